@@ -1,0 +1,216 @@
+"""Reader / writer for plan files (include/chiml_plan.h): the flattened per-rank output of the
+propagator constructor -- update lists, pole constants, CPML lists, sources, detectors -- i.e.
+exactly what the C ABI in include/chiml_gpu.h consumes.
+
+The record layouts mirror the reference's own PODs:
+  ChimlRun        == std::pair<std::array<int,6>, std::array<double,4>>  (reference UTIL/typedefs.hpp:14)
+  ChimlPsiParams  == updatePsiParams   (reference PML/parallelPML.hpp:18-26)
+  ChimlGridParams == updateGridParams  (reference PML/parallelPML.hpp:30-38)
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+PLAN_VERSION = 1
+
+MODE_TE, MODE_TM, MODE_3D = 0, 1, 2
+LIST_U, LIST_D, LIST_LORD, LIST_ORDIPD, LIST_ORDIPP = 0, 1, 2, 3, 4
+FIELD_NAMES = ["Ex", "Ey", "Ez", "Hx", "Hy", "Hz", "Dx", "Dy", "Dz"]
+
+RUN_DTYPE = np.dtype([("n", "<i4"), ("ind", "<i4"), ("ind_i", "<i4"), ("ind_j", "<i4"), ("ind_k", "<i4"),
+                      ("obj", "<i4"), ("pf", "<f8", (4,))])
+PSI_DTYPE = np.dtype([("transSz", "<i4"), ("stride", "<i4"), ("ind", "<i4"), ("indOff", "<i4"),
+                      ("b", "<f8"), ("c", "<f8")])
+GRIDP_DTYPE = np.dtype([("nAx", "<i4"), ("stride", "<i4"), ("ind", "<i4"), ("indOff", "<i4"),
+                        ("Db", "<f8"), ("DbField", "<f8")])
+assert RUN_DTYPE.itemsize == 56 and PSI_DTYPE.itemsize == 32 and GRIDP_DTYPE.itemsize == 32
+
+_GRID_FMT = "<i3i3dd5i4x" + "i3iiiiid"   # ChimlGridDesc (natural alignment, 72 bytes) + packed ChimlPlanGrid tail
+_GRID_SIZE = struct.calcsize(_GRID_FMT)
+
+
+@dataclass
+class PlanObject:
+    obj: int
+    npoles: int
+    use_or_dip: int
+    ml: int
+    eps_inf: float
+    mu_inf: float
+    alpha: np.ndarray
+    xi: np.ndarray
+    gamma: np.ndarray
+    dip: np.ndarray  # (npoles, 3)
+
+
+@dataclass
+class PlanCpml:
+    comp: int
+    part: int
+    has_psi: int
+    psi: np.ndarray
+    grid: np.ndarray
+
+
+@dataclass
+class PlanSource:
+    field: int
+    loc: Tuple[int, int, int]
+    sz: Tuple[int, int, int]
+    amp: np.ndarray
+
+
+@dataclass
+class PlanDetector:
+    detector: int
+    field: int
+    loc: Tuple[int, int, int]     # global coordinates of the stored (grown) box
+    sz: Tuple[int, int, int]
+    offset: Tuple[int, int, int]
+    every: int
+    type: int
+    conv: float
+    t_conv: float
+
+
+@dataclass
+class Plan:
+    mode: int = MODE_3D
+    ln: Tuple[int, int, int] = (0, 0, 0)
+    d: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    dt: float = 0.0
+    has_D: int = 0
+    pml_on_D: int = 0
+    n_objects: int = 1
+    rank: int = 0
+    nranks: int = 1
+    y_start: int = 0
+    n_global: Tuple[int, int, int] = (0, 0, 0)
+    n_steps: int = 0
+    n_lor_poles: int = 0
+    n_ordip_poles: int = 0
+    t_max: float = 0.0
+    lists: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)   # (kind, comp) -> RUN_DTYPE array
+    objects: List[PlanObject] = field(default_factory=list)
+    cpml: List[PlanCpml] = field(default_factory=list)
+    sources: List[PlanSource] = field(default_factory=list)
+    detectors: List[PlanDetector] = field(default_factory=list)
+
+    @property
+    def ncell(self) -> int:
+        return self.ln[0] * self.ln[1] * self.ln[2]
+
+    def fields_present(self) -> List[int]:
+        """E/H(/D) components that exist in this mode (parallelFDTDField.hpp:391-443)."""
+        if self.mode == MODE_TE:
+            f = [0, 1, 5]
+        elif self.mode == MODE_TM:
+            f = [2, 3, 4]
+        else:
+            f = [0, 1, 2, 3, 4, 5]
+        if self.has_D:
+            f += [6 + c for c in f if c < 3]
+        return f
+
+    def get_list(self, kind: int, comp: int) -> np.ndarray:
+        return self.lists.get((kind, comp), np.zeros(0, dtype=RUN_DTYPE))
+
+
+def read_plan(path: str) -> Plan:
+    data = open(path, "rb").read()
+    pos = 0
+    plan = Plan()
+    first = True
+    while pos < len(data):
+        tag = data[pos:pos + 8].decode("ascii").strip()
+        (nbytes,) = struct.unpack_from("<Q", data, pos + 8)
+        payload = data[pos + 16:pos + 16 + nbytes]
+        pos += 16 + nbytes
+        if first:
+            if tag != "CHIMLPLN":
+                raise ValueError(f"{path}: not a plan file")
+            (ver,) = struct.unpack_from("<i", payload, 0)
+            if ver != PLAN_VERSION:
+                raise ValueError(f"{path}: plan version {ver} != {PLAN_VERSION}")
+            first = False
+            continue
+        if tag == "GRID":
+            v = struct.unpack_from(_GRID_FMT, payload, 0)
+            plan.mode = v[0]; plan.ln = tuple(v[1:4]); plan.d = tuple(v[4:7]); plan.dt = v[7]
+            plan.has_D, plan.pml_on_D, plan.n_objects, plan.rank, plan.nranks = v[8:13]
+            plan.y_start = v[13]; plan.n_global = tuple(v[14:17]); plan.n_steps = v[17]
+            plan.n_lor_poles = v[18]; plan.n_ordip_poles = v[19]; plan.t_max = v[21]
+        elif tag == "UPLIST":
+            kind, comp, n = struct.unpack_from("<iiQ", payload, 0)
+            plan.lists[(kind, comp)] = np.frombuffer(payload, dtype=RUN_DTYPE, count=n, offset=16).copy()
+        elif tag == "OBJECT":
+            obj, npoles, use_or_dip, ml, eps_inf, mu_inf = struct.unpack_from("<iiiidd", payload, 0)
+            off = 32
+            arrs = []
+            for _ in range(3):
+                arrs.append(np.frombuffer(payload, dtype="<f8", count=npoles, offset=off).copy()); off += 8 * npoles
+            dip = np.frombuffer(payload, dtype="<f8", count=3 * npoles, offset=off).copy().reshape(npoles, 3)
+            plan.objects.append(PlanObject(obj, npoles, use_or_dip, ml, eps_inf, mu_inf, arrs[0], arrs[1], arrs[2], dip))
+        elif tag == "CPML":
+            comp, part, has_psi, _pad, npsi, ngrid = struct.unpack_from("<iiiiQQ", payload, 0)
+            psi = np.frombuffer(payload, dtype=PSI_DTYPE, count=npsi, offset=32).copy()
+            grid = np.frombuffer(payload, dtype=GRIDP_DTYPE, count=ngrid, offset=32 + 32 * npsi).copy()
+            plan.cpml.append(PlanCpml(comp, part, has_psi, psi, grid))
+        elif tag == "SOURCE":
+            v = struct.unpack_from("<i3i3ii", payload, 0)
+            amp = np.frombuffer(payload, dtype="<f8", count=v[7], offset=32).copy()
+            plan.sources.append(PlanSource(v[0], tuple(v[1:4]), tuple(v[4:7]), amp))
+        elif tag == "DETECTOR":
+            v = struct.unpack_from("<ii3i3i3iiiidd", payload, 0)
+            plan.detectors.append(PlanDetector(v[0], v[1], tuple(v[2:5]), tuple(v[5:8]), tuple(v[8:11]), v[11], v[12], v[14], v[15]))
+    return plan
+
+
+def _rec(tag: str, payload: bytes) -> bytes:
+    return tag.ljust(8).encode("ascii") + struct.pack("<Q", len(payload)) + payload
+
+
+def write_plan(path: str, plan: Plan) -> None:
+    out = [_rec("CHIMLPLN", struct.pack("<i", PLAN_VERSION))]
+    out.append(_rec("GRID", struct.pack(_GRID_FMT, plan.mode, *plan.ln, *plan.d, plan.dt, plan.has_D, plan.pml_on_D,
+                                        plan.n_objects, plan.rank, plan.nranks, plan.y_start, *plan.n_global,
+                                        plan.n_steps, plan.n_lor_poles, plan.n_ordip_poles, 0, plan.t_max)))
+    for (kind, comp), runs in sorted(plan.lists.items()):
+        runs = np.ascontiguousarray(runs, dtype=RUN_DTYPE)
+        out.append(_rec("UPLIST", struct.pack("<iiQ", kind, comp, len(runs)) + runs.tobytes()))
+    for o in plan.objects:
+        out.append(_rec("OBJECT", struct.pack("<iiiidd", o.obj, o.npoles, o.use_or_dip, o.ml, o.eps_inf, o.mu_inf)
+                        + np.asarray(o.alpha, "<f8").tobytes() + np.asarray(o.xi, "<f8").tobytes()
+                        + np.asarray(o.gamma, "<f8").tobytes() + np.asarray(o.dip, "<f8").tobytes()))
+    for c in plan.cpml:
+        out.append(_rec("CPML", struct.pack("<iiiiQQ", c.comp, c.part, c.has_psi, 0, len(c.psi), len(c.grid))
+                        + np.ascontiguousarray(c.psi, PSI_DTYPE).tobytes() + np.ascontiguousarray(c.grid, GRIDP_DTYPE).tobytes()))
+    for s in plan.sources:
+        out.append(_rec("SOURCE", struct.pack("<i3i3ii", s.field, *s.loc, *s.sz, len(s.amp)) + np.asarray(s.amp, "<f8").tobytes()))
+    for d in plan.detectors:
+        out.append(_rec("DETECTOR", struct.pack("<ii3i3i3iiiidd", d.detector, d.field, *d.loc, *d.sz, *d.offset, d.every, d.type, 0,
+                                                d.conv, d.t_conv)))
+    with open(path, "wb") as f:
+        f.write(b"".join(out))
+
+
+def read_dump(path: str) -> Dict[Tuple[int, str], Tuple[Tuple[int, int, int], int, np.ndarray]]:
+    """Field dump written by oracle/ref_driver.cpp --dump: {(rank, name): (ln, y_start, array[y][z][x])}."""
+    data = open(path, "rb").read()
+    if data[:8] != b"CHIMLDMP":
+        raise ValueError(f"{path}: not a field dump")
+    pos = 12
+    out = {}
+    while pos < len(data):
+        rank = struct.unpack_from("<i", data, pos)[0]
+        name = data[pos + 4:pos + 20].split(b"\0")[0].decode()
+        lnx, lny, lnz, ys = struct.unpack_from("<4i", data, pos + 20)
+        n = lnx * lny * lnz
+        arr = np.frombuffer(data, dtype="<f8", count=n, offset=pos + 36).copy().reshape(lny, lnz, lnx)
+        out[(rank, name)] = ((lnx, lny, lnz), ys, arr)
+        pos += 36 + 8 * n
+    return out

@@ -1,0 +1,155 @@
+/* chiml_gpu.h -- C ABI of the B200 (sm_100a) time-stepping engine for chiML's FDTD hot path.
+ *
+ * This is the drop-in boundary: a maintainer of the reference replaces the body of
+ * parallelFDTDFieldBase<double>::step() (reference src/FDTD_MANAGER/parallelFDTDField.hpp:1228-1303)
+ * by calls into this library, handing over the data structures the reference constructor has
+ * already built -- its run-length "update lists", CPML parameter lists, per-object pole constants,
+ * source boxes and detector boxes -- unchanged.  Plain C types only; no exceptions cross the
+ * boundary: every function returns 0 on success or a non-zero ChimlStatus, and
+ * chiml_gpu_last_error() returns the message of the last failure on that context.
+ *
+ * Index space.  Every `ind` below is the reference's own local linear index
+ *     ind = x + ln[0] * ( z + ln[2] * y )           (GRID/parallelGrid.hpp:363,563)
+ * over the ghost-inclusive local extents ln = (nx+2, ny_loc+2, nz+2) (2-D: ln[2] = 1).  The device
+ * stores rows padded to 128 bytes; that is invisible here.
+ *
+ * Threading: one host thread per context; contexts are independent.  All device work of a context
+ * runs on streams it owns; calls are asynchronous unless stated otherwise.
+ */
+#ifndef CHIML_GPU_H
+#define CHIML_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ChimlCtx ChimlCtx;
+
+typedef enum ChimlStatus
+{
+    CHIML_OK = 0,
+    CHIML_ERR_ARG = 1,         /* bad argument / inconsistent list */
+    CHIML_ERR_CUDA = 2,        /* CUDA runtime error (message in chiml_gpu_last_error) */
+    CHIML_ERR_UNSUPPORTED = 3, /* list describes something outside the supported hot path */
+    CHIML_ERR_STATE = 4,       /* call order (e.g. step before commit) */
+    CHIML_ERR_NO_DEVICE = 5    /* no CUDA device: there is deliberately no CPU fallback */
+} ChimlStatus;
+
+/* field components, in the reference's order E_[0..2], H_[0..2], D_[0..2] (parallelFDTDField.hpp:173-176) */
+typedef enum ChimlField
+{
+    CHIML_EX = 0, CHIML_EY = 1, CHIML_EZ = 2,
+    CHIML_HX = 3, CHIML_HY = 4, CHIML_HZ = 5,
+    CHIML_DX = 6, CHIML_DY = 7, CHIML_DZ = 8,
+    CHIML_NFIELDS = 9
+} ChimlField;
+
+/* CompCell.pol / size_z selection of parallelFDTDField.hpp:391,418 */
+typedef enum ChimlMode { CHIML_MODE_TE = 0 /* Ex,Ey,Hz */, CHIML_MODE_TM = 1 /* Ez,Hx,Hy */, CHIML_MODE_3D = 2 } ChimlMode;
+
+typedef struct ChimlGridDesc
+{
+    int32_t mode;       /* ChimlMode */
+    int32_t ln[3];      /* ghost-inclusive local extents (parallelGrid::ln_vec_) */
+    double  d[3];       /* grid spacing d_ */
+    double  dt;         /* time step dt_ */
+    int32_t has_D;      /* D_ grids exist ("disp", parallelFDTDField.hpp:375-402) */
+    int32_t pml_on_D;   /* dielectricMatInPML_: the E-side CPML acts on D (parallelFDTDField.cpp:68-77) */
+    int32_t n_objects;  /* objArr_.size() (object 0 is the vacuum background) */
+    int32_t rank;       /* y-slab index of this context (mpiInterface::rank) */
+    int32_t nranks;     /* number of y-slabs */
+} ChimlGridDesc;
+
+/* One x-contiguous run: layout-identical to the reference's
+ * std::pair<std::array<int,6>, std::array<double,4>> (UTIL/typedefs.hpp:14,
+ * filled by populateUpLists, parallelFDTDField.hpp:628-649):
+ *   {n, ind, ind_i, ind_j, ind_k, obj}  {1.0, -dt/(eps d_j), -dt/(eps d_k), eps}          */
+typedef struct ChimlRun
+{
+    int32_t n, ind, ind_i, ind_j, ind_k, obj;
+    double  pf[4];
+} ChimlRun;
+
+/* layout-identical to updatePsiParams / updateGridParams (PML/parallelPML.hpp:18-38) */
+typedef struct ChimlPsiParams  { int32_t transSz, stride, ind, indOff; double b, c; } ChimlPsiParams;
+typedef struct ChimlGridParams { int32_t nAx, stride, ind, indOff; double Db, DbField; } ChimlGridParams;
+
+typedef enum ChimlListKind
+{
+    CHIML_LIST_U      = 0, /* upE_[c] / upH_[c]: direct curl update                 (updateE/updateH :1308-1323) */
+    CHIML_LIST_D      = 1, /* upD_[c]: curl accumulated into D                       (updateD :1338-1343)        */
+    CHIML_LIST_LORD   = 2, /* upLorD_[c]: isotropic pole update + D->E               (updatePolE :1355-1361, D2E :1456-1459) */
+    CHIML_LIST_ORDIPD = 3, /* upOrDipD_[c]: oriented-dipole D->E (node->edge average) (D2E :1465-1466)            */
+    CHIML_LIST_ORDIPP = 4  /* upOrDipP_: oriented-dipole pole update at nodes; comp ignored (updatePolE :1350-1354) */
+} ChimlListKind;
+
+/* ---- life cycle ------------------------------------------------------------------------------ */
+int  chiml_gpu_device_count(void);
+int  chiml_gpu_create(const ChimlGridDesc* desc, int device, ChimlCtx** out);
+void chiml_gpu_destroy(ChimlCtx* ctx);
+const char* chiml_gpu_last_error(const ChimlCtx* ctx); /* ctx may be NULL: last create() failure */
+
+/* ---- setup (before commit) -------------------------------------------------------------------- */
+/* comp: 0..2 = Ex,Ey,Ez   3..5 = Hx,Hy,Hz */
+int chiml_gpu_set_update_list(ChimlCtx* ctx, int kind, int comp, const ChimlRun* runs, size_t n);
+
+/* Pole constants of object `obj`: Obj::alpha()/xi()/gamma() after setUpConsts(dt) (OBJECTS/Obj.cpp:299-371).
+ * dip: 3*npoles doubles (x,y,z per pole) for oriented-dipole objects with a position-independent
+ * dipole direction (ISOTROPIC -> 1,1,1; UNIDIRECTIONAL -> dipE; parallelFDTDField.hpp:998-1020), or NULL. */
+int chiml_gpu_set_object(ChimlCtx* ctx, int obj, int npoles, const double* alpha, const double* xi, const double* gamma,
+                         int use_or_dip, const double* dip);
+
+/* One half of parallelCPML<T>::updateGrid() (PML/parallelPML.hpp:693-697) for component comp:
+ *   part 0 = addGrid_j_(updateListGrid_k_, updateListPsi_j_, grid_i, psi_j, grid_k)
+ *   part 1 = addGrid_k_(updateListGrid_j_, updateListPsi_k_, grid_i, psi_k, grid_j)
+ * has_psi = 0 selects pmlUpdateFxnReal::addGridOnly (PML/parallelPML.cpp:23-30). */
+int chiml_gpu_set_cpml(ChimlCtx* ctx, int comp, int part, int has_psi,
+                       const ChimlPsiParams* psi, size_t npsi, const ChimlGridParams* grid, size_t ngrid);
+
+/* Soft source box in local ghost-inclusive coordinates (SalveSource of SOURCE/parallelSource.hpp,
+ * built by genDatStruct, parallelSourceNormal.hpp:100): field[box] += amp each step, where the host
+ * passes amp = dt * Re(sum_p pulse_p(t)) (parallelSourceNormal.cpp:15-37).  Returns the source slot. */
+int chiml_gpu_add_source(ChimlCtx* ctx, int field, const int32_t loc[3], const int32_t sz[3], int* slot);
+
+/* Time-domain detector sampling (DTC/parallelStorageDTC.cpp:17-44): every `every` steps after the
+ * step, and once at commit time (t = 0, parallelFDTDField.cpp:832-833), the raw values of `field`
+ * in the box loc..loc+sz (local ghost-inclusive coordinates) are appended to a device ring that
+ * chiml_gpu_read_detector drains.  The Yee-offset averaging and SI factors stay on the host. */
+int chiml_gpu_add_detector(ChimlCtx* ctx, int field, const int32_t loc[3], const int32_t sz[3], int every, int* slot);
+
+/* Freeze the setup: paints the per-cell update maps from the lists, builds the CPML coefficient
+ * tables and compact psi / polarisation pools, zeroes all state. */
+int chiml_gpu_commit(ChimlCtx* ctx);
+
+/* ---- stepping ---------------------------------------------------------------------------------- */
+/* n leap-frog steps in the reference's order (step(), :1228-1303).  src_amp: n * n_sources doubles,
+ * step-major (may be NULL when there are no sources). */
+int chiml_gpu_step_n(ChimlCtx* ctx, int n, const double* src_amp);
+int chiml_gpu_sync(ChimlCtx* ctx);
+/* same as step_n but bracketed by CUDA events on the context's stream; returns device milliseconds */
+int chiml_gpu_step_n_timed(ChimlCtx* ctx, int n, const double* src_amp, float* ms);
+/* number of kernels this context has launched since creation */
+int64_t chiml_gpu_launch_count(const ChimlCtx* ctx);
+
+/* ---- state access (synchronous) ---------------------------------------------------------------- */
+/* host buffers use the reference's logical layout, ln[0]*ln[1]*ln[2] doubles, ghosts included */
+int chiml_gpu_upload_field(ChimlCtx* ctx, int field, const double* host);
+int chiml_gpu_download_field(ChimlCtx* ctx, int field, double* host);
+/* isotropic pole state lorP_[c][p] / prevLorP_[c][p] expanded to the logical full grid (zeros elsewhere) */
+int chiml_gpu_download_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host);
+int chiml_gpu_upload_pole(ChimlCtx* ctx, int comp, int pole, int prev, const double* host);
+/* CPML psi of component comp, part 0/1, expanded to the logical full grid */
+int chiml_gpu_download_psi(ChimlCtx* ctx, int comp, int part, double* host);
+/* copies up to cap samples (each sz[0]*sz[1]*sz[2] doubles, x fastest then z then y) and reports how many exist */
+int chiml_gpu_read_detector(ChimlCtx* ctx, int slot, double* out, size_t cap_samples, size_t* n_samples);
+
+/* bytes of device memory held by the context */
+size_t chiml_gpu_device_bytes(const ChimlCtx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHIML_GPU_H */

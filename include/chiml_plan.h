@@ -1,0 +1,73 @@
+/* chiml_plan.h -- on-disk form of everything the C ABI in chiml_gpu.h consumes ("plan file").
+ *
+ * A plan is the flattened output of the propagator constructor for ONE y-slab (rank): grid
+ * description, update lists, object pole constants, CPML lists, source boxes with their per-step
+ * amplitudes, detector boxes.  It is written by the host side of this repository
+ * (chiml_b200/host, `chiml --dump-plan`) and -- for parity tests -- by oracle/ref_driver.cpp from the
+ * internals of the unmodified reference, so the two can be compared list by list.
+ *
+ * File = sequence of records, little endian:  char tag[8] | uint64 nbytes | payload[nbytes]
+ * The first record is CHIMLPLN (payload: int32 version).  Unknown tags are skipped by readers.
+ */
+#ifndef CHIML_PLAN_H
+#define CHIML_PLAN_H
+
+#include "chiml_gpu.h"
+
+#define CHIML_PLAN_VERSION 1
+
+#pragma pack(push, 1)
+typedef struct ChimlPlanGrid          /* tag "GRID    " */
+{
+    ChimlGridDesc desc;
+    int32_t y_start;      /* parallelGrid::procLoc(1): global row of local row 1 */
+    int32_t n_global[3];  /* n_vec_ (points per direction, no ghosts) */
+    int32_t n_steps;      /* ceil(tMax/dt) (main.cpp:54) */
+    int32_t n_lor_poles;  /* max over components of lorP_[c].size() */
+    int32_t n_ordip_poles;/* max over components of orDipLorP_[c].size() */
+    int32_t pad;
+    double  t_max;
+} ChimlPlanGrid;
+
+typedef struct ChimlPlanListHdr       /* tag "UPLIST  ": header + n * ChimlRun */
+{
+    int32_t kind, comp;
+    uint64_t n;
+} ChimlPlanListHdr;
+
+typedef struct ChimlPlanObjectHdr     /* tag "OBJECT  ": header + alpha[np] xi[np] gamma[np] dip[3 np] */
+{
+    int32_t obj, npoles, use_or_dip, ml;
+    double  eps_inf, mu_inf;
+} ChimlPlanObjectHdr;
+
+typedef struct ChimlPlanCpmlHdr       /* tag "CPML    ": header + npsi * ChimlPsiParams + ngrid * ChimlGridParams */
+{
+    int32_t comp, part, has_psi, pad;
+    uint64_t npsi, ngrid;
+} ChimlPlanCpmlHdr;
+
+typedef struct ChimlPlanSourceHdr     /* tag "SOURCE  ": header + n_steps amplitudes (dt * Re sum pulse(t_k)) */
+{
+    int32_t field;
+    int32_t loc[3];
+    int32_t sz[3];
+    int32_t n_steps;
+} ChimlPlanSourceHdr;
+
+typedef struct ChimlPlanDetector      /* tag "DETECTOR": one stored field box of a time-domain detector */
+{
+    int32_t detector;     /* index into dtcArr_ */
+    int32_t field;
+    int32_t loc[3];       /* GLOBAL grid coordinates (no ghosts) of the stored box */
+    int32_t sz[3];        /* already grown by the Yee offset (parallelStorageDTC.hpp:62-63) */
+    int32_t offset[3];
+    int32_t every;        /* timeInterval_ in steps */
+    int32_t type;         /* DTCTYPE as int */
+    int32_t pad;
+    double  conv;         /* convFactor_ */
+    double  t_conv;       /* tConv_ */
+} ChimlPlanDetector;
+#pragma pack(pop)
+
+#endif /* CHIML_PLAN_H */

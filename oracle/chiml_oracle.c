@@ -1,0 +1,479 @@
+/* TEST INFRASTRUCTURE ONLY -- see chiml_oracle.h.  CPU restatement of the reference hot path.
+ * Build: gcc -std=c99 -O2 -ffp-contract=off (oracle/Makefile).  All `file:line` citations are
+ * relative to the reference tree (/root/reference/src). */
+#define _POSIX_C_SOURCE 200809L
+#include "chiml_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define MAX_POLES 16
+#define MAX_SRC 64
+
+typedef struct { ChimlRun* r; size_t n; } RunList;
+typedef struct { int has_psi, present; ChimlPsiParams* psi; size_t npsi; ChimlGridParams* grid; size_t ngrid; double* psi_grid; } CpmlPart;
+typedef struct { int npoles, use_or_dip; double alpha[MAX_POLES], xi[MAX_POLES], gamma[MAX_POLES], dip[MAX_POLES][3]; } ObjConst;
+typedef struct { int field; int32_t loc[3], sz[3]; } SrcBox;
+
+struct OracleSim
+{
+    ChimlGridDesc g;
+    size_t ncell;
+    double* f[CHIML_NFIELDS];
+    RunList up[5][6];              /* [kind][comp] */
+    CpmlPart pml[6][2];
+    ObjConst* obj;
+    int npoles;                    /* number of allocated isotropic pole grids = max over objects (lorP_[c].size()) */
+    int nordip;                    /* number of allocated oriented-dipole pole grids */
+    double* P[3][MAX_POLES];       /* lorP_[c][p] */
+    double* Pprev[3][MAX_POLES];   /* prevLorP_[c][p] */
+    double* oP[3][MAX_POLES];      /* orDipLorP_[c][p] */
+    double* oPprev[3][MAX_POLES];  /* prevOrDipLorP_[c][p] */
+    double* dipgrid[3][MAX_POLES]; /* dipP_[c][p] (static) */
+    SrcBox src[MAX_SRC];
+    int nsrc;
+    int committed;
+    /* threading */
+    int nthreads;
+    pthread_barrier_t bar;
+    const double* src_amp;
+    int nsteps;
+};
+
+static int comp_exists(const OracleSim* s, int field)
+{
+    int c = field % 3, isH = (field >= 3 && field < 6);
+    if(field >= 6 && !s->g.has_D) return 0;
+    if(s->g.mode == CHIML_MODE_3D) return 1;
+    if(s->g.mode == CHIML_MODE_TE) return isH ? (c == 2) : (c != 2);   /* Ex,Ey,Hz (parallelFDTDField.hpp:391-396) */
+    return isH ? (c != 2) : (c == 2);                                    /* Ez,Hx,Hy (:418-423) */
+}
+
+OracleSim* oracle_create(const ChimlGridDesc* desc)
+{
+    OracleSim* s = (OracleSim*)calloc(1, sizeof(OracleSim));
+    if(!s) return NULL;
+    s->g = *desc;
+    s->ncell = (size_t)desc->ln[0] * (size_t)desc->ln[1] * (size_t)desc->ln[2];
+    s->obj = (ObjConst*)calloc((size_t)(desc->n_objects > 0 ? desc->n_objects : 1), sizeof(ObjConst));
+    for(int fld = 0; fld < CHIML_NFIELDS; ++fld)
+        if(comp_exists(s, fld)) s->f[fld] = (double*)calloc(s->ncell, sizeof(double));
+    return s;
+}
+
+void oracle_destroy(OracleSim* s)
+{
+    if(!s) return;
+    for(int i = 0; i < CHIML_NFIELDS; ++i) free(s->f[i]);
+    for(int k = 0; k < 5; ++k) for(int c = 0; c < 6; ++c) free(s->up[k][c].r);
+    for(int c = 0; c < 6; ++c) for(int p = 0; p < 2; ++p) { free(s->pml[c][p].psi); free(s->pml[c][p].grid); free(s->pml[c][p].psi_grid); }
+    for(int c = 0; c < 3; ++c) for(int p = 0; p < MAX_POLES; ++p) { free(s->P[c][p]); free(s->Pprev[c][p]); free(s->oP[c][p]); free(s->oPprev[c][p]); free(s->dipgrid[c][p]); }
+    free(s->obj);
+    free(s);
+}
+
+int oracle_set_update_list(OracleSim* s, int kind, int comp, const ChimlRun* runs, size_t n)
+{
+    if(kind < 0 || kind > 4 || comp < 0 || comp > 5) return CHIML_ERR_ARG;
+    RunList* l = &s->up[kind][comp];
+    free(l->r);
+    l->r = (ChimlRun*)malloc((n ? n : 1) * sizeof(ChimlRun));
+    if(n) memcpy(l->r, runs, n * sizeof(ChimlRun));
+    l->n = n;
+    return 0;
+}
+
+int oracle_set_object(OracleSim* s, int obj, int npoles, const double* alpha, const double* xi, const double* gamma, int use_or_dip, const double* dip)
+{
+    if(obj < 0 || obj >= s->g.n_objects || npoles < 0 || npoles > MAX_POLES) return CHIML_ERR_ARG;
+    ObjConst* o = &s->obj[obj];
+    o->npoles = npoles;
+    o->use_or_dip = use_or_dip;
+    for(int p = 0; p < npoles; ++p)
+    {
+        o->alpha[p] = alpha[p]; o->xi[p] = xi[p]; o->gamma[p] = gamma[p];
+        for(int k = 0; k < 3; ++k) o->dip[p][k] = dip ? dip[3 * p + k] : 0.0;
+    }
+    return 0;
+}
+
+int oracle_set_cpml(OracleSim* s, int comp, int part, int has_psi, const ChimlPsiParams* psi, size_t npsi, const ChimlGridParams* grid, size_t ngrid)
+{
+    if(comp < 0 || comp > 5 || part < 0 || part > 1) return CHIML_ERR_ARG;
+    CpmlPart* p = &s->pml[comp][part];
+    free(p->psi); free(p->grid);
+    p->psi = (ChimlPsiParams*)malloc((npsi ? npsi : 1) * sizeof(ChimlPsiParams));
+    p->grid = (ChimlGridParams*)malloc((ngrid ? ngrid : 1) * sizeof(ChimlGridParams));
+    if(npsi) memcpy(p->psi, psi, npsi * sizeof(ChimlPsiParams));
+    if(ngrid) memcpy(p->grid, grid, ngrid * sizeof(ChimlGridParams));
+    p->npsi = npsi; p->ngrid = ngrid; p->has_psi = has_psi; p->present = 1;
+    return 0;
+}
+
+int oracle_add_source(OracleSim* s, int field, const int32_t loc[3], const int32_t sz[3])
+{
+    if(s->nsrc >= MAX_SRC || field < 0 || field >= CHIML_NFIELDS || !s->f[field]) return CHIML_ERR_ARG;
+    SrcBox* b = &s->src[s->nsrc++];
+    b->field = field;
+    for(int k = 0; k < 3; ++k) { b->loc[k] = loc[k]; b->sz[k] = sz[k]; }
+    return 0;
+}
+
+/* Grid allocation mirrors the constructor: one P / prevP grid per pole index up to the largest pole
+ * count of any object (parallelFDTDField.hpp:448-479), oriented-dipole grids likewise (:498-545), and
+ * full-size psi grids (PML/parallelPML.hpp:143-156).  dipP_ grids: setupDipMoments (:960-1023) for
+ * ISOTROPIC / UNIDIRECTIONAL orientations, evaluated from the node-centred object map which is
+ * recovered here from the oriented-dipole node list (cells outside it are never read). */
+int oracle_commit(OracleSim* s)
+{
+    s->npoles = 0; s->nordip = 0;
+    for(int o = 0; o < s->g.n_objects; ++o)
+    {
+        if(s->obj[o].npoles > s->npoles) s->npoles = s->obj[o].npoles;
+        if(s->obj[o].use_or_dip && s->obj[o].npoles > s->nordip) s->nordip = s->obj[o].npoles;
+    }
+    for(int c = 0; c < 3; ++c)
+    {
+        if(!s->f[CHIML_DX + c]) continue;
+        for(int p = 0; p < s->npoles; ++p)
+        {
+            s->P[c][p] = (double*)calloc(s->ncell, sizeof(double));
+            s->Pprev[c][p] = (double*)calloc(s->ncell, sizeof(double));
+        }
+        for(int p = 0; p < s->nordip; ++p)
+        {
+            s->oP[c][p] = (double*)calloc(s->ncell, sizeof(double));
+            s->oPprev[c][p] = (double*)calloc(s->ncell, sizeof(double));
+            s->dipgrid[c][p] = (double*)calloc(s->ncell, sizeof(double));
+        }
+    }
+    const RunList* nl = &s->up[CHIML_LIST_ORDIPP][0];
+    for(size_t e = 0; e < nl->n; ++e)
+    {
+        const ChimlRun* r = &nl->r[e];
+        const ObjConst* o = &s->obj[r->obj];
+        for(int c = 0; c < 3; ++c)
+            for(int p = 0; p < o->npoles && p < s->nordip; ++p)
+                if(s->dipgrid[c][p])
+                    for(int i = 0; i < r->n; ++i) s->dipgrid[c][p][r->ind + i] = o->dip[p][c];
+    }
+    for(int c = 0; c < 6; ++c)
+        for(int p = 0; p < 2; ++p)
+            if(s->pml[c][p].present && s->pml[c][p].has_psi)
+                s->pml[c][p].psi_grid = (double*)calloc(s->ncell, sizeof(double));
+    s->committed = 1;
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * BLAS level-1 restated (reference semantics: UTIL/utilities_MKL.hpp wrappers over daxpy_/dscal_/dcopy_)
+ * ------------------------------------------------------------------------------------------- */
+static inline void axpy(int n, double a, const double* x, int incx, double* y, int incy)
+{ for(int i = 0; i < n; ++i) y[(size_t)i * incy] = y[(size_t)i * incy] + a * x[(size_t)i * incx]; }
+static inline void scal(int n, double a, double* x, int incx)
+{ for(int i = 0; i < n; ++i) x[(size_t)i * incx] = a * x[(size_t)i * incx]; }
+
+/* UTIL/FDTD_up_eq.cpp:10-35 (OneCompCurlJ, OneCompCurlK, TwoCompCurl): the variant is selected by which
+ * neighbour grids exist, as the constructor does (FDTD_MANAGER/parallelFDTDField.cpp:94-105,263-274). */
+static void curl_run(const ChimlRun* r, double* Ui, const double* Vj, const double* Vk)
+{
+    if(Vj)
+    {
+        axpy(r->n,        r->pf[2], Vj + r->ind,   1, Ui + r->ind, 1);
+        axpy(r->n, -1.0 * r->pf[2], Vj + r->ind_k, 1, Ui + r->ind, 1);
+    }
+    if(Vk)
+    {
+        axpy(r->n, -1.0 * r->pf[1], Vk + r->ind,   1, Ui + r->ind, 1);
+        axpy(r->n,        r->pf[1], Vk + r->ind_j, 1, Ui + r->ind, 1);
+    }
+}
+
+/* UTIL/FDTD_up_eq.cpp:425-448 UpdateLorPol */
+static void lor_pol_run(const ChimlRun* r, const double* Ei, double** P, double** Pprev, const ObjConst* o, double* jstore)
+{
+    for(int pp = 0; pp < o->npoles; ++pp)
+    {
+        memcpy(jstore, P[pp] + r->ind, (size_t)r->n * sizeof(double));
+        scal(r->n, o->alpha[pp], P[pp] + r->ind, 1);
+        axpy(r->n, o->xi[pp], Pprev[pp] + r->ind, 1, P[pp] + r->ind, 1);
+        axpy(r->n, o->gamma[pp], Ei + r->ind, 1, P[pp] + r->ind, 1);
+        memcpy(Pprev[pp] + r->ind, jstore, (size_t)r->n * sizeof(double));
+    }
+}
+
+/* UTIL/FDTD_up_eq.cpp:450-631 UpdateLorPolOrDip / ...XY / ...Z; multAvg = x*y/2.0 (UTIL/utilityFxns.hpp:38).
+ * have[c] tells which E components exist (3-D: all; TE: x,y; TM: z). */
+static void lor_pol_ordip_run(const OracleSim* s, const ChimlRun* r, const ObjConst* o, double* scratch)
+{
+    const int n = r->n;
+    double* dotU = scratch;
+    double* dotF = scratch + n;
+    const int has_x = s->f[CHIML_EX] != NULL, has_z = s->f[CHIML_EZ] != NULL;
+    const int offs[3] = { r->ind_i, r->ind_j, r->ind_k };
+    for(int pp = 0; pp < o->npoles; ++pp)
+    {
+        double* jst[3] = { scratch + 2 * n, scratch + 3 * n, scratch + 4 * n };
+        for(int c = 0; c < 3; ++c)
+            if(s->f[c]) memcpy(jst[c], s->oP[c][pp] + r->ind, (size_t)n * sizeof(double));
+        for(int c = 0; c < 3; ++c)
+        {
+            if(!s->f[c]) continue;
+            scal(n, o->alpha[pp], s->oP[c][pp] + r->ind, 1);
+            axpy(n, o->xi[pp], s->oPprev[c][pp] + r->ind, 1, s->oP[c][pp] + r->ind, 1);
+        }
+        if(has_x)
+        {
+            /* 3-D (UpdateLorPolOrDip) or TE (UpdateLorPolOrDipXY): x and y (and z) contributions, in this order */
+            int first = 1;
+            for(int c = 0; c < 3; ++c)
+            {
+                if(!s->f[c]) continue;
+                const double* dip = s->dipgrid[c][pp] + r->ind;
+                const double* E0 = s->f[c] + r->ind;
+                const double* E1 = s->f[c] + offs[c];
+                if(first)
+                {
+                    for(int i = 0; i < n; ++i) dotU[i] = dip[i] * E0[i] / 2.0;
+                    for(int i = 0; i < n; ++i) dotF[i] = dip[i] * E1[i] / 2.0;
+                    axpy(n, 1.0, dotF, 1, dotU, 1);
+                    first = 0;
+                }
+                else
+                {
+                    for(int i = 0; i < n; ++i) dotF[i] = dip[i] * E0[i] / 2.0;
+                    axpy(n, 1.0, dotF, 1, dotU, 1);
+                    for(int i = 0; i < n; ++i) dotF[i] = dip[i] * E1[i] / 2.0;
+                    axpy(n, 1.0, dotF, 1, dotU, 1);
+                }
+            }
+            for(int c = 0; c < 3; ++c)
+            {
+                if(!s->f[c]) continue;
+                const double* dip = s->dipgrid[c][pp] + r->ind;
+                for(int i = 0; i < n; ++i) dotF[i] = dip[i] * dotU[i];
+                axpy(n, o->gamma[pp], dotF, 1, s->oP[c][pp] + r->ind, 1);
+            }
+        }
+        else if(has_z)
+        {
+            /* TM (UpdateLorPolOrDipZ :606-631): dotU = dip_z * Ez, P_z += gamma * dotU */
+            const double* dip = s->dipgrid[2][pp] + r->ind;
+            const double* E0 = s->f[CHIML_EZ] + r->ind;
+            for(int i = 0; i < n; ++i) dotU[i] = dip[i] * E0[i];
+            axpy(n, o->gamma[pp], dotU, 1, s->oP[2][pp] + r->ind, 1);
+        }
+        for(int c = 0; c < 3; ++c)
+            if(s->f[c]) memcpy(s->oPprev[c][pp] + r->ind, jst[c], (size_t)n * sizeof(double));
+    }
+}
+
+/* UTIL/FDTD_up_eq.cpp:838-848 DtoU: sums over ALL allocated pole grids */
+static void dtou_run(const ChimlRun* r, const double* Di, double* Ui, double** P, int nP)
+{
+    const double eps = r->pf[3];
+    memcpy(Ui + r->ind, Di + r->ind, (size_t)r->n * sizeof(double));
+    scal(r->n, 1.0 / eps, Ui + r->ind, 1);
+    for(int pp = 0; pp < nP; ++pp)
+        axpy(r->n, -1.0 / eps, P[pp] + r->ind, 1, Ui + r->ind, 1);
+}
+
+/* UTIL/FDTD_up_eq.cpp:862-889 orDipDtoU (node->edge average) and orDipDtoUZ (2-D TM Ez) */
+static void ordip_dtou_run(const ChimlRun* r, const double* Di, double* Ui, double** P, int nP, int zvariant)
+{
+    const double eps = r->pf[3];
+    memcpy(Ui + r->ind, Di + r->ind, (size_t)r->n * sizeof(double));
+    scal(r->n, 1.0 / eps, Ui + r->ind, 1);
+    for(int pp = 0; pp < nP; ++pp)
+    {
+        if(zvariant)
+            axpy(r->n, -1.0 / eps, P[pp] + r->ind, 1, Ui + r->ind, 1);
+        else
+        {
+            axpy(r->n, -0.5 / eps, P[pp] + r->ind,   1, Ui + r->ind, 1);
+            axpy(r->n, -0.5 / eps, P[pp] + r->ind_i, 1, Ui + r->ind, 1);
+        }
+    }
+}
+
+/* PML/parallelPML.cpp:32-40 updatePsiField */
+static void psi_entry(const ChimlPsiParams* p, double* psi, const double* V)
+{
+    scal(p->transSz,        p->b, psi + p->ind, p->stride);
+    axpy(p->transSz,        p->c, V + p->ind,    p->stride, psi + p->ind, p->stride);
+    axpy(p->transSz, -1.0 * p->c, V + p->indOff, p->stride, psi + p->ind, p->stride);
+}
+/* PML/parallelPML.cpp:12-30 addPsi / addGridOnly (the grid part) */
+static void pml_grid_entry(const ChimlGridParams* p, double* Ui, const double* psi, const double* V)
+{
+    axpy(p->nAx,        p->DbField, V + p->ind,    p->stride, Ui + p->ind, p->stride);
+    axpy(p->nAx, -1.0 * p->DbField, V + p->indOff, p->stride, Ui + p->ind, p->stride);
+    if(psi)
+        axpy(p->nAx, p->Db, psi + p->ind, p->stride, Ui + p->ind, p->stride);
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * step(): FDTD_MANAGER/parallelFDTDField.hpp:1228-1303, restricted to the lists covered here
+ * (no magnetic / chiral media, no TFSF).  Work inside each phase is split over threads by list
+ * entry; entries of one list write disjoint cells, and phases are separated by barriers.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { OracleSim* s; int tid; } Worker;
+
+#define SPLIT(n, lo, hi) size_t lo = (size_t)(n) * (size_t)tid / (size_t)nt, hi = (size_t)(n) * (size_t)(tid + 1) / (size_t)nt
+#define BARRIER() do { if(nt > 1) pthread_barrier_wait(&s->bar); } while(0)
+
+static void pml_component(OracleSim* s, int comp, double* target, int tid, int nt)
+{
+    /* parallelCPML<T>::updateGrid (PML/parallelPML.hpp:693-697): part 0 then part 1 */
+    const int isE = comp < 3;
+    const int i = comp % 3;
+    const int base = isE ? CHIML_HX : CHIML_EX;           /* the PML of an E component is driven by H and vice versa */
+    for(int part = 0; part < 2; ++part)
+    {
+        CpmlPart* p = &s->pml[comp][part];
+        if(!p->present) { continue; }
+        /* part 0: psi_j driven by grid_k; part 1: psi_k driven by grid_j (:695-696) */
+        const double* V = s->f[base + (part == 0 ? (i + 2) % 3 : (i + 1) % 3)];
+        if(!V) continue;
+        if(p->has_psi)
+        {
+            SPLIT(p->npsi, lo, hi);
+            for(size_t e = lo; e < hi; ++e) psi_entry(&p->psi[e], p->psi_grid, V);
+        }
+        BARRIER();
+        {
+            SPLIT(p->ngrid, lo, hi);
+            for(size_t e = lo; e < hi; ++e) pml_grid_entry(&p->grid[e], target, p->has_psi ? p->psi_grid : NULL, V);
+        }
+        BARRIER();
+    }
+}
+
+static void step_worker(OracleSim* s, int tid, int nt)
+{
+    const int lnx = s->g.ln[0], lnz = s->g.ln[2];
+    double* scratch = (double*)malloc((size_t)(6 * lnx + 8) * sizeof(double));
+    for(int step = 0; step < s->nsteps; ++step)
+    {
+        /* updateH (:1308-1313) */
+        for(int i = 0; i < 3; ++i)
+        {
+            double* H = s->f[CHIML_HX + i];
+            if(!H) continue;
+            RunList* l = &s->up[CHIML_LIST_U][3 + i];
+            SPLIT(l->n, lo, hi);
+            for(size_t e = lo; e < hi; ++e) curl_run(&l->r[e], H, s->f[CHIML_EX + (i + 1) % 3], s->f[CHIML_EX + (i + 2) % 3]);
+        }
+        BARRIER();
+        /* updateHPML_ (:1258-1259) */
+        for(int i = 0; i < 3; ++i)
+            if(s->f[CHIML_HX + i]) pml_component(s, 3 + i, s->f[CHIML_HX + i], tid, nt);
+        /* src->addPul (:1261-1262, SOURCE/parallelSourceNormal.cpp:15-37): grid[box] += dt*Re(pulse), amp precomputed */
+        if(tid == 0)
+        {
+            for(int q = 0; q < s->nsrc; ++q)
+            {
+                const SrcBox* b = &s->src[q];
+                const double amp = s->src_amp[(size_t)step * (size_t)s->nsrc + q];
+                double* G = s->f[b->field];
+                for(int y = 0; y < b->sz[1]; ++y)
+                    for(int z = 0; z < b->sz[2]; ++z)
+                        for(int x = 0; x < b->sz[0]; ++x)
+                        {
+                            size_t ind = (size_t)(b->loc[0] + x) + (size_t)lnx * ((size_t)(b->loc[2] + z) + (size_t)lnz * (size_t)(b->loc[1] + y));
+                            G[ind] = G[ind] + amp;
+                        }
+            }
+        }
+        BARRIER();
+        /* updatePolE (:1348-1365): oriented-dipole poles at nodes, then isotropic poles per component */
+        {
+            RunList* l = &s->up[CHIML_LIST_ORDIPP][0];
+            SPLIT(l->n, lo, hi);
+            for(size_t e = lo; e < hi; ++e) lor_pol_ordip_run(s, &l->r[e], &s->obj[l->r[e].obj], scratch);
+        }
+        for(int i = 0; i < 3; ++i)
+        {
+            if(!s->f[CHIML_EX + i] || !s->f[CHIML_DX + i]) continue;
+            RunList* l = &s->up[CHIML_LIST_LORD][i];
+            SPLIT(l->n, lo, hi);
+            for(size_t e = lo; e < hi; ++e) lor_pol_run(&l->r[e], s->f[CHIML_EX + i], s->P[i], s->Pprev[i], &s->obj[l->r[e].obj], scratch);
+        }
+        BARRIER();
+        /* updateD (:1338-1343) and updateE (:1318-1323) */
+        for(int i = 0; i < 3; ++i)
+        {
+            if(!s->f[CHIML_EX + i]) continue;
+            const double* Hj = s->f[CHIML_HX + (i + 1) % 3];
+            const double* Hk = s->f[CHIML_HX + (i + 2) % 3];
+            if(s->f[CHIML_DX + i])
+            {
+                RunList* l = &s->up[CHIML_LIST_D][i];
+                SPLIT(l->n, lo, hi);
+                for(size_t e = lo; e < hi; ++e) curl_run(&l->r[e], s->f[CHIML_DX + i], Hj, Hk);
+            }
+            RunList* l = &s->up[CHIML_LIST_U][i];
+            SPLIT(l->n, lo, hi);
+            for(size_t e = lo; e < hi; ++e) curl_run(&l->r[e], s->f[CHIML_EX + i], Hj, Hk);
+        }
+        BARRIER();
+        /* updateEPML_ (:1279-1280): acts on D when material reaches the PML (parallelFDTDField.cpp:68-77,239-246) */
+        for(int i = 0; i < 3; ++i)
+            if(s->f[CHIML_EX + i]) pml_component(s, i, s->g.pml_on_D ? s->f[CHIML_DX + i] : s->f[CHIML_EX + i], tid, nt);
+        /* D2E (:1452-1473) */
+        for(int i = 0; i < 3; ++i)
+        {
+            if(!s->f[CHIML_EX + i] || !s->f[CHIML_DX + i]) continue;
+            RunList* l = &s->up[CHIML_LIST_LORD][i];
+            {
+                SPLIT(l->n, lo, hi);
+                for(size_t e = lo; e < hi; ++e) dtou_run(&l->r[e], s->f[CHIML_DX + i], s->f[CHIML_EX + i], s->P[i], s->npoles);
+            }
+            l = &s->up[CHIML_LIST_ORDIPD][i];
+            {
+                /* orDipDtoUZ only for Ez without Hz (FDTD_MANAGER/parallelFDTDField.cpp:293-296) */
+                const int zvariant = (i == 2 && !s->f[CHIML_HZ]);
+                SPLIT(l->n, lo, hi);
+                for(size_t e = lo; e < hi; ++e) ordip_dtou_run(&l->r[e], s->f[CHIML_DX + i], s->f[CHIML_EX + i], s->oP[i], s->nordip, zvariant);
+            }
+        }
+        BARRIER();
+    }
+    free(scratch);
+}
+
+static void* thread_main(void* arg)
+{
+    Worker* w = (Worker*)arg;
+    step_worker(w->s, w->tid, w->s->nthreads);
+    return NULL;
+}
+
+int oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads)
+{
+    if(!s->committed) return CHIML_ERR_STATE;
+    if(nthreads < 1) nthreads = 1;
+    s->nthreads = nthreads;
+    s->src_amp = src_amp;
+    s->nsteps = n;
+    if(nthreads == 1)
+    {
+        step_worker(s, 0, 1);
+        return 0;
+    }
+    pthread_barrier_init(&s->bar, NULL, (unsigned)nthreads);
+    pthread_t* th = (pthread_t*)malloc((size_t)nthreads * sizeof(pthread_t));
+    Worker* w = (Worker*)malloc((size_t)nthreads * sizeof(Worker));
+    for(int t = 0; t < nthreads; ++t) { w[t].s = s; w[t].tid = t; pthread_create(&th[t], NULL, thread_main, &w[t]); }
+    for(int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    pthread_barrier_destroy(&s->bar);
+    free(th); free(w);
+    return 0;
+}
+
+double* oracle_field(OracleSim* s, int field) { return (field >= 0 && field < CHIML_NFIELDS) ? s->f[field] : NULL; }
+double* oracle_pole(OracleSim* s, int comp, int pole, int prev) { return (comp < 0 || comp > 2 || pole < 0 || pole >= MAX_POLES) ? NULL : (prev ? s->Pprev[comp][pole] : s->P[comp][pole]); }
+double* oracle_ordip_pole(OracleSim* s, int comp, int pole, int prev) { return (comp < 0 || comp > 2 || pole < 0 || pole >= MAX_POLES) ? NULL : (prev ? s->oPprev[comp][pole] : s->oP[comp][pole]); }
+double* oracle_psi(OracleSim* s, int comp, int part) { return (comp < 0 || comp > 5 || part < 0 || part > 1) ? NULL : s->pml[comp][part].psi_grid; }
+int oracle_n_poles(OracleSim* s) { return s->npoles; }

@@ -1,0 +1,52 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of chiML's time-stepping hot path.
+ *
+ * Nothing under oracle/ is product code: it is imported only by tests/, by
+ * __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs, and only as the
+ * checker.  The product (chiml_b200/) never links, imports or executes it.
+ *
+ * What it restates: parallelFDTDFieldBase<double>::step() (reference
+ * src/FDTD_MANAGER/parallelFDTDField.hpp:1228-1303) and the arithmetic it calls, as plain loops that
+ * perform the same rounded operations in the same order as the reference's BLAS-level-1 call
+ * chains (compile with -ffp-contract=off).  Each function cites the reference lines it follows.
+ * It consumes the same flattened inputs as the C ABI (include/chiml_gpu.h): the reference's own
+ * update lists, CPML lists and pole constants.
+ *
+ * Parity pinning: the reference ships no tests or golden vectors, so this
+ * restatement is pinned against the reference ITSELF: oracle/_ref/chiml_ref is the unmodified
+ * reference compiled in place (oracle/Makefile), and tests/test_oracle_vs_ref.py requires
+ * bit-identical fields between the two on the committed cases.
+ */
+#ifndef CHIML_ORACLE_H
+#define CHIML_ORACLE_H
+
+#include "../include/chiml_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OracleSim OracleSim;
+
+OracleSim* oracle_create(const ChimlGridDesc* desc);
+void oracle_destroy(OracleSim* s);
+int  oracle_set_update_list(OracleSim* s, int kind, int comp, const ChimlRun* runs, size_t n);
+int  oracle_set_object(OracleSim* s, int obj, int npoles, const double* alpha, const double* xi, const double* gamma,
+                       int use_or_dip, const double* dip);
+int  oracle_set_cpml(OracleSim* s, int comp, int part, int has_psi, const ChimlPsiParams* psi, size_t npsi,
+                     const ChimlGridParams* grid, size_t ngrid);
+int  oracle_add_source(OracleSim* s, int field, const int32_t loc[3], const int32_t sz[3]);
+int  oracle_commit(OracleSim* s);
+/* nthreads > 1: rows of every list are split over POSIX threads (same arithmetic per cell) */
+int  oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads);
+
+/* direct pointers to the full-size logical arrays (ln[0]*ln[1]*ln[2] doubles), NULL if absent */
+double* oracle_field(OracleSim* s, int field);
+double* oracle_pole(OracleSim* s, int comp, int pole, int prev);
+double* oracle_ordip_pole(OracleSim* s, int comp, int pole, int prev);
+double* oracle_psi(OracleSim* s, int comp, int part);
+int     oracle_n_poles(OracleSim* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -8,18 +8,30 @@
 // wall-clock seconds of the step loop as JSON.  Used to pin the restated oracle and as the
 // `--impl reference` CPU arm of bench.py.
 //
-// usage: chiml_ref <input.json> [--ranks R] [--steps N] [--dump FILE] [--no-output] [--quiet]
+// usage: chiml_ref <input.json> [--ranks R] [--steps N] [--dump FILE] [--plan PREFIX] [--no-output] [--quiet]
+//   --plan PREFIX writes PREFIX.rank<r>.plan (include/chiml_plan.h) from the constructed propagator, before stepping
 //
 // dump file layout (little endian): magic "CHIMLDMP" | int32 nranks | then per rank, per grid:
 //   int32 rank | char name[16] | int32 lnx, lny, lnz | int32 yStart(global row of local row 1) | float64 data[lnx*lny*lnz]
 // with the reference's own index order x + lnx*(z + lnz*y), ghost cells included.
-#include <FDTD_MANAGER/parallelFDTDField.hpp>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
 #include <sstream>
 #include <thread>
+#include <boost/mpi.hpp>
+#include <unordered_map>
+#include <functional>
+#include <iomanip>
+// The plan dump reads the propagator's protected update lists; the reference offers no accessor for
+// them, so this TEST driver opens the classes up (the reference sources themselves stay untouched).
+#define protected public
+#define private public
+#include <FDTD_MANAGER/parallelFDTDField.hpp>
+#undef protected
+#undef private
+#include "../include/chiml_plan.h"
 
 namespace mpi = boost::mpi;
 
@@ -29,6 +41,7 @@ struct Options
     int ranks = 1;
     int steps = -1;
     std::string dump;
+    std::string plan;
     bool output = true;
     bool quiet = false;
 };
@@ -61,6 +74,182 @@ static void grabGrid(int rank, const std::string& name, std::shared_ptr<parallel
     g_dumps.push_back(std::move(d));
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// plan dump (include/chiml_plan.h) from the reference's own data structures
+// ---------------------------------------------------------------------------------------------
+static void putRec(std::ofstream& out, const char* tag, const std::string& payload)
+{
+    char t[8];
+    std::memset(t, ' ', 8);
+    std::memcpy(t, tag, std::min<size_t>(8, std::strlen(tag)));
+    uint64_t n = payload.size();
+    out.write(t, 8);
+    out.write(reinterpret_cast<const char*>(&n), 8);
+    out.write(payload.data(), std::streamsize(n));
+}
+template <typename T> static void app(std::string& s, const T& v) { s.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
+template <typename T> static void appVec(std::string& s, const std::vector<T>& v) { if(!v.empty()) s.append(reinterpret_cast<const char*>(v.data()), v.size() * sizeof(T)); }
+
+static void putList(std::ofstream& out, int kind, int comp, const upLists& l)
+{
+    static_assert(sizeof(upLists::value_type) == sizeof(ChimlRun), "upLists entry must be layout-identical to ChimlRun");
+    std::string p;
+    ChimlPlanListHdr h; h.kind = kind; h.comp = comp; h.n = l.size();
+    app(p, h);
+    if(!l.empty()) p.append(reinterpret_cast<const char*>(l.data()), l.size() * sizeof(ChimlRun));
+    putRec(out, "UPLIST", p);
+}
+
+static void putCpml(std::ofstream& out, int comp, std::shared_ptr<parallelCPML<double>> pml)
+{
+    static_assert(sizeof(updatePsiParams) == sizeof(ChimlPsiParams), "updatePsiParams layout");
+    static_assert(sizeof(updateGridParams) == sizeof(ChimlGridParams), "updateGridParams layout");
+    if(!pml) return;
+    for(int part = 0; part < 2; ++part)
+    {
+        const std::vector<updatePsiParams>&  psi  = part == 0 ? pml->updateListPsi_j_  : pml->updateListPsi_k_;
+        const std::vector<updateGridParams>& grid = part == 0 ? pml->updateListGrid_k_ : pml->updateListGrid_j_;
+        bool hasPsi  = part == 0 ? bool(pml->psi_j_)  : bool(pml->psi_k_);
+        bool hasGrid = part == 0 ? bool(pml->grid_k_) : bool(pml->grid_j_);
+        if(!hasGrid) continue;
+        std::string p;
+        ChimlPlanCpmlHdr h; h.comp = comp; h.part = part; h.has_psi = hasPsi ? 1 : 0; h.pad = 0; h.npsi = psi.size(); h.ngrid = grid.size();
+        app(p, h);
+        if(!psi.empty())  p.append(reinterpret_cast<const char*>(psi.data()),  psi.size()  * sizeof(ChimlPsiParams));
+        if(!grid.empty()) p.append(reinterpret_cast<const char*>(grid.data()), grid.size() * sizeof(ChimlGridParams));
+        putRec(out, "CPML", p);
+    }
+}
+
+static int fieldId(parallelFDTDFieldReal& FF, const std::shared_ptr<parallelGrid<double>>& g)
+{
+    for(int i = 0; i < 3; ++i)
+    {
+        if(g && g == FF.E_[i]) return CHIML_EX + i;
+        if(g && g == FF.H_[i]) return CHIML_HX + i;
+        if(g && g == FF.D_[i]) return CHIML_DX + i;
+    }
+    return -1;
+}
+
+static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const parallelProgramInputs& IP, int nSteps)
+{
+    std::ofstream out(fname.c_str(), std::ios::binary);
+    { std::string p; int32_t v = CHIML_PLAN_VERSION; app(p, v); putRec(out, "CHIMLPLN", p); }
+    std::shared_ptr<parallelGrid<double>> g0 = FF.E_[0] ? FF.E_[0] : FF.E_[2];
+    ChimlPlanGrid pg;
+    std::memset(&pg, 0, sizeof(pg));
+    pg.desc.mode = (FF.E_[0] && FF.E_[2]) ? CHIML_MODE_3D : (FF.E_[0] ? CHIML_MODE_TE : CHIML_MODE_TM);
+    for(int i = 0; i < 3; ++i) { pg.desc.ln[i] = g0->ln_vec(i); pg.desc.d[i] = FF.d_[i]; pg.n_global[i] = FF.n_vec_[i]; }
+    pg.desc.dt = FF.dt_;
+    pg.desc.has_D = (FF.D_[0] || FF.D_[2]) ? 1 : 0;
+    pg.desc.pml_on_D = FF.dielectricMatInPML_ ? 1 : 0;
+    pg.desc.n_objects = int(FF.objArr_.size());
+    pg.desc.rank = FF.gridComm_->rank();
+    pg.desc.nranks = FF.gridComm_->size();
+    pg.y_start = g0->procLoc(1);
+    pg.n_steps = nSteps;
+    pg.n_lor_poles = int(std::max(FF.lorP_[0].size(), FF.lorP_[2].size()));
+    pg.n_ordip_poles = int(std::max(FF.orDipLorP_[0].size(), FF.orDipLorP_[2].size()));
+    pg.t_max = IP.tMax_;
+    { std::string p; app(p, pg); putRec(out, "GRID", p); }
+
+    if(FF.magMatInPML_) throw std::runtime_error("plan dump: magnetic material in the PML is outside the covered hot path");
+    for(int c = 0; c < 3; ++c)
+    {
+        if(!FF.upB_[c].empty() || !FF.upLorB_[c].empty() || !FF.upChiD_[c].empty() || !FF.upChiB_[c].empty() || !FF.upOrDipB_[c].empty()
+           || !FF.upOrDipChiD_[c].empty() || !FF.upOrDipChiB_[c].empty())
+            throw std::runtime_error("plan dump: magnetic / chiral update lists are outside the covered hot path");
+        putList(out, CHIML_LIST_U, c, FF.upE_[c]);
+        putList(out, CHIML_LIST_U, 3 + c, FF.upH_[c]);
+        putList(out, CHIML_LIST_D, c, FF.upD_[c]);
+        putList(out, CHIML_LIST_LORD, c, FF.upLorD_[c]);
+        putList(out, CHIML_LIST_ORDIPD, c, FF.upOrDipD_[c]);
+    }
+    if(!FF.upOrDipM_.empty() || !FF.upChiOrDipP_.empty() || !FF.upChiOrDipM_.empty())
+        throw std::runtime_error("plan dump: magnetic / chiral oriented-dipole lists are outside the covered hot path");
+    putList(out, CHIML_LIST_ORDIPP, 0, FF.upOrDipP_);
+
+    for(size_t oo = 0; oo < FF.objArr_.size(); ++oo)
+    {
+        auto& obj = FF.objArr_[oo];
+        ChimlPlanObjectHdr h;
+        h.obj = int(oo); h.npoles = int(obj->gamma().size()); h.use_or_dip = obj->useOrdDip() ? 1 : 0; h.ml = obj->ML() ? 1 : 0;
+        h.eps_inf = obj->epsInfty(); h.mu_inf = obj->muInfty();
+        std::string p; app(p, h);
+        appVec(p, obj->alpha()); appVec(p, obj->xi()); appVec(p, obj->gamma());
+        std::vector<double> dip(3 * size_t(h.npoles), 0.0);
+        if(h.use_or_dip)
+        {
+            for(int pp = 0; pp < h.npoles; ++pp)
+            {
+                MAT_DIP_ORIENTAITON ori = obj->dipOr(pp);
+                if(ori == MAT_DIP_ORIENTAITON::ISOTROPIC) { dip[3*pp] = dip[3*pp+1] = dip[3*pp+2] = 1.0; }
+                else if(ori == MAT_DIP_ORIENTAITON::UNIDIRECTIONAL) { for(int k = 0; k < 3; ++k) dip[3*pp+k] = obj->dipE(pp)[k]; }
+                else throw std::runtime_error("plan dump: position-dependent dipole orientation (REL_TO_NORM) is outside the covered hot path");
+            }
+        }
+        appVec(p, dip);
+        putRec(out, "OBJECT", p);
+    }
+    for(int c = 0; c < 3; ++c)
+    {
+        putCpml(out, c, FF.EPML_[c]);
+        putCpml(out, 3 + c, FF.HPML_[c]);
+    }
+    // sources: the box this rank adds to, and the per-step amplitude dt*Re(sum pulse(t_k)) with t_k accumulated as step() does
+    for(auto& srcBase : FF.srcArr_)
+    {
+        auto src = std::dynamic_pointer_cast<parallelSourceNormalReal>(srcBase);
+        if(!src) throw std::runtime_error("plan dump: only normal (axis-aligned) soft sources are on the covered hot path");
+        if(!src->slave_) continue;
+        ChimlPlanSourceHdr h;
+        h.field = fieldId(FF, src->grid_);
+        // undo the (length, trans1, trans2) permutation of genDatStruct so loc/sz are plain x,y,z
+        std::array<int,3> sz = {{1, 1, 1}};
+        const SalveSource& sl = *src->slave_;
+        int ax1 = sl.addVec1_[0] ? 0 : (sl.addVec1_[1] ? 1 : 2);
+        int ax2 = sl.addVec2_[0] ? 0 : (sl.addVec2_[1] ? 1 : 2);
+        int longAxis = 3 - ax1 - ax2;
+        sz[longAxis] = sl.sz_[0];
+        sz[ax1] = sl.sz_[1];
+        sz[ax2] = sl.sz_[2];
+        for(int k = 0; k < 3; ++k) { h.loc[k] = sl.loc_[k]; h.sz[k] = sz[k]; }
+        h.n_steps = nSteps;
+        std::vector<double> amp(nSteps);
+        double t = 0.0;
+        for(int k = 0; k < nSteps; ++k)
+        {
+            cplx pulVal = 0.0;
+            for(auto& pul : src->pulse_) pulVal += pul->pulse(t);
+            amp[k] = FF.dt_ * std::real(pulVal);
+            t += FF.dt_;
+        }
+        std::string p; app(p, h); appVec(p, amp);
+        putRec(out, "SOURCE", p);
+    }
+    int dd = 0;
+    for(auto& dtc : FF.dtcArr_)
+    {
+        for(auto& f : dtc->fields_)
+        {
+            ChimlPlanDetector d;
+            std::memset(&d, 0, sizeof(d));
+            d.detector = dd;
+            d.field = fieldId(FF, f->grid_);
+            for(int k = 0; k < 3; ++k) { d.loc[k] = f->loc_[k]; d.sz[k] = f->sz_[k]; d.offset[k] = f->offSet_[k]; }
+            d.every = dtc->timeInterval_;
+            d.type = int(dtc->type_);
+            d.conv = dtc->convFactor_;
+            d.t_conv = dtc->tConv_;
+            std::string p; app(p, d);
+            putRec(out, "DETECTOR", p);
+        }
+        ++dd;
+    }
+}
+
 static void rankMain(int rank, const Options& opt)
 {
     mpi::shim::myRank() = rank;
@@ -89,6 +278,9 @@ static void rankMain(int rank, const Options& opt)
     parallelFDTDFieldReal FF(IP, gridComm);
     int nSteps = int(std::ceil(IP.tMax_ / IP.dt_));
     if(opt.steps >= 0) nSteps = opt.steps;
+
+    if(!opt.plan.empty())
+        writePlan(opt.plan + ".rank" + std::to_string(rank) + ".plan", FF, IP, nSteps);
 
     gridComm->barrier();
     auto t0 = std::chrono::steady_clock::now();
@@ -157,6 +349,7 @@ int main(int argc, char** argv)
         if(s == "--ranks" && a + 1 < argc) opt.ranks = std::atoi(argv[++a]);
         else if(s == "--steps" && a + 1 < argc) opt.steps = std::atoi(argv[++a]);
         else if(s == "--dump" && a + 1 < argc) opt.dump = argv[++a];
+        else if(s == "--plan" && a + 1 < argc) opt.plan = argv[++a];
         else if(s == "--no-output") opt.output = false;
         else if(s == "--quiet") opt.quiet = true;
         else if(opt.input.empty()) opt.input = s;
@@ -164,7 +357,7 @@ int main(int argc, char** argv)
     }
     if(opt.input.empty() || opt.ranks < 1)
     {
-        std::fprintf(stderr, "usage: chiml_ref <input.json> [--ranks R] [--steps N] [--dump FILE] [--no-output] [--quiet]\n");
+        std::fprintf(stderr, "usage: chiml_ref <input.json> [--ranks R] [--steps N] [--dump FILE] [--plan PREFIX] [--no-output] [--quiet]\n");
         return 2;
     }
     std::streambuf* oldCout = nullptr;
