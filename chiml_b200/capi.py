@@ -1,0 +1,251 @@
+"""ctypes binding of the C ABI (include/chiml_gpu.h) of the B200 engine.
+
+PyTorch is not involved in the product path: the shared library owns its device memory and
+streams.  This module fails loudly when the CUDA library is missing or no GPU is visible -- there
+is no CPU fallback (the CPU oracle under oracle/ is test infrastructure and is never imported here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import plan as P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libchiml_b200.so")
+
+STATUS = {0: "OK", 1: "ERR_ARG", 2: "ERR_CUDA", 3: "ERR_UNSUPPORTED", 4: "ERR_STATE", 5: "ERR_NO_DEVICE"}
+
+EXPORTED_SYMBOLS = [
+    "chiml_gpu_device_count", "chiml_gpu_create", "chiml_gpu_destroy", "chiml_gpu_last_error",
+    "chiml_gpu_set_update_list", "chiml_gpu_set_object", "chiml_gpu_set_cpml", "chiml_gpu_add_source",
+    "chiml_gpu_add_detector", "chiml_gpu_commit", "chiml_gpu_step_n", "chiml_gpu_sync", "chiml_gpu_step_n_timed",
+    "chiml_gpu_launch_count", "chiml_gpu_upload_field", "chiml_gpu_download_field", "chiml_gpu_download_pole",
+    "chiml_gpu_upload_pole", "chiml_gpu_download_ordip_pole", "chiml_gpu_download_psi", "chiml_gpu_read_detector",
+    "chiml_gpu_device_bytes",
+]
+
+
+class ChimlError(RuntimeError):
+    pass
+
+
+class GridDesc(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("ln", C.c_int32 * 3), ("d", C.c_double * 3), ("dt", C.c_double),
+                ("has_D", C.c_int32), ("pml_on_D", C.c_int32), ("n_objects", C.c_int32), ("rank", C.c_int32),
+                ("nranks", C.c_int32)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Load chiml_b200/libchiml_b200.so (built in-tree by __graft_entry__.build / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ChimlError(f"{LIB_PATH} is missing: build it with `make -C chiml_b200/csrc` (nvcc, sm_100a). "
+                         "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.chiml_gpu_device_count.restype = i
+    L.chiml_gpu_create.argtypes = [C.POINTER(GridDesc), i, C.POINTER(vp)]
+    L.chiml_gpu_destroy.argtypes = [vp]
+    L.chiml_gpu_destroy.restype = None
+    L.chiml_gpu_last_error.argtypes = [vp]
+    L.chiml_gpu_last_error.restype = C.c_char_p
+    L.chiml_gpu_set_update_list.argtypes = [vp, i, i, vp, sz]
+    L.chiml_gpu_set_object.argtypes = [vp, i, i, vp, vp, vp, i, vp]
+    L.chiml_gpu_set_cpml.argtypes = [vp, i, i, i, vp, sz, vp, sz]
+    L.chiml_gpu_add_source.argtypes = [vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(i)]
+    L.chiml_gpu_add_detector.argtypes = [vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i, C.POINTER(i)]
+    L.chiml_gpu_commit.argtypes = [vp]
+    L.chiml_gpu_step_n.argtypes = [vp, i, vp]
+    L.chiml_gpu_sync.argtypes = [vp]
+    L.chiml_gpu_step_n_timed.argtypes = [vp, i, vp, C.POINTER(C.c_float)]
+    L.chiml_gpu_launch_count.argtypes = [vp]
+    L.chiml_gpu_launch_count.restype = C.c_int64
+    L.chiml_gpu_upload_field.argtypes = [vp, i, vp]
+    L.chiml_gpu_download_field.argtypes = [vp, i, vp]
+    L.chiml_gpu_download_pole.argtypes = [vp, i, i, i, vp]
+    L.chiml_gpu_upload_pole.argtypes = [vp, i, i, i, vp]
+    L.chiml_gpu_download_ordip_pole.argtypes = [vp, i, i, i, vp]
+    L.chiml_gpu_download_psi.argtypes = [vp, i, i, vp]
+    L.chiml_gpu_read_detector.argtypes = [vp, i, vp, sz, C.POINTER(sz)]
+    L.chiml_gpu_device_bytes.argtypes = [vp]
+    L.chiml_gpu_device_bytes.restype = sz
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return lib().chiml_gpu_device_count()
+
+
+def _ptr(a: Optional[np.ndarray]):
+    if a is None or a.size == 0:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class GpuSim:
+    """One y-slab of the propagator on one GPU, configured from a Plan (the reference's own lists)."""
+
+    def __init__(self, plan: P.Plan, device: int = 0, detectors: bool = True):
+        L = lib()
+        self.plan = plan
+        g = GridDesc()
+        g.mode = plan.mode
+        g.ln[:] = plan.ln
+        g.d[:] = plan.d
+        g.dt = plan.dt
+        g.has_D, g.pml_on_D, g.n_objects, g.rank, g.nranks = plan.has_D, plan.pml_on_D, plan.n_objects, plan.rank, plan.nranks
+        h = C.c_void_p()
+        rc = L.chiml_gpu_create(C.byref(g), device, C.byref(h))
+        if rc != 0:
+            raise ChimlError(f"chiml_gpu_create: {STATUS.get(rc, rc)}: {L.chiml_gpu_last_error(None).decode()}")
+        self.h = h
+        self.steps_done = 0
+        self.det_slots = []
+        try:
+            for (kind, comp), runs in plan.lists.items():
+                runs = np.ascontiguousarray(runs, dtype=P.RUN_DTYPE)
+                self._chk(L.chiml_gpu_set_update_list(self.h, kind, comp, _ptr(runs), len(runs)))
+            for o in plan.objects:
+                a, x, gm, dp = (np.ascontiguousarray(v, dtype=np.float64) for v in (o.alpha, o.xi, o.gamma, o.dip))
+                self._chk(L.chiml_gpu_set_object(self.h, o.obj, o.npoles, _ptr(a), _ptr(x), _ptr(gm), o.use_or_dip, _ptr(dp)))
+            for c in plan.cpml:
+                psi = np.ascontiguousarray(c.psi, dtype=P.PSI_DTYPE)
+                grid = np.ascontiguousarray(c.grid, dtype=P.GRIDP_DTYPE)
+                self._chk(L.chiml_gpu_set_cpml(self.h, c.comp, c.part, c.has_psi, _ptr(psi), len(psi), _ptr(grid), len(grid)))
+            for s in plan.sources:
+                slot = C.c_int()
+                self._chk(L.chiml_gpu_add_source(self.h, s.field, (C.c_int32 * 3)(*s.loc), (C.c_int32 * 3)(*s.sz), C.byref(slot)))
+            if detectors:
+                for d in plan.detectors:
+                    box = local_box(plan, d.loc, d.sz)
+                    if box is None:
+                        self.det_slots.append(-1)
+                        continue
+                    slot = C.c_int()
+                    self._chk(L.chiml_gpu_add_detector(self.h, d.field, (C.c_int32 * 3)(*box[0]), (C.c_int32 * 3)(*box[1]), d.every, C.byref(slot)))
+                    self.det_slots.append(slot.value)
+            self._chk(L.chiml_gpu_commit(self.h))
+        except Exception:
+            self.close()
+            raise
+
+    def _chk(self, rc: int) -> None:
+        if rc != 0:
+            msg = lib().chiml_gpu_last_error(self.h).decode()
+            raise ChimlError(f"{STATUS.get(rc, rc)}: {msg}")
+
+    # ---- stepping -----------------------------------------------------------------------------------
+    def src_amp(self, start: int, n: int) -> np.ndarray:
+        ns = len(self.plan.sources)
+        amp = np.zeros((n, max(ns, 1)), dtype=np.float64)
+        for q, s in enumerate(self.plan.sources):
+            seg = s.amp[start:start + n]
+            amp[:len(seg), q] = seg
+        return amp
+
+    def step_n(self, n: int, amp: Optional[np.ndarray] = None) -> None:
+        if amp is None:
+            amp = self.src_amp(self.steps_done, n)
+        amp = np.ascontiguousarray(amp, dtype=np.float64)
+        self._chk(lib().chiml_gpu_step_n(self.h, n, _ptr(amp) if len(self.plan.sources) else None))
+        self.steps_done += n
+
+    def step_n_timed(self, n: int, amp: Optional[np.ndarray] = None) -> float:
+        if amp is None:
+            amp = self.src_amp(self.steps_done, n)
+        amp = np.ascontiguousarray(amp, dtype=np.float64)
+        ms = C.c_float()
+        self._chk(lib().chiml_gpu_step_n_timed(self.h, n, _ptr(amp) if len(self.plan.sources) else None, C.byref(ms)))
+        self.steps_done += n
+        return float(ms.value)
+
+    def sync(self) -> None:
+        self._chk(lib().chiml_gpu_sync(self.h))
+
+    # ---- state ----------------------------------------------------------------------------------------
+    def _shape(self):
+        lnx, lny, lnz = self.plan.ln
+        return (lny, lnz, lnx)
+
+    def field(self, f: int) -> np.ndarray:
+        out = np.empty(self._shape(), dtype=np.float64)
+        self._chk(lib().chiml_gpu_download_field(self.h, f, _ptr(out)))
+        return out
+
+    def set_field(self, f: int, a: np.ndarray) -> None:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert a.shape == self._shape()
+        self._chk(lib().chiml_gpu_upload_field(self.h, f, _ptr(a)))
+
+    def pole(self, comp: int, pole: int, prev: int = 0) -> np.ndarray:
+        out = np.empty(self._shape(), dtype=np.float64)
+        self._chk(lib().chiml_gpu_download_pole(self.h, comp, pole, prev, _ptr(out)))
+        return out
+
+    def set_pole(self, comp: int, pole: int, prev: int, a: np.ndarray) -> None:
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self._chk(lib().chiml_gpu_upload_pole(self.h, comp, pole, prev, _ptr(a)))
+
+    def ordip_pole(self, comp: int, pole: int, prev: int = 0) -> np.ndarray:
+        out = np.empty(self._shape(), dtype=np.float64)
+        self._chk(lib().chiml_gpu_download_ordip_pole(self.h, comp, pole, prev, _ptr(out)))
+        return out
+
+    def psi(self, comp: int, part: int) -> np.ndarray:
+        out = np.empty(self._shape(), dtype=np.float64)
+        self._chk(lib().chiml_gpu_download_psi(self.h, comp, part, _ptr(out)))
+        return out
+
+    def detector(self, index: int) -> np.ndarray:
+        """All samples of plan.detectors[index] so far: array (n_samples, sy, sz, sx)."""
+        slot = self.det_slots[index]
+        if slot < 0:
+            return np.zeros((0, 0, 0, 0))
+        n = C.c_size_t()
+        self._chk(lib().chiml_gpu_read_detector(self.h, slot, None, 0, C.byref(n)))
+        box = local_box(self.plan, self.plan.detectors[index].loc, self.plan.detectors[index].sz)
+        sx, sy, sz = box[1]
+        out = np.empty((n.value, sy, sz, sx), dtype=np.float64)
+        self._chk(lib().chiml_gpu_read_detector(self.h, slot, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def launch_count(self) -> int:
+        return int(lib().chiml_gpu_launch_count(self.h))
+
+    def device_bytes(self) -> int:
+        return int(lib().chiml_gpu_device_bytes(self.h))
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            lib().chiml_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def local_box(plan: P.Plan, gloc, gsz):
+    """Intersection of a box given in global grid coordinates with this rank's slab, in local
+    ghost-inclusive coordinates (the +1 ghost offset of parallelGrid, y shifted by y_start)."""
+    x0, y0, z0 = gloc
+    sx, sy, sz = gsz
+    ly0 = y0 - plan.y_start + 1
+    ly1 = ly0 + sy
+    lo, hi = max(ly0, 1), min(ly1, plan.ln[1] - 1)
+    if hi <= lo:
+        return None
+    zl = z0 + 1 if plan.ln[2] > 1 else 0
+    return (x0 + 1, lo, zl), (sx, hi - lo, sz if plan.ln[2] > 1 else 1)

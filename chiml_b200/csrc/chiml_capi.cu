@@ -1,0 +1,891 @@
+// C ABI (include/chiml_gpu.h) of the B200 FDTD engine: setup from the reference's lists, commit
+// (painting + pools), stepping, state access.  There is no CPU fallback: without a CUDA device
+// chiml_gpu_create fails with CHIML_ERR_NO_DEVICE.
+#include "chiml_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+using namespace chiml;
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if(_e != cudaSuccess) {                                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e);                               \
+            return CHIML_ERR_CUDA;                                                                       \
+        }                                                                                                \
+    } while(0)
+
+static int fail(ChimlCtx* ctx, int code, const std::string& msg) { ctx->err = msg; return code; }
+
+static bool field_exists(const ChimlCtx* ctx, int f)
+{
+    const int c = f % 3;
+    const bool isH = f >= 3 && f < 6;
+    if(f >= 6 && !ctx->g.has_D) return false;
+    if(ctx->g.mode == CHIML_MODE_3D) return true;
+    if(ctx->g.mode == CHIML_MODE_TE) return isH ? c == 2 : c != 2;
+    return isH ? c != 2 : c == 2;
+}
+
+template <typename T> static int dev_alloc(ChimlCtx* ctx, T** p, size_t n, bool zero = true)
+{
+    if(n == 0) n = 1;
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    ctx->dev_bytes += n * sizeof(T);
+    if(zero) CK(cudaMemsetAsync(*p, 0, n * sizeof(T), ctx->stream));
+    return 0;
+}
+template <typename T> static int dev_upload(ChimlCtx* ctx, T** p, const std::vector<T>& v)
+{
+    int rc = dev_alloc(ctx, p, v.size(), false);
+    if(rc) return rc;
+    if(!v.empty()) CK(cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// logical linear offset (+-1, +-lx, +-lx*lz) -> (dx, dy, dz)
+static bool decode_offset(const ChimlCtx* ctx, long off, int d[3])
+{
+    d[0] = d[1] = d[2] = 0;
+    if(off == 0) return true;
+    const long a = off < 0 ? -off : off;
+    const int s = off < 0 ? -1 : 1;
+    if(a == 1) { d[0] = s; return true; }
+    if(ctx->lz > 1 && a == ctx->lx) { d[2] = s; return true; }
+    if(a == (long)ctx->lx * ctx->lz) { d[1] = s; return true; }
+    return false;
+}
+static long phys_offset(const ChimlCtx* ctx, const int d[3]) { return d[0] + ctx->px * (d[2] + (long)ctx->lz * d[1]); }
+
+extern "C" {
+
+int chiml_gpu_device_count(void)
+{
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* chiml_gpu_last_error(const ChimlCtx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int chiml_gpu_create(const ChimlGridDesc* desc, int device, ChimlCtx** out)
+{
+    if(!desc || !out) { g_create_err = "null argument"; return CHIML_ERR_ARG; }
+    *out = nullptr;
+    if(desc->ln[0] < 3 || desc->ln[1] < 3 || desc->ln[2] < 1 || desc->mode < 0 || desc->mode > 2 || desc->n_objects < 1)
+    { g_create_err = "bad grid description"; return CHIML_ERR_ARG; }
+    if((desc->mode == CHIML_MODE_3D) != (desc->ln[2] > 1))
+    { g_create_err = "mode / ln[2] mismatch: 3-D needs ln[2] > 1, 2-D needs ln[2] == 1"; return CHIML_ERR_ARG; }
+    int ndev = chiml_gpu_device_count();
+    if(ndev <= 0) { g_create_err = "no CUDA device visible: this engine has no CPU fallback"; return CHIML_ERR_NO_DEVICE; }
+    if(device < 0 || device >= ndev) { g_create_err = "device index out of range"; return CHIML_ERR_ARG; }
+    ChimlCtx* ctx = new ChimlCtx();
+    ctx->g = *desc;
+    ctx->device = device;
+    ctx->lx = desc->ln[0]; ctx->ly = desc->ln[1]; ctx->lz = desc->ln[2];
+    ctx->px = ((long)ctx->lx + 15) / 16 * 16;
+    ctx->plane = ctx->px * ctx->lz;
+    ctx->nphys = (size_t)ctx->plane * ctx->ly;
+    ctx->nlogical = (size_t)ctx->lx * ctx->ly * ctx->lz;
+    ctx->objs.resize(desc->n_objects);
+    cudaError_t e = cudaSetDevice(device);
+    if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+    if(e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if(e != cudaSuccess) { g_create_err = std::string("CUDA init: ") + cudaGetErrorString(e); delete ctx; return CHIML_ERR_CUDA; }
+    *out = ctx;
+    return CHIML_OK;
+}
+
+void chiml_gpu_destroy(ChimlCtx* ctx)
+{
+    if(!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for(auto& p : ctx->d_field) cudaFree(p);
+    for(int c = 0; c < 6; ++c)
+    {
+        cudaFree(ctx->d_info[c]); cudaFree(ctx->d_cls[c]);
+        for(int k = 0; k < 2; ++k)
+        {
+            PmlPartDev& pp = ctx->pml[c][k];
+            cudaFree(pp.d_F); cudaFree(pp.d_b); cudaFree(pp.d_c); cudaFree(pp.d_cmap); cudaFree(pp.d_psi);
+        }
+    }
+    for(int c = 0; c < 3; ++c)
+    {
+        cudaFree(ctx->span[c].d_xmin); cudaFree(ctx->span[c].d_xmax); cudaFree(ctx->span[c].d_base);
+        for(int p = 0; p < MAX_POLES; ++p)
+            for(int k = 0; k < 2; ++k) { cudaFree(ctx->d_P[c][p][k]); cudaFree(ctx->d_oP[c][p][k]); }
+    }
+    cudaFree(ctx->d_info_node); cudaFree(ctx->d_cls_node);
+    cudaFree(ctx->span_node.d_xmin); cudaFree(ctx->span_node.d_xmax); cudaFree(ctx->span_node.d_base);
+    cudaFree(ctx->d_src_amp);
+    for(auto& d : ctx->detectors) cudaFree(d.d_ring);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int chiml_gpu_set_update_list(ChimlCtx* ctx, int kind, int comp, const ChimlRun* runs, size_t n)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_update_list after commit");
+    if(kind < 0 || kind > 4 || comp < 0 || comp > 5 || (n && !runs)) return fail(ctx, CHIML_ERR_ARG, "set_update_list: bad kind/comp");
+    if(kind != CHIML_LIST_U && comp > 2 && n) return fail(ctx, CHIML_ERR_UNSUPPORTED, "magnetic dispersive lists (upB_/upLorB_) are outside the covered hot path");
+    const long ncell = (long)ctx->nlogical;
+    for(size_t i = 0; i < n; ++i)
+    {
+        const ChimlRun& r = runs[i];
+        if(r.n < 1 || r.ind < 0 || (long)r.ind + r.n > ncell || r.obj < 0 || r.obj >= ctx->g.n_objects)
+            return fail(ctx, CHIML_ERR_ARG, "set_update_list: run outside the grid or bad object index");
+        if((r.ind % ctx->lx) + r.n > ctx->lx) return fail(ctx, CHIML_ERR_ARG, "set_update_list: run crosses a row end");
+    }
+    ctx->lists[kind][comp].runs.assign(runs, runs + n);
+    return CHIML_OK;
+}
+
+int chiml_gpu_set_object(ChimlCtx* ctx, int obj, int npoles, const double* alpha, const double* xi, const double* gamma, int use_or_dip, const double* dip)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_object after commit");
+    if(obj < 0 || obj >= ctx->g.n_objects || npoles < 0) return fail(ctx, CHIML_ERR_ARG, "set_object: bad index");
+    if(npoles > MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_object: more than 12 poles per object");
+    HostObj& o = ctx->objs[obj];
+    o.npoles = npoles; o.use_or_dip = use_or_dip;
+    o.alpha.assign(alpha, alpha + npoles); o.xi.assign(xi, xi + npoles); o.gamma.assign(gamma, gamma + npoles);
+    o.dip.assign(3 * (size_t)npoles, 0.0);
+    if(dip) o.dip.assign(dip, dip + 3 * (size_t)npoles);
+    return CHIML_OK;
+}
+
+int chiml_gpu_set_cpml(ChimlCtx* ctx, int comp, int part, int has_psi, const ChimlPsiParams* psi, size_t npsi, const ChimlGridParams* grid, size_t ngrid)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_cpml after commit");
+    if(comp < 0 || comp > 5 || part < 0 || part > 1) return fail(ctx, CHIML_ERR_ARG, "set_cpml: bad comp/part");
+    HostPml& h = ctx->hpml[comp][part];
+    h.present = 1; h.has_psi = has_psi;
+    h.psi.assign(psi, psi + npsi);
+    h.grid.assign(grid, grid + ngrid);
+    return CHIML_OK;
+}
+
+int chiml_gpu_add_source(ChimlCtx* ctx, int field, const int32_t loc[3], const int32_t sz[3], int* slot)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "add_source after commit");
+    if(field < 0 || field >= 6 || !field_exists(ctx, field)) return fail(ctx, CHIML_ERR_ARG, "add_source: field absent in this mode");
+    if((int)ctx->sources.size() >= MAX_SOURCES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "too many sources");
+    SourceDev s; s.field = field;
+    const int ln[3] = {ctx->lx, ctx->ly, ctx->lz};
+    for(int k = 0; k < 3; ++k)
+    {
+        if(sz[k] < 1 || loc[k] < 0 || loc[k] + sz[k] > ln[k]) return fail(ctx, CHIML_ERR_ARG, "add_source: box outside the local grid");
+        s.loc[k] = loc[k]; s.sz[k] = sz[k];
+    }
+    if(slot) *slot = (int)ctx->sources.size();
+    ctx->sources.push_back(s);
+    return CHIML_OK;
+}
+
+int chiml_gpu_add_detector(ChimlCtx* ctx, int field, const int32_t loc[3], const int32_t sz[3], int every, int* slot)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "add_detector after commit");
+    if(field < 0 || field >= CHIML_NFIELDS || !field_exists(ctx, field)) return fail(ctx, CHIML_ERR_ARG, "add_detector: field absent in this mode");
+    if(every < 1) return fail(ctx, CHIML_ERR_ARG, "add_detector: interval must be >= 1 step");
+    DetectorDev d; d.field = field; d.every = every;
+    const int ln[3] = {ctx->lx, ctx->ly, ctx->lz};
+    for(int k = 0; k < 3; ++k)
+    {
+        if(sz[k] < 1 || loc[k] < 0 || loc[k] + sz[k] > ln[k]) return fail(ctx, CHIML_ERR_ARG, "add_detector: box outside the local grid");
+        d.loc[k] = loc[k]; d.sz[k] = sz[k];
+    }
+    d.sample_len = (size_t)sz[0] * sz[1] * sz[2];
+    if(slot) *slot = (int)ctx->detectors.size();
+    ctx->detectors.push_back(d);
+    return CHIML_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// commit helpers
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct ClassKey
+{
+    double pf1, pf2, eps; int npoles, ordip; std::vector<double> consts;
+    bool operator<(const ClassKey& o) const
+    {
+        return std::tie(pf1, pf2, eps, npoles, ordip, consts) < std::tie(o.pf1, o.pf2, o.eps, o.npoles, o.ordip, o.consts);
+    }
+};
+
+struct ClassBuilder
+{
+    std::map<ClassKey, int> ids;
+    std::vector<ClassEntry> entries;
+    ClassBuilder() { ClassEntry z; std::memset(&z, 0, sizeof(z)); entries.push_back(z); }
+    // returns 0 on overflow
+    int get(const ChimlRun& r, const HostObj& o, bool withPoles)
+    {
+        ClassKey k;
+        k.pf1 = r.pf[1]; k.pf2 = r.pf[2]; k.eps = r.pf[3];
+        k.npoles = withPoles ? o.npoles : 0;
+        k.ordip = withPoles ? o.use_or_dip : 0;
+        if(withPoles)
+        {
+            k.consts = o.alpha;
+            k.consts.insert(k.consts.end(), o.xi.begin(), o.xi.end());
+            k.consts.insert(k.consts.end(), o.gamma.begin(), o.gamma.end());
+            k.consts.insert(k.consts.end(), o.dip.begin(), o.dip.end());
+        }
+        auto it = ids.find(k);
+        if(it != ids.end()) return it->second;
+        if((int)entries.size() > MAX_CLASSES) return 0;
+        ClassEntry e; std::memset(&e, 0, sizeof(e));
+        e.pf1 = k.pf1; e.pf2 = k.pf2;
+        e.inv_eps = 1.0 / k.eps; e.neg_inv_eps = -1.0 / k.eps; e.neg_half_inv_eps = -0.5 / k.eps;
+        e.npoles = k.npoles;
+        for(int p = 0; p < k.npoles; ++p)
+        {
+            e.alpha[p] = o.alpha[p]; e.xi[p] = o.xi[p]; e.gamma[p] = o.gamma[p];
+            for(int q = 0; q < 3; ++q) e.dip[p][q] = o.dip[3 * p + q];
+        }
+        int id = (int)entries.size();
+        entries.push_back(e);
+        ids[k] = id;
+        return id;
+    }
+};
+
+int paint_list(ChimlCtx* ctx, const std::vector<ChimlRun>& runs, const std::vector<uint8_t>& cls, uint16_t flags, uint16_t* d_info, int* d_err)
+{
+    if(runs.empty()) return 0;
+    ChimlRun* d_runs = nullptr; uint8_t* d_cls = nullptr;
+    CK(cudaMalloc((void**)&d_runs, runs.size() * sizeof(ChimlRun)));
+    CK(cudaMalloc((void**)&d_cls, cls.size()));
+    CK(cudaMemcpyAsync(d_runs, runs.data(), runs.size() * sizeof(ChimlRun), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_cls, cls.data(), cls.size(), cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 256;
+    const size_t blocks = std::min<size_t>((runs.size() * 32 + threads - 1) / threads, 148 * 16);
+    k_paint_runs<<<(unsigned)blocks, threads, 0, ctx->stream>>>(d_runs, d_cls, runs.size(), flags, d_info, ctx->lx, ctx->px, d_err);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_runs); cudaFree(d_cls);
+    return 0;
+}
+
+int paint_lines(ChimlCtx* ctx, const std::vector<int4>& lines, uint16_t flags, uint16_t* d_info, int* d_err)
+{
+    if(lines.empty()) return 0;
+    int4* d_lines = nullptr;
+    CK(cudaMalloc((void**)&d_lines, lines.size() * sizeof(int4)));
+    CK(cudaMemcpyAsync(d_lines, lines.data(), lines.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+    const int threads = 256;
+    const size_t blocks = std::min<size_t>((lines.size() * 32 + threads - 1) / threads, 148 * 16);
+    k_paint_lines<<<(unsigned)blocks, threads, 0, ctx->stream>>>(d_lines, lines.size(), flags, d_info, ctx->lx, ctx->px, d_err);
+    ++ctx->launches;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_lines);
+    return 0;
+}
+
+// per-row x-spans of the runs whose object carries poles
+int build_spans(ChimlCtx* ctx, const std::vector<const std::vector<ChimlRun>*>& lists, bool ordipOnly, SpanTable& sp)
+{
+    const size_t nrows = (size_t)ctx->ly * ctx->lz;
+    sp.h_xmin.assign(nrows, -1); sp.h_xmax.assign(nrows, -1); sp.h_base.assign(nrows, 0);
+    for(auto* l : lists)
+        for(const ChimlRun& r : *l)
+        {
+            const HostObj& o = ctx->objs[r.obj];
+            if(o.npoles == 0) continue;
+            if(ordipOnly && !o.use_or_dip) continue;
+            const size_t row = (size_t)(r.ind / ctx->lx);
+            const int x0 = r.ind % ctx->lx, x1 = x0 + r.n - 1;
+            if(sp.h_xmin[row] < 0 || x0 < sp.h_xmin[row]) sp.h_xmin[row] = x0;
+            if(x1 > sp.h_xmax[row]) sp.h_xmax[row] = x1;
+        }
+    int64_t total = 0;
+    for(size_t row = 0; row < nrows; ++row)
+        if(sp.h_xmin[row] >= 0) { sp.h_base[row] = total; total += sp.h_xmax[row] - sp.h_xmin[row] + 1; }
+    sp.total = total;
+    int rc;
+    if((rc = dev_upload(ctx, &sp.d_xmin, sp.h_xmin))) return rc;
+    if((rc = dev_upload(ctx, &sp.d_xmax, sp.h_xmax))) return rc;
+    if((rc = dev_upload(ctx, &sp.d_base, sp.h_base))) return rc;
+    return 0;
+}
+
+int coord_of(const ChimlCtx* ctx, long ind, int axis)
+{
+    if(axis == 0) return (int)(ind % ctx->lx);
+    if(axis == 2) return (int)((ind / ctx->lx) % ctx->lz);
+    return (int)(ind / ((long)ctx->lx * ctx->lz));
+}
+int stride_axis(const ChimlCtx* ctx, int stride)
+{
+    if(stride == 1) return 0;
+    if(ctx->lz > 1 && stride == ctx->lx) return 2;
+    if(stride == ctx->lx * ctx->lz) return 1;
+    return -1;
+}
+
+// Build the device form of one CPML part from the reference's two lists.
+int build_pml_part(ChimlCtx* ctx, int comp, int part, int* d_err)
+{
+    const HostPml& h = ctx->hpml[comp][part];
+    PmlPartDev& pp = ctx->pml[comp][part];
+    if(!h.present || (h.psi.empty() && h.grid.empty())) return 0;
+    const int i = comp % 3;
+    const bool isE = comp < 3;
+    // part 0 is driven by grid_k, part 1 by grid_j (PML/parallelPML.hpp:695-696); E components are driven by H and vice versa
+    pp.vfield = (isE ? CHIML_HX : CHIML_EX) + (part == 0 ? (i + 2) % 3 : (i + 1) % 3);
+    if(!field_exists(ctx, pp.vfield)) return fail(ctx, CHIML_ERR_ARG, "set_cpml: the field driving this CPML part does not exist in this mode");
+    const int ln[3] = {ctx->lx, ctx->ly, ctx->lz};
+    const long ncell = (long)ctx->nlogical;
+    // stencil offset and derivative axis: identical for every entry of both lists
+    bool haveOff = false;
+    auto checkOff = [&](long off) -> bool {
+        if(!haveOff) { pp.off_logical = off; haveOff = true; return true; }
+        return pp.off_logical == off;
+    };
+    for(const auto& e : h.psi)  if(!checkOff((long)e.indOff - e.ind)) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_cpml: psi entries with different stencil offsets");
+    for(const auto& e : h.grid) if(!checkOff((long)e.indOff - e.ind)) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_cpml: grid entries with different stencil offsets");
+    int dd[3];
+    if(!decode_offset(ctx, pp.off_logical, dd) || pp.off_logical == 0) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_cpml: stencil offset is not one cell along an axis");
+    pp.axis = dd[0] ? 0 : (dd[1] ? 1 : 2);
+    const int L = ln[pp.axis];
+    std::vector<double> F(L, 0.0), b(L, 0.0), c(L, 0.0);
+    std::vector<char> Fset(L, 0), bset(L, 0);
+    pp.has_psi = h.has_psi;
+    pp.present = 1;
+    bool dbSet = false;
+    std::vector<int4> psiLines, gridLines;
+    for(const auto& e : h.psi)
+    {
+        const int sa = stride_axis(ctx, e.stride);
+        if(e.transSz < 1 || sa < 0 || e.ind < 0 || (long)e.ind + (long)(e.transSz - 1) * e.stride >= ncell)
+            return fail(ctx, CHIML_ERR_ARG, "set_cpml: psi entry outside the grid");
+        if(sa == pp.axis) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_cpml: psi line runs along its own normal axis");
+        const int co = coord_of(ctx, e.ind, pp.axis);
+        if(bset[co] && (b[co] != e.b || c[co] != e.c)) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_cpml: psi coefficients are not a function of the coordinate along the slab normal");
+        b[co] = e.b; c[co] = e.c; bset[co] = 1;
+        psiLines.push_back(make_int4(e.transSz, e.stride, e.ind, 0));
+    }
+    for(const auto& e : h.grid)
+    {
+        const int sa = stride_axis(ctx, e.stride);
+        if(e.nAx < 1 || sa < 0 || e.ind < 0 || (long)e.ind + (long)(e.nAx - 1) * e.stride >= ncell)
+            return fail(ctx, CHIML_ERR_ARG, "set_cpml: grid entry outside the grid");
+        if(dbSet && pp.Db != e.Db) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_cpml: Db differs between grid entries");
+        pp.Db = e.Db; dbSet = true;
+        const int co0 = coord_of(ctx, e.ind, pp.axis);
+        const int nco = sa == pp.axis ? e.nAx : 1;
+        for(int k = 0; k < nco; ++k)
+        {
+            const int co = co0 + k;
+            if(co >= L) return fail(ctx, CHIML_ERR_ARG, "set_cpml: grid entry leaves the grid");
+            if(Fset[co] && F[co] != e.DbField) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_cpml: DbField is not a function of the coordinate along the derivative axis");
+            F[co] = e.DbField; Fset[co] = 1;
+        }
+        gridLines.push_back(make_int4(e.nAx, e.stride, e.ind, 0));
+    }
+    // compact psi coordinates
+    pp.h_cmap.assign(L, -1);
+    pp.nact = 0;
+    for(int co = 0; co < L; ++co) if(bset[co]) pp.h_cmap[co] = pp.nact++;
+    int rc;
+    if((rc = dev_upload(ctx, &pp.d_F, F))) return rc;
+    if((rc = dev_upload(ctx, &pp.d_b, b))) return rc;
+    if((rc = dev_upload(ctx, &pp.d_c, c))) return rc;
+    if((rc = dev_upload(ctx, &pp.d_cmap, pp.h_cmap))) return rc;
+    if(pp.has_psi && pp.nact > 0)
+    {
+        if(pp.axis == 0) { pp.psi_pitch = ((long)pp.nact + 1) / 2 * 2; pp.psi_count = pp.psi_pitch * ctx->lz * (long)ctx->ly; }
+        else if(pp.axis == 1) { pp.psi_pitch = ctx->px; pp.psi_count = ctx->px * ctx->lz * (long)pp.nact; }
+        else { pp.psi_pitch = ctx->px; pp.psi_count = ctx->px * (long)pp.nact * ctx->ly; }
+        if((rc = dev_alloc(ctx, &pp.d_psi, (size_t)pp.psi_count))) return rc;
+    }
+    if((rc = paint_lines(ctx, psiLines, part == 0 ? F_PS0 : F_PS1, ctx->d_info[comp], d_err))) return rc;
+    if((rc = paint_lines(ctx, gridLines, part == 0 ? F_PG0 : F_PG1, ctx->d_info[comp], d_err))) return rc;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int chiml_gpu_commit(ChimlCtx* ctx)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "commit called twice");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    int* d_err = nullptr;
+    if((rc = dev_alloc(ctx, &d_err, 1))) return rc;
+
+    // fields (+1 padded row of slack on either side is not needed: every stencil point of an updated cell lies inside the ghost-inclusive grid)
+    for(int f = 0; f < CHIML_NFIELDS; ++f)
+        if(field_exists(ctx, f) && (rc = dev_alloc(ctx, &ctx->d_field[f], ctx->nphys))) return rc;
+
+    // --- update lists -> class tables + painted cell info -------------------------------------------------
+    for(int comp = 0; comp < 6; ++comp)
+    {
+        if(!field_exists(ctx, comp))
+        {
+            for(int k = 0; k < 5; ++k)
+                if(k != CHIML_LIST_ORDIPP && !ctx->lists[k][comp].runs.empty())
+                    return fail(ctx, CHIML_ERR_ARG, "update list given for a field component that does not exist in this mode");
+            continue;
+        }
+        if((rc = dev_alloc(ctx, &ctx->d_info[comp], ctx->nphys))) return rc;
+        ClassBuilder cb;
+        const bool isE = comp < 3;
+        if(isE && !ctx->g.has_D)
+            for(int k : {CHIML_LIST_D, CHIML_LIST_LORD, CHIML_LIST_ORDIPD})
+                if(!ctx->lists[k][comp].runs.empty()) return fail(ctx, CHIML_ERR_ARG, "D-type update list given but has_D = 0");
+        // stencil offsets must be uniform per component
+        bool haveOff = false;
+        struct { int kind; uint16_t flags; bool poles; } plan[4] = {
+            {CHIML_LIST_U, F_CURL, false}, {CHIML_LIST_D, (uint16_t)(F_CURL | F_ISD), true},
+            {CHIML_LIST_LORD, F_D2E, true}, {CHIML_LIST_ORDIPD, F_ORD2E, true}};
+        for(auto& pl : plan)
+        {
+            const auto& runs = ctx->lists[pl.kind][comp].runs;
+            if(runs.empty()) continue;
+            std::vector<uint8_t> cls(runs.size());
+            for(size_t e = 0; e < runs.size(); ++e)
+            {
+                const ChimlRun& r = runs[e];
+                if(pl.kind == CHIML_LIST_U || pl.kind == CHIML_LIST_D)
+                {
+                    const long oj = (long)r.ind_j - r.ind, ok = (long)r.ind_k - r.ind;
+                    if(!haveOff) { ctx->off_j[comp] = oj; ctx->off_k[comp] = ok; haveOff = true; }
+                    else if(ctx->off_j[comp] != oj || ctx->off_k[comp] != ok)
+                        return fail(ctx, CHIML_ERR_UNSUPPORTED, "update list: stencil offsets differ between runs of one component");
+                }
+                if(pl.kind == CHIML_LIST_ORDIPD)
+                {
+                    const long oi = (long)r.ind_i - r.ind;
+                    if(e == 0) ctx->ordip_off[comp] = oi;
+                    else if(ctx->ordip_off[comp] != oi) return fail(ctx, CHIML_ERR_UNSUPPORTED, "oriented-dipole list: node offsets differ between runs");
+                }
+                if(r.pf[3] == 0.0 && pl.kind != CHIML_LIST_U) return fail(ctx, CHIML_ERR_ARG, "update list: eps = 0 in a D-type run");
+                const HostObj& o = ctx->objs[r.obj];
+                // E-side D-type runs of isotropic objects carry the object's poles in their class (so that the
+                // D-run and the LorD-run of one cell agree); oriented-dipole objects keep theirs on the node grid
+                const bool usePoles = isE && pl.poles && !o.use_or_dip;
+                int id = cb.get(r, o, usePoles);
+                if(id == 0) return fail(ctx, CHIML_ERR_UNSUPPORTED, "more than 255 distinct material classes for one field component");
+                cls[e] = (uint8_t)id;
+            }
+            if((rc = paint_list(ctx, runs, cls, pl.flags, ctx->d_info[comp], d_err))) return rc;
+        }
+        ctx->ncls[comp] = (int)cb.entries.size();
+        if((rc = dev_upload(ctx, &ctx->d_cls[comp], cb.entries))) return rc;
+        int dj[3], dk[3];
+        if(haveOff && (!decode_offset(ctx, ctx->off_j[comp], dj) || !decode_offset(ctx, ctx->off_k[comp], dk)))
+            return fail(ctx, CHIML_ERR_UNSUPPORTED, "update list: stencil offset is not one cell along an axis");
+    }
+    // a D-run and a LorD/OrDipD run covering the same cell must agree on the class byte: the D-run was keyed with poles too
+    // --- isotropic pole pools -----------------------------------------------------------------------------
+    for(int c = 0; c < 3; ++c)
+    {
+        if(!field_exists(ctx, c) || !ctx->g.has_D) continue;
+        int np = 0;
+        for(const ChimlRun& r : ctx->lists[CHIML_LIST_LORD][c].runs)
+            if(!ctx->objs[r.obj].use_or_dip) np = std::max(np, ctx->objs[r.obj].npoles);
+        ctx->npoles_comp[c] = np;
+        std::vector<const std::vector<ChimlRun>*> ls = {&ctx->lists[CHIML_LIST_LORD][c].runs};
+        if((rc = build_spans(ctx, ls, false, ctx->span[c]))) return rc;
+        for(int p = 0; p < np; ++p)
+            for(int k = 0; k < 2; ++k)
+                if((rc = dev_alloc(ctx, &ctx->d_P[c][p][k], (size_t)ctx->span[c].total))) return rc;
+    }
+    // --- oriented-dipole node grid ------------------------------------------------------------------------
+    {
+        const auto& runs = ctx->lists[CHIML_LIST_ORDIPP][0].runs;
+        if(!runs.empty())
+        {
+            if(!ctx->g.has_D) return fail(ctx, CHIML_ERR_ARG, "oriented-dipole node list given but has_D = 0");
+            if((rc = dev_alloc(ctx, &ctx->d_info_node, ctx->nphys))) return rc;
+            ClassBuilder cb;
+            std::vector<uint8_t> cls(runs.size());
+            for(size_t e = 0; e < runs.size(); ++e)
+            {
+                const ChimlRun& r = runs[e];
+                const long o3[3] = {(long)r.ind_i - r.ind, (long)r.ind_j - r.ind, (long)r.ind_k - r.ind};
+                for(int k = 0; k < 3; ++k)
+                {
+                    if(e == 0) ctx->node_off[k] = o3[k];
+                    else if(ctx->node_off[k] != o3[k]) return fail(ctx, CHIML_ERR_UNSUPPORTED, "oriented-dipole node list: offsets differ between runs");
+                }
+                const HostObj& o = ctx->objs[r.obj];
+                ChimlRun key = r; key.pf[1] = key.pf[2] = 0.0; key.pf[3] = 1.0;   // node classes depend on the pole constants only
+                int id = cb.get(key, o, true);
+                if(id == 0) return fail(ctx, CHIML_ERR_UNSUPPORTED, "more than 255 distinct oriented-dipole material classes");
+                cls[e] = (uint8_t)id;
+                ctx->nordip = std::max(ctx->nordip, o.npoles);
+            }
+            if((rc = paint_list(ctx, runs, cls, 0x0100, ctx->d_info_node, d_err))) return rc;
+            ctx->ncls_node = (int)cb.entries.size();
+            if((rc = dev_upload(ctx, &ctx->d_cls_node, cb.entries))) return rc;
+            std::vector<const std::vector<ChimlRun>*> ls = {&runs};
+            if((rc = build_spans(ctx, ls, true, ctx->span_node))) return rc;
+            for(int c = 0; c < 3; ++c)
+                if(field_exists(ctx, c))
+                    for(int p = 0; p < ctx->nordip; ++p)
+                        for(int k = 0; k < 2; ++k)
+                            if((rc = dev_alloc(ctx, &ctx->d_oP[c][p][k], (size_t)ctx->span_node.total))) return rc;
+        }
+        else
+            for(int c = 0; c < 3; ++c)
+                if(!ctx->lists[CHIML_LIST_ORDIPD][c].runs.empty())
+                    return fail(ctx, CHIML_ERR_ARG, "oriented-dipole D->E list given without the node list");
+    }
+    // --- CPML ---------------------------------------------------------------------------------------------
+    for(int comp = 0; comp < 6; ++comp)
+        for(int part = 0; part < 2; ++part)
+        {
+            if(ctx->hpml[comp][part].present && !field_exists(ctx, comp))
+                return fail(ctx, CHIML_ERR_ARG, "CPML lists given for a field component that does not exist in this mode");
+            if(field_exists(ctx, comp) && (rc = build_pml_part(ctx, comp, part, d_err))) return rc;
+        }
+    if(ctx->g.pml_on_D && !ctx->g.has_D) return fail(ctx, CHIML_ERR_ARG, "pml_on_D needs has_D");
+
+    int h_err = 0;
+    CK(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_err);
+    if(h_err == 1) return fail(ctx, CHIML_ERR_UNSUPPORTED, "lists disagree on the material of a cell (different eps / prefactors for the same cell)");
+    if(h_err == 2) return fail(ctx, CHIML_ERR_ARG, "an update list covers a cell twice");
+    if(h_err == 3) return fail(ctx, CHIML_ERR_ARG, "a CPML list covers a cell twice");
+
+    // detectors: ring buffers sized on first use; sample at t = 0 (FDTD_MANAGER/parallelFDTDField.cpp:832-833)
+    ctx->committed = true;
+    for(size_t d = 0; d < ctx->detectors.size(); ++d)
+    {
+        DetectorDev& dt = ctx->detectors[d];
+        dt.cap = 4096;
+        if((rc = dev_alloc(ctx, &dt.d_ring, dt.cap * dt.sample_len, false))) return rc;
+        k_detector<<<(unsigned)std::min<size_t>((dt.sample_len + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+            ctx->d_field[dt.field], dt.loc[0], dt.loc[2], dt.loc[1], dt.sz[0], dt.sz[2], dt.sz[1], ctx->lz, ctx->px, dt.d_ring);
+        ++ctx->launches;
+        dt.count = 1;
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    // host copies of the big lists are no longer needed
+    for(auto& k : ctx->lists) for(auto& l : k) { l.runs.clear(); l.runs.shrink_to_fit(); }
+    return CHIML_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// stepping
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
+{
+    std::memset(&a, 0, sizeof(a));
+    a.lx = ctx->lx; a.ly = ctx->ly; a.lz = ctx->lz; a.px = ctx->px;
+    a.pml_on_D = ctx->g.pml_on_D;
+    a.nsp_xmin = ctx->span_node.d_xmin; a.nsp_xmax = ctx->span_node.d_xmax; a.nsp_base = ctx->span_node.d_base;
+    const int cur = ctx->pcur, prv = 1 - ctx->pcur;
+    for(int i = 0; i < 3; ++i)
+    {
+        const int comp = isE ? i : 3 + i;
+        CompArgs& ca = a.c[i];
+        if(!ctx->d_field[comp]) continue;
+        ca.info = ctx->d_info[comp];
+        ca.cls = ctx->d_cls[comp];
+        ca.U = ctx->d_field[comp];
+        ca.D = isE ? ctx->d_field[CHIML_DX + i] : nullptr;
+        const int base = isE ? CHIML_HX : CHIML_EX;
+        ca.Vj = ctx->d_field[base + (i + 1) % 3];
+        ca.Vk = ctx->d_field[base + (i + 2) % 3];
+        int d[3];
+        decode_offset(ctx, ctx->off_j[comp], d); ca.offJ = phys_offset(ctx, d);
+        decode_offset(ctx, ctx->off_k[comp], d); ca.offK = phys_offset(ctx, d);
+        for(int part = 0; part < 2; ++part)
+        {
+            const PmlPartDev& pp = ctx->pml[comp][part];
+            PmlArgs& pa = ca.pml[part];
+            pa.present = pp.present;
+            if(!pp.present) continue;
+            pa.V = ctx->d_field[pp.vfield];
+            pa.F = pp.d_F; pa.b = pp.d_b; pa.c = pp.d_c; pa.cmap = pp.d_cmap; pa.psi = pp.d_psi;
+            pa.Db = pp.Db; pa.psi_pitch = pp.psi_pitch; pa.axis = pp.axis; pa.nact = pp.nact; pa.has_psi = pp.has_psi;
+            decode_offset(ctx, pp.off_logical, d); pa.off = phys_offset(ctx, d);
+        }
+        if(isE)
+        {
+            ca.sp_xmin = ctx->span[i].d_xmin; ca.sp_base = ctx->span[i].d_base;
+            for(int p = 0; p < MAX_POLES; ++p) { ca.Pcur[p] = ctx->d_P[i][p][cur]; ca.Pnew[p] = ctx->d_P[i][p][prv]; }
+            ca.nordip = ctx->nordip;
+            // after the node kernel of this step the new oriented-dipole P lives in buffer `prv`
+            for(int p = 0; p < MAX_POLES; ++p) ca.oP[p] = ctx->d_oP[i][p][prv];
+            decode_offset(ctx, ctx->ordip_off[i], d);
+            ca.ord_dx = d[0]; ca.ord_dy = d[1]; ca.ord_dz = d[2];
+            // orDipDtoUZ is bound for Ez when there is no Hz (FDTD_MANAGER/parallelFDTDField.cpp:293-296)
+            ca.ord_zvariant = (i == 2 && !ctx->d_field[CHIML_HZ]) ? 1 : 0;
+        }
+    }
+}
+
+int launch_step(ChimlCtx* ctx, long long k, int nsrc)
+{
+    const dim3 block(64, ctx->lz > 1 ? 4 : 1, 1);
+    const dim3 grid((ctx->lx + block.x - 1) / block.x, (ctx->lz + block.y - 1) / block.y, ctx->ly);
+    StepArgs a;
+    // H half step: updateH + updateHPML_ (step() items 4 and 6)
+    fill_step_args(ctx, false, a);
+    k_update<false><<<grid, block, 0, ctx->stream>>>(a);
+    ++ctx->launches;
+    // sources (item 7): all sources, E and H alike, are injected here
+    for(int q = 0; q < nsrc; ++q)
+    {
+        const SourceDev& s = ctx->sources[q];
+        const long n = (long)s.sz[0] * s.sz[1] * s.sz[2];
+        k_source<<<(unsigned)std::min<long>((n + 255) / 256, 2048), 256, 0, ctx->stream>>>(
+            ctx->d_field[s.field], s.loc[0], s.loc[2], s.loc[1], s.sz[0], s.sz[2], s.sz[1], ctx->lz, ctx->px, ctx->d_src_amp + k * nsrc + q);
+        ++ctx->launches;
+    }
+    // oriented-dipole poles at the nodes (item 10, first loop)
+    if(ctx->d_info_node)
+    {
+        NodeArgs na;
+        std::memset(&na, 0, sizeof(na));
+        na.info = ctx->d_info_node; na.cls = ctx->d_cls_node;
+        na.lx = ctx->lx; na.ly = ctx->ly; na.lz = ctx->lz; na.px = ctx->px;
+        na.sp_xmin = ctx->span_node.d_xmin; na.sp_base = ctx->span_node.d_base;
+        const int cur = ctx->pcur, prv = 1 - ctx->pcur;
+        for(int c = 0; c < 3; ++c)
+        {
+            na.E[c] = ctx->d_field[c];
+            int d[3];
+            decode_offset(ctx, ctx->node_off[c], d);
+            na.eoff[c] = phys_offset(ctx, d);
+            for(int p = 0; p < MAX_POLES; ++p) { na.Pcur[c][p] = ctx->d_oP[c][p][cur]; na.Pnew[c][p] = ctx->d_oP[c][p][prv]; }
+        }
+        k_ordip_poles<<<grid, block, 0, ctx->stream>>>(na);
+        ++ctx->launches;
+    }
+    // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
+    fill_step_args(ctx, true, a);
+    k_update<true><<<grid, block, 0, ctx->stream>>>(a);
+    ++ctx->launches;
+    ctx->pcur = 1 - ctx->pcur;
+    ++ctx->step_count;
+    // detectors (item 18)
+    for(auto& dt : ctx->detectors)
+    {
+        if(ctx->step_count % dt.every != 0) continue;
+        if(dt.count >= dt.cap)
+        {
+            double* bigger = nullptr;
+            if(cudaMalloc((void**)&bigger, 2 * dt.cap * dt.sample_len * sizeof(double)) != cudaSuccess) return CHIML_ERR_CUDA;
+            cudaMemcpyAsync(bigger, dt.d_ring, dt.cap * dt.sample_len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(dt.d_ring);
+            ctx->dev_bytes += dt.cap * dt.sample_len * sizeof(double);
+            dt.d_ring = bigger; dt.cap *= 2;
+        }
+        k_detector<<<(unsigned)std::min<size_t>((dt.sample_len + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+            ctx->d_field[dt.field], dt.loc[0], dt.loc[2], dt.loc[1], dt.sz[0], dt.sz[2], dt.sz[1], ctx->lz, ctx->px, dt.d_ring + dt.count * dt.sample_len);
+        ++ctx->launches;
+        ++dt.count;
+    }
+    return 0;
+}
+
+int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "step before commit");
+    if(n < 0) return fail(ctx, CHIML_ERR_ARG, "negative step count");
+    CK(cudaSetDevice(ctx->device));
+    const int nsrc = (int)ctx->sources.size();
+    if(nsrc > 0)
+    {
+        if(!src_amp) return fail(ctx, CHIML_ERR_ARG, "sources registered but no amplitudes given");
+        const size_t need = (size_t)n * nsrc;
+        if(need > ctx->src_amp_cap)
+        {
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_src_amp);
+            CK(cudaMalloc((void**)&ctx->d_src_amp, need * sizeof(double)));
+            ctx->src_amp_cap = need;
+        }
+        CK(cudaMemcpyAsync(ctx->d_src_amp, src_amp, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for(int k = 0; k < n; ++k)
+    {
+        int rc = launch_step(ctx, k, nsrc);
+        if(rc) return fail(ctx, rc, "launch failed");
+    }
+    CK(cudaGetLastError());
+    return CHIML_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int chiml_gpu_step_n(ChimlCtx* ctx, int n, const double* src_amp) { return step_n_impl(ctx, n, src_amp); }
+
+int chiml_gpu_sync(ChimlCtx* ctx)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CHIML_OK;
+}
+
+int chiml_gpu_step_n_timed(ChimlCtx* ctx, int n, const double* src_amp, float* ms)
+{
+    if(!ctx || !ms) return CHIML_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = step_n_impl(ctx, n, src_amp);
+    if(rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return CHIML_OK;
+}
+
+int64_t chiml_gpu_launch_count(const ChimlCtx* ctx) { return ctx ? ctx->launches : 0; }
+size_t chiml_gpu_device_bytes(const ChimlCtx* ctx) { return ctx ? ctx->dev_bytes : 0; }
+
+int chiml_gpu_upload_field(ChimlCtx* ctx, int field, const double* host)
+{
+    if(!ctx || !host) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "upload before commit");
+    if(field < 0 || field >= CHIML_NFIELDS || !ctx->d_field[field]) return fail(ctx, CHIML_ERR_ARG, "upload_field: field absent");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(ctx->d_field[field], ctx->px * sizeof(double), host, ctx->lx * sizeof(double), ctx->lx * sizeof(double),
+                         (size_t)ctx->ly * ctx->lz, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CHIML_OK;
+}
+
+int chiml_gpu_download_field(ChimlCtx* ctx, int field, double* host)
+{
+    if(!ctx || !host) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "download before commit");
+    if(field < 0 || field >= CHIML_NFIELDS || !ctx->d_field[field]) return fail(ctx, CHIML_ERR_ARG, "download_field: field absent");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(host, ctx->lx * sizeof(double), ctx->d_field[field], ctx->px * sizeof(double), ctx->lx * sizeof(double),
+                         (size_t)ctx->ly * ctx->lz, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CHIML_OK;
+}
+
+static int pole_xfer(ChimlCtx* ctx, int comp, int pole, int prev, double* host, const double* hostIn)
+{
+    if(!ctx || (!host && !hostIn)) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "pole access before commit");
+    if(comp < 0 || comp > 2 || pole < 0 || pole >= MAX_POLES) return fail(ctx, CHIML_ERR_ARG, "pole access: bad comp/pole");
+    CK(cudaSetDevice(ctx->device));
+    const SpanTable& sp = ctx->span[comp];
+    double* pool = ctx->d_P[comp][pole][prev ? 1 - ctx->pcur : ctx->pcur];
+    if(host) std::fill(host, host + ctx->nlogical, 0.0);
+    if(!pool || sp.total == 0) return CHIML_OK;
+    std::vector<double> tmp((size_t)sp.total);
+    if(host) { CK(cudaMemcpyAsync(tmp.data(), pool, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
+    const size_t nrows = (size_t)ctx->ly * ctx->lz;
+    for(size_t row = 0; row < nrows; ++row)
+    {
+        if(sp.h_xmin[row] < 0) continue;
+        const int w = sp.h_xmax[row] - sp.h_xmin[row] + 1;
+        if(host) std::copy_n(&tmp[(size_t)sp.h_base[row]], w, host + row * ctx->lx + sp.h_xmin[row]);
+        else     std::copy_n(hostIn + row * ctx->lx + sp.h_xmin[row], w, &tmp[(size_t)sp.h_base[row]]);
+    }
+    if(hostIn) { CK(cudaMemcpyAsync(pool, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); CK(cudaStreamSynchronize(ctx->stream)); }
+    return CHIML_OK;
+}
+
+int chiml_gpu_download_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host) { return pole_xfer(ctx, comp, pole, prev, host, nullptr); }
+int chiml_gpu_upload_pole(ChimlCtx* ctx, int comp, int pole, int prev, const double* host) { return pole_xfer(ctx, comp, pole, prev, nullptr, host); }
+
+int chiml_gpu_download_ordip_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host)
+{
+    if(!ctx || !host) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "pole access before commit");
+    if(comp < 0 || comp > 2 || pole < 0 || pole >= MAX_POLES) return fail(ctx, CHIML_ERR_ARG, "pole access: bad comp/pole");
+    CK(cudaSetDevice(ctx->device));
+    const SpanTable& sp = ctx->span_node;
+    double* pool = ctx->d_oP[comp][pole][prev ? 1 - ctx->pcur : ctx->pcur];
+    std::fill(host, host + ctx->nlogical, 0.0);
+    if(!pool || sp.total == 0) return CHIML_OK;
+    std::vector<double> tmp((size_t)sp.total);
+    CK(cudaMemcpyAsync(tmp.data(), pool, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t nrows = (size_t)ctx->ly * ctx->lz;
+    for(size_t row = 0; row < nrows; ++row)
+        if(sp.h_xmin[row] >= 0)
+            std::copy_n(&tmp[(size_t)sp.h_base[row]], sp.h_xmax[row] - sp.h_xmin[row] + 1, host + row * ctx->lx + sp.h_xmin[row]);
+    return CHIML_OK;
+}
+
+int chiml_gpu_download_psi(ChimlCtx* ctx, int comp, int part, double* host)
+{
+    if(!ctx || !host) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "psi access before commit");
+    if(comp < 0 || comp > 5 || part < 0 || part > 1) return fail(ctx, CHIML_ERR_ARG, "download_psi: bad comp/part");
+    CK(cudaSetDevice(ctx->device));
+    const PmlPartDev& pp = ctx->pml[comp][part];
+    std::fill(host, host + ctx->nlogical, 0.0);
+    if(!pp.d_psi) return CHIML_OK;
+    std::vector<double> tmp((size_t)pp.psi_count);
+    CK(cudaMemcpyAsync(tmp.data(), pp.d_psi, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for(int y = 0; y < ctx->ly; ++y)
+        for(int z = 0; z < ctx->lz; ++z)
+            for(int x = 0; x < ctx->lx; ++x)
+            {
+                const int co = pp.axis == 0 ? x : (pp.axis == 1 ? y : z);
+                const int cc = pp.h_cmap[co];
+                if(cc < 0) continue;
+                long ip;
+                if(pp.axis == 0)      ip = cc + pp.psi_pitch * (z + (long)ctx->lz * y);
+                else if(pp.axis == 1) ip = x + ctx->px * (z + (long)ctx->lz * cc);
+                else                  ip = x + ctx->px * (cc + (long)pp.nact * y);
+                host[x + (size_t)ctx->lx * (z + (size_t)ctx->lz * y)] = tmp[(size_t)ip];
+            }
+    return CHIML_OK;
+}
+
+int chiml_gpu_read_detector(ChimlCtx* ctx, int slot, double* out, size_t cap_samples, size_t* n_samples)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "read_detector before commit");
+    if(slot < 0 || slot >= (int)ctx->detectors.size()) return fail(ctx, CHIML_ERR_ARG, "read_detector: bad slot");
+    CK(cudaSetDevice(ctx->device));
+    const DetectorDev& dt = ctx->detectors[slot];
+    CK(cudaStreamSynchronize(ctx->stream));
+    if(n_samples) *n_samples = dt.count;
+    const size_t n = std::min(cap_samples, dt.count);
+    if(out && n) CK(cudaMemcpy(out, dt.d_ring, n * dt.sample_len * sizeof(double), cudaMemcpyDeviceToHost));
+    return CHIML_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,147 @@
+// Internal context of the B200 FDTD engine (not part of the C ABI).
+//
+// Device data layout (DESIGN.md "Data layout in HBM"):
+//   * every field component is one SoA buffer, logical index (x, z, y) with x fastest, rows padded to a
+//     multiple of 16 doubles (128 B) -> physical index  x + px * (z + lz * y)
+//   * per component a uint16 "cell info" plane painted from the reference's update lists:
+//       low byte  = material class (index into a small table of prefactors / pole constants)
+//       high byte = flags: which of the reference's per-run operations apply to the cell
+//   * CPML psi arrays exist only inside the slabs (the axis normal to the slab is compressed)
+//   * polarisation (pole) state exists only on the x-span of dispersive cells of each grid row
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/chiml_gpu.h"
+
+namespace chiml {
+
+constexpr int MAX_POLES = 12;     // poles per material class (largest built-in metal has 6)
+constexpr int MAX_SOURCES = 32;
+constexpr int MAX_CLASSES = 255;
+
+// cell-info flags (high byte)
+constexpr uint16_t F_CURL  = 0x0100;  // interior curl run covers the cell (upE_/upH_/upD_)
+constexpr uint16_t F_ISD   = 0x0200;  // ... and accumulates into D (upD_)
+constexpr uint16_t F_PG0   = 0x0400;  // CPML part 0 grid term   (updateListGrid_k_)
+constexpr uint16_t F_PS0   = 0x0800;  // CPML part 0 psi update  (updateListPsi_j_)
+constexpr uint16_t F_PG1   = 0x1000;  // CPML part 1 grid term   (updateListGrid_j_)
+constexpr uint16_t F_PS1   = 0x2000;  // CPML part 1 psi update  (updateListPsi_k_)
+constexpr uint16_t F_D2E   = 0x4000;  // isotropic pole update + D->E (upLorD_)
+constexpr uint16_t F_ORD2E = 0x8000;  // oriented-dipole D->E (upOrDipD_)
+constexpr uint16_t CLS_MASK = 0x00FF;
+
+struct ClassEntry
+{
+    double pf1, pf2;            // prefactors[1], prefactors[2] of the run
+    double inv_eps;             // 1.0/eps           (DtoU dscal factor)
+    double neg_inv_eps;         // -1.0/eps          (DtoU daxpy factor)
+    double neg_half_inv_eps;    // -0.5/eps          (orDipDtoU daxpy factor)
+    int npoles;
+    int pad;
+    double alpha[MAX_POLES], xi[MAX_POLES], gamma[MAX_POLES];
+    double dip[MAX_POLES][3];
+};
+
+// compact storage of per-row x-spans (pole state)
+struct SpanTable
+{
+    int32_t* d_xmin = nullptr;   // per logical row (z + lz*y): first x of the span, or -1
+    int32_t* d_xmax = nullptr;
+    int64_t* d_base = nullptr;   // offset of the span in the pool
+    int64_t total = 0;
+    std::vector<int32_t> h_xmin, h_xmax;
+    std::vector<int64_t> h_base;
+};
+
+struct PmlPartDev
+{
+    int present = 0;
+    int has_psi = 0;
+    int axis = -1;               // derivative axis: 0 x, 1 y, 2 z
+    int vfield = -1;             // ChimlField driving this part
+    long off_logical = 0;        // indOff - ind (logical)
+    double Db = 0.0;
+    int nact = 0;                // number of coordinates along `axis` with an active psi
+    long psi_pitch = 0, psi_count = 0;
+    double* d_F = nullptr;       // per coordinate along axis
+    double* d_b = nullptr;
+    double* d_c = nullptr;
+    int32_t* d_cmap = nullptr;   // coordinate -> compact coordinate (or -1)
+    double* d_psi = nullptr;
+    std::vector<int32_t> h_cmap;
+};
+
+struct SourceDev { int field; int32_t loc[3], sz[3]; };
+struct DetectorDev
+{
+    int field; int32_t loc[3], sz[3]; int every;
+    size_t sample_len = 0;
+    double* d_ring = nullptr; size_t cap = 0; size_t count = 0;
+};
+
+struct HostList { std::vector<ChimlRun> runs; };
+struct HostPml { int present = 0, has_psi = 0; std::vector<ChimlPsiParams> psi; std::vector<ChimlGridParams> grid; };
+struct HostObj { int npoles = 0, use_or_dip = 0; std::vector<double> alpha, xi, gamma, dip; };
+
+} // namespace chiml
+
+struct ChimlCtx
+{
+    ChimlGridDesc g{};
+    int device = 0;
+    int lx = 0, ly = 0, lz = 0;
+    long px = 0;                 // padded row pitch (doubles)
+    long plane = 0;              // px * lz
+    size_t nphys = 0;            // px * lz * ly
+    size_t nlogical = 0;
+    bool committed = false;
+    std::string err;
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    // state
+    double* d_field[CHIML_NFIELDS] = {};
+    uint16_t* d_info[6] = {};
+    chiml::ClassEntry* d_cls[6] = {};
+    int ncls[6] = {};
+    chiml::PmlPartDev pml[6][2];
+
+    // isotropic poles: per E component pools [pole][cur/prev]
+    chiml::SpanTable span[3];
+    int npoles_comp[3] = {};
+    double* d_P[3][chiml::MAX_POLES][2] = {};
+    int pcur = 0;                // which of the two buffers currently holds P (the other holds prevP)
+
+    // oriented-dipole poles at nodes
+    uint16_t* d_info_node = nullptr;
+    chiml::ClassEntry* d_cls_node = nullptr;
+    int ncls_node = 0;
+    chiml::SpanTable span_node;
+    int nordip = 0;
+    double* d_oP[3][chiml::MAX_POLES][2] = {};
+    long node_off[3] = {};       // logical offsets ind_i-ind, ind_j-ind, ind_k-ind of the node list
+    long ordip_off[3] = {};      // logical offset ind_i-ind of upOrDipD_[c]
+
+    // curl offsets per component (logical): ind_j - ind, ind_k - ind
+    long off_j[6] = {}, off_k[6] = {};
+
+    std::vector<chiml::SourceDev> sources;
+    double* d_src_amp = nullptr; size_t src_amp_cap = 0;
+    std::vector<chiml::DetectorDev> detectors;
+
+    // host-side copies of the setup until commit
+    chiml::HostList lists[5][6];
+    chiml::HostPml hpml[6][2];
+    std::vector<chiml::HostObj> objs;
+
+    long long step_count = 0;
+    int64_t launches = 0;
+    size_t dev_bytes = 0;
+};

@@ -141,6 +141,8 @@ int chiml_gpu_download_field(ChimlCtx* ctx, int field, double* host);
 /* isotropic pole state lorP_[c][p] / prevLorP_[c][p] expanded to the logical full grid (zeros elsewhere) */
 int chiml_gpu_download_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host);
 int chiml_gpu_upload_pole(ChimlCtx* ctx, int comp, int pole, int prev, const double* host);
+/* oriented-dipole pole state orDipLorP_[c][p] / prevOrDipLorP_[c][p] (node-centred), expanded likewise */
+int chiml_gpu_download_ordip_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host);
 /* CPML psi of component comp, part 0/1, expanded to the logical full grid */
 int chiml_gpu_download_psi(ChimlCtx* ctx, int comp, int part, double* host);
 /* copies up to cap samples (each sz[0]*sz[1]*sz[2] doubles, x fastest then z then y) and reports how many exist */

@@ -1,0 +1,75 @@
+"""Regenerates the committed golden fixtures from the UNMODIFIED reference (oracle/_ref/chiml_ref,
+built in place from /root/reference by oracle/Makefile).  Run here (the container that has
+/root/reference); the fixtures travel to the GPU box.
+
+For every case:   <case>.json          the chiML input (chiml_b200.inputs builders)
+                  <case>.rank0.plan    the reference constructor's own lists (include/chiml_plan.h)
+                  <case>.expect.npz    every public field / pole grid of the reference after n_steps
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from chiml_b200 import inputs as I  # noqa: E402
+from chiml_b200 import plan as P    # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "chiml_ref")
+RES = 100
+DT = I.default_dt(RES)
+
+
+def _short_pulse(cfg):
+    for s in cfg["SourceList"]:
+        for p in s["PulseList"]:
+            p["t_0"] = 0.25
+            p["cutoff"] = 2.5
+    return cfg
+
+
+def cases():
+    c = {}
+    c["te_vacuum"] = I.c1_te_vacuum(n=47, steps=150, pml_cells=8, out="out/te")
+    c["tm_drude"] = I.c2_tm_drude(n=63, steps=100, pml_cells=8, rod=(20, 6), nfreq=0, out="out/tm")
+    c["tm_au"] = I.c2_tm_drude(n=63, steps=100, pml_cells=8, rod=(20, 6), material="Au", nfreq=0, out="out/tmau")
+    c["vac3d"] = I.config(I.comp_cell([21 / RES, 17 / RES, 23 / RES], RES, 60 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+                          [I.normal_source("Ez", [0, 0, 0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])], [],
+                          [I.detector([0.03, 0, 0], [0, 0, 0], "Ez", "out/v3/dtc", time_int=DT * 1.0000001)])
+    c["lorentz3d"] = I.config(I.comp_cell([23 / RES, 19 / RES, 21 / RES], RES, 60 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+                              [I.normal_source("Ez", [0, 0, 0.04], [0.05, 0.04, 0], [I.gaussian_pulse(1.5, 1.0)])],
+                              [I.block([0.08, 0.06, 0.05], [0.01, 0, -0.02], eps=2.0, pols=[I.lorentz_pole(1.2, 0.1, 2.0), I.lorentz_pole(0.5, 0.05, 3.0)]),
+                               I.sphere(0.04, [-0.03, 0.02, 0.03], eps=1.5, pols=[I.lorentz_pole(0.7, 0.2, 1.0)])],
+                              [I.detector([0.03, 0, 0], [0, 0, 0], "Ez", "out/l3/dtc", time_int=DT * 1.0000001)])
+    c["aniso_slab3d"] = I.c3_aniso_slab(n=23, steps=50, pml_cells=5, slab_cells=6, out="out/c3")
+    c["kappa3d"] = I.config(I.comp_cell([19 / RES, 21 / RES, 17 / RES], RES, 50 * DT - 0.5 * DT, "Ex"),
+                            I.pml([5 / RES, 6 / RES, 4 / RES], a_max=0.2, ma=2.0, m=3.5, sig_opt_rat=0.9, kappa_max=3.0),
+                            [I.normal_source("Ey", [0, 0, 0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
+                            [I.block([0.06, 0.3, 0.05], [0.0, 0.0, 0.0], eps=3.0)],
+                            [I.detector([0.03, 0, 0], [0, 0, 0], "Ey", "out/k3/dtc", time_int=DT * 1.0000001)])
+    return {k: _short_pulse(v) for k, v in c.items()}
+
+
+def main():
+    if not os.path.exists(REF):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "-j8"], check=True)
+    work = os.path.join(HERE, "_work")
+    os.makedirs(work, exist_ok=True)
+    for name, cfg in cases().items():
+        jpath = os.path.join(HERE, name + ".json")
+        I.write(cfg, jpath)
+        I.write(cfg, os.path.join(work, name + ".json"))   # the reference prefixes "stripped_" to the name as given: run on a cwd-relative copy
+        subprocess.run([REF, name + ".json", "--dump", os.path.join(work, name + ".dump"), "--plan", os.path.join(HERE, name),
+                        "--quiet", "--no-output"], check=True, cwd=work, stdout=subprocess.DEVNULL)
+        dump = P.read_dump(os.path.join(work, name + ".dump"))
+        arrays = {nm: arr for (rank, nm), (ln, ys, arr) in dump.items() if rank == 0}
+        np.savez_compressed(os.path.join(HERE, name + ".expect.npz"), **arrays)
+        print(name, {k: v.shape for k, v in list(arrays.items())[:1]}, len(arrays), "arrays",
+              os.path.getsize(os.path.join(HERE, name + ".expect.npz")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

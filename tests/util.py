@@ -1,0 +1,52 @@
+"""Shared helpers of the parity tests."""
+import glob
+import os
+
+import numpy as np
+
+from chiml_b200 import plan as P
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p)[:-len(".rank0.plan")] for p in glob.glob(os.path.join(GOLDEN, "*.rank0.plan")))
+
+
+def load_plan(case: str) -> P.Plan:
+    return P.read_plan(os.path.join(GOLDEN, case + ".rank0.plan"))
+
+
+def load_expect(case: str):
+    with np.load(os.path.join(GOLDEN, case + ".expect.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def state_array(sim, name: str):
+    """Fetch the array the reference dump calls `name` (oracle/ref_driver.cpp grabGrid names) from an
+    OracleSim or a GpuSim (both expose field / pole / ordip_pole)."""
+    if name in P.FIELD_NAMES:
+        return sim.field(P.FIELD_NAMES.index(name))
+    if name.startswith("poP"):
+        return sim.ordip_pole("xyz".index(name[3]), int(name[4:]), 1)
+    if name.startswith("oP"):
+        return sim.ordip_pole("xyz".index(name[2]), int(name[3:]), 0)
+    if name.startswith("pP"):
+        return sim.pole("xyz".index(name[2]), int(name[3:]), 1)
+    if name.startswith("P"):
+        return sim.pole("xyz".index(name[1]), int(name[2:]), 0)
+    raise KeyError(name)
+
+
+def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
+    den = float(np.linalg.norm(b.ravel()))
+    num = float(np.linalg.norm((a - b).ravel()))
+    return num / den if den > 0 else num
+
+
+def state_names(plan: P.Plan):
+    names = [P.FIELD_NAMES[f] for f in plan.fields_present()]
+    for c in range(3):
+        if (6 + c) in plan.fields_present():
+            for p in range(plan.n_lor_poles):
+                names += [f"P{'xyz'[c]}{p}", f"pP{'xyz'[c]}{p}"]
+            for p in range(plan.n_ordip_poles):
+                names += [f"oP{'xyz'[c]}{p}", f"poP{'xyz'[c]}{p}"]
+    return names
