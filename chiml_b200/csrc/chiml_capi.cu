@@ -110,10 +110,10 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for(auto& p : ctx->d_field) cudaFree(p);
+    for(auto& p : ctx->d_field_base) cudaFree(p);
     for(int c = 0; c < 6; ++c)
     {
-        cudaFree(ctx->d_info[c]); cudaFree(ctx->d_cls[c]);
+        cudaFree(ctx->d_info[c]); cudaFree(ctx->d_cls[c]); cudaFree(ctx->d_pf[c]);
         for(int k = 0; k < 2; ++k)
         {
             PmlPartDev& pp = ctx->pml[c][k];
@@ -129,6 +129,7 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     cudaFree(ctx->d_info_node); cudaFree(ctx->d_cls_node);
     cudaFree(ctx->span_node.d_xmin); cudaFree(ctx->span_node.d_xmax); cudaFree(ctx->span_node.d_base);
     cudaFree(ctx->d_src_amp);
+    cudaFree(ctx->d_tiledesc[0]); cudaFree(ctx->d_tiledesc[1]);
     for(auto& d : ctx->detectors) cudaFree(d.d_ring);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -369,6 +370,8 @@ int build_pml_part(ChimlCtx* ctx, int comp, int part, int* d_err)
     int dd[3];
     if(!decode_offset(ctx, pp.off_logical, dd) || pp.off_logical == 0) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_cpml: stencil offset is not one cell along an axis");
     pp.axis = dd[0] ? 0 : (dd[1] ? 1 : 2);
+    // part 0 differentiates along j = (i+1)%3, part 1 along k = (i+2)%3 (PML/parallelPML.hpp:124-141,679,687); the kernel relies on it
+    if(pp.axis != (i + 1 + part) % 3) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_cpml: derivative axis of the list does not match the part (j for part 0, k for part 1)");
     const int L = ln[pp.axis];
     std::vector<double> F(L, 0.0), b(L, 0.0), c(L, 0.0);
     std::vector<char> Fset(L, 0), bset(L, 0);
@@ -440,8 +443,15 @@ int chiml_gpu_commit(ChimlCtx* ctx)
     if((rc = dev_alloc(ctx, &d_err, 1))) return rc;
 
     // fields (+1 padded row of slack on either side is not needed: every stencil point of an updated cell lies inside the ghost-inclusive grid)
+    // one plane (+ a row) of zeroed slack on either side: the kernels load the stencil neighbours of ghost and
+    // padding cells unconditionally
+    ctx->guard = (size_t)ctx->plane + 32;
     for(int f = 0; f < CHIML_NFIELDS; ++f)
-        if(field_exists(ctx, f) && (rc = dev_alloc(ctx, &ctx->d_field[f], ctx->nphys))) return rc;
+        if(field_exists(ctx, f))
+        {
+            if((rc = dev_alloc(ctx, &ctx->d_field_base[f], ctx->nphys + 2 * ctx->guard))) return rc;
+            ctx->d_field[f] = ctx->d_field_base[f] + ctx->guard;
+        }
 
     // --- update lists -> class tables + painted cell info -------------------------------------------------
     for(int comp = 0; comp < 6; ++comp)
@@ -460,7 +470,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
             for(int k : {CHIML_LIST_D, CHIML_LIST_LORD, CHIML_LIST_ORDIPD})
                 if(!ctx->lists[k][comp].runs.empty()) return fail(ctx, CHIML_ERR_ARG, "D-type update list given but has_D = 0");
         // stencil offsets must be uniform per component
-        bool haveOff = false;
+        bool& haveOff = ctx->have_off[comp];
         struct { int kind; uint16_t flags; bool poles; } plan[4] = {
             {CHIML_LIST_U, F_CURL, false}, {CHIML_LIST_D, (uint16_t)(F_CURL | F_ISD), true},
             {CHIML_LIST_LORD, F_D2E, true}, {CHIML_LIST_ORDIPD, F_ORD2E, true}};
@@ -498,6 +508,9 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         }
         ctx->ncls[comp] = (int)cb.entries.size();
         if((rc = dev_upload(ctx, &ctx->d_cls[comp], cb.entries))) return rc;
+        std::vector<double2> pf(cb.entries.size());
+        for(size_t k = 0; k < pf.size(); ++k) pf[k] = make_double2(cb.entries[k].pf1, cb.entries[k].pf2);
+        if((rc = dev_upload(ctx, &ctx->d_pf[comp], pf))) return rc;
         int dj[3], dk[3];
         if(haveOff && (!decode_offset(ctx, ctx->off_j[comp], dj) || !decode_offset(ctx, ctx->off_k[comp], dk)))
             return fail(ctx, CHIML_ERR_UNSUPPORTED, "update list: stencil offset is not one cell along an axis");
@@ -567,6 +580,20 @@ int chiml_gpu_commit(ChimlCtx* ctx)
             if(field_exists(ctx, comp) && (rc = build_pml_part(ctx, comp, part, d_err))) return rc;
         }
     if(ctx->g.pml_on_D && !ctx->g.has_D) return fail(ctx, CHIML_ERR_ARG, "pml_on_D needs has_D");
+    // The kernels feed the CPML parts with the stencil values of the curl: part 0 (grid_k, derivative along j) must use
+    // the offset of ind_j, part 1 (grid_j, derivative along k) the offset of ind_k (true for the reference: both follow derivOff)
+    for(int comp = 0; comp < 6; ++comp)
+    {
+        long* offs[2] = {&ctx->off_j[comp], &ctx->off_k[comp]};
+        for(int part = 0; part < 2; ++part)
+        {
+            const PmlPartDev& pp = ctx->pml[comp][part];
+            if(!pp.present) continue;
+            if(!ctx->have_off[comp] && *offs[part] == 0) *offs[part] = pp.off_logical;
+            else if(*offs[part] != pp.off_logical)
+                return fail(ctx, CHIML_ERR_UNSUPPORTED, "CPML stencil offset differs from the curl stencil offset of the same component");
+        }
+    }
 
     int h_err = 0;
     CK(cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -576,6 +603,39 @@ int chiml_gpu_commit(ChimlCtx* ctx)
     if(h_err == 2) return fail(ctx, CHIML_ERR_ARG, "an update list covers a cell twice");
     if(h_err == 3) return fail(ctx, CHIML_ERR_ARG, "a CPML list covers a cell twice");
 
+    // The kernels hard-wire the reference's stencil (derivOff, FDTD_MANAGER/parallelFDTDField.cpp:80-82,248-250):
+    // component c reads grid_k one cell along axis j=(c+1)%3 (ind_j) and grid_j one cell along axis k=(c+2)%3 (ind_k),
+    // backwards for E and forwards for H.  Refuse lists that say otherwise.
+    {
+        const long strideL[3] = {1, (long)ctx->lx * ctx->lz, ctx->lx};   // logical strides of x, y, z
+        for(int comp = 0; comp < 6; ++comp)
+        {
+            if(!field_exists(ctx, comp)) continue;
+            const int i = comp % 3, s = comp < 3 ? -1 : 1, base = comp < 3 ? CHIML_HX : CHIML_EX;
+            const bool hasVj = field_exists(ctx, base + (i + 1) % 3), hasVk = field_exists(ctx, base + (i + 2) % 3);
+            const bool anyList = ctx->have_off[comp] || ctx->pml[comp][0].present || ctx->pml[comp][1].present;
+            if(!anyList) continue;
+            if(hasVk && ctx->off_j[comp] != 0 && ctx->off_j[comp] != s * strideL[(i + 1) % 3])
+                return fail(ctx, CHIML_ERR_UNSUPPORTED, "update list: ind_j is not the reference's Yee stencil neighbour");
+            if(hasVj && ctx->off_k[comp] != 0 && ctx->off_k[comp] != s * strideL[(i + 2) % 3])
+                return fail(ctx, CHIML_ERR_UNSUPPORTED, "update list: ind_k is not the reference's Yee stencil neighbour");
+        }
+    }
+    // tile descriptors (one per k_update block): uniform interior tiles skip the cell-info planes altogether
+    {
+        const dim3 tb(32, ctx->lz > 1 ? TILE_Z : 1, 1);
+        const unsigned nxt = (ctx->lx + TILE_X - 1) / TILE_X, nzt = (ctx->lz + tb.y - 1) / tb.y;
+        const size_t ntiles = (size_t)nxt * nzt * ctx->ly;
+        for(int fam = 0; fam < 2; ++fam)
+        {
+            if((rc = dev_alloc(ctx, &ctx->d_tiledesc[fam], ntiles))) return rc;
+            const int b0 = fam == 0 ? 0 : 3;
+            k_tile_desc<<<(unsigned)ntiles, tb, 0, ctx->stream>>>(ctx->d_info[b0], ctx->d_info[b0 + 1], ctx->d_info[b0 + 2], ctx->d_tiledesc[fam],
+                                                                 nxt, nzt, ctx->lx, ctx->lz, ctx->px);
+            ++ctx->launches;
+        }
+        CK(cudaGetLastError());
+    }
     // detectors: ring buffers sized on first use; sample at t = 0 (FDTD_MANAGER/parallelFDTDField.cpp:832-833)
     ctx->committed = true;
     for(size_t d = 0; d < ctx->detectors.size(); ++d)
@@ -609,6 +669,7 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
     a.pml_on_D = ctx->g.pml_on_D;
     a.nsp_xmin = ctx->span_node.d_xmin; a.nsp_xmax = ctx->span_node.d_xmax; a.nsp_base = ctx->span_node.d_base;
     const int cur = ctx->pcur, prv = 1 - ctx->pcur;
+    for(int i = 0; i < 3; ++i) a.fam[i] = ctx->d_field[(isE ? CHIML_HX : CHIML_EX) + i];
     for(int i = 0; i < 3; ++i)
     {
         const int comp = isE ? i : 3 + i;
@@ -616,6 +677,7 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
         if(!ctx->d_field[comp]) continue;
         ca.info = ctx->d_info[comp];
         ca.cls = ctx->d_cls[comp];
+        ca.pf = ctx->d_pf[comp];
         ca.U = ctx->d_field[comp];
         ca.D = isE ? ctx->d_field[CHIML_DX + i] : nullptr;
         const int base = isE ? CHIML_HX : CHIML_EX;
@@ -630,10 +692,8 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
             PmlArgs& pa = ca.pml[part];
             pa.present = pp.present;
             if(!pp.present) continue;
-            pa.V = ctx->d_field[pp.vfield];
             pa.F = pp.d_F; pa.b = pp.d_b; pa.c = pp.d_c; pa.cmap = pp.d_cmap; pa.psi = pp.d_psi;
             pa.Db = pp.Db; pa.psi_pitch = pp.psi_pitch; pa.axis = pp.axis; pa.nact = pp.nact; pa.has_psi = pp.has_psi;
-            decode_offset(ctx, pp.off_logical, d); pa.off = phys_offset(ctx, d);
         }
         if(isE)
         {
@@ -652,12 +712,28 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
 
 int launch_step(ChimlCtx* ctx, long long k, int nsrc)
 {
-    const dim3 block(64, ctx->lz > 1 ? 4 : 1, 1);
-    const dim3 grid((ctx->lx + block.x - 1) / block.x, (ctx->lz + block.y - 1) / block.y, ctx->ly);
+    // each thread owns two x-adjacent cells; blocks are ordered y-fastest within an (x, z) tile column
+    const dim3 block(32, ctx->lz > 1 ? TILE_Z : 1, 1);
+    const unsigned nxt = (ctx->lx + 2 * block.x - 1) / (2 * block.x), nzt = (ctx->lz + block.y - 1) / block.y;
+    // y chunks: enough blocks for ~4 waves of 2 resident blocks per SM, but at least 16 planes per block so that the
+    // one-plane pipeline prologue stays below ~6 %
+    const unsigned columns = nxt * nzt;
+    static const int ycEnv = getenv("CHIML_YCHUNK") ? atoi(getenv("CHIML_YCHUNK")) : 0;
+    unsigned nchunks = std::max(1u, (148u * 2u * 4u + columns - 1) / columns);
+    int ychunk = std::max(16, (ctx->ly + (int)nchunks - 1) / (int)nchunks);
+    if(ycEnv > 0) ychunk = ycEnv;
+    ychunk = std::min(ychunk, ctx->ly);
+    nchunks = (ctx->ly + ychunk - 1) / ychunk;
+    const dim3 grid(columns * nchunks, 1, 1);
+    const dim3 nblock(64, ctx->lz > 1 ? 4 : 1, 1);
+    const dim3 ngrid((ctx->lx + nblock.x - 1) / nblock.x, (ctx->lz + nblock.y - 1) / nblock.y, ctx->ly);
     StepArgs a;
     // H half step: updateH + updateHPML_ (step() items 4 and 6)
     fill_step_args(ctx, false, a);
-    k_update<false><<<grid, block, 0, ctx->stream>>>(a);
+    a.nxt = nxt; a.nzt = nzt; a.ychunk = ychunk; a.tiledesc = ctx->d_tiledesc[1];
+    if(ctx->g.mode == CHIML_MODE_3D)      k_update<false, CHIML_MODE_3D><<<grid, block, 0, ctx->stream>>>(a);
+    else if(ctx->g.mode == CHIML_MODE_TE) k_update<false, CHIML_MODE_TE><<<grid, block, 0, ctx->stream>>>(a);
+    else                                  k_update<false, CHIML_MODE_TM><<<grid, block, 0, ctx->stream>>>(a);
     ++ctx->launches;
     // sources (item 7): all sources, E and H alike, are injected here
     for(int q = 0; q < nsrc; ++q)
@@ -685,12 +761,15 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
             na.eoff[c] = phys_offset(ctx, d);
             for(int p = 0; p < MAX_POLES; ++p) { na.Pcur[c][p] = ctx->d_oP[c][p][cur]; na.Pnew[c][p] = ctx->d_oP[c][p][prv]; }
         }
-        k_ordip_poles<<<grid, block, 0, ctx->stream>>>(na);
+        k_ordip_poles<<<ngrid, nblock, 0, ctx->stream>>>(na);
         ++ctx->launches;
     }
     // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
     fill_step_args(ctx, true, a);
-    k_update<true><<<grid, block, 0, ctx->stream>>>(a);
+    a.nxt = nxt; a.nzt = nzt; a.ychunk = ychunk; a.tiledesc = ctx->d_tiledesc[0];
+    if(ctx->g.mode == CHIML_MODE_3D)      k_update<true, CHIML_MODE_3D><<<grid, block, 0, ctx->stream>>>(a);
+    else if(ctx->g.mode == CHIML_MODE_TE) k_update<true, CHIML_MODE_TE><<<grid, block, 0, ctx->stream>>>(a);
+    else                                  k_update<true, CHIML_MODE_TM><<<grid, block, 0, ctx->stream>>>(a);
     ++ctx->launches;
     ctx->pcur = 1 - ctx->pcur;
     ++ctx->step_count;

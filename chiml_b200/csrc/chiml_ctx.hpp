@@ -107,9 +107,14 @@ struct ChimlCtx
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     // state
-    double* d_field[CHIML_NFIELDS] = {};
+    double* d_field[CHIML_NFIELDS] = {};       // points `guard` doubles into d_field_base
+    double* d_field_base[CHIML_NFIELDS] = {};
+    size_t guard = 0;
+    bool have_off[6] = {};
     uint16_t* d_info[6] = {};
     chiml::ClassEntry* d_cls[6] = {};
+    double2* d_pf[6] = {};       // {pf1, pf2} per class (interior fast path)
+    unsigned* d_tiledesc[2] = {};  // per-tile descriptors, [0] E family, [1] H family
     int ncls[6] = {};
     chiml::PmlPartDev pml[6][2];
 

@@ -13,14 +13,12 @@ namespace chiml {
 
 struct PmlArgs
 {
-    const double* V;      // field driving this part (grid_k for part 0, grid_j for part 1)
     const double* F;      // DbField per coordinate along `axis`
     const double* b;
     const double* c;
     const int32_t* cmap;  // coordinate -> compact psi coordinate
     double* psi;
     double Db;
-    long off;             // physical offset of the second stencil point
     long psi_pitch;
     int axis;
     int nact;
@@ -32,6 +30,7 @@ struct CompArgs
 {
     const uint16_t* info;
     const ClassEntry* cls;
+    const double2* pf;    // compact copy of {pf1, pf2} per class for the interior fast path
     double* U;            // E_c or H_c
     double* D;            // D_c (E components of dispersive runs) or nullptr
     const double* Vj;     // grid_j, used with offK  (UTIL/FDTD_up_eq.cpp:29-30)
@@ -53,6 +52,7 @@ struct CompArgs
 struct StepArgs
 {
     CompArgs c[3];
+    const double* fam[3];        // the three components of the OTHER family (H for the E half step, E for the H half step)
     // node span table (oriented dipoles)
     const int32_t* nsp_xmin;
     const int32_t* nsp_xmax;
@@ -60,6 +60,9 @@ struct StepArgs
     int lx, ly, lz;
     long px;
     int pml_on_D;
+    unsigned nxt, nzt;           // x tiles, z tiles
+    int ychunk;                  // planes marched by one block
+    const unsigned* tiledesc;    // per-tile descriptors of this family
 };
 
 struct NodeArgs
@@ -89,149 +92,9 @@ __device__ __forceinline__ double node_value(const StepArgs& a, const double* po
     return pool[a.nsp_base[row] + (x - xmin)];
 }
 
-template <bool IS_E>
-__device__ __forceinline__ void update_component(const StepArgs& a, const CompArgs& ca, long r, long row, int x, int y, int z)
-{
-    const uint16_t info = ca.info[r];
-    if(info == 0) return;
-    const ClassEntry& ce = ca.cls[info & CLS_MASK];
-
-    double u = ca.U[r];
-    double pn[MAX_POLES];
-    int np = 0;
-
-    // updatePolE, isotropic poles (FDTD_MANAGER/parallelFDTDField.hpp:1355-1361 -> UTIL/FDTD_up_eq.cpp:435-446):
-    // tmp = P; P = alpha*P; P += xi*Pprev; P += gamma*E^n; Pprev = tmp
-    if(IS_E && (info & F_D2E))
-    {
-        np = ce.npoles;
-        if(np > 0)
-        {
-            const long ip = ca.sp_base[row] + (x - ca.sp_xmin[row]);
-#pragma unroll
-            for(int p = 0; p < MAX_POLES; ++p)
-            {
-                if(p < np)
-                {
-                    double t = dm(ce.alpha[p], ca.Pcur[p][ip]);
-                    t = axpy1(t, ce.xi[p], ca.Pnew[p][ip]);
-                    t = axpy1(t, ce.gamma[p], u);
-                    ca.Pnew[p][ip] = t;
-                    pn[p] = t;
-                }
-            }
-        }
-    }
-
-    const bool pmlCell = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
-    const bool pmlOnD = IS_E && a.pml_on_D;
-    const bool needD = IS_E && ((info & (F_ISD | F_D2E | F_ORD2E)) || (pmlOnD && pmlCell));
-    double dv = needD ? ca.D[r] : 0.0;
-    bool dDirty = false;
-
-    // updateD / updateE / updateH: TwoCompCurl, OneCompCurlJ, OneCompCurlK (UTIL/FDTD_up_eq.cpp:10-35)
-    if(info & F_CURL)
-    {
-        double t = (IS_E && (info & F_ISD)) ? dv : u;
-        if(ca.Vj)
-        {
-            t = axpy1(t,  ce.pf2, ca.Vj[r]);
-            t = axpy1(t, -ce.pf2, ca.Vj[r + ca.offK]);
-        }
-        if(ca.Vk)
-        {
-            t = axpy1(t, -ce.pf1, ca.Vk[r]);
-            t = axpy1(t,  ce.pf1, ca.Vk[r + ca.offJ]);
-        }
-        if(IS_E && (info & F_ISD)) { dv = t; dDirty = true; } else u = t;
-    }
-
-    // parallelCPML<T>::updateGrid (PML/parallelPML.hpp:693-697): part 0 then part 1; each part is
-    // updatePsiField then the grid daxpys (PML/parallelPML.cpp:12-40)
-    if(pmlCell)
-    {
-        double t = pmlOnD ? dv : u;
-#pragma unroll
-        for(int part = 0; part < 2; ++part)
-        {
-            const PmlArgs& pp = ca.pml[part];
-            const uint16_t fg = part == 0 ? F_PG0 : F_PG1;
-            const uint16_t fs = part == 0 ? F_PS0 : F_PS1;
-            if(!(info & (fg | fs))) continue;
-            const double vr = pp.V[r];
-            const double vo = pp.V[r + pp.off];
-            const int coord = pp.axis == 0 ? x : (pp.axis == 1 ? y : z);
-            double ps = 0.0;
-            if(info & fs)
-            {
-                const int cc = pp.cmap[coord];
-                long ip;
-                if(pp.axis == 0)      ip = cc + pp.psi_pitch * (z + (long)a.lz * y);
-                else if(pp.axis == 1) ip = x + a.px * (z + (long)a.lz * cc);
-                else                  ip = x + a.px * (cc + (long)pp.nact * y);
-                const double cv = pp.c[coord];
-                ps = dm(pp.b[coord], pp.psi[ip]);
-                ps = axpy1(ps,  cv, vr);
-                ps = axpy1(ps, -cv, vo);
-                pp.psi[ip] = ps;
-            }
-            if(info & fg)
-            {
-                const double Fv = pp.F[coord];
-                t = axpy1(t,  Fv, vr);
-                t = axpy1(t, -Fv, vo);
-                if(info & fs) t = axpy1(t, pp.Db, ps);
-            }
-        }
-        if(pmlOnD) { dv = t; dDirty = true; } else u = t;
-    }
-
-    // D2E (FDTD_MANAGER/parallelFDTDField.hpp:1452-1473)
-    if(IS_E && (info & F_D2E))
-    {
-        // DtoU (UTIL/FDTD_up_eq.cpp:838-848): E = D; E *= 1/eps; E += (-1/eps) P_p for every pole grid
-        u = dm(ce.inv_eps, dv);
-#pragma unroll
-        for(int p = 0; p < MAX_POLES; ++p)
-            if(p < np) u = axpy1(u, ce.neg_inv_eps, pn[p]);
-    }
-    else if(IS_E && (info & F_ORD2E))
-    {
-        // orDipDtoU / orDipDtoUZ (UTIL/FDTD_up_eq.cpp:862-889)
-        u = dm(ce.inv_eps, dv);
-        for(int p = 0; p < ca.nordip; ++p)
-        {
-            const double p0 = node_value(a, ca.oP[p], x, y, z);
-            if(ca.ord_zvariant)
-                u = axpy1(u, ce.neg_inv_eps, p0);
-            else
-            {
-                const double p1 = node_value(a, ca.oP[p], x + ca.ord_dx, y + ca.ord_dy, z + ca.ord_dz);
-                u = axpy1(u, ce.neg_half_inv_eps, p0);
-                u = axpy1(u, ce.neg_half_inv_eps, p1);
-            }
-        }
-    }
-
-    ca.U[r] = u;
-    if(dDirty) ca.D[r] = dv;
-}
-
-// One thread per cell; the three components that share a cell index share their neighbour loads
-// through L1.  grid = (ceil(lx/BX), ceil(lz/BZ), ly).
-template <bool IS_E>
-__global__ void __launch_bounds__(256) k_update(const __grid_constant__ StepArgs a)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int z = blockIdx.y * blockDim.y + threadIdx.y;
-    const int y = blockIdx.z;
-    if(x >= a.lx || z >= a.lz) return;
-    const long row = z + (long)a.lz * y;
-    const long r = x + a.px * row;
-#pragma unroll
-    for(int c = 0; c < 3; ++c)
-        if(a.c[c].U) update_component<IS_E>(a, a.c[c], r, row, x, y, z);
-}
+} // namespace chiml
+#include "chiml_update.cuh"
+namespace chiml {
 
 // updatePolE, oriented-dipole poles at the integer nodes
 // (FDTD_MANAGER/parallelFDTDField.hpp:1350-1354 -> UTIL/FDTD_up_eq.cpp:450-631)
