@@ -129,7 +129,7 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     cudaFree(ctx->d_info_node); cudaFree(ctx->d_cls_node);
     cudaFree(ctx->span_node.d_xmin); cudaFree(ctx->span_node.d_xmax); cudaFree(ctx->span_node.d_base);
     cudaFree(ctx->d_src_amp);
-    cudaFree(ctx->d_tiledesc[0]); cudaFree(ctx->d_tiledesc[1]);
+    for(auto& f : ctx->d_tiles) for(auto& p : f) cudaFree(p);
     for(auto& d : ctx->detectors) cudaFree(d.d_ring);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -507,6 +507,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
             if((rc = paint_list(ctx, runs, cls, pl.flags, ctx->d_info[comp], d_err))) return rc;
         }
         ctx->ncls[comp] = (int)cb.entries.size();
+        ctx->h_cls[comp] = cb.entries;
         if((rc = dev_upload(ctx, &ctx->d_cls[comp], cb.entries))) return rc;
         std::vector<double2> pf(cb.entries.size());
         for(size_t k = 0; k < pf.size(); ++k) pf[k] = make_double2(cb.entries[k].pf1, cb.entries[k].pf2);
@@ -621,20 +622,60 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 return fail(ctx, CHIML_ERR_UNSUPPORTED, "update list: ind_k is not the reference's Yee stencil neighbour");
         }
     }
-    // tile descriptors (one per k_update block): uniform interior tiles skip the cell-info planes altogether
+    // tile classification -> compact work lists for k_fast / k_uniform / k_general (chiml_update.cuh)
     {
         const dim3 tb(32, ctx->lz > 1 ? TILE_Z : 1, 1);
         const unsigned nxt = (ctx->lx + TILE_X - 1) / TILE_X, nzt = (ctx->lz + tb.y - 1) / tb.y;
         const size_t ntiles = (size_t)nxt * nzt * ctx->ly;
+        TileSummary* d_sum = nullptr;
+        CK(cudaMalloc((void**)&d_sum, ntiles * sizeof(TileSummary)));
+        std::vector<TileSummary> sum(ntiles);
         for(int fam = 0; fam < 2; ++fam)
         {
-            if((rc = dev_alloc(ctx, &ctx->d_tiledesc[fam], ntiles))) return rc;
             const int b0 = fam == 0 ? 0 : 3;
-            k_tile_desc<<<(unsigned)ntiles, tb, 0, ctx->stream>>>(ctx->d_info[b0], ctx->d_info[b0 + 1], ctx->d_info[b0 + 2], ctx->d_tiledesc[fam],
-                                                                 nxt, nzt, ctx->lx, ctx->lz, ctx->px);
+            k_tile_summary<<<(unsigned)ntiles, tb, 0, ctx->stream>>>(ctx->d_info[b0], ctx->d_info[b0 + 1], ctx->d_info[b0 + 2], d_sum, nxt, nzt, ctx->lz, ctx->px);
             ++ctx->launches;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(sum.data(), d_sum, ntiles * sizeof(TileSummary), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            std::vector<TileRec> lists[3];
+            for(size_t tIdx = 0; tIdx < ntiles; ++tIdx)
+            {
+                const TileSummary& ts = sum[tIdx];
+                if(!(ts.count[0] | ts.count[1] | ts.count[2])) continue;
+                TileRec rec;
+                std::memset(&rec, 0, sizeof(rec));
+                rec.x0 = (int)(tIdx % nxt) * TILE_X;
+                rec.z0 = (int)((tIdx / nxt) % nzt) * (int)tb.y;
+                rec.y = (int)(tIdx / ((size_t)nxt * nzt));
+                bool fast = true, uniform = true;
+                for(int c = 0; c < 3; ++c)
+                {
+                    if(!ts.count[c]) continue;
+                    const unsigned rc_ = ts.rect[c];
+                    const unsigned area = (((rc_ >> 8) & 0xFF) - (rc_ & 0xFF)) * ((rc_ >> 24) - ((rc_ >> 16) & 0xFF));
+                    const unsigned inf = ts.info[c];
+                    const ClassEntry& ce = ctx->h_cls[b0 + c][inf & CLS_MASK];
+                    const bool rectFull = ts.same[c] && area == ts.count[c];
+                    if(!rectFull) { fast = uniform = false; continue; }
+                    if((inf & 0xFF00u) != F_CURL) fast = false;
+                    if((inf & F_ORD2E) || ((inf & F_D2E) && ce.npoles > 0)) uniform = false;
+                    rec.rect[c] = rc_;
+                    rec.info[c] = inf;
+                    rec.pf[c] = make_double2(ce.pf1, ce.pf2);
+                    rec.inv_eps[c] = ce.inv_eps;
+                }
+                lists[fast ? 0 : (uniform ? 1 : 2)].push_back(rec);
+            }
+            for(int k = 0; k < 3; ++k)
+            {
+                ctx->ntiles[fam][k] = (unsigned)lists[k].size();
+                TileRec* d = nullptr;
+                if((rc = dev_upload(ctx, &d, lists[k]))) return rc;
+                ctx->d_tiles[fam][k] = d;
+            }
         }
-        CK(cudaGetLastError());
+        cudaFree(d_sum);
     }
     // detectors: ring buffers sized on first use; sample at t = 0 (FDTD_MANAGER/parallelFDTDField.cpp:832-833)
     ctx->committed = true;
@@ -710,31 +751,32 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
     }
 }
 
+template <bool IS_E, int MODE>
+void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block)
+{
+    const int fam = IS_E ? 0 : 1;
+    if(ctx->ntiles[fam][0]) { k_fast<IS_E, MODE><<<ctx->ntiles[fam][0], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0]); ++ctx->launches; }
+    if(ctx->ntiles[fam][1]) { k_uniform<IS_E, MODE><<<ctx->ntiles[fam][1], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1]); ++ctx->launches; }
+    if(ctx->ntiles[fam][2]) { k_general<IS_E, MODE><<<ctx->ntiles[fam][2], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2]); ++ctx->launches; }
+}
+template <bool IS_E>
+void launch_family(ChimlCtx* ctx, const StepArgs& a, const dim3 block)
+{
+    if(ctx->g.mode == CHIML_MODE_3D)      launch_family_mode<IS_E, CHIML_MODE_3D>(ctx, a, block);
+    else if(ctx->g.mode == CHIML_MODE_TE) launch_family_mode<IS_E, CHIML_MODE_TE>(ctx, a, block);
+    else                                  launch_family_mode<IS_E, CHIML_MODE_TM>(ctx, a, block);
+}
+
 int launch_step(ChimlCtx* ctx, long long k, int nsrc)
 {
-    // each thread owns two x-adjacent cells; blocks are ordered y-fastest within an (x, z) tile column
+    // one block per tile of the compact lists built at commit
     const dim3 block(32, ctx->lz > 1 ? TILE_Z : 1, 1);
-    const unsigned nxt = (ctx->lx + 2 * block.x - 1) / (2 * block.x), nzt = (ctx->lz + block.y - 1) / block.y;
-    // y chunks: enough blocks for ~4 waves of 2 resident blocks per SM, but at least 16 planes per block so that the
-    // one-plane pipeline prologue stays below ~6 %
-    const unsigned columns = nxt * nzt;
-    static const int ycEnv = getenv("CHIML_YCHUNK") ? atoi(getenv("CHIML_YCHUNK")) : 0;
-    unsigned nchunks = std::max(1u, (148u * 2u * 4u + columns - 1) / columns);
-    int ychunk = std::max(16, (ctx->ly + (int)nchunks - 1) / (int)nchunks);
-    if(ycEnv > 0) ychunk = ycEnv;
-    ychunk = std::min(ychunk, ctx->ly);
-    nchunks = (ctx->ly + ychunk - 1) / ychunk;
-    const dim3 grid(columns * nchunks, 1, 1);
     const dim3 nblock(64, ctx->lz > 1 ? 4 : 1, 1);
     const dim3 ngrid((ctx->lx + nblock.x - 1) / nblock.x, (ctx->lz + nblock.y - 1) / nblock.y, ctx->ly);
     StepArgs a;
     // H half step: updateH + updateHPML_ (step() items 4 and 6)
     fill_step_args(ctx, false, a);
-    a.nxt = nxt; a.nzt = nzt; a.ychunk = ychunk; a.tiledesc = ctx->d_tiledesc[1];
-    if(ctx->g.mode == CHIML_MODE_3D)      k_update<false, CHIML_MODE_3D><<<grid, block, 0, ctx->stream>>>(a);
-    else if(ctx->g.mode == CHIML_MODE_TE) k_update<false, CHIML_MODE_TE><<<grid, block, 0, ctx->stream>>>(a);
-    else                                  k_update<false, CHIML_MODE_TM><<<grid, block, 0, ctx->stream>>>(a);
-    ++ctx->launches;
+    launch_family<false>(ctx, a, block);
     // sources (item 7): all sources, E and H alike, are injected here
     for(int q = 0; q < nsrc; ++q)
     {
@@ -766,11 +808,7 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
     }
     // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
     fill_step_args(ctx, true, a);
-    a.nxt = nxt; a.nzt = nzt; a.ychunk = ychunk; a.tiledesc = ctx->d_tiledesc[0];
-    if(ctx->g.mode == CHIML_MODE_3D)      k_update<true, CHIML_MODE_3D><<<grid, block, 0, ctx->stream>>>(a);
-    else if(ctx->g.mode == CHIML_MODE_TE) k_update<true, CHIML_MODE_TE><<<grid, block, 0, ctx->stream>>>(a);
-    else                                  k_update<true, CHIML_MODE_TM><<<grid, block, 0, ctx->stream>>>(a);
-    ++ctx->launches;
+    launch_family<true>(ctx, a, block);
     ctx->pcur = 1 - ctx->pcur;
     ++ctx->step_count;
     // detectors (item 18)

@@ -114,7 +114,10 @@ struct ChimlCtx
     uint16_t* d_info[6] = {};
     chiml::ClassEntry* d_cls[6] = {};
     double2* d_pf[6] = {};       // {pf1, pf2} per class (interior fast path)
-    unsigned* d_tiledesc[2] = {};  // per-tile descriptors, [0] E family, [1] H family
+    // compact tile lists per family ([0] E, [1] H) and kind ([0] fast, [1] uniform, [2] general); element type chiml::TileRec
+    void* d_tiles[2][3] = {};
+    unsigned ntiles[2][3] = {};
+    std::vector<chiml::ClassEntry> h_cls[6];
     int ncls[6] = {};
     chiml::PmlPartDev pml[6][2];
 

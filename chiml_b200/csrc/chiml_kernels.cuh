@@ -60,9 +60,22 @@ struct StepArgs
     int lx, ly, lz;
     long px;
     int pml_on_D;
-    unsigned nxt, nzt;           // x tiles, z tiles
-    int ychunk;                  // planes marched by one block
-    const unsigned* tiledesc;    // per-tile descriptors of this family
+};
+
+constexpr int TILE_X = 64;   // cells per tile row (32 lanes x 2 cells)
+constexpr int TILE_Z = 8;    // rows per tile (3-D); 2-D grids use 1
+
+// one work item of k_fast / k_uniform / k_general (built at commit time, 128 bytes)
+struct TileRec
+{
+    int x0, z0, y, pad0;
+    unsigned rect[3];            // per component: xlo | xhi<<8 | zlo<<16 | zhi<<24 (tile-local, hi exclusive); 0 = no cell of this component
+    unsigned pad1;
+    unsigned info[3];            // per component: the one info value of its cells (k_uniform)
+    unsigned pad2;
+    double2 pf[3];               // per component: {pf1, pf2} of its class
+    double inv_eps[3];           // per component: 1/eps of its class (pole-free D->E)
+    double pad3;
 };
 
 struct NodeArgs

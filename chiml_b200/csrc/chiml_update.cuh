@@ -1,16 +1,25 @@
-// The fused half-step kernel (H half step: updateH + updateHPML_; E half step: updatePolE (isotropic),
+// The fused half-step kernels (H half step: updateH + updateHPML_; E half step: updatePolE (isotropic),
 // updateD, updateE, updateEPML_, D2E) -- reference FDTD_MANAGER/parallelFDTDField.hpp:1228-1303.
 // Included by chiml_kernels.cuh.
+//
+// Work decomposition.  The grid is cut into tiles of TILE_X x TILE_Z cells of one y plane; one thread
+// block processes one tile, each thread two x-adjacent cells and every component of the family at
+// them.  At commit time every tile of every family is classified from the painted cell-info planes:
+//   FAST     every component's updated cells form a rectangle of plain interior curl cells of one class
+//   UNIFORM  every component's updated cells form a rectangle with ONE info value whose flags need no
+//            per-cell data beyond the CPML coordinate tables (curl, D target, CPML parts, pole-free D->E)
+//   GENERAL  anything else (dispersive cells, material boundaries, ...): per-cell info is read
+// and three compact tile lists per family are built.  k_fast / k_uniform never read the cell-info
+// planes and run block-uniform straight-line code with all loads issued up front; they are small
+// (about 60 registers) so that enough warps are resident to cover HBM latency.  The stencil is the
+// reference's (derivOff of FDTD_MANAGER/parallelFDTDField.cpp:80-82,248-250): component c reads
+// grid_j = other[(c+1)%3] one cell along axis (c+2)%3 and grid_k = other[(c+2)%3] one cell along
+// axis (c+1)%3, backwards for E, forwards for H; chiml_gpu_commit verifies that the lists agree.
+// Field arrays carry one plane of zeroed slack on either side, so the unconditional neighbour loads
+// of ghost / padding cells stay in bounds.
 #pragma once
 
 namespace chiml {
-
-constexpr int TILE_X = 64;   // cells per tile row (32 lanes x 2 cells)
-constexpr int TILE_Z = 8;    // rows per tile (3-D); 2-D grids use 1
-
-// tile descriptor (one uint32 per tile, per family, per plane): status in the top byte, the
-// uniform class of each component in the three low bytes
-constexpr unsigned TD_GENERAL = 0u, TD_UNIFORM = 1u, TD_EMPTY = 2u;
 
 // which components exist (FDTD_MANAGER/parallelFDTDField.hpp:391-443): TE = Ex,Ey,Hz; TM = Ez,Hx,Hy
 template <int MODE> __host__ __device__ constexpr bool has_E(int c) { return MODE == CHIML_MODE_3D || (MODE == CHIML_MODE_TE ? c != 2 : c == 2); }
@@ -18,10 +27,13 @@ template <int MODE> __host__ __device__ constexpr bool has_H(int c) { return MOD
 template <bool IS_E, int MODE> __host__ __device__ constexpr bool has_own(int c) { return IS_E ? has_E<MODE>(c) : has_H<MODE>(c); }
 template <bool IS_E, int MODE> __host__ __device__ constexpr bool has_other(int c) { return IS_E ? has_H<MODE>(c) : has_E<MODE>(c); }
 
-// General path: one field component C of one cell.  u = current value of U[r]; (vj_r, vj_n) = grid_j at
-// ind and ind_k, (vk_r, vk_n) = grid_k at ind and ind_j -- the four stencil values of TwoCompCurl, which
-// are also the stencil values of the two CPML parts (part 0: grid_k, derivative along j = (C+1)%3;
-// part 1: grid_j, derivative along k = (C+2)%3).  Returns true when U[r] must be written back.
+// ---------------------------------------------------------------------------------------------------
+// general path: one field component C of one cell, driven by its cell-info word
+// ---------------------------------------------------------------------------------------------------
+// u = current value of U[r]; (vj_r, vj_n) = grid_j at ind and ind_k, (vk_r, vk_n) = grid_k at ind and ind_j --
+// the four stencil values of TwoCompCurl, which are also the stencil values of the two CPML parts (part 0:
+// grid_k, derivative along j = (C+1)%3; part 1: grid_j, derivative along k = (C+2)%3).
+// Returns true when U[r] must be written back.
 template <bool IS_E, int MODE, int C>
 __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& ca, const unsigned info, double& u,
                                             const double vj_r, const double vj_n, const double vk_r, const double vk_n,
@@ -155,6 +167,9 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// shared pieces of the three tile kernels
+// ---------------------------------------------------------------------------------------------------
 // Values of V at the stencil neighbour of cells (x, x+1): one cell along AXIS in direction SIGN.
 // own2 = V[r], V[r+1].  Row pitch and plane stride are multiples of 16 doubles, so the y / z
 // neighbours are aligned 16-byte loads; the x neighbour needs one extra scalar.
@@ -166,6 +181,227 @@ __device__ __forceinline__ double2 neighbour2(const double* __restrict__ V, cons
     return *reinterpret_cast<const double2*>(V + r + off);
 }
 
+// all loads of one thread: own family u, other family v at r, and the six stencil neighbours
+template <bool IS_E, int MODE>
+struct PairLoads
+{
+    double2 u[3], v[3], nj[3], nk[3];
+    __device__ __forceinline__ void load(const StepArgs& a, const long r)
+    {
+        constexpr int S = IS_E ? -1 : 1;
+        const long plane = a.px * a.lz;
+#pragma unroll
+        for(int c = 0; c < 3; ++c) u[c] = v[c] = nj[c] = nk[c] = make_double2(0.0, 0.0);
+#pragma unroll
+        for(int c = 0; c < 3; ++c)
+        {
+            if(has_own<IS_E, MODE>(c)) u[c] = *reinterpret_cast<const double2*>(a.c[c].U + r);
+            if(has_other<IS_E, MODE>(c)) v[c] = *reinterpret_cast<const double2*>(a.fam[c] + r);
+        }
+        // component c: grid_j = other[(c+1)%3] along axis (c+2)%3; grid_k = other[(c+2)%3] along axis (c+1)%3
+        if(has_own<IS_E, MODE>(0))
+        {
+            if(has_other<IS_E, MODE>(1)) nj[0] = neighbour2<2, S>(a.fam[1], r, a.px, plane, v[1]);
+            if(has_other<IS_E, MODE>(2)) nk[0] = neighbour2<1, S>(a.fam[2], r, a.px, plane, v[2]);
+        }
+        if(has_own<IS_E, MODE>(1))
+        {
+            if(has_other<IS_E, MODE>(2)) nj[1] = neighbour2<0, S>(a.fam[2], r, a.px, plane, v[2]);
+            if(has_other<IS_E, MODE>(0)) nk[1] = neighbour2<2, S>(a.fam[0], r, a.px, plane, v[0]);
+        }
+        if(has_own<IS_E, MODE>(2))
+        {
+            if(has_other<IS_E, MODE>(0)) nj[2] = neighbour2<1, S>(a.fam[0], r, a.px, plane, v[0]);
+            if(has_other<IS_E, MODE>(1)) nk[2] = neighbour2<0, S>(a.fam[1], r, a.px, plane, v[1]);
+        }
+    }
+};
+
+// rectangle of updated cells of one component inside the tile: bytes xlo, xhi, zlo, zhi (hi exclusive)
+__device__ __forceinline__ void rect_mask(const unsigned rect, const int xl, const int zl, bool& m0, bool& m1)
+{
+    const int xlo = rect & 0xFF, xhi = (rect >> 8) & 0xFF, zlo = (rect >> 16) & 0xFF, zhi = rect >> 24;
+    const bool zin = zl >= zlo && zl < zhi;
+    m0 = zin && xl >= xlo && xl < xhi;
+    m1 = zin && xl + 1 >= xlo && xl + 1 < xhi;
+}
+__device__ __forceinline__ void store_pair(double* p, const double2 t, const bool m0, const bool m1)
+{
+    if(m0 && m1) *reinterpret_cast<double2*>(p) = t;
+    else if(m0) p[0] = t.x;
+    else if(m1) p[1] = t.y;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_fast: tiles whose updated cells are plain interior curl cells (TwoCompCurl / OneCompCurlJ / K)
+// ---------------------------------------------------------------------------------------------------
+template <bool IS_E, int MODE>
+__global__ void __launch_bounds__(256, 4) k_fast(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+{
+    const TileRec& t = tiles[blockIdx.x];
+    const int xl = 2 * threadIdx.x, zl = threadIdx.y;
+    const int x = t.x0 + xl, z = t.z0 + zl;
+    if(x >= a.px || z >= a.lz) return;
+    const long r = x + a.px * (z + (long)a.lz * t.y);
+    PairLoads<IS_E, MODE> L;
+    L.load(a, r);
+#pragma unroll
+    for(int c = 0; c < 3; ++c)
+    {
+        if(!has_own<IS_E, MODE>(c)) continue;
+        const unsigned rect = t.rect[c];
+        if(rect == 0) continue;                       // nothing of this component in the tile
+        bool m0, m1;
+        rect_mask(rect, xl, zl, m0, m1);
+        const double2 pf = t.pf[c];                   // {pf1, pf2}
+        const double2 vj = L.v[(c + 1) % 3], vk = L.v[(c + 2) % 3];
+        double2 w = L.u[c];
+        if(has_other<IS_E, MODE>((c + 1) % 3))
+        {
+            w.x = axpy1(w.x,  pf.y, vj.x);      w.y = axpy1(w.y,  pf.y, vj.y);
+            w.x = axpy1(w.x, -pf.y, L.nj[c].x); w.y = axpy1(w.y, -pf.y, L.nj[c].y);
+        }
+        if(has_other<IS_E, MODE>((c + 2) % 3))
+        {
+            w.x = axpy1(w.x, -pf.x, vk.x);      w.y = axpy1(w.y, -pf.x, vk.y);
+            w.x = axpy1(w.x,  pf.x, L.nk[c].x); w.y = axpy1(w.y,  pf.x, L.nk[c].y);
+        }
+        store_pair(a.c[c].U + r, w, m0, m1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_uniform: tiles where each component has ONE info value over a rectangle: curl into E/H or D, CPML parts
+// (psi recursion + grid terms) on E/H or D, pole-free D->E.  Block-uniform control flow, no cell-info reads.
+// ---------------------------------------------------------------------------------------------------
+template <bool IS_E, int MODE, int C>
+__device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t, const PairLoads<IS_E, MODE>& L,
+                                             const long r, const long row, const int x, const int y, const int z, const int xl, const int zl)
+{
+    if(!has_own<IS_E, MODE>(C)) return;
+    const unsigned rect = t.rect[C];
+    if(rect == 0) return;
+    const unsigned info = t.info[C];
+    const CompArgs& ca = a.c[C];
+    constexpr bool HAS_VJ = has_other<IS_E, MODE>((C + 1) % 3);
+    constexpr bool HAS_VK = has_other<IS_E, MODE>((C + 2) % 3);
+    bool m0, m1;
+    rect_mask(rect, xl, zl, m0, m1);
+    const double2 vj = L.v[(C + 1) % 3], vk = L.v[(C + 2) % 3];
+    const double2 nj = L.nj[C], nk = L.nk[C];
+    double2 u = L.u[C];
+
+    const bool pmlCell = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
+    const bool pmlOnD = IS_E && a.pml_on_D;
+    const bool needD = IS_E && ((info & (F_ISD | F_D2E)) || (pmlOnD && pmlCell));
+    double2 dv = make_double2(0.0, 0.0);
+    if(needD) dv = *reinterpret_cast<const double2*>(ca.D + r);
+    bool dDirty = false;
+
+    if(info & F_CURL)
+    {
+        const double2 pf = t.pf[C];
+        double2 w = (IS_E && (info & F_ISD)) ? dv : u;
+        if(HAS_VJ)
+        {
+            w.x = axpy1(w.x,  pf.y, vj.x); w.y = axpy1(w.y,  pf.y, vj.y);
+            w.x = axpy1(w.x, -pf.y, nj.x); w.y = axpy1(w.y, -pf.y, nj.y);
+        }
+        if(HAS_VK)
+        {
+            w.x = axpy1(w.x, -pf.x, vk.x); w.y = axpy1(w.y, -pf.x, vk.y);
+            w.x = axpy1(w.x,  pf.x, nk.x); w.y = axpy1(w.y,  pf.x, nk.y);
+        }
+        if(IS_E && (info & F_ISD)) { dv = w; dDirty = true; } else u = w;
+    }
+    if(pmlCell)
+    {
+        double2 w = pmlOnD ? dv : u;
+#pragma unroll
+        for(int part = 0; part < 2; ++part)
+        {
+            if(part == 0 ? !HAS_VK : !HAS_VJ) continue;
+            const PmlArgs& pp = ca.pml[part];
+            const unsigned fg = part == 0 ? F_PG0 : F_PG1;
+            const unsigned fs = part == 0 ? F_PS0 : F_PS1;
+            if(!(info & (fg | fs))) continue;
+            constexpr int AX0 = (C + 1) % 3, AX1 = (C + 2) % 3;
+            const int axis = part == 0 ? AX0 : AX1;
+            const double2 vr = part == 0 ? vk : vj;
+            const double2 vo = part == 0 ? nk : nj;
+            double2 ps = make_double2(0.0, 0.0);
+            double2 Fv, bv, cv;
+            if(axis == 0)
+            {
+                Fv = *reinterpret_cast<const double2*>(pp.F + x);
+                if(info & fs) { bv = *reinterpret_cast<const double2*>(pp.b + x); cv = *reinterpret_cast<const double2*>(pp.c + x); }
+            }
+            else
+            {
+                const int coord = axis == 1 ? y : z;
+                const double f = pp.F[coord];
+                Fv = make_double2(f, f);
+                if(info & fs) { const double bb = pp.b[coord], cc = pp.c[coord]; bv = make_double2(bb, bb); cv = make_double2(cc, cc); }
+            }
+            if(info & fs)
+            {
+                if(axis == 0)
+                {
+                    const int2 cc = *reinterpret_cast<const int2*>(pp.cmap + x);
+                    const long base = pp.psi_pitch * row;
+                    if(m0) { double p = dm(bv.x, pp.psi[base + cc.x]); p = axpy1(p, cv.x, vr.x); p = axpy1(p, -cv.x, vo.x); pp.psi[base + cc.x] = p; ps.x = p; }
+                    if(m1) { double p = dm(bv.y, pp.psi[base + cc.y]); p = axpy1(p, cv.y, vr.y); p = axpy1(p, -cv.y, vo.y); pp.psi[base + cc.y] = p; ps.y = p; }
+                }
+                else
+                {
+                    const int cc = pp.cmap[axis == 1 ? y : z];
+                    const long ip = axis == 1 ? x + a.px * (z + (long)a.lz * cc) : x + a.px * (cc + (long)pp.nact * y);
+                    double2 p = *reinterpret_cast<const double2*>(pp.psi + ip);
+                    p.x = dm(bv.x, p.x);            p.y = dm(bv.y, p.y);
+                    p.x = axpy1(p.x,  cv.x, vr.x);  p.y = axpy1(p.y,  cv.y, vr.y);
+                    p.x = axpy1(p.x, -cv.x, vo.x);  p.y = axpy1(p.y, -cv.y, vo.y);
+                    store_pair(pp.psi + ip, p, m0, m1);
+                    ps = p;
+                }
+            }
+            if(info & fg)
+            {
+                w.x = axpy1(w.x,  Fv.x, vr.x); w.y = axpy1(w.y,  Fv.y, vr.y);
+                w.x = axpy1(w.x, -Fv.x, vo.x); w.y = axpy1(w.y, -Fv.y, vo.y);
+                if(info & fs) { w.x = axpy1(w.x, pp.Db, ps.x); w.y = axpy1(w.y, pp.Db, ps.y); }
+            }
+        }
+        if(pmlOnD) { dv = w; dDirty = true; } else u = w;
+    }
+    if(IS_E && (info & F_D2E))
+    {
+        // DtoU with no pole grids contributing (UTIL/FDTD_up_eq.cpp:838-843): E = (1/eps) * D
+        const double ie = t.inv_eps[C];
+        u.x = dm(ie, dv.x); u.y = dm(ie, dv.y);
+    }
+    store_pair(ca.U + r, u, m0, m1);
+    if(dDirty) store_pair(ca.D + r, dv, m0, m1);
+}
+
+template <bool IS_E, int MODE>
+__global__ void __launch_bounds__(256, 3) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+{
+    const TileRec& t = tiles[blockIdx.x];
+    const int xl = 2 * threadIdx.x, zl = threadIdx.y;
+    const int x = t.x0 + xl, z = t.z0 + zl, y = t.y;
+    if(x >= a.px || z >= a.lz) return;
+    const long row = z + (long)a.lz * y;
+    const long r = x + a.px * row;
+    PairLoads<IS_E, MODE> L;
+    L.load(a, r);
+    uniform_comp<IS_E, MODE, 0>(a, t, L, r, row, x, y, z, xl, zl);
+    uniform_comp<IS_E, MODE, 1>(a, t, L, r, row, x, y, z, xl, zl);
+    uniform_comp<IS_E, MODE, 2>(a, t, L, r, row, x, y, z, xl, zl);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_general: everything else, per cell
+// ---------------------------------------------------------------------------------------------------
 template <bool IS_E, int MODE, int C>
 __device__ __forceinline__ void general_pair(const StepArgs& a, double2 u, const double2 vj, const double2 nj, const double2 vk, const double2 nk,
                                              const long r, const long row, const int x, const int y, const int z)
@@ -175,216 +411,76 @@ __device__ __forceinline__ void general_pair(const StepArgs& a, double2 u, const
     const ushort2 info = *reinterpret_cast<const ushort2*>(ca.info + r);
     const bool w0 = update_cell<IS_E, MODE, C>(a, ca, info.x, u.x, vj.x, nj.x, vk.x, nk.x, r, row, x, y, z);
     const bool w1 = update_cell<IS_E, MODE, C>(a, ca, info.y, u.y, vj.y, nj.y, vk.y, nk.y, r + 1, row, x + 1, y, z);
-    if(w0 && w1) *reinterpret_cast<double2*>(ca.U + r) = u;
-    else if(w0) ca.U[r] = u.x;
-    else if(w1) ca.U[r + 1] = u.y;
-}
-
-// TwoCompCurl / OneCompCurlJ / OneCompCurlK on both cells of the pair (UTIL/FDTD_up_eq.cpp:10-35)
-template <bool IS_E, int MODE, int C>
-__device__ __forceinline__ void fast_pair(const StepArgs& a, const unsigned cls, double2 t, const double2 vj, const double2 nj, const double2 vk, const double2 nk, const long r)
-{
-    if(!has_own<IS_E, MODE>(C)) return;
-    const CompArgs& ca = a.c[C];
-    const double2 pf = ca.pf[cls];          // {pf1, pf2}
-    if(has_other<IS_E, MODE>((C + 1) % 3))
-    {
-        t.x = axpy1(t.x,  pf.y, vj.x); t.y = axpy1(t.y,  pf.y, vj.y);
-        t.x = axpy1(t.x, -pf.y, nj.x); t.y = axpy1(t.y, -pf.y, nj.y);
-    }
-    if(has_other<IS_E, MODE>((C + 2) % 3))
-    {
-        t.x = axpy1(t.x, -pf.x, vk.x); t.y = axpy1(t.y, -pf.x, vk.y);
-        t.x = axpy1(t.x,  pf.x, nk.x); t.y = axpy1(t.y,  pf.x, nk.y);
-    }
-    *reinterpret_cast<double2*>(ca.U + r) = t;
-}
-
-// Fused half step, y-marching.  A block owns one (x, z) tile column (TILE_X x TILE_Z cells) and marches
-// through a chunk of y planes; each thread owns two x-adjacent cells and all components at them.
-//   * Register pipelining: while plane y is being computed, every load of plane y+1 (own fields, the
-//     other family, its x and z stencil neighbours) is already in flight, so HBM latency is hidden by
-//     design rather than by occupancy.  The y stencil neighbour never touches memory again: the E
-//     half step keeps the previous plane of H in registers, the H half step reads E one plane ahead.
-//     Each field value therefore crosses HBM once per half step (plus a one-row z halo per tile).
-//   * A per-tile, per-plane descriptor built at commit time says whether every cell of the tile is a
-//     plain interior curl cell of one material class: such tiles (the bulk of the domain) never read
-//     the cell-info planes and run straight-line code; CPML / dispersive / boundary tiles take the
-//     general path (update_cell).
-// The stencil is the reference's (derivOff of FDTD_MANAGER/parallelFDTDField.cpp:80-82,248-250):
-// component c reads grid_j = other[(c+1)%3] one cell along axis (c+2)%3 and grid_k = other[(c+2)%3] one
-// cell along axis (c+1)%3, backwards for E, forwards for H; chiml_gpu_commit verifies the lists agree.
-// Field arrays carry one plane of zeroed slack on either side, so the look-ahead loads and the
-// neighbour loads of ghost / padding cells stay in bounds.
-template <bool IS_E, int MODE>
-struct Stage
-{
-    double2 u[3];      // own family at the two cells
-    double2 v[3];      // other family at the two cells (E half step only; the H half step rotates v separately)
-    double  xs[2];     // the extra scalar of the two x-neighbour pairs: other[2] (for c=1), other[1] (for c=2)
-    double2 zn[2];     // the two z neighbours: other[1] (for c=0), other[0] (for c=1)
-};
-
-template <bool IS_E, int MODE>
-__device__ __forceinline__ void load_other(const StepArgs& a, const long r, double2 (&v)[3])
-{
-#pragma unroll
-    for(int c = 0; c < 3; ++c)
-        if(has_other<IS_E, MODE>(c)) v[c] = *reinterpret_cast<const double2*>(a.fam[c] + r);
+    store_pair(ca.U + r, u, w0, w1);
 }
 
 template <bool IS_E, int MODE>
-__device__ __forceinline__ void load_stage(const StepArgs& a, const long r, Stage<IS_E, MODE>& st)
+__global__ void __launch_bounds__(256, 2) k_general(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
 {
-    constexpr int S = IS_E ? -1 : 1;
-    constexpr bool IS3D = MODE == CHIML_MODE_3D;
-#pragma unroll
-    for(int c = 0; c < 3; ++c)
-        if(has_own<IS_E, MODE>(c)) st.u[c] = *reinterpret_cast<const double2*>(a.c[c].U + r);
-    if(IS_E) load_other<IS_E, MODE>(a, r, st.v);
-    const long xo = S > 0 ? 2 : -1;
-    if(has_own<IS_E, MODE>(1) && has_other<IS_E, MODE>(2)) st.xs[0] = a.fam[2][r + xo];
-    if(has_own<IS_E, MODE>(2) && has_other<IS_E, MODE>(1)) st.xs[1] = a.fam[1][r + xo];
-    if(IS3D)
-    {
-        st.zn[0] = *reinterpret_cast<const double2*>(a.fam[1] + r + S * a.px);
-        st.zn[1] = *reinterpret_cast<const double2*>(a.fam[0] + r + S * a.px);
-    }
-}
-
-template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(256, 2) k_update(const __grid_constant__ StepArgs a)
-{
-    constexpr int S = IS_E ? -1 : 1;
-    // block -> (x tile, z tile, y chunk); x tiles fastest so that concurrently running blocks stream neighbouring rows
-    unsigned b = blockIdx.x;
-    const unsigned xt = b % a.nxt;  b /= a.nxt;
-    const unsigned zt = b % a.nzt;
-    const int y0 = (int)(b / a.nzt) * a.ychunk;
-    const int y1 = min(y0 + a.ychunk, a.ly);
-    const int x = 2 * (xt * 32 + threadIdx.x);
-    const int z = zt * blockDim.y + threadIdx.y;
+    const TileRec& t = tiles[blockIdx.x];
+    const int x = t.x0 + 2 * threadIdx.x, z = t.z0 + threadIdx.y, y = t.y;
     if(x >= a.px || z >= a.lz) return;
-    const long plane = a.px * a.lz;
-    long r = x + a.px * (z + (long)a.lz * y0);
-    const unsigned* tdp = a.tiledesc + ((size_t)y0 * a.nzt + zt) * a.nxt + xt;
-    const size_t tdStride = (size_t)a.nzt * a.nxt;
-
-    Stage<IS_E, MODE> cur, nxt;
-    double2 vy[3];     // E: other family one plane back (y-1); H: other family one plane ahead (y+1)
-    double2 vy2[3];    // H: other family two planes ahead, in flight
-#pragma unroll
-    for(int c = 0; c < 3; ++c)
-    {
-        cur.u[c] = cur.v[c] = nxt.u[c] = nxt.v[c] = vy[c] = vy2[c] = make_double2(0.0, 0.0);
-    }
-    cur.xs[0] = cur.xs[1] = nxt.xs[0] = nxt.xs[1] = 0.0;
-    cur.zn[0] = cur.zn[1] = nxt.zn[0] = nxt.zn[1] = make_double2(0.0, 0.0);
-
-    // prologue
-    load_stage<IS_E, MODE>(a, r, cur);
-    if(IS_E) load_other<IS_E, MODE>(a, r - plane, vy);
-    else { load_other<IS_E, MODE>(a, r, cur.v); load_other<IS_E, MODE>(a, r + plane, vy); }
-    unsigned td = *tdp;
-
-#pragma unroll 1
-    for(int y = y0; y < y1; ++y)
-    {
-        // ---- issue every load of plane y+1 (and, for H, the other family of plane y+2) -------------------------
-        const long rn = r + plane;
-        unsigned tdn = TD_EMPTY << 24;
-        if(y + 1 < y1)
-        {
-            load_stage<IS_E, MODE>(a, rn, nxt);
-            if(!IS_E) load_other<IS_E, MODE>(a, rn + plane, vy2);
-            tdn = tdp[tdStride];
-        }
-        // ---- compute plane y -----------------------------------------------------------------------------------
-        const unsigned status = td >> 24;
-        if(status != TD_EMPTY)
-        {
-            // component c: grid_j = other[(c+1)%3] along axis (c+2)%3 ; grid_k = other[(c+2)%3] along axis (c+1)%3
-            const double2 nj0 = cur.zn[0];                                                     // other[1] along z
-            const double2 nk0 = vy[2];                                                         // other[2] along y
-            const double2 nj1 = S > 0 ? make_double2(cur.v[2].y, cur.xs[0]) : make_double2(cur.xs[0], cur.v[2].x);   // other[2] along x
-            const double2 nk1 = cur.zn[1];                                                     // other[0] along z
-            const double2 nj2 = vy[0];                                                         // other[0] along y
-            const double2 nk2 = S > 0 ? make_double2(cur.v[1].y, cur.xs[1]) : make_double2(cur.xs[1], cur.v[1].x);   // other[1] along x
-            if(status == TD_UNIFORM)
-            {
-                fast_pair<IS_E, MODE, 0>(a, td & 0xFFu,         cur.u[0], cur.v[1], nj0, cur.v[2], nk0, r);
-                fast_pair<IS_E, MODE, 1>(a, (td >> 8) & 0xFFu,  cur.u[1], cur.v[2], nj1, cur.v[0], nk1, r);
-                fast_pair<IS_E, MODE, 2>(a, (td >> 16) & 0xFFu, cur.u[2], cur.v[0], nj2, cur.v[1], nk2, r);
-            }
-            else
-            {
-                const long row = z + (long)a.lz * y;
-                general_pair<IS_E, MODE, 0>(a, cur.u[0], cur.v[1], nj0, cur.v[2], nk0, r, row, x, y, z);
-                general_pair<IS_E, MODE, 1>(a, cur.u[1], cur.v[2], nj1, cur.v[0], nk1, r, row, x, y, z);
-                general_pair<IS_E, MODE, 2>(a, cur.u[2], cur.v[0], nj2, cur.v[1], nk2, r, row, x, y, z);
-            }
-        }
-        // ---- rotate ----------------------------------------------------------------------------------------------
-        if(IS_E)
-        {
-#pragma unroll
-            for(int c = 0; c < 3; ++c) vy[c] = cur.v[c];
-            cur = nxt;
-        }
-        else
-        {
-#pragma unroll
-            for(int c = 0; c < 3; ++c) { nxt.v[c] = vy[c]; vy[c] = vy2[c]; }
-            cur = nxt;
-        }
-        td = tdn;
-        tdp += tdStride;
-        r = rn;
-    }
+    const long row = z + (long)a.lz * y;
+    const long r = x + a.px * row;
+    PairLoads<IS_E, MODE> L;
+    L.load(a, r);
+    general_pair<IS_E, MODE, 0>(a, L.u[0], L.v[1], L.nj[0], L.v[2], L.nk[0], r, row, x, y, z);
+    general_pair<IS_E, MODE, 1>(a, L.u[1], L.v[2], L.nj[1], L.v[0], L.nk[1], r, row, x, y, z);
+    general_pair<IS_E, MODE, 2>(a, L.u[2], L.v[0], L.nj[2], L.v[1], L.nk[2], r, row, x, y, z);
 }
 
-// Commit-time classification of the tiles of one family (one block per tile, same shape as k_update).
-__global__ void k_tile_desc(const uint16_t* i0, const uint16_t* i1, const uint16_t* i2, unsigned* desc,
-                            unsigned nxt, unsigned nzt, int lx, int lz, long px)
+// ---------------------------------------------------------------------------------------------------
+// commit-time tile summary: per tile and component the bounding rectangle of non-zero info cells, their
+// count, the first non-zero info value and whether all non-zero values are equal.  One block per tile.
+// ---------------------------------------------------------------------------------------------------
+struct TileSummary { unsigned rect[3]; unsigned info[3]; unsigned count[3]; unsigned same[3]; };
+
+__global__ void k_tile_summary(const uint16_t* i0, const uint16_t* i1, const uint16_t* i2, TileSummary* out,
+                               unsigned nxt, unsigned nzt, int lz, long px)
 {
     const unsigned tile = blockIdx.x;
     const unsigned xt = tile % nxt, zt = (tile / nxt) % nzt, y = tile / (nxt * nzt);
-    const int x = 2 * (xt * 32 + threadIdx.x);
-    const int z = zt * blockDim.y + threadIdx.y;
-    __shared__ unsigned first[3];
-    __shared__ int mixed, nonzero;
+    const int xl = 2 * threadIdx.x, zl = threadIdx.y;
+    const int x = xt * TILE_X + xl, z = zt * blockDim.y + zl;
+    __shared__ unsigned s_xlo[3], s_xhi[3], s_zlo[3], s_zhi[3], s_cnt[3], s_first[3], s_diff[3];
     const uint16_t* ip[3] = {i0, i1, i2};
-    if(threadIdx.x == 0 && threadIdx.y == 0)
+    if(threadIdx.x < 3 && threadIdx.y == 0)
     {
-        mixed = 0; nonzero = 0;
-        const long r0 = (long)(2 * xt * 32) + px * ((long)zt * blockDim.y + (long)lz * y);
-        for(int c = 0; c < 3; ++c) first[c] = ip[c] ? ip[c][r0] : 0u;
+        const int c = threadIdx.x;
+        s_xlo[c] = 255; s_xhi[c] = 0; s_zlo[c] = 255; s_zhi[c] = 0; s_cnt[c] = 0; s_first[c] = 0; s_diff[c] = 0;
     }
     __syncthreads();
+    unsigned v[3][2] = {{0, 0}, {0, 0}, {0, 0}};
     if(z < lz && x < px)
     {
         const long r = x + px * (z + (long)lz * y);
         for(int c = 0; c < 3; ++c)
         {
             if(!ip[c]) continue;
-            const unsigned v0 = ip[c][r], v1 = ip[c][r + 1];
-            if(v0 != first[c] || v1 != first[c]) mixed = 1;
-            if(v0 | v1) nonzero = 1;
+            v[c][0] = ip[c][r]; v[c][1] = ip[c][r + 1];
+            for(int k = 0; k < 2; ++k)
+                if(v[c][k])
+                {
+                    atomicMin(&s_xlo[c], (unsigned)(xl + k)); atomicMax(&s_xhi[c], (unsigned)(xl + k + 1));
+                    atomicMin(&s_zlo[c], (unsigned)zl);       atomicMax(&s_zhi[c], (unsigned)(zl + 1));
+                    atomicAdd(&s_cnt[c], 1u);
+                    atomicMax(&s_first[c], v[c][k]);   // any representative: the largest value
+                }
         }
     }
-    else if(z < lz) mixed = 1;      // tile reaches past the padded row: cannot be uniform
     __syncthreads();
-    if(threadIdx.x == 0 && threadIdx.y == 0)
+    for(int c = 0; c < 3; ++c)
+        for(int k = 0; k < 2; ++k)
+            if(v[c][k] && v[c][k] != s_first[c]) s_diff[c] = 1;
+    __syncthreads();
+    if(threadIdx.x < 3 && threadIdx.y == 0)
     {
-        unsigned d;
-        bool simple = !mixed;
-        for(int c = 0; c < 3; ++c)
-            if(ip[c] && (first[c] & 0xFF00u) != F_CURL) simple = false;
-        // a tile whose last rows lie beyond lz is still uniform: those threads exit in k_update
-        if(!nonzero) d = TD_EMPTY << 24;
-        else if(simple) d = (TD_UNIFORM << 24) | (first[0] & 0xFFu) | ((first[1] & 0xFFu) << 8) | ((first[2] & 0xFFu) << 16);
-        else d = TD_GENERAL << 24;
-        desc[tile] = d;
+        const int c = threadIdx.x;
+        TileSummary& o = out[tile];
+        o.count[c] = s_cnt[c];
+        o.info[c] = s_first[c];
+        o.same[c] = s_diff[c] ? 0u : 1u;
+        o.rect[c] = s_cnt[c] ? (s_xlo[c] | (s_xhi[c] << 8) | (s_zlo[c] << 16) | (s_zhi[c] << 24)) : 0u;
     }
 }
 
