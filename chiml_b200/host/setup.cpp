@@ -1,0 +1,837 @@
+// See setup.hpp.  Reference lines are cited at each piece of logic; indices are the reference's
+// (local, ghost-inclusive, x + lnx*(z + lnz*y)).
+#include "setup.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <thread>
+
+namespace chiml_host {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// slab geometry
+// ---------------------------------------------------------------------------------------------------
+struct Geom
+{
+    int rank, nranks;
+    bool last;             // rank == size-1
+    bool twoD;
+    int n[3];              // n_vec_: grid points per direction (2-D: n[2] = 1)
+    int ln[3];             // local ghost-inclusive extents
+    int yStart;            // procLoc(1)
+    double d[3], dt;
+    int thick[3];          // pmlThickness_
+    int mn[3], pl[3];      // local CPML thicknesses (parallelCPML::findLnVecs, PML/parallelPML.hpp:280-308)
+    int ind(int x, int y, int z) const { return x + ln[0] * (z + y * ln[2]); }
+    int procLoc(int dir) const { return dir == 1 ? yStart : 0; }
+};
+
+// the eight staggered maps of the constructor (parallelFDTDField.hpp:264-272): offset of the sample point
+// inside the cell and which directions are one point short
+struct GridSpec { double off[3]; int endOff[3]; bool E; };
+const GridSpec SPEC_NODE_P = {{0.0, 0.0, 0.0}, {0, 0, 0}, true};
+const GridSpec SPEC_COMP[6] = {
+    {{0.5, 0.0, 0.0}, {1, 0, 0}, true},  {{0.0, 0.5, 0.0}, {0, 1, 0}, true},  {{0.0, 0.0, 0.5}, {0, 0, 1}, true},
+    {{0.0, 0.5, 0.5}, {0, 1, 1}, false}, {{0.5, 0.0, 0.5}, {1, 0, 1}, false}, {{0.5, 0.5, 0.0}, {1, 1, 0}, false}};
+// derivOff (parallelFDTDField.cpp:80-82,248-250)
+const int DERIV_OFF[6][3] = {{0, -1, 0}, {0, 0, -1}, {-1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 0}};
+
+bool comp_exists(int mode, int comp)
+{
+    const int c = comp % 3;
+    const bool isH = comp >= 3;
+    if(mode == CHIML_MODE_3D) return true;
+    if(mode == CHIML_MODE_TE) return isH ? c == 2 : c != 2;
+    return isH ? c != 2 : c == 2;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// object maps, one row at a time (replaces setupPhysFields, parallelFDTDField.hpp:867-947)
+// ---------------------------------------------------------------------------------------------------
+class Rasteriser
+{
+public:
+    Rasteriser(const Inputs& IP, const Geom& g) : IP_(IP), g_(g)
+    {
+        for(int d = 0; d < 3; ++d) cen_[d] = (g.n[d] - g.n[d] % 2) / 2.0;
+        for(size_t oo = 1; oo < IP.objArr_.size(); ++oo)
+        {
+            const Obj& o = *IP.objArr_[oo];
+            if(!o.relevant()) continue;
+            Cull c;
+            c.obj = (int)oo;
+            c.sameGeo = o.geoParam_ == o.geoParamML_;
+            const std::array<double, 3> h = o.halfExtent(o.geoParamML_);
+            for(int d = 0; d < 3; ++d)
+            {
+                // global index g with |(g + off - cen)*d - loc| <= h + margin, off in [0, 0.5]
+                const double marg = 2.0 * g.d[d];
+                c.lo[d] = std::isfinite(h[d]) ? (long)std::floor((o.location_[d] - h[d] - marg) / g.d[d] + cen_[d]) - 1 : std::numeric_limits<long>::min() / 2;
+                c.hi[d] = std::isfinite(h[d]) ? (long)std::ceil((o.location_[d] + h[d] + marg) / g.d[d] + cen_[d]) + 1 : std::numeric_limits<long>::max() / 2;
+            }
+            cull_.push_back(c);
+        }
+    }
+
+    // object id of the last relevant object containing the sample point at GLOBAL indices (gx, gy, gz); 0 = background
+    int idAt(const GridSpec& s, long gx, long gy, long gz) const
+    {
+        int id = 0;
+        const std::array<double, 3> pt = {{(gx + s.off[0] - cen_[0]) * g_.d[0], (gy + s.off[1] - cen_[1]) * g_.d[1], (gz + s.off[2] - cen_[2]) * g_.d[2]}};
+        for(const Cull& c : cull_)
+        {
+            if(gx < c.lo[0] || gx > c.hi[0] || gy < c.lo[1] || gy > c.hi[1] || gz < c.lo[2] || gz > c.hi[2]) continue;
+            const Obj& o = *IP_.objArr_[c.obj];
+            if(o.isObj(pt, g_.d[0], o.geoParamML_)) id = c.obj;
+        }
+        return id;
+    }
+
+    // one local row (jj, kk) of the object-id and eps/mu maps, including the -1 / 0.0 border marks
+    void row(const GridSpec& s, int jj, int kk, int* obj, double* eps) const
+    {
+        const int lx = g_.ln[0], ly = g_.ln[1], lz = g_.ln[2];
+        std::fill(obj, obj + lx, 0);
+        std::fill(eps, eps + lx, 1.0);
+        const int zmin = g_.twoD ? 0 : 1, zmax = g_.twoD ? 1 : lz - 1;
+        if(jj >= 1 && jj < ly - 1 && kk >= zmin && kk < zmax)
+        {
+            const long gy = (long)(jj - 1) + g_.yStart, gz = (long)(kk - 1);
+            const double py = (gy + s.off[1] - cen_[1]) * g_.d[1], pz = (gz + s.off[2] - cen_[2]) * g_.d[2];
+            for(const Cull& c : cull_)
+            {
+                if(gy < c.lo[1] || gy > c.hi[1] || gz < c.lo[2] || gz > c.hi[2]) continue;
+                const Obj& o = *IP_.objArr_[c.obj];
+                const int x0 = (int)std::max<long>(1, c.lo[0] + 1), x1 = (int)std::min<long>(lx - 2, c.hi[0] + 1);
+                const double val = s.E ? o.eps_infty_ : o.mu_infty_;
+                for(int ii = x0; ii <= x1; ++ii)
+                {
+                    const std::array<double, 3> pt = {{((ii - 1) + s.off[0] - cen_[0]) * g_.d[0], py, pz}};
+                    const bool inML = o.isObj(pt, g_.d[0], o.geoParamML_);
+                    if(inML) obj[ii] = c.obj;
+                    if(c.sameGeo ? inML : o.isObj(pt, g_.d[0], o.geoParam_)) eps[ii] = val;
+                }
+            }
+        }
+        // borders between processes / domain edge are marked -1; the short last line additionally gets eps = 0 (:900-945)
+        if(!g_.twoD)
+        {
+            if(kk == 0 || kk == lz - 1) std::fill(obj, obj + lx, -1);
+            if(s.endOff[2] == 1 && kk == lz - 2) { std::fill(obj, obj + lx, -1); std::fill(eps, eps + lx, 0.0); }
+        }
+        if(jj == 0 || jj == ly - 1) std::fill(obj, obj + lx, -1);
+        if(s.endOff[1] == 1 && g_.last && g_.n[1] + 2 * g_.nranks > 3 && jj == ly - 2) { std::fill(obj, obj + lx, -1); std::fill(eps, eps + lx, 0.0); }
+        obj[0] = -1; obj[lx - 1] = -1;
+        if(s.endOff[0] == 1 && g_.n[0] + 2 > 3) { obj[lx - 2] = -1; eps[lx - 2] = 0.0; }
+    }
+
+private:
+    struct Cull { int obj; bool sameGeo; long lo[3], hi[3]; };
+    const Inputs& IP_;
+    const Geom& g_;
+    double cen_[3];
+    std::vector<Cull> cull_;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// does material reach into the CPML?  (parallelFDTDField.hpp:275-370, including its loop-bound quirk:
+// min/max of the PML-normal index are overwritten inside the (jj,kk) loops, so the lower slab is
+// scanned only on the first transverse line and the upper slab on every line)
+// ---------------------------------------------------------------------------------------------------
+bool dielectric_in_pml(const Inputs& IP, const int n_vec[3], const double d[3])
+{
+    bool dielectricMatInPML = false;
+    for(int pp = 0; pp < 3 && !dielectricMatInPML; ++pp)
+    {
+        const int cor_ii = pp, cor_jj = (pp + 1) % 3, cor_kk = (pp + 2) % 3;
+        int mn[3], mx[3];
+        for(int k = 0; k < 3; ++k) { mn[k] = (int)(-1 * (double)n_vec[k] / 2); mx[k] = (int)((double)n_vec[k] / 2); }
+        mx[cor_ii] = (int)(IP.pmlThickness_[cor_ii] - n_vec[cor_ii] / 2.0);
+        for(const auto& obj : IP.objArr_)
+        {
+            if(obj->eps_infty_ == 1.0 && obj->mu_infty_ == 1.0 && obj->gamma_.size() < 1 && !obj->ML_) continue;
+            const bool dielcMat = !(obj->eps_infty_ == 1.0 && obj->gamma_.size() < 1);
+            if(!dielcMat) { /* the loops below could only clear nothing */ }
+            // bounding box of the object in the centred integer coordinates of this scan, for culling
+            const std::array<double, 3> h = obj->halfExtent(obj->geoParam_);
+            long lo[3], hi[3];
+            for(int k = 0; k < 3; ++k)
+            {
+                lo[k] = std::isfinite(h[k]) ? (long)std::floor((obj->location_[k] - h[k]) / d[k]) - 2 : std::numeric_limits<long>::min() / 2;
+                hi[k] = std::isfinite(h[k]) ? (long)std::ceil((obj->location_[k] + h[k]) / d[k]) + 2 : std::numeric_limits<long>::max() / 2;
+            }
+            auto scan = [&](int jj, int kk, int i0, int i1) {
+                if(dielectricMatInPML || !dielcMat) return;
+                if(jj < lo[cor_jj] || jj > hi[cor_jj] || kk < lo[cor_kk] || kk > hi[cor_kk]) return;
+                for(int ii = (int)std::max<long>(i0, lo[cor_ii]); ii < i1 && ii <= hi[cor_ii] && !dielectricMatInPML; ++ii)
+                {
+                    std::array<double, 3> pt = {{0, 0, 0}};
+                    pt[cor_ii] = static_cast<double>(ii) * d[cor_ii];
+                    pt[cor_jj] = static_cast<double>(jj) * d[cor_jj];
+                    pt[cor_kk] = static_cast<double>(kk) * d[cor_kk];
+                    pt[0] += d[0] / 2.0;                                        // Ex point
+                    if(obj->isObj(pt, d[0], obj->geoParam_)) { dielectricMatInPML = true; break; }
+                    pt[1] += d[1] / 2.0;                                        // (Hz point: magnetic test, never sets anything here)
+                    pt[0] -= d[0] / 2.0;                                        // Ey point
+                    if(obj->isObj(pt, d[0], obj->geoParam_)) { dielectricMatInPML = true; break; }
+                    pt[2] += d[2] / 2.0;                                        // (Hx point)
+                    pt[1] -= d[0] / 2.0;                                        // Ez point (the reference subtracts d_[0] here)
+                    if(obj->isObj(pt, d[0], obj->geoParam_)) { dielectricMatInPML = true; break; }
+                }
+            };
+            for(int jj = mn[cor_jj]; jj < mx[cor_jj]; ++jj)
+                for(int kk = mn[cor_kk]; kk < mx[cor_kk]; ++kk)
+                {
+                    scan(jj, kk, mn[cor_ii], mx[cor_ii]);
+                    mn[cor_ii] = n_vec[cor_ii] / 2 - IP.pmlThickness_[cor_ii];
+                    mx[cor_ii] = n_vec[cor_ii] / 2;
+                    scan(jj, kk, mn[cor_ii], mx[cor_ii]);
+                }
+        }
+    }
+    return dielectricMatInPML;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// update lists of one map (initializeList / getBlasLists / fillBlasLists / populateUpLists,
+// parallelFDTDField.hpp:628-682,751-856)
+// ---------------------------------------------------------------------------------------------------
+struct Box { int mn[3], mx[3]; bool includeU; bool curl; };
+struct RawRun { int x, y, z, n, obj; double eps; };
+
+struct ListSet { std::vector<ChimlRun> U, D, LorD, OrDipD; };
+
+void build_lists(const Inputs& IP, const Geom& g, const Rasteriser& ras, const GridSpec& spec, bool E, const int derivOff[3], const int fieldEnd[3],
+                 double dj, double dk, bool matInPML, bool orDipField, int nthreads, ListSet& out)
+{
+    const int lx = g.ln[0];
+    int mn[3] = {1, 1, g.twoD ? 0 : 1};
+    int mx[3] = {g.ln[0] - 1 - fieldEnd[0], g.ln[1] - 1, g.twoD ? 1 : g.ln[2] - 1 - fieldEnd[2]};
+    if(g.last) mx[1] -= fieldEnd[1];
+    // getBlasLists (:802-856)
+    const bool inc = E && matInPML;    // (E && dielectricMatInPML_) || (!E && magMatInPML_); no magnetic media here
+    int PML_x_left = inc ? g.mn[0] : 0, PML_x_right = inc ? g.pl[0] : 0;
+    if(PML_x_right != 0) PML_x_right -= fieldEnd[0];
+    int PML_y_bot = inc ? g.mn[1] : 0, PML_y_top = inc ? g.pl[1] : 0;
+    if(PML_y_top != 0 && g.last) PML_y_top -= fieldEnd[1];
+    int PML_z_back = (!g.twoD && inc) ? g.mn[2] : 0, PML_z_front = (!g.twoD && inc) ? g.pl[2] : 0;
+    if(PML_z_front != 0) PML_z_front -= fieldEnd[2];
+    const bool incU = !matInPML;
+    std::vector<Box> boxes = {
+        {{mn[0], mn[1], mn[2]}, {mx[0], mn[1] + PML_y_bot, mx[2]}, incU, false},
+        {{mn[0], mx[1] - PML_y_top, mn[2]}, {mx[0], mx[1], mx[2]}, incU, false},
+        {{mn[0], mn[1] + PML_y_bot, mn[2]}, {mx[0], mx[1] - PML_y_top, mn[2] + PML_z_back}, incU, false},
+        {{mn[0], mn[1] + PML_y_bot, mx[2] - PML_z_front}, {mx[0], mx[1] - PML_y_top, mx[2]}, incU, false},
+        {{mn[0], mn[1] + PML_y_bot, mn[2] + PML_z_back}, {mn[0] + PML_x_left, mx[1] - PML_y_top, mx[2] - PML_z_front}, incU, false},
+        {{mx[0] - PML_x_right, mn[1] + PML_y_bot, mn[2] + PML_z_back}, {mx[0], mx[1] - PML_y_top, mx[2] - PML_z_front}, incU, false},
+        {{mn[0] + PML_x_left, mn[1] + PML_y_bot, mn[2] + PML_z_back}, {mx[0] - PML_x_right, mx[1] - PML_y_top, mx[2] - PML_z_front}, true, false}};
+    {
+        Box c; c.includeU = true; c.curl = true;
+        for(int k = 0; k < 3; ++k) { c.mn[k] = mn[k]; c.mx[k] = mx[k]; }
+        c.mn[0] += g.mn[0]; c.mx[0] -= g.pl[0]; if(g.pl[0] != 0) c.mx[0] += fieldEnd[0];
+        c.mn[1] += g.mn[1]; c.mx[1] -= g.pl[1]; if(g.pl[1] != 0 && g.last) c.mx[1] += fieldEnd[1];
+        c.mn[2] += g.twoD ? 0 : g.mn[2]; c.mx[2] -= g.twoD ? 0 : g.pl[2]; if(!g.twoD && g.pl[2] != 0) c.mx[2] += fieldEnd[2];
+        boxes.push_back(c);
+    }
+    const int nb = (int)boxes.size();
+    if(nthreads < 1) nthreads = 1;
+    const int ny = std::max(0, mx[1] - mn[1]);
+    nthreads = std::max(1, std::min(nthreads, ny));
+    // per thread, per box, per kind: raw runs in (y, z, x) order
+    enum { K_U = 0, K_D = 1, K_ORD = 2 };
+    std::vector<std::vector<std::vector<RawRun>>> raw(nthreads, std::vector<std::vector<RawRun>>(nb * 3));
+    auto work = [&](int t) {
+        std::vector<int> obj(lx);
+        std::vector<double> eps(lx);
+        const int y0 = mn[1] + (int)((long)ny * t / nthreads), y1 = mn[1] + (int)((long)ny * (t + 1) / nthreads);
+        for(int jj = y0; jj < y1; ++jj)
+            for(int kk = mn[2]; kk < mx[2]; ++kk)
+            {
+                bool have = false;
+                for(int b = 0; b < nb; ++b)
+                {
+                    const Box& bx = boxes[b];
+                    if(jj < bx.mn[1] || jj >= bx.mx[1] || kk < bx.mn[2] || kk >= bx.mx[2] || bx.mx[0] <= bx.mn[0]) continue;
+                    if(!have) { ras.row(spec, jj, kk, obj.data(), eps.data()); have = true; }
+                    int ii = bx.mn[0];
+                    while(ii < bx.mx[0])
+                    {
+                        const int iistore = ii;
+                        while((ii < bx.mx[0] - 1) && (obj[ii] == obj[ii + 1]) && (eps[ii] == eps[ii + 1])) ++ii;
+                        const int id = obj[iistore];
+                        const Obj& o = *IP.objArr_[id < 0 ? 0 : id];
+                        int kind;
+                        if(o.useOrientedDipols_ && E && o.gamma_.size() > 0) kind = K_ORD;                       // fillBlasLists :767-773
+                        else if(bx.includeU && (!E || (o.gamma_.size() < 1 && !o.ML_))) kind = K_U;                // :776-777
+                        else kind = K_D;
+                        raw[t][b * 3 + kind].push_back({iistore, jj, kk, ii - iistore + 1, id, eps[iistore]});
+                        ++ii;
+                    }
+                }
+            }
+    };
+    if(nthreads == 1) work(0);
+    else
+    {
+        std::vector<std::thread> th;
+        for(int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+        for(auto& x : th) x.join();
+    }
+    // populateUpLists (:628-649)
+    auto emit = [&](std::vector<ChimlRun>& dst, const RawRun& r, bool upUList) {
+        ChimlRun u;
+        const double ep_mu = upUList ? r.eps : 1.0;
+        const int x = r.x, y = r.y, z = r.z;
+        u.n = r.n; u.ind = g.ind(x, y, z); u.obj = r.obj;
+        if(!orDipField)
+        {
+            if(g.ln[2] == 1)
+            {
+                u.ind_i = g.ind(x - derivOff[1], y - derivOff[2], z);
+                u.ind_j = g.ind(x + derivOff[0], y + derivOff[1], z);
+                u.ind_k = g.ind(x + derivOff[2], y + derivOff[0], z);
+            }
+            else
+            {
+                u.ind_i = g.ind(x - derivOff[1], y - derivOff[2], z - derivOff[0]);
+                u.ind_j = g.ind(x + derivOff[0], y + derivOff[1], z + derivOff[2]);
+                u.ind_k = g.ind(x + derivOff[2], y + derivOff[0], z + derivOff[1]);
+            }
+        }
+        else
+        {
+            u.ind_i = g.ind(x + derivOff[0], y, z);
+            u.ind_j = g.ind(x, y + derivOff[1], z);
+            u.ind_k = g.ind(x, y, z + derivOff[2]);
+        }
+        u.pf[0] = 1.0; u.pf[1] = -1.0 * g.dt / (ep_mu * dj); u.pf[2] = -1.0 * g.dt / (ep_mu * dk); u.pf[3] = r.eps;
+        dst.push_back(u);
+    };
+    for(int b = 0; b < nb; ++b)
+        for(int t = 0; t < nthreads; ++t)
+        {
+            if(boxes[b].curl)
+            {
+                for(const RawRun& r : raw[t][b * 3 + K_U]) emit(out.U, r, true);
+                // the curl pass files every non-U run under upD (getBlasLists :855 passes upDLists four times)
+            }
+            else
+            {
+                for(const RawRun& r : raw[t][b * 3 + K_D]) emit(out.LorD, r, false);
+                for(const RawRun& r : raw[t][b * 3 + K_ORD]) emit(out.OrDipD, r, false);
+            }
+        }
+    // upD keeps the reference's order inside the curl box: runs of all non-U kinds interleaved in (y, z, x) order
+    {
+        const int b = nb - 1;
+        for(int t = 0; t < nthreads; ++t)
+        {
+            const auto& dRuns = raw[t][b * 3 + K_D];
+            const auto& oRuns = raw[t][b * 3 + K_ORD];
+            size_t i = 0, j = 0;
+            auto before = [](const RawRun& p, const RawRun& q) { return p.y != q.y ? p.y < q.y : (p.z != q.z ? p.z < q.z : p.x < q.x); };
+            while(i < dRuns.size() || j < oRuns.size())
+            {
+                if(j >= oRuns.size() || (i < dRuns.size() && before(dRuns[i], oRuns[j]))) emit(out.D, dRuns[i++], false);
+                else emit(out.D, oRuns[j++], false);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CPML (parallelCPML constructor and list builders, PML/parallelPML.hpp:102-182,192-275,321-451,462-656,708-765)
+// ---------------------------------------------------------------------------------------------------
+struct CpmlBuilder
+{
+    const Inputs& IP;
+    const Geom& g;
+    const Rasteriser& ras;
+    int comp;
+    bool E;
+    int i_, j_, k_;
+    int sh[3];                 // one point short in direction d (fieldEnd)
+    bool hasGrid[2];           // part 0 needs grid_k, part 1 needs grid_j
+    std::vector<double> eta[3][2];   // [direction][0 = minus side, 1 = plus side]
+    std::vector<ChimlPsiParams> psi[2];
+    std::vector<ChimlGridParams> grid[2];
+
+    double kappa(double ii, double iiMax) const { return (0.0 <= ii && ii <= iiMax) ? 1.0 + (IP.pmlKappaMax_ - 1.0) * std::pow((iiMax - ii) / iiMax, IP.pmlM_) : 1.0; }
+    double sigma(double ii, double iiMax, double eta_eff, double sigmaMax) const { return (0.0 <= ii && ii <= iiMax) ? sigmaMax / eta_eff * pow((iiMax - ii) / iiMax, IP.pmlM_) : 0.0; }
+    double aVal(double ii, double iiMax) const { return (0.0 <= ii && ii <= iiMax) ? IP.pmlAMax_ * std::pow(ii / iiMax, IP.pmlMa_) : 0.0; }
+    double b(double sig, double a, double kap) const { return std::exp(-1.0 * (sig / kap + a) * g.dt); }
+    double c(double sig, double a, double kap) const { return (sig == 0 && a == 0) ? 0 : sig * (b(sig, a, kap) - 1.0) / (kap * (sig + kap * a)); }
+
+    // genEtaEff / genEtaEffVal (:192-275): product of the plane means of eps_inf and mu_inf of the objects on the plane
+    void genEta(int dir, bool pl)
+    {
+        const GridSpec& spec = SPEC_COMP[comp];
+        int planeSzTemp[3] = {g.n[0] - sh[0], g.n[1] - sh[1], g.n[2] - sh[2]};
+        if(g.twoD) planeSzTemp[2] = 1;
+        const int lo = pl ? g.n[dir] - g.thick[dir] : 0, hi = pl ? g.n[dir] : g.thick[dir];
+        std::vector<double>& out = eta[dir][pl ? 1 : 0];
+        for(int ii = lo; ii < hi; ++ii)
+        {
+            double eps_sum = 0.0, mu_sum = 0.0;
+            double N;
+            auto add = [&](int id) {
+                // ids on the sampled planes are never -1: the short last line is excluded by planeSzTemp
+                eps_sum += IP.objArr_[id]->eps_infty_ / N;
+                mu_sum += IP.objArr_[id]->mu_infty_ / N;
+            };
+            const long zoff = 0;
+            if(dir == 0)
+            {
+                N = static_cast<double>(planeSzTemp[2] * planeSzTemp[1]);
+                for(int yy = 0; yy < planeSzTemp[1]; ++yy)
+                    for(int zz = 0; zz < planeSzTemp[2]; ++zz) add(ras.idAt(spec, ii, yy, zz + zoff));
+            }
+            else if(dir == 1)
+            {
+                N = static_cast<double>(planeSzTemp[0] * planeSzTemp[2]);
+                for(int zz = 0; zz < planeSzTemp[2]; ++zz)
+                    for(int xx = 0; xx < planeSzTemp[0]; ++xx) add(ras.idAt(spec, xx, ii, zz + zoff));
+            }
+            else
+            {
+                N = static_cast<double>(planeSzTemp[0] * planeSzTemp[1]);
+                for(int yy = 0; yy < planeSzTemp[1]; ++yy)
+                    for(int xx = 0; xx < planeSzTemp[0]; ++xx) add(ras.idAt(spec, xx, yy, ii));
+            }
+            const double etaSum = eps_sum * mu_sum;
+            const double etaVal = (etaSum != 0.00) ? etaSum : 0;
+            if((int)out.size() < g.thick[dir] && etaVal != 0.0) out.push_back(etaVal);
+        }
+    }
+
+    // getPsiUpList (:321-451)
+    void psiList(int dir, bool pl, int startPt, int nDir, int dirMax, std::vector<ChimlPsiParams>& list)
+    {
+        ChimlPsiParams param;
+        int transSz2 = 1, cor_norm = dir, cor_trans1, cor_trans2, trans1FieldOff = 0, trans2FieldOff = 0, ccStart = 0;
+        const double sigmaMax = IP.pmlSigOptRat_ * 0.8 * (IP.pmlM_ + 1) / g.d[dir];
+        if(dir == 0)
+        {
+            cor_trans1 = g.twoD ? 1 : 2; cor_trans2 = g.twoD ? 2 : 1;
+            param.stride = g.ln[0];
+            if(sh[1] && g.last) (g.twoD ? trans1FieldOff : trans2FieldOff) = 1;
+            if(sh[2]) (g.twoD ? trans2FieldOff : trans1FieldOff) = 1;
+            if(sh[0]) { if(pl) ccStart = 1; else dirMax -= 1; }
+        }
+        else if(dir == 1)
+        {
+            cor_trans1 = 0; cor_trans2 = 2; param.stride = 1;
+            if(sh[0]) trans1FieldOff = 1;
+            if(sh[2]) trans2FieldOff = 1;
+            if(pl && g.last && sh[1]) ccStart = 1;
+            if(!pl && startPt + dirMax == nDir && sh[1]) dirMax -= 1;
+        }
+        else
+        {
+            cor_trans1 = 0; cor_trans2 = 1; param.stride = 1;
+            if(sh[0]) trans1FieldOff = 1;
+            if(sh[1] && g.last) trans2FieldOff = 1;
+            if(sh[2]) { if(pl) ccStart = 1; else dirMax -= 1; }
+        }
+        const std::vector<double>& eta_eff = eta[dir][pl ? 1 : 0];
+        param.transSz = g.ln[cor_trans1] - 2 - trans1FieldOff;
+        transSz2 = g.ln[cor_trans2] - 2 - trans2FieldOff;
+        if(g.twoD && cor_trans2 == 2) transSz2 = 1;
+        const double distOff = E ? 0.0 : 0.5;
+        int loc[3] = {-1, -1, -1};
+        loc[cor_trans1] = 1;
+        for(int cc = ccStart; cc < dirMax; ++cc)
+        {
+            loc[cor_norm] = pl ? g.ln[cor_norm] - 2 - cc : cc + 1;
+            double dist = g.procLoc(cor_norm) + (loc[cor_norm] - 1) + distOff;
+            if(pl) dist = g.n[cor_norm] - 1 - dist;
+            const double sig = sigma(dist, static_cast<double>(nDir - 1), eta_eff.at((size_t)dist), sigmaMax);
+            const double kap = kappa(dist, static_cast<double>(nDir - 1));
+            const double a = aVal(dist, static_cast<double>(nDir - 1));
+            param.b = b(sig, a, kap);
+            param.c = c(sig, a, kap) / g.d[cor_norm];
+            if(!E) param.c *= -1.0;
+            for(int jj = 0; jj < transSz2; ++jj)
+            {
+                loc[cor_trans2] = 1 + jj;
+                if(g.twoD) loc[2] = 0;
+                int locOff[3] = {loc[0], loc[1], loc[2]};
+                locOff[cor_norm] += E ? -1 : 1;
+                param.ind = g.ind(loc[0], loc[1], loc[2]);
+                param.indOff = g.ind(locOff[0], locOff[1], locOff[2]);
+                list.push_back(param);
+            }
+        }
+    }
+
+    // getGridUpList + getAxLists (:462-656)
+    void gridList(int dir, int derivDir, bool pl, std::vector<ChimlGridParams>& list)
+    {
+        ChimlGridParams param;
+        int mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+        const int cor_ii = dir, cor_jj = (dir + 1) % 3, cor_kk = (dir + 2) % 3;
+        int off_ii = 0;
+        param.Db = g.dt;
+        double DbFieldBase = g.dt;
+        int offset[3] = {0, 0, 0};
+        param.stride = dir == 0 ? g.ln[0] : 1;
+        if(dir == 1)
+        {
+            if(pl && g.last && sh[1]) off_ii = -1;
+            if(!pl) off_ii = 1;
+        }
+        else
+        {
+            if(pl && sh[dir]) off_ii = -1;
+            else if(!pl) off_ii = 1;
+        }
+        // signs from Taflove ch. 7 (:555-581), by component: 0 Ex 1 Ey 2 Ez 3 Hx 4 Hy 5 Hz
+        if(derivDir == 0)      { if(comp == 5 || comp == 1) param.Db *= -1.0; if(comp == 4 || comp == 1) DbFieldBase *= -1.0; }
+        else if(derivDir == 1) { if(comp == 3 || comp == 2) param.Db *= -1.0; if(comp == 5 || comp == 2) DbFieldBase *= -1.0; }
+        else                   { if(comp == 4 || comp == 0) param.Db *= -1.0; if(comp == 3 || comp == 0) DbFieldBase *= -1.0; }
+        DbFieldBase /= g.d[derivDir];
+        offset[derivDir] = E ? -1 : 1;
+        mn[cor_ii] += pl ? g.ln[cor_ii] - g.pl[cor_ii] - 1 : 1;
+        mx[cor_ii] += off_ii + (pl ? g.ln[cor_ii] - 1 : g.mn[cor_ii]);
+        mn[cor_jj] = 1; mx[cor_jj] = g.ln[cor_jj] - 1;
+        mn[cor_kk] = 1; mx[cor_kk] = g.ln[cor_kk] - 1;
+        auto trim = [&](int ax) {
+            mn[ax] += g.mn[ax];
+            mx[ax] -= g.pl[ax] - ((E || (ax == 1 && !g.last)) ? 0 : 1);
+        };
+        if(dir == i_) { trim(cor_jj); trim(cor_kk); }
+        else if(derivDir != cor_ii) trim(derivDir);
+        if(cor_ii != 0 && sh[0]) mx[0] -= 1;
+        if(cor_ii != 1 && g.last && sh[1]) mx[1] -= 1;
+        if(cor_ii != 2 && !g.twoD && sh[2]) mx[2] -= 1;
+        if(g.twoD) { mn[2] = 0; mx[2] = 1; }
+        const double distOff = E ? 0.0 : 0.5;
+        auto push = [&](int x, int y, int z, int n) {
+            const int ax[3] = {x, y, z};
+            double dist = g.procLoc(derivDir) + ax[derivDir] - 1 + distOff;
+            if(pl) dist = g.n[derivDir] - 1 - dist;
+            const double kap = kappa(dist, static_cast<double>(g.thick[derivDir] - 1));
+            param.DbField = DbFieldBase / kap;
+            param.ind = g.ind(x, y, z);
+            param.indOff = g.ind(x + offset[0], y + offset[1], z + offset[2]);
+            param.nAx = n;
+            list.push_back(param);
+        };
+        if(param.stride == 1)
+        {
+            for(int kk = mn[2]; kk < mx[2]; ++kk)
+                for(int jj = mn[1]; jj < mx[1]; ++jj) push(mn[0], jj, kk, mx[0] - mn[0]);
+        }
+        else if(g.twoD)
+        {
+            for(int kk = mn[2]; kk < mx[2]; ++kk)
+                for(int ii = mn[0]; ii < mx[0]; ++ii) push(ii, mn[1], kk, mx[1] - mn[1]);
+        }
+        else
+        {
+            for(int jj = mn[1]; jj < mx[1]; ++jj)
+                for(int ii = mn[0]; ii < mx[0]; ++ii) push(ii, jj, mn[2], mx[2] - mn[2]);
+        }
+    }
+
+    // initalizeLists (:669-689) for the six faces in the constructor's order (:176-181)
+    void build()
+    {
+        for(int dir = 0; dir < 3; ++dir)
+        {
+            if(dir == 2 && g.twoD) continue;
+            genEta(dir, false);
+            genEta(dir, true);
+        }
+        for(int dir = 0; dir < 3; ++dir)
+            for(int side = 0; side < 2; ++side)
+            {
+                const bool pl = side == 1;
+                const int ln_pml = pl ? g.pl[dir] : g.mn[dir];
+                if(ln_pml == 0) continue;
+                const int startPt = pl ? g.procLoc(dir) + g.ln[dir] - 2 : g.procLoc(dir);
+                if(hasGrid[0])
+                {
+                    if(dir == j_) psiList(dir, pl, startPt, g.thick[dir], ln_pml, psi[0]);
+                    gridList(dir, j_, pl, grid[0]);
+                }
+                if(hasGrid[1])
+                {
+                    if(dir == k_) psiList(dir, pl, startPt, g.thick[dir], ln_pml, psi[1]);
+                    gridList(dir, k_, pl, grid[1]);
+                }
+            }
+    }
+};
+
+// DTCTYPE -> stored field (single-component types; parallelFDTDField.cpp:689-826)
+int detector_field(DTCTYPE t)
+{
+    switch(t)
+    {
+        case DTCTYPE::EX: return CHIML_EX; case DTCTYPE::EY: return CHIML_EY; case DTCTYPE::EZ: return CHIML_EZ;
+        case DTCTYPE::HX: return CHIML_HX; case DTCTYPE::HY: return CHIML_HY; case DTCTYPE::HZ: return CHIML_HZ;
+        case DTCTYPE::DX: return CHIML_DX; case DTCTYPE::DY: return CHIML_DY; case DTCTYPE::DZ: return CHIML_DZ;
+        default: throw std::logic_error("power / polarisation detectors are outside the covered hot path");
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------
+SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads)
+{
+    if(nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+    SlabPlan P;
+    Geom g;
+    g.rank = rank; g.nranks = nranks; g.last = rank == nranks - 1;
+    g.twoD = IP.size_[2] == 0;
+    for(int k = 0; k < 3; ++k)
+    {
+        g.n[k] = static_cast<int>(std::floor(IP.size_[k] / IP.d_[k] + 0.5)) + 1;   // toN_vec, parallelFDTDField.hpp:1714
+        g.d[k] = IP.d_[k];
+        g.thick[k] = IP.pmlThickness_[k];
+    }
+    g.dt = IP.dt_;
+    // equal-height y-slabs (mpiInterface::getLocxLocyLocz(int,int,int), MPI/mpiInterface.cpp:55-58)
+    const int base = g.n[1] / nranks, rem = g.n[1] % nranks;
+    const int nyloc = base + (rank < rem ? 1 : 0);
+    g.yStart = rank * base + std::min(rank, rem);
+    if(nyloc < 1) throw std::logic_error("a y-slab is empty: fewer grid rows than ranks");
+    g.ln[0] = g.n[0] + 2; g.ln[1] = nyloc + 2; g.ln[2] = g.twoD ? 1 : g.n[2] + 2;
+    // findLnVecs (PML/parallelPML.hpp:280-308)
+    for(int k = 0; k < 3; ++k) { g.mn[k] = 0; g.pl[k] = 0; }
+    for(int k = 0; k < 3; ++k)
+    {
+        if(k == 2 && g.twoD) continue;
+        const int loc = g.procLoc(k), lsz = g.ln[k] - 2;
+        if(loc < g.thick[k]) g.mn[k] = loc + lsz < g.thick[k] ? lsz : g.thick[k] - loc;
+        if(loc + lsz > g.n[k] - g.thick[k]) g.pl[k] = loc > g.n[k] - g.thick[k] ? lsz : loc + lsz - (g.n[k] - g.thick[k]);
+    }
+    for(auto& obj : IP.objArr_)
+        if(obj->alpha_.empty() && obj->dipOr_.empty()) obj->setUpConsts(IP.dt_);
+
+    const int mode = !g.twoD ? CHIML_MODE_3D
+                             : ((IP.pol_ == POLARIZATION::HZ || IP.pol_ == POLARIZATION::EX || IP.pol_ == POLARIZATION::EY) ? CHIML_MODE_TE : CHIML_MODE_TM);
+    const int nvec[3] = {g.n[0], g.n[1], g.n[2]};
+    P.dielectricMatInPML = dielectric_in_pml(IP, nvec, g.d);
+    bool disp = P.dielectricMatInPML;
+    int nLor = 0, nOrDip = 0;
+    for(const auto& obj : IP.objArr_)
+    {
+        if(obj->gamma_.size() > 0 || obj->ML_ || obj->eps_infty_ > 1.0) disp = true;
+        if(obj->mu_infty_ > 1.0) throw std::logic_error("magnetic materials are outside the covered hot path");
+        nLor = std::max(nLor, (int)obj->gamma_.size());
+        if(obj->useOrientedDipols_) nOrDip = std::max(nOrDip, (int)obj->gamma_.size());
+    }
+
+    std::memset(&P.grid, 0, sizeof(P.grid));
+    P.grid.desc.mode = mode;
+    for(int k = 0; k < 3; ++k) { P.grid.desc.ln[k] = g.ln[k]; P.grid.desc.d[k] = g.d[k]; P.grid.n_global[k] = g.n[k]; }
+    P.grid.desc.dt = g.dt;
+    P.grid.desc.has_D = disp ? 1 : 0;
+    P.grid.desc.pml_on_D = P.dielectricMatInPML ? 1 : 0;
+    P.grid.desc.n_objects = (int)IP.objArr_.size();
+    P.grid.desc.rank = rank; P.grid.desc.nranks = nranks;
+    P.grid.y_start = g.yStart;
+    P.grid.n_steps = int(std::ceil(IP.tMax_ / IP.dt_));
+    P.grid.n_lor_poles = disp ? nLor : 0;
+    P.grid.n_ordip_poles = disp ? nOrDip : 0;
+    P.grid.t_max = IP.tMax_;
+
+    Rasteriser ras(IP, g);
+    // ---- update lists (parallelFDTDField.cpp:80-92,248-261) ----
+    for(int comp = 0; comp < 6; ++comp)
+    {
+        if(!comp_exists(mode, comp)) continue;
+        const int i = comp % 3;
+        const double dj = g.d[(i + 1) % 3], dk = g.d[(i + 2) % 3];
+        ListSet ls;
+        build_lists(IP, g, ras, SPEC_COMP[comp], comp < 3, DERIV_OFF[comp], SPEC_COMP[comp].endOff, dj, dk, P.dielectricMatInPML, false, nthreads, ls);
+        P.lists[CHIML_LIST_U][comp] = std::move(ls.U);
+        if(comp < 3)
+        {
+            P.lists[CHIML_LIST_D][comp] = std::move(ls.D);
+            P.lists[CHIML_LIST_LORD][comp] = std::move(ls.LorD);
+            P.lists[CHIML_LIST_ORDIPD][comp] = std::move(ls.OrDipD);
+        }
+    }
+    if(disp && nOrDip > 0)
+    {
+        // node-centred oriented-dipole list (parallelFDTDField.cpp:83-87,252-256): dipP_ exists for the in-plane components
+        // whenever an oriented-dipole object carries electric poles
+        const int dOff[3] = {-1, -1, -1}, fEnd[3] = {0, 0, 0};
+        ListSet ls;
+        build_lists(IP, g, ras, SPEC_NODE_P, true, dOff, fEnd, g.d[0], g.d[0], P.dielectricMatInPML, true, nthreads, ls);
+        P.lists[CHIML_LIST_ORDIPP][0] = std::move(ls.OrDipD);
+    }
+    // ---- objects ----
+    for(const auto& obj : IP.objArr_)
+    {
+        PlanObject o;
+        o.npoles = (int)obj->gamma_.size(); o.use_or_dip = obj->useOrientedDipols_ ? 1 : 0; o.ml = obj->ML_ ? 1 : 0;
+        o.eps_inf = obj->eps_infty_; o.mu_inf = obj->mu_infty_;
+        o.alpha = obj->alpha_; o.xi = obj->xi_; o.gamma = obj->gamma_;
+        o.dip.assign(3 * (size_t)o.npoles, 0.0);
+        if(o.use_or_dip)
+            for(int p = 0; p < o.npoles; ++p)
+                for(int k = 0; k < 3; ++k) o.dip[3 * p + k] = obj->dipOr_[p] == DIPOR::ISOTROPIC ? 1.0 : obj->dipE_[p][k];   // setupDipMoments :998-1007
+        P.objects.push_back(o);
+    }
+    // ---- CPML (parallelFDTDField.cpp:60-77,229-246) ----
+    for(int comp = 0; comp < 6; ++comp)
+    {
+        if(!comp_exists(mode, comp)) continue;
+        const int i = comp % 3;
+        CpmlBuilder cb{IP, g, ras, comp, comp < 3, i, (i + 1) % 3, (i + 2) % 3, {SPEC_COMP[comp].endOff[0], SPEC_COMP[comp].endOff[1], SPEC_COMP[comp].endOff[2]}, {false, false}, {}, {}, {}};
+        const int other = comp < 3 ? 3 : 0;
+        cb.hasGrid[0] = comp_exists(mode, other + (i + 2) % 3);   // grid_k
+        cb.hasGrid[1] = comp_exists(mode, other + (i + 1) % 3);   // grid_j
+        cb.build();
+        for(int part = 0; part < 2; ++part)
+        {
+            if(!cb.hasGrid[part]) continue;
+            // psi_j exists unless 2-D and j == Z; psi_k likewise (PML/parallelPML.hpp:143-156)
+            const int axis = part == 0 ? cb.j_ : cb.k_;
+            PlanCpml pc;
+            pc.comp = comp; pc.part = part; pc.has_psi = (!g.twoD || axis != 2) ? 1 : 0;
+            pc.psi = std::move(cb.psi[part]); pc.grid = std::move(cb.grid[part]);
+            P.cpml.push_back(std::move(pc));
+        }
+    }
+    // ---- sources (parallelFDTDField.cpp:457-560; SOURCE/parallelSourceNormal.hpp:69-140) ----
+    for(const SourceInput& s : IP.sources_)
+    {
+        const int field = (int)s.pol;   // EX..HZ share the ChimlField numbering
+        if(!comp_exists(mode, field)) throw std::logic_error("a source acts on a field component that does not exist in this mode");
+        PlanSource ps;
+        ps.field = field;
+        bool inside = true;
+        for(int k = 0; k < 3; ++k)
+        {
+            const int pl = g.procLoc(k), lsz = g.ln[k] - 2;
+            int l;
+            if(s.loc[k] >= pl && s.loc[k] < pl + lsz) l = s.loc[k] - pl + 1;
+            else if(s.loc[k] < pl && s.loc[k] + s.sz[k] > pl) l = 1;
+            else l = -1;
+            if(k == 2 && g.twoD) l = 0;
+            ps.loc[k] = l;
+            if(l == -1) inside = false;
+        }
+        if(!inside) continue;
+        for(int k = 0; k < 3; ++k)
+        {
+            const int pl = g.procLoc(k);
+            if(s.sz[k] + s.loc[k] > pl + g.ln[k] - 2) ps.sz[k] = g.ln[k] - ps.loc[k] - 1;
+            else ps.sz[k] = s.loc[k] + s.sz[k] - (pl + ps.loc[k] - 1);
+            if(k == 2 && g.twoD) ps.sz[k] = 1;
+        }
+        ps.amp.resize(P.grid.n_steps);
+        double t = 0.0;
+        for(int k = 0; k < P.grid.n_steps; ++k)
+        {
+            cplx pulVal = 0.0;
+            for(size_t p = 0; p < s.shapes.size(); ++p) pulVal += pulseValue(s.shapes[p], t, s.fxn[p]);
+            ps.amp[k] = g.dt * std::real(pulVal);
+            t += g.dt;
+        }
+        P.sources.push_back(std::move(ps));
+    }
+    // ---- detectors (DTC/parallelDTC.hpp:44-93, parallelStorageDTC.hpp:51-80) ----
+    int dd = 0;
+    for(const DetectorInput& d : IP.detectors_)
+    {
+        PlanDetector pd;
+        pd.detector = dd++;
+        pd.field = detector_field(d.type);
+        if(!comp_exists(mode, pd.field % 3 + (pd.field >= 3 && pd.field < 6 ? 3 : 0))) throw std::logic_error("a detector samples a field component that does not exist in this mode");
+        for(int k = 0; k < 3; ++k) { pd.loc[k] = d.loc[k]; pd.sz[k] = d.sz[k]; pd.offset[k] = 0; }
+        pd.every = static_cast<int>(std::floor(d.timeInt / IP.dt_));
+        if(pd.every == 0) throw std::logic_error("The time step of a detector is less than the main grid or set to 0.");
+        pd.type = (int)d.type;
+        pd.conv = 1.0; pd.t_conv = 1.0;
+        if(d.SI)
+        {
+            pd.t_conv *= IP.a_ / SPEED_OF_LIGHT;
+            pd.conv = (IP.I0_ / IP.a_);
+            if(d.type == DTCTYPE::EX || d.type == DTCTYPE::EY || d.type == DTCTYPE::EZ) pd.conv /= EPS0() * SPEED_OF_LIGHT;
+        }
+        P.detectors.push_back(pd);
+    }
+    return P;
+}
+
+// ---------------------------------------------------------------------------------------------------
+namespace {
+void put_rec(std::ofstream& out, const char* tag, const std::string& payload)
+{
+    char t[8];
+    std::memset(t, ' ', 8);
+    std::memcpy(t, tag, std::min<size_t>(8, std::strlen(tag)));
+    const uint64_t n = payload.size();
+    out.write(t, 8);
+    out.write(reinterpret_cast<const char*>(&n), 8);
+    out.write(payload.data(), (std::streamsize)n);
+}
+template <typename T> void app(std::string& s, const T& v) { s.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
+template <typename T> void app_vec(std::string& s, const std::vector<T>& v) { if(!v.empty()) s.append(reinterpret_cast<const char*>(v.data()), v.size() * sizeof(T)); }
+}
+
+void SlabPlan::write(const std::string& path) const
+{
+    std::ofstream out(path.c_str(), std::ios::binary);
+    if(!out) throw std::runtime_error("cannot write " + path);
+    { std::string p; int32_t v = CHIML_PLAN_VERSION; app(p, v); put_rec(out, "CHIMLPLN", p); }
+    { std::string p; app(p, grid); put_rec(out, "GRID", p); }
+    // same record order as oracle/ref_driver.cpp
+    for(int c = 0; c < 3; ++c)
+    {
+        const int kinds[5] = {CHIML_LIST_U, CHIML_LIST_U, CHIML_LIST_D, CHIML_LIST_LORD, CHIML_LIST_ORDIPD};
+        const int comps[5] = {c, 3 + c, c, c, c};
+        for(int k = 0; k < 5; ++k)
+        {
+            std::string p;
+            ChimlPlanListHdr h; h.kind = kinds[k]; h.comp = comps[k]; h.n = lists[kinds[k]][comps[k]].size();
+            app(p, h); app_vec(p, lists[kinds[k]][comps[k]]);
+            put_rec(out, "UPLIST", p);
+        }
+    }
+    { std::string p; ChimlPlanListHdr h; h.kind = CHIML_LIST_ORDIPP; h.comp = 0; h.n = lists[CHIML_LIST_ORDIPP][0].size(); app(p, h); app_vec(p, lists[CHIML_LIST_ORDIPP][0]); put_rec(out, "UPLIST", p); }
+    for(size_t oo = 0; oo < objects.size(); ++oo)
+    {
+        const PlanObject& o = objects[oo];
+        ChimlPlanObjectHdr h; h.obj = (int)oo; h.npoles = o.npoles; h.use_or_dip = o.use_or_dip; h.ml = o.ml; h.eps_inf = o.eps_inf; h.mu_inf = o.mu_inf;
+        std::string p; app(p, h); app_vec(p, o.alpha); app_vec(p, o.xi); app_vec(p, o.gamma); app_vec(p, o.dip);
+        put_rec(out, "OBJECT", p);
+    }
+    for(const PlanCpml& c : cpml)
+    {
+        ChimlPlanCpmlHdr h; h.comp = c.comp; h.part = c.part; h.has_psi = c.has_psi; h.pad = 0; h.npsi = c.psi.size(); h.ngrid = c.grid.size();
+        std::string p; app(p, h); app_vec(p, c.psi); app_vec(p, c.grid);
+        put_rec(out, "CPML", p);
+    }
+    for(const PlanSource& s : sources)
+    {
+        ChimlPlanSourceHdr h; h.field = s.field;
+        for(int k = 0; k < 3; ++k) { h.loc[k] = s.loc[k]; h.sz[k] = s.sz[k]; }
+        h.n_steps = (int)s.amp.size();
+        std::string p; app(p, h); app_vec(p, s.amp);
+        put_rec(out, "SOURCE", p);
+    }
+    for(const PlanDetector& d : detectors)
+    {
+        ChimlPlanDetector r; std::memset(&r, 0, sizeof(r));
+        r.detector = d.detector; r.field = d.field;
+        for(int k = 0; k < 3; ++k) { r.loc[k] = d.loc[k]; r.sz[k] = d.sz[k]; r.offset[k] = d.offset[k]; }
+        r.every = d.every; r.type = d.type; r.conv = d.conv; r.t_conv = d.t_conv;
+        std::string p; app(p, r);
+        put_rec(out, "DETECTOR", p);
+    }
+}
+
+} // namespace chiml_host

@@ -1,0 +1,43 @@
+// Host-side construction of everything chiml_gpu.h consumes, for one y-slab: object maps -> update
+// lists, CPML lists, pole constants, source boxes + amplitudes, detector boxes.  This is the work of
+// the reference's propagator constructor (FDTD_MANAGER/parallelFDTDField.hpp:214-617,
+// parallelFDTDField.cpp:13-852; PML/parallelPML.hpp:102-656) with a different architecture: the
+// reference materialises eight full-size object-id and eps grids per rank; here rows of those maps
+// are generated on the fly (one x-row at a time, objects culled by bounding box) and turned straight
+// into run-length lists, so a 2048 x 256 x 1024 slab needs megabytes of host memory, not tens of
+// gigabytes, and the row loop runs on all host threads.
+#pragma once
+
+#include <array>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/chiml_plan.h"
+#include "inputs.hpp"
+
+namespace chiml_host {
+
+struct PlanCpml { int comp, part, has_psi; std::vector<ChimlPsiParams> psi; std::vector<ChimlGridParams> grid; };
+struct PlanObject { int npoles, use_or_dip, ml; double eps_inf, mu_inf; std::vector<double> alpha, xi, gamma, dip; };
+struct PlanSource { int field; int32_t loc[3], sz[3]; std::vector<double> amp; };
+struct PlanDetector { int detector, field; int32_t loc[3], sz[3], offset[3]; int every, type; double conv, t_conv; };
+
+// The flattened propagator of one rank ("plan", include/chiml_plan.h)
+struct SlabPlan
+{
+    ChimlPlanGrid grid;
+    std::vector<ChimlRun> lists[5][6];      // [ChimlListKind][component]
+    std::vector<PlanObject> objects;
+    std::vector<PlanCpml> cpml;
+    std::vector<PlanSource> sources;
+    std::vector<PlanDetector> detectors;
+    bool dielectricMatInPML = false;
+
+    void write(const std::string& path) const;
+};
+
+// Builds the plan of y-slab `rank` of `nranks` (equal-height slabs, mpiInterface::getLocxLocyLocz(int,int,int)).
+SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads = 0);
+
+} // namespace chiml_host

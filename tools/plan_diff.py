@@ -1,0 +1,76 @@
+"""Compare two plan files record by record (development tool): host-built vs reference-built."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+from chiml_b200 import plan as P
+
+
+def diff(a: P.Plan, b: P.Plan, verbose=True):
+    bad = []
+    for k in ("mode", "ln", "d", "dt", "has_D", "pml_on_D", "n_objects", "rank", "nranks", "y_start", "n_global", "n_steps",
+              "n_lor_poles", "n_ordip_poles", "t_max"):
+        if getattr(a, k) != getattr(b, k):
+            bad.append(f"grid.{k}: {getattr(a, k)} != {getattr(b, k)}")
+    for key in sorted(set(a.lists) | set(b.lists)):
+        la, lb = a.get_list(*key), b.get_list(*key)
+        if len(la) != len(lb):
+            bad.append(f"list{key}: len {len(la)} != {len(lb)}")
+            n = min(len(la), len(lb))
+            idx = [i for i in range(n) if la[i] != lb[i]][:1]
+            if idx:
+                bad.append(f"   first diff at {idx[0]}: {la[idx[0]]} vs {lb[idx[0]]}")
+            elif n < len(la): bad.append(f"   extra in A: {la[n]}")
+            elif n < len(lb): bad.append(f"   extra in B: {lb[n]}")
+        elif la.tobytes() != lb.tobytes():
+            i = next(i for i in range(len(la)) if la[i] != lb[i])
+            bad.append(f"list{key}: first diff at {i}: {la[i]} vs {lb[i]}")
+    if len(a.objects) != len(b.objects):
+        bad.append(f"objects: {len(a.objects)} != {len(b.objects)}")
+    for oa, ob in zip(a.objects, b.objects):
+        for k in ("obj", "npoles", "use_or_dip", "ml", "eps_inf", "mu_inf"):
+            if getattr(oa, k) != getattr(ob, k):
+                bad.append(f"object {oa.obj}.{k}: {getattr(oa, k)} != {getattr(ob, k)}")
+        for k in ("alpha", "xi", "gamma", "dip"):
+            if np.asarray(getattr(oa, k)).tobytes() != np.asarray(getattr(ob, k)).tobytes():
+                bad.append(f"object {oa.obj}.{k}: {getattr(oa, k)} != {getattr(ob, k)}")
+    ca = {(c.comp, c.part): c for c in a.cpml}
+    cb = {(c.comp, c.part): c for c in b.cpml}
+    for key in sorted(set(ca) | set(cb)):
+        if key not in ca or key not in cb:
+            bad.append(f"cpml{key}: present only in {'A' if key in ca else 'B'}")
+            continue
+        x, y = ca[key], cb[key]
+        if x.has_psi != y.has_psi:
+            bad.append(f"cpml{key}.has_psi {x.has_psi} != {y.has_psi}")
+        for nm in ("psi", "grid"):
+            u, v = getattr(x, nm), getattr(y, nm)
+            if len(u) != len(v):
+                bad.append(f"cpml{key}.{nm}: len {len(u)} != {len(v)}")
+            elif u.tobytes() != v.tobytes():
+                i = next(i for i in range(len(u)) if u[i] != v[i])
+                bad.append(f"cpml{key}.{nm}: first diff at {i}/{len(u)}: {u[i]} vs {v[i]}")
+    if len(a.sources) != len(b.sources):
+        bad.append(f"sources: {len(a.sources)} != {len(b.sources)}")
+    for i, (sa, sb) in enumerate(zip(a.sources, b.sources)):
+        if (sa.field, sa.loc, sa.sz) != (sb.field, sb.loc, sb.sz):
+            bad.append(f"source {i}: {(sa.field, sa.loc, sa.sz)} != {(sb.field, sb.loc, sb.sz)}")
+        if sa.amp.tobytes() != sb.amp.tobytes():
+            n = min(len(sa.amp), len(sb.amp))
+            j = next((j for j in range(n) if sa.amp[j] != sb.amp[j]), n)
+            bad.append(f"source {i}: amp len {len(sa.amp)} vs {len(sb.amp)}, first diff at {j}: "
+                       f"{sa.amp[j] if j < len(sa.amp) else None!r} vs {sb.amp[j] if j < len(sb.amp) else None!r}")
+    if len(a.detectors) != len(b.detectors):
+        bad.append(f"detectors: {len(a.detectors)} != {len(b.detectors)}")
+    for i, (da, db) in enumerate(zip(a.detectors, b.detectors)):
+        if da != db:
+            bad.append(f"detector {i}: {da} != {db}")
+    return bad
+
+
+if __name__ == "__main__":
+    bad = diff(P.read_plan(sys.argv[1]), P.read_plan(sys.argv[2]))
+    print("\n".join(bad) if bad else "plans identical")
+    sys.exit(1 if bad else 0)
