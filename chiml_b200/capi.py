@@ -25,7 +25,8 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_add_detector", "chiml_gpu_commit", "chiml_gpu_step_n", "chiml_gpu_sync", "chiml_gpu_step_n_timed",
     "chiml_gpu_launch_count", "chiml_gpu_upload_field", "chiml_gpu_download_field", "chiml_gpu_download_pole",
     "chiml_gpu_upload_pole", "chiml_gpu_download_ordip_pole", "chiml_gpu_download_psi", "chiml_gpu_read_detector",
-    "chiml_gpu_device_bytes",
+    "chiml_gpu_device_bytes", "chiml_gpu_set_kernel_timing", "chiml_gpu_n_kernel_kinds", "chiml_gpu_kernel_stat",
+    "chiml_gpu_reset_kernel_stats", "chiml_gpu_read_detector_range",
 ]
 
 
@@ -37,6 +38,11 @@ class GridDesc(C.Structure):
     _fields_ = [("mode", C.c_int32), ("ln", C.c_int32 * 3), ("d", C.c_double * 3), ("dt", C.c_double),
                 ("has_D", C.c_int32), ("pml_on_D", C.c_int32), ("n_objects", C.c_int32), ("rank", C.c_int32),
                 ("nranks", C.c_int32)]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("timed_launches", C.c_int64), ("ms_total", C.c_double),
+                ("alg_bytes_per_launch", C.c_double)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -76,8 +82,13 @@ def lib() -> C.CDLL:
     L.chiml_gpu_download_ordip_pole.argtypes = [vp, i, i, i, vp]
     L.chiml_gpu_download_psi.argtypes = [vp, i, i, vp]
     L.chiml_gpu_read_detector.argtypes = [vp, i, vp, sz, C.POINTER(sz)]
+    L.chiml_gpu_read_detector_range.argtypes = [vp, i, sz, sz, vp, C.POINTER(sz)]
     L.chiml_gpu_device_bytes.argtypes = [vp]
     L.chiml_gpu_device_bytes.restype = sz
+    L.chiml_gpu_set_kernel_timing.argtypes = [vp, i]
+    L.chiml_gpu_n_kernel_kinds.restype = i
+    L.chiml_gpu_kernel_stat.argtypes = [vp, i, C.POINTER(KernelStat)]
+    L.chiml_gpu_reset_kernel_stats.argtypes = [vp]
     _lib = L
     return L
 
@@ -217,6 +228,31 @@ class GpuSim:
         sx, sy, sz = box[1]
         out = np.empty((n.value, sy, sz, sx), dtype=np.float64)
         self._chk(lib().chiml_gpu_read_detector(self.h, slot, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def detector_range(self, index: int, first: int, n: int, out: np.ndarray) -> int:
+        """Copies samples [first, first+n) of plan.detectors[index] into `out` (host buffer); returns how many existed."""
+        slot = self.det_slots[index]
+        if slot < 0:
+            return 0
+        m = C.c_size_t()
+        self._chk(lib().chiml_gpu_read_detector_range(self.h, slot, first, n, _ptr(out), C.byref(m)))
+        return int(m.value)
+
+    def set_kernel_timing(self, on: bool) -> None:
+        self._chk(lib().chiml_gpu_set_kernel_timing(self.h, 1 if on else 0))
+
+    def reset_kernel_stats(self) -> None:
+        self._chk(lib().chiml_gpu_reset_kernel_stats(self.h))
+
+    def kernel_stats(self):
+        """[{name, launches, timed_launches, ms_total, alg_bytes_per_launch}] for every kernel of the step loop."""
+        out = []
+        for k in range(lib().chiml_gpu_n_kernel_kinds()):
+            ks = KernelStat()
+            self._chk(lib().chiml_gpu_kernel_stat(self.h, k, C.byref(ks)))
+            out.append({"name": ks.name.decode(), "launches": int(ks.launches), "timed_launches": int(ks.timed_launches),
+                        "ms_total": float(ks.ms_total), "alg_bytes_per_launch": float(ks.alg_bytes_per_launch)})
         return out
 
     def launch_count(self) -> int:

@@ -131,6 +131,8 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     cudaFree(ctx->d_src_amp);
     for(auto& f : ctx->d_tiles) for(auto& p : f) cudaFree(p);
     for(auto& d : ctx->detectors) cudaFree(d.d_ring);
+    for(auto& v : ctx->ev_pending) for(auto& pr : v) { cudaEventDestroy(pr[0]); cudaEventDestroy(pr[1]); }
+    for(auto& e : ctx->ev_pool) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -555,6 +557,9 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 if(id == 0) return fail(ctx, CHIML_ERR_UNSUPPORTED, "more than 255 distinct oriented-dipole material classes");
                 cls[e] = (uint8_t)id;
                 ctx->nordip = std::max(ctx->nordip, o.npoles);
+                int ncomp = 0;
+                for(int c = 0; c < 3; ++c) ncomp += field_exists(ctx, c) ? 1 : 0;
+                ctx->kstat[K_ORDIP_POLES].alg_bytes += 24.0 * ncomp * (double)r.n * o.npoles;   // P, prevP read, new P written
             }
             if((rc = paint_list(ctx, runs, cls, 0x0100, ctx->d_info_node, d_err))) return rc;
             ctx->ncls_node = (int)cb.entries.size();
@@ -633,12 +638,14 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         for(int fam = 0; fam < 2; ++fam)
         {
             const int b0 = fam == 0 ? 0 : 3;
-            k_tile_summary<<<(unsigned)ntiles, tb, 0, ctx->stream>>>(ctx->d_info[b0], ctx->d_info[b0 + 1], ctx->d_info[b0 + 2], d_sum, nxt, nzt, ctx->lz, ctx->px);
+            k_tile_summary<<<(unsigned)ntiles, tb, 0, ctx->stream>>>(ctx->d_info[b0], ctx->d_info[b0 + 1], ctx->d_info[b0 + 2], d_sum, nxt, nzt, ctx->lz, ctx->px,
+                                                                     ctx->d_cls[b0], ctx->d_cls[b0 + 1], ctx->d_cls[b0 + 2], fam == 0 ? 1 : 0, ctx->g.pml_on_D);
             ++ctx->launches;
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(sum.data(), d_sum, ntiles * sizeof(TileSummary), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             std::vector<TileRec> lists[3];
+            double listBytes[3] = {0.0, 0.0, 0.0};
             for(size_t tIdx = 0; tIdx < ntiles; ++tIdx)
             {
                 const TileSummary& ts = sum[tIdx];
@@ -666,9 +673,11 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                     rec.inv_eps[c] = ce.inv_eps;
                 }
                 lists[fast ? 0 : (uniform ? 1 : 2)].push_back(rec);
+                listBytes[fast ? 0 : (uniform ? 1 : 2)] += ts.bytes;
             }
             for(int k = 0; k < 3; ++k)
             {
+                ctx->kstat[(fam == 0 ? K_E_FAST : K_H_FAST) + k].alg_bytes = listBytes[k];
                 ctx->ntiles[fam][k] = (unsigned)lists[k].size();
                 TileRec* d = nullptr;
                 if((rc = dev_upload(ctx, &d, lists[k]))) return rc;
@@ -751,13 +760,37 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
     }
 }
 
+// Brackets one launch with CUDA events on the context's stream when kernel timing is on, and counts it.
+struct LaunchScope
+{
+    ChimlCtx* ctx; int kind; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    static cudaEvent_t get(ChimlCtx* ctx)
+    {
+        cudaEvent_t e = nullptr;
+        if(!ctx->ev_pool.empty()) { e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    LaunchScope(ChimlCtx* c, int k) : ctx(c), kind(k)
+    {
+        if(ctx->timing) { e0 = get(ctx); e1 = get(ctx); cudaEventRecord(e0, ctx->stream); }
+    }
+    ~LaunchScope()
+    {
+        ++ctx->launches;
+        ++ctx->kstat[kind].launches;
+        if(e0) { cudaEventRecord(e1, ctx->stream); ctx->ev_pending[kind].push_back({e0, e1}); }
+    }
+};
+
 template <bool IS_E, int MODE>
 void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block)
 {
     const int fam = IS_E ? 0 : 1;
-    if(ctx->ntiles[fam][0]) { k_fast<IS_E, MODE><<<ctx->ntiles[fam][0], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0]); ++ctx->launches; }
-    if(ctx->ntiles[fam][1]) { k_uniform<IS_E, MODE><<<ctx->ntiles[fam][1], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1]); ++ctx->launches; }
-    if(ctx->ntiles[fam][2]) { k_general<IS_E, MODE><<<ctx->ntiles[fam][2], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2]); ++ctx->launches; }
+    const int k0 = IS_E ? K_E_FAST : K_H_FAST;
+    if(ctx->ntiles[fam][0]) { LaunchScope ls(ctx, k0);     k_fast<IS_E, MODE><<<ctx->ntiles[fam][0], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0]); }
+    if(ctx->ntiles[fam][1]) { LaunchScope ls(ctx, k0 + 1); k_uniform<IS_E, MODE><<<ctx->ntiles[fam][1], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1]); }
+    if(ctx->ntiles[fam][2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE><<<ctx->ntiles[fam][2], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2]); }
 }
 template <bool IS_E>
 void launch_family(ChimlCtx* ctx, const StepArgs& a, const dim3 block)
@@ -782,9 +815,9 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
     {
         const SourceDev& s = ctx->sources[q];
         const long n = (long)s.sz[0] * s.sz[1] * s.sz[2];
+        LaunchScope ls(ctx, K_SOURCE);
         k_source<<<(unsigned)std::min<long>((n + 255) / 256, 2048), 256, 0, ctx->stream>>>(
             ctx->d_field[s.field], s.loc[0], s.loc[2], s.loc[1], s.sz[0], s.sz[2], s.sz[1], ctx->lz, ctx->px, ctx->d_src_amp + k * nsrc + q);
-        ++ctx->launches;
     }
     // oriented-dipole poles at the nodes (item 10, first loop)
     if(ctx->d_info_node)
@@ -803,8 +836,8 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
             na.eoff[c] = phys_offset(ctx, d);
             for(int p = 0; p < MAX_POLES; ++p) { na.Pcur[c][p] = ctx->d_oP[c][p][cur]; na.Pnew[c][p] = ctx->d_oP[c][p][prv]; }
         }
+        LaunchScope ls(ctx, K_ORDIP_POLES);
         k_ordip_poles<<<ngrid, nblock, 0, ctx->stream>>>(na);
-        ++ctx->launches;
     }
     // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
     fill_step_args(ctx, true, a);
@@ -825,9 +858,11 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
             ctx->dev_bytes += dt.cap * dt.sample_len * sizeof(double);
             dt.d_ring = bigger; dt.cap *= 2;
         }
-        k_detector<<<(unsigned)std::min<size_t>((dt.sample_len + 255) / 256, 1024), 256, 0, ctx->stream>>>(
-            ctx->d_field[dt.field], dt.loc[0], dt.loc[2], dt.loc[1], dt.sz[0], dt.sz[2], dt.sz[1], ctx->lz, ctx->px, dt.d_ring + dt.count * dt.sample_len);
-        ++ctx->launches;
+        {
+            LaunchScope ls(ctx, K_DETECTOR);
+            k_detector<<<(unsigned)std::min<size_t>((dt.sample_len + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+                ctx->d_field[dt.field], dt.loc[0], dt.loc[2], dt.loc[1], dt.sz[0], dt.sz[2], dt.sz[1], ctx->lz, ctx->px, dt.d_ring + dt.count * dt.sample_len);
+        }
         ++dt.count;
     }
     return 0;
@@ -890,6 +925,50 @@ int chiml_gpu_step_n_timed(ChimlCtx* ctx, int n, const double* src_amp, float* m
 }
 
 int64_t chiml_gpu_launch_count(const ChimlCtx* ctx) { return ctx ? ctx->launches : 0; }
+
+int chiml_gpu_set_kernel_timing(ChimlCtx* ctx, int on)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    ctx->timing = on != 0;
+    return CHIML_OK;
+}
+
+int chiml_gpu_n_kernel_kinds(void) { return K_NKINDS; }
+
+int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out)
+{
+    static const char* names[K_NKINDS] = {"k_fast<E>", "k_uniform<E>", "k_general<E>", "k_fast<H>", "k_uniform<H>", "k_general<H>",
+                                          "k_ordip_poles", "k_source", "k_detector"};
+    if(!ctx || !out || kind < 0 || kind >= K_NKINDS) return CHIML_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    KernelStat& ks = ctx->kstat[kind];
+    for(auto& pr : ctx->ev_pending[kind])
+    {
+        float ms = 0.f;
+        if(cudaEventElapsedTime(&ms, pr[0], pr[1]) == cudaSuccess) { ks.ms_total += ms; ++ks.timed; }
+        ctx->ev_pool.push_back(pr[0]); ctx->ev_pool.push_back(pr[1]);
+    }
+    ctx->ev_pending[kind].clear();
+    std::memset(out, 0, sizeof(*out));
+    std::snprintf(out->name, sizeof(out->name), "%s", names[kind]);
+    out->launches = ks.launches; out->timed_launches = ks.timed; out->ms_total = ks.ms_total; out->alg_bytes_per_launch = ks.alg_bytes;
+    return CHIML_OK;
+}
+
+int chiml_gpu_reset_kernel_stats(ChimlCtx* ctx)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for(int k = 0; k < K_NKINDS; ++k)
+    {
+        for(auto& pr : ctx->ev_pending[k]) { ctx->ev_pool.push_back(pr[0]); ctx->ev_pool.push_back(pr[1]); }
+        ctx->ev_pending[k].clear();
+        ctx->kstat[k].launches = 0; ctx->kstat[k].ms_total = 0.0; ctx->kstat[k].timed = 0;
+    }
+    return CHIML_OK;
+}
 size_t chiml_gpu_device_bytes(const ChimlCtx* ctx) { return ctx ? ctx->dev_bytes : 0; }
 
 int chiml_gpu_upload_field(ChimlCtx* ctx, int field, const double* host)
@@ -1002,6 +1081,21 @@ int chiml_gpu_read_detector(ChimlCtx* ctx, int slot, double* out, size_t cap_sam
     if(n_samples) *n_samples = dt.count;
     const size_t n = std::min(cap_samples, dt.count);
     if(out && n) CK(cudaMemcpy(out, dt.d_ring, n * dt.sample_len * sizeof(double), cudaMemcpyDeviceToHost));
+    return CHIML_OK;
+}
+
+int chiml_gpu_read_detector_range(ChimlCtx* ctx, int slot, size_t first, size_t n, double* out, size_t* n_read)
+{
+    if(!ctx || !out) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "read_detector_range before commit");
+    if(slot < 0 || slot >= (int)ctx->detectors.size()) return fail(ctx, CHIML_ERR_ARG, "read_detector_range: bad slot");
+    CK(cudaSetDevice(ctx->device));
+    const DetectorDev& dt = ctx->detectors[slot];
+    const size_t avail = first < dt.count ? dt.count - first : 0;
+    const size_t m = std::min(n, avail);
+    if(m) CK(cudaMemcpyAsync(out, dt.d_ring + first * dt.sample_len, m * dt.sample_len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if(n_read) *n_read = m;
     return CHIML_OK;
 }
 

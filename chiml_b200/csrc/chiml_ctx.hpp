@@ -85,6 +85,10 @@ struct DetectorDev
     double* d_ring = nullptr; size_t cap = 0; size_t count = 0;
 };
 
+// kernels of the step loop, for launch / time / algorithmic-byte accounting
+enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_NKINDS };
+struct KernelStat { int64_t launches = 0; double ms_total = 0.0; double alg_bytes = 0.0; int64_t timed = 0; };
+
 struct HostList { std::vector<ChimlRun> runs; };
 struct HostPml { int present = 0, has_psi = 0; std::vector<ChimlPsiParams> psi; std::vector<ChimlGridParams> grid; };
 struct HostObj { int npoles = 0, use_or_dip = 0; std::vector<double> alpha, xi, gamma, dip; };
@@ -152,4 +156,10 @@ struct ChimlCtx
     long long step_count = 0;
     int64_t launches = 0;
     size_t dev_bytes = 0;
+
+    // per-kernel device timing (chiml_gpu_set_kernel_timing / chiml_gpu_kernel_stat)
+    bool timing = false;
+    chiml::KernelStat kstat[chiml::K_NKINDS];
+    std::vector<cudaEvent_t> ev_pool;                         // recycled events
+    std::vector<std::array<cudaEvent_t, 2>> ev_pending[chiml::K_NKINDS];
 };

@@ -433,11 +433,30 @@ __global__ void __launch_bounds__(256, 2) k_general(const __grid_constant__ Step
 // commit-time tile summary: per tile and component the bounding rectangle of non-zero info cells, their
 // count, the first non-zero info value and whether all non-zero values are equal.  One block per tile.
 // ---------------------------------------------------------------------------------------------------
-struct TileSummary { unsigned rect[3]; unsigned info[3]; unsigned count[3]; unsigned same[3]; };
+struct TileSummary { unsigned rect[3]; unsigned info[3]; unsigned count[3]; unsigned same[3]; unsigned bytes; unsigned pad[3]; };
+
+// algorithmic bytes one field-component cell moves per step: 16 B RW + 8 B cross-read when it is
+// updated, +16 B when its D value is read and written, +24 B per isotropic pole, +16 B per psi value touched
+__device__ __forceinline__ unsigned cell_alg_bytes(const unsigned info, const ClassEntry* cls, const bool isE, const bool pmlOnD)
+{
+    if(info == 0) return 0;
+    const bool pml = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
+    unsigned b = 0;
+    if((info & F_CURL) || (info & (F_PG0 | F_PG1))) b += 24;
+    if(isE && ((info & (F_ISD | F_D2E | F_ORD2E)) || (pmlOnD && pml))) b += 16;
+    if(isE && (info & F_D2E)) b += 24u * (unsigned)cls[info & CLS_MASK].npoles;
+    if(info & F_PS0) b += 16;
+    if(info & F_PS1) b += 16;
+    return b;
+}
 
 __global__ void k_tile_summary(const uint16_t* i0, const uint16_t* i1, const uint16_t* i2, TileSummary* out,
-                               unsigned nxt, unsigned nzt, int lz, long px)
+                               unsigned nxt, unsigned nzt, int lz, long px,
+                               const ClassEntry* c0, const ClassEntry* c1, const ClassEntry* c2, int isE, int pmlOnD)
 {
+    __shared__ unsigned s_bytes;
+    const ClassEntry* cp[3] = {c0, c1, c2};
+    if(threadIdx.x == 0 && threadIdx.y == 0) s_bytes = 0;
     const unsigned tile = blockIdx.x;
     const unsigned xt = tile % nxt, zt = (tile / nxt) % nzt, y = tile / (nxt * nzt);
     const int xl = 2 * threadIdx.x, zl = threadIdx.y;
@@ -461,6 +480,7 @@ __global__ void k_tile_summary(const uint16_t* i0, const uint16_t* i1, const uin
             for(int k = 0; k < 2; ++k)
                 if(v[c][k])
                 {
+                    atomicAdd(&s_bytes, cell_alg_bytes(v[c][k], cp[c], isE != 0, pmlOnD != 0));
                     atomicMin(&s_xlo[c], (unsigned)(xl + k)); atomicMax(&s_xhi[c], (unsigned)(xl + k + 1));
                     atomicMin(&s_zlo[c], (unsigned)zl);       atomicMax(&s_zhi[c], (unsigned)(zl + 1));
                     atomicAdd(&s_cnt[c], 1u);
@@ -481,6 +501,7 @@ __global__ void k_tile_summary(const uint16_t* i0, const uint16_t* i1, const uin
         o.info[c] = s_first[c];
         o.same[c] = s_diff[c] ? 0u : 1u;
         o.rect[c] = s_cnt[c] ? (s_xlo[c] | (s_xhi[c] << 8) | (s_zlo[c] << 16) | (s_zhi[c] << 24)) : 0u;
+        if(c == 0) o.bytes = s_bytes;
     }
 }
 

@@ -188,3 +188,31 @@ def c4_plasmonic_ml(n: int = 767, steps: int = 500, res: int = 100, pml_cells: i
                   [normal_source("Ex", [0.0, 0.0, half_z - (pml_cells + 10) / res], [span_x, span_y, 0.0], [gaussian_pulse(1.5 * 2.0 / 1.86, 1.0)])],
                   objs,
                   [detector([0.0, 0.0, zs], [0.0, 0.0, 0.0], "Ex", out + "/dtc", time_int=dt * 1.0000001)])
+
+
+def c5_aniso_ml(nx: int = 2047, ny: int = 255, nz: int = 1023, steps: int = 200, res: int = 100, pml_cells: int = 20, slab_cells: int = 40,
+                sheet: bool = True, sheet_margin: int = 20, out: str = "output_data/c5") -> Dict:
+    """C5: the C3 anisotropic (oriented-dipole Lorentz) slab through the PML plus the C4 two-level emitter sheet (one node
+    thick, 10 cells above the slab, inside the non-PML interior), Ex dipole in the slab, point detectors.  nx, ny, nz are
+    cells per side of the WHOLE grid (points = cells + 1); the y-slab decomposition cuts ny."""
+    dt = default_dt(res)
+    s2 = 1.0 / math.sqrt(2.0)
+    pole = lorentz_pole(sigma_p=1.5, gamma=0.05, omega=2.5, dip_or_e="unidirectional", dir_dip_e=[s2, s2, 0.0])
+    objs = [block([(nx + 2) / res, (ny + 2) / res, slab_cells / res], [0.0, 0.0, 0.0], eps=2.25, pols=[pole])]
+    # the sheet is one node thick: put it exactly on a grid node (nodes sit at (k - cells/2) * d, half-integers for odd cell counts)
+    zs = (math.floor(nz / 2.0 + slab_cells / 2 + 10) - nz / 2.0) / res
+    if sheet:
+        mx, my = nx - 2 * pml_cells - 2 * sheet_margin, ny - 2 * pml_cells - 2 * sheet_margin
+        if mx < 1 or my < 1:
+            raise ValueError("c5_aniso_ml: grid too small for the emitter sheet")
+        objs.append(ml_block([mx / res, my / res, 0.0], [0.0, 0.0, zs], mol_den=1e25, e_levels_ev=[0.0, 2.0], dipole_debye=10.0,
+                             relax_rate=1e12, dephasing_rate=1e13, dtc_levs=[3], pop_fname_base=out + "/qe_"))
+    q = min(40, nx // 6) / res
+    qy = min(40, ny // 6) / res
+    dets = [detector([q, 0.0, 0.0], [0.0, 0.0, 0.0], "Ex", out + "/dtc_a", time_int=dt * 1.0000001),
+            detector([0.0, qy, zs], [0.0, 0.0, 0.0], "Ey", out + "/dtc_b", time_int=dt * 1.0000001),
+            detector([q, qy, 0.0], [0.0, 0.0, 0.0], "Hz", out + "/dtc_c", time_int=dt * 1.0000001)]
+    return config(comp_cell([nx / res, ny / res, nz / res], res, steps * dt - 0.5 * dt, "Ex"),
+                  pml([pml_cells / res] * 3),
+                  [normal_source("Ex", [0.0, 0.0, 0.0], [0.0, 0.0, 0.0], [gaussian_pulse(1.5, 1.0)])],
+                  objs, dets)

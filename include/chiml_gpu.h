@@ -134,6 +134,24 @@ int chiml_gpu_step_n_timed(ChimlCtx* ctx, int n, const double* src_amp, float* m
 /* number of kernels this context has launched since creation */
 int64_t chiml_gpu_launch_count(const ChimlCtx* ctx);
 
+/* ---- accounting --------------------------------------------------------------------------------- */
+/* Per-kernel statistics of the step loop.  With kernel timing on, every launch made by chiml_gpu_step_n is bracketed by
+ * CUDA events on the context's stream; chiml_gpu_kernel_stat synchronises and returns, for kernel `kind`
+ * (0 <= kind < chiml_gpu_n_kernel_kinds()), the number of launches, the summed device time of the timed ones and the
+ * ALGORITHMIC bytes one launch moves (time-varying state only, counted from the painted cells). */
+typedef struct ChimlKernelStat
+{
+    char    name[32];
+    int64_t launches;
+    int64_t timed_launches;
+    double  ms_total;
+    double  alg_bytes_per_launch;
+} ChimlKernelStat;
+int chiml_gpu_set_kernel_timing(ChimlCtx* ctx, int on);
+int chiml_gpu_n_kernel_kinds(void);
+int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out);
+int chiml_gpu_reset_kernel_stats(ChimlCtx* ctx);
+
 /* ---- state access (synchronous) ---------------------------------------------------------------- */
 /* host buffers use the reference's logical layout, ln[0]*ln[1]*ln[2] doubles, ghosts included */
 int chiml_gpu_upload_field(ChimlCtx* ctx, int field, const double* host);
@@ -147,6 +165,8 @@ int chiml_gpu_download_ordip_pole(ChimlCtx* ctx, int comp, int pole, int prev, d
 int chiml_gpu_download_psi(ChimlCtx* ctx, int comp, int part, double* host);
 /* copies up to cap samples (each sz[0]*sz[1]*sz[2] doubles, x fastest then z then y) and reports how many exist */
 int chiml_gpu_read_detector(ChimlCtx* ctx, int slot, double* out, size_t cap_samples, size_t* n_samples);
+/* samples [first, first+n) only (what a host loop that drains the detector after every step reads); *n_read = how many existed */
+int chiml_gpu_read_detector_range(ChimlCtx* ctx, int slot, size_t first, size_t n, double* out, size_t* n_read);
 
 /* bytes of device memory held by the context */
 size_t chiml_gpu_device_bytes(const ChimlCtx* ctx);

@@ -8,7 +8,7 @@
 // wall-clock seconds of the step loop as JSON.  Used to pin the restated oracle and as the
 // `--impl reference` CPU arm of bench.py.
 //
-// usage: chiml_ref <input.json> [--ranks R] [--steps N] [--dump FILE] [--plan PREFIX] [--no-output] [--quiet]
+// usage: chiml_ref <input.json> [--ranks R] [--steps N] [--warmup W (untimed steps before the N timed ones)] [--dump FILE] [--plan PREFIX] [--no-output] [--quiet]
 //   --plan PREFIX writes PREFIX.rank<r>.plan (include/chiml_plan.h) from the constructed propagator, before stepping
 //
 // dump file layout (little endian): magic "CHIMLDMP" | int32 nranks | then per rank, per grid:
@@ -40,6 +40,7 @@ struct Options
     std::string input;
     int ranks = 1;
     int steps = -1;
+    int warmup = 0;
     std::string dump;
     std::string plan;
     bool output = true;
@@ -282,6 +283,8 @@ static void rankMain(int rank, const Options& opt)
     if(!opt.plan.empty())
         writePlan(opt.plan + ".rank" + std::to_string(rank) + ".plan", FF, IP, nSteps);
 
+    for(int tt = 0; tt < opt.warmup; ++tt)
+        FF.step();
     gridComm->barrier();
     auto t0 = std::chrono::steady_clock::now();
     for(int tt = 0; tt < nSteps; ++tt)
@@ -292,8 +295,7 @@ static void rankMain(int rank, const Options& opt)
     {
         g_stepSeconds = std::chrono::duration<double>(t1 - t0).count();
         g_nStepsRun = nSteps;
-        g_cells = long(FF.E_[0] ? FF.E_[0]->x() - 2 : FF.E_[2]->x() - 2) * long(FF.E_[0] ? FF.E_[0]->y() - 2 : FF.E_[2]->y() - 2)
-                * long( (FF.E_[0] ? FF.E_[0]->z() : FF.E_[2]->z()) == 1 ? 1 : (FF.E_[0] ? FF.E_[0]->z() - 2 : FF.E_[2]->z() - 2) );
+        g_cells = long(FF.n_vec_[0]) * long(FF.n_vec_[1]) * long(FF.n_vec_[2] > 1 ? FF.n_vec_[2] : 1);   // grid points, PML included
     }
 
     if(!opt.dump.empty())
@@ -340,14 +342,30 @@ static void rankMain(int rank, const Options& opt)
     gridComm->barrier();
 }
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void segvHandler(int sig)
+{
+    void* frames[64];
+    int n = backtrace(frames, 64);
+    const char msg[] = "chiml_ref: fatal signal, backtrace:\n";
+    (void)!write(2, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 int main(int argc, char** argv)
 {
+    signal(SIGSEGV, segvHandler);
+    signal(SIGABRT, segvHandler);
     Options opt;
     for(int a = 1; a < argc; ++a)
     {
         std::string s = argv[a];
         if(s == "--ranks" && a + 1 < argc) opt.ranks = std::atoi(argv[++a]);
         else if(s == "--steps" && a + 1 < argc) opt.steps = std::atoi(argv[++a]);
+        else if(s == "--warmup" && a + 1 < argc) opt.warmup = std::atoi(argv[++a]);
         else if(s == "--dump" && a + 1 < argc) opt.dump = argv[++a];
         else if(s == "--plan" && a + 1 < argc) opt.plan = argv[++a];
         else if(s == "--no-output") opt.output = false;
