@@ -122,12 +122,12 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     }
     for(int c = 0; c < 3; ++c)
     {
-        cudaFree(ctx->span[c].d_xmin); cudaFree(ctx->span[c].d_xmax); cudaFree(ctx->span[c].d_base);
+        cudaFree(ctx->span[c].d_xmin); cudaFree(ctx->span[c].d_xmax); cudaFree(ctx->span[c].d_base); cudaFree(ctx->span[c].d_rows);
         for(int p = 0; p < MAX_POLES; ++p)
             for(int k = 0; k < 2; ++k) { cudaFree(ctx->d_P[c][p][k]); cudaFree(ctx->d_oP[c][p][k]); }
     }
     cudaFree(ctx->d_info_node); cudaFree(ctx->d_cls_node);
-    cudaFree(ctx->span_node.d_xmin); cudaFree(ctx->span_node.d_xmax); cudaFree(ctx->span_node.d_base);
+    cudaFree(ctx->span_node.d_xmin); cudaFree(ctx->span_node.d_xmax); cudaFree(ctx->span_node.d_base); cudaFree(ctx->span_node.d_rows);
     cudaFree(ctx->d_src_amp);
     for(auto& f : ctx->d_tiles) for(auto& p : f) cudaFree(p);
     for(auto& d : ctx->detectors) cudaFree(d.d_ring);
@@ -327,7 +327,17 @@ int build_spans(ChimlCtx* ctx, const std::vector<const std::vector<ChimlRun>*>& 
     for(size_t row = 0; row < nrows; ++row)
         if(sp.h_xmin[row] >= 0) { sp.h_base[row] = total; total += sp.h_xmax[row] - sp.h_xmin[row] + 1; }
     sp.total = total;
+    std::vector<int32_t> rows;
+    sp.max_width = 0;
+    for(size_t row = 0; row < nrows; ++row)
+        if(sp.h_xmin[row] >= 0)
+        {
+            rows.push_back((int32_t)row);
+            sp.max_width = std::max(sp.max_width, sp.h_xmax[row] - (sp.h_xmin[row] & ~1) + 1);
+        }
+    sp.nrows_used = (int)rows.size();
     int rc;
+    if((rc = dev_upload(ctx, &sp.d_rows, rows))) return rc;
     if((rc = dev_upload(ctx, &sp.d_xmin, sp.h_xmin))) return rc;
     if((rc = dev_upload(ctx, &sp.d_xmax, sp.h_xmax))) return rc;
     if((rc = dev_upload(ctx, &sp.d_base, sp.h_base))) return rc;
@@ -804,8 +814,6 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
 {
     // one block per tile of the compact lists built at commit
     const dim3 block(32, ctx->lz > 1 ? TILE_Z : 1, 1);
-    const dim3 nblock(64, ctx->lz > 1 ? 4 : 1, 1);
-    const dim3 ngrid((ctx->lx + nblock.x - 1) / nblock.x, (ctx->lz + nblock.y - 1) / nblock.y, ctx->ly);
     StepArgs a;
     // H half step: updateH + updateHPML_ (step() items 4 and 6)
     fill_step_args(ctx, false, a);
@@ -826,7 +834,8 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
         std::memset(&na, 0, sizeof(na));
         na.info = ctx->d_info_node; na.cls = ctx->d_cls_node;
         na.lx = ctx->lx; na.ly = ctx->ly; na.lz = ctx->lz; na.px = ctx->px;
-        na.sp_xmin = ctx->span_node.d_xmin; na.sp_base = ctx->span_node.d_base;
+        na.sp_xmin = ctx->span_node.d_xmin; na.sp_xmax = ctx->span_node.d_xmax; na.sp_base = ctx->span_node.d_base;
+        na.rows = ctx->span_node.d_rows;
         const int cur = ctx->pcur, prv = 1 - ctx->pcur;
         for(int c = 0; c < 3; ++c)
         {
@@ -837,7 +846,8 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
             for(int p = 0; p < MAX_POLES; ++p) { na.Pcur[c][p] = ctx->d_oP[c][p][cur]; na.Pnew[c][p] = ctx->d_oP[c][p][prv]; }
         }
         LaunchScope ls(ctx, K_ORDIP_POLES);
-        k_ordip_poles<<<ngrid, nblock, 0, ctx->stream>>>(na);
+        const dim3 ng((ctx->span_node.max_width + 255) / 256, ctx->span_node.nrows_used, 1);
+        if(ng.y > 0) k_ordip_poles<<<ng, 256, 0, ctx->stream>>>(na);
     }
     // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
     fill_step_args(ctx, true, a);

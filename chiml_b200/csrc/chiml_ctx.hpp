@@ -57,6 +57,8 @@ struct SpanTable
     int64_t total = 0;
     std::vector<int32_t> h_xmin, h_xmax;
     std::vector<int64_t> h_base;
+    int32_t* d_rows = nullptr;   // compact list of rows with a span
+    int nrows_used = 0, max_width = 0;
 };
 
 struct PmlPartDev

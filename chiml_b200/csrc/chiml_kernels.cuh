@@ -85,7 +85,9 @@ struct NodeArgs
     const double* E[3];
     long eoff[3];                // physical offsets of the second averaging point per component
     const int32_t* sp_xmin;
+    const int32_t* sp_xmax;
     const int64_t* sp_base;
+    const int32_t* rows;         // compact list of the grid rows (z + lz*y) that hold node cells
     const double* Pcur[3][MAX_POLES];
     double* Pnew[3][MAX_POLES];
     int lx, ly, lz;
@@ -113,11 +115,11 @@ namespace chiml {
 // (FDTD_MANAGER/parallelFDTDField.hpp:1350-1354 -> UTIL/FDTD_up_eq.cpp:450-631)
 __global__ void __launch_bounds__(256) k_ordip_poles(const __grid_constant__ NodeArgs a)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int z = blockIdx.y * blockDim.y + threadIdx.y;
-    const int y = blockIdx.z;
-    if(x >= a.lx || z >= a.lz) return;
-    const long row = z + (long)a.lz * y;
+    // one block per 256-cell chunk of one row of the compact row list: only rows that hold node cells are visited
+    const long row = a.rows[blockIdx.y];
+    const int xmin = a.sp_xmin[row];
+    const int x = (xmin & ~1) + blockIdx.x * blockDim.x + threadIdx.x;
+    if(x < xmin || x > a.sp_xmax[row]) return;
     const long r = x + a.px * row;
     const uint16_t info = a.info[r];
     if(info == 0) return;
