@@ -26,7 +26,8 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_launch_count", "chiml_gpu_upload_field", "chiml_gpu_download_field", "chiml_gpu_download_pole",
     "chiml_gpu_upload_pole", "chiml_gpu_download_ordip_pole", "chiml_gpu_download_psi", "chiml_gpu_read_detector",
     "chiml_gpu_device_bytes", "chiml_gpu_set_kernel_timing", "chiml_gpu_n_kernel_kinds", "chiml_gpu_kernel_stat",
-    "chiml_gpu_reset_kernel_stats", "chiml_gpu_read_detector_range",
+    "chiml_gpu_reset_kernel_stats", "chiml_gpu_read_detector_range", "chiml_gpu_add_emitters",
+    "chiml_gpu_download_emitter_state", "chiml_gpu_download_emitter_pol", "chiml_gpu_read_population",
 ]
 
 
@@ -38,6 +39,34 @@ class GridDesc(C.Structure):
     _fields_ = [("mode", C.c_int32), ("ln", C.c_int32 * 3), ("d", C.c_double * 3), ("dt", C.c_double),
                 ("has_D", C.c_int32), ("pml_on_D", C.c_int32), ("n_objects", C.c_int32), ("rank", C.c_int32),
                 ("nranks", C.c_int32)]
+
+
+class EmitterDesc(C.Structure):
+    """include/chiml_gpu.h ChimlEmitterDesc"""
+    _fields_ = [("nlevel", C.c_int32), ("nsys", C.c_int32), ("nemit", C.c_int32), ("box_lo", C.c_int32 * 3), ("box_n", C.c_int32 * 3),
+                ("dt", C.c_double), ("inv_hbar", C.c_double), ("na", C.c_double),
+                ("h0", C.c_void_p), ("weight", C.c_void_p), ("mu", C.c_void_p), ("gam_ptr", C.c_void_p), ("gam_col", C.c_void_p),
+                ("gam_val", C.c_void_p), ("loc", C.c_void_p), ("eps", C.c_void_p), ("npop", C.c_int32), ("pop_level", C.c_void_p),
+                ("pop_every", C.c_int32), ("npoints", C.c_int32)]
+
+
+def emitter_desc(e: "P.PlanEmitter", keep: list) -> EmitterDesc:
+    """C struct of one plan emitter record; the numpy arrays it points to are appended to `keep`."""
+    d = EmitterDesc()
+    d.nlevel, d.nsys, d.nemit = e.nlevel, e.nsys, e.nemit
+    d.box_lo[:] = e.box_lo
+    d.box_n[:] = e.box_n
+    d.dt, d.inv_hbar, d.na = e.dt, e.inv_hbar, e.na
+    arrs = {"h0": np.ascontiguousarray(e.h0, np.complex128), "weight": np.ascontiguousarray(e.weight, np.float64),
+            "mu": np.ascontiguousarray(e.mu, np.complex128), "gam_ptr": np.ascontiguousarray(e.gam_ptr, np.int32),
+            "gam_col": np.ascontiguousarray(e.gam_col, np.int32), "gam_val": np.ascontiguousarray(e.gam_val, np.float64),
+            "loc": np.ascontiguousarray(e.loc, np.int32), "eps": np.ascontiguousarray(e.eps, np.float64),
+            "pop_level": np.ascontiguousarray(e.pop_level, np.int32)}
+    for k, a in arrs.items():
+        keep.append(a)
+        setattr(d, k, a.ctypes.data if a.size else None)
+    d.npop, d.pop_every, d.npoints = e.npop, e.pop_every, e.npoints
+    return d
 
 
 class KernelStat(C.Structure):
@@ -83,6 +112,10 @@ def lib() -> C.CDLL:
     L.chiml_gpu_download_psi.argtypes = [vp, i, i, vp]
     L.chiml_gpu_read_detector.argtypes = [vp, i, vp, sz, C.POINTER(sz)]
     L.chiml_gpu_read_detector_range.argtypes = [vp, i, sz, sz, vp, C.POINTER(sz)]
+    L.chiml_gpu_add_emitters.argtypes = [vp, C.POINTER(EmitterDesc), C.POINTER(i)]
+    L.chiml_gpu_download_emitter_state.argtypes = [vp, i, i, i, vp]
+    L.chiml_gpu_download_emitter_pol.argtypes = [vp, i, i, vp]
+    L.chiml_gpu_read_population.argtypes = [vp, i, i, vp, sz, C.POINTER(sz)]
     L.chiml_gpu_device_bytes.argtypes = [vp]
     L.chiml_gpu_device_bytes.restype = sz
     L.chiml_gpu_set_kernel_timing.argtypes = [vp, i]
@@ -136,6 +169,11 @@ class GpuSim:
             for s in plan.sources:
                 slot = C.c_int()
                 self._chk(L.chiml_gpu_add_source(self.h, s.field, (C.c_int32 * 3)(*s.loc), (C.c_int32 * 3)(*s.sz), C.byref(slot)))
+            keep = []
+            for e in plan.emitters:
+                slot = C.c_int()
+                d = emitter_desc(e, keep)
+                self._chk(L.chiml_gpu_add_emitters(self.h, C.byref(d), C.byref(slot)))
             if detectors:
                 for d in plan.detectors:
                     box = local_box(plan, d.loc, d.sz)
@@ -238,6 +276,27 @@ class GpuSim:
         m = C.c_size_t()
         self._chk(lib().chiml_gpu_read_detector_range(self.h, slot, first, n, _ptr(out), C.byref(m)))
         return int(m.value)
+
+    def emitter_state(self, slot: int, sys: int, which: int) -> np.ndarray:
+        """(nemit, N*N) complex: rho (which=0) or d rho/dt at n, n-1, n-2, n-3 (which=1..4) of level system `sys`."""
+        e = self.plan.emitters[slot]
+        out = np.empty((e.nemit, e.nlevel * e.nlevel, 2), dtype=np.float64)
+        self._chk(lib().chiml_gpu_download_emitter_state(self.h, slot, sys, which, _ptr(out)))
+        return out[..., 0] + 1j * out[..., 1]
+
+    def emitter_P(self, slot: int, comp: int) -> np.ndarray:
+        e = self.plan.emitters[slot]
+        out = np.empty((e.box_n[1] + 2, e.pz, e.box_n[0] + 2), dtype=np.float64)
+        self._chk(lib().chiml_gpu_download_emitter_pol(self.h, slot, comp, _ptr(out)))
+        return out
+
+    def population(self, slot: int, det: int) -> np.ndarray:
+        n = C.c_size_t()
+        self._chk(lib().chiml_gpu_read_population(self.h, slot, det, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 2), dtype=np.float64)
+        if n.value:
+            self._chk(lib().chiml_gpu_read_population(self.h, slot, det, _ptr(out), n.value, C.byref(n)))
+        return out[:, 0] + 1j * out[:, 1]
 
     def set_kernel_timing(self, on: bool) -> None:
         self._chk(lib().chiml_gpu_set_kernel_timing(self.h, 1 if on else 0))

@@ -131,6 +131,14 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     cudaFree(ctx->d_src_amp);
     for(auto& f : ctx->d_tiles) for(auto& p : f) cudaFree(p);
     for(auto& d : ctx->detectors) cudaFree(d.d_ring);
+    for(auto& em : ctx->emitters)
+    {
+        cudaFree(em.d_h0); cudaFree(em.d_mu); cudaFree(em.d_gam_val); cudaFree(em.d_eps); cudaFree(em.d_gam_ptr); cudaFree(em.d_gam_col); cudaFree(em.d_loc);
+        for(auto& p : em.d_P) cudaFree(p);
+        cudaFree(em.d_rho);
+        for(auto& p : em.d_f) cudaFree(p);
+        cudaFree(em.d_pop_partial); cudaFree(em.d_pop);
+    }
     for(auto& v : ctx->ev_pending) for(auto& pr : v) { cudaEventDestroy(pr[0]); cudaEventDestroy(pr[1]); }
     for(auto& e : ctx->ev_pool) cudaEventDestroy(e);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -216,6 +224,52 @@ int chiml_gpu_add_detector(ChimlCtx* ctx, int field, const int32_t loc[3], const
     d.sample_len = (size_t)sz[0] * sz[1] * sz[2];
     if(slot) *slot = (int)ctx->detectors.size();
     ctx->detectors.push_back(d);
+    return CHIML_OK;
+}
+
+int chiml_gpu_add_emitters(ChimlCtx* ctx, const ChimlEmitterDesc* d, int* slot)
+{
+    if(!ctx || !d) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "add_emitters after commit");
+    if(d->nlevel < 2 || d->nlevel > 6) return fail(ctx, CHIML_ERR_UNSUPPORTED, "add_emitters: 2 <= nlevel <= 6 supported");
+    if(d->nsys < 1 || d->nemit < 0 || d->npop < 0 || d->npop > EMIT_MAX_POP || d->pop_every < 1)
+        return fail(ctx, CHIML_ERR_ARG, "add_emitters: bad counts (at most 8 population detectors per object)");
+    if(!d->h0 || !d->weight || !d->mu || !d->gam_ptr || !d->eps || (d->nemit && !d->loc) || (d->npop && !d->pop_level))
+        return fail(ctx, CHIML_ERR_ARG, "add_emitters: null array");
+    if(!ctx->g.has_D) return fail(ctx, CHIML_ERR_ARG, "add_emitters: emitter objects are D-cells, has_D must be set");
+    EmitterDev em;
+    em.d = *d;
+    const int n2 = d->nlevel * d->nlevel;
+    em.n2 = n2;
+    const bool threeD = ctx->lz > 1;
+    em.pz = threeD ? d->box_n[2] + 2 : 2;
+    em.pbox = (size_t)(d->box_n[0] + 2) * (size_t)(d->box_n[1] + 2) * (size_t)em.pz;
+    const int ln[3] = {ctx->lx, ctx->ly, ctx->lz};
+    for(int k = 0; k < 3; ++k)
+    {
+        if(!threeD && k == 2) continue;
+        if(d->box_n[k] < 1 || d->box_lo[k] < 0 || d->box_lo[k] + d->box_n[k] + 2 > ln[k])
+            return fail(ctx, CHIML_ERR_ARG, "add_emitters: emitter box (plus its one-node rim) leaves the local grid");
+    }
+    for(int e = 0; e < d->nemit; ++e)
+        for(int k = 0; k < 3; ++k)
+            if(d->loc[3 * e + k] < 0 || d->loc[3 * e + k] >= (k == 2 && !threeD ? 1 : d->box_n[k]))
+                return fail(ctx, CHIML_ERR_ARG, "add_emitters: emitter outside its box");
+    const int nnz = d->gam_ptr[n2];
+    for(int k = 0; k < nnz; ++k) if(d->gam_col[k] < 0 || d->gam_col[k] >= n2) return fail(ctx, CHIML_ERR_ARG, "add_emitters: gam column out of range");
+    for(int p = 0; p < d->npop; ++p) if(d->pop_level[p] < 0 || d->pop_level[p] >= n2) return fail(ctx, CHIML_ERR_ARG, "add_emitters: population level out of range");
+    em.h_h0.assign(d->h0, d->h0 + (size_t)d->nsys * n2 * 2);
+    em.h_weight.assign(d->weight, d->weight + d->nsys);
+    em.h_mu.assign(d->mu, d->mu + (size_t)3 * n2 * 2);
+    em.h_gam_ptr.assign(d->gam_ptr, d->gam_ptr + n2 + 1);
+    if(nnz) { em.h_gam_col.assign(d->gam_col, d->gam_col + nnz); em.h_gam_val.assign(d->gam_val, d->gam_val + nnz); }
+    if(d->nemit) em.h_loc.assign(d->loc, d->loc + (size_t)3 * d->nemit);
+    em.h_eps.assign(d->eps, d->eps + em.pbox);
+    if(d->npop) em.h_pop_level.assign(d->pop_level, d->pop_level + d->npop);
+    for(int c = 0; c < 3; ++c)
+        for(int k = 0; k < 2 * n2; ++k) if(em.h_mu[(size_t)c * n2 * 2 + k] != 0.0) em.mu_present[c] = 1;
+    if(slot) *slot = (int)ctx->emitters.size();
+    ctx->emitters.push_back(std::move(em));
     return CHIML_OK;
 }
 
@@ -696,6 +750,31 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         }
         cudaFree(d_sum);
     }
+    // emitters: constants, P boxes, SoA density state (rho_00 = weight of the level system, ML/density.hpp:57-60)
+    for(EmitterDev& em : ctx->emitters)
+    {
+        if((rc = dev_upload(ctx, &em.d_h0, em.h_h0))) return rc;
+        if((rc = dev_upload(ctx, &em.d_mu, em.h_mu))) return rc;
+        if((rc = dev_upload(ctx, &em.d_gam_ptr, em.h_gam_ptr))) return rc;
+        if((rc = dev_upload(ctx, &em.d_gam_col, em.h_gam_col))) return rc;
+        if((rc = dev_upload(ctx, &em.d_gam_val, em.h_gam_val))) return rc;
+        if((rc = dev_upload(ctx, &em.d_loc, em.h_loc))) return rc;
+        if((rc = dev_upload(ctx, &em.d_eps, em.h_eps))) return rc;
+        for(int c = 0; c < 3; ++c) if((rc = dev_alloc(ctx, &em.d_P[c], em.pbox))) return rc;
+        const size_t per = (size_t)em.d.nsys * em.n2 * 2 * (size_t)std::max(em.d.nemit, 1);
+        std::vector<double> rho0(per, 0.0);
+        for(int sy = 0; sy < em.d.nsys; ++sy)
+            for(int e = 0; e < em.d.nemit; ++e) rho0[((size_t)sy * em.n2 * 2) * em.d.nemit + e] = em.h_weight[sy];
+        if((rc = dev_upload(ctx, &em.d_rho, rho0))) return rc;
+        for(int k = 0; k < 4; ++k) if((rc = dev_alloc(ctx, &em.d_f[k], per))) return rc;
+        em.nblocks = (em.d.nemit + 127) / 128;
+        if((rc = dev_alloc(ctx, &em.d_pop_partial, (size_t)std::max(em.d.npop, 1) * std::max(em.nblocks, 1) * 2))) return rc;
+        em.pop_cap = 4096;
+        if((rc = dev_alloc(ctx, &em.d_pop, (size_t)std::max(em.d.npop, 1) * em.pop_cap * 2))) return rc;
+        ctx->kstat[K_EMIT_DENSITY].alg_bytes += (double)em.d.nemit * (em.d.nsys * 96.0 * em.d.nlevel * em.d.nlevel + 48.0 + 24.0);
+        ctx->kstat[K_EMIT_ADDP].alg_bytes += 0.0;   // its E read-modify-write is the field traffic already counted for the E half step
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     // detectors: ring buffers sized on first use; sample at t = 0 (FDTD_MANAGER/parallelFDTDField.cpp:832-833)
     ctx->committed = true;
     for(size_t d = 0; d < ctx->detectors.size(); ++d)
@@ -810,6 +889,80 @@ void launch_family(ChimlCtx* ctx, const StepArgs& a, const dim3 block)
     else                                  launch_family_mode<IS_E, CHIML_MODE_TM>(ctx, a, block);
 }
 
+template <int N>
+void launch_density(ChimlCtx* ctx, const EmitArgs& ea, int nblocks)
+{
+    k_emit_density<N><<<nblocks, 128, 0, ctx->stream>>>(ea);
+}
+
+int launch_emitters(ChimlCtx* ctx, EmitterDev& em)
+{
+    const bool threeD = ctx->lz > 1;
+    {
+        AddPArgs pa;
+        std::memset(&pa, 0, sizeof(pa));
+        for(int c = 0; c < 3; ++c) { pa.E[c] = ctx->d_field[c]; pa.P[c] = em.d_P[c]; }
+        pa.eps = em.d_eps;
+        for(int k = 0; k < 3; ++k) pa.box_lo[k] = em.d.box_lo[k];
+        pa.nx = em.d.box_n[0] + 1; pa.ny = em.d.box_n[1] + 1; pa.nz = threeD ? em.d.box_n[2] + 1 : 1;
+        pa.bx = em.d.box_n[0] + 2; pa.bz = em.pz; pa.zoff = threeD ? 1 : 0;
+        pa.lz = ctx->lz; pa.px = ctx->px;
+        const long n = (long)pa.nx * pa.ny * pa.nz;
+        LaunchScope ls(ctx, K_EMIT_ADDP);
+        k_emit_addP<<<(unsigned)std::min<long>((n + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(pa);
+    }
+    const int sample = (em.tstep % em.d.pop_every) == 0 && em.d.npop > 0;
+    if(em.d.nemit > 0)
+    {
+        EmitArgs ea;
+        std::memset(&ea, 0, sizeof(ea));
+        for(int c = 0; c < 3; ++c) { ea.E[c] = ctx->d_field[c]; ea.P[c] = em.d_P[c]; ea.mu_present[c] = em.mu_present[c]; }
+        ea.lz = ctx->lz; ea.px = ctx->px; ea.threeD = threeD ? 1 : 0; ea.tm = (!ctx->d_field[CHIML_EX]) ? 1 : 0;
+        ea.nemit = em.d.nemit; ea.nsys = em.d.nsys; ea.nlevel = em.d.nlevel;
+        for(int k = 0; k < 3; ++k) ea.box_lo[k] = em.d.box_lo[k];
+        ea.bx = em.d.box_n[0] + 2; ea.bz = em.pz;
+        ea.dt = em.d.dt; ea.inv_hbar = em.d.inv_hbar; ea.na = em.d.na;
+        ea.h0 = em.d_h0; ea.mu = em.d_mu; ea.gam_ptr = em.d_gam_ptr; ea.gam_col = em.d_gam_col; ea.gam_val = em.d_gam_val;
+        ea.loc = em.d_loc; ea.eps = em.d_eps;
+        ea.rho = em.d_rho;
+        for(int k = 0; k < 4; ++k) ea.f[k] = em.d_f[(em.fbase + k) % 4];
+        ea.npop = em.d.npop; ea.sample = sample;
+        for(int p = 0; p < em.d.npop; ++p) ea.pop_level[p] = em.h_pop_level[p];
+        ea.pop_partial = em.d_pop_partial;
+        {
+            LaunchScope ls(ctx, K_EMIT_DENSITY);
+            switch(em.d.nlevel)
+            {
+                case 2: launch_density<2>(ctx, ea, em.nblocks); break;
+                case 3: launch_density<3>(ctx, ea, em.nblocks); break;
+                case 4: launch_density<4>(ctx, ea, em.nblocks); break;
+                case 5: launch_density<5>(ctx, ea, em.nblocks); break;
+                default: launch_density<6>(ctx, ea, em.nblocks); break;
+            }
+        }
+        em.fbase = (em.fbase + 3) % 4;   // the slot that held f_{n-3} now holds the new f_n
+    }
+    if(sample)
+    {
+        if(em.pop_n >= em.pop_cap)
+        {
+            double* bigger = nullptr;
+            const size_t ncap = 2 * em.pop_cap;
+            if(cudaMalloc((void**)&bigger, (size_t)em.d.npop * ncap * 2 * sizeof(double)) != cudaSuccess) return CHIML_ERR_CUDA;
+            for(int p = 0; p < em.d.npop; ++p)
+                cudaMemcpyAsync(bigger + (size_t)p * ncap * 2, em.d_pop + (size_t)p * em.pop_cap * 2, em.pop_n * 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(em.d_pop);
+            em.d_pop = bigger; em.pop_cap = ncap;
+        }
+        LaunchScope ls(ctx, K_EMIT_POP);
+        k_emit_pop_reduce<<<1, 256, 0, ctx->stream>>>(em.d_pop_partial, em.d.nemit > 0 ? em.nblocks : 0, em.d.npop, 0.0, (double)em.d.npoints, em.d_pop, em.pop_cap, em.pop_n);
+        ++em.pop_n;
+    }
+    ++em.tstep;
+    return 0;
+}
+
 int launch_step(ChimlCtx* ctx, long long k, int nsrc)
 {
     // one block per tile of the compact lists built at commit
@@ -852,6 +1005,12 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
     // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
     fill_step_args(ctx, true, a);
     launch_family<true>(ctx, a, block);
+    // qe->addQE() for every emitter object (item 16)
+    for(EmitterDev& em : ctx->emitters)
+    {
+        int rc = launch_emitters(ctx, em);
+        if(rc) return rc;
+    }
     ctx->pcur = 1 - ctx->pcur;
     ++ctx->step_count;
     // detectors (item 18)
@@ -948,7 +1107,7 @@ int chiml_gpu_n_kernel_kinds(void) { return K_NKINDS; }
 int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out)
 {
     static const char* names[K_NKINDS] = {"k_fast<E>", "k_uniform<E>", "k_general<E>", "k_fast<H>", "k_uniform<H>", "k_general<H>",
-                                          "k_ordip_poles", "k_source", "k_detector"};
+                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce"};
     if(!ctx || !out || kind < 0 || kind >= K_NKINDS) return CHIML_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1091,6 +1250,51 @@ int chiml_gpu_read_detector(ChimlCtx* ctx, int slot, double* out, size_t cap_sam
     if(n_samples) *n_samples = dt.count;
     const size_t n = std::min(cap_samples, dt.count);
     if(out && n) CK(cudaMemcpy(out, dt.d_ring, n * dt.sample_len * sizeof(double), cudaMemcpyDeviceToHost));
+    return CHIML_OK;
+}
+
+int chiml_gpu_download_emitter_state(ChimlCtx* ctx, int slot, int sys, int which, double* out)
+{
+    if(!ctx || !out) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "download_emitter_state before commit");
+    if(slot < 0 || slot >= (int)ctx->emitters.size()) return fail(ctx, CHIML_ERR_ARG, "download_emitter_state: bad slot");
+    const EmitterDev& em = ctx->emitters[slot];
+    if(sys < 0 || sys >= em.d.nsys || which < 0 || which > 4) return fail(ctx, CHIML_ERR_ARG, "download_emitter_state: bad sys/which");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double* src = which == 0 ? em.d_rho : em.d_f[(em.fbase + which - 1) % 4];
+    const size_t ne = (size_t)em.d.nemit, n2r = (size_t)em.n2 * 2;
+    std::vector<double> soa(n2r * ne);
+    if(ne) CK(cudaMemcpy(soa.data(), src + (size_t)sys * n2r * ne, soa.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for(size_t e = 0; e < ne; ++e)
+        for(size_t k = 0; k < n2r; ++k) out[e * n2r + k] = soa[k * ne + e];
+    return CHIML_OK;
+}
+
+int chiml_gpu_download_emitter_pol(ChimlCtx* ctx, int slot, int comp, double* out)
+{
+    if(!ctx || !out) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "download_emitter_pol before commit");
+    if(slot < 0 || slot >= (int)ctx->emitters.size() || comp < 0 || comp > 2) return fail(ctx, CHIML_ERR_ARG, "download_emitter_pol: bad slot/comp");
+    const EmitterDev& em = ctx->emitters[slot];
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, em.d_P[comp], em.pbox * sizeof(double), cudaMemcpyDeviceToHost));
+    return CHIML_OK;
+}
+
+int chiml_gpu_read_population(ChimlCtx* ctx, int slot, int det, double* out, size_t cap_samples, size_t* n_samples)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "read_population before commit");
+    if(slot < 0 || slot >= (int)ctx->emitters.size()) return fail(ctx, CHIML_ERR_ARG, "read_population: bad slot");
+    const EmitterDev& em = ctx->emitters[slot];
+    if(det < 0 || det >= em.d.npop) return fail(ctx, CHIML_ERR_ARG, "read_population: bad detector");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if(n_samples) *n_samples = em.pop_n;
+    const size_t n = std::min(cap_samples, em.pop_n);
+    if(out && n) CK(cudaMemcpy(out, em.d_pop + (size_t)det * em.pop_cap * 2, n * 2 * sizeof(double), cudaMemcpyDeviceToHost));
     return CHIML_OK;
 }
 

@@ -88,8 +88,28 @@ struct DetectorDev
 };
 
 // kernels of the step loop, for launch / time / algorithmic-byte accounting
-enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_NKINDS };
+enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_NKINDS };
 struct KernelStat { int64_t launches = 0; double ms_total = 0.0; double alg_bytes = 0.0; int64_t timed = 0; };
+
+// one parallelQE object on the device (chiml_emitters.cuh)
+struct EmitterDev
+{
+    ChimlEmitterDesc d{};            // scalars; the pointer members are not used after add_emitters
+    int n2 = 0, pz = 0;
+    size_t pbox = 0;
+    std::vector<double> h_h0, h_weight, h_mu, h_gam_val, h_eps;
+    std::vector<int32_t> h_gam_ptr, h_gam_col, h_loc, h_pop_level;
+    double *d_h0 = nullptr, *d_mu = nullptr, *d_gam_val = nullptr, *d_eps = nullptr;
+    int32_t *d_gam_ptr = nullptr, *d_gam_col = nullptr, *d_loc = nullptr;
+    double* d_P[3] = {};
+    double* d_rho = nullptr;
+    double* d_f[4] = {};             // ring of derivative histories
+    int fbase = 0;                   // d_f[(fbase + k) % 4] holds d rho/dt at step n-k
+    int mu_present[3] = {};
+    double* d_pop_partial = nullptr; int nblocks = 0;
+    double* d_pop = nullptr; size_t pop_cap = 0, pop_n = 0;
+    long tstep = 0;
+};
 
 struct HostList { std::vector<ChimlRun> runs; };
 struct HostPml { int present = 0, has_psi = 0; std::vector<ChimlPsiParams> psi; std::vector<ChimlGridParams> grid; };
@@ -149,6 +169,7 @@ struct ChimlCtx
     std::vector<chiml::SourceDev> sources;
     double* d_src_amp = nullptr; size_t src_amp_cap = 0;
     std::vector<chiml::DetectorDev> detectors;
+    std::vector<chiml::EmitterDev> emitters;
 
     // host-side copies of the setup until commit
     chiml::HostList lists[5][6];

@@ -109,6 +109,7 @@ __device__ __forceinline__ double node_value(const StepArgs& a, const double* po
 
 } // namespace chiml
 #include "chiml_update.cuh"
+#include "chiml_emitters.cuh"
 namespace chiml {
 
 // updatePolE, oriented-dipole poles at the integer nodes

@@ -82,6 +82,28 @@ def ml_block(size: Sequence[float], loc: Sequence[float], mol_den: float, e_leve
     return o
 
 
+def ml_object(size: Sequence[float], loc: Sequence[float], mol_den: float, basis: Sequence[Sequence[int]], levels: List[Dict],
+              couplings_debye: Sequence[float], relaxations: List[Dict], eps: float = 1.0, dtc_levs: Sequence[int] = (),
+              pop_fname_base: str = "output_data/qe_", pop_every: int = 1) -> Dict:
+    """General emitter block: `basis` = [(l, m), ...]; `levels` = Energy_Levels entries ({"E_cen": [...eV], "weights": [...],
+    "levs_described": k}); `couplings_debye` = N*N transition dipoles; `relaxations` = [{"state_i", "state_f", "rate", "dephasing_rate"}]
+    (rates in s^-1) -- INPUTS/parallelInputs.cpp:427-666."""
+    o = block(size, loc, eps=eps)
+    o["Basis_Set"] = [{"l": int(l), "m": int(m)} for l, m in basis]
+    o["mol_den"] = mol_den
+    o["Energy_Levels"] = [{"distribution": "delta_fxn", "E_cen": list(lv["E_cen"]), "weights": list(lv.get("weights", [1.0] * len(lv["E_cen"]))),
+                           "nstates": 1, "levs_described": int(lv.get("levs_described", 1))} for lv in levels]
+    o["couplings"] = list(couplings_debye)
+    o["gam"] = []
+    o["RelaxationOperators"] = [{"state_i": r["state_i"], "state_f": r["state_f"], "rate": r["rate"], "del_omg": 0.0, "radiative": False,
+                                 "dephasing_rate": r.get("dephasing_rate", 0.0)} for r in relaxations]
+    o["dtc_levs"] = list(dtc_levs)
+    o["levDTC_timeInt"] = pop_every
+    o["dtc_pop_fname_base"] = pop_fname_base
+    o["output_pol"] = False
+    return o
+
+
 def detector(loc: Sequence[float], size: Sequence[float], typ: str, fname: str, dtc_class: str = "txt", time_int: float = 0.0, si: bool = False) -> Dict:
     return {"loc": list(loc), "size": list(size), "SI": si, "dtc_class": dtc_class, "fname": fname, "type": typ, "txt_dat_type": "real",
             "txt_format_type": "none", "Time_Interval": time_int, "timeIntegrateMap": False, "t_start": 0.0, "t_end": 1e8}

@@ -78,6 +78,38 @@ class PlanDetector:
 
 
 @dataclass
+class PlanEmitter:
+    """One parallelQE object restricted to this slab (include/chiml_gpu.h ChimlEmitterDesc)."""
+    object: int
+    nlevel: int
+    nsys: int
+    nemit: int
+    box_lo: Tuple[int, int, int]
+    box_n: Tuple[int, int, int]
+    pz: int
+    npop: int
+    pop_every: int
+    npoints: int
+    dt: float
+    inv_hbar: float
+    na: float
+    h0: np.ndarray        # (nsys, N*N) complex
+    weight: np.ndarray    # (nsys,)
+    mu: np.ndarray        # (3, N*N) complex
+    gam_ptr: np.ndarray   # (N*N+1,) int32
+    gam_col: np.ndarray
+    gam_val: np.ndarray
+    loc: np.ndarray       # (nemit, 3) int32
+    eps: np.ndarray       # (n1+2, pz, n0+2)
+    pop_level: np.ndarray
+
+
+_EMIT_FMT = "<4i3i3i4i2i3d"
+_EMIT_SIZE = struct.calcsize(_EMIT_FMT)
+assert _EMIT_SIZE == 88
+
+
+@dataclass
 class Plan:
     mode: int = MODE_3D
     ln: Tuple[int, int, int] = (0, 0, 0)
@@ -99,6 +131,7 @@ class Plan:
     cpml: List[PlanCpml] = field(default_factory=list)
     sources: List[PlanSource] = field(default_factory=list)
     detectors: List[PlanDetector] = field(default_factory=list)
+    emitters: List[PlanEmitter] = field(default_factory=list)
 
     @property
     def ncell(self) -> int:
@@ -167,6 +200,31 @@ def read_plan(path: str) -> Plan:
         elif tag == "DETECTOR":
             v = struct.unpack_from("<ii3i3i3iiiidd", payload, 0)
             plan.detectors.append(PlanDetector(v[0], v[1], tuple(v[2:5]), tuple(v[5:8]), tuple(v[8:11]), v[11], v[12], v[14], v[15]))
+        elif tag == "EMITTER":
+            v = struct.unpack_from(_EMIT_FMT, payload, 0)
+            obj, N, nsys, nemit = v[0:4]
+            lo, bn = tuple(v[4:7]), tuple(v[7:10])
+            nnz, npop, pop_every, npoints, pz = v[10], v[11], v[12], v[13], v[14]
+            dt, inv_hbar, na = v[16], v[17], v[18]
+            off = _EMIT_SIZE
+            n2 = N * N
+
+            def take(dtype, count):
+                nonlocal off
+                a = np.frombuffer(payload, dtype=dtype, count=count, offset=off).copy()
+                off += a.nbytes
+                return a
+            h0 = take("<c16", nsys * n2).reshape(nsys, n2)
+            weight = take("<f8", nsys)
+            mu = take("<c16", 3 * n2).reshape(3, n2)
+            gptr = take("<i4", n2 + 1)
+            gcol = take("<i4", nnz)
+            gval = take("<f8", nnz)
+            loc = take("<i4", 3 * nemit).reshape(nemit, 3)
+            eps = take("<f8", (bn[0] + 2) * (bn[1] + 2) * pz).reshape(bn[1] + 2, pz, bn[0] + 2)
+            pl = take("<i4", npop)
+            plan.emitters.append(PlanEmitter(obj, N, nsys, nemit, lo, bn, pz, npop, pop_every, npoints, dt, inv_hbar, na, h0, weight, mu,
+                                             gptr, gcol, gval, loc, eps, pl))
     return plan
 
 
@@ -194,6 +252,14 @@ def write_plan(path: str, plan: Plan) -> None:
     for d in plan.detectors:
         out.append(_rec("DETECTOR", struct.pack("<ii3i3i3iiiidd", d.detector, d.field, *d.loc, *d.sz, *d.offset, d.every, d.type, 0,
                                                 d.conv, d.t_conv)))
+    for e in plan.emitters:
+        out.append(_rec("EMITTER", struct.pack(_EMIT_FMT, e.object, e.nlevel, e.nsys, e.nemit, *e.box_lo, *e.box_n, len(e.gam_col), e.npop,
+                                               e.pop_every, e.npoints, e.pz, 0, e.dt, e.inv_hbar, e.na)
+                        + np.ascontiguousarray(e.h0, "<c16").tobytes() + np.ascontiguousarray(e.weight, "<f8").tobytes()
+                        + np.ascontiguousarray(e.mu, "<c16").tobytes() + np.ascontiguousarray(e.gam_ptr, "<i4").tobytes()
+                        + np.ascontiguousarray(e.gam_col, "<i4").tobytes() + np.ascontiguousarray(e.gam_val, "<f8").tobytes()
+                        + np.ascontiguousarray(e.loc, "<i4").tobytes() + np.ascontiguousarray(e.eps, "<f8").tobytes()
+                        + np.ascontiguousarray(e.pop_level, "<i4").tobytes()))
     with open(path, "wb") as f:
         f.write(b"".join(out))
 

@@ -120,6 +120,39 @@ int chiml_gpu_add_source(ChimlCtx* ctx, int field, const int32_t loc[3], const i
  * chiml_gpu_read_detector drains.  The Yee-offset averaging and SI factors stay on the host. */
 int chiml_gpu_add_detector(ChimlCtx* ctx, int field, const int32_t loc[3], const int32_t sz[3], int every, int* slot);
 
+/* Quantum-emitter cells of one parallelQE object (ML/parallelQE.hpp): every listed grid node carries, per level system
+ * (= per Hamiltonian of levelSys_), an N x N density matrix propagated by PCABAM4 (:751-770) under H = H0 - mu.E (ML/Hamiltonian.cpp:59-69)
+ * with the relaxation super-operator gam_ (:727-744), and feeds P = na Re<rho|mu> back into E (addQE :682-718).  Emitters are owned by the
+ * slab that owns their node (the reference spreads them over all ranks, :394-420, and ships E / P boxes around; results are identical).
+ * All complex arrays are (re, im) pairs, matrices row-major as the reference stores them. */
+typedef struct ChimlEmitterDesc
+{
+    int32_t nlevel;            /* N = nlevel_ */
+    int32_t nsys;              /* levelSys_.size() */
+    int32_t nemit;             /* emitters (nodes) of this object inside this slab */
+    int32_t box_lo[3];         /* local ghost-inclusive coordinates of the box corner = emitter-box minimum minus one node
+                                  (SendEFieldRecvPField::loc_ after the procLoc shift, parallelQE.hpp:518-570) */
+    int32_t box_n[3];          /* emitter bounding box n_vec = max - min + 1 (2-D: box_n[2] = 1) */
+    double  dt;                /* dt_ */
+    double  inv_hbar;          /* imag(one_over_hbar_) = 1/hbar_ (:201) */
+    double  na;                /* na_ : molecular density * a^3 */
+    const double* h0;          /* nsys * N*N complex : Hamiltonian::h0_ of every level system */
+    const double* weight;      /* nsys : initial rho_00 (energyWeights_[q].second, density.hpp:57-60) */
+    const double* mu;          /* 3 * N*N complex : x_, y_, z_expectation_ (dipole matrices times couplings, Hamiltonian.cpp:28-41) */
+    const int32_t* gam_ptr;    /* N*N + 1 : CSR row pointers of gam_ ...                                                  */
+    const int32_t* gam_col;    /* ... columns and values in the ITERATION ORDER of the reference's unordered_map rows (:740-742) */
+    const double*  gam_val;
+    const int32_t* loc;        /* 3 * nemit : emitter nodes relative to the box minimum (Density::x(), y(), z() after :477-484), in the
+                                  reference's order */
+    const double*  eps;        /* (box_n[0]+2)*(box_n[1]+2)*pz : eps_ (epsRelOrDip_) over the P box, index x + (n0+2)*(z + pz*y),
+                                  pz = box_n[2]+2 in 3-D, 2 in 2-D (the shape of P_, :470) */
+    int32_t npop;              /* population detectors (QEPopDtc) */
+    const int32_t* pop_level;  /* npop : flat index into rho (QEPopDtc::level_, QEPopDtc.hpp:67) */
+    int32_t pop_every;         /* timeInt_ in steps */
+    int32_t npoints;           /* QEPopDtc::npoints_ = emitters of the whole object (all slabs) */
+} ChimlEmitterDesc;
+int chiml_gpu_add_emitters(ChimlCtx* ctx, const ChimlEmitterDesc* desc, int* slot);
+
 /* Freeze the setup: paints the per-cell update maps from the lists, builds the CPML coefficient
  * tables and compact psi / polarisation pools, zeroes all state. */
 int chiml_gpu_commit(ChimlCtx* ctx);
@@ -167,6 +200,14 @@ int chiml_gpu_download_psi(ChimlCtx* ctx, int comp, int part, double* host);
 int chiml_gpu_read_detector(ChimlCtx* ctx, int slot, double* out, size_t cap_samples, size_t* n_samples);
 /* samples [first, first+n) only (what a host loop that drains the detector after every step reads); *n_read = how many existed */
 int chiml_gpu_read_detector_range(ChimlCtx* ctx, int slot, size_t first, size_t n, double* out, size_t* n_read);
+
+/* emitter state of level system `sys`: which = 0 rho, 1..4 = d rho/dt at n, n-1, n-2, n-3; out = nemit * N*N complex, emitter-major */
+int chiml_gpu_download_emitter_state(ChimlCtx* ctx, int slot, int sys, int which, double* out);
+/* the emitter polarisation box P_[comp] (shape as ChimlEmitterDesc::eps) */
+int chiml_gpu_download_emitter_pol(ChimlCtx* ctx, int slot, int comp, double* out);
+/* population detector `det` of emitter set `slot`: complex samples sum_emitters rho[level] / npoints of THIS slab's emitters
+ * (QEPopDtc::accumPop; the host adds the slabs, QEPopDtc::toFile).  out = cap_samples complex. */
+int chiml_gpu_read_population(ChimlCtx* ctx, int slot, int det, double* out, size_t cap_samples, size_t* n_samples);
 
 /* bytes of device memory held by the context */
 size_t chiml_gpu_device_bytes(const ChimlCtx* ctx);

@@ -68,6 +68,17 @@ typedef struct ChimlPlanDetector      /* tag "DETECTOR": one stored field box of
     double  conv;         /* convFactor_ */
     double  t_conv;       /* tConv_ */
 } ChimlPlanDetector;
+typedef struct ChimlPlanEmitterHdr    /* tag "EMITTER ": header, then in this order: h0[nsys*N*N*2] weight[nsys] mu[3*N*N*2]
+                                         gam_ptr[N*N+1] gam_col[nnz] gam_val[nnz] loc[3*nemit] eps[(n0+2)(n1+2)pz] pop_level[npop] */
+{
+    int32_t object;       /* index into qeArr_ */
+    int32_t nlevel, nsys, nemit;
+    int32_t box_lo[3];
+    int32_t box_n[3];
+    int32_t nnz, npop, pop_every, npoints;
+    int32_t pz, pad;
+    double  dt, inv_hbar, na;
+} ChimlPlanEmitterHdr;
 #pragma pack(pop)
 
 #endif /* CHIML_PLAN_H */

@@ -16,6 +16,24 @@ typedef struct { int has_psi, present; ChimlPsiParams* psi; size_t npsi; ChimlGr
 typedef struct { int npoles, use_or_dip; double alpha[MAX_POLES], xi[MAX_POLES], gamma[MAX_POLES], dip[MAX_POLES][3]; } ObjConst;
 typedef struct { int field; int32_t loc[3], sz[3]; } SrcBox;
 
+/* one parallelQE object (ML/parallelQE.hpp): owned copies of the ChimlEmitterDesc arrays + state */
+#define MAX_QE 8
+#define MAX_N2 64
+typedef struct
+{
+    ChimlEmitterDesc d;
+    int n2, pz;
+    size_t pbox;
+    double *h0, *weight, *mu, *gam_val, *eps;
+    int32_t *gam_ptr, *gam_col, *loc, *pop_level;
+    double* P[3];          /* P_[c] boxes */
+    double* st[5];         /* [w][sys][emitter][n2][re,im]: density_, density_deriv_n_, _n_minus_1_, _2_, _3_ (ML/density.hpp:24-28) */
+    double* pop;           /* [det][sample][re,im] */
+    size_t pop_cap, pop_n;
+    double* curpop;        /* [det][re,im] */
+    long tstep;
+} QESet;
+
 struct OracleSim
 {
     ChimlGridDesc g;
@@ -39,6 +57,8 @@ struct OracleSim
     pthread_barrier_t bar;
     const double* src_amp;
     int nsteps;
+    QESet qe[MAX_QE];
+    int nqe;
 };
 
 static int comp_exists(const OracleSim* s, int field)
@@ -320,6 +340,233 @@ static void pml_grid_entry(const ChimlGridParams* p, double* Ui, const double* p
  * ------------------------------------------------------------------------------------------- */
 typedef struct { OracleSim* s; int tid; } Worker;
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Maxwell-Liouville emitters (ML/parallelQE.hpp, ML/Hamiltonian.cpp, ML/density.hpp, UTIL/FDTD_up_eq.cpp:1367-1473).
+ * Complex arithmetic follows the BLAS the reference is linked against in oracle/_ref (oracle/ref_shim/blas_shim.cpp):
+ * the conventional 4-multiply complex product, netlib loop order in zgemm.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { double re, im; } cx;
+static cx cmul(cx a, cx b) { cx r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
+static cx cadd(cx a, cx b) { cx r; r.re = a.re + b.re; r.im = a.im + b.im; return r; }
+
+/* zaxpy_(n, cplx(a,0), x, 1, y, 1) */
+static void zaxpy_real(int n, double a, const cx* x, cx* y)
+{
+    cx ca; ca.re = a; ca.im = 0.0;
+    for(int k = 0; k < n; ++k) y[k] = cadd(y[k], cmul(ca, x[k]));
+}
+
+int oracle_add_emitters(OracleSim* s, const ChimlEmitterDesc* d)
+{
+    if(s->nqe >= MAX_QE || d->nlevel < 1 || d->nlevel * d->nlevel > MAX_N2) return CHIML_ERR_ARG;
+    QESet* q = &s->qe[s->nqe++];
+    memset(q, 0, sizeof(*q));
+    q->d = *d;
+    const int n2 = d->nlevel * d->nlevel;
+    q->n2 = n2;
+    q->pz = s->g.ln[2] > 1 ? d->box_n[2] + 2 : 2;                       /* P_ shape, ML/parallelQE.hpp:470 */
+    q->pbox = (size_t)(d->box_n[0] + 2) * (size_t)(d->box_n[1] + 2) * (size_t)q->pz;
+#define DUP(dst, src, n, T) do { const size_t cnt_ = (size_t)(n); dst = (T*)malloc((cnt_ > 0 ? cnt_ : 1) * sizeof(T)); if(cnt_ > 0) memcpy(dst, src, cnt_ * sizeof(T)); } while(0)
+    DUP(q->h0, d->h0, (size_t)d->nsys * n2 * 2, double);
+    DUP(q->weight, d->weight, (size_t)d->nsys, double);
+    DUP(q->mu, d->mu, (size_t)3 * n2 * 2, double);
+    DUP(q->gam_ptr, d->gam_ptr, (size_t)n2 + 1, int32_t);
+    DUP(q->gam_col, d->gam_col, (size_t)d->gam_ptr[n2], int32_t);
+    DUP(q->gam_val, d->gam_val, (size_t)d->gam_ptr[n2], double);
+    DUP(q->loc, d->loc, (size_t)3 * d->nemit, int32_t);
+    DUP(q->eps, d->eps, q->pbox, double);
+    DUP(q->pop_level, d->pop_level, (size_t)d->npop, int32_t);
+#undef DUP
+    for(int c = 0; c < 3; ++c) q->P[c] = (double*)calloc(q->pbox, sizeof(double));
+    const size_t per = (size_t)d->nsys * (size_t)d->nemit * (size_t)n2 * 2;
+    for(int w = 0; w < 5; ++w) q->st[w] = (double*)calloc(per ? per : 1, sizeof(double));
+    /* Density::initializeDensity(weight): rho_00 = weight of the level system (ML/density.hpp:57-60, parallelQE.hpp:428-429) */
+    for(int sy = 0; sy < d->nsys; ++sy)
+        for(int e = 0; e < d->nemit; ++e)
+            q->st[0][(((size_t)sy * d->nemit + e) * n2) * 2] = d->weight[sy];
+    q->curpop = (double*)calloc((size_t)(d->npop ? d->npop : 1) * 2, sizeof(double));
+    q->pop_cap = 1024;
+    q->pop = (double*)calloc((size_t)(d->npop ? d->npop : 1) * q->pop_cap * 2, sizeof(double));
+    return 0;
+}
+
+/* Hamiltonian::getHam (ML/Hamiltonian.cpp:59-69): H = h0 + Ex (-mu_x) + Ey (-mu_y) + Ez (-mu_z); a direction whose dipole matrix
+ * is identically zero is skipped (:42-55) */
+static void qe_get_ham(const QESet* q, int sys, const double e[3], cx* H)
+{
+    const int n2 = q->n2;
+    const cx* h0 = (const cx*)q->h0 + (size_t)sys * n2;
+    for(int k = 0; k < n2; ++k) H[k] = h0[k];
+    if(e[0] == 0.0 && e[1] == 0.0 && e[2] == 0.0) return;
+    for(int c = 0; c < 3; ++c)
+    {
+        const cx* mu = (const cx*)q->mu + (size_t)c * n2;
+        int allzero = 1;
+        for(int k = 0; k < n2; ++k) if(mu[k].re != 0.0 || mu[k].im != 0.0) allzero = 0;
+        if(allzero) continue;
+        cx a; a.re = e[c]; a.im = 0.0;
+        for(int k = 0; k < n2; ++k)
+        {
+            cx neg; neg.re = -mu[k].re; neg.im = -mu[k].im;      /* neg_?_expectation_ = expectation * (-1.0 * coupling) */
+            H[k] = cadd(H[k], cmul(a, neg));
+        }
+    }
+}
+
+/* parallelQEBase::denDeriv, MKL branch (ML/parallelQE.hpp:727-744): T = zgemm(i/hbar, H, rho) (column-major call on row-major data),
+ * out = T + T^H (mkl_zomatadd 'R','N','C'), then the sparse relaxation rows */
+static void qe_den_deriv(const QESet* q, const cx* H, const cx* den, cx* out)
+{
+    const int N = q->d.nlevel, n2 = q->n2;
+    cx T[MAX_N2];
+    cx alpha; alpha.re = 0.0; alpha.im = q->d.inv_hbar;
+    for(int j = 0; j < N; ++j)
+    {
+        for(int i = 0; i < N; ++i) { T[i + j * N].re = 0.0; T[i + j * N].im = 0.0; }
+        for(int l = 0; l < N; ++l)
+        {
+            const cx temp = cmul(alpha, den[l + j * N]);
+            for(int i = 0; i < N; ++i) T[i + j * N] = cadd(T[i + j * N], cmul(temp, H[i + l * N]));
+        }
+    }
+    cx one; one.re = 1.0; one.im = 0.0;
+    for(int i = 0; i < N; ++i)
+        for(int j = 0; j < N; ++j)
+        {
+            cx b; b.re = T[j * N + i].re; b.im = -T[j * N + i].im;
+            out[i * N + j] = cadd(cmul(one, T[i * N + j]), cmul(one, b));
+        }
+    for(int ii = 0; ii < n2; ++ii)
+        for(int k = q->gam_ptr[ii]; k < q->gam_ptr[ii + 1]; ++k)
+        {
+            const cx v = den[q->gam_col[k]];
+            out[ii].re = out[ii].re + v.re * q->gam_val[k];
+            out[ii].im = out[ii].im + v.im * q->gam_val[k];
+        }
+}
+
+/* parallelQEBase::addQE (:682-718) + updateDensity (:614-678) on the slab that owns the nodes */
+static void qe_add(OracleSim* s, QESet* q)
+{
+    const ChimlEmitterDesc* d = &q->d;
+    const int lnx = s->g.ln[0], lnz = s->g.ln[2];
+    const int threeD = lnz > 1;
+    const int zOff = threeD ? 1 : 0;
+    const int bx = d->box_n[0] + 2, bz = q->pz;
+    const int n2 = q->n2;
+#define PB(i, j, k) ((size_t)(i) + (size_t)bx * ((size_t)(k) + (size_t)bz * (size_t)(j)))
+#define GI(x, y, z) ((size_t)(x) + (size_t)lnx * ((size_t)(z) + (size_t)lnz * (size_t)(y)))
+    /* addP (UTIL/FDTD_up_eq.cpp:1367-1380): E += -0.5 P[n]/eps[n], then E += -0.5 P[n+off]/eps[n+off] */
+    for(int c = 0; c < 3; ++c)
+    {
+        double* E = s->f[CHIML_EX + c];
+        if(!E) continue;
+        const int off[3] = { c == 0 ? 1 : 0, c == 1 ? 1 : 0, c == 2 ? zOff : 0 };
+        const int nx = d->box_n[0] + 1, ny = d->box_n[1] + 1, nz = threeD ? d->box_n[2] + 1 : 1;
+        for(int jj = 0; jj < nz; ++jj)
+            for(int ii = 0; ii < ny; ++ii)
+                for(int i = 0; i < nx; ++i)
+                {
+                    const size_t g = GI(d->box_lo[0] + i, d->box_lo[1] + ii, threeD ? d->box_lo[2] + jj : 0);
+                    const double t1 = -0.5 * q->P[c][PB(i, ii, jj)] / q->eps[PB(i, ii, jj)];
+                    E[g] = E[g] + 1.0 * t1;
+                    const double t2 = -0.5 * q->P[c][PB(i + off[0], ii + off[1], jj + off[2])] / q->eps[PB(i + off[0], ii + off[1], jj + off[2])];
+                    E[g] = E[g] + 1.0 * t2;
+                }
+    }
+    /* zeroP_ */
+    for(int c = 0; c < 3; ++c) if(s->f[CHIML_EX + c]) memset(q->P[c], 0, q->pbox * sizeof(double));
+    const int sample = (q->tstep % d->pop_every) == 0;
+    cx H[MAX_N2], pred[MAX_N2], fpred[MAX_N2];
+    const double dt = d->dt;
+    for(int sy = 0; sy < d->nsys; ++sy)
+        for(int e = 0; e < d->nemit; ++e)
+        {
+            const int* l = &q->loc[3 * e];
+            /* getE_TE / getE_TM (UTIL/FDTD_up_eq.cpp:1398-1430): the node field */
+            double ev[3] = {0.0, 0.0, 0.0};
+            const int gx = d->box_lo[0] + 1 + l[0], gy = d->box_lo[1] + 1 + l[1], gz = threeD ? d->box_lo[2] + 1 + l[2] : 0;
+            for(int c = 0; c < 3; ++c)
+            {
+                const double* E = s->f[CHIML_EX + c];
+                if(!E) continue;
+                if(c == 2 && !s->f[CHIML_EX]) ev[c] = E[GI(gx, gy, gz)];                         /* TM: copied */
+                else ev[c] = 0.5 * E[GI(gx, gy, gz)] + 0.5 * E[GI(gx - (c == 0), gy - (c == 1), gz - (c == 2 ? zOff : 0))];
+            }
+            const size_t base = (((size_t)sy * d->nemit + e) * n2);
+            cx* rho = (cx*)q->st[0] + base;
+            cx* f0 = (cx*)q->st[1] + base; cx* f1 = (cx*)q->st[2] + base; cx* f2 = (cx*)q->st[3] + base; cx* f3 = (cx*)q->st[4] + base;
+            /* PCABAM4 (:751-770) */
+            for(int k = 0; k < n2; ++k) pred[k] = rho[k];
+            zaxpy_real(n2,  55.0 * dt / 24.0, f0, pred);
+            zaxpy_real(n2, -59.0 * dt / 24.0, f1, pred);
+            zaxpy_real(n2,  37.0 * dt / 24.0, f2, pred);
+            zaxpy_real(n2,  -9.0 * dt / 24.0, f3, pred);
+            qe_get_ham(q, sy, ev, H);
+            qe_den_deriv(q, H, pred, fpred);
+            zaxpy_real(n2,  9.0 * dt / 24.0, fpred, rho);
+            zaxpy_real(n2, 19.0 * dt / 24.0, f0, rho);
+            zaxpy_real(n2, -5.0 * dt / 24.0, f1, rho);
+            zaxpy_real(n2,        dt / 24.0, f2, rho);
+            for(int k = 0; k < n2; ++k) { f3[k] = f2[k]; f2[k] = f1[k]; f1[k] = f0[k]; }   /* Density::moveDensity */
+            qe_den_deriv(q, H, rho, f0);
+            /* QEPopDtc::inPop (ML/QEPopDtc.hpp:67): the FLAT index level_ */
+            if(sample)
+                for(int p = 0; p < d->npop; ++p)
+                {
+                    q->curpop[2 * p] = q->curpop[2 * p] + rho[q->pop_level[p]].re;
+                    q->curpop[2 * p + 1] = q->curpop[2 * p + 1] + rho[q->pop_level[p]].im;
+                }
+            /* updateQEPol (UTIL/FDTD_up_eq.hpp:620): P += na * Re(zdotc(rho, mu_c)) */
+            for(int c = 0; c < 3; ++c)
+            {
+                if(!s->f[CHIML_EX + c]) continue;
+                const cx* mu = (const cx*)q->mu + (size_t)c * n2;
+                cx acc; acc.re = 0.0; acc.im = 0.0;
+                for(int k = 0; k < n2; ++k)
+                {
+                    cx cj; cj.re = rho[k].re; cj.im = -rho[k].im;
+                    acc = cadd(acc, cmul(cj, mu[k]));
+                }
+                const size_t pi = PB(l[0] + 1, l[1] + 1, l[2] - 1 + zOff + 1);
+                q->P[c][pi] = q->P[c][pi] + d->na * acc.re;
+            }
+        }
+    /* QEPopDtc::accumPop (ML/QEPopDtc.cpp:28-35) */
+    if(sample && d->npop > 0)
+    {
+        if(q->pop_n >= q->pop_cap)
+        {
+            double* np_ = (double*)calloc((size_t)d->npop * q->pop_cap * 2 * 2, sizeof(double));
+            for(int p = 0; p < d->npop; ++p) memcpy(np_ + (size_t)p * q->pop_cap * 2 * 2, q->pop + (size_t)p * q->pop_cap * 2, q->pop_n * 2 * sizeof(double));
+            free(q->pop); q->pop = np_; q->pop_cap *= 2;
+        }
+        for(int p = 0; p < d->npop; ++p)
+        {
+            /* complex / double */
+            q->pop[((size_t)p * q->pop_cap + q->pop_n) * 2] = q->curpop[2 * p] / (double)d->npoints;
+            q->pop[((size_t)p * q->pop_cap + q->pop_n) * 2 + 1] = q->curpop[2 * p + 1] / (double)d->npoints;
+        }
+        ++q->pop_n;
+    }
+    for(int p = 0; p < d->npop; ++p) { q->curpop[2 * p] = 0.0; q->curpop[2 * p + 1] = 0.0; }
+    ++q->tstep;
+#undef PB
+#undef GI
+}
+
+double* oracle_emitter_state(OracleSim* s, int slot, int which) { return (slot < 0 || slot >= s->nqe || which < 0 || which > 4) ? NULL : s->qe[slot].st[which]; }
+double* oracle_emitter_P(OracleSim* s, int slot, int comp) { return (slot < 0 || slot >= s->nqe || comp < 0 || comp > 2) ? NULL : s->qe[slot].P[comp]; }
+size_t  oracle_population(OracleSim* s, int slot, int det, double* out, size_t cap)
+{
+    if(slot < 0 || slot >= s->nqe || det < 0 || det >= s->qe[slot].d.npop) return 0;
+    QESet* q = &s->qe[slot];
+    size_t n = q->pop_n < cap ? q->pop_n : cap;
+    if(out && n) memcpy(out, q->pop + (size_t)det * q->pop_cap * 2, n * 2 * sizeof(double));
+    return q->pop_n;
+}
+
 #define SPLIT(n, lo, hi) size_t lo = (size_t)(n) * (size_t)tid / (size_t)nt, hi = (size_t)(n) * (size_t)(tid + 1) / (size_t)nt
 #define BARRIER() do { if(nt > 1) pthread_barrier_wait(&s->bar); } while(0)
 
@@ -438,6 +685,10 @@ static void step_worker(OracleSim* s, int tid, int nt)
                 for(size_t e = lo; e < hi; ++e) ordip_dtou_run(&l->r[e], s->f[CHIML_DX + i], s->f[CHIML_EX + i], s->oP[i], s->nordip, zvariant);
             }
         }
+        BARRIER();
+        /* qe->addQE() for every emitter object (:1282-1283); serial, as each reference rank runs it */
+        if(tid == 0)
+            for(int q = 0; q < s->nqe; ++q) qe_add(s, &s->qe[q]);
         BARRIER();
     }
     free(scratch);

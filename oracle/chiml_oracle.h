@@ -35,6 +35,7 @@ int  oracle_set_object(OracleSim* s, int obj, int npoles, const double* alpha, c
 int  oracle_set_cpml(OracleSim* s, int comp, int part, int has_psi, const ChimlPsiParams* psi, size_t npsi,
                      const ChimlGridParams* grid, size_t ngrid);
 int  oracle_add_source(OracleSim* s, int field, const int32_t loc[3], const int32_t sz[3]);
+int  oracle_add_emitters(OracleSim* s, const ChimlEmitterDesc* d);
 int  oracle_commit(OracleSim* s);
 /* nthreads > 1: rows of every list are split over POSIX threads (same arithmetic per cell) */
 int  oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads);
@@ -45,6 +46,10 @@ double* oracle_pole(OracleSim* s, int comp, int pole, int prev);
 double* oracle_ordip_pole(OracleSim* s, int comp, int pole, int prev);
 double* oracle_psi(OracleSim* s, int comp, int part);
 int     oracle_n_poles(OracleSim* s);
+/* emitter state [sys][emitter][N*N][re,im] (which: 0 rho, 1..4 derivative histories), P boxes, population series */
+double* oracle_emitter_state(OracleSim* s, int slot, int which);
+double* oracle_emitter_P(OracleSim* s, int slot, int comp);
+size_t  oracle_population(OracleSim* s, int slot, int det, double* out, size_t cap);
 
 #ifdef __cplusplus
 }

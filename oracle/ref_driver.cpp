@@ -134,6 +134,7 @@ static int fieldId(parallelFDTDFieldReal& FF, const std::shared_ptr<parallelGrid
     return -1;
 }
 
+static void putEmitters(std::ofstream& out, parallelFDTDFieldReal& FF);
 static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const parallelProgramInputs& IP, int nSteps)
 {
     std::ofstream out(fname.c_str(), std::ios::binary);
@@ -249,6 +250,62 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
         }
         ++dd;
     }
+    if(!FF.qeArr_.empty() && FF.gridComm_->size() == 1) putEmitters(out, FF);
+}
+
+// EMITTER records: one per parallelQE object, from the object's own members (single-rank runs only: with more ranks the
+// reference spreads emitters over ranks irrespective of where their node lives, ML/parallelQE.hpp:394-420)
+static void putEmitters(std::ofstream& out, parallelFDTDFieldReal& FF)
+{
+    int qq = 0;
+    for(auto& qe : FF.qeArr_)
+    {
+        if(!qe->sameProcCalc_) throw std::runtime_error("plan dump: emitter sets need a single-rank run");
+        ChimlPlanEmitterHdr h;
+        std::memset(&h, 0, sizeof(h));
+        h.object = qq;
+        h.nlevel = qe->nlevel_;
+        h.nsys = int(qe->levelSys_.size());
+        h.nemit = int(qe->levelSys_[0].den_.size());
+        auto eg = qe->e_[0] ? qe->e_[0] : qe->e_[2];
+        auto Pg = qe->P_[0] ? qe->P_[0] : qe->P_[2];
+        h.box_n[0] = eg->x(); h.box_n[1] = eg->y(); h.box_n[2] = eg->z();
+        for(int k = 0; k < 3; ++k) h.box_lo[k] = qe->sameProcCalc_->loc_[k];
+        h.pz = Pg->z();
+        h.dt = qe->dt_; h.inv_hbar = std::imag(qe->one_over_hbar_); h.na = qe->na_;
+        std::vector<int32_t> gptr(1, 0), gcol; std::vector<double> gval;
+        for(auto& row : qe->gam_)
+        {
+            for(auto it = row.begin(); it != row.end(); ++it) { gcol.push_back(it->first); gval.push_back(it->second); }
+            gptr.push_back(int32_t(gcol.size()));
+        }
+        while(int(gptr.size()) < h.nlevel * h.nlevel + 1) gptr.push_back(gptr.back());
+        h.nnz = int(gcol.size());
+        h.npop = int(qe->dtcPopArr_.size());
+        h.pop_every = h.npop ? qe->dtcPopArr_[0]->timeInt_ : 1;
+        h.npoints = h.npop ? qe->dtcPopArr_[0]->npoints_ : h.nemit;
+        std::string p; app(p, h);
+        const int n2 = h.nlevel * h.nlevel;
+        for(auto& ls : qe->levelSys_) p.append(reinterpret_cast<const char*>(ls.ham_->h0_.data()), n2 * sizeof(cplx));
+        for(auto& ew : qe->energyWeights_) app(p, ew.second);
+        auto& ham = *qe->levelSys_[0].ham_;
+        p.append(reinterpret_cast<const char*>(ham.x_expectation_.data()), n2 * sizeof(cplx));
+        p.append(reinterpret_cast<const char*>(ham.y_expectation_.data()), n2 * sizeof(cplx));
+        p.append(reinterpret_cast<const char*>(ham.z_expectation_.data()), n2 * sizeof(cplx));
+        appVec(p, gptr); appVec(p, gcol); appVec(p, gval);
+        for(auto& den : qe->levelSys_[0].den_) { int32_t l[3] = {den.x(), den.y(), den.z()}; p.append(reinterpret_cast<const char*>(l), sizeof(l)); }
+        for(int y = 0; y < Pg->y(); ++y)
+            for(int z = 0; z < Pg->z(); ++z)
+                for(int x = 0; x < Pg->x(); ++x)
+                {
+                    double e = qe->eps_->z() == 1 ? qe->eps_->point(h.box_lo[0] + x, h.box_lo[1] + y, 0)
+                                                  : qe->eps_->point(h.box_lo[0] + x, h.box_lo[1] + y, h.box_lo[2] + z);
+                    app(p, e);
+                }
+        for(auto& d : qe->dtcPopArr_) { int32_t lv = d->level_; app(p, lv); }
+        putRec(out, "EMITTER", p);
+        ++qq;
+    }
 }
 
 static void rankMain(int rank, const Options& opt)
@@ -317,6 +374,46 @@ static void rankMain(int rank, const Options& opt)
                 grabGrid(rank, std::string("oP") + c[i] + std::to_string(p), FF.orDipLorP_[i][p]);
                 grabGrid(rank, std::string("poP") + c[i] + std::to_string(p), FF.prevOrDipLorP_[i][p]);
             }
+        }
+    }
+
+    if(!opt.dump.empty() && FF.gridComm_->size() == 1)
+    {
+        // emitter state: rho and the four derivative histories per level system, the P boxes, the population series
+        int qq = 0;
+        for(auto& qe : FF.qeArr_)
+        {
+            const int n2 = qe->nlevel_ * qe->nlevel_;
+            for(size_t ss = 0; ss < qe->levelSys_.size(); ++ss)
+                for(int w = 0; w < 5; ++w)
+                {
+                    GridDump d; d.rank = rank; d.name = "q" + std::to_string(qq) + "s" + std::to_string(ss) + "w" + std::to_string(w);
+                    d.ln[0] = 2 * n2; d.ln[1] = int(qe->levelSys_[ss].den_.size()); d.ln[2] = 1; d.yStart = 0;
+                    for(auto& den : qe->levelSys_[ss].den_)
+                    {
+                        std::vector<cplx>& v = w == 0 ? den.density_ : w == 1 ? den.density_deriv_n_ : w == 2 ? den.density_deriv_n_minus_1_
+                                             : w == 3 ? den.density_deriv_n_minus_2_ : den.density_deriv_n_minus_3_;
+                        for(auto& c : v) { d.data.push_back(c.real()); d.data.push_back(c.imag()); }
+                    }
+                    std::lock_guard<std::mutex> lk(g_dumpMtx); g_dumps.push_back(std::move(d));
+                }
+            for(int c = 0; c < 3; ++c)
+            {
+                if(!qe->P_[c] || !qe->E_[c]) continue;
+                GridDump d; d.rank = rank; d.name = "q" + std::to_string(qq) + "P" + std::string(1, "xyz"[c]);
+                d.ln[0] = qe->P_[c]->x(); d.ln[1] = qe->P_[c]->y(); d.ln[2] = qe->P_[c]->z(); d.yStart = 0;
+                d.data.assign(&qe->P_[c]->point(0), &qe->P_[c]->point(0) + qe->P_[c]->size());
+                std::lock_guard<std::mutex> lk(g_dumpMtx); g_dumps.push_back(std::move(d));
+            }
+            int dd = 0;
+            for(auto& dtc : qe->dtcPopArr_)
+            {
+                GridDump d; d.rank = rank; d.name = "q" + std::to_string(qq) + "pop" + std::to_string(dd++);
+                d.ln[0] = 2; d.ln[1] = int(dtc->allPop_.size()); d.ln[2] = 1; d.yStart = 0;
+                for(auto& c : dtc->allPop_) { d.data.push_back(c.real()); d.data.push_back(c.imag()); }
+                std::lock_guard<std::mutex> lk(g_dumpMtx); g_dumps.push_back(std::move(d));
+            }
+            ++qq;
         }
     }
 

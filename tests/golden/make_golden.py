@@ -50,7 +50,38 @@ def cases():
                             [I.normal_source("Ey", [0, 0, 0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
                             [I.block([0.06, 0.3, 0.05], [0.0, 0.0, 0.0], eps=3.0)],
                             [I.detector([0.03, 0, 0], [0, 0, 0], "Ey", "out/k3/dtc", time_int=DT * 1.0000001)])
-    return {k: _short_pulse(v) for k, v in c.items()}
+    c = {k: _short_pulse(v) for k, v in c.items()}
+    # ---- Maxwell-Liouville emitter cases (sources in vacuum: a source inside a D-cell is overwritten by D->E) ----
+    relax1 = [{"state_i": 1, "state_f": 0, "rate": 1e12, "dephasing_rate": 1e13}]
+    two = lambda sz, loc, lv: I.ml_object(sz, loc, 1e25, [(0, 0), (1, 0)], [{"E_cen": [0.0]}, {"E_cen": [2.0]}], [0, 10.0, 10.0, 0], relax1,  # noqa: E731
+                                          eps=1.5, dtc_levs=lv)
+    pulse = lambda f, a: I.gaussian_pulse(f, 1.0, intensity=a, t_0=0.25, cutoff=2.5)  # noqa: E731
+    c["ml3d_two"] = I.config(I.comp_cell([23 / RES, 19 / RES, 21 / RES], RES, 60 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+                             [I.normal_source("Ez", [-0.05, -0.04, -0.04], [0, 0, 0], [pulse(1.5, 3e13)])],
+                             [I.block([0.08, 0.06, 0.05], [0.05, 0, -0.03], eps=2.0), two([0.05, 0.04, 0.02], [-0.005, 0.005, 0.015], [3, 1])],
+                             [I.detector([0.03, 0, 0], [0, 0, 0], "Ez", "out/m2/dtc", time_int=DT * 1.0000001)])
+    four = I.ml_object([0.05, 0.04, 0.02], [-0.005, 0.005, 0.015], 1e25, [(0, 0), (1, -1), (1, 0), (1, 1)],
+                       [{"E_cen": [0.0]}, {"E_cen": [1.9, 2.1], "weights": [0.6, 0.4], "levs_described": 3}],
+                       [0, 10, 8, 6, 10, 0, 0, 0, 8, 0, 0, 0, 6, 0, 0, 0],
+                       [{"state_i": 1, "state_f": 0, "rate": 1e12, "dephasing_rate": 1e13}, {"state_i": 2, "state_f": 0, "rate": 2e12, "dephasing_rate": 0.5e13},
+                        {"state_i": 3, "state_f": 0, "rate": 1.5e12}], eps=1.2, dtc_levs=[5, 0], pop_every=2)
+    c["ml3d_four"] = I.config(I.comp_cell([23 / RES, 19 / RES, 21 / RES], RES, 60 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+                              [I.normal_source("Ez", [-0.05, -0.04, -0.04], [0, 0, 0], [pulse(1.5, 3e13)]),
+                               I.normal_source("Ex", [0.04, -0.04, 0.04], [0, 0, 0], [pulse(1.2, 2e13)])],
+                              [I.block([0.08, 0.06, 0.05], [0.05, 0, -0.03], eps=2.0), four],
+                              [I.detector([0.03, 0, 0], [0, 0, 0], "Ez", "out/m4/dtc", time_int=DT * 1.0000001)])
+    c["ml_tm"] = I.config(I.comp_cell([47 / RES, 39 / RES, 0], RES, 80 * DT - 0.5 * DT, "Ez"), I.pml([8 / RES, 8 / RES, 0]),
+                          [I.normal_source("Ez", [-0.1, -0.08, 0], [0, 0, 0], [pulse(1.5, 3e13)])],
+                          [two([0.08, 0.06, 0.0], [0.02, 0.01, 0.0], [3])],
+                          [I.detector([0.03, 0, 0], [0, 0, 0], "Ez", "out/mtm/dtc", time_int=DT * 1.0000001)])
+    pxy = I.ml_object([0.08, 0.06, 0.0], [0.02, 0.01, 0.0], 1e25, [(0, 0), (1, -1), (1, 1)], [{"E_cen": [0.0]}, {"E_cen": [2.0], "levs_described": 2}],
+                      [0, 10, 10, 10, 0, 0, 10, 0, 0], [{"state_i": 1, "state_f": 0, "rate": 1e12, "dephasing_rate": 1e13},
+                                                         {"state_i": 2, "state_f": 0, "rate": 1e12}], eps=1.5, dtc_levs=[4])
+    c["ml_te"] = I.config(I.comp_cell([47 / RES, 39 / RES, 0], RES, 80 * DT - 0.5 * DT, "Hz"), I.pml([8 / RES, 8 / RES, 0]),
+                          [I.normal_source("Ex", [-0.1, -0.08, 0], [0, 0, 0], [pulse(1.5, 3e13)])],
+                          [pxy],
+                          [I.detector([0.03, 0, 0], [0, 0, 0], "Ex", "out/mte/dtc", time_int=DT * 1.0000001)])
+    return c
 
 
 def main():

@@ -32,6 +32,34 @@ def grid_desc(plan: P.Plan) -> GridDesc:
     return g
 
 
+class EmitterDesc(C.Structure):
+    """include/chiml_gpu.h ChimlEmitterDesc"""
+    _fields_ = [("nlevel", C.c_int32), ("nsys", C.c_int32), ("nemit", C.c_int32), ("box_lo", C.c_int32 * 3), ("box_n", C.c_int32 * 3),
+                ("dt", C.c_double), ("inv_hbar", C.c_double), ("na", C.c_double),
+                ("h0", C.c_void_p), ("weight", C.c_void_p), ("mu", C.c_void_p), ("gam_ptr", C.c_void_p), ("gam_col", C.c_void_p),
+                ("gam_val", C.c_void_p), ("loc", C.c_void_p), ("eps", C.c_void_p), ("npop", C.c_int32), ("pop_level", C.c_void_p),
+                ("pop_every", C.c_int32), ("npoints", C.c_int32)]
+
+
+def emitter_desc(e: P.PlanEmitter, keep: list) -> EmitterDesc:
+    """Builds the C struct from a plan record; the numpy arrays it points to are appended to `keep`."""
+    d = EmitterDesc()
+    d.nlevel, d.nsys, d.nemit = e.nlevel, e.nsys, e.nemit
+    d.box_lo[:] = e.box_lo
+    d.box_n[:] = e.box_n
+    d.dt, d.inv_hbar, d.na = e.dt, e.inv_hbar, e.na
+    arrs = {"h0": np.ascontiguousarray(e.h0, np.complex128), "weight": np.ascontiguousarray(e.weight, np.float64),
+            "mu": np.ascontiguousarray(e.mu, np.complex128), "gam_ptr": np.ascontiguousarray(e.gam_ptr, np.int32),
+            "gam_col": np.ascontiguousarray(e.gam_col, np.int32), "gam_val": np.ascontiguousarray(e.gam_val, np.float64),
+            "loc": np.ascontiguousarray(e.loc, np.int32), "eps": np.ascontiguousarray(e.eps, np.float64),
+            "pop_level": np.ascontiguousarray(e.pop_level, np.int32)}
+    for k, a in arrs.items():
+        keep.append(a)
+        setattr(d, k, a.ctypes.data if a.size else None)
+    d.npop, d.pop_every, d.npoints = e.npop, e.pop_every, e.npoints
+    return d
+
+
 _lib = None
 
 
@@ -62,6 +90,13 @@ def lib() -> C.CDLL:
             getattr(L, fn).restype = C.POINTER(C.c_double)
             getattr(L, fn).argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.oracle_n_poles.argtypes = [C.c_void_p]
+        L.oracle_add_emitters.argtypes = [C.c_void_p, C.POINTER(EmitterDesc)]
+        L.oracle_emitter_state.restype = C.POINTER(C.c_double)
+        L.oracle_emitter_state.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.oracle_emitter_P.restype = C.POINTER(C.c_double)
+        L.oracle_emitter_P.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.oracle_population.restype = C.c_size_t
+        L.oracle_population.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -94,6 +129,9 @@ class OracleSim:
             loc = (C.c_int32 * 3)(*s.loc)
             sz = (C.c_int32 * 3)(*s.sz)
             self._chk(L.oracle_add_source(self.h, s.field, loc, sz))
+        for e in plan.emitters:
+            d = emitter_desc(e, self._keep)
+            self._chk(L.oracle_add_emitters(self.h, C.byref(d)))
         self._chk(L.oracle_commit(self.h))
         self.steps_done = 0
 
@@ -134,6 +172,24 @@ class OracleSim:
 
     def psi(self, comp: int, part: int):
         return self._view(lib().oracle_psi(self.h, comp, part))
+
+    def emitter_state(self, slot: int, sys: int, which: int) -> np.ndarray:
+        """(nemit, N*N) complex view of rho (which=0) or a derivative history (1..4) of level system `sys`."""
+        e = self.plan.emitters[slot]
+        p = lib().oracle_emitter_state(self.h, slot, which)
+        a = np.ctypeslib.as_array(p, shape=(e.nsys, e.nemit, e.nlevel * e.nlevel, 2))
+        return a[sys, :, :, 0] + 1j * a[sys, :, :, 1]
+
+    def emitter_P(self, slot: int, comp: int) -> np.ndarray:
+        e = self.plan.emitters[slot]
+        p = lib().oracle_emitter_P(self.h, slot, comp)
+        return np.ctypeslib.as_array(p, shape=(e.box_n[1] + 2, e.pz, e.box_n[0] + 2))
+
+    def population(self, slot: int, det: int) -> np.ndarray:
+        n = lib().oracle_population(self.h, slot, det, None, 0)
+        out = np.zeros((n, 2))
+        lib().oracle_population(self.h, slot, det, _ptr(out) if n else None, n)
+        return out[:, 0] + 1j * out[:, 1]
 
     def n_poles(self) -> int:
         return lib().oracle_n_poles(self.h)

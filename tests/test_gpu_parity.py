@@ -12,6 +12,7 @@ from oracle_api import OracleSim
 pytestmark = pytest.mark.gpu
 
 TOL_L2 = 1e-10
+TOL_DTC = 1e-9
 
 
 @pytest.mark.parametrize("case", util.CASES)
@@ -22,6 +23,13 @@ def test_gpu_matches_reference_fixture(case):
     sim.step_n(plan.n_steps)
     for name, ref in expect.items():
         got = util.state_array(sim, name)
+        assert got.shape == ref.shape, f"{case}/{name}: shape {got.shape} != {ref.shape}"
+        if "pop" in name:
+            # population detector = a sum over all emitters: the GPU reduces in tree order, so the bar is the detector
+            # tolerance of BASELINE.md (max relative error <= 1e-9), not bit equality
+            scale = np.abs(ref).max()
+            assert np.abs(got - ref).max() <= TOL_DTC * max(scale, 1e-300), f"{case}/{name}: max rel {np.abs(got - ref).max() / scale:.3e}"
+            continue
         assert util.rel_l2(got, ref) <= TOL_L2, f"{case}/{name}: rel L2 {util.rel_l2(got, ref):.3e}"
         assert np.array_equal(got, ref), f"{case}/{name}: not bit-identical, max |diff| {np.abs(got - ref).max():.3e}"
     assert sim.launch_count() > 0
@@ -47,6 +55,13 @@ def test_gpu_matches_oracle_from_random_state(case, oracle_lib):
         assert np.array_equal(g, c), f"{case}/{util.P.FIELD_NAMES[f]}: rel L2 {util.rel_l2(g, c):.3e}"
     for comp, part in [(c.comp, c.part) for c in plan.cpml if c.has_psi]:
         assert np.array_equal(gpu.psi(comp, part), cpu.psi(comp, part)), f"{case}: psi comp {comp} part {part}"
+    for q, e in enumerate(plan.emitters):
+        for sy in range(e.nsys):
+            for w in range(5):
+                assert np.array_equal(gpu.emitter_state(q, sy, w), cpu.emitter_state(q, sy, w)), f"{case}: emitter set {q} system {sy} array {w}"
+        for c in range(3):
+            if c in plan.fields_present():
+                assert np.array_equal(gpu.emitter_P(q, c), cpu.emitter_P(q, c)), f"{case}: emitter P {q}/{c}"
     gpu.close(); cpu.close()
 
 

@@ -19,7 +19,7 @@ def test_oracle_matches_reference_bitwise(case, oracle_lib):
     for name, ref in expect.items():
         got = util.state_array(sim, name)
         assert got is not None, f"{case}: oracle has no array {name}"
-        assert np.abs(ref).max() > 0 or name[0] in "pPo", f"{case}: reference array {name} is all zero - fixture does not exercise it"
+        assert np.abs(ref).max() > 0 or name[0] in "pPoq", f"{case}: reference array {name} is all zero - fixture does not exercise it"
         assert np.array_equal(got, ref), f"{case}/{name}: max |diff| = {np.abs(got - ref).max():.3e}"
     sim.close()
 

@@ -24,6 +24,25 @@ def state_array(sim, name: str):
     OracleSim or a GpuSim (both expose field / pole / ordip_pole)."""
     if name in P.FIELD_NAMES:
         return sim.field(P.FIELD_NAMES.index(name))
+    if name.startswith("q"):
+        # emitter arrays of the reference dump: q<slot>s<sys>w<which> (states), q<slot>P<c> (P boxes), q<slot>pop<det>
+        import re
+        m = re.fullmatch(r"q(\d+)s(\d+)w(\d)", name)
+        if m:
+            a = sim.emitter_state(int(m.group(1)), int(m.group(2)), int(m.group(3)))
+            out = np.empty((a.shape[0], 1, 2 * a.shape[1]))
+            out[:, 0, 0::2], out[:, 0, 1::2] = a.real, a.imag
+            return out
+        m = re.fullmatch(r"q(\d+)P([xyz])", name)
+        if m:
+            return np.asarray(sim.emitter_P(int(m.group(1)), "xyz".index(m.group(2))))
+        m = re.fullmatch(r"q(\d+)pop(\d+)", name)
+        if m:
+            a = sim.population(int(m.group(1)), int(m.group(2)))
+            out = np.empty((a.shape[0], 1, 2))
+            out[:, 0, 0], out[:, 0, 1] = a.real, a.imag
+            return out
+        raise KeyError(name)
     if name.startswith("poP"):
         return sim.ordip_pole("xyz".index(name[3]), int(name[4:]), 1)
     if name.startswith("oP"):
@@ -49,4 +68,7 @@ def state_names(plan: P.Plan):
                 names += [f"P{'xyz'[c]}{p}", f"pP{'xyz'[c]}{p}"]
             for p in range(plan.n_ordip_poles):
                 names += [f"oP{'xyz'[c]}{p}", f"poP{'xyz'[c]}{p}"]
+    for q, e in enumerate(plan.emitters):
+        names += [f"q{q}s{s}w{w}" for s in range(e.nsys) for w in range(5)]
+        names += [f"q{q}P{'xyz'[c]}" for c in range(3) if c in plan.fields_present()]
     return names
