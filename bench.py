@@ -38,7 +38,7 @@ from chiml_b200 import inputs as I  # noqa: E402
 
 METRIC = "fp64_cell_updates_per_s"
 UNIT = "Mcell/s"
-WORKLOAD_HAS_EMITTERS = False    # flipped when the emitter (Maxwell-Liouville) path is part of the engine
+WORKLOAD_HAS_EMITTERS = True     # the two-level emitter sheet of C4/C5 is part of the workload
 PLAN_TOOL = os.path.join(ROOT, "chiml_b200", "chiml_plan")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "chiml_ref")
 

@@ -65,4 +65,5 @@ def census(plan: P.Plan) -> Census:
             comp_cells += int(c.grid["nAx"].sum())
         if c.has_psi:
             psi_cells += int(c.psi["transSz"].sum())
-    return Census(cells, comp_cells, d_cells, pole_cells, psi_cells)
+    emitter_bytes = sum(e.nemit * (e.nsys * 96 * e.nlevel * e.nlevel + 96) for e in plan.emitters)
+    return Census(cells, comp_cells, d_cells, pole_cells, psi_cells, emitter_bytes)

@@ -771,7 +771,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         if((rc = dev_alloc(ctx, &em.d_pop_partial, (size_t)std::max(em.d.npop, 1) * std::max(em.nblocks, 1) * 2))) return rc;
         em.pop_cap = 4096;
         if((rc = dev_alloc(ctx, &em.d_pop, (size_t)std::max(em.d.npop, 1) * em.pop_cap * 2))) return rc;
-        ctx->kstat[K_EMIT_DENSITY].alg_bytes += (double)em.d.nemit * (em.d.nsys * 96.0 * em.d.nlevel * em.d.nlevel + 48.0 + 24.0);
+        ctx->kstat[K_EMIT_DENSITY].alg_bytes += (double)em.d.nemit * (em.d.nsys * 96.0 * em.d.nlevel * em.d.nlevel + 96.0)   /* rho RW, 4 histories R, 1 W; 6 E reads, 3 P RMW */;
         ctx->kstat[K_EMIT_ADDP].alg_bytes += 0.0;   // its E read-modify-write is the field traffic already counted for the E half step
         CK(cudaStreamSynchronize(ctx->stream));
     }

@@ -470,9 +470,22 @@ Inputs::Inputs(const Json& IP)
                 for(const auto& g : gv.second.child("g").kids) gam.push_back(g.second.value<double>() * a_ / SPEED_OF_LIGHT);
                 q.gam.push_back(gam);
             }
-            for(int zz = 0; zz < nz; ++zz)
-                for(int yy = 0; yy < ny; ++yy)
-                    for(int xx = 0; xx < nx; ++xx)
+            // same scan order as the reference (z outermost, x innermost, :596-614), restricted to the object's bounding box
+            int lo[3] = {0, 0, 0}, hi[3] = {nx, ny, nz};
+            {
+                const std::array<double, 3> h = obj->halfExtent(obj->geoParam_);
+                const int nn[3] = {nx, ny, nz};
+                for(int k = 0; k < 3; ++k)
+                    if(std::isfinite(h[k]))
+                    {
+                        const double c = (nn[k] - 1) / 2.0;
+                        lo[k] = std::max(0, (int)std::floor((obj->location_[k] - h[k]) / d_[k] + c) - 2);
+                        hi[k] = std::min(nn[k], (int)std::ceil((obj->location_[k] + h[k]) / d_[k] + c) + 3);
+                    }
+            }
+            for(int zz = lo[2]; zz < hi[2]; ++zz)
+                for(int yy = lo[1]; yy < hi[1]; ++yy)
+                    for(int xx = lo[0]; xx < hi[0]; ++xx)
                     {
                         std::array<double, 3> loc = {{static_cast<double>(xx - (nx - 1) / 2.0) * d_[0], static_cast<double>(yy - (ny - 1) / 2.0) * d_[1],
                                                       static_cast<double>(zz - (nz - 1) / 2.0) * d_[2]}};

@@ -8,6 +8,7 @@
 #include <fstream>
 #include <limits>
 #include <thread>
+#include <unordered_map>
 
 namespace chiml_host {
 
@@ -90,6 +91,21 @@ public:
             if(o.isObj(pt, g_.d[0], o.geoParamML_)) id = c.obj;
         }
         return id;
+    }
+
+    // eps (or mu) map value at GLOBAL indices, without the border marks of row(): the value of the last relevant object whose
+    // (non-enlarged) geometry contains the sample point, 1 elsewhere (parallelFDTDField.hpp:891-894)
+    double epsAt(const GridSpec& s, long gx, long gy, long gz) const
+    {
+        double v = 1.0;
+        const std::array<double, 3> pt = {{(gx + s.off[0] - cen_[0]) * g_.d[0], (gy + s.off[1] - cen_[1]) * g_.d[1], (gz + s.off[2] - cen_[2]) * g_.d[2]}};
+        for(const Cull& c : cull_)
+        {
+            if(gx < c.lo[0] || gx > c.hi[0] || gy < c.lo[1] || gy > c.hi[1] || gz < c.lo[2] || gz > c.hi[2]) continue;
+            const Obj& o = *IP_.objArr_[c.obj];
+            if(o.isObj(pt, g_.d[0], o.geoParam_)) v = s.E ? o.eps_infty_ : o.mu_infty_;
+        }
+        return v;
     }
 
     // one local row (jj, kk) of the object-id and eps/mu maps, including the -1 / 0.0 border marks
@@ -581,6 +597,8 @@ int detector_field(DTCTYPE t)
     }
 }
 
+#include "emitters.inc"
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------
@@ -763,6 +781,8 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads)
         }
         P.detectors.push_back(pd);
     }
+    // ---- emitters (parallelFDTDField.cpp:412-454) ----
+    build_emitters(IP, g, ras, mode, P);
     return P;
 }
 
@@ -831,6 +851,18 @@ void SlabPlan::write(const std::string& path) const
         r.every = d.every; r.type = d.type; r.conv = d.conv; r.t_conv = d.t_conv;
         std::string p; app(p, r);
         put_rec(out, "DETECTOR", p);
+    }
+    for(const PlanEmitter& e : emitters)
+    {
+        ChimlPlanEmitterHdr h; std::memset(&h, 0, sizeof(h));
+        h.object = e.object; h.nlevel = e.nlevel; h.nsys = e.nsys; h.nemit = e.nemit;
+        for(int k = 0; k < 3; ++k) { h.box_lo[k] = e.box_lo[k]; h.box_n[k] = e.box_n[k]; }
+        h.nnz = (int)e.gam_col.size(); h.npop = (int)e.pop_level.size(); h.pop_every = e.pop_every; h.npoints = e.npoints;
+        h.pz = e.pz; h.dt = e.dt; h.inv_hbar = e.inv_hbar; h.na = e.na;
+        std::string p; app(p, h);
+        app_vec(p, e.h0); app_vec(p, e.weight); app_vec(p, e.mu); app_vec(p, e.gam_ptr); app_vec(p, e.gam_col); app_vec(p, e.gam_val);
+        app_vec(p, e.loc); app_vec(p, e.eps); app_vec(p, e.pop_level);
+        put_rec(out, "EMITTER", p);
     }
 }
 

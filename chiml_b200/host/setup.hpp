@@ -23,6 +23,17 @@ struct PlanObject { int npoles, use_or_dip, ml; double eps_inf, mu_inf; std::vec
 struct PlanSource { int field; int32_t loc[3], sz[3]; std::vector<double> amp; };
 struct PlanDetector { int detector, field; int32_t loc[3], sz[3], offset[3]; int every, type; double conv, t_conv; };
 
+// one parallelQE object restricted to the slab (include/chiml_gpu.h ChimlEmitterDesc)
+struct PlanEmitter
+{
+    int object = 0, nlevel = 0, nsys = 0, nemit = 0;
+    int32_t box_lo[3] = {0, 0, 0}, box_n[3] = {0, 0, 0};
+    int pz = 0, pop_every = 1, npoints = 0;
+    double dt = 0, inv_hbar = 0, na = 0;
+    std::vector<double> h0, weight, mu, gam_val, eps;
+    std::vector<int32_t> gam_ptr, gam_col, loc, pop_level;
+};
+
 // The flattened propagator of one rank ("plan", include/chiml_plan.h)
 struct SlabPlan
 {
@@ -32,6 +43,7 @@ struct SlabPlan
     std::vector<PlanCpml> cpml;
     std::vector<PlanSource> sources;
     std::vector<PlanDetector> detectors;
+    std::vector<PlanEmitter> emitters;
     bool dielectricMatInPML = false;
 
     void write(const std::string& path) const;

@@ -1,0 +1,68 @@
+"""The host-side setup of this repository (chiml_b200/host: JSON -> update lists, CPML lists, pole constants, sources,
+detectors, emitter sets) must reproduce, record for record and bit for bit, what the UNMODIFIED reference's constructors built
+for the same JSON (the committed <case>.rank0.plan files were dumped from the reference's own data structures by
+oracle/ref_driver.cpp)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+TOOL = os.path.join(ROOT, "chiml_b200", "chiml_plan")
+
+
+@pytest.fixture(scope="session")
+def plan_tool():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host")], check=True, stdout=subprocess.DEVNULL)
+    return TOOL
+
+
+@pytest.mark.parametrize("case", util.CASES)
+def test_host_plan_equals_reference_plan(case, plan_tool, tmp_path):
+    import plan_diff
+    from chiml_b200 import plan as P
+    out = str(tmp_path / case)
+    subprocess.run([plan_tool, os.path.join(util.GOLDEN, case + ".json"), out], check=True)
+    bad = plan_diff.diff(P.read_plan(out + ".rank0.plan"), util.load_plan(case))
+    assert not bad, "\n".join(bad[:20])
+
+
+@pytest.mark.parametrize("case,nranks", [("aniso_slab3d", 2), ("ml3d_two", 2), ("tm_au", 3)])
+def test_slab_plans_tile_the_single_rank_plan(case, nranks, plan_tool, tmp_path):
+    """y-slab decomposition: the update-list cells of the slabs, mapped back to global rows, are exactly the cells of the
+    single-rank plan (same prefactors), and every emitter is owned by exactly one slab."""
+    import numpy as np
+    from chiml_b200 import plan as P
+    out = str(tmp_path / case)
+    subprocess.run([plan_tool, os.path.join(util.GOLDEN, case + ".json"), out, "--ranks", str(nranks)], check=True)
+    whole = util.load_plan(case)
+    slabs = [P.read_plan(f"{out}.rank{r}.plan") for r in range(nranks)]
+    lnx, lny, lnz = whole.ln
+    assert sum(s.ln[1] - 2 for s in slabs) == lny - 2
+    for key, runs in whole.lists.items():
+        def cells(plan, runs, ys):
+            m = {}
+            for r in runs:
+                row, x0 = divmod(int(r["ind"]), plan.ln[0])
+                y, z = divmod(row, plan.ln[2])
+                for i in range(int(r["n"])):
+                    m[(x0 + i, y + ys, z)] = (float(r["pf"][1]), float(r["pf"][2]), float(r["pf"][3]))
+            return m
+        ref = cells(whole, runs, 0)
+        got = {}
+        for s in slabs:
+            part = cells(s, s.get_list(*key), s.y_start)
+            assert not (set(part) & set(got)), f"list {key}: a cell is owned by two slabs"
+            got.update(part)
+        assert got == ref, f"list {key}: slabs do not tile the single-rank list"
+    if whole.emitters:
+        tot = sum(e.nemit for s in slabs for e in s.emitters)
+        assert tot == whole.emitters[0].nemit
+        for s in slabs:
+            for e in s.emitters:
+                assert e.npoints == whole.emitters[0].npoints
+                np.testing.assert_array_equal(e.gam_val, whole.emitters[0].gam_val)

@@ -67,6 +67,19 @@ def diff(a: P.Plan, b: P.Plan, verbose=True):
     for i, (da, db) in enumerate(zip(a.detectors, b.detectors)):
         if da != db:
             bad.append(f"detector {i}: {da} != {db}")
+    if len(a.emitters) != len(b.emitters):
+        bad.append(f"emitters: {len(a.emitters)} != {len(b.emitters)}")
+    for i, (ea, eb) in enumerate(zip(a.emitters, b.emitters)):
+        for k in ("object", "nlevel", "nsys", "nemit", "box_lo", "box_n", "pz", "npop", "pop_every", "npoints", "dt", "inv_hbar", "na"):
+            if getattr(ea, k) != getattr(eb, k):
+                bad.append(f"emitter {i}.{k}: {getattr(ea, k)!r} != {getattr(eb, k)!r}")
+        for k in ("h0", "weight", "mu", "gam_ptr", "gam_col", "gam_val", "loc", "eps", "pop_level"):
+            u, v = np.asarray(getattr(ea, k)), np.asarray(getattr(eb, k))
+            if u.shape != v.shape:
+                bad.append(f"emitter {i}.{k}: shape {u.shape} != {v.shape}")
+            elif u.tobytes() != v.tobytes():
+                j = np.flatnonzero(u.ravel() != v.ravel())
+                bad.append(f"emitter {i}.{k}: {len(j)} entries differ, first at {j[:1]}: {u.ravel()[j[:1]]} vs {v.ravel()[j[:1]]}")
     return bad
 
 
