@@ -475,9 +475,16 @@ int main(int argc, char** argv)
         std::fprintf(stderr, "usage: chiml_ref <input.json> [--ranks R] [--steps N] [--dump FILE] [--plan PREFIX] [--no-output] [--quiet]\n");
         return 2;
     }
+    // --quiet: the reference prints from every rank; ranks are threads here, so the sink must be stateless (a shared
+    // std::ostringstream is a data race that crashes with many ranks)
+    struct NullBuf : std::streambuf
+    {
+        int overflow(int c) override { return traits_type::not_eof(c); }
+        std::streamsize xsputn(const char*, std::streamsize n) override { return n; }
+    };
+    static NullBuf sink;
     std::streambuf* oldCout = nullptr;
-    std::ostringstream sink;
-    if(opt.quiet) oldCout = std::cout.rdbuf(sink.rdbuf());
+    if(opt.quiet) oldCout = std::cout.rdbuf(&sink);
 
     mpi::shim::world().nranks = opt.ranks;
     std::vector<std::thread> threads;
