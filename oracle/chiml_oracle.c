@@ -59,6 +59,7 @@ struct OracleSim
     int nsteps;
     QESet qe[MAX_QE];
     int nqe;
+    int phase_mask;                /* bit 0: H half step + sources, 1: node poles, 2: E half step + emitter addP, 3: emitter density */
 };
 
 static int comp_exists(const OracleSim* s, int field)
@@ -447,7 +448,8 @@ static void qe_den_deriv(const QESet* q, const cx* H, const cx* den, cx* out)
 }
 
 /* parallelQEBase::addQE (:682-718) + updateDensity (:614-678) on the slab that owns the nodes */
-static void qe_add(OracleSim* s, QESet* q)
+/* part: 1 = addP only, 2 = density update only, 3 = both (addQE) */
+static void qe_add(OracleSim* s, QESet* q, int part)
 {
     const ChimlEmitterDesc* d = &q->d;
     const int lnx = s->g.ln[0], lnz = s->g.ln[2];
@@ -458,7 +460,7 @@ static void qe_add(OracleSim* s, QESet* q)
 #define PB(i, j, k) ((size_t)(i) + (size_t)bx * ((size_t)(k) + (size_t)bz * (size_t)(j)))
 #define GI(x, y, z) ((size_t)(x) + (size_t)lnx * ((size_t)(z) + (size_t)lnz * (size_t)(y)))
     /* addP (UTIL/FDTD_up_eq.cpp:1367-1380): E += -0.5 P[n]/eps[n], then E += -0.5 P[n+off]/eps[n+off] */
-    for(int c = 0; c < 3; ++c)
+    for(int c = 0; c < 3 && (part & 1); ++c)
     {
         double* E = s->f[CHIML_EX + c];
         if(!E) continue;
@@ -475,8 +477,15 @@ static void qe_add(OracleSim* s, QESet* q)
                     E[g] = E[g] + 1.0 * t2;
                 }
     }
-    /* zeroP_ */
-    for(int c = 0; c < 3; ++c) if(s->f[CHIML_EX + c]) memset(q->P[c], 0, q->pbox * sizeof(double));
+    if(!(part & 2)) return;
+    /* zeroP_ (only the entries of this slab's emitters can be non-zero; rim rows owned by a neighbouring slab are kept) */
+    for(int c = 0; c < 3; ++c)
+        if(s->f[CHIML_EX + c])
+            for(int e = 0; e < d->nemit; ++e)
+            {
+                const int* l = &q->loc[3 * e];
+                q->P[c][PB(l[0] + 1, l[1] + 1, l[2] - 1 + zOff + 1)] = 0.0;
+            }
     const int sample = (q->tstep % d->pop_every) == 0;
     cx H[MAX_N2], pred[MAX_N2], fpred[MAX_N2];
     const double dt = d->dt;
@@ -604,7 +613,7 @@ static void step_worker(OracleSim* s, int tid, int nt)
     for(int step = 0; step < s->nsteps; ++step)
     {
         /* updateH (:1308-1313) */
-        for(int i = 0; i < 3; ++i)
+        for(int i = 0; i < 3 && (s->phase_mask & 1); ++i)
         {
             double* H = s->f[CHIML_HX + i];
             if(!H) continue;
@@ -614,10 +623,10 @@ static void step_worker(OracleSim* s, int tid, int nt)
         }
         BARRIER();
         /* updateHPML_ (:1258-1259) */
-        for(int i = 0; i < 3; ++i)
+        for(int i = 0; i < 3 && (s->phase_mask & 1); ++i)
             if(s->f[CHIML_HX + i]) pml_component(s, 3 + i, s->f[CHIML_HX + i], tid, nt);
         /* src->addPul (:1261-1262, SOURCE/parallelSourceNormal.cpp:15-37): grid[box] += dt*Re(pulse), amp precomputed */
-        if(tid == 0)
+        if(tid == 0 && (s->phase_mask & 1))
         {
             for(int q = 0; q < s->nsrc; ++q)
             {
@@ -635,12 +644,13 @@ static void step_worker(OracleSim* s, int tid, int nt)
         }
         BARRIER();
         /* updatePolE (:1348-1365): oriented-dipole poles at nodes, then isotropic poles per component */
+        if(s->phase_mask & 2)
         {
             RunList* l = &s->up[CHIML_LIST_ORDIPP][0];
             SPLIT(l->n, lo, hi);
             for(size_t e = lo; e < hi; ++e) lor_pol_ordip_run(s, &l->r[e], &s->obj[l->r[e].obj], scratch);
         }
-        for(int i = 0; i < 3; ++i)
+        for(int i = 0; i < 3 && (s->phase_mask & 4); ++i)
         {
             if(!s->f[CHIML_EX + i] || !s->f[CHIML_DX + i]) continue;
             RunList* l = &s->up[CHIML_LIST_LORD][i];
@@ -649,7 +659,7 @@ static void step_worker(OracleSim* s, int tid, int nt)
         }
         BARRIER();
         /* updateD (:1338-1343) and updateE (:1318-1323) */
-        for(int i = 0; i < 3; ++i)
+        for(int i = 0; i < 3 && (s->phase_mask & 4); ++i)
         {
             if(!s->f[CHIML_EX + i]) continue;
             const double* Hj = s->f[CHIML_HX + (i + 1) % 3];
@@ -666,10 +676,10 @@ static void step_worker(OracleSim* s, int tid, int nt)
         }
         BARRIER();
         /* updateEPML_ (:1279-1280): acts on D when material reaches the PML (parallelFDTDField.cpp:68-77,239-246) */
-        for(int i = 0; i < 3; ++i)
+        for(int i = 0; i < 3 && (s->phase_mask & 4); ++i)
             if(s->f[CHIML_EX + i]) pml_component(s, i, s->g.pml_on_D ? s->f[CHIML_DX + i] : s->f[CHIML_EX + i], tid, nt);
         /* D2E (:1452-1473) */
-        for(int i = 0; i < 3; ++i)
+        for(int i = 0; i < 3 && (s->phase_mask & 4); ++i)
         {
             if(!s->f[CHIML_EX + i] || !s->f[CHIML_DX + i]) continue;
             RunList* l = &s->up[CHIML_LIST_LORD][i];
@@ -687,8 +697,10 @@ static void step_worker(OracleSim* s, int tid, int nt)
         }
         BARRIER();
         /* qe->addQE() for every emitter object (:1282-1283); serial, as each reference rank runs it */
-        if(tid == 0)
-            for(int q = 0; q < s->nqe; ++q) qe_add(s, &s->qe[q]);
+        if(tid == 0 && (s->phase_mask & 4))
+            for(int q = 0; q < s->nqe; ++q) qe_add(s, &s->qe[q], 1);
+        if(tid == 0 && (s->phase_mask & 8))
+            for(int q = 0; q < s->nqe; ++q) qe_add(s, &s->qe[q], 2);
         BARRIER();
     }
     free(scratch);
@@ -708,6 +720,7 @@ int oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads)
     s->nthreads = nthreads;
     s->src_amp = src_amp;
     s->nsteps = n;
+    s->phase_mask = 15;
     if(nthreads == 1)
     {
         step_worker(s, 0, 1);
@@ -720,6 +733,19 @@ int oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads)
     for(int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
     pthread_barrier_destroy(&s->bar);
     free(th); free(w);
+    return 0;
+}
+
+/* one phase of ONE step (y-slab runs exchange ghost rows between the phases): 0 = H half step + sources, 1 = oriented-dipole
+ * node poles, 2 = E half step + emitter addP, 3 = emitter density update.  src_amp = the n_sources amplitudes of this step. */
+int oracle_step_phase(OracleSim* s, int phase, const double* src_amp)
+{
+    if(!s->committed || phase < 0 || phase > 3) return CHIML_ERR_STATE;
+    s->nthreads = 1;
+    s->src_amp = src_amp;
+    s->nsteps = 1;
+    s->phase_mask = 1 << phase;
+    step_worker(s, 0, 1);
     return 0;
 }
 

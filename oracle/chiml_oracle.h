@@ -40,6 +40,9 @@ int  oracle_commit(OracleSim* s);
 /* nthreads > 1: rows of every list are split over POSIX threads (same arithmetic per cell) */
 int  oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads);
 
+/* one phase of one step, for y-slab runs that exchange ghost rows between phases (see chiml_oracle.c) */
+int  oracle_step_phase(OracleSim* s, int phase, const double* src_amp);
+
 /* direct pointers to the full-size logical arrays (ln[0]*ln[1]*ln[2] doubles), NULL if absent */
 double* oracle_field(OracleSim* s, int field);
 double* oracle_pole(OracleSim* s, int comp, int pole, int prev);

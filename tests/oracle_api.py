@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
         L.oracle_add_source.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.oracle_commit.argtypes = [C.c_void_p]
         L.oracle_step_n.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.oracle_step_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         for fn in ("oracle_field", "oracle_psi"):
             getattr(L, fn).restype = C.POINTER(C.c_double)
         L.oracle_field.argtypes = [C.c_void_p, C.c_int]
@@ -154,6 +155,13 @@ class OracleSim:
         amp = np.ascontiguousarray(amp, dtype=np.float64)
         self._chk(lib().oracle_step_n(self.h, n, _ptr(amp), nthreads))
         self.steps_done += n
+
+    def step_phase(self, phase: int, amp: np.ndarray) -> None:
+        """One phase of one step (chiml_b200/slab.py); amp = the amplitudes of this step, shape (1, n_sources)."""
+        amp = np.ascontiguousarray(amp, dtype=np.float64)
+        self._chk(lib().oracle_step_phase(self.h, phase, _ptr(amp)))
+        if phase == 3:
+            self.steps_done += 1
 
     def _view(self, p) -> np.ndarray | None:
         if not p:

@@ -1,0 +1,90 @@
+"""World_size-N worker of the slab tests (launched with torch.distributed.run, backend gloo): every rank builds the plan of
+its y-slab with the host-side setup, steps the CPU checker through chiml_b200.slab.step_slab, and rank 0 compares the gathered
+owned rows with the single-rank output of the reference (tests/golden/<case>.expect.npz) bit for bit."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import util  # noqa: E402
+from chiml_b200 import plan as P, slab  # noqa: E402
+from oracle_api import OracleSim  # noqa: E402
+
+
+def main():
+    case = sys.argv[1]
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    work = tempfile.mkdtemp(prefix=f"slab_{case}_r{rank}_")
+    subprocess.run([os.path.join(ROOT, "chiml_b200", "chiml_plan"), os.path.join(util.GOLDEN, case + ".json"), os.path.join(work, case),
+                    "--ranks", str(world), "--only", str(rank)], check=True)
+    plan = P.read_plan(os.path.join(work, f"{case}.rank{rank}.plan"))
+    whole = util.load_plan(case)
+    sim = OracleSim(plan)
+
+    def send(to, arr):
+        dist.send(torch.from_numpy(arr), dst=to)
+
+    def recv(frm, out):
+        t = torch.from_numpy(out)
+        dist.recv(t, src=frm)
+
+    for k in range(whole.n_steps):
+        slab.step_slab(sim, plan, sim.src_amp(k, 1), send, recv)
+
+    # gather owned rows on rank 0
+    ny = plan.ln[1] - 2
+    names = [n for n in util.state_names(whole) if not n.startswith("q")]
+    mine = {n: np.ascontiguousarray(util.state_array(sim, n)[1:ny + 1]) for n in names}
+    emit = []
+    for q, e in enumerate(plan.emitters):
+        coords = np.stack([e.box_lo[0] + e.loc[:, 0], e.box_lo[1] + e.loc[:, 1] + plan.y_start, e.box_lo[2] + e.loc[:, 2]], axis=1) if e.nemit else np.zeros((0, 3), int)
+        emit.append((e.object, coords, [[sim.emitter_state(q, sy, w).copy() for w in range(5)] for sy in range(e.nsys)]))
+    gathered = [None] * world
+    dist.gather_object((plan.y_start, mine, emit), gathered if rank == 0 else None, dst=0)
+    ok = True
+    if rank == 0:
+        expect = util.load_expect(case)
+        gathered.sort(key=lambda t: t[0])
+        for n in names:
+            got = np.concatenate([g[1][n] for g in gathered], axis=0)
+            ref = expect[n][1:-1]
+            if not np.array_equal(got, ref):
+                ok = False
+                print(f"MISMATCH {case}/{n}: max |diff| {np.abs(got - ref).max():.3e} of {np.abs(ref).max():.3e}")
+        for q, e in enumerate(whole.emitters):
+            gcoord = np.stack([e.box_lo[0] + e.loc[:, 0], e.box_lo[1] + e.loc[:, 1], e.box_lo[2] + e.loc[:, 2]], axis=1)
+            index = {tuple(c): i for i, c in enumerate(gcoord)}
+            seen = 0
+            for _, _, em in gathered:
+                for obj, coords, states in em:
+                    if obj != e.object:
+                        continue
+                    idx = np.array([index[tuple(c)] for c in coords], dtype=int)
+                    seen += len(idx)
+                    for sy in range(e.nsys):
+                        for w in range(5):
+                            r = expect[f"q{q}s{sy}w{w}"][:, 0, :]
+                            ref = (r[:, 0::2] + 1j * r[:, 1::2])[idx]
+                            if not np.array_equal(states[sy][w], ref):
+                                ok = False
+                                print(f"MISMATCH {case}/q{q}s{sy}w{w}: max |diff| {np.abs(states[sy][w] - ref).max():.3e}")
+            if seen != e.nemit:
+                ok = False
+                print(f"MISMATCH {case}: {seen} emitters over the slabs, {e.nemit} in the single-rank run")
+        print("SLAB_OK" if ok else "SLAB_FAIL")
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

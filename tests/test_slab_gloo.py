@@ -1,0 +1,22 @@
+"""N > 1 path on CPU (world_size 2 and 3, backend gloo): the y-slab plans of the host-side setup, stepped by the CPU checker
+through the ghost-row exchange protocol of chiml_b200/slab.py (the protocol the CUDA engine implements with peer-to-peer
+stores), must reproduce the single-rank output of the reference bit for bit -- fields, pole grids and emitter density
+matrices, including an emitter block and an oriented-dipole slab cut by the slab boundary."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("case,world", [("aniso_slab3d", 2), ("ml3d_two", 2), ("ml3d_four", 3), ("ml_te", 2)])
+def test_slab_protocol_matches_single_rank_reference(case, world):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host")], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, stdout=subprocess.DEVNULL)
+    port = 29650 + (hash((case, world)) % 200)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py"), case],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SLAB_OK" in r.stdout, (r.stdout[-3000:] + r.stderr[-3000:])
