@@ -28,6 +28,7 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_device_bytes", "chiml_gpu_set_kernel_timing", "chiml_gpu_n_kernel_kinds", "chiml_gpu_kernel_stat",
     "chiml_gpu_reset_kernel_stats", "chiml_gpu_read_detector_range", "chiml_gpu_add_emitters",
     "chiml_gpu_download_emitter_state", "chiml_gpu_download_emitter_pol", "chiml_gpu_read_population",
+    "chiml_gpu_halo_export", "chiml_gpu_halo_bind",
 ]
 
 
@@ -112,6 +113,8 @@ def lib() -> C.CDLL:
     L.chiml_gpu_download_psi.argtypes = [vp, i, i, vp]
     L.chiml_gpu_read_detector.argtypes = [vp, i, vp, sz, C.POINTER(sz)]
     L.chiml_gpu_read_detector_range.argtypes = [vp, i, sz, sz, vp, C.POINTER(sz)]
+    L.chiml_gpu_halo_export.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.chiml_gpu_halo_bind.argtypes = [vp, C.c_char_p, sz, C.c_char_p, sz]
     L.chiml_gpu_add_emitters.argtypes = [vp, C.POINTER(EmitterDesc), C.POINTER(i)]
     L.chiml_gpu_download_emitter_state.argtypes = [vp, i, i, i, vp]
     L.chiml_gpu_download_emitter_pol.argtypes = [vp, i, i, vp]
@@ -267,6 +270,22 @@ class GpuSim:
         out = np.empty((n.value, sy, sz, sx), dtype=np.float64)
         self._chk(lib().chiml_gpu_read_detector(self.h, slot, _ptr(out), n.value, C.byref(n)))
         return out
+
+    # ---- y-slabs -----------------------------------------------------------------------------------
+    def halo_export(self) -> bytes:
+        n = C.c_size_t()
+        self._chk(lib().chiml_gpu_halo_export(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        self._chk(lib().chiml_gpu_halo_export(self.h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def halo_bind(self, dist, rank: int, world: int) -> None:
+        """Exchanges the export blobs through torch.distributed (any backend) and binds the neighbours."""
+        blobs = [None] * world
+        dist.all_gather_object(blobs, self.halo_export())
+        lower = blobs[rank - 1] if rank > 0 else None
+        upper = blobs[rank + 1] if rank < world - 1 else None
+        self._chk(lib().chiml_gpu_halo_bind(self.h, lower, len(lower) if lower else 0, upper, len(upper) if upper else 0))
 
     def detector_range(self, index: int, first: int, n: int, out: np.ndarray) -> int:
         """Copies samples [first, first+n) of plan.detectors[index] into `out` (host buffer); returns how many existed."""

@@ -43,6 +43,13 @@ template <typename T> static int dev_alloc(ChimlCtx* ctx, T** p, size_t n, bool 
     if(zero) CK(cudaMemsetAsync(*p, 0, n * sizeof(T), ctx->stream));
     return 0;
 }
+// buffers a neighbouring slab maps with CUDA IPC: whole multiples of 2 MiB, so that the driver never sub-allocates them
+template <typename T> static int dev_alloc_ipc(ChimlCtx* ctx, T** p, size_t n)
+{
+    if(ctx->g.nranks <= 1) return dev_alloc(ctx, p, n);
+    const size_t bytes = ((std::max<size_t>(n, 1) * sizeof(T) + IPC_GRANULE - 1) / IPC_GRANULE) * IPC_GRANULE;
+    return dev_alloc(ctx, reinterpret_cast<char**>(p), bytes);
+}
 template <typename T> static int dev_upload(ChimlCtx* ctx, T** p, const std::vector<T>& v)
 {
     int rc = dev_alloc(ctx, p, v.size(), false);
@@ -98,6 +105,9 @@ int chiml_gpu_create(const ChimlGridDesc* desc, int device, ChimlCtx** out)
     ctx->objs.resize(desc->n_objects);
     cudaError_t e = cudaSetDevice(device);
     if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->hstream, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming);
+    if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_push, cudaEventDisableTiming);
     if(e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if(e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
     if(e != cudaSuccess) { g_create_err = std::string("CUDA init: ") + cudaGetErrorString(e); delete ctx; return CHIML_ERR_CUDA; }
@@ -141,7 +151,13 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     }
     for(auto& v : ctx->ev_pending) for(auto& pr : v) { cudaEventDestroy(pr[0]); cudaEventDestroy(pr[1]); }
     for(auto& e : ctx->ev_pool) cudaEventDestroy(e);
+    cudaStreamSynchronize(ctx->hstream);
+    for(HaloPeer* pr : {&ctx->lower, &ctx->upper}) for(void* b : pr->opened) cudaIpcCloseMemHandle(b);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_push_counter);
+    for(auto& g : ctx->d_oPy_ghost) cudaFree(g);
+    cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_push);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->hstream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -515,7 +531,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
     for(int f = 0; f < CHIML_NFIELDS; ++f)
         if(field_exists(ctx, f))
         {
-            if((rc = dev_alloc(ctx, &ctx->d_field_base[f], ctx->nphys + 2 * ctx->guard))) return rc;
+            if((rc = dev_alloc_ipc(ctx, &ctx->d_field_base[f], ctx->nphys + 2 * ctx->guard))) return rc;
             ctx->d_field[f] = ctx->d_field_base[f] + ctx->guard;
         }
 
@@ -739,6 +755,14 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 lists[fast ? 0 : (uniform ? 1 : 2)].push_back(rec);
                 listBytes[fast ? 0 : (uniform ? 1 : 2)] += ts.bytes;
             }
+            // tiles of a row that a neighbouring slab reads go first: they are launched on their own, ahead of the halo push
+            const bool hasLower = ctx->g.rank > 0, hasUpper = ctx->g.rank < ctx->g.nranks - 1;
+            for(int k = 0; k < 3; ++k)
+            {
+                auto isB = [&](const TileRec& t) { return (hasLower && t.y == 1) || (hasUpper && t.y == ctx->ly - 2); };
+                auto mid = std::stable_partition(lists[k].begin(), lists[k].end(), isB);
+                ctx->nbound[fam][k] = (unsigned)(mid - lists[k].begin());
+            }
             for(int k = 0; k < 3; ++k)
             {
                 ctx->kstat[(fam == 0 ? K_E_FAST : K_H_FAST) + k].alg_bytes = listBytes[k];
@@ -750,6 +774,15 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         }
         cudaFree(d_sum);
     }
+    // y-slab halo: flag words, push counters, the dense ghost row of node P_y (filled by the slab above)
+    if(ctx->g.nranks > 1)
+    {
+        if((rc = dev_alloc_ipc(ctx, &ctx->d_flags, (size_t)HF_NFLAGS))) return rc;
+        if((rc = dev_alloc(ctx, &ctx->d_push_counter, 16))) return rc;
+        if(ctx->g.rank < ctx->g.nranks - 1)
+            for(int p = 0; p < ctx->nordip; ++p)
+                if((rc = dev_alloc_ipc(ctx, &ctx->d_oPy_ghost[p], (size_t)ctx->lx * ctx->lz))) return rc;
+    }
     // emitters: constants, P boxes, SoA density state (rho_00 = weight of the level system, ML/density.hpp:57-60)
     for(EmitterDev& em : ctx->emitters)
     {
@@ -760,7 +793,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         if((rc = dev_upload(ctx, &em.d_gam_val, em.h_gam_val))) return rc;
         if((rc = dev_upload(ctx, &em.d_loc, em.h_loc))) return rc;
         if((rc = dev_upload(ctx, &em.d_eps, em.h_eps))) return rc;
-        for(int c = 0; c < 3; ++c) if((rc = dev_alloc(ctx, &em.d_P[c], em.pbox))) return rc;
+        for(int c = 0; c < 3; ++c) if((rc = dev_alloc_ipc(ctx, &em.d_P[c], em.pbox))) return rc;
         const size_t per = (size_t)em.d.nsys * em.n2 * 2 * (size_t)std::max(em.d.nemit, 1);
         std::vector<double> rho0(per, 0.0);
         for(int sy = 0; sy < em.d.nsys; ++sy)
@@ -840,7 +873,7 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
             for(int p = 0; p < MAX_POLES; ++p) { ca.Pcur[p] = ctx->d_P[i][p][cur]; ca.Pnew[p] = ctx->d_P[i][p][prv]; }
             ca.nordip = ctx->nordip;
             // after the node kernel of this step the new oriented-dipole P lives in buffer `prv`
-            for(int p = 0; p < MAX_POLES; ++p) ca.oP[p] = ctx->d_oP[i][p][prv];
+            for(int p = 0; p < MAX_POLES; ++p) { ca.oP[p] = ctx->d_oP[i][p][prv]; ca.oPg[p] = i == 1 ? ctx->d_oPy_ghost[p] : nullptr; }
             decode_offset(ctx, ctx->ordip_off[i], d);
             ca.ord_dx = d[0]; ca.ord_dy = d[1]; ca.ord_dz = d[2];
             // orDipDtoUZ is bound for Ez when there is no Hz (FDTD_MANAGER/parallelFDTDField.cpp:293-296)
@@ -872,21 +905,29 @@ struct LaunchScope
     }
 };
 
+// part 0: every tile; part 1: the slab-boundary tiles (front of each list); part 2: the rest
 template <bool IS_E, int MODE>
-void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block)
+void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int part)
 {
     const int fam = IS_E ? 0 : 1;
     const int k0 = IS_E ? K_E_FAST : K_H_FAST;
-    if(ctx->ntiles[fam][0]) { LaunchScope ls(ctx, k0);     k_fast<IS_E, MODE><<<ctx->ntiles[fam][0], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0]); }
-    if(ctx->ntiles[fam][1]) { LaunchScope ls(ctx, k0 + 1); k_uniform<IS_E, MODE><<<ctx->ntiles[fam][1], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1]); }
-    if(ctx->ntiles[fam][2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE><<<ctx->ntiles[fam][2], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2]); }
+    unsigned first[3], count[3];
+    for(int k = 0; k < 3; ++k)
+    {
+        const unsigned n = ctx->ntiles[fam][k], nb = ctx->nbound[fam][k];
+        first[k] = part == 2 ? nb : 0;
+        count[k] = part == 0 ? n : (part == 1 ? nb : n - nb);
+    }
+    if(count[0]) { LaunchScope ls(ctx, k0);     k_fast<IS_E, MODE><<<count[0], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0] + first[0]); }
+    if(count[1]) { LaunchScope ls(ctx, k0 + 1); k_uniform<IS_E, MODE><<<count[1], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1] + first[1]); }
+    if(count[2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE><<<count[2], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2]); }
 }
 template <bool IS_E>
-void launch_family(ChimlCtx* ctx, const StepArgs& a, const dim3 block)
+void launch_family(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int part)
 {
-    if(ctx->g.mode == CHIML_MODE_3D)      launch_family_mode<IS_E, CHIML_MODE_3D>(ctx, a, block);
-    else if(ctx->g.mode == CHIML_MODE_TE) launch_family_mode<IS_E, CHIML_MODE_TE>(ctx, a, block);
-    else                                  launch_family_mode<IS_E, CHIML_MODE_TM>(ctx, a, block);
+    if(ctx->g.mode == CHIML_MODE_3D)      launch_family_mode<IS_E, CHIML_MODE_3D>(ctx, a, block, part);
+    else if(ctx->g.mode == CHIML_MODE_TE) launch_family_mode<IS_E, CHIML_MODE_TE>(ctx, a, block, part);
+    else                                  launch_family_mode<IS_E, CHIML_MODE_TM>(ctx, a, block, part);
 }
 
 template <int N>
@@ -895,22 +936,52 @@ void launch_density(ChimlCtx* ctx, const EmitArgs& ea, int nblocks)
     k_emit_density<N><<<nblocks, 128, 0, ctx->stream>>>(ea);
 }
 
-int launch_emitters(ChimlCtx* ctx, EmitterDev& em)
+// rows of [y0, y1) that are / are not slab-boundary rows (local row 1 with a slab below, row ly-2 with a slab above)
+struct RowSeg { int y0, y1; };
+int split_rows(const ChimlCtx* ctx, int y0, int y1, int part, RowSeg out[3])
+{
+    if(part == 0) { out[0] = {y0, y1}; return y1 > y0 ? 1 : 0; }
+    const int bl = ctx->g.rank > 0 ? 1 : -1, bu = ctx->g.rank < ctx->g.nranks - 1 ? ctx->ly - 2 : -1;
+    int n = 0;
+    if(part == 1)
+    {
+        if(bl >= y0 && bl < y1) out[n++] = {bl, bl + 1};
+        if(bu >= y0 && bu < y1 && bu != bl) out[n++] = {bu, bu + 1};
+        return n;
+    }
+    int a = y0;
+    for(int b : {bl, bu})
+        if(b >= a && b < y1) { if(b > a) out[n++] = {a, b}; a = b + 1; }
+    if(a < y1) out[n++] = {a, y1};
+    return n;
+}
+
+void launch_addP(ChimlCtx* ctx, EmitterDev& em, int part)
 {
     const bool threeD = ctx->lz > 1;
+    AddPArgs pa;
+    std::memset(&pa, 0, sizeof(pa));
+    for(int c = 0; c < 3; ++c) { pa.E[c] = ctx->d_field[c]; pa.P[c] = em.d_P[c]; }
+    pa.eps = em.d_eps;
+    for(int k = 0; k < 3; ++k) pa.box_lo[k] = em.d.box_lo[k];
+    pa.nx = em.d.box_n[0] + 1; pa.ny = em.d.box_n[1] + 1; pa.nz = threeD ? em.d.box_n[2] + 1 : 1;
+    pa.bx = em.d.box_n[0] + 2; pa.bz = em.pz; pa.zoff = threeD ? 1 : 0;
+    pa.lz = ctx->lz; pa.px = ctx->px;
+    RowSeg seg[3];
+    const int nseg = split_rows(ctx, pa.box_lo[1], pa.box_lo[1] + pa.ny, part, seg);
+    for(int i = 0; i < nseg; ++i)
     {
-        AddPArgs pa;
-        std::memset(&pa, 0, sizeof(pa));
-        for(int c = 0; c < 3; ++c) { pa.E[c] = ctx->d_field[c]; pa.P[c] = em.d_P[c]; }
-        pa.eps = em.d_eps;
-        for(int k = 0; k < 3; ++k) pa.box_lo[k] = em.d.box_lo[k];
-        pa.nx = em.d.box_n[0] + 1; pa.ny = em.d.box_n[1] + 1; pa.nz = threeD ? em.d.box_n[2] + 1 : 1;
-        pa.bx = em.d.box_n[0] + 2; pa.bz = em.pz; pa.zoff = threeD ? 1 : 0;
-        pa.lz = ctx->lz; pa.px = ctx->px;
-        const long n = (long)pa.nx * pa.ny * pa.nz;
+        pa.iy0 = seg[i].y0 - pa.box_lo[1]; pa.iy1 = seg[i].y1 - pa.box_lo[1];
+        const long n = (long)pa.nx * (pa.iy1 - pa.iy0) * pa.nz;
+        if(n <= 0) continue;
         LaunchScope ls(ctx, K_EMIT_ADDP);
         k_emit_addP<<<(unsigned)std::min<long>((n + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(pa);
     }
+}
+
+int launch_density_step(ChimlCtx* ctx, EmitterDev& em)
+{
+    const bool threeD = ctx->lz > 1;
     const int sample = (em.tstep % em.d.pop_every) == 0 && em.d.npop > 0;
     if(em.d.nemit > 0)
     {
@@ -963,53 +1034,114 @@ int launch_emitters(ChimlCtx* ctx, EmitterDev& em)
     return 0;
 }
 
+void launch_sources(ChimlCtx* ctx, long long k, int nsrc, int part)
+{
+    for(int q = 0; q < nsrc; ++q)
+    {
+        const SourceDev& s = ctx->sources[q];
+        RowSeg seg[3];
+        const int nseg = split_rows(ctx, s.loc[1], s.loc[1] + s.sz[1], part, seg);
+        for(int i = 0; i < nseg; ++i)
+        {
+            const int sy = seg[i].y1 - seg[i].y0;
+            const long n = (long)s.sz[0] * sy * s.sz[2];
+            if(n <= 0) continue;
+            LaunchScope ls(ctx, K_SOURCE);
+            k_source<<<(unsigned)std::min<long>((n + 255) / 256, 2048), 256, 0, ctx->stream>>>(
+                ctx->d_field[s.field], s.loc[0], s.loc[2], seg[i].y0, s.sz[0], s.sz[2], sy, ctx->lz, ctx->px, ctx->d_src_amp + k * nsrc + q);
+        }
+    }
+}
+
+void launch_node_poles(ChimlCtx* ctx)
+{
+    if(!ctx->d_info_node) return;
+    NodeArgs na;
+    std::memset(&na, 0, sizeof(na));
+    na.info = ctx->d_info_node; na.cls = ctx->d_cls_node;
+    na.lx = ctx->lx; na.ly = ctx->ly; na.lz = ctx->lz; na.px = ctx->px;
+    na.sp_xmin = ctx->span_node.d_xmin; na.sp_xmax = ctx->span_node.d_xmax; na.sp_base = ctx->span_node.d_base;
+    na.rows = ctx->span_node.d_rows;
+    const int cur = ctx->pcur, prv = 1 - ctx->pcur;
+    for(int c = 0; c < 3; ++c)
+    {
+        na.E[c] = ctx->d_field[c];
+        int d[3];
+        decode_offset(ctx, ctx->node_off[c], d);
+        na.eoff[c] = phys_offset(ctx, d);
+        for(int p = 0; p < MAX_POLES; ++p) { na.Pcur[c][p] = ctx->d_oP[c][p][cur]; na.Pnew[c][p] = ctx->d_oP[c][p][prv]; }
+    }
+    LaunchScope ls(ctx, K_ORDIP_POLES);
+    const dim3 ng((ctx->span_node.max_width + 255) / 256, ctx->span_node.nrows_used, 1);
+    if(ng.y > 0) k_ordip_poles<<<ng, 256, 0, ctx->stream>>>(na);
+}
+
+// ---- halo helpers (chiml_halo.cuh) ------------------------------------------------------------------
+void halo_wait(ChimlCtx* ctx, std::initializer_list<std::pair<int, long long>> flags)
+{
+    HaloWaitArgs w;
+    std::memset(&w, 0, sizeof(w));
+    for(auto& f : flags)
+        if(f.second > 0) { w.flag[w.n] = ctx->d_flags + f.first; w.value[w.n] = (int)f.second; ++w.n; }
+    if(w.n == 0) return;
+    w.error = ctx->d_flags + HF_ERROR;
+    LaunchScope ls(ctx, K_HALO_WAIT);
+    k_halo_wait<<<1, 1, 0, ctx->stream>>>(w);
+}
+
+// the halo stream picks up after everything launched so far on the compute stream
+void halo_fork(ChimlCtx* ctx)
+{
+    cudaEventRecord(ctx->ev_main, ctx->stream);
+    cudaStreamWaitEvent(ctx->hstream, ctx->ev_main, 0);
+}
+
+void halo_push(ChimlCtx* ctx, const HaloPeer& peer, std::initializer_list<HaloSeg> segs, std::initializer_list<int> flags, long long value)
+{
+    HaloPushArgs pa;
+    std::memset(&pa, 0, sizeof(pa));
+    long total = 0;
+    for(auto& sg : segs) if(sg.src && sg.dst && sg.n > 0) { pa.seg[pa.nseg++] = sg; total += sg.n; }
+    for(int f : flags) pa.peer_flag[pa.nflag++] = peer.flags + f;
+    pa.value = (int)value;
+    pa.counter = ctx->d_push_counter + (ctx->push_slot++ % 16);
+    const unsigned blocks = (unsigned)std::max<long>(1, std::min<long>((total / 2 + 255) / 256, 64));
+    ++ctx->launches; ++ctx->kstat[K_HALO_PUSH].launches;
+    k_halo_push<<<blocks, 256, 0, ctx->hstream>>>(pa);
+    ctx->push_pending = true;
+}
+
+int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc);
+
 int launch_step(ChimlCtx* ctx, long long k, int nsrc)
 {
     // one block per tile of the compact lists built at commit
     const dim3 block(32, ctx->lz > 1 ? TILE_Z : 1, 1);
     StepArgs a;
-    // H half step: updateH + updateHPML_ (step() items 4 and 6)
-    fill_step_args(ctx, false, a);
-    launch_family<false>(ctx, a, block);
-    // sources (item 7): all sources, E and H alike, are injected here
-    for(int q = 0; q < nsrc; ++q)
+    if(ctx->g.nranks > 1)
     {
-        const SourceDev& s = ctx->sources[q];
-        const long n = (long)s.sz[0] * s.sz[1] * s.sz[2];
-        LaunchScope ls(ctx, K_SOURCE);
-        k_source<<<(unsigned)std::min<long>((n + 255) / 256, 2048), 256, 0, ctx->stream>>>(
-            ctx->d_field[s.field], s.loc[0], s.loc[2], s.loc[1], s.sz[0], s.sz[2], s.sz[1], ctx->lz, ctx->px, ctx->d_src_amp + k * nsrc + q);
-    }
-    // oriented-dipole poles at the nodes (item 10, first loop)
-    if(ctx->d_info_node)
-    {
-        NodeArgs na;
-        std::memset(&na, 0, sizeof(na));
-        na.info = ctx->d_info_node; na.cls = ctx->d_cls_node;
-        na.lx = ctx->lx; na.ly = ctx->ly; na.lz = ctx->lz; na.px = ctx->px;
-        na.sp_xmin = ctx->span_node.d_xmin; na.sp_xmax = ctx->span_node.d_xmax; na.sp_base = ctx->span_node.d_base;
-        na.rows = ctx->span_node.d_rows;
-        const int cur = ctx->pcur, prv = 1 - ctx->pcur;
-        for(int c = 0; c < 3; ++c)
-        {
-            na.E[c] = ctx->d_field[c];
-            int d[3];
-            decode_offset(ctx, ctx->node_off[c], d);
-            na.eoff[c] = phys_offset(ctx, d);
-            for(int p = 0; p < MAX_POLES; ++p) { na.Pcur[c][p] = ctx->d_oP[c][p][cur]; na.Pnew[c][p] = ctx->d_oP[c][p][prv]; }
-        }
-        LaunchScope ls(ctx, K_ORDIP_POLES);
-        const dim3 ng((ctx->span_node.max_width + 255) / 256, ctx->span_node.nrows_used, 1);
-        if(ng.y > 0) k_ordip_poles<<<ng, 256, 0, ctx->stream>>>(na);
-    }
-    // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
-    fill_step_args(ctx, true, a);
-    launch_family<true>(ctx, a, block);
-    // qe->addQE() for every emitter object (item 16)
-    for(EmitterDev& em : ctx->emitters)
-    {
-        int rc = launch_emitters(ctx, em);
+        int rc = launch_step_slabs(ctx, k, nsrc);
         if(rc) return rc;
+    }
+    else
+    {
+        // H half step: updateH + updateHPML_ (step() items 4 and 6)
+        fill_step_args(ctx, false, a);
+        launch_family<false>(ctx, a, block, 0);
+        // sources (item 7): all sources, E and H alike, are injected here
+        launch_sources(ctx, k, nsrc, 0);
+        // oriented-dipole poles at the nodes (item 10, first loop)
+        launch_node_poles(ctx);
+        // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
+        fill_step_args(ctx, true, a);
+        launch_family<true>(ctx, a, block, 0);
+        // qe->addQE() for every emitter object (item 16)
+        for(EmitterDev& em : ctx->emitters)
+        {
+            launch_addP(ctx, em, 0);
+            int rc = launch_density_step(ctx, em);
+            if(rc) return rc;
+        }
     }
     ctx->pcur = 1 - ctx->pcur;
     ++ctx->step_count;
@@ -1034,6 +1166,110 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
         }
         ++dt.count;
     }
+    return 0;
+}
+
+// One time step of one y-slab of several (protocol and its proof of equivalence: chiml_b200/slab.py, tests/test_slab_gloo.py).
+// kk = number of the step being taken, counted from 1: the value published in the neighbours' flags.
+int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
+{
+    if(!ctx->halo_bound) return CHIML_ERR_STATE;
+    const dim3 block(32, ctx->lz > 1 ? TILE_Z : 1, 1);
+    const long long kk = ctx->step_count + 1;
+    const bool lo = ctx->lower.present, up = ctx->upper.present;
+    const long rowN = ctx->plane;                                    // one (x, z) plane of doubles, padded
+    const long top = (long)(ctx->ly - 2) * ctx->plane, ghostTop = (long)(ctx->ly - 1) * ctx->plane;
+    const bool haveEy = ctx->d_field[CHIML_EY] != nullptr;
+    const bool needEy = haveEy && (ctx->d_info_node || !ctx->emitters.empty() || true);
+    StepArgs a;
+    // pushes of the previous step read rows this step overwrites
+    if(ctx->push_pending) { cudaStreamWaitEvent(ctx->stream, ctx->ev_push, 0); ctx->push_pending = false; }
+
+    // ---- H half step: boundary rows first (they read the ghost E row the slab above pushed at the end of the last step)
+    if(up) halo_wait(ctx, {{HF_E_FROM_UPPER, kk - 1}});
+    fill_step_args(ctx, false, a);
+    launch_family<false>(ctx, a, block, 1);
+    launch_sources(ctx, k, nsrc, 1);
+    if(up)
+    {
+        halo_fork(ctx);
+        const HaloPeer& p = ctx->upper;
+        halo_push(ctx, p, {{ctx->d_field[CHIML_HX] ? ctx->d_field[CHIML_HX] + top : nullptr, p.field[CHIML_HX], rowN},
+                           {ctx->d_field[CHIML_HZ] ? ctx->d_field[CHIML_HZ] + top : nullptr, p.field[CHIML_HZ], rowN}}, {HF_H_FROM_LOWER}, kk);
+    }
+    launch_family<false>(ctx, a, block, 2);
+    launch_sources(ctx, k, nsrc, 2);
+
+    // ---- oriented-dipole poles at the nodes (read Ey of ghost row 0: pushed by the slab below after its last E half step)
+    if(lo && needEy) halo_wait(ctx, {{HF_EY_FROM_LOWER, kk - 1}});
+    launch_node_poles(ctx);
+    if(lo && ctx->d_info_node && ctx->nordip > 0 && haveEy)
+    {
+        halo_fork(ctx);
+        NodePushArgs np;
+        std::memset(&np, 0, sizeof(np));
+        np.npoles = ctx->nordip;
+        for(int p = 0; p < ctx->nordip; ++p) { np.pool[p] = ctx->d_oP[1][p][1 - ctx->pcur]; np.dst[p] = ctx->lower.oPy_ghost[p]; }
+        np.sp_xmin = ctx->span_node.d_xmin; np.sp_xmax = ctx->span_node.d_xmax; np.sp_base = ctx->span_node.d_base;
+        np.lx = ctx->lx; np.lz = ctx->lz;
+        np.peer_flag = ctx->lower.flags + HF_OP_FROM_UPPER; np.value = (int)kk;
+        np.counter = ctx->d_push_counter + (ctx->push_slot++ % 16);
+        ++ctx->launches; ++ctx->kstat[K_HALO_PUSH].launches;
+        k_halo_push_nodes<<<32, 256, 0, ctx->hstream>>>(np);
+        ctx->push_pending = true;
+    }
+
+    // ---- E half step: boundary rows first
+    bool recvQP = false;
+    for(size_t q = 0; q < ctx->emitters.size(); ++q)
+        if(up && q < ctx->upper.emitPy.size() && ctx->emitters[q].d.box_lo[1] + ctx->emitters[q].d.box_n[1] + 1 == ctx->ly - 1) recvQP = true;
+    halo_wait(ctx, {{HF_H_FROM_LOWER, lo ? kk : 0}, {HF_OP_FROM_UPPER, (up && ctx->d_info_node && ctx->nordip > 0 && haveEy) ? kk : 0},
+                    {HF_QP_FROM_UPPER, recvQP ? kk - 1 : 0}});
+    fill_step_args(ctx, true, a);
+    launch_family<true>(ctx, a, block, 1);
+    for(EmitterDev& em : ctx->emitters) launch_addP(ctx, em, 1);
+    halo_fork(ctx);
+    if(lo)
+    {
+        const HaloPeer& p = ctx->lower;
+        const long pg = (long)(p.ly - 1) * ctx->plane;     // its upper ghost row
+        halo_push(ctx, p, {{ctx->d_field[CHIML_EX] ? ctx->d_field[CHIML_EX] + ctx->plane : nullptr, p.field[CHIML_EX] ? p.field[CHIML_EX] + pg : nullptr, rowN},
+                           {ctx->d_field[CHIML_EZ] ? ctx->d_field[CHIML_EZ] + ctx->plane : nullptr, p.field[CHIML_EZ] ? p.field[CHIML_EZ] + pg : nullptr, rowN}},
+                  {HF_E_FROM_UPPER}, kk);
+    }
+    if(up && haveEy)
+        halo_push(ctx, ctx->upper, {{ctx->d_field[CHIML_EY] + top, ctx->upper.field[CHIML_EY], rowN}}, {HF_EY_FROM_LOWER}, kk);
+    launch_family<true>(ctx, a, block, 2);
+    for(EmitterDev& em : ctx->emitters) launch_addP(ctx, em, 2);
+
+    // ---- emitter density update (averages Ey[r], Ey[r - y]: needs this step's Ey in ghost row 0)
+    if(!ctx->emitters.empty())
+    {
+        if(lo && haveEy) halo_wait(ctx, {{HF_EY_FROM_LOWER, kk}});
+        for(EmitterDev& em : ctx->emitters)
+        {
+            int rc = launch_density_step(ctx, em);
+            if(rc) return rc;
+        }
+        if(lo && haveEy)
+        {
+            std::vector<size_t> qs;
+            for(size_t q = 0; q < ctx->emitters.size(); ++q)
+                if(ctx->emitters[q].d.box_lo[1] == 0 && q < ctx->lower.emitPy.size() && ctx->lower.emitPy[q]) qs.push_back(q);
+            if(!qs.empty()) halo_fork(ctx);
+            for(size_t i = 0; i < qs.size(); ++i)
+            {
+                EmitterDev& em = ctx->emitters[qs[i]];
+                const long rowP = (long)(em.d.box_n[0] + 2) * em.pz;
+                double* dst = ctx->lower.emitPy[qs[i]] + (long)(ctx->lower.emit_bn1[qs[i]] + 1) * rowP;
+                // the flag is published with the last set only: pushes run in order on the halo stream
+                if(i + 1 == qs.size()) halo_push(ctx, ctx->lower, {{em.d_P[1] + rowP, dst, rowP}}, {HF_QP_FROM_UPPER}, kk);
+                else                   halo_push(ctx, ctx->lower, {{em.d_P[1] + rowP, dst, rowP}}, {}, kk);
+            }
+        }
+    }
+    (void)ghostTop;
+    if(ctx->push_pending) cudaEventRecord(ctx->ev_push, ctx->hstream);
     return 0;
 }
 
@@ -1077,6 +1313,141 @@ int chiml_gpu_sync(ChimlCtx* ctx)
     if(!ctx) return CHIML_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->hstream));
+    if(ctx->d_flags)
+    {
+        int err = 0;
+        CK(cudaMemcpy(&err, ctx->d_flags + HF_ERROR, sizeof(int), cudaMemcpyDeviceToHost));
+        if(err) return fail(ctx, CHIML_ERR_STATE, "a neighbouring slab did not deliver its ghost row within 30 s (halo wait timed out)");
+    }
+    return CHIML_OK;
+}
+
+// ---- y-slab binding ------------------------------------------------------------------------------
+namespace {
+struct HaloBlobHdr
+{
+    uint32_t magic; int32_t rank, nranks, lx, ly, lz; int64_t px; int64_t guard; int32_t nordip, nsets; int32_t has_field[6];
+};
+struct HaloBlobSet { cudaIpcMemHandle_t h; int32_t has, box_lo1, box_n1, rowlen; };
+constexpr uint32_t HALO_MAGIC = 0x4F4C4148u;   // "HALO"
+}
+
+int chiml_gpu_halo_export(ChimlCtx* ctx, void* blob, size_t cap, size_t* size)
+{
+    if(!ctx || !size) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "halo_export before commit");
+    if(ctx->g.nranks <= 1) return fail(ctx, CHIML_ERR_ARG, "halo_export: the grid description names a single slab");
+    CK(cudaSetDevice(ctx->device));
+    const size_t need = sizeof(HaloBlobHdr) + (6 + 1 + MAX_POLES) * sizeof(cudaIpcMemHandle_t) + ctx->emitters.size() * sizeof(HaloBlobSet);
+    *size = need;
+    if(!blob) return CHIML_OK;
+    if(cap < need) return fail(ctx, CHIML_ERR_ARG, "halo_export: buffer too small");
+    std::vector<char> out(need, 0);
+    HaloBlobHdr h{};
+    h.magic = HALO_MAGIC; h.rank = ctx->g.rank; h.nranks = ctx->g.nranks; h.lx = ctx->lx; h.ly = ctx->ly; h.lz = ctx->lz; h.px = ctx->px;
+    h.guard = (int64_t)ctx->guard; h.nordip = ctx->nordip; h.nsets = (int32_t)ctx->emitters.size();
+    cudaIpcMemHandle_t* hs = reinterpret_cast<cudaIpcMemHandle_t*>(out.data() + sizeof(HaloBlobHdr));
+    for(int f = 0; f < 6; ++f)
+        if(ctx->d_field_base[f]) { h.has_field[f] = 1; CK(cudaIpcGetMemHandle(&hs[f], ctx->d_field_base[f])); }
+    CK(cudaIpcGetMemHandle(&hs[6], ctx->d_flags));
+    for(int p = 0; p < MAX_POLES; ++p)
+        if(ctx->d_oPy_ghost[p]) CK(cudaIpcGetMemHandle(&hs[7 + p], ctx->d_oPy_ghost[p]));
+    HaloBlobSet* sets = reinterpret_cast<HaloBlobSet*>(out.data() + sizeof(HaloBlobHdr) + (7 + MAX_POLES) * sizeof(cudaIpcMemHandle_t));
+    for(size_t q = 0; q < ctx->emitters.size(); ++q)
+    {
+        const EmitterDev& em = ctx->emitters[q];
+        sets[q].box_lo1 = em.d.box_lo[1]; sets[q].box_n1 = em.d.box_n[1]; sets[q].rowlen = (em.d.box_n[0] + 2) * em.pz;
+        if(em.d_P[1] && ctx->d_field[CHIML_EY]) { sets[q].has = 1; CK(cudaIpcGetMemHandle(&sets[q].h, em.d_P[1])); }
+    }
+    std::memcpy(out.data(), &h, sizeof(h));
+    std::memcpy(blob, out.data(), need);
+    return CHIML_OK;
+}
+
+static int halo_open_peer(ChimlCtx* ctx, const void* blob, size_t size, bool isLower, HaloPeer& peer)
+{
+    if(size < sizeof(HaloBlobHdr)) return fail(ctx, CHIML_ERR_ARG, "halo_bind: truncated blob");
+    HaloBlobHdr h;
+    std::memcpy(&h, blob, sizeof(h));
+    if(h.magic != HALO_MAGIC) return fail(ctx, CHIML_ERR_ARG, "halo_bind: not a halo blob");
+    if(h.nranks != ctx->g.nranks || h.rank != ctx->g.rank + (isLower ? -1 : 1)) return fail(ctx, CHIML_ERR_ARG, "halo_bind: blob is not from the neighbouring slab");
+    if(h.lx != ctx->lx || h.lz != ctx->lz || h.px != ctx->px) return fail(ctx, CHIML_ERR_ARG, "halo_bind: neighbour has different x / z extents");
+    const size_t need = sizeof(HaloBlobHdr) + (7 + MAX_POLES) * sizeof(cudaIpcMemHandle_t) + (size_t)h.nsets * sizeof(HaloBlobSet);
+    if(size < need) return fail(ctx, CHIML_ERR_ARG, "halo_bind: truncated blob");
+    const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>((const char*)blob + sizeof(HaloBlobHdr));
+    auto open = [&](const cudaIpcMemHandle_t& hh, void** out) -> int {
+        CK(cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess));
+        peer.opened.push_back(*out);
+        return 0;
+    };
+    int rc;
+    peer.ly = h.ly;
+    for(int f = 0; f < 6; ++f)
+    {
+        if(!h.has_field[f]) continue;
+        // only the arrays this slab writes into: E_x, E_z of the slab below; H_x, H_z, E_y of the slab above
+        const bool needIt = isLower ? (f == CHIML_EX || f == CHIML_EZ) : (f == CHIML_HX || f == CHIML_HZ || f == CHIML_EY);
+        if(!needIt) continue;
+        void* base = nullptr;
+        if((rc = open(hs[f], &base))) return rc;
+        peer.field[f] = reinterpret_cast<double*>(base) + h.guard;
+    }
+    { void* base = nullptr; if((rc = open(hs[6], &base))) return rc; peer.flags = reinterpret_cast<int*>(base); }
+    if(isLower)
+    {
+        if(h.nordip != ctx->nordip) return fail(ctx, CHIML_ERR_ARG, "halo_bind: neighbour has a different number of oriented-dipole poles");
+        for(int p = 0; p < h.nordip; ++p) { void* base = nullptr; if((rc = open(hs[7 + p], &base))) return rc; peer.oPy_ghost[p] = reinterpret_cast<double*>(base); }
+        const HaloBlobSet* sets = reinterpret_cast<const HaloBlobSet*>((const char*)blob + sizeof(HaloBlobHdr) + (7 + MAX_POLES) * sizeof(cudaIpcMemHandle_t));
+        peer.emitPy.assign(ctx->emitters.size(), nullptr);
+        peer.emit_bn1.assign(ctx->emitters.size(), 0);
+        // emitter sets are matched by position: both slabs list the objects that touch them in input order; match by row length
+        // and by the rim condition (our first row is inside the object, their top rim is their ghost row)
+        for(size_t q = 0; q < ctx->emitters.size(); ++q)
+        {
+            const EmitterDev& em = ctx->emitters[q];
+            if(em.d.box_lo[1] != 0) continue;
+            int match = -1;
+            for(int j = 0; j < h.nsets; ++j)
+                if(sets[j].has && sets[j].rowlen == (em.d.box_n[0] + 2) * em.pz && sets[j].box_lo1 + sets[j].box_n1 + 1 == h.ly - 1) { match = j; break; }
+            if(match < 0) return fail(ctx, CHIML_ERR_ARG, "halo_bind: an emitter object reaches this slab's first row but the slab below has no matching set");
+            void* base = nullptr;
+            if((rc = open(sets[match].h, &base))) return rc;
+            peer.emitPy[q] = reinterpret_cast<double*>(base);
+            peer.emit_bn1[q] = sets[match].box_n1;
+        }
+    }
+    else
+    {
+        const HaloBlobSet* sets = reinterpret_cast<const HaloBlobSet*>((const char*)blob + sizeof(HaloBlobHdr) + (7 + MAX_POLES) * sizeof(cudaIpcMemHandle_t));
+        peer.emitPy.assign(ctx->emitters.size(), nullptr);   // non-null marks "the slab above pushes into this set's rim"
+        for(size_t q = 0; q < ctx->emitters.size(); ++q)
+        {
+            const EmitterDev& em = ctx->emitters[q];
+            if(em.d.box_lo[1] + em.d.box_n[1] + 1 != ctx->ly - 1) continue;
+            bool found = false;
+            for(int j = 0; j < h.nsets; ++j) if(sets[j].has && sets[j].box_lo1 == 0 && sets[j].rowlen == (em.d.box_n[0] + 2) * em.pz) found = true;
+            if(!found) return fail(ctx, CHIML_ERR_ARG, "halo_bind: an emitter box ends in this slab's ghost row but the slab above has no matching set");
+            peer.emitPy[q] = em.d_P[1];
+        }
+    }
+    peer.present = true;
+    return CHIML_OK;
+}
+
+int chiml_gpu_halo_bind(ChimlCtx* ctx, const void* lower_blob, size_t lower_size, const void* upper_blob, size_t upper_size)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "halo_bind before commit");
+    if(ctx->halo_bound) return fail(ctx, CHIML_ERR_STATE, "halo_bind called twice");
+    CK(cudaSetDevice(ctx->device));
+    const bool needLower = ctx->g.rank > 0, needUpper = ctx->g.rank < ctx->g.nranks - 1;
+    if(needLower != (lower_blob != nullptr) || needUpper != (upper_blob != nullptr))
+        return fail(ctx, CHIML_ERR_ARG, "halo_bind: exactly the existing neighbours must be given (none below slab 0, none above the last slab)");
+    int rc;
+    if(needLower && (rc = halo_open_peer(ctx, lower_blob, lower_size, true, ctx->lower))) return rc;
+    if(needUpper && (rc = halo_open_peer(ctx, upper_blob, upper_size, false, ctx->upper))) return rc;
+    ctx->halo_bound = true;
     return CHIML_OK;
 }
 

@@ -88,7 +88,7 @@ struct DetectorDev
 };
 
 // kernels of the step loop, for launch / time / algorithmic-byte accounting
-enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_NKINDS };
+enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_NKINDS };
 struct KernelStat { int64_t launches = 0; double ms_total = 0.0; double alg_bytes = 0.0; int64_t timed = 0; };
 
 // one parallelQE object on the device (chiml_emitters.cuh)
@@ -109,6 +109,22 @@ struct EmitterDev
     double* d_pop_partial = nullptr; int nblocks = 0;
     double* d_pop = nullptr; size_t pop_cap = 0, pop_n = 0;
     long tstep = 0;
+};
+
+// ---- y-slab halo (chiml_halo.cuh): flags the neighbours write into this context's memory, one 32-bit step counter each
+enum HaloFlag { HF_H_FROM_LOWER = 0, HF_OP_FROM_UPPER, HF_E_FROM_UPPER, HF_EY_FROM_LOWER, HF_QP_FROM_UPPER, HF_ERROR, HF_NFLAGS = 16 };
+constexpr size_t IPC_GRANULE = 2u << 20;     // exported buffers are whole 2 MiB allocations (never sub-allocated by the driver)
+
+struct HaloPeer                   // one neighbouring slab, as mapped into this process
+{
+    bool present = false;
+    int ly = 0;                   // its ghost-inclusive slab height
+    double* field[6] = {};        // its E / H arrays (logical origin, like ChimlCtx::d_field)
+    double* oPy_ghost[MAX_POLES] = {};   // its dense ghost row of node P_y (only the slab below needs ours: we write theirs)
+    std::vector<double*> emitPy;  // its emitter P_y boxes, per emitter set (nullptr when that set does not exchange)
+    std::vector<int> emit_bn1;    // box_n[1] of those sets
+    int* flags = nullptr;         // its flag array
+    std::vector<void*> opened;    // bases returned by cudaIpcOpenMemHandle
 };
 
 struct HostList { std::vector<ChimlRun> runs; };
@@ -179,6 +195,18 @@ struct ChimlCtx
     long long step_count = 0;
     int64_t launches = 0;
     size_t dev_bytes = 0;
+
+    // y-slab halo
+    cudaStream_t hstream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_push = nullptr;
+    bool push_pending = false;
+    int* d_flags = nullptr;                      // HF_NFLAGS ints, exported
+    unsigned* d_push_counter = nullptr;          // block counters of the push kernels
+    int push_slot = 0;
+    double* d_oPy_ghost[chiml::MAX_POLES] = {};  // dense (lx * lz) ghost row ny+1 of node P_y per pole, written by the slab above
+    chiml::HaloPeer lower, upper;
+    bool halo_bound = false;
+    unsigned nbound[2][3] = {};                  // tiles of each list that touch a slab-boundary row (sorted to the front)
 
     // per-kernel device timing (chiml_gpu_set_kernel_timing / chiml_gpu_kernel_stat)
     bool timing = false;

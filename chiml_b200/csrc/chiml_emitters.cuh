@@ -261,15 +261,16 @@ struct AddPArgs
     int bx, bz;
     int zoff;                  // zOff_
     int lz; long px;
+    int iy0, iy1;              // box rows [iy0, iy1) handled by this launch (slab-boundary rows go first, see chiml_halo.cuh)
 };
 __global__ void k_emit_addP(const __grid_constant__ AddPArgs a)
 {
-    const long n = (long)a.nx * a.ny * a.nz;
+    const long n = (long)a.nx * (a.iy1 - a.iy0) * a.nz;
     for(long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     {
         const int ix = (int)(i % a.nx);
         const int iz = (int)((i / a.nx) % a.nz);
-        const int iy = (int)(i / ((long)a.nx * a.nz));
+        const int iy = a.iy0 + (int)(i / ((long)a.nx * a.nz));
         const long g = (a.box_lo[0] + ix) + a.px * ((a.lz > 1 ? a.box_lo[2] + iz : 0) + (long)a.lz * (a.box_lo[1] + iy));
         const long p0 = ix + (long)a.bx * (iz + (long)a.bz * iy);
         const double ep0 = a.eps[p0];

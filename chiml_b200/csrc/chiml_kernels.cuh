@@ -44,6 +44,7 @@ struct CompArgs
     double* Pnew[MAX_POLES];     // the buffer that held prevP receives the new P
     // oriented-dipole D->E
     const double* oP[MAX_POLES]; // node-centred pole state AFTER this step's node update
+    const double* oPg[MAX_POLES];// dense ghost row ny+1 of that state (written by the slab above), or nullptr
     int nordip;
     int ord_dx, ord_dy, ord_dz;  // node offset r + e_c of orDipDtoU
     int ord_zvariant;            // orDipDtoUZ (2-D TM Ez)
@@ -99,8 +100,9 @@ __device__ __forceinline__ double da(double a, double b) { return __dadd_rn(a, b
 // y <- y + a*x with separately rounded product and sum (daxpy semantics)
 __device__ __forceinline__ double axpy1(double y, double a, double x) { return __dadd_rn(y, __dmul_rn(a, x)); }
 
-__device__ __forceinline__ double node_value(const StepArgs& a, const double* pool, int x, int y, int z)
+__device__ __forceinline__ double node_value(const StepArgs& a, const double* pool, const double* ghost, int x, int y, int z)
 {
+    if(ghost && y == a.ly - 1) return ghost[x + (long)a.lx * z];
     const long row = z + (long)a.lz * y;
     const int xmin = a.nsp_xmin[row];
     if(xmin < 0 || x < xmin || x > a.nsp_xmax[row]) return 0.0;
@@ -110,6 +112,7 @@ __device__ __forceinline__ double node_value(const StepArgs& a, const double* po
 } // namespace chiml
 #include "chiml_update.cuh"
 #include "chiml_emitters.cuh"
+#include "chiml_halo.cuh"
 namespace chiml {
 
 // updatePolE, oriented-dipole poles at the integer nodes

@@ -151,12 +151,12 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
         u = dm(ce.inv_eps, dv);
         for(int p = 0; p < ca.nordip; ++p)
         {
-            const double p0 = node_value(a, ca.oP[p], x, y, z);
+            const double p0 = node_value(a, ca.oP[p], ca.oPg[p], x, y, z);
             if(ca.ord_zvariant)
                 u = axpy1(u, ce.neg_inv_eps, p0);
             else
             {
-                const double p1 = node_value(a, ca.oP[p], x + ca.ord_dx, y + ca.ord_dy, z + ca.ord_dz);
+                const double p1 = node_value(a, ca.oP[p], ca.oPg[p], x + ca.ord_dx, y + ca.ord_dy, z + ca.ord_dz);
                 u = axpy1(u, ce.neg_half_inv_eps, p0);
                 u = axpy1(u, ce.neg_half_inv_eps, p1);
             }

@@ -157,6 +157,15 @@ int chiml_gpu_add_emitters(ChimlCtx* ctx, const ChimlEmitterDesc* desc, int* slo
  * tables and compact psi / polarisation pools, zeroes all state. */
 int chiml_gpu_commit(ChimlCtx* ctx);
 
+/* ---- y-slabs (one context per GPU, one process per context) ---------------------------------------------------------------
+ * Replaces parallelGrid::transferDat (GRID/parallelGrid.hpp:738-770) and the E / P box transfers of the emitter code
+ * (ML/parallelQE.hpp:618-645,694-715): after commit every slab exports an opaque blob (CUDA IPC handles of the rows its neighbours
+ * write, plus layout); the host transports the blobs (MPI, torch.distributed, a file ...) and hands each slab the blobs of the slab
+ * below (rank-1) and above (rank+1), NULL where there is none.  From then on chiml_gpu_step_n exchanges ghost rows by peer-to-peer
+ * stores over NVLink, boundary rows first, overlapped with the interior update.  All slabs must step in lock-step (same n). */
+int chiml_gpu_halo_export(ChimlCtx* ctx, void* blob, size_t cap, size_t* size);   /* blob == NULL: only reports the size */
+int chiml_gpu_halo_bind(ChimlCtx* ctx, const void* lower_blob, size_t lower_size, const void* upper_blob, size_t upper_size);
+
 /* ---- stepping ---------------------------------------------------------------------------------- */
 /* n leap-frog steps in the reference's order (step(), :1228-1303).  src_amp: n * n_sources doubles,
  * step-major (may be NULL when there are no sources). */

@@ -1,0 +1,103 @@
+"""One process per GPU (torch.distributed.run): every rank builds its y-slab plan, binds the CUDA engine's native halo
+(peer-to-peer stores over NVLink), steps, and rank 0 compares the gathered owned rows with the single-rank output of the
+reference (tests/golden/<case>.expect.npz) bit for bit.  usage: slab_gpu_worker.py <case> [<case> ...]"""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import util  # noqa: E402
+from chiml_b200 import capi, plan as P  # noqa: E402
+
+
+def run_case(case, rank, world, local):
+    work = tempfile.mkdtemp(prefix=f"slabgpu_{case}_r{rank}_")
+    subprocess.run([os.path.join(ROOT, "chiml_b200", "chiml_plan"), os.path.join(util.GOLDEN, case + ".json"), os.path.join(work, case),
+                    "--ranks", str(world), "--only", str(rank)], check=True)
+    plan = P.read_plan(os.path.join(work, f"{case}.rank{rank}.plan"))
+    whole = util.load_plan(case)
+    sim = capi.GpuSim(plan, device=local)
+    sim.halo_bind(dist, rank, world)
+    # several calls of uneven length: the flags count steps across calls
+    done = 0
+    for n in (1, 2, whole.n_steps - 3):
+        sim.step_n(n)
+        done += n
+    sim.sync()
+    ny = plan.ln[1] - 2
+    names = [n for n in util.state_names(whole) if not n.startswith("q")]
+    mine = {n: np.ascontiguousarray(util.state_array(sim, n)[1:ny + 1]) for n in names}
+    emit = []
+    for q, e in enumerate(plan.emitters):
+        coords = np.stack([e.box_lo[0] + e.loc[:, 0], e.box_lo[1] + e.loc[:, 1] + plan.y_start, e.box_lo[2] + e.loc[:, 2]], axis=1) if e.nemit else np.zeros((0, 3), int)
+        emit.append((e.object, coords, [[sim.emitter_state(q, sy, w).copy() for w in range(5)] for sy in range(e.nsys)],
+                     [sim.population(q, d) for d in range(e.npop)]))
+    launches = sim.launch_count()
+    sim.close()
+    gathered = [None] * world
+    dist.gather_object((plan.y_start, mine, emit), gathered if rank == 0 else None, dst=0)
+    ok = True
+    if rank == 0:
+        expect = util.load_expect(case)
+        gathered.sort(key=lambda t: t[0])
+        for n in names:
+            got = np.concatenate([g[1][n] for g in gathered], axis=0)
+            ref = expect[n][1:-1]
+            if not np.array_equal(got, ref):
+                ok = False
+                print(f"MISMATCH {case}/{n}: max |diff| {np.abs(got - ref).max():.3e} of {np.abs(ref).max():.3e}")
+        for q, e in enumerate(whole.emitters):
+            gcoord = np.stack([e.box_lo[0] + e.loc[:, 0], e.box_lo[1] + e.loc[:, 1], e.box_lo[2] + e.loc[:, 2]], axis=1)
+            index = {tuple(c): i for i, c in enumerate(gcoord)}
+            seen = 0
+            pops = None
+            for _, _, em in gathered:
+                for obj, coords, states, pop in em:
+                    if obj != e.object:
+                        continue
+                    idx = np.array([index[tuple(c)] for c in coords], dtype=int)
+                    seen += len(idx)
+                    pops = pop if pops is None else [a + b for a, b in zip(pops, pop)]   # the host adds the slabs (QEPopDtc::toFile)
+                    for sy in range(e.nsys):
+                        for w in range(5):
+                            r = expect[f"q{q}s{sy}w{w}"][:, 0, :]
+                            ref = (r[:, 0::2] + 1j * r[:, 1::2])[idx]
+                            if not np.array_equal(states[sy][w], ref):
+                                ok = False
+                                print(f"MISMATCH {case}/q{q}s{sy}w{w}: max |diff| {np.abs(states[sy][w] - ref).max():.3e}")
+            if seen != e.nemit:
+                ok = False
+                print(f"MISMATCH {case}: {seen} emitters over the slabs, {e.nemit} in the single-rank run")
+            for d in range(e.npop):
+                r = expect[f"q{q}pop{d}"][:, 0, :]
+                ref = r[:, 0] + 1j * r[:, 1]
+                if pops is None or len(pops[d]) != len(ref) or np.abs(pops[d] - ref).max() > 1e-9 * max(np.abs(ref).max(), 1e-300):
+                    ok = False
+                    print(f"MISMATCH {case}/q{q}pop{d}")
+        print(f"{case}: {'SLAB_GPU_OK' if ok else 'SLAB_GPU_FAIL'} ({world} slabs, {launches} launches on rank 0)")
+    return ok
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    ok = True
+    for case in sys.argv[1:]:
+        ok = run_case(case, rank, world, local) and ok
+        dist.barrier()
+    import torch
+    flag = torch.tensor([1 if ok else 0])
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
