@@ -968,7 +968,11 @@ void launch_addP(ChimlCtx* ctx, EmitterDev& em, int part)
     pa.bx = em.d.box_n[0] + 2; pa.bz = em.pz; pa.zoff = threeD ? 1 : 0;
     pa.lz = ctx->lz; pa.px = ctx->px;
     RowSeg seg[3];
-    const int nseg = split_rows(ctx, pa.box_lo[1], pa.box_lo[1] + pa.ny, part, seg);
+    // with several slabs the box may reach into a ghost row: that row belongs to the neighbour, which updates it and pushes it here
+    // (adding P to it locally could land after the push and spoil it)
+    const int r0 = ctx->g.nranks > 1 ? std::max(pa.box_lo[1], 1) : pa.box_lo[1];
+    const int r1 = ctx->g.nranks > 1 ? std::min(pa.box_lo[1] + pa.ny, ctx->ly - 1) : pa.box_lo[1] + pa.ny;
+    const int nseg = split_rows(ctx, r0, r1, part, seg);
     for(int i = 0; i < nseg; ++i)
     {
         pa.iy0 = seg[i].y0 - pa.box_lo[1]; pa.iy1 = seg[i].y1 - pa.box_lo[1];
@@ -1034,13 +1038,17 @@ int launch_density_step(ChimlCtx* ctx, EmitterDev& em)
     return 0;
 }
 
+// part 0: all sources; part 1: H-field sources on slab-boundary rows (they must be in the row before it is pushed, and nothing of
+// the H half step reads H); part 2: the rest -- E-field sources always come after the whole H half step, which reads E
 void launch_sources(ChimlCtx* ctx, long long k, int nsrc, int part)
 {
     for(int q = 0; q < nsrc; ++q)
     {
         const SourceDev& s = ctx->sources[q];
+        const bool isH = s.field >= CHIML_HX && s.field <= CHIML_HZ;
+        if(part == 1 && !isH) continue;
         RowSeg seg[3];
-        const int nseg = split_rows(ctx, s.loc[1], s.loc[1] + s.sz[1], part, seg);
+        const int nseg = split_rows(ctx, s.loc[1], s.loc[1] + s.sz[1], (part == 2 && !isH) ? 0 : part, seg);
         for(int i = 0; i < nseg; ++i)
         {
             const int sy = seg[i].y1 - seg[i].y0;
