@@ -1414,7 +1414,7 @@ static int halo_open_peer(ChimlCtx* ctx, const void* blob, size_t size, bool isL
         for(size_t q = 0; q < ctx->emitters.size(); ++q)
         {
             const EmitterDev& em = ctx->emitters[q];
-            if(em.d.box_lo[1] != 0) continue;
+            if(em.d.box_lo[1] != 0 || !ctx->d_field[CHIML_EY]) continue;   // only P_y couples across a slab boundary
             int match = -1;
             for(int j = 0; j < h.nsets; ++j)
                 if(sets[j].has && sets[j].rowlen == (em.d.box_n[0] + 2) * em.pz && sets[j].box_lo1 + sets[j].box_n1 + 1 == h.ly - 1) { match = j; break; }
@@ -1432,7 +1432,7 @@ static int halo_open_peer(ChimlCtx* ctx, const void* blob, size_t size, bool isL
         for(size_t q = 0; q < ctx->emitters.size(); ++q)
         {
             const EmitterDev& em = ctx->emitters[q];
-            if(em.d.box_lo[1] + em.d.box_n[1] + 1 != ctx->ly - 1) continue;
+            if(em.d.box_lo[1] + em.d.box_n[1] + 1 != ctx->ly - 1 || !ctx->d_field[CHIML_EY]) continue;
             bool found = false;
             for(int j = 0; j < h.nsets; ++j) if(sets[j].has && sets[j].box_lo1 == 0 && sets[j].rowlen == (em.d.box_n[0] + 2) * em.pz) found = true;
             if(!found) return fail(ctx, CHIML_ERR_ARG, "halo_bind: an emitter box ends in this slab's ghost row but the slab above has no matching set");
