@@ -195,6 +195,7 @@ def b200_arm(args):
         raise SystemExit("bench.py: no CUDA device visible; the engine has no CPU fallback")
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)

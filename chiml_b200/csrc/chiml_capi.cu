@@ -1188,7 +1188,7 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
     const long rowN = ctx->plane;                                    // one (x, z) plane of doubles, padded
     const long top = (long)(ctx->ly - 2) * ctx->plane, ghostTop = (long)(ctx->ly - 1) * ctx->plane;
     const bool haveEy = ctx->d_field[CHIML_EY] != nullptr;
-    const bool needEy = haveEy && (ctx->d_info_node || !ctx->emitters.empty() || true);
+    const bool needEy = haveEy;
     StepArgs a;
     // pushes of the previous step read rows this step overwrites
     if(ctx->push_pending) { cudaStreamWaitEvent(ctx->stream, ctx->ev_push, 0); ctx->push_pending = false; }
@@ -1230,7 +1230,7 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
     // ---- E half step: boundary rows first
     bool recvQP = false;
     for(size_t q = 0; q < ctx->emitters.size(); ++q)
-        if(up && q < ctx->upper.emitPy.size() && ctx->emitters[q].d.box_lo[1] + ctx->emitters[q].d.box_n[1] + 1 == ctx->ly - 1) recvQP = true;
+        if(up && haveEy && q < ctx->upper.emitPy.size() && ctx->upper.emitPy[q]) recvQP = true;
     halo_wait(ctx, {{HF_H_FROM_LOWER, lo ? kk : 0}, {HF_OP_FROM_UPPER, (up && ctx->d_info_node && ctx->nordip > 0 && haveEy) ? kk : 0},
                     {HF_QP_FROM_UPPER, recvQP ? kk - 1 : 0}});
     fill_step_args(ctx, true, a);
