@@ -69,7 +69,7 @@ constexpr int TILE_Z = 8;    // rows per tile (3-D); 2-D grids use 1
 // one work item of k_fast / k_uniform / k_general (built at commit time, 128 bytes)
 struct TileRec
 {
-    int x0, z0, y, pad0;
+    int x0, z0, y, ny;           // ny: number of consecutive y planes the block marches over (k_fast); 1 elsewhere
     unsigned rect[3];            // per component: xlo | xhi<<8 | zlo<<16 | zhi<<24 (tile-local, hi exclusive); 0 = no cell of this component
     unsigned pad1;
     unsigned info[3];            // per component: the one info value of its cells (k_uniform)

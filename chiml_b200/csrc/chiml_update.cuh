@@ -235,38 +235,105 @@ __device__ __forceinline__ void store_pair(double* p, const double2 t, const boo
 // ---------------------------------------------------------------------------------------------------
 // k_fast: tiles whose updated cells are plain interior curl cells (TwoCompCurl / OneCompCurlJ / K)
 // ---------------------------------------------------------------------------------------------------
+// The block marches along y over the t.ny planes of its tile column.  The two stencil neighbours that lie one plane away in y
+// (E half step: H_z[y-1] for E_x, H_x[y-1] for E_z; H half step: E_z[y+1] for H_x, E_x[y+1] for H_z) are carried in registers
+// from one plane to the next, so every array crosses HBM exactly once per half step however far apart in time the tiles of
+// neighbouring planes would otherwise run (a whole y plane of tiles is ~150 MB of traffic: more than L2 holds).
 template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(256, 4) k_fast(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+__global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
 {
     const TileRec& t = tiles[blockIdx.x];
     const int xl = 2 * threadIdx.x, zl = threadIdx.y;
     const int x = t.x0 + xl, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
-    const long r = x + a.px * (z + (long)a.lz * t.y);
-    PairLoads<IS_E, MODE> L;
-    L.load(a, r);
+    constexpr int S = IS_E ? -1 : 1;
+    const long plane = a.px * a.lz;
+    long r = x + a.px * (z + (long)a.lz * t.y);
+    const int ny = t.ny;
+    bool m0[3], m1[3];
+    double2 pf[3];
 #pragma unroll
     for(int c = 0; c < 3; ++c)
     {
-        if(!has_own<IS_E, MODE>(c)) continue;
-        const unsigned rect = t.rect[c];
-        if(rect == 0) continue;                       // nothing of this component in the tile
-        bool m0, m1;
-        rect_mask(rect, xl, zl, m0, m1);
-        const double2 pf = t.pf[c];                   // {pf1, pf2}
-        const double2 vj = L.v[(c + 1) % 3], vk = L.v[(c + 2) % 3];
-        double2 w = L.u[c];
-        if(has_other<IS_E, MODE>((c + 1) % 3))
+        m0[c] = m1[c] = false;
+        if(has_own<IS_E, MODE>(c) && t.rect[c] != 0) rect_mask(t.rect[c], xl, zl, m0[c], m1[c]);
+        pf[c] = t.pf[c];
+    }
+    const double* __restrict__ f0 = a.fam[0];
+    const double* __restrict__ f1 = a.fam[1];
+    const double* __restrict__ f2 = a.fam[2];
+    // carried planes of the y-coupled arrays: E half step: the plane below; H half step: the current plane (loaded as "next" before)
+    constexpr bool Y0 = has_own<IS_E, MODE>(2) && has_other<IS_E, MODE>(0);   // own z reads other x one plane away
+    constexpr bool Y2 = has_own<IS_E, MODE>(0) && has_other<IS_E, MODE>(2);   // own x reads other z one plane away
+    double2 c0 = make_double2(0.0, 0.0), c2 = make_double2(0.0, 0.0);
+    if(IS_E)
+    {
+        if(Y0) c0 = *reinterpret_cast<const double2*>(f0 + r - plane);
+        if(Y2) c2 = *reinterpret_cast<const double2*>(f2 + r - plane);
+    }
+    else
+    {
+        if(Y0) c0 = *reinterpret_cast<const double2*>(f0 + r);
+        if(Y2) c2 = *reinterpret_cast<const double2*>(f2 + r);
+    }
+    for(int iy = 0; iy < ny; ++iy, r += plane)
+    {
+        double2 v[3], nj[3], nk[3], u[3];
+#pragma unroll
+        for(int c = 0; c < 3; ++c) v[c] = nj[c] = nk[c] = u[c] = make_double2(0.0, 0.0);
+#pragma unroll
+        for(int c = 0; c < 3; ++c)
+            if(has_own<IS_E, MODE>(c)) u[c] = *reinterpret_cast<const double2*>(a.c[c].U + r);
+        double2 n0 = make_double2(0.0, 0.0), n2 = make_double2(0.0, 0.0);   // H half step: the plane above
+        if(IS_E)
         {
-            w.x = axpy1(w.x,  pf.y, vj.x);      w.y = axpy1(w.y,  pf.y, vj.y);
-            w.x = axpy1(w.x, -pf.y, L.nj[c].x); w.y = axpy1(w.y, -pf.y, L.nj[c].y);
+            if(has_other<IS_E, MODE>(0)) v[0] = *reinterpret_cast<const double2*>(f0 + r);
+            if(has_other<IS_E, MODE>(2)) v[2] = *reinterpret_cast<const double2*>(f2 + r);
         }
-        if(has_other<IS_E, MODE>((c + 2) % 3))
+        else
         {
-            w.x = axpy1(w.x, -pf.x, vk.x);      w.y = axpy1(w.y, -pf.x, vk.y);
-            w.x = axpy1(w.x,  pf.x, L.nk[c].x); w.y = axpy1(w.y,  pf.x, L.nk[c].y);
+            if(Y0) { v[0] = c0; n0 = *reinterpret_cast<const double2*>(f0 + r + plane); }
+            else if(has_other<IS_E, MODE>(0)) v[0] = *reinterpret_cast<const double2*>(f0 + r);
+            if(Y2) { v[2] = c2; n2 = *reinterpret_cast<const double2*>(f2 + r + plane); }
+            else if(has_other<IS_E, MODE>(2)) v[2] = *reinterpret_cast<const double2*>(f2 + r);
         }
-        store_pair(a.c[c].U + r, w, m0, m1);
+        if(has_other<IS_E, MODE>(1)) v[1] = *reinterpret_cast<const double2*>(f1 + r);
+        // component c: grid_j = other[(c+1)%3] along axis (c+2)%3; grid_k = other[(c+2)%3] along axis (c+1)%3
+        if(has_own<IS_E, MODE>(0))
+        {
+            if(has_other<IS_E, MODE>(1)) nj[0] = neighbour2<2, S>(f1, r, a.px, plane, v[1]);
+            if(has_other<IS_E, MODE>(2)) nk[0] = IS_E ? c2 : n2;
+        }
+        if(has_own<IS_E, MODE>(1))
+        {
+            if(has_other<IS_E, MODE>(2)) nj[1] = neighbour2<0, S>(f2, r, a.px, plane, v[2]);
+            if(has_other<IS_E, MODE>(0)) nk[1] = neighbour2<2, S>(f0, r, a.px, plane, v[0]);
+        }
+        if(has_own<IS_E, MODE>(2))
+        {
+            if(has_other<IS_E, MODE>(0)) nj[2] = IS_E ? c0 : n0;
+            if(has_other<IS_E, MODE>(1)) nk[2] = neighbour2<0, S>(f1, r, a.px, plane, v[1]);
+        }
+#pragma unroll
+        for(int c = 0; c < 3; ++c)
+        {
+            if(!has_own<IS_E, MODE>(c)) continue;
+            if(!(m0[c] || m1[c])) continue;
+            const double2 vj = v[(c + 1) % 3], vk = v[(c + 2) % 3];
+            double2 w = u[c];
+            if(has_other<IS_E, MODE>((c + 1) % 3))
+            {
+                w.x = axpy1(w.x,  pf[c].y, vj.x);    w.y = axpy1(w.y,  pf[c].y, vj.y);
+                w.x = axpy1(w.x, -pf[c].y, nj[c].x); w.y = axpy1(w.y, -pf[c].y, nj[c].y);
+            }
+            if(has_other<IS_E, MODE>((c + 2) % 3))
+            {
+                w.x = axpy1(w.x, -pf[c].x, vk.x);    w.y = axpy1(w.y, -pf[c].x, vk.y);
+                w.x = axpy1(w.x,  pf[c].x, nk[c].x); w.y = axpy1(w.y,  pf[c].x, nk[c].y);
+            }
+            store_pair(a.c[c].U + r, w, m0[c], m1[c]);
+        }
+        if(IS_E) { c0 = v[0]; c2 = v[2]; } else { if(Y0) c0 = n0; if(Y2) c2 = n2; }
     }
 }
 
