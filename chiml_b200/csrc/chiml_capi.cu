@@ -762,25 +762,29 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 constexpr int MARCH_NY = 32;
                 const bool hasLo = ctx->g.rank > 0, hasUp = ctx->g.rank < ctx->g.nranks - 1;
                 auto isBnd = [&](const TileRec& t) { return (hasLo && t.y == 1) || (hasUp && t.y == ctx->ly - 2); };
-                std::vector<TileRec>& fl = lists[0];
-                std::stable_sort(fl.begin(), fl.end(), [](const TileRec& p, const TileRec& q) {
-                    return std::tie(p.z0, p.x0, p.y) < std::tie(q.z0, q.x0, q.y); });
-                std::vector<TileRec> merged;
-                for(const TileRec& t : fl)
+                for(int kind = 0; kind < 2; ++kind)      // FAST and UNIFORM lists
                 {
-                    if(!merged.empty())
+                    std::vector<TileRec>& fl = lists[kind];
+                    std::stable_sort(fl.begin(), fl.end(), [](const TileRec& p, const TileRec& q) {
+                        return std::tie(p.z0, p.x0, p.y) < std::tie(q.z0, q.x0, q.y); });
+                    std::vector<TileRec> merged;
+                    for(const TileRec& t : fl)
                     {
-                        TileRec& m = merged.back();
-                        const bool same = m.x0 == t.x0 && m.z0 == t.z0 && m.y + m.ny == t.y && m.ny < MARCH_NY && !isBnd(m) && !isBnd(t) &&
-                                          std::memcmp(m.rect, t.rect, sizeof(m.rect)) == 0 && std::memcmp(m.pf, t.pf, sizeof(m.pf)) == 0;
-                        if(same) { ++m.ny; continue; }
+                        if(!merged.empty())
+                        {
+                            TileRec& m = merged.back();
+                            const bool same = m.x0 == t.x0 && m.z0 == t.z0 && m.y + m.ny == t.y && m.ny < MARCH_NY && !isBnd(m) && !isBnd(t) &&
+                                              std::memcmp(m.rect, t.rect, sizeof(m.rect)) == 0 && std::memcmp(m.pf, t.pf, sizeof(m.pf)) == 0 &&
+                                              std::memcmp(m.info, t.info, sizeof(m.info)) == 0 && std::memcmp(m.inv_eps, t.inv_eps, sizeof(m.inv_eps)) == 0;
+                            if(same) { ++m.ny; continue; }
+                        }
+                        merged.push_back(t);
                     }
-                    merged.push_back(t);
+                    // launch order: by first plane, then z, then x -- neighbouring blocks stream neighbouring rows
+                    std::stable_sort(merged.begin(), merged.end(), [](const TileRec& p, const TileRec& q) {
+                        return std::tie(p.y, p.z0, p.x0) < std::tie(q.y, q.z0, q.x0); });
+                    fl.swap(merged);
                 }
-                // launch order: by first plane, then z, then x -- neighbouring blocks stream neighbouring rows
-                std::stable_sort(merged.begin(), merged.end(), [](const TileRec& p, const TileRec& q) {
-                    return std::tie(p.y, p.z0, p.x0) < std::tie(q.y, q.z0, q.x0); });
-                fl.swap(merged);
             }
             // tiles of a row that a neighbouring slab reads go first: they are launched on their own, ahead of the halo push
             const bool hasLower = ctx->g.rank > 0, hasUpper = ctx->g.rank < ctx->g.nranks - 1;

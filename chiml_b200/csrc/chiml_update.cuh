@@ -450,20 +450,85 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
     if(dDirty) store_pair(ca.D + r, dv, m0, m1);
 }
 
+// One plane of loads for a block that marches along y (see k_fast): fills L for the plane at r; c0 / c2 carry the y-coupled arrays
+// from plane to plane (E half step: the plane below; H half step: the current plane, loaded as "next" one iteration earlier).
 template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(256, 3) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+__device__ __forceinline__ void march_load(const StepArgs& a, const long r, const long plane, double2& c0, double2& c2, PairLoads<IS_E, MODE>& L)
+{
+    constexpr int S = IS_E ? -1 : 1;
+    constexpr bool Y0 = has_own<IS_E, MODE>(2) && has_other<IS_E, MODE>(0);
+    constexpr bool Y2 = has_own<IS_E, MODE>(0) && has_other<IS_E, MODE>(2);
+    const double* __restrict__ f0 = a.fam[0];
+    const double* __restrict__ f1 = a.fam[1];
+    const double* __restrict__ f2 = a.fam[2];
+#pragma unroll
+    for(int c = 0; c < 3; ++c) L.u[c] = L.v[c] = L.nj[c] = L.nk[c] = make_double2(0.0, 0.0);
+#pragma unroll
+    for(int c = 0; c < 3; ++c)
+        if(has_own<IS_E, MODE>(c)) L.u[c] = *reinterpret_cast<const double2*>(a.c[c].U + r);
+    double2 n0 = make_double2(0.0, 0.0), n2 = make_double2(0.0, 0.0);
+    if(IS_E)
+    {
+        if(has_other<IS_E, MODE>(0)) L.v[0] = *reinterpret_cast<const double2*>(f0 + r);
+        if(has_other<IS_E, MODE>(2)) L.v[2] = *reinterpret_cast<const double2*>(f2 + r);
+    }
+    else
+    {
+        if(Y0) { L.v[0] = c0; n0 = *reinterpret_cast<const double2*>(f0 + r + plane); }
+        else if(has_other<IS_E, MODE>(0)) L.v[0] = *reinterpret_cast<const double2*>(f0 + r);
+        if(Y2) { L.v[2] = c2; n2 = *reinterpret_cast<const double2*>(f2 + r + plane); }
+        else if(has_other<IS_E, MODE>(2)) L.v[2] = *reinterpret_cast<const double2*>(f2 + r);
+    }
+    if(has_other<IS_E, MODE>(1)) L.v[1] = *reinterpret_cast<const double2*>(f1 + r);
+    if(has_own<IS_E, MODE>(0))
+    {
+        if(has_other<IS_E, MODE>(1)) L.nj[0] = neighbour2<2, S>(f1, r, a.px, plane, L.v[1]);
+        if(has_other<IS_E, MODE>(2)) L.nk[0] = IS_E ? c2 : n2;
+    }
+    if(has_own<IS_E, MODE>(1))
+    {
+        if(has_other<IS_E, MODE>(2)) L.nj[1] = neighbour2<0, S>(f2, r, a.px, plane, L.v[2]);
+        if(has_other<IS_E, MODE>(0)) L.nk[1] = neighbour2<2, S>(f0, r, a.px, plane, L.v[0]);
+    }
+    if(has_own<IS_E, MODE>(2))
+    {
+        if(has_other<IS_E, MODE>(0)) L.nj[2] = IS_E ? c0 : n0;
+        if(has_other<IS_E, MODE>(1)) L.nk[2] = neighbour2<0, S>(f1, r, a.px, plane, L.v[1]);
+    }
+    if(IS_E) { c0 = L.v[0]; c2 = L.v[2]; } else { if(Y0) c0 = n0; if(Y2) c2 = n2; }
+}
+template <bool IS_E, int MODE>
+__device__ __forceinline__ void march_init(const StepArgs& a, const long r, const long plane, double2& c0, double2& c2)
+{
+    constexpr bool Y0 = has_own<IS_E, MODE>(2) && has_other<IS_E, MODE>(0);
+    constexpr bool Y2 = has_own<IS_E, MODE>(0) && has_other<IS_E, MODE>(2);
+    c0 = c2 = make_double2(0.0, 0.0);
+    const long o = IS_E ? r - plane : r;
+    if(Y0) c0 = *reinterpret_cast<const double2*>(a.fam[0] + o);
+    if(Y2) c2 = *reinterpret_cast<const double2*>(a.fam[2] + o);
+}
+
+template <bool IS_E, int MODE>
+__global__ void __launch_bounds__(256, 2) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
 {
     const TileRec& t = tiles[blockIdx.x];
     const int xl = 2 * threadIdx.x, zl = threadIdx.y;
-    const int x = t.x0 + xl, z = t.z0 + zl, y = t.y;
+    const int x = t.x0 + xl, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
-    const long row = z + (long)a.lz * y;
-    const long r = x + a.px * row;
-    PairLoads<IS_E, MODE> L;
-    L.load(a, r);
-    uniform_comp<IS_E, MODE, 0>(a, t, L, r, row, x, y, z, xl, zl);
-    uniform_comp<IS_E, MODE, 1>(a, t, L, r, row, x, y, z, xl, zl);
-    uniform_comp<IS_E, MODE, 2>(a, t, L, r, row, x, y, z, xl, zl);
+    const long plane = a.px * a.lz;
+    long r = x + a.px * (z + (long)a.lz * t.y);
+    double2 c0, c2;
+    march_init<IS_E, MODE>(a, r, plane, c0, c2);
+    for(int iy = 0; iy < t.ny; ++iy, r += plane)
+    {
+        const int y = t.y + iy;
+        const long row = z + (long)a.lz * y;
+        PairLoads<IS_E, MODE> L;
+        march_load<IS_E, MODE>(a, r, plane, c0, c2, L);
+        uniform_comp<IS_E, MODE, 0>(a, t, L, r, row, x, y, z, xl, zl);
+        uniform_comp<IS_E, MODE, 1>(a, t, L, r, row, x, y, z, xl, zl);
+        uniform_comp<IS_E, MODE, 2>(a, t, L, r, row, x, y, z, xl, zl);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
