@@ -361,10 +361,55 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
     const bool pmlCell = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
     const bool pmlOnD = IS_E && a.pml_on_D;
     const bool needD = IS_E && ((info & (F_ISD | F_D2E)) || (pmlOnD && pmlCell));
+
+    // ---- every load of this component is issued here, before any arithmetic waits on one of them -------------------------
     double2 dv = make_double2(0.0, 0.0);
     if(needD) dv = *reinterpret_cast<const double2*>(ca.D + r);
-    bool dDirty = false;
+    double2 psv[2], Fv[2], bv[2], cv[2];
+    long pip[2] = {0, 0};
+    int2 pcc[2];
+#pragma unroll
+    for(int part = 0; part < 2; ++part)
+    {
+        psv[part] = Fv[part] = bv[part] = cv[part] = make_double2(0.0, 0.0);
+        pcc[part] = make_int2(0, 0);
+        if(part == 0 ? !HAS_VK : !HAS_VJ) continue;
+        const PmlArgs& pp = ca.pml[part];
+        const unsigned fg = part == 0 ? F_PG0 : F_PG1;
+        const unsigned fs = part == 0 ? F_PS0 : F_PS1;
+        if(!(info & (fg | fs))) continue;
+        constexpr int AX0 = (C + 1) % 3, AX1 = (C + 2) % 3;
+        const int axis = part == 0 ? AX0 : AX1;
+        if(axis == 0)
+        {
+            Fv[part] = *reinterpret_cast<const double2*>(pp.F + x);
+            if(info & fs)
+            {
+                bv[part] = *reinterpret_cast<const double2*>(pp.b + x);
+                cv[part] = *reinterpret_cast<const double2*>(pp.c + x);
+                pcc[part] = *reinterpret_cast<const int2*>(pp.cmap + x);
+                pip[part] = pp.psi_pitch * row;
+                if(m0) psv[part].x = pp.psi[pip[part] + pcc[part].x];
+                if(m1) psv[part].y = pp.psi[pip[part] + pcc[part].y];
+            }
+        }
+        else
+        {
+            const int coord = axis == 1 ? y : z;
+            const double f = pp.F[coord];
+            Fv[part] = make_double2(f, f);
+            if(info & fs)
+            {
+                const double bb = pp.b[coord], cc = pp.c[coord];
+                bv[part] = make_double2(bb, bb); cv[part] = make_double2(cc, cc);
+                const int cm = pp.cmap[coord];
+                pip[part] = axis == 1 ? x + a.px * (z + (long)a.lz * cm) : x + a.px * (cm + (long)pp.nact * y);
+                psv[part] = *reinterpret_cast<const double2*>(pp.psi + pip[part]);
+            }
+        }
+    }
 
+    bool dDirty = false;
     if(info & F_CURL)
     {
         const double2 pf = t.pf[C];
@@ -397,44 +442,24 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
             const double2 vr = part == 0 ? vk : vj;
             const double2 vo = part == 0 ? nk : nj;
             double2 ps = make_double2(0.0, 0.0);
-            double2 Fv, bv, cv;
-            if(axis == 0)
-            {
-                Fv = *reinterpret_cast<const double2*>(pp.F + x);
-                if(info & fs) { bv = *reinterpret_cast<const double2*>(pp.b + x); cv = *reinterpret_cast<const double2*>(pp.c + x); }
-            }
-            else
-            {
-                const int coord = axis == 1 ? y : z;
-                const double f = pp.F[coord];
-                Fv = make_double2(f, f);
-                if(info & fs) { const double bb = pp.b[coord], cc = pp.c[coord]; bv = make_double2(bb, bb); cv = make_double2(cc, cc); }
-            }
             if(info & fs)
             {
+                double2 p = psv[part];
+                p.x = dm(bv[part].x, p.x);            p.y = dm(bv[part].y, p.y);
+                p.x = axpy1(p.x,  cv[part].x, vr.x);  p.y = axpy1(p.y,  cv[part].y, vr.y);
+                p.x = axpy1(p.x, -cv[part].x, vo.x);  p.y = axpy1(p.y, -cv[part].y, vo.y);
                 if(axis == 0)
                 {
-                    const int2 cc = *reinterpret_cast<const int2*>(pp.cmap + x);
-                    const long base = pp.psi_pitch * row;
-                    if(m0) { double p = dm(bv.x, pp.psi[base + cc.x]); p = axpy1(p, cv.x, vr.x); p = axpy1(p, -cv.x, vo.x); pp.psi[base + cc.x] = p; ps.x = p; }
-                    if(m1) { double p = dm(bv.y, pp.psi[base + cc.y]); p = axpy1(p, cv.y, vr.y); p = axpy1(p, -cv.y, vo.y); pp.psi[base + cc.y] = p; ps.y = p; }
+                    if(m0) pp.psi[pip[part] + pcc[part].x] = p.x;
+                    if(m1) pp.psi[pip[part] + pcc[part].y] = p.y;
                 }
-                else
-                {
-                    const int cc = pp.cmap[axis == 1 ? y : z];
-                    const long ip = axis == 1 ? x + a.px * (z + (long)a.lz * cc) : x + a.px * (cc + (long)pp.nact * y);
-                    double2 p = *reinterpret_cast<const double2*>(pp.psi + ip);
-                    p.x = dm(bv.x, p.x);            p.y = dm(bv.y, p.y);
-                    p.x = axpy1(p.x,  cv.x, vr.x);  p.y = axpy1(p.y,  cv.y, vr.y);
-                    p.x = axpy1(p.x, -cv.x, vo.x);  p.y = axpy1(p.y, -cv.y, vo.y);
-                    store_pair(pp.psi + ip, p, m0, m1);
-                    ps = p;
-                }
+                else store_pair(pp.psi + pip[part], p, m0, m1);
+                ps = p;
             }
             if(info & fg)
             {
-                w.x = axpy1(w.x,  Fv.x, vr.x); w.y = axpy1(w.y,  Fv.y, vr.y);
-                w.x = axpy1(w.x, -Fv.x, vo.x); w.y = axpy1(w.y, -Fv.y, vo.y);
+                w.x = axpy1(w.x,  Fv[part].x, vr.x); w.y = axpy1(w.y,  Fv[part].y, vr.y);
+                w.x = axpy1(w.x, -Fv[part].x, vo.x); w.y = axpy1(w.y, -Fv[part].y, vo.y);
                 if(info & fs) { w.x = axpy1(w.x, pp.Db, ps.x); w.y = axpy1(w.y, pp.Db, ps.y); }
             }
         }
@@ -508,27 +533,73 @@ __device__ __forceinline__ void march_init(const StepArgs& a, const long r, cons
     if(Y2) c2 = *reinterpret_cast<const double2*>(a.fam[2] + o);
 }
 
+// One component per thread (blockDim.z selects it): each thread issues the <= 8 independent loads of ITS component at once -- own
+// value, the two driving arrays at the cell, their two stencil neighbours, D, psi -- so a plane costs one memory latency instead
+// of one per component, and three times as many warps are resident.  The driving arrays are shared between components; the
+// second reader hits L1.  y-coupled neighbours are carried in registers while the block marches along y (see k_fast).
+template <bool IS_E, int MODE, int C>
+__device__ __forceinline__ void comp_march_init(const StepArgs& a, const long r, const long plane, double2& carry)
+{
+    // component 0 reads other[2] one plane away in y (grid_k), component 2 reads other[0] (grid_j); component 1 has no y neighbour
+    carry = make_double2(0.0, 0.0);
+    constexpr int SRC = C == 0 ? 2 : 0;
+    if(C != 1 && has_other<IS_E, MODE>(SRC)) carry = *reinterpret_cast<const double2*>(a.fam[SRC] + (IS_E ? r - plane : r));
+}
+template <bool IS_E, int MODE, int C>
+__device__ __forceinline__ void comp_march_load(const StepArgs& a, const long r, const long plane, double2& carry, PairLoads<IS_E, MODE>& L)
+{
+    constexpr int S = IS_E ? -1 : 1;
+    constexpr int J = (C + 1) % 3, K = (C + 2) % 3;           // grid_j = other[J] (neighbour along axis K), grid_k = other[K] (along axis J)
+    const double* __restrict__ fj = a.fam[J];
+    const double* __restrict__ fk = a.fam[K];
+    L.u[C] = *reinterpret_cast<const double2*>(a.c[C].U + r);
+    L.v[J] = L.v[K] = L.nj[C] = L.nk[C] = make_double2(0.0, 0.0);
+    // which of the two driving arrays is the y-coupled one: axis K == 1 -> grid_j (C == 2); axis J == 1 -> grid_k (C == 0)
+    constexpr bool JY = K == 1, KY = J == 1;
+    double2 nextPlane = make_double2(0.0, 0.0);
+    if(has_other<IS_E, MODE>(J))
+    {
+        if(JY && !IS_E) { L.v[J] = carry; nextPlane = *reinterpret_cast<const double2*>(fj + r + plane); }
+        else L.v[J] = *reinterpret_cast<const double2*>(fj + r);
+    }
+    if(has_other<IS_E, MODE>(K))
+    {
+        if(KY && !IS_E) { L.v[K] = carry; nextPlane = *reinterpret_cast<const double2*>(fk + r + plane); }
+        else L.v[K] = *reinterpret_cast<const double2*>(fk + r);
+    }
+    if(has_other<IS_E, MODE>(J)) L.nj[C] = JY ? (IS_E ? carry : nextPlane) : neighbour2<K, S>(fj, r, a.px, plane, L.v[J]);
+    if(has_other<IS_E, MODE>(K)) L.nk[C] = KY ? (IS_E ? carry : nextPlane) : neighbour2<J, S>(fk, r, a.px, plane, L.v[K]);
+    if(JY && has_other<IS_E, MODE>(J)) carry = IS_E ? L.v[J] : nextPlane;
+    if(KY && has_other<IS_E, MODE>(K)) carry = IS_E ? L.v[K] : nextPlane;
+}
+
+template <bool IS_E, int MODE, int C>
+__device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& t, const int xl, const int zl, const int x, const int z)
+{
+    if(!has_own<IS_E, MODE>(C) || t.rect[C] == 0) return;
+    const long plane = a.px * a.lz;
+    long r = x + a.px * (z + (long)a.lz * t.y);
+    double2 carry;
+    comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
+    for(int iy = 0; iy < t.ny; ++iy, r += plane)
+    {
+        const int y = t.y + iy;
+        PairLoads<IS_E, MODE> L;
+        comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L);
+        uniform_comp<IS_E, MODE, C>(a, t, L, r, z + (long)a.lz * y, x, y, z, xl, zl);
+    }
+}
+
 template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(256, 2) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+__global__ void __launch_bounds__(768, 1) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
 {
     const TileRec& t = tiles[blockIdx.x];
     const int xl = 2 * threadIdx.x, zl = threadIdx.y;
     const int x = t.x0 + xl, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
-    const long plane = a.px * a.lz;
-    long r = x + a.px * (z + (long)a.lz * t.y);
-    double2 c0, c2;
-    march_init<IS_E, MODE>(a, r, plane, c0, c2);
-    for(int iy = 0; iy < t.ny; ++iy, r += plane)
-    {
-        const int y = t.y + iy;
-        const long row = z + (long)a.lz * y;
-        PairLoads<IS_E, MODE> L;
-        march_load<IS_E, MODE>(a, r, plane, c0, c2, L);
-        uniform_comp<IS_E, MODE, 0>(a, t, L, r, row, x, y, z, xl, zl);
-        uniform_comp<IS_E, MODE, 1>(a, t, L, r, row, x, y, z, xl, zl);
-        uniform_comp<IS_E, MODE, 2>(a, t, L, r, row, x, y, z, xl, zl);
-    }
+    if(threadIdx.z == 0)      uniform_march<IS_E, MODE, 0>(a, t, xl, zl, x, z);
+    else if(threadIdx.z == 1) uniform_march<IS_E, MODE, 1>(a, t, xl, zl, x, z);
+    else                      uniform_march<IS_E, MODE, 2>(a, t, xl, zl, x, z);
 }
 
 // ---------------------------------------------------------------------------------------------------
