@@ -40,6 +40,8 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
                                             const long r, const long row, const int x, const int y, const int z)
 {
     if(info == 0) return false;
+    // D is needed by almost every cell of a general E tile: fetch it before anything that depends on the class table
+    const double dIn = (IS_E && ca.D) ? ca.D[r] : 0.0;
     const ClassEntry& ce = ca.cls[info & CLS_MASK];
     constexpr bool HAS_VJ = has_other<IS_E, MODE>((C + 1) % 3);
     constexpr bool HAS_VK = has_other<IS_E, MODE>((C + 2) % 3);
@@ -73,7 +75,7 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
     const bool pmlCell = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
     const bool pmlOnD = IS_E && a.pml_on_D;
     const bool needD = IS_E && ((info & (F_ISD | F_D2E | F_ORD2E)) || (pmlOnD && pmlCell));
-    double dv = needD ? ca.D[r] : 0.0;
+    double dv = needD ? dIn : 0.0;
     bool dDirty = false;
 
     // updateD / updateE / updateH: TwoCompCurl, OneCompCurlJ, OneCompCurlK (UTIL/FDTD_up_eq.cpp:10-35)
@@ -617,19 +619,31 @@ __device__ __forceinline__ void general_pair(const StepArgs& a, double2 u, const
     store_pair(ca.U + r, u, w0, w1);
 }
 
-template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(256, 2) k_general(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+// one component per thread (threadIdx.z), like k_uniform: the loads of a component do not queue behind the arithmetic of another
+template <bool IS_E, int MODE, int C>
+__device__ __forceinline__ void general_comp(const StepArgs& a, const TileRec& t, const int x, const int z)
 {
-    const TileRec& t = tiles[blockIdx.x];
-    const int x = t.x0 + 2 * threadIdx.x, z = t.z0 + threadIdx.y, y = t.y;
-    if(x >= a.px || z >= a.lz) return;
+    if(!has_own<IS_E, MODE>(C)) return;
+    const long plane = a.px * a.lz;
+    const int y = t.y;
     const long row = z + (long)a.lz * y;
     const long r = x + a.px * row;
+    double2 carry;
+    comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
     PairLoads<IS_E, MODE> L;
-    L.load(a, r);
-    general_pair<IS_E, MODE, 0>(a, L.u[0], L.v[1], L.nj[0], L.v[2], L.nk[0], r, row, x, y, z);
-    general_pair<IS_E, MODE, 1>(a, L.u[1], L.v[2], L.nj[1], L.v[0], L.nk[1], r, row, x, y, z);
-    general_pair<IS_E, MODE, 2>(a, L.u[2], L.v[0], L.nj[2], L.v[1], L.nk[2], r, row, x, y, z);
+    comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L);
+    general_pair<IS_E, MODE, C>(a, L.u[C], L.v[(C + 1) % 3], L.nj[C], L.v[(C + 2) % 3], L.nk[C], r, row, x, y, z);
+}
+
+template <bool IS_E, int MODE>
+__global__ void __launch_bounds__(768, 1) k_general(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+{
+    const TileRec& t = tiles[blockIdx.x];
+    const int x = t.x0 + 2 * threadIdx.x, z = t.z0 + threadIdx.y;
+    if(x >= a.px || z >= a.lz) return;
+    if(threadIdx.z == 0)      general_comp<IS_E, MODE, 0>(a, t, x, z);
+    else if(threadIdx.z == 1) general_comp<IS_E, MODE, 1>(a, t, x, z);
+    else                      general_comp<IS_E, MODE, 2>(a, t, x, z);
 }
 
 // ---------------------------------------------------------------------------------------------------
