@@ -592,13 +592,33 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
     }
 }
 
-template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(768, 1) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+// The E half step (D and psi arrays per component) gains from the split; the H half step, whose traffic is mostly the shared driving
+// arrays, is faster with all three components in one thread (measured: profiles/README.md), so it is launched with blockDim.z = 1.
+template <bool IS_E, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
 {
     const TileRec& t = tiles[blockIdx.x];
     const int xl = 2 * threadIdx.x, zl = threadIdx.y;
     const int x = t.x0 + xl, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
+    if(!SPLIT)
+    {
+        const long plane = a.px * a.lz;
+        long r = x + a.px * (z + (long)a.lz * t.y);
+        double2 c0, c2;
+        march_init<IS_E, MODE>(a, r, plane, c0, c2);
+        for(int iy = 0; iy < t.ny; ++iy, r += plane)
+        {
+            const int y = t.y + iy;
+            const long row = z + (long)a.lz * y;
+            PairLoads<IS_E, MODE> L;
+            march_load<IS_E, MODE>(a, r, plane, c0, c2, L);
+            uniform_comp<IS_E, MODE, 0>(a, t, L, r, row, x, y, z, xl, zl);
+            uniform_comp<IS_E, MODE, 1>(a, t, L, r, row, x, y, z, xl, zl);
+            uniform_comp<IS_E, MODE, 2>(a, t, L, r, row, x, y, z, xl, zl);
+        }
+        return;
+    }
     if(threadIdx.z == 0)      uniform_march<IS_E, MODE, 0>(a, t, xl, zl, x, z);
     else if(threadIdx.z == 1) uniform_march<IS_E, MODE, 1>(a, t, xl, zl, x, z);
     else                      uniform_march<IS_E, MODE, 2>(a, t, xl, zl, x, z);
@@ -635,12 +655,24 @@ __device__ __forceinline__ void general_comp(const StepArgs& a, const TileRec& t
     general_pair<IS_E, MODE, C>(a, L.u[C], L.v[(C + 1) % 3], L.nj[C], L.v[(C + 2) % 3], L.nk[C], r, row, x, y, z);
 }
 
-template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(768, 1) k_general(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+template <bool IS_E, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_general(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
 {
     const TileRec& t = tiles[blockIdx.x];
     const int x = t.x0 + 2 * threadIdx.x, z = t.z0 + threadIdx.y;
     if(x >= a.px || z >= a.lz) return;
+    if(!SPLIT)
+    {
+        const int y = t.y;
+        const long row = z + (long)a.lz * y;
+        const long r = x + a.px * row;
+        PairLoads<IS_E, MODE> L;
+        L.load(a, r);
+        general_pair<IS_E, MODE, 0>(a, L.u[0], L.v[1], L.nj[0], L.v[2], L.nk[0], r, row, x, y, z);
+        general_pair<IS_E, MODE, 1>(a, L.u[1], L.v[2], L.nj[1], L.v[0], L.nk[1], r, row, x, y, z);
+        general_pair<IS_E, MODE, 2>(a, L.u[2], L.v[0], L.nj[2], L.v[1], L.nk[2], r, row, x, y, z);
+        return;
+    }
     if(threadIdx.z == 0)      general_comp<IS_E, MODE, 0>(a, t, x, z);
     else if(threadIdx.z == 1) general_comp<IS_E, MODE, 1>(a, t, x, z);
     else                      general_comp<IS_E, MODE, 2>(a, t, x, z);
