@@ -729,7 +729,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
             for(size_t tIdx = 0; tIdx < ntiles; ++tIdx)
             {
                 const TileSummary& ts = sum[tIdx];
-                if(!(ts.count[0] | ts.count[1] | ts.count[2])) continue;
+                if(!(ts.total[0] | ts.total[1] | ts.total[2])) continue;
                 TileRec rec;
                 std::memset(&rec, 0, sizeof(rec));
                 rec.x0 = (int)(tIdx % nxt) * TILE_X;
@@ -737,21 +737,23 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 rec.y = (int)(tIdx / ((size_t)nxt * nzt));
                 rec.ny = 1;
                 bool fast = true, uniform = true;
+                auto area = [](unsigned rc_) { return (((rc_ >> 8) & 0xFF) - (rc_ & 0xFF)) * ((rc_ >> 24) - ((rc_ >> 16) & 0xFF)); };
                 for(int c = 0; c < 3; ++c)
                 {
-                    if(!ts.count[c]) continue;
-                    const unsigned rc_ = ts.rect[c];
-                    const unsigned area = (((rc_ >> 8) & 0xFF) - (rc_ & 0xFF)) * ((rc_ >> 24) - ((rc_ >> 16) & 0xFF));
-                    const unsigned inf = ts.info[c];
-                    const ClassEntry& ce = ctx->h_cls[b0 + c][inf & CLS_MASK];
-                    const bool rectFull = ts.same[c] && area == ts.count[c];
-                    if(!rectFull) { fast = uniform = false; continue; }
-                    if((inf & 0xFF00u) != F_CURL) fast = false;
-                    if((inf & F_ORD2E) || ((inf & F_D2E) && ce.npoles > 0)) uniform = false;
-                    rec.rect[c] = rc_;
-                    rec.info[c] = inf;
-                    rec.pf[c] = make_double2(ce.pf1, ce.pf2);
-                    rec.inv_eps[c] = ce.inv_eps;
+                    if(!ts.total[c]) continue;
+                    const bool two = ts.countB[c] > 0;
+                    const bool full = !ts.other[c] && area(ts.rect[c]) == ts.count[c] && (!two || area(ts.rectB[c]) == ts.countB[c]) &&
+                                      ts.count[c] + ts.countB[c] == ts.total[c];
+                    if(!full) { fast = uniform = false; continue; }
+                    for(int w = 0; w < (two ? 2 : 1); ++w)
+                    {
+                        const unsigned inf = w == 0 ? ts.info[c] : ts.infoB[c];
+                        const ClassEntry& ce = ctx->h_cls[b0 + c][inf & CLS_MASK];
+                        if((inf & 0xFF00u) != F_CURL || two) fast = false;
+                        if((inf & F_ORD2E) || ((inf & F_D2E) && ce.npoles > 0)) uniform = false;
+                        if(w == 0) { rec.rect[c] = ts.rect[c]; rec.info[c] = inf; rec.pf[c] = make_double2(ce.pf1, ce.pf2); rec.inv_eps[c] = ce.inv_eps; }
+                        else       { rec.rectB[c] = ts.rectB[c]; rec.infoB[c] = inf; rec.pfB[c] = make_double2(ce.pf1, ce.pf2); rec.inv_epsB[c] = ce.inv_eps; }
+                    }
                 }
                 lists[fast ? 0 : (uniform ? 1 : 2)].push_back(rec);
                 listBytes[fast ? 0 : (uniform ? 1 : 2)] += ts.bytes;
@@ -775,7 +777,9 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                             TileRec& m = merged.back();
                             const bool same = m.x0 == t.x0 && m.z0 == t.z0 && m.y + m.ny == t.y && m.ny < MARCH_NY && !isBnd(m) && !isBnd(t) &&
                                               std::memcmp(m.rect, t.rect, sizeof(m.rect)) == 0 && std::memcmp(m.pf, t.pf, sizeof(m.pf)) == 0 &&
-                                              std::memcmp(m.info, t.info, sizeof(m.info)) == 0 && std::memcmp(m.inv_eps, t.inv_eps, sizeof(m.inv_eps)) == 0;
+                                              std::memcmp(m.info, t.info, sizeof(m.info)) == 0 && std::memcmp(m.inv_eps, t.inv_eps, sizeof(m.inv_eps)) == 0 &&
+                                              std::memcmp(m.rectB, t.rectB, sizeof(m.rectB)) == 0 && std::memcmp(m.infoB, t.infoB, sizeof(m.infoB)) == 0 &&
+                                              std::memcmp(m.pfB, t.pfB, sizeof(m.pfB)) == 0 && std::memcmp(m.inv_epsB, t.inv_epsB, sizeof(m.inv_epsB)) == 0;
                             if(same) { ++m.ny; continue; }
                         }
                         merged.push_back(t);

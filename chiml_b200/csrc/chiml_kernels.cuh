@@ -66,7 +66,7 @@ struct StepArgs
 constexpr int TILE_X = 64;   // cells per tile row (32 lanes x 2 cells)
 constexpr int TILE_Z = 8;    // rows per tile (3-D); 2-D grids use 1
 
-// one work item of k_fast / k_uniform / k_general (built at commit time, 128 bytes)
+// one work item of k_fast / k_uniform / k_general (built at commit time)
 struct TileRec
 {
     int x0, z0, y, ny;           // ny: number of consecutive y planes the block marches over (k_fast); 1 elsewhere
@@ -77,6 +77,12 @@ struct TileRec
     double2 pf[3];               // per component: {pf1, pf2} of its class
     double inv_eps[3];           // per component: 1/eps of its class (pole-free D->E)
     double pad3;
+    // second rectangle of a component (k_uniform only; rectB == 0 when the tile has one info value)
+    unsigned rectB[3]; unsigned pad4;
+    unsigned infoB[3]; unsigned pad5;
+    double2 pfB[3];
+    double inv_epsB[3];
+    double pad6;
 };
 
 struct NodeArgs

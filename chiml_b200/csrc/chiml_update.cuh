@@ -344,18 +344,16 @@ __global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArg
 // (psi recursion + grid terms) on E/H or D, pole-free D->E.  Block-uniform control flow, no cell-info reads.
 // ---------------------------------------------------------------------------------------------------
 template <bool IS_E, int MODE, int C>
-__device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t, const PairLoads<IS_E, MODE>& L,
+__device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned rect, const unsigned info, const double2 pfc, const double inv_eps,
+                                             const PairLoads<IS_E, MODE>& L,
                                              const long r, const long row, const int x, const int y, const int z, const int xl, const int zl)
 {
-    if(!has_own<IS_E, MODE>(C)) return;
-    const unsigned rect = t.rect[C];
-    if(rect == 0) return;
-    const unsigned info = t.info[C];
     const CompArgs& ca = a.c[C];
     constexpr bool HAS_VJ = has_other<IS_E, MODE>((C + 1) % 3);
     constexpr bool HAS_VK = has_other<IS_E, MODE>((C + 2) % 3);
     bool m0, m1;
     rect_mask(rect, xl, zl, m0, m1);
+    if(!(m0 || m1)) return;
     const double2 vj = L.v[(C + 1) % 3], vk = L.v[(C + 2) % 3];
     const double2 nj = L.nj[C], nk = L.nk[C];
     double2 u = L.u[C];
@@ -414,7 +412,7 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
     bool dDirty = false;
     if(info & F_CURL)
     {
-        const double2 pf = t.pf[C];
+        const double2 pf = pfc;
         double2 w = (IS_E && (info & F_ISD)) ? dv : u;
         if(HAS_VJ)
         {
@@ -470,11 +468,28 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
     if(IS_E && (info & F_D2E))
     {
         // DtoU with no pole grids contributing (UTIL/FDTD_up_eq.cpp:838-843): E = (1/eps) * D
-        const double ie = t.inv_eps[C];
+        const double ie = inv_eps;
         u.x = dm(ie, dv.x); u.y = dm(ie, dv.y);
     }
     store_pair(ca.U + r, u, m0, m1);
     if(dDirty) store_pair(ca.D + r, dv, m0, m1);
+}
+
+// a UNIFORM tile holds, per component, one or two rectangles of cells with one info value each (two: a tile cut by a CPML or
+// material boundary); a thread whose two cells lie in different rectangles runs the body once per rectangle
+template <bool IS_E, int MODE, int C>
+__device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t, const PairLoads<IS_E, MODE>& L,
+                                             const long r, const long row, const int x, const int y, const int z, const int xl, const int zl)
+{
+    if(!has_own<IS_E, MODE>(C)) return;
+#pragma unroll 1
+    for(int w = 0; w < 2; ++w)
+    {
+        const unsigned rect = w == 0 ? t.rect[C] : t.rectB[C];
+        if(rect == 0) continue;
+        uniform_rect<IS_E, MODE, C>(a, rect, w == 0 ? t.info[C] : t.infoB[C], w == 0 ? t.pf[C] : t.pfB[C], w == 0 ? t.inv_eps[C] : t.inv_epsB[C],
+                                    L, r, row, x, y, z, xl, zl);
+    }
 }
 
 // One plane of loads for a block that marches along y (see k_fast): fills L for the plane at r; c0 / c2 carry the y-coupled arrays
@@ -578,7 +593,7 @@ __device__ __forceinline__ void comp_march_load(const StepArgs& a, const long r,
 template <bool IS_E, int MODE, int C>
 __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& t, const int xl, const int zl, const int x, const int z)
 {
-    if(!has_own<IS_E, MODE>(C) || t.rect[C] == 0) return;
+    if(!has_own<IS_E, MODE>(C) || (t.rect[C] == 0 && t.rectB[C] == 0)) return;
     const long plane = a.px * a.lz;
     long r = x + a.px * (z + (long)a.lz * t.y);
     double2 carry;
@@ -682,7 +697,15 @@ __global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_general(co
 // commit-time tile summary: per tile and component the bounding rectangle of non-zero info cells, their
 // count, the first non-zero info value and whether all non-zero values are equal.  One block per tile.
 // ---------------------------------------------------------------------------------------------------
-struct TileSummary { unsigned rect[3]; unsigned info[3]; unsigned count[3]; unsigned same[3]; unsigned bytes; unsigned pad[3]; };
+// per component: the (up to) two distinct non-zero info values of the tile -- A = the largest, B = the smallest -- with the bounding
+// rectangle and cell count of each, the total count, and whether a third value occurs
+struct TileSummary
+{
+    unsigned rect[3], info[3], count[3];        // value A
+    unsigned rectB[3], infoB[3], countB[3];     // value B (0 when the tile has one value)
+    unsigned total[3], other[3];
+    unsigned bytes; unsigned pad[3];
+};
 
 // algorithmic bytes one field-component cell moves per step: 16 B RW + 8 B cross-read when it is
 // updated, +16 B when its D value is read and written, +24 B per isotropic pole, +16 B per psi value touched
@@ -710,12 +733,13 @@ __global__ void k_tile_summary(const uint16_t* i0, const uint16_t* i1, const uin
     const unsigned xt = tile % nxt, zt = (tile / nxt) % nzt, y = tile / (nxt * nzt);
     const int xl = 2 * threadIdx.x, zl = threadIdx.y;
     const int x = xt * TILE_X + xl, z = zt * blockDim.y + zl;
-    __shared__ unsigned s_xlo[3], s_xhi[3], s_zlo[3], s_zhi[3], s_cnt[3], s_first[3], s_diff[3];
+    __shared__ unsigned s_lo[2][3][2], s_hi[2][3][2], s_cnt[2][3], s_tot[3], s_vmax[3], s_vmin[3], s_other[3];
     const uint16_t* ip[3] = {i0, i1, i2};
     if(threadIdx.x < 3 && threadIdx.y == 0)
     {
         const int c = threadIdx.x;
-        s_xlo[c] = 255; s_xhi[c] = 0; s_zlo[c] = 255; s_zhi[c] = 0; s_cnt[c] = 0; s_first[c] = 0; s_diff[c] = 0;
+        for(int k = 0; k < 2; ++k) { s_lo[k][c][0] = s_lo[k][c][1] = 255; s_hi[k][c][0] = s_hi[k][c][1] = 0; s_cnt[k][c] = 0; }
+        s_tot[c] = 0; s_vmax[c] = 0; s_vmin[c] = 0xFFFFFFFFu; s_other[c] = 0;
     }
     __syncthreads();
     unsigned v[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -730,26 +754,32 @@ __global__ void k_tile_summary(const uint16_t* i0, const uint16_t* i1, const uin
                 if(v[c][k])
                 {
                     atomicAdd(&s_bytes, cell_alg_bytes(v[c][k], cp[c], isE != 0, pmlOnD != 0));
-                    atomicMin(&s_xlo[c], (unsigned)(xl + k)); atomicMax(&s_xhi[c], (unsigned)(xl + k + 1));
-                    atomicMin(&s_zlo[c], (unsigned)zl);       atomicMax(&s_zhi[c], (unsigned)(zl + 1));
-                    atomicAdd(&s_cnt[c], 1u);
-                    atomicMax(&s_first[c], v[c][k]);   // any representative: the largest value
+                    atomicAdd(&s_tot[c], 1u);
+                    atomicMax(&s_vmax[c], v[c][k]);
+                    atomicMin(&s_vmin[c], v[c][k]);
                 }
         }
     }
     __syncthreads();
     for(int c = 0; c < 3; ++c)
         for(int k = 0; k < 2; ++k)
-            if(v[c][k] && v[c][k] != s_first[c]) s_diff[c] = 1;
+        {
+            if(!v[c][k]) continue;
+            const int w = v[c][k] == s_vmax[c] ? 0 : (v[c][k] == s_vmin[c] ? 1 : -1);
+            if(w < 0) { s_other[c] = 1; continue; }
+            atomicMin(&s_lo[w][c][0], (unsigned)(xl + k)); atomicMax(&s_hi[w][c][0], (unsigned)(xl + k + 1));
+            atomicMin(&s_lo[w][c][1], (unsigned)zl);       atomicMax(&s_hi[w][c][1], (unsigned)(zl + 1));
+            atomicAdd(&s_cnt[w][c], 1u);
+        }
     __syncthreads();
     if(threadIdx.x < 3 && threadIdx.y == 0)
     {
         const int c = threadIdx.x;
         TileSummary& o = out[tile];
-        o.count[c] = s_cnt[c];
-        o.info[c] = s_first[c];
-        o.same[c] = s_diff[c] ? 0u : 1u;
-        o.rect[c] = s_cnt[c] ? (s_xlo[c] | (s_xhi[c] << 8) | (s_zlo[c] << 16) | (s_zhi[c] << 24)) : 0u;
+        auto pack = [&](int w) { return s_cnt[w][c] ? (s_lo[w][c][0] | (s_hi[w][c][0] << 8) | (s_lo[w][c][1] << 16) | (s_hi[w][c][1] << 24)) : 0u; };
+        o.total[c] = s_tot[c]; o.other[c] = s_other[c];
+        o.count[c] = s_cnt[0][c]; o.info[c] = s_tot[c] ? s_vmax[c] : 0u; o.rect[c] = pack(0);
+        o.countB[c] = s_cnt[1][c]; o.infoB[c] = s_cnt[1][c] ? s_vmin[c] : 0u; o.rectB[c] = pack(1);
         if(c == 0) o.bytes = s_bytes;
     }
 }
