@@ -365,14 +365,16 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
     // ---- every load of this component is issued here, before any arithmetic waits on one of them -------------------------
     double2 dv = make_double2(0.0, 0.0);
     if(needD) dv = *reinterpret_cast<const double2*>(ca.D + r);
-    double2 psv[2], Fv[2], bv[2], cv[2];
+    // coefficients: per-x pairs for the part whose derivative runs along x (at most one of the two), scalars for the other
+    double2 psv[2];
+    double2 Fx = make_double2(0.0, 0.0), bx = make_double2(0.0, 0.0), cx = make_double2(0.0, 0.0);
+    double Fs[2] = {0.0, 0.0}, bs[2] = {0.0, 0.0}, cs[2] = {0.0, 0.0};
     long pip[2] = {0, 0};
-    int2 pcc[2];
+    int2 pcc = make_int2(0, 0);
 #pragma unroll
     for(int part = 0; part < 2; ++part)
     {
-        psv[part] = Fv[part] = bv[part] = cv[part] = make_double2(0.0, 0.0);
-        pcc[part] = make_int2(0, 0);
+        psv[part] = make_double2(0.0, 0.0);
         if(part == 0 ? !HAS_VK : !HAS_VJ) continue;
         const PmlArgs& pp = ca.pml[part];
         const unsigned fg = part == 0 ? F_PG0 : F_PG1;
@@ -382,26 +384,24 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
         const int axis = part == 0 ? AX0 : AX1;
         if(axis == 0)
         {
-            Fv[part] = *reinterpret_cast<const double2*>(pp.F + x);
+            Fx = *reinterpret_cast<const double2*>(pp.F + x);
             if(info & fs)
             {
-                bv[part] = *reinterpret_cast<const double2*>(pp.b + x);
-                cv[part] = *reinterpret_cast<const double2*>(pp.c + x);
-                pcc[part] = *reinterpret_cast<const int2*>(pp.cmap + x);
+                bx = *reinterpret_cast<const double2*>(pp.b + x);
+                cx = *reinterpret_cast<const double2*>(pp.c + x);
+                pcc = *reinterpret_cast<const int2*>(pp.cmap + x);
                 pip[part] = pp.psi_pitch * row;
-                if(m0) psv[part].x = pp.psi[pip[part] + pcc[part].x];
-                if(m1) psv[part].y = pp.psi[pip[part] + pcc[part].y];
+                if(m0) psv[part].x = pp.psi[pip[part] + pcc.x];
+                if(m1) psv[part].y = pp.psi[pip[part] + pcc.y];
             }
         }
         else
         {
             const int coord = axis == 1 ? y : z;
-            const double f = pp.F[coord];
-            Fv[part] = make_double2(f, f);
+            Fs[part] = pp.F[coord];
             if(info & fs)
             {
-                const double bb = pp.b[coord], cc = pp.c[coord];
-                bv[part] = make_double2(bb, bb); cv[part] = make_double2(cc, cc);
+                bs[part] = pp.b[coord]; cs[part] = pp.c[coord];
                 const int cm = pp.cmap[coord];
                 pip[part] = axis == 1 ? x + a.px * (z + (long)a.lz * cm) : x + a.px * (cm + (long)pp.nact * y);
                 psv[part] = *reinterpret_cast<const double2*>(pp.psi + pip[part]);
@@ -444,22 +444,25 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
             double2 ps = make_double2(0.0, 0.0);
             if(info & fs)
             {
+                const double2 bq = axis == 0 ? bx : make_double2(bs[part], bs[part]);
+                const double2 cq = axis == 0 ? cx : make_double2(cs[part], cs[part]);
                 double2 p = psv[part];
-                p.x = dm(bv[part].x, p.x);            p.y = dm(bv[part].y, p.y);
-                p.x = axpy1(p.x,  cv[part].x, vr.x);  p.y = axpy1(p.y,  cv[part].y, vr.y);
-                p.x = axpy1(p.x, -cv[part].x, vo.x);  p.y = axpy1(p.y, -cv[part].y, vo.y);
+                p.x = dm(bq.x, p.x);            p.y = dm(bq.y, p.y);
+                p.x = axpy1(p.x,  cq.x, vr.x);  p.y = axpy1(p.y,  cq.y, vr.y);
+                p.x = axpy1(p.x, -cq.x, vo.x);  p.y = axpy1(p.y, -cq.y, vo.y);
                 if(axis == 0)
                 {
-                    if(m0) pp.psi[pip[part] + pcc[part].x] = p.x;
-                    if(m1) pp.psi[pip[part] + pcc[part].y] = p.y;
+                    if(m0) pp.psi[pip[part] + pcc.x] = p.x;
+                    if(m1) pp.psi[pip[part] + pcc.y] = p.y;
                 }
                 else store_pair(pp.psi + pip[part], p, m0, m1);
                 ps = p;
             }
             if(info & fg)
             {
-                w.x = axpy1(w.x,  Fv[part].x, vr.x); w.y = axpy1(w.y,  Fv[part].y, vr.y);
-                w.x = axpy1(w.x, -Fv[part].x, vo.x); w.y = axpy1(w.y, -Fv[part].y, vo.y);
+                const double2 Fq = axis == 0 ? Fx : make_double2(Fs[part], Fs[part]);
+                w.x = axpy1(w.x,  Fq.x, vr.x); w.y = axpy1(w.y,  Fq.y, vr.y);
+                w.x = axpy1(w.x, -Fq.x, vo.x); w.y = axpy1(w.y, -Fq.y, vo.y);
                 if(info & fs) { w.x = axpy1(w.x, pp.Db, ps.x); w.y = axpy1(w.y, pp.Db, ps.y); }
             }
         }
@@ -481,14 +484,16 @@ template <bool IS_E, int MODE, int C>
 __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t, const PairLoads<IS_E, MODE>& L,
                                              const long r, const long row, const int x, const int y, const int z, const int xl, const int zl)
 {
-    if(!has_own<IS_E, MODE>(C)) return;
-#pragma unroll 1
-    for(int w = 0; w < 2; ++w)
+    if constexpr(has_own<IS_E, MODE>(C))
     {
-        const unsigned rect = w == 0 ? t.rect[C] : t.rectB[C];
-        if(rect == 0) continue;
-        uniform_rect<IS_E, MODE, C>(a, rect, w == 0 ? t.info[C] : t.infoB[C], w == 0 ? t.pf[C] : t.pfB[C], w == 0 ? t.inv_eps[C] : t.inv_epsB[C],
-                                    L, r, row, x, y, z, xl, zl);
+#pragma unroll 1
+        for(int w = 0; w < 2; ++w)
+        {
+            const unsigned rect = w == 0 ? t.rect[C] : t.rectB[C];
+            if(rect == 0) continue;
+            uniform_rect<IS_E, MODE, C>(a, rect, w == 0 ? t.info[C] : t.infoB[C], w == 0 ? t.pf[C] : t.pfB[C], w == 0 ? t.inv_eps[C] : t.inv_epsB[C],
+                                        L, r, row, x, y, z, xl, zl);
+        }
     }
 }
 
@@ -563,13 +568,14 @@ __device__ __forceinline__ void comp_march_init(const StepArgs& a, const long r,
     if(C != 1 && has_other<IS_E, MODE>(SRC)) carry = *reinterpret_cast<const double2*>(a.fam[SRC] + (IS_E ? r - plane : r));
 }
 template <bool IS_E, int MODE, int C>
-__device__ __forceinline__ void comp_march_load(const StepArgs& a, const long r, const long plane, double2& carry, PairLoads<IS_E, MODE>& L)
+__device__ __forceinline__ void comp_march_load(const StepArgs& a, const long r, const long plane, double2& carry, PairLoads<IS_E, MODE>& L, const bool needU = true)
 {
     constexpr int S = IS_E ? -1 : 1;
     constexpr int J = (C + 1) % 3, K = (C + 2) % 3;           // grid_j = other[J] (neighbour along axis K), grid_k = other[K] (along axis J)
     const double* __restrict__ fj = a.fam[J];
     const double* __restrict__ fk = a.fam[K];
-    L.u[C] = *reinterpret_cast<const double2*>(a.c[C].U + r);
+    L.u[C] = make_double2(0.0, 0.0);
+    if(needU) L.u[C] = *reinterpret_cast<const double2*>(a.c[C].U + r);   // not needed where D->E overwrites E
     L.v[J] = L.v[K] = L.nj[C] = L.nk[C] = make_double2(0.0, 0.0);
     // which of the two driving arrays is the y-coupled one: axis K == 1 -> grid_j (C == 2); axis J == 1 -> grid_k (C == 0)
     constexpr bool JY = K == 1, KY = J == 1;
@@ -598,11 +604,12 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
     long r = x + a.px * (z + (long)a.lz * t.y);
     double2 carry;
     comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
+    const bool needU = !IS_E || (t.rect[C] != 0 && !(t.info[C] & F_D2E)) || (t.rectB[C] != 0 && !(t.infoB[C] & F_D2E));
     for(int iy = 0; iy < t.ny; ++iy, r += plane)
     {
         const int y = t.y + iy;
         PairLoads<IS_E, MODE> L;
-        comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L);
+        comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L, needU);
         uniform_comp<IS_E, MODE, C>(a, t, L, r, z + (long)a.lz * y, x, y, z, xl, zl);
     }
 }
