@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_device_bytes", "chiml_gpu_set_kernel_timing", "chiml_gpu_n_kernel_kinds", "chiml_gpu_kernel_stat",
     "chiml_gpu_reset_kernel_stats", "chiml_gpu_read_detector_range", "chiml_gpu_add_emitters",
     "chiml_gpu_download_emitter_state", "chiml_gpu_download_emitter_pol", "chiml_gpu_read_population",
-    "chiml_gpu_halo_export", "chiml_gpu_halo_bind",
+    "chiml_gpu_halo_export", "chiml_gpu_halo_bind", "chiml_gpu_add_dft", "chiml_gpu_step_n_dft", "chiml_gpu_download_dft",
 ]
 
 
@@ -115,6 +115,9 @@ def lib() -> C.CDLL:
     L.chiml_gpu_read_detector_range.argtypes = [vp, i, sz, sz, vp, C.POINTER(sz)]
     L.chiml_gpu_halo_export.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.chiml_gpu_halo_bind.argtypes = [vp, C.c_char_p, sz, C.c_char_p, sz]
+    L.chiml_gpu_add_dft.argtypes = [vp, i, i, i, i, i, i, vp, sz, sz, C.POINTER(i)]
+    L.chiml_gpu_step_n_dft.argtypes = [vp, i, vp, vp]
+    L.chiml_gpu_download_dft.argtypes = [vp, i, vp, vp]
     L.chiml_gpu_add_emitters.argtypes = [vp, C.POINTER(EmitterDesc), C.POINTER(i)]
     L.chiml_gpu_download_emitter_state.argtypes = [vp, i, i, i, vp]
     L.chiml_gpu_download_emitter_pol.argtypes = [vp, i, i, vp]
@@ -177,6 +180,10 @@ class GpuSim:
                 slot = C.c_int()
                 d = emitter_desc(e, keep)
                 self._chk(L.chiml_gpu_add_emitters(self.h, C.byref(d), C.byref(slot)))
+            for d in plan.dfts:
+                lines = np.ascontiguousarray(d.lines, dtype=np.int32)
+                slot = C.c_int()
+                self._chk(L.chiml_gpu_add_dft(self.h, d.field, d.group, d.every, d.nfreq, d.npts, d.stride, _ptr(lines), len(lines), d.acc_len, C.byref(slot)))
             if detectors:
                 for d in plan.detectors:
                     box = local_box(plan, d.loc, d.sz)
@@ -209,7 +216,11 @@ class GpuSim:
         if amp is None:
             amp = self.src_amp(self.steps_done, n)
         amp = np.ascontiguousarray(amp, dtype=np.float64)
-        self._chk(lib().chiml_gpu_step_n(self.h, n, _ptr(amp) if len(self.plan.sources) else None))
+        if self.plan.dfts:
+            tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, n))
+            self._chk(lib().chiml_gpu_step_n_dft(self.h, n, _ptr(amp) if len(self.plan.sources) else None, _ptr(tw)))
+        else:
+            self._chk(lib().chiml_gpu_step_n(self.h, n, _ptr(amp) if len(self.plan.sources) else None))
         self.steps_done += n
 
     def step_n_timed(self, n: int, amp: Optional[np.ndarray] = None) -> float:
@@ -316,6 +327,13 @@ class GpuSim:
         if n.value:
             self._chk(lib().chiml_gpu_read_population(self.h, slot, det, _ptr(out), n.value, C.byref(n)))
         return out[:, 0] + 1j * out[:, 1]
+
+    def dft(self, slot: int) -> np.ndarray:
+        """Complex accumulator of DFT set `slot` (fInReal_ + i fInCplx_)."""
+        d = self.plan.dfts[slot]
+        re, im = np.empty(d.acc_len), np.empty(d.acc_len)
+        self._chk(lib().chiml_gpu_download_dft(self.h, slot, _ptr(re), _ptr(im)))
+        return re + 1j * im
 
     def set_kernel_timing(self, on: bool) -> None:
         self._chk(lib().chiml_gpu_set_kernel_timing(self.h, 1 if on else 0))

@@ -141,6 +141,8 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     cudaFree(ctx->d_src_amp);
     for(auto& f : ctx->d_tiles) for(auto& p : f) cudaFree(p);
     for(auto& d : ctx->detectors) cudaFree(d.d_ring);
+    for(auto& d : ctx->dfts) { cudaFree(d.d_lines); cudaFree(d.d_re); cudaFree(d.d_im); }
+    cudaFree(ctx->d_tw);
     for(auto& em : ctx->emitters)
     {
         cudaFree(em.d_h0); cudaFree(em.d_mu); cudaFree(em.d_gam_val); cudaFree(em.d_eps); cudaFree(em.d_gam_ptr); cudaFree(em.d_gam_col); cudaFree(em.d_loc);
@@ -240,6 +242,29 @@ int chiml_gpu_add_detector(ChimlCtx* ctx, int field, const int32_t loc[3], const
     d.sample_len = (size_t)sz[0] * sz[1] * sz[2];
     if(slot) *slot = (int)ctx->detectors.size();
     ctx->detectors.push_back(d);
+    return CHIML_OK;
+}
+
+int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq, int npts, int stride, const ChimlDftLine* lines, size_t nlines, size_t acc_len, int* slot)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "add_dft after commit");
+    if(field < 0 || field >= CHIML_NFIELDS || !field_exists(ctx, field)) return fail(ctx, CHIML_ERR_ARG, "add_dft: field absent in this mode");
+    if(group < 0 || group > 255 || every < 1 || nfreq < 1 || npts < 1 || (nlines && !lines)) return fail(ctx, CHIML_ERR_ARG, "add_dft: bad argument");
+    if((int)ctx->dft_group_nfreq.size() <= group) ctx->dft_group_nfreq.resize(group + 1, 0);
+    if(ctx->dft_group_nfreq[group] != 0 && ctx->dft_group_nfreq[group] != nfreq) return fail(ctx, CHIML_ERR_ARG, "add_dft: the sets of one group must share the frequency list");
+    ctx->dft_group_nfreq[group] = nfreq;
+    for(size_t l = 0; l < nlines; ++l)
+    {
+        const long last = (long)lines[l].ind + (long)(npts - 1) * stride;
+        if(lines[l].ind < 0 || last >= (long)ctx->nlogical || last < 0) return fail(ctx, CHIML_ERR_ARG, "add_dft: line leaves the grid");
+        if(lines[l].out < 0 || (size_t)lines[l].out + (size_t)nfreq * npts > acc_len) return fail(ctx, CHIML_ERR_ARG, "add_dft: line leaves the accumulator");
+    }
+    DftDev d;
+    d.field = field; d.group = group; d.every = every; d.nfreq = nfreq; d.npts = npts; d.stride = stride; d.nlines = nlines; d.acc_len = acc_len;
+    d.h_lines.assign(lines, lines + nlines);
+    if(slot) *slot = (int)ctx->dfts.size();
+    ctx->dfts.push_back(std::move(d));
     return CHIML_OK;
 }
 
@@ -843,6 +868,12 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         ctx->kstat[K_EMIT_ADDP].alg_bytes += 0.0;   // its E read-modify-write is the field traffic already counted for the E half step
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    for(DftDev& d : ctx->dfts)
+    {
+        if((rc = dev_upload(ctx, &d.d_lines, d.h_lines))) return rc;
+        if((rc = dev_alloc(ctx, &d.d_re, d.acc_len))) return rc;
+        if((rc = dev_alloc(ctx, &d.d_im, d.acc_len))) return rc;
+    }
     // detectors: ring buffers sized on first use; sample at t = 0 (FDTD_MANAGER/parallelFDTDField.cpp:832-833)
     ctx->committed = true;
     for(size_t d = 0; d < ctx->detectors.size(); ++d)
@@ -1209,6 +1240,21 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
         }
         ++dt.count;
     }
+    // flux->fieldIn(tcur_) (item 18, :1300-1302)
+    if(!ctx->dfts.empty())
+    {
+        size_t per_step = 0;
+        std::vector<size_t> goff(ctx->dft_group_nfreq.size(), 0);
+        for(size_t g = 0; g < ctx->dft_group_nfreq.size(); ++g) { goff[g] = per_step; per_step += 2 * (size_t)ctx->dft_group_nfreq[g]; }
+        for(DftDev& d : ctx->dfts)
+        {
+            if(ctx->step_count % d.every != 0 || d.nlines == 0) continue;
+            const size_t n = d.nlines * (size_t)d.npts * d.nfreq;
+            LaunchScope ls(ctx, K_DFT);
+            k_dft<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(
+                ctx->d_field[d.field], d.d_lines, d.nlines, d.npts, d.stride, d.nfreq, ctx->d_tw + (size_t)k * per_step + goff[d.group], d.d_re, d.d_im, ctx->lx, ctx->px);
+        }
+    }
     return 0;
 }
 
@@ -1316,12 +1362,27 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
     return 0;
 }
 
-int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp)
+int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles = nullptr)
 {
     if(!ctx) return CHIML_ERR_ARG;
     if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "step before commit");
     if(n < 0) return fail(ctx, CHIML_ERR_ARG, "negative step count");
     CK(cudaSetDevice(ctx->device));
+    if(!ctx->dfts.empty())
+    {
+        if(!twiddles) return fail(ctx, CHIML_ERR_ARG, "running-DFT sets are registered: step with chiml_gpu_step_n_dft and the twiddle factors");
+        size_t per_step = 0;
+        for(int nf : ctx->dft_group_nfreq) per_step += 2 * (size_t)nf;
+        const size_t need = per_step * (size_t)n;
+        if(need > ctx->tw_cap)
+        {
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_tw);
+            CK(cudaMalloc((void**)&ctx->d_tw, std::max<size_t>(need, 1) * sizeof(double)));
+            ctx->tw_cap = need;
+        }
+        if(need) CK(cudaMemcpyAsync(ctx->d_tw, twiddles, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
     const int nsrc = (int)ctx->sources.size();
     if(nsrc > 0)
     {
@@ -1350,6 +1411,23 @@ int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp)
 extern "C" {
 
 int chiml_gpu_step_n(ChimlCtx* ctx, int n, const double* src_amp) { return step_n_impl(ctx, n, src_amp); }
+int chiml_gpu_step_n_dft(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles) { return step_n_impl(ctx, n, src_amp, twiddles); }
+
+int chiml_gpu_download_dft(ChimlCtx* ctx, int slot, double* re, double* im)
+{
+    if(!ctx || !re || !im) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "download_dft before commit");
+    if(slot < 0 || slot >= (int)ctx->dfts.size()) return fail(ctx, CHIML_ERR_ARG, "download_dft: bad slot");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const DftDev& d = ctx->dfts[slot];
+    if(d.acc_len)
+    {
+        CK(cudaMemcpy(re, d.d_re, d.acc_len * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(im, d.d_im, d.acc_len * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return CHIML_OK;
+}
 
 int chiml_gpu_sync(ChimlCtx* ctx)
 {
@@ -1521,7 +1599,7 @@ int chiml_gpu_n_kernel_kinds(void) { return K_NKINDS; }
 int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out)
 {
     static const char* names[K_NKINDS] = {"k_fast<E>", "k_uniform<E>", "k_general<E>", "k_fast<H>", "k_uniform<H>", "k_general<H>",
-                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce"};
+                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft"};
     if(!ctx || !out || kind < 0 || kind >= K_NKINDS) return CHIML_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));

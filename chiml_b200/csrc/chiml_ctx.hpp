@@ -88,7 +88,7 @@ struct DetectorDev
 };
 
 // kernels of the step loop, for launch / time / algorithmic-byte accounting
-enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_NKINDS };
+enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_NKINDS };
 struct KernelStat { int64_t launches = 0; double ms_total = 0.0; double alg_bytes = 0.0; int64_t timed = 0; };
 
 // one parallelQE object on the device (chiml_emitters.cuh)
@@ -125,6 +125,16 @@ struct HaloPeer                   // one neighbouring slab, as mapped into this 
     std::vector<int> emit_bn1;    // box_n[1] of those sets
     int* flags = nullptr;         // its flag array
     std::vector<void*> opened;    // bases returned by cudaIpcOpenMemHandle
+};
+
+// one stored field of a flux / frequency detector (running DFT)
+struct DftDev
+{
+    int field = 0, group = 0, every = 1, nfreq = 0, npts = 0, stride = 1;
+    size_t nlines = 0, acc_len = 0;
+    std::vector<ChimlDftLine> h_lines;
+    ChimlDftLine* d_lines = nullptr;
+    double *d_re = nullptr, *d_im = nullptr;
 };
 
 struct HostList { std::vector<ChimlRun> runs; };
@@ -186,6 +196,9 @@ struct ChimlCtx
     double* d_src_amp = nullptr; size_t src_amp_cap = 0;
     std::vector<chiml::DetectorDev> detectors;
     std::vector<chiml::EmitterDev> emitters;
+    std::vector<chiml::DftDev> dfts;
+    std::vector<int> dft_group_nfreq;            // nfreq of every group, in group order
+    double* d_tw = nullptr; size_t tw_cap = 0;   // twiddles of the current step_n_dft call
 
     // host-side copies of the setup until commit
     chiml::HostList lists[5][6];

@@ -9,6 +9,7 @@ The record layouts mirror the reference's own PODs:
 """
 from __future__ import annotations
 
+import math
 import struct
 from dataclasses import dataclass, field
 from typing import Dict, List, Tuple
@@ -104,6 +105,20 @@ class PlanEmitter:
     pop_level: np.ndarray
 
 
+@dataclass
+class PlanDft:
+    """One stored field of a flux object (include/chiml_gpu.h chiml_gpu_add_dft)."""
+    field: int
+    group: int
+    every: int
+    nfreq: int
+    npts: int
+    stride: int
+    acc_len: int
+    freq: np.ndarray      # (nfreq,) the group's freqList_ (angular, FDTD units)
+    lines: np.ndarray     # (nlines, 2) int32: grid index, accumulator index
+
+
 _EMIT_FMT = "<4i3i3i4i2i3d"
 _EMIT_SIZE = struct.calcsize(_EMIT_FMT)
 assert _EMIT_SIZE == 88
@@ -132,6 +147,7 @@ class Plan:
     sources: List[PlanSource] = field(default_factory=list)
     detectors: List[PlanDetector] = field(default_factory=list)
     emitters: List[PlanEmitter] = field(default_factory=list)
+    dfts: List[PlanDft] = field(default_factory=list)
 
     @property
     def ncell(self) -> int:
@@ -200,6 +216,11 @@ def read_plan(path: str) -> Plan:
         elif tag == "DETECTOR":
             v = struct.unpack_from("<ii3i3i3iiiidd", payload, 0)
             plan.detectors.append(PlanDetector(v[0], v[1], tuple(v[2:5]), tuple(v[5:8]), tuple(v[8:11]), v[11], v[12], v[14], v[15]))
+        elif tag == "DFT":
+            fld, group, every, nfreq, npts, stride, nlines, acc_len = struct.unpack_from("<6iQQ", payload, 0)
+            freq = np.frombuffer(payload, dtype="<f8", count=nfreq, offset=40).copy()
+            lines = np.frombuffer(payload, dtype="<i4", count=2 * nlines, offset=40 + 8 * nfreq).copy().reshape(nlines, 2)
+            plan.dfts.append(PlanDft(fld, group, every, nfreq, npts, stride, acc_len, freq, lines))
         elif tag == "EMITTER":
             v = struct.unpack_from(_EMIT_FMT, payload, 0)
             obj, N, nsys, nemit = v[0:4]
@@ -226,6 +247,27 @@ def read_plan(path: str) -> Plan:
             plan.emitters.append(PlanEmitter(obj, N, nsys, nemit, lo, bn, pz, npop, pop_every, npoints, dt, inv_hbar, na, h0, weight, mu,
                                              gptr, gcol, gval, loc, eps, pl))
     return plan
+
+
+def dft_twiddles(plan: "Plan", start: int, n: int) -> np.ndarray:
+    """exp(-i freq t) for steps start .. start+n-1 (t = time after the step, as parallelFluxDTC::fieldIn gets tcur_,
+    DTC/parallelFlux.hpp:298): shape (n, sum of nfreq over groups, 2), evaluated like the reference (std::exp of a complex)."""
+    groups = {}
+    for d in plan.dfts:
+        groups[d.group] = d.freq
+    if not groups:
+        return np.zeros((n, 0, 2))
+    freq = np.concatenate([groups[g] for g in sorted(groups)])
+    out = np.empty((n, len(freq), 2))
+    t = 0.0
+    for k in range(start + n):          # tcur_ is accumulated step by step (tcur_ += dt_)
+        t += plan.dt
+        if k >= start:
+            # std::exp(cplx(0, y)) = (cos y, sin y) from libm: use the same library functions, not numpy's own complex exp
+            for j, fr in enumerate(freq):
+                y = -1.0 * t * float(fr)
+                out[k - start, j, 0], out[k - start, j, 1] = math.cos(y), math.sin(y)
+    return out
 
 
 def _rec(tag: str, payload: bytes) -> bytes:
@@ -260,6 +302,9 @@ def write_plan(path: str, plan: Plan) -> None:
                         + np.ascontiguousarray(e.gam_col, "<i4").tobytes() + np.ascontiguousarray(e.gam_val, "<f8").tobytes()
                         + np.ascontiguousarray(e.loc, "<i4").tobytes() + np.ascontiguousarray(e.eps, "<f8").tobytes()
                         + np.ascontiguousarray(e.pop_level, "<i4").tobytes()))
+    for d in plan.dfts:
+        out.append(_rec("DFT", struct.pack("<6iQQ", d.field, d.group, d.every, d.nfreq, d.npts, d.stride, len(d.lines), d.acc_len)
+                        + np.ascontiguousarray(d.freq, "<f8").tobytes() + np.ascontiguousarray(d.lines, "<i4").tobytes()))
     with open(path, "wb") as f:
         f.write(b"".join(out))
 

@@ -153,6 +153,17 @@ typedef struct ChimlEmitterDesc
 } ChimlEmitterDesc;
 int chiml_gpu_add_emitters(ChimlCtx* ctx, const ChimlEmitterDesc* desc, int* slot);
 
+/* Running discrete Fourier transform of one stored field of a flux / frequency detector (parallelStorageFreqDTCReal::fieldIn,
+ * DTC/parallelStorageFreqDTC.cpp:21-30; driven by parallelFluxDTC::fieldIn, DTC/parallelFlux.hpp:296-312): every `every` steps, after
+ * the step, for every line l and point i < npts and frequency f < nfreq
+ *     acc_re[lines[l].out + f + nfreq*i] += tw_re[f] * field[lines[l].ind + i*stride]      (the two dger_ rank-1 updates)
+ *     acc_im[lines[l].out + f + nfreq*i] += tw_im[f] * field[lines[l].ind + i*stride]
+ * with tw = exp(-i freq t) computed by the HOST for the time after the step (so that its rounding is the host's) and passed to
+ * chiml_gpu_step_n_dft.  `group` = index of the flux object: all stored fields of one object share its twiddles. */
+typedef struct ChimlDftLine { int32_t ind, out; } ChimlDftLine;   /* the (grid index, accumulator index) pairs of fInGridInds_ */
+int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq, int npts, int stride,
+                      const ChimlDftLine* lines, size_t nlines, size_t acc_len, int* slot);
+
 /* Freeze the setup: paints the per-cell update maps from the lists, builds the CPML coefficient
  * tables and compact psi / polarisation pools, zeroes all state. */
 int chiml_gpu_commit(ChimlCtx* ctx);
@@ -170,6 +181,9 @@ int chiml_gpu_halo_bind(ChimlCtx* ctx, const void* lower_blob, size_t lower_size
 /* n leap-frog steps in the reference's order (step(), :1228-1303).  src_amp: n * n_sources doubles,
  * step-major (may be NULL when there are no sources). */
 int chiml_gpu_step_n(ChimlCtx* ctx, int n, const double* src_amp);
+/* same with running-DFT sets: twiddles = for every step k < n, for every group g in order, nfreq_g complex (re, im) numbers
+ * exp(-i freq t_k), t_k = time after step k (only read on the steps the group samples).  chiml_gpu_step_n fails when DFT sets exist. */
+int chiml_gpu_step_n_dft(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles);
 int chiml_gpu_sync(ChimlCtx* ctx);
 /* same as step_n but bracketed by CUDA events on the context's stream; returns device milliseconds */
 int chiml_gpu_step_n_timed(ChimlCtx* ctx, int n, const double* src_amp, float* ms);
@@ -217,6 +231,9 @@ int chiml_gpu_download_emitter_pol(ChimlCtx* ctx, int slot, int comp, double* ou
 /* population detector `det` of emitter set `slot`: complex samples sum_emitters rho[level] / npoints of THIS slab's emitters
  * (QEPopDtc::accumPop; the host adds the slabs, QEPopDtc::toFile).  out = cap_samples complex. */
 int chiml_gpu_read_population(ChimlCtx* ctx, int slot, int det, double* out, size_t cap_samples, size_t* n_samples);
+
+/* accumulators of DFT set `slot`: acc_len doubles each (fInReal_, fInCplx_) */
+int chiml_gpu_download_dft(ChimlCtx* ctx, int slot, double* re, double* im);
 
 /* bytes of device memory held by the context */
 size_t chiml_gpu_device_bytes(const ChimlCtx* ctx);

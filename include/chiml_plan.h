@@ -79,6 +79,11 @@ typedef struct ChimlPlanEmitterHdr    /* tag "EMITTER ": header, then in this or
     int32_t pz, pad;
     double  dt, inv_hbar, na;
 } ChimlPlanEmitterHdr;
+typedef struct ChimlPlanDftHdr        /* tag "DFT     ": header, freq[nfreq] doubles (group's freqList_), then nlines ChimlDftLine */
+{
+    int32_t field, group, every, nfreq, npts, stride;
+    uint64_t nlines, acc_len;
+} ChimlPlanDftHdr;
 #pragma pack(pop)
 
 #endif /* CHIML_PLAN_H */

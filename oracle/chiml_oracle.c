@@ -34,6 +34,10 @@ typedef struct
     long tstep;
 } QESet;
 
+/* one stored field of a flux / frequency detector (DTC/parallelStorageFreqDTC.cpp:21-30) */
+#define MAX_DFT 64
+typedef struct { int field, group, every, nfreq, npts, stride; size_t nlines, acc_len; ChimlDftLine* lines; double *re, *im; } DftSet;
+
 struct OracleSim
 {
     ChimlGridDesc g;
@@ -59,6 +63,11 @@ struct OracleSim
     int nsteps;
     QESet qe[MAX_QE];
     int nqe;
+    DftSet dft[MAX_DFT];
+    int ndft;
+    int dft_group_nfreq[256];
+    const double* twiddles;        /* of the current oracle_step_n_dft call */
+    long step_count;
     int phase_mask;                /* bit 0: H half step + sources, 1: node poles, 2: E half step + emitter addP, 3: emitter density */
 };
 
@@ -701,6 +710,32 @@ static void step_worker(OracleSim* s, int tid, int nt)
             for(int q = 0; q < s->nqe; ++q) qe_add(s, &s->qe[q], 1);
         if(tid == 0 && (s->phase_mask & 8))
             for(int q = 0; q < s->nqe; ++q) qe_add(s, &s->qe[q], 2);
+        /* flux->fieldIn(tcur_) (:1300-1302): two dger_ rank-1 updates per line, F(f, i) += 1.0 * tw[f] * u[i] */
+        if(tid == 0 && (s->phase_mask & 8))
+        {
+            ++s->step_count;
+            size_t per_step = 0, goff[256];
+            for(int g = 0; g < 256; ++g) { goff[g] = per_step; per_step += 2 * (size_t)s->dft_group_nfreq[g]; }
+            for(int q = 0; q < s->ndft; ++q)
+            {
+                DftSet* d = &s->dft[q];
+                if(s->step_count % d->every != 0) continue;
+                const double* tw = s->twiddles + (size_t)step * per_step + goff[d->group];
+                const double* G = s->f[d->field];
+                for(size_t l = 0; l < d->nlines; ++l)
+                    for(int i = 0; i < d->npts; ++i)
+                    {
+                        const double u = G[(size_t)d->lines[l].ind + (size_t)i * (size_t)d->stride];
+                        const double t = 1.0 * u;
+                        for(int f = 0; f < d->nfreq; ++f)
+                        {
+                            const size_t o = (size_t)d->lines[l].out + (size_t)f + (size_t)d->nfreq * (size_t)i;
+                            d->re[o] = d->re[o] + tw[2 * f] * t;
+                            d->im[o] = d->im[o] + tw[2 * f + 1] * t;
+                        }
+                    }
+            }
+        }
         BARRIER();
     }
     free(scratch);
@@ -713,9 +748,31 @@ static void* thread_main(void* arg)
     return NULL;
 }
 
+int oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads);
+int oracle_add_dft(OracleSim* s, int field, int group, int every, int nfreq, int npts, int stride, const ChimlDftLine* lines, size_t nlines, size_t acc_len)
+{
+    if(s->ndft >= MAX_DFT || group < 0 || group > 255 || field < 0 || field >= CHIML_NFIELDS || !s->f[field]) return CHIML_ERR_ARG;
+    DftSet* d = &s->dft[s->ndft++];
+    d->field = field; d->group = group; d->every = every; d->nfreq = nfreq; d->npts = npts; d->stride = stride; d->nlines = nlines; d->acc_len = acc_len;
+    d->lines = (ChimlDftLine*)malloc((nlines ? nlines : 1) * sizeof(ChimlDftLine));
+    if(nlines) memcpy(d->lines, lines, nlines * sizeof(ChimlDftLine));
+    d->re = (double*)calloc(acc_len ? acc_len : 1, sizeof(double));
+    d->im = (double*)calloc(acc_len ? acc_len : 1, sizeof(double));
+    s->dft_group_nfreq[group] = nfreq;
+    return 0;
+}
+double* oracle_dft(OracleSim* s, int slot, int imag) { return (slot < 0 || slot >= s->ndft) ? NULL : (imag ? s->dft[slot].im : s->dft[slot].re); }
+
+int oracle_step_n_dft(OracleSim* s, int n, const double* src_amp, const double* twiddles, int nthreads)
+{
+    s->twiddles = twiddles;
+    return oracle_step_n(s, n, src_amp, nthreads);
+}
+
 int oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads)
 {
     if(!s->committed) return CHIML_ERR_STATE;
+    if(s->ndft > 0 && !s->twiddles) return CHIML_ERR_ARG;
     if(nthreads < 1) nthreads = 1;
     s->nthreads = nthreads;
     s->src_amp = src_amp;

@@ -251,6 +251,27 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
         ++dd;
     }
     if(!FF.qeArr_.empty() && FF.gridComm_->size() == 1) putEmitters(out, FF);
+    // DFT records: every stored field of every flux object, in the order parallelFluxDTC::fieldIn walks them (DTC/parallelFlux.hpp:296-312)
+    int group = 0;
+    for(auto& flux : FF.fluxArr_)
+    {
+        for(auto& fp : flux->fInParam_)
+            for(auto* vec : {&fp.Ej_dtc_, &fp.Ek_dtc_, &fp.Hj_dtc_, &fp.Hk_dtc_})
+                for(auto& dtc : *vec)
+                {
+                    auto real = std::dynamic_pointer_cast<parallelStorageFreqDTCReal>(dtc);
+                    if(!real || !real->fieldInFreq_) continue;
+                    ChimlPlanDftHdr h; std::memset(&h, 0, sizeof(h));
+                    h.field = fieldId(FF, real->grid_); h.group = group; h.every = flux->timeInt_; h.nfreq = real->nfreq_;
+                    h.npts = real->fieldInFreq_->sz_[0]; h.stride = real->fieldInFreq_->stride_;
+                    h.nlines = real->fieldInFreq_->fInGridInds_.size() / 2; h.acc_len = real->fInReal_.size();
+                    std::string p; app(p, h); appVec(p, flux->freqList_);
+                    for(size_t ii = 0; ii + 1 < real->fieldInFreq_->fInGridInds_.size(); ii += 2)
+                    { ChimlDftLine l; l.ind = real->fieldInFreq_->fInGridInds_[ii]; l.out = real->fieldInFreq_->fInGridInds_[ii + 1]; app(p, l); }
+                    putRec(out, "DFT", p);
+                }
+        ++group;
+    }
 }
 
 // EMITTER records: one per parallelQE object, from the object's own members (single-rank runs only: with more ranks the
@@ -415,6 +436,28 @@ static void rankMain(int rank, const Options& opt)
             }
             ++qq;
         }
+    }
+
+    if(!opt.dump.empty())
+    {
+        int slot = 0;
+        for(auto& flux : FF.fluxArr_)
+            for(auto& fp : flux->fInParam_)
+                for(auto* vec : {&fp.Ej_dtc_, &fp.Ek_dtc_, &fp.Hj_dtc_, &fp.Hk_dtc_})
+                    for(auto& dtc : *vec)
+                    {
+                        auto real = std::dynamic_pointer_cast<parallelStorageFreqDTCReal>(dtc);
+                        if(!real || !real->fieldInFreq_) continue;
+                        for(int im = 0; im < 2; ++im)
+                        {
+                            GridDump d; d.rank = rank; d.name = "dft" + std::to_string(slot) + (im ? "i" : "r");
+                            const std::vector<double>& v = im ? real->fInCplx_ : real->fInReal_;
+                            d.ln[0] = int(v.size()); d.ln[1] = 1; d.ln[2] = 1; d.yStart = 0;
+                            d.data = v;
+                            std::lock_guard<std::mutex> lk(g_dumpMtx); g_dumps.push_back(std::move(d));
+                        }
+                        ++slot;
+                    }
     }
 
     if(opt.output)

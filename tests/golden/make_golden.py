@@ -81,6 +81,8 @@ def cases():
                           [I.normal_source("Ex", [-0.1, -0.08, 0], [0, 0, 0], [pulse(1.5, 3e13)])],
                           [pxy],
                           [I.detector([0.03, 0, 0], [0, 0, 0], "Ex", "out/mte/dtc", time_int=DT * 1.0000001)])
+    # ---- running DFT on the four edges of a flux box around a Drude rod (DTC/parallelFlux.hpp, parallelStorageFreqDTC.cpp:21-30) ----
+    c["tm_flux"] = _short_pulse(I.c2_tm_drude(n=63, steps=100, pml_cells=8, rod=(20, 6), nfreq=5, out="out/tmflux"))
     return c
 
 

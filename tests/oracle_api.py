@@ -83,6 +83,10 @@ def lib() -> C.CDLL:
         L.oracle_commit.argtypes = [C.c_void_p]
         L.oracle_step_n.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_step_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_add_dft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
+        L.oracle_step_n_dft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_dft.restype = C.POINTER(C.c_double)
+        L.oracle_dft.argtypes = [C.c_void_p, C.c_int, C.c_int]
         for fn in ("oracle_field", "oracle_psi"):
             getattr(L, fn).restype = C.POINTER(C.c_double)
         L.oracle_field.argtypes = [C.c_void_p, C.c_int]
@@ -130,6 +134,9 @@ class OracleSim:
             loc = (C.c_int32 * 3)(*s.loc)
             sz = (C.c_int32 * 3)(*s.sz)
             self._chk(L.oracle_add_source(self.h, s.field, loc, sz))
+        for d in plan.dfts:
+            lines = np.ascontiguousarray(d.lines, dtype=np.int32)
+            self._chk(L.oracle_add_dft(self.h, d.field, d.group, d.every, d.nfreq, d.npts, d.stride, _ptr(lines), len(lines), d.acc_len))
         for e in plan.emitters:
             d = emitter_desc(e, self._keep)
             self._chk(L.oracle_add_emitters(self.h, C.byref(d)))
@@ -153,7 +160,11 @@ class OracleSim:
         if amp is None:
             amp = self.src_amp(self.steps_done, n)
         amp = np.ascontiguousarray(amp, dtype=np.float64)
-        self._chk(lib().oracle_step_n(self.h, n, _ptr(amp), nthreads))
+        if self.plan.dfts:
+            tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, n))
+            self._chk(lib().oracle_step_n_dft(self.h, n, _ptr(amp), _ptr(tw), nthreads))
+        else:
+            self._chk(lib().oracle_step_n(self.h, n, _ptr(amp), nthreads))
         self.steps_done += n
 
     def step_phase(self, phase: int, amp: np.ndarray) -> None:
@@ -198,6 +209,12 @@ class OracleSim:
         out = np.zeros((n, 2))
         lib().oracle_population(self.h, slot, det, _ptr(out) if n else None, n)
         return out[:, 0] + 1j * out[:, 1]
+
+    def dft(self, slot: int) -> np.ndarray:
+        d = self.plan.dfts[slot]
+        re = np.ctypeslib.as_array(lib().oracle_dft(self.h, slot, 0), shape=(max(d.acc_len, 1),))[:d.acc_len]
+        im = np.ctypeslib.as_array(lib().oracle_dft(self.h, slot, 1), shape=(max(d.acc_len, 1),))[:d.acc_len]
+        return re + 1j * im
 
     def n_poles(self) -> int:
         return lib().oracle_n_poles(self.h)

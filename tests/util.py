@@ -24,6 +24,9 @@ def state_array(sim, name: str):
     OracleSim or a GpuSim (both expose field / pole / ordip_pole)."""
     if name in P.FIELD_NAMES:
         return sim.field(P.FIELD_NAMES.index(name))
+    if name.startswith("dft"):
+        a = sim.dft(int(name[3:-1]))
+        return (a.imag if name.endswith("i") else a.real).reshape(1, 1, -1).copy()
     if name.startswith("q"):
         # emitter arrays of the reference dump: q<slot>s<sys>w<which> (states), q<slot>P<c> (P boxes), q<slot>pop<det>
         import re
@@ -68,6 +71,8 @@ def state_names(plan: P.Plan):
                 names += [f"P{'xyz'[c]}{p}", f"pP{'xyz'[c]}{p}"]
             for p in range(plan.n_ordip_poles):
                 names += [f"oP{'xyz'[c]}{p}", f"poP{'xyz'[c]}{p}"]
+    for k in range(len(plan.dfts)):
+        names += [f"dft{k}r", f"dft{k}i"]
     for q, e in enumerate(plan.emitters):
         names += [f"q{q}s{s}w{w}" for s in range(e.nsys) for w in range(5)]
         names += [f"q{q}P{'xyz'[c]}" for c in range(3) if c in plan.fields_present()]

@@ -80,6 +80,14 @@ def diff(a: P.Plan, b: P.Plan, verbose=True):
             elif u.tobytes() != v.tobytes():
                 j = np.flatnonzero(u.ravel() != v.ravel())
                 bad.append(f"emitter {i}.{k}: {len(j)} entries differ, first at {j[:1]}: {u.ravel()[j[:1]]} vs {v.ravel()[j[:1]]}")
+    if len(a.dfts) != len(b.dfts):
+        bad.append(f"dft sets: {len(a.dfts)} != {len(b.dfts)}")
+    for i, (da, db) in enumerate(zip(a.dfts, b.dfts)):
+        for k in ("field", "group", "every", "nfreq", "npts", "stride", "acc_len"):
+            if getattr(da, k) != getattr(db, k):
+                bad.append(f"dft {i}.{k}: {getattr(da, k)} != {getattr(db, k)}")
+        if da.freq.tobytes() != db.freq.tobytes() or da.lines.tobytes() != db.lines.tobytes():
+            bad.append(f"dft {i}: frequency list or line list differs")
     return bad
 
 
