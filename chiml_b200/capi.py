@@ -75,6 +75,27 @@ class KernelStat(C.Structure):
                 ("alg_bytes_per_launch", C.c_double)]
 
 
+class _Tolerant:
+    """Attribute access on the CDLL that yields a dummy for symbols an OLDER build of the library lacks (development aid for A/B
+    timing of two builds through CHIML_B200_LIB); calling such a symbol raises."""
+
+    class _Missing:
+        def __init__(self, name):
+            self.name = name
+
+        def __call__(self, *a):
+            raise ChimlError(f"{self.name} is not exported by this build of the library")
+
+    def __init__(self, dll):
+        object.__setattr__(self, "_dll", dll)
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._dll, name)
+        except AttributeError:
+            return _Tolerant._Missing(name)
+
+
 _lib: Optional[C.CDLL] = None
 
 
@@ -86,7 +107,7 @@ def lib() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ChimlError(f"{LIB_PATH} is missing: build it with `make -C chiml_b200/csrc` (nvcc, sm_100a). "
                          "There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = _Tolerant(C.CDLL(os.environ.get("CHIML_B200_LIB", LIB_PATH)))
     vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
     L.chiml_gpu_device_count.restype = i
     L.chiml_gpu_create.argtypes = [C.POINTER(GridDesc), i, C.POINTER(vp)]

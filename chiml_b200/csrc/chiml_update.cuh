@@ -365,16 +365,14 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
     // ---- every load of this component is issued here, before any arithmetic waits on one of them -------------------------
     double2 dv = make_double2(0.0, 0.0);
     if(needD) dv = *reinterpret_cast<const double2*>(ca.D + r);
-    // coefficients: per-x pairs for the part whose derivative runs along x (at most one of the two), scalars for the other
-    double2 psv[2];
-    double2 Fx = make_double2(0.0, 0.0), bx = make_double2(0.0, 0.0), cx = make_double2(0.0, 0.0);
-    double Fs[2] = {0.0, 0.0}, bs[2] = {0.0, 0.0}, cs[2] = {0.0, 0.0};
+    double2 psv[2], Fv[2], bv[2], cv[2];
     long pip[2] = {0, 0};
-    int2 pcc = make_int2(0, 0);
+    int2 pcc[2];
 #pragma unroll
     for(int part = 0; part < 2; ++part)
     {
-        psv[part] = make_double2(0.0, 0.0);
+        psv[part] = Fv[part] = bv[part] = cv[part] = make_double2(0.0, 0.0);
+        pcc[part] = make_int2(0, 0);
         if(part == 0 ? !HAS_VK : !HAS_VJ) continue;
         const PmlArgs& pp = ca.pml[part];
         const unsigned fg = part == 0 ? F_PG0 : F_PG1;
@@ -384,24 +382,26 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
         const int axis = part == 0 ? AX0 : AX1;
         if(axis == 0)
         {
-            Fx = *reinterpret_cast<const double2*>(pp.F + x);
+            Fv[part] = *reinterpret_cast<const double2*>(pp.F + x);
             if(info & fs)
             {
-                bx = *reinterpret_cast<const double2*>(pp.b + x);
-                cx = *reinterpret_cast<const double2*>(pp.c + x);
-                pcc = *reinterpret_cast<const int2*>(pp.cmap + x);
+                bv[part] = *reinterpret_cast<const double2*>(pp.b + x);
+                cv[part] = *reinterpret_cast<const double2*>(pp.c + x);
+                pcc[part] = *reinterpret_cast<const int2*>(pp.cmap + x);
                 pip[part] = pp.psi_pitch * row;
-                if(m0) psv[part].x = pp.psi[pip[part] + pcc.x];
-                if(m1) psv[part].y = pp.psi[pip[part] + pcc.y];
+                if(m0) psv[part].x = pp.psi[pip[part] + pcc[part].x];
+                if(m1) psv[part].y = pp.psi[pip[part] + pcc[part].y];
             }
         }
         else
         {
             const int coord = axis == 1 ? y : z;
-            Fs[part] = pp.F[coord];
+            const double f = pp.F[coord];
+            Fv[part] = make_double2(f, f);
             if(info & fs)
             {
-                bs[part] = pp.b[coord]; cs[part] = pp.c[coord];
+                const double bb = pp.b[coord], cc = pp.c[coord];
+                bv[part] = make_double2(bb, bb); cv[part] = make_double2(cc, cc);
                 const int cm = pp.cmap[coord];
                 pip[part] = axis == 1 ? x + a.px * (z + (long)a.lz * cm) : x + a.px * (cm + (long)pp.nact * y);
                 psv[part] = *reinterpret_cast<const double2*>(pp.psi + pip[part]);
@@ -444,25 +444,22 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
             double2 ps = make_double2(0.0, 0.0);
             if(info & fs)
             {
-                const double2 bq = axis == 0 ? bx : make_double2(bs[part], bs[part]);
-                const double2 cq = axis == 0 ? cx : make_double2(cs[part], cs[part]);
                 double2 p = psv[part];
-                p.x = dm(bq.x, p.x);            p.y = dm(bq.y, p.y);
-                p.x = axpy1(p.x,  cq.x, vr.x);  p.y = axpy1(p.y,  cq.y, vr.y);
-                p.x = axpy1(p.x, -cq.x, vo.x);  p.y = axpy1(p.y, -cq.y, vo.y);
+                p.x = dm(bv[part].x, p.x);            p.y = dm(bv[part].y, p.y);
+                p.x = axpy1(p.x,  cv[part].x, vr.x);  p.y = axpy1(p.y,  cv[part].y, vr.y);
+                p.x = axpy1(p.x, -cv[part].x, vo.x);  p.y = axpy1(p.y, -cv[part].y, vo.y);
                 if(axis == 0)
                 {
-                    if(m0) pp.psi[pip[part] + pcc.x] = p.x;
-                    if(m1) pp.psi[pip[part] + pcc.y] = p.y;
+                    if(m0) pp.psi[pip[part] + pcc[part].x] = p.x;
+                    if(m1) pp.psi[pip[part] + pcc[part].y] = p.y;
                 }
                 else store_pair(pp.psi + pip[part], p, m0, m1);
                 ps = p;
             }
             if(info & fg)
             {
-                const double2 Fq = axis == 0 ? Fx : make_double2(Fs[part], Fs[part]);
-                w.x = axpy1(w.x,  Fq.x, vr.x); w.y = axpy1(w.y,  Fq.y, vr.y);
-                w.x = axpy1(w.x, -Fq.x, vo.x); w.y = axpy1(w.y, -Fq.y, vo.y);
+                w.x = axpy1(w.x,  Fv[part].x, vr.x); w.y = axpy1(w.y,  Fv[part].y, vr.y);
+                w.x = axpy1(w.x, -Fv[part].x, vo.x); w.y = axpy1(w.y, -Fv[part].y, vo.y);
                 if(info & fs) { w.x = axpy1(w.x, pp.Db, ps.x); w.y = axpy1(w.y, pp.Db, ps.y); }
             }
         }

@@ -17,7 +17,7 @@ def declared_symbols():
 
 
 def test_library_exports_every_declared_symbol():
-    L = capi.lib()
+    L = capi.lib()._dll          # the raw CDLL: the wrapper tolerates missing symbols of older builds
     names = declared_symbols()
     assert len(names) >= 20
     for n in names:
