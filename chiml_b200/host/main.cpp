@@ -1,0 +1,236 @@
+// chiml: the host driver of the B200 engine -- the counterpart of the reference's src/main.cpp:11-128.  Reads the same JSON input,
+// builds the propagator's lists on the host (build_plan), hands them to the CUDA library through the C ABI (include/chiml_gpu.h),
+// runs the time loop on the GPU, and writes the detector / population files the reference writes (TXT detectors,
+// DTC/parallelDTC_TXT.cpp:25-55; level populations, ML/QEPopDtc.cpp:37-61).
+//
+//   chiml <input.json> [--device D] [--steps N] [--rank R --nranks N --rendezvous DIR]
+//
+// One process drives one GPU.  With --nranks > 1 each process takes one y-slab; the halo blobs are exchanged through files in the
+// rendezvous directory (any shared directory), after which the slabs talk over NVLink only.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+#include <sys/stat.h>
+
+#include "../../include/chiml_gpu.h"
+#include "setup.hpp"
+
+using namespace chiml_host;
+
+static void check(ChimlCtx* ctx, int rc, const char* what)
+{
+    if(rc != CHIML_OK) throw std::runtime_error(std::string(what) + ": " + chiml_gpu_last_error(ctx));
+}
+
+static void make_dirs(const std::string& file)
+{
+    for(size_t i = 1; i < file.size(); ++i)
+        if(file[i] == '/') mkdir(file.substr(0, i).c_str(), 0777);
+}
+
+static std::vector<char> read_file_when_ready(const std::string& path)
+{
+    for(int tries = 0; tries < 6000; ++tries)
+    {
+        std::ifstream in(path.c_str(), std::ios::binary);
+        if(in) { std::vector<char> v((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>()); if(!v.empty()) return v; }
+        std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    }
+    throw std::runtime_error("rendezvous: " + path + " did not appear");
+}
+
+// local ghost-inclusive box of a detector's stored field inside this slab (parallelStorageDTC::genDatStruct); false if outside
+static bool local_box(const SlabPlan& P, const PlanDetector& d, int32_t loc[3], int32_t sz[3])
+{
+    const int ly = P.grid.desc.ln[1], lz = P.grid.desc.ln[2];
+    const int y0 = d.loc[1] - P.grid.y_start + 1, y1 = y0 + d.sz[1];
+    const int lo = std::max(y0, 1), hi = std::min(y1, ly - 1);
+    if(hi <= lo) return false;
+    loc[0] = d.loc[0] + 1; loc[1] = lo; loc[2] = lz > 1 ? d.loc[2] + 1 : 0;
+    sz[0] = d.sz[0]; sz[1] = hi - lo; sz[2] = lz > 1 ? d.sz[2] : 1;
+    return true;
+}
+
+int main(int argc, char** argv)
+{
+    std::string input, rendezvous;
+    int device = 0, rank = 0, nranks = 1, steps = -1;
+    for(int a = 1; a < argc; ++a)
+    {
+        const std::string s = argv[a];
+        auto next = [&]() -> const char* { if(a + 1 >= argc) throw std::runtime_error("missing value after " + s); return argv[++a]; };
+        try
+        {
+            if(s == "--device") device = std::atoi(next());
+            else if(s == "--rank") rank = std::atoi(next());
+            else if(s == "--nranks") nranks = std::atoi(next());
+            else if(s == "--rendezvous") rendezvous = next();
+            else if(s == "--steps") steps = std::atoi(next());
+            else if(input.empty()) input = s;
+            else throw std::runtime_error("unknown argument " + s);
+        }
+        catch(std::exception& e) { std::fprintf(stderr, "chiml: %s\n", e.what()); return 2; }
+    }
+    if(input.empty()) { std::fprintf(stderr, "usage: chiml <input.json> [--device D] [--steps N] [--rank R --nranks N --rendezvous DIR]\n"); return 2; }
+    ChimlCtx* ctx = nullptr;
+    try
+    {
+        Json root = read_input_file(input);
+        Inputs IP(root);
+        SlabPlan P = build_plan(IP, rank, nranks);
+        if(rank == 0) std::cout << "I TOOK ALL THE INPUT PARAMETERS" << std::endl;
+
+        if(chiml_gpu_create(&P.grid.desc, device, &ctx) != CHIML_OK) throw std::runtime_error(std::string("chiml_gpu_create: ") + chiml_gpu_last_error(nullptr));
+        for(int kind = 0; kind < 5; ++kind)
+            for(int comp = 0; comp < 6; ++comp)
+                if(!P.lists[kind][comp].empty())
+                    check(ctx, chiml_gpu_set_update_list(ctx, kind, comp, P.lists[kind][comp].data(), P.lists[kind][comp].size()), "set_update_list");
+        for(size_t o = 0; o < P.objects.size(); ++o)
+            check(ctx, chiml_gpu_set_object(ctx, (int)o, P.objects[o].npoles, P.objects[o].alpha.data(), P.objects[o].xi.data(), P.objects[o].gamma.data(),
+                                            P.objects[o].use_or_dip, P.objects[o].dip.data()), "set_object");
+        for(const PlanCpml& c : P.cpml)
+            check(ctx, chiml_gpu_set_cpml(ctx, c.comp, c.part, c.has_psi, c.psi.data(), c.psi.size(), c.grid.data(), c.grid.size()), "set_cpml");
+        for(const PlanSource& s : P.sources) check(ctx, chiml_gpu_add_source(ctx, s.field, s.loc, s.sz, nullptr), "add_source");
+        std::vector<int> detSlot(P.detectors.size(), -1);
+        for(size_t d = 0; d < P.detectors.size(); ++d)
+        {
+            int32_t loc[3], sz[3];
+            if(local_box(P, P.detectors[d], loc, sz)) check(ctx, chiml_gpu_add_detector(ctx, P.detectors[d].field, loc, sz, P.detectors[d].every, &detSlot[d]), "add_detector");
+        }
+        for(const PlanEmitter& e : P.emitters)
+        {
+            ChimlEmitterDesc d;
+            std::memset(&d, 0, sizeof(d));
+            d.nlevel = e.nlevel; d.nsys = e.nsys; d.nemit = e.nemit;
+            for(int k = 0; k < 3; ++k) { d.box_lo[k] = e.box_lo[k]; d.box_n[k] = e.box_n[k]; }
+            d.dt = e.dt; d.inv_hbar = e.inv_hbar; d.na = e.na;
+            d.h0 = e.h0.data(); d.weight = e.weight.data(); d.mu = e.mu.data();
+            d.gam_ptr = e.gam_ptr.data(); d.gam_col = e.gam_col.data(); d.gam_val = e.gam_val.data();
+            d.loc = e.loc.data(); d.eps = e.eps.data();
+            d.npop = (int)e.pop_level.size(); d.pop_level = e.pop_level.data(); d.pop_every = e.pop_every; d.npoints = e.npoints;
+            check(ctx, chiml_gpu_add_emitters(ctx, &d, nullptr), "add_emitters");
+        }
+        check(ctx, chiml_gpu_commit(ctx), "commit");
+
+        if(nranks > 1)
+        {
+            if(rendezvous.empty()) throw std::runtime_error("--nranks > 1 needs --rendezvous DIR");
+            size_t n = 0;
+            check(ctx, chiml_gpu_halo_export(ctx, nullptr, 0, &n), "halo_export");
+            std::vector<char> mine(n);
+            check(ctx, chiml_gpu_halo_export(ctx, mine.data(), n, &n), "halo_export");
+            const std::string my = rendezvous + "/halo." + std::to_string(rank);
+            { std::ofstream out((my + ".tmp").c_str(), std::ios::binary); out.write(mine.data(), (std::streamsize)n); }
+            std::rename((my + ".tmp").c_str(), my.c_str());
+            std::vector<char> lower, upper;
+            if(rank > 0) lower = read_file_when_ready(rendezvous + "/halo." + std::to_string(rank - 1));
+            if(rank + 1 < nranks) upper = read_file_when_ready(rendezvous + "/halo." + std::to_string(rank + 1));
+            check(ctx, chiml_gpu_halo_bind(ctx, lower.empty() ? nullptr : lower.data(), lower.size(), upper.empty() ? nullptr : upper.data(), upper.size()), "halo_bind");
+        }
+        if(rank == 0) std::cout << "made FF" << std::endl;
+
+        const int nSteps = steps >= 0 ? steps : P.grid.n_steps;
+        const int nsrc = (int)P.sources.size();
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<double> amp;
+        for(int done = 0; done < nSteps;)
+        {
+            const int n = std::min(256, nSteps - done);
+            amp.assign((size_t)n * std::max(nsrc, 1), 0.0);
+            for(int k = 0; k < n; ++k)
+                for(int q = 0; q < nsrc; ++q)
+                    if((size_t)(done + k) < P.sources[q].amp.size()) amp[(size_t)k * nsrc + q] = P.sources[q].amp[done + k];
+            check(ctx, chiml_gpu_step_n(ctx, n, nsrc ? amp.data() : nullptr), "step_n");
+            done += n;
+        }
+        check(ctx, chiml_gpu_sync(ctx), "sync");
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::cout << std::setw(9) << sec << "\t" << rank << "\t" << P.grid.y_start << std::endl;   // main.cpp:59-65 (wall clock here)
+
+        // ---- detector files (DTC/parallelDTC_TXT.cpp:25-55); a detector cut by a slab boundary is written by each slab for its part
+        for(size_t d = 0; d < P.detectors.size(); ++d)
+        {
+            if(detSlot[d] < 0) continue;
+            const PlanDetector& pd = P.detectors[d];
+            const DetectorInput& di = IP.detectors_[pd.detector];
+            if(di.cls != DTCCLASS::TXT) continue;
+            int32_t loc[3], sz[3];
+            local_box(P, pd, loc, sz);
+            const size_t len = (size_t)sz[0] * sz[1] * sz[2];
+            size_t ns = 0;
+            check(ctx, chiml_gpu_read_detector(ctx, detSlot[d], nullptr, 0, &ns), "read_detector");
+            std::vector<double> data(ns * len);
+            check(ctx, chiml_gpu_read_detector(ctx, detSlot[d], data.data(), ns, &ns), "read_detector");
+            std::string name = di.name;
+            if(nranks > 1) name += ".rank" + std::to_string(rank);
+            make_dirs(name);
+            std::ofstream out(name.c_str());
+            out << "# time\tx\ty\tz\tfield" << std::endl;
+            double rsl[3];
+            for(int k = 0; k < 3; ++k)
+            {
+                // realSpaceLoc_ (DTC/parallelDTC.hpp:61): d * (loc - (n_vec - 2 np - n_vec % 2) / 2) with the ghost-inclusive global n_vec;
+                // a 2-D grid has n_vec(z) = 1 and np(z) = 1, which makes the bracket -1
+                const int n = P.grid.n_global[k];
+                const int half = (k == 2 && P.grid.desc.ln[2] == 1) ? -1 : (n - n % 2) / 2;
+                rsl[k] = P.grid.desc.d[k] * (pd.loc[k] - half);
+            }
+            if(di.SI) for(int k = 0; k < 3; ++k) rsl[k] *= IP.a_ * IP.a_;     // scaled twice in the reference (parallelDTC.hpp:69,82)
+            for(size_t s = 0; s < ns; ++s)
+            {
+                const double t = (double)(s * (size_t)pd.every) * P.grid.desc.dt;
+                out << std::setprecision(6) << t * pd.t_conv << "\t" << rsl[0] << "\t" << rsl[1] << "\t" << rsl[2];
+                // sample layout: x fastest, then z, then y; the reference prints y outermost, then z, then x
+                for(size_t i = 0; i < len; ++i)
+                {
+                    double point = 0.0;
+                    point = point + (pd.conv / 2.0) * data[s * len + i];
+                    point = point + (pd.conv / 2.0) * data[s * len + i];     // single-component detectors: offset 0, the same cell twice
+                    out << "\t" << std::setw(24) << std::setprecision(18) << point;
+                }
+                out << '\n';
+            }
+        }
+        // ---- level populations (ML/QEPopDtc.cpp:37-61)
+        for(size_t q = 0; q < P.emitters.size(); ++q)
+        {
+            const PlanEmitter& e = P.emitters[q];
+            const QEInput& qi = IP.qes_[e.object];
+            for(size_t dd = 0; dd < e.pop_level.size(); ++dd)
+            {
+                size_t ns = 0;
+                check(ctx, chiml_gpu_read_population(ctx, (int)q, (int)dd, nullptr, 0, &ns), "read_population");
+                std::vector<double> pop(2 * ns);
+                check(ctx, chiml_gpu_read_population(ctx, (int)q, (int)dd, pop.data(), ns, &ns), "read_population");
+                std::string name = qi.dtcPopFiles[dd];
+                if(nranks > 1) name += ".rank" + std::to_string(rank);
+                make_dirs(name);
+                std::ofstream out(name.c_str());
+                for(size_t tt = 0; tt < ns; ++tt)
+                {
+                    const double re = pop[2 * tt], im = pop[2 * tt + 1];
+                    out << std::setw(9) << std::setprecision(9) << tt * e.pop_every * e.dt << "\t" << std::setw(16) << std::setprecision(16) << re << "\t"
+                        << std::setw(16) << std::setprecision(16) << im << "\t" << std::setw(16) << std::setprecision(16) << std::abs(std::complex<double>(re, im)) << std::endl;
+                }
+            }
+        }
+        chiml_gpu_destroy(ctx);
+    }
+    catch(std::exception& e)
+    {
+        std::fprintf(stderr, "chiml: %s\n", e.what());
+        if(ctx) chiml_gpu_destroy(ctx);
+        return 1;
+    }
+    return 0;
+}
