@@ -552,6 +552,30 @@ __device__ __forceinline__ void march_init(const StepArgs& a, const long r, cons
     if(Y2) c2 = *reinterpret_cast<const double2*>(a.fam[2] + o);
 }
 
+// L2 prefetch of one 128-byte line (fire and forget: holds no register and no shared memory).  The marching kernels touch every
+// array at a fixed plane stride, so the lines of the plane two steps ahead are requested while the current plane is computed; the
+// demand loads then pay L2 latency instead of HBM latency, which is what the UNIFORM kernels (few warps, many arrays) are short of.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+constexpr int PREFETCH_PLANES = 2;
+
+// psi lines of component C of a UNIFORM tile at plane y (address arithmetic of uniform_rect), for the rectangle with this info
+template <bool IS_E, int MODE, int C>
+__device__ __forceinline__ void prefetch_psi(const StepArgs& a, const unsigned info, const int x, const int y, const int z)
+{
+    const CompArgs& ca = a.c[C];
+#pragma unroll
+    for(int part = 0; part < 2; ++part)
+    {
+        const unsigned fs = part == 0 ? F_PS0 : F_PS1;
+        if(!(info & fs)) continue;
+        constexpr int AX0 = (C + 1) % 3, AX1 = (C + 2) % 3;
+        const int axis = part == 0 ? AX0 : AX1;
+        const PmlArgs& pp = ca.pml[part];
+        if(axis == 1)      { const int cm = pp.cmap[y]; if(cm >= 0) prefetch_l2(pp.psi + x + a.px * (z + (long)a.lz * cm)); }
+        else if(axis == 2) { const int cm = pp.cmap[z]; if(cm >= 0) prefetch_l2(pp.psi + x + a.px * (cm + (long)pp.nact * y)); }
+    }
+}
+
 // One component per thread (blockDim.z selects it): each thread issues the <= 8 independent loads of ITS component at once -- own
 // value, the two driving arrays at the cell, their two stencil neighbours, D, psi -- so a plane costs one memory latency instead
 // of one per component, and three times as many warps are resident.  The driving arrays are shared between components; the
@@ -602,9 +626,22 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
     double2 carry;
     comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
     const bool needU = !IS_E || (t.rect[C] != 0 && !(t.info[C] & F_D2E)) || (t.rectB[C] != 0 && !(t.infoB[C] & F_D2E));
+    const unsigned anyInfo = (t.rect[C] ? t.info[C] : 0u) | (t.rectB[C] ? t.infoB[C] : 0u);
+    const bool anyD = IS_E && a.c[C].D && ((anyInfo & (F_ISD | F_D2E)) || (a.pml_on_D && (anyInfo & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
+    const bool leader = (threadIdx.x & 7) == 0;      // one lane per 128-byte line
     for(int iy = 0; iy < t.ny; ++iy, r += plane)
     {
         const int y = t.y + iy;
+        if(leader && iy + PREFETCH_PLANES < t.ny)
+        {
+            const long rp = r + PREFETCH_PLANES * plane;
+            if(has_other<IS_E, MODE>((C + 1) % 3)) prefetch_l2(a.fam[(C + 1) % 3] + rp);
+            if(has_other<IS_E, MODE>((C + 2) % 3)) prefetch_l2(a.fam[(C + 2) % 3] + rp);
+            if(needU) prefetch_l2(a.c[C].U + rp);
+            if(anyD) prefetch_l2(a.c[C].D + rp);
+            if(t.rect[C])  prefetch_psi<IS_E, MODE, C>(a, t.info[C], x, y + PREFETCH_PLANES, z);
+            if(t.rectB[C]) prefetch_psi<IS_E, MODE, C>(a, t.infoB[C], x, y + PREFETCH_PLANES, z);
+        }
         PairLoads<IS_E, MODE> L;
         comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L, needU);
         uniform_comp<IS_E, MODE, C>(a, t, L, r, z + (long)a.lz * y, x, y, z, xl, zl);
@@ -626,10 +663,27 @@ __global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_uniform(co
         long r = x + a.px * (z + (long)a.lz * t.y);
         double2 c0, c2;
         march_init<IS_E, MODE>(a, r, plane, c0, c2);
+        const bool leader = (threadIdx.x & 7) == 0;
         for(int iy = 0; iy < t.ny; ++iy, r += plane)
         {
             const int y = t.y + iy;
             const long row = z + (long)a.lz * y;
+            if(leader && iy + PREFETCH_PLANES < t.ny)
+            {
+                const long rp = r + PREFETCH_PLANES * plane;
+#pragma unroll
+                for(int c = 0; c < 3; ++c)
+                {
+                    if(has_other<IS_E, MODE>(c)) prefetch_l2(a.fam[c] + rp + (IS_E ? 0 : plane));
+                    if(has_own<IS_E, MODE>(c)) prefetch_l2(a.c[c].U + rp);
+                }
+                if(t.rect[0])  prefetch_psi<IS_E, MODE, 0>(a, t.info[0], x, y + PREFETCH_PLANES, z);
+                if(t.rectB[0]) prefetch_psi<IS_E, MODE, 0>(a, t.infoB[0], x, y + PREFETCH_PLANES, z);
+                if(t.rect[1])  prefetch_psi<IS_E, MODE, 1>(a, t.info[1], x, y + PREFETCH_PLANES, z);
+                if(t.rectB[1]) prefetch_psi<IS_E, MODE, 1>(a, t.infoB[1], x, y + PREFETCH_PLANES, z);
+                if(t.rect[2])  prefetch_psi<IS_E, MODE, 2>(a, t.info[2], x, y + PREFETCH_PLANES, z);
+                if(t.rectB[2]) prefetch_psi<IS_E, MODE, 2>(a, t.infoB[2], x, y + PREFETCH_PLANES, z);
+            }
             PairLoads<IS_E, MODE> L;
             march_load<IS_E, MODE>(a, r, plane, c0, c2, L);
             uniform_comp<IS_E, MODE, 0>(a, t, L, r, row, x, y, z, xl, zl);
