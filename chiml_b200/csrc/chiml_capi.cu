@@ -986,20 +986,7 @@ void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int 
         count[k] = part == 0 ? n : (part == 1 ? nb : n - nb);
     }
     if(count[0]) { LaunchScope ls(ctx, k0);     k_fast<IS_E, MODE><<<count[0], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0] + first[0]); }
-    if(count[1])
-    {
-        LaunchScope ls(ctx, k0 + 1);
-        static const bool usePipe = std::getenv("CHIML_NO_PIPE") == nullptr;
-        if(IS_E && usePipe && block.y == TILE_Z)
-        {
-            // E half step of UNIFORM tiles: asynchronous shared-memory pipeline (chiml_pipe.cuh), 192 KB of slots per block
-            static bool attr[3] = {false, false, false};
-            if(!attr[MODE]) { cudaFuncSetAttribute(k_uniform_pipe<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM); attr[MODE] = true; }
-            k_uniform_pipe<MODE><<<count[1], dim3(block.x, block.y, 3), PIPE_SMEM, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1] + first[1]);
-        }
-        else
-            k_uniform<IS_E, MODE, IS_E><<<count[1], dim3(block.x, block.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1] + first[1]);
-    }
+    if(count[1]) { LaunchScope ls(ctx, k0 + 1); k_uniform<IS_E, MODE, IS_E><<<count[1], dim3(block.x, block.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1] + first[1]); }
     if(count[2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE, IS_E><<<count[2], dim3(block.x, block.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2]); }
 }
 template <bool IS_E>
