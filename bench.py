@@ -284,6 +284,7 @@ def b200_arm(args):
         sim.sync()
         barrier()
         e2e_s = allmax(time.perf_counter() - t0)
+        h2d, d2h = allsum(float(h2d)), allsum(float(d2h))     # whole job: the source / detector cells live in one or two slabs
         clk = clocks.stop()
         e2e_value = cells_total * K / e2e_s / 1e6
 
