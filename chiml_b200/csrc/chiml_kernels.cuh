@@ -117,7 +117,6 @@ __device__ __forceinline__ double node_value(const StepArgs& a, const double* po
 
 } // namespace chiml
 #include "chiml_update.cuh"
-#include "chiml_cells.cuh"
 #include "chiml_emitters.cuh"
 #include "chiml_halo.cuh"
 namespace chiml {
