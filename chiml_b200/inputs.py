@@ -190,7 +190,8 @@ def c3_aniso_slab(n: int = 511, steps: int = 1000, res: int = 100, pml_cells: in
 
 
 def c4_plasmonic_ml(n: int = 767, steps: int = 500, res: int = 100, pml_cells: int = 20, cube: int = 40, pitch: int = 70, narray: int = 10,
-                    sheet: int = 1000, metal: str = "Au", out: str = "output_data/c4", ny: Optional[int] = None, nz: Optional[int] = None) -> Dict:
+                    sheet: int = 1000, metal: str = "Au", out: str = "output_data/c4", ny: Optional[int] = None, nz: Optional[int] = None,
+                    sheet_gap: int = 10, src_margin: int = 10) -> Dict:
     """C4: narray x narray metal cubes under a one-node-thick two-level emitter sheet, Ez plane source."""
     dt = default_dt(res)
     ny = n if ny is None else ny
@@ -200,14 +201,17 @@ def c4_plasmonic_ml(n: int = 767, steps: int = 500, res: int = 100, pml_cells: i
     for iy in range(narray):
         for ix in range(narray):
             objs.append(block([cube / res] * 3, [(x0 + ix * pitch) / res, (x0 + iy * pitch) / res, 0.0], material=metal))
-    zs = (cube / 2 + 10) / res
+    # one node thick: exactly on a grid node (nodes sit at (k - cells/2) * d, half-integers for odd cell counts)
+    zs = (math.floor(nz / 2.0 + cube / 2 + sheet_gap) - nz / 2.0) / res
     objs.append(ml_block([(sheet - 1) / res, (sheet - 1) / res, 0.0], [0.0, 0.0, zs], mol_den=1e25, e_levels_ev=[0.0, 2.0], dipole_debye=10.0,
                          relax_rate=1e12, dephasing_rate=1e13, dtc_levs=[3], pop_fname_base=out + "/qe_"))
     half_z = nz / res / 2.0
-    span_x, span_y = (n - 2 * pml_cells - 20) / res, (ny - 2 * pml_cells - 20) / res
+    mx_, my_ = min(10, (n - 2 * pml_cells) // 4), min(10, (ny - 2 * pml_cells) // 4)      # source margin to the CPML, in cells
+    span_x, span_y = (n - 2 * pml_cells - 2 * mx_) / res, (ny - 2 * pml_cells - 2 * my_) / res
+    src_z = half_z - (pml_cells + src_margin) / res        # keep it outside the emitter object's 3-cell buffer: a source inside a D-cell is overwritten
     return config(comp_cell([n / res, ny / res, nz / res], res, steps * dt - 0.5 * dt, "Ez"),
                   pml([pml_cells / res] * 3),
-                  [normal_source("Ex", [0.0, 0.0, half_z - (pml_cells + 10) / res], [span_x, span_y, 0.0], [gaussian_pulse(1.5 * 2.0 / 1.86, 1.0)])],
+                  [normal_source("Ex", [0.0, 0.0, src_z], [span_x, span_y, 0.0], [gaussian_pulse(1.5 * 2.0 / 1.86, 1.0)])],
                   objs,
                   [detector([0.0, 0.0, zs], [0.0, 0.0, 0.0], "Ex", out + "/dtc", time_int=dt * 1.0000001)])
 

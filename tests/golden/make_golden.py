@@ -81,6 +81,12 @@ def cases():
                           [I.normal_source("Ex", [-0.1, -0.08, 0], [0, 0, 0], [pulse(1.5, 3e13)])],
                           [pxy],
                           [I.detector([0.03, 0, 0], [0, 0, 0], "Ex", "out/mte/dtc", time_int=DT * 1.0000001)])
+    # ---- C4 in miniature: built-in 6-pole Au cubes under a two-level emitter sheet, Ex plane source, CPML on every face ----
+    c4 = I.c4_plasmonic_ml(n=27, ny=25, nz=37, steps=60, pml_cells=5, cube=6, pitch=10, narray=2, sheet=12, out="out/c4s", sheet_gap=3, src_margin=2)
+    for s_ in c4["SourceList"]:
+        for p_ in s_["PulseList"]:
+            p_["Field_Intensity"] = 3e13
+    c["c4_small"] = _short_pulse(c4)
     # ---- running DFT on the four edges of a flux box around a Drude rod (DTC/parallelFlux.hpp, parallelStorageFreqDTC.cpp:21-30) ----
     c["tm_flux"] = _short_pulse(I.c2_tm_drude(n=63, steps=100, pml_cells=8, rod=(20, 6), nfreq=5, out="out/tmflux"))
     return c
