@@ -52,9 +52,19 @@ def parse_args():
     ap.add_argument("--nx", type=int, default=2048, help="grid points along x (whole grid)")
     ap.add_argument("--ny-per-gpu", type=int, default=256, help="grid points along y per GPU (y-slab height)")
     ap.add_argument("--nz", type=int, default=1024, help="grid points along z")
+    ap.add_argument("--workload", default="c5", choices=["c5", "c1", "c2", "c3", "c4"],
+                    help="c5 (default) is the bench contract; c1..c4 are the other BASELINE.md configurations at full size, for the record "
+                         "(single GPU, no CPU baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--keep", action="store_true", help="keep the scratch directory")
     return ap.parse_args()
+
+
+OTHER = {"c1": ("C1: 2-D TE vacuum 512x512, Hz dipole, CPML 20, Hz detector", lambda steps: I.c1_te_vacuum(n=511, steps=steps)),
+         "c2": ("C2: 2-D TM Drude nanorod 2048x2048, CPML 20, Ez line source (flux accumulators not built by the host setup yet)",
+                lambda steps: I.c2_tm_drude(n=2047, steps=steps, nfreq=0)),
+         "c3": ("C3: 3-D anisotropic (oriented-dipole Lorentz) slab waveguide 512^3, CPML all faces", lambda steps: I.c3_aniso_slab(n=511, steps=steps)),
+         "c4": ("C4: 3-D 10x10 Au (6-pole) cubes + two-level emitter sheet (1e6 emitters), 768^3", lambda steps: I.c4_plasmonic_ml(n=767, steps=steps))}
 
 
 def workload_cfg(nx_pts: int, ny_pts: int, nz_pts: int, steps: int):
@@ -227,7 +237,13 @@ def b200_arm(args):
     try:
         # the input a user would write, then the host-side setup (C++) for this rank's y-slab
         total_steps = W + 3 * K + 8
-        cfg = workload_cfg(nx, nyg * world, nz, total_steps)
+        if args.workload != "c5":
+            if world != 1:
+                raise SystemExit("bench.py: --workload c1..c4 are single-GPU record runs")
+            cfg = OTHER[args.workload][1](total_steps)
+            args.no_cpu_baseline = True
+        else:
+            cfg = workload_cfg(nx, nyg * world, nz, total_steps)
         jpath = os.path.join(work, "bench.json")
         I.write(cfg, jpath)
         t0 = time.time()
@@ -318,7 +334,7 @@ def b200_arm(args):
 
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(nx, nyg, nz, world), "l2": "inputs_larger_than_L2 (every state array > 4 GB)" if cells_local * 8 > 2.5e8 else "small grid: arrays may fit L2",
+                "config": {"workload": workload_name(nx, nyg, nz, world) if args.workload == "c5" else OTHER[args.workload][0], "l2": "inputs_larger_than_L2 (every state array > 4 GB)" if cells_local * 8 > 2.5e8 else "small grid: arrays may fit L2",
                            "census_rank0": cs.as_dict(), "device_GB_rank0": sim.device_bytes() / 1e9, "setup_s_rank0": round(setup_s, 1),
                            "fields": "zero initial state driven by the dipole source (reference behaviour); timing is data-independent"},
                 "clocks": clk,
