@@ -986,7 +986,14 @@ void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int 
         count[k] = part == 0 ? n : (part == 1 ? nb : n - nb);
     }
     if(count[0]) { LaunchScope ls(ctx, k0);     k_fast<IS_E, MODE><<<count[0], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0] + first[0]); }
-    if(count[1]) { LaunchScope ls(ctx, k0 + 1); k_uniform<IS_E, MODE, IS_E><<<count[1], dim3(block.x, block.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1] + first[1]); }
+    if(count[1])
+    {
+        // 3-D: two half-tile blocks per tile (chiml_update.cuh, UNIFORM_SPLIT_Z); 2-D tiles are a single row
+        LaunchScope ls(ctx, k0 + 1);
+        const unsigned zsplit = block.y == TILE_Z ? UNIFORM_SPLIT_Z : 1;
+        if(zsplit == 1) k_uniform_rows<IS_E, MODE, IS_E><<<count[1], dim3(block.x, block.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1] + first[1]);
+        else k_uniform<IS_E, MODE, IS_E><<<count[1] * zsplit, dim3(block.x, block.y / zsplit, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1] + first[1]);
+    }
     if(count[2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE, IS_E><<<count[2], dim3(block.x, block.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2]); }
 }
 template <bool IS_E>

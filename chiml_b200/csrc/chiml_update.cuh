@@ -494,6 +494,8 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
     }
 }
 
+constexpr int UNIFORM_SPLIT_Z = 2;     // blocks per 3-D tile in k_uniform (2-D grids have one row per tile and are launched unsplit)
+
 // One plane of loads for a block that marches along y (see k_fast): fills L for the plane at r; c0 / c2 carry the y-coupled arrays
 // from plane to plane (E half step: the plane below; H half step: the current plane, loaded as "next" one iteration earlier).
 template <bool IS_E, int MODE>
@@ -651,10 +653,8 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
 // The E half step (D and psi arrays per component) gains from the split; the H half step, whose traffic is mostly the shared driving
 // arrays, is faster with all three components in one thread (measured: profiles/README.md), so it is launched with blockDim.z = 1.
 template <bool IS_E, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+__device__ __forceinline__ void uniform_body(const StepArgs& a, const TileRec& t, const int xl, const int zl)
 {
-    const TileRec& t = tiles[blockIdx.x];
-    const int xl = 2 * threadIdx.x, zl = threadIdx.y;
     const int x = t.x0 + xl, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
     if(!SPLIT)
@@ -695,6 +695,21 @@ __global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_uniform(co
     if(threadIdx.z == 0)      uniform_march<IS_E, MODE, 0>(a, t, xl, zl, x, z);
     else if(threadIdx.z == 1) uniform_march<IS_E, MODE, 1>(a, t, xl, zl, x, z);
     else                      uniform_march<IS_E, MODE, 2>(a, t, xl, zl, x, z);
+}
+
+// Half tiles: a block owns 4 of the 8 z rows of a tile (blockIdx.x % UNIFORM_SPLIT_Z selects which), so that TWO (SPLIT) or FOUR (joint)
+// independent blocks share an SM.  All warps of one block march in lock-step -- they issue their loads together and wait together --
+// and with a single resident block the SM idles for a full HBM latency per plane; independent blocks drift apart and fill the gaps.
+template <bool IS_E, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 384 : 128, SPLIT ? 2 : 4) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+{
+    uniform_body<IS_E, MODE, SPLIT>(a, tiles[blockIdx.x / UNIFORM_SPLIT_Z], 2 * threadIdx.x, threadIdx.y + (TILE_Z / UNIFORM_SPLIT_Z) * (blockIdx.x % UNIFORM_SPLIT_Z));
+}
+// 2-D grids: a tile is one row of 64 cells
+template <bool IS_E, int MODE, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 96 : 32) k_uniform_rows(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+{
+    uniform_body<IS_E, MODE, SPLIT>(a, tiles[blockIdx.x], 2 * threadIdx.x, threadIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------------
