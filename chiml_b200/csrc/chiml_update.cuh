@@ -343,11 +343,15 @@ __global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArg
 // k_uniform: tiles where each component has ONE info value over a rectangle: curl into E/H or D, CPML parts
 // (psi recursion + grid terms) on E/H or D, pole-free D->E.  Block-uniform control flow, no cell-info reads.
 // ---------------------------------------------------------------------------------------------------
-template <bool IS_E, int MODE, int C>
-__device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned rect, const unsigned info, const double2 pfc, const double inv_eps,
+constexpr unsigned FL_RUNTIME = 0xFFFFFFFFu;
+
+// FL: the flag byte of the rectangle's info value as a compile-time constant (every `flags & X` below folds away), or FL_RUNTIME
+template <bool IS_E, int MODE, int C, unsigned FL>
+__device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned rect, const unsigned info_rt, const double2 pfc, const double inv_eps,
                                              const PairLoads<IS_E, MODE>& L,
                                              const long r, const long row, const int x, const int y, const int z, const int xl, const int zl)
 {
+    const unsigned info = FL == FL_RUNTIME ? info_rt : FL;
     const CompArgs& ca = a.c[C];
     constexpr bool HAS_VJ = has_other<IS_E, MODE>((C + 1) % 3);
     constexpr bool HAS_VK = has_other<IS_E, MODE>((C + 2) % 3);
@@ -488,8 +492,53 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
         {
             const unsigned rect = w == 0 ? t.rect[C] : t.rectB[C];
             if(rect == 0) continue;
-            uniform_rect<IS_E, MODE, C>(a, rect, w == 0 ? t.info[C] : t.infoB[C], w == 0 ? t.pf[C] : t.pfB[C], w == 0 ? t.inv_eps[C] : t.inv_epsB[C],
-                                        L, r, row, x, y, z, xl, zl);
+            const unsigned info = w == 0 ? t.info[C] : t.infoB[C];
+            const double2 pfc = w == 0 ? t.pf[C] : t.pfB[C];
+            const double ie = w == 0 ? t.inv_eps[C] : t.inv_epsB[C];
+            // the flag combinations the reference's lists produce for pole-free cells get a body compiled for exactly that combination
+            // (the flag tests, dead branches and zero-initialised operands of the generic body are most of its instructions)
+#define CHIML_UCASE(F) case (F): uniform_rect<IS_E, MODE, C, (F)>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl); break;
+            constexpr bool VJ = has_other<IS_E, MODE>((C + 1) % 3), VK = has_other<IS_E, MODE>((C + 2) % 3);
+            switch(info & 0xFF00u)
+            {
+                CHIML_UCASE(F_CURL)
+                default:
+                    if constexpr(IS_E)
+                    {
+                        switch(info & 0xFF00u)
+                        {
+                            CHIML_UCASE(F_CURL | F_ISD | F_D2E)
+                            default:
+                                if constexpr(VJ && VK)
+                                    switch(info & 0xFF00u)
+                                    {
+                                        CHIML_UCASE(F_PG0 | F_PG1 | F_D2E)
+                                        CHIML_UCASE(F_PG0 | F_PS0 | F_PG1 | F_D2E)
+                                        CHIML_UCASE(F_PG0 | F_PG1 | F_PS1 | F_D2E)
+                                        CHIML_UCASE(F_PG0 | F_PS0 | F_PG1 | F_PS1 | F_D2E)
+                                        CHIML_UCASE(F_PG0 | F_PG1)
+                                        CHIML_UCASE(F_PG0 | F_PS0 | F_PG1)
+                                        CHIML_UCASE(F_PG0 | F_PG1 | F_PS1)
+                                        CHIML_UCASE(F_PG0 | F_PS0 | F_PG1 | F_PS1)
+                                        default: uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl);
+                                    }
+                                else uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl);
+                        }
+                    }
+                    else if constexpr(VJ && VK)
+                    {
+                        switch(info & 0xFF00u)
+                        {
+                            CHIML_UCASE(F_PG0 | F_PG1)
+                            CHIML_UCASE(F_PG0 | F_PS0 | F_PG1)
+                            CHIML_UCASE(F_PG0 | F_PG1 | F_PS1)
+                            CHIML_UCASE(F_PG0 | F_PS0 | F_PG1 | F_PS1)
+                            default: uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl);
+                        }
+                    }
+                    else uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl);
+            }
+#undef CHIML_UCASE
         }
     }
 }
@@ -630,7 +679,7 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
     const bool needU = !IS_E || (t.rect[C] != 0 && !(t.info[C] & F_D2E)) || (t.rectB[C] != 0 && !(t.infoB[C] & F_D2E));
     const unsigned anyInfo = (t.rect[C] ? t.info[C] : 0u) | (t.rectB[C] ? t.infoB[C] : 0u);
     const bool anyD = IS_E && a.c[C].D && ((anyInfo & (F_ISD | F_D2E)) || (a.pml_on_D && (anyInfo & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
-    const bool leader = (threadIdx.x & 7) == 0;      // one lane per 128-byte line
+    const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector (the prefetch unit of L2)
     for(int iy = 0; iy < t.ny; ++iy, r += plane)
     {
         const int y = t.y + iy;
@@ -663,7 +712,7 @@ __device__ __forceinline__ void uniform_body(const StepArgs& a, const TileRec& t
         long r = x + a.px * (z + (long)a.lz * t.y);
         double2 c0, c2;
         march_init<IS_E, MODE>(a, r, plane, c0, c2);
-        const bool leader = (threadIdx.x & 7) == 0;
+        const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector
         for(int iy = 0; iy < t.ny; ++iy, r += plane)
         {
             const int y = t.y + iy;
