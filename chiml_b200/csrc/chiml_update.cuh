@@ -346,18 +346,68 @@ __global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArg
 constexpr unsigned FL_RUNTIME = 0xFFFFFFFFu;
 
 // FL: the flag byte of the rectangle's info value as a compile-time constant (every `flags & X` below folds away), or FL_RUNTIME
-template <bool IS_E, int MODE, int C, unsigned FL>
+// CPML coefficients that do not change from plane to plane: per-x pairs (derivative along x), z scalars (along z)
+struct PmlCoef { double2 F[2], b[2], c[2]; int2 cc[2]; int cmz[2]; };
+
+template <bool IS_E, int MODE, int C>
+__device__ __forceinline__ void pml_coef_static(const StepArgs& a, const unsigned info, const int x, const int z, PmlCoef& k)
+{
+    const CompArgs& ca = a.c[C];
+#pragma unroll
+    for(int part = 0; part < 2; ++part)
+    {
+        k.F[part] = k.b[part] = k.c[part] = make_double2(0.0, 0.0);
+        k.cc[part] = make_int2(0, 0); k.cmz[part] = 0;
+        if(part == 0 ? !has_other<IS_E, MODE>((C + 2) % 3) : !has_other<IS_E, MODE>((C + 1) % 3)) continue;
+        const PmlArgs& pp = ca.pml[part];
+        const unsigned fg = part == 0 ? F_PG0 : F_PG1, fs = part == 0 ? F_PS0 : F_PS1;
+        if(!(info & (fg | fs))) continue;
+        constexpr int AX0 = (C + 1) % 3, AX1 = (C + 2) % 3;
+        const int axis = part == 0 ? AX0 : AX1;
+        if(axis == 0)
+        {
+            k.F[part] = *reinterpret_cast<const double2*>(pp.F + x);
+            if(info & fs)
+            {
+                k.b[part] = *reinterpret_cast<const double2*>(pp.b + x);
+                k.c[part] = *reinterpret_cast<const double2*>(pp.c + x);
+                k.cc[part] = *reinterpret_cast<const int2*>(pp.cmap + x);
+            }
+        }
+        else if(axis == 2)
+        {
+            const double f = pp.F[z];
+            k.F[part] = make_double2(f, f);
+            if(info & fs)
+            {
+                const double bb = pp.b[z], cc = pp.c[z];
+                k.b[part] = make_double2(bb, bb); k.c[part] = make_double2(cc, cc);
+                k.cmz[part] = pp.cmap[z];
+            }
+        }
+    }
+}
+
+// HOISTED: the caller marches a column of planes and passes the masks and the plane-independent coefficients it computed once
+template <bool IS_E, int MODE, int C, unsigned FL, bool HOISTED = false>
 __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned rect, const unsigned info_rt, const double2 pfc, const double inv_eps,
                                              const PairLoads<IS_E, MODE>& L,
-                                             const long r, const long row, const int x, const int y, const int z, const int xl, const int zl)
+                                             const long r, const long row, const int x, const int y, const int z, const int xl, const int zl,
+                                             const bool hm0 = false, const bool hm1 = false, const PmlCoef* hc = nullptr)
 {
     const unsigned info = FL == FL_RUNTIME ? info_rt : FL;
     const CompArgs& ca = a.c[C];
     constexpr bool HAS_VJ = has_other<IS_E, MODE>((C + 1) % 3);
     constexpr bool HAS_VK = has_other<IS_E, MODE>((C + 2) % 3);
-    bool m0, m1;
-    rect_mask(rect, xl, zl, m0, m1);
-    if(!(m0 || m1)) return;
+    bool m0 = hm0, m1 = hm1;
+    PmlCoef own;
+    if(!HOISTED)
+    {
+        rect_mask(rect, xl, zl, m0, m1);
+        if(!(m0 || m1)) return;
+        pml_coef_static<IS_E, MODE, C>(a, info, x, z, own);
+    }
+    const PmlCoef& kc = HOISTED ? *hc : own;
     const double2 vj = L.v[(C + 1) % 3], vk = L.v[(C + 2) % 3];
     const double2 nj = L.nj[C], nk = L.nk[C];
     double2 u = L.u[C];
@@ -375,8 +425,8 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
 #pragma unroll
     for(int part = 0; part < 2; ++part)
     {
-        psv[part] = Fv[part] = bv[part] = cv[part] = make_double2(0.0, 0.0);
-        pcc[part] = make_int2(0, 0);
+        psv[part] = make_double2(0.0, 0.0);
+        Fv[part] = kc.F[part]; bv[part] = kc.b[part]; cv[part] = kc.c[part]; pcc[part] = kc.cc[part];
         if(part == 0 ? !HAS_VK : !HAS_VJ) continue;
         const PmlArgs& pp = ca.pml[part];
         const unsigned fg = part == 0 ? F_PG0 : F_PG1;
@@ -386,30 +436,30 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
         const int axis = part == 0 ? AX0 : AX1;
         if(axis == 0)
         {
-            Fv[part] = *reinterpret_cast<const double2*>(pp.F + x);
             if(info & fs)
             {
-                bv[part] = *reinterpret_cast<const double2*>(pp.b + x);
-                cv[part] = *reinterpret_cast<const double2*>(pp.c + x);
-                pcc[part] = *reinterpret_cast<const int2*>(pp.cmap + x);
                 pip[part] = pp.psi_pitch * row;
                 if(m0) psv[part].x = pp.psi[pip[part] + pcc[part].x];
                 if(m1) psv[part].y = pp.psi[pip[part] + pcc[part].y];
             }
         }
-        else
+        else if(axis == 1)
         {
-            const int coord = axis == 1 ? y : z;
-            const double f = pp.F[coord];
+            const double f = pp.F[y];
             Fv[part] = make_double2(f, f);
             if(info & fs)
             {
-                const double bb = pp.b[coord], cc = pp.c[coord];
+                const double bb = pp.b[y], cc = pp.c[y];
                 bv[part] = make_double2(bb, bb); cv[part] = make_double2(cc, cc);
-                const int cm = pp.cmap[coord];
-                pip[part] = axis == 1 ? x + a.px * (z + (long)a.lz * cm) : x + a.px * (cm + (long)pp.nact * y);
+                const int cm = pp.cmap[y];
+                pip[part] = x + a.px * (z + (long)a.lz * cm);
                 psv[part] = *reinterpret_cast<const double2*>(pp.psi + pip[part]);
             }
+        }
+        else if(info & fs)
+        {
+            pip[part] = x + a.px * (kc.cmz[part] + (long)pp.nact * y);
+            psv[part] = *reinterpret_cast<const double2*>(pp.psi + pip[part]);
         }
     }
 
@@ -668,10 +718,69 @@ __device__ __forceinline__ void comp_march_load(const StepArgs& a, const long r,
     if(KY && has_other<IS_E, MODE>(K)) carry = IS_E ? L.v[K] : nextPlane;
 }
 
+// a column of planes of a single-rectangle tile with the flag byte known at compile time: masks, prefactors and the plane-independent
+// CPML coefficients are set up once, the plane loop holds only loads, the reference's arithmetic and stores
+template <bool IS_E, int MODE, int C, unsigned FL>
+__device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec& t, const int xl, const int zl, const int x, const int z)
+{
+    bool m0, m1;
+    rect_mask(t.rect[C], xl, zl, m0, m1);
+    if(!(m0 || m1)) return;
+    PmlCoef kc;
+    pml_coef_static<IS_E, MODE, C>(a, FL, x, z, kc);
+    const double2 pfc = t.pf[C];
+    const double ie = t.inv_eps[C];
+    const long plane = a.px * a.lz;
+    long r = x + a.px * (z + (long)a.lz * t.y);
+    double2 carry;
+    comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
+    constexpr bool needU = !IS_E || !(FL & F_D2E);
+    const bool anyD = IS_E && a.c[C].D && ((FL & (F_ISD | F_D2E)) || (a.pml_on_D && (FL & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
+    const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector (the prefetch unit of L2)
+    const int ny = t.ny, y0 = t.y;
+    for(int iy = 0; iy < ny; ++iy, r += plane)
+    {
+        const int y = y0 + iy;
+        if(leader && iy + PREFETCH_PLANES < ny)
+        {
+            const long rp = r + PREFETCH_PLANES * plane;
+            if(has_other<IS_E, MODE>((C + 1) % 3)) prefetch_l2(a.fam[(C + 1) % 3] + rp);
+            if(has_other<IS_E, MODE>((C + 2) % 3)) prefetch_l2(a.fam[(C + 2) % 3] + rp);
+            if(needU) prefetch_l2(a.c[C].U + rp);
+            if(anyD) prefetch_l2(a.c[C].D + rp);
+            prefetch_psi<IS_E, MODE, C>(a, FL, x, y + PREFETCH_PLANES, z);
+        }
+        PairLoads<IS_E, MODE> L;
+        comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L, needU);
+        uniform_rect<IS_E, MODE, C, FL, true>(a, 0u, FL, pfc, ie, L, r, z + (long)a.lz * y, x, y, z, xl, zl, m0, m1, &kc);
+    }
+}
+
 template <bool IS_E, int MODE, int C>
 __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& t, const int xl, const int zl, const int x, const int z)
 {
     if(!has_own<IS_E, MODE>(C) || (t.rect[C] == 0 && t.rectB[C] == 0)) return;
+    if constexpr(has_own<IS_E, MODE>(C) && has_other<IS_E, MODE>((C + 1) % 3) && has_other<IS_E, MODE>((C + 2) % 3))
+    {
+        if(t.rectB[C] == 0)
+        {
+#define CHIML_COL(F) case (F): uniform_column<IS_E, MODE, C, (F)>(a, t, xl, zl, x, z); return;
+            switch(t.info[C] & 0xFF00u)
+            {
+                CHIML_COL(F_PG0 | F_PG1 | F_D2E)
+                CHIML_COL(F_PG0 | F_PS0 | F_PG1 | F_D2E)
+                CHIML_COL(F_PG0 | F_PG1 | F_PS1 | F_D2E)
+                CHIML_COL(F_PG0 | F_PS0 | F_PG1 | F_PS1 | F_D2E)
+                CHIML_COL(F_CURL | F_ISD | F_D2E)
+                CHIML_COL(F_PG0 | F_PG1)
+                CHIML_COL(F_PG0 | F_PS0 | F_PG1)
+                CHIML_COL(F_PG0 | F_PG1 | F_PS1)
+                CHIML_COL(F_PG0 | F_PS0 | F_PG1 | F_PS1)
+                default: break;
+            }
+#undef CHIML_COL
+        }
+    }
     const long plane = a.px * a.lz;
     long r = x + a.px * (z + (long)a.lz * t.y);
     double2 carry;
