@@ -776,7 +776,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                         const unsigned inf = w == 0 ? ts.info[c] : ts.infoB[c];
                         const ClassEntry& ce = ctx->h_cls[b0 + c][inf & CLS_MASK];
                         if((inf & 0xFF00u) != F_CURL || two) fast = false;
-                        if((inf & F_ORD2E) || ((inf & F_D2E) && ce.npoles > 0)) uniform = false;
+                        if((inf & F_D2E) && ce.npoles > 0) uniform = false;     // isotropic poles: per-cell pole pools (k_general)
                         if(w == 0) { rec.rect[c] = ts.rect[c]; rec.info[c] = inf; rec.pf[c] = make_double2(ce.pf1, ce.pf2); rec.inv_eps[c] = ce.inv_eps; }
                         else       { rec.rectB[c] = ts.rectB[c]; rec.infoB[c] = inf; rec.pfB[c] = make_double2(ce.pf1, ce.pf2); rec.inv_epsB[c] = ce.inv_eps; }
                     }
@@ -991,8 +991,9 @@ void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int 
         // 3-D: two half-tile blocks per tile (chiml_update.cuh, UNIFORM_SPLIT_Z); 2-D tiles are a single row
         LaunchScope ls(ctx, k0 + 1);
         const unsigned zsplit = block.y == TILE_Z ? UNIFORM_SPLIT_Z : 1;
-        if(zsplit == 1) k_uniform_rows<IS_E, MODE, IS_E><<<count[1], dim3(block.x, block.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1] + first[1]);
-        else k_uniform<IS_E, MODE, IS_E><<<count[1] * zsplit, dim3(block.x, block.y / zsplit, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][1] + first[1]);
+        const TileRec* tl = (const TileRec*)ctx->d_tiles[fam][1] + first[1];
+        if(zsplit == 1) k_uniform_rows<IS_E, MODE><<<count[1], dim3(block.x, block.y, 3), 0, ctx->stream>>>(a, tl);
+        else k_uniform<IS_E, MODE><<<count[1] * zsplit, dim3(block.x, block.y / zsplit, 3), 0, ctx->stream>>>(a, tl);
     }
     if(count[2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE, IS_E><<<count[2], dim3(block.x, block.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2]); }
 }

@@ -115,6 +115,21 @@ __device__ __forceinline__ double node_value(const StepArgs& a, const double* po
     return pool[a.nsp_base[row] + (x - xmin)];
 }
 
+// the same for the two x-adjacent cells of a thread: one span lookup per row
+__device__ __forceinline__ double2 node_pair(const StepArgs& a, const double* pool, const double* ghost, int x, int y, int z)
+{
+    if(ghost && y == a.ly - 1) return make_double2(ghost[x + (long)a.lx * z], ghost[x + 1 + (long)a.lx * z]);
+    const long row = z + (long)a.lz * y;
+    const int xmin = a.nsp_xmin[row];
+    double2 v = make_double2(0.0, 0.0);
+    if(xmin < 0) return v;
+    const int xmax = a.nsp_xmax[row];
+    const double* p = pool + a.nsp_base[row] - xmin;
+    if(x >= xmin && x <= xmax) v.x = p[x];
+    if(x + 1 >= xmin && x + 1 <= xmax) v.y = p[x + 1];
+    return v;
+}
+
 } // namespace chiml
 #include "chiml_update.cuh"
 #include "chiml_emitters.cuh"

@@ -414,7 +414,7 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
 
     const bool pmlCell = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
     const bool pmlOnD = IS_E && a.pml_on_D;
-    const bool needD = IS_E && ((info & (F_ISD | F_D2E)) || (pmlOnD && pmlCell));
+    const bool needD = IS_E && ((info & (F_ISD | F_D2E | F_ORD2E)) || (pmlOnD && pmlCell));
 
     // ---- every load of this component is issued here, before any arithmetic waits on one of them -------------------------
     double2 dv = make_double2(0.0, 0.0);
@@ -525,6 +525,24 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
         const double ie = inv_eps;
         u.x = dm(ie, dv.x); u.y = dm(ie, dv.y);
     }
+    else if(IS_E && (info & F_ORD2E))
+    {
+        // orDipDtoU / orDipDtoUZ (UTIL/FDTD_up_eq.cpp:862-889): E = D/eps - (1/2eps) sum_p (P_p[r] + P_p[r + e_c]), P at the nodes.
+        // -1/eps and -0.5/eps are -(1/eps) and -(0.5 * (1/eps)) exactly (sign flip and scaling by a power of two commute with rounding)
+        const double ie = inv_eps, nie = -inv_eps, nhie = -0.5 * inv_eps;
+        u.x = dm(ie, dv.x); u.y = dm(ie, dv.y);
+        for(int p = 0; p < ca.nordip; ++p)
+        {
+            const double2 p0 = node_pair(a, ca.oP[p], ca.oPg[p], x, y, z);
+            if(ca.ord_zvariant) { u.x = axpy1(u.x, nie, p0.x); u.y = axpy1(u.y, nie, p0.y); }
+            else
+            {
+                const double2 p1 = node_pair(a, ca.oP[p], ca.oPg[p], x + ca.ord_dx, y + ca.ord_dy, z + ca.ord_dz);
+                u.x = axpy1(u.x, nhie, p0.x); u.y = axpy1(u.y, nhie, p0.y);
+                u.x = axpy1(u.x, nhie, p1.x); u.y = axpy1(u.y, nhie, p1.y);
+            }
+        }
+    }
     store_pair(ca.U + r, u, m0, m1);
     if(dDirty) store_pair(ca.D + r, dv, m0, m1);
 }
@@ -594,64 +612,6 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
 }
 
 constexpr int UNIFORM_SPLIT_Z = 2;     // blocks per 3-D tile in k_uniform (2-D grids have one row per tile and are launched unsplit)
-
-// One plane of loads for a block that marches along y (see k_fast): fills L for the plane at r; c0 / c2 carry the y-coupled arrays
-// from plane to plane (E half step: the plane below; H half step: the current plane, loaded as "next" one iteration earlier).
-template <bool IS_E, int MODE>
-__device__ __forceinline__ void march_load(const StepArgs& a, const long r, const long plane, double2& c0, double2& c2, PairLoads<IS_E, MODE>& L)
-{
-    constexpr int S = IS_E ? -1 : 1;
-    constexpr bool Y0 = has_own<IS_E, MODE>(2) && has_other<IS_E, MODE>(0);
-    constexpr bool Y2 = has_own<IS_E, MODE>(0) && has_other<IS_E, MODE>(2);
-    const double* __restrict__ f0 = a.fam[0];
-    const double* __restrict__ f1 = a.fam[1];
-    const double* __restrict__ f2 = a.fam[2];
-#pragma unroll
-    for(int c = 0; c < 3; ++c) L.u[c] = L.v[c] = L.nj[c] = L.nk[c] = make_double2(0.0, 0.0);
-#pragma unroll
-    for(int c = 0; c < 3; ++c)
-        if(has_own<IS_E, MODE>(c)) L.u[c] = *reinterpret_cast<const double2*>(a.c[c].U + r);
-    double2 n0 = make_double2(0.0, 0.0), n2 = make_double2(0.0, 0.0);
-    if(IS_E)
-    {
-        if(has_other<IS_E, MODE>(0)) L.v[0] = *reinterpret_cast<const double2*>(f0 + r);
-        if(has_other<IS_E, MODE>(2)) L.v[2] = *reinterpret_cast<const double2*>(f2 + r);
-    }
-    else
-    {
-        if(Y0) { L.v[0] = c0; n0 = *reinterpret_cast<const double2*>(f0 + r + plane); }
-        else if(has_other<IS_E, MODE>(0)) L.v[0] = *reinterpret_cast<const double2*>(f0 + r);
-        if(Y2) { L.v[2] = c2; n2 = *reinterpret_cast<const double2*>(f2 + r + plane); }
-        else if(has_other<IS_E, MODE>(2)) L.v[2] = *reinterpret_cast<const double2*>(f2 + r);
-    }
-    if(has_other<IS_E, MODE>(1)) L.v[1] = *reinterpret_cast<const double2*>(f1 + r);
-    if(has_own<IS_E, MODE>(0))
-    {
-        if(has_other<IS_E, MODE>(1)) L.nj[0] = neighbour2<2, S>(f1, r, a.px, plane, L.v[1]);
-        if(has_other<IS_E, MODE>(2)) L.nk[0] = IS_E ? c2 : n2;
-    }
-    if(has_own<IS_E, MODE>(1))
-    {
-        if(has_other<IS_E, MODE>(2)) L.nj[1] = neighbour2<0, S>(f2, r, a.px, plane, L.v[2]);
-        if(has_other<IS_E, MODE>(0)) L.nk[1] = neighbour2<2, S>(f0, r, a.px, plane, L.v[0]);
-    }
-    if(has_own<IS_E, MODE>(2))
-    {
-        if(has_other<IS_E, MODE>(0)) L.nj[2] = IS_E ? c0 : n0;
-        if(has_other<IS_E, MODE>(1)) L.nk[2] = neighbour2<0, S>(f1, r, a.px, plane, L.v[1]);
-    }
-    if(IS_E) { c0 = L.v[0]; c2 = L.v[2]; } else { if(Y0) c0 = n0; if(Y2) c2 = n2; }
-}
-template <bool IS_E, int MODE>
-__device__ __forceinline__ void march_init(const StepArgs& a, const long r, const long plane, double2& c0, double2& c2)
-{
-    constexpr bool Y0 = has_own<IS_E, MODE>(2) && has_other<IS_E, MODE>(0);
-    constexpr bool Y2 = has_own<IS_E, MODE>(0) && has_other<IS_E, MODE>(2);
-    c0 = c2 = make_double2(0.0, 0.0);
-    const long o = IS_E ? r - plane : r;
-    if(Y0) c0 = *reinterpret_cast<const double2*>(a.fam[0] + o);
-    if(Y2) c2 = *reinterpret_cast<const double2*>(a.fam[2] + o);
-}
 
 // L2 prefetch of one 128-byte line (fire and forget: holds no register and no shared memory).  The marching kernels touch every
 // array at a fixed plane stride, so the lines of the plane two steps ahead are requested while the current plane is computed; the
@@ -734,8 +694,8 @@ __device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec&
     long r = x + a.px * (z + (long)a.lz * t.y);
     double2 carry;
     comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
-    constexpr bool needU = !IS_E || !(FL & F_D2E);
-    const bool anyD = IS_E && a.c[C].D && ((FL & (F_ISD | F_D2E)) || (a.pml_on_D && (FL & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
+    constexpr bool needU = !IS_E || !(FL & (F_D2E | F_ORD2E));
+    const bool anyD = IS_E && a.c[C].D && ((FL & (F_ISD | F_D2E | F_ORD2E)) || (a.pml_on_D && (FL & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
     const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector (the prefetch unit of L2)
     const int ny = t.ny, y0 = t.y;
     for(int iy = 0; iy < ny; ++iy, r += plane)
@@ -772,6 +732,7 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
                 CHIML_COL(F_PG0 | F_PG1 | F_PS1 | F_D2E)
                 CHIML_COL(F_PG0 | F_PS0 | F_PG1 | F_PS1 | F_D2E)
                 CHIML_COL(F_CURL | F_ISD | F_D2E)
+                CHIML_COL(F_CURL | F_ISD | F_ORD2E)
                 CHIML_COL(F_PG0 | F_PG1)
                 CHIML_COL(F_PG0 | F_PS0 | F_PG1)
                 CHIML_COL(F_PG0 | F_PG1 | F_PS1)
@@ -785,9 +746,9 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
     long r = x + a.px * (z + (long)a.lz * t.y);
     double2 carry;
     comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
-    const bool needU = !IS_E || (t.rect[C] != 0 && !(t.info[C] & F_D2E)) || (t.rectB[C] != 0 && !(t.infoB[C] & F_D2E));
+    const bool needU = !IS_E || (t.rect[C] != 0 && !(t.info[C] & (F_D2E | F_ORD2E))) || (t.rectB[C] != 0 && !(t.infoB[C] & (F_D2E | F_ORD2E)));
     const unsigned anyInfo = (t.rect[C] ? t.info[C] : 0u) | (t.rectB[C] ? t.infoB[C] : 0u);
-    const bool anyD = IS_E && a.c[C].D && ((anyInfo & (F_ISD | F_D2E)) || (a.pml_on_D && (anyInfo & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
+    const bool anyD = IS_E && a.c[C].D && ((anyInfo & (F_ISD | F_D2E | F_ORD2E)) || (a.pml_on_D && (anyInfo & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
     const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector (the prefetch unit of L2)
     for(int iy = 0; iy < t.ny; ++iy, r += plane)
     {
@@ -808,66 +769,31 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
     }
 }
 
-// The E half step (D and psi arrays per component) gains from the split; the H half step, whose traffic is mostly the shared driving
-// arrays, is faster with all three components in one thread (measured: profiles/README.md), so it is launched with blockDim.z = 1.
-template <bool IS_E, int MODE, bool SPLIT>
+// One component per thread for both half steps: with the flag-specialised column bodies the split wins for H as well (2.33 vs
+// 2.78 ms, profiles/README.md), although the three component threads re-read the shared driving arrays through L1.
+template <bool IS_E, int MODE>
 __device__ __forceinline__ void uniform_body(const StepArgs& a, const TileRec& t, const int xl, const int zl)
 {
     const int x = t.x0 + xl, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
-    if(!SPLIT)
-    {
-        const long plane = a.px * a.lz;
-        long r = x + a.px * (z + (long)a.lz * t.y);
-        double2 c0, c2;
-        march_init<IS_E, MODE>(a, r, plane, c0, c2);
-        const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector
-        for(int iy = 0; iy < t.ny; ++iy, r += plane)
-        {
-            const int y = t.y + iy;
-            const long row = z + (long)a.lz * y;
-            if(leader && iy + PREFETCH_PLANES < t.ny)
-            {
-                const long rp = r + PREFETCH_PLANES * plane;
-#pragma unroll
-                for(int c = 0; c < 3; ++c)
-                {
-                    if(has_other<IS_E, MODE>(c)) prefetch_l2(a.fam[c] + rp + (IS_E ? 0 : plane));
-                    if(has_own<IS_E, MODE>(c)) prefetch_l2(a.c[c].U + rp);
-                }
-                if(t.rect[0])  prefetch_psi<IS_E, MODE, 0>(a, t.info[0], x, y + PREFETCH_PLANES, z);
-                if(t.rectB[0]) prefetch_psi<IS_E, MODE, 0>(a, t.infoB[0], x, y + PREFETCH_PLANES, z);
-                if(t.rect[1])  prefetch_psi<IS_E, MODE, 1>(a, t.info[1], x, y + PREFETCH_PLANES, z);
-                if(t.rectB[1]) prefetch_psi<IS_E, MODE, 1>(a, t.infoB[1], x, y + PREFETCH_PLANES, z);
-                if(t.rect[2])  prefetch_psi<IS_E, MODE, 2>(a, t.info[2], x, y + PREFETCH_PLANES, z);
-                if(t.rectB[2]) prefetch_psi<IS_E, MODE, 2>(a, t.infoB[2], x, y + PREFETCH_PLANES, z);
-            }
-            PairLoads<IS_E, MODE> L;
-            march_load<IS_E, MODE>(a, r, plane, c0, c2, L);
-            uniform_comp<IS_E, MODE, 0>(a, t, L, r, row, x, y, z, xl, zl);
-            uniform_comp<IS_E, MODE, 1>(a, t, L, r, row, x, y, z, xl, zl);
-            uniform_comp<IS_E, MODE, 2>(a, t, L, r, row, x, y, z, xl, zl);
-        }
-        return;
-    }
     if(threadIdx.z == 0)      uniform_march<IS_E, MODE, 0>(a, t, xl, zl, x, z);
     else if(threadIdx.z == 1) uniform_march<IS_E, MODE, 1>(a, t, xl, zl, x, z);
     else                      uniform_march<IS_E, MODE, 2>(a, t, xl, zl, x, z);
 }
 
-// Half tiles: a block owns 4 of the 8 z rows of a tile (blockIdx.x % UNIFORM_SPLIT_Z selects which), so that TWO (SPLIT) or FOUR (joint)
-// independent blocks share an SM.  All warps of one block march in lock-step -- they issue their loads together and wait together --
+// Half tiles: a block owns 4 of the 8 z rows of a tile (blockIdx.x % UNIFORM_SPLIT_Z selects which), so that two independent blocks
+// share an SM.  All warps of one block march in lock-step -- they issue their loads together and wait together --
 // and with a single resident block the SM idles for a full HBM latency per plane; independent blocks drift apart and fill the gaps.
-template <bool IS_E, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 384 : 128, SPLIT ? 2 : 4) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+template <bool IS_E, int MODE>
+__global__ void __launch_bounds__(384, 2) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
 {
-    uniform_body<IS_E, MODE, SPLIT>(a, tiles[blockIdx.x / UNIFORM_SPLIT_Z], 2 * threadIdx.x, threadIdx.y + (TILE_Z / UNIFORM_SPLIT_Z) * (blockIdx.x % UNIFORM_SPLIT_Z));
+    uniform_body<IS_E, MODE>(a, tiles[blockIdx.x / UNIFORM_SPLIT_Z], 2 * threadIdx.x, threadIdx.y + (TILE_Z / UNIFORM_SPLIT_Z) * (blockIdx.x % UNIFORM_SPLIT_Z));
 }
 // 2-D grids: a tile is one row of 64 cells
-template <bool IS_E, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 96 : 32) k_uniform_rows(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+template <bool IS_E, int MODE>
+__global__ void __launch_bounds__(96) k_uniform_rows(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
 {
-    uniform_body<IS_E, MODE, SPLIT>(a, tiles[blockIdx.x], 2 * threadIdx.x, threadIdx.y);
+    uniform_body<IS_E, MODE>(a, tiles[blockIdx.x], 2 * threadIdx.x, threadIdx.y);
 }
 
 // ---------------------------------------------------------------------------------------------------
