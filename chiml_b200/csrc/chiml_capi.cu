@@ -985,17 +985,21 @@ void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int 
         first[k] = part == 2 ? nb : 0;
         count[k] = part == 0 ? n : (part == 1 ? nb : n - nb);
     }
-    if(count[0]) { LaunchScope ls(ctx, k0);     k_fast<IS_E, MODE><<<count[0], block, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0] + first[0]); }
+    // 2-D grids: one-row tiles, ROWS_2D of them per block (chiml_update.cuh tile_of_thread)
+    const bool twoD = MODE != CHIML_MODE_3D;
+    auto nblk = [&](unsigned n) { return twoD ? (n + ROWS_2D - 1) / ROWS_2D : n; };
+    const dim3 blk(block.x, twoD ? ROWS_2D : block.y, 1);
+    if(count[0]) { LaunchScope ls(ctx, k0);     k_fast<IS_E, MODE><<<nblk(count[0]), blk, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0] + first[0], count[0]); }
     if(count[1])
     {
         // 3-D: two half-tile blocks per tile (chiml_update.cuh, UNIFORM_SPLIT_Z); 2-D tiles are a single row
         LaunchScope ls(ctx, k0 + 1);
         const unsigned zsplit = block.y == TILE_Z ? UNIFORM_SPLIT_Z : 1;
         const TileRec* tl = (const TileRec*)ctx->d_tiles[fam][1] + first[1];
-        if(zsplit == 1) k_uniform_rows<IS_E, MODE><<<count[1], dim3(block.x, block.y, 3), 0, ctx->stream>>>(a, tl);
+        if(zsplit == 1) k_uniform_rows<IS_E, MODE><<<nblk(count[1]), dim3(blk.x, blk.y, 3), 0, ctx->stream>>>(a, tl, count[1]);
         else k_uniform<IS_E, MODE><<<count[1] * zsplit, dim3(block.x, block.y / zsplit, 3), 0, ctx->stream>>>(a, tl);
     }
-    if(count[2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE, IS_E><<<count[2], dim3(block.x, block.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2]); }
+    if(count[2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE, IS_E><<<nblk(count[2]), dim3(blk.x, blk.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2], count[2]); }
 }
 template <bool IS_E>
 void launch_family(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int part)

@@ -219,6 +219,17 @@ struct PairLoads
     }
 };
 
+// Which tile and which tile row a thread works on.  3-D: one block per tile, threadIdx.y = z row.  2-D grids have one-row tiles: a
+// block takes ROWS_2D consecutive tiles of the list, one per threadIdx.y (the warps of these kernels never synchronise).
+constexpr int ROWS_2D = 8;
+template <int MODE>
+__device__ __forceinline__ bool tile_of_thread(const unsigned ntiles, unsigned& tile, int& zl)
+{
+    if(MODE == CHIML_MODE_3D) { tile = blockIdx.x; zl = threadIdx.y; return true; }
+    tile = blockIdx.x * ROWS_2D + threadIdx.y; zl = 0;
+    return tile < ntiles;
+}
+
 // rectangle of updated cells of one component inside the tile: bytes xlo, xhi, zlo, zhi (hi exclusive)
 __device__ __forceinline__ void rect_mask(const unsigned rect, const int xl, const int zl, bool& m0, bool& m1)
 {
@@ -242,10 +253,12 @@ __device__ __forceinline__ void store_pair(double* p, const double2 t, const boo
 // from one plane to the next, so every array crosses HBM exactly once per half step however far apart in time the tiles of
 // neighbouring planes would otherwise run (a whole y plane of tiles is ~150 MB of traffic: more than L2 holds).
 template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+__global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles, const unsigned ntiles)
 {
-    const TileRec& t = tiles[blockIdx.x];
-    const int xl = 2 * threadIdx.x, zl = threadIdx.y;
+    unsigned ti; int zl;
+    if(!tile_of_thread<MODE>(ntiles, ti, zl)) return;
+    const TileRec& t = tiles[ti];
+    const int xl = 2 * threadIdx.x;
     const int x = t.x0 + xl, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
     constexpr int S = IS_E ? -1 : 1;
@@ -791,9 +804,10 @@ __global__ void __launch_bounds__(384, 2) k_uniform(const __grid_constant__ Step
 }
 // 2-D grids: a tile is one row of 64 cells
 template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(96) k_uniform_rows(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+__global__ void __launch_bounds__(32 * ROWS_2D * 3) k_uniform_rows(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles, const unsigned ntiles)
 {
-    uniform_body<IS_E, MODE>(a, tiles[blockIdx.x], 2 * threadIdx.x, threadIdx.y);
+    const unsigned ti = blockIdx.x * ROWS_2D + threadIdx.y;
+    if(ti < ntiles) uniform_body<IS_E, MODE>(a, tiles[ti], 2 * threadIdx.x, 0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -828,10 +842,12 @@ __device__ __forceinline__ void general_comp(const StepArgs& a, const TileRec& t
 }
 
 template <bool IS_E, int MODE, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_general(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+__global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_general(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles, const unsigned ntiles)
 {
-    const TileRec& t = tiles[blockIdx.x];
-    const int x = t.x0 + 2 * threadIdx.x, z = t.z0 + threadIdx.y;
+    unsigned ti; int zl;
+    if(!tile_of_thread<MODE>(ntiles, ti, zl)) return;
+    const TileRec& t = tiles[ti];
+    const int x = t.x0 + 2 * threadIdx.x, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
     if(!SPLIT)
     {
