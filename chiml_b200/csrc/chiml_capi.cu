@@ -787,7 +787,9 @@ int chiml_gpu_commit(ChimlCtx* ctx)
             // FAST tiles that are stacked along y with identical rectangles and prefactors become one work item: the block marches
             // over up to MARCH_NY planes carrying the y-neighbour planes in registers (k_fast).  Slab-boundary planes stay single.
             {
-                constexpr int MARCH_NY = 32;
+                // column length: long enough to amortise the carried planes, short enough that a small grid still yields several
+                // work items per SM (a 512 x 512 grid has only ~4600 tiles per half step)
+                const int MARCH_NY = (int)std::max<size_t>(1, std::min<size_t>(32, ntiles / (148 * 8)));
                 const bool hasLo = ctx->g.rank > 0, hasUp = ctx->g.rank < ctx->g.nranks - 1;
                 auto isBnd = [&](const TileRec& t) { return (hasLo && t.y == 1) || (hasUp && t.y == ctx->ly - 2); };
                 for(int kind = 0; kind < 2; ++kind)      // FAST and UNIFORM lists
