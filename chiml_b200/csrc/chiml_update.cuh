@@ -476,6 +476,24 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
         }
     }
 
+    // oriented-dipole node polarisation of the first two poles, issued with the other loads when the flag byte is a compile-time
+    // constant (span lookup -> pool value is a dependent chain of two memory latencies; left to the end it is paid on top of
+    // everything else; in the generic body the extra live registers cost more than they save)
+    constexpr bool HOIST_NODE = IS_E && FL != FL_RUNTIME && (FL & F_ORD2E) != 0;
+    constexpr int NODE_HOIST = 2;
+    double2 np0[NODE_HOIST], np1[NODE_HOIST];
+    if constexpr(HOIST_NODE)
+    {
+#pragma unroll
+        for(int p = 0; p < NODE_HOIST; ++p)
+        {
+            np0[p] = np1[p] = make_double2(0.0, 0.0);
+            if(p >= ca.nordip) continue;
+            np0[p] = node_pair(a, ca.oP[p], ca.oPg[p], x, y, z);
+            if(!ca.ord_zvariant) np1[p] = node_pair(a, ca.oP[p], ca.oPg[p], x + ca.ord_dx, y + ca.ord_dy, z + ca.ord_dz);
+        }
+    }
+
     bool dDirty = false;
     if(info & F_CURL)
     {
@@ -546,11 +564,16 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
         u.x = dm(ie, dv.x); u.y = dm(ie, dv.y);
         for(int p = 0; p < ca.nordip; ++p)
         {
-            const double2 p0 = node_pair(a, ca.oP[p], ca.oPg[p], x, y, z);
+            double2 p0, p1 = make_double2(0.0, 0.0);
+            if(HOIST_NODE && p < NODE_HOIST) { p0 = np0[p & (NODE_HOIST - 1)]; p1 = np1[p & (NODE_HOIST - 1)]; }
+            else
+            {
+                p0 = node_pair(a, ca.oP[p], ca.oPg[p], x, y, z);
+                if(!ca.ord_zvariant) p1 = node_pair(a, ca.oP[p], ca.oPg[p], x + ca.ord_dx, y + ca.ord_dy, z + ca.ord_dz);
+            }
             if(ca.ord_zvariant) { u.x = axpy1(u.x, nie, p0.x); u.y = axpy1(u.y, nie, p0.y); }
             else
             {
-                const double2 p1 = node_pair(a, ca.oP[p], ca.oPg[p], x + ca.ord_dx, y + ca.ord_dy, z + ca.ord_dz);
                 u.x = axpy1(u.x, nhie, p0.x); u.y = axpy1(u.y, nhie, p0.y);
                 u.x = axpy1(u.x, nhie, p1.x); u.y = axpy1(u.y, nhie, p1.y);
             }
