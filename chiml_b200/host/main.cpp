@@ -163,7 +163,7 @@ int main(int argc, char** argv)
             if(detSlot[d] < 0) continue;
             const PlanDetector& pd = P.detectors[d];
             const DetectorInput& di = IP.detectors_[pd.detector];
-            if(di.cls != DTCCLASS::TXT) continue;
+            if(di.cls != DTCCLASS::TXT && di.cls != DTCCLASS::BIN) continue;
             int32_t loc[3], sz[3];
             local_box(P, pd, loc, sz);
             const size_t len = (size_t)sz[0] * sz[1] * sz[2];
@@ -174,6 +174,34 @@ int main(int argc, char** argv)
             std::string name = di.name;
             if(nranks > 1) name += ".rank" + std::to_string(rank);
             make_dirs(name);
+            if(di.cls == DTCCLASS::BIN)
+            {
+                // DTC/parallelDTC_BIN.cpp:12-52: int sz[3], int loc[3], then per sample: double t, rows of sz[0] doubles, z outer, y inner
+                std::ofstream out(name.c_str(), std::ios::out | std::ios::binary);
+                const int32_t hsz[3] = {sz[0], sz[1], sz[2]}, hloc[3] = {pd.loc[0], pd.loc[1] + (loc[1] - (pd.loc[1] - P.grid.y_start + 1)), pd.loc[2]};
+                out.write(reinterpret_cast<const char*>(hsz), sizeof(hsz));
+                out.write(reinterpret_cast<const char*>(hloc), sizeof(hloc));
+                std::vector<double> rowv((size_t)sz[0]);
+                for(size_t s = 0; s < ns; ++s)
+                {
+                    const double tt = (double)(s * (size_t)pd.every) * P.grid.desc.dt * pd.t_conv;
+                    out.write(reinterpret_cast<const char*>(&tt), sizeof(tt));
+                    for(int kk = 0; kk < sz[2]; ++kk)
+                        for(int jj = 0; jj < sz[1]; ++jj)
+                        {
+                            for(int ii = 0; ii < sz[0]; ++ii)
+                            {
+                                const double f = data[s * len + (size_t)ii + (size_t)sz[0] * ((size_t)kk + (size_t)sz[2] * (size_t)jj)];
+                                double point = 0.0;
+                                point = point + (pd.conv / 2.0) * f;
+                                point = point + (pd.conv / 2.0) * f;
+                                rowv[(size_t)ii] = point;
+                            }
+                            out.write(reinterpret_cast<const char*>(rowv.data()), (std::streamsize)(rowv.size() * sizeof(double)));
+                        }
+                }
+                continue;
+            }
             std::ofstream out(name.c_str());
             out << "# time\tx\ty\tz\tfield" << std::endl;
             double rsl[3];

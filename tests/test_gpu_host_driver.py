@@ -15,19 +15,24 @@ pytestmark = pytest.mark.gpu
 
 FILES = {"te_vacuum": {"out/te/dtc_field_0.dat": "dtc_field_0.dat"},
          "ml3d_two": {"out/m2/dtc_field_0.dat": "dtc_field_0.dat", "output_data/qe_0_level_3.dat": "qe_0_level_3.dat",
-                      "output_data/qe_0_level_1.dat": "qe_0_level_1.dat"}}
+                      "output_data/qe_0_level_1.dat": "qe_0_level_1.dat"},
+         # a 4 x 3 x 3 box written by a BIN detector (DTC/parallelDTC_BIN.cpp) and an SI-scaled TXT detector
+         "vac3d_bin": {"out/vb/dtc_field_0.dat": "dtc_field_0.dat", "out/vb/dtc_field_1.dat": "dtc_field_1.dat"}}
 
 
 @pytest.mark.parametrize("case", sorted(FILES))
 def test_host_driver_writes_the_reference_files(case, tmp_path):
     exe = os.path.join(ROOT, "chiml_b200", "chiml")
     assert os.path.exists(exe), "build it with make -C chiml_b200/host"
-    shutil.copy(os.path.join(GOLDEN, case + ".json"), tmp_path / (case + ".json"))
+    src = os.path.join(GOLDEN, case + ".json")
+    if not os.path.exists(src):
+        src = os.path.join(GOLDEN, "out_expected", case, case + ".json")
+    shutil.copy(src, tmp_path / (case + ".json"))
     r = subprocess.run([exe, case + ".json"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     for produced, expected in FILES[case].items():
-        got = open(tmp_path / produced).read()
-        ref = open(os.path.join(GOLDEN, "out_expected", case, expected)).read()
+        got = open(tmp_path / produced, "rb").read()
+        ref = open(os.path.join(GOLDEN, "out_expected", case, expected), "rb").read()
         if "level" in produced:
             a, b = np.loadtxt(tmp_path / produced), np.loadtxt(os.path.join(GOLDEN, "out_expected", case, expected))
             assert a.shape == b.shape
