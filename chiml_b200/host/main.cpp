@@ -174,6 +174,12 @@ int main(int argc, char** argv)
             std::string name = di.name;
             if(nranks > 1) name += ".rank" + std::to_string(rank);
             make_dirs(name);
+            // sample times: the reference passes tcur_, which it accumulates step by step (tcur_ += dt_, parallelFDTDField.hpp:1290)
+            std::vector<double> times(1, 0.0);
+            {
+                double tcur = 0.0;
+                for(long st = 1; times.size() < ns; ++st) { tcur += P.grid.desc.dt; if(st % pd.every == 0) times.push_back(tcur); }
+            }
             if(di.cls == DTCCLASS::BIN)
             {
                 // DTC/parallelDTC_BIN.cpp:12-52: int sz[3], int loc[3], then per sample: double t, rows of sz[0] doubles, z outer, y inner
@@ -184,7 +190,7 @@ int main(int argc, char** argv)
                 std::vector<double> rowv((size_t)sz[0]);
                 for(size_t s = 0; s < ns; ++s)
                 {
-                    const double tt = (double)(s * (size_t)pd.every) * P.grid.desc.dt * pd.t_conv;
+                    const double tt = times[s] * pd.t_conv;
                     out.write(reinterpret_cast<const char*>(&tt), sizeof(tt));
                     for(int kk = 0; kk < sz[2]; ++kk)
                         for(int jj = 0; jj < sz[1]; ++jj)
@@ -216,7 +222,7 @@ int main(int argc, char** argv)
             if(di.SI) for(int k = 0; k < 3; ++k) rsl[k] *= IP.a_ * IP.a_;     // scaled twice in the reference (parallelDTC.hpp:69,82)
             for(size_t s = 0; s < ns; ++s)
             {
-                const double t = (double)(s * (size_t)pd.every) * P.grid.desc.dt;
+                const double t = times[s];
                 out << std::setprecision(6) << t * pd.t_conv << "\t" << rsl[0] << "\t" << rsl[1] << "\t" << rsl[2];
                 // sample layout: x fastest, then z, then y; the reference prints y outermost, then z, then x
                 for(size_t i = 0; i < len; ++i)
