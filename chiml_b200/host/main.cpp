@@ -9,6 +9,7 @@
 // rendezvous directory (any shared directory), after which the slabs talk over NVLink only.
 #include <chrono>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -120,6 +121,12 @@ int main(int argc, char** argv)
             d.npop = (int)e.pop_level.size(); d.pop_level = e.pop_level.data(); d.pop_every = e.pop_every; d.npoints = e.npoints;
             check(ctx, chiml_gpu_add_emitters(ctx, &d, nullptr), "add_emitters");
         }
+        std::vector<int> dftSlot(P.dfts.size(), -1);
+        for(size_t q = 0; q < P.dfts.size(); ++q)
+        {
+            const PlanDft& d = P.dfts[q];
+            check(ctx, chiml_gpu_add_dft(ctx, d.field, d.group, d.every, d.nfreq, d.npts, d.stride, d.lines.data(), d.lines.size(), d.acc_len, &dftSlot[q]), "add_dft");
+        }
         check(ctx, chiml_gpu_commit(ctx), "commit");
 
         if(nranks > 1)
@@ -142,7 +149,10 @@ int main(int argc, char** argv)
         const int nSteps = steps >= 0 ? steps : P.grid.n_steps;
         const int nsrc = (int)P.sources.size();
         const auto t0 = std::chrono::steady_clock::now();
-        std::vector<double> amp;
+        std::vector<double> amp, twiddles;
+        size_t ntw = 0;                                   // complex twiddles per step: all flux regions, region order
+        for(const FluxInput& f : IP.fluxes_) ntw += f.freqs.size();
+        double tFlux = 0.0;                               // the reference's tcur_ (tcur_ += dt_, parallelFDTDField.hpp:1290)
         for(int done = 0; done < nSteps;)
         {
             const int n = std::min(256, nSteps - done);
@@ -150,7 +160,24 @@ int main(int argc, char** argv)
             for(int k = 0; k < n; ++k)
                 for(int q = 0; q < nsrc; ++q)
                     if((size_t)(done + k) < P.sources[q].amp.size()) amp[(size_t)k * nsrc + q] = P.sources[q].amp[done + k];
-            check(ctx, chiml_gpu_step_n(ctx, n, nsrc ? amp.data() : nullptr), "step_n");
+            if(P.dfts.empty() && ntw == 0) check(ctx, chiml_gpu_step_n(ctx, n, nsrc ? amp.data() : nullptr), "step_n");
+            else
+            {
+                // fftFact_ = exp(i * (-t * freq)) with the time after the step (parallelFluxDTC::fieldIn, DTC/parallelFlux.hpp:298)
+                twiddles.resize((size_t)n * ntw * 2);
+                for(int k = 0; k < n; ++k)
+                {
+                    tFlux += P.grid.desc.dt;
+                    size_t j = (size_t)k * ntw;
+                    for(const FluxInput& f : IP.fluxes_)
+                        for(double freq : f.freqs)
+                        {
+                            const std::complex<double> w = std::exp(std::complex<double>(0.0, -1.0 * tFlux * freq));
+                            twiddles[2 * j] = w.real(); twiddles[2 * j + 1] = w.imag(); ++j;
+                        }
+                }
+                check(ctx, chiml_gpu_step_n_dft(ctx, n, nsrc ? amp.data() : nullptr, twiddles.data()), "step_n_dft");
+            }
             done += n;
         }
         check(ctx, chiml_gpu_sync(ctx), "sync");
@@ -233,6 +260,36 @@ int main(int argc, char** argv)
                     out << "\t" << std::setw(24) << std::setprecision(18) << point;
                 }
                 out << '\n';
+            }
+        }
+        // ---- frequency-domain fields of the flux regions: one file per region and slab holding every stored field's accumulators
+        // (fInReal_ / fInCplx_ of parallelStorageFreqDTCReal) in the order parallelFluxDTC::fieldIn walks them.  The Poynting-vector
+        // integration of getFlux() is post-processing on these arrays and is not part of the time-stepping path.
+        for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff)
+        {
+            std::string name = IP.fluxes_[ff].name + ".dft";
+            if(nranks > 1) name += ".rank" + std::to_string(rank);
+            make_dirs(name);
+            std::ofstream out(name.c_str(), std::ios::out | std::ios::binary);
+            const char magic[8] = {'C', 'H', 'I', 'M', 'L', 'D', 'F', 'T'};
+            out.write(magic, 8);
+            int32_t nsets = 0;
+            for(const PlanDft& d : P.dfts) nsets += d.group == (int)ff;
+            const int32_t hdr[2] = {nsets, (int32_t)IP.fluxes_[ff].freqs.size()};
+            out.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
+            out.write(reinterpret_cast<const char*>(IP.fluxes_[ff].freqs.data()), (std::streamsize)(IP.fluxes_[ff].freqs.size() * sizeof(double)));
+            for(size_t q = 0; q < P.dfts.size(); ++q)
+            {
+                const PlanDft& d = P.dfts[q];
+                if(d.group != (int)ff) continue;
+                std::vector<double> re(d.acc_len), im(d.acc_len);
+                check(ctx, chiml_gpu_download_dft(ctx, dftSlot[q], re.data(), im.data()), "download_dft");
+                const int32_t sh[4] = {d.field, d.npts, (int32_t)d.lines.size(), d.every};
+                const uint64_t len = d.acc_len;
+                out.write(reinterpret_cast<const char*>(sh), sizeof(sh));
+                out.write(reinterpret_cast<const char*>(&len), sizeof(len));
+                out.write(reinterpret_cast<const char*>(re.data()), (std::streamsize)(len * sizeof(double)));
+                out.write(reinterpret_cast<const char*>(im.data()), (std::streamsize)(len * sizeof(double)));
             }
         }
         // ---- level populations (ML/QEPopDtc.cpp:37-61)

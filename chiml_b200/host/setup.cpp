@@ -598,6 +598,7 @@ int detector_field(DTCTYPE t)
 }
 
 #include "emitters.inc"
+#include "flux.inc"
 
 } // namespace
 
@@ -783,6 +784,8 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads)
     }
     // ---- emitters (parallelFDTDField.cpp:412-454) ----
     build_emitters(IP, g, ras, mode, P);
+    // ---- flux regions: running-DFT sets (parallelFDTDField.cpp:650-682) ----
+    build_fluxes(IP, g, mode, P);
     return P;
 }
 
@@ -863,6 +866,14 @@ void SlabPlan::write(const std::string& path) const
         app_vec(p, e.h0); app_vec(p, e.weight); app_vec(p, e.mu); app_vec(p, e.gam_ptr); app_vec(p, e.gam_col); app_vec(p, e.gam_val);
         app_vec(p, e.loc); app_vec(p, e.eps); app_vec(p, e.pop_level);
         put_rec(out, "EMITTER", p);
+    }
+    for(const PlanDft& d : dfts)
+    {
+        ChimlPlanDftHdr h; std::memset(&h, 0, sizeof(h));
+        h.field = d.field; h.group = d.group; h.every = d.every; h.nfreq = d.nfreq; h.npts = d.npts; h.stride = d.stride;
+        h.nlines = d.lines.size(); h.acc_len = d.acc_len;
+        std::string p; app(p, h); app_vec(p, d.freq); app_vec(p, d.lines);
+        put_rec(out, "DFT", p);
     }
 }
 

@@ -34,6 +34,15 @@ struct PlanEmitter
     std::vector<int32_t> gam_ptr, gam_col, loc, pop_level;
 };
 
+// one stored field of a flux region: a running-DFT set (include/chiml_gpu.h chiml_gpu_add_dft)
+struct PlanDft
+{
+    int field = 0, group = 0, every = 1, nfreq = 0, npts = 0, stride = 1;
+    uint64_t acc_len = 0;
+    std::vector<double> freq;
+    std::vector<ChimlDftLine> lines;
+};
+
 // The flattened propagator of one rank ("plan", include/chiml_plan.h)
 struct SlabPlan
 {
@@ -44,6 +53,7 @@ struct SlabPlan
     std::vector<PlanSource> sources;
     std::vector<PlanDetector> detectors;
     std::vector<PlanEmitter> emitters;
+    std::vector<PlanDft> dfts;
     bool dielectricMatInPML = false;
 
     void write(const std::string& path) const;

@@ -89,6 +89,21 @@ def cases():
     c["c4_small"] = _short_pulse(c4)
     # ---- running DFT on the four edges of a flux box around a Drude rod (DTC/parallelFlux.hpp, parallelStorageFreqDTC.cpp:21-30) ----
     c["tm_flux"] = _short_pulse(I.c2_tm_drude(n=63, steps=100, pml_cells=8, rod=(20, 6), nfreq=5, out="out/tmflux"))
+    # ---- every surface kind of a flux region: 3-D box (six faces), single X / Y / Z planes, unequal sampling intervals ----
+    c["flux3d"] = _short_pulse(I.config(
+        I.comp_cell([21 / RES, 17 / RES, 23 / RES], RES, 50 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+        [I.normal_source("Ez", [-0.03, 0, 0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
+        [I.block([0.04, 0.04, 0.04], [0.02, 0.0, 0.0], eps=2.0, pols=[I.lorentz_pole(1.2, 0.1, 2.0)])],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Ez", "out/f3/dtc", time_int=DT * 1.0000001)],
+        [I.flux("out/f3/box", [0.02, 0.0, 0.0], [0.06, 0.06, 0.08], 1.5, 1.0, 3),
+         dict(I.flux("out/f3/px", [0.05, 0.0, 0.01], [0.0, 0.06, 0.08], 1.5, 1.0, 4), Time_Interval=2.0 * DT),
+         I.flux("out/f3/py", [0.0, 0.04, 0.0], [0.1, 0.0, 0.06], 1.2, 0.6, 3),
+         dict(I.flux("out/f3/pz", [0.01, 0.0, -0.05], [0.08, 0.06, 0.0], 1.5, 1.0, 5), Time_Interval=3.0 * DT)]))
+    te = I.c1_te_vacuum(n=47, steps=80, pml_cells=8, out="out/tef")
+    te["FluxList"] = [I.flux("out/tef/box", [0.0, 0.0, 0.0], [0.2, 0.14, 0.0], 1.5, 1.0, 4),
+                      I.flux("out/tef/lx", [0.1, 0.0, 0.0], [0.0, 0.2, 0.0], 1.5, 1.0, 3),
+                      dict(I.flux("out/tef/ly", [0.0, -0.08, 0.0], [0.22, 0.0, 0.0], 1.5, 1.0, 3), Time_Interval=2.0 * DT)]
+    c["te_flux"] = _short_pulse(te)
     return c
 
 
@@ -97,7 +112,10 @@ def main():
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref", "-j8"], check=True)
     work = os.path.join(HERE, "_work")
     os.makedirs(work, exist_ok=True)
+    only = set(sys.argv[1:])            # python make_golden.py [case ...]: regenerate only the named cases
     for name, cfg in cases().items():
+        if only and name not in only:
+            continue
         jpath = os.path.join(HERE, name + ".json")
         I.write(cfg, jpath)
         I.write(cfg, os.path.join(work, name + ".json"))   # the reference prefixes "stripped_" to the name as given: run on a cwd-relative copy

@@ -39,3 +39,46 @@ def test_host_driver_writes_the_reference_files(case, tmp_path):
             assert np.abs(a - b).max() <= 1e-9 * max(np.abs(b).max(), 1e-300)
         else:
             assert got == ref, f"{produced} differs from the reference's file"
+
+
+def _read_dft_file(path):
+    """chiml_b200/host/main.cpp: "CHIMLDFT", int32 nsets, int32 nfreq, freq[nfreq], then per stored field int32 field, npts, nlines, every,
+    uint64 len, re[len], im[len]."""
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"CHIMLDFT"
+    nsets, nfreq = np.frombuffer(raw, "<i4", 2, 8)
+    pos = 16 + 8 * int(nfreq)
+    sets = []
+    for _ in range(int(nsets)):
+        n = int(np.frombuffer(raw, "<u8", 1, pos + 16)[0])
+        re = np.frombuffer(raw, "<f8", n, pos + 24)
+        im = np.frombuffer(raw, "<f8", n, pos + 24 + 8 * n)
+        sets.append((re, im))
+        pos += 24 + 16 * n
+    assert pos == len(raw)
+    return sets
+
+
+@pytest.mark.parametrize("case,regions", [("flux3d", ["out/f3/box", "out/f3/px", "out/f3/py", "out/f3/pz"]),
+                                          ("te_flux", ["out/tef/box", "out/tef/lx", "out/tef/ly"]), ("tm_flux", None)])
+def test_host_driver_flux_accumulators_equal_the_reference(case, regions, tmp_path):
+    """JSON -> flux surfaces -> running DFT on the GPU -> files: every accumulator of every stored field of every flux region equals,
+    bit for bit, fInReal_ / fInCplx_ of the reference's parallelStorageFreqDTCReal objects after the same run (<case>.expect.npz,
+    arrays dft<slot>r / dft<slot>i in the order parallelFluxDTC::fieldIn walks them)."""
+    import json
+    exe = os.path.join(ROOT, "chiml_b200", "chiml")
+    assert os.path.exists(exe), "build it with make -C chiml_b200/host"
+    shutil.copy(os.path.join(GOLDEN, case + ".json"), tmp_path / (case + ".json"))
+    if regions is None:
+        regions = [f["name"] for f in json.load(open(os.path.join(GOLDEN, case + ".json")))["FluxList"]]
+    r = subprocess.run([exe, case + ".json"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    expect = np.load(os.path.join(GOLDEN, case + ".expect.npz"))
+    slot = 0
+    for name in regions:
+        for re, im in _read_dft_file(tmp_path / (name + ".dft")):
+            ref_re, ref_im = expect[f"dft{slot}r"].ravel(), expect[f"dft{slot}i"].ravel()
+            assert np.abs(ref_re).max() > 0, f"{case}: accumulator {slot} of the reference is all zero"
+            assert np.array_equal(re, ref_re) and np.array_equal(im, ref_im), f"{case}: {name} stored field {slot} differs from the reference"
+            slot += 1
+    assert f"dft{slot}r" not in expect.files and slot > 0

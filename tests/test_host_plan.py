@@ -28,9 +28,6 @@ def test_host_plan_equals_reference_plan(case, plan_tool, tmp_path):
     out = str(tmp_path / case)
     subprocess.run([plan_tool, os.path.join(util.GOLDEN, case + ".json"), out], check=True)
     bad = plan_diff.diff(P.read_plan(out + ".rank0.plan"), util.load_plan(case))
-    # known gap: the host-side setup does not build the running-DFT sets of flux objects yet; the CUDA path
-    # itself is covered with the sets dumped from the reference (tests/golden/tm_flux)
-    bad = [b for b in bad if not b.startswith("dft")]
     assert not bad, "\n".join(bad[:20])
 
 
