@@ -150,8 +150,11 @@ int main(int argc, char** argv)
         const int nsrc = (int)P.sources.size();
         const auto t0 = std::chrono::steady_clock::now();
         std::vector<double> amp, twiddles;
-        size_t ntw = 0;                                   // complex twiddles per step: all flux regions, region order
-        for(const FluxInput& f : IP.fluxes_) ntw += f.freqs.size();
+        // complex twiddles per step: the flux regions that have a stored field on this slab, region order (chiml_gpu_step_n_dft)
+        std::vector<char> fluxHere(IP.fluxes_.size(), 0);
+        for(const PlanDft& d : P.dfts) fluxHere[d.group] = 1;
+        size_t ntw = 0;
+        for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff) if(fluxHere[ff]) ntw += IP.fluxes_[ff].freqs.size();
         double tFlux = 0.0;                               // the reference's tcur_ (tcur_ += dt_, parallelFDTDField.hpp:1290)
         for(int done = 0; done < nSteps;)
         {
@@ -160,7 +163,7 @@ int main(int argc, char** argv)
             for(int k = 0; k < n; ++k)
                 for(int q = 0; q < nsrc; ++q)
                     if((size_t)(done + k) < P.sources[q].amp.size()) amp[(size_t)k * nsrc + q] = P.sources[q].amp[done + k];
-            if(P.dfts.empty() && ntw == 0) check(ctx, chiml_gpu_step_n(ctx, n, nsrc ? amp.data() : nullptr), "step_n");
+            if(P.dfts.empty()) check(ctx, chiml_gpu_step_n(ctx, n, nsrc ? amp.data() : nullptr), "step_n");
             else
             {
                 // fftFact_ = exp(i * (-t * freq)) with the time after the step (parallelFluxDTC::fieldIn, DTC/parallelFlux.hpp:298)
@@ -169,9 +172,10 @@ int main(int argc, char** argv)
                 {
                     tFlux += P.grid.desc.dt;
                     size_t j = (size_t)k * ntw;
-                    for(const FluxInput& f : IP.fluxes_)
-                        for(double freq : f.freqs)
+                    for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff)
+                        for(double freq : IP.fluxes_[ff].freqs)
                         {
+                            if(!fluxHere[ff]) break;
                             const std::complex<double> w = std::exp(std::complex<double>(0.0, -1.0 * tFlux * freq));
                             twiddles[2 * j] = w.real(); twiddles[2 * j + 1] = w.imag(); ++j;
                         }

@@ -798,12 +798,20 @@ int oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads)
 int oracle_step_phase(OracleSim* s, int phase, const double* src_amp)
 {
     if(!s->committed || phase < 0 || phase > 3) return CHIML_ERR_STATE;
+    if(phase == 3 && s->ndft > 0 && !s->twiddles) return CHIML_ERR_ARG;
     s->nthreads = 1;
     s->src_amp = src_amp;
     s->nsteps = 1;
     s->phase_mask = 1 << phase;
     step_worker(s, 0, 1);
     return 0;
+}
+
+/* same for runs with running-DFT sets: twiddles = the step's exp(-i freq t) of every group (read in phase 3) */
+int oracle_step_phase_dft(OracleSim* s, int phase, const double* src_amp, const double* twiddles)
+{
+    s->twiddles = twiddles;
+    return oracle_step_phase(s, phase, src_amp);
 }
 
 double* oracle_field(OracleSim* s, int field) { return (field >= 0 && field < CHIML_NFIELDS) ? s->f[field] : NULL; }

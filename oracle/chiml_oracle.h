@@ -45,6 +45,7 @@ int  oracle_step_n_dft(OracleSim* s, int n, const double* src_amp, const double*
 double* oracle_dft(OracleSim* s, int slot, int imag);
 /* one phase of one step, for y-slab runs that exchange ghost rows between phases (see chiml_oracle.c) */
 int  oracle_step_phase(OracleSim* s, int phase, const double* src_amp);
+int  oracle_step_phase_dft(OracleSim* s, int phase, const double* src_amp, const double* twiddles);
 
 /* direct pointers to the full-size logical arrays (ln[0]*ln[1]*ln[2] doubles), NULL if absent */
 double* oracle_field(OracleSim* s, int field);

@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
         L.oracle_step_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_add_dft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
         L.oracle_step_n_dft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_step_phase_dft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.oracle_dft.restype = C.POINTER(C.c_double)
         L.oracle_dft.argtypes = [C.c_void_p, C.c_int, C.c_int]
         for fn in ("oracle_field", "oracle_psi"):
@@ -170,7 +171,12 @@ class OracleSim:
     def step_phase(self, phase: int, amp: np.ndarray) -> None:
         """One phase of one step (chiml_b200/slab.py); amp = the amplitudes of this step, shape (1, n_sources)."""
         amp = np.ascontiguousarray(amp, dtype=np.float64)
-        self._chk(lib().oracle_step_phase(self.h, phase, _ptr(amp)))
+        if self.plan.dfts:
+            if phase == 3:
+                self._tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, 1))
+            self._chk(lib().oracle_step_phase_dft(self.h, phase, _ptr(amp), _ptr(self._tw) if phase == 3 else None))
+        else:
+            self._chk(lib().oracle_step_phase(self.h, phase, _ptr(amp)))
         if phase == 3:
             self.steps_done += 1
 

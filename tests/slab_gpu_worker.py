@@ -31,8 +31,10 @@ def run_case(case, rank, world, local):
         done += n
     sim.sync()
     ny = plan.ln[1] - 2
-    names = [n for n in util.state_names(whole) if not n.startswith("q")]
+    names = [n for n in util.state_names(whole) if not n.startswith("q") and not n.startswith("dft")]
     mine = {n: np.ascontiguousarray(util.state_array(sim, n)[1:ny + 1]) for n in names}
+    # running-DFT accumulators of this slab's parts of the flux surfaces, keyed by (region, field, global point, frequency)
+    mine["__dft__"] = util.dft_point_map(plan, [sim.dft(k) for k in range(len(plan.dfts))])
     emit = []
     for q, e in enumerate(plan.emitters):
         coords = np.stack([e.box_lo[0] + e.loc[:, 0], e.box_lo[1] + e.loc[:, 1] + plan.y_start, e.box_lo[2] + e.loc[:, 2]], axis=1) if e.nemit else np.zeros((0, 3), int)
@@ -52,6 +54,23 @@ def run_case(case, rank, world, local):
             if not np.array_equal(got, ref):
                 ok = False
                 print(f"MISMATCH {case}/{n}: max |diff| {np.abs(got - ref).max():.3e} of {np.abs(ref).max():.3e}")
+        if whole.dfts:
+            ref = util.dft_point_map(whole, [expect[f"dft{k}r"].ravel() + 1j * expect[f"dft{k}i"].ravel() for k in range(len(whole.dfts))])
+            got = {}
+            for g in gathered:
+                for key, v in g[1]["__dft__"].items():
+                    if key in got and got[key] != v:
+                        ok = False
+                        print(f"MISMATCH {case}: accumulator {key} differs between slabs")
+                    got[key] = v
+            if set(got) != set(ref):
+                ok = False
+                print(f"MISMATCH {case}: the slabs hold {len(got)} DFT accumulators, the single-rank run {len(ref)}")
+            else:
+                nbad = sum(1 for key in ref if ref[key] != got[key])
+                if nbad:
+                    ok = False
+                    print(f"MISMATCH {case}: {nbad} of {len(ref)} DFT accumulators differ from the reference")
         for q, e in enumerate(whole.emitters):
             gcoord = np.stack([e.box_lo[0] + e.loc[:, 0], e.box_lo[1] + e.loc[:, 1], e.box_lo[2] + e.loc[:, 2]], axis=1)
             index = {tuple(c): i for i, c in enumerate(gcoord)}

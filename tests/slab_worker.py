@@ -41,8 +41,9 @@ def main():
 
     # gather owned rows on rank 0
     ny = plan.ln[1] - 2
-    names = [n for n in util.state_names(whole) if not n.startswith("q")]
+    names = [n for n in util.state_names(whole) if not n.startswith("q") and not n.startswith("dft")]
     mine = {n: np.ascontiguousarray(util.state_array(sim, n)[1:ny + 1]) for n in names}
+    mine["__dft__"] = util.dft_point_map(plan, [sim.dft(k) for k in range(len(plan.dfts))])
     emit = []
     for q, e in enumerate(plan.emitters):
         coords = np.stack([e.box_lo[0] + e.loc[:, 0], e.box_lo[1] + e.loc[:, 1] + plan.y_start, e.box_lo[2] + e.loc[:, 2]], axis=1) if e.nemit else np.zeros((0, 3), int)
@@ -59,6 +60,21 @@ def main():
             if not np.array_equal(got, ref):
                 ok = False
                 print(f"MISMATCH {case}/{n}: max |diff| {np.abs(got - ref).max():.3e} of {np.abs(ref).max():.3e}")
+        if whole.dfts:
+            # running-DFT accumulators of the flux regions: the slabs' parts, keyed by (region, field, global point, frequency),
+            # are together exactly the single-rank reference's accumulators
+            ref = util.dft_point_map(whole, [expect[f"dft{k}r"].ravel() + 1j * expect[f"dft{k}i"].ravel() for k in range(len(whole.dfts))])
+            got = {}
+            for g in gathered:
+                got.update(g[1]["__dft__"])
+            if set(got) != set(ref):
+                ok = False
+                print(f"MISMATCH {case}: the slabs hold {len(got)} DFT accumulators, the single-rank run {len(ref)}")
+            else:
+                nbad = sum(1 for key in ref if ref[key] != got[key])
+                if nbad:
+                    ok = False
+                    print(f"MISMATCH {case}: {nbad} of {len(ref)} DFT accumulators differ from the reference")
         for q, e in enumerate(whole.emitters):
             gcoord = np.stack([e.box_lo[0] + e.loc[:, 0], e.box_lo[1] + e.loc[:, 1], e.box_lo[2] + e.loc[:, 2]], axis=1)
             index = {tuple(c): i for i, c in enumerate(gcoord)}

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 def test_two_slabs_over_nvlink_match_single_rank_reference():
     if capi.device_count() < 2:
         pytest.skip("needs two GPUs")
-    cases = ["vac3d", "aniso_slab3d", "lorentz3d", "ml3d_two", "ml3d_four", "ml_te", "ml_tm", "tm_au", "te_vacuum", "c4_small"]
+    cases = ["vac3d", "aniso_slab3d", "lorentz3d", "ml3d_two", "ml3d_four", "ml_te", "ml_tm", "tm_au", "te_vacuum", "c4_small", "flux3d", "te_flux", "tm_flux"]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29733", os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
                        capture_output=True, text=True, timeout=900)

@@ -77,3 +77,28 @@ def state_names(plan: P.Plan):
         names += [f"q{q}s{s}w{w}" for s in range(e.nsys) for w in range(5)]
         names += [f"q{q}P{'xyz'[c]}" for c in range(3) if c in plan.fields_present()]
     return names
+
+
+def dft_point_map(plan: P.Plan, accs):
+    """Running-DFT accumulators keyed by what they ARE rather than by where a rank stores them: (flux region, field, global grid
+    point, frequency) -> complex value.  `accs[k]` = complex accumulator array of plan.dfts[k].  An accumulator is a pure function
+    of its key (a field sample times the region's twiddle, summed over the sampled steps), so maps of different slab
+    decompositions of the same run must agree entry for entry; entries reached through two stored fields (box edges) must agree
+    with each other."""
+    lnx, lny, lnz = plan.ln
+    out = {}
+    for d, acc in zip(plan.dfts, accs):
+        for li, (ind, o) in enumerate(d.lines):
+            if li > 0 and ind == 0 and o == 0:
+                continue                      # unfilled tail entries of fInGridInds_
+            for i in range(d.npts):
+                g = int(ind) + i * d.stride
+                row, x = divmod(g, lnx)
+                y, z = divmod(row, lnz)
+                for f in range(d.nfreq):
+                    key = (d.group, d.field, x, y + plan.y_start, z, f)
+                    v = complex(acc[int(o) + f + d.nfreq * i])
+                    if key in out and out[key] != v:
+                        raise AssertionError(f"accumulator {key} stored twice with different values")
+                    out[key] = v
+    return out
