@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <string>
 #include <tuple>
 
 using namespace chiml;
@@ -752,6 +753,9 @@ int chiml_gpu_commit(ChimlCtx* ctx)
             CK(cudaStreamSynchronize(ctx->stream));
             std::vector<TileRec> lists[3];
             double listBytes[3] = {0.0, 0.0, 0.0};
+            // CHIML_B200_DEBUG_TILES=1: why tiles ended up in the GENERAL list (development aid, printed once per half step at commit)
+            const bool dbgTiles = std::getenv("CHIML_B200_DEBUG_TILES") != nullptr;
+            std::map<std::string, std::pair<size_t, double>> dbgWhy;
             for(size_t tIdx = 0; tIdx < ntiles; ++tIdx)
             {
                 const TileSummary& ts = sum[tIdx];
@@ -764,46 +768,83 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 rec.ny = 1;
                 bool fast = true, uniform = true;
                 auto area = [](unsigned rc_) { return (((rc_ >> 8) & 0xFF) - (rc_ & 0xFF)) * ((rc_ >> 24) - ((rc_ >> 16) & 0xFF)); };
+                // a component's cells must fall into at most TS_NV rectangles of one info value each; a record carries two of them
+                // per component, so a tile cut by several CPML / material boundaries becomes up to TS_NV / 2 records (k_uniform blocks)
+                int nvals[3] = {0, 0, 0}, nrec = 1;
                 for(int c = 0; c < 3; ++c)
                 {
                     if(!ts.total[c]) continue;
-                    const bool two = ts.countB[c] > 0;
-                    const bool full = !ts.other[c] && area(ts.rect[c]) == ts.count[c] && (!two || area(ts.rectB[c]) == ts.countB[c]) &&
-                                      ts.count[c] + ts.countB[c] == ts.total[c];
-                    if(!full) { fast = uniform = false; continue; }
-                    for(int w = 0; w < (two ? 2 : 1); ++w)
+                    bool full = !ts.other[c];
+                    for(int w = 0; w < TS_NV && ts.count[c][w]; ++w) { ++nvals[c]; full = full && area(ts.rect[c][w]) == ts.count[c][w]; }
+                    if(!full)
                     {
-                        const unsigned inf = w == 0 ? ts.info[c] : ts.infoB[c];
+                        if(dbgTiles && uniform)
+                        {
+                            char key[200];
+                            std::snprintf(key, sizeof(key), "c%d %s xt=%d zt=%d %04x(%u) %04x(%u) %04x(%u) total=%u", c, ts.other[c] ? ">6 values" : "non-rect",
+                                          (int)(tIdx % nxt), (int)((tIdx / nxt) % nzt), ts.info[c][0], ts.count[c][0], ts.info[c][1], ts.count[c][1],
+                                          ts.info[c][2], ts.count[c][2], ts.total[c]);
+                            auto& e = dbgWhy[key]; ++e.first; e.second += ts.bytes;
+                        }
+                        fast = uniform = false; continue;
+                    }
+                    nrec = std::max(nrec, (nvals[c] + 1) / 2);
+                    for(int w = 0; w < nvals[c]; ++w)
+                    {
+                        const unsigned inf = ts.info[c][w];
                         const ClassEntry& ce = ctx->h_cls[b0 + c][inf & CLS_MASK];
-                        if((inf & 0xFF00u) != F_CURL || two) fast = false;
+                        if((inf & 0xFF00u) != F_CURL || nvals[c] > 1) fast = false;
                         if((inf & F_D2E) && ce.npoles > 0) uniform = false;     // isotropic poles: per-cell pole pools (k_general)
-                        if(w == 0) { rec.rect[c] = ts.rect[c]; rec.info[c] = inf; rec.pf[c] = make_double2(ce.pf1, ce.pf2); rec.inv_eps[c] = ce.inv_eps; }
-                        else       { rec.rectB[c] = ts.rectB[c]; rec.infoB[c] = inf; rec.pfB[c] = make_double2(ce.pf1, ce.pf2); rec.inv_epsB[c] = ce.inv_eps; }
                     }
                 }
-                lists[fast ? 0 : (uniform ? 1 : 2)].push_back(rec);
-                listBytes[fast ? 0 : (uniform ? 1 : 2)] += ts.bytes;
+                if(!uniform) { lists[2].push_back(rec); listBytes[2] += ts.bytes; continue; }
+                for(int k = 0; k < nrec; ++k)
+                {
+                    TileRec part = rec;
+                    part.part = (unsigned)k;
+                    for(int c = 0; c < 3; ++c)
+                        for(int w = 2 * k; w < std::min(nvals[c], 2 * k + 2); ++w)
+                        {
+                            const unsigned inf = ts.info[c][w];
+                            const ClassEntry& ce = ctx->h_cls[b0 + c][inf & CLS_MASK];
+                            if(w == 2 * k) { part.rect[c] = ts.rect[c][w]; part.info[c] = inf; part.pf[c] = make_double2(ce.pf1, ce.pf2); part.inv_eps[c] = ce.inv_eps; }
+                            else           { part.rectB[c] = ts.rect[c][w]; part.infoB[c] = inf; part.pfB[c] = make_double2(ce.pf1, ce.pf2); part.inv_epsB[c] = ce.inv_eps; }
+                        }
+                    lists[fast ? 0 : 1].push_back(part);
+                }
+                listBytes[fast ? 0 : 1] += ts.bytes;
+            }
+            if(dbgTiles)
+            {
+                std::fprintf(stderr, "[chiml tiles] %s: fast %zu (%.3f GB) uniform %zu (%.3f GB) general %zu (%.3f GB)\n", fam == 0 ? "E" : "H",
+                             lists[0].size(), listBytes[0] / 1e9, lists[1].size(), listBytes[1] / 1e9, lists[2].size(), listBytes[2] / 1e9);
+                std::vector<std::pair<double, std::string>> top;
+                for(auto& kv : dbgWhy) top.push_back({kv.second.second, kv.first + " tiles=" + std::to_string(kv.second.first)});
+                std::sort(top.rbegin(), top.rend());
+                for(size_t i = 0; i < top.size() && i < 24; ++i) std::fprintf(stderr, "[chiml tiles]   %.4f GB  %s\n", top[i].first / 1e9, top[i].second.c_str());
             }
             // FAST tiles that are stacked along y with identical rectangles and prefactors become one work item: the block marches
             // over up to MARCH_NY planes carrying the y-neighbour planes in registers (k_fast).  Slab-boundary planes stay single.
             {
                 // column length: long enough to amortise the carried planes, short enough that a small grid still yields several
                 // work items per SM (a 512 x 512 grid has only ~4600 tiles per half step)
-                const int MARCH_NY = (int)std::max<size_t>(1, std::min<size_t>(32, ntiles / (148 * 8)));
+                                const size_t marchCap = ntiles / (148 * 8);
                 const bool hasLo = ctx->g.rank > 0, hasUp = ctx->g.rank < ctx->g.nranks - 1;
                 auto isBnd = [&](const TileRec& t) { return (hasLo && t.y == 1) || (hasUp && t.y == ctx->ly - 2); };
                 for(int kind = 0; kind < 2; ++kind)      // FAST and UNIFORM lists
                 {
+                    // measured on the C5 slab (profiles/README.md r1z): 64 planes for the vacuum kernel, 32 for the UNIFORM ones
+                    const int MARCH_NY = (int)std::max<size_t>(1, std::min<size_t>(kind == 0 ? 64 : 32, marchCap));
                     std::vector<TileRec>& fl = lists[kind];
                     std::stable_sort(fl.begin(), fl.end(), [](const TileRec& p, const TileRec& q) {
-                        return std::tie(p.z0, p.x0, p.y) < std::tie(q.z0, q.x0, q.y); });
+                        return std::tie(p.z0, p.x0, p.part, p.y) < std::tie(q.z0, q.x0, q.part, q.y); });
                     std::vector<TileRec> merged;
                     for(const TileRec& t : fl)
                     {
                         if(!merged.empty())
                         {
                             TileRec& m = merged.back();
-                            const bool same = m.x0 == t.x0 && m.z0 == t.z0 && m.y + m.ny == t.y && m.ny < MARCH_NY && !isBnd(m) && !isBnd(t) &&
+                            const bool same = m.x0 == t.x0 && m.z0 == t.z0 && m.part == t.part && m.y + m.ny == t.y && m.ny < MARCH_NY && !isBnd(m) && !isBnd(t) &&
                                               std::memcmp(m.rect, t.rect, sizeof(m.rect)) == 0 && std::memcmp(m.pf, t.pf, sizeof(m.pf)) == 0 &&
                                               std::memcmp(m.info, t.info, sizeof(m.info)) == 0 && std::memcmp(m.inv_eps, t.inv_eps, sizeof(m.inv_eps)) == 0 &&
                                               std::memcmp(m.rectB, t.rectB, sizeof(m.rectB)) == 0 && std::memcmp(m.infoB, t.infoB, sizeof(m.infoB)) == 0 &&
@@ -994,12 +1035,12 @@ void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int 
     if(count[0]) { LaunchScope ls(ctx, k0);     k_fast<IS_E, MODE><<<nblk(count[0]), blk, 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][0] + first[0], count[0]); }
     if(count[1])
     {
-        // 3-D: two half-tile blocks per tile (chiml_update.cuh, UNIFORM_SPLIT_Z); 2-D tiles are a single row
+        // 3-D: one block per (tile, z part, component) (chiml_update.cuh k_uniform); 2-D tiles are a single row
         LaunchScope ls(ctx, k0 + 1);
-        const unsigned zsplit = block.y == TILE_Z ? UNIFORM_SPLIT_Z : 1;
+        constexpr unsigned zsplit = uniform_split<IS_E>();
         const TileRec* tl = (const TileRec*)ctx->d_tiles[fam][1] + first[1];
-        if(zsplit == 1) k_uniform_rows<IS_E, MODE><<<nblk(count[1]), dim3(blk.x, blk.y, 3), 0, ctx->stream>>>(a, tl, count[1]);
-        else k_uniform<IS_E, MODE><<<count[1] * zsplit, dim3(block.x, block.y / zsplit, 3), 0, ctx->stream>>>(a, tl);
+        if(twoD) k_uniform_rows<IS_E, MODE><<<nblk(count[1]), dim3(blk.x, blk.y, 3), 0, ctx->stream>>>(a, tl, count[1]);
+        else k_uniform<IS_E, MODE><<<count[1] * zsplit * 3, dim3(block.x, block.y / zsplit, 1), 0, ctx->stream>>>(a, tl);
     }
     if(count[2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE, IS_E><<<nblk(count[2]), dim3(blk.x, blk.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2], count[2]); }
 }

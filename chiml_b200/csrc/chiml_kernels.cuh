@@ -71,7 +71,7 @@ struct TileRec
 {
     int x0, z0, y, ny;           // ny: number of consecutive y planes the block marches over (k_fast); 1 elsewhere
     unsigned rect[3];            // per component: xlo | xhi<<8 | zlo<<16 | zhi<<24 (tile-local, hi exclusive); 0 = no cell of this component
-    unsigned pad1;
+    unsigned part;               // which record of its tile this is (a tile with more than two info values per component has several)
     unsigned info[3];            // per component: the one info value of its cells (k_uniform)
     unsigned pad2;
     double2 pf[3];               // per component: {pf1, pf2} of its class

@@ -647,13 +647,31 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
     }
 }
 
-constexpr int UNIFORM_SPLIT_Z = 2;     // blocks per 3-D tile in k_uniform (2-D grids have one row per tile and are launched unsplit)
+// k_uniform geometry per half step: blocks per 3-D tile along z, and resident blocks per SM the register budget is set for
+// (measured on the C5 slab, profiles/README.md r1x/r1y; 2-D grids have one row per tile and use k_uniform_rows)
+#ifndef CHIML_SPLIT_E
+#define CHIML_SPLIT_E 1
+#endif
+#ifndef CHIML_OCC_E
+#define CHIML_OCC_E 4
+#endif
+#ifndef CHIML_SPLIT_H
+#define CHIML_SPLIT_H 1
+#endif
+#ifndef CHIML_OCC_H
+#define CHIML_OCC_H 4
+#endif
+#ifndef CHIML_PREFETCH_PLANES
+#define CHIML_PREFETCH_PLANES 1
+#endif
+template <bool IS_E> __host__ __device__ constexpr int uniform_split() { return IS_E ? CHIML_SPLIT_E : CHIML_SPLIT_H; }
+template <bool IS_E> __host__ __device__ constexpr int uniform_occ() { return IS_E ? CHIML_OCC_E : CHIML_OCC_H; }
 
 // L2 prefetch of one 128-byte line (fire and forget: holds no register and no shared memory).  The marching kernels touch every
 // array at a fixed plane stride, so the lines of the plane two steps ahead are requested while the current plane is computed; the
 // demand loads then pay L2 latency instead of HBM latency, which is what the UNIFORM kernels (few warps, many arrays) are short of.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-constexpr int PREFETCH_PLANES = 2;
+constexpr int PREFETCH_PLANES = CHIML_PREFETCH_PLANES;
 
 // psi lines of component C of a UNIFORM tile at plane y (address arithmetic of uniform_rect), for the rectangle with this info
 template <bool IS_E, int MODE, int C>
@@ -717,15 +735,14 @@ __device__ __forceinline__ void comp_march_load(const StepArgs& a, const long r,
 // a column of planes of a single-rectangle tile with the flag byte known at compile time: masks, prefactors and the plane-independent
 // CPML coefficients are set up once, the plane loop holds only loads, the reference's arithmetic and stores
 template <bool IS_E, int MODE, int C, unsigned FL>
-__device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec& t, const int xl, const int zl, const int x, const int z)
+__device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec& t, const unsigned rect, const double2 pfc, const double ie,
+                                               const int xl, const int zl, const int x, const int z)
 {
     bool m0, m1;
-    rect_mask(t.rect[C], xl, zl, m0, m1);
+    rect_mask(rect, xl, zl, m0, m1);
     if(!(m0 || m1)) return;
     PmlCoef kc;
     pml_coef_static<IS_E, MODE, C>(a, FL, x, z, kc);
-    const double2 pfc = t.pf[C];
-    const double ie = t.inv_eps[C];
     const long plane = a.px * a.lz;
     long r = x + a.px * (z + (long)a.lz * t.y);
     double2 carry;
@@ -758,11 +775,29 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
     if(!has_own<IS_E, MODE>(C) || (t.rect[C] == 0 && t.rectB[C] == 0)) return;
     if constexpr(has_own<IS_E, MODE>(C) && has_other<IS_E, MODE>((C + 1) % 3) && has_other<IS_E, MODE>((C + 2) % 3))
     {
-        if(t.rectB[C] == 0)
+        // a warp is one z row of the tile.  When all its cells lie in ONE of the tile's rectangles (every warp of a one-rectangle tile;
+        // in a tile cut along z every warp) it takes the column path of that rectangle; a row cut along x stays on the generic path
+        // (letting the two halves of a warp run two column bodies one after the other costs more than it saves: r2b, profiles/README.md)
+        unsigned rect = t.rect[C], info = t.info[C];
+        double2 pfc = t.pf[C];
+        double ie = t.inv_eps[C];
+        bool single = t.rectB[C] == 0;
+        if(!single)
         {
-#define CHIML_COL(F) case (F): uniform_column<IS_E, MODE, C, (F)>(a, t, xl, zl, x, z); return;
-            switch(t.info[C] & 0xFF00u)
+            bool a0, a1, b0, b1;
+            rect_mask(t.rect[C], xl, zl, a0, a1);
+            rect_mask(t.rectB[C], xl, zl, b0, b1);
+            const unsigned lanes = __activemask();
+            const bool inA = a0 || a1, inB = b0 || b1;
+            if(__all_sync(lanes, !inB)) { if(!inA) return; single = true; }
+            else if(__all_sync(lanes, !inA)) { if(!inB) return; rect = t.rectB[C]; info = t.infoB[C]; pfc = t.pfB[C]; ie = t.inv_epsB[C]; single = true; }
+        }
+        if(single)
+        {
+#define CHIML_COL(F) case (F): uniform_column<IS_E, MODE, C, (F)>(a, t, rect, pfc, ie, xl, zl, x, z); return;
+            switch(info & 0xFF00u)
             {
+                CHIML_COL(F_CURL)
                 CHIML_COL(F_PG0 | F_PG1 | F_D2E)
                 CHIML_COL(F_PG0 | F_PS0 | F_PG1 | F_D2E)
                 CHIML_COL(F_PG0 | F_PG1 | F_PS1 | F_D2E)
@@ -808,29 +843,33 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
 // One component per thread for both half steps: with the flag-specialised column bodies the split wins for H as well (2.33 vs
 // 2.78 ms, profiles/README.md), although the three component threads re-read the shared driving arrays through L1.
 template <bool IS_E, int MODE>
-__device__ __forceinline__ void uniform_body(const StepArgs& a, const TileRec& t, const int xl, const int zl)
+__device__ __forceinline__ void uniform_body(const StepArgs& a, const TileRec& t, const int xl, const int zl, const int comp)
 {
     const int x = t.x0 + xl, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
-    if(threadIdx.z == 0)      uniform_march<IS_E, MODE, 0>(a, t, xl, zl, x, z);
-    else if(threadIdx.z == 1) uniform_march<IS_E, MODE, 1>(a, t, xl, zl, x, z);
-    else                      uniform_march<IS_E, MODE, 2>(a, t, xl, zl, x, z);
+    if(comp == 0)      uniform_march<IS_E, MODE, 0>(a, t, xl, zl, x, z);
+    else if(comp == 1) uniform_march<IS_E, MODE, 1>(a, t, xl, zl, x, z);
+    else               uniform_march<IS_E, MODE, 2>(a, t, xl, zl, x, z);
 }
 
-// Half tiles: a block owns 4 of the 8 z rows of a tile (blockIdx.x % UNIFORM_SPLIT_Z selects which), so that two independent blocks
-// share an SM.  All warps of one block march in lock-step -- they issue their loads together and wait together --
-// and with a single resident block the SM idles for a full HBM latency per plane; independent blocks drift apart and fill the gaps.
+// One component per BLOCK: blockIdx.x % 3 selects it, so a block runs a single code body (the flag-specialised column of its
+// component) and the three blocks of a tile are neighbours in the grid -- they run at about the same time on different SMs and
+// share the driving arrays through L2.  Against one component per thread z-index inside one block (12 warps marching in
+// lock-step through three different bodies) this is 8-15 % faster: smaller independent blocks drift apart and fill each other's
+// memory-latency gaps, and each scheduler holds one body instead of three.  A block owns TILE_Z / split z rows of the tile.
 template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(384, 2) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
+__global__ void __launch_bounds__(32 * TILE_Z / uniform_split<IS_E>(), uniform_occ<IS_E>()) k_uniform(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles)
 {
-    uniform_body<IS_E, MODE>(a, tiles[blockIdx.x / UNIFORM_SPLIT_Z], 2 * threadIdx.x, threadIdx.y + (TILE_Z / UNIFORM_SPLIT_Z) * (blockIdx.x % UNIFORM_SPLIT_Z));
+    constexpr int SPLIT = uniform_split<IS_E>(), ROWS = TILE_Z / SPLIT;
+    const unsigned b = blockIdx.x / 3;
+    uniform_body<IS_E, MODE>(a, tiles[b / SPLIT], 2 * threadIdx.x, threadIdx.y + ROWS * (b % SPLIT), blockIdx.x % 3);
 }
 // 2-D grids: a tile is one row of 64 cells
 template <bool IS_E, int MODE>
 __global__ void __launch_bounds__(32 * ROWS_2D * 3) k_uniform_rows(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles, const unsigned ntiles)
 {
     const unsigned ti = blockIdx.x * ROWS_2D + threadIdx.y;
-    if(ti < ntiles) uniform_body<IS_E, MODE>(a, tiles[ti], 2 * threadIdx.x, 0);
+    if(ti < ntiles) uniform_body<IS_E, MODE>(a, tiles[ti], 2 * threadIdx.x, 0, threadIdx.z);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -893,14 +932,14 @@ __global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_general(co
 // commit-time tile summary: per tile and component the bounding rectangle of non-zero info cells, their
 // count, the first non-zero info value and whether all non-zero values are equal.  One block per tile.
 // ---------------------------------------------------------------------------------------------------
-// per component: the (up to) two distinct non-zero info values of the tile -- A = the largest, B = the smallest -- with the bounding
-// rectangle and cell count of each, the total count, and whether a third value occurs
+// per component: the (up to) TS_NV distinct non-zero info values of the tile in descending order, each with the bounding
+// rectangle and count of its cells; the total count, and whether more than TS_NV values occur
+constexpr int TS_NV = 6;
 struct TileSummary
 {
-    unsigned rect[3], info[3], count[3];        // value A
-    unsigned rectB[3], infoB[3], countB[3];     // value B (0 when the tile has one value)
+    unsigned info[3][TS_NV], rect[3][TS_NV], count[3][TS_NV];
     unsigned total[3], other[3];
-    unsigned bytes; unsigned pad[3];
+    unsigned bytes; unsigned pad;
 };
 
 // algorithmic bytes one field-component cell moves per step: 16 B RW + 8 B cross-read when it is
@@ -929,13 +968,13 @@ __global__ void k_tile_summary(const uint16_t* i0, const uint16_t* i1, const uin
     const unsigned xt = tile % nxt, zt = (tile / nxt) % nzt, y = tile / (nxt * nzt);
     const int xl = 2 * threadIdx.x, zl = threadIdx.y;
     const int x = xt * TILE_X + xl, z = zt * blockDim.y + zl;
-    __shared__ unsigned s_lo[2][3][2], s_hi[2][3][2], s_cnt[2][3], s_tot[3], s_vmax[3], s_vmin[3], s_other[3];
+    __shared__ unsigned s_lo[TS_NV][3][2], s_hi[TS_NV][3][2], s_cnt[TS_NV][3], s_val[TS_NV][3], s_tot[3], s_other[3];
     const uint16_t* ip[3] = {i0, i1, i2};
     if(threadIdx.x < 3 && threadIdx.y == 0)
     {
         const int c = threadIdx.x;
-        for(int k = 0; k < 2; ++k) { s_lo[k][c][0] = s_lo[k][c][1] = 255; s_hi[k][c][0] = s_hi[k][c][1] = 0; s_cnt[k][c] = 0; }
-        s_tot[c] = 0; s_vmax[c] = 0; s_vmin[c] = 0xFFFFFFFFu; s_other[c] = 0;
+        for(int k = 0; k < TS_NV; ++k) { s_lo[k][c][0] = s_lo[k][c][1] = 255; s_hi[k][c][0] = s_hi[k][c][1] = 0; s_cnt[k][c] = 0; s_val[k][c] = 0; }
+        s_tot[c] = 0; s_other[c] = 0;
     }
     __syncthreads();
     unsigned v[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -951,31 +990,40 @@ __global__ void k_tile_summary(const uint16_t* i0, const uint16_t* i1, const uin
                 {
                     atomicAdd(&s_bytes, cell_alg_bytes(v[c][k], cp[c], isE != 0, pmlOnD != 0));
                     atomicAdd(&s_tot[c], 1u);
-                    atomicMax(&s_vmax[c], v[c][k]);
-                    atomicMin(&s_vmin[c], v[c][k]);
                 }
         }
     }
-    __syncthreads();
+    // distinct values, largest first: value w is the maximum of the values below value w-1
+    for(int w = 0; w < TS_NV; ++w)
+    {
+        for(int c = 0; c < 3; ++c)
+            for(int k = 0; k < 2; ++k)
+                if(v[c][k] && (w == 0 || v[c][k] < s_val[w - 1][c])) atomicMax(&s_val[w][c], v[c][k]);
+        __syncthreads();
+        for(int c = 0; c < 3; ++c)
+            for(int k = 0; k < 2; ++k)
+            {
+                if(!v[c][k] || v[c][k] != s_val[w][c]) continue;
+                atomicMin(&s_lo[w][c][0], (unsigned)(xl + k)); atomicMax(&s_hi[w][c][0], (unsigned)(xl + k + 1));
+                atomicMin(&s_lo[w][c][1], (unsigned)zl);       atomicMax(&s_hi[w][c][1], (unsigned)(zl + 1));
+                atomicAdd(&s_cnt[w][c], 1u);
+            }
+        __syncthreads();
+    }
     for(int c = 0; c < 3; ++c)
         for(int k = 0; k < 2; ++k)
-        {
-            if(!v[c][k]) continue;
-            const int w = v[c][k] == s_vmax[c] ? 0 : (v[c][k] == s_vmin[c] ? 1 : -1);
-            if(w < 0) { s_other[c] = 1; continue; }
-            atomicMin(&s_lo[w][c][0], (unsigned)(xl + k)); atomicMax(&s_hi[w][c][0], (unsigned)(xl + k + 1));
-            atomicMin(&s_lo[w][c][1], (unsigned)zl);       atomicMax(&s_hi[w][c][1], (unsigned)(zl + 1));
-            atomicAdd(&s_cnt[w][c], 1u);
-        }
+            if(v[c][k] && v[c][k] < s_val[TS_NV - 1][c]) s_other[c] = 1;
     __syncthreads();
     if(threadIdx.x < 3 && threadIdx.y == 0)
     {
         const int c = threadIdx.x;
         TileSummary& o = out[tile];
-        auto pack = [&](int w) { return s_cnt[w][c] ? (s_lo[w][c][0] | (s_hi[w][c][0] << 8) | (s_lo[w][c][1] << 16) | (s_hi[w][c][1] << 24)) : 0u; };
         o.total[c] = s_tot[c]; o.other[c] = s_other[c];
-        o.count[c] = s_cnt[0][c]; o.info[c] = s_tot[c] ? s_vmax[c] : 0u; o.rect[c] = pack(0);
-        o.countB[c] = s_cnt[1][c]; o.infoB[c] = s_cnt[1][c] ? s_vmin[c] : 0u; o.rectB[c] = pack(1);
+        for(int w = 0; w < TS_NV; ++w)
+        {
+            o.count[c][w] = s_cnt[w][c]; o.info[c][w] = s_cnt[w][c] ? s_val[w][c] : 0u;
+            o.rect[c][w] = s_cnt[w][c] ? (s_lo[w][c][0] | (s_hi[w][c][0] << 8) | (s_lo[w][c][1] << 16) | (s_hi[w][c][1] << 24)) : 0u;
+        }
         if(c == 0) o.bytes = s_bytes;
     }
 }
