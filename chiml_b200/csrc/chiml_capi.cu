@@ -768,14 +768,45 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 rec.ny = 1;
                 bool fast = true, uniform = true;
                 auto area = [](unsigned rc_) { return (((rc_ >> 8) & 0xFF) - (rc_ & 0xFF)) * ((rc_ >> 24) - ((rc_ >> 16) & 0xFF)); };
-                // a component's cells must fall into at most TS_NV rectangles of one info value each; a record carries two of them
-                // per component, so a tile cut by several CPML / material boundaries becomes up to TS_NV / 2 records (k_uniform blocks)
-                int nvals[3] = {0, 0, 0}, nrec = 1;
+                // a component's cells must fall into a few rectangles of one info value each; a record carries two of them per component,
+                // so a tile cut by several CPML / material boundaries becomes several records (k_uniform blocks)
+                struct Val { unsigned info, rect; };
+                std::vector<Val> vals[3];
                 for(int c = 0; c < 3; ++c)
                 {
                     if(!ts.total[c]) continue;
                     bool full = !ts.other[c];
-                    for(int w = 0; w < TS_NV && ts.count[c][w]; ++w) { ++nvals[c]; full = full && area(ts.rect[c][w]) == ts.count[c][w]; }
+                    int nv = 0;
+                    while(nv < TS_NV && ts.count[c][nv]) ++nv;
+                    for(int w = 0; w < nv && full; ++w)
+                    {
+                        const unsigned rw = ts.rect[c][w];
+                        if(area(rw) == ts.count[c][w]) { vals[c].push_back({ts.info[c][w], rw}); continue; }
+                        // not a rectangle: an object narrower than the tile leaves the surrounding value on both sides of it (or two
+                        // objects share a tile).  If another value fills a full-height (full-width) rectangle strictly inside this
+                        // value's bounding box and the two strips beside it hold exactly this value's cells, the strips are rectangles
+                        bool split = false;
+                        for(int h = 0; h < nv && !split; ++h)
+                        {
+                            if(h == w || area(ts.rect[c][h]) != ts.count[c][h]) continue;
+                            const unsigned rh = ts.rect[c][h];
+                            const unsigned wx0 = rw & 0xFF, wx1 = (rw >> 8) & 0xFF, wz0 = (rw >> 16) & 0xFF, wz1 = rw >> 24;
+                            const unsigned hx0 = rh & 0xFF, hx1 = (rh >> 8) & 0xFF, hz0 = (rh >> 16) & 0xFF, hz1 = rh >> 24;
+                            if(hz0 == wz0 && hz1 == wz1 && hx0 > wx0 && hx1 < wx1 && ((hx0 - wx0) + (wx1 - hx1)) * (wz1 - wz0) == ts.count[c][w])
+                            {
+                                vals[c].push_back({ts.info[c][w], wx0 | (hx0 << 8) | (wz0 << 16) | (wz1 << 24)});
+                                vals[c].push_back({ts.info[c][w], hx1 | (wx1 << 8) | (wz0 << 16) | (wz1 << 24)});
+                                split = true;
+                            }
+                            else if(hx0 == wx0 && hx1 == wx1 && hz0 > wz0 && hz1 < wz1 && ((hz0 - wz0) + (wz1 - hz1)) * (wx1 - wx0) == ts.count[c][w])
+                            {
+                                vals[c].push_back({ts.info[c][w], wx0 | (wx1 << 8) | (wz0 << 16) | (hz0 << 24)});
+                                vals[c].push_back({ts.info[c][w], wx0 | (wx1 << 8) | (hz1 << 16) | (wz1 << 24)});
+                                split = true;
+                            }
+                        }
+                        if(!split) full = false;
+                    }
                     if(!full)
                     {
                         if(dbgTiles && uniform)
@@ -788,27 +819,31 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                         }
                         fast = uniform = false; continue;
                     }
-                    nrec = std::max(nrec, (nvals[c] + 1) / 2);
-                    for(int w = 0; w < nvals[c]; ++w)
-                    {
-                        const unsigned inf = ts.info[c][w];
-                        const ClassEntry& ce = ctx->h_cls[b0 + c][inf & CLS_MASK];
-                        if((inf & 0xFF00u) != F_CURL || nvals[c] > 1) fast = false;
-                        if((inf & F_D2E) && ce.npoles > 0) uniform = false;     // isotropic poles: per-cell pole pools (k_general)
-                    }
+                    for(const Val& v : vals[c])
+                        if((v.info & 0xFF00u) != F_CURL || vals[c].size() > 1) fast = false;
                 }
                 if(!uniform) { lists[2].push_back(rec); listBytes[2] += ts.bytes; continue; }
+                // a record holds two rectangles per component when the tile is cut along z only (every warp, one z row, then lies in one
+                // rectangle and takes the column path); a tile that is cut along x gets one record per rectangle, so that no warp has to
+                // run the two-rectangle body
+                int per = 2;
+                for(int c = 0; c < 3; ++c)
+                    for(size_t w = 1; w < vals[c].size(); ++w)
+                        if((vals[c][w].rect & 0xFFFFu) != (vals[c][0].rect & 0xFFFFu)) per = 1;
+                int nrec = 1;
+                for(int c = 0; c < 3; ++c) nrec = std::max(nrec, ((int)vals[c].size() + per - 1) / per);
                 for(int k = 0; k < nrec; ++k)
                 {
                     TileRec part = rec;
                     part.part = (unsigned)k;
                     for(int c = 0; c < 3; ++c)
-                        for(int w = 2 * k; w < std::min(nvals[c], 2 * k + 2); ++w)
+                        for(int w = per * k; w < std::min((int)vals[c].size(), per * k + per); ++w)
                         {
-                            const unsigned inf = ts.info[c][w];
+                            const unsigned inf = vals[c][w].info;
                             const ClassEntry& ce = ctx->h_cls[b0 + c][inf & CLS_MASK];
-                            if(w == 2 * k) { part.rect[c] = ts.rect[c][w]; part.info[c] = inf; part.pf[c] = make_double2(ce.pf1, ce.pf2); part.inv_eps[c] = ce.inv_eps; }
-                            else           { part.rectB[c] = ts.rect[c][w]; part.infoB[c] = inf; part.pfB[c] = make_double2(ce.pf1, ce.pf2); part.inv_epsB[c] = ce.inv_eps; }
+                            const unsigned npc = (fam == 0 && (inf & F_D2E)) ? (unsigned)ce.npoles << (8 * c) : 0u;    // isotropic poles of the class
+                            if(w == per * k) { part.rect[c] = vals[c][w].rect; part.info[c] = inf; part.pf[c] = make_double2(ce.pf1, ce.pf2); part.inv_eps[c] = ce.inv_eps; part.np |= npc; }
+                            else           { part.rectB[c] = vals[c][w].rect; part.infoB[c] = inf; part.pfB[c] = make_double2(ce.pf1, ce.pf2); part.inv_epsB[c] = ce.inv_eps; part.npB |= npc; }
                         }
                     lists[fast ? 0 : 1].push_back(part);
                 }

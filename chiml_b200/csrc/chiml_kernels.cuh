@@ -73,13 +73,13 @@ struct TileRec
     unsigned rect[3];            // per component: xlo | xhi<<8 | zlo<<16 | zhi<<24 (tile-local, hi exclusive); 0 = no cell of this component
     unsigned part;               // which record of its tile this is (a tile with more than two info values per component has several)
     unsigned info[3];            // per component: the one info value of its cells (k_uniform)
-    unsigned pad2;
+    unsigned np;                 // isotropic poles of the classes of rect (bits 0-7, 8-15, 16-23: components 0, 1, 2)
     double2 pf[3];               // per component: {pf1, pf2} of its class
     double inv_eps[3];           // per component: 1/eps of its class (pole-free D->E)
     double pad3;
     // second rectangle of a component (k_uniform only; rectB == 0 when the tile has one info value)
     unsigned rectB[3]; unsigned pad4;
-    unsigned infoB[3]; unsigned pad5;
+    unsigned infoB[3]; unsigned npB;   // npB: as np, for rectB
     double2 pfB[3];
     double inv_epsB[3];
     double pad6;

@@ -402,12 +402,14 @@ __device__ __forceinline__ void pml_coef_static(const StepArgs& a, const unsigne
 }
 
 // HOISTED: the caller marches a column of planes and passes the masks and the plane-independent coefficients it computed once
-template <bool IS_E, int MODE, int C, unsigned FL, bool HOISTED = false>
+// PT: isotropic poles known at compile time (0 none, 1 some) or decided by `np` at run time (-1)
+template <bool IS_E, int MODE, int C, unsigned FL, bool HOISTED = false, int PT = -1>
 __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned rect, const unsigned info_rt, const double2 pfc, const double inv_eps,
                                              const PairLoads<IS_E, MODE>& L,
                                              const long r, const long row, const int x, const int y, const int z, const int xl, const int zl,
-                                             const bool hm0 = false, const bool hm1 = false, const PmlCoef* hc = nullptr)
+                                             const int np = 0, const bool hm0 = false, const bool hm1 = false, const PmlCoef* hc = nullptr)
 {
+    // info_rt: the rectangle's info value (class bits always valid); its flag byte equals FL when FL is a compile-time constant
     const unsigned info = FL == FL_RUNTIME ? info_rt : FL;
     const CompArgs& ca = a.c[C];
     constexpr bool HAS_VJ = has_other<IS_E, MODE>((C + 1) % 3);
@@ -424,6 +426,7 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
     const double2 vj = L.v[(C + 1) % 3], vk = L.v[(C + 2) % 3];
     const double2 nj = L.nj[C], nk = L.nk[C];
     double2 u = L.u[C];
+    const double2 uOld = u;          // E^n: what the isotropic poles are driven by (they are updated before E in the reference)
 
     const bool pmlCell = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
     const bool pmlOnD = IS_E && a.pml_on_D;
@@ -552,9 +555,34 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
     }
     if(IS_E && (info & F_D2E))
     {
-        // DtoU with no pole grids contributing (UTIL/FDTD_up_eq.cpp:838-843): E = (1/eps) * D
+        // DtoU (UTIL/FDTD_up_eq.cpp:838-848): E = (1/eps) * D, then E += (-1/eps) P_p for every isotropic pole p, in pole order
         const double ie = inv_eps;
         u.x = dm(ie, dv.x); u.y = dm(ie, dv.y);
+        if(PT == 1 || (PT == -1 && np > 0))
+        {
+            // updatePolE (parallelFDTDField.hpp:1355-1361 -> UTIL/FDTD_up_eq.cpp:435-446): P = alpha P + xi P_prev + gamma E^n, written into
+            // the buffer that held P_prev.  The reference runs this before the D update; nothing it reads is written by that update, so
+            // doing it here, pole by pole straight into the D->E sum, gives the same bits without holding the new P values in registers
+            const ClassEntry& ce = ca.cls[info_rt & CLS_MASK];
+            const long ip = ca.sp_base[row] + (x - ca.sp_xmin[row]);
+            const double nie = ce.neg_inv_eps;
+#pragma unroll 2
+            for(int p = 0; p < np; ++p)
+            {
+                const double al = ce.alpha[p], xi = ce.xi[p], ga = ce.gamma[p];
+                const double* __restrict__ pc = ca.Pcur[p] + ip;
+                double* __restrict__ pn = ca.Pnew[p] + ip;
+                double c0 = 0.0, c1 = 0.0, o0 = 0.0, o1 = 0.0;
+                if(m0) { c0 = pc[0]; o0 = pn[0]; }
+                if(m1) { c1 = pc[1]; o1 = pn[1]; }
+                double t0 = dm(al, c0), t1 = dm(al, c1);
+                t0 = axpy1(t0, xi, o0);       t1 = axpy1(t1, xi, o1);
+                t0 = axpy1(t0, ga, uOld.x);   t1 = axpy1(t1, ga, uOld.y);
+                if(m0) pn[0] = t0;
+                if(m1) pn[1] = t1;
+                u.x = axpy1(u.x, nie, t0);    u.y = axpy1(u.y, nie, t1);
+            }
+        }
     }
     else if(IS_E && (info & F_ORD2E))
     {
@@ -599,9 +627,10 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
             const unsigned info = w == 0 ? t.info[C] : t.infoB[C];
             const double2 pfc = w == 0 ? t.pf[C] : t.pfB[C];
             const double ie = w == 0 ? t.inv_eps[C] : t.inv_epsB[C];
+            const int np = (int)(((w == 0 ? t.np : t.npB) >> (8 * C)) & 0xFFu);
             // the flag combinations the reference's lists produce for pole-free cells get a body compiled for exactly that combination
             // (the flag tests, dead branches and zero-initialised operands of the generic body are most of its instructions)
-#define CHIML_UCASE(F) case (F): uniform_rect<IS_E, MODE, C, (F)>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl); break;
+#define CHIML_UCASE(F) case (F): uniform_rect<IS_E, MODE, C, (F)>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl, np); break;
             constexpr bool VJ = has_other<IS_E, MODE>((C + 1) % 3), VK = has_other<IS_E, MODE>((C + 2) % 3);
             switch(info & 0xFF00u)
             {
@@ -624,9 +653,9 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
                                         CHIML_UCASE(F_PG0 | F_PS0 | F_PG1)
                                         CHIML_UCASE(F_PG0 | F_PG1 | F_PS1)
                                         CHIML_UCASE(F_PG0 | F_PS0 | F_PG1 | F_PS1)
-                                        default: uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl);
+                                        default: uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl, np);
                                     }
-                                else uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl);
+                                else uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl, np);
                         }
                     }
                     else if constexpr(VJ && VK)
@@ -637,10 +666,10 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
                             CHIML_UCASE(F_PG0 | F_PS0 | F_PG1)
                             CHIML_UCASE(F_PG0 | F_PG1 | F_PS1)
                             CHIML_UCASE(F_PG0 | F_PS0 | F_PG1 | F_PS1)
-                            default: uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl);
+                            default: uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl, np);
                         }
                     }
-                    else uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl);
+                    else uniform_rect<IS_E, MODE, C, FL_RUNTIME>(a, rect, info, pfc, ie, L, r, row, x, y, z, xl, zl, np);
             }
 #undef CHIML_UCASE
         }
@@ -734,9 +763,9 @@ __device__ __forceinline__ void comp_march_load(const StepArgs& a, const long r,
 
 // a column of planes of a single-rectangle tile with the flag byte known at compile time: masks, prefactors and the plane-independent
 // CPML coefficients are set up once, the plane loop holds only loads, the reference's arithmetic and stores
-template <bool IS_E, int MODE, int C, unsigned FL>
-__device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec& t, const unsigned rect, const double2 pfc, const double ie,
-                                               const int xl, const int zl, const int x, const int z)
+template <bool IS_E, int MODE, int C, unsigned FL, bool POLES>
+__device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec& t, const unsigned rect, const unsigned info, const double2 pfc, const double ie,
+                                               const int np, const int xl, const int zl, const int x, const int z)
 {
     bool m0, m1;
     rect_mask(rect, xl, zl, m0, m1);
@@ -747,7 +776,7 @@ __device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec&
     long r = x + a.px * (z + (long)a.lz * t.y);
     double2 carry;
     comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
-    constexpr bool needU = !IS_E || !(FL & (F_D2E | F_ORD2E));
+    constexpr bool needU = !IS_E || !(FL & (F_D2E | F_ORD2E)) || POLES;      // poles are driven by E^n
     const bool anyD = IS_E && a.c[C].D && ((FL & (F_ISD | F_D2E | F_ORD2E)) || (a.pml_on_D && (FL & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
     const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector (the prefetch unit of L2)
     const int ny = t.ny, y0 = t.y;
@@ -765,7 +794,7 @@ __device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec&
         }
         PairLoads<IS_E, MODE> L;
         comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L, needU);
-        uniform_rect<IS_E, MODE, C, FL, true>(a, 0u, FL, pfc, ie, L, r, z + (long)a.lz * y, x, y, z, xl, zl, m0, m1, &kc);
+        uniform_rect<IS_E, MODE, C, FL, true, POLES ? 1 : 0>(a, 0u, info, pfc, ie, L, r, z + (long)a.lz * y, x, y, z, xl, zl, np, m0, m1, &kc);
     }
 }
 
@@ -781,6 +810,7 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
         unsigned rect = t.rect[C], info = t.info[C];
         double2 pfc = t.pf[C];
         double ie = t.inv_eps[C];
+        int np = (int)((t.np >> (8 * C)) & 0xFFu);
         bool single = t.rectB[C] == 0;
         if(!single)
         {
@@ -790,11 +820,13 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
             const unsigned lanes = __activemask();
             const bool inA = a0 || a1, inB = b0 || b1;
             if(__all_sync(lanes, !inB)) { if(!inA) return; single = true; }
-            else if(__all_sync(lanes, !inA)) { if(!inB) return; rect = t.rectB[C]; info = t.infoB[C]; pfc = t.pfB[C]; ie = t.inv_epsB[C]; single = true; }
+            else if(__all_sync(lanes, !inA)) { if(!inB) return; rect = t.rectB[C]; info = t.infoB[C]; pfc = t.pfB[C]; ie = t.inv_epsB[C]; np = (int)((t.npB >> (8 * C)) & 0xFFu); single = true; }
         }
         if(single)
         {
-#define CHIML_COL(F) case (F): uniform_column<IS_E, MODE, C, (F)>(a, t, rect, pfc, ie, xl, zl, x, z); return;
+#define CHIML_COL(F) case (F): \
+                if constexpr(IS_E && (((F) & F_D2E) != 0)) { if(np > 0) { uniform_column<IS_E, MODE, C, (F), true>(a, t, rect, info, pfc, ie, np, xl, zl, x, z); return; } } \
+                uniform_column<IS_E, MODE, C, (F), false>(a, t, rect, info, pfc, ie, np, xl, zl, x, z); return;
             switch(info & 0xFF00u)
             {
                 CHIML_COL(F_CURL)
@@ -804,6 +836,10 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
                 CHIML_COL(F_PG0 | F_PS0 | F_PG1 | F_PS1 | F_D2E)
                 CHIML_COL(F_CURL | F_ISD | F_D2E)
                 CHIML_COL(F_CURL | F_ISD | F_ORD2E)
+                CHIML_COL(F_PG0 | F_PG1 | F_ORD2E)
+                CHIML_COL(F_PG0 | F_PS0 | F_PG1 | F_ORD2E)
+                CHIML_COL(F_PG0 | F_PG1 | F_PS1 | F_ORD2E)
+                CHIML_COL(F_PG0 | F_PS0 | F_PG1 | F_PS1 | F_ORD2E)
                 CHIML_COL(F_PG0 | F_PG1)
                 CHIML_COL(F_PG0 | F_PS0 | F_PG1)
                 CHIML_COL(F_PG0 | F_PG1 | F_PS1)
@@ -817,7 +853,8 @@ __device__ __forceinline__ void uniform_march(const StepArgs& a, const TileRec& 
     long r = x + a.px * (z + (long)a.lz * t.y);
     double2 carry;
     comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
-    const bool needU = !IS_E || (t.rect[C] != 0 && !(t.info[C] & (F_D2E | F_ORD2E))) || (t.rectB[C] != 0 && !(t.infoB[C] & (F_D2E | F_ORD2E)));
+    const bool needU = !IS_E || (t.rect[C] != 0 && !(t.info[C] & (F_D2E | F_ORD2E))) || (t.rectB[C] != 0 && !(t.infoB[C] & (F_D2E | F_ORD2E))) ||
+                       (((t.np | t.npB) >> (8 * C)) & 0xFFu) != 0;
     const unsigned anyInfo = (t.rect[C] ? t.info[C] : 0u) | (t.rectB[C] ? t.infoB[C] : 0u);
     const bool anyD = IS_E && a.c[C].D && ((anyInfo & (F_ISD | F_D2E | F_ORD2E)) || (a.pml_on_D && (anyInfo & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
     const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector (the prefetch unit of L2)
