@@ -332,7 +332,8 @@ class GpuSim:
         """(nemit, N*N) complex: rho (which=0) or d rho/dt at n, n-1, n-2, n-3 (which=1..4) of level system `sys`."""
         e = self.plan.emitters[slot]
         out = np.empty((e.nemit, e.nlevel * e.nlevel, 2), dtype=np.float64)
-        self._chk(lib().chiml_gpu_download_emitter_state(self.h, slot, sys, which, _ptr(out)))
+        if e.nemit:          # a slab that holds only the rim of the object has a set without emitters
+            self._chk(lib().chiml_gpu_download_emitter_state(self.h, slot, sys, which, _ptr(out)))
         return out[..., 0] + 1j * out[..., 1]
 
     def emitter_P(self, slot: int, comp: int) -> np.ndarray:

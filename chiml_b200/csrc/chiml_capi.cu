@@ -291,7 +291,10 @@ int chiml_gpu_add_emitters(ChimlCtx* ctx, const ChimlEmitterDesc* d, int* slot)
     for(int k = 0; k < 3; ++k)
     {
         if(!threeD && k == 2) continue;
-        if(d->box_n[k] < 1 || d->box_lo[k] < 0 || d->box_lo[k] + d->box_n[k] + 2 > ln[k])
+        // a slab whose last owned row lies just below the object holds a set without emitters and without box rows (box_n[1] == 0):
+        // its E_y in that row still feels P_y of the object's first row, which the slab above pushes into this set's rim
+        const int nmin = (k == 1 && d->nemit == 0 && ctx->g.nranks > 1) ? 0 : 1;
+        if(d->box_n[k] < nmin || d->box_lo[k] < 0 || d->box_lo[k] + d->box_n[k] + 2 > ln[k])
             return fail(ctx, CHIML_ERR_ARG, "add_emitters: emitter box (plus its one-node rim) leaves the local grid");
     }
     for(int e = 0; e < d->nemit; ++e)
