@@ -866,7 +866,8 @@ int chiml_gpu_commit(ChimlCtx* ctx)
             {
                 // column length: long enough to amortise the carried planes, short enough that a small grid still yields several
                 // work items per SM (a 512 x 512 grid has only ~4600 tiles per half step)
-                                const size_t marchCap = ntiles / (148 * 8);
+                // (2-D grids pack ROWS_2D one-row tiles into a block, so they need that many more columns for the same number of blocks)
+                const size_t marchCap = ntiles / (148 * 8 * (ctx->lz > 1 ? 1 : ROWS_2D));
                 const bool hasLo = ctx->g.rank > 0, hasUp = ctx->g.rank < ctx->g.nranks - 1;
                 auto isBnd = [&](const TileRec& t) { return (hasLo && t.y == 1) || (hasUp && t.y == ctx->ly - 2); };
                 for(int kind = 0; kind < 2; ++kind)      // FAST and UNIFORM lists
