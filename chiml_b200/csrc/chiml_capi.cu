@@ -785,28 +785,27 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                     {
                         const unsigned rw = ts.rect[c][w];
                         if(area(rw) == ts.count[c][w]) { vals[c].push_back({ts.info[c][w], rw}); continue; }
-                        // not a rectangle: an object narrower than the tile leaves the surrounding value on both sides of it (or two
-                        // objects share a tile).  If another value fills a full-height (full-width) rectangle strictly inside this
-                        // value's bounding box and the two strips beside it hold exactly this value's cells, the strips are rectangles
+                        // not a rectangle: another value's rectangle is cut out of this value's bounding box (an object narrower than the
+                        // tile, an object corner or edge inside the tile, two objects sharing a tile).  With exactly one such hole that
+                        // lies inside the box, box minus hole is at most four rectangles -- the full-width strips below and above the hole
+                        // and the pieces left and right of it; if their areas add up to this value's cell count they hold exactly its
+                        // cells (all of them lie in the box, none in the hole, which its own value fills completely)
                         bool split = false;
+                        const unsigned wx0 = rw & 0xFF, wx1 = (rw >> 8) & 0xFF, wz0 = (rw >> 16) & 0xFF, wz1 = rw >> 24;
                         for(int h = 0; h < nv && !split; ++h)
                         {
                             if(h == w || area(ts.rect[c][h]) != ts.count[c][h]) continue;
                             const unsigned rh = ts.rect[c][h];
-                            const unsigned wx0 = rw & 0xFF, wx1 = (rw >> 8) & 0xFF, wz0 = (rw >> 16) & 0xFF, wz1 = rw >> 24;
                             const unsigned hx0 = rh & 0xFF, hx1 = (rh >> 8) & 0xFF, hz0 = (rh >> 16) & 0xFF, hz1 = rh >> 24;
-                            if(hz0 == wz0 && hz1 == wz1 && hx0 > wx0 && hx1 < wx1 && ((hx0 - wx0) + (wx1 - hx1)) * (wz1 - wz0) == ts.count[c][w])
-                            {
-                                vals[c].push_back({ts.info[c][w], wx0 | (hx0 << 8) | (wz0 << 16) | (wz1 << 24)});
-                                vals[c].push_back({ts.info[c][w], hx1 | (wx1 << 8) | (wz0 << 16) | (wz1 << 24)});
-                                split = true;
-                            }
-                            else if(hx0 == wx0 && hx1 == wx1 && hz0 > wz0 && hz1 < wz1 && ((hz0 - wz0) + (wz1 - hz1)) * (wx1 - wx0) == ts.count[c][w])
-                            {
-                                vals[c].push_back({ts.info[c][w], wx0 | (wx1 << 8) | (wz0 << 16) | (hz0 << 24)});
-                                vals[c].push_back({ts.info[c][w], wx0 | (wx1 << 8) | (hz1 << 16) | (wz1 << 24)});
-                                split = true;
-                            }
+                            if(hx0 < wx0 || hx1 > wx1 || hz0 < wz0 || hz1 > wz1) continue;                    // not inside the box
+                            if(area(rw) - area(rh) != ts.count[c][w]) continue;                               // other values in the box too
+                            auto put = [&](unsigned x0, unsigned x1, unsigned z0, unsigned z1) {
+                                if(x1 > x0 && z1 > z0) vals[c].push_back({ts.info[c][w], x0 | (x1 << 8) | (z0 << 16) | (z1 << 24)}); };
+                            put(wx0, wx1, wz0, hz0);     // strip below the hole (smaller z), full width
+                            put(wx0, wx1, hz1, wz1);     // strip above
+                            put(wx0, hx0, hz0, hz1);     // left of the hole
+                            put(hx1, wx1, hz0, hz1);     // right of the hole
+                            split = true;
                         }
                         if(!split) full = false;
                     }
