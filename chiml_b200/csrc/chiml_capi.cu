@@ -770,46 +770,13 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 rec.y = (int)(tIdx / ((size_t)nxt * nzt));
                 rec.ny = 1;
                 bool fast = true, uniform = true;
-                auto area = [](unsigned rc_) { return (((rc_ >> 8) & 0xFF) - (rc_ & 0xFF)) * ((rc_ >> 24) - ((rc_ >> 16) & 0xFF)); };
                 // a component's cells must fall into a few rectangles of one info value each; a record carries two of them per component,
                 // so a tile cut by several CPML / material boundaries becomes several records (k_uniform blocks)
-                struct Val { unsigned info, rect; };
-                std::vector<Val> vals[3];
+                std::vector<TileVal> vals[3];
                 for(int c = 0; c < 3; ++c)
                 {
                     if(!ts.total[c]) continue;
-                    bool full = !ts.other[c];
-                    int nv = 0;
-                    while(nv < TS_NV && ts.count[c][nv]) ++nv;
-                    for(int w = 0; w < nv && full; ++w)
-                    {
-                        const unsigned rw = ts.rect[c][w];
-                        if(area(rw) == ts.count[c][w]) { vals[c].push_back({ts.info[c][w], rw}); continue; }
-                        // not a rectangle: another value's rectangle is cut out of this value's bounding box (an object narrower than the
-                        // tile, an object corner or edge inside the tile, two objects sharing a tile).  With exactly one such hole that
-                        // lies inside the box, box minus hole is at most four rectangles -- the full-width strips below and above the hole
-                        // and the pieces left and right of it; if their areas add up to this value's cell count they hold exactly its
-                        // cells (all of them lie in the box, none in the hole, which its own value fills completely)
-                        bool split = false;
-                        const unsigned wx0 = rw & 0xFF, wx1 = (rw >> 8) & 0xFF, wz0 = (rw >> 16) & 0xFF, wz1 = rw >> 24;
-                        for(int h = 0; h < nv && !split; ++h)
-                        {
-                            if(h == w || area(ts.rect[c][h]) != ts.count[c][h]) continue;
-                            const unsigned rh = ts.rect[c][h];
-                            const unsigned hx0 = rh & 0xFF, hx1 = (rh >> 8) & 0xFF, hz0 = (rh >> 16) & 0xFF, hz1 = rh >> 24;
-                            if(hx0 < wx0 || hx1 > wx1 || hz0 < wz0 || hz1 > wz1) continue;                    // not inside the box
-                            if(area(rw) - area(rh) != ts.count[c][w]) continue;                               // other values in the box too
-                            auto put = [&](unsigned x0, unsigned x1, unsigned z0, unsigned z1) {
-                                if(x1 > x0 && z1 > z0) vals[c].push_back({ts.info[c][w], x0 | (x1 << 8) | (z0 << 16) | (z1 << 24)}); };
-                            put(wx0, wx1, wz0, hz0);     // strip below the hole (smaller z), full width
-                            put(wx0, wx1, hz1, wz1);     // strip above
-                            put(wx0, hx0, hz0, hz1);     // left of the hole
-                            put(hx1, wx1, hz0, hz1);     // right of the hole
-                            split = true;
-                        }
-                        if(!split) full = false;
-                    }
-                    if(!full)
+                    if(!tile_rectangles(ts, c, vals[c]))          // chiml_tiles.hpp
                     {
                         if(dbgTiles && uniform)
                         {
@@ -821,17 +788,11 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                         }
                         fast = uniform = false; continue;
                     }
-                    for(const Val& v : vals[c])
+                    for(const TileVal& v : vals[c])
                         if((v.info & 0xFF00u) != F_CURL || vals[c].size() > 1) fast = false;
                 }
                 if(!uniform) { lists[2].push_back(rec); listBytes[2] += ts.bytes; continue; }
-                // a record holds two rectangles per component when the tile is cut along z only (every warp, one z row, then lies in one
-                // rectangle and takes the column path); a tile that is cut along x gets one record per rectangle, so that no warp has to
-                // run the two-rectangle body
-                int per = 2;
-                for(int c = 0; c < 3; ++c)
-                    for(size_t w = 1; w < vals[c].size(); ++w)
-                        if((vals[c][w].rect & 0xFFFFu) != (vals[c][0].rect & 0xFFFFu)) per = 1;
+                const int per = rectangles_per_record(vals);
                 int nrec = 1;
                 for(int c = 0; c < 3; ++c) nrec = std::max(nrec, ((int)vals[c].size() + per - 1) / per);
                 for(int k = 0; k < nrec; ++k)

@@ -131,6 +131,7 @@ __device__ __forceinline__ double2 node_pair(const StepArgs& a, const double* po
 }
 
 } // namespace chiml
+#include "chiml_tiles.hpp"
 #include "chiml_update.cuh"
 #include "chiml_emitters.cuh"
 #include "chiml_halo.cuh"

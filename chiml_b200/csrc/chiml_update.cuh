@@ -969,15 +969,7 @@ __global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_general(co
 // commit-time tile summary: per tile and component the bounding rectangle of non-zero info cells, their
 // count, the first non-zero info value and whether all non-zero values are equal.  One block per tile.
 // ---------------------------------------------------------------------------------------------------
-// per component: the (up to) TS_NV distinct non-zero info values of the tile in descending order, each with the bounding
-// rectangle and count of its cells; the total count, and whether more than TS_NV values occur
-constexpr int TS_NV = 6;
-struct TileSummary
-{
-    unsigned info[3][TS_NV], rect[3][TS_NV], count[3][TS_NV];
-    unsigned total[3], other[3];
-    unsigned bytes; unsigned pad;
-};
+// TileSummary: chiml_tiles.hpp
 
 // algorithmic bytes one field-component cell moves per step: 16 B RW + 8 B cross-read when it is
 // updated, +16 B when its D value is read and written, +24 B per isotropic pole, +16 B per psi value touched

@@ -1,0 +1,126 @@
+// CPU check of chiml_b200/csrc/chiml_tiles.hpp (no CUDA): synthetic 64 x 8 tiles of info values -> the same summary k_tile_summary
+// computes on the device (distinct values in descending order, bounding rectangle and count of each) -> tile_rectangles.  Whenever
+// the decomposition is accepted, the rectangles must be pairwise disjoint, every cell of a rectangle must carry the rectangle's value
+// and every non-zero cell must be covered: that is what lets k_uniform skip the per-cell info plane.  Designed cases (object narrower
+// than the tile, edges, corners, CPML transition layers) must be accepted; random paintings exercise the rejections.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <set>
+#include <vector>
+
+#include "../../chiml_b200/csrc/chiml_tiles.hpp"
+
+using namespace chiml;
+constexpr int TX = 64, TZ = 8;
+struct Tile { unsigned v[TZ][TX]; };
+
+static void paint(Tile& t, int x0, int x1, int z0, int z1, unsigned val)
+{
+    for(int z = std::max(z0, 0); z < std::min(z1, TZ); ++z)
+        for(int x = std::max(x0, 0); x < std::min(x1, TX); ++x) t.v[z][x] = val;
+}
+
+// restatement of k_tile_summary for one component (chiml_update.cuh)
+static TileSummary summarise(const Tile& t)
+{
+    TileSummary s;
+    std::memset(&s, 0, sizeof(s));
+    std::set<unsigned, std::greater<unsigned>> vals;
+    for(int z = 0; z < TZ; ++z)
+        for(int x = 0; x < TX; ++x)
+            if(t.v[z][x]) { vals.insert(t.v[z][x]); ++s.total[0]; }
+    int w = 0;
+    for(unsigned val : vals)
+    {
+        if(w == TS_NV) { s.other[0] = 1; break; }
+        unsigned x0 = 255, x1 = 0, z0 = 255, z1 = 0, n = 0;
+        for(int z = 0; z < TZ; ++z)
+            for(int x = 0; x < TX; ++x)
+                if(t.v[z][x] == val) { x0 = std::min<unsigned>(x0, x); x1 = std::max<unsigned>(x1, x + 1); z0 = std::min<unsigned>(z0, z); z1 = std::max<unsigned>(z1, z + 1); ++n; }
+        s.info[0][w] = val; s.count[0][w] = n; s.rect[0][w] = rect_pack(x0, x1, z0, z1);
+        ++w;
+    }
+    return s;
+}
+
+// true = accepted and verified, false = rejected; exits on a wrong decomposition
+static bool check(const Tile& t, const char* what)
+{
+    const TileSummary s = summarise(t);
+    std::vector<TileVal> vals;
+    if(!tile_rectangles(s, 0, vals)) return false;
+    int cover[TZ][TX];
+    std::memset(cover, 0, sizeof(cover));
+    for(const TileVal& v : vals)
+    {
+        const unsigned x0 = v.rect & 0xFF, x1 = (v.rect >> 8) & 0xFF, z0 = (v.rect >> 16) & 0xFF, z1 = v.rect >> 24;
+        if(x1 > (unsigned)TX || z1 > (unsigned)TZ || x0 >= x1 || z0 >= z1) { std::printf("FAIL %s: bad rectangle\n", what); std::exit(1); }
+        for(unsigned z = z0; z < z1; ++z)
+            for(unsigned x = x0; x < x1; ++x)
+            {
+                if(t.v[z][x] != v.info) { std::printf("FAIL %s: rectangle of value %x holds a cell of value %x at (%u, %u)\n", what, v.info, t.v[z][x], x, z); std::exit(1); }
+                if(cover[z][x]++) { std::printf("FAIL %s: cell (%u, %u) in two rectangles\n", what, x, z); std::exit(1); }
+            }
+    }
+    for(int z = 0; z < TZ; ++z)
+        for(int x = 0; x < TX; ++x)
+            if(t.v[z][x] && !cover[z][x]) { std::printf("FAIL %s: cell (%d, %d) of value %x not covered\n", what, x, z, t.v[z][x]); std::exit(1); }
+    return true;
+}
+
+static void must_accept(const Tile& t, const char* what, size_t nrect)
+{
+    if(!check(t, what)) { std::printf("FAIL %s: a decomposable tile was rejected\n", what); std::exit(1); }
+    std::vector<TileVal> vals;
+    const TileSummary s = summarise(t);
+    tile_rectangles(s, 0, vals);
+    if(vals.size() != nrect) { std::printf("FAIL %s: %zu rectangles, expected %zu\n", what, vals.size(), nrect); std::exit(1); }
+}
+
+int main()
+{
+    Tile t;
+    auto fill = [&](unsigned val) { paint(t, 0, TX, 0, TZ, val); };
+    fill(0x0101); must_accept(t, "one value", 1);
+    fill(0x0101); paint(t, 0, 21, 0, TZ, 0x3400); must_accept(t, "x cut", 2);
+    fill(0x0101); paint(t, 0, TX, 0, 4, 0x3400); paint(t, 0, TX, 4, 5, 0x1400); must_accept(t, "CPML transition layer along z", 3);
+    fill(0x0101); paint(t, 12, 52, 0, TZ, 0x4302); must_accept(t, "object narrower than the tile", 3);
+    fill(0x0101); paint(t, 24, TX, 2, TZ, 0x4302); must_accept(t, "object corner", 3);
+    fill(0x0101); paint(t, 20, 44, 3, TZ, 0x4302); must_accept(t, "object edge (notch)", 4);
+    fill(0x0101); paint(t, 20, 44, 2, 6, 0x4302); must_accept(t, "object inside the tile", 5);
+    fill(0x4302); paint(t, 30, 36, 0, TZ, 0x0101); must_accept(t, "gap between two objects", 3);
+    fill(0x0101); paint(t, 0, 1, 0, TZ, 0); paint(t, 1, 21, 0, TZ, 0x3400); must_accept(t, "ghost column + CPML + interior", 2);
+    {
+        // 3 x 3 arrangement (CPML corner with transition layers): nine values exceed TS_NV -> must be rejected, not mis-decomposed
+        unsigned val = 0x100;
+        const int xs[4] = {0, 20, 21, TX}, zs[4] = {0, 4, 5, TZ};
+        for(int a = 0; a < 3; ++a) for(int b = 0; b < 3; ++b) paint(t, xs[a], xs[a + 1], zs[b], zs[b + 1], val += 0x100);
+        if(check(t, "nine values")) { std::printf("FAIL nine values accepted\n"); return 1; }
+    }
+    {
+        // two holes in one value: not handled -> rejected
+        fill(0x0101); paint(t, 5, 15, 0, TZ, 0x4302); paint(t, 40, 50, 0, TZ, 0x4302);
+        check(t, "two objects");     // either outcome is fine as long as an accepted decomposition is exact (it is verified inside)
+    }
+    std::mt19937 rng(12345);
+    long accepted = 0, rejected = 0;
+    for(int it = 0; it < 200000; ++it)
+    {
+        fill(rng() % 4 == 0 ? 0u : 0x0101u);
+        const int nr = 1 + rng() % 4;
+        for(int k = 0; k < nr; ++k)
+        {
+            int x0 = (int)(rng() % (TX + 8)) - 4, x1 = x0 + 1 + (int)(rng() % TX), z0 = (int)(rng() % (TZ + 2)) - 1, z1 = z0 + 1 + (int)(rng() % TZ);
+            if(rng() % 3 == 0) { x0 = 0; x1 = TX; }
+            if(rng() % 3 == 0) { z0 = 0; z1 = TZ; }
+            paint(t, x0, x1, z0, z1, (rng() % 5) * 0x1100u + (rng() % 2));
+        }
+        (check(t, "random painting") ? accepted : rejected)++;
+    }
+    if(accepted < 20000 || rejected < 1000) { std::printf("FAIL: the random paintings do not exercise both outcomes (%ld accepted, %ld rejected)\n", accepted, rejected); return 1; }
+    std::printf("TILE_RECTS_OK %ld accepted %ld rejected\n", accepted, rejected);
+    return 0;
+}
