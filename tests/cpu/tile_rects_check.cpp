@@ -101,9 +101,10 @@ int main()
         if(check(t, "nine values")) { std::printf("FAIL nine values accepted\n"); return 1; }
     }
     {
-        // two holes in one value: not handled -> rejected
-        fill(0x0101); paint(t, 5, 15, 0, TZ, 0x4302); paint(t, 40, 50, 0, TZ, 0x4302);
-        check(t, "two objects");     // either outcome is fine as long as an accepted decomposition is exact (it is verified inside)
+        // two objects of ONE material: neither the material nor the background fills a rectangle, each is the other's hole -> rejected
+        // today; either outcome is fine as long as an accepted decomposition is exact (verified inside check)
+        fill(0x0101); paint(t, 5, 15, 0, TZ, 0x4302); paint(t, 40, 50, 0, TZ, 0x4302); check(t, "two objects of one material");
+        fill(0x0101); paint(t, 5, 15, 0, TZ, 0x4302); paint(t, 40, 50, 2, TZ, 0x4402); must_accept(t, "two objects of two materials", 7);
     }
     std::mt19937 rng(12345);
     long accepted = 0, rejected = 0;
