@@ -1,0 +1,208 @@
+// Flux spectra of a single-rank run from the running-DFT accumulators of the flux regions: the surface-averaged frequency-domain
+// fields, the Poynting integrand E x conj(H) on every surface, its Simpson integral, and the <flux name>.dat file.  Restates
+// parallelFluxDTC::combineField / getFlux / simps / simps2D (DTC/parallelFlux.hpp:325-602) for one process, with the same complex
+// expressions in the same order, so that the files equal the reference's character for character when the accumulators do.
+// This is post-processing after the time loop: the hot path only produces the accumulators (chiml_gpu_add_dft).
+#include <array>
+#include <cmath>
+#include <complex>
+#include <fstream>
+#include <iomanip>
+#include <stdexcept>
+#include <vector>
+
+#include "setup.hpp"
+
+namespace chiml_host {
+
+namespace {
+
+// netlib zaxpy with the product written out (what the reference links against here computes the same two expressions)
+inline cplx cmul(const cplx& a, const cplx& b) { return cplx(a.real() * b.real() - a.imag() * b.imag(), a.real() * b.imag() + a.imag() * b.real()); }
+
+// parallelFluxDTC::simps (DTC/parallelFlux.hpp:548-570)
+cplx simps(const cplx* integrand, int n, double d)
+{
+    if(n == 1) return integrand[0] * d;
+    cplx result(0.0, 0.0);
+    if(n % 2 == 0)
+    {
+        for(int ii = 0; ii < (n - 2) / 2; ii++) result += d / 6.0 * (integrand[ii * 2] + 4.0 * integrand[ii * 2 + 1] + integrand[(ii + 1) * 2]);
+        for(int ii = 1; ii < (n) / 2; ii++) result += d / 6.0 * (integrand[ii * 2 - 1] + 4.0 * integrand[ii * 2] + integrand[ii * 2 + 1]);
+        result += d / 4.0 * (integrand[0] + integrand[1] + integrand[n - 1] + integrand[n - 2]);
+    }
+    else
+    {
+        for(int ii = 0; ii < (n - 1) / 2; ii++) result += d / 3.0 * (integrand[ii * 2] + 4.0 * integrand[ii * 2 + 1] + integrand[(ii + 1) * 2]);
+    }
+    return result;
+}
+
+// a complex grid {nx, ny} stored x fastest; simps2D (:578-591)
+cplx simps2D(const std::vector<cplx>& g, int nx, int ny, double dx, double dy)
+{
+    if(ny > 1 && nx > 1)
+    {
+        std::vector<cplx> result(ny, 0.0);
+        for(int jj = 0; jj < ny; ++jj) result[jj] = simps(&g[(size_t)jj * nx], nx, dx);
+        return simps(result.data(), (int)result.size(), dy);
+    }
+    else if(nx > 1) return simps(g.data(), nx, dx);
+    else if(ny > 1) return simps(g.data(), ny, dy);
+    return cplx(0.0, 0.0);      // a one-point surface: the reference returns nothing here
+}
+
+struct Storage { const PlanDft* d; const std::vector<double>* re; const std::vector<double>* im; };
+struct Surface
+{
+    int dir = 0; bool plus = true;
+    std::vector<Storage> role[4];       // Ej, Ek, Hj, Hk
+};
+
+} // namespace
+
+void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std::vector<double>>& re, const std::vector<std::vector<double>>& im, long nSteps)
+{
+    if(P.grid.desc.nranks != 1) throw std::logic_error("flux files are written by single-rank runs (several slabs write their accumulators)");
+    const bool twoD = P.grid.desc.ln[2] == 1;
+    const bool threeD = P.grid.desc.mode == CHIML_MODE_3D;
+    for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff)
+    {
+        const FluxInput& fx = IP.fluxes_[ff];
+        const int nfreq = (int)fx.freqs.size();
+        std::vector<Surface> surf;
+        for(size_t q = 0; q < P.dfts.size(); ++q)
+        {
+            const PlanDft& d = P.dfts[q];
+            if(d.group != (int)ff) continue;
+            if((int)surf.size() <= d.surface) surf.resize(d.surface + 1);
+            surf[d.surface].dir = d.dir; surf[d.surface].plus = d.plus;
+            surf[d.surface].role[d.role].push_back({&d, &re[q], &im[q]});
+        }
+        if(surf.empty()) continue;
+        // t_step_: how often fieldIn ran -- once in the propagator's constructor on the zero fields (parallelFDTDField.cpp:836-837),
+        // then after every timeInt-th step
+        const long nt = nSteps / fx.timeInt + 1;
+        // unit conversions of the constructor (:146-173)
+        double fluxConv = fx.weight, freqConv = 1.0;
+        if(fx.SI)
+        {
+            freqConv = SPEED_OF_LIGHT / IP.a_;
+            fluxConv = IP.I0_ / IP.a_ * IP.I0_ / (EPS0() * IP.a_ * SPEED_OF_LIGHT);
+        }
+        freqConv /= (M_PI * 2.0);
+
+        // ---- combineField: the stored fields of a surface averaged onto the face centres, per role a grid {nfreq, sz[tc1], sz[cor]}
+        struct Face { int nx = 0, ny = 0; double dx = 0, dy = 0; std::vector<cplx> g[4]; bool has[4] = {false, false, false, false}; double weight = 1.0; };
+        std::vector<Face> faces(surf.size());
+        for(size_t vv = 0; vv < surf.size(); ++vv)
+        {
+            const Surface& s = surf[vv];
+            int cor, tc1;
+            std::array<int, 3> sz = fx.sz;
+            if(s.dir == 0) { if(twoD) { cor = 1; tc1 = 2; } else { cor = 2; tc1 = 1; } sz[0] = 1; }
+            else if(s.dir == 1) { cor = 0; tc1 = 2; sz[1] = 1; }
+            else { cor = 0; tc1 = 1; sz[2] = 1; }
+            const int corJ = (s.dir + 1) % 3, corK = (s.dir + 2) % 3;
+            Face& F = faces[vv];
+            F.nx = sz[cor]; F.ny = sz[tc1]; F.dx = P.grid.desc.d[cor]; F.dy = P.grid.desc.d[tc1];
+            F.weight = s.plus ? 1.0 : -1.0;
+            const int addIndex[2] = {0, 0};                      // one process: the surface starts in this process
+            for(int r = 0; r < 4; ++r)
+            {
+                const std::vector<Storage>& arr = s.role[r];
+                if(arr.empty()) continue;
+                F.has[r] = true;
+                F.g[r].assign((size_t)nfreq * F.nx * F.ny, cplx(0.0, 0.0));
+                const int corJK = (r == 0 || r == 3) ? corJ : corK;                 // Ej, Hk: corJ; Ek, Hj: corK
+                for(const Storage& st : arr)
+                {
+                    const int outY = st.d->nlines, outZ = st.d->npts;
+                    // constructSzProcOffsetLists (:176-242): two shifted windows in 3-D (both in-plane fields exist), one otherwise
+                    std::vector<std::array<int, 9>> ent(threeD ? 2 : 1, std::array<int, 9>{{0, outY, outZ, 0, 0, 0, 0, 0, 0}});
+                    if(threeD)
+                    {
+                        const int end = st.d->gloc[corJK] + st.d->gsz[corJK] - 1;
+                        const bool inside = (0 <= end) && (end < P.grid.n_global[corJK]);      // procLoc = 0, ln_vec - 2 = points of the grid
+                        if(cor == corJK)
+                        {
+                            if(addIndex[1] == 0) { ent[1][6] = 1; ent[1][4] = 1; } else ent[0][8] = 1;
+                            if(inside) ent[0][4] = 1;
+                        }
+                        else if(tc1 == corJK)
+                        {
+                            if(addIndex[0] == 0) { ent[1][5] = 1; ent[1][3] = 1; } else ent[0][7] = 1;
+                            if(inside) ent[0][3] = 1;
+                        }
+                    }
+                    const cplx w(1.0 / (static_cast<double>(arr.size() * ent.size())), 0.0);
+                    for(const auto& e : ent)
+                        for(int jj = 0; jj < e[2] - e[4]; ++jj)
+                            for(int ii = 0; ii < e[1] - e[3]; ++ii)
+                            {
+                                const size_t src = (size_t)nfreq * ((size_t)(jj + e[6]) + (size_t)(ii + e[5]) * outZ);
+                                const size_t dst = (size_t)nfreq * ((size_t)(jj + addIndex[1] + e[8]) + (size_t)(ii + addIndex[0] + e[7]) * F.nx);
+                                if(dst + nfreq > F.g[r].size() || src + nfreq > st.re->size()) throw std::logic_error("flux output: a stored field does not fit its surface");
+                                for(int f = 0; f < nfreq; ++f)
+                                    F.g[r][dst + f] = F.g[r][dst + f] + cmul(w, cplx((*st.re)[src + f], (*st.im)[src + f]));
+                            }
+                }
+            }
+        }
+
+        // ---- getFlux (:406-540)
+        std::ofstream f((fx.name + ".dat").c_str());
+        f << "#" << std::setw(16) << "freq\tabs(incd)\treal(incd)\timag(incd)";
+        if(faces.size() > 1)
+        {
+            f << std::setw(16) << "\tabs(right)\treal(right)\timag(right)\tabs(left)\treal(left)\timag(left)\tabs(top)\treal(top)\timag(top)\tabs(bot)\treal(bot)\timag(bot)";
+            if(fx.sz[0] > 1 && fx.sz[1] > 1 && fx.sz[2] > 1) f << std::setw(16) << "\tabs(front)\treal(front)\timag(front)\tabs(back)\treal(back)\timag(back)";
+        }
+        f << std::setw(16) << "freq\tabs(total)\treal(total)\timag(total)\n";
+        for(int kf = 0; kf < nfreq; ++kf)
+        {
+            cplx flux(0.0, 0.0);
+            // no TFSF surface on this path: the incident fields are empty and every incident spectrum is zero (:433-460)
+            const cplx Ex_inc(0.0, 0.0), Ey_inc(0.0, 0.0), Ez_inc(0.0, 0.0), Hx_inc(0.0, 0.0), Hy_inc(0.0, 0.0), Hz_inc(0.0, 0.0);
+            const double incConv = 1.0;
+            cplx flux_incd = std::pow(incConv * (Ey_inc * std::conj(Hz_inc) - Ez_inc * std::conj(Hy_inc)) / (std::pow(static_cast<double>(nt * fx.timeInt), 2.0)), 2.0);
+            flux_incd += std::pow(incConv * (Ez_inc * std::conj(Hx_inc) - Ex_inc * std::conj(Hz_inc)) / (std::pow(static_cast<double>(nt * fx.timeInt), 2.0)), 2.0);
+            flux_incd += std::pow(incConv * (Ex_inc * std::conj(Hy_inc) - Ey_inc * std::conj(Hx_inc)) / (std::pow(static_cast<double>(nt * fx.timeInt), 2.0)), 2.0);
+            flux_incd = std::sqrt(flux_incd);
+            std::vector<std::vector<cplx>> ijk(faces.size());
+            for(size_t vv = 0; vv < faces.size(); ++vv)
+            {
+                const Face& F = faces[vv];
+                const size_t n = (size_t)F.nx * F.ny;
+                ijk[vv].assign(n, cplx(0.0, 0.0));
+                std::vector<cplx> ikj(n, cplx(0.0, 0.0));
+                if(F.has[0])          // Ej conj(Hk)
+                    for(size_t e = 0; e < n; ++e)
+                        ijk[vv][e] = F.g[0][kf + (size_t)nfreq * e] * std::conj(F.g[3][kf + (size_t)nfreq * e]) / std::pow(static_cast<double>(nt), 2.0);
+                if(F.has[1])          // minus Ek conj(Hj)
+                    for(size_t e = 0; e < n; ++e)
+                    {
+                        ikj[e] = F.g[1][kf + (size_t)nfreq * e] * std::conj(F.g[2][kf + (size_t)nfreq * e]) / std::pow(static_cast<double>(nt), 2.0);
+                        ijk[vv][e] = ijk[vv][e] + cmul(cplx(-1.0, 0.0), ikj[e]);
+                    }
+            }
+            f << std::setw(18) << std::setprecision(15) << freqConv * fx.freqs[kf] << "\t" << std::setw(16) << std::setprecision(15) << std::abs(flux_incd) << "\t"
+              << std::setw(16) << std::setprecision(15) << std::abs(std::real(flux_incd)) << "\t" << std::setw(16) << std::setprecision(15) << std::imag(flux_incd) << "\t";
+            for(size_t vv = 0; vv < faces.size(); ++vv)
+            {
+                const Face& F = faces[vv];
+                const cplx tempFlux = fluxConv * F.weight * simps2D(ijk[vv], F.nx, F.ny, F.dx, F.dy);
+                flux += tempFlux;
+                f << std::setw(16) << std::setprecision(15) << std::abs(tempFlux) << "\t" << std::setw(16) << std::setprecision(15) << std::real(tempFlux) << "\t"
+                  << std::setw(16) << std::setprecision(15) << std::imag(tempFlux) << "\t";
+            }
+            if(faces.size() > 1)
+                f << std::setw(16) << std::setprecision(15) << std::abs(flux) << "\t" << std::setw(16) << std::setprecision(15) << std::real(flux) << "\t"
+                  << std::setw(16) << std::setprecision(15) << std::imag(flux) << std::endl;
+            else
+                f << std::endl;
+        }
+    }
+}
+
+} // namespace chiml_host

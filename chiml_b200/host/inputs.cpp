@@ -558,6 +558,8 @@ Inputs::Inputs(const Json& IP)
             for(int k = 0; k < nFreq; ++k) f.freqs[k] = 2.0 * M_PI / (lamL + k * dLam);
         }
         else throw std::logic_error("All fluxes must either have fcen and fwidth defined or lamL and lamR defined");
+        f.SI = fj.get<bool>("SI", false);
+        f.crossSec = fj.get<bool>("cross_sec", false);
         fluxes_.push_back(f);
     }
 }

@@ -101,7 +101,7 @@ struct DetectorInput
 
 struct FluxInput
 {
-    std::string name; std::array<int, 3> loc, sz; double weight; int timeInt; std::vector<double> freqs;
+    std::string name; std::array<int, 3> loc, sz; double weight; int timeInt; std::vector<double> freqs; bool SI = false, crossSec = false;
 };
 
 class Inputs

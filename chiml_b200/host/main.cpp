@@ -269,6 +269,7 @@ int main(int argc, char** argv)
         // ---- frequency-domain fields of the flux regions: one file per region and slab holding every stored field's accumulators
         // (fInReal_ / fInCplx_ of parallelStorageFreqDTCReal) in the order parallelFluxDTC::fieldIn walks them.  The Poynting-vector
         // integration of getFlux() is post-processing on these arrays and is not part of the time-stepping path.
+        std::vector<std::vector<double>> dftRe(P.dfts.size()), dftIm(P.dfts.size());
         for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff)
         {
             std::string name = IP.fluxes_[ff].name + ".dft";
@@ -294,8 +295,11 @@ int main(int argc, char** argv)
                 out.write(reinterpret_cast<const char*>(&len), sizeof(len));
                 out.write(reinterpret_cast<const char*>(re.data()), (std::streamsize)(len * sizeof(double)));
                 out.write(reinterpret_cast<const char*>(im.data()), (std::streamsize)(len * sizeof(double)));
+                dftRe[q].swap(re); dftIm[q].swap(im);
             }
         }
+        // flux spectra (parallelFluxDTC::getFlux): one process holds whole surfaces; several slabs leave their accumulator files
+        if(nranks == 1 && !IP.fluxes_.empty()) write_flux_files(IP, P, dftRe, dftIm, nSteps);
         // ---- level populations (ML/QEPopDtc.cpp:37-61)
         for(size_t q = 0; q < P.emitters.size(); ++q)
         {

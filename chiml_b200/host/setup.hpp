@@ -41,6 +41,13 @@ struct PlanDft
     uint64_t acc_len = 0;
     std::vector<double> freq;
     std::vector<ChimlDftLine> lines;
+    // where the set sits in its flux region (not part of the plan file; used by the flux output, flux_out.cpp)
+    int surface = 0;            // index into the region's surface list (parallelFluxDTC::fInParam_)
+    int role = 0;               // 0 Ej, 1 Ek, 2 Hj, 3 Hk of that surface
+    int dir = 0;                // normal of the surface: 0 x, 1 y, 2 z
+    bool plus = true;           // the face at loc + sz - 1 (weight +1) or at loc (weight -1)
+    int nlines = 0;             // fInParam::sz_[1]
+    std::array<int, 3> gloc = {0, 0, 0}, gsz = {0, 0, 0};   // the storage's box in global grid points (parallelStorageFreqDTC::loc_, sz_)
 };
 
 // The flattened propagator of one rank ("plan", include/chiml_plan.h)
@@ -61,5 +68,9 @@ struct SlabPlan
 
 // Builds the plan of y-slab `rank` of `nranks` (equal-height slabs, mpiInterface::getLocxLocyLocz(int,int,int)).
 SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads = 0);
+
+// Flux spectra files of a single-rank run (parallelFluxDTC::getFlux, DTC/parallelFlux.hpp:406-540): re[k] / im[k] = accumulators of
+// P.dfts[k] (fInReal_ / fInCplx_), nSteps = time steps taken.  Writes <flux name>.dat for every flux region.
+void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std::vector<double>>& re, const std::vector<std::vector<double>>& im, long nSteps);
 
 } // namespace chiml_host

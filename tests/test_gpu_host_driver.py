@@ -81,4 +81,8 @@ def test_host_driver_flux_accumulators_equal_the_reference(case, regions, tmp_pa
             assert np.abs(ref_re).max() > 0, f"{case}: accumulator {slot} of the reference is all zero"
             assert np.array_equal(re, ref_re) and np.array_equal(im, ref_im), f"{case}: {name} stored field {slot} differs from the reference"
             slot += 1
+        # ... and the flux spectrum the driver derives from them is the reference's <flux name>.dat, character for character
+        got = open(tmp_path / (name + ".dat"), "rb").read()
+        ref = open(os.path.join(GOLDEN, "out_expected", case, os.path.basename(name) + ".dat"), "rb").read()
+        assert got == ref, f"{case}: {name}.dat differs from the reference's file"
     assert f"dft{slot}r" not in expect.files and slot > 0
