@@ -45,3 +45,51 @@ def test_flux_files_from_reference_accumulators_equal_reference_files(case, tmp_
         got = open(tmp_path / (name + ".dat"), "rb").read()
         ref = open(os.path.join(util.GOLDEN, "out_expected", case, os.path.basename(name) + ".dat"), "rb").read()
         assert got == ref, f"{case}: {name}.dat differs from the reference's file"
+
+
+@pytest.mark.parametrize("case,nranks", [("flux3d", 3), ("te_flux", 2), ("tm_flux", 4)])
+def test_flux_files_from_slab_accumulator_parts(case, nranks, tmp_path):
+    """Several slabs: every rank's driver writes the accumulators of ITS parts of the flux surfaces (<name>.dft.rank<r>);
+    `chiml_flux --ranks N` puts the parts together (an accumulator is identified by region, surface, stored field and global grid
+    point) and must write the same files as a single-rank run.  The parts are cut here from the reference's single-rank accumulators
+    through the slab plans of the host-side setup -- that the engines produce exactly these parts is what tests/test_slab_gloo.py
+    and tests/test_gpu_slabs.py check."""
+    from chiml_b200 import plan as P
+    host = os.path.join(ROOT, "chiml_b200", "host")
+    subprocess.run(["make", "-C", host, os.path.join("..", "chiml_flux"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
+    cfg = json.load(open(os.path.join(util.GOLDEN, case + ".json")))
+    whole = util.load_plan(case)
+    exp = util.load_expect(case)
+    ref = util.dft_point_map(whole, [exp[f"dft{k}r"].ravel() + 1j * exp[f"dft{k}i"].ravel() for k in range(len(whole.dfts))])
+    subprocess.run([os.path.join(ROOT, "chiml_b200", "chiml_plan"), os.path.join(util.GOLDEN, case + ".json"), str(tmp_path / "p"), "--ranks", str(nranks)], check=True)
+    for r in range(nranks):
+        slab = P.read_plan(str(tmp_path / f"p.rank{r}.plan"))
+        lnx, lny, lnz = slab.ln
+        for g, fl in enumerate(cfg["FluxList"]):
+            sets = [d for d in slab.dfts if d.group == g]
+            if not sets:
+                continue
+            path = str(tmp_path / (fl["name"] + f".dft.rank{r}"))
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "wb") as f:
+                freq = np.asarray(sets[0].freq, "<f8")
+                f.write(b"CHIMLDFT" + struct.pack("<ii", len(sets), len(freq)) + freq.tobytes())
+                for d in sets:
+                    acc = np.zeros(d.acc_len, dtype=complex)
+                    for li, (ind, o) in enumerate(d.lines):
+                        if li > 0 and ind == 0 and o == 0:
+                            continue
+                        for i in range(d.npts):
+                            row, x = divmod(int(ind) + i * d.stride, lnx)
+                            y, z = divmod(row, lnz)
+                            for k in range(d.nfreq):
+                                acc[int(o) + k + d.nfreq * i] = ref[(d.group, d.field, x, y + slab.y_start, z, k)]
+                    f.write(struct.pack("<iiii", d.field, d.npts, len(d.lines), d.every) + struct.pack("<Q", d.acc_len))
+                    f.write(np.asarray(acc.real, "<f8").tobytes() + np.asarray(acc.imag, "<f8").tobytes())
+    r = subprocess.run([os.path.join(ROOT, "chiml_b200", "chiml_flux"), os.path.join(util.GOLDEN, case + ".json"), "--ranks", str(nranks)],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for fl in cfg["FluxList"]:
+        got = open(tmp_path / (fl["name"] + ".dat"), "rb").read()
+        want = open(os.path.join(util.GOLDEN, "out_expected", case, os.path.basename(fl["name"]) + ".dat"), "rb").read()
+        assert got == want, f"{case}: {fl['name']}.dat from {nranks} slabs differs from the reference's file"
