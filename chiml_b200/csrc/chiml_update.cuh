@@ -791,6 +791,13 @@ __device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec&
             if(needU) prefetch_l2(a.c[C].U + rp);
             if(anyD) prefetch_l2(a.c[C].D + rp);
             prefetch_psi<IS_E, MODE, C>(a, FL, x, y + PREFETCH_PLANES, z);
+            if constexpr(POLES)
+            {
+                // the pole pools are read pole after pole (two poles' loads in flight at a time): have them wait in L2
+                const long rowp = z + (long)a.lz * (y + PREFETCH_PLANES);
+                const long ipp = a.c[C].sp_base[rowp] + (x - a.c[C].sp_xmin[rowp]);
+                for(int p = 0; p < np; ++p) { prefetch_l2(a.c[C].Pcur[p] + ipp); prefetch_l2(a.c[C].Pnew[p] + ipp); }
+            }
         }
         PairLoads<IS_E, MODE> L;
         comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L, needU);
