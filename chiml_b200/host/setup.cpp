@@ -400,7 +400,8 @@ struct CpmlBuilder
                 eps_sum += IP.objArr_[id]->eps_infty_ / N;
                 mu_sum += IP.objArr_[id]->mu_infty_ / N;
             };
-            const long zoff = 0;
+            // a 2-D map has one z layer, kk = 0, whose sample point the reference puts at z = (kk - 1) d = -d (parallelFDTDField.hpp:890)
+            const long zoff = g.twoD ? -1 : 0;
             if(dir == 0)
             {
                 N = static_cast<double>(planeSzTemp[2] * planeSzTemp[1]);
@@ -694,6 +695,9 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads)
     {
         PlanObject o;
         o.npoles = (int)obj->gamma_.size(); o.use_or_dip = obj->useOrientedDipols_ ? 1 : 0; o.ml = obj->ML_ ? 1 : 0;
+        if(g.twoD && o.use_or_dip && o.npoles > 0 && !o.ml)
+            throw std::logic_error("oriented-dipole (unidirectional) poles on a 2-D grid are outside the covered hot path: the reference's update "
+                                   "lists for them index z neighbours a 2-D grid does not have (its own parallelGrid::getInd assertion fails)");
         o.eps_inf = obj->eps_infty_; o.mu_inf = obj->mu_infty_;
         o.alpha = obj->alpha_; o.xi = obj->xi_; o.gamma = obj->gamma_;
         o.dip.assign(3 * (size_t)o.npoles, 0.0);

@@ -1,0 +1,64 @@
+"""Random chiML inputs for the host-setup fuzz test (tests/test_host_plan_fuzz.py): 2-D TE / TM and 3-D cells with random CPML
+parameters, blocks and spheres of random dielectric / Lorentz / Drude / oriented-dipole (3-D only) media that may reach into the
+CPML, a random source box, detector box and flux regions (boxes, planes, lines, unequal sampling intervals)."""
+import random
+
+from chiml_b200 import inputs as I
+
+RES = 100
+DT = I.default_dt(RES)
+
+
+def rnd_case(seed):
+    r=random.Random(seed)
+    mode=r.choice(["3d","te","tm"])
+    if mode=="3d":
+        n=[r.randint(17,27) for _ in range(3)]; pol="Ex"
+    else:
+        n=[r.randint(31,55), r.randint(31,55), 0]; pol="Hz" if mode=="te" else "Ez"
+    size=[k/RES for k in n]
+    steps=10
+    pmlc=[r.randint(3,6) for _ in range(3)]
+    if mode!="3d": pmlc[2]=0
+    pml=I.pml([c/RES for c in pmlc], a_max=r.choice([0.25,0.1]), ma=r.choice([1.0,2.0]), m=r.choice([3.0,3.5]), kappa_max=r.choice([1.0,2.5]))
+    objs=[]
+    for _ in range(r.randint(0,3)):
+        loc=[r.uniform(-0.3,0.3)*size[k] for k in range(3)]
+        if mode!="3d": loc[2]=0.0
+        pols=[]
+        kind=r.choice(["eps","lor","uni","drude"]) if mode=="3d" else r.choice(["eps","lor","drude"])
+        if kind=="lor": pols=[I.lorentz_pole(r.uniform(0.3,1.5), r.uniform(0.02,0.2), r.uniform(1,3)) for _ in range(r.randint(1,2))]
+        if kind=="uni" :
+            v=[r.uniform(-1,1) for _ in range(3)]
+            if mode=="tm": v=[0,0,1.0]
+            if mode=="te": v[2]=0.0
+            nn=sum(x*x for x in v)**0.5 or 1.0
+            pols=[I.lorentz_pole(r.uniform(0.3,1.5), r.uniform(0.02,0.2), r.uniform(1,3), dip_or_e="unidirectional", dir_dip_e=[x/nn for x in v])]
+        if kind=="drude": pols=[I.drude_pole(r.uniform(5,9), r.uniform(0.05,0.2))]
+        eps=r.choice([1.0,2.0,2.25,4.0])
+        if r.random()<0.5:
+            sz=[r.uniform(0.1,0.6)*size[k] for k in range(3)]
+            if mode!="3d": sz[2]=0.0
+            objs.append(I.block(sz, loc, eps=eps, pols=pols))
+        else:
+            objs.append(I.sphere(r.uniform(0.08,0.25)*min(s for s in size if s>0), loc, eps=eps, pols=pols))
+    srcpol={"3d":r.choice(["Ex","Ey","Ez","Hx","Hz"]),"te":r.choice(["Hz","Ex","Ey"]),"tm":r.choice(["Ez","Hx","Hy"])}[mode]
+    sloc=[r.uniform(-0.2,0.2)*size[k] for k in range(3)]; ssz=[r.choice([0.0, r.uniform(0,0.3)*size[k]]) for k in range(3)]
+    if mode!="3d": sloc[2]=0.0; ssz[2]=0.0
+    srcs=[I.normal_source(srcpol, sloc, ssz, [I.gaussian_pulse(1.5,1.0,t_0=0.25,cutoff=2.5)])]
+    dets=[]
+    dpol={"3d":r.choice(["Ex","Ey","Ez","Hx","Hy","Hz"]),"te":r.choice(["Hz","Ex","Ey"]),"tm":r.choice(["Ez","Hx","Hy"])}[mode]
+    dloc=[r.uniform(-0.2,0.2)*size[k] for k in range(3)]; dsz=[r.choice([0.0, r.uniform(0,0.2)*size[k]]) for k in range(3)]
+    if mode!="3d": dloc[2]=0.0; dsz[2]=0.0
+    dets.append(I.detector(dloc, dsz, dpol, f"out/fz{seed}/d", time_int=DT*r.choice([1.0000001,2.0000001])))
+    fluxes=[]
+    for k in range(r.randint(0,2)):
+        floc=[r.uniform(-0.1,0.1)*size[j] for j in range(3)]
+        fsz=[r.uniform(0.2,0.5)*size[j] for j in range(3)]
+        if r.random()<0.5: fsz[r.randrange(3 if mode=="3d" else 2)]=0.0
+        if mode!="3d": floc[2]=0.0; fsz[2]=0.0
+        fl=I.flux(f"out/fz{seed}/f{k}", floc, fsz, 1.5, 1.0, r.randint(3,5))
+        if r.random()<0.5: fl["Time_Interval"]=2.0*DT
+        fluxes.append(fl)
+    return I.config(I.comp_cell(size, RES, steps*DT-0.5*DT, pol), pml, srcs, objs, dets, fluxes)
+

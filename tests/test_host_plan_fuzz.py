@@ -1,0 +1,34 @@
+"""Fuzz of the host-side setup against the UNMODIFIED reference's constructors: for random inputs (tests/fuzz/gen_inputs.py) the
+plan written by chiml_b200/chiml_plan must equal, record for record and bit for bit, the plan oracle/_ref/chiml_ref dumps from the
+reference's own data structures (update lists, CPML lists and coefficients, pole constants, source / detector boxes, flux DFT sets).
+Needs the reference build (oracle/_ref/chiml_ref, made by oracle/Makefile where /root/reference exists; it travels to the GPU box);
+skipped without it.  This test found the 2-D CPML coefficient bug for curved objects reaching into the CPML (sample point at z = -d)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "fuzz"))
+REF = os.path.join(ROOT, "oracle", "_ref", "chiml_ref")
+TOOL = os.path.join(ROOT, "chiml_b200", "chiml_plan")
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="needs the reference build oracle/_ref/chiml_ref")
+@pytest.mark.parametrize("seed", [1, 2, 5, 9, 11, 27, 33, 50, 64, 101, 150, 207])
+def test_random_input_host_plan_equals_reference_plan(seed, tmp_path):
+    import gen_inputs
+    import plan_diff
+    from chiml_b200 import inputs as I, plan as P
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
+    cfg = gen_inputs.rnd_case(seed)
+    I.write(cfg, str(tmp_path / "c.json"))
+    r = subprocess.run([REF, "c.json", "--steps", "0", "--plan", str(tmp_path / "ref"), "--quiet", "--no-output"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "host")], check=True)
+    bad = plan_diff.diff(P.read_plan(str(tmp_path / "host.rank0.plan")), P.read_plan(str(tmp_path / "ref.rank0.plan")))
+    # the reference was asked for 0 steps: its plan has no source amplitudes and n_steps = 0
+    bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
+    assert not bad, "\n".join(bad[:20])
