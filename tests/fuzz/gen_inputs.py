@@ -9,7 +9,25 @@ RES = 100
 DT = I.default_dt(RES)
 
 
-def rnd_case(seed):
+def rnd_pulse(r):
+    """One pulse of a random profile, with time constants of a few time steps so that a short run samples its shape
+    (UTIL/PulseFxn.hpp; parameters as parallelInputs.cpp:560-640 reads them)."""
+    prof = r.choice(["gaussian", "BH", "rectangle", "continuous", "ramped_cont", "ricker"])
+    p = {"profile": prof, "Field_Intensity": r.choice([1.0, 3e13]), "fcen": r.uniform(0.8, 40.0)}
+    if prof == "gaussian":
+        p.update(fwidth=r.uniform(20.0, 200.0), cutoff=r.uniform(1.5, 4.0), t_0=r.uniform(0.0, 0.02))
+    elif prof == "BH":
+        p.update(fwidth=r.uniform(20.0, 200.0), tau=r.uniform(0.01, 0.05), t_0=r.uniform(0.0, 0.02))   # fwidth is read even when tau is given
+    elif prof == "rectangle":
+        p.update(tau=r.uniform(0.005, 0.03), t_0=r.uniform(0.0, 0.02), n=r.choice([10, 30]))
+    elif prof == "ramped_cont":
+        p.update(ramp_val=r.uniform(10.0, 200.0))
+    elif prof == "ricker":
+        p.update(fwidth=r.uniform(20.0, 200.0), cutoff=r.uniform(0.005, 0.03))
+    return p
+
+
+def rnd_case(seed, steps=10, pulses="gaussian"):
     r=random.Random(seed)
     mode=r.choice(["3d","te","tm"])
     if mode=="3d":
@@ -17,7 +35,6 @@ def rnd_case(seed):
     else:
         n=[r.randint(31,55), r.randint(31,55), 0]; pol="Hz" if mode=="te" else "Ez"
     size=[k/RES for k in n]
-    steps=10
     pmlc=[r.randint(3,6) for _ in range(3)]
     if mode!="3d": pmlc[2]=0
     pml=I.pml([c/RES for c in pmlc], a_max=r.choice([0.25,0.1]), ma=r.choice([1.0,2.0]), m=r.choice([3.0,3.5]), kappa_max=r.choice([1.0,2.5]))
@@ -45,7 +62,10 @@ def rnd_case(seed):
     srcpol={"3d":r.choice(["Ex","Ey","Ez","Hx","Hz"]),"te":r.choice(["Hz","Ex","Ey"]),"tm":r.choice(["Ez","Hx","Hy"])}[mode]
     sloc=[r.uniform(-0.2,0.2)*size[k] for k in range(3)]; ssz=[r.choice([0.0, r.uniform(0,0.3)*size[k]]) for k in range(3)]
     if mode!="3d": sloc[2]=0.0; ssz[2]=0.0
-    srcs=[I.normal_source(srcpol, sloc, ssz, [I.gaussian_pulse(1.5,1.0,t_0=0.25,cutoff=2.5)])]
+    if pulses == "gaussian":
+        srcs=[I.normal_source(srcpol, sloc, ssz, [I.gaussian_pulse(1.5,1.0,t_0=0.25,cutoff=2.5)])]
+    else:
+        srcs=[I.normal_source(srcpol, sloc, ssz, [rnd_pulse(r) for _ in range(r.randint(1, 2))])]
     dets=[]
     dpol={"3d":r.choice(["Ex","Ey","Ez","Hx","Hy","Hz"]),"te":r.choice(["Hz","Ex","Ey"]),"tm":r.choice(["Ez","Hx","Hy"])}[mode]
     dloc=[r.uniform(-0.2,0.2)*size[k] for k in range(3)]; dsz=[r.choice([0.0, r.uniform(0,0.2)*size[k]]) for k in range(3)]
