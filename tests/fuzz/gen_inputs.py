@@ -82,3 +82,59 @@ def rnd_case(seed, steps=10, pulses="gaussian"):
         fluxes.append(fl)
     return I.config(I.comp_cell(size, RES, steps*DT-0.5*DT, pol), pml, srcs, objs, dets, fluxes)
 
+
+
+def rnd_ml_case(seed):
+    """A random Maxwell-Liouville emitter block (two, three or four levels; one or two level systems with weights; random energies,
+    couplings, relaxation and dephasing rates, density, background eps, population detectors) in a small 3-D, TE or TM cell."""
+    r = random.Random(1000 + seed)
+    kind = r.choice(["two3d", "four3d", "twotm", "threete"])
+    e1 = r.uniform(1.5, 2.5)
+    cen = [e1] if r.random() < 0.5 else [e1 - r.uniform(0.05, 0.2), e1 + r.uniform(0.05, 0.2)]
+    lev1 = {"E_cen": cen}
+    if len(cen) == 2:
+        w = r.uniform(0.2, 0.8)
+        lev1["weights"] = [w, 1.0 - w]
+    c = r.uniform(2.0, 15.0)
+    rate = lambda: r.choice([1e12, 2e12, 5e11])      # noqa: E731
+    deph = lambda: r.choice([1e13, 5e12])            # noqa: E731
+    if kind in ("two3d", "twotm"):
+        basis, levels, coup = [(0, 0), (1, 0)], [{"E_cen": [0.0]}, lev1], [0, c, c, 0]
+        relax = [{"state_i": 1, "state_f": 0, "rate": rate(), "dephasing_rate": deph()}]
+        nlev = 2
+    elif kind == "threete":
+        lev1["levs_described"] = 2
+        basis, levels, coup = [(0, 0), (1, -1), (1, 1)], [{"E_cen": [0.0]}, lev1], [0, c, c, c, 0, 0, c, 0, 0]
+        relax = [{"state_i": 1, "state_f": 0, "rate": rate(), "dephasing_rate": deph()}, {"state_i": 2, "state_f": 0, "rate": rate()}]
+        nlev = 3
+    else:
+        lev1["levs_described"] = 3
+        c2, c3 = r.uniform(2.0, 15.0), r.uniform(2.0, 15.0)
+        basis, levels = [(0, 0), (1, -1), (1, 0), (1, 1)], [{"E_cen": [0.0]}, lev1]
+        coup = [0, c, c2, c3, c, 0, 0, 0, c2, 0, 0, 0, c3, 0, 0, 0]
+        relax = [{"state_i": 1, "state_f": 0, "rate": rate(), "dephasing_rate": deph()}, {"state_i": 2, "state_f": 0, "rate": rate(), "dephasing_rate": deph()},
+                 {"state_i": 3, "state_f": 0, "rate": rate()}]
+        nlev = 4
+    dtc_levs = sorted(r.sample(range(nlev * nlev), r.randint(1, 2)))
+    eps = r.choice([1.0, 1.2, 1.5])
+    den = r.choice([1e24, 1e25, 3e25])
+    if kind in ("two3d", "four3d"):
+        n = [r.randint(21, 25), r.randint(17, 21), r.randint(19, 23)]
+        size = [k / RES for k in n]
+        pml = I.pml([5 / RES] * 3)
+        sz = [r.randint(3, 6) / RES, r.randint(3, 5) / RES, r.randint(2, 4) / RES]
+        loc = [r.randint(-2, 2) / RES + 0.005 * (k % 2 == 0) for k in range(3)]
+        obj = I.ml_object(sz, loc, den, basis, levels, coup, relax, eps=eps, dtc_levs=dtc_levs, pop_every=r.choice([1, 2]))
+        src = I.normal_source("Ez", [-0.05, -0.04, -0.04], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0, intensity=3e13, t_0=0.25, cutoff=2.5)])
+        det = I.detector([0.03, 0, 0], [0, 0, 0], "Ez", f"out/ml{seed}/d", time_int=DT * 1.0000001)
+        return I.config(I.comp_cell(size, RES, 4 * DT - 0.5 * DT, "Ex"), pml, [src], [obj], [det])
+    n = [r.randint(41, 49), r.randint(35, 41), 0]
+    size = [k / RES for k in n]
+    pml = I.pml([8 / RES, 8 / RES, 0])
+    sz = [r.randint(5, 9) / RES, r.randint(4, 7) / RES, 0.0]
+    loc = [r.randint(-3, 3) / RES, r.randint(-3, 3) / RES, 0.0]
+    obj = I.ml_object(sz, loc, den, basis, levels, coup, relax, eps=eps, dtc_levs=dtc_levs, pop_every=r.choice([1, 2]))
+    pol, spol = ("Ez", "Ez") if kind == "twotm" else ("Hz", "Ex")
+    src = I.normal_source(spol, [-0.1, -0.08, 0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0, intensity=3e13, t_0=0.25, cutoff=2.5)])
+    det = I.detector([0.03, 0, 0], [0, 0, 0], spol, f"out/ml{seed}/d", time_int=DT * 1.0000001)
+    return I.config(I.comp_cell(size, RES, 4 * DT - 0.5 * DT, pol), pml, [src], [obj], [det])

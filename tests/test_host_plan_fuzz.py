@@ -53,3 +53,25 @@ def test_random_pulse_shapes_give_the_reference_source_amplitudes(seed, tmp_path
     subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "host")], check=True)
     bad = plan_diff.diff(P.read_plan(str(tmp_path / "host.rank0.plan")), P.read_plan(str(tmp_path / "ref.rank0.plan")))
     assert not bad, "\n".join(bad[:20])
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="needs the reference build oracle/_ref/chiml_ref")
+@pytest.mark.parametrize("seed", [0, 1, 6, 7, 11, 13, 19, 23])
+def test_random_emitter_blocks_give_the_reference_emitter_sets(seed, tmp_path):
+    """Random Maxwell-Liouville blocks (2 / 3 / 4 levels, one or two weighted level systems, random energies, couplings, rates,
+    density, background eps; 3-D, TE, TM): Hamiltonians, dipole operators, Lindblad rows, emitter positions, eps boxes and population
+    detectors built by the host setup equal what the reference's parallelQE constructor built."""
+    import gen_inputs
+    import plan_diff
+    from chiml_b200 import inputs as I, plan as P
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
+    cfg = gen_inputs.rnd_ml_case(seed)
+    I.write(cfg, str(tmp_path / "c.json"))
+    r = subprocess.run([REF, "c.json", "--steps", "0", "--plan", str(tmp_path / "ref"), "--quiet", "--no-output"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "host")], check=True)
+    host, ref = P.read_plan(str(tmp_path / "host.rank0.plan")), P.read_plan(str(tmp_path / "ref.rank0.plan"))
+    assert len(ref.emitters) == 1 and ref.emitters[0].nemit > 0
+    bad = plan_diff.diff(host, ref)
+    bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
+    assert not bad, "\n".join(bad[:20])
