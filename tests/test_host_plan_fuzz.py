@@ -75,3 +75,20 @@ def test_random_emitter_blocks_give_the_reference_emitter_sets(seed, tmp_path):
     bad = plan_diff.diff(host, ref)
     bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
     assert not bad, "\n".join(bad[:20])
+
+
+@pytest.mark.parametrize("seed,nranks", [(1, 2), (2, 3), (5, 2), (9, 4), (11, 3), (27, 2), (50, 3), (64, 4), (101, 2), (150, 3)])
+def test_random_input_slab_plans_tile_the_single_rank_plan(seed, nranks, tmp_path):
+    """Random inputs cut into 2-4 y-slabs by the host setup: update lists, emitters and flux DFT lines of the slabs are a partition
+    of the single-rank plan's (no reference needed: this is the property the multi-GPU runs rely on)."""
+    import gen_inputs
+    import util
+    from chiml_b200 import inputs as I, plan as P
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
+    cfg = gen_inputs.rnd_case(seed)
+    I.write(cfg, str(tmp_path / "c.json"))
+    subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "one")], check=True)
+    subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "many"), "--ranks", str(nranks)], check=True)
+    whole = P.read_plan(str(tmp_path / "one.rank0.plan"))
+    slabs = [P.read_plan(str(tmp_path / f"many.rank{r}.plan")) for r in range(nranks)]
+    util.assert_slabs_tile_whole(whole, slabs)

@@ -102,3 +102,48 @@ def dft_point_map(plan: P.Plan, accs):
                         raise AssertionError(f"accumulator {key} stored twice with different values")
                     out[key] = v
     return out
+
+
+def assert_slabs_tile_whole(whole, slabs):
+    """y-slab decomposition of the host-side setup: the update-list cells of the slab plans, mapped back to global rows, are exactly
+    the cells of the single-rank plan (same prefactors), every emitter is owned by exactly one slab, and the running-DFT lines of the
+    slabs cover the single-rank sets' points exactly once."""
+    lnx, lny, lnz = whole.ln
+    assert sum(s.ln[1] - 2 for s in slabs) == lny - 2
+    for key, runs in whole.lists.items():
+        def cells(plan, runs, ys):
+            m = {}
+            for r in runs:
+                row, x0 = divmod(int(r["ind"]), plan.ln[0])
+                y, z = divmod(row, plan.ln[2])
+                for i in range(int(r["n"])):
+                    m[(x0 + i, y + ys, z)] = (float(r["pf"][1]), float(r["pf"][2]), float(r["pf"][3]))
+            return m
+        ref = cells(whole, runs, 0)
+        got = {}
+        for s in slabs:
+            part = cells(s, s.get_list(*key), s.y_start)
+            assert not (set(part) & set(got)), f"list {key}: a cell is owned by two slabs"
+            got.update(part)
+        assert got == ref, f"list {key}: slabs do not tile the single-rank list"
+    if whole.emitters:
+        assert sum(e.nemit for s in slabs for e in s.emitters) == sum(e.nemit for e in whole.emitters)
+
+    def dft_points(plan):
+        pts = {}
+        for d in plan.dfts:
+            for li, (ind, o) in enumerate(d.lines):
+                if li > 0 and ind == 0 and o == 0:
+                    continue
+                for i in range(d.npts):
+                    row, x = divmod(int(ind) + i * d.stride, plan.ln[0])
+                    y, z = divmod(row, plan.ln[2])
+                    key = (d.group, d.field, x, y + plan.y_start, z)
+                    pts[key] = pts.get(key, 0) + 1
+        return pts
+    ref = dft_points(whole)
+    got = {}
+    for s in slabs:
+        for k, v in dft_points(s).items():
+            got[k] = got.get(k, 0) + v
+    assert got == ref, "the slabs' running-DFT lines do not cover the single-rank sets exactly"
