@@ -603,8 +603,61 @@ int detector_field(DTCTYPE t)
 
 } // namespace
 
+// First rows of the y-slabs as the reference cuts them: rows are weighted by an operation count per grid point (base cost, poles of
+// the objects at the three E positions, CPML layers, flux surfaces) and every slab gets about the mean weight
+// (parallelFDTDField.hpp:1097-1210 setupWeightsGrid, MPI/mpiInterface.cpp:21-53 getLocxLocyLocz(weights)).  Used with
+// `chiml_plan --split reference`; the engine itself is indifferent to where the cuts are.
+std::vector<int> reference_split(const Inputs& IP, const Geom& g, int nranks)
+{
+    const int n0 = g.n[0], n1 = g.n[1], n2 = g.n[2];
+    std::vector<double> w(n1, 3.0 * 276.0 * n0 * n2);          // `IP.size_[2] != 1 ? 276.0 : 184.0` is 276 for every input
+    for(const auto& obj : IP.objArr_)
+    {
+        const double dbAdd = obj->useOrientedDipols_ ? 189.0 : 169.0;
+        const double add = dbAdd * obj->gamma_.size() + (obj->pols_.size() > 0 ? 30.0 : 0.0);
+        if(add == 0.0) continue;
+        for(int jj = 0; jj < n1; ++jj)
+            for(int ii = 0; ii < n0; ++ii)
+                for(int kk = 0; kk < n2; ++kk)
+                {
+                    std::array<double, 3> pt = {{(ii - (n0 - 1) / 2.0 + 0.5) * g.d[0], (jj - (n1 - 1) / 2.0) * g.d[1], (kk - (n2 - 1) / 2.0) * g.d[2]}};
+                    if(obj->isObj(pt, g.d[0], obj->geoParam_)) w[jj] += add;
+                    pt[1] += 0.5 * g.d[1]; pt[0] -= 0.5 * g.d[0];
+                    if(obj->isObj(pt, g.d[0], obj->geoParam_)) w[jj] += add;
+                    pt[1] -= 0.5 * g.d[1]; pt[2] += 0.5 * g.d[2];
+                    if(obj->isObj(pt, g.d[0], obj->geoParam_)) w[jj] += add;
+                }
+    }
+    // CPML layers: x layers on the Ey, Ez maps (every row alike), y layers on Ex, Ez, z layers on Ex, Ey
+    for(int jj = 0; jj < n1; ++jj) w[jj] += 2.0 * 2.0 * g.thick[0] * 79.0 * n2;
+    for(int yy = 0; yy < g.thick[1]; ++yy) { w[yy] += 2.0 * 79.0 * n0 * n2; w[n1 - 1 - yy] += 2.0 * 79.0 * n0 * n2; }
+    if(!g.twoD) for(int jj = 0; jj < n1; ++jj) w[jj] += 2.0 * 2.0 * g.thick[2] * 79.0 * n0;
+    if(!g.twoD)
+        for(const FluxInput& f : IP.fluxes_)
+        {
+            const double fw = f.freqs.size() * 3 + 20.0;
+            for(int yy = 0; yy < f.sz[1]; ++yy) w[f.loc[1] + yy] += 3.0 * fw * (2.0 * f.sz[0] + 2.0 * f.sz[2]);
+            for(int zz = 0; zz < f.sz[2]; ++zz) { w[f.loc[1]] += 3.0 * fw * f.sz[0]; w[f.loc[1] + f.sz[1] - 1] += 3.0 * fw * f.sz[0]; }
+        }
+    double sum = 0.0;
+    for(double v : w) sum += v;
+    const double avg = sum / static_cast<double>(nranks);
+    std::vector<int> start(nranks + 1, 0);
+    start[nranks] = n1;
+    double val = 0.0;
+    int curY = 0;
+    for(int cc = 0; cc < nranks - 1; ++cc)
+    {
+        curY = start[cc];
+        while(val + w[curY] / 2.0 < avg || curY == start[cc]) { val += w[curY]; curY++; }
+        val -= avg;
+        start[cc + 1] = curY;
+    }
+    return start;
+}
+
 // ---------------------------------------------------------------------------------------------------
-SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads)
+SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referenceSplit)
 {
     if(nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
     SlabPlan P;
@@ -620,8 +673,17 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads)
     g.dt = IP.dt_;
     // equal-height y-slabs (mpiInterface::getLocxLocyLocz(int,int,int), MPI/mpiInterface.cpp:55-58)
     const int base = g.n[1] / nranks, rem = g.n[1] % nranks;
-    const int nyloc = base + (rank < rem ? 1 : 0);
+    int nyloc = base + (rank < rem ? 1 : 0);
     g.yStart = rank * base + std::min(rank, rem);
+    if(referenceSplit && nranks > 1)
+    {
+        // the reference's cost-weighted cuts instead (pole constants must exist: the weights count poles)
+        for(auto& obj : IP.objArr_)
+            if(obj->alpha_.empty() && obj->dipOr_.empty()) obj->setUpConsts(IP.dt_);
+        g.twoD = IP.size_[2] == 0;
+        const std::vector<int> start = reference_split(IP, g, nranks);
+        g.yStart = start[rank]; nyloc = start[rank + 1] - start[rank];
+    }
     if(nyloc < 1) throw std::logic_error("a y-slab is empty: fewer grid rows than ranks");
     g.ln[0] = g.n[0] + 2; g.ln[1] = nyloc + 2; g.ln[2] = g.twoD ? 1 : g.n[2] + 2;
     // findLnVecs (PML/parallelPML.hpp:280-308)

@@ -67,7 +67,8 @@ struct SlabPlan
 };
 
 // Builds the plan of y-slab `rank` of `nranks` (equal-height slabs, mpiInterface::getLocxLocyLocz(int,int,int)).
-SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads = 0);
+// referenceSplit: cut the slabs where the reference's cost-weighted decomposition cuts them instead of at equal heights
+SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads = 0, bool referenceSplit = false);
 
 // Flux spectra files of a single-rank run (parallelFluxDTC::getFlux, DTC/parallelFlux.hpp:406-540): re[k] / im[k] = accumulators of
 // P.dfts[k] (fInReal_ / fInCplx_), nSteps = time steps taken.  Writes <flux name>.dat for every flux region.

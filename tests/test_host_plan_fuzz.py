@@ -92,3 +92,25 @@ def test_random_input_slab_plans_tile_the_single_rank_plan(seed, nranks, tmp_pat
     whole = P.read_plan(str(tmp_path / "one.rank0.plan"))
     slabs = [P.read_plan(str(tmp_path / f"many.rank{r}.plan")) for r in range(nranks)]
     util.assert_slabs_tile_whole(whole, slabs)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="needs the reference build oracle/_ref/chiml_ref")
+@pytest.mark.parametrize("seed,nranks", [(1, 2), (2, 3), (3, 4), (5, 2), (9, 3), (11, 4), (27, 2), (50, 3), (64, 4), (101, 2), (150, 3), (207, 4)])
+def test_random_input_slab_plans_equal_the_reference_ranks_plans(seed, nranks, tmp_path):
+    """Several ranks: with the reference's cost-weighted cuts (`chiml_plan --split reference`, setupWeightsGrid + getLocxLocyLocz
+    restated in host/setup.cpp) every rank's plan -- slab extents, update lists, CPML lists, local source / detector boxes, flux DFT
+    sets -- equals what that rank of the reference built (the reference's ranks run as threads of oracle/_ref/chiml_ref)."""
+    import gen_inputs
+    import plan_diff
+    from chiml_b200 import inputs as I, plan as P
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
+    cfg = gen_inputs.rnd_case(seed)
+    I.write(cfg, str(tmp_path / "c.json"))
+    r = subprocess.run([REF, "c.json", "--ranks", str(nranks), "--steps", "0", "--plan", str(tmp_path / "ref"), "--quiet", "--no-output"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "host"), "--ranks", str(nranks), "--split", "reference"], check=True)
+    for rk in range(nranks):
+        bad = plan_diff.diff(P.read_plan(str(tmp_path / f"host.rank{rk}.plan")), P.read_plan(str(tmp_path / f"ref.rank{rk}.plan")))
+        bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
+        assert not bad, f"rank {rk}:\n" + "\n".join(bad[:20])
