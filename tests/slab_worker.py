@@ -22,11 +22,30 @@ def main():
     case = sys.argv[1]
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    work = tempfile.mkdtemp(prefix=f"slab_{case}_r{rank}_")
-    subprocess.run([os.path.join(ROOT, "chiml_b200", "chiml_plan"), os.path.join(util.GOLDEN, case + ".json"), os.path.join(work, case),
-                    "--ranks", str(world), "--only", str(rank)], check=True)
+    work = tempfile.mkdtemp(prefix=f"slab_{case.replace(':', '_')}_r{rank}_")
+    tool = os.path.join(ROOT, "chiml_b200", "chiml_plan")
+    fuzz = case.startswith("fuzz:")
+    if fuzz:
+        # fuzz:<seed>[:ml] -- a random input (tests/fuzz/gen_inputs.py); the expected arrays come from the single-rank oracle
+        sys.path.insert(0, os.path.join(ROOT, "tests", "fuzz"))
+        import gen_inputs
+        from chiml_b200 import inputs as I
+        parts = case.split(":")
+        cfg = gen_inputs.rnd_ml_case(int(parts[1])) if len(parts) > 2 else gen_inputs.rnd_case(int(parts[1]), steps=12, pulses="random")
+        if len(parts) > 2:
+            cfg["CompCell"]["tLim"] = 12 * gen_inputs.DT - 0.5 * gen_inputs.DT
+        src = os.path.join(work, "c.json")
+        I.write(cfg, src)
+        case = "c"
+    else:
+        src = os.path.join(util.GOLDEN, case + ".json")
+    subprocess.run([tool, src, os.path.join(work, case), "--ranks", str(world), "--only", str(rank)], check=True)
     plan = P.read_plan(os.path.join(work, f"{case}.rank{rank}.plan"))
-    whole = util.load_plan(case)
+    if fuzz:
+        subprocess.run([tool, src, os.path.join(work, "whole")], check=True)
+        whole = P.read_plan(os.path.join(work, "whole.rank0.plan"))
+    else:
+        whole = util.load_plan(case)
     sim = OracleSim(plan)
 
     def send(to, arr):
@@ -52,7 +71,12 @@ def main():
     dist.gather_object((plan.y_start, mine, emit), gathered if rank == 0 else None, dst=0)
     ok = True
     if rank == 0:
-        expect = util.load_expect(case)
+        if fuzz:
+            one = OracleSim(whole)
+            one.step_n(whole.n_steps)
+            expect = {n: util.state_array(one, n) for n in util.state_names(whole)}
+        else:
+            expect = util.load_expect(case)
         gathered.sort(key=lambda t: t[0])
         for n in names:
             got = np.concatenate([g[1][n] for g in gathered], axis=0)

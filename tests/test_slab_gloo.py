@@ -12,7 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("case,world", [("aniso_slab3d", 2), ("ml3d_two", 2), ("ml3d_four", 3), ("ml_te", 2), ("c4_small", 2), ("flux3d", 3), ("te_flux", 2),
-                                        ("tm_flux", 2)])
+                                        ("tm_flux", 2),
+                                        # random inputs (tests/fuzz/gen_inputs.py), expected arrays from the single-rank oracle
+                                        ("fuzz:4", 4), ("fuzz:12", 3), ("fuzz:33", 3), ("fuzz:10:ml", 4), ("fuzz:14:ml", 2)])
 def test_slab_protocol_matches_single_rank_reference(case, world):
     subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host")], check=True, stdout=subprocess.DEVNULL)
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, stdout=subprocess.DEVNULL)
