@@ -22,6 +22,7 @@ pytestmark = pytest.mark.gpu
 def run_case(cfg, tmp_path, steps):
     from chiml_b200 import inputs as I, plan as P
     I.write(cfg, str(tmp_path / "c.json"))
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
     subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "p")], check=True)
     plan = P.read_plan(str(tmp_path / "p.rank0.plan"))
     rng = np.random.default_rng(4321)
