@@ -720,10 +720,11 @@ __device__ __forceinline__ void prefetch_psi(const StepArgs& a, const unsigned i
     }
 }
 
-// One component per thread (blockDim.z selects it): each thread issues the <= 8 independent loads of ITS component at once -- own
-// value, the two driving arrays at the cell, their two stencil neighbours, D, psi -- so a plane costs one memory latency instead
-// of one per component, and three times as many warps are resident.  The driving arrays are shared between components; the
-// second reader hits L1.  y-coupled neighbours are carried in registers while the block marches along y (see k_fast).
+// One component per thread (k_uniform: the block's component, blockIdx.x % 3; k_uniform_rows / k_general<E>: threadIdx.z): each
+// thread issues the <= 8 independent loads of ITS component at once -- own value, the two driving arrays at the cell, their two
+// stencil neighbours, D, psi -- so a plane costs one memory latency instead of one per component.  The driving arrays are shared
+// between components; the other readers hit L1 / L2.  y-coupled neighbours are carried in registers while the block marches
+// along y (see k_fast).
 template <bool IS_E, int MODE, int C>
 __device__ __forceinline__ void comp_march_init(const StepArgs& a, const long r, const long plane, double2& carry)
 {
@@ -931,7 +932,7 @@ __device__ __forceinline__ void general_pair(const StepArgs& a, double2 u, const
     store_pair(ca.U + r, u, w0, w1);
 }
 
-// one component per thread (threadIdx.z), like k_uniform: the loads of a component do not queue behind the arithmetic of another
+// one component per thread (threadIdx.z): the loads of a component do not queue behind the arithmetic of another
 template <bool IS_E, int MODE, int C>
 __device__ __forceinline__ void general_comp(const StepArgs& a, const TileRec& t, const int x, const int z)
 {
