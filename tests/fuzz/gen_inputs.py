@@ -138,3 +138,18 @@ def rnd_ml_case(seed):
     src = I.normal_source(spol, [-0.1, -0.08, 0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0, intensity=3e13, t_0=0.25, cutoff=2.5)])
     det = I.detector([0.03, 0, 0], [0, 0, 0], spol, f"out/ml{seed}/d", time_int=DT * 1.0000001)
     return I.config(I.comp_cell(size, RES, 4 * DT - 0.5 * DT, pol), pml, [src], [obj], [det])
+
+
+def rnd_case_rotated(seed, steps=10, pulses="gaussian"):
+    """rnd_case with its objects turned: blocks get random orientation angles (orPhi, and orTheta in 3-D), spheres become cylinders
+    of random radius, length and orientation (OBJECTS/Obj.cpp: RealSpace2ObjectSpace, block / cylinder isObj)."""
+    cfg = rnd_case(seed, steps=steps, pulses=pulses)
+    r = random.Random(5000 + seed)
+    three_d = cfg["CompCell"]["size"][2] != 0
+    for o in cfg["ObjectList"]:
+        o["orPhi"] = r.uniform(-90.0, 90.0)
+        o["orTheta"] = r.uniform(20.0, 160.0) if three_d else 90.0
+        if o["shape"] == "sphere":
+            rad = o.pop("radius")
+            o.update(shape="cylinder", radius=rad * r.uniform(0.6, 1.0), length=rad * r.uniform(1.0, 3.0))
+    return cfg

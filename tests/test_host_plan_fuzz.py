@@ -114,3 +114,23 @@ def test_random_input_slab_plans_equal_the_reference_ranks_plans(seed, nranks, t
         bad = plan_diff.diff(P.read_plan(str(tmp_path / f"host.rank{rk}.plan")), P.read_plan(str(tmp_path / f"ref.rank{rk}.plan")))
         bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
         assert not bad, f"rank {rk}:\n" + "\n".join(bad[:20])
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="needs the reference build oracle/_ref/chiml_ref")
+@pytest.mark.parametrize("seed", [1, 2, 5, 9, 11, 12, 17, 27, 33, 50])
+def test_rotated_blocks_and_cylinders_give_the_reference_plan(seed, tmp_path):
+    """Objects with random orientation angles and cylinders (tests/fuzz/gen_inputs.rnd_case_rotated): the host's rasterisation of
+    tilted shapes equals the reference's, list for list."""
+    import gen_inputs
+    import plan_diff
+    from chiml_b200 import inputs as I, plan as P
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
+    cfg = gen_inputs.rnd_case_rotated(seed)
+    assert cfg["ObjectList"]
+    I.write(cfg, str(tmp_path / "c.json"))
+    r = subprocess.run([REF, "c.json", "--steps", "0", "--plan", str(tmp_path / "ref"), "--quiet", "--no-output"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "host")], check=True)
+    bad = plan_diff.diff(P.read_plan(str(tmp_path / "host.rank0.plan")), P.read_plan(str(tmp_path / "ref.rank0.plan")))
+    bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
+    assert not bad, "\n".join(bad[:20])
