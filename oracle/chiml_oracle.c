@@ -35,7 +35,7 @@ typedef struct
 } QESet;
 
 /* one stored field of a flux / frequency detector (DTC/parallelStorageFreqDTC.cpp:21-30) */
-#define MAX_DFT 64
+#define MAX_DFT 512
 typedef struct { int field, group, every, nfreq, npts, stride; size_t nlines, acc_len; ChimlDftLine* lines; double *re, *im; } DftSet;
 
 struct OracleSim
