@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_reset_kernel_stats", "chiml_gpu_read_detector_range", "chiml_gpu_add_emitters",
     "chiml_gpu_download_emitter_state", "chiml_gpu_download_emitter_pol", "chiml_gpu_read_population",
     "chiml_gpu_halo_export", "chiml_gpu_halo_bind", "chiml_gpu_add_dft", "chiml_gpu_step_n_dft", "chiml_gpu_download_dft",
+    "chiml_gpu_set_march",
 ]
 
 
@@ -121,6 +122,7 @@ def lib() -> C.CDLL:
     L.chiml_gpu_add_source.argtypes = [vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(i)]
     L.chiml_gpu_add_detector.argtypes = [vp, i, C.POINTER(C.c_int32), C.POINTER(C.c_int32), i, C.POINTER(i)]
     L.chiml_gpu_commit.argtypes = [vp]
+    L.chiml_gpu_set_march.argtypes = [vp, i, i]
     L.chiml_gpu_step_n.argtypes = [vp, i, vp]
     L.chiml_gpu_sync.argtypes = [vp]
     L.chiml_gpu_step_n_timed.argtypes = [vp, i, vp, C.POINTER(C.c_float)]
@@ -166,7 +168,8 @@ def _ptr(a: Optional[np.ndarray]):
 class GpuSim:
     """One y-slab of the propagator on one GPU, configured from a Plan (the reference's own lists)."""
 
-    def __init__(self, plan: P.Plan, device: int = 0, detectors: bool = True):
+    def __init__(self, plan: P.Plan, device: int = 0, detectors: bool = True, march=None):
+        """march: None (automatic column length), an int, or (fast, uniform) planes per column of the y-marching kernels."""
         L = lib()
         self.plan = plan
         g = GridDesc()
@@ -214,6 +217,9 @@ class GpuSim:
                     slot = C.c_int()
                     self._chk(L.chiml_gpu_add_detector(self.h, d.field, (C.c_int32 * 3)(*box[0]), (C.c_int32 * 3)(*box[1]), d.every, C.byref(slot)))
                     self.det_slots.append(slot.value)
+            if march is not None:
+                mf, mu = (march, march) if isinstance(march, int) else march
+                self._chk(L.chiml_gpu_set_march(self.h, mf, mu))
             self._chk(L.chiml_gpu_commit(self.h))
         except Exception:
             self.close()

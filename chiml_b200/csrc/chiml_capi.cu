@@ -198,6 +198,25 @@ int chiml_gpu_set_object(ChimlCtx* ctx, int obj, int npoles, const double* alpha
     return CHIML_OK;
 }
 
+int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_ordip_pole_count after commit");
+    if(n_poles_global < 0) return fail(ctx, CHIML_ERR_ARG, "set_ordip_pole_count: negative count");
+    if(n_poles_global > MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_ordip_pole_count: more than 12 poles per object");
+    ctx->nordip_global = n_poles_global;
+    return CHIML_OK;
+}
+
+int chiml_gpu_set_march(ChimlCtx* ctx, int fast_planes, int uniform_planes)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_march after commit");
+    if(fast_planes < 0 || uniform_planes < 0) return fail(ctx, CHIML_ERR_ARG, "set_march: negative column length");
+    ctx->march_fast = fast_planes; ctx->march_uniform = uniform_planes;
+    return CHIML_OK;
+}
+
 int chiml_gpu_set_cpml(ChimlCtx* ctx, int comp, int part, int has_psi, const ChimlPsiParams* psi, size_t npsi, const ChimlGridParams* grid, size_t ngrid)
 {
     if(!ctx) return CHIML_ERR_ARG;
@@ -646,6 +665,8 @@ int chiml_gpu_commit(ChimlCtx* ctx)
     // --- oriented-dipole node grid ------------------------------------------------------------------------
     {
         const auto& runs = ctx->lists[CHIML_LIST_ORDIPP][0].runs;
+        ctx->nordip = ctx->g.nranks > 1 ? ctx->nordip_global : 0;
+        for(const ChimlRun& r : runs) ctx->nordip = std::max(ctx->nordip, ctx->objs[r.obj].npoles);
         if(!runs.empty())
         {
             if(!ctx->g.has_D) return fail(ctx, CHIML_ERR_ARG, "oriented-dipole node list given but has_D = 0");
@@ -666,7 +687,6 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 int id = cb.get(key, o, true);
                 if(id == 0) return fail(ctx, CHIML_ERR_UNSUPPORTED, "more than 255 distinct oriented-dipole material classes");
                 cls[e] = (uint8_t)id;
-                ctx->nordip = std::max(ctx->nordip, o.npoles);
                 int ncomp = 0;
                 for(int c = 0; c < 3; ++c) ncomp += field_exists(ctx, c) ? 1 : 0;
                 ctx->kstat[K_ORDIP_POLES].alg_bytes += 24.0 * ncomp * (double)r.n * o.npoles;   // P, prevP read, new P written
@@ -682,7 +702,9 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                         for(int k = 0; k < 2; ++k)
                             if((rc = dev_alloc(ctx, &ctx->d_oP[c][p][k], (size_t)ctx->span_node.total))) return rc;
         }
-        else
+        else if(ctx->nordip == 0)
+            // (with several slabs a slab may hold edge cells of an object whose nodes all lie in the slab above: its D->E then reads
+            // the ghost row only, and the global pole count says how many)
             for(int c = 0; c < 3; ++c)
                 if(!ctx->lists[CHIML_LIST_ORDIPD][c].runs.empty())
                     return fail(ctx, CHIML_ERR_ARG, "oriented-dipole D->E list given without the node list");
@@ -833,7 +855,18 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 for(int kind = 0; kind < 2; ++kind)      // FAST and UNIFORM lists
                 {
                     // measured on the C5 slab (profiles/README.md r1z): 64 planes for the vacuum kernel, 32 for the UNIFORM ones
-                    const int MARCH_NY = (int)std::max<size_t>(1, std::min<size_t>(kind == 0 ? 64 : 32, marchCap));
+                    int MARCH_NY = (int)std::max<size_t>(1, std::min<size_t>(kind == 0 ? 64 : 32, marchCap));
+                    // forced column length (chiml_gpu_set_march, else CHIML_B200_MARCH_NY="fast[,uniform]"): the parity tests use it to
+                    // run the carried-plane code of the marching kernels on grids that are too small to get columns on their own
+                    int forced = kind == 0 ? ctx->march_fast : ctx->march_uniform;
+                    if(forced <= 0)
+                        if(const char* ev = std::getenv("CHIML_B200_MARCH_NY"))
+                        {
+                            int f0 = 0, f1 = 0;
+                            const int got = std::sscanf(ev, "%d,%d", &f0, &f1);
+                            if(got >= 1) forced = (kind == 0 || got < 2) ? f0 : f1;
+                        }
+                    if(forced > 0) MARCH_NY = std::min(forced, 1 << 20);
                     std::vector<TileRec>& fl = lists[kind];
                     std::stable_sort(fl.begin(), fl.end(), [](const TileRec& p, const TileRec& q) {
                         return std::tie(p.z0, p.x0, p.part, p.y) < std::tie(q.z0, q.x0, q.part, q.y); });
@@ -1347,8 +1380,9 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
     // ---- oriented-dipole poles at the nodes (read Ey of ghost row 0: pushed by the slab below after its last E half step)
     if(lo && needEy) halo_wait(ctx, {{HF_EY_FROM_LOWER, kk - 1}});
     launch_node_poles(ctx);
-    if(lo && ctx->d_info_node && ctx->nordip > 0 && haveEy)
+    if(lo && ctx->nordip > 0 && haveEy)
     {
+        // every slab pushes, zeros where it holds no node cell: the count is the whole grid's (chiml_gpu_set_ordip_pole_count)
         halo_fork(ctx);
         NodePushArgs np;
         std::memset(&np, 0, sizeof(np));
@@ -1367,7 +1401,7 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
     bool recvQP = false;
     for(size_t q = 0; q < ctx->emitters.size(); ++q)
         if(up && haveEy && q < ctx->upper.emitPy.size() && ctx->upper.emitPy[q]) recvQP = true;
-    halo_wait(ctx, {{HF_H_FROM_LOWER, lo ? kk : 0}, {HF_OP_FROM_UPPER, (up && ctx->d_info_node && ctx->nordip > 0 && haveEy) ? kk : 0},
+    halo_wait(ctx, {{HF_H_FROM_LOWER, lo ? kk : 0}, {HF_OP_FROM_UPPER, (up && ctx->nordip > 0 && haveEy) ? kk : 0},
                     {HF_QP_FROM_UPPER, recvQP ? kk - 1 : 0}});
     fill_step_args(ctx, true, a);
     launch_family<true>(ctx, a, block, 1);
@@ -1505,7 +1539,12 @@ struct HaloBlobHdr
 {
     uint32_t magic; int32_t rank, nranks, lx, ly, lz; int64_t px; int64_t guard; int32_t nordip, nsets; int32_t has_field[6];
 };
-struct HaloBlobSet { cudaIpcMemHandle_t h; int32_t has, box_lo1, box_n1, rowlen; };
+struct HaloBlobSet { cudaIpcMemHandle_t h; int32_t has, box_lo1, box_n1, rowlen, object, box_lo0, box_lo2, box_n0, box_n2; };
+// the set of the neighbouring slab that belongs to the same emitter object: same object index, same x / z box
+inline bool same_object(const HaloBlobSet& s, const chiml::EmitterDev& em)
+{
+    return s.object == em.d.object && s.box_lo0 == em.d.box_lo[0] && s.box_lo2 == em.d.box_lo[2] && s.box_n0 == em.d.box_n[0] && s.box_n2 == em.d.box_n[2];
+}
 constexpr uint32_t HALO_MAGIC = 0x4F4C4148u;   // "HALO"
 }
 
@@ -1534,6 +1573,7 @@ int chiml_gpu_halo_export(ChimlCtx* ctx, void* blob, size_t cap, size_t* size)
     {
         const EmitterDev& em = ctx->emitters[q];
         sets[q].box_lo1 = em.d.box_lo[1]; sets[q].box_n1 = em.d.box_n[1]; sets[q].rowlen = (em.d.box_n[0] + 2) * em.pz;
+        sets[q].object = em.d.object; sets[q].box_lo0 = em.d.box_lo[0]; sets[q].box_lo2 = em.d.box_lo[2]; sets[q].box_n0 = em.d.box_n[0]; sets[q].box_n2 = em.d.box_n[2];
         if(em.d_P[1] && ctx->d_field[CHIML_EY]) { sets[q].has = 1; CK(cudaIpcGetMemHandle(&sets[q].h, em.d_P[1])); }
     }
     std::memcpy(out.data(), &h, sizeof(h));
@@ -1572,21 +1612,27 @@ static int halo_open_peer(ChimlCtx* ctx, const void* blob, size_t size, bool isL
     { void* base = nullptr; if((rc = open(hs[6], &base))) return rc; peer.flags = reinterpret_cast<int*>(base); }
     if(isLower)
     {
-        if(h.nordip != ctx->nordip) return fail(ctx, CHIML_ERR_ARG, "halo_bind: neighbour has a different number of oriented-dipole poles");
+        if(h.nordip != ctx->nordip)
+            return fail(ctx, CHIML_ERR_ARG, "halo_bind: neighbour counts a different number of oriented-dipole pole grids: give every slab the count of "
+                                            "the whole grid with chiml_gpu_set_ordip_pole_count");
         for(int p = 0; p < h.nordip; ++p) { void* base = nullptr; if((rc = open(hs[7 + p], &base))) return rc; peer.oPy_ghost[p] = reinterpret_cast<double*>(base); }
         const HaloBlobSet* sets = reinterpret_cast<const HaloBlobSet*>((const char*)blob + sizeof(HaloBlobHdr) + (7 + MAX_POLES) * sizeof(cudaIpcMemHandle_t));
         peer.emitPy.assign(ctx->emitters.size(), nullptr);
         peer.emit_bn1.assign(ctx->emitters.size(), 0);
-        // emitter sets are matched by position: both slabs list the objects that touch them in input order; match by row length
-        // and by the rim condition (our first row is inside the object, their top rim is their ghost row)
+        // a set of ours whose first row is inside the object pairs with THE set of the same object below whose top rim is its ghost row
+        // (same object index and x / z box; every set of the neighbour is paired at most once)
+        std::vector<char> used((size_t)std::max(h.nsets, 0), 0);
         for(size_t q = 0; q < ctx->emitters.size(); ++q)
         {
             const EmitterDev& em = ctx->emitters[q];
             if(em.d.box_lo[1] != 0 || !ctx->d_field[CHIML_EY]) continue;   // only P_y couples across a slab boundary
-            int match = -1;
+            int match = -1, nmatch = 0;
             for(int j = 0; j < h.nsets; ++j)
-                if(sets[j].has && sets[j].rowlen == (em.d.box_n[0] + 2) * em.pz && sets[j].box_lo1 + sets[j].box_n1 + 1 == h.ly - 1) { match = j; break; }
+                if(sets[j].has && !used[j] && same_object(sets[j], em) && sets[j].rowlen == (em.d.box_n[0] + 2) * em.pz && sets[j].box_lo1 + sets[j].box_n1 + 1 == h.ly - 1)
+                { if(match < 0) match = j; ++nmatch; }
             if(match < 0) return fail(ctx, CHIML_ERR_ARG, "halo_bind: an emitter object reaches this slab's first row but the slab below has no matching set");
+            if(nmatch > 1) return fail(ctx, CHIML_ERR_ARG, "halo_bind: several emitter sets of the slab below match one set of this slab: give every object its own ChimlEmitterDesc::object");
+            used[match] = 1;
             void* base = nullptr;
             if((rc = open(sets[match].h, &base))) return rc;
             peer.emitPy[q] = reinterpret_cast<double*>(base);
@@ -1601,9 +1647,10 @@ static int halo_open_peer(ChimlCtx* ctx, const void* blob, size_t size, bool isL
         {
             const EmitterDev& em = ctx->emitters[q];
             if(em.d.box_lo[1] + em.d.box_n[1] + 1 != ctx->ly - 1 || !ctx->d_field[CHIML_EY]) continue;
-            bool found = false;
-            for(int j = 0; j < h.nsets; ++j) if(sets[j].has && sets[j].box_lo1 == 0 && sets[j].rowlen == (em.d.box_n[0] + 2) * em.pz) found = true;
-            if(!found) return fail(ctx, CHIML_ERR_ARG, "halo_bind: an emitter box ends in this slab's ghost row but the slab above has no matching set");
+            int nmatch = 0;
+            for(int j = 0; j < h.nsets; ++j) if(sets[j].has && sets[j].box_lo1 == 0 && same_object(sets[j], em) && sets[j].rowlen == (em.d.box_n[0] + 2) * em.pz) ++nmatch;
+            if(nmatch == 0) return fail(ctx, CHIML_ERR_ARG, "halo_bind: an emitter box ends in this slab's ghost row but the slab above has no matching set");
+            if(nmatch > 1) return fail(ctx, CHIML_ERR_ARG, "halo_bind: several emitter sets of the slab above match one set of this slab: give every object its own ChimlEmitterDesc::object");
             peer.emitPy[q] = em.d_P[1];
         }
     }

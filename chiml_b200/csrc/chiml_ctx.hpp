@@ -154,6 +154,7 @@ struct ChimlCtx
     size_t nlogical = 0;
     bool committed = false;
     std::string err;
+    int march_fast = 0, march_uniform = 0;   // chiml_gpu_set_march: planes per column of k_fast / k_uniform (0 = automatic)
 
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -184,7 +185,8 @@ struct ChimlCtx
     chiml::ClassEntry* d_cls_node = nullptr;
     int ncls_node = 0;
     chiml::SpanTable span_node;
-    int nordip = 0;
+    int nordip = 0;              // pole grids of the whole grid: max(this slab's node list, chiml_gpu_set_ordip_pole_count)
+    int nordip_global = 0;
     double* d_oP[3][chiml::MAX_POLES][2] = {};
     long node_off[3] = {};       // logical offsets ind_i-ind, ind_j-ind, ind_k-ind of the node list
     long ordip_off[3] = {};      // logical offset ind_i-ind of upOrDipD_[c]

@@ -150,6 +150,8 @@ typedef struct ChimlEmitterDesc
     const int32_t* pop_level;  /* npop : flat index into rho (QEPopDtc::level_, QEPopDtc.hpp:67) */
     int32_t pop_every;         /* timeInt_ in steps */
     int32_t npoints;           /* QEPopDtc::npoints_ = emitters of the whole object (all slabs) */
+    int32_t object;            /* index of the object in qeArr_: with several slabs it pairs the sets of ONE object across a slab boundary
+                                  (two emitter species filling the same region have equal boxes and differ only in this) */
 } ChimlEmitterDesc;
 int chiml_gpu_add_emitters(ChimlCtx* ctx, const ChimlEmitterDesc* desc, int* slot);
 
@@ -163,6 +165,18 @@ int chiml_gpu_add_emitters(ChimlCtx* ctx, const ChimlEmitterDesc* desc, int* slo
 typedef struct ChimlDftLine { int32_t ind, out; } ChimlDftLine;   /* the (grid index, accumulator index) pairs of fInGridInds_ */
 int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq, int npts, int stride,
                       const ChimlDftLine* lines, size_t nlines, size_t acc_len, int* slot);
+
+/* Number of oriented-dipole pole grids of the WHOLE grid, orDipLorP_[c].size() = the largest pole count of any oriented-dipole
+ * object (parallelFDTDField.hpp:452-478): every rank of the reference allocates and exchanges that many, whether or not its own slab
+ * holds such an object.  Needed with several slabs only -- a slab that holds no oriented-dipole cell, or objects with fewer poles
+ * than its neighbour's, still exchanges that many node P_y ghost rows.  0 (default) = this slab's own list decides. */
+int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global);
+
+/* Column length of the y-marching kernels: how many stacked y planes of equal content one thread block walks, carrying the y-coupled
+ * neighbour planes in registers (k_fast / k_uniform).  0 = automatic (from the grid size, up to 64 / 32).  Results do not depend on
+ * it; it exists for tuning and so that the parity tests can force long columns on small grids (the environment variable
+ * CHIML_B200_MARCH_NY="fast[,uniform]" does the same for contexts that never call this). */
+int chiml_gpu_set_march(ChimlCtx* ctx, int fast_planes, int uniform_planes);
 
 /* Freeze the setup: paints the per-cell update maps from the lists, builds the CPML coefficient
  * tables and compact psi / polarisation pools, zeroes all state. */

@@ -14,12 +14,21 @@ pytestmark = pytest.mark.gpu
 TOL_L2 = 1e-10
 TOL_DTC = 1e-9
 
+# Column lengths of the y-marching kernels (chiml_gpu_set_march).  The fixtures are too small to get columns from the automatic
+# choice (it keeps >= 8 work items per SM), so without forcing it the register-carried neighbour planes of k_fast / k_uniform --
+# the code that moves ~100 % of the bytes of the large configurations -- would run with one plane only.  2, 3 and 7 put the column
+# seams at different planes; WHOLE merges every stack of equal tiles into one column (up to the full height of the grid).
+WHOLE = 1 << 20
+MARCH = [None, 2, 3, 7, WHOLE]
+MARCH_IDS = ["auto", "ny2", "ny3", "ny7", "whole"]
 
+
+@pytest.mark.parametrize("march", MARCH, ids=MARCH_IDS)
 @pytest.mark.parametrize("case", util.CASES)
-def test_gpu_matches_reference_fixture(case):
+def test_gpu_matches_reference_fixture(case, march):
     plan = util.load_plan(case)
     expect = util.load_expect(case)
-    sim = capi.GpuSim(plan)
+    sim = capi.GpuSim(plan, march=march)
     sim.step_n(plan.n_steps)
     for name, ref in expect.items():
         got = util.state_array(sim, name)
@@ -36,12 +45,13 @@ def test_gpu_matches_reference_fixture(case):
     sim.close()
 
 
+@pytest.mark.parametrize("march", MARCH, ids=MARCH_IDS)
 @pytest.mark.parametrize("case", util.CASES)
-def test_gpu_matches_oracle_from_random_state(case, oracle_lib):
+def test_gpu_matches_oracle_from_random_state(case, march, oracle_lib):
     """Seeded random fill of every state array (so nothing is identically zero), then N steps."""
     plan = util.load_plan(case)
     rng = np.random.default_rng(1234)
-    gpu, cpu = capi.GpuSim(plan), OracleSim(plan)
+    gpu, cpu = capi.GpuSim(plan, march=march), OracleSim(plan)
     lnx, lny, lnz = plan.ln
     for f in plan.fields_present():
         a = rng.uniform(-1.0, 1.0, size=(lny, lnz, lnx))

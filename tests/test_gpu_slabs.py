@@ -15,25 +15,37 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def test_two_slabs_over_nvlink_match_single_rank_reference():
+def _env(march):
+    """Forced column length of the y-marching kernels for the worker processes (CHIML_B200_MARCH_NY, include/chiml_gpu.h
+    chiml_gpu_set_march): slab-boundary planes stay single-plane work items, the columns next to them carry their y neighbours."""
+    env = dict(os.environ)
+    env.pop("CHIML_B200_MARCH_NY", None)
+    if march:
+        env["CHIML_B200_MARCH_NY"] = march
+    return env
+
+
+@pytest.mark.parametrize("march", [None, "5"], ids=["auto", "ny5"])
+def test_two_slabs_over_nvlink_match_single_rank_reference(march):
     if capi.device_count() < 2:
         pytest.skip("needs two GPUs")
     cases = ["vac3d", "aniso_slab3d", "lorentz3d", "ml3d_two", "ml3d_four", "ml_te", "ml_tm", "tm_au", "te_vacuum", "c4_small", "flux3d", "te_flux", "tm_flux"]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29733", os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=_env(march))
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     for c in cases:
         assert f"{c}: SLAB_GPU_OK" in r.stdout, r.stdout[-4000:]
 
 
-def test_four_slabs_match_single_rank_reference_even_on_one_gpu():
+@pytest.mark.parametrize("march", [None, "3", "1048576"], ids=["auto", "ny3", "whole"])
+def test_four_slabs_match_single_rank_reference_even_on_one_gpu(march):
     """Four slabs on however many GPUs there are (ranks wrap around the devices).  c4_small at four slabs has a slab that holds
     only the rim of the emitter sheet (an emitter set without emitters), flux3d has flux surfaces cut by slab boundaries."""
     cases = ["aniso_slab3d", "ml3d_two", "c4_small", "flux3d"]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
                         "--master-port", "29734", os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=_env(march))
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     for c in cases:
         assert f"{c}: SLAB_GPU_OK" in r.stdout, r.stdout[-4000:]
