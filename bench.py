@@ -55,6 +55,11 @@ def parse_args():
     ap.add_argument("--workload", default="c5", choices=["c5", "c1", "c2", "c3", "c4"],
                     help="c5 (default) is the bench contract; c1..c4 are the other BASELINE.md configurations at full size, for the record "
                          "(single GPU, no CPU baseline)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the bench contract): --ny-per-gpu rows per GPU; strong: the fixed BASELINE C5 grid nx x --ny-total x nz "
+                         "cut into N y-slabs (2048 x 2048 x 1024 needs >= 4 GPUs: ~52 GB of state per 2048 x 256 x 1024 slab)")
+    ap.add_argument("--ny-total", type=int, default=2048, help="grid points along y of the fixed grid of --scaling strong")
+    ap.add_argument("--no-halo-parity", action="store_true", help="N > 1: skip the bit-exactness check of the native halo before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--keep", action="store_true", help="keep the scratch directory")
     return ap.parse_args()
@@ -71,10 +76,35 @@ def workload_cfg(nx_pts: int, ny_pts: int, nz_pts: int, steps: int):
     return I.c5_aniso_ml(nx=nx_pts - 1, ny=ny_pts - 1, nz=nz_pts - 1, steps=steps, sheet=WORKLOAD_HAS_EMITTERS, out="bench_out/c5")
 
 
-def workload_name(nx, nyg, nz, n):
+def workload_name(nx, nyg, nz, n, scaling="weak"):
     sheet = " + two-level emitter sheet" if WORKLOAD_HAS_EMITTERS else ""
-    return (f"C5 weak-scaling slab: 3-D anisotropic (oriented-dipole Lorentz) slab waveguide{sheet} + CPML 20 cells, "
+    kind = "weak-scaling slab" if scaling == "weak" else "strong scaling of the fixed grid"
+    return (f"C5 {kind}: 3-D anisotropic (oriented-dipole Lorentz) slab waveguide{sheet} + CPML 20 cells, "
             f"{nx}x{nyg}x{nz} grid points per GPU ({nx}x{nyg * n}x{nz} total)")
+
+
+# N > 1: fixtures stepped across the N ranks over the native halo right before the timed region and compared with the committed
+# single-rank output of the unmodified reference (tests/golden/<case>.expect.npz): oriented-dipole slab through the CPML (node P_y
+# ghost rows), Au cubes under an emitter sheet (emitter P_y rim, a slab that holds only the rim), finite oriented-dipole objects
+# with different pole counts (slabs without node cells)
+HALO_PARITY_CASES = ["aniso_slab3d", "c4_small", "aniso_mixed3d"]
+
+
+def halo_parity(dist, rank, world, local):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import slab_gpu_worker
+    import torch
+    log = lambda m: print(m, file=sys.stderr)   # noqa: E731
+    ok = True
+    for case in HALO_PARITY_CASES:
+        ok = slab_gpu_worker.run_case(case, rank, world, local, log=log) and ok
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+    dist.broadcast(flag, src=0)
+    if int(flag.item()) != 1:
+        raise SystemExit("bench.py: the native halo does not reproduce the single-rank reference fixtures -- refusing to time it")
+    return {"result": "bit-identical", "cases": HALO_PARITY_CASES, "slabs": world,
+            "against": "tests/golden/<case>.expect.npz (single-rank output of the unmodified reference)"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -163,7 +193,7 @@ def run_reference(sample_pts, steps: int, warmup: int, work: str):
     cells = nx * ny * nz
     sec = out["step_seconds"]
     return cells * steps / sec / 1e6, sec / steps * 1e3, {
-        "cores": ranks, "kind": "reference",
+        "cores": ranks, "kind": "reference", "cells": cells,
         "sample": f"same workload at {nx}x{ny}x{nz} grid points ({cells / 1e6:.1f} Mcell), {steps} timed steps after {warmup} warm-up, "
                   f"{ranks} y-slab ranks as threads on {cores} host cores; {wall:.0f} s wall including the reference's setup"}
 
@@ -176,9 +206,12 @@ def reference_arm(args):
     try:
         sample = (384, 0, 192)
         v, ms, info = run_reference(sample, args.steps, args.warmup, work)
+        full_cells = args.nx * args.ny_per_gpu * args.gpus * args.nz
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.nx, args.ny_per_gpu, args.nz, args.gpus), "reference_sample": info["sample"]},
+                "config": {"workload": workload_name(args.nx, args.ny_per_gpu, args.nz, args.gpus), "reference_sample": info["sample"],
+                           "reference_sample_cells": info["cells"], "reference_sample_reduction": round(full_cells / info["cells"], 2),
+                           "same_config": False},
                 "cpu_baseline": dict(info, value=v, unit=UNIT),
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -243,6 +276,13 @@ def b200_arm(args):
             cfg = OTHER[args.workload][1](total_steps)
             args.no_cpu_baseline = True
         else:
+            if args.scaling == "strong":
+                if args.ny_total % world:
+                    raise SystemExit(f"bench.py: --scaling strong needs --ny-total ({args.ny_total}) divisible by the number of GPUs")
+                nyg = args.ny_total // world
+                if nx * nyg * nz > 2048 * 768 * 1024:
+                    raise SystemExit(f"bench.py: a {nx}x{nyg}x{nz} slab (~{52 * nx * nyg * nz / (2048 * 256 * 1024):.0f} GB of state) does not fit one "
+                                     "B200: strong scaling of the fixed C5 grid starts at 4 GPUs")
             cfg = workload_cfg(nx, nyg * world, nz, total_steps)
         jpath = os.path.join(work, "bench.json")
         I.write(cfg, jpath)
@@ -254,8 +294,11 @@ def b200_arm(args):
         cs = census.census(plan)
         sim = capi.GpuSim(plan, device=local)
         setup_s = time.time() - t0
+        parity = None
         if world > 1:
             sim.halo_bind(dist, rank, world)
+            if not args.no_halo_parity:
+                parity = halo_parity(dist, rank, world, local)
         cells_local = cs.cells
         cells_total = allsum(float(cells_local))
 
@@ -294,6 +337,7 @@ def b200_arm(args):
             for di in range(ndet):
                 got = sim.detector_range(di, det_next[di], 1, det_buf[di])
                 det_next[di] += got
+                sim.consume_detector(di, det_next[di])      # read, then consume: the device ring stays at its initial size
                 d2h += got * det_buf[di].nbytes
             if ndet == 0:
                 sim.sync()
@@ -304,43 +348,70 @@ def b200_arm(args):
         clk = clocks.stop()
         e2e_value = cells_total * K / e2e_s / 1e6
 
-        # ---- roofline of the dominant kernel ----
+        # ---- roofline of the dominant kernel, on the rank that moves the most bytes ----
+        # (slabs with a neighbour lose a y-CPML face: the end slabs of a weak-scaling run carry more psi traffic than the middle ones,
+        # and rank 0 of an N-GPU run less than the single GPU of N = 1)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        timed = [s for s in stats if s["timed_launches"] > 0]
-        dom = max(timed, key=lambda s: s["ms_total"])
-        dom_ms = dom["ms_total"] / dom["timed_launches"]
-        achieved = dom["alg_bytes_per_launch"] / (dom_ms * 1e-3) / 1e9
-        kernels = [{"name": s["name"], "launches_per_step": s["launches"] / K, "avg_ms": s["ms_total"] / s["timed_launches"],
-                    "share_of_step": s["ms_total"] / (ms if world == 1 else max(ms, 1e-9)),
-                    "alg_GB_per_launch": s["alg_bytes_per_launch"] / 1e9,
-                    "alg_GBps": s["alg_bytes_per_launch"] / (s["ms_total"] / s["timed_launches"] * 1e-3) / 1e9 if s["alg_bytes_per_launch"] else None}
-                   for s in timed]
-        step_bytes = cs.bytes_per_step
-        step_gbps = step_bytes * K / (ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom["name"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        mine = {"rank": rank, "bytes_per_step": cs.bytes_per_step, "cells": cells_local, "stats": stats, "census": cs.as_dict()}
+        ranks_info = [mine]
+        if dist is not None:
+            ranks_info = [None] * world
+            dist.all_gather_object(ranks_info, mine)
+        heavy = max(ranks_info, key=lambda r: r["bytes_per_step"])
+        ms_step = ms / K
+
+        def kernel_rows(st):
+            rows = []
+            for s_ in st:
+                if s_["timed_launches"] <= 0:
+                    continue
+                t_step = s_["ms_total"] / K                       # device time of ALL launches of this kernel in one step
+                rows.append({"name": s_["name"], "launches_per_step": s_["launches"] / K, "ms_per_step": t_step,
+                             "avg_launch_ms": s_["ms_total"] / s_["timed_launches"], "share_of_step": t_step / ms_step,
+                             "alg_GB_per_step": s_["alg_bytes_per_step"] / 1e9,
+                             "alg_GBps": s_["alg_bytes_per_step"] / (t_step * 1e-3) / 1e9 if s_["alg_bytes_per_step"] else None})
+            return rows
+        kernels = kernel_rows(heavy["stats"])
+        dom = max(kernels, key=lambda k_: k_["ms_per_step"])
+        achieved = dom["alg_GBps"] or 0.0
+        per_rank = [{"rank": r["rank"], "alg_bytes_per_step": r["bytes_per_step"], "achieved": r["bytes_per_step"] / (ms_step * 1e-3) / 1e9,
+                     "frac": r["bytes_per_step"] / (ms_step * 1e-3) / 1e9 / peak} for r in ranks_info]
+        step_bytes = heavy["bytes_per_step"]
+        step_gbps = step_bytes / (ms_step * 1e-3) / 1e9
+        sig = f"{args.workload}:{args.scaling}:{nx}x{nyg}x{nz}:n{world}"
+        roofline = {"bound": "hbm", "kernel": dom["name"], "rank": heavy["rank"], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src,
-                    "whole_step": {"alg_bytes_per_step_per_gpu": step_bytes, "achieved": step_gbps, "frac": step_gbps / peak},
+                    "how": "algorithmic bytes all launches of the kernel move in one step / their summed device time in one step (CUDA events around "
+                           "every launch), on the rank with the most bytes per step",
+                    "whole_step": {"alg_bytes_per_step_per_gpu": step_bytes, "achieved": step_gbps, "frac": step_gbps / peak,
+                                   "per_rank": per_rank, "min_frac": min(r["frac"] for r in per_rank)},
                     "kernels": kernels}
+        # DRAM traffic per launch is an ncu measurement: it is quoted only for the configuration it was captured on
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
-                roofline["traffic"] = json.load(open(tr)).get(dom["name"])
+                tj = json.load(open(tr))
+                if tj.get("_config") == sig:
+                    roofline["traffic"] = tj.get(dom["name"])
+                    roofline["traffic_source"] = tj.get("_comment")
             except Exception:
                 pass
 
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(nx, nyg, nz, world) if args.workload == "c5" else OTHER[args.workload][0], "l2": "inputs_larger_than_L2 (every state array > 4 GB)" if cells_local * 8 > 2.5e8 else "small grid: arrays may fit L2",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(nx, nyg, nz, world, args.scaling) if args.workload == "c5" else OTHER[args.workload][0], "signature": sig, "l2": "inputs_larger_than_L2 (every state array > 4 GB)" if cells_local * 8 > 2.5e8 else "small grid: arrays may fit L2",
                            "census_rank0": cs.as_dict(), "device_GB_rank0": sim.device_bytes() / 1e9, "setup_s_rank0": round(setup_s, 1),
                            "fields": "zero initial state driven by the dipole source (reference behaviour); timing is data-independent"},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K, "ms_per_step": e2e_s / K * 1e3},
                 "gpu_launches": int(launches),
                 "roofline": roofline}
+        if parity is not None:
+            line["halo_parity"] = parity
         sim.close()
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             try:

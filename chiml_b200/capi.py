@@ -29,7 +29,8 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_reset_kernel_stats", "chiml_gpu_read_detector_range", "chiml_gpu_add_emitters",
     "chiml_gpu_download_emitter_state", "chiml_gpu_download_emitter_pol", "chiml_gpu_read_population",
     "chiml_gpu_halo_export", "chiml_gpu_halo_bind", "chiml_gpu_add_dft", "chiml_gpu_step_n_dft", "chiml_gpu_download_dft",
-    "chiml_gpu_set_march",
+    "chiml_gpu_set_march", "chiml_gpu_set_ordip_pole_count", "chiml_gpu_reserve_steps", "chiml_gpu_consume_detector",
+    "chiml_gpu_consume_population",
 ]
 
 
@@ -49,7 +50,7 @@ class EmitterDesc(C.Structure):
                 ("dt", C.c_double), ("inv_hbar", C.c_double), ("na", C.c_double),
                 ("h0", C.c_void_p), ("weight", C.c_void_p), ("mu", C.c_void_p), ("gam_ptr", C.c_void_p), ("gam_col", C.c_void_p),
                 ("gam_val", C.c_void_p), ("loc", C.c_void_p), ("eps", C.c_void_p), ("npop", C.c_int32), ("pop_level", C.c_void_p),
-                ("pop_every", C.c_int32), ("npoints", C.c_int32)]
+                ("pop_every", C.c_int32), ("npoints", C.c_int32), ("object", C.c_int32)]
 
 
 def emitter_desc(e: "P.PlanEmitter", keep: list) -> EmitterDesc:
@@ -68,12 +69,13 @@ def emitter_desc(e: "P.PlanEmitter", keep: list) -> EmitterDesc:
         keep.append(a)
         setattr(d, k, a.ctypes.data if a.size else None)
     d.npop, d.pop_every, d.npoints = e.npop, e.pop_every, e.npoints
+    d.object = e.object
     return d
 
 
 class KernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("timed_launches", C.c_int64), ("ms_total", C.c_double),
-                ("alg_bytes_per_launch", C.c_double)]
+                ("alg_bytes_per_launch", C.c_double), ("alg_bytes_per_step", C.c_double)]
 
 
 class _Tolerant:
@@ -125,7 +127,11 @@ def lib() -> C.CDLL:
     L.chiml_gpu_set_march.argtypes = [vp, i, i]
     L.chiml_gpu_step_n.argtypes = [vp, i, vp]
     L.chiml_gpu_sync.argtypes = [vp]
-    L.chiml_gpu_step_n_timed.argtypes = [vp, i, vp, C.POINTER(C.c_float)]
+    L.chiml_gpu_step_n_timed.argtypes = [vp, i, vp, vp, C.POINTER(C.c_float)]
+    L.chiml_gpu_set_ordip_pole_count.argtypes = [vp, i]
+    L.chiml_gpu_reserve_steps.argtypes = [vp, C.c_longlong]
+    L.chiml_gpu_consume_detector.argtypes = [vp, i, sz]
+    L.chiml_gpu_consume_population.argtypes = [vp, i, sz]
     L.chiml_gpu_launch_count.argtypes = [vp]
     L.chiml_gpu_launch_count.restype = C.c_int64
     L.chiml_gpu_upload_field.argtypes = [vp, i, vp]
@@ -217,6 +223,8 @@ class GpuSim:
                     slot = C.c_int()
                     self._chk(L.chiml_gpu_add_detector(self.h, d.field, (C.c_int32 * 3)(*box[0]), (C.c_int32 * 3)(*box[1]), d.every, C.byref(slot)))
                     self.det_slots.append(slot.value)
+            if plan.nranks > 1:
+                self._chk(L.chiml_gpu_set_ordip_pole_count(self.h, plan.n_ordip_poles))
             if march is not None:
                 mf, mu = (march, march) if isinstance(march, int) else march
                 self._chk(L.chiml_gpu_set_march(self.h, mf, mu))
@@ -255,7 +263,8 @@ class GpuSim:
             amp = self.src_amp(self.steps_done, n)
         amp = np.ascontiguousarray(amp, dtype=np.float64)
         ms = C.c_float()
-        self._chk(lib().chiml_gpu_step_n_timed(self.h, n, _ptr(amp) if len(self.plan.sources) else None, C.byref(ms)))
+        tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, n)) if self.plan.dfts else None
+        self._chk(lib().chiml_gpu_step_n_timed(self.h, n, _ptr(amp) if len(self.plan.sources) else None, _ptr(tw), C.byref(ms)))
         self.steps_done += n
         return float(ms.value)
 
@@ -334,6 +343,16 @@ class GpuSim:
         self._chk(lib().chiml_gpu_read_detector_range(self.h, slot, first, n, _ptr(out), C.byref(m)))
         return int(m.value)
 
+    def consume_detector(self, index: int, upto: int) -> None:
+        if self.det_slots[index] >= 0:
+            self._chk(lib().chiml_gpu_consume_detector(self.h, self.det_slots[index], upto))
+
+    def consume_population(self, slot: int, upto: int) -> None:
+        self._chk(lib().chiml_gpu_consume_population(self.h, slot, upto))
+
+    def reserve_steps(self, n: int) -> None:
+        self._chk(lib().chiml_gpu_reserve_steps(self.h, n))
+
     def emitter_state(self, slot: int, sys: int, which: int) -> np.ndarray:
         """(nemit, N*N) complex: rho (which=0) or d rho/dt at n, n-1, n-2, n-3 (which=1..4) of level system `sys`."""
         e = self.plan.emitters[slot]
@@ -376,7 +395,8 @@ class GpuSim:
             ks = KernelStat()
             self._chk(lib().chiml_gpu_kernel_stat(self.h, k, C.byref(ks)))
             out.append({"name": ks.name.decode(), "launches": int(ks.launches), "timed_launches": int(ks.timed_launches),
-                        "ms_total": float(ks.ms_total), "alg_bytes_per_launch": float(ks.alg_bytes_per_launch)})
+                        "ms_total": float(ks.ms_total), "alg_bytes_per_launch": float(ks.alg_bytes_per_launch),
+                        "alg_bytes_per_step": float(ks.alg_bytes_per_step)})
         return out
 
     def launch_count(self) -> int:

@@ -190,6 +190,7 @@ int chiml_gpu_set_object(ChimlCtx* ctx, int obj, int npoles, const double* alpha
     if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_object after commit");
     if(obj < 0 || obj >= ctx->g.n_objects || npoles < 0) return fail(ctx, CHIML_ERR_ARG, "set_object: bad index");
     if(npoles > MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_object: more than 12 poles per object");
+    if(npoles > 0 && (!alpha || !xi || !gamma)) return fail(ctx, CHIML_ERR_ARG, "set_object: null pole constants");
     HostObj& o = ctx->objs[obj];
     o.npoles = npoles; o.use_or_dip = use_or_dip;
     o.alpha.assign(alpha, alpha + npoles); o.xi.assign(xi, xi + npoles); o.gamma.assign(gamma, gamma + npoles);
@@ -222,6 +223,7 @@ int chiml_gpu_set_cpml(ChimlCtx* ctx, int comp, int part, int has_psi, const Chi
     if(!ctx) return CHIML_ERR_ARG;
     if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_cpml after commit");
     if(comp < 0 || comp > 5 || part < 0 || part > 1) return fail(ctx, CHIML_ERR_ARG, "set_cpml: bad comp/part");
+    if((npsi && !psi) || (ngrid && !grid)) return fail(ctx, CHIML_ERR_ARG, "set_cpml: null list");
     HostPml& h = ctx->hpml[comp][part];
     h.present = 1; h.has_psi = has_psi;
     h.psi.assign(psi, psi + npsi);
@@ -233,6 +235,7 @@ int chiml_gpu_add_source(ChimlCtx* ctx, int field, const int32_t loc[3], const i
 {
     if(!ctx) return CHIML_ERR_ARG;
     if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "add_source after commit");
+    if(!loc || !sz) return fail(ctx, CHIML_ERR_ARG, "add_source: null box");
     if(field < 0 || field >= 6 || !field_exists(ctx, field)) return fail(ctx, CHIML_ERR_ARG, "add_source: field absent in this mode");
     if((int)ctx->sources.size() >= MAX_SOURCES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "too many sources");
     SourceDev s; s.field = field;
@@ -251,6 +254,7 @@ int chiml_gpu_add_detector(ChimlCtx* ctx, int field, const int32_t loc[3], const
 {
     if(!ctx) return CHIML_ERR_ARG;
     if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "add_detector after commit");
+    if(!loc || !sz) return fail(ctx, CHIML_ERR_ARG, "add_detector: null box");
     if(field < 0 || field >= CHIML_NFIELDS || !field_exists(ctx, field)) return fail(ctx, CHIML_ERR_ARG, "add_detector: field absent in this mode");
     if(every < 1) return fail(ctx, CHIML_ERR_ARG, "add_detector: interval must be >= 1 step");
     DetectorDev d; d.field = field; d.every = every;
@@ -955,7 +959,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
     for(size_t d = 0; d < ctx->detectors.size(); ++d)
     {
         DetectorDev& dt = ctx->detectors[d];
-        dt.cap = 4096;
+        dt.cap = std::min<size_t>(4096, std::max<size_t>(8, (64u << 20) / (dt.sample_len * sizeof(double))));   // grows on demand (reserve_rings)
         if((rc = dev_alloc(ctx, &dt.d_ring, dt.cap * dt.sample_len, false))) return rc;
         k_detector<<<(unsigned)std::min<size_t>((dt.sample_len + 255) / 256, 1024), 256, 0, ctx->stream>>>(
             ctx->d_field[dt.field], dt.loc[0], dt.loc[2], dt.loc[1], dt.sz[0], dt.sz[2], dt.sz[1], ctx->lz, ctx->px, dt.d_ring);
@@ -1173,19 +1177,8 @@ int launch_density_step(ChimlCtx* ctx, EmitterDev& em)
     }
     if(sample)
     {
-        if(em.pop_n >= em.pop_cap)
-        {
-            double* bigger = nullptr;
-            const size_t ncap = 2 * em.pop_cap;
-            if(cudaMalloc((void**)&bigger, (size_t)em.d.npop * ncap * 2 * sizeof(double)) != cudaSuccess) return CHIML_ERR_CUDA;
-            for(int p = 0; p < em.d.npop; ++p)
-                cudaMemcpyAsync(bigger + (size_t)p * ncap * 2, em.d_pop + (size_t)p * em.pop_cap * 2, em.pop_n * 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
-            cudaFree(em.d_pop);
-            em.d_pop = bigger; em.pop_cap = ncap;
-        }
         LaunchScope ls(ctx, K_EMIT_POP);
-        k_emit_pop_reduce<<<1, 256, 0, ctx->stream>>>(em.d_pop_partial, em.d.nemit > 0 ? em.nblocks : 0, em.d.npop, 0.0, (double)em.d.npoints, em.d_pop, em.pop_cap, em.pop_n);
+        k_emit_pop_reduce<<<1, 256, 0, ctx->stream>>>(em.d_pop_partial, em.d.nemit > 0 ? em.nblocks : 0, em.d.npop, 0.0, (double)em.d.npoints, em.d_pop, em.pop_cap, em.pop_n % em.pop_cap);
         ++em.pop_n;
     }
     ++em.tstep;
@@ -1311,20 +1304,10 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
     for(auto& dt : ctx->detectors)
     {
         if(ctx->step_count % dt.every != 0) continue;
-        if(dt.count >= dt.cap)
-        {
-            double* bigger = nullptr;
-            if(cudaMalloc((void**)&bigger, 2 * dt.cap * dt.sample_len * sizeof(double)) != cudaSuccess) return CHIML_ERR_CUDA;
-            cudaMemcpyAsync(bigger, dt.d_ring, dt.cap * dt.sample_len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
-            cudaFree(dt.d_ring);
-            ctx->dev_bytes += dt.cap * dt.sample_len * sizeof(double);
-            dt.d_ring = bigger; dt.cap *= 2;
-        }
         {
             LaunchScope ls(ctx, K_DETECTOR);
             k_detector<<<(unsigned)std::min<size_t>((dt.sample_len + 255) / 256, 1024), 256, 0, ctx->stream>>>(
-                ctx->d_field[dt.field], dt.loc[0], dt.loc[2], dt.loc[1], dt.sz[0], dt.sz[2], dt.sz[1], ctx->lz, ctx->px, dt.d_ring + dt.count * dt.sample_len);
+                ctx->d_field[dt.field], dt.loc[0], dt.loc[2], dt.loc[1], dt.sz[0], dt.sz[2], dt.sz[1], ctx->lz, ctx->px, dt.d_ring + (dt.count % dt.cap) * dt.sample_len);
         }
         ++dt.count;
     }
@@ -1451,6 +1434,56 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
     return 0;
 }
 
+// samples a detector with interval `every` takes during steps (sc, sc + n]
+size_t samples_in(long long sc, long long n, int every) { return (size_t)((sc + n) / every - sc / every); }
+
+// Makes room in the detector and population rings for the samples of the next n steps, so that the step loop itself never allocates
+// or synchronises.  A ring grows only when the host has not consumed what it holds (chiml_gpu_consume_detector / _population).
+int reserve_rings(ChimlCtx* ctx, long long n)
+{
+    for(DetectorDev& dt : ctx->detectors)
+    {
+        const size_t need = dt.count - dt.base + samples_in(ctx->step_count, n, dt.every);
+        if(need <= dt.cap) continue;
+        const size_t ncap = std::max(need, 2 * dt.cap);
+        double* bigger = nullptr;
+        CK(cudaMalloc((void**)&bigger, ncap * dt.sample_len * sizeof(double)));
+        for(size_t s = dt.base; s < dt.count; )      // unwrap: sample s moves from slot s % cap to slot s % ncap, in contiguous pieces
+        {
+            const size_t run = std::min({dt.count - s, dt.cap - s % dt.cap, ncap - s % ncap});
+            CK(cudaMemcpyAsync(bigger + (s % ncap) * dt.sample_len, dt.d_ring + (s % dt.cap) * dt.sample_len, run * dt.sample_len * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            s += run;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(dt.d_ring);
+        ctx->dev_bytes += (ncap - dt.cap) * dt.sample_len * sizeof(double);
+        dt.d_ring = bigger; dt.cap = ncap;
+    }
+    for(EmitterDev& em : ctx->emitters)
+    {
+        if(em.d.npop == 0) continue;
+        // sampled on the steps whose number, counted from 0, is a multiple of the interval: multiples of e in [tstep, tstep + n)
+        const long long e = em.d.pop_every;
+        const size_t need = em.pop_n - em.pop_base + (size_t)((em.tstep + n + e - 1) / e - (em.tstep + e - 1) / e);
+        if(need <= em.pop_cap) continue;
+        const size_t ncap = std::max(need, 2 * em.pop_cap);
+        double* bigger = nullptr;
+        CK(cudaMalloc((void**)&bigger, (size_t)em.d.npop * ncap * 2 * sizeof(double)));
+        for(int p = 0; p < em.d.npop; ++p)
+            for(size_t s = em.pop_base; s < em.pop_n; )
+            {
+                const size_t run = std::min({em.pop_n - s, em.pop_cap - s % em.pop_cap, ncap - s % ncap});
+                CK(cudaMemcpyAsync(bigger + ((size_t)p * ncap + s % ncap) * 2, em.d_pop + ((size_t)p * em.pop_cap + s % em.pop_cap) * 2, run * 2 * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+                s += run;
+            }
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(em.d_pop);
+        ctx->dev_bytes += (size_t)em.d.npop * (ncap - em.pop_cap) * 2 * sizeof(double);
+        em.d_pop = bigger; em.pop_cap = ncap;
+    }
+    return 0;
+}
+
 int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles = nullptr)
 {
     if(!ctx) return CHIML_ERR_ARG;
@@ -1472,6 +1505,7 @@ int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp, const double* twidd
         }
         if(need) CK(cudaMemcpyAsync(ctx->d_tw, twiddles, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
+    { int rc = reserve_rings(ctx, n); if(rc) return rc; }
     const int nsrc = (int)ctx->sources.size();
     if(nsrc > 0)
     {
@@ -1674,12 +1708,12 @@ int chiml_gpu_halo_bind(ChimlCtx* ctx, const void* lower_blob, size_t lower_size
     return CHIML_OK;
 }
 
-int chiml_gpu_step_n_timed(ChimlCtx* ctx, int n, const double* src_amp, float* ms)
+int chiml_gpu_step_n_timed(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles, float* ms)
 {
     if(!ctx || !ms) return CHIML_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    int rc = step_n_impl(ctx, n, src_amp);
+    int rc = step_n_impl(ctx, n, src_amp, twiddles);
     if(rc) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev1));
@@ -1715,7 +1749,10 @@ int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out)
     ctx->ev_pending[kind].clear();
     std::memset(out, 0, sizeof(*out));
     std::snprintf(out->name, sizeof(out->name), "%s", names[kind]);
-    out->launches = ks.launches; out->timed_launches = ks.timed; out->ms_total = ks.ms_total; out->alg_bytes_per_launch = ks.alg_bytes;
+    out->launches = ks.launches; out->timed_launches = ks.timed; out->ms_total = ks.ms_total;
+    out->alg_bytes_per_step = ks.alg_bytes;
+    const long long steps = ctx->step_count - ctx->stat_step0;
+    out->alg_bytes_per_launch = (ks.launches > 0 && steps > 0) ? ks.alg_bytes * (double)steps / (double)ks.launches : ks.alg_bytes;
     return CHIML_OK;
 }
 
@@ -1730,6 +1767,7 @@ int chiml_gpu_reset_kernel_stats(ChimlCtx* ctx)
         ctx->ev_pending[k].clear();
         ctx->kstat[k].launches = 0; ctx->kstat[k].ms_total = 0.0; ctx->kstat[k].timed = 0;
     }
+    ctx->stat_step0 = ctx->step_count;
     return CHIML_OK;
 }
 size_t chiml_gpu_device_bytes(const ChimlCtx* ctx) { return ctx ? ctx->dev_bytes : 0; }
@@ -1833,6 +1871,20 @@ int chiml_gpu_download_psi(ChimlCtx* ctx, int comp, int part, double* host)
     return CHIML_OK;
 }
 
+} // extern "C"
+// copies samples [first, first + n) of a detector ring to the host (the stream is idle: the callers synchronise first)
+static int ring_read(ChimlCtx* ctx, const DetectorDev& dt, size_t first, size_t n, double* out)
+{
+    for(size_t s = first, done = 0; done < n; )
+    {
+        const size_t run = std::min(n - done, dt.cap - s % dt.cap);
+        CK(cudaMemcpy(out + done * dt.sample_len, dt.d_ring + (s % dt.cap) * dt.sample_len, run * dt.sample_len * sizeof(double), cudaMemcpyDeviceToHost));
+        s += run; done += run;
+    }
+    return CHIML_OK;
+}
+extern "C" {
+
 int chiml_gpu_read_detector(ChimlCtx* ctx, int slot, double* out, size_t cap_samples, size_t* n_samples)
 {
     if(!ctx) return CHIML_ERR_ARG;
@@ -1841,10 +1893,38 @@ int chiml_gpu_read_detector(ChimlCtx* ctx, int slot, double* out, size_t cap_sam
     CK(cudaSetDevice(ctx->device));
     const DetectorDev& dt = ctx->detectors[slot];
     CK(cudaStreamSynchronize(ctx->stream));
-    if(n_samples) *n_samples = dt.count;
-    const size_t n = std::min(cap_samples, dt.count);
-    if(out && n) CK(cudaMemcpy(out, dt.d_ring, n * dt.sample_len * sizeof(double), cudaMemcpyDeviceToHost));
+    if(n_samples) *n_samples = dt.count - dt.base;
+    const size_t n = std::min(cap_samples, dt.count - dt.base);
+    return out && n ? ring_read(ctx, dt, dt.base, n, out) : CHIML_OK;
+}
+
+int chiml_gpu_consume_detector(ChimlCtx* ctx, int slot, size_t upto)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "consume_detector before commit");
+    if(slot < 0 || slot >= (int)ctx->detectors.size()) return fail(ctx, CHIML_ERR_ARG, "consume_detector: bad slot");
+    DetectorDev& dt = ctx->detectors[slot];
+    dt.base = std::min(std::max(dt.base, upto), dt.count);
     return CHIML_OK;
+}
+
+int chiml_gpu_consume_population(ChimlCtx* ctx, int slot, size_t upto)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "consume_population before commit");
+    if(slot < 0 || slot >= (int)ctx->emitters.size()) return fail(ctx, CHIML_ERR_ARG, "consume_population: bad slot");
+    EmitterDev& em = ctx->emitters[slot];
+    em.pop_base = std::min(std::max(em.pop_base, upto), em.pop_n);
+    return CHIML_OK;
+}
+
+int chiml_gpu_reserve_steps(ChimlCtx* ctx, long long n_steps)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "reserve_steps before commit");
+    if(n_steps < 0) return fail(ctx, CHIML_ERR_ARG, "reserve_steps: negative step count");
+    CK(cudaSetDevice(ctx->device));
+    return reserve_rings(ctx, n_steps);
 }
 
 int chiml_gpu_download_emitter_state(ChimlCtx* ctx, int slot, int sys, int which, double* out)
@@ -1886,9 +1966,14 @@ int chiml_gpu_read_population(ChimlCtx* ctx, int slot, int det, double* out, siz
     if(det < 0 || det >= em.d.npop) return fail(ctx, CHIML_ERR_ARG, "read_population: bad detector");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    if(n_samples) *n_samples = em.pop_n;
-    const size_t n = std::min(cap_samples, em.pop_n);
-    if(out && n) CK(cudaMemcpy(out, em.d_pop + (size_t)det * em.pop_cap * 2, n * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    if(n_samples) *n_samples = em.pop_n - em.pop_base;
+    const size_t n = std::min(cap_samples, em.pop_n - em.pop_base);
+    for(size_t s = em.pop_base, done = 0; out && done < n; )
+    {
+        const size_t run = std::min(n - done, em.pop_cap - s % em.pop_cap);
+        CK(cudaMemcpy(out + 2 * done, em.d_pop + ((size_t)det * em.pop_cap + s % em.pop_cap) * 2, run * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+        s += run; done += run;
+    }
     return CHIML_OK;
 }
 
@@ -1899,12 +1984,11 @@ int chiml_gpu_read_detector_range(ChimlCtx* ctx, int slot, size_t first, size_t 
     if(slot < 0 || slot >= (int)ctx->detectors.size()) return fail(ctx, CHIML_ERR_ARG, "read_detector_range: bad slot");
     CK(cudaSetDevice(ctx->device));
     const DetectorDev& dt = ctx->detectors[slot];
-    const size_t avail = first < dt.count ? dt.count - first : 0;
+    const size_t avail = (first >= dt.base && first < dt.count) ? dt.count - first : 0;    // consumed samples are gone
     const size_t m = std::min(n, avail);
-    if(m) CK(cudaMemcpyAsync(out, dt.d_ring + first * dt.sample_len, m * dt.sample_len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     if(n_read) *n_read = m;
-    return CHIML_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return m ? ring_read(ctx, dt, first, m, out) : CHIML_OK;
 }
 
 } // extern "C"

@@ -84,7 +84,8 @@ struct DetectorDev
 {
     int field; int32_t loc[3], sz[3]; int every;
     size_t sample_len = 0;
-    double* d_ring = nullptr; size_t cap = 0; size_t count = 0;
+    // ring of samples: sample s (counted from the t = 0 sample) lives in slot s % cap; samples [base, count) are retained
+    double* d_ring = nullptr; size_t cap = 0; size_t count = 0; size_t base = 0;
 };
 
 // kernels of the step loop, for launch / time / algorithmic-byte accounting
@@ -107,7 +108,7 @@ struct EmitterDev
     int fbase = 0;                   // d_f[(fbase + k) % 4] holds d rho/dt at step n-k
     int mu_present[3] = {};
     double* d_pop_partial = nullptr; int nblocks = 0;
-    double* d_pop = nullptr; size_t pop_cap = 0, pop_n = 0;
+    double* d_pop = nullptr; size_t pop_cap = 0, pop_n = 0, pop_base = 0;   // ring like DetectorDev's: [npop][pop_cap] complex
     long tstep = 0;
 };
 
@@ -225,6 +226,7 @@ struct ChimlCtx
 
     // per-kernel device timing (chiml_gpu_set_kernel_timing / chiml_gpu_kernel_stat)
     bool timing = false;
+    long long stat_step0 = 0;                                 // step_count at the last chiml_gpu_reset_kernel_stats
     chiml::KernelStat kstat[chiml::K_NKINDS];
     std::vector<cudaEvent_t> ev_pool;                         // recycled events
     std::vector<std::array<cudaEvent_t, 2>> ev_pending[chiml::K_NKINDS];

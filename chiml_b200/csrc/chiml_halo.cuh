@@ -67,10 +67,11 @@ __global__ void __launch_bounds__(256) k_halo_push_nodes(const __grid_constant__
     {
         const int x = (int)(i % a.lx), z = (int)(i / a.lx);
         const long row = z + (long)a.lz * 1;
-        const int xmin = a.sp_xmin[row];
+        // a slab without node cells (no span table) pushes zeros: the neighbour waits for this row whatever it holds
+        const int xmin = a.sp_xmin ? a.sp_xmin[row] : -1;
         const bool in = xmin >= 0 && x >= xmin && x <= a.sp_xmax[row];
         const long ip = in ? a.sp_base[row] + (x - xmin) : 0;
-        for(int p = 0; p < a.npoles; ++p) a.dst[p][i] = in ? a.pool[p][ip] : 0.0;
+        for(int p = 0; p < a.npoles; ++p) a.dst[p][i] = (in && a.pool[p]) ? a.pool[p][ip] : 0.0;
     }
     __threadfence_system();
     __syncthreads();

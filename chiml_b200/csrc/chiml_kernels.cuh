@@ -109,6 +109,7 @@ __device__ __forceinline__ double axpy1(double y, double a, double x) { return _
 __device__ __forceinline__ double node_value(const StepArgs& a, const double* pool, const double* ghost, int x, int y, int z)
 {
     if(ghost && y == a.ly - 1) return ghost[x + (long)a.lx * z];
+    if(!pool) return 0.0;           // a pole grid of the whole grid that this slab holds no cell of
     const long row = z + (long)a.lz * y;
     const int xmin = a.nsp_xmin[row];
     if(xmin < 0 || x < xmin || x > a.nsp_xmax[row]) return 0.0;
@@ -119,6 +120,7 @@ __device__ __forceinline__ double node_value(const StepArgs& a, const double* po
 __device__ __forceinline__ double2 node_pair(const StepArgs& a, const double* pool, const double* ghost, int x, int y, int z)
 {
     if(ghost && y == a.ly - 1) return make_double2(ghost[x + (long)a.lx * z], ghost[x + 1 + (long)a.lx * z]);
+    if(!pool) return make_double2(0.0, 0.0);
     const long row = z + (long)a.lz * y;
     const int xmin = a.nsp_xmin[row];
     double2 v = make_double2(0.0, 0.0);

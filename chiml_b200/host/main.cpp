@@ -3,10 +3,11 @@
 // runs the time loop on the GPU, and writes the detector / population files the reference writes (TXT detectors,
 // DTC/parallelDTC_TXT.cpp:25-55; level populations, ML/QEPopDtc.cpp:37-61).
 //
-//   chiml <input.json> [--device D] [--steps N] [--rank R --nranks N --rendezvous DIR]
+//   chiml <input.json> [--device D] [--steps N] [--rank R --nranks N --rendezvous DIR [--run-id ID]]
 //
 // One process drives one GPU.  With --nranks > 1 each process takes one y-slab; the halo blobs are exchanged through files in the
-// rendezvous directory (any shared directory), after which the slabs talk over NVLink only.
+// rendezvous directory (any shared directory), after which the slabs talk over NVLink only.  The blob files carry the run id in
+// their names (give every launch its own: a blob left behind by a killed run holds dead IPC handles) and are removed at the end.
 #include <chrono>
 #include <cmath>
 #include <complex>
@@ -64,7 +65,7 @@ static bool local_box(const SlabPlan& P, const PlanDetector& d, int32_t loc[3], 
 
 int main(int argc, char** argv)
 {
-    std::string input, rendezvous;
+    std::string input, rendezvous, runId = "0";
     int device = 0, rank = 0, nranks = 1, steps = -1;
     for(int a = 1; a < argc; ++a)
     {
@@ -76,14 +77,16 @@ int main(int argc, char** argv)
             else if(s == "--rank") rank = std::atoi(next());
             else if(s == "--nranks") nranks = std::atoi(next());
             else if(s == "--rendezvous") rendezvous = next();
+            else if(s == "--run-id") runId = next();
             else if(s == "--steps") steps = std::atoi(next());
             else if(input.empty()) input = s;
             else throw std::runtime_error("unknown argument " + s);
         }
         catch(std::exception& e) { std::fprintf(stderr, "chiml: %s\n", e.what()); return 2; }
     }
-    if(input.empty()) { std::fprintf(stderr, "usage: chiml <input.json> [--device D] [--steps N] [--rank R --nranks N --rendezvous DIR]\n"); return 2; }
+    if(input.empty()) { std::fprintf(stderr, "usage: chiml <input.json> [--device D] [--steps N] [--rank R --nranks N --rendezvous DIR [--run-id ID]]\n"); return 2; }
     ChimlCtx* ctx = nullptr;
+    std::string myBlob;
     try
     {
         Json root = read_input_file(input);
@@ -108,10 +111,12 @@ int main(int argc, char** argv)
             int32_t loc[3], sz[3];
             if(local_box(P, P.detectors[d], loc, sz)) check(ctx, chiml_gpu_add_detector(ctx, P.detectors[d].field, loc, sz, P.detectors[d].every, &detSlot[d]), "add_detector");
         }
+        if(nranks > 1) check(ctx, chiml_gpu_set_ordip_pole_count(ctx, P.grid.n_ordip_poles), "set_ordip_pole_count");
         for(const PlanEmitter& e : P.emitters)
         {
             ChimlEmitterDesc d;
             std::memset(&d, 0, sizeof(d));
+            d.object = e.object;
             d.nlevel = e.nlevel; d.nsys = e.nsys; d.nemit = e.nemit;
             for(int k = 0; k < 3; ++k) { d.box_lo[k] = e.box_lo[k]; d.box_n[k] = e.box_n[k]; }
             d.dt = e.dt; d.inv_hbar = e.inv_hbar; d.na = e.na;
@@ -136,12 +141,15 @@ int main(int argc, char** argv)
             check(ctx, chiml_gpu_halo_export(ctx, nullptr, 0, &n), "halo_export");
             std::vector<char> mine(n);
             check(ctx, chiml_gpu_halo_export(ctx, mine.data(), n, &n), "halo_export");
-            const std::string my = rendezvous + "/halo." + std::to_string(rank);
+            const std::string stem = rendezvous + "/halo." + runId + ".";
+            const std::string my = stem + std::to_string(rank);
+            myBlob = my;
+            std::remove(my.c_str());
             { std::ofstream out((my + ".tmp").c_str(), std::ios::binary); out.write(mine.data(), (std::streamsize)n); }
             std::rename((my + ".tmp").c_str(), my.c_str());
             std::vector<char> lower, upper;
-            if(rank > 0) lower = read_file_when_ready(rendezvous + "/halo." + std::to_string(rank - 1));
-            if(rank + 1 < nranks) upper = read_file_when_ready(rendezvous + "/halo." + std::to_string(rank + 1));
+            if(rank > 0) lower = read_file_when_ready(stem + std::to_string(rank - 1));
+            if(rank + 1 < nranks) upper = read_file_when_ready(stem + std::to_string(rank + 1));
             check(ctx, chiml_gpu_halo_bind(ctx, lower.empty() ? nullptr : lower.data(), lower.size(), upper.empty() ? nullptr : upper.data(), upper.size()), "halo_bind");
         }
         if(rank == 0) std::cout << "made FF" << std::endl;
@@ -156,6 +164,41 @@ int main(int argc, char** argv)
         size_t ntw = 0;
         for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff) if(fluxHere[ff]) ntw += IP.fluxes_[ff].freqs.size();
         double tFlux = 0.0;                               // the reference's tcur_ (tcur_ += dt_, parallelFDTDField.hpp:1290)
+        // detector and population samples are drained from the device rings after every chunk of steps (read, then consume), so the
+        // rings keep their initial size however long the run is
+        std::vector<std::vector<double>> detData(P.detectors.size());
+        std::vector<std::vector<std::vector<double>>> popData(P.emitters.size());
+        for(size_t q = 0; q < P.emitters.size(); ++q) popData[q].resize(P.emitters[q].pop_level.size());
+        auto drain = [&]() {
+            for(size_t d = 0; d < P.detectors.size(); ++d)
+            {
+                if(detSlot[d] < 0) continue;
+                int32_t loc[3], sz[3];
+                local_box(P, P.detectors[d], loc, sz);
+                const size_t len = (size_t)sz[0] * sz[1] * sz[2];
+                size_t ns = 0;
+                check(ctx, chiml_gpu_read_detector(ctx, detSlot[d], nullptr, 0, &ns), "read_detector");
+                if(ns == 0) continue;
+                const size_t have = detData[d].size();
+                detData[d].resize(have + ns * len);
+                check(ctx, chiml_gpu_read_detector(ctx, detSlot[d], detData[d].data() + have, ns, &ns), "read_detector");
+                check(ctx, chiml_gpu_consume_detector(ctx, detSlot[d], have / len + ns), "consume_detector");
+            }
+            for(size_t q = 0; q < P.emitters.size(); ++q)
+            {
+                size_t total = 0;
+                for(size_t dd = 0; dd < P.emitters[q].pop_level.size(); ++dd)
+                {
+                    size_t ns = 0;
+                    check(ctx, chiml_gpu_read_population(ctx, (int)q, (int)dd, nullptr, 0, &ns), "read_population");
+                    const size_t have = popData[q][dd].size();
+                    popData[q][dd].resize(have + 2 * ns);
+                    if(ns) check(ctx, chiml_gpu_read_population(ctx, (int)q, (int)dd, popData[q][dd].data() + have, ns, &ns), "read_population");
+                    total = have / 2 + ns;
+                }
+                if(!P.emitters[q].pop_level.empty()) check(ctx, chiml_gpu_consume_population(ctx, (int)q, total), "consume_population");
+            }
+        };
         for(int done = 0; done < nSteps;)
         {
             const int n = std::min(256, nSteps - done);
@@ -183,8 +226,11 @@ int main(int argc, char** argv)
                 check(ctx, chiml_gpu_step_n_dft(ctx, n, nsrc ? amp.data() : nullptr, twiddles.data()), "step_n_dft");
             }
             done += n;
+            drain();
         }
         check(ctx, chiml_gpu_sync(ctx), "sync");
+        drain();                                          // nSteps == 0: the t = 0 samples
+        if(!myBlob.empty()) std::remove(myBlob.c_str());  // every neighbour has bound long ago: the slabs step in lock-step
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::cout << std::setw(9) << sec << "\t" << rank << "\t" << P.grid.y_start << std::endl;   // main.cpp:59-65 (wall clock here)
 
@@ -198,10 +244,8 @@ int main(int argc, char** argv)
             int32_t loc[3], sz[3];
             local_box(P, pd, loc, sz);
             const size_t len = (size_t)sz[0] * sz[1] * sz[2];
-            size_t ns = 0;
-            check(ctx, chiml_gpu_read_detector(ctx, detSlot[d], nullptr, 0, &ns), "read_detector");
-            std::vector<double> data(ns * len);
-            check(ctx, chiml_gpu_read_detector(ctx, detSlot[d], data.data(), ns, &ns), "read_detector");
+            const std::vector<double>& data = detData[d];
+            const size_t ns = data.size() / len;
             std::string name = di.name;
             if(nranks > 1) name += ".rank" + std::to_string(rank);
             make_dirs(name);
@@ -307,10 +351,8 @@ int main(int argc, char** argv)
             const QEInput& qi = IP.qes_[e.object];
             for(size_t dd = 0; dd < e.pop_level.size(); ++dd)
             {
-                size_t ns = 0;
-                check(ctx, chiml_gpu_read_population(ctx, (int)q, (int)dd, nullptr, 0, &ns), "read_population");
-                std::vector<double> pop(2 * ns);
-                check(ctx, chiml_gpu_read_population(ctx, (int)q, (int)dd, pop.data(), ns, &ns), "read_population");
+                const std::vector<double>& pop = popData[q][dd];
+                const size_t ns = pop.size() / 2;
                 std::string name = qi.dtcPopFiles[dd];
                 if(nranks > 1) name += ".rank" + std::to_string(rank);
                 make_dirs(name);

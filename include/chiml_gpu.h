@@ -117,7 +117,8 @@ int chiml_gpu_add_source(ChimlCtx* ctx, int field, const int32_t loc[3], const i
 /* Time-domain detector sampling (DTC/parallelStorageDTC.cpp:17-44): every `every` steps after the
  * step, and once at commit time (t = 0, parallelFDTDField.cpp:832-833), the raw values of `field`
  * in the box loc..loc+sz (local ghost-inclusive coordinates) are appended to a device ring that
- * chiml_gpu_read_detector drains.  The Yee-offset averaging and SI factors stay on the host. */
+ * chiml_gpu_read_detector[_range] reads and chiml_gpu_consume_detector drains.  The Yee-offset averaging and SI factors stay on
+ * the host. */
 int chiml_gpu_add_detector(ChimlCtx* ctx, int field, const int32_t loc[3], const int32_t sz[3], int every, int* slot);
 
 /* Quantum-emitter cells of one parallelQE object (ML/parallelQE.hpp): every listed grid node carries, per level system
@@ -199,8 +200,14 @@ int chiml_gpu_step_n(ChimlCtx* ctx, int n, const double* src_amp);
  * exp(-i freq t_k), t_k = time after step k (only read on the steps the group samples).  chiml_gpu_step_n fails when DFT sets exist. */
 int chiml_gpu_step_n_dft(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles);
 int chiml_gpu_sync(ChimlCtx* ctx);
-/* same as step_n but bracketed by CUDA events on the context's stream; returns device milliseconds */
-int chiml_gpu_step_n_timed(ChimlCtx* ctx, int n, const double* src_amp, float* ms);
+/* same as step_n / step_n_dft (twiddles may be NULL when no running-DFT set is registered) but bracketed by CUDA events on the
+ * context's stream; returns device milliseconds */
+int chiml_gpu_step_n_timed(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles, float* ms);
+/* Detector and population samples go to device rings.  chiml_gpu_step_n makes room for the samples of its n steps BEFORE it launches
+ * anything (a ring whose retained samples leave no room is re-allocated there, once, never inside the step loop); a host that drains
+ * the rings -- read, then consume -- between calls keeps them at their initial size for runs of any length.  reserve_steps does the
+ * same sizing ahead of time for the next n_steps steps (e.g. for the whole run, when nothing is read before the end). */
+int chiml_gpu_reserve_steps(ChimlCtx* ctx, long long n_steps);
 /* number of kernels this context has launched since creation */
 int64_t chiml_gpu_launch_count(const ChimlCtx* ctx);
 
@@ -215,7 +222,9 @@ typedef struct ChimlKernelStat
     int64_t launches;
     int64_t timed_launches;
     double  ms_total;
-    double  alg_bytes_per_launch;
+    double  alg_bytes_per_launch;  /* alg_bytes_per_step / launches per step (a slab with neighbours launches every tile list twice: the
+                                      slab-boundary rows first, then the interior) */
+    double  alg_bytes_per_step;    /* bytes all launches of this kernel move in ONE time step */
 } ChimlKernelStat;
 int chiml_gpu_set_kernel_timing(ChimlCtx* ctx, int on);
 int chiml_gpu_n_kernel_kinds(void);
@@ -233,10 +242,14 @@ int chiml_gpu_upload_pole(ChimlCtx* ctx, int comp, int pole, int prev, const dou
 int chiml_gpu_download_ordip_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host);
 /* CPML psi of component comp, part 0/1, expanded to the logical full grid */
 int chiml_gpu_download_psi(ChimlCtx* ctx, int comp, int part, double* host);
-/* copies up to cap samples (each sz[0]*sz[1]*sz[2] doubles, x fastest then z then y) and reports how many exist */
+/* copies up to cap samples (each sz[0]*sz[1]*sz[2] doubles, x fastest then z then y), oldest retained sample first, and reports how
+ * many are retained (= all samples since commit when nothing was consumed; sample 0 is the one taken at t = 0) */
 int chiml_gpu_read_detector(ChimlCtx* ctx, int slot, double* out, size_t cap_samples, size_t* n_samples);
-/* samples [first, first+n) only (what a host loop that drains the detector after every step reads); *n_read = how many existed */
+/* samples [first, first+n) by absolute number (what a host loop that drains the detector after every step reads); *n_read = how
+ * many of them are retained */
 int chiml_gpu_read_detector_range(ChimlCtx* ctx, int slot, size_t first, size_t n, double* out, size_t* n_read);
+/* releases every sample with absolute number < upto: its ring slots are reused by later samples */
+int chiml_gpu_consume_detector(ChimlCtx* ctx, int slot, size_t upto);
 
 /* emitter state of level system `sys`: which = 0 rho, 1..4 = d rho/dt at n, n-1, n-2, n-3; out = nemit * N*N complex, emitter-major */
 int chiml_gpu_download_emitter_state(ChimlCtx* ctx, int slot, int sys, int which, double* out);
@@ -245,6 +258,8 @@ int chiml_gpu_download_emitter_pol(ChimlCtx* ctx, int slot, int comp, double* ou
 /* population detector `det` of emitter set `slot`: complex samples sum_emitters rho[level] / npoints of THIS slab's emitters
  * (QEPopDtc::accumPop; the host adds the slabs, QEPopDtc::toFile).  out = cap_samples complex. */
 int chiml_gpu_read_population(ChimlCtx* ctx, int slot, int det, double* out, size_t cap_samples, size_t* n_samples);
+/* releases the samples with absolute number < upto of EVERY population detector of emitter set `slot` (they share one ring) */
+int chiml_gpu_consume_population(ChimlCtx* ctx, int slot, size_t upto);
 
 /* accumulators of DFT set `slot`: acc_len doubles each (fInReal_, fInCplx_) */
 int chiml_gpu_download_dft(ChimlCtx* ctx, int slot, double* re, double* im);

@@ -81,6 +81,22 @@ def cases():
                           [I.normal_source("Ex", [-0.1, -0.08, 0], [0, 0, 0], [pulse(1.5, 3e13)])],
                           [pxy],
                           [I.detector([0.03, 0, 0], [0, 0, 0], "Ex", "out/mte/dtc", time_int=DT * 1.0000001)])
+    # (two emitter objects in one input cannot be run by the reference: every parallelQE is handed the energy levels of ALL
+    # emitter objects, parallelFDTDField.cpp:424, and its constructor then reads h0 out of bounds, ML/parallelQE.hpp:221-229 --
+    # tests/test_gpu_slabs.py covers several emitter sets per slab against the oracle instead)
+    # ---- oriented-dipole objects of finite y extent with different pole counts: with several slabs some slabs hold no node cell,
+    # some hold the one-pole film, some the two-pole block; every slab still exchanges the whole grid's two node P_y rows ----
+    s2_ = 1.0 / np.sqrt(2.0)
+    filmA = I.block([0.3, 0.07, 0.06], [0.0, -0.045, 0.0], eps=2.25,
+                    pols=[I.lorentz_pole(1.5, 0.05, 2.5, dip_or_e="unidirectional", dir_dip_e=[s2_, s2_, 0.0])])
+    blockB = I.block([0.10, 0.06, 0.08], [0.01, 0.045, 0.0], eps=1.8,
+                     pols=[I.lorentz_pole(0.9, 0.1, 2.0, dip_or_e="unidirectional", dir_dip_e=[0.0, 0.6, 0.8]),
+                           I.lorentz_pole(0.4, 0.02, 3.1, dip_or_e="unidirectional", dir_dip_e=[0.0, 0.6, 0.8])])
+    c["aniso_mixed3d"] = _short_pulse(I.config(
+        I.comp_cell([23 / RES, 23 / RES, 21 / RES], RES, 50 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+        [I.normal_source("Ey", [0.0, 0.0, 0.0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
+        [filmA, blockB],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Ey", "out/am/dtc", time_int=DT * 1.0000001)]))
     # ---- C4 in miniature: built-in 6-pole Au cubes under a two-level emitter sheet, Ex plane source, CPML on every face ----
     c4 = I.c4_plasmonic_ml(n=27, ny=25, nz=37, steps=60, pml_cells=5, cube=6, pitch=10, narray=2, sheet=12, out="out/c4s", sheet_gap=3, src_margin=2)
     for s_ in c4["SourceList"]:

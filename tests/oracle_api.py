@@ -38,7 +38,7 @@ class EmitterDesc(C.Structure):
                 ("dt", C.c_double), ("inv_hbar", C.c_double), ("na", C.c_double),
                 ("h0", C.c_void_p), ("weight", C.c_void_p), ("mu", C.c_void_p), ("gam_ptr", C.c_void_p), ("gam_col", C.c_void_p),
                 ("gam_val", C.c_void_p), ("loc", C.c_void_p), ("eps", C.c_void_p), ("npop", C.c_int32), ("pop_level", C.c_void_p),
-                ("pop_every", C.c_int32), ("npoints", C.c_int32)]
+                ("pop_every", C.c_int32), ("npoints", C.c_int32), ("object", C.c_int32)]
 
 
 def emitter_desc(e: P.PlanEmitter, keep: list) -> EmitterDesc:
@@ -57,6 +57,7 @@ def emitter_desc(e: P.PlanEmitter, keep: list) -> EmitterDesc:
         keep.append(a)
         setattr(d, k, a.ctypes.data if a.size else None)
     d.npop, d.pop_every, d.npoints = e.npop, e.pop_every, e.npoints
+    d.object = e.object
     return d
 
 

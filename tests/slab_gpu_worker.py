@@ -16,12 +16,41 @@ import util  # noqa: E402
 from chiml_b200 import capi, plan as P  # noqa: E402
 
 
-def run_case(case, rank, world, local):
+def add_second_species(plan):
+    """A second emitter species in the SAME region: every emitter set of the plan is duplicated with another object index, density
+    and dipole strength.  The two sets of a slab then have equal boxes, so across a slab boundary only ChimlEmitterDesc::object
+    tells them apart (chiml_gpu_halo_bind).  The reference cannot run two emitter objects in one input (tests/golden/make_golden.py),
+    so the expected result comes from the single-rank oracle."""
+    import dataclasses
+    plan.emitters += [dataclasses.replace(e, object=e.object + 100, na=0.6 * e.na, mu=0.7 * e.mu) for e in plan.emitters]
+
+
+def oracle_expect(whole, names):
+    """State arrays of the single-rank oracle after whole.n_steps steps, keyed like a reference dump."""
+    from oracle_api import OracleSim
+    cpu = OracleSim(whole)
+    cpu.step_n(whole.n_steps)
+    out = {n: np.array(util.state_array(cpu, n)) for n in names}
+    for q, e in enumerate(whole.emitters):
+        for d in range(e.npop):
+            a = cpu.population(q, d)
+            out[f"q{q}pop{d}"] = np.stack([a.real, a.imag], axis=1)[:, None, :]
+    cpu.close()
+    return out
+
+
+def run_case(case, rank, world, local, log=print):
+    """Returns True when the gathered slabs equal the single-rank result bit for bit (rank 0 decides; other ranks return True).
+    `log` receives the per-case verdict and any mismatch lines (bench.py sends them to stderr)."""
+    case, pair = (case[:-5], True) if case.endswith("+pair") else (case, False)
     work = tempfile.mkdtemp(prefix=f"slabgpu_{case}_r{rank}_")
     subprocess.run([os.path.join(ROOT, "chiml_b200", "chiml_plan"), os.path.join(util.GOLDEN, case + ".json"), os.path.join(work, case),
                     "--ranks", str(world), "--only", str(rank)], check=True)
     plan = P.read_plan(os.path.join(work, f"{case}.rank{rank}.plan"))
     whole = util.load_plan(case)
+    if pair:
+        add_second_species(plan)
+        add_second_species(whole)
     sim = capi.GpuSim(plan, device=local)
     sim.halo_bind(dist, rank, world)
     # several calls of uneven length: the flags count steps across calls
@@ -46,14 +75,14 @@ def run_case(case, rank, world, local):
     dist.gather_object((plan.y_start, mine, emit), gathered if rank == 0 else None, dst=0)
     ok = True
     if rank == 0:
-        expect = util.load_expect(case)
+        expect = oracle_expect(whole, util.state_names(whole)) if pair else util.load_expect(case)
         gathered.sort(key=lambda t: t[0])
         for n in names:
             got = np.concatenate([g[1][n] for g in gathered], axis=0)
             ref = expect[n][1:-1]
             if not np.array_equal(got, ref):
                 ok = False
-                print(f"MISMATCH {case}/{n}: max |diff| {np.abs(got - ref).max():.3e} of {np.abs(ref).max():.3e}")
+                log(f"MISMATCH {case}/{n}: max |diff| {np.abs(got - ref).max():.3e} of {np.abs(ref).max():.3e}")
         if whole.dfts:
             ref = util.dft_point_map(whole, [expect[f"dft{k}r"].ravel() + 1j * expect[f"dft{k}i"].ravel() for k in range(len(whole.dfts))])
             got = {}
@@ -61,16 +90,16 @@ def run_case(case, rank, world, local):
                 for key, v in g[1]["__dft__"].items():
                     if key in got and got[key] != v:
                         ok = False
-                        print(f"MISMATCH {case}: accumulator {key} differs between slabs")
+                        log(f"MISMATCH {case}: accumulator {key} differs between slabs")
                     got[key] = v
             if set(got) != set(ref):
                 ok = False
-                print(f"MISMATCH {case}: the slabs hold {len(got)} DFT accumulators, the single-rank run {len(ref)}")
+                log(f"MISMATCH {case}: the slabs hold {len(got)} DFT accumulators, the single-rank run {len(ref)}")
             else:
                 nbad = sum(1 for key in ref if ref[key] != got[key])
                 if nbad:
                     ok = False
-                    print(f"MISMATCH {case}: {nbad} of {len(ref)} DFT accumulators differ from the reference")
+                    log(f"MISMATCH {case}: {nbad} of {len(ref)} DFT accumulators differ from the reference")
         for q, e in enumerate(whole.emitters):
             gcoord = np.stack([e.box_lo[0] + e.loc[:, 0], e.box_lo[1] + e.loc[:, 1], e.box_lo[2] + e.loc[:, 2]], axis=1)
             index = {tuple(c): i for i, c in enumerate(gcoord)}
@@ -89,17 +118,17 @@ def run_case(case, rank, world, local):
                             ref = (r[:, 0::2] + 1j * r[:, 1::2])[idx]
                             if not np.array_equal(states[sy][w], ref):
                                 ok = False
-                                print(f"MISMATCH {case}/q{q}s{sy}w{w}: max |diff| {np.abs(states[sy][w] - ref).max():.3e}")
+                                log(f"MISMATCH {case}/q{q}s{sy}w{w}: max |diff| {np.abs(states[sy][w] - ref).max():.3e}")
             if seen != e.nemit:
                 ok = False
-                print(f"MISMATCH {case}: {seen} emitters over the slabs, {e.nemit} in the single-rank run")
+                log(f"MISMATCH {case}: {seen} emitters over the slabs, {e.nemit} in the single-rank run")
             for d in range(e.npop):
                 r = expect[f"q{q}pop{d}"][:, 0, :]
                 ref = r[:, 0] + 1j * r[:, 1]
                 if pops is None or len(pops[d]) != len(ref) or np.abs(pops[d] - ref).max() > 1e-9 * max(np.abs(ref).max(), 1e-300):
                     ok = False
-                    print(f"MISMATCH {case}/q{q}pop{d}")
-        print(f"{case}: {'SLAB_GPU_OK' if ok else 'SLAB_GPU_FAIL'} ({world} slabs, {launches} launches on rank 0)")
+                    log(f"MISMATCH {case}/q{q}pop{d}")
+        log(f"{case}{'+pair' if pair else ''}: {'SLAB_GPU_OK' if ok else 'SLAB_GPU_FAIL'} ({world} slabs, {launches} launches on rank 0)")
     return ok
 
 

@@ -95,3 +95,46 @@ def test_detector_series_matches_oracle(case, oracle_lib):
     assert np.max(np.abs(got - ref)) <= 1e-9 * scale
     assert np.array_equal(got, ref)
     gpu.close(); cpu.close()
+
+
+def test_detector_and_population_rings_wrap_and_grow(oracle_lib):
+    """Sample rings (include/chiml_gpu.h: read, then consume): a host that drains after every call keeps the rings at their initial
+    size over a run of 3 x the ring capacity (device memory does not grow, samples wrap around); a host that never consumes gets the
+    same series from rings that were re-allocated -- at the start of a call, with the retained samples unwrapped."""
+    plan = util.load_plan("ml_tm")
+    total, chunk = 12500, 700
+    a, b = capi.GpuSim(plan), capi.GpuSim(plan)
+    bytes0 = a.device_bytes()
+    det, pop = [], []
+    done = 0
+    while done < total:
+        n = min(chunk, total - done)
+        a.step_n(n); b.step_n(n)
+        d = a.detector(0)
+        det.append(d)
+        a.consume_detector(0, sum(len(x) for x in det))
+        p = a.population(0, 0)
+        pop.append(p)
+        a.consume_population(0, sum(len(x) for x in pop))
+        done += n
+    assert a.device_bytes() == bytes0, "a drained ring must not grow"
+    assert b.device_bytes() > bytes0, "an undrained ring of 12 501 samples must have grown beyond its 4096 slots"
+    det, pop = np.concatenate(det), np.concatenate(pop)
+    assert det.shape[0] == total + 1 and pop.shape[0] == total
+    assert np.array_equal(det, b.detector(0))
+    assert np.array_equal(pop, b.population(0, 0))
+    # consumed samples are gone, later ones are still addressable by absolute number
+    out = np.empty((4,) + det.shape[1:])
+    assert a.detector_range(0, 10, 4, out) == 0
+    b.consume_detector(0, total - 2)
+    assert b.detector_range(0, total - 2, 4, out) == 3 and np.array_equal(out[:3], det[total - 2:])
+    # the first steps agree with the CPU oracle (the series is not merely self-consistent)
+    cpu = OracleSim(plan)
+    d0 = plan.detectors[0]
+    (x0, y0, z0), _ = capi.local_box(plan, d0.loc, d0.sz)
+    ref = [cpu.field(d0.field)[y0, z0, x0]]
+    for _ in range(50):
+        cpu.step_n(1)
+        ref.append(cpu.field(d0.field)[y0, z0, x0])
+    assert np.array_equal(det[:51, 0, 0, 0], np.array(ref))
+    a.close(); b.close(); cpu.close()

@@ -29,7 +29,7 @@ def _env(march):
 def test_two_slabs_over_nvlink_match_single_rank_reference(march):
     if capi.device_count() < 2:
         pytest.skip("needs two GPUs")
-    cases = ["vac3d", "aniso_slab3d", "lorentz3d", "ml3d_two", "ml3d_four", "ml_te", "ml_tm", "tm_au", "te_vacuum", "c4_small", "flux3d", "te_flux", "tm_flux"]
+    cases = ["vac3d", "aniso_slab3d", "lorentz3d", "ml3d_two", "ml3d_four", "ml_te", "ml_tm", "tm_au", "te_vacuum", "c4_small", "flux3d", "te_flux", "tm_flux", "aniso_mixed3d", "ml3d_two+pair", "c4_small+pair"]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29733", os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
                        capture_output=True, text=True, timeout=900, env=_env(march))
@@ -42,10 +42,24 @@ def test_two_slabs_over_nvlink_match_single_rank_reference(march):
 def test_four_slabs_match_single_rank_reference_even_on_one_gpu(march):
     """Four slabs on however many GPUs there are (ranks wrap around the devices).  c4_small at four slabs has a slab that holds
     only the rim of the emitter sheet (an emitter set without emitters), flux3d has flux surfaces cut by slab boundaries."""
-    cases = ["aniso_slab3d", "ml3d_two", "c4_small", "flux3d"]
+    cases = ["aniso_slab3d", "ml3d_two", "c4_small", "flux3d", "aniso_mixed3d", "ml3d_two+pair", "ml_te+pair"]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
                         "--master-port", "29734", os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
                        capture_output=True, text=True, timeout=900, env=_env(march))
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    for c in cases:
+        assert f"{c}: SLAB_GPU_OK" in r.stdout, r.stdout[-4000:]
+
+
+def test_eight_slabs_of_three_rows_match_single_rank_reference():
+    """The cases bench.py steps across its N ranks before it times anything (HALO_PARITY_CASES), at the largest N: slabs of three
+    grid rows -- every row but one is a slab-boundary row -- sharing however many GPUs there are."""
+    sys.path.insert(0, ROOT)
+    import bench
+    cases = bench.HALO_PARITY_CASES
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=8", "--master-addr", "127.0.0.1",
+                        "--master-port", "29735", os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
+                       capture_output=True, text=True, timeout=900, env=_env(None))
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     for c in cases:
         assert f"{c}: SLAB_GPU_OK" in r.stdout, r.stdout[-4000:]

@@ -13,6 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("case,world", [("aniso_slab3d", 2), ("ml3d_two", 2), ("ml3d_four", 3), ("ml_te", 2), ("c4_small", 2), ("flux3d", 3), ("te_flux", 2),
                                         ("tm_flux", 2),
+                                        # oriented-dipole objects of finite y extent and different pole counts: slabs without node cells
+                                        ("aniso_mixed3d", 4), ("aniso_mixed3d", 3),
                                         # random inputs (tests/fuzz/gen_inputs.py), expected arrays from the single-rank oracle
                                         ("fuzz:4", 4), ("fuzz:12", 3), ("fuzz:33", 3), ("fuzz:10:ml", 4), ("fuzz:14:ml", 2)])
 def test_slab_protocol_matches_single_rank_reference(case, world):
