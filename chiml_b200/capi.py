@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_download_emitter_state", "chiml_gpu_download_emitter_pol", "chiml_gpu_read_population",
     "chiml_gpu_halo_export", "chiml_gpu_halo_bind", "chiml_gpu_add_dft", "chiml_gpu_step_n_dft", "chiml_gpu_download_dft",
     "chiml_gpu_set_march", "chiml_gpu_set_ordip_pole_count", "chiml_gpu_reserve_steps", "chiml_gpu_consume_detector",
-    "chiml_gpu_consume_population",
+    "chiml_gpu_consume_population", "chiml_gpu_set_persistent",
 ]
 
 
@@ -129,6 +129,7 @@ def lib() -> C.CDLL:
     L.chiml_gpu_sync.argtypes = [vp]
     L.chiml_gpu_step_n_timed.argtypes = [vp, i, vp, vp, C.POINTER(C.c_float)]
     L.chiml_gpu_set_ordip_pole_count.argtypes = [vp, i]
+    L.chiml_gpu_set_persistent.argtypes = [vp, i]
     L.chiml_gpu_reserve_steps.argtypes = [vp, C.c_longlong]
     L.chiml_gpu_consume_detector.argtypes = [vp, i, sz]
     L.chiml_gpu_consume_population.argtypes = [vp, i, sz]
@@ -174,7 +175,7 @@ def _ptr(a: Optional[np.ndarray]):
 class GpuSim:
     """One y-slab of the propagator on one GPU, configured from a Plan (the reference's own lists)."""
 
-    def __init__(self, plan: P.Plan, device: int = 0, detectors: bool = True, march=None):
+    def __init__(self, plan: P.Plan, device: int = 0, detectors: bool = True, march=None, persistent: Optional[bool] = None):
         """march: None (automatic column length), an int, or (fast, uniform) planes per column of the y-marching kernels."""
         L = lib()
         self.plan = plan
@@ -225,6 +226,8 @@ class GpuSim:
                     self.det_slots.append(slot.value)
             if plan.nranks > 1:
                 self._chk(L.chiml_gpu_set_ordip_pole_count(self.h, plan.n_ordip_poles))
+            if persistent is not None:
+                self._chk(L.chiml_gpu_set_persistent(self.h, 1 if persistent else 0))
             if march is not None:
                 mf, mu = (march, march) if isinstance(march, int) else march
                 self._chk(L.chiml_gpu_set_march(self.h, mf, mu))

@@ -157,7 +157,7 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     for(auto& e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamSynchronize(ctx->hstream);
     for(HaloPeer* pr : {&ctx->lower, &ctx->upper}) for(void* b : pr->opened) cudaIpcCloseMemHandle(b);
-    cudaFree(ctx->d_flags); cudaFree(ctx->d_push_counter);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_push_counter); cudaFree(ctx->d_persist_sa);
     for(auto& g : ctx->d_oPy_ghost) cudaFree(g);
     cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_push);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -206,6 +206,13 @@ int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global)
     if(n_poles_global < 0) return fail(ctx, CHIML_ERR_ARG, "set_ordip_pole_count: negative count");
     if(n_poles_global > MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_ordip_pole_count: more than 12 poles per object");
     ctx->nordip_global = n_poles_global;
+    return CHIML_OK;
+}
+
+int chiml_gpu_set_persistent(ChimlCtx* ctx, int on)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    ctx->persist_mode = on ? 1 : 0;
     return CHIML_OK;
 }
 
@@ -286,8 +293,12 @@ int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq,
         if(lines[l].out < 0 || (size_t)lines[l].out + (size_t)nfreq * npts > acc_len) return fail(ctx, CHIML_ERR_ARG, "add_dft: line leaves the accumulator");
     }
     DftDev d;
-    d.field = field; d.group = group; d.every = every; d.nfreq = nfreq; d.npts = npts; d.stride = stride; d.nlines = nlines; d.acc_len = acc_len;
-    d.h_lines.assign(lines, lines + nlines);
+    d.field = field; d.group = group; d.every = every; d.nfreq = nfreq; d.npts = npts; d.stride = stride; d.acc_len = acc_len;
+    // fInGridInds_ is sized for the whole surface; a rank that holds part of it leaves the tail (0, 0).  Those entries would all add
+    // the (zero) corner ghost cell into accumulator 0 -- harmless on the CPU, a read-modify-write race with the real line 0 here
+    for(size_t l = 0; l < nlines; ++l)
+        if(l == 0 || lines[l].ind != 0 || lines[l].out != 0) d.h_lines.push_back(lines[l]);
+    d.nlines = d.h_lines.size();
     if(slot) *slot = (int)ctx->dfts.size();
     ctx->dfts.push_back(std::move(d));
     return CHIML_OK;
@@ -348,6 +359,30 @@ int chiml_gpu_add_emitters(ChimlCtx* ctx, const ChimlEmitterDesc* d, int* slot)
 // commit helpers
 // ---------------------------------------------------------------------------------------------------
 namespace {
+
+// lanes per emitter of the density kernel (chiml_emitters.cuh): 0 = one thread per emitter (N = 2, 3: no or small spills; N = 6: more
+// elements than a warp has lanes), else the group kernel (N = 4, 5).  CHIML_B200_EMIT_KERNEL=thread|group overrides (tests, A/B).
+int emitter_group(int nlevel)
+{
+    const int g = nlevel == 2 ? 4 : (nlevel <= 4 ? 16 : 32);
+    if(nlevel > 5) return 0;
+    if(const char* ev = std::getenv("CHIML_B200_EMIT_KERNEL")) return std::strcmp(ev, "group") == 0 ? g : 0;
+    return nlevel >= 4 ? g : 0;
+}
+
+// algorithmic bytes one field-component cell with this info value moves per step (the host twin of cell_alg_bytes, chiml_update.cuh)
+double info_alg_bytes(const unsigned info, const ClassEntry* cls, const bool isE, const bool pmlOnD)
+{
+    if(info == 0) return 0.0;
+    const bool pml = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
+    double b = 0.0;
+    if((info & F_CURL) || (info & (F_PG0 | F_PG1))) b += 24;
+    if(isE && ((info & (F_ISD | F_D2E | F_ORD2E)) || (pmlOnD && pml))) b += 16;
+    if(isE && (info & F_D2E)) b += 24.0 * cls[info & CLS_MASK].npoles;
+    if(info & F_PS0) b += 16;
+    if(info & F_PS1) b += 16;
+    return b;
+}
 
 struct ClassKey
 {
@@ -446,9 +481,16 @@ int build_spans(ChimlCtx* ctx, const std::vector<const std::vector<ChimlRun>*>& 
             if(sp.h_xmin[row] < 0 || x0 < sp.h_xmin[row]) sp.h_xmin[row] = x0;
             if(x1 > sp.h_xmax[row]) sp.h_xmax[row] = x1;
         }
+    // spans start at an even x and have an even length, so that the pool offset of an even x is even: the kernels access the
+    // pools two cells (16 bytes, aligned) at a time.  The padding cells are never updated and stay zero.
     int64_t total = 0;
     for(size_t row = 0; row < nrows; ++row)
-        if(sp.h_xmin[row] >= 0) { sp.h_base[row] = total; total += sp.h_xmax[row] - sp.h_xmin[row] + 1; }
+        if(sp.h_xmin[row] >= 0)
+        {
+            sp.h_xmin[row] &= ~1;
+            sp.h_xmax[row] |= 1;
+            sp.h_base[row] = total; total += sp.h_xmax[row] - sp.h_xmin[row] + 1;
+        }
     sp.total = total;
     std::vector<int32_t> rows;
     sp.max_width = 0;
@@ -456,7 +498,7 @@ int build_spans(ChimlCtx* ctx, const std::vector<const std::vector<ChimlRun>*>& 
         if(sp.h_xmin[row] >= 0)
         {
             rows.push_back((int32_t)row);
-            sp.max_width = std::max(sp.max_width, sp.h_xmax[row] - (sp.h_xmin[row] & ~1) + 1);
+            sp.max_width = std::max(sp.max_width, sp.h_xmax[row] - sp.h_xmin[row] + 1);
         }
     sp.nrows_used = (int)rows.size();
     int rc;
@@ -795,7 +837,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 rec.z0 = (int)((tIdx / nxt) % nzt) * (int)tb.y;
                 rec.y = (int)(tIdx / ((size_t)nxt * nzt));
                 rec.ny = 1;
-                bool fast = true, uniform = true;
+                bool uniform = true;
                 // a component's cells must fall into a few rectangles of one info value each; a record carries two of them per component,
                 // so a tile cut by several CPML / material boundaries becomes several records (k_uniform blocks)
                 std::vector<TileVal> vals[3];
@@ -812,19 +854,21 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                                           ts.info[c][2], ts.count[c][2], ts.total[c]);
                             auto& e = dbgWhy[key]; ++e.first; e.second += ts.bytes;
                         }
-                        fast = uniform = false; continue;
+                        uniform = false; continue;
                     }
-                    for(const TileVal& v : vals[c])
-                        if((v.info & 0xFF00u) != F_CURL || vals[c].size() > 1) fast = false;
                 }
                 if(!uniform) { lists[2].push_back(rec); listBytes[2] += ts.bytes; continue; }
                 const int per = rectangles_per_record(vals);
                 int nrec = 1;
                 for(int c = 0; c < 3; ++c) nrec = std::max(nrec, ((int)vals[c].size() + per - 1) / per);
+                double tileBytes = 0.0;
                 for(int k = 0; k < nrec; ++k)
                 {
                     TileRec part = rec;
                     part.part = (unsigned)k;
+                    // a record whose rectangles are all plain curl cells is a k_fast record (all three components per thread)
+                    bool recFast = nrec == 1;
+                    double recBytes = 0.0;
                     for(int c = 0; c < 3; ++c)
                         for(int w = per * k; w < std::min((int)vals[c].size(), per * k + per); ++w)
                         {
@@ -832,11 +876,54 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                             const ClassEntry& ce = ctx->h_cls[b0 + c][inf & CLS_MASK];
                             const unsigned npc = (fam == 0 && (inf & F_D2E)) ? (unsigned)ce.npoles << (8 * c) : 0u;    // isotropic poles of the class
                             if(w == per * k) { part.rect[c] = vals[c][w].rect; part.info[c] = inf; part.pf[c] = make_double2(ce.pf1, ce.pf2); part.inv_eps[c] = ce.inv_eps; part.np |= npc; }
-                            else           { part.rectB[c] = vals[c][w].rect; part.infoB[c] = inf; part.pfB[c] = make_double2(ce.pf1, ce.pf2); part.inv_epsB[c] = ce.inv_eps; part.npB |= npc; }
+                            else           { part.rectB[c] = vals[c][w].rect; part.infoB[c] = inf; part.pfB[c] = make_double2(ce.pf1, ce.pf2); part.inv_epsB[c] = ce.inv_eps; part.npB |= npc; recFast = false; }
+                            if((inf & 0xFF00u) != F_CURL) recFast = false;
+                            recBytes += (double)rect_area(vals[c][w].rect) * info_alg_bytes(inf, ctx->h_cls[b0 + c].data(), fam == 0, ctx->g.pml_on_D != 0);
                         }
-                    lists[fast ? 0 : 1].push_back(part);
+                    lists[recFast ? 0 : 1].push_back(part);
+                    listBytes[recFast ? 0 : 1] += recBytes;
+                    tileBytes += recBytes;
                 }
-                listBytes[fast ? 0 : 1] += ts.bytes;
+                if(tileBytes != (double)ts.bytes) return fail(ctx, CHIML_ERR_STATE, "internal: the records of a tile do not account for its cells");
+            }
+            // (Cutting x-runs of equal records afresh from the start of the run, so that only the last record of a run is partial, was
+            // measured and dropped: record origins that are not multiples of 64 cells cost k_fast 8 % on EVERY interior tile --
+            // profiles/README.md r2_07.)
+            // narrow UNIFORM records of two z-adjacent tiles become one record worked on by half-warps (k_uniform, REC_WIDE2)
+            if(ctx->lz > 1 && uniform_split<true>() == 1 && uniform_split<false>() == 1 && !std::getenv("CHIML_B200_NO_WIDE2"))
+            {
+                std::vector<TileRec>& ul = lists[1];
+                std::map<std::tuple<int, int, int, unsigned>, size_t> at;
+                for(size_t i = 0; i < ul.size(); ++i) at[std::make_tuple(ul[i].y, ul[i].z0, ul[i].x0, ul[i].part)] = i;
+                std::vector<char> dead(ul.size(), 0);
+                for(size_t i = 0; i < ul.size(); ++i)
+                {
+                    TileRec& p = ul[i];
+                    if(dead[i] || p.z0 % (2 * TILE_Z) != 0) continue;
+                    auto it = at.find(std::make_tuple(p.y, p.z0 + TILE_Z, p.x0, p.part));
+                    if(it == at.end() || dead[it->second]) continue;
+                    const TileRec& q = ul[it->second];
+                    unsigned xlo = 255, xhi = 0;
+                    bool ok = true;
+                    for(int c = 0; c < 3 && ok; ++c)
+                    {
+                        if(p.rectB[c] || q.rectB[c] || (p.rect[c] == 0) != (q.rect[c] == 0)) { ok = false; break; }
+                        if(!p.rect[c]) continue;
+                        ok = (p.rect[c] & 0xFFFFu) == (q.rect[c] & 0xFFFFu) && (p.rect[c] >> 24) == (unsigned)TILE_Z && ((q.rect[c] >> 16) & 0xFFu) == 0u &&
+                             p.info[c] == q.info[c] && std::memcmp(&p.pf[c], &q.pf[c], sizeof(double2)) == 0 && p.inv_eps[c] == q.inv_eps[c];
+                        xlo = std::min(xlo, p.rect[c] & 0xFFu); xhi = std::max(xhi, (p.rect[c] >> 8) & 0xFFu);
+                    }
+                    if(!ok || p.np != q.np || xhi <= xlo || xhi - (xlo & ~1u) > 32u) continue;
+                    for(int c = 0; c < 3; ++c)
+                        if(p.rect[c]) p.rect[c] = (p.rect[c] & 0x00FFFFFFu) | (((unsigned)TILE_Z + (q.rect[c] >> 24)) << 24);
+                    p.part |= REC_WIDE2;
+                    p.pad4 = xlo & ~1u;
+                    dead[it->second] = 1;
+                }
+                std::vector<TileRec> kept;
+                kept.reserve(ul.size());
+                for(size_t i = 0; i < ul.size(); ++i) if(!dead[i]) kept.push_back(ul[i]);
+                ul.swap(kept);
             }
             if(dbgTiles)
             {
@@ -937,10 +1024,15 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         const size_t per = (size_t)em.d.nsys * em.n2 * 2 * (size_t)std::max(em.d.nemit, 1);
         std::vector<double> rho0(per, 0.0);
         for(int sy = 0; sy < em.d.nsys; ++sy)
-            for(int e = 0; e < em.d.nemit; ++e) rho0[((size_t)sy * em.n2 * 2) * em.d.nemit + e] = em.h_weight[sy];
+            for(int e = 0; e < em.d.nemit; ++e)      // element (sys, e, k = 0), real part, in the layout of the kernel that will run
+                rho0[em.group ? ((size_t)sy * em.d.nemit + e) * em.n2 * 2 : ((size_t)sy * em.n2 * 2) * em.d.nemit + e] = em.h_weight[sy];
         if((rc = dev_upload(ctx, &em.d_rho, rho0))) return rc;
         for(int k = 0; k < 4; ++k) if((rc = dev_alloc(ctx, &em.d_f[k], per))) return rc;
-        em.nblocks = (em.d.nemit + 127) / 128;
+        em.group = emitter_group(em.d.nlevel);
+        const int epb = em.group ? 128 / em.group : 128;
+        em.nblocks = (em.d.nemit + epb - 1) / epb;
+        em.gam_maxrow = 0;
+        for(int ii = 0; ii < em.n2; ++ii) em.gam_maxrow = std::max(em.gam_maxrow, em.h_gam_ptr[ii + 1] - em.h_gam_ptr[ii]);
         if((rc = dev_alloc(ctx, &em.d_pop_partial, (size_t)std::max(em.d.npop, 1) * std::max(em.nblocks, 1) * 2))) return rc;
         em.pop_cap = 4096;
         if((rc = dev_alloc(ctx, &em.d_pop, (size_t)std::max(em.d.npop, 1) * em.pop_cap * 2))) return rc;
@@ -1088,11 +1180,12 @@ void launch_family(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int part)
     else                                  launch_family_mode<IS_E, CHIML_MODE_TM>(ctx, a, block, part);
 }
 
-template <int N>
-void launch_density(ChimlCtx* ctx, const EmitArgs& ea, int nblocks)
+template <int N, int G>
+void launch_density_g(ChimlCtx* ctx, const EmitArgs& ea)
 {
-    k_emit_density<N><<<nblocks, 128, 0, ctx->stream>>>(ea);
+    k_emit_density_g<N, G><<<(ea.nemit + 128 / G - 1) / (128 / G), 128, 0, ctx->stream>>>(ea);
 }
+
 
 // rows of [y0, y1) that are / are not slab-boundary rows (local row 1 with a slab below, row ly-2 with a slab above)
 struct RowSeg { int y0, y1; };
@@ -1164,13 +1257,18 @@ int launch_density_step(ChimlCtx* ctx, EmitterDev& em)
         ea.pop_partial = em.d_pop_partial;
         {
             LaunchScope ls(ctx, K_EMIT_DENSITY);
-            switch(em.d.nlevel)
+            ea.gam_maxrow = em.gam_maxrow;
+            switch(em.d.nlevel * (em.group ? 10 : 1))
             {
-                case 2: launch_density<2>(ctx, ea, em.nblocks); break;
-                case 3: launch_density<3>(ctx, ea, em.nblocks); break;
-                case 4: launch_density<4>(ctx, ea, em.nblocks); break;
-                case 5: launch_density<5>(ctx, ea, em.nblocks); break;
-                default: launch_density<6>(ctx, ea, em.nblocks); break;
+                case 2:  k_emit_density<2><<<em.nblocks, 128, 0, ctx->stream>>>(ea); break;
+                case 3:  k_emit_density<3><<<em.nblocks, 128, 0, ctx->stream>>>(ea); break;
+                case 4:  k_emit_density<4><<<em.nblocks, 128, 0, ctx->stream>>>(ea); break;
+                case 5:  k_emit_density<5><<<em.nblocks, 128, 0, ctx->stream>>>(ea); break;
+                case 6:  k_emit_density<6><<<em.nblocks, 128, 0, ctx->stream>>>(ea); break;
+                case 20: launch_density_g<2, 4>(ctx, ea); break;
+                case 30: launch_density_g<3, 16>(ctx, ea); break;
+                case 40: launch_density_g<4, 16>(ctx, ea); break;
+                default: launch_density_g<5, 32>(ctx, ea); break;
             }
         }
         em.fbase = (em.fbase + 3) % 4;   // the slot that held f_{n-3} now holds the new f_n
@@ -1437,6 +1535,105 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
 // samples a detector with interval `every` takes during steps (sc, sc + n]
 size_t samples_in(long long sc, long long n, int every) { return (size_t)((sc + n) / every - sc / every); }
 
+// ---- 2-D grids: all n steps in one cooperative launch (chiml_persist.cuh) ------------------------------------------------------
+template <int MODE> int persist_occupancy(int* perSM)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(perSM, k_steps_2d<MODE>, 256, 0) == cudaSuccess ? 0 : 1;
+}
+
+bool persist_eligible(ChimlCtx* ctx)
+{
+    if(ctx->persist_mode == 0 || std::getenv("CHIML_B200_NO_PERSIST")) return false;
+    if(ctx->g.mode == CHIML_MODE_3D || ctx->g.nranks > 1 || !ctx->emitters.empty() || ctx->d_info_node) return false;
+    if((int)ctx->detectors.size() > P2D_MAX_DET || (int)ctx->dfts.size() > P2D_MAX_DFT) return false;
+    // sources are injected by one grid-wide pass: two boxes on the same field must not overlap (the launch path adds them one after the other)
+    for(size_t i = 0; i < ctx->sources.size(); ++i)
+        for(size_t j = i + 1; j < ctx->sources.size(); ++j)
+        {
+            const SourceDev &p = ctx->sources[i], &q = ctx->sources[j];
+            bool apart = p.field != q.field;
+            for(int k = 0; k < 3; ++k) if(p.loc[k] + p.sz[k] <= q.loc[k] || q.loc[k] + q.sz[k] <= p.loc[k]) apart = true;
+            if(!apart) return false;
+        }
+    if(ctx->persist_blocks < 0)
+    {
+        ctx->persist_blocks = 0;
+        int coop = 0, sms = 0, perSM = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        const int bad = ctx->g.mode == CHIML_MODE_TE ? persist_occupancy<CHIML_MODE_TE>(&perSM) : persist_occupancy<CHIML_MODE_TM>(&perSM);
+        if(coop && !bad && perSM > 0) ctx->persist_blocks = sms * std::min(perSM, 4);
+        cudaGetLastError();
+    }
+    return ctx->persist_blocks > 0;
+}
+
+int launch_steps_2d(ChimlCtx* ctx, int n, int nsrc)
+{
+    Persist2DArgs pa;
+    std::memset(&pa, 0, sizeof(pa));
+    if(!ctx->d_persist_sa)
+    {
+        // the argument blocks of the two half steps, the E one for either parity of the pole buffers: uploaded once
+        StepArgs sa[3];
+        const int keep = ctx->pcur;
+        fill_step_args(ctx, false, sa[0]);
+        ctx->pcur = 0; fill_step_args(ctx, true, sa[1]);
+        ctx->pcur = 1; fill_step_args(ctx, true, sa[2]);
+        ctx->pcur = keep;
+        CK(cudaMalloc(&ctx->d_persist_sa, sizeof(sa))); ctx->dev_bytes += sizeof(sa);
+        // ON THE CONTEXT'S STREAM: a synchronous cudaMemcpy from pageable memory returns once the data is staged, the DMA follows on the
+        // legacy stream -- which a non-blocking stream does not wait for; with a busy copy engine the kernel below then read the argument
+        // blocks of whichever simulation owned this allocation before
+        CK(cudaMemcpyAsync(ctx->d_persist_sa, sa, sizeof(sa), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    pa.sa = reinterpret_cast<const StepArgs*>(ctx->d_persist_sa);
+    pa.pcur0 = ctx->pcur;
+    for(int fam = 0; fam < 2; ++fam)
+        for(int k = 0; k < 3; ++k) { pa.tiles[fam][k] = (const TileRec*)ctx->d_tiles[fam][k]; pa.ntiles[fam][k] = ctx->ntiles[fam][k]; }
+    pa.nsteps = n; pa.nsrc = nsrc; pa.step0 = ctx->step_count;
+    for(int q = 0; q < nsrc; ++q) pa.src[q] = ctx->sources[q];
+    pa.src_amp = ctx->d_src_amp;
+    for(int f = 0; f < CHIML_NFIELDS; ++f) pa.field[f] = ctx->d_field[f];
+    pa.ndet = (int)ctx->detectors.size();
+    for(int d = 0; d < pa.ndet; ++d)
+    {
+        const DetectorDev& dt = ctx->detectors[d];
+        P2DDetector& o = pa.det[d];
+        o.field = dt.field; o.every = dt.every; o.ring = dt.d_ring; o.cap = dt.cap; o.count0 = dt.count; o.sample_len = dt.sample_len;
+        for(int k = 0; k < 3; ++k) { o.loc[k] = dt.loc[k]; o.sz[k] = dt.sz[k]; }
+    }
+    pa.ndft = (int)ctx->dfts.size();
+    size_t per_step = 0;
+    std::vector<size_t> goff(ctx->dft_group_nfreq.size(), 0);
+    for(size_t g = 0; g < ctx->dft_group_nfreq.size(); ++g) { goff[g] = per_step; per_step += 2 * (size_t)ctx->dft_group_nfreq[g]; }
+    for(int q = 0; q < pa.ndft; ++q)
+    {
+        const DftDev& d = ctx->dfts[q];
+        P2DDft& o = pa.dft[q];
+        o.field = d.field; o.group = d.group; o.every = d.every; o.nfreq = d.nfreq; o.npts = d.npts; o.stride = d.stride;
+        o.lines = d.d_lines; o.nlines = d.nlines; o.re = d.d_re; o.im = d.d_im; o.tw_off = goff[d.group];
+    }
+    pa.tw = ctx->d_tw; pa.tw_per_step = per_step;
+    pa.lx = ctx->lx; pa.lz = ctx->lz; pa.px = ctx->px;
+    // no more blocks than there are work items in the largest phase (8 warps per block, one item per warp at a time)
+    unsigned items = 1;
+    for(int fam = 0; fam < 2; ++fam) items = std::max(items, ctx->ntiles[fam][0] + 3 * ctx->ntiles[fam][1] + 3 * ctx->ntiles[fam][2]);
+    const unsigned blocks = std::max(1u, std::min((unsigned)ctx->persist_blocks, (items + 7) / 8));
+    void* args[] = {&pa};
+    {
+        LaunchScope ls(ctx, K_STEPS_2D);
+        const void* fn = ctx->g.mode == CHIML_MODE_TE ? (const void*)k_steps_2d<CHIML_MODE_TE> : (const void*)k_steps_2d<CHIML_MODE_TM>;
+        CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(32, 8, 1), args, 0, ctx->stream));
+    }
+    // host bookkeeping of what the launch does on the device
+    for(DetectorDev& dt : ctx->detectors) dt.count += samples_in(ctx->step_count, n, dt.every);
+    ctx->step_count += n;
+    if(n & 1) ctx->pcur = 1 - ctx->pcur;
+    return 0;
+}
+
+
 // Makes room in the detector and population rings for the samples of the next n steps, so that the step loop itself never allocates
 // or synchronises.  A ring grows only when the host has not consumed what it holds (chiml_gpu_consume_detector / _population).
 int reserve_rings(ChimlCtx* ctx, long long n)
@@ -1520,11 +1717,18 @@ int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp, const double* twidd
         }
         CK(cudaMemcpyAsync(ctx->d_src_amp, src_amp, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    for(int k = 0; k < n; ++k)
+    // (a call of one or two steps costs the same either way: seven short launches against one cooperative launch)
+    if(n > 2 && persist_eligible(ctx))
     {
-        int rc = launch_step(ctx, k, nsrc);
-        if(rc) return fail(ctx, rc, "launch failed");
+        int rc = launch_steps_2d(ctx, n, nsrc);
+        if(rc) return rc;
     }
+    else
+        for(int k = 0; k < n; ++k)
+        {
+            int rc = launch_step(ctx, k, nsrc);
+            if(rc) return fail(ctx, rc, "launch failed");
+        }
     CK(cudaGetLastError());
     return CHIML_OK;
 }
@@ -1735,7 +1939,7 @@ int chiml_gpu_n_kernel_kinds(void) { return K_NKINDS; }
 int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out)
 {
     static const char* names[K_NKINDS] = {"k_fast<E>", "k_uniform<E>", "k_general<E>", "k_fast<H>", "k_uniform<H>", "k_general<H>",
-                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft"};
+                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft", "k_steps_2d"};
     if(!ctx || !out || kind < 0 || kind >= K_NKINDS) return CHIML_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1812,7 +2016,7 @@ static int pole_xfer(ChimlCtx* ctx, int comp, int pole, int prev, double* host, 
     for(size_t row = 0; row < nrows; ++row)
     {
         if(sp.h_xmin[row] < 0) continue;
-        const int w = sp.h_xmax[row] - sp.h_xmin[row] + 1;
+        const int w = std::min(sp.h_xmax[row], ctx->lx - 1) - sp.h_xmin[row] + 1;     // the span's padding cell may lie beyond the logical row
         if(host) std::copy_n(&tmp[(size_t)sp.h_base[row]], w, host + row * ctx->lx + sp.h_xmin[row]);
         else     std::copy_n(hostIn + row * ctx->lx + sp.h_xmin[row], w, &tmp[(size_t)sp.h_base[row]]);
     }
@@ -1839,7 +2043,7 @@ int chiml_gpu_download_ordip_pole(ChimlCtx* ctx, int comp, int pole, int prev, d
     const size_t nrows = (size_t)ctx->ly * ctx->lz;
     for(size_t row = 0; row < nrows; ++row)
         if(sp.h_xmin[row] >= 0)
-            std::copy_n(&tmp[(size_t)sp.h_base[row]], sp.h_xmax[row] - sp.h_xmin[row] + 1, host + row * ctx->lx + sp.h_xmin[row]);
+            std::copy_n(&tmp[(size_t)sp.h_base[row]], std::min(sp.h_xmax[row], ctx->lx - 1) - sp.h_xmin[row] + 1, host + row * ctx->lx + sp.h_xmin[row]);
     return CHIML_OK;
 }
 
@@ -1938,8 +2142,14 @@ int chiml_gpu_download_emitter_state(ChimlCtx* ctx, int slot, int sys, int which
     CK(cudaStreamSynchronize(ctx->stream));
     const double* src = which == 0 ? em.d_rho : em.d_f[(em.fbase + which - 1) % 4];
     const size_t ne = (size_t)em.d.nemit, n2r = (size_t)em.n2 * 2;
+    if(ne == 0) return CHIML_OK;
+    if(em.group)      // AoS (sys, e, k, re/im): the layout asked for
+    {
+        CK(cudaMemcpy(out, src + (size_t)sys * n2r * ne, n2r * ne * sizeof(double), cudaMemcpyDeviceToHost));
+        return CHIML_OK;
+    }
     std::vector<double> soa(n2r * ne);
-    if(ne) CK(cudaMemcpy(soa.data(), src + (size_t)sys * n2r * ne, soa.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(soa.data(), src + (size_t)sys * n2r * ne, soa.size() * sizeof(double), cudaMemcpyDeviceToHost));
     for(size_t e = 0; e < ne; ++e)
         for(size_t k = 0; k < n2r; ++k) out[e * n2r + k] = soa[k * ne + e];
     return CHIML_OK;

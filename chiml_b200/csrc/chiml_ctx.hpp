@@ -89,7 +89,7 @@ struct DetectorDev
 };
 
 // kernels of the step loop, for launch / time / algorithmic-byte accounting
-enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_NKINDS };
+enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_STEPS_2D, K_NKINDS };
 struct KernelStat { int64_t launches = 0; double ms_total = 0.0; double alg_bytes = 0.0; int64_t timed = 0; };
 
 // one parallelQE object on the device (chiml_emitters.cuh)
@@ -108,6 +108,8 @@ struct EmitterDev
     int fbase = 0;                   // d_f[(fbase + k) % 4] holds d rho/dt at step n-k
     int mu_present[3] = {};
     double* d_pop_partial = nullptr; int nblocks = 0;
+    int gam_maxrow = 0;              // longest row of gam_
+    int group = 0;                   // lanes per emitter of k_emit_density_g (AoS state), or 0: k_emit_density, one thread per emitter (SoA state)
     double* d_pop = nullptr; size_t pop_cap = 0, pop_n = 0, pop_base = 0;   // ring like DetectorDev's: [npop][pop_cap] complex
     long tstep = 0;
 };
@@ -207,6 +209,11 @@ struct ChimlCtx
     chiml::HostList lists[5][6];
     chiml::HostPml hpml[6][2];
     std::vector<chiml::HostObj> objs;
+
+    // persistent multi-step kernel of 2-D grids (chiml_persist.cuh)
+    void* d_persist_sa = nullptr;                // 3 StepArgs
+    int persist_blocks = -1;                     // resident grid size, 0 = not available, -1 = not asked yet
+    int persist_mode = 1;                        // chiml_gpu_set_persistent
 
     long long step_count = 0;
     int64_t launches = 0;

@@ -176,7 +176,7 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
 // own2 = V[r], V[r+1].  Row pitch and plane stride are multiples of 16 doubles, so the y / z
 // neighbours are aligned 16-byte loads; the x neighbour needs one extra scalar.
 template <int AXIS, int SIGN>
-__device__ __forceinline__ double2 neighbour2(const double* __restrict__ V, const long r, const long px, const long plane, const double2 own2)
+__device__ __forceinline__ double2 neighbour2(const double* V, const long r, const long px, const long plane, const double2 own2)
 {
     if(AXIS == 0) return SIGN > 0 ? make_double2(own2.y, V[r + 2]) : make_double2(V[r - 1], own2.x);
     const long off = (AXIS == 2 ? px : plane) * SIGN;
@@ -253,12 +253,8 @@ __device__ __forceinline__ void store_pair(double* p, const double2 t, const boo
 // from one plane to the next, so every array crosses HBM exactly once per half step however far apart in time the tiles of
 // neighbouring planes would otherwise run (a whole y plane of tiles is ~150 MB of traffic: more than L2 holds).
 template <bool IS_E, int MODE>
-__global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles, const unsigned ntiles)
+__device__ __forceinline__ void fast_tile(const StepArgs& a, const TileRec& t, const int xl, const int zl)
 {
-    unsigned ti; int zl;
-    if(!tile_of_thread<MODE>(ntiles, ti, zl)) return;
-    const TileRec& t = tiles[ti];
-    const int xl = 2 * threadIdx.x;
     const int x = t.x0 + xl, z = t.z0 + zl;
     if(x >= a.px || z >= a.lz) return;
     constexpr int S = IS_E ? -1 : 1;
@@ -274,9 +270,12 @@ __global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArg
         if(has_own<IS_E, MODE>(c) && t.rect[c] != 0) rect_mask(t.rect[c], xl, zl, m0[c], m1[c]);
         pf[c] = t.pf[c];
     }
-    const double* __restrict__ f0 = a.fam[0];
-    const double* __restrict__ f1 = a.fam[1];
-    const double* __restrict__ f2 = a.fam[2];
+    // restrict WITHOUT const: the no-alias promise lets the loads move above the stores, but the loads stay coherent ld.global (a
+    // const restrict pointer makes them ld.global.nc, which the persistent multi-step kernel k_steps_2d must not use: there the
+    // arrays read in one half step are written in the other half step of the same launch)
+    double* __restrict__ f0 = const_cast<double*>(a.fam[0]);
+    double* __restrict__ f1 = const_cast<double*>(a.fam[1]);
+    double* __restrict__ f2 = const_cast<double*>(a.fam[2]);
     // carried planes of the y-coupled arrays: E half step: the plane below; H half step: the current plane (loaded as "next" before)
     constexpr bool Y0 = has_own<IS_E, MODE>(2) && has_other<IS_E, MODE>(0);   // own z reads other x one plane away
     constexpr bool Y2 = has_own<IS_E, MODE>(0) && has_other<IS_E, MODE>(2);   // own x reads other z one plane away
@@ -352,6 +351,14 @@ __global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArg
     }
 }
 
+template <bool IS_E, int MODE>
+__global__ void __launch_bounds__(256, 2) k_fast(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles, const unsigned ntiles)
+{
+    unsigned ti; int zl;
+    if(!tile_of_thread<MODE>(ntiles, ti, zl)) return;
+    fast_tile<IS_E, MODE>(a, tiles[ti], 2 * threadIdx.x, zl);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // k_uniform: tiles where each component has ONE info value over a rectangle: curl into E/H or D, CPML parts
 // (psi recursion + grid terms) on E/H or D, pole-free D->E.  Block-uniform control flow, no cell-info reads.
@@ -407,7 +414,7 @@ template <bool IS_E, int MODE, int C, unsigned FL, bool HOISTED = false, int PT 
 __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned rect, const unsigned info_rt, const double2 pfc, const double inv_eps,
                                              const PairLoads<IS_E, MODE>& L,
                                              const long r, const long row, const int x, const int y, const int z, const int xl, const int zl,
-                                             const int np = 0, const bool hm0 = false, const bool hm1 = false, const PmlCoef* hc = nullptr)
+                                             const int np = 0, const bool hm0 = false, const bool hm1 = false, const PmlCoef* hc = nullptr, const int ycm = -2)
 {
     // info_rt: the rectangle's info value (class bits always valid); its flag byte equals FL when FL is a compile-time constant
     const unsigned info = FL == FL_RUNTIME ? info_rt : FL;
@@ -467,7 +474,9 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
             {
                 const double bb = pp.b[y], cc = pp.c[y];
                 bv[part] = make_double2(bb, bb); cv[part] = make_double2(cc, cc);
-                const int cm = pp.cmap[y];
+                // ycm: the compact y coordinate of this plane, fetched by the marching caller one plane ahead (so that the psi load does
+                // not wait for a table lookup first)
+                const int cm = ycm != -2 ? ycm : pp.cmap[y];
                 pip[part] = x + a.px * (z + (long)a.lz * cm);
                 psv[part] = *reinterpret_cast<const double2*>(pp.psi + pip[part]);
             }
@@ -570,16 +579,16 @@ __device__ __forceinline__ void uniform_rect(const StepArgs& a, const unsigned r
             for(int p = 0; p < np; ++p)
             {
                 const double al = ce.alpha[p], xi = ce.xi[p], ga = ce.gamma[p];
-                const double* __restrict__ pc = ca.Pcur[p] + ip;
+                double* __restrict__ pc = const_cast<double*>(ca.Pcur[p]) + ip;     // not const: see k_fast
                 double* __restrict__ pn = ca.Pnew[p] + ip;
-                double c0 = 0.0, c1 = 0.0, o0 = 0.0, o1 = 0.0;
-                if(m0) { c0 = pc[0]; o0 = pn[0]; }
-                if(m1) { c1 = pc[1]; o1 = pn[1]; }
-                double t0 = dm(al, c0), t1 = dm(al, c1);
-                t0 = axpy1(t0, xi, o0);       t1 = axpy1(t1, xi, o1);
+                // the row spans of the pools start at an even x with an even length (build_spans): ip is even, both cells of the pair lie
+                // inside the span whenever one of them is updated -> one aligned 16-byte access per pool
+                const double2 cc = *reinterpret_cast<const double2*>(pc);
+                const double2 oo = *reinterpret_cast<const double2*>(pn);
+                double t0 = dm(al, cc.x), t1 = dm(al, cc.y);
+                t0 = axpy1(t0, xi, oo.x);     t1 = axpy1(t1, xi, oo.y);
                 t0 = axpy1(t0, ga, uOld.x);   t1 = axpy1(t1, ga, uOld.y);
-                if(m0) pn[0] = t0;
-                if(m1) pn[1] = t1;
+                store_pair(pn, make_double2(t0, t1), m0, m1);
                 u.x = axpy1(u.x, nie, t0);    u.y = axpy1(u.y, nie, t1);
             }
         }
@@ -690,6 +699,9 @@ __device__ __forceinline__ void uniform_comp(const StepArgs& a, const TileRec& t
 #ifndef CHIML_OCC_H
 #define CHIML_OCC_H 4
 #endif
+#ifndef CHIML_PIPE_Y
+#define CHIML_PIPE_Y 0      // measured equal on the C5 slab and on one-axis CPML probes (profiles/README.md r2_05): the L2 prefetch already covers it
+#endif
 #ifndef CHIML_PREFETCH_PLANES
 #define CHIML_PREFETCH_PLANES 1
 #endif
@@ -738,8 +750,8 @@ __device__ __forceinline__ void comp_march_load(const StepArgs& a, const long r,
 {
     constexpr int S = IS_E ? -1 : 1;
     constexpr int J = (C + 1) % 3, K = (C + 2) % 3;           // grid_j = other[J] (neighbour along axis K), grid_k = other[K] (along axis J)
-    const double* __restrict__ fj = a.fam[J];
-    const double* __restrict__ fk = a.fam[K];
+    double* __restrict__ fj = const_cast<double*>(a.fam[J]);      // not const: see k_fast
+    double* __restrict__ fk = const_cast<double*>(a.fam[K]);
     L.u[C] = make_double2(0.0, 0.0);
     if(needU) L.u[C] = *reinterpret_cast<const double2*>(a.c[C].U + r);   // not needed where D->E overwrites E
     L.v[J] = L.v[K] = L.nj[C] = L.nk[C] = make_double2(0.0, 0.0);
@@ -781,9 +793,16 @@ __device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec&
     const bool anyD = IS_E && a.c[C].D && ((FL & (F_ISD | F_D2E | F_ORD2E)) || (a.pml_on_D && (FL & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
     const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector (the prefetch unit of L2)
     const int ny = t.ny, y0 = t.y;
+    // psi of the y-normal slabs is stored under a compact y coordinate: it is looked up one plane ahead (CHIML_PIPE_Y)
+    constexpr int YPART = C == 0 ? 0 : 1;
+    constexpr bool YPSI = CHIML_PIPE_Y && C != 1 && ((FL & (YPART == 0 ? F_PS0 : F_PS1)) != 0);
+    int cmNext = -2;
+    if constexpr(YPSI) cmNext = a.c[C].pml[YPART].cmap[y0];
     for(int iy = 0; iy < ny; ++iy, r += plane)
     {
         const int y = y0 + iy;
+        const int cmCur = cmNext;
+        if constexpr(YPSI) if(iy + 1 < ny) cmNext = a.c[C].pml[YPART].cmap[y + 1];
         if(leader && iy + PREFETCH_PLANES < ny)
         {
             const long rp = r + PREFETCH_PLANES * plane;
@@ -802,7 +821,7 @@ __device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec&
         }
         PairLoads<IS_E, MODE> L;
         comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L, needU);
-        uniform_rect<IS_E, MODE, C, FL, true, POLES ? 1 : 0>(a, 0u, info, pfc, ie, L, r, z + (long)a.lz * y, x, y, z, xl, zl, np, m0, m1, &kc);
+        uniform_rect<IS_E, MODE, C, FL, true, POLES ? 1 : 0>(a, 0u, info, pfc, ie, L, r, z + (long)a.lz * y, x, y, z, xl, zl, np, m0, m1, &kc, YPSI ? cmCur : -2);
     }
 }
 
@@ -907,7 +926,12 @@ __global__ void __launch_bounds__(32 * TILE_Z / uniform_split<IS_E>(), uniform_o
 {
     constexpr int SPLIT = uniform_split<IS_E>(), ROWS = TILE_Z / SPLIT;
     const unsigned b = blockIdx.x / 3;
-    uniform_body<IS_E, MODE>(a, tiles[b / SPLIT], 2 * threadIdx.x, threadIdx.y + ROWS * (b % SPLIT), blockIdx.x % 3);
+    const TileRec& t = tiles[b / SPLIT];
+    int xl = 2 * threadIdx.x, zl = threadIdx.y + ROWS * (b % SPLIT);
+    // narrow records (CPML faces normal to x: 20 of the 64 cells of a row): two z-adjacent tiles in one record, half a warp per row,
+    // so that 10 of 16 lanes work instead of 10 of 32 (the x-face columns ran at 3.5 TB/s against 5.2 for the other faces)
+    if(SPLIT == 1 && (t.part & REC_WIDE2)) { xl = (int)t.pad4 + 2 * (threadIdx.x & 15); zl = 2 * threadIdx.y + (threadIdx.x >> 4); }
+    uniform_body<IS_E, MODE>(a, t, xl, zl, blockIdx.x % 3);
 }
 // 2-D grids: a tile is one row of 64 cells
 template <bool IS_E, int MODE>

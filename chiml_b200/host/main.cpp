@@ -240,10 +240,20 @@ int main(int argc, char** argv)
             if(detSlot[d] < 0) continue;
             const PlanDetector& pd = P.detectors[d];
             const DetectorInput& di = IP.detectors_[pd.detector];
-            if(di.cls != DTCCLASS::TXT && di.cls != DTCCLASS::BIN) continue;
+            if(di.cls != DTCCLASS::TXT && di.cls != DTCCLASS::BIN && di.cls != DTCCLASS::COUT) continue;
             int32_t loc[3], sz[3];
             local_box(P, pd, loc, sz);
             const size_t len = (size_t)sz[0] * sz[1] * sz[2];
+            // outputCollectFunction_ (DTC/parallelDTCOutputFxn.hpp): field value or |field|^2, added twice with half the factor each (the cell
+            // and its Yee-offset partner: single-component detectors have offset 0)
+            const bool power = di.type == DTCTYPE::EPOW || di.type == DTCTYPE::HPOW;
+            auto collect = [&](const double f) {
+                double point = 0.0;
+                const double v = power ? std::pow(std::abs(f), 2.0) : f;
+                point = point + (pd.conv / 2.0) * v;
+                point = point + (pd.conv / 2.0) * v;
+                return point;
+            };
             const std::vector<double>& data = detData[d];
             const size_t ns = data.size() / len;
             std::string name = di.name;
@@ -272,19 +282,13 @@ int main(int argc, char** argv)
                         {
                             for(int ii = 0; ii < sz[0]; ++ii)
                             {
-                                const double f = data[s * len + (size_t)ii + (size_t)sz[0] * ((size_t)kk + (size_t)sz[2] * (size_t)jj)];
-                                double point = 0.0;
-                                point = point + (pd.conv / 2.0) * f;
-                                point = point + (pd.conv / 2.0) * f;
-                                rowv[(size_t)ii] = point;
+                                rowv[(size_t)ii] = collect(data[s * len + (size_t)ii + (size_t)sz[0] * ((size_t)kk + (size_t)sz[2] * (size_t)jj)]);
                             }
                             out.write(reinterpret_cast<const char*>(rowv.data()), (std::streamsize)(rowv.size() * sizeof(double)));
                         }
                 }
                 continue;
             }
-            std::ofstream out(name.c_str());
-            out << "# time\tx\ty\tz\tfield" << std::endl;
             double rsl[3];
             for(int k = 0; k < 3; ++k)
             {
@@ -295,18 +299,31 @@ int main(int argc, char** argv)
                 rsl[k] = P.grid.desc.d[k] * (pd.loc[k] - half);
             }
             if(di.SI) for(int k = 0; k < 3; ++k) rsl[k] *= IP.a_ * IP.a_;     // scaled twice in the reference (parallelDTC.hpp:69,82)
+            if(di.cls == DTCCLASS::COUT)
+            {
+                // DTC/parallelDTC_COUT.cpp:18-41: to the console with the stream's default formatting, z and y descending, one line per row
+                // (the reference prints while it steps; here the samples of the whole run follow the run)
+                for(size_t s = 0; s < ns; ++s)
+                {
+                    std::cout << times[s] * pd.t_conv << "\t" << rsl[0] << "\t" << rsl[1] << '\t' << rsl[2] << '\t' << std::endl;
+                    for(int kk = sz[2] - 1; kk >= 0; --kk)
+                        for(int jj = sz[1] - 1; jj >= 0; --jj)
+                        {
+                            for(int ii = 0; ii < sz[0]; ++ii)
+                                std::cout << "\t" << collect(data[s * len + (size_t)ii + (size_t)sz[0] * ((size_t)kk + (size_t)sz[2] * (size_t)jj)]);
+                            std::cout << std::endl;
+                        }
+                }
+                continue;
+            }
+            std::ofstream out(name.c_str());
+            out << "# time\tx\ty\tz\tfield" << std::endl;
             for(size_t s = 0; s < ns; ++s)
             {
                 const double t = times[s];
                 out << std::setprecision(6) << t * pd.t_conv << "\t" << rsl[0] << "\t" << rsl[1] << "\t" << rsl[2];
                 // sample layout: x fastest, then z, then y; the reference prints y outermost, then z, then x
-                for(size_t i = 0; i < len; ++i)
-                {
-                    double point = 0.0;
-                    point = point + (pd.conv / 2.0) * data[s * len + i];
-                    point = point + (pd.conv / 2.0) * data[s * len + i];     // single-component detectors: offset 0, the same cell twice
-                    out << "\t" << std::setw(24) << std::setprecision(18) << point;
-                }
+                for(size_t i = 0; i < len; ++i) out << "\t" << std::setw(24) << std::setprecision(18) << collect(data[s * len + i]);
                 out << '\n';
             }
         }

@@ -586,9 +586,15 @@ struct CpmlBuilder
     }
 };
 
-// DTCTYPE -> stored field (single-component types; parallelFDTDField.cpp:689-826)
-int detector_field(DTCTYPE t)
+// DTCTYPE -> stored field (parallelFDTDField.cpp:689-826).  Power detectors whose components sit at different Yee positions (E power
+// in 3-D / TE, H power in 3-D / TM) are refused: the reference loops over the box of its FIRST stored field and indexes the boxes of
+// the others -- which are grown along other axes -- with it (DTC/parallelDTC_TXT.cpp:38-50), reading past their ends.
+int detector_field(DTCTYPE t, int mode)
 {
+    if(t == DTCTYPE::HPOW && mode == CHIML_MODE_TE) return CHIML_HZ;      // H power of a TE grid: Hz alone, offset 0 (:812-815)
+    if(t == DTCTYPE::EPOW && mode == CHIML_MODE_TM) return CHIML_EZ;      // E power of a TM grid: Ez alone, offset 0 (:816-819)
+    if(t == DTCTYPE::EPOW || t == DTCTYPE::HPOW)
+        throw std::logic_error("power detectors over several field components: the reference indexes the stored boxes out of bounds; not reproduced");
     switch(t)
     {
         case DTCTYPE::EX: return CHIML_EX; case DTCTYPE::EY: return CHIML_EY; case DTCTYPE::EZ: return CHIML_EZ;
@@ -833,7 +839,7 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
     {
         PlanDetector pd;
         pd.detector = dd++;
-        pd.field = detector_field(d.type);
+        pd.field = detector_field(d.type, mode);
         if(!comp_exists(mode, pd.field % 3 + (pd.field >= 3 && pd.field < 6 ? 3 : 0))) throw std::logic_error("a detector samples a field component that does not exist in this mode");
         for(int k = 0; k < 3; ++k) { pd.loc[k] = d.loc[k]; pd.sz[k] = d.sz[k]; pd.offset[k] = 0; }
         pd.every = static_cast<int>(std::floor(d.timeInt / IP.dt_));
@@ -846,6 +852,7 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
             pd.conv = (IP.I0_ / IP.a_);
             if(d.type == DTCTYPE::EX || d.type == DTCTYPE::EY || d.type == DTCTYPE::EZ) pd.conv /= EPS0() * SPEED_OF_LIGHT;
         }
+        if(d.type == DTCTYPE::EPOW || d.type == DTCTYPE::HPOW) pd.conv *= pd.conv;     // power: the square of the field factor (DTC/parallelDTC.hpp:87-91)
         P.detectors.push_back(pd);
     }
     // ---- emitters (parallelFDTDField.cpp:412-454) ----

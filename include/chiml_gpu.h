@@ -179,6 +179,11 @@ int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global);
  * CHIML_B200_MARCH_NY="fast[,uniform]" does the same for contexts that never call this). */
 int chiml_gpu_set_march(ChimlCtx* ctx, int fast_planes, int uniform_planes);
 
+/* 2-D grids (single slab, no emitters) run all n steps of a chiml_gpu_step_n call in ONE cooperative launch with grid-wide barriers
+ * between the phases of a step (csrc/chiml_persist.cuh) instead of 6-8 launches per step; results are identical.  on = 0 selects
+ * the launch-per-phase path (also: environment variable CHIML_B200_NO_PERSIST).  May be called at any time. */
+int chiml_gpu_set_persistent(ChimlCtx* ctx, int on);
+
 /* Freeze the setup: paints the per-cell update maps from the lists, builds the CPML coefficient
  * tables and compact psi / polarisation pools, zeroes all state. */
 int chiml_gpu_commit(ChimlCtx* ctx);

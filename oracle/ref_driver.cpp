@@ -8,8 +8,14 @@
 // wall-clock seconds of the step loop as JSON.  Used to pin the restated oracle and as the
 // `--impl reference` CPU arm of bench.py.
 //
-// usage: chiml_ref <input.json> [--ranks R] [--steps N] [--warmup W (untimed steps before the N timed ones)] [--dump FILE] [--plan PREFIX] [--no-output] [--quiet]
+// usage: chiml_ref <input.json> [--ranks R] [--steps N] [--warmup W (untimed steps before the N timed ones)] [--dump FILE] [--plan PREFIX] [--no-output] [--quiet] [--gpu]
 //   --plan PREFIX writes PREFIX.rank<r>.plan (include/chiml_plan.h) from the constructed propagator, before stepping
+//   --gpu         THE DROP-IN, COMPILED: the unmodified reference constructs everything, its lists go straight to the C ABI of
+//                 chiml_b200/libchiml_b200.so (loaded with dlopen: this binary stays runnable without CUDA), the time loop runs on the
+//                 GPU, and the reference's own writers (dtc->output / toFile, flux->getFlux, dtcPop->toFile) produce the files.  This
+//                 is the bindGpu() / step() stub of INTEGRATION.md as code (reference FDTD_MANAGER/parallelFDTDField.hpp:1228-1303,
+//                 main.cpp:54-118).  Single rank: the ranks of this driver are threads of one process, and CUDA IPC -- what the slabs'
+//                 halo binds with -- needs one process per slab.
 //
 // dump file layout (little endian): magic "CHIMLDMP" | int32 nranks | then per rank, per grid:
 //   int32 rank | char name[16] | int32 lnx, lny, lnz | int32 yStart(global row of local row 1) | float64 data[lnx*lny*lnz]
@@ -32,6 +38,8 @@
 #undef protected
 #undef private
 #include "../include/chiml_plan.h"
+#include <dlfcn.h>
+#include <unistd.h>
 
 namespace mpi = boost::mpi;
 
@@ -45,6 +53,7 @@ struct Options
     std::string plan;
     bool output = true;
     bool quiet = false;
+    bool gpu = false;
 };
 
 struct GridDump
@@ -329,6 +338,321 @@ static void putEmitters(std::ofstream& out, parallelFDTDFieldReal& FF)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// --gpu: the reference's propagator bound to the CUDA engine through the C ABI
+// ---------------------------------------------------------------------------------------------
+struct GpuApi
+{
+    void* lib = nullptr;
+#define CHIML_API(name) decltype(&::name) name = nullptr;
+    CHIML_API(chiml_gpu_create) CHIML_API(chiml_gpu_destroy) CHIML_API(chiml_gpu_last_error) CHIML_API(chiml_gpu_set_update_list)
+    CHIML_API(chiml_gpu_set_object) CHIML_API(chiml_gpu_set_cpml) CHIML_API(chiml_gpu_add_source) CHIML_API(chiml_gpu_add_detector)
+    CHIML_API(chiml_gpu_add_emitters) CHIML_API(chiml_gpu_add_dft) CHIML_API(chiml_gpu_commit) CHIML_API(chiml_gpu_step_n)
+    CHIML_API(chiml_gpu_step_n_dft) CHIML_API(chiml_gpu_sync) CHIML_API(chiml_gpu_read_detector_range) CHIML_API(chiml_gpu_consume_detector)
+    CHIML_API(chiml_gpu_read_population) CHIML_API(chiml_gpu_download_dft) CHIML_API(chiml_gpu_download_field) CHIML_API(chiml_gpu_download_pole)
+    CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
+    CHIML_API(chiml_gpu_download_emitter_pol)
+#undef CHIML_API
+    void load()
+    {
+        const char* env = std::getenv("CHIML_B200_LIB");
+        std::string path = env ? env : "";
+        if(path.empty())
+        {
+            char exe[4096]; ssize_t n = readlink("/proc/self/exe", exe, sizeof(exe) - 1);
+            std::string dir = n > 0 ? std::string(exe, size_t(n)) : std::string(".");
+            dir = dir.substr(0, dir.find_last_of('/'));                 // .../oracle/_ref
+            path = dir + "/../../chiml_b200/libchiml_b200.so";
+        }
+        lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if(!lib) throw std::runtime_error(std::string("--gpu: cannot load ") + path + ": " + dlerror());
+#define CHIML_API(name) name = reinterpret_cast<decltype(&::name)>(dlsym(lib, #name)); if(!name) throw std::runtime_error("--gpu: " #name " missing in the library");
+        CHIML_API(chiml_gpu_create) CHIML_API(chiml_gpu_destroy) CHIML_API(chiml_gpu_last_error) CHIML_API(chiml_gpu_set_update_list)
+        CHIML_API(chiml_gpu_set_object) CHIML_API(chiml_gpu_set_cpml) CHIML_API(chiml_gpu_add_source) CHIML_API(chiml_gpu_add_detector)
+        CHIML_API(chiml_gpu_add_emitters) CHIML_API(chiml_gpu_add_dft) CHIML_API(chiml_gpu_commit) CHIML_API(chiml_gpu_step_n)
+        CHIML_API(chiml_gpu_step_n_dft) CHIML_API(chiml_gpu_sync) CHIML_API(chiml_gpu_read_detector_range) CHIML_API(chiml_gpu_consume_detector)
+        CHIML_API(chiml_gpu_read_population) CHIML_API(chiml_gpu_download_dft) CHIML_API(chiml_gpu_download_field) CHIML_API(chiml_gpu_download_pole)
+        CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
+        CHIML_API(chiml_gpu_download_emitter_pol)
+#undef CHIML_API
+    }
+};
+
+struct GpuBinding
+{
+    GpuApi api;
+    ChimlCtx* ctx = nullptr;
+    std::vector<std::vector<int>> dtcSlots;                // per detector, per stored field: device slot
+    std::vector<std::vector<std::array<int, 6>>> dtcBox;   // ... and its local box (loc, sz)
+    std::vector<size_t> dtcSamples;                        // samples read so far per detector
+    struct DftRef { std::shared_ptr<parallelStorageFreqDTCReal> st; int slot; };
+    std::vector<DftRef> dfts;
+    std::vector<char> fluxHere;
+    void check(int rc, const char* what) { if(rc != CHIML_OK) throw std::runtime_error(std::string(what) + ": " + api.chiml_gpu_last_error(ctx)); }
+};
+
+// what a maintainer adds at the end of parallelFDTDFieldReal's constructor (INTEGRATION.md bindGpu)
+static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
+{
+    B.api.load();
+    GpuApi& A = B.api;
+    ChimlGridDesc g;
+    std::memset(&g, 0, sizeof(g));
+    g.mode = (FF.E_[0] && FF.E_[2]) ? CHIML_MODE_3D : (FF.E_[0] ? CHIML_MODE_TE : CHIML_MODE_TM);
+    auto ref = FF.E_[0] ? FF.E_[0] : FF.E_[2];
+    for(int k = 0; k < 3; ++k) { g.ln[k] = ref->ln_vec(k); g.d[k] = FF.d_[k]; }
+    g.dt = FF.dt_; g.has_D = (FF.D_[0] || FF.D_[2]) ? 1 : 0; g.pml_on_D = FF.dielectricMatInPML_ ? 1 : 0; g.n_objects = int(FF.objArr_.size());
+    g.rank = 0; g.nranks = 1;
+    if(A.chiml_gpu_create(&g, 0, &B.ctx) != CHIML_OK) throw std::runtime_error(std::string("chiml_gpu_create: ") + A.chiml_gpu_last_error(nullptr));
+    if(FF.magMatInPML_ || !FF.tfsfArr_.empty()) throw std::runtime_error("--gpu: magnetic materials in the PML / TFSF sources are outside the covered hot path");
+
+    static_assert(sizeof(upLists::value_type) == sizeof(ChimlRun), "upLists entries are handed over as ChimlRun");
+    auto put = [&](int kind, int comp, const upLists& l) {
+        B.check(A.chiml_gpu_set_update_list(B.ctx, kind, comp, reinterpret_cast<const ChimlRun*>(l.data()), l.size()), "set_update_list"); };
+    for(int c = 0; c < 3; ++c)
+    {
+        if(!FF.upB_[c].empty() || !FF.upLorB_[c].empty() || !FF.upChiD_[c].empty() || !FF.upChiB_[c].empty() || !FF.upOrDipB_[c].empty())
+            throw std::runtime_error("--gpu: magnetic / chiral update lists are outside the covered hot path");
+        put(CHIML_LIST_U, c, FF.upE_[c]);   put(CHIML_LIST_U, 3 + c, FF.upH_[c]);
+        put(CHIML_LIST_D, c, FF.upD_[c]);   put(CHIML_LIST_LORD, c, FF.upLorD_[c]);
+        put(CHIML_LIST_ORDIPD, c, FF.upOrDipD_[c]);
+    }
+    put(CHIML_LIST_ORDIPP, 0, FF.upOrDipP_);
+    for(size_t oo = 0; oo < FF.objArr_.size(); ++oo)
+    {
+        auto& obj = FF.objArr_[oo];
+        const int np = int(obj->gamma().size());
+        std::vector<double> dip(3 * size_t(np), 0.0);
+        if(obj->useOrdDip())
+            for(int pp = 0; pp < np; ++pp)
+            {
+                MAT_DIP_ORIENTAITON ori = obj->dipOr(pp);
+                if(ori == MAT_DIP_ORIENTAITON::ISOTROPIC) dip[3 * pp] = dip[3 * pp + 1] = dip[3 * pp + 2] = 1.0;
+                else if(ori == MAT_DIP_ORIENTAITON::UNIDIRECTIONAL) for(int k = 0; k < 3; ++k) dip[3 * pp + k] = obj->dipE(pp)[k];
+                else throw std::runtime_error("--gpu: position-dependent dipole orientation (REL_TO_NORM) is outside the covered hot path");
+            }
+        B.check(A.chiml_gpu_set_object(B.ctx, int(oo), np, obj->alpha().data(), obj->xi().data(), obj->gamma().data(), obj->useOrdDip() ? 1 : 0, dip.data()), "set_object");
+    }
+    static_assert(sizeof(updatePsiParams) == sizeof(ChimlPsiParams) && sizeof(updateGridParams) == sizeof(ChimlGridParams), "CPML list layouts");
+    for(int c = 0; c < 3; ++c)
+        for(int side = 0; side < 2; ++side)
+        {
+            auto pml = side == 0 ? FF.EPML_[c] : FF.HPML_[c];
+            if(!pml) continue;
+            const int comp = side == 0 ? c : 3 + c;
+            if(pml->grid_k_)
+                B.check(A.chiml_gpu_set_cpml(B.ctx, comp, 0, pml->psi_j_ ? 1 : 0, reinterpret_cast<const ChimlPsiParams*>(pml->updateListPsi_j_.data()), pml->updateListPsi_j_.size(),
+                                             reinterpret_cast<const ChimlGridParams*>(pml->updateListGrid_k_.data()), pml->updateListGrid_k_.size()), "set_cpml");
+            if(pml->grid_j_)
+                B.check(A.chiml_gpu_set_cpml(B.ctx, comp, 1, pml->psi_k_ ? 1 : 0, reinterpret_cast<const ChimlPsiParams*>(pml->updateListPsi_k_.data()), pml->updateListPsi_k_.size(),
+                                             reinterpret_cast<const ChimlGridParams*>(pml->updateListGrid_j_.data()), pml->updateListGrid_j_.size()), "set_cpml");
+        }
+    for(auto& srcBase : FF.srcArr_)
+    {
+        auto src = std::dynamic_pointer_cast<parallelSourceNormalReal>(srcBase);
+        if(!src) throw std::runtime_error("--gpu: only normal (axis-aligned) soft sources are on the covered hot path");
+        if(!src->slave_) throw std::runtime_error("--gpu: a source without a local box on a single rank");
+        const SalveSource& sl = *src->slave_;
+        const int ax1 = sl.addVec1_[0] ? 0 : (sl.addVec1_[1] ? 1 : 2), ax2 = sl.addVec2_[0] ? 0 : (sl.addVec2_[1] ? 1 : 2);
+        int32_t loc[3], sz[3] = {1, 1, 1};
+        sz[3 - ax1 - ax2] = sl.sz_[0]; sz[ax1] = sl.sz_[1]; sz[ax2] = sl.sz_[2];
+        for(int k = 0; k < 3; ++k) loc[k] = sl.loc_[k];
+        B.check(A.chiml_gpu_add_source(B.ctx, fieldId(FF, src->grid_), loc, sz, nullptr), "add_source");
+    }
+    const bool threeD = g.mode == CHIML_MODE_3D;
+    for(auto& dtc : FF.dtcArr_)
+    {
+        std::vector<int> slots; std::vector<std::array<int, 6>> boxes;
+        for(auto& f : dtc->fields_)
+        {
+            // stored box in global no-ghost coordinates, already grown by the Yee offset (DTC/parallelStorageDTC.hpp:51-80) -> local ghost-inclusive
+            int32_t loc[3] = {f->loc_[0] + 1, f->loc_[1] - ref->procLoc(1) + 1, threeD ? f->loc_[2] + 1 : 0};
+            int32_t sz[3] = {f->sz_[0], f->sz_[1], threeD ? f->sz_[2] : 1};
+            int slot = -1;
+            B.check(A.chiml_gpu_add_detector(B.ctx, fieldId(FF, f->grid_), loc, sz, dtc->timeInterval_, &slot), "add_detector");
+            slots.push_back(slot); boxes.push_back({{loc[0], loc[1], loc[2], sz[0], sz[1], sz[2]}});
+        }
+        B.dtcSlots.push_back(slots); B.dtcBox.push_back(boxes); B.dtcSamples.push_back(1);    // sample 0 = t = 0, written by the constructor already
+    }
+    // emitters: the EMITTER record of the plan dump is exactly ChimlEmitterDesc + arrays; reuse that extraction through a memory stream
+    // (kept in one place: putEmitters) -- done below by the caller, which owns the buffers
+    int group = 0;
+    B.fluxHere.assign(FF.fluxArr_.size(), 0);
+    for(auto& flux : FF.fluxArr_)
+    {
+        for(auto& fp : flux->fInParam_)
+            for(auto* vec : {&fp.Ej_dtc_, &fp.Ek_dtc_, &fp.Hj_dtc_, &fp.Hk_dtc_})
+                for(auto& dtc : *vec)
+                {
+                    auto st = std::dynamic_pointer_cast<parallelStorageFreqDTCReal>(dtc);
+                    if(!st || !st->fieldInFreq_) continue;
+                    static_assert(sizeof(ChimlDftLine) == 2 * sizeof(int), "fInGridInds_ is a list of (grid index, accumulator index) pairs");
+                    int slot = -1;
+                    B.check(A.chiml_gpu_add_dft(B.ctx, fieldId(FF, st->grid_), group, flux->timeInt_, st->nfreq_, st->fieldInFreq_->sz_[0], st->fieldInFreq_->stride_,
+                                                reinterpret_cast<const ChimlDftLine*>(st->fieldInFreq_->fInGridInds_.data()), st->fieldInFreq_->fInGridInds_.size() / 2,
+                                                st->fInReal_.size(), &slot), "add_dft");
+                    B.dfts.push_back({st, slot});
+                    B.fluxHere[group] = 1;
+                }
+        ++group;
+    }
+}
+
+// emitter objects: ChimlEmitterDesc from the members of parallelQEBase (what putEmitters writes into a plan file)
+struct EmitterBuffers
+{
+    std::vector<double> h0, weight, mu, gval, eps; std::vector<int32_t> gptr, gcol, loc, pop;
+};
+static void bindEmitters(parallelFDTDFieldReal& FF, GpuBinding& B, std::vector<EmitterBuffers>& keep)
+{
+    int qq = 0;
+    for(auto& qe : FF.qeArr_)
+    {
+        if(!qe->sameProcCalc_) throw std::runtime_error("--gpu: emitter sets need a single-rank run");
+        keep.emplace_back();
+        EmitterBuffers& b = keep.back();
+        ChimlEmitterDesc d;
+        std::memset(&d, 0, sizeof(d));
+        d.object = qq++;
+        d.nlevel = qe->nlevel_; d.nsys = int(qe->levelSys_.size()); d.nemit = int(qe->levelSys_[0].den_.size());
+        auto eg = qe->e_[0] ? qe->e_[0] : qe->e_[2];
+        auto Pg = qe->P_[0] ? qe->P_[0] : qe->P_[2];
+        d.box_n[0] = eg->x(); d.box_n[1] = eg->y(); d.box_n[2] = eg->z();
+        for(int k = 0; k < 3; ++k) d.box_lo[k] = qe->sameProcCalc_->loc_[k];
+        d.dt = qe->dt_; d.inv_hbar = std::imag(qe->one_over_hbar_); d.na = qe->na_;
+        const int n2 = d.nlevel * d.nlevel;
+        for(auto& ls : qe->levelSys_) for(int k = 0; k < n2; ++k) { b.h0.push_back(ls.ham_->h0_[k].real()); b.h0.push_back(ls.ham_->h0_[k].imag()); }
+        for(auto& ew : qe->energyWeights_) b.weight.push_back(ew.second);
+        auto& ham = *qe->levelSys_[0].ham_;
+        for(auto* v : {&ham.x_expectation_, &ham.y_expectation_, &ham.z_expectation_}) for(int k = 0; k < n2; ++k) { b.mu.push_back((*v)[k].real()); b.mu.push_back((*v)[k].imag()); }
+        b.gptr.push_back(0);
+        for(auto& row : qe->gam_) { for(auto it = row.begin(); it != row.end(); ++it) { b.gcol.push_back(it->first); b.gval.push_back(it->second); } b.gptr.push_back(int32_t(b.gcol.size())); }
+        while(int(b.gptr.size()) < n2 + 1) b.gptr.push_back(b.gptr.back());
+        for(auto& den : qe->levelSys_[0].den_) { b.loc.push_back(den.x()); b.loc.push_back(den.y()); b.loc.push_back(den.z()); }
+        for(int y = 0; y < Pg->y(); ++y)
+            for(int z = 0; z < Pg->z(); ++z)
+                for(int x = 0; x < Pg->x(); ++x)
+                    b.eps.push_back(qe->eps_->z() == 1 ? qe->eps_->point(d.box_lo[0] + x, d.box_lo[1] + y, 0) : qe->eps_->point(d.box_lo[0] + x, d.box_lo[1] + y, d.box_lo[2] + z));
+        for(auto& p : qe->dtcPopArr_) b.pop.push_back(p->level_);
+        d.h0 = b.h0.data(); d.weight = b.weight.data(); d.mu = b.mu.data(); d.gam_ptr = b.gptr.data(); d.gam_col = b.gcol.data(); d.gam_val = b.gval.data();
+        d.loc = b.loc.data(); d.eps = b.eps.data(); d.npop = int(b.pop.size()); d.pop_level = b.pop.data();
+        d.pop_every = d.npop ? qe->dtcPopArr_[0]->timeInt_ : 1;
+        d.npoints = d.npop ? qe->dtcPopArr_[0]->npoints_ : d.nemit;
+        B.check(B.api.chiml_gpu_add_emitters(B.ctx, &d, nullptr), "add_emitters");
+    }
+}
+
+// the body of parallelFDTDFieldBase<double>::step() with the engine behind it (INTEGRATION.md step())
+static void gpuStep(parallelFDTDFieldReal& FF, GpuBinding& B)
+{
+    GpuApi& A = B.api;
+    std::vector<double> amp;                                  // SOURCE/parallelSourceNormal.cpp:15-37: dt * Re(sum pulse(t))
+    for(auto& srcBase : FF.srcArr_)
+    {
+        auto src = std::dynamic_pointer_cast<parallelSourceNormalReal>(srcBase);
+        cplx p = 0.0;
+        for(auto& pul : src->pulse_) p += pul->pulse(FF.tcur_);
+        amp.push_back(FF.dt_ * std::real(p));
+    }
+    if(B.dfts.empty()) B.check(A.chiml_gpu_step_n(B.ctx, 1, amp.empty() ? nullptr : amp.data()), "step_n");
+    else
+    {
+        std::vector<double> tw;                               // parallelFluxDTC::fieldIn: fftFact_ = exp(i * (-t * freq)), t = time after the step
+        const double t = FF.tcur_ + FF.dt_;
+        for(size_t ff = 0; ff < FF.fluxArr_.size(); ++ff)
+            if(B.fluxHere[ff])
+                for(double f : FF.fluxArr_[ff]->freqList_) { const cplx w = std::exp(cplx(0.0, -1.0 * t * f)); tw.push_back(w.real()); tw.push_back(w.imag()); }
+        B.check(A.chiml_gpu_step_n_dft(B.ctx, 1, amp.empty() ? nullptr : amp.data(), tw.data()), "step_n_dft");
+    }
+    FF.tcur_ += FF.dt_;
+    ++FF.t_step_;
+    // detectors: the sampled boxes come back from the device ring into the reference's own grids, and its own writer formats them
+    for(size_t d = 0; d < FF.dtcArr_.size(); ++d)
+    {
+        auto& dtc = FF.dtcArr_[d];
+        if(FF.t_step_ % dtc->timeInt() != 0) continue;
+        for(size_t f = 0; f < dtc->fields_.size(); ++f)
+        {
+            const auto& bx = B.dtcBox[d][f];
+            std::vector<double> buf(size_t(bx[3]) * bx[4] * bx[5]);
+            size_t got = 0;
+            B.check(A.chiml_gpu_read_detector_range(B.ctx, B.dtcSlots[d][f], B.dtcSamples[d], 1, buf.data(), &got), "read_detector_range");
+            if(got != 1) throw std::runtime_error("--gpu: detector sample missing");
+            B.check(A.chiml_gpu_consume_detector(B.ctx, B.dtcSlots[d][f], B.dtcSamples[d] + 1), "consume_detector");
+            auto& grid = dtc->fields_[f]->grid_;
+            size_t i = 0;                                     // sample layout: x fastest, then z, then y
+            for(int y = 0; y < bx[4]; ++y)
+                for(int z = 0; z < bx[5]; ++z)
+                    for(int x = 0; x < bx[3]; ++x) grid->point(bx[0] + x, bx[1] + y, bx[2] + z) = buf[i++];
+        }
+        ++B.dtcSamples[d];
+        dtc->output(FF.tcur_);
+    }
+    // flux->fieldIn(tcur_) ran on the device (the running-DFT sets); what is left of it on the host is its sample counter, which
+    // getFlux normalises with (DTC/parallelFlux.hpp:313,418)
+    for(auto& flux : FF.fluxArr_)
+        if(FF.t_step_ % flux->timeInt() == 0) ++flux->t_step_;
+}
+
+// after the loop (main.cpp:67-118): accumulators, populations and -- for the state dump of the tests -- every grid come back
+static void gpuFinish(parallelFDTDFieldReal& FF, GpuBinding& B)
+{
+    GpuApi& A = B.api;
+    B.check(A.chiml_gpu_sync(B.ctx), "sync");
+    for(auto& d : B.dfts) B.check(A.chiml_gpu_download_dft(B.ctx, d.slot, d.st->fInReal_.data(), d.st->fInCplx_.data()), "download_dft");
+    int qq = 0;
+    for(auto& qe : FF.qeArr_)
+    {
+        int dd = 0;
+        for(auto& pop : qe->dtcPopArr_)
+        {
+            size_t ns = 0;
+            B.check(A.chiml_gpu_read_population(B.ctx, qq, dd, nullptr, 0, &ns), "read_population");
+            std::vector<double> v(2 * ns);
+            if(ns) B.check(A.chiml_gpu_read_population(B.ctx, qq, dd, v.data(), ns, &ns), "read_population");
+            pop->allPop_.clear();
+            for(size_t k = 0; k < ns; ++k) pop->allPop_.push_back(cplx(v[2 * k], v[2 * k + 1]));
+            ++dd;
+        }
+        // density matrices, their derivative histories and the polarisation boxes, for callers that look at them (the state dump)
+        const int n2 = qe->nlevel_ * qe->nlevel_;
+        for(size_t ss = 0; ss < qe->levelSys_.size(); ++ss)
+            for(int w = 0; w < 5; ++w)
+            {
+                std::vector<double> st(2 * size_t(n2) * qe->levelSys_[ss].den_.size());
+                if(st.empty()) continue;
+                B.check(A.chiml_gpu_download_emitter_state(B.ctx, qq, int(ss), w, st.data()), "download_emitter_state");
+                size_t e = 0;
+                for(auto& den : qe->levelSys_[ss].den_)
+                {
+                    std::vector<cplx>& v = w == 0 ? den.density_ : w == 1 ? den.density_deriv_n_ : w == 2 ? den.density_deriv_n_minus_1_
+                                         : w == 3 ? den.density_deriv_n_minus_2_ : den.density_deriv_n_minus_3_;
+                    for(int k = 0; k < n2; ++k) v[k] = cplx(st[2 * (e * n2 + k)], st[2 * (e * n2 + k) + 1]);
+                    ++e;
+                }
+            }
+        for(int c = 0; c < 3; ++c)
+            if(qe->P_[c] && qe->E_[c]) B.check(A.chiml_gpu_download_emitter_pol(B.ctx, qq, c, &qe->P_[c]->point(0)), "download_emitter_pol");
+        ++qq;
+    }
+    for(int c = 0; c < 3; ++c)
+    {
+        if(FF.E_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_EX + c, &FF.E_[c]->point(0)), "download_field");
+        if(FF.H_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_HX + c, &FF.H_[c]->point(0)), "download_field");
+        if(FF.D_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_DX + c, &FF.D_[c]->point(0)), "download_field");
+        for(size_t p = 0; p < FF.lorP_[c].size(); ++p)
+        {
+            B.check(A.chiml_gpu_download_pole(B.ctx, c, int(p), 0, &FF.lorP_[c][p]->point(0)), "download_pole");
+            B.check(A.chiml_gpu_download_pole(B.ctx, c, int(p), 1, &FF.prevLorP_[c][p]->point(0)), "download_pole");
+        }
+        for(size_t p = 0; p < FF.orDipLorP_[c].size(); ++p)
+        {
+            B.check(A.chiml_gpu_download_ordip_pole(B.ctx, c, int(p), 0, &FF.orDipLorP_[c][p]->point(0)), "download_ordip_pole");
+            B.check(A.chiml_gpu_download_ordip_pole(B.ctx, c, int(p), 1, &FF.prevOrDipLorP_[c][p]->point(0)), "download_ordip_pole");
+        }
+    }
+}
+
 static void rankMain(int rank, const Options& opt)
 {
     mpi::shim::myRank() = rank;
@@ -361,12 +685,22 @@ static void rankMain(int rank, const Options& opt)
     if(!opt.plan.empty())
         writePlan(opt.plan + ".rank" + std::to_string(rank) + ".plan", FF, IP, nSteps);
 
+    GpuBinding gpu;
+    std::vector<EmitterBuffers> emitterBuffers;
+    if(opt.gpu)
+    {
+        if(gridComm->size() != 1) throw std::runtime_error("--gpu runs a single rank (one process per slab is needed for the CUDA IPC halo)");
+        bindGpu(FF, gpu);
+        bindEmitters(FF, gpu, emitterBuffers);
+        gpu.check(gpu.api.chiml_gpu_commit(gpu.ctx), "commit");
+    }
     for(int tt = 0; tt < opt.warmup; ++tt)
-        FF.step();
+        if(opt.gpu) gpuStep(FF, gpu); else FF.step();
     gridComm->barrier();
     auto t0 = std::chrono::steady_clock::now();
     for(int tt = 0; tt < nSteps; ++tt)
-        FF.step();
+        if(opt.gpu) gpuStep(FF, gpu); else FF.step();
+    if(opt.gpu) gpuFinish(FF, gpu);
     gridComm->barrier();
     auto t1 = std::chrono::steady_clock::now();
     if(rank == 0)
@@ -479,6 +813,11 @@ static void rankMain(int rank, const Options& opt)
                 dtcPop->toFile();
         }
     }
+    if(opt.gpu)
+    {
+        if(rank == 0 && !opt.quiet) std::fprintf(stderr, "chiml_ref --gpu: %lld kernel launches\n", (long long)gpu.api.chiml_gpu_launch_count(gpu.ctx));
+        gpu.api.chiml_gpu_destroy(gpu.ctx);
+    }
     gridComm->barrier();
 }
 
@@ -510,6 +849,7 @@ int main(int argc, char** argv)
         else if(s == "--plan" && a + 1 < argc) opt.plan = argv[++a];
         else if(s == "--no-output") opt.output = false;
         else if(s == "--quiet") opt.quiet = true;
+        else if(s == "--gpu") opt.gpu = true;
         else if(opt.input.empty()) opt.input = s;
         else { std::fprintf(stderr, "chiml_ref: unknown argument %s\n", s.c_str()); return 2; }
     }

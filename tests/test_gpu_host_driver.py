@@ -20,6 +20,22 @@ FILES = {"te_vacuum": {"out/te/dtc_field_0.dat": "dtc_field_0.dat"},
          "vac3d_bin": {"out/vb/dtc_field_0.dat": "dtc_field_0.dat", "out/vb/dtc_field_1.dat": "dtc_field_1.dat"}}
 
 
+def test_power_and_console_detectors(tmp_path):
+    """H-power detector (|Hz|^2 with the squared SI factor, DTC/parallelDTC.hpp:87-91) written as TXT, and a console (COUT) detector
+    whose lines must equal the ones the reference printed (tests/golden/make_out_expected.py)."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_out_expected import cout_lines
+    exe = os.path.join(ROOT, "chiml_b200", "chiml")
+    shutil.copy(os.path.join(GOLDEN, "out_expected", "te_hpow", "te_hpow.json"), tmp_path / "te_hpow.json")
+    r = subprocess.run([exe, "te_hpow.json"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = open(tmp_path / "out" / "hp" / "pow_field_0.dat", "rb").read()
+    assert got == open(os.path.join(GOLDEN, "out_expected", "te_hpow", "pow_field_0.dat"), "rb").read()
+    assert b"e-" in got and got.count(b"\n") == 32                      # 60 steps, every second one, + t = 0, + header
+    assert cout_lines(r.stdout) == open(os.path.join(GOLDEN, "out_expected", "te_hpow", "cout.txt")).read()
+
+
 @pytest.mark.parametrize("case", sorted(FILES))
 def test_host_driver_writes_the_reference_files(case, tmp_path):
     exe = os.path.join(ROOT, "chiml_b200", "chiml")

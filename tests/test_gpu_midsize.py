@@ -29,9 +29,9 @@ def _plan(cfg):
     return P.read_plan(os.path.join(work, "p.rank0.plan"))
 
 
-def _compare(plan, march, steps=10, seed=99):
+def _compare(plan, march, steps=10, seed=99, persistent=None):
     rng = np.random.default_rng(seed)
-    gpu, cpu = capi.GpuSim(plan, march=march), OracleSim(plan)
+    gpu, cpu = capi.GpuSim(plan, march=march, persistent=persistent), OracleSim(plan)
     lnx, lny, lnz = plan.ln
     for f in plan.fields_present():
         a = rng.uniform(-1.0, 1.0, size=(lny, lnz, lnx))
@@ -81,8 +81,10 @@ def test_c2_drude_rod_2048sq(march, oracle_lib):
     """BASELINE C2 at full size (2-D TM, Drude nanorod, CPML, flux box with running DFT): eight one-row tiles per block, each warp
     marching its own column (automatic column length 6)."""
     plan = _plan(I.c2_tm_drude(n=2047, steps=10, nfreq=8, out="mid_out/c2"))
-    stats = _compare(plan, march)
+    stats = _compare(plan, march, persistent=False)
     assert stats["k_fast<E>"] > 0 and stats["k_dft"] > 0
+    stats = _compare(plan, march)               # default for 2-D grids: every step in one cooperative launch (csrc/chiml_persist.cuh)
+    assert stats["k_steps_2d"] == 1 and stats["k_fast<E>"] == 0
 
 
 def test_c1_te_vacuum_1024sq_whole_columns(oracle_lib):

@@ -75,6 +75,59 @@ def test_gpu_matches_oracle_from_random_state(case, march, oracle_lib):
     gpu.close(); cpu.close()
 
 
+@pytest.mark.parametrize("kernel", ["thread", "group"])
+@pytest.mark.parametrize("case", ["ml3d_two", "ml3d_four", "ml_te", "ml_tm", "c4_small"])
+def test_both_density_kernels_match_reference_fixture(case, kernel, monkeypatch):
+    """The density matrices are propagated by one thread per emitter (N = 2, 3, 6) or by a group of lanes per emitter exchanging
+    operands with warp shuffles (N = 4, 5), csrc/chiml_emitters.cuh; CHIML_B200_EMIT_KERNEL forces either for N <= 5.  Both must
+    reproduce the reference bit for bit (two levels, three levels in TE, four levels with two level systems, TM)."""
+    monkeypatch.setenv("CHIML_B200_EMIT_KERNEL", kernel)
+    plan = util.load_plan(case)
+    expect = util.load_expect(case)
+    sim = capi.GpuSim(plan)
+    sim.step_n(plan.n_steps)
+    for name, ref in expect.items():
+        got = util.state_array(sim, name)
+        if "pop" in name:
+            assert np.abs(got - ref).max() <= TOL_DTC * max(np.abs(ref).max(), 1e-300), f"{case}/{name}"
+        else:
+            assert np.array_equal(got, ref), f"{case}/{name} ({kernel} kernel): max |diff| {np.abs(got - ref).max():.3e}"
+    sim.close()
+
+
+TWO_D = [c for c in util.CASES if util.load_plan(c).ln[2] == 1]
+
+
+@pytest.mark.parametrize("march", [None, 3], ids=["auto", "ny3"])
+@pytest.mark.parametrize("case", TWO_D)
+def test_2d_launch_per_phase_path_matches_reference_fixture(case, march):
+    """2-D grids without emitters step through the persistent cooperative kernel by default (csrc/chiml_persist.cuh; every other test
+    of a 2-D case runs it); this one selects the launch-per-phase path, and both must reproduce the reference's output -- including
+    the detector series and the running-DFT accumulators, which the persistent kernel samples inside other phases."""
+    plan = util.load_plan(case)
+    expect = util.load_expect(case)
+    a, b = capi.GpuSim(plan, march=march, persistent=False), capi.GpuSim(plan, march=march, persistent=True)
+    for sim in (a, b):
+        for n in (3, 4, plan.n_steps - 7):      # several calls: the sample counters and the P buffer parity carry over
+            sim.step_n(n)
+    for name, ref in expect.items():
+        if "pop" in name:
+            continue
+        for tag, sim in (("launch path", a), ("persistent kernel", b)):
+            got = util.state_array(sim, name)
+            assert np.array_equal(got, ref), f"{case}/{name} ({tag}): {int((got != ref).sum())} of {got.size} values differ, max |diff| {np.abs(got - ref).max():.3e}"
+    for d in range(len(plan.detectors)):
+        da, db = a.detector(d), b.detector(d)
+        assert da.shape[0] == plan.n_steps // plan.detectors[d].every + 1
+        assert np.array_equal(da, db), f"{case}: detector {d}"
+    sa = {k["name"]: k["launches"] for k in a.kernel_stats()}
+    sb = {k["name"]: k["launches"] for k in b.kernel_stats()}
+    assert sa["k_steps_2d"] == 0
+    if not plan.emitters:
+        assert sb["k_steps_2d"] == 3 and sb["k_fast<E>"] == 0, sb
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("case", ["te_vacuum", "vac3d"])
 def test_detector_series_matches_oracle(case, oracle_lib):
     plan = util.load_plan(case)

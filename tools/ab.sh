@@ -11,7 +11,7 @@ for lib in "$@"; do
 import json, sys
 try:
     d = json.loads(open(sys.argv[2]).read().strip().splitlines()[-1])
-    ks = {k["name"]: k["avg_ms"] for k in d["roofline"]["kernels"]}
+    ks = {k["name"]: k["ms_per_step"] for k in d["roofline"]["kernels"]}
     print(f'{sys.argv[1]:>16s} {d["ms_per_step"]:7.3f} ms  ' + "  ".join(f'{n}={ks[n]:.3f}' for n in ("k_fast<E>", "k_uniform<E>", "k_general<E>", "k_fast<H>", "k_uniform<H>", "k_general<H>", "k_ordip_poles") if n in ks))
 except Exception as e:
     print(sys.argv[1], "FAILED", e)
