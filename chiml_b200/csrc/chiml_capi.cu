@@ -3,6 +3,7 @@
 // chiml_gpu_create fails with CHIML_ERR_NO_DEVICE.
 #include "chiml_kernels.cuh"
 
+#include <cuda.h>          // CUtensorMap and the prototype of cuTensorMapEncodeTiled (resolved at run time: no -lcuda)
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -157,7 +158,7 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     for(auto& e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamSynchronize(ctx->hstream);
     for(HaloPeer* pr : {&ctx->lower, &ctx->upper}) for(void* b : pr->opened) cudaIpcCloseMemHandle(b);
-    cudaFree(ctx->d_flags); cudaFree(ctx->d_push_counter); cudaFree(ctx->d_persist_sa);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_push_counter); cudaFree(ctx->d_persist_sa); cudaFree(ctx->d_tmaps);
     for(auto& g : ctx->d_oPy_ghost) cudaFree(g);
     cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_push);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -606,6 +607,52 @@ int build_pml_part(ChimlCtx* ctx, int comp, int part, int* d_err)
     return 0;
 }
 
+// TMA descriptors of one-row boxes (64 x 1 x 1 doubles) of every field array and psi array, for the row prefetch of the UNIFORM
+// marching kernels (chiml_update.cuh tma_prefetch_row).  cuTensorMapEncodeTiled is looked up in the driver at run time; when it is
+// missing (or CHIML_B200_NO_TMA is set) the kernels fall back to per-lane prefetch.global.L2.
+int build_tensor_maps(ChimlCtx* ctx)
+{
+    if(ctx->lz <= 1 || std::getenv("CHIML_B200_NO_TMA")) return 0;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
+    { cudaGetLastError(); return 0; }
+    EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
+    static_assert(sizeof(CUtensorMap) == TMAP_BYTES, "CUtensorMap is 128 bytes");
+    std::vector<CUtensorMap> maps(TMAP_COUNT);
+    std::memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+    auto make = [&](CUtensorMap& m, double* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t pitch0, cuuint64_t pitch1) -> bool {
+        const cuuint64_t dims[3] = {d0, d1, d2};
+        const cuuint64_t strides[2] = {pitch0 * sizeof(double), pitch1 * sizeof(double)};       // of dimensions 1 and 2, in bytes
+        const cuuint32_t box[3] = {(cuuint32_t)std::min<cuuint64_t>(d0, TILE_X), 1, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        return encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool ok = true;
+    for(int f = 0; f < CHIML_NFIELDS && ok; ++f)
+        if(ctx->d_field[f]) ok = make(maps[f], ctx->d_field[f], (cuuint64_t)ctx->px, (cuuint64_t)ctx->lz, (cuuint64_t)ctx->ly, (cuuint64_t)ctx->px, (cuuint64_t)ctx->plane);
+    for(int comp = 0; comp < 6 && ok; ++comp)
+        for(int part = 0; part < 2 && ok; ++part)
+        {
+            const PmlPartDev& pp = ctx->pml[comp][part];
+            if(!pp.d_psi) continue;
+            CUtensorMap& m = maps[TMAP_PSI0 + 2 * comp + part];
+            // the compact layouts of build_pml_part: x-normal slabs cc + pitch * (z + lz * y); y-normal x + px * (z + lz * cc); z-normal x + px * (cc + nact * y)
+            if(pp.axis == 0)      ok = make(m, pp.d_psi, (cuuint64_t)pp.psi_pitch, (cuuint64_t)ctx->lz * ctx->ly, 1, (cuuint64_t)pp.psi_pitch, (cuuint64_t)pp.psi_pitch * ctx->lz * ctx->ly);
+            else if(pp.axis == 1) ok = make(m, pp.d_psi, (cuuint64_t)ctx->px, (cuuint64_t)ctx->lz, (cuuint64_t)pp.nact, (cuuint64_t)ctx->px, (cuuint64_t)ctx->plane);
+            else                  ok = make(m, pp.d_psi, (cuuint64_t)ctx->px, (cuuint64_t)pp.nact, (cuuint64_t)ctx->ly, (cuuint64_t)ctx->px, (cuuint64_t)ctx->px * pp.nact);
+        }
+    if(!ok) return 0;            // a layout the encoder refuses (e.g. a stride that is no multiple of 16 bytes): per-lane prefetch instead
+    CK(cudaMalloc(&ctx->d_tmaps, maps.size() * sizeof(CUtensorMap)));
+    ctx->dev_bytes += maps.size() * sizeof(CUtensorMap);
+    CK(cudaMemcpyAsync(ctx->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -1001,6 +1048,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         }
         cudaFree(d_sum);
     }
+    if((rc = build_tensor_maps(ctx))) return rc;
     // y-slab halo: flag words, push counters, the dense ghost row of node P_y (filled by the slab above)
     if(ctx->g.nranks > 1)
     {
@@ -1013,6 +1061,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
     // emitters: constants, P boxes, SoA density state (rho_00 = weight of the level system, ML/density.hpp:57-60)
     for(EmitterDev& em : ctx->emitters)
     {
+        em.group = emitter_group(em.d.nlevel);       // which density kernel, hence which state layout
         if((rc = dev_upload(ctx, &em.d_h0, em.h_h0))) return rc;
         if((rc = dev_upload(ctx, &em.d_mu, em.h_mu))) return rc;
         if((rc = dev_upload(ctx, &em.d_gam_ptr, em.h_gam_ptr))) return rc;
@@ -1028,7 +1077,6 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 rho0[em.group ? ((size_t)sy * em.d.nemit + e) * em.n2 * 2 : ((size_t)sy * em.n2 * 2) * em.d.nemit + e] = em.h_weight[sy];
         if((rc = dev_upload(ctx, &em.d_rho, rho0))) return rc;
         for(int k = 0; k < 4; ++k) if((rc = dev_alloc(ctx, &em.d_f[k], per))) return rc;
-        em.group = emitter_group(em.d.nlevel);
         const int epb = em.group ? 128 / em.group : 128;
         em.nblocks = (em.d.nemit + epb - 1) / epb;
         em.gam_maxrow = 0;
@@ -1077,6 +1125,7 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
     std::memset(&a, 0, sizeof(a));
     a.lx = ctx->lx; a.ly = ctx->ly; a.lz = ctx->lz; a.px = ctx->px;
     a.pml_on_D = ctx->g.pml_on_D;
+    a.tmaps = reinterpret_cast<const unsigned char*>(ctx->d_tmaps);
     a.nsp_xmin = ctx->span_node.d_xmin; a.nsp_xmax = ctx->span_node.d_xmax; a.nsp_base = ctx->span_node.d_base;
     const int cur = ctx->pcur, prv = 1 - ctx->pcur;
     for(int i = 0; i < 3; ++i) a.fam[i] = ctx->d_field[(isE ? CHIML_HX : CHIML_EX) + i];

@@ -210,6 +210,7 @@ struct ChimlCtx
     chiml::HostPml hpml[6][2];
     std::vector<chiml::HostObj> objs;
 
+    void* d_tmaps = nullptr;                     // TMA descriptors of the field and psi arrays (chiml_kernels.cuh TMAP_*), 3-D grids
     // persistent multi-step kernel of 2-D grids (chiml_persist.cuh)
     void* d_persist_sa = nullptr;                // 3 StepArgs
     int persist_blocks = -1;                     // resident grid size, 0 = not available, -1 = not asked yet

@@ -61,7 +61,11 @@ struct StepArgs
     int lx, ly, lz;
     long px;
     int pml_on_D;
+    // TMA descriptors (CUtensorMap, 128 bytes each, in global memory) of one-row boxes (64 x 1 x 1 doubles) of the nine field arrays
+    // [0..8] and of the psi arrays [9 + 2*comp + part]; nullptr = none (2-D grids, CHIML_B200_NO_TMA): chiml_update.cuh tma_prefetch_row
+    const unsigned char* tmaps;
 };
+constexpr int TMAP_BYTES = 128, TMAP_PSI0 = 9, TMAP_COUNT = 9 + 12;
 
 constexpr unsigned REC_WIDE2 = 0x80000000u;   // TileRec::part flag: the record spans two z-adjacent tiles, half a warp per row, x origin pad4
 constexpr int TILE_X = 64;   // cells per tile row (32 lanes x 2 cells)

@@ -712,6 +712,15 @@ template <bool IS_E> __host__ __device__ constexpr int uniform_occ() { return IS
 // array at a fixed plane stride, so the lines of the plane two steps ahead are requested while the current plane is computed; the
 // demand loads then pay L2 latency instead of HBM latency, which is what the UNIFORM kernels (few warps, many arrays) are short of.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+// The same through the TMA unit: ONE instruction of ONE lane asks for a whole 64-cell row (512 bytes, four L2 lines) of a tile,
+// described by a tensor map of the array (chiml_gpu_commit builds them); coordinates are (x, z-like, y-like) of the array's own
+// layout, out-of-range parts of the box are skipped by the hardware.  Replaces sixteen prefetch.global.L2 plus their address
+// arithmetic per row and array.
+__device__ __forceinline__ void tma_prefetch_row(const unsigned char* tmaps, const int map, const int c0, const int c1, const int c2)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 :: "l"(tmaps + (size_t)map * TMAP_BYTES), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 constexpr int PREFETCH_PLANES = CHIML_PREFETCH_PLANES;
 
 // psi lines of component C of a UNIFORM tile at plane y (address arithmetic of uniform_rect), for the rectangle with this info
@@ -729,6 +738,27 @@ __device__ __forceinline__ void prefetch_psi(const StepArgs& a, const unsigned i
         const PmlArgs& pp = ca.pml[part];
         if(axis == 1)      { const int cm = pp.cmap[y]; if(cm >= 0) prefetch_l2(pp.psi + x + a.px * (z + (long)a.lz * cm)); }
         else if(axis == 2) { const int cm = pp.cmap[z]; if(cm >= 0) prefetch_l2(pp.psi + x + a.px * (cm + (long)pp.nact * y)); }
+    }
+}
+
+// the same by TMA row prefetch: x0 = first cell of the tile row; the psi arrays' tensor maps follow their compact layouts
+// (y-normal slabs: (x, z, compact y); z-normal: (x, compact z, y); x-normal: (compact x, z + lz * y, -))
+template <bool IS_E, int MODE, int C>
+__device__ __forceinline__ void tma_prefetch_psi(const StepArgs& a, const unsigned info, const int x0, const int y, const int z)
+{
+    const CompArgs& ca = a.c[C];
+#pragma unroll
+    for(int part = 0; part < 2; ++part)
+    {
+        const unsigned fs = part == 0 ? F_PS0 : F_PS1;
+        if(!(info & fs)) continue;
+        constexpr int AX0 = (C + 1) % 3, AX1 = (C + 2) % 3;
+        const int axis = part == 0 ? AX0 : AX1;
+        const PmlArgs& pp = ca.pml[part];
+        const int map = TMAP_PSI0 + 2 * ((IS_E ? 0 : 3) + C) + part;
+        if(axis == 1)      { const int cm = pp.cmap[y]; if(cm >= 0) tma_prefetch_row(a.tmaps, map, x0, z, cm); }
+        else if(axis == 2) { const int cm = pp.cmap[z]; if(cm >= 0) tma_prefetch_row(a.tmaps, map, x0, cm, y); }
+        else               tma_prefetch_row(a.tmaps, map, 0, z + a.lz * y, 0);
     }
 }
 
@@ -792,6 +822,9 @@ __device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec&
     constexpr bool needU = !IS_E || !(FL & (F_D2E | F_ORD2E)) || POLES;      // poles are driven by E^n
     const bool anyD = IS_E && a.c[C].D && ((FL & (F_ISD | F_D2E | F_ORD2E)) || (a.pml_on_D && (FL & (F_PG0 | F_PS0 | F_PG1 | F_PS1))));
     const bool leader = (threadIdx.x & 1) == 0;      // one lane per 32-byte sector (the prefetch unit of L2)
+    // the first live lane of this lane's tile row (live = updates a cell: the others have left above)
+    const unsigned liveLanes = __activemask() & ((t.part & REC_WIDE2) ? (threadIdx.x < 16 ? 0x0000FFFFu : 0xFFFF0000u) : 0xFFFFFFFFu);
+    const bool rowLeader = (int)(threadIdx.x & 31) == __ffs(liveLanes) - 1;
     const int ny = t.ny, y0 = t.y;
     // psi of the y-normal slabs is stored under a compact y coordinate: it is looked up one plane ahead (CHIML_PIPE_Y)
     constexpr int YPART = C == 0 ? 0 : 1;
@@ -803,7 +836,22 @@ __device__ __forceinline__ void uniform_column(const StepArgs& a, const TileRec&
         const int y = y0 + iy;
         const int cmCur = cmNext;
         if constexpr(YPSI) if(iy + 1 < ny) cmNext = a.c[C].pml[YPART].cmap[y + 1];
-        if(leader && iy + PREFETCH_PLANES < ny)
+        if(MODE == CHIML_MODE_3D && !POLES && a.tmaps != nullptr)
+        {
+            // one lane per tile row (a warp of a REC_WIDE2 record covers two rows: one lane per half-warp) asks the TMA unit for the
+            // whole next row of every array the column streams
+            if(rowLeader && iy + PREFETCH_PLANES < ny)
+            {
+                const int yp = y + PREFETCH_PLANES, x0 = t.x0;
+                constexpr int FB = IS_E ? CHIML_HX : CHIML_EX, OB = IS_E ? CHIML_EX : CHIML_HX;
+                if(has_other<IS_E, MODE>((C + 1) % 3)) tma_prefetch_row(a.tmaps, FB + (C + 1) % 3, x0, z, yp);
+                if(has_other<IS_E, MODE>((C + 2) % 3)) tma_prefetch_row(a.tmaps, FB + (C + 2) % 3, x0, z, yp);
+                if(needU) tma_prefetch_row(a.tmaps, OB + C, x0, z, yp);
+                if(anyD) tma_prefetch_row(a.tmaps, CHIML_DX + C, x0, z, yp);
+                tma_prefetch_psi<IS_E, MODE, C>(a, FL, x0, yp, z);
+            }
+        }
+        else if(leader && iy + PREFETCH_PLANES < ny)
         {
             const long rp = r + PREFETCH_PLANES * plane;
             if(has_other<IS_E, MODE>((C + 1) % 3)) prefetch_l2(a.fam[(C + 1) % 3] + rp);

@@ -202,6 +202,28 @@ void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std
             else
                 f << std::endl;
         }
+        // ---- saveFields (DTC/parallelFlux.hpp:616-659): nfreq, the region's size, the number of surfaces per role, then per role and
+        // surface the grid extents {nfreq, sz[transCor1], sz[cor]} and its complex values.  The reference walks every entry of
+        // Ej_freq_ .. Hk_freq_, also the null ones of 2-D grids (a TE / TM surface stores one E and one H field): it can only save 3-D
+        // regions, and so does this.
+        if(fx.save)
+        {
+            for(const Face& F : faces)
+                for(int r = 0; r < 4; ++r)
+                    if(!F.has[r]) throw std::logic_error("flux save: the reference dereferences the missing in-plane field of a 2-D surface here; 3-D flux regions only");
+            std::ofstream sf((fx.name + "_fields.dat").c_str(), std::ios::binary | std::ios::out);
+            const int32_t hdr[4] = {nfreq, fx.sz[0], fx.sz[1], fx.sz[2]};
+            sf.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
+            const int32_t cnt[4] = {(int32_t)faces.size(), (int32_t)faces.size(), (int32_t)faces.size(), (int32_t)faces.size()};
+            sf.write(reinterpret_cast<const char*>(cnt), sizeof(cnt));
+            for(int r = 0; r < 4; ++r)
+                for(const Face& F : faces)
+                {
+                    const int32_t nv[3] = {nfreq, F.ny, F.nx};
+                    sf.write(reinterpret_cast<const char*>(nv), sizeof(nv));
+                    sf.write(reinterpret_cast<const char*>(F.g[r].data()), (std::streamsize)(F.g[r].size() * sizeof(cplx)));
+                }
+        }
     }
 }
 

@@ -560,6 +560,7 @@ Inputs::Inputs(const Json& IP)
         else throw std::logic_error("All fluxes must either have fcen and fwidth defined or lamL and lamR defined");
         f.SI = fj.get<bool>("SI", false);
         f.crossSec = fj.get<bool>("cross_sec", false);
+        f.save = fj.get<bool>("save", false);
         fluxes_.push_back(f);
     }
 }

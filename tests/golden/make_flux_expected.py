@@ -11,6 +11,18 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.path.join(ROOT, "oracle", "_ref", "chiml_ref")
 CASES = ["tm_flux", "te_flux", "flux3d"]
 
+# flux3d_save: flux3d with "save" set on the 3-D box region: the reference then also writes <name>_fields.dat (saveFields,
+# DTC/parallelFlux.hpp:616-659), the frequency-domain surface fields a later run subtracts as incident fields
+cfg = json.load(open(os.path.join(HERE, "flux3d.json")))
+cfg["FluxList"][0]["save"] = True
+os.makedirs(os.path.join(HERE, "out_expected", "flux3d_save"), exist_ok=True)
+json.dump(cfg, open(os.path.join(HERE, "out_expected", "flux3d_save", "flux3d_save.json"), "w"), indent=1)
+work = tempfile.mkdtemp(prefix="fluxref_")
+shutil.copy(os.path.join(HERE, "out_expected", "flux3d_save", "flux3d_save.json"), work)
+subprocess.run([REF, "flux3d_save.json", "--quiet"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+shutil.copy(os.path.join(work, cfg["FluxList"][0]["name"] + "_fields.dat"), os.path.join(HERE, "out_expected", "flux3d_save", "box_fields.dat"))
+print("flux3d_save", os.path.getsize(os.path.join(HERE, "out_expected", "flux3d_save", "box_fields.dat")), "bytes")
+
 for case in CASES:
     work = tempfile.mkdtemp(prefix="fluxref_")
     shutil.copy(os.path.join(HERE, case + ".json"), work)

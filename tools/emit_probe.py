@@ -18,9 +18,9 @@ n, nz = sheet + 60, 47
 work = tempfile.mkdtemp(prefix="emit_probe_")
 relax1 = [{"state_i": 1, "state_f": 0, "rate": 1e12, "dephasing_rate": 1e13}]
 objs = {
-    "N2": I.ml_object([(sheet - 1) / res, (sheet - 1) / res, 0.0], [0, 0, 0.005], 1e25, [(0, 0), (1, 0)], [{"E_cen": [0.0]}, {"E_cen": [2.0]}],
+    "N2": I.ml_object([(sheet - 1) / res, (sheet - 1) / res, 0.0], [0, 0, 0.0], 1e25, [(0, 0), (1, 0)], [{"E_cen": [0.0]}, {"E_cen": [2.0]}],
                       [0, 10.0, 10.0, 0], relax1, eps=1.0, dtc_levs=[3]),
-    "N4": I.ml_object([(sheet - 1) / res, (sheet - 1) / res, 0.0], [0, 0, 0.005], 1e25, [(0, 0), (1, -1), (1, 0), (1, 1)],
+    "N4": I.ml_object([(sheet - 1) / res, (sheet - 1) / res, 0.0], [0, 0, 0.0], 1e25, [(0, 0), (1, -1), (1, 0), (1, 1)],
                       [{"E_cen": [0.0]}, {"E_cen": [1.9, 2.1], "weights": [0.6, 0.4], "levs_described": 3}],
                       [0, 10, 8, 6, 10, 0, 0, 0, 8, 0, 0, 0, 6, 0, 0, 0],
                       [{"state_i": 1, "state_f": 0, "rate": 1e12, "dephasing_rate": 1e13}, {"state_i": 2, "state_f": 0, "rate": 2e12, "dephasing_rate": 0.5e13},
