@@ -9,6 +9,7 @@
 #include <fstream>
 #include <iomanip>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 #include "setup.hpp"
@@ -92,6 +93,36 @@ void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std
         }
         freqConv /= (M_PI * 2.0);
 
+        // ---- loadFields(-1.0) (DTC/parallelFlux.hpp:664-722, called by the constructor, parallelFlux.cpp:70): the surface fields an
+        // earlier run saved (normally the same cell without the scatterer) are read into Ej_freq_ .. Hk_freq_ and scaled by -1, so that
+        // combineField below ADDS this run's fields to minus the incident ones.  Same order as saveFields: per role, per surface.
+        std::vector<std::vector<cplx>> loaded[4];
+        std::vector<std::array<int32_t, 3>> loadedN[4];
+        if(fx.load)
+        {
+            std::ifstream lf(fx.incdFile.c_str(), std::ios::binary | std::ios::in);
+            if(!lf) throw std::logic_error("flux load: cannot open " + fx.incdFile);
+            int32_t hdr[4], cnt[4];
+            lf.read(reinterpret_cast<char*>(hdr), sizeof(hdr));
+            lf.read(reinterpret_cast<char*>(cnt), sizeof(cnt));
+            if(nfreq != hdr[0] || fx.sz[0] != hdr[1] || fx.sz[1] != hdr[2] || fx.sz[2] != hdr[3])
+                throw std::logic_error("Given incident fields do not match size and frequency numbers for the current calculations");
+            for(int r = 0; r < 4; ++r)
+                if(cnt[r] != (int32_t)surf.size()) throw std::logic_error("The size of the field vectors of the saved fields are not the same as those in the current calculation");
+            for(int r = 0; r < 4; ++r)
+                for(size_t vv = 0; vv < surf.size(); ++vv)
+                {
+                    std::array<int32_t, 3> nv;
+                    lf.read(reinterpret_cast<char*>(nv.data()), sizeof(int32_t) * 3);
+                    if(!lf || nv[0] < 0 || nv[1] < 0 || nv[2] < 0) throw std::logic_error("flux load: " + fx.incdFile + " is truncated");
+                    std::vector<cplx> v((size_t)nv[0] * nv[1] * nv[2]);
+                    lf.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * sizeof(cplx)));
+                    if(!lf) throw std::logic_error("flux load: " + fx.incdFile + " is truncated");
+                    for(cplx& c : v) c = cmul(cplx(-1.0, 0.0), c);             // zscal_(size, weight = -1.0)
+                    loaded[r].push_back(std::move(v)); loadedN[r].push_back(nv);
+                }
+        }
+
         // ---- combineField: the stored fields of a surface averaged onto the face centres, per role a grid {nfreq, sz[tc1], sz[cor]}
         struct Face { int nx = 0, ny = 0; double dx = 0, dy = 0; std::vector<cplx> g[4]; bool has[4] = {false, false, false, false}; double weight = 1.0; };
         std::vector<Face> faces(surf.size());
@@ -114,6 +145,14 @@ void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std
                 if(arr.empty()) continue;
                 F.has[r] = true;
                 F.g[r].assign((size_t)nfreq * F.nx * F.ny, cplx(0.0, 0.0));
+                if(fx.load)
+                {
+                    static const char* roleName[4] = {"Ej_freq_", "Ek_freq_", "Hj_freq_", "Hk_freq_"};
+                    const std::array<int32_t, 3>& nv = loadedN[r][vv];
+                    if(nv[0] != nfreq || nv[1] != F.ny || nv[2] != F.nx)
+                        throw std::logic_error(std::string("When loading in a ") + roleName[r] + " field in a flux region, one of the size elements did not agree with the file.");
+                    F.g[r] = loaded[r][vv];
+                }
                 const int corJK = (r == 0 || r == 3) ? corJ : corK;                 // Ej, Hk: corJ; Ek, Hj: corK
                 for(const Storage& st : arr)
                 {

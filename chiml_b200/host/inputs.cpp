@@ -561,6 +561,9 @@ Inputs::Inputs(const Json& IP)
         f.SI = fj.get<bool>("SI", false);
         f.crossSec = fj.get<bool>("cross_sec", false);
         f.save = fj.get<bool>("save", false);
+        f.load = fj.get<bool>("load", false);
+        f.incdFile = fj.get<std::string>("incd_fileds", "");           // the reference's spelling (INPUTS/parallelInputs.cpp:828)
+        if(f.load && f.incdFile.empty()) throw std::logic_error("Trying to load in file without a valid path, in the " + std::to_string(fluxes_.size()) + " flux detector");
         fluxes_.push_back(f);
     }
 }

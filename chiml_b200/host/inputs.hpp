@@ -101,7 +101,7 @@ struct DetectorInput
 
 struct FluxInput
 {
-    std::string name; std::array<int, 3> loc, sz; double weight; int timeInt; std::vector<double> freqs; bool SI = false, crossSec = false, save = false;
+    std::string name; std::array<int, 3> loc, sz; double weight; int timeInt; std::vector<double> freqs; bool SI = false, crossSec = false, save = false, load = false; std::string incdFile;
 };
 
 class Inputs

@@ -23,6 +23,30 @@ subprocess.run([REF, "flux3d_save.json", "--quiet"], cwd=work, check=True, stdou
 shutil.copy(os.path.join(work, cfg["FluxList"][0]["name"] + "_fields.dat"), os.path.join(HERE, "out_expected", "flux3d_save", "box_fields.dat"))
 print("flux3d_save", os.path.getsize(os.path.join(HERE, "out_expected", "flux3d_save", "box_fields.dat")), "bytes")
 
+# flux3d_load: the usual two-run normalisation.  Run 1 = flux3d WITHOUT its scatterer, box region saved -> empty_fields.dat; run 2 =
+# flux3d with "load" on the box region, which starts its surface fields from minus the saved ones (loadFields(-1.0),
+# DTC/parallelFlux.hpp:664-722): box.dat then holds the flux of the scattered field alone.
+out = os.path.join(HERE, "out_expected", "flux3d_load")
+os.makedirs(out, exist_ok=True)
+cfg = json.load(open(os.path.join(HERE, "flux3d.json")))
+cfg["ObjectList"] = []
+cfg["FluxList"] = cfg["FluxList"][:1]
+cfg["FluxList"][0]["save"] = True
+work = tempfile.mkdtemp(prefix="fluxref_")
+json.dump(cfg, open(os.path.join(work, "empty.json"), "w"), indent=1)
+subprocess.run([REF, "empty.json", "--quiet"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+shutil.copy(os.path.join(work, cfg["FluxList"][0]["name"] + "_fields.dat"), os.path.join(out, "empty_fields.dat"))
+cfg = json.load(open(os.path.join(HERE, "flux3d.json")))
+cfg["FluxList"][0]["load"] = True
+cfg["FluxList"][0]["incd_fileds"] = "empty_fields.dat"
+json.dump(cfg, open(os.path.join(out, "flux3d_load.json"), "w"), indent=1)
+work = tempfile.mkdtemp(prefix="fluxref_")
+shutil.copy(os.path.join(out, "flux3d_load.json"), work)
+shutil.copy(os.path.join(out, "empty_fields.dat"), work)
+subprocess.run([REF, "flux3d_load.json", "--quiet"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+shutil.copy(os.path.join(work, cfg["FluxList"][0]["name"] + ".dat"), os.path.join(out, "box.dat"))
+print("flux3d_load", open(os.path.join(out, "box.dat")).read()[:400])
+
 for case in CASES:
     work = tempfile.mkdtemp(prefix="fluxref_")
     shutil.copy(os.path.join(HERE, case + ".json"), work)

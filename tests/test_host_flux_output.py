@@ -93,3 +93,42 @@ def test_flux_files_from_slab_accumulator_parts(case, nranks, tmp_path):
         got = open(tmp_path / (fl["name"] + ".dat"), "rb").read()
         want = open(os.path.join(util.GOLDEN, "out_expected", case, os.path.basename(fl["name"]) + ".dat"), "rb").read()
         assert got == want, f"{case}: {fl['name']}.dat from {nranks} slabs differs from the reference's file"
+
+
+def _flux_tool(tmp_path, json_path, case="flux3d", extra=()):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_flux")], check=True, stdout=subprocess.DEVNULL)
+    write_dft_files(case, str(tmp_path))
+    return subprocess.run([os.path.join(ROOT, "chiml_b200", "chiml_flux"), json_path, *extra], cwd=tmp_path, capture_output=True, text=True)
+
+
+def test_saved_surface_fields_equal_the_reference_file(tmp_path):
+    """"save": true on a 3-D flux box: <name>_fields.dat (parallelFluxDTC::saveFields, DTC/parallelFlux.hpp:616-659) byte for byte."""
+    d = os.path.join(util.GOLDEN, "out_expected", "flux3d_save")
+    r = _flux_tool(tmp_path, os.path.join(d, "flux3d_save.json"))
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "out/f3/box_fields.dat", "rb").read() == open(os.path.join(d, "box_fields.dat"), "rb").read()
+
+
+def test_loaded_incident_fields_are_subtracted_like_the_reference(tmp_path):
+    """"load": true: the surface fields start from minus the fields an earlier run saved (loadFields(-1.0), :664-722; here the
+    reference's own save of the cell without the scatterer) and the spectrum file equals the reference's for that input."""
+    import shutil
+    d = os.path.join(util.GOLDEN, "out_expected", "flux3d_load")
+    shutil.copy(os.path.join(d, "empty_fields.dat"), tmp_path)
+    r = _flux_tool(tmp_path, os.path.join(d, "flux3d_load.json"))
+    assert r.returncode == 0, r.stderr
+    assert open(tmp_path / "out/f3/box.dat", "rb").read() == open(os.path.join(d, "box.dat"), "rb").read()
+    # the other regions of the input load nothing and stay as in the plain run
+    assert open(tmp_path / "out/f3/px.dat", "rb").read() == open(os.path.join(util.GOLDEN, "out_expected", "flux3d", "px.dat"), "rb").read()
+
+
+def test_load_refuses_fields_of_another_region(tmp_path):
+    import shutil
+    d = os.path.join(util.GOLDEN, "out_expected", "flux3d_load")
+    cfg = json.load(open(os.path.join(d, "flux3d_load.json")))
+    cfg["FluxList"][1]["load"] = True
+    cfg["FluxList"][1]["incd_fileds"] = "empty_fields.dat"          # a 3-frequency box file for the 4-frequency plane
+    json.dump(cfg, open(tmp_path / "bad.json", "w"))
+    shutil.copy(os.path.join(d, "empty_fields.dat"), tmp_path)
+    r = _flux_tool(tmp_path, str(tmp_path / "bad.json"))
+    assert r.returncode != 0 and "do not match size and frequency" in (r.stderr + r.stdout)
