@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_download_emitter_state", "chiml_gpu_download_emitter_pol", "chiml_gpu_read_population",
     "chiml_gpu_halo_export", "chiml_gpu_halo_bind", "chiml_gpu_add_dft", "chiml_gpu_step_n_dft", "chiml_gpu_download_dft",
     "chiml_gpu_set_march", "chiml_gpu_set_ordip_pole_count", "chiml_gpu_reserve_steps", "chiml_gpu_consume_detector",
-    "chiml_gpu_consume_population", "chiml_gpu_set_persistent",
+    "chiml_gpu_consume_population", "chiml_gpu_set_persistent", "chiml_gpu_set_periodic",
 ]
 
 
@@ -145,6 +145,7 @@ def lib() -> C.CDLL:
     L.chiml_gpu_read_detector_range.argtypes = [vp, i, sz, sz, vp, C.POINTER(sz)]
     L.chiml_gpu_halo_export.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.chiml_gpu_halo_bind.argtypes = [vp, C.c_char_p, sz, C.c_char_p, sz]
+    L.chiml_gpu_set_periodic.argtypes = [vp, i, vp]
     L.chiml_gpu_add_dft.argtypes = [vp, i, i, i, i, i, i, vp, sz, sz, C.POINTER(i)]
     L.chiml_gpu_step_n_dft.argtypes = [vp, i, vp, vp]
     L.chiml_gpu_download_dft.argtypes = [vp, i, vp, vp]
@@ -224,6 +225,8 @@ class GpuSim:
                     slot = C.c_int()
                     self._chk(L.chiml_gpu_add_detector(self.h, d.field, (C.c_int32 * 3)(*box[0]), (C.c_int32 * 3)(*box[1]), d.every, C.byref(slot)))
                     self.det_slots.append(slot.value)
+            for comp, w in sorted(plan.periodic.items()):
+                self._chk(L.chiml_gpu_set_periodic(self.h, comp, (C.c_int32 * 7)(*w)))
             if plan.nranks > 1:
                 self._chk(L.chiml_gpu_set_ordip_pole_count(self.h, plan.n_ordip_poles))
             if persistent is not None:

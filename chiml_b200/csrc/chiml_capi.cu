@@ -210,6 +210,22 @@ int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global)
     return CHIML_OK;
 }
 
+int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* w)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_periodic after commit");
+    if(comp < 0 || comp > 5 || !w) return fail(ctx, CHIML_ERR_ARG, "set_periodic: component 0..5 and a wrap description");
+    if(!field_exists(ctx, comp)) return fail(ctx, CHIML_ERR_ARG, "set_periodic: the component does not exist in this mode");
+    if(ctx->g.nranks > 1) return fail(ctx, CHIML_ERR_UNSUPPORTED, "periodic boundaries are covered for single-slab runs only");
+    const bool twoD = ctx->lz == 1;
+    // the images must lie inside the arrays and the box must have an inside
+    if(w->xmax < 2 || w->ymax < 2 || w->xmax > ctx->lx - 1 || w->ymax > ctx->ly - 1 || w->nx != w->xmax - 1 || w->ny != w->ymax ||
+       (twoD ? (w->zmin != 0) : (w->zmin != 1 || w->zmax < 2 || w->zmax > ctx->lz - 1 || w->nz != w->zmax - 1)))
+        return fail(ctx, CHIML_ERR_ARG, "set_periodic: the wrap box does not fit the grid (expected the arguments of applBCE_/applBCH_)");
+    ctx->wrap[comp] = *w; ctx->has_wrap[comp] = true; ctx->periodic = true;
+    return 0;
+}
+
 int chiml_gpu_set_persistent(ChimlCtx* ctx, int on)
 {
     if(!ctx) return CHIML_ERR_ARG;
@@ -662,6 +678,16 @@ int chiml_gpu_commit(ChimlCtx* ctx)
     if(!ctx) return CHIML_ERR_ARG;
     if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "commit called twice");
     CK(cudaSetDevice(ctx->device));
+    if(ctx->periodic)
+    {
+        // the reference also wraps the node-centred oriented-dipole pole grids (applBCOrDip_, parallelFDTDField.hpp:1362-1363): the compact
+        // node pools hold no ghost nodes
+        bool ordip = !ctx->lists[CHIML_LIST_ORDIPP][0].runs.empty();
+        for(int c = 0; c < 3; ++c) ordip = ordip || !ctx->lists[CHIML_LIST_ORDIPD][c].runs.empty();
+        if(ordip) return fail(ctx, CHIML_ERR_UNSUPPORTED, "oriented-dipole media under periodic boundaries are outside the covered hot path");
+        for(int comp = 0; comp < 6; ++comp)
+            if(field_exists(ctx, comp) && !ctx->has_wrap[comp]) return fail(ctx, CHIML_ERR_ARG, "periodic boundaries: set_periodic must be called for every field component");
+    }
     int rc;
     int* d_err = nullptr;
     if((rc = dev_alloc(ctx, &d_err, 1))) return rc;
@@ -1355,6 +1381,28 @@ void launch_sources(ChimlCtx* ctx, long long k, int nsrc, int part)
     }
 }
 
+// applBCH_ / applBCE_ (step() items 9 and 17): periodic wrap copies of the three components of one family
+void launch_wraps(ChimlCtx* ctx, bool isE)
+{
+    if(!ctx->periodic) return;
+    WrapArgs wa;
+    std::memset(&wa, 0, sizeof(wa));
+    wa.lz = ctx->lz; wa.px = ctx->px;
+    long most = 0;
+    for(int i = 0; i < 3; ++i)
+    {
+        const int comp = (isE ? 0 : 3) + i;
+        if(!ctx->has_wrap[comp] || !ctx->d_field[comp]) continue;
+        const ChimlWrap& w = ctx->wrap[comp];
+        wa.f[wa.n] = ctx->d_field[comp]; wa.w[wa.n] = w; ++wa.n;
+        const long X = w.xmax + 1, Y = w.ymax + 1, Z = w.zmax - w.zmin + 2;
+        most = std::max(most, w.zmin != 0 ? 2 * (X * Z + X * (Y - 2) + (Y - 2) * (Z - 2)) : 2L * (w.xmax - 1 + w.ymax));
+    }
+    if(wa.n == 0) return;
+    LaunchScope ls(ctx, K_WRAP);
+    k_wrap<<<dim3((unsigned)std::max<long>(1, std::min<long>((most + 255) / 256, 148 * 4)), wa.n, 1), 256, 0, ctx->stream>>>(wa);
+}
+
 void launch_node_poles(ChimlCtx* ctx)
 {
     if(!ctx->d_info_node) return;
@@ -1432,6 +1480,8 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
         launch_family<false>(ctx, a, block, 0);
         // sources (item 7): all sources, E and H alike, are injected here
         launch_sources(ctx, k, nsrc, 0);
+        // periodic boundaries of H (item 9)
+        launch_wraps(ctx, false);
         // oriented-dipole poles at the nodes (item 10, first loop)
         launch_node_poles(ctx);
         // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
@@ -1444,6 +1494,8 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
             int rc = launch_density_step(ctx, em);
             if(rc) return rc;
         }
+        // periodic boundaries of E (item 17)
+        launch_wraps(ctx, true);
     }
     ctx->pcur = 1 - ctx->pcur;
     ++ctx->step_count;
@@ -1665,6 +1717,8 @@ int launch_steps_2d(ChimlCtx* ctx, int n, int nsrc)
     }
     pa.tw = ctx->d_tw; pa.tw_per_step = per_step;
     pa.lx = ctx->lx; pa.lz = ctx->lz; pa.px = ctx->px;
+    pa.periodic = ctx->periodic ? 1 : 0;
+    for(int c = 0; c < 6; ++c) { pa.wrap[c] = ctx->wrap[c]; pa.has_wrap[c] = ctx->has_wrap[c] && ctx->d_field[c] ? 1 : 0; }
     // no more blocks than there are work items in the largest phase (8 warps per block, one item per warp at a time)
     unsigned items = 1;
     for(int fam = 0; fam < 2; ++fam) items = std::max(items, ctx->ntiles[fam][0] + 3 * ctx->ntiles[fam][1] + 3 * ctx->ntiles[fam][2]);
@@ -1988,7 +2042,7 @@ int chiml_gpu_n_kernel_kinds(void) { return K_NKINDS; }
 int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out)
 {
     static const char* names[K_NKINDS] = {"k_fast<E>", "k_uniform<E>", "k_general<E>", "k_fast<H>", "k_uniform<H>", "k_general<H>",
-                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft", "k_steps_2d"};
+                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft", "k_steps_2d", "k_wrap"};
     if(!ctx || !out || kind < 0 || kind >= K_NKINDS) return CHIML_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -89,7 +89,7 @@ struct DetectorDev
 };
 
 // kernels of the step loop, for launch / time / algorithmic-byte accounting
-enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_STEPS_2D, K_NKINDS };
+enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_STEPS_2D, K_WRAP, K_NKINDS };
 struct KernelStat { int64_t launches = 0; double ms_total = 0.0; double alg_bytes = 0.0; int64_t timed = 0; };
 
 // one parallelQE object on the device (chiml_emitters.cuh)
@@ -209,6 +209,11 @@ struct ChimlCtx
     chiml::HostList lists[5][6];
     chiml::HostPml hpml[6][2];
     std::vector<chiml::HostObj> objs;
+
+    // periodic boundaries (chiml_gpu_set_periodic): wrap copies per component after its half step
+    ChimlWrap wrap[6] = {};
+    bool has_wrap[6] = {};
+    bool periodic = false;
 
     void* d_tmaps = nullptr;                     // TMA descriptors of the field and psi arrays (chiml_kernels.cuh TMAP_*), 3-D grids
     // persistent multi-step kernel of 2-D grids (chiml_persist.cuh)

@@ -220,6 +220,52 @@ __global__ void k_source(double* field, int lx0, int lz0, int ly0, int sx, int s
     }
 }
 
+// Periodic wrap copies of up to three components in one launch (applyBC1Proc, UTIL/FDTD_up_eq.cpp:1058-1116; blockIdx.y = component).
+// The reference's sequence of dcopy_ calls amounts to: every ghost cell of the box [0, xmax] x [0, ymax] x [zmin-1, zmax] takes the
+// value of its periodic image inside the box (x = 0 <- xmax-1, x = xmax <- 1, likewise y and z); every source is an inner cell, so
+// the copies are independent.  3-D: the shell is walked as y faces (whole planes), z faces (rows 1 .. ymax-1), x faces (the rest).
+// 2-D (zmin = 0): rows 0 and ymax over x in [1, xmax-1], columns 0 and xmax over y in [1, ymax] (the cells (0, 0), (xmax, 0) stay as they
+// are, as in the reference).
+struct WrapArgs { double* f[3]; ChimlWrap w[3]; int n; int lz; long px; };
+__global__ void k_wrap(WrapArgs a)
+{
+    const int c = blockIdx.y;
+    if(c >= a.n) return;
+    double* F = a.f[c];
+    const ChimlWrap w = a.w[c];
+    const long px = a.px, lz = a.lz;
+    const long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x, istep = (long)gridDim.x * blockDim.x;
+    if(w.zmin != 0)
+    {
+        const long X = w.xmax + 1, Y = w.ymax + 1, Z = w.zmax - w.zmin + 2;
+        const long nA = 2 * X * Z, nB = 2 * X * (Y - 2), nC = 2 * (Y - 2) * (Z - 2);
+        for(long i = i0; i < nA + nB + nC; i += istep)
+        {
+            int x, y, z;
+            if(i < nA)           { x = (int)(i % X); const long r = i / X; z = (int)(r % Z) + w.zmin - 1; y = (r / Z) ? w.ymax : 0; }
+            else if(i < nA + nB) { const long j = i - nA; x = (int)(j % X); const long r = j / X; y = (int)(r % (Y - 2)) + 1; z = (r / (Y - 2)) ? w.zmax : w.zmin - 1; }
+            else                 { const long j = i - nA - nB; z = (int)(j % (Z - 2)) + w.zmin; const long r = j / (Z - 2); y = (int)(r % (Y - 2)) + 1; x = (r / (Y - 2)) ? w.xmax : 0; }
+            const int sx = x == 0 ? w.xmax - 1 : (x == w.xmax ? 1 : x);
+            const int sy = y == 0 ? w.ymax - 1 : (y == w.ymax ? 1 : y);
+            const int sz = z == w.zmin - 1 ? w.zmax - 1 : (z == w.zmax ? w.zmin : z);
+            F[x + px * (z + lz * y)] = F[sx + px * (sz + lz * sy)];
+        }
+    }
+    else
+    {
+        const long nR = 2L * (w.xmax - 1), nC = 2L * w.ymax;
+        for(long i = i0; i < nR + nC; i += istep)
+        {
+            int x, y;
+            if(i < nR) { x = (int)(i % (w.xmax - 1)) + 1; y = (i / (w.xmax - 1)) ? w.ymax : 0; }
+            else       { const long j = i - nR; y = (int)(j % w.ymax) + 1; x = (j / w.ymax) ? w.xmax : 0; }
+            const int sx = x == 0 ? w.xmax - 1 : (x == w.xmax ? 1 : x);
+            const int sy = y == 0 ? w.ymax - 1 : (y == w.ymax ? 1 : y);
+            F[x + px * (long)y] = F[sx + px * (long)sy];
+        }
+    }
+}
+
 // detector sampling (DTC/parallelStorageDTC.cpp:17-44): copy the box into the ring, x fastest, then z, then y
 __global__ void k_detector(const double* field, int lx0, int lz0, int ly0, int sx, int sz, int sy, int lz, long px, double* out)
 {

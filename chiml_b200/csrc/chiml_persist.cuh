@@ -10,6 +10,7 @@
 //        taken after the previous step: the H half        step only reads H)
 //        step only reads E)
 //
+// (periodic boundaries add the wrap copies of H after the sources and of E after the E half step, each behind its own barrier)
 // Three barriers per step instead of seven launches; small grids stay in L2 between the phases.  The work items are the tile records
 // of the launch-per-phase kernels (same device functions, same arithmetic, same results): a warp takes one record (k_fast), one
 // (record, component) pair (k_uniform_rows / k_general) at a time.
@@ -40,7 +41,32 @@ struct Persist2DArgs
     P2DDft dft[P2D_MAX_DFT];
     const double* tw; unsigned long long tw_per_step;
     int lx, lz; long px;
+    int periodic;                  // wrap copies (chiml_gpu_set_periodic) of the components that exist
+    ChimlWrap wrap[6]; int has_wrap[6];
 };
+
+// applyBC1Proc on a 2-D grid (k_wrap, chiml_kernels.cuh): rows 0 and ymax over x in [1, xmax-1], columns 0 and xmax over y in [1, ymax],
+// each ghost cell from its periodic image inside
+__device__ __forceinline__ void p2d_wraps(const Persist2DArgs& p, const bool isE, const unsigned long long gt, const unsigned long long nt)
+{
+    for(int i = 0; i < 3; ++i)
+    {
+        const int comp = (isE ? 0 : 3) + i;
+        if(!p.has_wrap[comp]) continue;
+        const ChimlWrap w = p.wrap[comp];
+        double* F = p.field[comp];
+        const unsigned long long nR = 2ull * (w.xmax - 1), nC = 2ull * w.ymax;
+        for(unsigned long long e = gt; e < nR + nC; e += nt)
+        {
+            int x, y;
+            if(e < nR) { x = (int)(e % (w.xmax - 1)) + 1; y = (e / (w.xmax - 1)) ? w.ymax : 0; }
+            else       { const unsigned long long j = e - nR; y = (int)(j % w.ymax) + 1; x = (j / w.ymax) ? w.xmax : 0; }
+            const int sx = x == 0 ? w.xmax - 1 : (x == w.xmax ? 1 : x);
+            const int sy = y == 0 ? w.ymax - 1 : (y == w.ymax ? 1 : y);
+            F[x + p.px * (long)y] = F[sx + p.px * (long)sy];
+        }
+    }
+}
 
 template <bool IS_E, int MODE>
 __device__ __forceinline__ void p2d_family(const StepArgs& a, const Persist2DArgs& p, const unsigned gw, const unsigned nw)
@@ -168,6 +194,12 @@ __global__ void __launch_bounds__(256) k_steps_2d(const __grid_constant__ Persis
             }
         }
         p2d_barrier(grid);
+        // ---- periodic boundaries of H (item 9)
+        if(p.periodic)
+        {
+            p2d_wraps(p, false, (unsigned long long)blockIdx.x * nthr + tid, (unsigned long long)gridDim.x * nthr);
+            p2d_barrier(grid);
+        }
         // ---- E half step: isotropic poles, updateD / updateE, updateEPML_, D2E (items 10-15); H-field samples of this step
         {
             const bool due = p2d_samples_due(p, count, true);
@@ -176,6 +208,12 @@ __global__ void __launch_bounds__(256) k_steps_2d(const __grid_constant__ Persis
             else p2d_family<true, MODE>(sh[1], p, blockIdx.x * lastw + threadIdx.y, gridDim.x * lastw);
         }
         p2d_barrier(grid);
+        // ---- periodic boundaries of E (item 17)
+        if(p.periodic)
+        {
+            p2d_wraps(p, true, (unsigned long long)blockIdx.x * nthr + tid, (unsigned long long)gridDim.x * nthr);
+            p2d_barrier(grid);
+        }
     }
     if(p.nsteps > 0) p2d_samples(p, p.step0 + p.nsteps, p.nsteps - 1, false, (unsigned long long)blockIdx.x * nthr + tid, (unsigned long long)gridDim.x * nthr);
 }

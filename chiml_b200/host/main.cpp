@@ -112,6 +112,7 @@ int main(int argc, char** argv)
             if(local_box(P, P.detectors[d], loc, sz)) check(ctx, chiml_gpu_add_detector(ctx, P.detectors[d].field, loc, sz, P.detectors[d].every, &detSlot[d]), "add_detector");
         }
         if(nranks > 1) check(ctx, chiml_gpu_set_ordip_pole_count(ctx, P.grid.n_ordip_poles), "set_ordip_pole_count");
+        for(const ChimlPlanPeriodic& pp : P.periodic) check(ctx, chiml_gpu_set_periodic(ctx, pp.comp, &pp.wrap), "set_periodic");
         for(const PlanEmitter& e : P.emitters)
         {
             ChimlEmitterDesc d;

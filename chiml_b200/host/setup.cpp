@@ -732,6 +732,23 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
     P.grid.n_ordip_poles = disp ? nOrDip : 0;
     P.grid.t_max = IP.tMax_;
 
+    // ---- periodic boundaries: the arguments step() hands to applBCE_ / applBCH_ (parallelFDTDField.hpp:1267-1269,1285-1287) with
+    // yEPBC_ / yHPBC_ of the single-process branch (parallelFDTDField.cpp:163-171,329-336) and zMinPBC_ / zMaxPBC_ (hpp:444-445) ----
+    if(IP.periodic_)
+    {
+        if(nranks > 1) throw std::logic_error("periodic boundaries are covered for single-slab runs (the reference's multi-rank periodic run takes applyBCProcMid on every rank, SURVEY.md B.5)");
+        if(nOrDip > 0) throw std::logic_error("oriented-dipole media under periodic boundaries are outside the covered hot path");
+        const int l0 = g.ln[0] - 2, l1 = g.ln[1] - 2;
+        const int zMin = g.twoD ? 0 : 1, zMax = g.twoD ? 1 : g.ln[2] - 2;
+        // y-limited components (fieldEnd[1] = 1: Ey, Hx, Hz) wrap at row ln_vec_[1], the others at ln_vec_[1] + 1
+        const int yE[3] = {l1 + 1, l1, l1 + 1}, yH[3] = {l1, l1 + 1, l1};
+        const ChimlWrap w[6] = {{l0 - 1, yE[0], zMax, l0, yE[0], zMin, zMax + 1},     {l0, yE[1], zMax, l0 + 1, yE[1], zMin, zMax + 1},
+                                {l0, yE[2], zMax - 1, l0 + 1, yE[2], zMin, zMax},     {l0, yH[0], zMax - 1, l0 + 1, yH[0], zMin, zMax},
+                                {l0 - 1, yH[1], zMax - 1, l0, yH[1], zMin, zMax},     {l0 - 1, yH[2], zMax, l0, yH[2], zMin, zMax + 1}};
+        for(int comp = 0; comp < 6; ++comp)
+            if(comp_exists(mode, comp)) { ChimlPlanPeriodic pp; pp.comp = comp; pp.wrap = w[comp]; P.periodic.push_back(pp); }
+    }
+
     Rasteriser ras(IP, g);
     // ---- update lists (parallelFDTDField.cpp:80-92,248-261) ----
     for(int comp = 0; comp < 6; ++comp)
@@ -884,6 +901,7 @@ void SlabPlan::write(const std::string& path) const
     if(!out) throw std::runtime_error("cannot write " + path);
     { std::string p; int32_t v = CHIML_PLAN_VERSION; app(p, v); put_rec(out, "CHIMLPLN", p); }
     { std::string p; app(p, grid); put_rec(out, "GRID", p); }
+    for(const ChimlPlanPeriodic& pp : periodic) { std::string p; app(p, pp); put_rec(out, "PERIODIC", p); }
     // same record order as oracle/ref_driver.cpp
     for(int c = 0; c < 3; ++c)
     {

@@ -61,6 +61,7 @@ struct SlabPlan
     std::vector<PlanDetector> detectors;
     std::vector<PlanEmitter> emitters;
     std::vector<PlanDft> dfts;
+    std::vector<ChimlPlanPeriodic> periodic;   // wrap copies per component (CompCell.PBC)
     bool dielectricMatInPML = false;
 
     void write(const std::string& path) const;

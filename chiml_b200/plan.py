@@ -148,6 +148,7 @@ class Plan:
     detectors: List[PlanDetector] = field(default_factory=list)
     emitters: List[PlanEmitter] = field(default_factory=list)
     dfts: List[PlanDft] = field(default_factory=list)
+    periodic: Dict[int, Tuple[int, ...]] = field(default_factory=dict)      # comp -> (nx, ny, nz, xmax, ymax, zmin, zmax) (ChimlWrap)
 
     @property
     def ncell(self) -> int:
@@ -221,6 +222,9 @@ def read_plan(path: str) -> Plan:
             freq = np.frombuffer(payload, dtype="<f8", count=nfreq, offset=40).copy()
             lines = np.frombuffer(payload, dtype="<i4", count=2 * nlines, offset=40 + 8 * nfreq).copy().reshape(nlines, 2)
             plan.dfts.append(PlanDft(fld, group, every, nfreq, npts, stride, acc_len, freq, lines))
+        elif tag == "PERIODIC":
+            v = struct.unpack_from("<8i", payload, 0)
+            plan.periodic[v[0]] = tuple(v[1:8])
         elif tag == "EMITTER":
             v = struct.unpack_from(_EMIT_FMT, payload, 0)
             obj, N, nsys, nemit = v[0:4]
@@ -305,6 +309,8 @@ def write_plan(path: str, plan: Plan) -> None:
     for d in plan.dfts:
         out.append(_rec("DFT", struct.pack("<6iQQ", d.field, d.group, d.every, d.nfreq, d.npts, d.stride, len(d.lines), d.acc_len)
                         + np.ascontiguousarray(d.freq, "<f8").tobytes() + np.ascontiguousarray(d.lines, "<i4").tobytes()))
+    for comp, w in sorted(plan.periodic.items()):
+        out.append(_rec("PERIODIC", struct.pack("<8i", comp, *w)))
     with open(path, "wb") as f:
         f.write(b"".join(out))
 

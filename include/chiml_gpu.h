@@ -167,6 +167,17 @@ typedef struct ChimlDftLine { int32_t ind, out; } ChimlDftLine;   /* the (grid i
 int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq, int npts, int stride,
                       const ChimlDftLine* lines, size_t nlines, size_t acc_len, int* slot);
 
+/* Periodic boundaries (CompCell.PBC with real fields, i.e. k-point = 0): after its half step every E / H component gets the wrap
+ * copies of applyBC1Proc (UTIL/FDTD_up_eq.cpp:1058-1116) -- every ghost cell of the box [0, xmax] x [0, ymax] x [zmin-1, zmax]
+ * receives the value of its periodic image inside (x = 0 <- xmax-1, x = xmax <- 1, likewise y and z; on 2-D grids, zmin = 0, rows
+ * first, then columns over rows 1 .. ymax).  The seven numbers are the arguments the reference passes to applBCH_[c] / applBCE_[c]
+ * (FDTD_MANAGER/parallelFDTDField.hpp:1267-1269,1285-1287; yHPBC_/yEPBC_/zMinPBC_/zMaxPBC_ from parallelFDTDField.cpp:153-171,
+ * 322-336, parallelFDTDField.hpp:444-445): for a component trimmed by one point along an axis (fieldEnd) the last, never updated
+ * point of that axis is the upper image.  comp 0..5 = Ex..Hz.  Single slab only (the reference's multi-rank periodic run takes
+ * applyBCProcMid on every rank); oriented-dipole media are refused together with it. */
+typedef struct ChimlWrap { int32_t nx, ny, nz, xmax, ymax, zmin, zmax; } ChimlWrap;
+int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* wrap);
+
 /* Number of oriented-dipole pole grids of the WHOLE grid, orDipLorP_[c].size() = the largest pole count of any oriented-dipole
  * object (parallelFDTDField.hpp:452-478): every rank of the reference allocates and exchanges that many, whether or not its own slab
  * holds such an object.  Needed with several slabs only -- a slab that holds no oriented-dipole cell, or objects with fewer poles

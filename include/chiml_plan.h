@@ -84,6 +84,11 @@ typedef struct ChimlPlanDftHdr        /* tag "DFT     ": header, freq[nfreq] dou
     int32_t field, group, every, nfreq, npts, stride;
     uint64_t nlines, acc_len;
 } ChimlPlanDftHdr;
+typedef struct ChimlPlanPeriodic      /* tag "PERIODIC": the wrap copies of one component (chiml_gpu_set_periodic) */
+{
+    int32_t comp;
+    ChimlWrap wrap;
+} ChimlPlanPeriodic;
 #pragma pack(pop)
 
 #endif /* CHIML_PLAN_H */

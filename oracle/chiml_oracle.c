@@ -69,6 +69,8 @@ struct OracleSim
     const double* twiddles;        /* of the current oracle_step_n_dft call */
     long step_count;
     int phase_mask;                /* bit 0: H half step + sources, 1: node poles, 2: E half step + emitter addP, 3: emitter density */
+    ChimlWrap wrap[6];             /* periodic wrap copies per component (applBCE_ / applBCH_ arguments) */
+    int has_wrap[6];
 };
 
 static int comp_exists(const OracleSim* s, int field)
@@ -615,6 +617,69 @@ static void pml_component(OracleSim* s, int comp, double* target, int tid, int n
     }
 }
 
+/* applyBC1Proc, real fields (UTIL/FDTD_up_eq.cpp:1058-1116): the periodic wrap copies of one component on a single process, in the
+ * reference's order of dcopy_ calls.  PT(x, y, z) = parallelGrid::point(x, y, z) (GRID/parallelGrid.hpp:363). */
+int oracle_set_periodic(OracleSim* s, int comp, const ChimlWrap* w)
+{
+    if(!s || comp < 0 || comp > 5 || !w || s->g.nranks != 1) return CHIML_ERR_ARG;
+    s->wrap[comp] = *w; s->has_wrap[comp] = 1;
+    return 0;
+}
+static void copy_strided(int n, const double* x, size_t incx, double* y, size_t incy) { for(int i = 0; i < n; ++i) y[(size_t)i * incy] = x[(size_t)i * incx]; }
+static void apply_bc_1proc(const OracleSim* s, double* F, const ChimlWrap* w)
+{
+    const size_t lx = (size_t)s->g.ln[0], lz = (size_t)s->g.ln[2];
+#define PT(x, y, z) (F + ((size_t)(x) + lx * ((size_t)(z) + lz * (size_t)(y))))
+    const int nx = w->nx, ny = w->ny, nz = w->nz, xmax = w->xmax, ymax = w->ymax, zmin = w->zmin, zmax = w->zmax;
+    if(zmin != 0)
+    {
+        for(int kk = zmin; kk <= nz; ++kk)
+        {
+            copy_strided(nx, PT(1, ymax - 1, kk), 1, PT(1, 0, kk), 1);
+            copy_strided(nx, PT(1, 1, kk), 1, PT(1, ymax, kk), 1);
+        }
+        for(int jj = 1; jj < ny; ++jj)
+        {
+            copy_strided(nz, PT(xmax - 1, jj, 1), lx, PT(0, jj, 1), lx);
+            copy_strided(nz, PT(1, jj, 1), lx, PT(xmax, jj, 1), lx);
+            copy_strided(nx, PT(1, jj, zmax - 1), 1, PT(1, jj, zmin - 1), 1);
+            copy_strided(nx, PT(1, jj, zmin), 1, PT(1, jj, zmax), 1);
+        }
+        /* X edges */
+        copy_strided(nx, PT(1, 1, zmin), 1, PT(1, ymax, zmax), 1);
+        copy_strided(nx, PT(1, ymax - 1, zmin), 1, PT(1, 0, zmax), 1);
+        copy_strided(nx, PT(1, 1, zmax - 1), 1, PT(1, ymax, zmin - 1), 1);
+        copy_strided(nx, PT(1, ymax - 1, zmax - 1), 1, PT(1, 0, zmin - 1), 1);
+        /* Y edges */
+        copy_strided(ny - 1, PT(1, 1, zmin), lx * lz, PT(xmax, 1, zmax), lx * lz);
+        copy_strided(ny - 1, PT(xmax - 1, 1, zmin), lx * lz, PT(0, 1, zmax), lx * lz);
+        copy_strided(ny - 1, PT(1, 1, zmax - 1), lx * lz, PT(xmax, 1, zmin - 1), lx * lz);
+        copy_strided(ny - 1, PT(xmax - 1, 1, zmax - 1), lx * lz, PT(0, 1, zmin - 1), lx * lz);
+        /* Z edges */
+        copy_strided(nz, PT(1, 1, 1), lx, PT(xmax, ymax, 1), lx);
+        copy_strided(nz, PT(xmax - 1, 1, 1), lx, PT(0, ymax, 1), lx);
+        copy_strided(nz, PT(1, ymax - 1, 1), lx, PT(xmax, 0, 1), lx);
+        copy_strided(nz, PT(xmax - 1, ymax - 1, 1), lx, PT(0, 0, 1), lx);
+        /* corners */
+        *PT(xmax, ymax, zmax) = *PT(1, 1, zmin);
+        *PT(0, ymax, zmax) = *PT(xmax - 1, 1, zmin);
+        *PT(xmax, 0, zmax) = *PT(1, ymax - 1, zmin);
+        *PT(0, 0, zmax) = *PT(xmax - 1, ymax - 1, zmin);
+        *PT(xmax, ymax, zmin - 1) = *PT(1, 1, zmax - 1);
+        *PT(0, ymax, zmin - 1) = *PT(xmax - 1, 1, zmax - 1);
+        *PT(xmax, 0, zmin - 1) = *PT(1, ymax - 1, zmax - 1);
+        *PT(0, 0, zmin - 1) = *PT(xmax - 1, ymax - 1, zmax - 1);
+    }
+    else
+    {
+        copy_strided(nx, PT(1, ymax - 1, 0), 1, PT(1, 0, 0), 1);
+        copy_strided(nx, PT(1, 1, 0), 1, PT(1, ymax, 0), 1);
+        copy_strided(ny, PT(xmax - 1, 1, 0), lx, PT(0, 1, 0), lx);
+        copy_strided(ny, PT(1, 1, 0), lx, PT(xmax, 1, 0), lx);
+    }
+#undef PT
+}
+
 static void step_worker(OracleSim* s, int tid, int nt)
 {
     const int lnx = s->g.ln[0], lnz = s->g.ln[2];
@@ -651,6 +716,10 @@ static void step_worker(OracleSim* s, int tid, int nt)
                         }
             }
         }
+        /* applBCH_ (:1267-1269): periodic wrap copies of the H components */
+        if(tid == 0 && (s->phase_mask & 1))
+            for(int i = 0; i < 3; ++i)
+                if(s->f[CHIML_HX + i] && s->has_wrap[3 + i]) apply_bc_1proc(s, s->f[CHIML_HX + i], &s->wrap[3 + i]);
         BARRIER();
         /* updatePolE (:1348-1365): oriented-dipole poles at nodes, then isotropic poles per component */
         if(s->phase_mask & 2)
@@ -710,6 +779,10 @@ static void step_worker(OracleSim* s, int tid, int nt)
             for(int q = 0; q < s->nqe; ++q) qe_add(s, &s->qe[q], 1);
         if(tid == 0 && (s->phase_mask & 8))
             for(int q = 0; q < s->nqe; ++q) qe_add(s, &s->qe[q], 2);
+        /* applBCE_ (:1285-1287) */
+        if(tid == 0 && (s->phase_mask & 8))
+            for(int i = 0; i < 3; ++i)
+                if(s->f[CHIML_EX + i] && s->has_wrap[i]) apply_bc_1proc(s, s->f[CHIML_EX + i], &s->wrap[i]);
         /* flux->fieldIn(tcur_) (:1300-1302): two dger_ rank-1 updates per line, F(f, i) += 1.0 * tw[f] * u[i] */
         if(tid == 0 && (s->phase_mask & 8))
         {

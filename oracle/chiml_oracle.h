@@ -37,6 +37,7 @@ int  oracle_set_cpml(OracleSim* s, int comp, int part, int has_psi, const ChimlP
 int  oracle_add_source(OracleSim* s, int field, const int32_t loc[3], const int32_t sz[3]);
 int  oracle_add_emitters(OracleSim* s, const ChimlEmitterDesc* d);
 int  oracle_add_dft(OracleSim* s, int field, int group, int every, int nfreq, int npts, int stride, const ChimlDftLine* lines, size_t nlines, size_t acc_len);
+int  oracle_set_periodic(OracleSim* s, int comp, const ChimlWrap* w);
 int  oracle_commit(OracleSim* s);
 /* nthreads > 1: rows of every list are split over POSIX threads (same arithmetic per cell) */
 int  oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads);

@@ -143,6 +143,21 @@ static int fieldId(parallelFDTDFieldReal& FF, const std::shared_ptr<parallelGrid
     return -1;
 }
 
+// the arguments step() passes to applBCH_[c] / applBCE_[c] (FDTD_MANAGER/parallelFDTDField.hpp:1267-1269,1285-1287), comp 0..5 = Ex..Hz
+static ChimlWrap wrapArgs(parallelFDTDFieldReal& FF, int comp)
+{
+    const int l0 = FF.ln_vec_[0], zMin = FF.zMinPBC_, zMax = FF.zMaxPBC_;
+    switch(comp)
+    {
+        case 0: return ChimlWrap{l0 - 1, FF.yEPBC_[0], zMax,     l0,     FF.yEPBC_[0], zMin, zMax + 1};
+        case 1: return ChimlWrap{l0,     FF.yEPBC_[1], zMax,     l0 + 1, FF.yEPBC_[1], zMin, zMax + 1};
+        case 2: return ChimlWrap{l0,     FF.yEPBC_[2], zMax - 1, l0 + 1, FF.yEPBC_[2], zMin, zMax};
+        case 3: return ChimlWrap{l0,     FF.yHPBC_[0], zMax - 1, l0 + 1, FF.yHPBC_[0], zMin, zMax};
+        case 4: return ChimlWrap{l0 - 1, FF.yHPBC_[1], zMax - 1, l0,     FF.yHPBC_[1], zMin, zMax};
+        default: return ChimlWrap{l0 - 1, FF.yHPBC_[2], zMax,    l0,     FF.yHPBC_[2], zMin, zMax + 1};
+    }
+}
+
 static void putEmitters(std::ofstream& out, parallelFDTDFieldReal& FF);
 static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const parallelProgramInputs& IP, int nSteps)
 {
@@ -165,6 +180,16 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
     pg.n_ordip_poles = int(std::max(FF.orDipLorP_[0].size(), FF.orDipLorP_[2].size()));
     pg.t_max = IP.tMax_;
     { std::string p; app(p, pg); putRec(out, "GRID", p); }
+    if(IP.periodic_)
+    {
+        if(FF.gridComm_->size() > 1) throw std::runtime_error("plan dump: periodic boundaries on several ranks are outside the covered hot path");
+        for(int comp = 0; comp < 6; ++comp)
+        {
+            if(!(comp < 3 ? FF.E_[comp] : FF.H_[comp - 3])) continue;
+            ChimlPlanPeriodic pp; pp.comp = comp; pp.wrap = wrapArgs(FF, comp);
+            std::string p; app(p, pp); putRec(out, "PERIODIC", p);
+        }
+    }
 
     if(FF.magMatInPML_) throw std::runtime_error("plan dump: magnetic material in the PML is outside the covered hot path");
     for(int c = 0; c < 3; ++c)
@@ -351,7 +376,7 @@ struct GpuApi
     CHIML_API(chiml_gpu_step_n_dft) CHIML_API(chiml_gpu_sync) CHIML_API(chiml_gpu_read_detector_range) CHIML_API(chiml_gpu_consume_detector)
     CHIML_API(chiml_gpu_read_population) CHIML_API(chiml_gpu_download_dft) CHIML_API(chiml_gpu_download_field) CHIML_API(chiml_gpu_download_pole)
     CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
-    CHIML_API(chiml_gpu_download_emitter_pol)
+    CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic)
 #undef CHIML_API
     void load()
     {
@@ -373,7 +398,7 @@ struct GpuApi
         CHIML_API(chiml_gpu_step_n_dft) CHIML_API(chiml_gpu_sync) CHIML_API(chiml_gpu_read_detector_range) CHIML_API(chiml_gpu_consume_detector)
         CHIML_API(chiml_gpu_read_population) CHIML_API(chiml_gpu_download_dft) CHIML_API(chiml_gpu_download_field) CHIML_API(chiml_gpu_download_pole)
         CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
-        CHIML_API(chiml_gpu_download_emitter_pol)
+        CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic)
 #undef CHIML_API
     }
 };
@@ -433,6 +458,14 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
             }
         B.check(A.chiml_gpu_set_object(B.ctx, int(oo), np, obj->alpha().data(), obj->xi().data(), obj->gamma().data(), obj->useOrdDip() ? 1 : 0, dip.data()), "set_object");
     }
+    // periodic boundaries: the arguments of applBCE_ / applBCH_ (single rank: applyBC1Proc)
+    if(FF.E_[0] ? FF.E_[0]->PBC() : FF.E_[2]->PBC())
+        for(int comp = 0; comp < 6; ++comp)
+            if(comp < 3 ? FF.E_[comp] : FF.H_[comp - 3])
+            {
+                const ChimlWrap w = wrapArgs(FF, comp);
+                B.check(A.chiml_gpu_set_periodic(B.ctx, comp, &w), "set_periodic");
+            }
     static_assert(sizeof(updatePsiParams) == sizeof(ChimlPsiParams) && sizeof(updateGridParams) == sizeof(ChimlGridParams), "CPML list layouts");
     for(int c = 0; c < 3; ++c)
         for(int side = 0; side < 2; ++side)

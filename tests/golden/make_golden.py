@@ -120,6 +120,30 @@ def cases():
                       I.flux("out/tef/lx", [0.1, 0.0, 0.0], [0.0, 0.2, 0.0], 1.5, 1.0, 3),
                       dict(I.flux("out/tef/ly", [0.0, -0.08, 0.0], [0.22, 0.0, 0.0], 1.5, 1.0, 3), Time_Interval=2.0 * DT)]
     c["te_flux"] = _short_pulse(te)
+    # ---- periodic boundaries, real fields (CompCell.PBC, k-point 0: applyBC1Proc, UTIL/FDTD_up_eq.cpp:1058-1116) ----
+    # 3-D: a Lorentz film spanning the periodic x / y faces with CPML in z only (the usual array set-up), an eps block against the +x
+    # face, a plane source; 120 steps let the wave go round the cell.  2-D: TM Drude rod and TE vacuum with CPML in y only.
+    c["pbc3d"] = _short_pulse(I.config(
+        I.comp_cell([21 / RES, 17 / RES, 25 / RES], RES, 120 * DT - 0.5 * DT, "Ex", pbc=True), I.pml([0.0, 0.0, 6 / RES]),
+        [I.normal_source("Ex", [0.0, 0.0, 0.07], [0.21, 0.17, 0.0], [I.gaussian_pulse(1.5, 1.0)]),
+         I.normal_source("Ez", [0.09, -0.07, -0.02], [0, 0, 0], [I.gaussian_pulse(1.2, 1.0)])],
+        [I.block([0.3, 0.3, 0.04], [0.0, 0.0, -0.02], eps=2.0, pols=[I.lorentz_pole(1.2, 0.1, 2.0), I.lorentz_pole(0.5, 0.05, 3.0)]),
+         I.block([0.06, 0.05, 0.05], [0.09, 0.02, 0.04], eps=3.0)],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Ex", "out/p3/dtc", time_int=DT * 1.0000001)]))
+    c["pbc3d_all"] = _short_pulse(I.config(
+        I.comp_cell([15 / RES, 19 / RES, 13 / RES], RES, 90 * DT - 0.5 * DT, "Ex", pbc=True), I.pml([0.0, 0.0, 0.0]),
+        [I.normal_source("Ey", [0.06, 0.08, -0.05], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
+        [I.sphere(0.05, [-0.06, -0.08, 0.05], eps=2.5, pols=[I.lorentz_pole(0.7, 0.2, 1.0)])],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Ey", "out/p3a/dtc", time_int=DT * 1.0000001)]))
+    tm = I.c2_tm_drude(n=63, steps=160, pml_cells=8, rod=(20, 6), nfreq=0, out="out/ptm")
+    tm["CompCell"]["PBC"] = True
+    tm["PML"]["thickness"] = [0.0, 8 / RES, 0.0]
+    c["pbc_tm"] = _short_pulse(tm)
+    te = I.c1_te_vacuum(n=47, steps=160, pml_cells=8, out="out/pte")
+    te["CompCell"]["PBC"] = True
+    te["PML"]["thickness"] = [8 / RES, 0.0, 0.0]
+    te["ObjectList"] = [I.block([0.1, 1.0, 0.0], [0.08, 0.0, 0.0], eps=2.2, pols=[I.lorentz_pole(0.8, 0.1, 2.0)])]
+    c["pbc_te"] = _short_pulse(te)
     return c
 
 

@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
         L.oracle_commit.argtypes = [C.c_void_p]
         L.oracle_step_n.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_step_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_set_periodic.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_add_dft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
         L.oracle_step_n_dft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_step_phase_dft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -142,6 +143,8 @@ class OracleSim:
         for e in plan.emitters:
             d = emitter_desc(e, self._keep)
             self._chk(L.oracle_add_emitters(self.h, C.byref(d)))
+        for comp, w in sorted(plan.periodic.items()):
+            self._chk(L.oracle_set_periodic(self.h, comp, (C.c_int32 * 7)(*w)))
         self._chk(L.oracle_commit(self.h))
         self.steps_done = 0
 

@@ -17,6 +17,8 @@ FILES = {"te_vacuum": {"out/te/dtc_field_0.dat": "dtc_field_0.dat"},
          "ml3d_two": {"out/m2/dtc_field_0.dat": "dtc_field_0.dat", "output_data/qe_0_level_3.dat": "qe_0_level_3.dat",
                       "output_data/qe_0_level_1.dat": "qe_0_level_1.dat"},
          # a 4 x 3 x 3 box written by a BIN detector (DTC/parallelDTC_BIN.cpp) and an SI-scaled TXT detector
+         # periodic boundaries (CompCell.PBC, real fields): JSON -> wrap descriptions -> k_wrap between the half steps
+         "pbc3d": {"out/p3/dtc_field_0.dat": "dtc_field_0.dat"}, "pbc_tm": {"out/ptm/dtc_field_0.dat": "dtc_field_0.dat"},
          "vac3d_bin": {"out/vb/dtc_field_0.dat": "dtc_field_0.dat", "out/vb/dtc_field_1.dat": "dtc_field_1.dat"}}
 
 

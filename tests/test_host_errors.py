@@ -53,7 +53,8 @@ def test_detector_outside_cell(tmp_path):
 
 @pytest.mark.parametrize("mutate,needle", [
     (lambda c: c.__setitem__("TFSF", [{"dummy": 1}]), "TFSF sources are outside the covered hot path"),
-    (lambda c: c["CompCell"].__setitem__("PBC", True), "periodic / complex-field runs are outside the covered hot path"),
+    (lambda c: (c["CompCell"].__setitem__("PBC", True), c["CompCell"].__setitem__("k-point", [0.3, 0.0, 0.0])), "complex-field (Bloch-periodic, k-point != 0) runs are outside the covered hot path"),
+    (lambda c: c["CompCell"].__setitem__("cplxFields", True), "complex-field"),
     (lambda c: c["ObjectList"].append(dict(I.block([0.1, 0.1, 0.0], [0, 0, 0]), mu=2.0)), "magnetic"),
 ])
 def test_out_of_scope_inputs_fail_loudly(mutate, needle, tmp_path):
@@ -67,3 +68,13 @@ def test_valid_input_builds(tmp_path):
     r = _run(_base(), tmp_path)
     assert r.returncode == 0, r.stderr
     assert os.path.exists(tmp_path / "out.rank0.plan")
+
+
+def test_periodic_run_on_several_slabs_is_refused(tmp_path):
+    """Real-field periodic boundaries are covered on one slab; the reference's multi-rank periodic run (applyBCProcMid on every rank,
+    SURVEY.md appendix B.5) is not reproduced, so the setup must say so instead of building slab plans."""
+    import shutil
+    import util
+    shutil.copy(os.path.join(util.GOLDEN, "pbc3d.json"), tmp_path / "pbc3d.json")
+    r = subprocess.run([TOOL, "pbc3d.json", "out", "--ranks", "2"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "single-slab" in r.stderr, r.stderr

@@ -14,6 +14,8 @@ def diff(a: P.Plan, b: P.Plan, verbose=True):
               "n_lor_poles", "n_ordip_poles", "t_max"):
         if getattr(a, k) != getattr(b, k):
             bad.append(f"grid.{k}: {getattr(a, k)} != {getattr(b, k)}")
+    if a.periodic != b.periodic:
+        bad.append(f"periodic: {a.periodic} != {b.periodic}")
     for key in sorted(set(a.lists) | set(b.lists)):
         la, lb = a.get_list(*key), b.get_list(*key)
         if len(la) != len(lb):
