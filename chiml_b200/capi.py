@@ -30,7 +30,8 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_download_emitter_state", "chiml_gpu_download_emitter_pol", "chiml_gpu_read_population",
     "chiml_gpu_halo_export", "chiml_gpu_halo_bind", "chiml_gpu_add_dft", "chiml_gpu_step_n_dft", "chiml_gpu_download_dft",
     "chiml_gpu_set_march", "chiml_gpu_set_ordip_pole_count", "chiml_gpu_reserve_steps", "chiml_gpu_consume_detector",
-    "chiml_gpu_consume_population", "chiml_gpu_set_persistent", "chiml_gpu_set_periodic",
+    "chiml_gpu_consume_population", "chiml_gpu_set_persistent", "chiml_gpu_set_periodic", "chiml_gpu_add_tfsf_surface",
+    "chiml_gpu_step_n_tfsf",
 ]
 
 
@@ -51,6 +52,33 @@ class EmitterDesc(C.Structure):
                 ("h0", C.c_void_p), ("weight", C.c_void_p), ("mu", C.c_void_p), ("gam_ptr", C.c_void_p), ("gam_col", C.c_void_p),
                 ("gam_val", C.c_void_p), ("loc", C.c_void_p), ("eps", C.c_void_p), ("npop", C.c_int32), ("pop_level", C.c_void_p),
                 ("pop_every", C.c_int32), ("npoints", C.c_int32), ("object", C.c_int32)]
+
+
+class TfsfSurface(C.Structure):
+    """include/chiml_gpu.h ChimlTfsfSurface"""
+    _fields_ = [("comp", C.c_int32), ("incd_offset", C.c_int32), ("incd_len", C.c_int32), ("n", C.c_int32), ("stride_incd", C.c_int32),
+                ("stride_main", C.c_int32), ("npairs_D", C.c_int32), ("npairs_U", C.c_int32), ("prefactor", C.c_double),
+                ("pairs_D", C.c_void_p), ("pairs_U", C.c_void_p), ("ep_mu", C.c_void_p)]
+
+
+def tfsf_surface(t: "P.PlanTfsfSurface", keep: list) -> TfsfSurface:
+    d = TfsfSurface()
+    d.comp, d.incd_offset, d.incd_len, d.n, d.stride_incd, d.stride_main = t.comp, t.incd_offset, t.incd_len, t.n, t.stride_incd, t.stride_main
+    d.npairs_D, d.npairs_U, d.prefactor = len(t.pairs_D), len(t.pairs_U), t.prefactor
+    pd, pu = np.ascontiguousarray(t.pairs_D, np.int32), np.ascontiguousarray(t.pairs_U, np.int32)
+    em = np.ascontiguousarray(t.ep_mu, np.float64) if t.ep_mu is not None else None
+    keep += [pd, pu, em]
+    d.pairs_D = pd.ctypes.data if pd.size else None
+    d.pairs_U = pu.ctypes.data if pu.size else None
+    d.ep_mu = em.ctypes.data if em is not None else None
+    return d
+
+
+def tfsf_rows(plan: "P.Plan", start: int, n: int) -> np.ndarray:
+    """Rows start .. start+n-1 of the incident-line table (recorded from the reference's own 1-D line, plan record TFSFLINE)."""
+    if plan.tfsf_lines is None or start + n > len(plan.tfsf_lines):
+        raise ValueError("the plan holds TFSF surfaces but no incident-line table for these steps")
+    return np.ascontiguousarray(plan.tfsf_lines[start:start + n], dtype=np.float64)
 
 
 def emitter_desc(e: "P.PlanEmitter", keep: list) -> EmitterDesc:
@@ -146,6 +174,8 @@ def lib() -> C.CDLL:
     L.chiml_gpu_halo_export.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.chiml_gpu_halo_bind.argtypes = [vp, C.c_char_p, sz, C.c_char_p, sz]
     L.chiml_gpu_set_periodic.argtypes = [vp, i, vp]
+    L.chiml_gpu_add_tfsf_surface.argtypes = [vp, C.POINTER(TfsfSurface)]
+    L.chiml_gpu_step_n_tfsf.argtypes = [vp, i, vp, vp, vp, sz]
     L.chiml_gpu_add_dft.argtypes = [vp, i, i, i, i, i, i, vp, sz, sz, C.POINTER(i)]
     L.chiml_gpu_step_n_dft.argtypes = [vp, i, vp, vp]
     L.chiml_gpu_download_dft.argtypes = [vp, i, vp, vp]
@@ -227,6 +257,9 @@ class GpuSim:
                     self.det_slots.append(slot.value)
             for comp, w in sorted(plan.periodic.items()):
                 self._chk(L.chiml_gpu_set_periodic(self.h, comp, (C.c_int32 * 7)(*w)))
+            for t in plan.tfsf:
+                d = tfsf_surface(t, keep)
+                self._chk(L.chiml_gpu_add_tfsf_surface(self.h, C.byref(d)))
             if plan.nranks > 1:
                 self._chk(L.chiml_gpu_set_ordip_pole_count(self.h, plan.n_ordip_poles))
             if persistent is not None:
@@ -257,7 +290,11 @@ class GpuSim:
         if amp is None:
             amp = self.src_amp(self.steps_done, n)
         amp = np.ascontiguousarray(amp, dtype=np.float64)
-        if self.plan.dfts:
+        if self.plan.tfsf:
+            tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, n)) if self.plan.dfts else None
+            rows = tfsf_rows(self.plan, self.steps_done, n)
+            self._chk(lib().chiml_gpu_step_n_tfsf(self.h, n, _ptr(amp) if len(self.plan.sources) else None, _ptr(tw), _ptr(rows), rows.shape[1]))
+        elif self.plan.dfts:
             tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, n))
             self._chk(lib().chiml_gpu_step_n_dft(self.h, n, _ptr(amp) if len(self.plan.sources) else None, _ptr(tw)))
         else:

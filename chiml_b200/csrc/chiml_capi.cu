@@ -158,7 +158,8 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     for(auto& e : ctx->ev_pool) cudaEventDestroy(e);
     cudaStreamSynchronize(ctx->hstream);
     for(HaloPeer* pr : {&ctx->lower, &ctx->upper}) for(void* b : pr->opened) cudaIpcCloseMemHandle(b);
-    cudaFree(ctx->d_flags); cudaFree(ctx->d_push_counter); cudaFree(ctx->d_persist_sa); cudaFree(ctx->d_tmaps);
+    cudaFree(ctx->d_flags); cudaFree(ctx->d_push_counter); cudaFree(ctx->d_persist_sa); cudaFree(ctx->d_tmaps); cudaFree(ctx->d_tfsf_incd);
+    for(auto& t : ctx->tfsf) { cudaFree(t.d_pairs_D); cudaFree(t.d_pairs_U); cudaFree(t.d_ep_mu); }
     for(auto& g : ctx->d_oPy_ghost) cudaFree(g);
     cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_push);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -208,6 +209,34 @@ int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global)
     if(n_poles_global > MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_ordip_pole_count: more than 12 poles per object");
     ctx->nordip_global = n_poles_global;
     return CHIML_OK;
+}
+
+int chiml_gpu_add_tfsf_surface(ChimlCtx* ctx, const ChimlTfsfSurface* t)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "add_tfsf_surface after commit");
+    if(!t || t->comp < 0 || t->comp > 5 || !field_exists(ctx, t->comp)) return fail(ctx, CHIML_ERR_ARG, "add_tfsf_surface: target component 0..5 of this mode");
+    if(ctx->g.nranks > 1) return fail(ctx, CHIML_ERR_UNSUPPORTED, "TFSF surfaces are covered for single-slab runs only");
+    if((t->n < 0 && (t->npairs_D > 0 || t->npairs_U > 0)) || t->npairs_D < 0 || t->npairs_U < 0 || t->incd_len < 1 || t->incd_offset < 0 || t->stride_main < 1 ||
+       (t->npairs_D > 0 && !t->pairs_D) || (t->npairs_U > 0 && !t->pairs_U))
+        return fail(ctx, CHIML_ERR_ARG, "add_tfsf_surface: inconsistent surface record");
+    if(t->npairs_D > 0 && (t->comp > 2 || !ctx->g.has_D)) return fail(ctx, CHIML_ERR_UNSUPPORTED, "add_tfsf_surface: D pairs need an E component and D grids (B targets are outside the covered hot path)");
+    // every incident index a pair reaches must lie inside its line
+    const long span = (long)(t->n - 1) * std::abs(t->stride_incd);
+    for(int side = 0; side < 2; ++side)
+    {
+        const int32_t* pr = side ? t->pairs_U : t->pairs_D;
+        for(int l = 0; l < (side ? t->npairs_U : t->npairs_D); ++l)
+            if(t->n > 0 && (pr[2 * l] < 0 || pr[2 * l] + span >= t->incd_len)) return fail(ctx, CHIML_ERR_ARG, "add_tfsf_surface: a pair reads outside its incident line");
+    }
+    TfsfDev d;
+    d.s = *t;
+    d.h_pairs_D.assign(t->pairs_D, t->pairs_D + 2 * (size_t)t->npairs_D);
+    d.h_pairs_U.assign(t->pairs_U, t->pairs_U + 2 * (size_t)t->npairs_U);
+    if(t->ep_mu) d.h_ep_mu.assign(t->ep_mu, t->ep_mu + t->incd_len);
+    d.s.pairs_D = nullptr; d.s.pairs_U = nullptr; d.s.ep_mu = nullptr;
+    ctx->tfsf.push_back(std::move(d));
+    return 0;
 }
 
 int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* w)
@@ -1074,6 +1103,31 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         }
         cudaFree(d_sum);
     }
+    // TFSF surfaces: pair lists and eps / mu lines to the device; no surface cell may lie inside the CPML
+    if(!ctx->tfsf.empty())
+    {
+        int* d_terr = nullptr;
+        if((rc = dev_alloc(ctx, &d_terr, 1))) return rc;
+        for(TfsfDev& t : ctx->tfsf)
+        {
+            if((rc = dev_upload(ctx, &t.d_pairs_D, t.h_pairs_D))) return rc;
+            if((rc = dev_upload(ctx, &t.d_pairs_U, t.h_pairs_U))) return rc;
+            if(!t.h_ep_mu.empty() && (rc = dev_upload(ctx, &t.d_ep_mu, t.h_ep_mu))) return rc;
+            for(int side = 0; side < 2; ++side)
+            {
+                const int np = side ? t.s.npairs_U : t.s.npairs_D;
+                if(np == 0 || t.s.n == 0) continue;
+                k_tfsf_check<<<(unsigned)std::min<long>(((long)np * t.s.n + 255) / 256, 1024), 256, 0, ctx->stream>>>(
+                    side ? t.d_pairs_U : t.d_pairs_D, np, t.s.n, t.s.stride_main, ctx->d_info[t.s.comp], ctx->lx, ctx->px, (long)ctx->nlogical, d_terr);
+            }
+        }
+        int h_terr = 0;
+        CK(cudaMemcpyAsync(&h_terr, d_terr, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_terr);
+        if(h_terr & 4) return fail(ctx, CHIML_ERR_ARG, "TFSF surface: a main-grid index lies outside the grid");
+        if(h_terr & 8) return fail(ctx, CHIML_ERR_UNSUPPORTED, "TFSF surface: a surface cell lies inside the CPML (the reference adds the incident field between the curl and the CPML terms)");
+    }
     if((rc = build_tensor_maps(ctx))) return rc;
     // y-slab halo: flag words, push counters, the dense ghost row of node P_y (filled by the slab above)
     if(ctx->g.nranks > 1)
@@ -1381,6 +1435,42 @@ void launch_sources(ChimlCtx* ctx, long long k, int nsrc, int part)
     }
 }
 
+// tfsf->updateFields() (step() item 5): the surface lists in the reference's order, grouped into waves of lists with distinct target arrays
+// (two surfaces of one component share the cells of the edge where they meet: their additions keep the reference's order)
+void launch_tfsf(ChimlCtx* ctx, long long k)
+{
+    if(ctx->tfsf.empty()) return;
+    std::vector<TfsfEntry> order[9];                 // per target array (E, H, D components), in surface order: H surfaces first
+    for(int pass = 0; pass < 2; ++pass)
+        for(const TfsfDev& t : ctx->tfsf)
+        {
+            if((t.s.comp >= 3) != (pass == 0)) continue;
+            for(int side = 0; side < 2; ++side)
+            {
+                const int np = side ? t.s.npairs_U : t.s.npairs_D;
+                if(np == 0 || t.s.n == 0) continue;
+                const int arr = side ? t.s.comp : CHIML_DX + t.s.comp;
+                TfsfEntry e;
+                e.target = ctx->d_field[arr]; e.pairs = side ? t.d_pairs_U : t.d_pairs_D; e.ep_mu = side ? t.d_ep_mu : nullptr;
+                e.npairs = np; e.n = t.s.n; e.stride_incd = t.s.stride_incd; e.stride_main = t.s.stride_main; e.incd_offset = t.s.incd_offset;
+                e.prefactor = t.s.prefactor;
+                order[arr].push_back(e);
+            }
+        }
+    size_t waves = 0;
+    for(auto& o : order) waves = std::max(waves, o.size());
+    for(size_t w = 0; w < waves; ++w)
+    {
+        TfsfArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.incd = ctx->d_tfsf_incd + (size_t)k * ctx->tfsf_per_step; a.lx = ctx->lx; a.px = ctx->px;
+        long most = 1;
+        for(auto& o : order) if(w < o.size()) { a.e[a.n++] = o[w]; most = std::max(most, (long)o[w].npairs * o[w].n); }
+        LaunchScope ls(ctx, K_TFSF);
+        k_tfsf<<<dim3((unsigned)std::min<long>((most + 255) / 256, 148 * 2), a.n, 1), 256, 0, ctx->stream>>>(a);
+    }
+}
+
 // applBCH_ / applBCE_ (step() items 9 and 17): periodic wrap copies of the three components of one family
 void launch_wraps(ChimlCtx* ctx, bool isE)
 {
@@ -1478,6 +1568,8 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
         // H half step: updateH + updateHPML_ (step() items 4 and 6)
         fill_step_args(ctx, false, a);
         launch_family<false>(ctx, a, block, 0);
+        // TFSF surfaces (item 5): H after its curl, E / D before theirs and before the soft sources
+        launch_tfsf(ctx, k);
         // sources (item 7): all sources, E and H alike, are injected here
         launch_sources(ctx, k, nsrc, 0);
         // periodic boundaries of H (item 9)
@@ -1645,6 +1737,7 @@ template <int MODE> int persist_occupancy(int* perSM)
 bool persist_eligible(ChimlCtx* ctx)
 {
     if(ctx->persist_mode == 0 || std::getenv("CHIML_B200_NO_PERSIST")) return false;
+    if(!ctx->tfsf.empty()) return false;      // the surface waves are separate launches
     if(ctx->g.mode == CHIML_MODE_3D || ctx->g.nranks > 1 || !ctx->emitters.empty() || ctx->d_info_node) return false;
     if((int)ctx->detectors.size() > P2D_MAX_DET || (int)ctx->dfts.size() > P2D_MAX_DFT) return false;
     // sources are injected by one grid-wide pass: two boxes on the same field must not overlap (the launch path adds them one after the other)
@@ -1784,12 +1877,28 @@ int reserve_rings(ChimlCtx* ctx, long long n)
     return 0;
 }
 
-int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles = nullptr)
+int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles = nullptr, const double* incd = nullptr, size_t incd_per_step = 0)
 {
     if(!ctx) return CHIML_ERR_ARG;
     if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "step before commit");
     if(n < 0) return fail(ctx, CHIML_ERR_ARG, "negative step count");
     CK(cudaSetDevice(ctx->device));
+    if(!ctx->tfsf.empty())
+    {
+        if(!incd) return fail(ctx, CHIML_ERR_ARG, "TFSF surfaces are registered: step with chiml_gpu_step_n_tfsf and the incident lines");
+        for(const TfsfDev& t : ctx->tfsf)
+            if((size_t)t.s.incd_offset + (size_t)t.s.incd_len > incd_per_step) return fail(ctx, CHIML_ERR_ARG, "step_n_tfsf: a surface's incident line does not fit the per-step table");
+        const size_t need = incd_per_step * (size_t)n;
+        if(need > ctx->tfsf_incd_cap)
+        {
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_tfsf_incd);
+            CK(cudaMalloc((void**)&ctx->d_tfsf_incd, std::max<size_t>(need, 1) * sizeof(double)));
+            ctx->tfsf_incd_cap = need;
+        }
+        if(need) CK(cudaMemcpyAsync(ctx->d_tfsf_incd, incd, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->tfsf_per_step = incd_per_step;
+    }
     if(!ctx->dfts.empty())
     {
         if(!twiddles) return fail(ctx, CHIML_ERR_ARG, "running-DFT sets are registered: step with chiml_gpu_step_n_dft and the twiddle factors");
@@ -1842,6 +1951,8 @@ extern "C" {
 
 int chiml_gpu_step_n(ChimlCtx* ctx, int n, const double* src_amp) { return step_n_impl(ctx, n, src_amp); }
 int chiml_gpu_step_n_dft(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles) { return step_n_impl(ctx, n, src_amp, twiddles); }
+int chiml_gpu_step_n_tfsf(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles, const double* incd, size_t incd_per_step)
+{ return step_n_impl(ctx, n, src_amp, twiddles, incd, incd_per_step); }
 
 int chiml_gpu_download_dft(ChimlCtx* ctx, int slot, double* re, double* im)
 {
@@ -2042,7 +2153,7 @@ int chiml_gpu_n_kernel_kinds(void) { return K_NKINDS; }
 int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out)
 {
     static const char* names[K_NKINDS] = {"k_fast<E>", "k_uniform<E>", "k_general<E>", "k_fast<H>", "k_uniform<H>", "k_general<H>",
-                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft", "k_steps_2d", "k_wrap"};
+                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft", "k_steps_2d", "k_wrap", "k_tfsf"};
     if(!ctx || !out || kind < 0 || kind >= K_NKINDS) return CHIML_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -89,7 +89,7 @@ struct DetectorDev
 };
 
 // kernels of the step loop, for launch / time / algorithmic-byte accounting
-enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_STEPS_2D, K_WRAP, K_NKINDS };
+enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_STEPS_2D, K_WRAP, K_TFSF, K_NKINDS };
 struct KernelStat { int64_t launches = 0; double ms_total = 0.0; double alg_bytes = 0.0; int64_t timed = 0; };
 
 // one parallelQE object on the device (chiml_emitters.cuh)
@@ -138,6 +138,16 @@ struct DftDev
     std::vector<ChimlDftLine> h_lines;
     ChimlDftLine* d_lines = nullptr;
     double *d_re = nullptr, *d_im = nullptr;
+};
+
+// one TFSF surface (chiml_gpu_add_tfsf_surface): host copies until commit, device copies after
+struct TfsfDev
+{
+    ChimlTfsfSurface s{};
+    std::vector<int32_t> h_pairs_D, h_pairs_U;
+    std::vector<double> h_ep_mu;
+    int32_t *d_pairs_D = nullptr, *d_pairs_U = nullptr;
+    double* d_ep_mu = nullptr;
 };
 
 struct HostList { std::vector<ChimlRun> runs; };
@@ -210,6 +220,10 @@ struct ChimlCtx
     chiml::HostPml hpml[6][2];
     std::vector<chiml::HostObj> objs;
 
+    // TFSF surfaces and the incident-line table of the current chiml_gpu_step_n_tfsf call
+    std::vector<chiml::TfsfDev> tfsf;
+    double* d_tfsf_incd = nullptr; size_t tfsf_incd_cap = 0; size_t tfsf_per_step = 0;
+    bool tfsf_table_ready = false;
     // periodic boundaries (chiml_gpu_set_periodic): wrap copies per component after its half step
     ChimlWrap wrap[6] = {};
     bool has_wrap[6] = {};

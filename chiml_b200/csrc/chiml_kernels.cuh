@@ -220,6 +220,45 @@ __global__ void k_source(double* field, int lx0, int lz0, int ly0, int sx, int s
     }
 }
 
+// TFSF surface corrections (tfsfUpdateFxnReal::addIncdFields / addIncdFieldsEPChange, SOURCE/parallelTFSF.cpp:77-105): one launch applies one
+// "wave" of surface lists -- at most one per target array, so no two entries touch the same cell -- blockIdx.y = entry.  For pair l and
+// element i:  target[main_l + i * stride_main] += prefactor * incd[incd_l + ix0 + i * stride_incd] (/ ep_mu[same index]); a negative
+// incident stride starts at the far end like the BLAS call it replaces (ix0 = (1 - n) * stride).  Main-grid indices are the reference's
+// logical ones (x + lx * row) and are mapped to the padded rows here.
+constexpr int TFSF_WAVE = 12;
+struct TfsfEntry { double* target; const int32_t* pairs; const double* ep_mu; int npairs, n, stride_incd, stride_main, incd_offset; double prefactor; };
+struct TfsfArgs { TfsfEntry e[TFSF_WAVE]; int n; const double* incd; int lx; long px; };
+__global__ void k_tfsf(TfsfArgs a)
+{
+    if((int)blockIdx.y >= a.n) return;
+    const TfsfEntry& t = a.e[blockIdx.y];
+    const double* incd = a.incd + t.incd_offset;
+    const long total = (long)t.npairs * t.n;
+    const long ix0 = t.stride_incd < 0 ? (long)(1 - t.n) * t.stride_incd : 0;
+    for(long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x)
+    {
+        const long l = q / t.n, i = q % t.n;
+        const long ii = t.pairs[2 * l] + ix0 + i * t.stride_incd;
+        const long m = t.pairs[2 * l + 1] + i * (long)t.stride_main;
+        double v = incd[ii];
+        if(t.ep_mu) v = v / t.ep_mu[ii];
+        const long r = (m % a.lx) + a.px * (m / a.lx);
+        t.target[r] = da(t.target[r], dm(t.prefactor, v));
+    }
+}
+// commit-time check: a surface cell inside the CPML (any of the four CPML flags of its component) cannot be reproduced, because the
+// reference adds the incident field between the curl and the CPML terms, which are one pass here
+__global__ void k_tfsf_check(const int32_t* pairs, int npairs, int n, int stride_main, const uint16_t* info, int lx, long px, long ncell, int* err)
+{
+    const long total = (long)npairs * n;
+    for(long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x)
+    {
+        const long m = pairs[2 * (q / n) + 1] + (q % n) * (long)stride_main;
+        if(m < 0 || m >= ncell) { atomicOr(err, 4); continue; }
+        if(info[(m % lx) + px * (m / lx)] & (F_PS0 | F_PS1 | F_PG0 | F_PG1)) atomicOr(err, 8);
+    }
+}
+
 // Periodic wrap copies of up to three components in one launch (applyBC1Proc, UTIL/FDTD_up_eq.cpp:1058-1116; blockIdx.y = component).
 // The reference's sequence of dcopy_ calls amounts to: every ghost cell of the box [0, xmax] x [0, ymax] x [zmin-1, zmax] takes the
 // value of its periodic image inside the box (x = 0 <- xmax-1, x = xmax <- 1, likewise y and z); every source is an inner cell, so

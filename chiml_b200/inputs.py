@@ -114,6 +114,14 @@ def flux(name: str, loc: Sequence[float], size: Sequence[float], fcen: float, fw
             "nfreq": nfreq, "weight": weight, "cross_sec": False}
 
 
+def tfsf(size: Sequence[float], loc: Sequence[float], pulses: List[Dict], m: Sequence[int] = (1, 0, 0), psi: float = 90.0, pml_thick: int = 10,
+         pml_a_max: float = 0.0, pml_m: float = 3.0, pml_ma: float = 1.0) -> Dict:
+    """A total-field / scattered-field box (write_json.write_tfsf_m_def; parsed at INPUTS/parallelInputs.cpp:219-408): plane wave along
+    the integer direction m, polarisation angle psi (degrees)."""
+    return {"loc": list(loc), "size": list(size), "m": list(m), "psi": psi, "PulseList": pulses, "circPol": "Ex", "ellpiticalKRat": 1.0,
+            "pmlThick": pml_thick, "pmlAMax": pml_a_max, "pmlM": pml_m, "pmlMa": pml_ma}
+
+
 def config(cell: Dict, pml_: Dict, sources: List[Dict], objects: List[Dict], detectors: List[Dict], fluxes: Optional[List[Dict]] = None) -> Dict:
     return {"CompCell": cell, "PML": pml_, "SourceList": sources, "TFSF": [], "ObjectList": objects, "DetectorList": detectors,
             "FluxList": fluxes or []}

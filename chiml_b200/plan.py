@@ -12,7 +12,7 @@ from __future__ import annotations
 import math
 import struct
 from dataclasses import dataclass, field
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
@@ -119,6 +119,21 @@ class PlanDft:
     lines: np.ndarray     # (nlines, 2) int32: grid index, accumulator index
 
 
+@dataclass
+class PlanTfsfSurface:
+    """One TFSF surface (include/chiml_gpu.h ChimlTfsfSurface)."""
+    comp: int
+    incd_offset: int
+    incd_len: int
+    n: int
+    stride_incd: int
+    stride_main: int
+    prefactor: float
+    pairs_D: np.ndarray   # (npairs, 2) int32: incident index, main-grid index
+    pairs_U: np.ndarray
+    ep_mu: Optional[np.ndarray]
+
+
 _EMIT_FMT = "<4i3i3i4i2i3d"
 _EMIT_SIZE = struct.calcsize(_EMIT_FMT)
 assert _EMIT_SIZE == 88
@@ -148,6 +163,8 @@ class Plan:
     detectors: List[PlanDetector] = field(default_factory=list)
     emitters: List[PlanEmitter] = field(default_factory=list)
     dfts: List[PlanDft] = field(default_factory=list)
+    tfsf: List[PlanTfsfSurface] = field(default_factory=list)
+    tfsf_lines: Optional[np.ndarray] = None     # (n_steps, per_step): the incident-line table of chiml_gpu_step_n_tfsf
     periodic: Dict[int, Tuple[int, ...]] = field(default_factory=dict)      # comp -> (nx, ny, nz, xmax, ymax, zmin, zmax) (ChimlWrap)
 
     @property
@@ -222,6 +239,16 @@ def read_plan(path: str) -> Plan:
             freq = np.frombuffer(payload, dtype="<f8", count=nfreq, offset=40).copy()
             lines = np.frombuffer(payload, dtype="<i4", count=2 * nlines, offset=40 + 8 * nfreq).copy().reshape(nlines, 2)
             plan.dfts.append(PlanDft(fld, group, every, nfreq, npts, stride, acc_len, freq, lines))
+        elif tag == "TFSFSURF":
+            v = struct.unpack_from("<10id", payload, 0)
+            off = 48
+            pd = np.frombuffer(payload, dtype="<i4", count=2 * v[6], offset=off).copy().reshape(v[6], 2); off += 8 * v[6]
+            pu = np.frombuffer(payload, dtype="<i4", count=2 * v[7], offset=off).copy().reshape(v[7], 2); off += 8 * v[7]
+            em = np.frombuffer(payload, dtype="<f8", count=v[2], offset=off).copy() if v[8] else None
+            plan.tfsf.append(PlanTfsfSurface(v[0], v[1], v[2], v[3], v[4], v[5], v[10], pd, pu, em))
+        elif tag == "TFSFLINE":
+            ns, per = struct.unpack_from("<ii", payload, 0)
+            plan.tfsf_lines = np.frombuffer(payload, dtype="<f8", count=ns * per, offset=8).copy().reshape(ns, per)
         elif tag == "PERIODIC":
             v = struct.unpack_from("<8i", payload, 0)
             plan.periodic[v[0]] = tuple(v[1:8])
@@ -309,6 +336,13 @@ def write_plan(path: str, plan: Plan) -> None:
     for d in plan.dfts:
         out.append(_rec("DFT", struct.pack("<6iQQ", d.field, d.group, d.every, d.nfreq, d.npts, d.stride, len(d.lines), d.acc_len)
                         + np.ascontiguousarray(d.freq, "<f8").tobytes() + np.ascontiguousarray(d.lines, "<i4").tobytes()))
+    for t in plan.tfsf:
+        out.append(_rec("TFSFSURF", struct.pack("<10id", t.comp, t.incd_offset, t.incd_len, t.n, t.stride_incd, t.stride_main, len(t.pairs_D), len(t.pairs_U),
+                                                1 if t.ep_mu is not None else 0, 0, t.prefactor)
+                        + np.ascontiguousarray(t.pairs_D, "<i4").tobytes() + np.ascontiguousarray(t.pairs_U, "<i4").tobytes()
+                        + (np.ascontiguousarray(t.ep_mu, "<f8").tobytes() if t.ep_mu is not None else b"")))
+    if plan.tfsf_lines is not None:
+        out.append(_rec("TFSFLINE", struct.pack("<ii", *plan.tfsf_lines.shape) + np.ascontiguousarray(plan.tfsf_lines, "<f8").tobytes()))
     for comp, w in sorted(plan.periodic.items()):
         out.append(_rec("PERIODIC", struct.pack("<8i", comp, *w)))
     with open(path, "wb") as f:

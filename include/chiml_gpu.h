@@ -178,6 +178,32 @@ int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq,
 typedef struct ChimlWrap { int32_t nx, ny, nz, xmax, ymax, zmin, zmax; } ChimlWrap;
 int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* wrap);
 
+/* Total-field / scattered-field plane-wave source (SOURCE/parallelTFSF.hpp).  The 1-D auxiliary incident line (parallelTFSFBase::step,
+ * :1148-1177: six complex 1-D fields with their own dispersion and CPML) does not depend on the main grid; it stays on the host --
+ * the reference's own object steps it -- and the device applies the surface corrections of updateFields() (:1058-1073).  One surface
+ * (paramStoreTFSF, :100-111, built by genSurface, :823-998) of target component comp (0..5 = Ex..Hz): for every pair
+ * (incd index, main index) of indsD_ / indsU_ and i < n = szTrans_[0]
+ *     target[ind_main + i * stride_main] += prefactor * Re(incd[ind_incd + i * stride_incd])                  (addIncdFields, parallelTFSF.cpp:77-83)
+ *     ... += prefactor * (Re(incd[..]) / ep_mu[ind_incd + i * stride_incd])   for the U pairs when ep_mu != NULL  (addIncdFieldsEPChange, :93-105)
+ * target = D_[comp] for the D pairs and E_/H_[comp] for the U pairs.  incd_offset selects the incident line inside the per-step table
+ * handed to chiml_gpu_step_n_tfsf.  E / D surfaces are applied before the E half step and before the soft sources, H surfaces after the
+ * H half step (step() item 5 sits between updateH and updateHPML_: a surface cell inside the CPML is refused).  Single slab only. */
+typedef struct ChimlTfsfSurface
+{
+    int32_t comp;             /* target component 0..5 */
+    int32_t incd_offset;      /* start of the surface's incident line inside one step's table */
+    int32_t incd_len;         /* length of that line (bounds check) */
+    int32_t n;                /* szTrans_[0] */
+    int32_t stride_incd;      /* strideIncd_ (may be negative) */
+    int32_t stride_main;      /* strideMain_ */
+    int32_t npairs_D, npairs_U;
+    double  prefactor;
+    const int32_t* pairs_D;   /* 2 * npairs_D: indsD_ */
+    const int32_t* pairs_U;   /* 2 * npairs_U: indsU_ */
+    const double*  ep_mu;     /* incd_len doubles (eps_[c] / mu_[c] along the line) or NULL */
+} ChimlTfsfSurface;
+int chiml_gpu_add_tfsf_surface(ChimlCtx* ctx, const ChimlTfsfSurface* s);
+
 /* Number of oriented-dipole pole grids of the WHOLE grid, orDipLorP_[c].size() = the largest pole count of any oriented-dipole
  * object (parallelFDTDField.hpp:452-478): every rank of the reference allocates and exchanges that many, whether or not its own slab
  * holds such an object.  Needed with several slabs only -- a slab that holds no oriented-dipole cell, or objects with fewer poles
@@ -215,6 +241,10 @@ int chiml_gpu_step_n(ChimlCtx* ctx, int n, const double* src_amp);
 /* same with running-DFT sets: twiddles = for every step k < n, for every group g in order, nfreq_g complex (re, im) numbers
  * exp(-i freq t_k), t_k = time after step k (only read on the steps the group samples).  chiml_gpu_step_n fails when DFT sets exist. */
 int chiml_gpu_step_n_dft(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles);
+/* same with TFSF surfaces: incd = for every step k < n a table of incd_per_step doubles holding the real parts of the incident lines the
+ * surfaces of that step read -- for an H surface the incident E line BEFORE the line's step k, for an E / D surface the incident H line
+ * AFTER it (updateFields: H surfaces, step(), E surfaces).  twiddles may be NULL without running-DFT sets. */
+int chiml_gpu_step_n_tfsf(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles, const double* incd, size_t incd_per_step);
 int chiml_gpu_sync(ChimlCtx* ctx);
 /* same as step_n / step_n_dft (twiddles may be NULL when no running-DFT set is registered) but bracketed by CUDA events on the
  * context's stream; returns device milliseconds */

@@ -89,6 +89,16 @@ typedef struct ChimlPlanPeriodic      /* tag "PERIODIC": the wrap copies of one 
     int32_t comp;
     ChimlWrap wrap;
 } ChimlPlanPeriodic;
+typedef struct ChimlPlanTfsfSurfaceHdr /* tag "TFSFSURF": header, pairs_D[2 npairs_D] pairs_U[2 npairs_U] int32, then ep_mu[incd_len] doubles if has_ep_mu */
+{
+    int32_t comp, incd_offset, incd_len, n, stride_incd, stride_main, npairs_D, npairs_U, has_ep_mu, pad;
+    double  prefactor;
+} ChimlPlanTfsfSurfaceHdr;
+typedef struct ChimlPlanTfsfLinesHdr   /* tag "TFSFLINE": header, then n_steps * per_step doubles (chiml_gpu_step_n_tfsf's table); written AFTER the
+                                          run by the reference driver (the line is stepped by the reference's own object) */
+{
+    int32_t n_steps, per_step;
+} ChimlPlanTfsfLinesHdr;
 #pragma pack(pop)
 
 #endif /* CHIML_PLAN_H */

@@ -38,6 +38,10 @@ typedef struct
 #define MAX_DFT 512
 typedef struct { int field, group, every, nfreq, npts, stride; size_t nlines, acc_len; ChimlDftLine* lines; double *re, *im; } DftSet;
 
+/* one TFSF surface (SOURCE/parallelTFSF.hpp:100-111) */
+#define MAX_TFSF 256
+typedef struct { ChimlTfsfSurface s; int32_t *pairs_D, *pairs_U; double* ep_mu; } TfsfSur;
+
 struct OracleSim
 {
     ChimlGridDesc g;
@@ -69,6 +73,10 @@ struct OracleSim
     const double* twiddles;        /* of the current oracle_step_n_dft call */
     long step_count;
     int phase_mask;                /* bit 0: H half step + sources, 1: node poles, 2: E half step + emitter addP, 3: emitter density */
+    TfsfSur tfsf[MAX_TFSF];        /* TFSF surfaces (paramStoreTFSF) */
+    int ntfsf;
+    const double* tfsf_incd;       /* of the current oracle_step_n_tfsf call: [step][per_step] */
+    size_t tfsf_per_step;
     ChimlWrap wrap[6];             /* periodic wrap copies per component (applBCE_ / applBCH_ arguments) */
     int has_wrap[6];
 };
@@ -617,6 +625,50 @@ static void pml_component(OracleSim* s, int comp, double* target, int tid, int n
     }
 }
 
+/* TFSF surfaces: tfsfUpdateFxnReal::addIncdFields / addIncdFieldsEPChange (SOURCE/parallelTFSF.cpp:77-105) on the records genSurface built
+ * (SOURCE/parallelTFSF.hpp:823-998).  The incident lines come from the caller (the reference's own 1-D line, stepped on the host). */
+int oracle_add_tfsf_surface(OracleSim* s, const ChimlTfsfSurface* t)
+{
+    if(!s || !t || s->ntfsf >= MAX_TFSF || t->comp < 0 || t->comp > 5 || !s->f[t->comp] || s->g.nranks != 1) return CHIML_ERR_ARG;
+    if(t->npairs_D > 0 && (t->comp > 2 || !s->f[CHIML_DX + t->comp])) return CHIML_ERR_ARG;
+    TfsfSur* q = &s->tfsf[s->ntfsf++];
+    q->s = *t;
+    q->pairs_D = (int32_t*)malloc((size_t)(2 * t->npairs_D + 1) * sizeof(int32_t));
+    q->pairs_U = (int32_t*)malloc((size_t)(2 * t->npairs_U + 1) * sizeof(int32_t));
+    if(t->npairs_D) memcpy(q->pairs_D, t->pairs_D, (size_t)(2 * t->npairs_D) * sizeof(int32_t));
+    if(t->npairs_U) memcpy(q->pairs_U, t->pairs_U, (size_t)(2 * t->npairs_U) * sizeof(int32_t));
+    q->ep_mu = NULL;
+    if(t->ep_mu) { q->ep_mu = (double*)malloc((size_t)t->incd_len * sizeof(double)); memcpy(q->ep_mu, t->ep_mu, (size_t)t->incd_len * sizeof(double)); }
+    return 0;
+}
+static void tfsf_add(OracleSim* s, const TfsfSur* q, const double* table)
+{
+    const double* incd = table + q->s.incd_offset;
+    const int n = q->s.n;
+    const long si = q->s.stride_incd, sm = q->s.stride_main;
+    /* daxpy_(n, prefactor, Re incd, 2 * strideIncd, grid, strideMain): a negative increment starts at the far end (BLAS convention),
+     * i.e. element i of x is x[(i - (n - 1)) * inc] ... walked together with element i of y */
+    double* D = q->s.comp < 3 ? s->f[CHIML_DX + q->s.comp] : NULL;
+    double* U = s->f[q->s.comp];
+    for(int l = 0; l < q->s.npairs_D; ++l)
+    {
+        const long i0 = q->pairs_D[2 * l], m0 = q->pairs_D[2 * l + 1];
+        const long ix0 = si < 0 ? (long)(1 - n) * si : 0;
+        for(int i = 0; i < n; ++i) D[m0 + i * sm] = D[m0 + i * sm] + q->s.prefactor * incd[i0 + ix0 + i * si];
+    }
+    for(int l = 0; l < q->s.npairs_U; ++l)
+    {
+        const long i0 = q->pairs_U[2 * l], m0 = q->pairs_U[2 * l + 1];
+        const long ix0 = si < 0 ? (long)(1 - n) * si : 0;
+        for(int i = 0; i < n; ++i)
+        {
+            double v = incd[i0 + ix0 + i * si];
+            if(q->ep_mu) v = v / q->ep_mu[i0 + ix0 + i * si];       /* dcopy (same negative-increment convention), then std::divides */
+            U[m0 + i * sm] = U[m0 + i * sm] + q->s.prefactor * v;
+        }
+    }
+}
+
 /* applyBC1Proc, real fields (UTIL/FDTD_up_eq.cpp:1058-1116): the periodic wrap copies of one component on a single process, in the
  * reference's order of dcopy_ calls.  PT(x, y, z) = parallelGrid::point(x, y, z) (GRID/parallelGrid.hpp:363). */
 int oracle_set_periodic(OracleSim* s, int comp, const ChimlWrap* w)
@@ -694,6 +746,14 @@ static void step_worker(OracleSim* s, int tid, int nt)
             RunList* l = &s->up[CHIML_LIST_U][3 + i];
             SPLIT(l->n, lo, hi);
             for(size_t e = lo; e < hi; ++e) curl_run(&l->r[e], H, s->f[CHIML_EX + (i + 1) % 3], s->f[CHIML_EX + (i + 2) % 3]);
+        }
+        BARRIER();
+        /* tfsf->updateFields() (:1238-1255, SOURCE/parallelTFSF.hpp:1058-1073): H surfaces, the line's own step (host), E surfaces */
+        if(tid == 0 && (s->phase_mask & 1) && s->ntfsf > 0)
+        {
+            const double* table = s->tfsf_incd + (size_t)step * s->tfsf_per_step;
+            for(int q = 0; q < s->ntfsf; ++q) if(s->tfsf[q].s.comp >= 3) tfsf_add(s, &s->tfsf[q], table);
+            for(int q = 0; q < s->ntfsf; ++q) if(s->tfsf[q].s.comp < 3) tfsf_add(s, &s->tfsf[q], table);
         }
         BARRIER();
         /* updateHPML_ (:1258-1259) */
@@ -836,6 +896,16 @@ int oracle_add_dft(OracleSim* s, int field, int group, int every, int nfreq, int
 }
 double* oracle_dft(OracleSim* s, int slot, int imag) { return (slot < 0 || slot >= s->ndft) ? NULL : (imag ? s->dft[slot].im : s->dft[slot].re); }
 
+int oracle_step_n_tfsf(OracleSim* s, int n, const double* src_amp, const double* twiddles, const double* incd, size_t incd_per_step, int nthreads)
+{
+    if(s->ntfsf > 0 && !incd) return CHIML_ERR_ARG;
+    for(int q = 0; q < s->ntfsf; ++q) if((size_t)(s->tfsf[q].s.incd_offset + s->tfsf[q].s.incd_len) > incd_per_step) return CHIML_ERR_ARG;
+    s->twiddles = twiddles; s->tfsf_incd = incd; s->tfsf_per_step = incd_per_step;
+    const int rc = oracle_step_n(s, n, src_amp, nthreads);
+    s->tfsf_incd = NULL;
+    return rc;
+}
+
 int oracle_step_n_dft(OracleSim* s, int n, const double* src_amp, const double* twiddles, int nthreads)
 {
     s->twiddles = twiddles;
@@ -846,6 +916,7 @@ int oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads)
 {
     if(!s->committed) return CHIML_ERR_STATE;
     if(s->ndft > 0 && !s->twiddles) return CHIML_ERR_ARG;
+    if(s->ntfsf > 0 && !s->tfsf_incd) return CHIML_ERR_ARG;
     if(nthreads < 1) nthreads = 1;
     s->nthreads = nthreads;
     s->src_amp = src_amp;

@@ -38,11 +38,13 @@ int  oracle_add_source(OracleSim* s, int field, const int32_t loc[3], const int3
 int  oracle_add_emitters(OracleSim* s, const ChimlEmitterDesc* d);
 int  oracle_add_dft(OracleSim* s, int field, int group, int every, int nfreq, int npts, int stride, const ChimlDftLine* lines, size_t nlines, size_t acc_len);
 int  oracle_set_periodic(OracleSim* s, int comp, const ChimlWrap* w);
+int  oracle_add_tfsf_surface(OracleSim* s, const ChimlTfsfSurface* t);
 int  oracle_commit(OracleSim* s);
 /* nthreads > 1: rows of every list are split over POSIX threads (same arithmetic per cell) */
 int  oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads);
 
 int  oracle_step_n_dft(OracleSim* s, int n, const double* src_amp, const double* twiddles, int nthreads);
+int  oracle_step_n_tfsf(OracleSim* s, int n, const double* src_amp, const double* twiddles, const double* incd, size_t incd_per_step, int nthreads);
 double* oracle_dft(OracleSim* s, int slot, int imag);
 /* one phase of one step, for y-slab runs that exchange ghost rows between phases (see chiml_oracle.c) */
 int  oracle_step_phase(OracleSim* s, int phase, const double* src_amp);

@@ -158,6 +158,83 @@ static ChimlWrap wrapArgs(parallelFDTDFieldReal& FF, int comp)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TFSF sources: the surfaces of every parallelTFSF object as ChimlTfsfSurface records and the layout of one step's incident-line
+// table (include/chiml_gpu.h chiml_gpu_step_n_tfsf): per TFSF object E_incd_[0..2] then H_incd_[0..2], real parts
+// ---------------------------------------------------------------------------------------------
+struct TfsfLayout
+{
+    std::vector<int> off, len;      // [6 * t + k], k = 0..2 E lines, 3..5 H lines
+    int perStep = 0;
+};
+static TfsfLayout tfsfLayout(parallelFDTDFieldReal& FF)
+{
+    TfsfLayout L;
+    for(auto& tfsf : FF.tfsfArr_)
+        for(int k = 0; k < 6; ++k)
+        {
+            auto& g = k < 3 ? tfsf->E_incd_[k] : tfsf->H_incd_[k - 3];
+            L.off.push_back(L.perStep);
+            L.len.push_back(g ? int(g->size()) : 0);
+            L.perStep += L.len.back();
+        }
+    return L;
+}
+// the E lines (what the H surfaces of the coming step read) or the H lines (what its E surfaces read, after the line's own step)
+static void tfsfGrab(parallelFDTDFieldReal& FF, const TfsfLayout& L, bool E, double* row)
+{
+    for(size_t t = 0; t < FF.tfsfArr_.size(); ++t)
+        for(int k = E ? 0 : 3; k < (E ? 3 : 6); ++k)
+        {
+            auto& g = k < 3 ? FF.tfsfArr_[t]->E_incd_[k] : FF.tfsfArr_[t]->H_incd_[k - 3];
+            for(int i = 0; i < L.len[6 * t + k]; ++i) row[L.off[6 * t + k] + i] = std::real(g->point(i));
+        }
+}
+struct TfsfSurfaceRec { ChimlTfsfSurface s; std::vector<double> epMu; };
+static std::vector<TfsfSurfaceRec> tfsfSurfaces(parallelFDTDFieldReal& FF, const TfsfLayout& L)
+{
+    std::vector<TfsfSurfaceRec> out;
+    for(size_t t = 0; t < FF.tfsfArr_.size(); ++t)
+    {
+        auto& tfsf = FF.tfsfArr_[t];
+        for(int side = 0; side < 2; ++side)          // updateFields(): H surfaces, then (after the line's step) E surfaces
+            for(int ii = 0; ii < 3; ++ii)
+            {
+                const bool E = side == 1;
+                auto& epMu = E ? tfsf->eps_[ii] : tfsf->mu_[ii];
+                // the constructor's choice between addIncdFields and addIncdFieldsEPChange (SOURCE/parallelTFSF.cpp:125-200)
+                const bool epChange = (E ? bool(tfsf->E_[ii]) : bool(tfsf->H_[ii])) && epMu &&
+                                      std::any_of(epMu->data(), epMu->data() + epMu->size(), [&](double a) { return a != epMu->point(0); });
+                for(auto& sur : (E ? tfsf->eSurfaces_[ii] : tfsf->hSurfaces_[ii]))
+                {
+                    TfsfSurfaceRec r;
+                    std::memset(&r.s, 0, sizeof(r.s));
+                    int k = -1;
+                    for(int q = 0; q < 3; ++q)
+                    {
+                        if(sur->incdField_ == tfsf->E_incd_[q]) k = q;
+                        if(sur->incdField_ == tfsf->H_incd_[q]) k = 3 + q;
+                    }
+                    if(k < 0) throw std::runtime_error("TFSF surface: unknown incident field");
+                    if(E != (k >= 3)) throw std::runtime_error("TFSF surface: an E surface reads an incident E line (or H / H)");
+                    if(!E && !sur->indsD_.empty()) throw std::runtime_error("TFSF surface inside a magnetic-dispersive medium (B target) is outside the covered hot path");
+                    r.s.comp = (E ? 0 : 3) + ii;
+                    r.s.incd_offset = L.off[6 * t + k]; r.s.incd_len = L.len[6 * t + k];
+                    r.s.n = sur->szTrans_[0]; r.s.stride_incd = sur->strideIncd_; r.s.stride_main = sur->strideMain_;
+                    r.s.npairs_D = int(sur->indsD_.size() / 2); r.s.npairs_U = int(sur->indsU_.size() / 2);
+                    r.s.prefactor = sur->prefactor_;
+                    r.s.pairs_D = sur->indsD_.data(); r.s.pairs_U = sur->indsU_.data();       // owned by the reference's surface object
+                    if(epChange) { r.epMu.assign(epMu->data(), epMu->data() + epMu->size()); r.epMu.resize(size_t(r.s.incd_len), 1.0); }
+                    out.push_back(std::move(r));
+                }
+            }
+    }
+    for(auto& r : out) r.s.ep_mu = r.epMu.empty() ? nullptr : r.epMu.data();
+    return out;
+}
+static std::vector<double> g_tfsfTable;          // rank 0's table rows of the steps taken (appended to the plan after the run)
+static int g_tfsfPerStep = 0;
+
 static void putEmitters(std::ofstream& out, parallelFDTDFieldReal& FF);
 static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const parallelProgramInputs& IP, int nSteps)
 {
@@ -191,6 +268,22 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
         }
     }
 
+    if(!FF.tfsfArr_.empty())
+    {
+        if(FF.gridComm_->size() > 1) throw std::runtime_error("plan dump: TFSF sources on several ranks are outside the covered hot path");
+        const TfsfLayout L = tfsfLayout(FF);
+        for(const TfsfSurfaceRec& r : tfsfSurfaces(FF, L))
+        {
+            ChimlPlanTfsfSurfaceHdr h; std::memset(&h, 0, sizeof(h));
+            h.comp = r.s.comp; h.incd_offset = r.s.incd_offset; h.incd_len = r.s.incd_len; h.n = r.s.n; h.stride_incd = r.s.stride_incd;
+            h.stride_main = r.s.stride_main; h.npairs_D = r.s.npairs_D; h.npairs_U = r.s.npairs_U; h.has_ep_mu = r.s.ep_mu ? 1 : 0; h.prefactor = r.s.prefactor;
+            std::string p; app(p, h);
+            p.append(reinterpret_cast<const char*>(r.s.pairs_D), size_t(r.s.npairs_D) * 8);
+            p.append(reinterpret_cast<const char*>(r.s.pairs_U), size_t(r.s.npairs_U) * 8);
+            if(r.s.ep_mu) p.append(reinterpret_cast<const char*>(r.s.ep_mu), size_t(r.s.incd_len) * 8);
+            putRec(out, "TFSFSURF", p);
+        }
+    }
     if(FF.magMatInPML_) throw std::runtime_error("plan dump: magnetic material in the PML is outside the covered hot path");
     for(int c = 0; c < 3; ++c)
     {
@@ -376,7 +469,7 @@ struct GpuApi
     CHIML_API(chiml_gpu_step_n_dft) CHIML_API(chiml_gpu_sync) CHIML_API(chiml_gpu_read_detector_range) CHIML_API(chiml_gpu_consume_detector)
     CHIML_API(chiml_gpu_read_population) CHIML_API(chiml_gpu_download_dft) CHIML_API(chiml_gpu_download_field) CHIML_API(chiml_gpu_download_pole)
     CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
-    CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic)
+    CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic) CHIML_API(chiml_gpu_add_tfsf_surface) CHIML_API(chiml_gpu_step_n_tfsf)
 #undef CHIML_API
     void load()
     {
@@ -398,7 +491,7 @@ struct GpuApi
         CHIML_API(chiml_gpu_step_n_dft) CHIML_API(chiml_gpu_sync) CHIML_API(chiml_gpu_read_detector_range) CHIML_API(chiml_gpu_consume_detector)
         CHIML_API(chiml_gpu_read_population) CHIML_API(chiml_gpu_download_dft) CHIML_API(chiml_gpu_download_field) CHIML_API(chiml_gpu_download_pole)
         CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
-        CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic)
+        CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic) CHIML_API(chiml_gpu_add_tfsf_surface) CHIML_API(chiml_gpu_step_n_tfsf)
 #undef CHIML_API
     }
 };
@@ -413,6 +506,8 @@ struct GpuBinding
     struct DftRef { std::shared_ptr<parallelStorageFreqDTCReal> st; int slot; };
     std::vector<DftRef> dfts;
     std::vector<char> fluxHere;
+    TfsfLayout tfsfL;                                      // TFSF: the incident-line table of one step and the surface records
+    std::vector<TfsfSurfaceRec> tfsfSurf;
     void check(int rc, const char* what) { if(rc != CHIML_OK) throw std::runtime_error(std::string(what) + ": " + api.chiml_gpu_last_error(ctx)); }
 };
 
@@ -429,7 +524,11 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
     g.dt = FF.dt_; g.has_D = (FF.D_[0] || FF.D_[2]) ? 1 : 0; g.pml_on_D = FF.dielectricMatInPML_ ? 1 : 0; g.n_objects = int(FF.objArr_.size());
     g.rank = 0; g.nranks = 1;
     if(A.chiml_gpu_create(&g, 0, &B.ctx) != CHIML_OK) throw std::runtime_error(std::string("chiml_gpu_create: ") + A.chiml_gpu_last_error(nullptr));
-    if(FF.magMatInPML_ || !FF.tfsfArr_.empty()) throw std::runtime_error("--gpu: magnetic materials in the PML / TFSF sources are outside the covered hot path");
+    if(FF.magMatInPML_) throw std::runtime_error("--gpu: magnetic materials in the PML are outside the covered hot path");
+    // TFSF sources: the surface records go to the device, the 1-D incident line stays with the reference's object (gpuStep)
+    B.tfsfL = tfsfLayout(FF);
+    B.tfsfSurf = tfsfSurfaces(FF, B.tfsfL);
+    for(const TfsfSurfaceRec& r : B.tfsfSurf) B.check(A.chiml_gpu_add_tfsf_surface(B.ctx, &r.s), "add_tfsf_surface");
 
     static_assert(sizeof(upLists::value_type) == sizeof(ChimlRun), "upLists entries are handed over as ChimlRun");
     auto put = [&](int kind, int comp, const upLists& l) {
@@ -587,16 +686,38 @@ static void gpuStep(parallelFDTDFieldReal& FF, GpuBinding& B)
         for(auto& pul : src->pulse_) p += pul->pulse(FF.tcur_);
         amp.push_back(FF.dt_ * std::real(p));
     }
-    if(B.dfts.empty()) B.check(A.chiml_gpu_step_n(B.ctx, 1, amp.empty() ? nullptr : amp.data()), "step_n");
-    else
+    std::vector<double> tfsfRow;
+    if(!FF.tfsfArr_.empty())
     {
-        std::vector<double> tw;                               // parallelFluxDTC::fieldIn: fftFact_ = exp(i * (-t * freq)), t = time after the step
+        // step() items around tfsf->updateFields() (FDTD_MANAGER/parallelFDTDField.hpp:1238-1255): the H surfaces read the incident E
+        // lines as they are now, the line takes its own step on the host, the E surfaces read the incident H lines after it; the
+        // incident-field series for the flux normalisation are recorded as the reference records them
+        tfsfRow.assign(size_t(B.tfsfL.perStep), 0.0);
+        tfsfGrab(FF, B.tfsfL, true, tfsfRow.data());
+        for(auto& tfsf : FF.tfsfArr_)
+        {
+            FF.H_incd_[0][2 * FF.t_step_ + 0] = tfsf->get_incd_Hx(); FF.H_incd_[0][2 * FF.t_step_ + 1] = tfsf->get_incd_Hx_off();
+            FF.H_incd_[1][2 * FF.t_step_ + 0] = tfsf->get_incd_Hy(); FF.H_incd_[1][2 * FF.t_step_ + 1] = tfsf->get_incd_Hy_off();
+            FF.H_incd_[2][2 * FF.t_step_ + 0] = tfsf->get_incd_Hz(); FF.H_incd_[2][2 * FF.t_step_ + 1] = tfsf->get_incd_Hz_off();
+            tfsf->step();
+            FF.E_incd_[0][2 * FF.t_step_ + 0] = tfsf->get_incd_Ex(); FF.E_incd_[0][2 * FF.t_step_ + 1] = tfsf->get_incd_Ex_off();
+            FF.E_incd_[1][2 * FF.t_step_ + 0] = tfsf->get_incd_Ey(); FF.E_incd_[1][2 * FF.t_step_ + 1] = tfsf->get_incd_Ey_off();
+            FF.E_incd_[2][2 * FF.t_step_ + 0] = tfsf->get_incd_Ez(); FF.E_incd_[2][2 * FF.t_step_ + 1] = tfsf->get_incd_Ez_off();
+        }
+        tfsfGrab(FF, B.tfsfL, false, tfsfRow.data());
+    }
+    std::vector<double> tw;                                   // parallelFluxDTC::fieldIn: fftFact_ = exp(i * (-t * freq)), t = time after the step
+    if(!B.dfts.empty())
+    {
         const double t = FF.tcur_ + FF.dt_;
         for(size_t ff = 0; ff < FF.fluxArr_.size(); ++ff)
             if(B.fluxHere[ff])
                 for(double f : FF.fluxArr_[ff]->freqList_) { const cplx w = std::exp(cplx(0.0, -1.0 * t * f)); tw.push_back(w.real()); tw.push_back(w.imag()); }
-        B.check(A.chiml_gpu_step_n_dft(B.ctx, 1, amp.empty() ? nullptr : amp.data(), tw.data()), "step_n_dft");
     }
+    if(!FF.tfsfArr_.empty())
+        B.check(A.chiml_gpu_step_n_tfsf(B.ctx, 1, amp.empty() ? nullptr : amp.data(), tw.empty() ? nullptr : tw.data(), tfsfRow.data(), tfsfRow.size()), "step_n_tfsf");
+    else if(B.dfts.empty()) B.check(A.chiml_gpu_step_n(B.ctx, 1, amp.empty() ? nullptr : amp.data()), "step_n");
+    else B.check(A.chiml_gpu_step_n_dft(B.ctx, 1, amp.empty() ? nullptr : amp.data(), tw.data()), "step_n_dft");
     FF.tcur_ += FF.dt_;
     ++FF.t_step_;
     // detectors: the sampled boxes come back from the device ring into the reference's own grids, and its own writer formats them
@@ -727,13 +848,31 @@ static void rankMain(int rank, const Options& opt)
         bindEmitters(FF, gpu, emitterBuffers);
         gpu.check(gpu.api.chiml_gpu_commit(gpu.ctx), "commit");
     }
-    for(int tt = 0; tt < opt.warmup; ++tt)
-        if(opt.gpu) gpuStep(FF, gpu); else FF.step();
+    // a CPU run that writes a plan also records what the TFSF surfaces read from the reference's 1-D incident line, step by step
+    const bool tfsfRecord = !FF.tfsfArr_.empty() && !opt.plan.empty() && !opt.gpu;
+    const TfsfLayout tfsfL = tfsfLayout(FF);
+    auto stepOnce = [&]() {
+        if(opt.gpu) { gpuStep(FF, gpu); return; }
+        if(!tfsfRecord) { FF.step(); return; }
+        std::vector<double> row(size_t(tfsfL.perStep), 0.0);
+        tfsfGrab(FF, tfsfL, true, row.data());
+        FF.step();
+        tfsfGrab(FF, tfsfL, false, row.data());
+        g_tfsfTable.insert(g_tfsfTable.end(), row.begin(), row.end());
+        g_tfsfPerStep = tfsfL.perStep;
+    };
+    for(int tt = 0; tt < opt.warmup; ++tt) stepOnce();
     gridComm->barrier();
     auto t0 = std::chrono::steady_clock::now();
-    for(int tt = 0; tt < nSteps; ++tt)
-        if(opt.gpu) gpuStep(FF, gpu); else FF.step();
+    for(int tt = 0; tt < nSteps; ++tt) stepOnce();
     if(opt.gpu) gpuFinish(FF, gpu);
+    if(tfsfRecord && g_tfsfPerStep > 0)
+    {
+        std::ofstream out((opt.plan + ".rank" + std::to_string(rank) + ".plan").c_str(), std::ios::binary | std::ios::app);
+        ChimlPlanTfsfLinesHdr h; h.n_steps = int(g_tfsfTable.size() / size_t(g_tfsfPerStep)); h.per_step = g_tfsfPerStep;
+        std::string p; app(p, h); appVec(p, g_tfsfTable);
+        putRec(out, "TFSFLINE", p);
+    }
     gridComm->barrier();
     auto t1 = std::chrono::steady_clock::now();
     if(rank == 0)

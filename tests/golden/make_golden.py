@@ -144,6 +144,36 @@ def cases():
     te["PML"]["thickness"] = [8 / RES, 0.0, 0.0]
     te["ObjectList"] = [I.block([0.1, 1.0, 0.0], [0.08, 0.0, 0.0], eps=2.2, pols=[I.lorentz_pole(0.8, 0.1, 2.0)])]
     c["pbc_te"] = _short_pulse(te)
+    # ---- TFSF plane-wave sources (SOURCE/parallelTFSF.hpp): the surface corrections run on the device, the 1-D incident line is the
+    # reference's own (its per-step values are recorded into the plan, record TFSFLINE).  2-D TM along +y over a Drude rod; 2-D TE
+    # along (1, 2) (incident strides 1 and 2) over a Lorentz block; 3-D along +z over a Lorentz sphere with a flux box around it
+    # (incident-field normalisation of getFlux); 3-D along +z through a Lorentz slab that cuts the box (D targets and
+    # addIncdFieldsEPChange); 3-D along (1, 0, 1).  (Directions with a negative component make the reference's own incident line
+    # overflow to inf / NaN within a few steps here, and m = (1, 0, 0) on a 2-D TM grid leaves its y faces without Hx corrections:
+    # such inputs are no fixtures.) ----
+    tp = lambda f: [I.gaussian_pulse(f, 1.0, t_0=0.25, cutoff=2.5)]  # noqa: E731
+    tm = I.c2_tm_drude(n=63, steps=120, pml_cells=8, rod=(20, 6), nfreq=0, out="out/ttm")
+    tm["SourceList"] = []
+    tm["TFSF"] = [I.tfsf([0.3, 0.3, 0.0], [0.0, 0.0, 0.0], tp(1.5), m=(0, 1, 0))]
+    c["tfsf_tm"] = tm
+    te = I.c1_te_vacuum(n=55, steps=120, pml_cells=8, out="out/tte")
+    te["SourceList"] = []
+    te["ObjectList"] = [I.block([0.08, 0.06, 0.0], [0.02, 0.01, 0.0], eps=2.2, pols=[I.lorentz_pole(0.8, 0.1, 2.0)])]
+    te["TFSF"] = [I.tfsf([0.26, 0.22, 0.0], [0.0, 0.0, 0.0], tp(1.5), m=(1, 2, 0), psi=0.0)]
+    c["tfsf_te"] = te
+    cell3 = lambda steps: I.comp_cell([25 / RES, 23 / RES, 27 / RES], RES, steps * DT - 0.5 * DT, "Ex")  # noqa: E731
+    ball = I.sphere(0.03, [0.0, 0.01, 0.0], eps=2.0, pols=[I.lorentz_pole(1.2, 0.1, 2.0)])
+    c["tfsf3d"] = I.config(cell3(70), I.pml([5 / RES] * 3), [], [ball],
+                           [I.detector([0.03, 0, 0], [0, 0, 0], "Ex", "out/t3/dtc", time_int=DT * 1.0000001)],
+                           [I.flux("out/t3/box", [0.0, 0.0, 0.0], [0.06, 0.06, 0.06], 1.5, 1.0, 3)])
+    c["tfsf3d"]["TFSF"] = [I.tfsf([0.1, 0.1, 0.12], [0.0, 0.0, 0.0], tp(1.5), m=(0, 0, 1), psi=90.0)]
+    c["tfsf3d_slab"] = I.config(cell3(70), I.pml([5 / RES] * 3), [I.normal_source("Ez", [0.02, -0.03, -0.03], [0, 0, 0], tp(1.2))],
+                                [I.block([1.0, 1.0, 0.04], [0.0, 0.0, 0.02], eps=2.2, pols=[I.lorentz_pole(0.8, 0.1, 2.0)])],
+                                [I.detector([0.03, 0, 0], [0, 0, 0], "Ey", "out/t3s/dtc", time_int=DT * 1.0000001)])
+    c["tfsf3d_slab"]["TFSF"] = [I.tfsf([0.1, 0.1, 0.12], [0.0, 0.0, 0.0], tp(1.5), m=(0, 0, 1), psi=60.0)]
+    c["tfsf3d_obl"] = I.config(cell3(60), I.pml([5 / RES] * 3), [], [ball],
+                               [I.detector([0.03, 0, 0], [0, 0, 0], "Ex", "out/t3o/dtc", time_int=DT * 1.0000001)])
+    c["tfsf3d_obl"]["TFSF"] = [I.tfsf([0.1, 0.1, 0.12], [0.0, 0.0, 0.0], tp(1.5), m=(1, 0, 1), psi=90.0)]
     return c
 
 

@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
         L.oracle_step_n.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_step_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_set_periodic.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_add_tfsf_surface.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_step_n_tfsf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         L.oracle_add_dft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
         L.oracle_step_n_dft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_step_phase_dft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -143,6 +145,10 @@ class OracleSim:
         for e in plan.emitters:
             d = emitter_desc(e, self._keep)
             self._chk(L.oracle_add_emitters(self.h, C.byref(d)))
+        for t in plan.tfsf:
+            from chiml_b200 import capi
+            d = capi.tfsf_surface(t, self._keep)
+            self._chk(L.oracle_add_tfsf_surface(self.h, C.byref(d)))
         for comp, w in sorted(plan.periodic.items()):
             self._chk(L.oracle_set_periodic(self.h, comp, (C.c_int32 * 7)(*w)))
         self._chk(L.oracle_commit(self.h))
@@ -165,7 +171,12 @@ class OracleSim:
         if amp is None:
             amp = self.src_amp(self.steps_done, n)
         amp = np.ascontiguousarray(amp, dtype=np.float64)
-        if self.plan.dfts:
+        if self.plan.tfsf:
+            from chiml_b200 import capi
+            tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, n)) if self.plan.dfts else None
+            rows = capi.tfsf_rows(self.plan, self.steps_done, n)
+            self._chk(lib().oracle_step_n_tfsf(self.h, n, _ptr(amp), _ptr(tw) if tw is not None else None, _ptr(rows), rows.shape[1], nthreads))
+        elif self.plan.dfts:
             tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, n))
             self._chk(lib().oracle_step_n_dft(self.h, n, _ptr(amp), _ptr(tw), nthreads))
         else:

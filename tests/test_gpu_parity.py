@@ -123,7 +123,7 @@ def test_2d_launch_per_phase_path_matches_reference_fixture(case, march):
     sa = {k["name"]: k["launches"] for k in a.kernel_stats()}
     sb = {k["name"]: k["launches"] for k in b.kernel_stats()}
     assert sa["k_steps_2d"] == 0
-    if not plan.emitters:
+    if not plan.emitters and not plan.tfsf:      # (emitters and TFSF surfaces take the launch path)
         assert sb["k_steps_2d"] == 3 and sb["k_fast<E>"] == 0, sb
     a.close(); b.close()
 
@@ -191,3 +191,40 @@ def test_detector_and_population_rings_wrap_and_grow(oracle_lib):
         ref.append(cpu.field(d0.field)[y0, z0, x0])
     assert np.array_equal(det[:51, 0, 0, 0], np.array(ref))
     a.close(); b.close(); cpu.close()
+
+
+@pytest.mark.parametrize("case", ["tfsf_te", "tfsf3d_obl", "tfsf3d_slab"])
+def test_tfsf_surface_variants_match_oracle(case, oracle_lib):
+    """Surface records the reference's fixtures cannot supply (directions with a negative component make its own incident line overflow):
+    negative incident strides -- read from the far end, like the BLAS call they replace -- and an eps / mu line on every surface
+    (addIncdFieldsEPChange, SOURCE/parallelTFSF.cpp:93-105).  Built from a fixture's records; GPU against the oracle, bit for bit."""
+    import copy
+    plan = copy.deepcopy(util.load_plan(case))
+    rng = np.random.default_rng(7)
+    for k, t in enumerate(plan.tfsf):
+        if k % 2 == 0:
+            t.stride_incd = -t.stride_incd if t.stride_incd else -1
+            span = (max(t.n, 1) - 1) * abs(t.stride_incd)
+            for pr in (t.pairs_D, t.pairs_U):
+                if len(pr):
+                    pr[:, 0] = np.minimum(pr[:, 0], t.incd_len - 1 - span)
+        if t.ep_mu is None and k % 3 != 1:
+            t.ep_mu = rng.uniform(1.0, 3.0, size=t.incd_len)
+    gpu, cpu = capi.GpuSim(plan), OracleSim(plan)
+    for n in (1, 2, 27):
+        gpu.step_n(n)
+        cpu.step_n(n)
+    for f in plan.fields_present():
+        g, c = gpu.field(f), cpu.field(f)
+        assert np.abs(c).max() > 0
+        assert np.array_equal(g, c), f"{case}/{util.P.FIELD_NAMES[f]}: rel L2 {util.rel_l2(g, c):.3e}"
+    gpu.close(); cpu.close()
+
+
+def test_tfsf_surface_inside_the_cpml_is_refused():
+    import copy
+    plan = copy.deepcopy(util.load_plan("tfsf_tm"))
+    t = next(t for t in plan.tfsf if len(t.pairs_U))
+    t.pairs_U[0, 1] = 2 + plan.ln[0] * 2          # a cell of the CPML corner
+    with pytest.raises(capi.ChimlError, match="inside the CPML"):
+        capi.GpuSim(plan)
