@@ -62,7 +62,8 @@ struct Surface
 
 } // namespace
 
-void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std::vector<double>>& re, const std::vector<std::vector<double>>& im, long nSteps)
+void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std::vector<double>>& re, const std::vector<std::vector<double>>& im, long nSteps,
+                      const std::vector<std::vector<cplx>>* incd)
 {
     if(P.grid.desc.nranks != 1) throw std::logic_error("flux files are written by single-rank runs (several slabs write their accumulators)");
     const bool twoD = P.grid.desc.ln[2] == 1;
@@ -90,6 +91,31 @@ void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std
         {
             freqConv = SPEED_OF_LIGHT / IP.a_;
             fluxConv = IP.I0_ / IP.a_ * IP.I0_ / (EPS0() * IP.a_ * SPEED_OF_LIGHT);
+        }
+        // the incident flux is scaled by the area of the region's faces unless cross sections are asked for (:156-172)
+        double incConvX = 1.0, incConvY = 1.0, incConvZ = 1.0;
+        if(fx.SI) incConvX = incConvY = incConvZ = IP.I0_ / IP.a_ * IP.I0_ / (EPS0() * IP.a_ * SPEED_OF_LIGHT);
+        if(!fx.crossSec)
+        {
+            auto norm1 = [&](int n, double d) { std::vector<cplx> ones(n, cplx(1.0, 0.0)); return std::real(simps(ones.data(), n, d)); };
+            auto norm2 = [&](int nx, int ny, double dx, double dy) {                       // simps2DNorm (:603-611)
+                std::vector<cplx> result(ny, 0.0);
+                for(int jj = 0; jj < ny; ++jj) { std::vector<cplx> ones(nx, cplx(1.0, 0.0)); result[jj] = simps(ones.data(), nx, dx); }
+                return std::real(simps(result.data(), (int)result.size(), dy));
+            };
+            const double* d = P.grid.desc.d;
+            if(threeD)
+            {
+                incConvX *= (fx.sz[2] > 1 && fx.sz[1] > 1) ? norm2(fx.sz[1], fx.sz[2], d[1], d[2]) : 0.0;
+                incConvY *= (fx.sz[0] > 1 && fx.sz[2] > 1) ? norm2(fx.sz[0], fx.sz[2], d[0], d[2]) : 0.0;
+                incConvZ *= (fx.sz[0] > 1 && fx.sz[1] > 1) ? norm2(fx.sz[0], fx.sz[1], d[0], d[1]) : 0.0;
+            }
+            else
+            {
+                incConvY *= norm1(fx.sz[0], d[0]);
+                incConvX *= norm1(fx.sz[1], d[1]);
+                incConvZ = 0.0;
+            }
         }
         freqConv /= (M_PI * 2.0);
 
@@ -201,12 +227,24 @@ void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std
         for(int kf = 0; kf < nfreq; ++kf)
         {
             cplx flux(0.0, 0.0);
-            // no TFSF surface on this path: the incident fields are empty and every incident spectrum is zero (:433-460)
-            const cplx Ex_inc(0.0, 0.0), Ey_inc(0.0, 0.0), Ez_inc(0.0, 0.0), Hx_inc(0.0, 0.0), Hy_inc(0.0, 0.0), Hz_inc(0.0, 0.0);
-            const double incConv = 1.0;
-            cplx flux_incd = std::pow(incConv * (Ey_inc * std::conj(Hz_inc) - Ez_inc * std::conj(Hy_inc)) / (std::pow(static_cast<double>(nt * fx.timeInt), 2.0)), 2.0);
-            flux_incd += std::pow(incConv * (Ez_inc * std::conj(Hx_inc) - Ex_inc * std::conj(Hz_inc)) / (std::pow(static_cast<double>(nt * fx.timeInt), 2.0)), 2.0);
-            flux_incd += std::pow(incConv * (Ex_inc * std::conj(Hy_inc) - Ey_inc * std::conj(Hx_inc)) / (std::pow(static_cast<double>(nt * fx.timeInt), 2.0)), 2.0);
+            // Fourier transform of the incident-field series of a TFSF source (:455-479): even entries (the field at the origin), then odd
+            // ones (its Yee-offset partner), each weighted 1/2; real fields keep the real part (getIncdField_).  Without a TFSF source the
+            // series are all zero.
+            cplx inc[6];
+            for(int s6 = 0; s6 < 6; ++s6)
+            {
+                inc[s6] = cplx(0.0, 0.0);
+                if(!incd || incd->size() != 6) continue;
+                const std::vector<cplx>& v = (*incd)[s6];
+                for(size_t tt = 0; tt < v.size(); tt += 2)
+                    inc[s6] += cplx(std::real(0.5 * v[tt])) * std::exp(cplx(0.0, fx.freqs[kf] * static_cast<double>(tt / 2) * (IP.dt_ / static_cast<double>(fx.timeInt))));
+                for(size_t tt = 1; tt < v.size(); tt += 2)
+                    inc[s6] += cplx(std::real(0.5 * v[tt])) * std::exp(cplx(0.0, fx.freqs[kf] * static_cast<double>(tt / 2) * (IP.dt_ / static_cast<double>(fx.timeInt))));
+            }
+            const cplx Ex_inc = inc[0], Ey_inc = inc[1], Ez_inc = inc[2], Hx_inc = inc[3], Hy_inc = inc[4], Hz_inc = inc[5];
+            cplx flux_incd = std::pow(incConvX * (Ey_inc * std::conj(Hz_inc) - Ez_inc * std::conj(Hy_inc)) / (std::pow(static_cast<double>(nt * fx.timeInt), 2.0)), 2.0);
+            flux_incd += std::pow(incConvY * (Ez_inc * std::conj(Hx_inc) - Ex_inc * std::conj(Hz_inc)) / (std::pow(static_cast<double>(nt * fx.timeInt), 2.0)), 2.0);
+            flux_incd += std::pow(incConvZ * (Ex_inc * std::conj(Hy_inc) - Ey_inc * std::conj(Hx_inc)) / (std::pow(static_cast<double>(nt * fx.timeInt), 2.0)), 2.0);
             flux_incd = std::sqrt(flux_incd);
             std::vector<std::vector<cplx>> ijk(faces.size());
             for(size_t vv = 0; vv < faces.size(); ++vv)
@@ -262,6 +300,164 @@ void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std
                     sf.write(reinterpret_cast<const char*>(nv), sizeof(nv));
                     sf.write(reinterpret_cast<const char*>(F.g[r].data()), (std::streamsize)(F.g[r].size() * sizeof(cplx)));
                 }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Frequency detectors (dtc_class "freq"): parallelDetectorFREQ_Base::collectFreqFields / fieldTranspose / toFile(incd, dt) / toMap(incd, dt)
+// (DTC/parallelDTC_FREQ.hpp:275-343, 384-447, 497-583) for one process, as main.cpp:74-107 calls them (the variants with incident fields,
+// whose series are all zero without a TFSF source: E_incd_ / H_incd_ hold 2 (nSteps + 1) zeros, FDTD_MANAGER/parallelFDTDField.hpp:250-255).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+// netlib zdotc with x = (1, 0) everywhere, as fieldOutFreqFunction / pwrOutFreqFunction call it (DTC/parallelDTCOutputFxn.cpp:9-18)
+cplx sum_ones(int n, const cplx* y)
+{
+    cplx sacc(0.0, 0.0);
+    const cplx one(1.0, 0.0);
+    for(int i = 0; i < n; ++i) sacc = sacc + cmul(std::conj(one), y[i]);
+    return sacc;
+}
+cplx field_out(int szFreq, const cplx* in, int, cplx*, int nt, double conv) { return conv * sum_ones(szFreq, in) / std::pow(static_cast<double>(nt), 1.0); }
+cplx power_out(int szFreq, const cplx* in, int szPwr, cplx* pwr, int nt, double conv)
+{
+    for(int i = 0; i < szPwr; ++i) pwr[i] = in[i] * std::conj(in[i]);
+    return conv * sum_ones(szFreq, pwr) / std::pow(static_cast<double>(nt), 2.0);
+}
+} // namespace
+
+void write_freq_detector_files(const Inputs& IP, const SlabPlan& P, const std::vector<std::vector<double>>& re, const std::vector<std::vector<double>>& im, long nSteps)
+{
+    if(IP.freqDtcs_.empty()) return;
+    if(P.grid.desc.nranks != 1) throw std::logic_error("frequency-detector files are written by single-rank runs");
+    for(size_t k = 0; k < IP.freqDtcs_.size(); ++k)
+    {
+        const FreqDtcInput& q = IP.freqDtcs_[k];
+        const int nfreq = (int)q.freqs.size();
+        const int szFreq = q.sz[0] * q.sz[1] * q.sz[2];
+        // the constructor's unit factors (:96-124)
+        double freqConv = 1.0, convFactor = 1.0;
+        if(q.SI)
+        {
+            convFactor = IP.I0_ / IP.a_;
+            if(q.type == DTCTYPE::EX || q.type == DTCTYPE::EY || q.type == DTCTYPE::EZ) convFactor /= EPS0() * SPEED_OF_LIGHT;
+            freqConv = SPEED_OF_LIGHT / IP.a_;
+        }
+        const bool pow = q.type == DTCTYPE::EPOW || q.type == DTCTYPE::HPOW;
+        if(pow) convFactor = std::pow(convFactor, 2.0);
+        freqConv /= (M_PI * 2.0);
+        auto toOut = pow ? power_out : field_out;
+        const int tStep = (int)(nSteps / q.timeInt + 1);        // output(): once in the propagator's constructor, then every timeInt-th step
+        // collectFreqFields + fieldTranspose: per stored field a {szFreq, nfreq} grid, point j of frequency f at j + szFreq * f.  The box
+        // point j = x + sz_x (z + sz_z y) is accumulator (line z + sz_z y, point x) of the volume storage; a 2-D grid stores no line at all
+        // (getLocalSzEl of the absent z axis is 0) and its fields stay zero
+        std::vector<std::vector<cplx>> trans;
+        int nIncd = 0;
+        for(size_t e = 0; e < P.dfts.size(); ++e)
+        {
+            const PlanDft& d = P.dfts[e];
+            if(d.freq_dtc != (int)k) continue;
+            std::vector<cplx> t((size_t)szFreq * nfreq, cplx(0.0, 0.0));
+            const size_t pts = d.acc_len / (size_t)std::max(nfreq, 1);
+            if(pts != 0 && pts != (size_t)szFreq) throw std::logic_error("frequency detector: the stored box does not match the detector's size");
+            for(size_t j = 0; j < pts; ++j)
+                for(int f = 0; f < nfreq; ++f) t[j + (size_t)szFreq * f] = cplx(re[e][f + (size_t)nfreq * j], im[e][f + (size_t)nfreq * j]);
+            trans.push_back(std::move(t));
+        }
+        // which incident series main.cpp hands over: three for the power types, one otherwise
+        nIncd = pow ? 3 : 1;
+        const size_t incdLen = 2 * ((size_t)P.grid.n_steps + 1);
+        auto incd_point = [&](int ii) {
+            cplx pt(0.0, 0.0);
+            const cplx zero(0.0, 0.0);
+            for(size_t tt = 0; tt < incdLen; tt += 2)
+                pt += std::real(0.5 * zero) * std::exp(cplx(0.0, -1.0 * q.freqs[ii] * static_cast<double>(tt / 2) * (IP.dt_ / static_cast<double>(q.timeInt))));
+            for(size_t tt = 1; tt < incdLen; tt += 2)
+                pt += std::real(0.5 * zero) * std::exp(cplx(0.0, -1.0 * q.freqs[ii] * static_cast<double>(tt / 2) * (IP.dt_ / static_cast<double>(q.timeInt))));
+            pt /= static_cast<double>(tStep * q.timeInt);
+            if(pow) pt *= std::conj(pt);
+            pt *= convFactor / 2.0;
+            return pt;
+        };
+        if(!q.outputMaps)
+        {
+            std::ofstream f(q.name.c_str());
+            f << "#" << std::setw(16) << "freq\tabs(incd)\treal(incd)\timag(incd)";
+            for(size_t nn = 1; nn < trans.size(); ++nn) f << "\tabs(field " << nn << ")\treal(field " << nn << ")\timag(field " << nn << ")";
+            if(trans.size() > 1) f << "\tabs(total)\treal(total)\timag(total)";
+            f << std::endl;
+            std::vector<cplx> pwr(szFreq, 0.0);
+            for(int ii = 0; ii < nfreq; ii++)
+            {
+                cplx incd_field(0.0, 0.0);
+                f << std::setw(16) << std::setprecision(12) << freqConv * q.freqs[ii];
+                for(int v = 0; v < nIncd; ++v)
+                {
+                    const cplx pt = incd_point(ii);
+                    f << "\t" << std::setw(16) << std::setprecision(12) << std::real(pt) << "\t" << std::setw(16) << std::setprecision(12) << std::imag(pt) << "\t"
+                      << std::setw(16) << std::setprecision(12) << std::abs(pt);
+                    incd_field += pt;
+                }
+                if(nIncd > 2)
+                    f << "\t" << std::setw(16) << std::setprecision(12) << std::real(incd_field) << "\t" << std::setw(16) << std::setprecision(12) << std::imag(incd_field) << "\t"
+                      << std::setw(16) << std::setprecision(12) << std::abs(incd_field);
+                cplx freq = 0;
+                for(auto& grid : trans)
+                {
+                    const cplx pt = toOut(szFreq, &grid[(size_t)szFreq * ii], (int)pwr.size(), pwr.data(), tStep, convFactor / 2.0);
+                    f << "\t" << std::setw(16) << std::setprecision(12) << std::real(pt) << "\t" << std::setw(16) << std::setprecision(12) << std::imag(pt) << "\t"
+                      << std::setw(16) << std::setprecision(12) << std::abs(pt);
+                    freq += pt;
+                }
+                if(trans.size() > 1)
+                    f << '\t' << std::setw(16) << std::setprecision(12) << std::real(freq) << "\t" << std::setw(16) << std::setprecision(12) << std::imag(freq) << "\t"
+                      << std::setw(16) << std::setprecision(12) << std::abs(freq) << std::endl;
+                else
+                    f << "\n";
+            }
+        }
+        else
+        {
+            for(int ii = 0; ii < nfreq; ii++)
+            {
+                std::vector<cplx> pwr(1, 0.0);
+                const std::string fileName = q.name + "." + std::to_string(freqConv * q.freqs[ii]);
+                std::ofstream f(fileName.c_str());
+                f << "#" << std::setw(16) << "x\ty\tz\tabs(incd)\treal(incd)\timag(incd)";
+                for(size_t nn = 1; nn < trans.size(); ++nn) f << "\tabs(field " << nn << ")\treal(field " << nn << ")\timag(field " << nn << ")";
+                if(trans.size() > 1) f << "\tabs(total)\treal(total)\timag(total)";
+                f << std::endl;
+                cplx incd_field(0.0, 0.0);
+                std::vector<double> outIncdToFile;
+                for(int v = 0; v < nIncd; ++v)
+                {
+                    const cplx pt = incd_point(ii);
+                    outIncdToFile.push_back(std::real(pt)); outIncdToFile.push_back(std::imag(pt)); outIncdToFile.push_back(std::abs(pt));
+                    incd_field += pt;
+                }
+                if(nIncd > 2) { outIncdToFile.push_back(std::real(incd_field)); outIncdToFile.push_back(std::imag(incd_field)); outIncdToFile.push_back(std::abs(incd_field)); }
+                for(int yy = 0; yy < q.sz[1]; ++yy)
+                    for(int zz = 0; zz < q.sz[2]; ++zz)
+                        for(int xx = 0; xx < q.sz[0]; ++xx)
+                        {
+                            f << std::setw(16) << xx << '\t' << yy << '\t' << zz;
+                            for(double val : outIncdToFile) f << "\t" << std::setw(16) << std::setprecision(12) << val;
+                            const int jj = xx + zz * q.sz[0] + yy * q.sz[0] * q.sz[2];
+                            cplx freq = 0;
+                            for(auto& grid : trans)
+                            {
+                                const cplx pt = toOut(1, &grid[(size_t)jj + (size_t)szFreq * ii], (int)pwr.size(), pwr.data(), tStep, convFactor / 2.0);
+                                f << "\t" << std::setw(16) << std::setprecision(12) << std::abs(pt) << "\t" << std::real(pt) << "\t" << std::imag(pt);
+                                freq += pt;
+                            }
+                            if(trans.size() > 1)
+                                f << '\t' << std::setw(16) << std::setprecision(12) << std::real(freq) << "\t" << std::setw(16) << std::setprecision(12) << std::imag(freq) << "\t"
+                                  << std::setw(16) << std::setprecision(12) << std::abs(freq) << std::endl;
+                            else
+                                f << "\n";
+                        }
+            }
         }
     }
 }

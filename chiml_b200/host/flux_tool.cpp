@@ -1,5 +1,6 @@
 // chiml_flux: the flux spectra files of a single-rank run from the accumulator files the driver wrote.
-// usage: chiml_flux <input.json> [--steps N] [--ranks R]   (run in the directory the relative output names of the input refer to)
+// usage: chiml_flux <input.json> [--steps N] [--ranks R] [--incd FILE]   (FILE: the incident-field series of a TFSF run, "CHIMLINC", int32 n, then six
+// series Ex Ey Ez Hx Hy Hz of n complex values, as the drop-in / the reference driver's --incd-dump writes them)   (run in the directory the relative output names of the input refer to)
 // Reads <flux name>.dft of every flux region (format: chiml_b200/host/main.cpp), writes <flux name>.dat like the reference's
 // parallelFluxDTC::getFlux.  The driver `chiml` calls the same function at the end of a single-rank run; this tool exists so that
 // accumulators of several slabs can be merged first, and so that the post-processing is testable without a GPU.
@@ -53,19 +54,35 @@ int main(int argc, char** argv)
     if(argc < 2) { std::fprintf(stderr, "usage: chiml_flux <input.json> [--steps N] [--ranks R]\n"); return 2; }
     long steps = -1;
     int nranks = 1;
+    std::string incdFile;
     for(int a = 2; a + 1 < argc; a += 2)
     {
         if(std::string(argv[a]) == "--steps") steps = std::atol(argv[a + 1]);
+        else if(std::string(argv[a]) == "--incd") incdFile = argv[a + 1];
         else if(std::string(argv[a]) == "--ranks") nranks = std::atoi(argv[a + 1]);
     }
     try
     {
         Json root = read_input_file(argv[1]);
-        Inputs IP(root);
+        Inputs IP(root, true);
         SlabPlan P = build_plan(IP, 0, 1);
+        std::vector<std::vector<std::complex<double>>> incd;
+        if(!incdFile.empty())
+        {
+            std::ifstream in(incdFile.c_str(), std::ios::binary);
+            char magic[8]; int32_t n = 0;
+            in.read(magic, 8); in.read(reinterpret_cast<char*>(&n), 4);
+            if(!in || std::memcmp(magic, "CHIMLINC", 8) != 0 || n < 0) throw std::runtime_error(incdFile + " is not an incident-series file");
+            incd.assign(6, std::vector<std::complex<double>>((size_t)n));
+            for(auto& v : incd) in.read(reinterpret_cast<char*>(v.data()), (std::streamsize)(v.size() * sizeof(std::complex<double>)));
+            if(!in) throw std::runtime_error(incdFile + " is truncated");
+        }
         std::vector<std::vector<double>> re(P.dfts.size()), im(P.dfts.size());
         if(nranks == 1)
+        {
             for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff) read_region(IP.fluxes_[ff].name + ".dft", P, (int)ff, re, im);
+            for(size_t k = 0; k < IP.freqDtcs_.size(); ++k) read_region(IP.freqDtcs_[k].name + ".dft", P, (int)(IP.fluxes_.size() + k), re, im);
+        }
         else
         {
             // several slabs: every slab wrote the accumulators of its parts of the surfaces (<name>.dft.rank<r>); an accumulator is
@@ -113,7 +130,9 @@ int main(int argc, char** argv)
             for(size_t q = 0; q < P.dfts.size(); ++q)
                 if(filled[q] != where[q].size()) throw std::runtime_error("the slabs' accumulator files do not cover a flux surface");
         }
-        write_flux_files(IP, P, re, im, steps >= 0 ? steps : P.grid.n_steps);
+        write_flux_files(IP, P, re, im, steps >= 0 ? steps : P.grid.n_steps, incd.empty() ? nullptr : &incd);
+        if(nranks == 1) write_freq_detector_files(IP, P, re, im, steps >= 0 ? steps : P.grid.n_steps);
+        else if(!IP.freqDtcs_.empty()) throw std::runtime_error("frequency-detector files are written by single-rank runs");
     }
     catch(std::exception& e) { std::fprintf(stderr, "chiml_flux: %s\n", e.what()); return 1; }
     return 0;

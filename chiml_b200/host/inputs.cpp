@@ -318,7 +318,7 @@ std::shared_ptr<Obj> Inputs::jsonToObject(const Json& o)
 // ---------------------------------------------------------------------------------------------------
 // Inputs
 // ---------------------------------------------------------------------------------------------------
-Inputs::Inputs(const Json& IP)
+Inputs::Inputs(const Json& IP, bool postProcessing)
 {
     periodic_ = IP.get<bool>("CompCell.PBC", false);
     pol_ = string2pol(IP.get<std::string>("CompCell.pol"));
@@ -350,7 +350,7 @@ Inputs::Inputs(const Json& IP)
         if(pmlThickness[ii] * 2 > size_[ii]) throw std::logic_error("PML size is larger than the cell size, this will lead to infinte fields.");
         pmlThickness_[ii] = find_pt(pmlThickness[ii], d_[ii]);
     }
-    if(IP.child("TFSF").size() > 0) throw std::logic_error("TFSF sources are outside the covered hot path (SURVEY.md section 8(f) rank 1)");
+    if(IP.child("TFSF").size() > 0 && !postProcessing) throw std::logic_error("TFSF sources are outside the covered hot path (SURVEY.md section 8(f) rank 1)");
 
     // ---- sources (parallelInputs.cpp:114-216) ----
     for(const auto& it : IP.child("SourceList").kids)
@@ -520,7 +520,7 @@ Inputs::Inputs(const Json& IP)
         d.name = dj.get<std::string>("fname") + "_field_" + std::to_string(ii) + ".dat";
         ++ii;
         d.cls = string2dtcclass(dj.get<std::string>("dtc_class", "cout"));
-        if(d.cls == DTCCLASS::FREQ || d.cls == DTCCLASS::BMP) throw std::logic_error("freq / bmp detectors are outside the covered hot path");
+        if(d.cls == DTCCLASS::BMP) throw std::logic_error("bmp detectors are outside the covered hot path");
         d.SI = dj.get<bool>("SI", true);
         d.timeInt = dj.get<double>("Time_Interval", dt_);
         const std::array<double, 3> tempSz = as_ptArr<double>(dj, "size");
@@ -530,6 +530,34 @@ Inputs::Inputs(const Json& IP)
         {
             if(locs[i] - tempSz[i] / 2.0 < -1.0 * size_[i] / 2.0 || locs[i] + tempSz[i] / 2.0 > size_[i] / 2.0) throw std::logic_error("A detector is outside the FDTD cell.");
             d.loc[i] = find_pt(locs[i] + size_[i] / 2.0 - tempSz[i] / 2.0, d_[i]);
+        }
+        if(d.cls == DTCCLASS::FREQ)
+        {
+            // the frequency list (parallelInputs.cpp:716-751)
+            FreqDtcInput q;
+            q.type = d.type; q.SI = d.SI; q.name = d.name; q.loc = d.loc; q.sz = d.sz;
+            q.outputMaps = dj.get<bool>("output_map", false);
+            q.timeInt = static_cast<int>(std::floor(d.timeInt / dt_ + 0.5));
+            const double fCen = dj.get<double>("fcen", -1.0), fWidth = dj.get<double>("fwidth", -1.0);
+            const double lamL = dj.get<double>("lamL", -1.0), lamR = dj.get<double>("lamR", -1.0);
+            const int nFreq = dj.get<int>("nfreq", -1);
+            if(nFreq < 1) throw std::logic_error("The freq detector regions need to have a number of frequencies specified");
+            q.freqs.assign(nFreq, 0.0);
+            if(fCen != -1.0 && fWidth != -1.0)
+            {
+                if(lamL != -1.0 && lamR != -1.0) throw std::logic_error("Both a freq and wavelength range is defined, please select one to define for the freq detector");
+                const double dOmg = fWidth / static_cast<double>(nFreq - 1);
+                for(int k = 0; k < nFreq; ++k) q.freqs[k] = (fCen - fWidth / 2.0 + k * dOmg) * 2.0 * M_PI;
+            }
+            else if(lamL != -1.0 && lamR != -1.0)
+            {
+                const double dLam = (lamR - lamL) / static_cast<double>(nFreq - 1);
+                for(int k = 0; k < nFreq; ++k) q.freqs[k] = 2.0 * M_PI / (lamL + k * dLam);
+            }
+            else throw std::logic_error("All frequency detectors must either have fcen and fwidth defined or lamL and lamR defined");
+            if(q.timeInt < 1) throw std::logic_error("The time step of a detector is less than the main grid or set to 0.");
+            freqDtcs_.push_back(q);
+            continue;
         }
         detectors_.push_back(d);
     }

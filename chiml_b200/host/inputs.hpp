@@ -99,6 +99,15 @@ struct DetectorInput
     double timeInt;
 };
 
+// a frequency-domain detector (dtc_class "freq", DTC/parallelDTC_FREQ.hpp): running DFT of the sampled fields over a box
+struct FreqDtcInput
+{
+    DTCTYPE type; bool SI, outputMaps; std::string name;
+    std::array<int, 3> loc, sz;
+    int timeInt;                      // floor(Time_Interval / dt + 0.5) (parallelFDTDField.cpp:1728)
+    std::vector<double> freqs;        // angular, FDTD units
+};
+
 struct FluxInput
 {
     std::string name; std::array<int, 3> loc, sz; double weight; int timeInt; std::vector<double> freqs; bool SI = false, crossSec = false, save = false, load = false; std::string incdFile;
@@ -108,6 +117,7 @@ class Inputs
 {
 public:
     bool periodic_ = false;
+    std::vector<FreqDtcInput> freqDtcs_;
     POLARIZATION pol_;
     int res_;
     double courant_, a_, tMax_, I0_;
@@ -121,7 +131,9 @@ public:
     std::vector<FluxInput> fluxes_;
     std::vector<QEInput> qes_;
 
-    explicit Inputs(const Json& IP);
+    // postProcessing: the input is only read for its grid, flux regions and detectors (chiml_flux); a TFSF block, which the host-side
+    // setup cannot turn into a plan, is then skipped instead of refused
+    explicit Inputs(const Json& IP, bool postProcessing = false);
     static int find_pt(double pt, double d) { return int(std::floor(pt / d + 0.5)); }   // parallelInputs.hpp:296
     double ev2FDTD(double eV) const { return eV / 4.135666e-15 * a_ / SPEED_OF_LIGHT; }   // parallelInputs.cpp:1181-1184
 

@@ -332,9 +332,12 @@ int main(int argc, char** argv)
         // (fInReal_ / fInCplx_ of parallelStorageFreqDTCReal) in the order parallelFluxDTC::fieldIn walks them.  The Poynting-vector
         // integration of getFlux() is post-processing on these arrays and is not part of the time-stepping path.
         std::vector<std::vector<double>> dftRe(P.dfts.size()), dftIm(P.dfts.size());
-        for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff)
+        // (the frequency detectors' groups follow the flux regions'; their accumulator files are <detector file>.dft)
+        for(size_t ff = 0; ff < IP.fluxes_.size() + IP.freqDtcs_.size(); ++ff)
         {
-            std::string name = IP.fluxes_[ff].name + ".dft";
+            const bool isFlux = ff < IP.fluxes_.size();
+            const std::vector<double>& freqs = isFlux ? IP.fluxes_[ff].freqs : IP.freqDtcs_[ff - IP.fluxes_.size()].freqs;
+            std::string name = (isFlux ? IP.fluxes_[ff].name : IP.freqDtcs_[ff - IP.fluxes_.size()].name) + ".dft";
             if(nranks > 1) name += ".rank" + std::to_string(rank);
             make_dirs(name);
             std::ofstream out(name.c_str(), std::ios::out | std::ios::binary);
@@ -342,9 +345,9 @@ int main(int argc, char** argv)
             out.write(magic, 8);
             int32_t nsets = 0;
             for(const PlanDft& d : P.dfts) nsets += d.group == (int)ff;
-            const int32_t hdr[2] = {nsets, (int32_t)IP.fluxes_[ff].freqs.size()};
+            const int32_t hdr[2] = {nsets, (int32_t)freqs.size()};
             out.write(reinterpret_cast<const char*>(hdr), sizeof(hdr));
-            out.write(reinterpret_cast<const char*>(IP.fluxes_[ff].freqs.data()), (std::streamsize)(IP.fluxes_[ff].freqs.size() * sizeof(double)));
+            out.write(reinterpret_cast<const char*>(freqs.data()), (std::streamsize)(freqs.size() * sizeof(double)));
             for(size_t q = 0; q < P.dfts.size(); ++q)
             {
                 const PlanDft& d = P.dfts[q];
@@ -362,6 +365,7 @@ int main(int argc, char** argv)
         }
         // flux spectra (parallelFluxDTC::getFlux): one process holds whole surfaces; several slabs leave their accumulator files
         if(nranks == 1 && !IP.fluxes_.empty()) write_flux_files(IP, P, dftRe, dftIm, nSteps);
+        if(nranks == 1) write_freq_detector_files(IP, P, dftRe, dftIm, nSteps);
         // ---- level populations (ML/QEPopDtc.cpp:37-61)
         for(size_t q = 0; q < P.emitters.size(); ++q)
         {

@@ -876,6 +876,7 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
     build_emitters(IP, g, ras, mode, P);
     // ---- flux regions: running-DFT sets (parallelFDTDField.cpp:650-682) ----
     build_fluxes(IP, g, mode, P);
+    build_freq_detectors(IP, g, mode, P);
     return P;
 }
 

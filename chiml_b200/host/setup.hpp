@@ -9,6 +9,7 @@
 #pragma once
 
 #include <array>
+#include <complex>
 #include <memory>
 #include <string>
 #include <vector>
@@ -42,6 +43,7 @@ struct PlanDft
     std::vector<double> freq;
     std::vector<ChimlDftLine> lines;
     // where the set sits in its flux region (not part of the plan file; used by the flux output, flux_out.cpp)
+    int freq_dtc = -1;          // >= 0: a stored field of frequency detector freq_dtc (Inputs::freqDtcs_), not of a flux region
     int surface = 0;            // index into the region's surface list (parallelFluxDTC::fInParam_)
     int role = 0;               // 0 Ej, 1 Ek, 2 Hj, 3 Hk of that surface
     int dir = 0;                // normal of the surface: 0 x, 1 y, 2 z
@@ -73,6 +75,12 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads = 0, bool ref
 
 // Flux spectra files of a single-rank run (parallelFluxDTC::getFlux, DTC/parallelFlux.hpp:406-540): re[k] / im[k] = accumulators of
 // P.dfts[k] (fInReal_ / fInCplx_), nSteps = time steps taken.  Writes <flux name>.dat for every flux region.
-void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std::vector<double>>& re, const std::vector<std::vector<double>>& im, long nSteps);
+// Files of the frequency detectors of a single-rank run (parallelDetectorFREQ_Base::toFile / toMap with incident fields, DTC/parallelDTC_FREQ.hpp:384-583,
+// as main.cpp:74-107 calls them; no TFSF source on this path: the incident columns are zero)
+void write_freq_detector_files(const Inputs& IP, const SlabPlan& P, const std::vector<std::vector<double>>& re, const std::vector<std::vector<double>>& im, long nSteps);
+// incd: the incident-field series of a TFSF run, E_incd_[0..2] then H_incd_[0..2] of the propagator (FDTD_MANAGER/parallelFDTDField.hpp:143-144,
+// 1240-1254: two values per step), or nullptr / empty vectors when there is none
+void write_flux_files(const Inputs& IP, const SlabPlan& P, const std::vector<std::vector<double>>& re, const std::vector<std::vector<double>>& im, long nSteps,
+                      const std::vector<std::vector<std::complex<double>>>* incd = nullptr);
 
 } // namespace chiml_host

@@ -109,6 +109,14 @@ def detector(loc: Sequence[float], size: Sequence[float], typ: str, fname: str, 
             "txt_format_type": "none", "Time_Interval": time_int, "timeIntegrateMap": False, "t_start": 0.0, "t_end": 1e8}
 
 
+def freq_detector(loc: Sequence[float], size: Sequence[float], typ: str, fname: str, fcen: float, fwidth: float, nfreq: int, time_int: float = 0.0,
+                  si: bool = False, output_map: bool = False) -> Dict:
+    """A frequency-domain detector (dtc_class "freq", parsed at INPUTS/parallelInputs.cpp:671-751): running DFT of the fields over a box."""
+    d = detector(loc, size, typ, fname, dtc_class="freq", time_int=time_int, si=si)
+    d.update({"fcen": fcen, "fwidth": fwidth, "nfreq": nfreq, "output_map": output_map})
+    return d
+
+
 def flux(name: str, loc: Sequence[float], size: Sequence[float], fcen: float, fwidth: float, nfreq: int, weight: float = 1.0) -> Dict:
     return {"name": name, "save": False, "load": False, "loc": list(loc), "size": list(size), "SI": False, "fcen": fcen, "fwidth": fwidth,
             "nfreq": nfreq, "weight": weight, "cross_sec": False}

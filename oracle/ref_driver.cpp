@@ -54,6 +54,7 @@ struct Options
     bool output = true;
     bool quiet = false;
     bool gpu = false;
+    std::string incdDump;      // --incd-dump FILE: the incident-field series E_incd_[0..2], H_incd_[0..2] after the run ("CHIMLINC", int32 n, 6 x n complex)
 };
 
 struct GridDump
@@ -235,6 +236,45 @@ static std::vector<TfsfSurfaceRec> tfsfSurfaces(parallelFDTDFieldReal& FF, const
 static std::vector<double> g_tfsfTable;          // rank 0's table rows of the steps taken (appended to the plan after the run)
 static int g_tfsfPerStep = 0;
 
+// every running-DFT storage of the propagator in the order step() feeds them (FDTD_MANAGER/parallelFDTDField.hpp:1297-1302): the stored fields
+// of the frequency detectors (dtcFreqArr_, DTC/parallelDTC_FREQ.hpp:258-264) after those of the flux objects (DTC/parallelFlux.hpp:296-312);
+// group = which twiddle list a storage uses: flux objects first, then frequency detectors
+struct DftStorageRef { std::shared_ptr<parallelStorageFreqDTCReal> st; int group; int every; const std::vector<double>* freq; };
+static std::vector<DftStorageRef> allDftStorages(parallelFDTDFieldReal& FF)
+{
+    std::vector<DftStorageRef> out;
+    int group = 0;
+    for(auto& flux : FF.fluxArr_)
+    {
+        for(auto& fp : flux->fInParam_)
+            for(auto* vec : {&fp.Ej_dtc_, &fp.Ek_dtc_, &fp.Hj_dtc_, &fp.Hk_dtc_})
+                for(auto& dtc : *vec)
+                {
+                    auto real = std::dynamic_pointer_cast<parallelStorageFreqDTCReal>(dtc);
+                    if(real && real->fieldInFreq_) out.push_back({real, group, flux->timeInt_, &flux->freqList_});
+                }
+        ++group;
+    }
+    for(auto& dtc : FF.dtcFreqArr_)
+    {
+        for(auto& g : dtc->gridsIn_)
+        {
+            auto real = std::dynamic_pointer_cast<parallelStorageFreqDTCReal>(g);
+            if(real && real->fieldInFreq_) out.push_back({real, group, dtc->timeInt_, &dtc->freqList_});
+        }
+        ++group;
+    }
+    return out;
+}
+// the frequency lists of the groups that hold a storage on this rank, in group order (the twiddles of one step follow this order)
+static std::vector<const std::vector<double>*> dftGroupFreqs(parallelFDTDFieldReal& FF)
+{
+    std::vector<const std::vector<double>*> out;
+    int last = -1;
+    for(const DftStorageRef& r : allDftStorages(FF)) if(r.group != last) { out.push_back(r.freq); last = r.group; }
+    return out;
+}
+
 static void putEmitters(std::ofstream& out, parallelFDTDFieldReal& FF);
 static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const parallelProgramInputs& IP, int nSteps)
 {
@@ -378,26 +418,18 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
         ++dd;
     }
     if(!FF.qeArr_.empty() && FF.gridComm_->size() == 1) putEmitters(out, FF);
-    // DFT records: every stored field of every flux object, in the order parallelFluxDTC::fieldIn walks them (DTC/parallelFlux.hpp:296-312)
-    int group = 0;
-    for(auto& flux : FF.fluxArr_)
+    // DFT records: every stored field of every flux object and frequency detector
+    for(const DftStorageRef& r : allDftStorages(FF))
     {
-        for(auto& fp : flux->fInParam_)
-            for(auto* vec : {&fp.Ej_dtc_, &fp.Ek_dtc_, &fp.Hj_dtc_, &fp.Hk_dtc_})
-                for(auto& dtc : *vec)
-                {
-                    auto real = std::dynamic_pointer_cast<parallelStorageFreqDTCReal>(dtc);
-                    if(!real || !real->fieldInFreq_) continue;
-                    ChimlPlanDftHdr h; std::memset(&h, 0, sizeof(h));
-                    h.field = fieldId(FF, real->grid_); h.group = group; h.every = flux->timeInt_; h.nfreq = real->nfreq_;
-                    h.npts = real->fieldInFreq_->sz_[0]; h.stride = real->fieldInFreq_->stride_;
-                    h.nlines = real->fieldInFreq_->fInGridInds_.size() / 2; h.acc_len = real->fInReal_.size();
-                    std::string p; app(p, h); appVec(p, flux->freqList_);
-                    for(size_t ii = 0; ii + 1 < real->fieldInFreq_->fInGridInds_.size(); ii += 2)
-                    { ChimlDftLine l; l.ind = real->fieldInFreq_->fInGridInds_[ii]; l.out = real->fieldInFreq_->fInGridInds_[ii + 1]; app(p, l); }
-                    putRec(out, "DFT", p);
-                }
-        ++group;
+        auto& real = r.st;
+        ChimlPlanDftHdr h; std::memset(&h, 0, sizeof(h));
+        h.field = fieldId(FF, real->grid_); h.group = r.group; h.every = r.every; h.nfreq = real->nfreq_;
+        h.npts = real->fieldInFreq_->sz_[0]; h.stride = real->fieldInFreq_->stride_;
+        h.nlines = real->fieldInFreq_->fInGridInds_.size() / 2; h.acc_len = real->fInReal_.size();
+        std::string p; app(p, h); appVec(p, *r.freq);
+        for(size_t ii = 0; ii + 1 < real->fieldInFreq_->fInGridInds_.size(); ii += 2)
+        { ChimlDftLine l; l.ind = real->fieldInFreq_->fInGridInds_[ii]; l.out = real->fieldInFreq_->fInGridInds_[ii + 1]; app(p, l); }
+        putRec(out, "DFT", p);
     }
 }
 
@@ -505,7 +537,7 @@ struct GpuBinding
     std::vector<size_t> dtcSamples;                        // samples read so far per detector
     struct DftRef { std::shared_ptr<parallelStorageFreqDTCReal> st; int slot; };
     std::vector<DftRef> dfts;
-    std::vector<char> fluxHere;
+    std::vector<const std::vector<double>*> dftFreqs;      // frequency lists of the groups with a storage here, in group order
     TfsfLayout tfsfL;                                      // TFSF: the incident-line table of one step and the surface records
     std::vector<TfsfSurfaceRec> tfsfSurf;
     void check(int rc, const char* what) { if(rc != CHIML_OK) throw std::runtime_error(std::string(what) + ": " + api.chiml_gpu_last_error(ctx)); }
@@ -608,26 +640,17 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
     }
     // emitters: the EMITTER record of the plan dump is exactly ChimlEmitterDesc + arrays; reuse that extraction through a memory stream
     // (kept in one place: putEmitters) -- done below by the caller, which owns the buffers
-    int group = 0;
-    B.fluxHere.assign(FF.fluxArr_.size(), 0);
-    for(auto& flux : FF.fluxArr_)
+    static_assert(sizeof(ChimlDftLine) == 2 * sizeof(int), "fInGridInds_ is a list of (grid index, accumulator index) pairs");
+    for(const DftStorageRef& r : allDftStorages(FF))
     {
-        for(auto& fp : flux->fInParam_)
-            for(auto* vec : {&fp.Ej_dtc_, &fp.Ek_dtc_, &fp.Hj_dtc_, &fp.Hk_dtc_})
-                for(auto& dtc : *vec)
-                {
-                    auto st = std::dynamic_pointer_cast<parallelStorageFreqDTCReal>(dtc);
-                    if(!st || !st->fieldInFreq_) continue;
-                    static_assert(sizeof(ChimlDftLine) == 2 * sizeof(int), "fInGridInds_ is a list of (grid index, accumulator index) pairs");
-                    int slot = -1;
-                    B.check(A.chiml_gpu_add_dft(B.ctx, fieldId(FF, st->grid_), group, flux->timeInt_, st->nfreq_, st->fieldInFreq_->sz_[0], st->fieldInFreq_->stride_,
-                                                reinterpret_cast<const ChimlDftLine*>(st->fieldInFreq_->fInGridInds_.data()), st->fieldInFreq_->fInGridInds_.size() / 2,
-                                                st->fInReal_.size(), &slot), "add_dft");
-                    B.dfts.push_back({st, slot});
-                    B.fluxHere[group] = 1;
-                }
-        ++group;
+        auto& st = r.st;
+        int slot = -1;
+        B.check(A.chiml_gpu_add_dft(B.ctx, fieldId(FF, st->grid_), r.group, r.every, st->nfreq_, st->fieldInFreq_->sz_[0], st->fieldInFreq_->stride_,
+                                    reinterpret_cast<const ChimlDftLine*>(st->fieldInFreq_->fInGridInds_.data()), st->fieldInFreq_->fInGridInds_.size() / 2,
+                                    st->fInReal_.size(), &slot), "add_dft");
+        B.dfts.push_back({st, slot});
     }
+    B.dftFreqs = dftGroupFreqs(FF);
 }
 
 // emitter objects: ChimlEmitterDesc from the members of parallelQEBase (what putEmitters writes into a plan file)
@@ -710,9 +733,8 @@ static void gpuStep(parallelFDTDFieldReal& FF, GpuBinding& B)
     if(!B.dfts.empty())
     {
         const double t = FF.tcur_ + FF.dt_;
-        for(size_t ff = 0; ff < FF.fluxArr_.size(); ++ff)
-            if(B.fluxHere[ff])
-                for(double f : FF.fluxArr_[ff]->freqList_) { const cplx w = std::exp(cplx(0.0, -1.0 * t * f)); tw.push_back(w.real()); tw.push_back(w.imag()); }
+        for(const std::vector<double>* fl : B.dftFreqs)
+            for(double f : *fl) { const cplx w = std::exp(cplx(0.0, -1.0 * t * f)); tw.push_back(w.real()); tw.push_back(w.imag()); }
     }
     if(!FF.tfsfArr_.empty())
         B.check(A.chiml_gpu_step_n_tfsf(B.ctx, 1, amp.empty() ? nullptr : amp.data(), tw.empty() ? nullptr : tw.data(), tfsfRow.data(), tfsfRow.size()), "step_n_tfsf");
@@ -746,6 +768,8 @@ static void gpuStep(parallelFDTDFieldReal& FF, GpuBinding& B)
     // getFlux normalises with (DTC/parallelFlux.hpp:313,418)
     for(auto& flux : FF.fluxArr_)
         if(FF.t_step_ % flux->timeInt() == 0) ++flux->t_step_;
+    for(auto& dtc : FF.dtcFreqArr_)                            // likewise parallelDetectorFREQ_Base::output (DTC/parallelDTC_FREQ.hpp:258-264)
+        if(FF.t_step_ % dtc->timeInt() == 0) ++dtc->t_step_;
 }
 
 // after the loop (main.cpp:67-118): accumulators, populations and -- for the state dump of the tests -- every grid come back
@@ -947,33 +971,56 @@ static void rankMain(int rank, const Options& opt)
     if(!opt.dump.empty())
     {
         int slot = 0;
-        for(auto& flux : FF.fluxArr_)
-            for(auto& fp : flux->fInParam_)
-                for(auto* vec : {&fp.Ej_dtc_, &fp.Ek_dtc_, &fp.Hj_dtc_, &fp.Hk_dtc_})
-                    for(auto& dtc : *vec)
-                    {
-                        auto real = std::dynamic_pointer_cast<parallelStorageFreqDTCReal>(dtc);
-                        if(!real || !real->fieldInFreq_) continue;
-                        for(int im = 0; im < 2; ++im)
-                        {
-                            GridDump d; d.rank = rank; d.name = "dft" + std::to_string(slot) + (im ? "i" : "r");
-                            const std::vector<double>& v = im ? real->fInCplx_ : real->fInReal_;
-                            d.ln[0] = int(v.size()); d.ln[1] = 1; d.ln[2] = 1; d.yStart = 0;
-                            d.data = v;
-                            std::lock_guard<std::mutex> lk(g_dumpMtx); g_dumps.push_back(std::move(d));
-                        }
-                        ++slot;
-                    }
+        for(const DftStorageRef& r : allDftStorages(FF))
+        {
+            for(int im = 0; im < 2; ++im)
+            {
+                GridDump d; d.rank = rank; d.name = "dft" + std::to_string(slot) + (im ? "i" : "r");
+                const std::vector<double>& v = im ? r.st->fInCplx_ : r.st->fInReal_;
+                d.ln[0] = int(v.size()); d.ln[1] = 1; d.ln[2] = 1; d.yStart = 0;
+                d.data = v;
+                std::lock_guard<std::mutex> lk(g_dumpMtx); g_dumps.push_back(std::move(d));
+            }
+            ++slot;
+        }
     }
 
+    if(!opt.incdDump.empty() && rank == 0)
+    {
+        std::ofstream out(opt.incdDump.c_str(), std::ios::binary);
+        const int32_t n = int32_t(FF.E_incd_[0].size());
+        out.write("CHIMLINC", 8); out.write(reinterpret_cast<const char*>(&n), 4);
+        for(int k = 0; k < 6; ++k)
+        {
+            const std::vector<cplx>& v = k < 3 ? FF.E_incd_[k] : FF.H_incd_[k - 3];
+            out.write(reinterpret_cast<const char*>(v.data()), std::streamsize(v.size() * sizeof(cplx)));
+        }
+    }
     if(opt.output)
     {
         for(auto& flux : FF.fluxArr())
             flux->getFlux(FF.ExIncd(), FF.EyIncd(), FF.EzIncd(), FF.HxIncd(), FF.HyIncd(), FF.HzIncd(), true);
-        for(auto& dtc : FF.dtcFreqArr())
+        for(auto& dtc : FF.dtcFreqArr())                      // main.cpp:74-107: the variant with incident fields first
         {
-            if(dtc->outputMaps()) dtc->toMap();
-            else dtc->toFile();
+            try
+            {
+                std::vector<std::vector<cplx>> incdFields;
+                if(dtc->type() == DTCTYPE::HPOW) incdFields = { FF.HxIncd(), FF.HyIncd(), FF.HzIncd() };
+                else if(dtc->type() == DTCTYPE::EPOW) incdFields = { FF.ExIncd(), FF.EyIncd(), FF.EzIncd() };
+                else if(dtc->type() == DTCTYPE::EX || dtc->type() == DTCTYPE::PX) incdFields = { FF.ExIncd() };
+                else if(dtc->type() == DTCTYPE::EY || dtc->type() == DTCTYPE::PY) incdFields = { FF.EyIncd() };
+                else if(dtc->type() == DTCTYPE::EZ || dtc->type() == DTCTYPE::PZ) incdFields = { FF.EzIncd() };
+                else if(dtc->type() == DTCTYPE::HX || dtc->type() == DTCTYPE::MX) incdFields = { FF.HxIncd() };
+                else if(dtc->type() == DTCTYPE::HY || dtc->type() == DTCTYPE::MY) incdFields = { FF.HyIncd() };
+                else if(dtc->type() == DTCTYPE::HZ || dtc->type() == DTCTYPE::MZ) incdFields = { FF.HzIncd() };
+                if(dtc->outputMaps()) dtc->toMap(incdFields, FF.dt());
+                else dtc->toFile(incdFields, FF.dt());
+            }
+            catch(std::exception& e)
+            {
+                if(dtc->outputMaps()) dtc->toMap();
+                else dtc->toFile();
+            }
         }
         for(auto& dtc : FF.dtcArr())
             dtc->toFile();
@@ -1022,6 +1069,7 @@ int main(int argc, char** argv)
         else if(s == "--no-output") opt.output = false;
         else if(s == "--quiet") opt.quiet = true;
         else if(s == "--gpu") opt.gpu = true;
+        else if(s == "--incd-dump" && a + 1 < argc) opt.incdDump = argv[++a];
         else if(opt.input.empty()) opt.input = s;
         else { std::fprintf(stderr, "chiml_ref: unknown argument %s\n", s.c_str()); return 2; }
     }

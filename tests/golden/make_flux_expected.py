@@ -47,6 +47,30 @@ subprocess.run([REF, "flux3d_load.json", "--quiet"], cwd=work, check=True, stdou
 shutil.copy(os.path.join(work, cfg["FluxList"][0]["name"] + ".dat"), os.path.join(out, "box.dat"))
 print("flux3d_load", open(os.path.join(out, "box.dat")).read()[:400])
 
+# freq3d: the files of the frequency detectors (parallelDetectorFREQ_Base::toFile / toMap with incident fields, as main.cpp:74-107 calls
+# them) beside a flux box
+work = tempfile.mkdtemp(prefix="fluxref_")
+shutil.copy(os.path.join(HERE, "freq3d.json"), work)
+subprocess.run([REF, "freq3d.json", "--quiet"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+out = os.path.join(HERE, "out_expected", "freq3d")
+os.makedirs(out, exist_ok=True)
+for n in sorted(os.listdir(os.path.join(work, "out", "fq"))):
+    if n.startswith("dtc_"):
+        continue
+    shutil.copy(os.path.join(work, "out", "fq", n), os.path.join(out, n))
+    print("freq3d", n)
+
+# tfsf3d: a flux box around a sphere lit by a TFSF plane wave: getFlux normalises with the incident-field series the propagator
+# recorded (DTC/parallelFlux.hpp:455-482); the series themselves (--incd-dump) are kept as the fixture the host-side post-processing reads
+work = tempfile.mkdtemp(prefix="fluxref_")
+shutil.copy(os.path.join(HERE, "tfsf3d.json"), work)
+subprocess.run([REF, "tfsf3d.json", "--quiet", "--incd-dump", "incd.bin"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+out = os.path.join(HERE, "out_expected", "tfsf3d")
+os.makedirs(out, exist_ok=True)
+shutil.copy(os.path.join(work, "out", "t3", "box.dat"), os.path.join(out, "box.dat"))
+shutil.copy(os.path.join(work, "incd.bin"), os.path.join(out, "incd.bin"))
+print("tfsf3d", open(os.path.join(out, "box.dat")).read()[:300])
+
 for case in CASES:
     work = tempfile.mkdtemp(prefix="fluxref_")
     shutil.copy(os.path.join(HERE, case + ".json"), work)

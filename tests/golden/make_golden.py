@@ -174,6 +174,17 @@ def cases():
     c["tfsf3d_obl"] = I.config(cell3(60), I.pml([5 / RES] * 3), [], [ball],
                                [I.detector([0.03, 0, 0], [0, 0, 0], "Ex", "out/t3o/dtc", time_int=DT * 1.0000001)])
     c["tfsf3d_obl"]["TFSF"] = [I.tfsf([0.1, 0.1, 0.12], [0.0, 0.0, 0.0], tp(1.5), m=(1, 0, 1), psi=90.0)]
+    # ---- frequency detectors (DTC/parallelDTC_FREQ.hpp): a field type over a box, an SI-scaled E-power type (three stored fields) every
+    # second step, a map output over a plane; beside a flux box, so that the twiddle groups of both kinds are in one run ----
+    c["freq3d"] = _short_pulse(I.config(
+        I.comp_cell([23 / RES, 19 / RES, 21 / RES], RES, 60 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+        [I.normal_source("Ez", [0, 0, 0.04], [0.05, 0.04, 0], [I.gaussian_pulse(1.5, 1.0)])],
+        [I.block([0.08, 0.06, 0.05], [0.01, 0, -0.02], eps=2.0, pols=[I.lorentz_pole(1.2, 0.1, 2.0)])],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Ez", "out/fq/dtc", time_int=DT * 1.0000001),
+         I.freq_detector([0.03, 0, 0], [0.02, 0.01, 0.03], "Ez", "out/fq/ez", 1.5, 1.0, 4, time_int=DT * 1.0000001),
+         I.freq_detector([0.0, 0.02, 0.0], [0.02, 0.0, 0.01], "E_pow", "out/fq/epow", 1.5, 1.0, 4, time_int=2 * DT * 1.0000001, si=True),
+         I.freq_detector([0.0, 0.0, 0.02], [0.02, 0.02, 0.0], "Hy", "out/fq/map", 1.5, 1.0, 2, time_int=DT * 1.0000001, output_map=True)],
+        [I.flux("out/fq/box", [0.0, 0.0, 0.0], [0.06, 0.06, 0.06], 1.5, 1.0, 3)]))
     return c
 
 

@@ -19,6 +19,9 @@ FILES = {"te_vacuum": {"out/te/dtc_field_0.dat": "dtc_field_0.dat"},
          # a 4 x 3 x 3 box written by a BIN detector (DTC/parallelDTC_BIN.cpp) and an SI-scaled TXT detector
          # periodic boundaries (CompCell.PBC, real fields): JSON -> wrap descriptions -> k_wrap between the half steps
          "pbc3d": {"out/p3/dtc_field_0.dat": "dtc_field_0.dat"}, "pbc_tm": {"out/ptm/dtc_field_0.dat": "dtc_field_0.dat"},
+         # frequency detectors (field, SI power over three fields, map output) beside a flux box: DFT sets on the GPU, files by the host
+         "freq3d": {"out/fq/ez_field_1.dat": "ez_field_1.dat", "out/fq/epow_field_2.dat": "epow_field_2.dat", "out/fq/box.dat": "box.dat",
+                    "out/fq/map_field_3.dat.1.000000": "map_field_3.dat.1.000000", "out/fq/map_field_3.dat.2.000000": "map_field_3.dat.2.000000"},
          "vac3d_bin": {"out/vb/dtc_field_0.dat": "dtc_field_0.dat", "out/vb/dtc_field_1.dat": "dtc_field_1.dat"}}
 
 

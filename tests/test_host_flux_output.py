@@ -132,3 +132,47 @@ def test_load_refuses_fields_of_another_region(tmp_path):
     shutil.copy(os.path.join(d, "empty_fields.dat"), tmp_path)
     r = _flux_tool(tmp_path, str(tmp_path / "bad.json"))
     assert r.returncode != 0 and "do not match size and frequency" in (r.stderr + r.stdout)
+
+
+def test_frequency_detector_files_equal_the_reference_files(tmp_path):
+    """dtc_class "freq" detectors (DTC/parallelDTC_FREQ.hpp): a field type over a box, an SI-scaled E-power type over three stored fields
+    sampled every second step, and a map output (one file per frequency) -- from the reference's accumulators, every file must equal the
+    reference's character for character; the flux box of the same input is written beside them."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_flux")], check=True, stdout=subprocess.DEVNULL)
+    case = "freq3d"
+    cfg = json.load(open(os.path.join(util.GOLDEN, case + ".json")))
+    plan = util.load_plan(case)
+    exp = util.load_expect(case)
+    freq_names = [d["fname"] + f"_field_{i}.dat" for i, d in enumerate(cfg["DetectorList"]) if d["dtc_class"] == "freq"]
+    names = [fl["name"] for fl in cfg["FluxList"]] + freq_names
+    for g, name in enumerate(names):
+        sets = [(k, d) for k, d in enumerate(plan.dfts) if d.group == g]
+        path = os.path.join(tmp_path, name + ".dft")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "wb") as f:
+            freq = np.asarray(sets[0][1].freq, "<f8")
+            f.write(b"CHIMLDFT" + struct.pack("<ii", len(sets), len(freq)) + freq.tobytes())
+            for k, d in sets:
+                re, im = exp[f"dft{k}r"].ravel(), exp[f"dft{k}i"].ravel()
+                f.write(struct.pack("<iiii", d.field, d.npts, len(d.lines), d.every) + struct.pack("<Q", len(re)))
+                f.write(np.asarray(re, "<f8").tobytes() + np.asarray(im, "<f8").tobytes())
+    r = subprocess.run([os.path.join(ROOT, "chiml_b200", "chiml_flux"), os.path.join(util.GOLDEN, case + ".json")], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = sorted(os.listdir(os.path.join(util.GOLDEN, "out_expected", case)))
+    assert len(want) >= 5
+    for n in want:
+        got = open(tmp_path / "out" / "fq" / n, "rb").read()
+        ref = open(os.path.join(util.GOLDEN, "out_expected", case, n), "rb").read()
+        assert got == ref, f"{n} differs from the reference's file"
+
+
+def test_incident_normalisation_of_a_tfsf_run_equals_the_reference_file(tmp_path):
+    """getFlux with incident fields (DTC/parallelFlux.hpp:455-482): the incident-field series of the TFSF source, Fourier transformed and
+    scaled by the area of the region's faces, fill the abs(incd) / real(incd) / imag(incd) columns.  Series and accumulators are the
+    reference's own (tests/golden/out_expected/tfsf3d/incd.bin, tfsf3d.expect.npz); the file must equal the reference's."""
+    d = os.path.join(util.GOLDEN, "out_expected", "tfsf3d")
+    r = _flux_tool(tmp_path, os.path.join(util.GOLDEN, "tfsf3d.json"), case="tfsf3d", extra=("--incd", os.path.join(d, "incd.bin")))
+    assert r.returncode == 0, r.stderr
+    got = open(tmp_path / "out/t3/box.dat", "rb").read()
+    assert got == open(os.path.join(d, "box.dat"), "rb").read()
+    assert float(got.split(b"\n")[1].split()[1]) > 0.0          # the incident column is not the all-zero one of a run without TFSF
