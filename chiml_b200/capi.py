@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_halo_export", "chiml_gpu_halo_bind", "chiml_gpu_add_dft", "chiml_gpu_step_n_dft", "chiml_gpu_download_dft",
     "chiml_gpu_set_march", "chiml_gpu_set_ordip_pole_count", "chiml_gpu_reserve_steps", "chiml_gpu_consume_detector",
     "chiml_gpu_consume_population", "chiml_gpu_set_persistent", "chiml_gpu_set_periodic", "chiml_gpu_add_tfsf_surface",
-    "chiml_gpu_step_n_tfsf",
+    "chiml_gpu_step_n_tfsf", "chiml_gpu_bind_imag", "chiml_gpu_step_n_cplx",
 ]
 
 
@@ -174,6 +174,8 @@ def lib() -> C.CDLL:
     L.chiml_gpu_halo_export.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.chiml_gpu_halo_bind.argtypes = [vp, C.c_char_p, sz, C.c_char_p, sz]
     L.chiml_gpu_set_periodic.argtypes = [vp, i, vp]
+    L.chiml_gpu_bind_imag.argtypes = [vp, vp, vp]
+    L.chiml_gpu_step_n_cplx.argtypes = [vp, i, vp, vp]
     L.chiml_gpu_add_tfsf_surface.argtypes = [vp, C.POINTER(TfsfSurface)]
     L.chiml_gpu_step_n_tfsf.argtypes = [vp, i, vp, vp, vp, sz]
     L.chiml_gpu_add_dft.argtypes = [vp, i, i, i, i, i, i, vp, sz, sz, C.POINTER(i)]
@@ -206,10 +208,12 @@ def _ptr(a: Optional[np.ndarray]):
 class GpuSim:
     """One y-slab of the propagator on one GPU, configured from a Plan (the reference's own lists)."""
 
-    def __init__(self, plan: P.Plan, device: int = 0, detectors: bool = True, march=None, persistent: Optional[bool] = None):
-        """march: None (automatic column length), an int, or (fast, uniform) planes per column of the y-marching kernels."""
+    def __init__(self, plan: P.Plan, device: int = 0, detectors: bool = True, march=None, persistent: Optional[bool] = None, _part: str = "re"):
+        """march: None (automatic column length), an int, or (fast, uniform) planes per column of the y-marching kernels.
+        A plan with complex fields (plan.cplx) builds a pair: this object holds the real parts, self.imag the imaginary parts."""
         L = lib()
         self.plan = plan
+        self.imag = None
         g = GridDesc()
         g.mode = plan.mode
         g.ln[:] = plan.ln
@@ -268,6 +272,9 @@ class GpuSim:
                 mf, mu = (march, march) if isinstance(march, int) else march
                 self._chk(L.chiml_gpu_set_march(self.h, mf, mu))
             self._chk(L.chiml_gpu_commit(self.h))
+            if plan.cplx and _part == "re":
+                self.imag = GpuSim(plan, device=device, detectors=detectors, march=march, persistent=persistent, _part="im")
+                self._chk(L.chiml_gpu_bind_imag(self.h, self.imag.h, (C.c_double * 3)(*plan.k_point)))
         except Exception:
             self.close()
             raise
@@ -286,10 +293,25 @@ class GpuSim:
             amp[:len(seg), q] = seg
         return amp
 
+    def src_amp_im(self, start: int, n: int) -> np.ndarray:
+        ns = len(self.plan.sources)
+        amp = np.zeros((n, max(ns, 1)), dtype=np.float64)
+        for q, s in enumerate(self.plan.sources):
+            seg = s.amp_im[start:start + n]
+            amp[:len(seg), q] = seg
+        return amp
+
     def step_n(self, n: int, amp: Optional[np.ndarray] = None) -> None:
         if amp is None:
             amp = self.src_amp(self.steps_done, n)
         amp = np.ascontiguousarray(amp, dtype=np.float64)
+        if self.plan.cplx:
+            amp_im = np.ascontiguousarray(self.src_amp_im(self.steps_done, n))
+            ns = len(self.plan.sources)
+            self._chk(lib().chiml_gpu_step_n_cplx(self.h, n, _ptr(amp) if ns else None, _ptr(amp_im) if ns else None))
+            self.steps_done += n
+            self.imag.steps_done += n
+            return
         if self.plan.tfsf:
             tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, n)) if self.plan.dfts else None
             rows = tfsf_rows(self.plan, self.steps_done, n)
@@ -449,6 +471,10 @@ class GpuSim:
         return int(lib().chiml_gpu_device_bytes(self.h))
 
     def close(self) -> None:
+        # (the imaginary part of a pair runs on the real part's stream: it goes first)
+        if getattr(self, "imag", None) is not None:
+            self.imag.close()
+            self.imag = None
         if getattr(self, "h", None):
             lib().chiml_gpu_destroy(self.h)
             self.h = None

@@ -6,6 +6,7 @@
 #include <cuda.h>          // CUtensorMap and the prototype of cuTensorMapEncodeTiled (resolved at run time: no -lcuda)
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -122,7 +123,9 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
 {
     if(!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if(ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if(ctx->imag) { ctx->imag->stream = nullptr; ctx->imag->real_part = nullptr; ctx->imag = nullptr; }      // the imaginary part ran on this context's stream
+    if(ctx->real_part) { ctx->real_part->imag = nullptr; ctx->real_part = nullptr; }
     for(auto& p : ctx->d_field_base) cudaFree(p);
     for(int c = 0; c < 6; ++c)
     {
@@ -164,7 +167,7 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
     cudaEventDestroy(ctx->ev_main); cudaEventDestroy(ctx->ev_push);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->hstream);
-    cudaStreamDestroy(ctx->stream);
+    if(ctx->stream && !ctx->is_imag_part) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -1493,6 +1496,47 @@ void launch_wraps(ChimlCtx* ctx, bool isE)
     k_wrap<<<dim3((unsigned)std::max<long>(1, std::min<long>((most + 255) / 256, 148 * 4)), wa.n, 1), 256, 0, ctx->stream>>>(wa);
 }
 
+// Bloch wrap copies of one family of a complex-field pair: phase table per component as the reference writes the arguments
+// (UTIL/FDTD_up_eq.cpp:1248-1324: exp(cplx(0, +-k_x dx xmax +- k_y dy ymax +- k_z dz zmax)), summed left to right, x then y then z)
+void launch_bloch(ChimlCtx* re, ChimlCtx* im, bool isE)
+{
+    BlochArgs ba;
+    std::memset(&ba, 0, sizeof(ba));
+    ba.lz = re->lz; ba.px = re->px;
+    long most = 0;
+    const double* k = re->k_point;
+    const double dx = re->g.d[0], dy = re->g.d[1], dz = re->g.d[2];
+    for(int i = 0; i < 3; ++i)
+    {
+        const int comp = (isE ? 0 : 3) + i;
+        if(!re->has_wrap[comp] || !re->d_field[comp] || !im->d_field[comp]) continue;
+        const ChimlWrap& w = re->wrap[comp];
+        const int q = ba.n++;
+        ba.fr[q] = re->d_field[comp]; ba.fi[q] = im->d_field[comp]; ba.w[q] = w;
+        for(int cz = -1; cz <= 1; ++cz)
+            for(int cy = -1; cy <= 1; ++cy)
+                for(int cx = -1; cx <= 1; ++cx)
+                {
+                    double arg = 0.0;
+                    bool first = true;
+                    // the first wrapped axis enters as k * d * max or -1.0 * k * d * max, the following ones are added or subtracted
+                    auto term = [&](int cdir, double kk, double dd, int mx) {
+                        if(cdir == 0) return;
+                        if(first) { arg = cdir > 0 ? kk * dd * mx : -1.0 * kk * dd * mx; first = false; }
+                        else arg = cdir > 0 ? arg + kk * dd * mx : arg - kk * dd * mx;
+                    };
+                    term(cx, k[0], dx, w.xmax); term(cy, k[1], dy, w.ymax); term(cz, k[2], dz, w.zmax);
+                    const std::complex<double> ph = std::exp(std::complex<double>(0.0, arg));
+                    ba.ph[q][(cx + 1) + 3 * (cy + 1) + 9 * (cz + 1)] = make_double2(ph.real(), ph.imag());
+                }
+        const long X = w.xmax + 1, Y = w.ymax + 1, Z = w.zmax - w.zmin + 2;
+        most = std::max(most, w.zmin != 0 ? 2 * (X * Z + X * (Y - 2) + (Y - 2) * (Z - 2)) : 2L * (w.xmax - 1 + w.ymax));
+    }
+    if(ba.n == 0) return;
+    LaunchScope ls(re, K_WRAP_BLOCH);
+    k_wrap_bloch<<<dim3((unsigned)std::max<long>(1, std::min<long>((most + 255) / 256, 148 * 4)), ba.n, 1), 256, 0, re->stream>>>(ba);
+}
+
 void launch_node_poles(ChimlCtx* ctx)
 {
     if(!ctx->d_info_node) return;
@@ -1553,7 +1597,9 @@ void halo_push(ChimlCtx* ctx, const HaloPeer& peer, std::initializer_list<HaloSe
 
 int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc);
 
-int launch_step(ChimlCtx* ctx, long long k, int nsrc)
+// section: 0 = the whole step; a complex-field pair interleaves its two parts: 1 = H half step without the wrap copies, 2 = E half step
+// without them, 3 = the end of the step (buffer flip, detectors, running DFT)
+int launch_step(ChimlCtx* ctx, long long k, int nsrc, int section = 0)
 {
     // one block per tile of the compact lists built at commit
     const dim3 block(32, ctx->lz > 1 ? TILE_Z : 1, 1);
@@ -1565,29 +1611,36 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc)
     }
     else
     {
-        // H half step: updateH + updateHPML_ (step() items 4 and 6)
-        fill_step_args(ctx, false, a);
-        launch_family<false>(ctx, a, block, 0);
-        // TFSF surfaces (item 5): H after its curl, E / D before theirs and before the soft sources
-        launch_tfsf(ctx, k);
-        // sources (item 7): all sources, E and H alike, are injected here
-        launch_sources(ctx, k, nsrc, 0);
-        // periodic boundaries of H (item 9)
-        launch_wraps(ctx, false);
-        // oriented-dipole poles at the nodes (item 10, first loop)
-        launch_node_poles(ctx);
-        // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
-        fill_step_args(ctx, true, a);
-        launch_family<true>(ctx, a, block, 0);
-        // qe->addQE() for every emitter object (item 16)
-        for(EmitterDev& em : ctx->emitters)
+        if(section == 0 || section == 1)
         {
-            launch_addP(ctx, em, 0);
-            int rc = launch_density_step(ctx, em);
-            if(rc) return rc;
+            // H half step: updateH + updateHPML_ (step() items 4 and 6)
+            fill_step_args(ctx, false, a);
+            launch_family<false>(ctx, a, block, 0);
+            // TFSF surfaces (item 5): H after its curl, E / D before theirs and before the soft sources
+            launch_tfsf(ctx, k);
+            // sources (item 7): all sources, E and H alike, are injected here
+            launch_sources(ctx, k, nsrc, 0);
+        }
+        // periodic boundaries of H (item 9)
+        if(section == 0) launch_wraps(ctx, false);
+        if(section == 0 || section == 2)
+        {
+            // oriented-dipole poles at the nodes (item 10, first loop)
+            launch_node_poles(ctx);
+            // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
+            fill_step_args(ctx, true, a);
+            launch_family<true>(ctx, a, block, 0);
+            // qe->addQE() for every emitter object (item 16)
+            for(EmitterDev& em : ctx->emitters)
+            {
+                launch_addP(ctx, em, 0);
+                int rc = launch_density_step(ctx, em);
+                if(rc) return rc;
+            }
         }
         // periodic boundaries of E (item 17)
-        launch_wraps(ctx, true);
+        if(section == 0) launch_wraps(ctx, true);
+        if(section == 1 || section == 2) return 0;
     }
     ctx->pcur = 1 - ctx->pcur;
     ++ctx->step_count;
@@ -1737,6 +1790,7 @@ template <int MODE> int persist_occupancy(int* perSM)
 bool persist_eligible(ChimlCtx* ctx)
 {
     if(ctx->persist_mode == 0 || std::getenv("CHIML_B200_NO_PERSIST")) return false;
+    if(ctx->imag || ctx->is_imag_part) return false;
     if(!ctx->tfsf.empty()) return false;      // the surface waves are separate launches
     if(ctx->g.mode == CHIML_MODE_3D || ctx->g.nranks > 1 || !ctx->emitters.empty() || ctx->d_info_node) return false;
     if((int)ctx->detectors.size() > P2D_MAX_DET || (int)ctx->dfts.size() > P2D_MAX_DFT) return false;
@@ -1877,11 +1931,55 @@ int reserve_rings(ChimlCtx* ctx, long long n)
     return 0;
 }
 
+int upload_src_amp(ChimlCtx* ctx, int n, const double* src_amp)
+{
+    const int nsrc = (int)ctx->sources.size();
+    if(nsrc == 0) return 0;
+    if(!src_amp) return fail(ctx, CHIML_ERR_ARG, "sources registered but no amplitudes given");
+    const size_t need = (size_t)n * nsrc;
+    if(need > ctx->src_amp_cap)
+    {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_src_amp);
+        CK(cudaMalloc((void**)&ctx->d_src_amp, need * sizeof(double)));
+        ctx->src_amp_cap = need;
+    }
+    if(need) CK(cudaMemcpyAsync(ctx->d_src_amp, src_amp, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// n steps of a complex-field pair: the two parts take every half step one after the other on one stream, the Bloch wrap copies couple them
+int step_n_pair(ChimlCtx* re, int n, const double* amp_re, const double* amp_im)
+{
+    if(!re) return CHIML_ERR_ARG;
+    ChimlCtx* const ctx = re;           // (the CK macro reports into `ctx`)
+    ChimlCtx* im = re->imag;
+    if(!im) return fail(re, CHIML_ERR_STATE, "step_n_cplx: no imaginary part is bound (chiml_gpu_bind_imag)");
+    if(n < 0) return fail(re, CHIML_ERR_ARG, "negative step count");
+    CK(cudaSetDevice(re->device));
+    int rc;
+    if((rc = reserve_rings(re, n)) || (rc = reserve_rings(im, n))) return rc;
+    if((rc = upload_src_amp(re, n, amp_re))) return rc;
+    if((rc = upload_src_amp(im, n, amp_im))) return fail(re, rc, "step_n_cplx: amplitudes of the imaginary part: " + im->err);
+    const int nsrc = (int)re->sources.size();
+    for(int k = 0; k < n; ++k)
+    {
+        if((rc = launch_step(re, k, nsrc, 1)) || (rc = launch_step(im, k, nsrc, 1))) return fail(re, rc, "launch failed");
+        launch_bloch(re, im, false);
+        if((rc = launch_step(re, k, nsrc, 2)) || (rc = launch_step(im, k, nsrc, 2))) return fail(re, rc, "launch failed");
+        launch_bloch(re, im, true);
+        if((rc = launch_step(re, k, nsrc, 3)) || (rc = launch_step(im, k, nsrc, 3))) return fail(re, rc, "launch failed");
+    }
+    CK(cudaGetLastError());
+    return CHIML_OK;
+}
+
 int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles = nullptr, const double* incd = nullptr, size_t incd_per_step = 0)
 {
     if(!ctx) return CHIML_ERR_ARG;
     if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "step before commit");
     if(n < 0) return fail(ctx, CHIML_ERR_ARG, "negative step count");
+    if(ctx->imag || ctx->is_imag_part) return fail(ctx, CHIML_ERR_STATE, "this context is one part of a complex-field pair: step it with chiml_gpu_step_n_cplx on the real part");
     CK(cudaSetDevice(ctx->device));
     if(!ctx->tfsf.empty())
     {
@@ -1916,19 +2014,7 @@ int step_n_impl(ChimlCtx* ctx, int n, const double* src_amp, const double* twidd
     }
     { int rc = reserve_rings(ctx, n); if(rc) return rc; }
     const int nsrc = (int)ctx->sources.size();
-    if(nsrc > 0)
-    {
-        if(!src_amp) return fail(ctx, CHIML_ERR_ARG, "sources registered but no amplitudes given");
-        const size_t need = (size_t)n * nsrc;
-        if(need > ctx->src_amp_cap)
-        {
-            CK(cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->d_src_amp);
-            CK(cudaMalloc((void**)&ctx->d_src_amp, need * sizeof(double)));
-            ctx->src_amp_cap = need;
-        }
-        CK(cudaMemcpyAsync(ctx->d_src_amp, src_amp, need * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    { int rc = upload_src_amp(ctx, n, src_amp); if(rc) return rc; }
     // (a call of one or two steps costs the same either way: seven short launches against one cooperative launch)
     if(n > 2 && persist_eligible(ctx))
     {
@@ -1951,6 +2037,38 @@ extern "C" {
 
 int chiml_gpu_step_n(ChimlCtx* ctx, int n, const double* src_amp) { return step_n_impl(ctx, n, src_amp); }
 int chiml_gpu_step_n_dft(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles) { return step_n_impl(ctx, n, src_amp, twiddles); }
+int chiml_gpu_step_n_cplx(ChimlCtx* re, int n, const double* src_amp_re, const double* src_amp_im) { return step_n_pair(re, n, src_amp_re, src_amp_im); }
+
+int chiml_gpu_bind_imag(ChimlCtx* re, ChimlCtx* im, const double* k_point)
+{
+    if(!re || !im || re == im) return CHIML_ERR_ARG;
+    if(!re->committed || !im->committed) return fail(re, CHIML_ERR_STATE, "bind_imag: both parts must be committed");
+    if(re->imag || re->is_imag_part || im->imag || im->is_imag_part) return fail(re, CHIML_ERR_STATE, "bind_imag: a context is already part of a pair");
+    if(!k_point) return fail(re, CHIML_ERR_ARG, "bind_imag: k-point");
+    if(re->device != im->device || re->lx != im->lx || re->ly != im->ly || re->lz != im->lz || re->g.mode != im->g.mode || re->g.has_D != im->g.has_D)
+        return fail(re, CHIML_ERR_ARG, "bind_imag: the two parts must be set up from the same lists on the same device");
+    if(re->g.nranks > 1 || im->g.nranks > 1) return fail(re, CHIML_ERR_UNSUPPORTED, "complex fields are covered for single-slab runs only");
+    if(!re->periodic || !im->periodic) return fail(re, CHIML_ERR_ARG, "bind_imag: complex fields belong to periodic runs: call chiml_gpu_set_periodic on both parts");
+    for(int c = 0; c < 6; ++c)
+        if(re->has_wrap[c] != im->has_wrap[c] || (re->has_wrap[c] && std::memcmp(&re->wrap[c], &im->wrap[c], sizeof(ChimlWrap)) != 0))
+            return fail(re, CHIML_ERR_ARG, "bind_imag: the two parts have different wrap descriptions");
+    for(ChimlCtx* c : {re, im})
+        if(!c->emitters.empty() || !c->dfts.empty() || !c->tfsf.empty())
+            return fail(re, CHIML_ERR_UNSUPPORTED, "complex fields with emitters / running-DFT sets / TFSF surfaces are outside the covered hot path");
+    if(re->sources.size() != im->sources.size()) return fail(re, CHIML_ERR_ARG, "bind_imag: the two parts have different sources");
+    ChimlCtx* const ctx = re;           // (the CK macro reports into `ctx`)
+    CK(cudaSetDevice(re->device));
+    CK(cudaStreamSynchronize(im->stream));
+    CK(cudaStreamSynchronize(re->stream));
+    cudaStreamDestroy(im->stream);
+    im->stream = re->stream;                       // one stream: the halves of the two parts and the wrap copies are ordered by it
+    im->is_imag_part = true;
+    im->real_part = re;
+    re->imag = im;
+    for(int k = 0; k < 3; ++k) re->k_point[k] = im->k_point[k] = k_point[k];
+    return 0;
+}
+
 int chiml_gpu_step_n_tfsf(ChimlCtx* ctx, int n, const double* src_amp, const double* twiddles, const double* incd, size_t incd_per_step)
 { return step_n_impl(ctx, n, src_amp, twiddles, incd, incd_per_step); }
 
@@ -2153,7 +2271,7 @@ int chiml_gpu_n_kernel_kinds(void) { return K_NKINDS; }
 int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out)
 {
     static const char* names[K_NKINDS] = {"k_fast<E>", "k_uniform<E>", "k_general<E>", "k_fast<H>", "k_uniform<H>", "k_general<H>",
-                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft", "k_steps_2d", "k_wrap", "k_tfsf"};
+                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft", "k_steps_2d", "k_wrap", "k_tfsf", "k_wrap_bloch"};
     if(!ctx || !out || kind < 0 || kind >= K_NKINDS) return CHIML_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -89,7 +89,7 @@ struct DetectorDev
 };
 
 // kernels of the step loop, for launch / time / algorithmic-byte accounting
-enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_STEPS_2D, K_WRAP, K_TFSF, K_NKINDS };
+enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_STEPS_2D, K_WRAP, K_TFSF, K_WRAP_BLOCH, K_NKINDS };
 struct KernelStat { int64_t launches = 0; double ms_total = 0.0; double alg_bytes = 0.0; int64_t timed = 0; };
 
 // one parallelQE object on the device (chiml_emitters.cuh)
@@ -220,6 +220,11 @@ struct ChimlCtx
     chiml::HostPml hpml[6][2];
     std::vector<chiml::HostObj> objs;
 
+    // complex fields: this context holds the real parts, `imag` the imaginary parts (chiml_gpu_bind_imag); the pair is stepped through this one
+    ChimlCtx* imag = nullptr;
+    ChimlCtx* real_part = nullptr;               // set in the imaginary part
+    bool is_imag_part = false;
+    double k_point[3] = {0.0, 0.0, 0.0};
     // TFSF surfaces and the incident-line table of the current chiml_gpu_step_n_tfsf call
     std::vector<chiml::TfsfDev> tfsf;
     double* d_tfsf_incd = nullptr; size_t tfsf_incd_cap = 0; size_t tfsf_per_step = 0;

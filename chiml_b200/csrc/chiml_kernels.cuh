@@ -305,6 +305,68 @@ __global__ void k_wrap(WrapArgs a)
     }
 }
 
+// Bloch-periodic wrap copies of complex fields held as a real and an imaginary array (applyBC1Proc, complex fields, UTIL/FDTD_up_eq.cpp:1248-1324):
+// the same ghost shell as k_wrap, every ghost cell = phase * image with phase = exp(i (+-kx dx xmax +- ky dy ymax +- kz dz zmax)) over the axes
+// that wrapped, ONE exponential of the summed argument as the reference evaluates it (table ph, index (sx+1) + 3 (sy+1) + 9 (sz+1), computed on
+// the host), product in netlib order.  The reference's corner assignments read row ymax AFTER it received the phased image of row 1: a corner
+// is phase_corner * (phase_y+ * F(x', 1, z')), for the corners at y = 0 too.  Likewise the 2-D columns run over rows 1 .. ymax, so their cell in
+// row ymax is phase_x * (phase_y+ * F(x', 1)).
+struct BlochArgs { double* fr[3]; double* fi[3]; ChimlWrap w[3]; double2 ph[3][27]; int n; int lz; long px; };
+__device__ __forceinline__ double2 cmul_rn(const double2 a, const double2 b)
+{ return make_double2(da(dm(a.x, b.x), -dm(a.y, b.y)), da(dm(a.x, b.y), dm(a.y, b.x))); }
+__global__ void k_wrap_bloch(const __grid_constant__ BlochArgs a)
+{
+    const int c = blockIdx.y;
+    if(c >= a.n) return;
+    double* R = a.fr[c]; double* I = a.fi[c];
+    const ChimlWrap w = a.w[c];
+    const long px = a.px, lz = a.lz;
+    const long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x, istep = (long)gridDim.x * blockDim.x;
+    const double2 phyPlus = a.ph[c][1 + 3 * 2 + 9 * 1];
+    if(w.zmin != 0)
+    {
+        const long X = w.xmax + 1, Y = w.ymax + 1, Z = w.zmax - w.zmin + 2;
+        const long nA = 2 * X * Z, nB = 2 * X * (Y - 2), nC = 2 * (Y - 2) * (Z - 2);
+        for(long i = i0; i < nA + nB + nC; i += istep)
+        {
+            int x, y, z;
+            if(i < nA)           { x = (int)(i % X); const long r = i / X; z = (int)(r % Z) + w.zmin - 1; y = (r / Z) ? w.ymax : 0; }
+            else if(i < nA + nB) { const long j = i - nA; x = (int)(j % X); const long r = j / X; y = (int)(r % (Y - 2)) + 1; z = (r / (Y - 2)) ? w.zmax : w.zmin - 1; }
+            else                 { const long j = i - nA - nB; z = (int)(j % (Z - 2)) + w.zmin; const long r = j / (Z - 2); y = (int)(r % (Y - 2)) + 1; x = (r / (Y - 2)) ? w.xmax : 0; }
+            const int cx = x == 0 ? -1 : (x == w.xmax ? 1 : 0), cy = y == 0 ? -1 : (y == w.ymax ? 1 : 0), cz = z == w.zmin - 1 ? -1 : (z == w.zmax ? 1 : 0);
+            const int sx = cx < 0 ? w.xmax - 1 : (cx > 0 ? 1 : x);
+            const int sz = cz < 0 ? w.zmax - 1 : (cz > 0 ? w.zmin : z);
+            const bool corner = cx != 0 && cy != 0 && cz != 0;
+            const int sy = corner ? 1 : (cy < 0 ? w.ymax - 1 : (cy > 0 ? 1 : y));
+            const long s = sx + px * (sz + lz * sy);
+            double2 v = make_double2(R[s], I[s]);
+            if(corner) v = cmul_rn(phyPlus, v);
+            v = cmul_rn(a.ph[c][(cx + 1) + 3 * (cy + 1) + 9 * (cz + 1)], v);
+            const long d = x + px * (z + lz * y);
+            R[d] = v.x; I[d] = v.y;
+        }
+    }
+    else
+    {
+        const long nR = 2L * (w.xmax - 1), nC = 2L * w.ymax;
+        for(long i = i0; i < nR + nC; i += istep)
+        {
+            int x, y;
+            if(i < nR) { x = (int)(i % (w.xmax - 1)) + 1; y = (i / (w.xmax - 1)) ? w.ymax : 0; }
+            else       { const long j = i - nR; y = (int)(j % w.ymax) + 1; x = (j / w.ymax) ? w.xmax : 0; }
+            const int cx = x == 0 ? -1 : (x == w.xmax ? 1 : 0), cy = y == 0 ? -1 : (y == w.ymax ? 1 : 0);
+            const int sx = cx < 0 ? w.xmax - 1 : (cx > 0 ? 1 : x);
+            const int sy = cy < 0 ? w.ymax - 1 : (cy > 0 ? 1 : y);
+            const long s = sx + px * (long)sy;
+            double2 v = make_double2(R[s], I[s]);
+            if(cx != 0 && cy != 0) { v = cmul_rn(phyPlus, v); v = cmul_rn(a.ph[c][(cx + 1) + 3 * 1 + 9 * 1], v); }       // column cell of row ymax: y first, then x
+            else v = cmul_rn(a.ph[c][(cx + 1) + 3 * (cy + 1) + 9 * 1], v);
+            const long d = x + px * (long)y;
+            R[d] = v.x; I[d] = v.y;
+        }
+    }
+}
+
 // detector sampling (DTC/parallelStorageDTC.cpp:17-44): copy the box into the ring, x fastest, then z, then y
 __global__ void k_detector(const double* field, int lx0, int lz0, int ly0, int sx, int sz, int sy, int lz, long px, double* out)
 {

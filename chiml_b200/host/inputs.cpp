@@ -328,11 +328,13 @@ Inputs::Inputs(const Json& IP, bool postProcessing)
     tMax_ = IP.get<double>("CompCell.tLim");
     I0_ = IP.get<double>("CompCell.I0", a_ * EPS0() * SPEED_OF_LIGHT);
     // periodic boundaries with a k-point switch the reference to complex fields (INPUTS/parallelInputs.cpp:108-112): real fields only here
-    bool kPoint = false;
+    // periodic boundaries with a k-point switch the reference to complex fields (INPUTS/parallelInputs.cpp:22-25,108-112)
+    k_point_ = as_ptArr<double>(IP, "CompCell.k-point", 0.0);
+    cplxFields_ = IP.get<bool>("CompCell.cplxFields", false);
     if(periodic_)
-        for(double kk : as_ptArr<double>(IP, "CompCell.k-point", 0.0)) if(kk != 0) kPoint = true;
-    if(IP.get<bool>("CompCell.cplxFields", false) || kPoint)
-        throw std::logic_error("complex-field (Bloch-periodic, k-point != 0) runs are outside the covered hot path (SURVEY.md section 8(f) rank 3)");
+        for(double kk : k_point_) if(kk != 0) cplxFields_ = true;
+    if(cplxFields_ && !periodic_)
+        throw std::logic_error("complex fields without periodic boundaries are outside the covered hot path (SURVEY.md section 8(f) rank 3)");
     size_ = as_ptArr<double>(IP, "CompCell.size");
     d_ = as_ptArr<double>(IP, "CompCell.stepSize", 1.0 / res_);
     dt_ = IP.get<double>("CompCell.dt", courant_ / std::sqrt(1.0 / (d_[0] * d_[0]) + 1.0 / (d_[1] * d_[1]) + 1.0 / (d_[2] * d_[2])));

@@ -117,6 +117,8 @@ class Inputs
 {
 public:
     bool periodic_ = false;
+    bool cplxFields_ = false;                     // Bloch-periodic run: the fields are complex (two real field sets coupled by the wrap copies)
+    std::array<double, 3> k_point_ = {{0.0, 0.0, 0.0}};
     std::vector<FreqDtcInput> freqDtcs_;
     POLARIZATION pol_;
     int res_;

@@ -86,6 +86,7 @@ int main(int argc, char** argv)
     }
     if(input.empty()) { std::fprintf(stderr, "usage: chiml <input.json> [--device D] [--steps N] [--rank R --nranks N --rendezvous DIR [--run-id ID]]\n"); return 2; }
     ChimlCtx* ctx = nullptr;
+    ChimlCtx* ctxIm = nullptr;            // complex fields: the imaginary parts (a second propagator over the same lists)
     std::string myBlob;
     try
     {
@@ -134,6 +135,27 @@ int main(int argc, char** argv)
             check(ctx, chiml_gpu_add_dft(ctx, d.field, d.group, d.every, d.nfreq, d.npts, d.stride, d.lines.data(), d.lines.size(), d.acc_len, &dftSlot[q]), "add_dft");
         }
         check(ctx, chiml_gpu_commit(ctx), "commit");
+        if(P.cplx)
+        {
+            // Bloch-periodic run: the imaginary parts of every array are a second context set up from the same lists (no detectors of its own:
+            // the reference's TXT / BIN writers print the real part of the collected field, DTC/parallelDTC_TXT.cpp:76-93), bound to the first
+            for(const PlanDetector& d : P.detectors)
+                if(d.type == (int)DTCTYPE::EPOW || d.type == (int)DTCTYPE::HPOW) throw std::runtime_error("power detectors of a complex-field run are outside the covered hot path");
+            if(chiml_gpu_create(&P.grid.desc, device, &ctxIm) != CHIML_OK) throw std::runtime_error(std::string("chiml_gpu_create: ") + chiml_gpu_last_error(nullptr));
+            for(int kind = 0; kind < 5; ++kind)
+                for(int comp = 0; comp < 6; ++comp)
+                    if(!P.lists[kind][comp].empty())
+                        check(ctxIm, chiml_gpu_set_update_list(ctxIm, kind, comp, P.lists[kind][comp].data(), P.lists[kind][comp].size()), "set_update_list");
+            for(size_t o = 0; o < P.objects.size(); ++o)
+                check(ctxIm, chiml_gpu_set_object(ctxIm, (int)o, P.objects[o].npoles, P.objects[o].alpha.data(), P.objects[o].xi.data(), P.objects[o].gamma.data(),
+                                                  P.objects[o].use_or_dip, P.objects[o].dip.data()), "set_object");
+            for(const PlanCpml& c : P.cpml)
+                check(ctxIm, chiml_gpu_set_cpml(ctxIm, c.comp, c.part, c.has_psi, c.psi.data(), c.psi.size(), c.grid.data(), c.grid.size()), "set_cpml");
+            for(const PlanSource& s : P.sources) check(ctxIm, chiml_gpu_add_source(ctxIm, s.field, s.loc, s.sz, nullptr), "add_source");
+            for(const ChimlPlanPeriodic& pp : P.periodic) check(ctxIm, chiml_gpu_set_periodic(ctxIm, pp.comp, &pp.wrap), "set_periodic");
+            check(ctxIm, chiml_gpu_commit(ctxIm), "commit");
+            check(ctx, chiml_gpu_bind_imag(ctx, ctxIm, P.k_point), "bind_imag");
+        }
 
         if(nranks > 1)
         {
@@ -160,10 +182,13 @@ int main(int argc, char** argv)
         const auto t0 = std::chrono::steady_clock::now();
         std::vector<double> amp, twiddles;
         // complex twiddles per step: the flux regions that have a stored field on this slab, region order (chiml_gpu_step_n_dft)
-        std::vector<char> fluxHere(IP.fluxes_.size(), 0);
+        // (the groups of the frequency detectors follow those of the flux regions)
+        const size_t nGroups = IP.fluxes_.size() + IP.freqDtcs_.size();
+        auto groupFreqs = [&](size_t g) -> const std::vector<double>& { return g < IP.fluxes_.size() ? IP.fluxes_[g].freqs : IP.freqDtcs_[g - IP.fluxes_.size()].freqs; };
+        std::vector<char> fluxHere(nGroups, 0);
         for(const PlanDft& d : P.dfts) fluxHere[d.group] = 1;
         size_t ntw = 0;
-        for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff) if(fluxHere[ff]) ntw += IP.fluxes_[ff].freqs.size();
+        for(size_t ff = 0; ff < nGroups; ++ff) if(fluxHere[ff]) ntw += groupFreqs(ff).size();
         double tFlux = 0.0;                               // the reference's tcur_ (tcur_ += dt_, parallelFDTDField.hpp:1290)
         // detector and population samples are drained from the device rings after every chunk of steps (read, then consume), so the
         // rings keep their initial size however long the run is
@@ -207,7 +232,15 @@ int main(int argc, char** argv)
             for(int k = 0; k < n; ++k)
                 for(int q = 0; q < nsrc; ++q)
                     if((size_t)(done + k) < P.sources[q].amp.size()) amp[(size_t)k * nsrc + q] = P.sources[q].amp[done + k];
-            if(P.dfts.empty()) check(ctx, chiml_gpu_step_n(ctx, n, nsrc ? amp.data() : nullptr), "step_n");
+            if(P.cplx)
+            {
+                std::vector<double> ampIm((size_t)n * std::max(nsrc, 1), 0.0);
+                for(int k = 0; k < n; ++k)
+                    for(int q = 0; q < nsrc; ++q)
+                        if((size_t)(done + k) < P.sources[q].amp_im.size()) ampIm[(size_t)k * nsrc + q] = P.sources[q].amp_im[done + k];
+                check(ctx, chiml_gpu_step_n_cplx(ctx, n, nsrc ? amp.data() : nullptr, nsrc ? ampIm.data() : nullptr), "step_n_cplx");
+            }
+            else if(P.dfts.empty()) check(ctx, chiml_gpu_step_n(ctx, n, nsrc ? amp.data() : nullptr), "step_n");
             else
             {
                 // fftFact_ = exp(i * (-t * freq)) with the time after the step (parallelFluxDTC::fieldIn, DTC/parallelFlux.hpp:298)
@@ -216,8 +249,8 @@ int main(int argc, char** argv)
                 {
                     tFlux += P.grid.desc.dt;
                     size_t j = (size_t)k * ntw;
-                    for(size_t ff = 0; ff < IP.fluxes_.size(); ++ff)
-                        for(double freq : IP.fluxes_[ff].freqs)
+                    for(size_t ff = 0; ff < nGroups; ++ff)
+                        for(double freq : groupFreqs(ff))
                         {
                             if(!fluxHere[ff]) break;
                             const std::complex<double> w = std::exp(std::complex<double>(0.0, -1.0 * tFlux * freq));
@@ -324,7 +357,10 @@ int main(int argc, char** argv)
                 const double t = times[s];
                 out << std::setprecision(6) << t * pd.t_conv << "\t" << rsl[0] << "\t" << rsl[1] << "\t" << rsl[2];
                 // sample layout: x fastest, then z, then y; the reference prints y outermost, then z, then x
-                for(size_t i = 0; i < len; ++i) out << "\t" << std::setw(24) << std::setprecision(18) << collect(data[s * len + i]);
+                // (the complex-field writer prints the real part of the collected value at the stream's default 6 digits, unpadded:
+                // DTC/parallelDTC_TXT.cpp:76-93 against :25-55)
+                if(P.cplx) for(size_t i = 0; i < len; ++i) out << "\t" << collect(data[s * len + i]);
+                else for(size_t i = 0; i < len; ++i) out << "\t" << std::setw(24) << std::setprecision(18) << collect(data[s * len + i]);
                 out << '\n';
             }
         }
@@ -387,11 +423,13 @@ int main(int argc, char** argv)
                 }
             }
         }
+        if(ctxIm) chiml_gpu_destroy(ctxIm);
         chiml_gpu_destroy(ctx);
     }
     catch(std::exception& e)
     {
         std::fprintf(stderr, "chiml: %s\n", e.what());
+        if(ctxIm) chiml_gpu_destroy(ctxIm);
         if(ctx) chiml_gpu_destroy(ctx);
         return 1;
     }

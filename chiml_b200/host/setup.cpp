@@ -748,6 +748,15 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
         for(int comp = 0; comp < 6; ++comp)
             if(comp_exists(mode, comp)) { ChimlPlanPeriodic pp; pp.comp = comp; pp.wrap = w[comp]; P.periodic.push_back(pp); }
     }
+    if(IP.cplxFields_)
+    {
+        // parallelFDTDFieldCplx: everything above and below is the same set-up; emitters, flux regions and frequency detectors of a
+        // complex run are not reproduced
+        if(!IP.qes_.empty() || !IP.fluxes_.empty() || !IP.freqDtcs_.empty())
+            throw std::logic_error("complex-field runs with emitters / flux regions / frequency detectors are outside the covered hot path");
+        P.cplx = true;
+        for(int k = 0; k < 3; ++k) P.k_point[k] = IP.k_point_[k];
+    }
 
     Rasteriser ras(IP, g);
     // ---- update lists (parallelFDTDField.cpp:80-92,248-261) ----
@@ -840,12 +849,14 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
             if(k == 2 && g.twoD) ps.sz[k] = 1;
         }
         ps.amp.resize(P.grid.n_steps);
+        if(IP.cplxFields_) ps.amp_im.resize(P.grid.n_steps);
         double t = 0.0;
         for(int k = 0; k < P.grid.n_steps; ++k)
         {
             cplx pulVal = 0.0;
             for(size_t p = 0; p < s.shapes.size(); ++p) pulVal += pulseValue(s.shapes[p], t, s.fxn[p]);
             ps.amp[k] = g.dt * std::real(pulVal);
+            if(IP.cplxFields_) ps.amp_im[k] = g.dt * std::imag(pulVal);      // parallelSourceNormalCplx::addPul: zaxpy_(n, dt_, pulVec_, ...)
             t += g.dt;
         }
         P.sources.push_back(std::move(ps));
@@ -902,6 +913,12 @@ void SlabPlan::write(const std::string& path) const
     if(!out) throw std::runtime_error("cannot write " + path);
     { std::string p; int32_t v = CHIML_PLAN_VERSION; app(p, v); put_rec(out, "CHIMLPLN", p); }
     { std::string p; app(p, grid); put_rec(out, "GRID", p); }
+    if(cplx)
+    {
+        ChimlPlanComplex pc; std::memset(&pc, 0, sizeof(pc));
+        pc.cplx = 1; for(int k = 0; k < 3; ++k) pc.k_point[k] = k_point[k];
+        std::string p; app(p, pc); put_rec(out, "COMPLEX", p);
+    }
     for(const ChimlPlanPeriodic& pp : periodic) { std::string p; app(p, pp); put_rec(out, "PERIODIC", p); }
     // same record order as oracle/ref_driver.cpp
     for(int c = 0; c < 3; ++c)
@@ -937,6 +954,7 @@ void SlabPlan::write(const std::string& path) const
         h.n_steps = (int)s.amp.size();
         std::string p; app(p, h); app_vec(p, s.amp);
         put_rec(out, "SOURCE", p);
+        if(cplx) { std::string q; const int32_t ns = (int32_t)s.amp_im.size(); app(q, ns); app_vec(q, s.amp_im); put_rec(out, "SRCIMAG", q); }
     }
     for(const PlanDetector& d : detectors)
     {

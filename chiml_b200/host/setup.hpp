@@ -21,7 +21,7 @@ namespace chiml_host {
 
 struct PlanCpml { int comp, part, has_psi; std::vector<ChimlPsiParams> psi; std::vector<ChimlGridParams> grid; };
 struct PlanObject { int npoles, use_or_dip, ml; double eps_inf, mu_inf; std::vector<double> alpha, xi, gamma, dip; };
-struct PlanSource { int field; int32_t loc[3], sz[3]; std::vector<double> amp; };
+struct PlanSource { int field; int32_t loc[3], sz[3]; std::vector<double> amp, amp_im; };     // amp_im: dt * Im(sum pulse), complex fields only
 struct PlanDetector { int detector, field; int32_t loc[3], sz[3], offset[3]; int every, type; double conv, t_conv; };
 
 // one parallelQE object restricted to the slab (include/chiml_gpu.h ChimlEmitterDesc)
@@ -64,6 +64,8 @@ struct SlabPlan
     std::vector<PlanEmitter> emitters;
     std::vector<PlanDft> dfts;
     std::vector<ChimlPlanPeriodic> periodic;   // wrap copies per component (CompCell.PBC)
+    bool cplx = false;                         // complex fields (k-point != 0)
+    double k_point[3] = {0.0, 0.0, 0.0};
     bool dielectricMatInPML = false;
 
     void write(const std::string& path) const;

@@ -63,6 +63,7 @@ class PlanSource:
     loc: Tuple[int, int, int]
     sz: Tuple[int, int, int]
     amp: np.ndarray
+    amp_im: Optional[np.ndarray] = None     # complex fields: dt * Im(sum pulse(t_k)) (record SRCIMAG)
 
 
 @dataclass
@@ -163,6 +164,8 @@ class Plan:
     detectors: List[PlanDetector] = field(default_factory=list)
     emitters: List[PlanEmitter] = field(default_factory=list)
     dfts: List[PlanDft] = field(default_factory=list)
+    cplx: bool = False                          # complex fields (record COMPLEX): real and imaginary parts are two field sets over the same lists
+    k_point: Tuple[float, float, float] = (0.0, 0.0, 0.0)
     tfsf: List[PlanTfsfSurface] = field(default_factory=list)
     tfsf_lines: Optional[np.ndarray] = None     # (n_steps, per_step): the incident-line table of chiml_gpu_step_n_tfsf
     periodic: Dict[int, Tuple[int, ...]] = field(default_factory=dict)      # comp -> (nx, ny, nz, xmax, ymax, zmin, zmax) (ChimlWrap)
@@ -239,6 +242,12 @@ def read_plan(path: str) -> Plan:
             freq = np.frombuffer(payload, dtype="<f8", count=nfreq, offset=40).copy()
             lines = np.frombuffer(payload, dtype="<i4", count=2 * nlines, offset=40 + 8 * nfreq).copy().reshape(nlines, 2)
             plan.dfts.append(PlanDft(fld, group, every, nfreq, npts, stride, acc_len, freq, lines))
+        elif tag == "COMPLEX":
+            v = struct.unpack_from("<ii3d", payload, 0)
+            plan.cplx = bool(v[0]); plan.k_point = tuple(v[2:5])
+        elif tag == "SRCIMAG":
+            (ns,) = struct.unpack_from("<i", payload, 0)
+            plan.sources[-1].amp_im = np.frombuffer(payload, dtype="<f8", count=ns, offset=4).copy()
         elif tag == "TFSFSURF":
             v = struct.unpack_from("<10id", payload, 0)
             off = 48
@@ -320,8 +329,12 @@ def write_plan(path: str, plan: Plan) -> None:
     for c in plan.cpml:
         out.append(_rec("CPML", struct.pack("<iiiiQQ", c.comp, c.part, c.has_psi, 0, len(c.psi), len(c.grid))
                         + np.ascontiguousarray(c.psi, PSI_DTYPE).tobytes() + np.ascontiguousarray(c.grid, GRIDP_DTYPE).tobytes()))
+    if plan.cplx:
+        out.append(_rec("COMPLEX", struct.pack("<ii3d", 1, 0, *plan.k_point)))
     for s in plan.sources:
         out.append(_rec("SOURCE", struct.pack("<i3i3ii", s.field, *s.loc, *s.sz, len(s.amp)) + np.asarray(s.amp, "<f8").tobytes()))
+        if s.amp_im is not None:
+            out.append(_rec("SRCIMAG", struct.pack("<i", len(s.amp_im)) + np.asarray(s.amp_im, "<f8").tobytes()))
     for d in plan.detectors:
         out.append(_rec("DETECTOR", struct.pack("<ii3i3i3iiiidd", d.detector, d.field, *d.loc, *d.sz, *d.offset, d.every, d.type, 0,
                                                 d.conv, d.t_conv)))

@@ -178,6 +178,16 @@ int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq,
 typedef struct ChimlWrap { int32_t nx, ny, nz, xmax, ymax, zmin, zmax; } ChimlWrap;
 int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* wrap);
 
+/* Complex fields (Bloch-periodic runs: a k-point switches the reference to parallelFDTDFieldCplx, INPUTS/parallelInputs.cpp:108-112).  Every operator
+ * of the step has real coefficients -- the reference's complex BLAS chains multiply by real factors -- so the real and the imaginary parts of all
+ * arrays evolve as two real propagators over the SAME lists, coupled only by the phase factors exp(i k.L) of the periodic wrap copies
+ * (applyBC1Proc, complex fields, UTIL/FDTD_up_eq.cpp:1248-1324) and driven by the real / imaginary parts of the pulse.  Two contexts set up
+ * identically (lists, objects, CPML, sources, detectors, chiml_gpu_set_periodic on both) and committed are bound into a pair; from then on
+ * chiml_gpu_step_n_cplx on the REAL part steps both (src_amp_re / src_amp_im: dt * Re / Im(sum pulse(t)) per step and source) and applies the Bloch
+ * wrap copies; state is read from either context as usual.  Single slab, no emitters, running-DFT sets or TFSF surfaces. */
+int chiml_gpu_bind_imag(ChimlCtx* re, ChimlCtx* im, const double* k_point /* 3 */);
+int chiml_gpu_step_n_cplx(ChimlCtx* re, int n, const double* src_amp_re, const double* src_amp_im);
+
 /* Total-field / scattered-field plane-wave source (SOURCE/parallelTFSF.hpp).  The 1-D auxiliary incident line (parallelTFSFBase::step,
  * :1148-1177: six complex 1-D fields with their own dispersion and CPML) does not depend on the main grid; it stays on the host --
  * the reference's own object steps it -- and the device applies the surface corrections of updateFields() (:1058-1073).  One surface

@@ -99,6 +99,13 @@ typedef struct ChimlPlanTfsfLinesHdr   /* tag "TFSFLINE": header, then n_steps *
 {
     int32_t n_steps, per_step;
 } ChimlPlanTfsfLinesHdr;
+typedef struct ChimlPlanComplex        /* tag "COMPLEX ": the propagator holds complex fields (Bloch-periodic run, parallelFDTDFieldCplx): every field / psi /
+                                          pole array has a real and an imaginary part, coupled only by the phase factors of the periodic wrap copies */
+{
+    int32_t cplx, pad;
+    double  k_point[3];                /* k_point_ */
+} ChimlPlanComplex;
+/* tag "SRCIMAG ": int32 n_steps, then n_steps doubles dt * Im(sum pulse(t_k)) of the SOURCE record before it (complex fields only) */
 #pragma pack(pop)
 
 #endif /* CHIML_PLAN_H */

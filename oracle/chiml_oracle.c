@@ -4,6 +4,8 @@
 #define _POSIX_C_SOURCE 200809L
 #include "chiml_oracle.h"
 
+#include <complex.h>
+#undef I
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -730,6 +732,102 @@ static void apply_bc_1proc(const OracleSim* s, double* F, const ChimlWrap* w)
         copy_strided(ny, PT(1, 1, 0), lx, PT(xmax, 1, 0), lx);
     }
 #undef PT
+}
+
+/* ---- complex fields (Bloch-periodic runs): the real and imaginary parts are two simulations over the same lists -- every operator of the
+ * step has real coefficients, so the reference's complex BLAS chains (zaxpy with a real factor etc.) act on the two parts separately --
+ * coupled only by the phase factors of the wrap copies.  applyBC1Proc, complex fields (UTIL/FDTD_up_eq.cpp:1248-1324), call by call:
+ * zcopy_ then zscal_ with exp(i k.L) (dest = phase * dest, netlib product), the corners as written there -- they read the already
+ * wrapped row ymax. */
+typedef struct { double re, im; } cxd;
+static cxd phase_of(double arg) { const double _Complex w = cexp(__builtin_complex(0.0, arg)); cxd r; r.re = creal(w); r.im = cimag(w); return r; }
+static void zcopy_scal(int n, const double* sr, const double* si, size_t incs, double* dr, double* di, size_t incd, cxd a)
+{
+    for(int i = 0; i < n; ++i)
+    {
+        const double xr = sr[(size_t)i * incs], xi = si[(size_t)i * incs];
+        dr[(size_t)i * incd] = a.re * xr - a.im * xi;
+        di[(size_t)i * incd] = a.re * xi + a.im * xr;
+    }
+}
+static void apply_bc_1proc_cplx(const OracleSim* s, double* R, double* Iq, const ChimlWrap* w, const double k[3])
+{
+    const size_t lx = (size_t)s->g.ln[0], lz = (size_t)s->g.ln[2];
+    const double dx = s->g.d[0], dy = s->g.d[1], dz = s->g.d[2];
+#define OF(x, y, z) ((size_t)(x) + lx * ((size_t)(z) + lz * (size_t)(y)))
+#define CS(n, sx, sy, sz, inc, tx, ty, tz, arg) zcopy_scal(n, R + OF(sx, sy, sz), Iq + OF(sx, sy, sz), inc, R + OF(tx, ty, tz), Iq + OF(tx, ty, tz), inc, phase_of(arg))
+    const int nx = w->nx, ny = w->ny, nz = w->nz, xmax = w->xmax, ymax = w->ymax, zmin = w->zmin, zmax = w->zmax;
+    if(zmin != 0)
+    {
+        for(int kk = zmin; kk <= nz; ++kk)
+        {
+            CS(nx, 1, ymax - 1, kk, 1, 1, 0, kk, -1.0 * k[1] * dy * ymax);
+            CS(nx, 1, 1, kk, 1, 1, ymax, kk, k[1] * dy * ymax);
+        }
+        for(int jj = 1; jj < ny; ++jj)
+        {
+            CS(nz, xmax - 1, jj, 1, lx, 0, jj, 1, -1.0 * k[0] * dx * xmax);
+            CS(nz, 1, jj, 1, lx, xmax, jj, 1, k[0] * dx * xmax);
+            CS(nx, 1, jj, zmax - 1, 1, 1, jj, zmin - 1, -1.0 * k[2] * dz * zmax);
+            CS(nx, 1, jj, zmin, 1, 1, jj, zmax, k[2] * dz * zmax);
+        }
+        /* Y edges */
+        CS(ny - 1, 1, 1, zmin, lx * lz, xmax, 1, zmax, k[0] * dx * xmax + k[2] * dz * zmax);
+        CS(ny - 1, xmax - 1, 1, zmin, lx * lz, 0, 1, zmax, -1.0 * k[0] * dx * xmax + k[2] * dz * zmax);
+        CS(ny - 1, 1, 1, zmax - 1, lx * lz, xmax, 1, zmin - 1, k[0] * dx * xmax - k[2] * dz * zmax);
+        CS(ny - 1, xmax - 1, 1, zmax - 1, lx * lz, 0, 1, zmin - 1, -1.0 * k[0] * dx * xmax - k[2] * dz * zmax);
+        /* X edges */
+        CS(nx, 1, 1, zmin, 1, 1, ymax, zmax, k[1] * dy * ymax + k[2] * dz * zmax);
+        CS(nx, 1, 1, zmax - 1, 1, 1, ymax, zmin - 1, k[1] * dy * ymax - k[2] * dz * zmax);
+        CS(nx, 1, ymax - 1, zmin, 1, 1, 0, zmax, -1.0 * k[1] * dy * ymax + k[2] * dz * zmax);
+        CS(nx, 1, ymax - 1, zmax - 1, 1, 1, 0, zmin - 1, -1.0 * k[1] * dy * ymax - k[2] * dz * zmax);
+        /* Z edges */
+        CS(nz, 1, 1, 1, lx, xmax, ymax, 1, k[0] * dx * xmax + k[1] * dy * ymax);
+        CS(nz, xmax - 1, 1, 1, lx, 0, ymax, 1, -1.0 * k[0] * dx * xmax + k[1] * dy * ymax);
+        CS(nz, 1, ymax - 1, 1, lx, xmax, 0, 1, k[0] * dx * xmax - k[1] * dy * ymax);
+        CS(nz, xmax - 1, ymax - 1, 1, lx, 0, 0, 1, -1.0 * k[0] * dx * xmax - k[1] * dy * ymax);
+        /* corners: every one of them reads row ymax, which the first loop has already filled with the phased image of row 1 */
+        CS(1, 1, ymax, zmin, 1, xmax, ymax, zmax, k[0] * dx * xmax + k[1] * dy * ymax + k[2] * dz * zmax);
+        CS(1, xmax - 1, ymax, zmin, 1, 0, ymax, zmax, -1.0 * k[0] * dx * xmax + k[1] * dy * ymax + k[2] * dz * zmax);
+        CS(1, 1, ymax, zmax - 1, 1, xmax, ymax, zmin - 1, k[0] * dx * xmax + k[1] * dy * ymax - k[2] * dz * zmax);
+        CS(1, xmax - 1, ymax, zmax - 1, 1, 0, ymax, zmin - 1, -1.0 * k[0] * dx * xmax + k[1] * dy * ymax - k[2] * dz * zmax);
+        CS(1, 1, ymax, zmin, 1, xmax, 0, zmax, k[0] * dx * xmax - k[1] * dy * ymax + k[2] * dz * zmax);
+        CS(1, xmax - 1, ymax, zmin, 1, 0, 0, zmax, -1.0 * k[0] * dx * xmax - k[1] * dy * ymax + k[2] * dz * zmax);
+        CS(1, 1, ymax, zmax - 1, 1, xmax, 0, zmin - 1, k[0] * dx * xmax - k[1] * dy * ymax - k[2] * dz * zmax);
+        CS(1, xmax - 1, ymax, zmax - 1, 1, 0, 0, zmin - 1, -1.0 * k[0] * dx * xmax - k[1] * dy * ymax - k[2] * dz * zmax);
+    }
+    else
+    {
+        CS(nx, 1, ymax - 1, 0, 1, 1, 0, 0, -1.0 * k[1] * dy * ymax);
+        CS(nx, 1, 1, 0, 1, 1, ymax, 0, k[1] * dy * ymax);
+        CS(ny, xmax - 1, 1, 0, lx, 0, 1, 0, -1.0 * k[0] * dx * xmax);
+        CS(ny, 1, 1, 0, lx, xmax, 1, 0, k[0] * dx * xmax);
+    }
+#undef CS
+#undef OF
+}
+int oracle_step_phase(OracleSim* s, int phase, const double* src_amp);
+/* n steps of a complex-field run: re / im = the two parts (no periodic wraps of their own, no running-DFT sets, no emitters), amp_re / amp_im =
+ * dt * Re / Im(sum pulse) per step and source, wrap / has_wrap = the applBCE_ / applBCH_ arguments per component */
+int oracle_pair_step_n(OracleSim* re, OracleSim* im, int n, const double* amp_re, const double* amp_im, const ChimlWrap* wrap, const int* has_wrap,
+                       const double* k_point)
+{
+    if(!re || !im || !wrap || !has_wrap || !k_point || re->ncell != im->ncell || re->ndft || im->ndft || re->nqe || im->nqe || re->ntfsf || im->ntfsf)
+        return CHIML_ERR_ARG;
+    for(int c = 0; c < 6; ++c) if(re->has_wrap[c] || im->has_wrap[c]) return CHIML_ERR_ARG;
+    const size_t ns = (size_t)re->nsrc;
+    for(int k = 0; k < n; ++k)
+    {
+        int rc;
+        if((rc = oracle_step_phase(re, 0, amp_re + (size_t)k * ns)) || (rc = oracle_step_phase(im, 0, amp_im + (size_t)k * ns))) return rc;
+        for(int i = 0; i < 3; ++i)          /* applBCH_ (FDTD_MANAGER/parallelFDTDField.hpp:1267-1269) */
+            if(re->f[CHIML_HX + i] && has_wrap[3 + i]) apply_bc_1proc_cplx(re, re->f[CHIML_HX + i], im->f[CHIML_HX + i], &wrap[3 + i], k_point);
+        for(int phase = 1; phase <= 3; ++phase)
+            if((rc = oracle_step_phase(re, phase, amp_re + (size_t)k * ns)) || (rc = oracle_step_phase(im, phase, amp_im + (size_t)k * ns))) return rc;
+        for(int i = 0; i < 3; ++i)          /* applBCE_ (:1285-1287) */
+            if(re->f[CHIML_EX + i] && has_wrap[i]) apply_bc_1proc_cplx(re, re->f[CHIML_EX + i], im->f[CHIML_EX + i], &wrap[i], k_point);
+    }
+    return 0;
 }
 
 static void step_worker(OracleSim* s, int tid, int nt)

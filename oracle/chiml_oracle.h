@@ -45,6 +45,9 @@ int  oracle_step_n(OracleSim* s, int n, const double* src_amp, int nthreads);
 
 int  oracle_step_n_dft(OracleSim* s, int n, const double* src_amp, const double* twiddles, int nthreads);
 int  oracle_step_n_tfsf(OracleSim* s, int n, const double* src_amp, const double* twiddles, const double* incd, size_t incd_per_step, int nthreads);
+/* complex fields (Bloch-periodic runs) as two real simulations coupled by the phase factors of the wrap copies (see chiml_oracle.c) */
+int  oracle_pair_step_n(OracleSim* re, OracleSim* im, int n, const double* amp_re, const double* amp_im, const ChimlWrap* wrap, const int* has_wrap,
+                        const double* k_point);
 double* oracle_dft(OracleSim* s, int slot, int imag);
 /* one phase of one step, for y-slab runs that exchange ghost rows between phases (see chiml_oracle.c) */
 int  oracle_step_phase(OracleSim* s, int phase, const double* src_amp);

@@ -85,6 +85,23 @@ static void grabGrid(int rank, const std::string& name, std::shared_ptr<parallel
     g_dumps.push_back(std::move(d));
 }
 
+// complex grids: the real part under the grid's name, the imaginary part under <name>_im
+static void grabGrid(int rank, const std::string& name, std::shared_ptr<parallelGrid<cplx>> g)
+{
+    if(!g) return;
+    for(int im = 0; im < 2; ++im)
+    {
+        GridDump d;
+        d.rank = rank;
+        d.name = name + (im ? "_im" : "");
+        d.ln[0] = g->local_x(); d.ln[1] = g->local_y(); d.ln[2] = g->local_z();
+        d.yStart = g->procLoc(1);
+        d.data.resize(size_t(g->size()));
+        for(int i = 0; i < g->size(); ++i) d.data[size_t(i)] = im ? std::imag(g->point(i)) : std::real(g->point(i));
+        std::lock_guard<std::mutex> lk(g_dumpMtx);
+        g_dumps.push_back(std::move(d));
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // plan dump (include/chiml_plan.h) from the reference's own data structures
@@ -112,7 +129,7 @@ static void putList(std::ofstream& out, int kind, int comp, const upLists& l)
     putRec(out, "UPLIST", p);
 }
 
-static void putCpml(std::ofstream& out, int comp, std::shared_ptr<parallelCPML<double>> pml)
+template <class T> static void putCpml(std::ofstream& out, int comp, std::shared_ptr<parallelCPML<T>> pml)
 {
     static_assert(sizeof(updatePsiParams) == sizeof(ChimlPsiParams), "updatePsiParams layout");
     static_assert(sizeof(updateGridParams) == sizeof(ChimlGridParams), "updateGridParams layout");
@@ -133,7 +150,7 @@ static void putCpml(std::ofstream& out, int comp, std::shared_ptr<parallelCPML<d
     }
 }
 
-static int fieldId(parallelFDTDFieldReal& FF, const std::shared_ptr<parallelGrid<double>>& g)
+template <class FFT, class T> static int fieldId(FFT& FF, const std::shared_ptr<parallelGrid<T>>& g)
 {
     for(int i = 0; i < 3; ++i)
     {
@@ -145,7 +162,7 @@ static int fieldId(parallelFDTDFieldReal& FF, const std::shared_ptr<parallelGrid
 }
 
 // the arguments step() passes to applBCH_[c] / applBCE_[c] (FDTD_MANAGER/parallelFDTDField.hpp:1267-1269,1285-1287), comp 0..5 = Ex..Hz
-static ChimlWrap wrapArgs(parallelFDTDFieldReal& FF, int comp)
+template <class FFT> static ChimlWrap wrapArgs(FFT& FF, int comp)
 {
     const int l0 = FF.ln_vec_[0], zMin = FF.zMinPBC_, zMax = FF.zMaxPBC_;
     switch(comp)
@@ -276,11 +293,25 @@ static std::vector<const std::vector<double>*> dftGroupFreqs(parallelFDTDFieldRe
 }
 
 static void putEmitters(std::ofstream& out, parallelFDTDFieldReal& FF);
-static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const parallelProgramInputs& IP, int nSteps)
+// real / complex propagator: the value type of its grids and the class of its soft sources
+template <class FFT> struct FieldTraits;
+template <> struct FieldTraits<parallelFDTDFieldReal> { typedef double value; typedef parallelSourceNormalReal source; static const bool cplx = false; };
+template <> struct FieldTraits<parallelFDTDFieldCplx> { typedef cplx value;   typedef parallelSourceNormalCplx source; static const bool cplx = true; };
+static void putTfsfRecords(std::ofstream& out, parallelFDTDFieldReal& FF);
+static void putTfsfRecords(std::ofstream&, parallelFDTDFieldCplx& FF)
+{ if(!FF.tfsfArr_.empty()) throw std::runtime_error("plan dump: TFSF sources with complex fields are outside the covered hot path"); }
+static void putEmittersAndDfts(std::ofstream& out, parallelFDTDFieldReal& FF);
+static void putEmittersAndDfts(std::ofstream&, parallelFDTDFieldCplx& FF)
 {
+    if(!FF.qeArr_.empty() || !FF.fluxArr_.empty() || !FF.dtcFreqArr_.empty())
+        throw std::runtime_error("plan dump: emitters / flux regions / frequency detectors with complex fields are outside the covered hot path");
+}
+template <class FFT> static void writePlan(const std::string& fname, FFT& FF, const parallelProgramInputs& IP, int nSteps)
+{
+    typedef FieldTraits<FFT> TR;
     std::ofstream out(fname.c_str(), std::ios::binary);
     { std::string p; int32_t v = CHIML_PLAN_VERSION; app(p, v); putRec(out, "CHIMLPLN", p); }
-    std::shared_ptr<parallelGrid<double>> g0 = FF.E_[0] ? FF.E_[0] : FF.E_[2];
+    std::shared_ptr<parallelGrid<typename TR::value>> g0 = FF.E_[0] ? FF.E_[0] : FF.E_[2];
     ChimlPlanGrid pg;
     std::memset(&pg, 0, sizeof(pg));
     pg.desc.mode = (FF.E_[0] && FF.E_[2]) ? CHIML_MODE_3D : (FF.E_[0] ? CHIML_MODE_TE : CHIML_MODE_TM);
@@ -297,6 +328,15 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
     pg.n_ordip_poles = int(std::max(FF.orDipLorP_[0].size(), FF.orDipLorP_[2].size()));
     pg.t_max = IP.tMax_;
     { std::string p; app(p, pg); putRec(out, "GRID", p); }
+    if(TR::cplx)
+    {
+        // complex fields (Bloch-periodic runs): every field array has a real and an imaginary part; the wrap copies carry the phase
+        // factors of the k-point (UTIL/FDTD_up_eq.cpp:1118-1324)
+        if(!IP.periodic_) throw std::runtime_error("plan dump: complex fields without periodic boundaries are outside the covered hot path");
+        ChimlPlanComplex pc; std::memset(&pc, 0, sizeof(pc));
+        pc.cplx = 1; for(int k = 0; k < 3; ++k) pc.k_point[k] = FF.k_point_[k];
+        std::string p; app(p, pc); putRec(out, "COMPLEX", p);
+    }
     if(IP.periodic_)
     {
         if(FF.gridComm_->size() > 1) throw std::runtime_error("plan dump: periodic boundaries on several ranks are outside the covered hot path");
@@ -308,22 +348,7 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
         }
     }
 
-    if(!FF.tfsfArr_.empty())
-    {
-        if(FF.gridComm_->size() > 1) throw std::runtime_error("plan dump: TFSF sources on several ranks are outside the covered hot path");
-        const TfsfLayout L = tfsfLayout(FF);
-        for(const TfsfSurfaceRec& r : tfsfSurfaces(FF, L))
-        {
-            ChimlPlanTfsfSurfaceHdr h; std::memset(&h, 0, sizeof(h));
-            h.comp = r.s.comp; h.incd_offset = r.s.incd_offset; h.incd_len = r.s.incd_len; h.n = r.s.n; h.stride_incd = r.s.stride_incd;
-            h.stride_main = r.s.stride_main; h.npairs_D = r.s.npairs_D; h.npairs_U = r.s.npairs_U; h.has_ep_mu = r.s.ep_mu ? 1 : 0; h.prefactor = r.s.prefactor;
-            std::string p; app(p, h);
-            p.append(reinterpret_cast<const char*>(r.s.pairs_D), size_t(r.s.npairs_D) * 8);
-            p.append(reinterpret_cast<const char*>(r.s.pairs_U), size_t(r.s.npairs_U) * 8);
-            if(r.s.ep_mu) p.append(reinterpret_cast<const char*>(r.s.ep_mu), size_t(r.s.incd_len) * 8);
-            putRec(out, "TFSFSURF", p);
-        }
-    }
+    putTfsfRecords(out, FF);
     if(FF.magMatInPML_) throw std::runtime_error("plan dump: magnetic material in the PML is outside the covered hot path");
     for(int c = 0; c < 3; ++c)
     {
@@ -370,7 +395,7 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
     // sources: the box this rank adds to, and the per-step amplitude dt*Re(sum pulse(t_k)) with t_k accumulated as step() does
     for(auto& srcBase : FF.srcArr_)
     {
-        auto src = std::dynamic_pointer_cast<parallelSourceNormalReal>(srcBase);
+        auto src = std::dynamic_pointer_cast<typename TR::source>(srcBase);
         if(!src) throw std::runtime_error("plan dump: only normal (axis-aligned) soft sources are on the covered hot path");
         if(!src->slave_) continue;
         ChimlPlanSourceHdr h;
@@ -386,17 +411,19 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
         sz[ax2] = sl.sz_[2];
         for(int k = 0; k < 3; ++k) { h.loc[k] = sl.loc_[k]; h.sz[k] = sz[k]; }
         h.n_steps = nSteps;
-        std::vector<double> amp(nSteps);
+        std::vector<double> amp(nSteps), ampIm(nSteps);
         double t = 0.0;
         for(int k = 0; k < nSteps; ++k)
         {
             cplx pulVal = 0.0;
             for(auto& pul : src->pulse_) pulVal += pul->pulse(t);
             amp[k] = FF.dt_ * std::real(pulVal);
+            ampIm[k] = FF.dt_ * std::imag(pulVal);           // complex fields: zaxpy_(n, dt_, pulVec_, ...) adds dt * pulse to both parts
             t += FF.dt_;
         }
         std::string p; app(p, h); appVec(p, amp);
         putRec(out, "SOURCE", p);
+        if(TR::cplx) { std::string q; int32_t ns = nSteps; app(q, ns); appVec(q, ampIm); putRec(out, "SRCIMAG", q); }   // belongs to the SOURCE record before it
     }
     int dd = 0;
     for(auto& dtc : FF.dtcArr_)
@@ -417,6 +444,31 @@ static void writePlan(const std::string& fname, parallelFDTDFieldReal& FF, const
         }
         ++dd;
     }
+    putEmittersAndDfts(out, FF);
+}
+
+static void putTfsfRecords(std::ofstream& out, parallelFDTDFieldReal& FF)
+{
+    if(!FF.tfsfArr_.empty())
+    {
+        if(FF.gridComm_->size() > 1) throw std::runtime_error("plan dump: TFSF sources on several ranks are outside the covered hot path");
+        const TfsfLayout L = tfsfLayout(FF);
+        for(const TfsfSurfaceRec& r : tfsfSurfaces(FF, L))
+        {
+            ChimlPlanTfsfSurfaceHdr h; std::memset(&h, 0, sizeof(h));
+            h.comp = r.s.comp; h.incd_offset = r.s.incd_offset; h.incd_len = r.s.incd_len; h.n = r.s.n; h.stride_incd = r.s.stride_incd;
+            h.stride_main = r.s.stride_main; h.npairs_D = r.s.npairs_D; h.npairs_U = r.s.npairs_U; h.has_ep_mu = r.s.ep_mu ? 1 : 0; h.prefactor = r.s.prefactor;
+            std::string p; app(p, h);
+            p.append(reinterpret_cast<const char*>(r.s.pairs_D), size_t(r.s.npairs_D) * 8);
+            p.append(reinterpret_cast<const char*>(r.s.pairs_U), size_t(r.s.npairs_U) * 8);
+            if(r.s.ep_mu) p.append(reinterpret_cast<const char*>(r.s.ep_mu), size_t(r.s.incd_len) * 8);
+            putRec(out, "TFSFSURF", p);
+        }
+    }
+}
+
+static void putEmittersAndDfts(std::ofstream& out, parallelFDTDFieldReal& FF)
+{
     if(!FF.qeArr_.empty() && FF.gridComm_->size() == 1) putEmitters(out, FF);
     // DFT records: every stored field of every flux object and frequency detector
     for(const DftStorageRef& r : allDftStorages(FF))
@@ -854,7 +906,45 @@ static void rankMain(int rank, const Options& opt)
         boost::filesystem::remove(filename);
 
     if(IP.cplxFields_)
-        throw std::runtime_error("chiml_ref: complex-field runs are outside the hot path covered here");
+    {
+        // Bloch-periodic run (k-point != 0 switches the reference to complex fields, INPUTS/parallelInputs.cpp:108-112): main.cpp:129-199 with
+        // parallelFDTDFieldCplx; plan and state dumps as for real fields, every grid as a real and an imaginary array
+        if(opt.gpu) throw std::runtime_error("chiml_ref --gpu: complex fields are driven by the host driver of this repository (two real field sets), not by this binding");
+        parallelFDTDFieldCplx FC(IP, gridComm);
+        int nStepsC = int(std::ceil(IP.tMax_ / IP.dt_));
+        if(opt.steps >= 0) nStepsC = opt.steps;
+        if(!opt.plan.empty()) writePlan(opt.plan + ".rank" + std::to_string(rank) + ".plan", FC, IP, nStepsC);
+        for(int tt = 0; tt < opt.warmup; ++tt) FC.step();
+        gridComm->barrier();
+        auto c0 = std::chrono::steady_clock::now();
+        for(int tt = 0; tt < nStepsC; ++tt) FC.step();
+        gridComm->barrier();
+        auto c1 = std::chrono::steady_clock::now();
+        if(rank == 0)
+        {
+            g_stepSeconds = std::chrono::duration<double>(c1 - c0).count();
+            g_nStepsRun = nStepsC;
+            g_cells = long(FC.n_vec_[0]) * long(FC.n_vec_[1]) * long(FC.n_vec_[2] > 1 ? FC.n_vec_[2] : 1);
+        }
+        if(!opt.dump.empty())
+        {
+            const char* c = "xyz";
+            for(int i = 0; i < 3; ++i)
+            {
+                grabGrid(rank, std::string("E") + c[i], FC.E_[i]);
+                grabGrid(rank, std::string("H") + c[i], FC.H_[i]);
+                grabGrid(rank, std::string("D") + c[i], FC.D_[i]);
+                for(size_t p = 0; p < FC.lorP_[i].size(); ++p)
+                {
+                    grabGrid(rank, std::string("P") + c[i] + std::to_string(p), FC.lorP_[i][p]);
+                    grabGrid(rank, std::string("pP") + c[i] + std::to_string(p), FC.prevLorP_[i][p]);
+                }
+            }
+        }
+        if(opt.output)
+            for(auto& dtc : FC.dtcArr()) dtc->toFile();
+        return;
+    }
 
     parallelFDTDFieldReal FF(IP, gridComm);
     int nSteps = int(std::ceil(IP.tMax_ / IP.dt_));

@@ -185,6 +185,33 @@ def cases():
          I.freq_detector([0.0, 0.02, 0.0], [0.02, 0.0, 0.01], "E_pow", "out/fq/epow", 1.5, 1.0, 4, time_int=2 * DT * 1.0000001, si=True),
          I.freq_detector([0.0, 0.0, 0.02], [0.02, 0.02, 0.0], "Hy", "out/fq/map", 1.5, 1.0, 2, time_int=DT * 1.0000001, output_map=True)],
         [I.flux("out/fq/box", [0.0, 0.0, 0.0], [0.06, 0.06, 0.06], 1.5, 1.0, 3)]))
+    # ---- Bloch-periodic runs: a k-point switches the reference to complex fields (parallelFDTDFieldCplx); the pulse is complex too.  3-D with a
+    # Lorentz film and CPML in z, k along x; 3-D periodic on all faces with a k-point in every direction (edges, corners); 2-D TM Drude rod,
+    # 2-D TE Lorentz block ----
+    def _bloch(cfg, k):
+        cfg = _short_pulse(cfg)
+        cfg["CompCell"]["PBC"] = True
+        cfg["CompCell"]["k-point"] = list(k)
+        return cfg
+    c["cplx3d"] = _bloch(I.config(
+        I.comp_cell([21 / RES, 17 / RES, 25 / RES], RES, 100 * DT - 0.5 * DT, "Ex", pbc=True), I.pml([0.0, 0.0, 6 / RES]),
+        [I.normal_source("Ex", [0.0, 0.0, 0.07], [0.21, 0.17, 0.0], [I.gaussian_pulse(1.5, 1.0)]),
+         I.normal_source("Ez", [0.09, -0.07, -0.02], [0, 0, 0], [I.gaussian_pulse(1.2, 1.0)])],
+        [I.block([0.3, 0.3, 0.04], [0.0, 0.0, -0.02], eps=2.0, pols=[I.lorentz_pole(1.2, 0.1, 2.0), I.lorentz_pole(0.5, 0.05, 3.0)]),
+         I.block([0.06, 0.05, 0.05], [0.09, 0.02, 0.04], eps=3.0)],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Ex", "out/c3/dtc", time_int=DT * 1.0000001)]), [0.7, 0.0, 0.0])
+    c["cplx3d_all"] = _bloch(I.config(
+        I.comp_cell([15 / RES, 19 / RES, 13 / RES], RES, 90 * DT - 0.5 * DT, "Ex", pbc=True), I.pml([0.0, 0.0, 0.0]),
+        [I.normal_source("Ey", [0.06, 0.08, -0.05], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
+        [I.sphere(0.05, [-0.06, -0.08, 0.05], eps=2.5, pols=[I.lorentz_pole(0.7, 0.2, 1.0)])],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Ey", "out/c3a/dtc", time_int=DT * 1.0000001)]), [0.4, -0.3, 0.6])
+    tm = I.c2_tm_drude(n=63, steps=160, pml_cells=8, rod=(20, 6), nfreq=0, out="out/ctm")
+    tm["PML"]["thickness"] = [0.0, 8 / RES, 0.0]
+    c["cplx_tm"] = _bloch(tm, [0.5, 0.0, 0.0])
+    te = I.c1_te_vacuum(n=47, steps=160, pml_cells=8, out="out/cte")
+    te["PML"]["thickness"] = [8 / RES, 0.0, 0.0]
+    te["ObjectList"] = [I.block([0.1, 1.0, 0.0], [0.08, 0.0, 0.0], eps=2.2, pols=[I.lorentz_pole(0.8, 0.1, 2.0)])]
+    c["cplx_te"] = _bloch(te, [0.0, -0.6, 0.0])
     return c
 
 

@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
         L.oracle_step_n.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_step_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_set_periodic.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_pair_step_n.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_add_tfsf_surface.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_step_n_tfsf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
         L.oracle_add_dft.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
@@ -118,10 +119,12 @@ def _ptr(a: np.ndarray):
 class OracleSim:
     """The oracle configured from a plan (the same inputs the C ABI gets)."""
 
-    def __init__(self, plan: P.Plan):
+    def __init__(self, plan: P.Plan, _part: str = "re"):
         L = lib()
         self.plan = plan
         self._keep = []
+        self.imag = None
+        self._part = _part
         g = grid_desc(plan)
         self.h = L.oracle_create(C.byref(g))
         if not self.h:
@@ -149,10 +152,14 @@ class OracleSim:
             from chiml_b200 import capi
             d = capi.tfsf_surface(t, self._keep)
             self._chk(L.oracle_add_tfsf_surface(self.h, C.byref(d)))
-        for comp, w in sorted(plan.periodic.items()):
-            self._chk(L.oracle_set_periodic(self.h, comp, (C.c_int32 * 7)(*w)))
+        if not plan.cplx:
+            for comp, w in sorted(plan.periodic.items()):
+                self._chk(L.oracle_set_periodic(self.h, comp, (C.c_int32 * 7)(*w)))
         self._chk(L.oracle_commit(self.h))
         self.steps_done = 0
+        if plan.cplx and _part == "re":
+            # complex fields: a second simulation over the same lists holds the imaginary parts; the pair is stepped through this one
+            self.imag = OracleSim(plan, _part="im")
 
     @staticmethod
     def _chk(rc):
@@ -167,10 +174,31 @@ class OracleSim:
             amp[:len(seg), q] = seg
         return amp
 
+    def src_amp_im(self, start: int, n: int) -> np.ndarray:
+        ns = len(self.plan.sources)
+        amp = np.zeros((n, max(ns, 1)), dtype=np.float64)
+        for q, s in enumerate(self.plan.sources):
+            seg = s.amp_im[start:start + n]
+            amp[:len(seg), q] = seg
+        return amp
+
     def step_n(self, n: int, nthreads: int = 1, amp: np.ndarray | None = None) -> None:
         if amp is None:
             amp = self.src_amp(self.steps_done, n)
         amp = np.ascontiguousarray(amp, dtype=np.float64)
+        if self.plan.cplx:
+            assert self.imag is not None, "the imaginary part of a complex-field pair is stepped through the real part"
+            amp_im = np.ascontiguousarray(self.src_amp_im(self.steps_done, n))
+            wraps = (C.c_int32 * 42)()
+            has = (C.c_int * 6)()
+            for comp, w in self.plan.periodic.items():
+                wraps[7 * comp:7 * comp + 7] = w
+                has[comp] = 1
+            k = (C.c_double * 3)(*self.plan.k_point)
+            self._chk(lib().oracle_pair_step_n(self.h, self.imag.h, n, _ptr(amp), _ptr(amp_im), wraps, has, k))
+            self.steps_done += n
+            self.imag.steps_done += n
+            return
         if self.plan.tfsf:
             from chiml_b200 import capi
             tw = np.ascontiguousarray(P.dft_twiddles(self.plan, self.steps_done, n)) if self.plan.dfts else None
@@ -241,6 +269,9 @@ class OracleSim:
         return lib().oracle_n_poles(self.h)
 
     def close(self):
+        if self.imag is not None:
+            self.imag.close()
+            self.imag = None
         if self.h:
             lib().oracle_destroy(self.h)
             self.h = None

@@ -22,6 +22,8 @@ FILES = {"te_vacuum": {"out/te/dtc_field_0.dat": "dtc_field_0.dat"},
          # frequency detectors (field, SI power over three fields, map output) beside a flux box: DFT sets on the GPU, files by the host
          "freq3d": {"out/fq/ez_field_1.dat": "ez_field_1.dat", "out/fq/epow_field_2.dat": "epow_field_2.dat", "out/fq/box.dat": "box.dat",
                     "out/fq/map_field_3.dat.1.000000": "map_field_3.dat.1.000000", "out/fq/map_field_3.dat.2.000000": "map_field_3.dat.2.000000"},
+         # Bloch-periodic runs (k-point != 0, complex fields): two real field sets on the device, coupled by k_wrap_bloch
+         "cplx3d": {"out/c3/dtc_field_0.dat": "dtc_field_0.dat"}, "cplx_tm": {"out/ctm/dtc_field_0.dat": "dtc_field_0.dat"},
          "vac3d_bin": {"out/vb/dtc_field_0.dat": "dtc_field_0.dat", "out/vb/dtc_field_1.dat": "dtc_field_1.dat"}}
 
 

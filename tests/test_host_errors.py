@@ -53,8 +53,7 @@ def test_detector_outside_cell(tmp_path):
 
 @pytest.mark.parametrize("mutate,needle", [
     (lambda c: c.__setitem__("TFSF", [{"dummy": 1}]), "TFSF sources are outside the covered hot path"),
-    (lambda c: (c["CompCell"].__setitem__("PBC", True), c["CompCell"].__setitem__("k-point", [0.3, 0.0, 0.0])), "complex-field (Bloch-periodic, k-point != 0) runs are outside the covered hot path"),
-    (lambda c: c["CompCell"].__setitem__("cplxFields", True), "complex-field"),
+    (lambda c: c["CompCell"].__setitem__("cplxFields", True), "complex fields without periodic boundaries"),
     (lambda c: c["ObjectList"].append(dict(I.block([0.1, 0.1, 0.0], [0, 0, 0]), mu=2.0)), "magnetic"),
 ])
 def test_out_of_scope_inputs_fail_loudly(mutate, needle, tmp_path):

@@ -22,6 +22,8 @@ def load_expect(case: str):
 def state_array(sim, name: str):
     """Fetch the array the reference dump calls `name` (oracle/ref_driver.cpp grabGrid names) from an
     OracleSim or a GpuSim (both expose field / pole / ordip_pole)."""
+    if name.endswith("_im"):
+        return state_array(sim.imag, name[:-3])          # complex fields: the imaginary part is the second simulation of the pair
     if name in P.FIELD_NAMES:
         return sim.field(P.FIELD_NAMES.index(name))
     if name.startswith("dft"):

@@ -14,6 +14,11 @@ def diff(a: P.Plan, b: P.Plan, verbose=True):
               "n_lor_poles", "n_ordip_poles", "t_max"):
         if getattr(a, k) != getattr(b, k):
             bad.append(f"grid.{k}: {getattr(a, k)} != {getattr(b, k)}")
+    if a.cplx != b.cplx or tuple(a.k_point) != tuple(b.k_point):
+        bad.append(f"complex: {a.cplx} {a.k_point} != {b.cplx} {b.k_point}")
+    for q, (sa, sb) in enumerate(zip(a.sources, b.sources)):
+        if (sa.amp_im is None) != (sb.amp_im is None) or (sa.amp_im is not None and np.asarray(sa.amp_im).tobytes() != np.asarray(sb.amp_im).tobytes()):
+            bad.append(f"source {q}: imaginary amplitudes differ")
     if a.periodic != b.periodic:
         bad.append(f"periodic: {a.periodic} != {b.periodic}")
     for key in sorted(set(a.lists) | set(b.lists)):
