@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_set_march", "chiml_gpu_set_ordip_pole_count", "chiml_gpu_reserve_steps", "chiml_gpu_consume_detector",
     "chiml_gpu_consume_population", "chiml_gpu_set_persistent", "chiml_gpu_set_periodic", "chiml_gpu_add_tfsf_surface",
     "chiml_gpu_step_n_tfsf", "chiml_gpu_bind_imag", "chiml_gpu_step_n_cplx",
+    "chiml_gpu_set_magnetic", "chiml_gpu_set_object_magnetic", "chiml_gpu_download_mag_pole",
 ]
 
 
@@ -174,6 +175,9 @@ def lib() -> C.CDLL:
     L.chiml_gpu_halo_export.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.chiml_gpu_halo_bind.argtypes = [vp, C.c_char_p, sz, C.c_char_p, sz]
     L.chiml_gpu_set_periodic.argtypes = [vp, i, vp]
+    L.chiml_gpu_set_magnetic.argtypes = [vp, i, i]
+    L.chiml_gpu_set_object_magnetic.argtypes = [vp, i, i, vp, vp, vp]
+    L.chiml_gpu_download_mag_pole.argtypes = [vp, i, i, i, vp]
     L.chiml_gpu_bind_imag.argtypes = [vp, vp, vp]
     L.chiml_gpu_step_n_cplx.argtypes = [vp, i, vp, vp]
     L.chiml_gpu_add_tfsf_surface.argtypes = [vp, C.POINTER(TfsfSurface)]
@@ -228,12 +232,17 @@ class GpuSim:
         self.steps_done = 0
         self.det_slots = []
         try:
+            if plan.has_B:
+                self._chk(L.chiml_gpu_set_magnetic(self.h, plan.has_B, plan.pml_on_B))
             for (kind, comp), runs in plan.lists.items():
                 runs = np.ascontiguousarray(runs, dtype=P.RUN_DTYPE)
                 self._chk(L.chiml_gpu_set_update_list(self.h, kind, comp, _ptr(runs), len(runs)))
             for o in plan.objects:
                 a, x, gm, dp = (np.ascontiguousarray(v, dtype=np.float64) for v in (o.alpha, o.xi, o.gamma, o.dip))
                 self._chk(L.chiml_gpu_set_object(self.h, o.obj, o.npoles, _ptr(a), _ptr(x), _ptr(gm), o.use_or_dip, _ptr(dp)))
+            for obj, (a, x, gm) in sorted(plan.mag_objects.items()):
+                a, x, gm = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, x, gm))
+                self._chk(L.chiml_gpu_set_object_magnetic(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm)))
             for c in plan.cpml:
                 psi = np.ascontiguousarray(c.psi, dtype=P.PSI_DTYPE)
                 grid = np.ascontiguousarray(c.grid, dtype=P.GRIDP_DTYPE)
@@ -359,6 +368,11 @@ class GpuSim:
     def set_pole(self, comp: int, pole: int, prev: int, a: np.ndarray) -> None:
         a = np.ascontiguousarray(a, dtype=np.float64)
         self._chk(lib().chiml_gpu_upload_pole(self.h, comp, pole, prev, _ptr(a)))
+
+    def mag_pole(self, comp: int, pole: int, prev: int = 0) -> np.ndarray:
+        out = np.empty(self._shape(), dtype=np.float64)
+        self._chk(lib().chiml_gpu_download_mag_pole(self.h, comp, pole, prev, _ptr(out)))
+        return out
 
     def ordip_pole(self, comp: int, pole: int, prev: int = 0) -> np.ndarray:
         out = np.empty(self._shape(), dtype=np.float64)

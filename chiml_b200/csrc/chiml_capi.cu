@@ -32,6 +32,7 @@ static int fail(ChimlCtx* ctx, int code, const std::string& msg) { ctx->err = ms
 static bool field_exists(const ChimlCtx* ctx, int f)
 {
     const int c = f % 3;
+    if(f >= CHIML_BX) return ctx->has_B && field_exists(ctx, CHIML_HX + c);       // B_[c] beside H_[c] (magnetic-dispersive media)
     const bool isH = f >= 3 && f < 6;
     if(f >= 6 && !ctx->g.has_D) return false;
     if(ctx->g.mode == CHIML_MODE_3D) return true;
@@ -136,11 +137,11 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
             cudaFree(pp.d_F); cudaFree(pp.d_b); cudaFree(pp.d_c); cudaFree(pp.d_cmap); cudaFree(pp.d_psi);
         }
     }
-    for(int c = 0; c < 3; ++c)
+    for(int c = 0; c < 6; ++c)
     {
         cudaFree(ctx->span[c].d_xmin); cudaFree(ctx->span[c].d_xmax); cudaFree(ctx->span[c].d_base); cudaFree(ctx->span[c].d_rows);
         for(int p = 0; p < MAX_POLES; ++p)
-            for(int k = 0; k < 2; ++k) { cudaFree(ctx->d_P[c][p][k]); cudaFree(ctx->d_oP[c][p][k]); }
+            for(int k = 0; k < 2; ++k) { cudaFree(ctx->d_P[c][p][k]); if(c < 3) cudaFree(ctx->d_oP[c][p][k]); }
     }
     cudaFree(ctx->d_info_node); cudaFree(ctx->d_cls_node);
     cudaFree(ctx->span_node.d_xmin); cudaFree(ctx->span_node.d_xmax); cudaFree(ctx->span_node.d_base); cudaFree(ctx->span_node.d_rows);
@@ -176,7 +177,8 @@ int chiml_gpu_set_update_list(ChimlCtx* ctx, int kind, int comp, const ChimlRun*
     if(!ctx) return CHIML_ERR_ARG;
     if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_update_list after commit");
     if(kind < 0 || kind > 4 || comp < 0 || comp > 5 || (n && !runs)) return fail(ctx, CHIML_ERR_ARG, "set_update_list: bad kind/comp");
-    if(kind != CHIML_LIST_U && comp > 2 && n) return fail(ctx, CHIML_ERR_UNSUPPORTED, "magnetic dispersive lists (upB_/upLorB_) are outside the covered hot path");
+    if(kind != CHIML_LIST_U && comp > 2 && n && !(ctx->has_B && (kind == CHIML_LIST_D || kind == CHIML_LIST_LORD)))
+        return fail(ctx, CHIML_ERR_UNSUPPORTED, "magnetic lists need chiml_gpu_set_magnetic(has_B = 1) first (upB_ / upLorB_); magnetic oriented-dipole lists are outside the covered hot path");
     const long ncell = (long)ctx->nlogical;
     for(size_t i = 0; i < n; ++i)
     {
@@ -212,6 +214,29 @@ int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global)
     if(n_poles_global > MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_ordip_pole_count: more than 12 poles per object");
     ctx->nordip_global = n_poles_global;
     return CHIML_OK;
+}
+
+int chiml_gpu_set_magnetic(ChimlCtx* ctx, int has_B, int pml_on_B)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_magnetic after commit");
+    if(pml_on_B && !has_B) return fail(ctx, CHIML_ERR_ARG, "set_magnetic: the CPML cannot act on B without B grids");
+    if(has_B && ctx->g.nranks > 1) return fail(ctx, CHIML_ERR_UNSUPPORTED, "magnetic-dispersive media are covered for single-slab runs only");
+    ctx->has_B = has_B ? 1 : 0; ctx->pml_on_B = pml_on_B ? 1 : 0;
+    return 0;
+}
+
+int chiml_gpu_set_object_magnetic(ChimlCtx* ctx, int obj, int npoles, const double* alpha, const double* xi, const double* gamma)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_object_magnetic after commit");
+    if(obj < 0 || obj >= (int)ctx->objs.size()) return fail(ctx, CHIML_ERR_ARG, "set_object_magnetic: object index out of range");
+    if(npoles < 0 || npoles > MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_object_magnetic: more poles than MAX_POLES");
+    if(npoles > 0 && (!alpha || !xi || !gamma)) return fail(ctx, CHIML_ERR_ARG, "set_object_magnetic: NULL constant array");
+    HostObj& o = ctx->objs[obj];
+    o.nmag = npoles;
+    o.malpha.assign(alpha, alpha + npoles); o.mxi.assign(xi, xi + npoles); o.mgamma.assign(gamma, gamma + npoles);
+    return 0;
 }
 
 int chiml_gpu_add_tfsf_surface(ChimlCtx* ctx, const ChimlTfsfSurface* t)
@@ -448,13 +473,20 @@ struct ClassBuilder
     std::vector<ClassEntry> entries;
     ClassBuilder() { ClassEntry z; std::memset(&z, 0, sizeof(z)); entries.push_back(z); }
     // returns 0 on overflow
-    int get(const ChimlRun& r, const HostObj& o, bool withPoles)
+    // magnetic: the run belongs to an H component: its poles are the object's magnetic ones (magAlpha, magXi, magGamma)
+    int get(const ChimlRun& r, const HostObj& o, bool withPoles, bool magnetic = false)
     {
         ClassKey k;
         k.pf1 = r.pf[1]; k.pf2 = r.pf[2]; k.eps = r.pf[3];
-        k.npoles = withPoles ? o.npoles : 0;
-        k.ordip = withPoles ? o.use_or_dip : 0;
-        if(withPoles)
+        k.npoles = withPoles ? (magnetic ? o.nmag : o.npoles) : 0;
+        k.ordip = (withPoles && !magnetic) ? o.use_or_dip : 0;
+        if(withPoles && magnetic)
+        {
+            k.consts = o.malpha;
+            k.consts.insert(k.consts.end(), o.mxi.begin(), o.mxi.end());
+            k.consts.insert(k.consts.end(), o.mgamma.begin(), o.mgamma.end());
+        }
+        else if(withPoles)
         {
             k.consts = o.alpha;
             k.consts.insert(k.consts.end(), o.xi.begin(), o.xi.end());
@@ -470,6 +502,7 @@ struct ClassBuilder
         e.npoles = k.npoles;
         for(int p = 0; p < k.npoles; ++p)
         {
+            if(magnetic) { e.alpha[p] = o.malpha[p]; e.xi[p] = o.mxi[p]; e.gamma[p] = o.mgamma[p]; continue; }
             e.alpha[p] = o.alpha[p]; e.xi[p] = o.xi[p]; e.gamma[p] = o.gamma[p];
             for(int q = 0; q < 3; ++q) e.dip[p][q] = o.dip[3 * p + q];
         }
@@ -515,7 +548,7 @@ int paint_lines(ChimlCtx* ctx, const std::vector<int4>& lines, uint16_t flags, u
 }
 
 // per-row x-spans of the runs whose object carries poles
-int build_spans(ChimlCtx* ctx, const std::vector<const std::vector<ChimlRun>*>& lists, bool ordipOnly, SpanTable& sp)
+int build_spans(ChimlCtx* ctx, const std::vector<const std::vector<ChimlRun>*>& lists, bool ordipOnly, SpanTable& sp, bool magnetic = false)
 {
     const size_t nrows = (size_t)ctx->ly * ctx->lz;
     sp.h_xmin.assign(nrows, -1); sp.h_xmax.assign(nrows, -1); sp.h_base.assign(nrows, 0);
@@ -523,7 +556,7 @@ int build_spans(ChimlCtx* ctx, const std::vector<const std::vector<ChimlRun>*>& 
         for(const ChimlRun& r : *l)
         {
             const HostObj& o = ctx->objs[r.obj];
-            if(o.npoles == 0) continue;
+            if((magnetic ? o.nmag : o.npoles) == 0) continue;
             if(ordipOnly && !o.use_or_dip) continue;
             const size_t row = (size_t)(r.ind / ctx->lx);
             const int x0 = r.ind % ctx->lx, x1 = x0 + r.n - 1;
@@ -748,9 +781,9 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         if((rc = dev_alloc(ctx, &ctx->d_info[comp], ctx->nphys))) return rc;
         ClassBuilder cb;
         const bool isE = comp < 3;
-        if(isE && !ctx->g.has_D)
+        if(isE ? !ctx->g.has_D : !ctx->has_B)
             for(int k : {CHIML_LIST_D, CHIML_LIST_LORD, CHIML_LIST_ORDIPD})
-                if(!ctx->lists[k][comp].runs.empty()) return fail(ctx, CHIML_ERR_ARG, "D-type update list given but has_D = 0");
+                if(!ctx->lists[k][comp].runs.empty()) return fail(ctx, CHIML_ERR_ARG, isE ? "D-type update list given but has_D = 0" : "B-type update list given but has_B = 0");
         // stencil offsets must be uniform per component
         bool& haveOff = ctx->have_off[comp];
         struct { int kind; uint16_t flags; bool poles; } plan[4] = {
@@ -781,8 +814,8 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 const HostObj& o = ctx->objs[r.obj];
                 // E-side D-type runs of isotropic objects carry the object's poles in their class (so that the
                 // D-run and the LorD-run of one cell agree); oriented-dipole objects keep theirs on the node grid
-                const bool usePoles = isE && pl.poles && !o.use_or_dip;
-                int id = cb.get(r, o, usePoles);
+                const bool usePoles = isE ? (pl.poles && !o.use_or_dip) : (pl.poles && ctx->has_B);
+                int id = cb.get(r, o, usePoles, !isE);
                 if(id == 0) return fail(ctx, CHIML_ERR_UNSUPPORTED, "more than 255 distinct material classes for one field component");
                 cls[e] = (uint8_t)id;
             }
@@ -800,15 +833,16 @@ int chiml_gpu_commit(ChimlCtx* ctx)
     }
     // a D-run and a LorD/OrDipD run covering the same cell must agree on the class byte: the D-run was keyed with poles too
     // --- isotropic pole pools -----------------------------------------------------------------------------
-    for(int c = 0; c < 3; ++c)
+    for(int c = 0; c < 6; ++c)
     {
-        if(!field_exists(ctx, c) || !ctx->g.has_D) continue;
+        if(!field_exists(ctx, c) || (c < 3 ? !ctx->g.has_D : !ctx->has_B)) continue;
         int np = 0;
         for(const ChimlRun& r : ctx->lists[CHIML_LIST_LORD][c].runs)
-            if(!ctx->objs[r.obj].use_or_dip) np = std::max(np, ctx->objs[r.obj].npoles);
+            if(c >= 3) np = std::max(np, ctx->objs[r.obj].nmag);
+            else if(!ctx->objs[r.obj].use_or_dip) np = std::max(np, ctx->objs[r.obj].npoles);
         ctx->npoles_comp[c] = np;
         std::vector<const std::vector<ChimlRun>*> ls = {&ctx->lists[CHIML_LIST_LORD][c].runs};
-        if((rc = build_spans(ctx, ls, false, ctx->span[c]))) return rc;
+        if((rc = build_spans(ctx, ls, false, ctx->span[c], c >= 3))) return rc;
         for(int p = 0; p < np; ++p)
             for(int k = 0; k < 2; ++k)
                 if((rc = dev_alloc(ctx, &ctx->d_P[c][p][k], (size_t)ctx->span[c].total))) return rc;
@@ -961,6 +995,9 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                         }
                         uniform = false; continue;
                     }
+                    // magnetic-dispersive cells (B targets, magnetic poles, B -> H) are worked on by the per-cell kernel only
+                    if(fam == 1)
+                        for(const TileVal& tv : vals[c]) if(tv.info & (F_ISD | F_D2E)) uniform = false;
                 }
                 if(!uniform) { lists[2].push_back(rec); listBytes[2] += ts.bytes; continue; }
                 const int per = rectangles_per_record(vals);
@@ -1207,7 +1244,7 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
 {
     std::memset(&a, 0, sizeof(a));
     a.lx = ctx->lx; a.ly = ctx->ly; a.lz = ctx->lz; a.px = ctx->px;
-    a.pml_on_D = ctx->g.pml_on_D;
+    a.pml_on_D = isE ? ctx->g.pml_on_D : ctx->pml_on_B;       // (for the H family: the CPML acts on B)
     a.tmaps = reinterpret_cast<const unsigned char*>(ctx->d_tmaps);
     a.nsp_xmin = ctx->span_node.d_xmin; a.nsp_xmax = ctx->span_node.d_xmax; a.nsp_base = ctx->span_node.d_base;
     const int cur = ctx->pcur, prv = 1 - ctx->pcur;
@@ -1221,7 +1258,7 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
         ca.cls = ctx->d_cls[comp];
         ca.pf = ctx->d_pf[comp];
         ca.U = ctx->d_field[comp];
-        ca.D = isE ? ctx->d_field[CHIML_DX + i] : nullptr;
+        ca.D = isE ? ctx->d_field[CHIML_DX + i] : (ctx->has_B ? ctx->d_field[CHIML_BX + i] : nullptr);
         const int base = isE ? CHIML_HX : CHIML_EX;
         ca.Vj = ctx->d_field[base + (i + 1) % 3];
         ca.Vk = ctx->d_field[base + (i + 2) % 3];
@@ -1236,6 +1273,11 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
             if(!pp.present) continue;
             pa.F = pp.d_F; pa.b = pp.d_b; pa.c = pp.d_c; pa.cmap = pp.d_cmap; pa.psi = pp.d_psi;
             pa.Db = pp.Db; pa.psi_pitch = pp.psi_pitch; pa.axis = pp.axis; pa.nact = pp.nact; pa.has_psi = pp.has_psi;
+        }
+        if(!isE && ctx->has_B)
+        {
+            ca.sp_xmin = ctx->span[3 + i].d_xmin; ca.sp_base = ctx->span[3 + i].d_base;
+            for(int p = 0; p < MAX_POLES; ++p) { ca.Pcur[p] = ctx->d_P[3 + i][p][cur]; ca.Pnew[p] = ctx->d_P[3 + i][p][prv]; }
         }
         if(isE)
         {
@@ -1302,7 +1344,14 @@ void launch_family_mode(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int 
         if(twoD) k_uniform_rows<IS_E, MODE><<<nblk(count[1]), dim3(blk.x, blk.y, 3), 0, ctx->stream>>>(a, tl, count[1]);
         else k_uniform<IS_E, MODE><<<count[1] * zsplit * 3, dim3(block.x, block.y / zsplit, 1), 0, ctx->stream>>>(a, tl);
     }
-    if(count[2]) { LaunchScope ls(ctx, k0 + 2); k_general<IS_E, MODE, IS_E><<<nblk(count[2]), dim3(blk.x, blk.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2], count[2]); }
+    if(count[2])
+    {
+        LaunchScope ls(ctx, k0 + 2);
+        if(!IS_E && ctx->has_B)       // magnetic-dispersive media: the H family with B targets, magnetic poles and B -> H
+            k_general<IS_E, MODE, IS_E, true><<<nblk(count[2]), dim3(blk.x, blk.y, 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2], count[2]);
+        else
+            k_general<IS_E, MODE, IS_E><<<nblk(count[2]), dim3(blk.x, blk.y, IS_E ? 3 : 1), 0, ctx->stream>>>(a, (const TileRec*)ctx->d_tiles[fam][2] + first[2], count[2]);
+    }
 }
 template <bool IS_E>
 void launch_family(ChimlCtx* ctx, const StepArgs& a, const dim3 block, int part)
@@ -1432,8 +1481,10 @@ void launch_sources(ChimlCtx* ctx, long long k, int nsrc, int part)
             const long n = (long)s.sz[0] * sy * s.sz[2];
             if(n <= 0) continue;
             LaunchScope ls(ctx, K_SOURCE);
+            // (a source into H on a cell of upLorB_ is overwritten by B2H in the reference, which runs after the sources: skipped there)
             k_source<<<(unsigned)std::min<long>((n + 255) / 256, 2048), 256, 0, ctx->stream>>>(
-                ctx->d_field[s.field], s.loc[0], s.loc[2], seg[i].y0, s.sz[0], s.sz[2], sy, ctx->lz, ctx->px, ctx->d_src_amp + k * nsrc + q);
+                ctx->d_field[s.field], s.loc[0], s.loc[2], seg[i].y0, s.sz[0], s.sz[2], sy, ctx->lz, ctx->px, ctx->d_src_amp + k * nsrc + q,
+                (isH && ctx->has_B) ? ctx->d_info[s.field] : nullptr);
         }
     }
 }
@@ -1791,6 +1842,7 @@ bool persist_eligible(ChimlCtx* ctx)
 {
     if(ctx->persist_mode == 0 || std::getenv("CHIML_B200_NO_PERSIST")) return false;
     if(ctx->imag || ctx->is_imag_part) return false;
+    if(ctx->has_B) return false;              // B / M cells take the launch path
     if(!ctx->tfsf.empty()) return false;      // the surface waves are separate launches
     if(ctx->g.mode == CHIML_MODE_3D || ctx->g.nranks > 1 || !ctx->emitters.empty() || ctx->d_info_node) return false;
     if((int)ctx->detectors.size() > P2D_MAX_DET || (int)ctx->dfts.size() > P2D_MAX_DFT) return false;
@@ -2336,7 +2388,7 @@ static int pole_xfer(ChimlCtx* ctx, int comp, int pole, int prev, double* host, 
 {
     if(!ctx || (!host && !hostIn)) return CHIML_ERR_ARG;
     if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "pole access before commit");
-    if(comp < 0 || comp > 2 || pole < 0 || pole >= MAX_POLES) return fail(ctx, CHIML_ERR_ARG, "pole access: bad comp/pole");
+    if(comp < 0 || comp > 5 || pole < 0 || pole >= MAX_POLES) return fail(ctx, CHIML_ERR_ARG, "pole access: bad comp/pole");
     CK(cudaSetDevice(ctx->device));
     const SpanTable& sp = ctx->span[comp];
     double* pool = ctx->d_P[comp][pole][prev ? 1 - ctx->pcur : ctx->pcur];
@@ -2356,8 +2408,9 @@ static int pole_xfer(ChimlCtx* ctx, int comp, int pole, int prev, double* host, 
     return CHIML_OK;
 }
 
-int chiml_gpu_download_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host) { return pole_xfer(ctx, comp, pole, prev, host, nullptr); }
-int chiml_gpu_upload_pole(ChimlCtx* ctx, int comp, int pole, int prev, const double* host) { return pole_xfer(ctx, comp, pole, prev, nullptr, host); }
+int chiml_gpu_download_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host) { return (comp < 0 || comp > 2) ? CHIML_ERR_ARG : pole_xfer(ctx, comp, pole, prev, host, nullptr); }
+int chiml_gpu_upload_pole(ChimlCtx* ctx, int comp, int pole, int prev, const double* host) { return (comp < 0 || comp > 2) ? CHIML_ERR_ARG : pole_xfer(ctx, comp, pole, prev, nullptr, host); }
+int chiml_gpu_download_mag_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host) { return (comp < 0 || comp > 2) ? CHIML_ERR_ARG : pole_xfer(ctx, 3 + comp, pole, prev, host, nullptr); }
 
 int chiml_gpu_download_ordip_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host)
 {

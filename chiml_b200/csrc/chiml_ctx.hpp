@@ -152,7 +152,7 @@ struct TfsfDev
 
 struct HostList { std::vector<ChimlRun> runs; };
 struct HostPml { int present = 0, has_psi = 0; std::vector<ChimlPsiParams> psi; std::vector<ChimlGridParams> grid; };
-struct HostObj { int npoles = 0, use_or_dip = 0; std::vector<double> alpha, xi, gamma, dip; };
+struct HostObj { int npoles = 0, use_or_dip = 0; std::vector<double> alpha, xi, gamma, dip; int nmag = 0; std::vector<double> malpha, mxi, mgamma; };
 
 } // namespace chiml
 
@@ -187,10 +187,11 @@ struct ChimlCtx
     int ncls[6] = {};
     chiml::PmlPartDev pml[6][2];
 
-    // isotropic poles: per E component pools [pole][cur/prev]
-    chiml::SpanTable span[3];
-    int npoles_comp[3] = {};
-    double* d_P[3][chiml::MAX_POLES][2] = {};
+    // isotropic poles: per component pools [pole][cur/prev]; [0..2] electric (P of Ex..Ez), [3..5] magnetic (M of Hx..Hz, has_B)
+    chiml::SpanTable span[6];
+    int npoles_comp[6] = {};
+    double* d_P[6][chiml::MAX_POLES][2] = {};
+    int has_B = 0, pml_on_B = 0;       // chiml_gpu_set_magnetic
     int pcur = 0;                // which of the two buffers currently holds P (the other holds prevP)
 
     // oriented-dipole poles at nodes

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) k_ordip_poles(const __grid_constant__ Nod
 }
 
 // src->addPul (SOURCE/parallelSourceNormal.cpp:15-37): grid[box] += dt*Re(sum pulse(t)); the product is formed on the host
-__global__ void k_source(double* field, int lx0, int lz0, int ly0, int sx, int sz, int sy, int lz, long px, const double* amp)
+__global__ void k_source(double* field, int lx0, int lz0, int ly0, int sx, int sz, int sy, int lz, long px, const double* amp, const uint16_t* skipInfo = nullptr)
 {
     const long n = (long)sx * sz * sy;
     const double av = *amp;
@@ -216,6 +216,7 @@ __global__ void k_source(double* field, int lx0, int lz0, int ly0, int sx, int s
         const int iz = (int)((i / sx) % sz);
         const int iy = (int)(i / ((long)sx * sz));
         const long r = (lx0 + ix) + px * ((lz0 + iz) + (long)lz * (ly0 + iy));
+        if(skipInfo && (skipInfo[r] & F_D2E)) continue;       // H = (B - sum M) / mu_inf has already replaced what the reference would add to
         field[r] = da(field[r], av);
     }
 }

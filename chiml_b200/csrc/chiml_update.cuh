@@ -34,14 +34,15 @@ template <bool IS_E, int MODE> __host__ __device__ constexpr bool has_other(int 
 // the four stencil values of TwoCompCurl, which are also the stencil values of the two CPML parts (part 0:
 // grid_k, derivative along j = (C+1)%3; part 1: grid_j, derivative along k = (C+2)%3).
 // Returns true when U[r] must be written back.
-template <bool IS_E, int MODE, int C>
+// DP: the family has D-like arrays and pole pools (always for E; for H only with magnetic-dispersive media: B, M, mu_inf)
+template <bool IS_E, int MODE, int C, bool DP = IS_E>
 __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& ca, const unsigned info, double& u,
                                             const double vj_r, const double vj_n, const double vk_r, const double vk_n,
                                             const long r, const long row, const int x, const int y, const int z)
 {
     if(info == 0) return false;
     // D is needed by almost every cell of a general E tile: fetch it before anything that depends on the class table
-    const double dIn = (IS_E && ca.D) ? ca.D[r] : 0.0;
+    const double dIn = (DP && ca.D) ? ca.D[r] : 0.0;
     const ClassEntry& ce = ca.cls[info & CLS_MASK];
     constexpr bool HAS_VJ = has_other<IS_E, MODE>((C + 1) % 3);
     constexpr bool HAS_VK = has_other<IS_E, MODE>((C + 2) % 3);
@@ -51,7 +52,7 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
 
     // updatePolE, isotropic poles (parallelFDTDField.hpp:1355-1361 -> UTIL/FDTD_up_eq.cpp:435-446):
     // tmp = P; P = alpha*P; P += xi*Pprev; P += gamma*E^n; Pprev = tmp
-    if(IS_E && (info & F_D2E))
+    if(DP && (info & F_D2E))
     {
         np = ce.npoles;
         if(np > 0)
@@ -73,15 +74,15 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
     }
 
     const bool pmlCell = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
-    const bool pmlOnD = IS_E && a.pml_on_D;
-    const bool needD = IS_E && ((info & (F_ISD | F_D2E | F_ORD2E)) || (pmlOnD && pmlCell));
+    const bool pmlOnD = DP && a.pml_on_D;
+    const bool needD = DP && ((info & (F_ISD | F_D2E | F_ORD2E)) || (pmlOnD && pmlCell));
     double dv = needD ? dIn : 0.0;
     bool dDirty = false;
 
     // updateD / updateE / updateH: TwoCompCurl, OneCompCurlJ, OneCompCurlK (UTIL/FDTD_up_eq.cpp:10-35)
     if(info & F_CURL)
     {
-        double t = (IS_E && (info & F_ISD)) ? dv : u;
+        double t = (DP && (info & F_ISD)) ? dv : u;
         if(HAS_VJ)
         {
             t = axpy1(t,  ce.pf2, vj_r);
@@ -92,7 +93,7 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
             t = axpy1(t, -ce.pf1, vk_r);
             t = axpy1(t,  ce.pf1, vk_n);
         }
-        if(IS_E && (info & F_ISD)) { dv = t; dDirty = true; } else u = t;
+        if(DP && (info & F_ISD)) { dv = t; dDirty = true; } else u = t;
     }
 
     // parallelCPML<T>::updateGrid (PML/parallelPML.hpp:693-697): part 0 then part 1; each part is
@@ -139,7 +140,7 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
     }
 
     // D2E (parallelFDTDField.hpp:1452-1473)
-    if(IS_E && (info & F_D2E))
+    if(DP && (info & F_D2E))
     {
         // DtoU (UTIL/FDTD_up_eq.cpp:838-848): E = D; E *= 1/eps; E += (-1/eps) P_p for every pole grid
         u = dm(ce.inv_eps, dv);
@@ -992,20 +993,20 @@ __global__ void __launch_bounds__(32 * ROWS_2D * 3) k_uniform_rows(const __grid_
 // ---------------------------------------------------------------------------------------------------
 // k_general: everything else, per cell
 // ---------------------------------------------------------------------------------------------------
-template <bool IS_E, int MODE, int C>
+template <bool IS_E, int MODE, int C, bool DP = IS_E>
 __device__ __forceinline__ void general_pair(const StepArgs& a, double2 u, const double2 vj, const double2 nj, const double2 vk, const double2 nk,
                                              const long r, const long row, const int x, const int y, const int z)
 {
     if(!has_own<IS_E, MODE>(C)) return;
     const CompArgs& ca = a.c[C];
     const ushort2 info = *reinterpret_cast<const ushort2*>(ca.info + r);
-    const bool w0 = update_cell<IS_E, MODE, C>(a, ca, info.x, u.x, vj.x, nj.x, vk.x, nk.x, r, row, x, y, z);
-    const bool w1 = update_cell<IS_E, MODE, C>(a, ca, info.y, u.y, vj.y, nj.y, vk.y, nk.y, r + 1, row, x + 1, y, z);
+    const bool w0 = update_cell<IS_E, MODE, C, DP>(a, ca, info.x, u.x, vj.x, nj.x, vk.x, nk.x, r, row, x, y, z);
+    const bool w1 = update_cell<IS_E, MODE, C, DP>(a, ca, info.y, u.y, vj.y, nj.y, vk.y, nk.y, r + 1, row, x + 1, y, z);
     store_pair(ca.U + r, u, w0, w1);
 }
 
 // one component per thread (threadIdx.z): the loads of a component do not queue behind the arithmetic of another
-template <bool IS_E, int MODE, int C>
+template <bool IS_E, int MODE, int C, bool DP = IS_E>
 __device__ __forceinline__ void general_comp(const StepArgs& a, const TileRec& t, const int x, const int z)
 {
     if(!has_own<IS_E, MODE>(C)) return;
@@ -1017,10 +1018,10 @@ __device__ __forceinline__ void general_comp(const StepArgs& a, const TileRec& t
     comp_march_init<IS_E, MODE, C>(a, r, plane, carry);
     PairLoads<IS_E, MODE> L;
     comp_march_load<IS_E, MODE, C>(a, r, plane, carry, L);
-    general_pair<IS_E, MODE, C>(a, L.u[C], L.v[(C + 1) % 3], L.nj[C], L.v[(C + 2) % 3], L.nk[C], r, row, x, y, z);
+    general_pair<IS_E, MODE, C, DP>(a, L.u[C], L.v[(C + 1) % 3], L.nj[C], L.v[(C + 2) % 3], L.nk[C], r, row, x, y, z);
 }
 
-template <bool IS_E, int MODE, bool SPLIT>
+template <bool IS_E, int MODE, bool SPLIT, bool DP = IS_E>
 __global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_general(const __grid_constant__ StepArgs a, const TileRec* __restrict__ tiles, const unsigned ntiles)
 {
     unsigned ti; int zl;
@@ -1035,14 +1036,14 @@ __global__ void __launch_bounds__(SPLIT ? 768 : 256, SPLIT ? 1 : 2) k_general(co
         const long r = x + a.px * row;
         PairLoads<IS_E, MODE> L;
         L.load(a, r);
-        general_pair<IS_E, MODE, 0>(a, L.u[0], L.v[1], L.nj[0], L.v[2], L.nk[0], r, row, x, y, z);
-        general_pair<IS_E, MODE, 1>(a, L.u[1], L.v[2], L.nj[1], L.v[0], L.nk[1], r, row, x, y, z);
-        general_pair<IS_E, MODE, 2>(a, L.u[2], L.v[0], L.nj[2], L.v[1], L.nk[2], r, row, x, y, z);
+        general_pair<IS_E, MODE, 0, DP>(a, L.u[0], L.v[1], L.nj[0], L.v[2], L.nk[0], r, row, x, y, z);
+        general_pair<IS_E, MODE, 1, DP>(a, L.u[1], L.v[2], L.nj[1], L.v[0], L.nk[1], r, row, x, y, z);
+        general_pair<IS_E, MODE, 2, DP>(a, L.u[2], L.v[0], L.nj[2], L.v[1], L.nk[2], r, row, x, y, z);
         return;
     }
-    if(threadIdx.z == 0)      general_comp<IS_E, MODE, 0>(a, t, x, z);
-    else if(threadIdx.z == 1) general_comp<IS_E, MODE, 1>(a, t, x, z);
-    else                      general_comp<IS_E, MODE, 2>(a, t, x, z);
+    if(threadIdx.z == 0)      general_comp<IS_E, MODE, 0, DP>(a, t, x, z);
+    else if(threadIdx.z == 1) general_comp<IS_E, MODE, 1, DP>(a, t, x, z);
+    else                      general_comp<IS_E, MODE, 2, DP>(a, t, x, z);
 }
 
 // ---------------------------------------------------------------------------------------------------

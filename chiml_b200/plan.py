@@ -20,7 +20,7 @@ PLAN_VERSION = 1
 
 MODE_TE, MODE_TM, MODE_3D = 0, 1, 2
 LIST_U, LIST_D, LIST_LORD, LIST_ORDIPD, LIST_ORDIPP = 0, 1, 2, 3, 4
-FIELD_NAMES = ["Ex", "Ey", "Ez", "Hx", "Hy", "Hz", "Dx", "Dy", "Dz"]
+FIELD_NAMES = ["Ex", "Ey", "Ez", "Hx", "Hy", "Hz", "Dx", "Dy", "Dz", "Bx", "By", "Bz"]
 
 RUN_DTYPE = np.dtype([("n", "<i4"), ("ind", "<i4"), ("ind_i", "<i4"), ("ind_j", "<i4"), ("ind_k", "<i4"),
                       ("obj", "<i4"), ("pf", "<f8", (4,))])
@@ -164,6 +164,10 @@ class Plan:
     detectors: List[PlanDetector] = field(default_factory=list)
     emitters: List[PlanEmitter] = field(default_factory=list)
     dfts: List[PlanDft] = field(default_factory=list)
+    has_B: int = 0                              # magnetic-dispersive media (record MAGNETIC): B grids exist
+    pml_on_B: int = 0
+    n_mag_poles: int = 0
+    mag_objects: Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray]] = field(default_factory=dict)   # obj -> (magAlpha, magXi, magGamma)
     cplx: bool = False                          # complex fields (record COMPLEX): real and imaginary parts are two field sets over the same lists
     k_point: Tuple[float, float, float] = (0.0, 0.0, 0.0)
     tfsf: List[PlanTfsfSurface] = field(default_factory=list)
@@ -184,6 +188,8 @@ class Plan:
             f = [0, 1, 2, 3, 4, 5]
         if self.has_D:
             f += [6 + c for c in f if c < 3]
+        if self.has_B:
+            f += [9 + (c - 3) for c in f if 3 <= c < 6]
         return f
 
     def get_list(self, kind: int, comp: int) -> np.ndarray:
@@ -242,6 +248,12 @@ def read_plan(path: str) -> Plan:
             freq = np.frombuffer(payload, dtype="<f8", count=nfreq, offset=40).copy()
             lines = np.frombuffer(payload, dtype="<i4", count=2 * nlines, offset=40 + 8 * nfreq).copy().reshape(nlines, 2)
             plan.dfts.append(PlanDft(fld, group, every, nfreq, npts, stride, acc_len, freq, lines))
+        elif tag == "MAGNETIC":
+            plan.has_B, plan.pml_on_B, plan.n_mag_poles, _ = struct.unpack_from("<4i", payload, 0)
+        elif tag == "OBJMAG":
+            obj, np_ = struct.unpack_from("<ii", payload, 0)
+            arrs = [np.frombuffer(payload, dtype="<f8", count=np_, offset=8 + 8 * np_ * k).copy() for k in range(3)]
+            plan.mag_objects[obj] = (arrs[0], arrs[1], arrs[2])
         elif tag == "COMPLEX":
             v = struct.unpack_from("<ii3d", payload, 0)
             plan.cplx = bool(v[0]); plan.k_point = tuple(v[2:5])
@@ -329,6 +341,10 @@ def write_plan(path: str, plan: Plan) -> None:
     for c in plan.cpml:
         out.append(_rec("CPML", struct.pack("<iiiiQQ", c.comp, c.part, c.has_psi, 0, len(c.psi), len(c.grid))
                         + np.ascontiguousarray(c.psi, PSI_DTYPE).tobytes() + np.ascontiguousarray(c.grid, GRIDP_DTYPE).tobytes()))
+    if plan.has_B:
+        out.append(_rec("MAGNETIC", struct.pack("<4i", plan.has_B, plan.pml_on_B, plan.n_mag_poles, 0)))
+        for obj, (a, x, g) in sorted(plan.mag_objects.items()):
+            out.append(_rec("OBJMAG", struct.pack("<ii", obj, len(a)) + np.asarray(a, "<f8").tobytes() + np.asarray(x, "<f8").tobytes() + np.asarray(g, "<f8").tobytes()))
     if plan.cplx:
         out.append(_rec("COMPLEX", struct.pack("<ii3d", 1, 0, *plan.k_point)))
     for s in plan.sources:

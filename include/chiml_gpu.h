@@ -44,7 +44,8 @@ typedef enum ChimlField
     CHIML_EX = 0, CHIML_EY = 1, CHIML_EZ = 2,
     CHIML_HX = 3, CHIML_HY = 4, CHIML_HZ = 5,
     CHIML_DX = 6, CHIML_DY = 7, CHIML_DZ = 8,
-    CHIML_NFIELDS = 9
+    CHIML_BX = 9, CHIML_BY = 10, CHIML_BZ = 11,   /* B_[0..2]: exist after chiml_gpu_set_magnetic(has_B = 1) */
+    CHIML_NFIELDS = 12
 } ChimlField;
 
 /* CompCell.pol / size_z selection of parallelFDTDField.hpp:391,418 */
@@ -177,6 +178,17 @@ int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq,
  * applyBCProcMid on every rank); oriented-dipole media are refused together with it. */
 typedef struct ChimlWrap { int32_t nx, ny, nz, xmax, ymax, zmin, zmax; } ChimlWrap;
 int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* wrap);
+
+/* Magnetic-dispersive media: the B / H / M mirror of the D / E / P path (updateMagH, updateB, B2H of step(), FDTD_MANAGER/parallelFDTDField.hpp:1230,
+ * 1234, 1264; :1328-1333, :1370-1387, :1478-1500).  has_B: B_ grids exist (:403-406, :429-432); pml_on_B: magMatInPML_, the H-side CPML acts on B
+ * (parallelFDTDField.cpp:229-246).  With has_B the H components accept the list kinds CHIML_LIST_D (upB_[c]: curl accumulated into B) and
+ * CHIML_LIST_LORD (upLorB_[c]: magnetic pole update with H^n at the start of the step, then H = (B - sum M) / mu_inf after the H-side CPML and
+ * the sources), comp 3..5.  Magnetic pole constants of an object: Obj::magAlpha() / magXi() / magGamma().  A soft source into H on a cell of
+ * upLorB_ is overwritten by B2H as in the reference.  Chiral media and magnetic oriented dipoles are refused. */
+int chiml_gpu_set_magnetic(ChimlCtx* ctx, int has_B, int pml_on_B);
+int chiml_gpu_set_object_magnetic(ChimlCtx* ctx, int obj, int npoles, const double* alpha, const double* xi, const double* gamma);
+/* magnetic pole state lorM_[c][p] / prevLorM_[c][p] (c = 0..2 for Hx..Hz) expanded to the logical full grid */
+int chiml_gpu_download_mag_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host);
 
 /* Complex fields (Bloch-periodic runs: a k-point switches the reference to parallelFDTDFieldCplx, INPUTS/parallelInputs.cpp:108-112).  Every operator
  * of the step has real coefficients -- the reference's complex BLAS chains multiply by real factors -- so the real and the imaginary parts of all

@@ -99,6 +99,14 @@ typedef struct ChimlPlanTfsfLinesHdr   /* tag "TFSFLINE": header, then n_steps *
 {
     int32_t n_steps, per_step;
 } ChimlPlanTfsfLinesHdr;
+typedef struct ChimlPlanMagnetic       /* tag "MAGNETIC": B_ grids exist / the H-side CPML acts on B (chiml_gpu_set_magnetic) */
+{
+    int32_t has_B, pml_on_B, n_mag_poles /* max over components of lorM_[c].size() */, pad;
+} ChimlPlanMagnetic;
+typedef struct ChimlPlanObjMagHdr      /* tag "OBJMAG  ": header + magAlpha[np] magXi[np] magGamma[np] of object obj */
+{
+    int32_t obj, npoles;
+} ChimlPlanObjMagHdr;
 typedef struct ChimlPlanComplex        /* tag "COMPLEX ": the propagator holds complex fields (Bloch-periodic run, parallelFDTDFieldCplx): every field / psi /
                                           pole array has a real and an imaginary part, coupled only by the phase factors of the periodic wrap copies */
 {

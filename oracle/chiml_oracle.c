@@ -59,6 +59,10 @@ struct OracleSim
     double* oP[3][MAX_POLES];      /* orDipLorP_[c][p] */
     double* oPprev[3][MAX_POLES];  /* prevOrDipLorP_[c][p] */
     double* dipgrid[3][MAX_POLES]; /* dipP_[c][p] (static) */
+    int has_B, pml_on_B, nmag;     /* magnetic-dispersive media: B grids exist, the H-side CPML acts on B, number of lorM_ grids */
+    double* M[3][MAX_POLES];       /* lorM_[c][p] */
+    double* Mprev[3][MAX_POLES];   /* prevLorM_[c][p] */
+    ObjConst* mobj;                /* magnetic pole constants per object (magAlpha, magXi, magGamma) */
     SrcBox src[MAX_SRC];
     int nsrc;
     int committed;
@@ -86,6 +90,7 @@ struct OracleSim
 static int comp_exists(const OracleSim* s, int field)
 {
     int c = field % 3, isH = (field >= 3 && field < 6);
+    if(field >= CHIML_BX) return 0;                 /* B grids are made by oracle_set_magnetic */
     if(field >= 6 && !s->g.has_D) return 0;
     if(s->g.mode == CHIML_MODE_3D) return 1;
     if(s->g.mode == CHIML_MODE_TE) return isH ? (c == 2) : (c != 2);   /* Ex,Ey,Hz (parallelFDTDField.hpp:391-396) */
@@ -140,6 +145,29 @@ int oracle_set_object(OracleSim* s, int obj, int npoles, const double* alpha, co
     return 0;
 }
 
+/* magnetic-dispersive media (include/chiml_gpu.h chiml_gpu_set_magnetic / chiml_gpu_set_object_magnetic) */
+int oracle_set_magnetic(OracleSim* s, int has_B, int pml_on_B)
+{
+    if(!s || s->committed) return CHIML_ERR_STATE;
+    s->has_B = has_B; s->pml_on_B = pml_on_B;
+    if(has_B)
+        for(int c = 0; c < 3; ++c)
+            if(s->f[CHIML_HX + c] && !s->f[CHIML_BX + c]) s->f[CHIML_BX + c] = (double*)calloc(s->ncell, sizeof(double));
+    if(!s->mobj) s->mobj = (ObjConst*)calloc((size_t)(s->g.n_objects > 0 ? s->g.n_objects : 1), sizeof(ObjConst));
+    return 0;
+}
+int oracle_set_object_magnetic(OracleSim* s, int obj, int npoles, const double* alpha, const double* xi, const double* gamma)
+{
+    if(!s || obj < 0 || obj >= s->g.n_objects || npoles < 0 || npoles > MAX_POLES) return CHIML_ERR_ARG;
+    if(!s->mobj) s->mobj = (ObjConst*)calloc((size_t)(s->g.n_objects > 0 ? s->g.n_objects : 1), sizeof(ObjConst));
+    ObjConst* o = &s->mobj[obj];
+    o->npoles = npoles;
+    for(int p = 0; p < npoles; ++p) { o->alpha[p] = alpha[p]; o->xi[p] = xi[p]; o->gamma[p] = gamma[p]; }
+    return 0;
+}
+double* oracle_mag_pole(OracleSim* s, int comp, int pole, int prev) { return (comp < 0 || comp > 2 || pole < 0 || pole >= MAX_POLES) ? NULL : (prev ? s->Mprev[comp][pole] : s->M[comp][pole]); }
+int oracle_n_mag_poles(OracleSim* s) { return s->nmag; }
+
 int oracle_set_cpml(OracleSim* s, int comp, int part, int has_psi, const ChimlPsiParams* psi, size_t npsi, const ChimlGridParams* grid, size_t ngrid)
 {
     if(comp < 0 || comp > 5 || part < 0 || part > 1) return CHIML_ERR_ARG;
@@ -188,6 +216,19 @@ int oracle_commit(OracleSim* s)
             s->oP[c][p] = (double*)calloc(s->ncell, sizeof(double));
             s->oPprev[c][p] = (double*)calloc(s->ncell, sizeof(double));
             s->dipgrid[c][p] = (double*)calloc(s->ncell, sizeof(double));
+        }
+    }
+    /* lorM_ / prevLorM_: as many grids per H component as the largest magnetic pole count of any object */
+    s->nmag = 0;
+    if(s->has_B && s->mobj)
+        for(int o = 0; o < s->g.n_objects; ++o) if(s->mobj[o].npoles > s->nmag) s->nmag = s->mobj[o].npoles;
+    for(int c = 0; c < 3 && s->has_B; ++c)
+    {
+        if(!s->f[CHIML_BX + c]) continue;
+        for(int p = 0; p < s->nmag; ++p)
+        {
+            s->M[c][p] = (double*)calloc(s->ncell, sizeof(double));
+            s->Mprev[c][p] = (double*)calloc(s->ncell, sizeof(double));
         }
     }
     const RunList* nl = &s->up[CHIML_LIST_ORDIPP][0];
@@ -836,11 +877,29 @@ static void step_worker(OracleSim* s, int tid, int nt)
     double* scratch = (double*)malloc((size_t)(6 * lnx + 8) * sizeof(double));
     for(int step = 0; step < s->nsteps; ++step)
     {
-        /* updateH (:1308-1313) */
+        /* updateMagH (:1230, :1370-1387): magnetic poles from H^n, before any H / B update of the step */
+        if(s->has_B)
+        {
+            for(int i = 0; i < 3 && (s->phase_mask & 1); ++i)
+            {
+                if(!s->f[CHIML_HX + i] || !s->f[CHIML_BX + i]) continue;
+                RunList* l = &s->up[CHIML_LIST_LORD][3 + i];
+                SPLIT(l->n, lo, hi);
+                for(size_t e = lo; e < hi; ++e) lor_pol_run(&l->r[e], s->f[CHIML_HX + i], s->M[i], s->Mprev[i], &s->mobj[l->r[e].obj], scratch);
+            }
+            BARRIER();
+        }
+        /* updateB (:1234, :1328-1333) and updateH (:1308-1313) */
         for(int i = 0; i < 3 && (s->phase_mask & 1); ++i)
         {
             double* H = s->f[CHIML_HX + i];
             if(!H) continue;
+            if(s->has_B && s->f[CHIML_BX + i])
+            {
+                RunList* lb = &s->up[CHIML_LIST_D][3 + i];
+                SPLIT(lb->n, lo, hi);
+                for(size_t e = lo; e < hi; ++e) curl_run(&lb->r[e], s->f[CHIML_BX + i], s->f[CHIML_EX + (i + 1) % 3], s->f[CHIML_EX + (i + 2) % 3]);
+            }
             RunList* l = &s->up[CHIML_LIST_U][3 + i];
             SPLIT(l->n, lo, hi);
             for(size_t e = lo; e < hi; ++e) curl_run(&l->r[e], H, s->f[CHIML_EX + (i + 1) % 3], s->f[CHIML_EX + (i + 2) % 3]);
@@ -856,7 +915,7 @@ static void step_worker(OracleSim* s, int tid, int nt)
         BARRIER();
         /* updateHPML_ (:1258-1259) */
         for(int i = 0; i < 3 && (s->phase_mask & 1); ++i)
-            if(s->f[CHIML_HX + i]) pml_component(s, 3 + i, s->f[CHIML_HX + i], tid, nt);
+            if(s->f[CHIML_HX + i]) pml_component(s, 3 + i, (s->has_B && s->pml_on_B) ? s->f[CHIML_BX + i] : s->f[CHIML_HX + i], tid, nt);   /* on B when magMatInPML_ (parallelFDTDField.cpp:229-246) */
         /* src->addPul (:1261-1262, SOURCE/parallelSourceNormal.cpp:15-37): grid[box] += dt*Re(pulse), amp precomputed */
         if(tid == 0 && (s->phase_mask & 1))
         {
@@ -873,6 +932,19 @@ static void step_worker(OracleSim* s, int tid, int nt)
                             G[ind] = G[ind] + amp;
                         }
             }
+        }
+        /* B2H (:1264, :1478-1500): H = B / mu_inf - sum M / mu_inf on the cells of upLorB_, after the sources */
+        if(s->has_B && (s->phase_mask & 1))
+        {
+            BARRIER();
+            for(int i = 0; i < 3; ++i)
+            {
+                if(!s->f[CHIML_HX + i] || !s->f[CHIML_BX + i]) continue;
+                RunList* l = &s->up[CHIML_LIST_LORD][3 + i];
+                SPLIT(l->n, lo, hi);
+                for(size_t e = lo; e < hi; ++e) dtou_run(&l->r[e], s->f[CHIML_BX + i], s->f[CHIML_HX + i], s->M[i], s->nmag);
+            }
+            BARRIER();
         }
         /* applBCH_ (:1267-1269): periodic wrap copies of the H components */
         if(tid == 0 && (s->phase_mask & 1))

@@ -38,6 +38,10 @@ int  oracle_add_source(OracleSim* s, int field, const int32_t loc[3], const int3
 int  oracle_add_emitters(OracleSim* s, const ChimlEmitterDesc* d);
 int  oracle_add_dft(OracleSim* s, int field, int group, int every, int nfreq, int npts, int stride, const ChimlDftLine* lines, size_t nlines, size_t acc_len);
 int  oracle_set_periodic(OracleSim* s, int comp, const ChimlWrap* w);
+int  oracle_set_magnetic(OracleSim* s, int has_B, int pml_on_B);
+int  oracle_set_object_magnetic(OracleSim* s, int obj, int npoles, const double* alpha, const double* xi, const double* gamma);
+double* oracle_mag_pole(OracleSim* s, int comp, int pole, int prev);
+int  oracle_n_mag_poles(OracleSim* s);
 int  oracle_add_tfsf_surface(OracleSim* s, const ChimlTfsfSurface* t);
 int  oracle_commit(OracleSim* s);
 /* nthreads > 1: rows of every list are split over POSIX threads (same arithmetic per cell) */

@@ -349,12 +349,32 @@ template <class FFT> static void writePlan(const std::string& fname, FFT& FF, co
     }
 
     putTfsfRecords(out, FF);
-    if(FF.magMatInPML_) throw std::runtime_error("plan dump: magnetic material in the PML is outside the covered hot path");
+    // magnetic-dispersive media: B grids, the H-side CPML on B, magnetic pole constants per object
+    const bool hasB = bool(FF.B_[0]) || bool(FF.B_[2]);
+    if(hasB)
+    {
+        ChimlPlanMagnetic pm; std::memset(&pm, 0, sizeof(pm));
+        pm.has_B = 1; pm.pml_on_B = FF.magMatInPML_ ? 1 : 0; pm.n_mag_poles = int(std::max(FF.lorM_[0].size(), FF.lorM_[2].size()));
+        std::string p; app(p, pm); putRec(out, "MAGNETIC", p);
+        for(size_t oo = 0; oo < FF.objArr_.size(); ++oo)
+        {
+            auto& obj = FF.objArr_[oo];
+            ChimlPlanObjMagHdr h; h.obj = int(oo); h.npoles = int(obj->magGamma().size());
+            std::string q; app(q, h); appVec(q, obj->magAlpha()); appVec(q, obj->magXi()); appVec(q, obj->magGamma());
+            putRec(out, "OBJMAG", q);
+        }
+    }
+    else if(FF.magMatInPML_) throw std::runtime_error("plan dump: magnetic material in the PML without B grids");
     for(int c = 0; c < 3; ++c)
     {
-        if(!FF.upB_[c].empty() || !FF.upLorB_[c].empty() || !FF.upChiD_[c].empty() || !FF.upChiB_[c].empty() || !FF.upOrDipB_[c].empty()
-           || !FF.upOrDipChiD_[c].empty() || !FF.upOrDipChiB_[c].empty())
-            throw std::runtime_error("plan dump: magnetic / chiral update lists are outside the covered hot path");
+        if(!FF.upChiD_[c].empty() || !FF.upChiB_[c].empty() || !FF.upOrDipB_[c].empty() || !FF.upOrDipChiD_[c].empty() || !FF.upOrDipChiB_[c].empty())
+            throw std::runtime_error("plan dump: chiral / magnetic oriented-dipole update lists are outside the covered hot path");
+        if(hasB)
+        {
+            putList(out, CHIML_LIST_D, 3 + c, FF.upB_[c]);
+            putList(out, CHIML_LIST_LORD, 3 + c, FF.upLorB_[c]);
+        }
+        else if(!FF.upB_[c].empty() || !FF.upLorB_[c].empty()) throw std::runtime_error("plan dump: magnetic update lists without B grids");
         putList(out, CHIML_LIST_U, c, FF.upE_[c]);
         putList(out, CHIML_LIST_U, 3 + c, FF.upH_[c]);
         putList(out, CHIML_LIST_D, c, FF.upD_[c]);
@@ -554,6 +574,7 @@ struct GpuApi
     CHIML_API(chiml_gpu_read_population) CHIML_API(chiml_gpu_download_dft) CHIML_API(chiml_gpu_download_field) CHIML_API(chiml_gpu_download_pole)
     CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
     CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic) CHIML_API(chiml_gpu_add_tfsf_surface) CHIML_API(chiml_gpu_step_n_tfsf)
+    CHIML_API(chiml_gpu_set_magnetic) CHIML_API(chiml_gpu_set_object_magnetic) CHIML_API(chiml_gpu_download_mag_pole)
 #undef CHIML_API
     void load()
     {
@@ -576,6 +597,7 @@ struct GpuApi
         CHIML_API(chiml_gpu_read_population) CHIML_API(chiml_gpu_download_dft) CHIML_API(chiml_gpu_download_field) CHIML_API(chiml_gpu_download_pole)
         CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
         CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic) CHIML_API(chiml_gpu_add_tfsf_surface) CHIML_API(chiml_gpu_step_n_tfsf)
+        CHIML_API(chiml_gpu_set_magnetic) CHIML_API(chiml_gpu_set_object_magnetic) CHIML_API(chiml_gpu_download_mag_pole)
 #undef CHIML_API
     }
 };
@@ -608,7 +630,9 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
     g.dt = FF.dt_; g.has_D = (FF.D_[0] || FF.D_[2]) ? 1 : 0; g.pml_on_D = FF.dielectricMatInPML_ ? 1 : 0; g.n_objects = int(FF.objArr_.size());
     g.rank = 0; g.nranks = 1;
     if(A.chiml_gpu_create(&g, 0, &B.ctx) != CHIML_OK) throw std::runtime_error(std::string("chiml_gpu_create: ") + A.chiml_gpu_last_error(nullptr));
-    if(FF.magMatInPML_) throw std::runtime_error("--gpu: magnetic materials in the PML are outside the covered hot path");
+    // magnetic-dispersive media: B grids, CPML on B, the lists upB_ / upLorB_ below, magnetic pole constants per object
+    const bool hasB = bool(FF.B_[0]) || bool(FF.B_[2]);
+    if(hasB) B.check(A.chiml_gpu_set_magnetic(B.ctx, 1, FF.magMatInPML_ ? 1 : 0), "set_magnetic");
     // TFSF sources: the surface records go to the device, the 1-D incident line stays with the reference's object (gpuStep)
     B.tfsfL = tfsfLayout(FF);
     B.tfsfSurf = tfsfSurfaces(FF, B.tfsfL);
@@ -619,8 +643,9 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
         B.check(A.chiml_gpu_set_update_list(B.ctx, kind, comp, reinterpret_cast<const ChimlRun*>(l.data()), l.size()), "set_update_list"); };
     for(int c = 0; c < 3; ++c)
     {
-        if(!FF.upB_[c].empty() || !FF.upLorB_[c].empty() || !FF.upChiD_[c].empty() || !FF.upChiB_[c].empty() || !FF.upOrDipB_[c].empty())
-            throw std::runtime_error("--gpu: magnetic / chiral update lists are outside the covered hot path");
+        if(!FF.upChiD_[c].empty() || !FF.upChiB_[c].empty() || !FF.upOrDipB_[c].empty())
+            throw std::runtime_error("--gpu: chiral / magnetic oriented-dipole update lists are outside the covered hot path");
+        if(hasB) { put(CHIML_LIST_D, 3 + c, FF.upB_[c]); put(CHIML_LIST_LORD, 3 + c, FF.upLorB_[c]); }
         put(CHIML_LIST_U, c, FF.upE_[c]);   put(CHIML_LIST_U, 3 + c, FF.upH_[c]);
         put(CHIML_LIST_D, c, FF.upD_[c]);   put(CHIML_LIST_LORD, c, FF.upLorD_[c]);
         put(CHIML_LIST_ORDIPD, c, FF.upOrDipD_[c]);
@@ -640,6 +665,7 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
                 else throw std::runtime_error("--gpu: position-dependent dipole orientation (REL_TO_NORM) is outside the covered hot path");
             }
         B.check(A.chiml_gpu_set_object(B.ctx, int(oo), np, obj->alpha().data(), obj->xi().data(), obj->gamma().data(), obj->useOrdDip() ? 1 : 0, dip.data()), "set_object");
+        if(hasB) B.check(A.chiml_gpu_set_object_magnetic(B.ctx, int(oo), int(obj->magGamma().size()), obj->magAlpha().data(), obj->magXi().data(), obj->magGamma().data()), "set_object_magnetic");
     }
     // periodic boundaries: the arguments of applBCE_ / applBCH_ (single rank: applyBC1Proc)
     if(FF.E_[0] ? FF.E_[0]->PBC() : FF.E_[2]->PBC())
@@ -870,6 +896,12 @@ static void gpuFinish(parallelFDTDFieldReal& FF, GpuBinding& B)
         if(FF.E_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_EX + c, &FF.E_[c]->point(0)), "download_field");
         if(FF.H_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_HX + c, &FF.H_[c]->point(0)), "download_field");
         if(FF.D_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_DX + c, &FF.D_[c]->point(0)), "download_field");
+        if(FF.B_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_BX + c, &FF.B_[c]->point(0)), "download_field");
+        for(size_t p = 0; p < FF.lorM_[c].size(); ++p)
+        {
+            B.check(A.chiml_gpu_download_mag_pole(B.ctx, c, int(p), 0, &FF.lorM_[c][p]->point(0)), "download_mag_pole");
+            B.check(A.chiml_gpu_download_mag_pole(B.ctx, c, int(p), 1, &FF.prevLorM_[c][p]->point(0)), "download_mag_pole");
+        }
         for(size_t p = 0; p < FF.lorP_[c].size(); ++p)
         {
             B.check(A.chiml_gpu_download_pole(B.ctx, c, int(p), 0, &FF.lorP_[c][p]->point(0)), "download_pole");
@@ -1005,6 +1037,11 @@ static void rankMain(int rank, const Options& opt)
             grabGrid(rank, std::string("H") + c[i], FF.H_[i]);
             grabGrid(rank, std::string("D") + c[i], FF.D_[i]);
             grabGrid(rank, std::string("B") + c[i], FF.B_[i]);
+            for(size_t p = 0; p < FF.lorM_[i].size(); ++p)
+            {
+                grabGrid(rank, std::string("M") + c[i] + std::to_string(p), FF.lorM_[i][p]);
+                grabGrid(rank, std::string("pM") + c[i] + std::to_string(p), FF.prevLorM_[i][p]);
+            }
             for(size_t p = 0; p < FF.lorP_[i].size(); ++p)
             {
                 grabGrid(rank, std::string("P") + c[i] + std::to_string(p), FF.lorP_[i][p]);

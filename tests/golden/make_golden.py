@@ -212,6 +212,28 @@ def cases():
     te["PML"]["thickness"] = [8 / RES, 0.0, 0.0]
     te["ObjectList"] = [I.block([0.1, 1.0, 0.0], [0.08, 0.0, 0.0], eps=2.2, pols=[I.lorentz_pole(0.8, 0.1, 2.0)])]
     c["cplx_te"] = _bloch(te, [0.0, -0.6, 0.0])
+    # ---- magnetic-dispersive media (B / H / M mirror of D / E / P: updateMagH, updateB, B2H): a block with mu = 1.5 and poles that are electric
+    # and magnetic beside a purely electric sphere, inside the CPML-free interior; the same block reaching through the CPML (magMatInPML_: the
+    # H-side CPML acts on B, every CPML cell becomes a B cell); 2-D TM (Hx, Hy magnetic) and TE (Hz magnetic) ----
+    magp = lambda sp, g, w, sm: I.lorentz_pole(sp, g, w, sigma_m=sm)  # noqa: E731
+    mblock = dict(I.block([0.08, 0.06, 0.05], [0.01, 0, -0.02], eps=2.0, pols=[magp(1.2, 0.1, 2.0, 0.6), magp(0.5, 0.05, 3.0, 0.3)]), mu=1.5)
+    c["mag3d"] = _short_pulse(I.config(
+        I.comp_cell([23 / RES, 19 / RES, 21 / RES], RES, 60 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+        [I.normal_source("Ez", [0, 0, 0.04], [0.05, 0.04, 0], [I.gaussian_pulse(1.5, 1.0)]),
+         I.normal_source("Hy", [0.02, 0.0, -0.02], [0, 0, 0], [I.gaussian_pulse(1.2, 1.0)])],
+        [mblock, I.sphere(0.03, [-0.04, 0.02, 0.04], eps=1.5, pols=[I.lorentz_pole(0.7, 0.2, 1.0)])],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Hy", "out/mg/dtc", time_int=DT * 1.0000001)]))
+    c["mag3d_pml"] = _short_pulse(I.config(
+        I.comp_cell([21 / RES, 19 / RES, 17 / RES], RES, 50 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES, 4 / RES, 5 / RES]),
+        [I.normal_source("Ey", [0.0, 0.0, 0.0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
+        [dict(I.block([0.5, 0.06, 0.05], [0.0, 0.01, 0.0], eps=1.0, pols=[magp(0.0, 0.1, 2.0, 0.8)]), mu=2.0)],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Hz", "out/mgp/dtc", time_int=DT * 1.0000001)]))
+    tm = I.c2_tm_drude(n=63, steps=100, pml_cells=8, rod=(20, 6), nfreq=0, out="out/mtm")
+    tm["ObjectList"] = [dict(I.block([0.2, 0.06, 0.0], [0.0, 0.05, 0.0], eps=2.0, pols=[magp(0.9, 0.1, 2.0, 0.7)]), mu=1.3)]
+    c["mag_tm"] = _short_pulse(tm)
+    te = I.c1_te_vacuum(n=47, steps=100, pml_cells=8, out="out/mte")
+    te["ObjectList"] = [dict(I.block([0.1, 0.1, 0.0], [0.1, -0.03, 0.0], eps=1.0, pols=[magp(0.0, 0.05, 1.8, 0.9)]), mu=1.8)]      # (off the Hz source: B2H overwrites a source inside)
+    c["mag_te"] = _short_pulse(te)
     return c
 
 

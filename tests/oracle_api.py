@@ -85,6 +85,10 @@ def lib() -> C.CDLL:
         L.oracle_step_n.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_step_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_set_periodic.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_set_magnetic.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.oracle_set_object_magnetic.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_mag_pole.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.oracle_mag_pole.restype = C.POINTER(C.c_double)
         L.oracle_pair_step_n.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_add_tfsf_surface.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_step_n_tfsf.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
@@ -135,6 +139,11 @@ class OracleSim:
         for o in plan.objects:
             a, x, gm, dp = (np.ascontiguousarray(v, dtype=np.float64) for v in (o.alpha, o.xi, o.gamma, o.dip))
             self._chk(L.oracle_set_object(self.h, o.obj, o.npoles, _ptr(a), _ptr(x), _ptr(gm), o.use_or_dip, _ptr(dp)))
+        if plan.has_B:
+            self._chk(L.oracle_set_magnetic(self.h, plan.has_B, plan.pml_on_B))
+            for obj, (a, x, gm) in sorted(plan.mag_objects.items()):
+                a, x, gm = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, x, gm))
+                self._chk(L.oracle_set_object_magnetic(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm)))
         for c in plan.cpml:
             psi, grid = np.ascontiguousarray(c.psi), np.ascontiguousarray(c.grid)
             self._chk(L.oracle_set_cpml(self.h, c.comp, c.part, c.has_psi, _ptr(psi), len(psi), _ptr(grid), len(grid)))
@@ -234,6 +243,9 @@ class OracleSim:
 
     def pole(self, comp: int, pole: int, prev: int = 0):
         return self._view(lib().oracle_pole(self.h, comp, pole, prev))
+
+    def mag_pole(self, comp: int, pole: int, prev: int = 0):
+        return self._view(lib().oracle_mag_pole(self.h, comp, pole, prev))
 
     def ordip_pole(self, comp: int, pole: int, prev: int = 0):
         return self._view(lib().oracle_ordip_pole(self.h, comp, pole, prev))

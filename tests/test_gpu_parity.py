@@ -123,7 +123,7 @@ def test_2d_launch_per_phase_path_matches_reference_fixture(case, march):
     sa = {k["name"]: k["launches"] for k in a.kernel_stats()}
     sb = {k["name"]: k["launches"] for k in b.kernel_stats()}
     assert sa["k_steps_2d"] == 0
-    if not plan.emitters and not plan.tfsf and not plan.cplx:      # (emitters, TFSF surfaces and complex-field pairs take the launch path)
+    if not plan.emitters and not plan.tfsf and not plan.cplx and not plan.has_B:      # (emitters, TFSF surfaces, complex-field pairs and magnetic media take the launch path)
         assert sb["k_steps_2d"] == 3 and sb["k_fast<E>"] == 0, sb
     a.close(); b.close()
 

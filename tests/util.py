@@ -48,6 +48,10 @@ def state_array(sim, name: str):
             out[:, 0, 0], out[:, 0, 1] = a.real, a.imag
             return out
         raise KeyError(name)
+    if name.startswith("pM"):
+        return sim.mag_pole("xyz".index(name[2]), int(name[3:]), 1)
+    if name.startswith("M"):
+        return sim.mag_pole("xyz".index(name[1]), int(name[2:]), 0)
     if name.startswith("poP"):
         return sim.ordip_pole("xyz".index(name[3]), int(name[4:]), 1)
     if name.startswith("oP"):
@@ -73,6 +77,9 @@ def state_names(plan: P.Plan):
                 names += [f"P{'xyz'[c]}{p}", f"pP{'xyz'[c]}{p}"]
             for p in range(plan.n_ordip_poles):
                 names += [f"oP{'xyz'[c]}{p}", f"poP{'xyz'[c]}{p}"]
+        if (9 + c) in plan.fields_present():
+            for p in range(plan.n_mag_poles):
+                names += [f"M{'xyz'[c]}{p}", f"pM{'xyz'[c]}{p}"]
     for k in range(len(plan.dfts)):
         names += [f"dft{k}r", f"dft{k}i"]
     for q, e in enumerate(plan.emitters):
