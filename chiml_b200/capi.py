@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_consume_population", "chiml_gpu_set_persistent", "chiml_gpu_set_periodic", "chiml_gpu_add_tfsf_surface",
     "chiml_gpu_step_n_tfsf", "chiml_gpu_bind_imag", "chiml_gpu_step_n_cplx",
     "chiml_gpu_set_magnetic", "chiml_gpu_set_object_magnetic", "chiml_gpu_download_mag_pole",
+    "chiml_gpu_set_object_chiral", "chiml_gpu_set_prev_copy", "chiml_gpu_download_chi_pole", "chiml_gpu_download_prev_field",
 ]
 
 
@@ -175,6 +176,10 @@ def lib() -> C.CDLL:
     L.chiml_gpu_halo_export.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.chiml_gpu_halo_bind.argtypes = [vp, C.c_char_p, sz, C.c_char_p, sz]
     L.chiml_gpu_set_periodic.argtypes = [vp, i, vp]
+    L.chiml_gpu_set_object_chiral.argtypes = [vp, i, i, vp, vp, vp, vp]
+    L.chiml_gpu_set_prev_copy.argtypes = [vp, vp, sz]
+    L.chiml_gpu_download_chi_pole.argtypes = [vp, i, i, i, vp]
+    L.chiml_gpu_download_prev_field.argtypes = [vp, i, vp]
     L.chiml_gpu_set_magnetic.argtypes = [vp, i, i]
     L.chiml_gpu_set_object_magnetic.argtypes = [vp, i, i, vp, vp, vp]
     L.chiml_gpu_download_mag_pole.argtypes = [vp, i, i, i, vp]
@@ -243,6 +248,12 @@ class GpuSim:
             for obj, (a, x, gm) in sorted(plan.mag_objects.items()):
                 a, x, gm = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, x, gm))
                 self._chk(L.chiml_gpu_set_object_magnetic(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm)))
+            for obj, arrs in sorted(plan.chi_objects.items()):
+                a, x, gm, gp = (np.ascontiguousarray(v, dtype=np.float64) for v in arrs)
+                self._chk(L.chiml_gpu_set_object_chiral(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm), _ptr(gp)))
+            if plan.prev_copy is not None:
+                rows = np.ascontiguousarray(plan.prev_copy, dtype=np.int32)
+                self._chk(L.chiml_gpu_set_prev_copy(self.h, _ptr(rows), len(rows)))
             for c in plan.cpml:
                 psi = np.ascontiguousarray(c.psi, dtype=P.PSI_DTYPE)
                 grid = np.ascontiguousarray(c.grid, dtype=P.GRIDP_DTYPE)
@@ -368,6 +379,16 @@ class GpuSim:
     def set_pole(self, comp: int, pole: int, prev: int, a: np.ndarray) -> None:
         a = np.ascontiguousarray(a, dtype=np.float64)
         self._chk(lib().chiml_gpu_upload_pole(self.h, comp, pole, prev, _ptr(a)))
+
+    def chi_pole(self, comp: int, pole: int, prev: int = 0) -> np.ndarray:
+        out = np.empty(self._shape(), dtype=np.float64)
+        self._chk(lib().chiml_gpu_download_chi_pole(self.h, comp, pole, prev, _ptr(out)))
+        return out
+
+    def prev_field(self, comp: int) -> np.ndarray:
+        out = np.empty(self._shape(), dtype=np.float64)
+        self._chk(lib().chiml_gpu_download_prev_field(self.h, comp, _ptr(out)))
+        return out
 
     def mag_pole(self, comp: int, pole: int, prev: int = 0) -> np.ndarray:
         out = np.empty(self._shape(), dtype=np.float64)

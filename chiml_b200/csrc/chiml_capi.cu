@@ -143,6 +143,12 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
         for(int p = 0; p < MAX_POLES; ++p)
             for(int k = 0; k < 2; ++k) { cudaFree(ctx->d_P[c][p][k]); if(c < 3) cudaFree(ctx->d_oP[c][p][k]); }
     }
+    for(int c = 0; c < 6; ++c)
+    {
+        cudaFree(ctx->d_prev_base[c]);
+        for(int p = 0; p < MAX_CHI; ++p) for(int k = 0; k < 2; ++k) cudaFree(ctx->d_chi[c][p][k]);
+    }
+    cudaFree(ctx->d_prev_rows);
     cudaFree(ctx->d_info_node); cudaFree(ctx->d_cls_node);
     cudaFree(ctx->span_node.d_xmin); cudaFree(ctx->span_node.d_xmax); cudaFree(ctx->span_node.d_base); cudaFree(ctx->span_node.d_rows);
     cudaFree(ctx->d_src_amp);
@@ -176,8 +182,10 @@ int chiml_gpu_set_update_list(ChimlCtx* ctx, int kind, int comp, const ChimlRun*
 {
     if(!ctx) return CHIML_ERR_ARG;
     if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_update_list after commit");
-    if(kind < 0 || kind > 4 || comp < 0 || comp > 5 || (n && !runs)) return fail(ctx, CHIML_ERR_ARG, "set_update_list: bad kind/comp");
-    if(kind != CHIML_LIST_U && comp > 2 && n && !(ctx->has_B && (kind == CHIML_LIST_D || kind == CHIML_LIST_LORD)))
+    if(kind < 0 || kind > 5 || comp < 0 || comp > 5 || (n && !runs)) return fail(ctx, CHIML_ERR_ARG, "set_update_list: bad kind/comp");
+    if(kind == CHIML_LIST_CHID && n && (ctx->g.mode != CHIML_MODE_3D || !ctx->g.has_D || !ctx->has_B || ctx->g.nranks > 1))
+        return fail(ctx, CHIML_ERR_UNSUPPORTED, "chiral lists need a 3-D grid with D and B grids (chiml_gpu_set_magnetic first) on a single slab");
+    if(kind != CHIML_LIST_U && comp > 2 && n && !(ctx->has_B && (kind == CHIML_LIST_D || kind == CHIML_LIST_LORD || kind == CHIML_LIST_CHID)))
         return fail(ctx, CHIML_ERR_UNSUPPORTED, "magnetic lists need chiml_gpu_set_magnetic(has_B = 1) first (upB_ / upLorB_); magnetic oriented-dipole lists are outside the covered hot path");
     const long ncell = (long)ctx->nlogical;
     for(size_t i = 0; i < n; ++i)
@@ -214,6 +222,34 @@ int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global)
     if(n_poles_global > MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_ordip_pole_count: more than 12 poles per object");
     ctx->nordip_global = n_poles_global;
     return CHIML_OK;
+}
+
+int chiml_gpu_set_object_chiral(ChimlCtx* ctx, int obj, int npoles, const double* alpha, const double* xi, const double* gamma, const double* gamma_prev)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_object_chiral after commit");
+    if(obj < 0 || obj >= (int)ctx->objs.size()) return fail(ctx, CHIML_ERR_ARG, "set_object_chiral: object index out of range");
+    if(npoles < 0 || npoles > MAX_CHI) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_object_chiral: more chiral poles than MAX_CHI");
+    if(npoles > 0 && (!alpha || !xi || !gamma || !gamma_prev)) return fail(ctx, CHIML_ERR_ARG, "set_object_chiral: NULL constant array");
+    HostObj& o = ctx->objs[obj];
+    o.nchi = npoles;
+    o.calpha.assign(alpha, alpha + npoles); o.cxi.assign(xi, xi + npoles); o.cgamma.assign(gamma, gamma + npoles); o.cgprev.assign(gamma_prev, gamma_prev + npoles);
+    return 0;
+}
+
+int chiml_gpu_set_prev_copy(ChimlCtx* ctx, const int32_t* rows, size_t nrows)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_prev_copy after commit");
+    if(nrows && !rows) return fail(ctx, CHIML_ERR_ARG, "set_prev_copy: NULL rows");
+    for(size_t q = 0; q < nrows; ++q)
+    {
+        const int32_t* b = rows + 4 * q;
+        if(b[0] < 0 || b[1] < 0 || b[1] + b[0] > ctx->lx || b[2] < 0 || b[2] >= ctx->ly || b[3] < 0 || b[3] >= ctx->lz)
+            return fail(ctx, CHIML_ERR_ARG, "set_prev_copy: a row leaves the grid");
+    }
+    ctx->h_prev_rows.assign(rows, rows + 4 * nrows);
+    return 0;
 }
 
 int chiml_gpu_set_magnetic(ChimlCtx* ctx, int has_B, int pml_on_B)
@@ -493,6 +529,16 @@ struct ClassBuilder
             k.consts.insert(k.consts.end(), o.gamma.begin(), o.gamma.end());
             k.consts.insert(k.consts.end(), o.dip.begin(), o.dip.end());
         }
+        // a chiral object's D / B run and its chiral run cover the same cells: both carry the chiral constants
+        const int nchi = withPoles ? o.nchi : 0;
+        if(nchi > 0)
+        {
+            k.consts.push_back(1e300);          // (separator: the lists above have variable length)
+            k.consts.insert(k.consts.end(), o.calpha.begin(), o.calpha.end());
+            k.consts.insert(k.consts.end(), o.cxi.begin(), o.cxi.end());
+            k.consts.insert(k.consts.end(), o.cgamma.begin(), o.cgamma.end());
+            k.consts.insert(k.consts.end(), o.cgprev.begin(), o.cgprev.end());
+        }
         auto it = ids.find(k);
         if(it != ids.end()) return it->second;
         if((int)entries.size() > MAX_CLASSES) return 0;
@@ -506,6 +552,13 @@ struct ClassBuilder
             e.alpha[p] = o.alpha[p]; e.xi[p] = o.xi[p]; e.gamma[p] = o.gamma[p];
             for(int q = 0; q < 3; ++q) e.dip[p][q] = o.dip[3 * p + q];
         }
+        e.nchi = nchi;
+        for(int p = 0; p < nchi; ++p)
+        {
+            e.chi_alpha[p] = o.calpha[p]; e.chi_xi[p] = o.cxi[p];
+            e.chi_g8[p] = o.cgamma[p] / 8.0; e.chi_gp8[p] = o.cgprev[p] / 8.0;      // daxpy_(n, gamma[pp] / 8.0, ...)
+        }
+        e.chi_fac = magnetic ? -1.0 / k.eps : -1.0 / (-1.0 * k.eps);               // chiDtoU: -1.0 / epMuInfty, epMuInfty = +mu (B2H) or -eps (D2E)
         int id = (int)entries.size();
         entries.push_back(e);
         ids[k] = id;
@@ -556,7 +609,7 @@ int build_spans(ChimlCtx* ctx, const std::vector<const std::vector<ChimlRun>*>& 
         for(const ChimlRun& r : *l)
         {
             const HostObj& o = ctx->objs[r.obj];
-            if((magnetic ? o.nmag : o.npoles) == 0) continue;
+            if((magnetic ? o.nmag : o.npoles) == 0 && o.nchi == 0) continue;
             if(ordipOnly && !o.use_or_dip) continue;
             const size_t row = (size_t)(r.ind / ctx->lx);
             const int x0 = r.ind % ctx->lx, x1 = x0 + r.n - 1;
@@ -713,7 +766,7 @@ int build_tensor_maps(ChimlCtx* ctx)
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
     bool ok = true;
-    for(int f = 0; f < CHIML_NFIELDS && ok; ++f)
+    for(int f = 0; f < TMAP_PSI0 && ok; ++f)
         if(ctx->d_field[f]) ok = make(maps[f], ctx->d_field[f], (cuuint64_t)ctx->px, (cuuint64_t)ctx->lz, (cuuint64_t)ctx->ly, (cuuint64_t)ctx->px, (cuuint64_t)ctx->plane);
     for(int comp = 0; comp < 6 && ok; ++comp)
         for(int part = 0; part < 2 && ok; ++part)
@@ -768,12 +821,30 @@ int chiml_gpu_commit(ChimlCtx* ctx)
             ctx->d_field[f] = ctx->d_field_base[f] + ctx->guard;
         }
 
+    // chiral media: prevE_ / prevH_ and the rows copied into them
+    {
+        bool anyChi = false;
+        for(int comp = 0; comp < 6; ++comp) anyChi = anyChi || !ctx->lists[CHIML_LIST_CHID][comp].runs.empty();
+        if(anyChi)
+        {
+            for(int c = 0; c < 6; ++c)
+            {
+                if((rc = dev_alloc(ctx, &ctx->d_prev_base[c], ctx->nphys + 2 * ctx->guard))) return rc;
+                ctx->d_prev[c] = ctx->d_prev_base[c] + ctx->guard;
+            }
+            std::vector<int4> rows(ctx->h_prev_rows.size() / 4);
+            for(size_t q = 0; q < rows.size(); ++q) rows[q] = make_int4(ctx->h_prev_rows[4 * q], ctx->h_prev_rows[4 * q + 1], ctx->h_prev_rows[4 * q + 2], ctx->h_prev_rows[4 * q + 3]);
+            ctx->n_prev_rows = rows.size();
+            if((rc = dev_upload(ctx, &ctx->d_prev_rows, rows))) return rc;
+        }
+    }
+
     // --- update lists -> class tables + painted cell info -------------------------------------------------
     for(int comp = 0; comp < 6; ++comp)
     {
         if(!field_exists(ctx, comp))
         {
-            for(int k = 0; k < 5; ++k)
+            for(int k = 0; k < 6; ++k)
                 if(k != CHIML_LIST_ORDIPP && !ctx->lists[k][comp].runs.empty())
                     return fail(ctx, CHIML_ERR_ARG, "update list given for a field component that does not exist in this mode");
             continue;
@@ -782,13 +853,13 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         ClassBuilder cb;
         const bool isE = comp < 3;
         if(isE ? !ctx->g.has_D : !ctx->has_B)
-            for(int k : {CHIML_LIST_D, CHIML_LIST_LORD, CHIML_LIST_ORDIPD})
+            for(int k : {CHIML_LIST_D, CHIML_LIST_LORD, CHIML_LIST_ORDIPD, CHIML_LIST_CHID})
                 if(!ctx->lists[k][comp].runs.empty()) return fail(ctx, CHIML_ERR_ARG, isE ? "D-type update list given but has_D = 0" : "B-type update list given but has_B = 0");
         // stencil offsets must be uniform per component
         bool& haveOff = ctx->have_off[comp];
-        struct { int kind; uint16_t flags; bool poles; } plan[4] = {
+        struct { int kind; uint16_t flags; bool poles; } plan[5] = {
             {CHIML_LIST_U, F_CURL, false}, {CHIML_LIST_D, (uint16_t)(F_CURL | F_ISD), true},
-            {CHIML_LIST_LORD, F_D2E, true}, {CHIML_LIST_ORDIPD, F_ORD2E, true}};
+            {CHIML_LIST_LORD, F_D2E, true}, {CHIML_LIST_ORDIPD, F_ORD2E, true}, {CHIML_LIST_CHID, F_D2E, true}};
         for(auto& pl : plan)
         {
             const auto& runs = ctx->lists[pl.kind][comp].runs;
@@ -803,6 +874,18 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                     if(!haveOff) { ctx->off_j[comp] = oj; ctx->off_k[comp] = ok; haveOff = true; }
                     else if(ctx->off_j[comp] != oj || ctx->off_k[comp] != ok)
                         return fail(ctx, CHIML_ERR_UNSUPPORTED, "update list: stencil offsets differ between runs of one component");
+                }
+                if(pl.kind == CHIML_LIST_CHID)
+                {
+                    // the eight-point stencil of UpdateChiral hangs on the entry's three neighbour indices: one geometry per component
+                    const long o3[3] = {(long)r.ind_i - r.ind, (long)r.ind_j - r.ind, (long)r.ind_k - r.ind};
+                    for(int q = 0; q < 3; ++q)
+                    {
+                        if(e == 0) ctx->chi_off[comp][q] = o3[q];
+                        else if(ctx->chi_off[comp][q] != o3[q]) return fail(ctx, CHIML_ERR_UNSUPPORTED, "chiral list: neighbour offsets differ between runs");
+                    }
+                    if(ctx->objs[r.obj].nchi == 0) return fail(ctx, CHIML_ERR_ARG, "chiral list: the object of a run has no chiral pole (chiml_gpu_set_object_chiral)");
+                    ctx->has_chi = true;
                 }
                 if(pl.kind == CHIML_LIST_ORDIPD)
                 {
@@ -836,16 +919,24 @@ int chiml_gpu_commit(ChimlCtx* ctx)
     for(int c = 0; c < 6; ++c)
     {
         if(!field_exists(ctx, c) || (c < 3 ? !ctx->g.has_D : !ctx->has_B)) continue;
-        int np = 0;
-        for(const ChimlRun& r : ctx->lists[CHIML_LIST_LORD][c].runs)
-            if(c >= 3) np = std::max(np, ctx->objs[r.obj].nmag);
-            else if(!ctx->objs[r.obj].use_or_dip) np = std::max(np, ctx->objs[r.obj].npoles);
+        int np = 0, nchi = 0;
+        for(int kind : {CHIML_LIST_LORD, CHIML_LIST_CHID})
+            for(const ChimlRun& r : ctx->lists[kind][c].runs)
+            {
+                if(c >= 3) np = std::max(np, ctx->objs[r.obj].nmag);
+                else if(!ctx->objs[r.obj].use_or_dip) np = std::max(np, ctx->objs[r.obj].npoles);
+                if(kind == CHIML_LIST_CHID) nchi = std::max(nchi, ctx->objs[r.obj].nchi);
+            }
         ctx->npoles_comp[c] = np;
-        std::vector<const std::vector<ChimlRun>*> ls = {&ctx->lists[CHIML_LIST_LORD][c].runs};
+        ctx->nchi_comp[c] = nchi;
+        std::vector<const std::vector<ChimlRun>*> ls = {&ctx->lists[CHIML_LIST_LORD][c].runs, &ctx->lists[CHIML_LIST_CHID][c].runs};
         if((rc = build_spans(ctx, ls, false, ctx->span[c], c >= 3))) return rc;
         for(int p = 0; p < np; ++p)
             for(int k = 0; k < 2; ++k)
                 if((rc = dev_alloc(ctx, &ctx->d_P[c][p][k], (size_t)ctx->span[c].total))) return rc;
+        for(int p = 0; p < nchi; ++p)
+            for(int k = 0; k < 2; ++k)
+                if((rc = dev_alloc(ctx, &ctx->d_chi[c][p][k], (size_t)ctx->span[c].total))) return rc;
     }
     // --- oriented-dipole node grid ------------------------------------------------------------------------
     {
@@ -998,6 +1089,9 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                     // magnetic-dispersive cells (B targets, magnetic poles, B -> H) are worked on by the per-cell kernel only
                     if(fam == 1)
                         for(const TileVal& tv : vals[c]) if(tv.info & (F_ISD | F_D2E)) uniform = false;
+                    // ... and so are the cells of chiral objects, in either family
+                    if(ctx->has_chi)
+                        for(const TileVal& tv : vals[c]) if(ctx->h_cls[b0 + c][tv.info & CLS_MASK].nchi > 0) uniform = false;
                 }
                 if(!uniform) { lists[2].push_back(rec); listBytes[2] += ts.bytes; continue; }
                 const int per = rectangles_per_record(vals);
@@ -1274,6 +1368,16 @@ void fill_step_args(ChimlCtx* ctx, bool isE, StepArgs& a)
             pa.F = pp.d_F; pa.b = pp.d_b; pa.c = pp.d_c; pa.cmap = pp.d_cmap; pa.psi = pp.d_psi;
             pa.Db = pp.Db; pa.psi_pitch = pp.psi_pitch; pa.axis = pp.axis; pa.nact = pp.nact; pa.has_psi = pp.has_psi;
         }
+        if(ctx->has_chi)
+        {
+            const int cc = (isE ? 0 : 3) + i;
+            for(int p = 0; p < MAX_CHI; ++p) { ca.chiCur[p] = ctx->d_chi[cc][p][cur]; ca.chiNew[p] = ctx->d_chi[cc][p][prv]; }
+            ca.oppPrev = ctx->d_prev[(isE ? 3 : 0) + i];                 // E_c is driven by H_c and prevH_c, H_c by E_c and prevE_c
+            int dd[3];
+            decode_offset(ctx, ctx->chi_off[cc][0], dd); ca.chi_oi = phys_offset(ctx, dd);
+            decode_offset(ctx, ctx->chi_off[cc][1], dd); ca.chi_oj = phys_offset(ctx, dd);
+            decode_offset(ctx, ctx->chi_off[cc][2], dd); ca.chi_ok = phys_offset(ctx, dd);
+        }
         if(!isE && ctx->has_B)
         {
             ca.sp_xmin = ctx->span[3 + i].d_xmin; ca.sp_base = ctx->span[3 + i].d_base;
@@ -1525,6 +1629,18 @@ void launch_tfsf(ChimlCtx* ctx, long long k)
     }
 }
 
+// copy2PrevFields_ after updateChiH (E -> prevE, right after the H family, whose chiral magnetisation read them) and after updateChiE (H -> prevH)
+void launch_prev_copy(ChimlCtx* ctx, bool copyE)
+{
+    if(!ctx->has_chi || ctx->n_prev_rows == 0) return;
+    PrevCopyArgs pa;
+    std::memset(&pa, 0, sizeof(pa));
+    for(int i = 0; i < 3; ++i) { pa.src[i] = ctx->d_field[(copyE ? CHIML_EX : CHIML_HX) + i]; pa.dst[i] = ctx->d_prev[(copyE ? 0 : 3) + i]; }
+    pa.rows = ctx->d_prev_rows; pa.nrows = (unsigned)ctx->n_prev_rows; pa.lz = ctx->lz; pa.px = ctx->px;
+    LaunchScope ls(ctx, K_PREV_COPY);
+    k_prev_copy<<<pa.nrows, 64, 0, ctx->stream>>>(pa);
+}
+
 // applBCH_ / applBCE_ (step() items 9 and 17): periodic wrap copies of the three components of one family
 void launch_wraps(ChimlCtx* ctx, bool isE)
 {
@@ -1667,6 +1783,7 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc, int section = 0)
             // H half step: updateH + updateHPML_ (step() items 4 and 6)
             fill_step_args(ctx, false, a);
             launch_family<false>(ctx, a, block, 0);
+            launch_prev_copy(ctx, true);        // (the chiral magnetisation of this step has read E and prevE: E -> prevE)
             // TFSF surfaces (item 5): H after its curl, E / D before theirs and before the soft sources
             launch_tfsf(ctx, k);
             // sources (item 7): all sources, E and H alike, are injected here
@@ -1681,6 +1798,7 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc, int section = 0)
             // E half step: isotropic poles, updateD/updateE, updateEPML_, D2E (items 10-15)
             fill_step_args(ctx, true, a);
             launch_family<true>(ctx, a, block, 0);
+            launch_prev_copy(ctx, false);       // (the chiral polarisation of this step has read H and prevH: H -> prevH)
             // qe->addQE() for every emitter object (item 16)
             for(EmitterDev& em : ctx->emitters)
             {
@@ -2323,7 +2441,7 @@ int chiml_gpu_n_kernel_kinds(void) { return K_NKINDS; }
 int chiml_gpu_kernel_stat(ChimlCtx* ctx, int kind, ChimlKernelStat* out)
 {
     static const char* names[K_NKINDS] = {"k_fast<E>", "k_uniform<E>", "k_general<E>", "k_fast<H>", "k_uniform<H>", "k_general<H>",
-                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft", "k_steps_2d", "k_wrap", "k_tfsf", "k_wrap_bloch"};
+                                          "k_ordip_poles", "k_source", "k_detector", "k_emit_addP", "k_emit_density", "k_emit_pop_reduce", "k_halo_push", "k_halo_wait", "k_dft", "k_steps_2d", "k_wrap", "k_tfsf", "k_wrap_bloch", "k_prev_copy"};
     if(!ctx || !out || kind < 0 || kind >= K_NKINDS) return CHIML_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -2410,6 +2528,41 @@ static int pole_xfer(ChimlCtx* ctx, int comp, int pole, int prev, double* host, 
 
 int chiml_gpu_download_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host) { return (comp < 0 || comp > 2) ? CHIML_ERR_ARG : pole_xfer(ctx, comp, pole, prev, host, nullptr); }
 int chiml_gpu_upload_pole(ChimlCtx* ctx, int comp, int pole, int prev, const double* host) { return (comp < 0 || comp > 2) ? CHIML_ERR_ARG : pole_xfer(ctx, comp, pole, prev, nullptr, host); }
+int chiml_gpu_download_chi_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host)
+{
+    if(!ctx || !host) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "pole access before commit");
+    if(comp < 0 || comp > 5 || pole < 0 || pole >= MAX_CHI) return fail(ctx, CHIML_ERR_ARG, "chiral pole access: bad comp/pole");
+    CK(cudaSetDevice(ctx->device));
+    const SpanTable& sp = ctx->span[comp];
+    double* pool = ctx->d_chi[comp][pole][prev ? 1 - ctx->pcur : ctx->pcur];
+    std::fill(host, host + ctx->nlogical, 0.0);
+    if(!pool || sp.total == 0) return CHIML_OK;
+    std::vector<double> tmp((size_t)sp.total);
+    CK(cudaMemcpyAsync(tmp.data(), pool, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t nrows = (size_t)ctx->ly * ctx->lz;
+    for(size_t row = 0; row < nrows; ++row)
+    {
+        if(sp.h_xmin[row] < 0) continue;
+        const int w = std::min(sp.h_xmax[row], ctx->lx - 1) - sp.h_xmin[row] + 1;
+        std::copy_n(&tmp[(size_t)sp.h_base[row]], w, host + row * ctx->lx + sp.h_xmin[row]);
+    }
+    return CHIML_OK;
+}
+
+int chiml_gpu_download_prev_field(ChimlCtx* ctx, int comp, double* host)
+{
+    if(!ctx || !host) return CHIML_ERR_ARG;
+    if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "download_prev_field before commit");
+    if(comp < 0 || comp > 5 || !ctx->d_prev[comp]) return fail(ctx, CHIML_ERR_ARG, "download_prev_field: no previous-field copy of this component (no chiral list)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(host, (size_t)ctx->lx * sizeof(double), ctx->d_prev[comp], (size_t)ctx->px * sizeof(double), (size_t)ctx->lx * sizeof(double),
+                         (size_t)ctx->ly * ctx->lz, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CHIML_OK;
+}
+
 int chiml_gpu_download_mag_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host) { return (comp < 0 || comp > 2) ? CHIML_ERR_ARG : pole_xfer(ctx, 3 + comp, pole, prev, host, nullptr); }
 
 int chiml_gpu_download_ordip_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host)

@@ -21,6 +21,7 @@
 
 namespace chiml {
 
+constexpr int MAX_CHI = 4;        // chiral poles per material class
 constexpr int MAX_POLES = 12;     // poles per material class (largest built-in metal has 6)
 constexpr int MAX_SOURCES = 32;
 constexpr int MAX_CLASSES = 255;
@@ -46,6 +47,10 @@ struct ClassEntry
     int pad;
     double alpha[MAX_POLES], xi[MAX_POLES], gamma[MAX_POLES];
     double dip[MAX_POLES][3];
+    // chiral poles of the class (UpdateChiral, UTIL/FDTD_up_eq.cpp:64-111; chiDtoU :920-925)
+    int nchi, pad2;
+    double chi_alpha[MAX_CHI], chi_xi[MAX_CHI], chi_g8[MAX_CHI], chi_gp8[MAX_CHI];   // chiAlpha, chiXi, chiGamma / 8.0, chiGammaPrev / 8.0
+    double chi_fac;             // -1.0 / (-1.0 * eps) for E (D2E passes -eps), -1.0 / mu for H
 };
 
 // compact storage of per-row x-spans (pole state)
@@ -89,7 +94,7 @@ struct DetectorDev
 };
 
 // kernels of the step loop, for launch / time / algorithmic-byte accounting
-enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_STEPS_2D, K_WRAP, K_TFSF, K_WRAP_BLOCH, K_NKINDS };
+enum KernelKind { K_E_FAST = 0, K_E_UNIFORM, K_E_GENERAL, K_H_FAST, K_H_UNIFORM, K_H_GENERAL, K_ORDIP_POLES, K_SOURCE, K_DETECTOR, K_EMIT_ADDP, K_EMIT_DENSITY, K_EMIT_POP, K_HALO_PUSH, K_HALO_WAIT, K_DFT, K_STEPS_2D, K_WRAP, K_TFSF, K_WRAP_BLOCH, K_PREV_COPY, K_NKINDS };
 struct KernelStat { int64_t launches = 0; double ms_total = 0.0; double alg_bytes = 0.0; int64_t timed = 0; };
 
 // one parallelQE object on the device (chiml_emitters.cuh)
@@ -152,7 +157,7 @@ struct TfsfDev
 
 struct HostList { std::vector<ChimlRun> runs; };
 struct HostPml { int present = 0, has_psi = 0; std::vector<ChimlPsiParams> psi; std::vector<ChimlGridParams> grid; };
-struct HostObj { int npoles = 0, use_or_dip = 0; std::vector<double> alpha, xi, gamma, dip; int nmag = 0; std::vector<double> malpha, mxi, mgamma; };
+struct HostObj { int npoles = 0, use_or_dip = 0; std::vector<double> alpha, xi, gamma, dip; int nmag = 0; std::vector<double> malpha, mxi, mgamma; int nchi = 0; std::vector<double> calpha, cxi, cgamma, cgprev; };
 
 } // namespace chiml
 
@@ -192,6 +197,15 @@ struct ChimlCtx
     int npoles_comp[6] = {};
     double* d_P[6][chiml::MAX_POLES][2] = {};
     int has_B = 0, pml_on_B = 0;       // chiml_gpu_set_magnetic
+    // chiral media: chiral pole pools over the same spans, previous-field copies, the rows copied after each half step
+    double* d_chi[6][chiml::MAX_CHI][2] = {};
+    double* d_prev[6] = {};            // prevE_[0..2], prevH_[0..2] (logical origin, guarded like d_field)
+    double* d_prev_base[6] = {};
+    int nchi_comp[6] = {};
+    long chi_off[6][3] = {};           // logical ind_i - ind, ind_j - ind, ind_k - ind of the CHID list of the component
+    std::vector<int32_t> h_prev_rows;  // copy2PrevFields_: 4 per row {length, x, y, z}
+    int4* d_prev_rows = nullptr; size_t n_prev_rows = 0;
+    bool has_chi = false;
     int pcur = 0;                // which of the two buffers currently holds P (the other holds prevP)
 
     // oriented-dipole poles at nodes
@@ -217,7 +231,7 @@ struct ChimlCtx
     double* d_tw = nullptr; size_t tw_cap = 0;   // twiddles of the current step_n_dft call
 
     // host-side copies of the setup until commit
-    chiml::HostList lists[5][6];
+    chiml::HostList lists[6][6];
     chiml::HostPml hpml[6][2];
     std::vector<chiml::HostObj> objs;
 

@@ -48,6 +48,11 @@ struct CompArgs
     int nordip;
     int ord_dx, ord_dy, ord_dz;  // node offset r + e_c of orDipDtoU
     int ord_zvariant;            // orDipDtoUZ (2-D TM Ez)
+    // chiral poles (pools over the same spans as the isotropic ones); the eight-point stencil on the other family's same component
+    const double* chiCur[MAX_CHI];
+    double* chiNew[MAX_CHI];
+    const double* oppPrev;       // previous value of the other family's component (prevH_[c] for E_c, prevE_[c] for H_c)
+    long chi_oi, chi_oj, chi_ok; // physical offsets of ind_i, ind_j, ind_k of the chiral list relative to ind
 };
 
 struct StepArgs
@@ -258,6 +263,20 @@ __global__ void k_tfsf_check(const int32_t* pairs, int npairs, int n, int stride
         if(m < 0 || m >= ncell) { atomicOr(err, 4); continue; }
         if(info[(m % lx) + px * (m / lx)] & (F_PS0 | F_PS1 | F_PG0 | F_PG1)) atomicOr(err, 8);
     }
+}
+
+// copy2PrevFields_ (FDTD_MANAGER/parallelFDTDField.hpp:1411-1416, 1441-1446): rows {length, x, y, z} of the three components of one family into
+// their prev grids, after the chiral update that read them
+struct PrevCopyArgs { const double* src[3]; double* dst[3]; const int4* rows; unsigned nrows; int lz; long px; };
+__global__ void k_prev_copy(PrevCopyArgs a)
+{
+    const unsigned q = blockIdx.x;
+    if(q >= a.nrows) return;
+    const int4 b = a.rows[q];
+    const long off = b.y + a.px * (b.w + (long)a.lz * b.z);
+    for(int c = 0; c < 3; ++c)
+        if(a.src[c] && a.dst[c])
+            for(int i = threadIdx.x; i < b.x; i += blockDim.x) a.dst[c][off + i] = a.src[c][off + i];
 }
 
 // Periodic wrap copies of up to three components in one launch (applyBC1Proc, UTIL/FDTD_up_eq.cpp:1058-1116; blockIdx.y = component).

@@ -73,6 +73,40 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
         }
     }
 
+    // updateChiE / updateChiH (:1392-1447 -> UpdateChiral, UTIL/FDTD_up_eq.cpp:64-111): chiral poles driven by the other family's component C at
+    // the eight corners r, j, k, j+k-r, i, i+j-r, i+k-r, i+j+k-2r of the list entry, current values then previous ones
+    double cn[MAX_CHI];
+    int nc = 0;
+    if(DP && (info & F_D2E))
+    {
+        nc = ce.nchi;
+        if(nc > 0)
+        {
+            const long ip = ca.sp_base[row] + (x - ca.sp_xmin[row]);
+            const long o2 = ca.chi_oi, o3 = ca.chi_oj, o4 = ca.chi_ok;
+            const long off8[8] = {0, o3, o4, o3 + o4, o2, o2 + o3, o2 + o4, o2 + o3 + o4};
+            const double* __restrict__ opp = a.fam[C];
+            double ov[8], pv[8];
+#pragma unroll
+            for(int k = 0; k < 8; ++k) { ov[k] = opp[r + off8[k]]; pv[k] = ca.oppPrev[r + off8[k]]; }
+#pragma unroll
+            for(int p = 0; p < MAX_CHI; ++p)
+            {
+                if(p < nc)
+                {
+                    double t = dm(ce.chi_alpha[p], ca.chiCur[p][ip]);
+                    t = axpy1(t, ce.chi_xi[p], ca.chiNew[p][ip]);
+#pragma unroll
+                    for(int k = 0; k < 8; ++k) t = axpy1(t, ce.chi_g8[p], ov[k]);
+#pragma unroll
+                    for(int k = 0; k < 8; ++k) t = axpy1(t, ce.chi_gp8[p], pv[k]);
+                    ca.chiNew[p][ip] = t;
+                    cn[p] = t;
+                }
+            }
+        }
+    }
+
     const bool pmlCell = (info & (F_PG0 | F_PS0 | F_PG1 | F_PS1)) != 0;
     const bool pmlOnD = DP && a.pml_on_D;
     const bool needD = DP && ((info & (F_ISD | F_D2E | F_ORD2E)) || (pmlOnD && pmlCell));
@@ -147,6 +181,10 @@ __device__ __forceinline__ bool update_cell(const StepArgs& a, const CompArgs& c
 #pragma unroll
         for(int p = 0; p < MAX_POLES; ++p)
             if(p < np) u = axpy1(u, ce.neg_inv_eps, pn[p]);
+        // chiDtoU (:920-925) with epMuInfty = -eps (E) / +mu (H)
+#pragma unroll
+        for(int p = 0; p < MAX_CHI; ++p)
+            if(p < nc) u = axpy1(u, ce.chi_fac, cn[p]);
     }
     else if(IS_E && (info & F_ORD2E))
     {

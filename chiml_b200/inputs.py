@@ -38,9 +38,10 @@ def normal_source(pol: str, loc: Sequence[float], size: Sequence[float], pulses:
 
 
 def lorentz_pole(sigma_p: float, gamma: float, omega: float, dip_or_e: str = "isotropic", dir_dip_e: Sequence[float] = (0.0, 0.0, 0.0),
-                 sigma_m: float = 0.0) -> Dict:
-    """sigma_m > 0 makes the pole a magnetic one as well (magnetisation M driven by H, OBJECTS/Obj.cpp setUpConsts)."""
-    return {"dipOrE": dip_or_e, "dipOrM": "isotropic", "sigma_p": sigma_p, "sigma_m": sigma_m, "tau": 0.0, "gamma": gamma,
+                 sigma_m: float = 0.0, tau: float = 0.0) -> Dict:
+    """sigma_m > 0 makes the pole a magnetic one as well (magnetisation M driven by H, OBJECTS/Obj.cpp setUpConsts); tau != 0 a chiral one
+    (cross terms between E and H, chiAlpha / chiXi / chiGamma / chiGammaPrev, OBJECTS/Obj.cpp:345-353)."""
+    return {"dipOrE": dip_or_e, "dipOrM": "isotropic", "sigma_p": sigma_p, "sigma_m": sigma_m, "tau": tau, "gamma": gamma,
             "omega": omega, "dirDipE": list(dir_dip_e), "dirDipM": [0.0, 0.0, 0.0]}
 
 

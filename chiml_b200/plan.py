@@ -19,7 +19,7 @@ import numpy as np
 PLAN_VERSION = 1
 
 MODE_TE, MODE_TM, MODE_3D = 0, 1, 2
-LIST_U, LIST_D, LIST_LORD, LIST_ORDIPD, LIST_ORDIPP = 0, 1, 2, 3, 4
+LIST_U, LIST_D, LIST_LORD, LIST_ORDIPD, LIST_ORDIPP, LIST_CHID = 0, 1, 2, 3, 4, 5
 FIELD_NAMES = ["Ex", "Ey", "Ez", "Hx", "Hy", "Hz", "Dx", "Dy", "Dz", "Bx", "By", "Bz"]
 
 RUN_DTYPE = np.dtype([("n", "<i4"), ("ind", "<i4"), ("ind_i", "<i4"), ("ind_j", "<i4"), ("ind_k", "<i4"),
@@ -168,11 +168,17 @@ class Plan:
     pml_on_B: int = 0
     n_mag_poles: int = 0
     mag_objects: Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray]] = field(default_factory=dict)   # obj -> (magAlpha, magXi, magGamma)
+    chi_objects: Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = field(default_factory=dict)   # obj -> (chiAlpha, chiXi, chiGamma, chiGammaPrev)
+    prev_copy: Optional[np.ndarray] = None      # (nrows, 4) int32: copy2PrevFields_ rows {length, x, y, z}
     cplx: bool = False                          # complex fields (record COMPLEX): real and imaginary parts are two field sets over the same lists
     k_point: Tuple[float, float, float] = (0.0, 0.0, 0.0)
     tfsf: List[PlanTfsfSurface] = field(default_factory=list)
     tfsf_lines: Optional[np.ndarray] = None     # (n_steps, per_step): the incident-line table of chiml_gpu_step_n_tfsf
     periodic: Dict[int, Tuple[int, ...]] = field(default_factory=dict)      # comp -> (nx, ny, nz, xmax, ymax, zmin, zmax) (ChimlWrap)
+
+    @property
+    def n_chi_poles(self) -> int:
+        return max([len(a[0]) for a in self.chi_objects.values()] + [0])
 
     @property
     def ncell(self) -> int:
@@ -254,6 +260,13 @@ def read_plan(path: str) -> Plan:
             obj, np_ = struct.unpack_from("<ii", payload, 0)
             arrs = [np.frombuffer(payload, dtype="<f8", count=np_, offset=8 + 8 * np_ * k).copy() for k in range(3)]
             plan.mag_objects[obj] = (arrs[0], arrs[1], arrs[2])
+        elif tag == "OBJCHI":
+            obj, np_ = struct.unpack_from("<ii", payload, 0)
+            arrs = [np.frombuffer(payload, dtype="<f8", count=np_, offset=8 + 8 * np_ * k).copy() for k in range(4)]
+            plan.chi_objects[obj] = tuple(arrs)
+        elif tag == "PREVCOPY":
+            (nr,) = struct.unpack_from("<Q", payload, 0)
+            plan.prev_copy = np.frombuffer(payload, dtype="<i4", count=4 * nr, offset=8).copy().reshape(nr, 4)
         elif tag == "COMPLEX":
             v = struct.unpack_from("<ii3d", payload, 0)
             plan.cplx = bool(v[0]); plan.k_point = tuple(v[2:5])
@@ -345,6 +358,10 @@ def write_plan(path: str, plan: Plan) -> None:
         out.append(_rec("MAGNETIC", struct.pack("<4i", plan.has_B, plan.pml_on_B, plan.n_mag_poles, 0)))
         for obj, (a, x, g) in sorted(plan.mag_objects.items()):
             out.append(_rec("OBJMAG", struct.pack("<ii", obj, len(a)) + np.asarray(a, "<f8").tobytes() + np.asarray(x, "<f8").tobytes() + np.asarray(g, "<f8").tobytes()))
+    for obj, arrs in sorted(plan.chi_objects.items()):
+        out.append(_rec("OBJCHI", struct.pack("<ii", obj, len(arrs[0])) + b"".join(np.asarray(a, "<f8").tobytes() for a in arrs)))
+    if plan.prev_copy is not None:
+        out.append(_rec("PREVCOPY", struct.pack("<Q", len(plan.prev_copy)) + np.ascontiguousarray(plan.prev_copy, "<i4").tobytes()))
     if plan.cplx:
         out.append(_rec("COMPLEX", struct.pack("<ii3d", 1, 0, *plan.k_point)))
     for s in plan.sources:

@@ -84,7 +84,10 @@ typedef enum ChimlListKind
     CHIML_LIST_D      = 1, /* upD_[c]: curl accumulated into D                       (updateD :1338-1343)        */
     CHIML_LIST_LORD   = 2, /* upLorD_[c]: isotropic pole update + D->E               (updatePolE :1355-1361, D2E :1456-1459) */
     CHIML_LIST_ORDIPD = 3, /* upOrDipD_[c]: oriented-dipole D->E (node->edge average) (D2E :1465-1466)            */
-    CHIML_LIST_ORDIPP = 4  /* upOrDipP_: oriented-dipole pole update at nodes; comp ignored (updatePolE :1350-1354) */
+    CHIML_LIST_ORDIPP = 4, /* upOrDipP_: oriented-dipole pole update at nodes; comp ignored (updatePolE :1350-1354) */
+    CHIML_LIST_CHID   = 5  /* upChiD_[c] (comp 0..2) / upChiB_[c] (comp 3..5): the cells of chiral objects -- achiral poles, chiral poles driven by the
+                              8-point average of the other family's same component and of its previous value, D->E / B->H with both (updateChiE /
+                              updateChiH :1392-1447, D2E :1460-1464, B2H :1484-1488); 3-D grids */
 } ChimlListKind;
 
 /* ---- life cycle ------------------------------------------------------------------------------ */
@@ -189,6 +192,19 @@ int chiml_gpu_set_magnetic(ChimlCtx* ctx, int has_B, int pml_on_B);
 int chiml_gpu_set_object_magnetic(ChimlCtx* ctx, int obj, int npoles, const double* alpha, const double* xi, const double* gamma);
 /* magnetic pole state lorM_[c][p] / prevLorM_[c][p] (c = 0..2 for Hx..Hz) expanded to the logical full grid */
 int chiml_gpu_download_mag_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host);
+
+/* Chiral media (UpdateChiral, UTIL/FDTD_up_eq.cpp:64-111; chiDtoU :920-925).  Per chiral pole p of an object, on the cells of CHIML_LIST_CHID:
+ *   E side:  chiP_p = chiAlpha_p chiP_p + chiXi_p chiP_p,prev + (chiGamma_p / 8) sum_8 H_i + (chiGammaPrev_p / 8) sum_8 H_i,prev ;  E_i += (+1/eps) chiP_p
+ *   H side:  chiM_p likewise from E_i and its previous value, before the H / B update of the step;                                H_i += (-1/mu) chiM_p
+ * where the eight points are r, ind_j, ind_k, ind_j+ind_k-r, ind_i, ind_i+ind_j-r, ind_i+ind_k-r, ind_i+ind_j+ind_k-2r of the list entry, and "previous"
+ * is the copy of the other family's fields taken right after the update that used them (copy2PrevFields_, parallelFDTDField.cpp:391-410: rows
+ * {length, x, y, z} of a box around every chiral object).  Constants: Obj::chiAlpha() / chiXi() / chiGamma() / chiGammaPrev().  Needs D and B grids
+ * (has_D, chiml_gpu_set_magnetic).  3-D grids, single slab; chiral oriented dipoles are refused. */
+int chiml_gpu_set_object_chiral(ChimlCtx* ctx, int obj, int npoles, const double* alpha, const double* xi, const double* gamma, const double* gamma_prev);
+int chiml_gpu_set_prev_copy(ChimlCtx* ctx, const int32_t* rows /* 4 per row: length, x, y, z */, size_t nrows);
+/* chiral pole state lorChiHP_[c][p] (comp 0..2) / lorChiEM_[c][p] (comp 3..5) and their previous values; the previous-field copies prevE_ / prevH_ */
+int chiml_gpu_download_chi_pole(ChimlCtx* ctx, int comp, int pole, int prev, double* host);
+int chiml_gpu_download_prev_field(ChimlCtx* ctx, int comp, double* host);
 
 /* Complex fields (Bloch-periodic runs: a k-point switches the reference to parallelFDTDFieldCplx, INPUTS/parallelInputs.cpp:108-112).  Every operator
  * of the step has real coefficients -- the reference's complex BLAS chains multiply by real factors -- so the real and the imaginary parts of all

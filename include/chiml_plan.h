@@ -107,6 +107,11 @@ typedef struct ChimlPlanObjMagHdr      /* tag "OBJMAG  ": header + magAlpha[np] 
 {
     int32_t obj, npoles;
 } ChimlPlanObjMagHdr;
+typedef struct ChimlPlanObjChiHdr      /* tag "OBJCHI  ": header + chiAlpha[np] chiXi[np] chiGamma[np] chiGammaPrev[np] of object obj */
+{
+    int32_t obj, npoles;
+} ChimlPlanObjChiHdr;
+/* tag "PREVCOPY": uint64 nrows, then nrows x {int32 length, x, y, z}: copy2PrevFields_ (local ghost-inclusive coordinates) */
 typedef struct ChimlPlanComplex        /* tag "COMPLEX ": the propagator holds complex fields (Bloch-periodic run, parallelFDTDFieldCplx): every field / psi /
                                           pole array has a real and an imaginary part, coupled only by the phase factors of the periodic wrap copies */
 {

@@ -49,7 +49,7 @@ struct OracleSim
     ChimlGridDesc g;
     size_t ncell;
     double* f[CHIML_NFIELDS];
-    RunList up[5][6];              /* [kind][comp] */
+    RunList up[6][6];              /* [kind][comp] */
     CpmlPart pml[6][2];
     ObjConst* obj;
     int npoles;                    /* number of allocated isotropic pole grids = max over objects (lorP_[c].size()) */
@@ -63,6 +63,13 @@ struct OracleSim
     double* M[3][MAX_POLES];       /* lorM_[c][p] */
     double* Mprev[3][MAX_POLES];   /* prevLorM_[c][p] */
     ObjConst* mobj;                /* magnetic pole constants per object (magAlpha, magXi, magGamma) */
+    /* chiral media */
+    ObjConst* cobj;                /* chiral constants per object: alpha = chiAlpha, xi = chiXi, gamma = chiGamma, dip[p][0] = chiGammaPrev */
+    int nchi;                      /* number of chiral pole grids = max over objects */
+    double* chi[6][MAX_POLES];     /* lorChiHP_[c][p] (0..2), lorChiEM_[c][p] (3..5) */
+    double* chiprev[6][MAX_POLES];
+    double* prevf[6];              /* prevE_[0..2], prevH_[0..2] */
+    int32_t* prevcopy; size_t nprevcopy;   /* copy2PrevFields_ rows {length, x, y, z} */
     SrcBox src[MAX_SRC];
     int nsrc;
     int committed;
@@ -113,7 +120,7 @@ void oracle_destroy(OracleSim* s)
 {
     if(!s) return;
     for(int i = 0; i < CHIML_NFIELDS; ++i) free(s->f[i]);
-    for(int k = 0; k < 5; ++k) for(int c = 0; c < 6; ++c) free(s->up[k][c].r);
+    for(int k = 0; k < 6; ++k) for(int c = 0; c < 6; ++c) free(s->up[k][c].r);
     for(int c = 0; c < 6; ++c) for(int p = 0; p < 2; ++p) { free(s->pml[c][p].psi); free(s->pml[c][p].grid); free(s->pml[c][p].psi_grid); }
     for(int c = 0; c < 3; ++c) for(int p = 0; p < MAX_POLES; ++p) { free(s->P[c][p]); free(s->Pprev[c][p]); free(s->oP[c][p]); free(s->oPprev[c][p]); free(s->dipgrid[c][p]); }
     free(s->obj);
@@ -122,7 +129,7 @@ void oracle_destroy(OracleSim* s)
 
 int oracle_set_update_list(OracleSim* s, int kind, int comp, const ChimlRun* runs, size_t n)
 {
-    if(kind < 0 || kind > 4 || comp < 0 || comp > 5) return CHIML_ERR_ARG;
+    if(kind < 0 || kind > 5 || comp < 0 || comp > 5) return CHIML_ERR_ARG;
     RunList* l = &s->up[kind][comp];
     free(l->r);
     l->r = (ChimlRun*)malloc((n ? n : 1) * sizeof(ChimlRun));
@@ -144,6 +151,28 @@ int oracle_set_object(OracleSim* s, int obj, int npoles, const double* alpha, co
     }
     return 0;
 }
+
+/* chiral media (include/chiml_gpu.h chiml_gpu_set_object_chiral / chiml_gpu_set_prev_copy) */
+int oracle_set_object_chiral(OracleSim* s, int obj, int npoles, const double* alpha, const double* xi, const double* gamma, const double* gamma_prev)
+{
+    if(!s || obj < 0 || obj >= s->g.n_objects || npoles < 0 || npoles > MAX_POLES) return CHIML_ERR_ARG;
+    if(!s->cobj) s->cobj = (ObjConst*)calloc((size_t)(s->g.n_objects > 0 ? s->g.n_objects : 1), sizeof(ObjConst));
+    ObjConst* o = &s->cobj[obj];
+    o->npoles = npoles;
+    for(int p = 0; p < npoles; ++p) { o->alpha[p] = alpha[p]; o->xi[p] = xi[p]; o->gamma[p] = gamma[p]; o->dip[p][0] = gamma_prev[p]; }
+    return 0;
+}
+int oracle_set_prev_copy(OracleSim* s, const int32_t* rows, size_t nrows)
+{
+    if(!s || (nrows && !rows)) return CHIML_ERR_ARG;
+    free(s->prevcopy);
+    s->prevcopy = (int32_t*)malloc((nrows ? nrows : 1) * 4 * sizeof(int32_t));
+    if(nrows) memcpy(s->prevcopy, rows, nrows * 4 * sizeof(int32_t));
+    s->nprevcopy = nrows;
+    return 0;
+}
+double* oracle_chi_pole(OracleSim* s, int comp, int pole, int prev) { return (comp < 0 || comp > 5 || pole < 0 || pole >= MAX_POLES) ? NULL : (prev ? s->chiprev[comp][pole] : s->chi[comp][pole]); }
+double* oracle_prev_field(OracleSim* s, int comp) { return (comp < 0 || comp > 5) ? NULL : s->prevf[comp]; }
 
 /* magnetic-dispersive media (include/chiml_gpu.h chiml_gpu_set_magnetic / chiml_gpu_set_object_magnetic) */
 int oracle_set_magnetic(OracleSim* s, int has_B, int pml_on_B)
@@ -229,6 +258,23 @@ int oracle_commit(OracleSim* s)
         {
             s->M[c][p] = (double*)calloc(s->ncell, sizeof(double));
             s->Mprev[c][p] = (double*)calloc(s->ncell, sizeof(double));
+        }
+    }
+    /* chiral media: lorChiHP_ / lorChiEM_ and their previous values, prevE_ / prevH_ (3-D: every component) */
+    s->nchi = 0;
+    if(s->cobj)
+        for(int o = 0; o < s->g.n_objects; ++o) if(s->cobj[o].npoles > s->nchi) s->nchi = s->cobj[o].npoles;
+    if(s->nchi > 0)
+    {
+        if(s->g.mode != CHIML_MODE_3D || !s->g.has_D || !s->has_B) return CHIML_ERR_UNSUPPORTED;
+        for(int c = 0; c < 6; ++c)
+        {
+            s->prevf[c] = (double*)calloc(s->ncell, sizeof(double));
+            for(int p = 0; p < s->nchi; ++p)
+            {
+                s->chi[c][p] = (double*)calloc(s->ncell, sizeof(double));
+                s->chiprev[c][p] = (double*)calloc(s->ncell, sizeof(double));
+            }
         }
     }
     const RunList* nl = &s->up[CHIML_LIST_ORDIPP][0];
@@ -360,6 +406,43 @@ static void dtou_run(const ChimlRun* r, const double* Di, double* Ui, double** P
     scal(r->n, 1.0 / eps, Ui + r->ind, 1);
     for(int pp = 0; pp < nP; ++pp)
         axpy(r->n, -1.0 / eps, P[pp] + r->ind, 1, Ui + r->ind, 1);
+}
+
+/* UpdateChiral (UTIL/FDTD_up_eq.cpp:64-111): chiral pole of component i driven by the other family's component i at the eight corners spanned
+ * by the entry's three neighbour indices, current and previous values */
+static void chiral_run(const ChimlRun* r, const double* O, const double* Oprev, double** C, double** Cprev, const ObjConst* o, double* jstore)
+{
+    const long i1 = r->ind, i2 = r->ind_i, i3 = r->ind_j, i4 = r->ind_k;
+    const long pts[8] = {i1, i3, i4, i3 + i4 - i1, i2, i2 + i3 - i1, i2 + i4 - i1, i2 + i3 + i4 - 2 * i1};
+    for(int pp = 0; pp < o->npoles; ++pp)
+    {
+        memcpy(jstore, C[pp] + i1, (size_t)r->n * sizeof(double));
+        scal(r->n, o->alpha[pp], C[pp] + i1, 1);
+        axpy(r->n, o->xi[pp], Cprev[pp] + i1, 1, C[pp] + i1, 1);
+        for(int k = 0; k < 8; ++k) axpy(r->n, o->gamma[pp] / 8.0, O + pts[k], 1, C[pp] + i1, 1);
+        for(int k = 0; k < 8; ++k) axpy(r->n, o->dip[pp][0] / 8.0, Oprev + pts[k], 1, C[pp] + i1, 1);
+        memcpy(Cprev[pp] + i1, jstore, (size_t)r->n * sizeof(double));
+    }
+}
+/* chiDtoU (:920-925) with epMuInfty as D2E / B2H pass it: -eps for E, +mu for H */
+static void chi_dtou_run(const ChimlRun* r, double epMuInfty, double* Ui, double** C, int nC)
+{
+    for(int pp = 0; pp < nC; ++pp) axpy(r->n, -1.0 / epMuInfty, C[pp] + r->ind, 1, Ui + r->ind, 1);
+}
+/* copy2PrevFields_ (FDTD_MANAGER/parallelFDTDField.hpp:1411-1416, 1441-1446): the three components of one family into their prev grids */
+static void prev_copy(OracleSim* s, int isE)
+{
+    const size_t lx = (size_t)s->g.ln[0], lz = (size_t)s->g.ln[2];
+    for(size_t q = 0; q < s->nprevcopy; ++q)
+    {
+        const int32_t* b = s->prevcopy + 4 * q;
+        const size_t off = (size_t)b[1] + lx * ((size_t)b[3] + lz * (size_t)b[2]);
+        for(int i = 0; i < 3; ++i)
+        {
+            const int f = (isE ? CHIML_EX : CHIML_HX) + i, pf = (isE ? 0 : 3) + i;
+            if(s->f[f] && s->prevf[pf]) memcpy(s->prevf[pf] + off, s->f[f] + off, (size_t)b[0] * sizeof(double));
+        }
+    }
 }
 
 /* UTIL/FDTD_up_eq.cpp:862-889 orDipDtoU (node->edge average) and orDipDtoUZ (2-D TM Ez) */
@@ -889,6 +972,23 @@ static void step_worker(OracleSim* s, int tid, int nt)
             }
             BARRIER();
         }
+        /* updateChiH (:1231, :1422-1447): achiral magnetic poles of the chiral cells, chiral magnetisation from E and prevE, then E -> prevE */
+        if(s->nchi > 0 && (s->phase_mask & 1))
+        {
+            for(int i = 0; i < 3; ++i)
+            {
+                RunList* l = &s->up[CHIML_LIST_CHID][3 + i];
+                SPLIT(l->n, lo, hi);
+                for(size_t e = lo; e < hi; ++e)
+                {
+                    lor_pol_run(&l->r[e], s->f[CHIML_HX + i], s->M[i], s->Mprev[i], &s->mobj[l->r[e].obj], scratch);
+                    chiral_run(&l->r[e], s->f[CHIML_EX + i], s->prevf[i], s->chi[3 + i], s->chiprev[3 + i], &s->cobj[l->r[e].obj], scratch);
+                }
+            }
+            BARRIER();
+            if(tid == 0) prev_copy(s, 1);
+            BARRIER();
+        }
         /* updateB (:1234, :1328-1333) and updateH (:1308-1313) */
         for(int i = 0; i < 3 && (s->phase_mask & 1); ++i)
         {
@@ -943,6 +1043,13 @@ static void step_worker(OracleSim* s, int tid, int nt)
                 RunList* l = &s->up[CHIML_LIST_LORD][3 + i];
                 SPLIT(l->n, lo, hi);
                 for(size_t e = lo; e < hi; ++e) dtou_run(&l->r[e], s->f[CHIML_BX + i], s->f[CHIML_HX + i], s->M[i], s->nmag);
+                RunList* lc = &s->up[CHIML_LIST_CHID][3 + i];
+                SPLIT(lc->n, lo2, hi2);
+                for(size_t e = lo2; e < hi2; ++e)
+                {
+                    dtou_run(&lc->r[e], s->f[CHIML_BX + i], s->f[CHIML_HX + i], s->M[i], s->nmag);
+                    chi_dtou_run(&lc->r[e], lc->r[e].pf[3], s->f[CHIML_HX + i], s->chi[3 + i], s->nchi);
+                }
             }
             BARRIER();
         }
@@ -966,6 +1073,23 @@ static void step_worker(OracleSim* s, int tid, int nt)
             for(size_t e = lo; e < hi; ++e) lor_pol_run(&l->r[e], s->f[CHIML_EX + i], s->P[i], s->Pprev[i], &s->obj[l->r[e].obj], scratch);
         }
         BARRIER();
+        /* updateChiE (:1273, :1392-1417): achiral poles of the chiral cells, chiral polarisation from H and prevH, then H -> prevH */
+        if(s->nchi > 0 && (s->phase_mask & 4))
+        {
+            for(int i = 0; i < 3; ++i)
+            {
+                RunList* l = &s->up[CHIML_LIST_CHID][i];
+                SPLIT(l->n, lo, hi);
+                for(size_t e = lo; e < hi; ++e)
+                {
+                    lor_pol_run(&l->r[e], s->f[CHIML_EX + i], s->P[i], s->Pprev[i], &s->obj[l->r[e].obj], scratch);
+                    chiral_run(&l->r[e], s->f[CHIML_HX + i], s->prevf[3 + i], s->chi[i], s->chiprev[i], &s->cobj[l->r[e].obj], scratch);
+                }
+            }
+            BARRIER();
+            if(tid == 0) prev_copy(s, 0);
+            BARRIER();
+        }
         /* updateD (:1338-1343) and updateE (:1318-1323) */
         for(int i = 0; i < 3 && (s->phase_mask & 4); ++i)
         {
@@ -994,6 +1118,16 @@ static void step_worker(OracleSim* s, int tid, int nt)
             {
                 SPLIT(l->n, lo, hi);
                 for(size_t e = lo; e < hi; ++e) dtou_run(&l->r[e], s->f[CHIML_DX + i], s->f[CHIML_EX + i], s->P[i], s->npoles);
+            }
+            if(s->nchi > 0)
+            {
+                RunList* lc = &s->up[CHIML_LIST_CHID][i];
+                SPLIT(lc->n, lo, hi);
+                for(size_t e = lo; e < hi; ++e)
+                {
+                    dtou_run(&lc->r[e], s->f[CHIML_DX + i], s->f[CHIML_EX + i], s->P[i], s->npoles);
+                    chi_dtou_run(&lc->r[e], -1.0 * lc->r[e].pf[3], s->f[CHIML_EX + i], s->chi[i], s->nchi);
+                }
             }
             l = &s->up[CHIML_LIST_ORDIPD][i];
             {

@@ -365,10 +365,34 @@ template <class FFT> static void writePlan(const std::string& fname, FFT& FF, co
         }
     }
     else if(FF.magMatInPML_) throw std::runtime_error("plan dump: magnetic material in the PML without B grids");
+    // chiral media: constants per object, the rows copied into prevE_ / prevH_
+    {
+        bool anyChi = false;
+        for(auto& obj : FF.objArr_) anyChi = anyChi || !obj->chiGamma().empty();
+        if(anyChi)
+        {
+            for(size_t oo = 0; oo < FF.objArr_.size(); ++oo)
+            {
+                auto& obj = FF.objArr_[oo];
+                ChimlPlanObjChiHdr h; h.obj = int(oo); h.npoles = int(obj->chiGamma().size());
+                std::string q; app(q, h); appVec(q, obj->chiAlpha()); appVec(q, obj->chiXi()); appVec(q, obj->chiGamma()); appVec(q, obj->chiGammaPrev());
+                putRec(out, "OBJCHI", q);
+            }
+            std::string q; uint64_t nr = FF.copy2PrevFields_.size(); app(q, nr);
+            for(auto& row : FF.copy2PrevFields_) for(int k = 0; k < 4; ++k) { int32_t v = row[k]; app(q, v); }
+            putRec(out, "PREVCOPY", q);
+        }
+    }
     for(int c = 0; c < 3; ++c)
     {
-        if(!FF.upChiD_[c].empty() || !FF.upChiB_[c].empty() || !FF.upOrDipB_[c].empty() || !FF.upOrDipChiD_[c].empty() || !FF.upOrDipChiB_[c].empty())
-            throw std::runtime_error("plan dump: chiral / magnetic oriented-dipole update lists are outside the covered hot path");
+        if(!FF.upOrDipB_[c].empty() || !FF.upOrDipChiD_[c].empty() || !FF.upOrDipChiB_[c].empty())
+            throw std::runtime_error("plan dump: magnetic / chiral oriented-dipole update lists are outside the covered hot path");
+        if(!FF.upChiD_[c].empty() || !FF.upChiB_[c].empty())
+        {
+            if(!hasB || !(FF.D_[0] && FF.D_[2])) throw std::runtime_error("plan dump: chiral lists need D and B grids on a 3-D grid");
+            putList(out, CHIML_LIST_CHID, c, FF.upChiD_[c]);
+            putList(out, CHIML_LIST_CHID, 3 + c, FF.upChiB_[c]);
+        }
         if(hasB)
         {
             putList(out, CHIML_LIST_D, 3 + c, FF.upB_[c]);
@@ -575,6 +599,7 @@ struct GpuApi
     CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
     CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic) CHIML_API(chiml_gpu_add_tfsf_surface) CHIML_API(chiml_gpu_step_n_tfsf)
     CHIML_API(chiml_gpu_set_magnetic) CHIML_API(chiml_gpu_set_object_magnetic) CHIML_API(chiml_gpu_download_mag_pole)
+    CHIML_API(chiml_gpu_set_object_chiral) CHIML_API(chiml_gpu_set_prev_copy) CHIML_API(chiml_gpu_download_chi_pole) CHIML_API(chiml_gpu_download_prev_field)
 #undef CHIML_API
     void load()
     {
@@ -598,6 +623,7 @@ struct GpuApi
         CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
         CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic) CHIML_API(chiml_gpu_add_tfsf_surface) CHIML_API(chiml_gpu_step_n_tfsf)
         CHIML_API(chiml_gpu_set_magnetic) CHIML_API(chiml_gpu_set_object_magnetic) CHIML_API(chiml_gpu_download_mag_pole)
+        CHIML_API(chiml_gpu_set_object_chiral) CHIML_API(chiml_gpu_set_prev_copy) CHIML_API(chiml_gpu_download_chi_pole) CHIML_API(chiml_gpu_download_prev_field)
 #undef CHIML_API
     }
 };
@@ -643,9 +669,10 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
         B.check(A.chiml_gpu_set_update_list(B.ctx, kind, comp, reinterpret_cast<const ChimlRun*>(l.data()), l.size()), "set_update_list"); };
     for(int c = 0; c < 3; ++c)
     {
-        if(!FF.upChiD_[c].empty() || !FF.upChiB_[c].empty() || !FF.upOrDipB_[c].empty())
-            throw std::runtime_error("--gpu: chiral / magnetic oriented-dipole update lists are outside the covered hot path");
+        if(!FF.upOrDipB_[c].empty() || !FF.upOrDipChiD_[c].empty() || !FF.upOrDipChiB_[c].empty())
+            throw std::runtime_error("--gpu: magnetic / chiral oriented-dipole update lists are outside the covered hot path");
         if(hasB) { put(CHIML_LIST_D, 3 + c, FF.upB_[c]); put(CHIML_LIST_LORD, 3 + c, FF.upLorB_[c]); }
+        if(!FF.upChiD_[c].empty() || !FF.upChiB_[c].empty()) { put(CHIML_LIST_CHID, c, FF.upChiD_[c]); put(CHIML_LIST_CHID, 3 + c, FF.upChiB_[c]); }   // chiral media
         put(CHIML_LIST_U, c, FF.upE_[c]);   put(CHIML_LIST_U, 3 + c, FF.upH_[c]);
         put(CHIML_LIST_D, c, FF.upD_[c]);   put(CHIML_LIST_LORD, c, FF.upLorD_[c]);
         put(CHIML_LIST_ORDIPD, c, FF.upOrDipD_[c]);
@@ -666,6 +693,8 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
             }
         B.check(A.chiml_gpu_set_object(B.ctx, int(oo), np, obj->alpha().data(), obj->xi().data(), obj->gamma().data(), obj->useOrdDip() ? 1 : 0, dip.data()), "set_object");
         if(hasB) B.check(A.chiml_gpu_set_object_magnetic(B.ctx, int(oo), int(obj->magGamma().size()), obj->magAlpha().data(), obj->magXi().data(), obj->magGamma().data()), "set_object_magnetic");
+        if(!obj->chiGamma().empty())
+            B.check(A.chiml_gpu_set_object_chiral(B.ctx, int(oo), int(obj->chiGamma().size()), obj->chiAlpha().data(), obj->chiXi().data(), obj->chiGamma().data(), obj->chiGammaPrev().data()), "set_object_chiral");
     }
     // periodic boundaries: the arguments of applBCE_ / applBCH_ (single rank: applyBC1Proc)
     if(FF.E_[0] ? FF.E_[0]->PBC() : FF.E_[2]->PBC())
@@ -675,6 +704,8 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
                 const ChimlWrap w = wrapArgs(FF, comp);
                 B.check(A.chiml_gpu_set_periodic(B.ctx, comp, &w), "set_periodic");
             }
+    if(!FF.copy2PrevFields_.empty())                 // chiral media: the rows copied into prevE_ / prevH_ (std::array<int,4> rows are 4 ints each)
+        B.check(A.chiml_gpu_set_prev_copy(B.ctx, reinterpret_cast<const int32_t*>(FF.copy2PrevFields_.data()), FF.copy2PrevFields_.size()), "set_prev_copy");
     static_assert(sizeof(updatePsiParams) == sizeof(ChimlPsiParams) && sizeof(updateGridParams) == sizeof(ChimlGridParams), "CPML list layouts");
     for(int c = 0; c < 3; ++c)
         for(int side = 0; side < 2; ++side)
@@ -897,6 +928,18 @@ static void gpuFinish(parallelFDTDFieldReal& FF, GpuBinding& B)
         if(FF.H_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_HX + c, &FF.H_[c]->point(0)), "download_field");
         if(FF.D_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_DX + c, &FF.D_[c]->point(0)), "download_field");
         if(FF.B_[c]) B.check(A.chiml_gpu_download_field(B.ctx, CHIML_BX + c, &FF.B_[c]->point(0)), "download_field");
+        if(FF.prevE_[c] && !FF.copy2PrevFields_.empty()) B.check(A.chiml_gpu_download_prev_field(B.ctx, c, &FF.prevE_[c]->point(0)), "download_prev_field");
+        if(FF.prevH_[c] && !FF.copy2PrevFields_.empty()) B.check(A.chiml_gpu_download_prev_field(B.ctx, 3 + c, &FF.prevH_[c]->point(0)), "download_prev_field");
+        for(size_t p = 0; p < FF.lorChiHP_[c].size(); ++p)
+        {
+            B.check(A.chiml_gpu_download_chi_pole(B.ctx, c, int(p), 0, &FF.lorChiHP_[c][p]->point(0)), "download_chi_pole");
+            B.check(A.chiml_gpu_download_chi_pole(B.ctx, c, int(p), 1, &FF.prevLorChiHP_[c][p]->point(0)), "download_chi_pole");
+        }
+        for(size_t p = 0; p < FF.lorChiEM_[c].size(); ++p)
+        {
+            B.check(A.chiml_gpu_download_chi_pole(B.ctx, 3 + c, int(p), 0, &FF.lorChiEM_[c][p]->point(0)), "download_chi_pole");
+            B.check(A.chiml_gpu_download_chi_pole(B.ctx, 3 + c, int(p), 1, &FF.prevLorChiEM_[c][p]->point(0)), "download_chi_pole");
+        }
         for(size_t p = 0; p < FF.lorM_[c].size(); ++p)
         {
             B.check(A.chiml_gpu_download_mag_pole(B.ctx, c, int(p), 0, &FF.lorM_[c][p]->point(0)), "download_mag_pole");
@@ -1037,6 +1080,18 @@ static void rankMain(int rank, const Options& opt)
             grabGrid(rank, std::string("H") + c[i], FF.H_[i]);
             grabGrid(rank, std::string("D") + c[i], FF.D_[i]);
             grabGrid(rank, std::string("B") + c[i], FF.B_[i]);
+            grabGrid(rank, std::string("vE") + c[i], FF.prevE_[i]);
+            grabGrid(rank, std::string("vH") + c[i], FF.prevH_[i]);
+            for(size_t p = 0; p < FF.lorChiHP_[i].size(); ++p)
+            {
+                grabGrid(rank, std::string("cP") + c[i] + std::to_string(p), FF.lorChiHP_[i][p]);
+                grabGrid(rank, std::string("cvP") + c[i] + std::to_string(p), FF.prevLorChiHP_[i][p]);
+            }
+            for(size_t p = 0; p < FF.lorChiEM_[i].size(); ++p)
+            {
+                grabGrid(rank, std::string("cM") + c[i] + std::to_string(p), FF.lorChiEM_[i][p]);
+                grabGrid(rank, std::string("cvM") + c[i] + std::to_string(p), FF.prevLorChiEM_[i][p]);
+            }
             for(size_t p = 0; p < FF.lorM_[i].size(); ++p)
             {
                 grabGrid(rank, std::string("M") + c[i] + std::to_string(p), FF.lorM_[i][p]);

@@ -234,6 +234,21 @@ def cases():
     te = I.c1_te_vacuum(n=47, steps=100, pml_cells=8, out="out/mte")
     te["ObjectList"] = [dict(I.block([0.1, 0.1, 0.0], [0.1, -0.03, 0.0], eps=1.0, pols=[magp(0.0, 0.05, 1.8, 0.9)]), mu=1.8)]      # (off the Hz source: B2H overwrites a source inside)
     c["mag_te"] = _short_pulse(te)
+    # ---- chiral media (the "chi" of chiML): a block whose poles are electric, magnetic and chiral (tau != 0: P gains a term driven by the 8-point
+    # average of H and of the previous H, M one driven by E) beside an achiral Lorentz sphere; and the same kind of block reaching through the CPML ----
+    chip = lambda sp, g, w, sm, tau: I.lorentz_pole(sp, g, w, sigma_m=sm, tau=tau)  # noqa: E731
+    c["chi3d"] = _short_pulse(I.config(
+        I.comp_cell([23 / RES, 19 / RES, 21 / RES], RES, 60 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+        [I.normal_source("Ez", [0, 0, 0.04], [0.05, 0.04, 0], [I.gaussian_pulse(1.5, 1.0)]),
+         I.normal_source("Hy", [0.06, 0.0, -0.04], [0, 0, 0], [I.gaussian_pulse(1.2, 1.0)])],
+        [dict(I.block([0.08, 0.06, 0.05], [0.01, 0, -0.02], eps=2.0, pols=[chip(1.2, 0.1, 2.0, 0.6, 0.3), chip(0.5, 0.05, 3.0, 0.3, -0.2)]), mu=1.5),
+         I.sphere(0.03, [-0.04, 0.02, 0.04], eps=1.5, pols=[I.lorentz_pole(0.7, 0.2, 1.0)])],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Hy", "out/ch/dtc", time_int=DT * 1.0000001)]))
+    c["chi3d_pml"] = _short_pulse(I.config(
+        I.comp_cell([21 / RES, 19 / RES, 17 / RES], RES, 50 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES, 4 / RES, 5 / RES]),
+        [I.normal_source("Ey", [0.0, 0.04, 0.0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
+        [dict(I.block([0.5, 0.06, 0.05], [0.0, -0.02, 0.0], eps=1.8, pols=[chip(0.9, 0.1, 2.0, 0.8, 0.4)]), mu=1.2)],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Hz", "out/chp/dtc", time_int=DT * 1.0000001)]))
     return c
 
 

@@ -85,6 +85,12 @@ def lib() -> C.CDLL:
         L.oracle_step_n.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_step_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_set_periodic.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_set_object_chiral.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_set_prev_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.oracle_chi_pole.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.oracle_chi_pole.restype = C.POINTER(C.c_double)
+        L.oracle_prev_field.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_prev_field.restype = C.POINTER(C.c_double)
         L.oracle_set_magnetic.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.oracle_set_object_magnetic.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_mag_pole.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -144,6 +150,12 @@ class OracleSim:
             for obj, (a, x, gm) in sorted(plan.mag_objects.items()):
                 a, x, gm = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, x, gm))
                 self._chk(L.oracle_set_object_magnetic(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm)))
+        for obj, arrs in sorted(plan.chi_objects.items()):
+            a, x, gm, gp = (np.ascontiguousarray(v, dtype=np.float64) for v in arrs)
+            self._chk(L.oracle_set_object_chiral(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm), _ptr(gp)))
+        if plan.prev_copy is not None:
+            rows = np.ascontiguousarray(plan.prev_copy, dtype=np.int32)
+            self._chk(L.oracle_set_prev_copy(self.h, _ptr(rows), len(rows)))
         for c in plan.cpml:
             psi, grid = np.ascontiguousarray(c.psi), np.ascontiguousarray(c.grid)
             self._chk(L.oracle_set_cpml(self.h, c.comp, c.part, c.has_psi, _ptr(psi), len(psi), _ptr(grid), len(grid)))
@@ -243,6 +255,12 @@ class OracleSim:
 
     def pole(self, comp: int, pole: int, prev: int = 0):
         return self._view(lib().oracle_pole(self.h, comp, pole, prev))
+
+    def chi_pole(self, comp: int, pole: int, prev: int = 0):
+        return self._view(lib().oracle_chi_pole(self.h, comp, pole, prev))
+
+    def prev_field(self, comp: int):
+        return self._view(lib().oracle_prev_field(self.h, comp))
 
     def mag_pole(self, comp: int, pole: int, prev: int = 0):
         return self._view(lib().oracle_mag_pole(self.h, comp, pole, prev))

@@ -15,6 +15,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
+def _free_port() -> int:
+    import socket
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return so.getsockname()[1]
+
+
 def _env(march):
     """Forced column length of the y-marching kernels for the worker processes (CHIML_B200_MARCH_NY, include/chiml_gpu.h
     chiml_gpu_set_march): slab-boundary planes stay single-plane work items, the columns next to them carry their y neighbours."""
@@ -31,7 +38,7 @@ def test_two_slabs_over_nvlink_match_single_rank_reference(march):
         pytest.skip("needs two GPUs")
     cases = ["vac3d", "aniso_slab3d", "lorentz3d", "ml3d_two", "ml3d_four", "ml_te", "ml_tm", "tm_au", "te_vacuum", "c4_small", "flux3d", "te_flux", "tm_flux", "aniso_mixed3d", "ml3d_two+pair", "c4_small+pair"]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29733", os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
+                        "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
                        capture_output=True, text=True, timeout=900, env=_env(march))
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     for c in cases:
@@ -44,7 +51,7 @@ def test_four_slabs_match_single_rank_reference_even_on_one_gpu(march):
     only the rim of the emitter sheet (an emitter set without emitters), flux3d has flux surfaces cut by slab boundaries."""
     cases = ["aniso_slab3d", "ml3d_two", "c4_small", "flux3d", "aniso_mixed3d", "ml3d_two+pair", "ml_te+pair"]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
-                        "--master-port", "29734", os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
+                        "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
                        capture_output=True, text=True, timeout=900, env=_env(march))
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     for c in cases:
@@ -58,7 +65,7 @@ def test_eight_slabs_of_three_rows_match_single_rank_reference():
     import bench
     cases = bench.HALO_PARITY_CASES
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=8", "--master-addr", "127.0.0.1",
-                        "--master-port", "29735", os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
+                        "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
                        capture_output=True, text=True, timeout=900, env=_env(None))
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     for c in cases:

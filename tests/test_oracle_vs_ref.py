@@ -40,4 +40,4 @@ def test_fixture_covers_every_list_kind():
     for case in util.CASES:
         plan = util.load_plan(case)
         kinds |= {k for (k, c), v in plan.lists.items() if len(v)}
-    assert kinds == {0, 1, 2, 3, 4}
+    assert kinds == {0, 1, 2, 3, 4, 5}

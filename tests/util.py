@@ -48,6 +48,13 @@ def state_array(sim, name: str):
             out[:, 0, 0], out[:, 0, 1] = a.real, a.imag
             return out
         raise KeyError(name)
+    # chiral media: vE / vH = prevE_ / prevH_; cP / cvP = lorChiHP_ / its previous value; cM / cvM = lorChiEM_ / previous
+    if name[:2] in ("vE", "vH") and len(name) == 3:
+        return sim.prev_field((0 if name[1] == "E" else 3) + "xyz".index(name[2]))
+    if name.startswith("cvP") or name.startswith("cvM"):
+        return sim.chi_pole((0 if name[2] == "P" else 3) + "xyz".index(name[3]), int(name[4:]), 1)
+    if name.startswith("cP") or name.startswith("cM"):
+        return sim.chi_pole((0 if name[1] == "P" else 3) + "xyz".index(name[2]), int(name[3:]), 0)
     if name.startswith("pM"):
         return sim.mag_pole("xyz".index(name[2]), int(name[3:]), 1)
     if name.startswith("M"):
@@ -80,6 +87,11 @@ def state_names(plan: P.Plan):
         if (9 + c) in plan.fields_present():
             for p in range(plan.n_mag_poles):
                 names += [f"M{'xyz'[c]}{p}", f"pM{'xyz'[c]}{p}"]
+    if plan.chi_objects:
+        names += [f"v{f}{c}" for f in "EH" for c in "xyz"]
+        for c in "xyz":
+            for p in range(plan.n_chi_poles):
+                names += [f"cP{c}{p}", f"cvP{c}{p}", f"cM{c}{p}", f"cvM{c}{p}"]
     for k in range(len(plan.dfts)):
         names += [f"dft{k}r", f"dft{k}i"]
     for q, e in enumerate(plan.emitters):
