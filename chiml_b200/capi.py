@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "chiml_gpu_consume_population", "chiml_gpu_set_persistent", "chiml_gpu_set_periodic", "chiml_gpu_add_tfsf_surface",
     "chiml_gpu_step_n_tfsf", "chiml_gpu_bind_imag", "chiml_gpu_step_n_cplx",
     "chiml_gpu_set_magnetic", "chiml_gpu_set_object_magnetic", "chiml_gpu_download_mag_pole",
-    "chiml_gpu_set_object_chiral", "chiml_gpu_set_prev_copy", "chiml_gpu_download_chi_pole", "chiml_gpu_download_prev_field",
+    "chiml_gpu_set_dip_grid", "chiml_gpu_set_object_chiral", "chiml_gpu_set_prev_copy", "chiml_gpu_download_chi_pole", "chiml_gpu_download_prev_field",
 ]
 
 
@@ -178,6 +178,7 @@ def lib() -> C.CDLL:
     L.chiml_gpu_set_periodic.argtypes = [vp, i, vp]
     L.chiml_gpu_set_object_chiral.argtypes = [vp, i, i, vp, vp, vp, vp]
     L.chiml_gpu_set_prev_copy.argtypes = [vp, vp, sz]
+    L.chiml_gpu_set_dip_grid.argtypes = [vp, i, i, vp]
     L.chiml_gpu_download_chi_pole.argtypes = [vp, i, i, i, vp]
     L.chiml_gpu_download_prev_field.argtypes = [vp, i, vp]
     L.chiml_gpu_set_magnetic.argtypes = [vp, i, i]
@@ -245,6 +246,9 @@ class GpuSim:
             for o in plan.objects:
                 a, x, gm, dp = (np.ascontiguousarray(v, dtype=np.float64) for v in (o.alpha, o.xi, o.gamma, o.dip))
                 self._chk(L.chiml_gpu_set_object(self.h, o.obj, o.npoles, _ptr(a), _ptr(x), _ptr(gm), o.use_or_dip, _ptr(dp)))
+            for (comp, pole), g in sorted(plan.dip_grids.items()):
+                g = np.ascontiguousarray(g, dtype=np.float64)
+                self._chk(L.chiml_gpu_set_dip_grid(self.h, comp, pole, _ptr(g)))
             for obj, (a, x, gm) in sorted(plan.mag_objects.items()):
                 a, x, gm = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, x, gm))
                 self._chk(L.chiml_gpu_set_object_magnetic(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm)))

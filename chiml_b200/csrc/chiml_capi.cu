@@ -142,6 +142,7 @@ void chiml_gpu_destroy(ChimlCtx* ctx)
         cudaFree(ctx->span[c].d_xmin); cudaFree(ctx->span[c].d_xmax); cudaFree(ctx->span[c].d_base); cudaFree(ctx->span[c].d_rows);
         for(int p = 0; p < MAX_POLES; ++p)
             for(int k = 0; k < 2; ++k) { cudaFree(ctx->d_P[c][p][k]); if(c < 3) cudaFree(ctx->d_oP[c][p][k]); }
+        if(c < 3) for(int p = 0; p < MAX_POLES; ++p) cudaFree(ctx->d_dipg[c][p]);
     }
     for(int c = 0; c < 6; ++c)
     {
@@ -211,6 +212,19 @@ int chiml_gpu_set_object(ChimlCtx* ctx, int obj, int npoles, const double* alpha
     o.alpha.assign(alpha, alpha + npoles); o.xi.assign(xi, xi + npoles); o.gamma.assign(gamma, gamma + npoles);
     o.dip.assign(3 * (size_t)npoles, 0.0);
     if(dip) o.dip.assign(dip, dip + 3 * (size_t)npoles);
+    return CHIML_OK;
+}
+
+int chiml_gpu_set_dip_grid(ChimlCtx* ctx, int comp, int pole, const double* grid)
+{
+    if(!ctx) return CHIML_ERR_ARG;
+    if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_dip_grid after commit");
+    if(!grid) return fail(ctx, CHIML_ERR_ARG, "set_dip_grid: null grid");
+    if(comp < 0 || comp > 2 || pole < 0) return fail(ctx, CHIML_ERR_ARG, "set_dip_grid: bad comp/pole");
+    if(pole >= MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_dip_grid: more than 12 poles per object");
+    if(!field_exists(ctx, comp)) return fail(ctx, CHIML_ERR_ARG, "set_dip_grid: the field component does not exist in this mode");
+    ctx->h_dipg[comp][pole].assign(grid, grid + ctx->nlogical);
+    ctx->has_dipg = true;
     return CHIML_OK;
 }
 
@@ -977,6 +991,25 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                     for(int p = 0; p < ctx->nordip; ++p)
                         for(int k = 0; k < 2; ++k)
                             if((rc = dev_alloc(ctx, &ctx->d_oP[c][p][k], (size_t)ctx->span_node.total))) return rc;
+            // position-dependent dipole grids: the values at the node cells, in pool order (cells of a span the list does not cover are never read)
+            for(int c = 0; c < 3; ++c)
+                for(int p = 0; p < MAX_POLES; ++p)
+                {
+                    std::vector<double>& hg = ctx->h_dipg[c][p];
+                    if(hg.empty()) continue;
+                    if(p < ctx->nordip && field_exists(ctx, c))
+                    {
+                        const SpanTable& sp = ctx->span_node;
+                        std::vector<double> tmp((size_t)sp.total, 0.0);
+                        const size_t nrows = (size_t)ctx->ly * ctx->lz;
+                        for(size_t row = 0; row < nrows; ++row)
+                            if(sp.h_xmin[row] >= 0)
+                                std::copy_n(hg.data() + row * ctx->lx + sp.h_xmin[row], std::min(sp.h_xmax[row], ctx->lx - 1) - sp.h_xmin[row] + 1, &tmp[(size_t)sp.h_base[row]]);
+                        if((rc = dev_upload(ctx, &ctx->d_dipg[c][p], tmp))) return rc;
+                        ctx->kstat[K_ORDIP_POLES].alg_bytes += 8.0 * (double)sp.total;
+                    }
+                    std::vector<double>().swap(hg);
+                }
         }
         else if(ctx->nordip == 0)
             // (with several slabs a slab may hold edge cells of an object whose nodes all lie in the slab above: its D->E then reads
@@ -1720,11 +1753,13 @@ void launch_node_poles(ChimlCtx* ctx)
         int d[3];
         decode_offset(ctx, ctx->node_off[c], d);
         na.eoff[c] = phys_offset(ctx, d);
-        for(int p = 0; p < MAX_POLES; ++p) { na.Pcur[c][p] = ctx->d_oP[c][p][cur]; na.Pnew[c][p] = ctx->d_oP[c][p][prv]; }
+        for(int p = 0; p < MAX_POLES; ++p) { na.Pcur[c][p] = ctx->d_oP[c][p][cur]; na.Pnew[c][p] = ctx->d_oP[c][p][prv]; na.dipg[c][p] = ctx->d_dipg[c][p]; }
     }
     LaunchScope ls(ctx, K_ORDIP_POLES);
     const dim3 ng((ctx->span_node.max_width + 255) / 256, ctx->span_node.nrows_used, 1);
-    if(ng.y > 0) k_ordip_poles<<<ng, 256, 0, ctx->stream>>>(na);
+    if(ng.y == 0) return;
+    if(ctx->has_dipg) k_ordip_poles<true><<<ng, 256, 0, ctx->stream>>>(na);
+    else              k_ordip_poles<false><<<ng, 256, 0, ctx->stream>>>(na);
 }
 
 // ---- halo helpers (chiml_halo.cuh) ------------------------------------------------------------------

@@ -107,6 +107,7 @@ struct NodeArgs
     const int32_t* rows;         // compact list of the grid rows (z + lz*y) that hold node cells
     const double* Pcur[3][MAX_POLES];
     double* Pnew[3][MAX_POLES];
+    const double* dipg[3][MAX_POLES];   // position-dependent dipole grids over the node spans (REL_TO_NORM), or nullptr: the class's direction
     int lx, ly, lz;
     long px;
 };
@@ -152,6 +153,8 @@ namespace chiml {
 
 // updatePolE, oriented-dipole poles at the integer nodes
 // (FDTD_MANAGER/parallelFDTDField.hpp:1350-1354 -> UTIL/FDTD_up_eq.cpp:450-631)
+// DIPG: the dipole vector of a node comes from the grids of setupDipMoments (parallelFDTDField.hpp:960-1048) instead of the object's class
+template <bool DIPG>
 __global__ void __launch_bounds__(256) k_ordip_poles(const __grid_constant__ NodeArgs a)
 {
     // one block per 256-cell chunk of one row of the compact row list: only rows that hold node cells are visited.
@@ -173,14 +176,18 @@ __global__ void __launch_bounds__(256) k_ordip_poles(const __grid_constant__ Nod
     const bool planar = a.E[0] != nullptr;     // 3-D or TE; otherwise the TM (Ez only) variant
     for(int p = 0; p < ce.npoles; ++p)
     {
-        double pc[3] = {0.0, 0.0, 0.0};
+        double pc[3] = {0.0, 0.0, 0.0}, dp3[3];
 #pragma unroll
         for(int c = 0; c < 3; ++c)
+        {
+            dp3[c] = ce.dip[p][c];
             if(a.E[c])
             {
                 pc[c] = dm(ce.alpha[p], a.Pcur[c][p][ip]);
                 pc[c] = axpy1(pc[c], ce.xi[p], a.Pnew[c][p][ip]);
+                if(DIPG && a.dipg[c][p]) dp3[c] = a.dipg[c][p][ip];
             }
+        }
         if(planar)
         {
             double dotU = 0.0;
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(256) k_ordip_poles(const __grid_constant__ Nod
             for(int c = 0; c < 3; ++c)
             {
                 if(!a.E[c]) continue;
-                const double dp = ce.dip[p][c];
+                const double dp = dp3[c];
                 const double t0 = __ddiv_rn(dm(dp, e0[c]), 2.0);   // multAvg: x*y/2.0 (UTIL/utilityFxns.hpp:38)
                 const double t1 = __ddiv_rn(dm(dp, e1[c]), 2.0);
                 if(first) { dotU = da(t0, t1); first = false; }
@@ -197,11 +204,11 @@ __global__ void __launch_bounds__(256) k_ordip_poles(const __grid_constant__ Nod
             }
 #pragma unroll
             for(int c = 0; c < 3; ++c)
-                if(a.E[c]) pc[c] = axpy1(pc[c], ce.gamma[p], dm(ce.dip[p][c], dotU));
+                if(a.E[c]) pc[c] = axpy1(pc[c], ce.gamma[p], dm(dp3[c], dotU));
         }
         else
         {
-            const double dotU = dm(ce.dip[p][2], e0[2]);
+            const double dotU = dm(dp3[2], e0[2]);
             pc[2] = axpy1(pc[2], ce.gamma[p], dotU);
         }
 #pragma unroll

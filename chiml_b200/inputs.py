@@ -38,11 +38,21 @@ def normal_source(pol: str, loc: Sequence[float], size: Sequence[float], pulses:
 
 
 def lorentz_pole(sigma_p: float, gamma: float, omega: float, dip_or_e: str = "isotropic", dir_dip_e: Sequence[float] = (0.0, 0.0, 0.0),
-                 sigma_m: float = 0.0, tau: float = 0.0) -> Dict:
+                 sigma_m: float = 0.0, tau: float = 0.0, pol_ang_e: Optional[float] = None, az_ang_e: Optional[float] = None, tan_iso: bool = False,
+                 dip_or_m: str = "isotropic") -> Dict:
     """sigma_m > 0 makes the pole a magnetic one as well (magnetisation M driven by H, OBJECTS/Obj.cpp setUpConsts); tau != 0 a chiral one
-    (cross terms between E and H, chiAlpha / chiXi / chiGamma / chiGammaPrev, OBJECTS/Obj.cpp:345-353)."""
-    return {"dipOrE": dip_or_e, "dipOrM": "isotropic", "sigma_p": sigma_p, "sigma_m": sigma_m, "tau": tau, "gamma": gamma,
-            "omega": omega, "dirDipE": list(dir_dip_e), "dirDipM": [0.0, 0.0, 0.0]}
+    (cross terms between E and H, chiAlpha / chiXi / chiGamma / chiGammaPrev, OBJECTS/Obj.cpp:345-353).  dip_or_e "normal" / "tangent" /
+    "rel_norm" orient the dipole relative to the object's surface normal (polar / azimuthal angles in degrees, INPUTS/parallelInputs.cpp:1329-1357;
+    tan_iso splits the pole into a lateral and a longitudinal tangent one)."""
+    d = {"dipOrE": dip_or_e, "dipOrM": dip_or_m, "sigma_p": sigma_p, "sigma_m": sigma_m, "tau": tau, "gamma": gamma,
+         "omega": omega, "dirDipE": list(dir_dip_e), "dirDipM": [0.0, 0.0, 0.0]}
+    if pol_ang_e is not None:
+        d["polAngRelNormE"] = pol_ang_e
+    if az_ang_e is not None:
+        d["azAngRelNormE"] = az_ang_e
+    if tan_iso:
+        d["tanIso"] = True
+    return d
 
 
 def ev_to_fdtd(ev: float, a: float = 1e-7) -> float:

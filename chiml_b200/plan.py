@@ -169,6 +169,7 @@ class Plan:
     n_mag_poles: int = 0
     mag_objects: Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray]] = field(default_factory=dict)   # obj -> (magAlpha, magXi, magGamma)
     chi_objects: Dict[int, Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = field(default_factory=dict)   # obj -> (chiAlpha, chiXi, chiGamma, chiGammaPrev)
+    dip_grids: Dict[Tuple[int, int], np.ndarray] = field(default_factory=dict)    # (comp, pole) -> dipP_[comp][pole], the whole ghost-inclusive grid (REL_TO_NORM orientations)
     prev_copy: Optional[np.ndarray] = None      # (nrows, 4) int32: copy2PrevFields_ rows {length, x, y, z}
     cplx: bool = False                          # complex fields (record COMPLEX): real and imaginary parts are two field sets over the same lists
     k_point: Tuple[float, float, float] = (0.0, 0.0, 0.0)
@@ -264,6 +265,9 @@ def read_plan(path: str) -> Plan:
             obj, np_ = struct.unpack_from("<ii", payload, 0)
             arrs = [np.frombuffer(payload, dtype="<f8", count=np_, offset=8 + 8 * np_ * k).copy() for k in range(4)]
             plan.chi_objects[obj] = tuple(arrs)
+        elif tag == "DIPGRID":
+            comp, pole = struct.unpack_from("<ii", payload, 0)
+            plan.dip_grids[(comp, pole)] = np.frombuffer(payload, dtype="<f8", offset=8).copy()
         elif tag == "PREVCOPY":
             (nr,) = struct.unpack_from("<Q", payload, 0)
             plan.prev_copy = np.frombuffer(payload, dtype="<i4", count=4 * nr, offset=8).copy().reshape(nr, 4)
@@ -360,6 +364,8 @@ def write_plan(path: str, plan: Plan) -> None:
             out.append(_rec("OBJMAG", struct.pack("<ii", obj, len(a)) + np.asarray(a, "<f8").tobytes() + np.asarray(x, "<f8").tobytes() + np.asarray(g, "<f8").tobytes()))
     for obj, arrs in sorted(plan.chi_objects.items()):
         out.append(_rec("OBJCHI", struct.pack("<ii", obj, len(arrs[0])) + b"".join(np.asarray(a, "<f8").tobytes() for a in arrs)))
+    for (comp, pole), g in sorted(plan.dip_grids.items()):
+        out.append(_rec("DIPGRID", struct.pack("<ii", comp, pole) + np.ascontiguousarray(g, "<f8").tobytes()))
     if plan.prev_copy is not None:
         out.append(_rec("PREVCOPY", struct.pack("<Q", len(plan.prev_copy)) + np.ascontiguousarray(plan.prev_copy, "<i4").tobytes()))
     if plan.cplx:

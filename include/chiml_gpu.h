@@ -248,6 +248,14 @@ int chiml_gpu_add_tfsf_surface(ChimlCtx* ctx, const ChimlTfsfSurface* s);
  * than its neighbour's, still exchanges that many node P_y ghost rows.  0 (default) = this slab's own list decides. */
 int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global);
 
+/* Position-dependent dipole orientations (MAT_DIP_ORIENTAITON::REL_TO_NORM: "normal", "tangent", polar / azimuthal angles relative to the surface
+ * normal, tanIso).  setupDipMoments (parallelFDTDField.hpp:960-1048) evaluates the object's surface gradient at every node; the result is the static
+ * grid dipP_[comp][pole] that UpdateLorPolOrDip* (UTIL/FDTD_up_eq.cpp:450-631) multiplies with, node by node.  grid = that array, the whole local
+ * ghost-inclusive grid (x fastest, then z, then y -- &dipP_[comp][pole]->point(0)); the engine keeps the values at the cells of CHIML_LIST_ORDIPP
+ * only.  Where a grid is given it replaces the per-object direction of chiml_gpu_set_object for this (comp, pole) on every node; give it for every
+ * component and pole the reference holds as soon as one pole of one object is oriented this way.  Before commit. */
+int chiml_gpu_set_dip_grid(ChimlCtx* ctx, int comp, int pole, const double* grid);
+
 /* Column length of the y-marching kernels: how many stacked y planes of equal content one thread block walks, carrying the y-coupled
  * neighbour planes in registers (k_fast / k_uniform).  0 = automatic (from the grid size, up to 64 / 32).  Results do not depend on
  * it; it exists for tuning and so that the parity tests can force long columns on small grids (the environment variable

@@ -111,6 +111,8 @@ typedef struct ChimlPlanObjChiHdr      /* tag "OBJCHI  ": header + chiAlpha[np] 
 {
     int32_t obj, npoles;
 } ChimlPlanObjChiHdr;
+/* tag "DIPGRID ": int32 comp, int32 pole, then ln[0]*ln[1]*ln[2] doubles: dipP_[comp][pole] of setupDipMoments (written only when a pole is oriented
+ * relative to the surface normal, REL_TO_NORM; then for every grid the reference holds) */
 /* tag "PREVCOPY": uint64 nrows, then nrows x {int32 length, x, y, z}: copy2PrevFields_ (local ghost-inclusive coordinates) */
 typedef struct ChimlPlanComplex        /* tag "COMPLEX ": the propagator holds complex fields (Bloch-periodic run, parallelFDTDFieldCplx): every field / psi /
                                           pole array has a real and an imaginary part, coupled only by the phase factors of the periodic wrap copies */

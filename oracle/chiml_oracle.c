@@ -59,6 +59,7 @@ struct OracleSim
     double* oP[3][MAX_POLES];      /* orDipLorP_[c][p] */
     double* oPprev[3][MAX_POLES];  /* prevOrDipLorP_[c][p] */
     double* dipgrid[3][MAX_POLES]; /* dipP_[c][p] (static) */
+    double* dipgiven[3][MAX_POLES];/* dipP_[c][p] as handed over by oracle_set_dip_grid (position-dependent orientations), or NULL */
     int has_B, pml_on_B, nmag;     /* magnetic-dispersive media: B grids exist, the H-side CPML acts on B, number of lorM_ grids */
     double* M[3][MAX_POLES];       /* lorM_[c][p] */
     double* Mprev[3][MAX_POLES];   /* prevLorM_[c][p] */
@@ -122,7 +123,7 @@ void oracle_destroy(OracleSim* s)
     for(int i = 0; i < CHIML_NFIELDS; ++i) free(s->f[i]);
     for(int k = 0; k < 6; ++k) for(int c = 0; c < 6; ++c) free(s->up[k][c].r);
     for(int c = 0; c < 6; ++c) for(int p = 0; p < 2; ++p) { free(s->pml[c][p].psi); free(s->pml[c][p].grid); free(s->pml[c][p].psi_grid); }
-    for(int c = 0; c < 3; ++c) for(int p = 0; p < MAX_POLES; ++p) { free(s->P[c][p]); free(s->Pprev[c][p]); free(s->oP[c][p]); free(s->oPprev[c][p]); free(s->dipgrid[c][p]); }
+    for(int c = 0; c < 3; ++c) for(int p = 0; p < MAX_POLES; ++p) { free(s->P[c][p]); free(s->Pprev[c][p]); free(s->oP[c][p]); free(s->oPprev[c][p]); free(s->dipgrid[c][p]); free(s->dipgiven[c][p]); }
     free(s->obj);
     free(s);
 }
@@ -149,6 +150,18 @@ int oracle_set_object(OracleSim* s, int obj, int npoles, const double* alpha, co
         o->alpha[p] = alpha[p]; o->xi[p] = xi[p]; o->gamma[p] = gamma[p];
         for(int k = 0; k < 3; ++k) o->dip[p][k] = dip ? dip[3 * p + k] : 0.0;
     }
+    return 0;
+}
+
+/* position-dependent dipole grids (include/chiml_gpu.h chiml_gpu_set_dip_grid): dipP_[comp][pole] of setupDipMoments
+ * (parallelFDTDField.hpp:960-1048) for REL_TO_NORM orientations, the whole ghost-inclusive grid as the reference holds it */
+int oracle_set_dip_grid(OracleSim* s, int comp, int pole, const double* grid)
+{
+    if(!s || !grid || comp < 0 || comp > 2 || pole < 0 || pole >= MAX_POLES) return CHIML_ERR_ARG;
+    if(s->committed) return CHIML_ERR_STATE;
+    free(s->dipgiven[comp][pole]);
+    s->dipgiven[comp][pole] = (double*)malloc(s->ncell * sizeof(double));
+    memcpy(s->dipgiven[comp][pole], grid, s->ncell * sizeof(double));
     return 0;
 }
 
@@ -287,6 +300,9 @@ int oracle_commit(OracleSim* s)
                 if(s->dipgrid[c][p])
                     for(int i = 0; i < r->n; ++i) s->dipgrid[c][p][r->ind + i] = o->dip[p][c];
     }
+    for(int c = 0; c < 3; ++c)
+        for(int p = 0; p < s->nordip; ++p)
+            if(s->dipgiven[c][p] && s->dipgrid[c][p]) memcpy(s->dipgrid[c][p], s->dipgiven[c][p], s->ncell * sizeof(double));
     for(int c = 0; c < 6; ++c)
         for(int p = 0; p < 2; ++p)
             if(s->pml[c][p].present && s->pml[c][p].has_psi)

@@ -39,6 +39,7 @@ int  oracle_add_emitters(OracleSim* s, const ChimlEmitterDesc* d);
 int  oracle_add_dft(OracleSim* s, int field, int group, int every, int nfreq, int npts, int stride, const ChimlDftLine* lines, size_t nlines, size_t acc_len);
 int  oracle_set_periodic(OracleSim* s, int comp, const ChimlWrap* w);
 int  oracle_set_object_chiral(OracleSim* s, int obj, int npoles, const double* alpha, const double* xi, const double* gamma, const double* gamma_prev);
+int  oracle_set_dip_grid(OracleSim* s, int comp, int pole, const double* grid);
 int  oracle_set_prev_copy(OracleSim* s, const int32_t* rows, size_t nrows);
 double* oracle_chi_pole(OracleSim* s, int comp, int pole, int prev);
 double* oracle_prev_field(OracleSim* s, int comp);

@@ -409,6 +409,7 @@ template <class FFT> static void writePlan(const std::string& fname, FFT& FF, co
         throw std::runtime_error("plan dump: magnetic / chiral oriented-dipole lists are outside the covered hot path");
     putList(out, CHIML_LIST_ORDIPP, 0, FF.upOrDipP_);
 
+    bool relToNorm = false;
     for(size_t oo = 0; oo < FF.objArr_.size(); ++oo)
     {
         auto& obj = FF.objArr_[oo];
@@ -425,12 +426,23 @@ template <class FFT> static void writePlan(const std::string& fname, FFT& FF, co
                 MAT_DIP_ORIENTAITON ori = obj->dipOr(pp);
                 if(ori == MAT_DIP_ORIENTAITON::ISOTROPIC) { dip[3*pp] = dip[3*pp+1] = dip[3*pp+2] = 1.0; }
                 else if(ori == MAT_DIP_ORIENTAITON::UNIDIRECTIONAL) { for(int k = 0; k < 3; ++k) dip[3*pp+k] = obj->dipE(pp)[k]; }
-                else throw std::runtime_error("plan dump: position-dependent dipole orientation (REL_TO_NORM) is outside the covered hot path");
+                else relToNorm = true;      // position-dependent: the grids of setupDipMoments follow as DIPGRID records
             }
         }
         appVec(p, dip);
         putRec(out, "OBJECT", p);
     }
+    // dipP_[c][p] (setupDipMoments, parallelFDTDField.hpp:960-1048) when any pole is oriented relative to the surface normal
+    if(relToNorm)
+        for(int c = 0; c < 3; ++c)
+            for(size_t pp = 0; pp < FF.dipP_[c].size(); ++pp)
+            {
+                int32_t hd[2] = {c, int32_t(pp)};
+                std::string q; app(q, hd);
+                const double* g = &FF.dipP_[c][pp]->point(0);
+                q.append(reinterpret_cast<const char*>(g), sizeof(double) * size_t(pg.desc.ln[0]) * size_t(pg.desc.ln[1]) * size_t(pg.desc.ln[2]));
+                putRec(out, "DIPGRID", q);
+            }
     for(int c = 0; c < 3; ++c)
     {
         putCpml(out, c, FF.EPML_[c]);
@@ -599,7 +611,7 @@ struct GpuApi
     CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
     CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic) CHIML_API(chiml_gpu_add_tfsf_surface) CHIML_API(chiml_gpu_step_n_tfsf)
     CHIML_API(chiml_gpu_set_magnetic) CHIML_API(chiml_gpu_set_object_magnetic) CHIML_API(chiml_gpu_download_mag_pole)
-    CHIML_API(chiml_gpu_set_object_chiral) CHIML_API(chiml_gpu_set_prev_copy) CHIML_API(chiml_gpu_download_chi_pole) CHIML_API(chiml_gpu_download_prev_field)
+    CHIML_API(chiml_gpu_set_dip_grid) CHIML_API(chiml_gpu_set_object_chiral) CHIML_API(chiml_gpu_set_prev_copy) CHIML_API(chiml_gpu_download_chi_pole) CHIML_API(chiml_gpu_download_prev_field)
 #undef CHIML_API
     void load()
     {
@@ -623,7 +635,7 @@ struct GpuApi
         CHIML_API(chiml_gpu_download_ordip_pole) CHIML_API(chiml_gpu_launch_count) CHIML_API(chiml_gpu_download_emitter_state)
         CHIML_API(chiml_gpu_download_emitter_pol) CHIML_API(chiml_gpu_set_periodic) CHIML_API(chiml_gpu_add_tfsf_surface) CHIML_API(chiml_gpu_step_n_tfsf)
         CHIML_API(chiml_gpu_set_magnetic) CHIML_API(chiml_gpu_set_object_magnetic) CHIML_API(chiml_gpu_download_mag_pole)
-        CHIML_API(chiml_gpu_set_object_chiral) CHIML_API(chiml_gpu_set_prev_copy) CHIML_API(chiml_gpu_download_chi_pole) CHIML_API(chiml_gpu_download_prev_field)
+        CHIML_API(chiml_gpu_set_dip_grid) CHIML_API(chiml_gpu_set_object_chiral) CHIML_API(chiml_gpu_set_prev_copy) CHIML_API(chiml_gpu_download_chi_pole) CHIML_API(chiml_gpu_download_prev_field)
 #undef CHIML_API
     }
 };
@@ -678,6 +690,7 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
         put(CHIML_LIST_ORDIPD, c, FF.upOrDipD_[c]);
     }
     put(CHIML_LIST_ORDIPP, 0, FF.upOrDipP_);
+    bool relToNorm = false;
     for(size_t oo = 0; oo < FF.objArr_.size(); ++oo)
     {
         auto& obj = FF.objArr_[oo];
@@ -689,13 +702,17 @@ static void bindGpu(parallelFDTDFieldReal& FF, GpuBinding& B)
                 MAT_DIP_ORIENTAITON ori = obj->dipOr(pp);
                 if(ori == MAT_DIP_ORIENTAITON::ISOTROPIC) dip[3 * pp] = dip[3 * pp + 1] = dip[3 * pp + 2] = 1.0;
                 else if(ori == MAT_DIP_ORIENTAITON::UNIDIRECTIONAL) for(int k = 0; k < 3; ++k) dip[3 * pp + k] = obj->dipE(pp)[k];
-                else throw std::runtime_error("--gpu: position-dependent dipole orientation (REL_TO_NORM) is outside the covered hot path");
+                else relToNorm = true;
             }
         B.check(A.chiml_gpu_set_object(B.ctx, int(oo), np, obj->alpha().data(), obj->xi().data(), obj->gamma().data(), obj->useOrdDip() ? 1 : 0, dip.data()), "set_object");
         if(hasB) B.check(A.chiml_gpu_set_object_magnetic(B.ctx, int(oo), int(obj->magGamma().size()), obj->magAlpha().data(), obj->magXi().data(), obj->magGamma().data()), "set_object_magnetic");
         if(!obj->chiGamma().empty())
             B.check(A.chiml_gpu_set_object_chiral(B.ctx, int(oo), int(obj->chiGamma().size()), obj->chiAlpha().data(), obj->chiXi().data(), obj->chiGamma().data(), obj->chiGammaPrev().data()), "set_object_chiral");
     }
+    if(relToNorm)       // orientations relative to the surface normal: the engine reads the reference's own dipP_ grids
+        for(int c = 0; c < 3; ++c)
+            for(size_t pp = 0; pp < FF.dipP_[c].size(); ++pp)
+                B.check(A.chiml_gpu_set_dip_grid(B.ctx, c, int(pp), &FF.dipP_[c][pp]->point(0)), "set_dip_grid");
     // periodic boundaries: the arguments of applBCE_ / applBCH_ (single rank: applyBC1Proc)
     if(FF.E_[0] ? FF.E_[0]->PBC() : FF.E_[2]->PBC())
         for(int comp = 0; comp < 6; ++comp)

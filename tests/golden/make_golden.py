@@ -249,6 +249,22 @@ def cases():
         [I.normal_source("Ey", [0.0, 0.04, 0.0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
         [dict(I.block([0.5, 0.06, 0.05], [0.0, -0.02, 0.0], eps=1.8, pols=[chip(0.9, 0.1, 2.0, 0.8, 0.4)]), mu=1.2)],
         [I.detector([0.03, 0, 0], [0, 0, 0], "Hz", "out/chp/dtc", time_int=DT * 1.0000001)]))
+    # ---- dipoles oriented relative to the surface normal (REL_TO_NORM: setupDipMoments evaluates the object's surface gradient at every node,
+    # parallelFDTDField.hpp:960-1048): a sphere with a "normal" and a "tangent" pole, a block with a pole at 30 / 60 degrees next to an isotropic
+    # oriented pole, a bar with tangent-isotropic poles reaching through the CPML (2-D grids: the reference's own constructor asserts on oriented dipoles) ----
+    reln = lambda sp, g, w, how, **kw: I.lorentz_pole(sp, g, w, dip_or_e=how, **kw)  # noqa: E731
+    c["dipnorm3d"] = _short_pulse(I.config(
+        I.comp_cell([23 / RES, 21 / RES, 21 / RES], RES, 50 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES] * 3),
+        [I.normal_source("Ey", [0.0, 0.0, 0.0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
+        [I.sphere(0.045, [-0.035, 0.01, 0.02], eps=1.6, pols=[reln(0.9, 0.1, 2.0, "normal"), reln(0.6, 0.05, 2.6, "tangent")]),
+         I.block([0.06, 0.07, 0.05], [0.05, -0.02, -0.02], eps=2.0,
+                 pols=[reln(0.8, 0.08, 1.8, "rel_norm", pol_ang_e=30.0, az_ang_e=60.0), I.lorentz_pole(0.3, 0.02, 3.1, dip_or_e="unidirectional", dir_dip_e=[0.6, 0.0, 0.8])])],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Ey", "out/dn/dtc", time_int=DT * 1.0000001)]))
+    c["dipnorm3d_pml"] = _short_pulse(I.config(
+        I.comp_cell([21 / RES, 19 / RES, 19 / RES], RES, 40 * DT - 0.5 * DT, "Ex"), I.pml([5 / RES, 4 / RES, 5 / RES]),
+        [I.normal_source("Ez", [0.0, 0.03, 0.0], [0, 0, 0], [I.gaussian_pulse(1.5, 1.0)])],
+        [I.block([0.5, 0.06, 0.07], [0.0, -0.02, 0.0], eps=1.8, pols=[reln(0.9, 0.1, 2.0, "tangent", tan_iso=True, dip_or_m="tangent")])],
+        [I.detector([0.03, 0, 0], [0, 0, 0], "Ez", "out/dnp/dtc", time_int=DT * 1.0000001)]))
     return c
 
 

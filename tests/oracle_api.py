@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
         L.oracle_set_periodic.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oracle_set_object_chiral.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_set_prev_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.oracle_set_dip_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oracle_chi_pole.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.oracle_chi_pole.restype = C.POINTER(C.c_double)
         L.oracle_prev_field.argtypes = [C.c_void_p, C.c_int]
@@ -150,6 +151,9 @@ class OracleSim:
             for obj, (a, x, gm) in sorted(plan.mag_objects.items()):
                 a, x, gm = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, x, gm))
                 self._chk(L.oracle_set_object_magnetic(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm)))
+        for (comp, pole), g in sorted(plan.dip_grids.items()):
+            g = np.ascontiguousarray(g, dtype=np.float64)
+            self._chk(L.oracle_set_dip_grid(self.h, comp, pole, _ptr(g)))
         for obj, arrs in sorted(plan.chi_objects.items()):
             a, x, gm, gp = (np.ascontiguousarray(v, dtype=np.float64) for v in arrs)
             self._chk(L.oracle_set_object_chiral(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm), _ptr(gp)))
