@@ -123,9 +123,10 @@ Obj::Obj(SHAPE s, double eps, double mu, std::vector<LorenzDipoleOscillator> pol
 
 void Obj::setUpConsts(double dt)
 {
+    constsSet_ = true;
     for(const auto& pol : pols_)
     {
-        if(pol.dipOrE_ != DIPOR::ISOTROPIC) useOrientedDipols_ = true;
+        if(pol.dipOrE_ != DIPOR::ISOTROPIC || pol.dipOrM_ != DIPOR::ISOTROPIC) useOrientedDipols_ = true;
         if(std::abs(pol.sigP_) != 0.0)
         {
             dipOr_.push_back(pol.dipOrE_);
@@ -133,6 +134,20 @@ void Obj::setUpConsts(double dt)
             alpha_.push_back(((2 - std::pow(pol.omg_ * dt, 2.0)) / (1 + pol.gam_ * dt)));
             xi_.push_back(((pol.gam_ * dt - 1) / (1 + pol.gam_ * dt)));
             gamma_.push_back(((pol.sigP_ * std::pow(pol.omg_ * dt, 2.0)) / (1 + pol.gam_ * dt)));
+        }
+        if(std::abs(pol.sigM_) != 0.0)
+        {
+            magAlpha_.push_back(((2 - std::pow(pol.omg_ * dt, 2.0)) / (1 + pol.gam_ * dt)));
+            magXi_.push_back(((pol.gam_ * dt - 1) / (1 + pol.gam_ * dt)));
+            magGamma_.push_back(((pol.sigM_ * std::pow(pol.omg_ * dt, 2.0)) / (1 + pol.gam_ * dt)));
+        }
+        if(std::abs(pol.tau_) != 0.0)
+        {
+            // the 1 / dt of the two gammas is the time derivative of the chiral interaction (OBJECTS/Obj.cpp:345-353)
+            chiAlpha_.push_back(((2 - std::pow(pol.omg_ * dt, 2.0)) / (1 + pol.gam_ * dt)));
+            chiXi_.push_back(((pol.gam_ * dt - 1) / (1 + pol.gam_ * dt)));
+            chiGamma_.push_back((-1.0 / dt) * ((pol.tau_ * std::pow(pol.omg_ * dt, 2.0)) / ((1 + pol.gam_ * dt))));
+            chiGammaPrev_.push_back((1.0 / dt) * ((pol.tau_ * std::pow(pol.omg_ * dt, 2.0)) / ((1 + pol.gam_ * dt))));
         }
     }
 }
@@ -263,8 +278,12 @@ std::shared_ptr<Obj> Inputs::jsonToObject(const Json& o)
             osc.gam_ = p.get<double>("gamma") * M_PI;
             osc.omg_ = p.get<double>("omega") * 2 * M_PI;
             osc.sigP_ = p.get<double>("sigma_p", 0.0);
-            if(p.get<double>("sigma_m", 0.0) != 0.0 || p.get<double>("tau", 0.0) != 0.0)
-                throw std::logic_error("magnetic / chiral poles are outside the covered hot path");
+            osc.sigM_ = p.get<double>("sigma_m", 0.0);
+            osc.tau_ = p.get<double>("tau", 0.0);
+            osc.dipOrM_ = string2dipor(p.get<std::string>("dipOrM", "isotropic"));
+            if((osc.sigM_ != 0.0 || osc.tau_ != 0.0) && (osc.dipOrE_ != DIPOR::ISOTROPIC || osc.dipOrM_ != DIPOR::ISOTROPIC))
+                throw std::logic_error("oriented magnetic / chiral dipoles are outside the covered hot path");
+            if(osc.dipOrM_ != DIPOR::ISOTROPIC) throw std::logic_error("oriented magnetic dipoles are outside the covered hot path");
             if(osc.dipOrE_ == DIPOR::UNIDIRECTIONAL)
             {
                 if(osc.sigP_ > 0.0) { osc.uVecDipE_ = as_ptArr<double>(p, "dirDipE"); normalize3(osc.uVecDipE_); }

@@ -33,8 +33,8 @@ enum class DTCTYPE { EX, EY, EZ, HX, HY, HZ, DX, DY, DZ, BX, BY, BZ, EPOW, HPOW,
 // one Lorentz pole (OBJECTS/Obj.hpp:18-39)
 struct LorenzDipoleOscillator
 {
-    DIPOR dipOrE_ = DIPOR::ISOTROPIC;
-    double sigP_ = 0.0, gam_ = 0.0, omg_ = 0.0;
+    DIPOR dipOrE_ = DIPOR::ISOTROPIC, dipOrM_ = DIPOR::ISOTROPIC;
+    double sigP_ = 0.0, sigM_ = 0.0, tau_ = 0.0, gam_ = 0.0, omg_ = 0.0;
     std::array<double, 3> uVecDipE_ = {{1.0, 1.0, 1.0}};
 };
 
@@ -52,6 +52,9 @@ public:
     std::array<double, 9> coordTransform_;
     std::vector<LorenzDipoleOscillator> pols_;
     std::vector<double> alpha_, xi_, gamma_;            // Obj::setUpConsts, OBJECTS/Obj.cpp:299-371
+    std::vector<double> magAlpha_, magXi_, magGamma_;   // magnetic poles (sigma_m != 0)
+    std::vector<double> chiAlpha_, chiXi_, chiGamma_, chiGammaPrev_;   // chiral poles (tau != 0)
+    bool constsSet_ = false;
     std::vector<DIPOR> dipOr_;
     std::vector<std::array<double, 3>> dipE_;
 
@@ -62,7 +65,7 @@ public:
     void addMLBuff(double d);
     // conservative half extents of the shape (geo) along the Cartesian axes; infinite where unbounded / not finite
     std::array<double, 3> halfExtent(const std::vector<double>& geo) const;
-    bool relevant() const { return ML_ || !gamma_.empty() || eps_infty_ != 1.0 || mu_infty_ != 1.0; }   // parallelFDTDField.hpp:880
+    bool relevant() const { return ML_ || !gamma_.empty() || !magGamma_.empty() || !chiGamma_.empty() || eps_infty_ != 1.0 || mu_infty_ != 1.0; }   // parallelFDTDField.hpp:880
 };
 
 struct EnergyLevel { std::vector<double> energyStates_, weights_; int nstates_ = 1, levDescribed_ = 1; };

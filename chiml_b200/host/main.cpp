@@ -96,13 +96,28 @@ int main(int argc, char** argv)
         if(rank == 0) std::cout << "I TOOK ALL THE INPUT PARAMETERS" << std::endl;
 
         if(chiml_gpu_create(&P.grid.desc, device, &ctx) != CHIML_OK) throw std::runtime_error(std::string("chiml_gpu_create: ") + chiml_gpu_last_error(nullptr));
-        for(int kind = 0; kind < 5; ++kind)
-            for(int comp = 0; comp < 6; ++comp)
-                if(!P.lists[kind][comp].empty())
-                    check(ctx, chiml_gpu_set_update_list(ctx, kind, comp, P.lists[kind][comp].data(), P.lists[kind][comp].size()), "set_update_list");
-        for(size_t o = 0; o < P.objects.size(); ++o)
-            check(ctx, chiml_gpu_set_object(ctx, (int)o, P.objects[o].npoles, P.objects[o].alpha.data(), P.objects[o].xi.data(), P.objects[o].gamma.data(),
-                                            P.objects[o].use_or_dip, P.objects[o].dip.data()), "set_object");
+        // update lists and material constants of every kind (B grids first: the H components take D-type lists only with them)
+        auto handOver = [&P](ChimlCtx* c) {
+            if(P.has_B) check(c, chiml_gpu_set_magnetic(c, 1, P.magMatInPML ? 1 : 0), "set_magnetic");
+            for(int kind = 0; kind < 6; ++kind)
+                for(int comp = 0; comp < 6; ++comp)
+                    if(!P.lists[kind][comp].empty())
+                        check(c, chiml_gpu_set_update_list(c, kind, comp, P.lists[kind][comp].data(), P.lists[kind][comp].size()), "set_update_list");
+            bool anyChi = false;
+            for(size_t o = 0; o < P.objects.size(); ++o)
+            {
+                const PlanObject& ob = P.objects[o];
+                check(c, chiml_gpu_set_object(c, (int)o, ob.npoles, ob.alpha.data(), ob.xi.data(), ob.gamma.data(), ob.use_or_dip, ob.dip.data()), "set_object");
+                if(P.has_B) check(c, chiml_gpu_set_object_magnetic(c, (int)o, (int)ob.magGamma.size(), ob.magAlpha.data(), ob.magXi.data(), ob.magGamma.data()), "set_object_magnetic");
+                if(!ob.chiGamma.empty())
+                {
+                    anyChi = true;
+                    check(c, chiml_gpu_set_object_chiral(c, (int)o, (int)ob.chiGamma.size(), ob.chiAlpha.data(), ob.chiXi.data(), ob.chiGamma.data(), ob.chiGammaPrev.data()), "set_object_chiral");
+                }
+            }
+            if(anyChi) check(c, chiml_gpu_set_prev_copy(c, reinterpret_cast<const int32_t*>(P.prev_copy.data()), P.prev_copy.size()), "set_prev_copy");
+        };
+        handOver(ctx);
         for(const PlanCpml& c : P.cpml)
             check(ctx, chiml_gpu_set_cpml(ctx, c.comp, c.part, c.has_psi, c.psi.data(), c.psi.size(), c.grid.data(), c.grid.size()), "set_cpml");
         for(const PlanSource& s : P.sources) check(ctx, chiml_gpu_add_source(ctx, s.field, s.loc, s.sz, nullptr), "add_source");
@@ -142,13 +157,7 @@ int main(int argc, char** argv)
             for(const PlanDetector& d : P.detectors)
                 if(d.type == (int)DTCTYPE::EPOW || d.type == (int)DTCTYPE::HPOW) throw std::runtime_error("power detectors of a complex-field run are outside the covered hot path");
             if(chiml_gpu_create(&P.grid.desc, device, &ctxIm) != CHIML_OK) throw std::runtime_error(std::string("chiml_gpu_create: ") + chiml_gpu_last_error(nullptr));
-            for(int kind = 0; kind < 5; ++kind)
-                for(int comp = 0; comp < 6; ++comp)
-                    if(!P.lists[kind][comp].empty())
-                        check(ctxIm, chiml_gpu_set_update_list(ctxIm, kind, comp, P.lists[kind][comp].data(), P.lists[kind][comp].size()), "set_update_list");
-            for(size_t o = 0; o < P.objects.size(); ++o)
-                check(ctxIm, chiml_gpu_set_object(ctxIm, (int)o, P.objects[o].npoles, P.objects[o].alpha.data(), P.objects[o].xi.data(), P.objects[o].gamma.data(),
-                                                  P.objects[o].use_or_dip, P.objects[o].dip.data()), "set_object");
+            handOver(ctxIm);
             for(const PlanCpml& c : P.cpml)
                 check(ctxIm, chiml_gpu_set_cpml(ctxIm, c.comp, c.part, c.has_psi, c.psi.data(), c.psi.size(), c.grid.data(), c.grid.size()), "set_cpml");
             for(const PlanSource& s : P.sources) check(ctxIm, chiml_gpu_add_source(ctxIm, s.field, s.loc, s.sz, nullptr), "add_source");

@@ -159,10 +159,19 @@ private:
 // min/max of the PML-normal index are overwritten inside the (jj,kk) loops, so the lower slab is
 // scanned only on the first transverse line and the upper slab on every line)
 // ---------------------------------------------------------------------------------------------------
-bool dielectric_in_pml(const Inputs& IP, const int n_vec[3], const double d[3])
+void materials_in_pml(const Inputs& IP, const int n_vec[3], const double d[3], bool& dielectricMatInPML, bool& magMatInPML)
 {
-    bool dielectricMatInPML = false;
-    for(int pp = 0; pp < 3 && !dielectricMatInPML; ++pp)
+    dielectricMatInPML = false; magMatInPML = false;
+    // a flag nobody can set is settled from the start: the scan stops once both are
+    bool anyDie = false, anyMag = false;
+    for(const auto& obj : IP.objArr_)
+    {
+        if(obj->eps_infty_ == 1.0 && obj->mu_infty_ == 1.0 && obj->gamma_.size() < 1 && obj->magGamma_.size() < 1 && obj->chiGamma_.size() < 1 && !obj->ML_) continue;
+        anyDie = anyDie || !(obj->eps_infty_ == 1.0 && obj->gamma_.size() < 1 && obj->chiGamma_.size() < 1);
+        anyMag = anyMag || !(obj->mu_infty_ == 1.0 && obj->magGamma_.size() < 1 && obj->chiGamma_.size() < 1);
+    }
+    auto settled = [&]() { return (dielectricMatInPML || !anyDie) && (magMatInPML || !anyMag); };
+    for(int pp = 0; pp < 3 && !settled(); ++pp)
     {
         const int cor_ii = pp, cor_jj = (pp + 1) % 3, cor_kk = (pp + 2) % 3;
         int mn[3], mx[3];
@@ -170,9 +179,9 @@ bool dielectric_in_pml(const Inputs& IP, const int n_vec[3], const double d[3])
         mx[cor_ii] = (int)(IP.pmlThickness_[cor_ii] - n_vec[cor_ii] / 2.0);
         for(const auto& obj : IP.objArr_)
         {
-            if(obj->eps_infty_ == 1.0 && obj->mu_infty_ == 1.0 && obj->gamma_.size() < 1 && !obj->ML_) continue;
-            const bool dielcMat = !(obj->eps_infty_ == 1.0 && obj->gamma_.size() < 1);
-            if(!dielcMat) { /* the loops below could only clear nothing */ }
+            if(obj->eps_infty_ == 1.0 && obj->mu_infty_ == 1.0 && obj->gamma_.size() < 1 && obj->magGamma_.size() < 1 && obj->chiGamma_.size() < 1 && !obj->ML_) continue;
+            const bool dielcMat = !(obj->eps_infty_ == 1.0 && obj->gamma_.size() < 1 && obj->chiGamma_.size() < 1);
+            const bool magMat = !(obj->mu_infty_ == 1.0 && obj->magGamma_.size() < 1 && obj->chiGamma_.size() < 1);
             // bounding box of the object in the centred integer coordinates of this scan, for culling
             const std::array<double, 3> h = obj->halfExtent(obj->geoParam_);
             long lo[3], hi[3];
@@ -182,22 +191,29 @@ bool dielectric_in_pml(const Inputs& IP, const int n_vec[3], const double d[3])
                 hi[k] = std::isfinite(h[k]) ? (long)std::ceil((obj->location_[k] + h[k]) / d[k]) + 2 : std::numeric_limits<long>::max() / 2;
             }
             auto scan = [&](int jj, int kk, int i0, int i1) {
-                if(dielectricMatInPML || !dielcMat) return;
+                const bool wantDie = dielcMat && !dielectricMatInPML, wantMag = magMat && !magMatInPML;
+                if(!wantDie && !wantMag) return;
                 if(jj < lo[cor_jj] || jj > hi[cor_jj] || kk < lo[cor_kk] || kk > hi[cor_kk]) return;
-                for(int ii = (int)std::max<long>(i0, lo[cor_ii]); ii < i1 && ii <= hi[cor_ii] && !dielectricMatInPML; ++ii)
+                for(int ii = (int)std::max<long>(i0, lo[cor_ii]); ii < i1 && ii <= hi[cor_ii]; ++ii)
                 {
+                    if(!(dielcMat && !dielectricMatInPML) && !(magMat && !magMatInPML)) break;
                     std::array<double, 3> pt = {{0, 0, 0}};
                     pt[cor_ii] = static_cast<double>(ii) * d[cor_ii];
                     pt[cor_jj] = static_cast<double>(jj) * d[cor_jj];
                     pt[cor_kk] = static_cast<double>(kk) * d[cor_kk];
+                    // the six Yee points of the cell, reached by the reference's chain of offsets (including its d_[0] / d_[2] slips)
                     pt[0] += d[0] / 2.0;                                        // Ex point
-                    if(obj->isObj(pt, d[0], obj->geoParam_)) { dielectricMatInPML = true; break; }
-                    pt[1] += d[1] / 2.0;                                        // (Hz point: magnetic test, never sets anything here)
+                    if(!dielectricMatInPML && dielcMat && obj->isObj(pt, d[0], obj->geoParam_)) dielectricMatInPML = true;
+                    pt[1] += d[1] / 2.0;                                        // Hz point
+                    if(!magMatInPML && magMat && obj->isObj(pt, d[0], obj->geoParam_)) magMatInPML = true;
                     pt[0] -= d[0] / 2.0;                                        // Ey point
-                    if(obj->isObj(pt, d[0], obj->geoParam_)) { dielectricMatInPML = true; break; }
-                    pt[2] += d[2] / 2.0;                                        // (Hx point)
+                    if(!dielectricMatInPML && dielcMat && obj->isObj(pt, d[0], obj->geoParam_)) dielectricMatInPML = true;
+                    pt[2] += d[2] / 2.0;                                        // Hx point
+                    if(!magMatInPML && magMat && obj->isObj(pt, d[0], obj->geoParam_)) magMatInPML = true;
                     pt[1] -= d[0] / 2.0;                                        // Ez point (the reference subtracts d_[0] here)
-                    if(obj->isObj(pt, d[0], obj->geoParam_)) { dielectricMatInPML = true; break; }
+                    if(!dielectricMatInPML && dielcMat && obj->isObj(pt, d[0], obj->geoParam_)) dielectricMatInPML = true;
+                    pt[0] += d[2] / 2.0;                                        // Hy point (the reference adds d_[2] here)
+                    if(!magMatInPML && magMat && obj->isObj(pt, d[0], obj->geoParam_)) magMatInPML = true;
                 }
             };
             for(int jj = mn[cor_jj]; jj < mx[cor_jj]; ++jj)
@@ -210,7 +226,6 @@ bool dielectric_in_pml(const Inputs& IP, const int n_vec[3], const double d[3])
                 }
         }
     }
-    return dielectricMatInPML;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -220,17 +235,19 @@ bool dielectric_in_pml(const Inputs& IP, const int n_vec[3], const double d[3])
 struct Box { int mn[3], mx[3]; bool includeU; bool curl; };
 struct RawRun { int x, y, z, n, obj; double eps; };
 
-struct ListSet { std::vector<ChimlRun> U, D, LorD, OrDipD; };
+struct ListSet { std::vector<ChimlRun> U, D, LorD, OrDipD, ChiD; std::vector<std::array<int, 5>> chiLocs; /* {n, x, y, z, obj} of the ChiD runs */ };
 
+// dieInPML / magInPML: dielectricMatInPML_ / magMatInPML_
 void build_lists(const Inputs& IP, const Geom& g, const Rasteriser& ras, const GridSpec& spec, bool E, const int derivOff[3], const int fieldEnd[3],
-                 double dj, double dk, bool matInPML, bool orDipField, int nthreads, ListSet& out)
+                 double dj, double dk, bool dieInPML, bool magInPML, bool orDipField, int nthreads, ListSet& out)
 {
     const int lx = g.ln[0];
     int mn[3] = {1, 1, g.twoD ? 0 : 1};
     int mx[3] = {g.ln[0] - 1 - fieldEnd[0], g.ln[1] - 1, g.twoD ? 1 : g.ln[2] - 1 - fieldEnd[2]};
     if(g.last) mx[1] -= fieldEnd[1];
     // getBlasLists (:802-856)
-    const bool inc = E && matInPML;    // (E && dielectricMatInPML_) || (!E && magMatInPML_); no magnetic media here
+    const bool matInPML = dieInPML || magInPML;
+    const bool inc = (E && dieInPML) || (!E && magInPML);
     int PML_x_left = inc ? g.mn[0] : 0, PML_x_right = inc ? g.pl[0] : 0;
     if(PML_x_right != 0) PML_x_right -= fieldEnd[0];
     int PML_y_bot = inc ? g.mn[1] : 0, PML_y_top = inc ? g.pl[1] : 0;
@@ -259,8 +276,8 @@ void build_lists(const Inputs& IP, const Geom& g, const Rasteriser& ras, const G
     const int ny = std::max(0, mx[1] - mn[1]);
     nthreads = std::max(1, std::min(nthreads, ny));
     // per thread, per box, per kind: raw runs in (y, z, x) order
-    enum { K_U = 0, K_D = 1, K_ORD = 2 };
-    std::vector<std::vector<std::vector<RawRun>>> raw(nthreads, std::vector<std::vector<RawRun>>(nb * 3));
+    enum { K_U = 0, K_D = 1, K_ORD = 2, K_CHI = 3, NK = 4 };
+    std::vector<std::vector<std::vector<RawRun>>> raw(nthreads, std::vector<std::vector<RawRun>>(nb * NK));
     auto work = [&](int t) {
         std::vector<int> obj(lx);
         std::vector<double> eps(lx);
@@ -282,10 +299,12 @@ void build_lists(const Inputs& IP, const Geom& g, const Rasteriser& ras, const G
                         const int id = obj[iistore];
                         const Obj& o = *IP.objArr_[id < 0 ? 0 : id];
                         int kind;
-                        if(o.useOrientedDipols_ && E && o.gamma_.size() > 0) kind = K_ORD;                       // fillBlasLists :767-773
-                        else if(bx.includeU && (!E || (o.gamma_.size() < 1 && !o.ML_))) kind = K_U;                // :776-777
+                        // fillBlasLists :767-779 (oriented magnetic / chiral dipoles are refused before this point)
+                        if(o.useOrientedDipols_ && E && o.gamma_.size() > 0) kind = K_ORD;
+                        else if(o.chiGamma_.size() > 0) kind = K_CHI;
+                        else if(bx.includeU && ((!E && o.magGamma_.size() < 1) || (E && o.gamma_.size() < 1 && !o.ML_))) kind = K_U;
                         else kind = K_D;
-                        raw[t][b * 3 + kind].push_back({iistore, jj, kk, ii - iistore + 1, id, eps[iistore]});
+                        raw[t][b * NK + kind].push_back({iistore, jj, kk, ii - iistore + 1, id, eps[iistore]});
                         ++ii;
                     }
                 }
@@ -333,13 +352,18 @@ void build_lists(const Inputs& IP, const Geom& g, const Rasteriser& ras, const G
         {
             if(boxes[b].curl)
             {
-                for(const RawRun& r : raw[t][b * 3 + K_U]) emit(out.U, r, true);
+                for(const RawRun& r : raw[t][b * NK + K_U]) emit(out.U, r, true);
                 // the curl pass files every non-U run under upD (getBlasLists :855 passes upDLists four times)
             }
             else
             {
-                for(const RawRun& r : raw[t][b * 3 + K_D]) emit(out.LorD, r, false);
-                for(const RawRun& r : raw[t][b * 3 + K_ORD]) emit(out.OrDipD, r, false);
+                for(const RawRun& r : raw[t][b * NK + K_D]) emit(out.LorD, r, false);
+                for(const RawRun& r : raw[t][b * NK + K_ORD]) emit(out.OrDipD, r, false);
+                for(const RawRun& r : raw[t][b * NK + K_CHI])
+                {
+                    emit(out.ChiD, r, false);
+                    out.chiLocs.push_back({{r.n, r.x, r.y, r.z, r.obj}});       // populateUpLists storeLocs (:645-646)
+                }
             }
         }
     // upD keeps the reference's order inside the curl box: runs of all non-U kinds interleaved in (y, z, x) order
@@ -347,14 +371,16 @@ void build_lists(const Inputs& IP, const Geom& g, const Rasteriser& ras, const G
         const int b = nb - 1;
         for(int t = 0; t < nthreads; ++t)
         {
-            const auto& dRuns = raw[t][b * 3 + K_D];
-            const auto& oRuns = raw[t][b * 3 + K_ORD];
-            size_t i = 0, j = 0;
+            const std::vector<RawRun>* rr[3] = {&raw[t][b * NK + K_D], &raw[t][b * NK + K_ORD], &raw[t][b * NK + K_CHI]};
+            size_t at[3] = {0, 0, 0};
             auto before = [](const RawRun& p, const RawRun& q) { return p.y != q.y ? p.y < q.y : (p.z != q.z ? p.z < q.z : p.x < q.x); };
-            while(i < dRuns.size() || j < oRuns.size())
+            for(;;)
             {
-                if(j >= oRuns.size() || (i < dRuns.size() && before(dRuns[i], oRuns[j]))) emit(out.D, dRuns[i++], false);
-                else emit(out.D, oRuns[j++], false);
+                int best = -1;
+                for(int k = 0; k < 3; ++k)
+                    if(at[k] < rr[k]->size() && (best < 0 || before((*rr[k])[at[k]], (*rr[best])[at[best]]))) best = k;
+                if(best < 0) break;
+                emit(out.D, (*rr[best])[at[best]++], false);
             }
         }
     }
@@ -685,7 +711,7 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
     {
         // the reference's cost-weighted cuts instead (pole constants must exist: the weights count poles)
         for(auto& obj : IP.objArr_)
-            if(obj->alpha_.empty() && obj->dipOr_.empty()) obj->setUpConsts(IP.dt_);
+            if(!obj->constsSet_) obj->setUpConsts(IP.dt_);
         g.twoD = IP.size_[2] == 0;
         const std::vector<int> start = reference_split(IP, g, nranks);
         g.yStart = start[rank]; nyloc = start[rank + 1] - start[rank];
@@ -702,21 +728,31 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
         if(loc + lsz > g.n[k] - g.thick[k]) g.pl[k] = loc > g.n[k] - g.thick[k] ? lsz : loc + lsz - (g.n[k] - g.thick[k]);
     }
     for(auto& obj : IP.objArr_)
-        if(obj->alpha_.empty() && obj->dipOr_.empty()) obj->setUpConsts(IP.dt_);
+        if(!obj->constsSet_) obj->setUpConsts(IP.dt_);
 
     const int mode = !g.twoD ? CHIML_MODE_3D
                              : ((IP.pol_ == POLARIZATION::HZ || IP.pol_ == POLARIZATION::EX || IP.pol_ == POLARIZATION::EY) ? CHIML_MODE_TE : CHIML_MODE_TM);
     const int nvec[3] = {g.n[0], g.n[1], g.n[2]};
-    P.dielectricMatInPML = dielectric_in_pml(IP, nvec, g.d);
-    bool disp = P.dielectricMatInPML;
-    int nLor = 0, nOrDip = 0;
+    materials_in_pml(IP, nvec, g.d, P.dielectricMatInPML, P.magMatInPML);
+    // which grids exist (parallelFDTDField.hpp:372-389): D for dispersive / chiral media, B for magnetic / chiral ones
+    bool disp = P.dielectricMatInPML, magnetic = P.magMatInPML, chiral = false;
+    int nLor = 0, nOrDip = 0, nMag = 0;
     for(const auto& obj : IP.objArr_)
     {
         if(obj->gamma_.size() > 0 || obj->ML_ || obj->eps_infty_ > 1.0) disp = true;
-        if(obj->mu_infty_ > 1.0) throw std::logic_error("magnetic materials are outside the covered hot path");
+        if(obj->magGamma_.size() > 0 || obj->mu_infty_ > 1.0) magnetic = true;
+        if(obj->chiGamma_.size() > 0) chiral = true;
+        if(obj->useOrientedDipols_ && (obj->magGamma_.size() > 0 || obj->chiGamma_.size() > 0))
+            throw std::logic_error("oriented-dipole objects with magnetic / chiral poles are outside the covered hot path");
         nLor = std::max(nLor, (int)obj->gamma_.size());
+        nMag = std::max(nMag, (int)obj->magGamma_.size());
         if(obj->useOrientedDipols_) nOrDip = std::max(nOrDip, (int)obj->gamma_.size());
     }
+    if(chiral && g.twoD) throw std::logic_error("chiral media on a 2-D grid are outside the covered hot path");
+    if((magnetic || chiral) && nranks > 1) throw std::logic_error("magnetic / chiral media are covered for single-slab runs");
+    if(chiral) disp = true;
+    P.has_B = magnetic || chiral;
+    P.n_mag_poles = P.has_B ? nMag : 0;
 
     std::memset(&P.grid, 0, sizeof(P.grid));
     P.grid.desc.mode = mode;
@@ -759,6 +795,7 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
     }
 
     Rasteriser ras(IP, g);
+    std::vector<std::array<int, 5>> chiLocs;
     // ---- update lists (parallelFDTDField.cpp:80-92,248-261) ----
     for(int comp = 0; comp < 6; ++comp)
     {
@@ -766,13 +803,40 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
         const int i = comp % 3;
         const double dj = g.d[(i + 1) % 3], dk = g.d[(i + 2) % 3];
         ListSet ls;
-        build_lists(IP, g, ras, SPEC_COMP[comp], comp < 3, DERIV_OFF[comp], SPEC_COMP[comp].endOff, dj, dk, P.dielectricMatInPML, false, nthreads, ls);
+        build_lists(IP, g, ras, SPEC_COMP[comp], comp < 3, DERIV_OFF[comp], SPEC_COMP[comp].endOff, dj, dk, P.dielectricMatInPML, P.magMatInPML, false, nthreads, ls);
         P.lists[CHIML_LIST_U][comp] = std::move(ls.U);
         if(comp < 3)
         {
             P.lists[CHIML_LIST_D][comp] = std::move(ls.D);
             P.lists[CHIML_LIST_LORD][comp] = std::move(ls.LorD);
             P.lists[CHIML_LIST_ORDIPD][comp] = std::move(ls.OrDipD);
+        }
+        else if(P.has_B)
+        {
+            // upB_ / upLorB_ (with B grids; without them an H component has nothing but upH_)
+            P.lists[CHIML_LIST_D][comp] = std::move(ls.D);
+            P.lists[CHIML_LIST_LORD][comp] = std::move(ls.LorD);
+        }
+        else if(!ls.D.empty() || !ls.LorD.empty()) throw std::logic_error("magnetic update lists without B grids");
+        P.lists[CHIML_LIST_CHID][comp] = std::move(ls.ChiD);
+        chiLocs.insert(chiLocs.end(), ls.chiLocs.begin(), ls.chiLocs.end());
+    }
+    // copy2PrevFields_ (parallelFDTDField.cpp:391-410): per chiral object the box of its ChiD / ChiB runs, one cell wider on every side
+    if(chiral)
+    {
+        for(int oo = 0; oo < (int)IP.objArr_.size(); ++oo)
+        {
+            if(IP.objArr_[oo]->chiGamma_.empty()) continue;
+            int mnC[3] = {g.n[0], g.n[1], g.n[2]}, mxC[3] = {0, 0, 0};
+            for(const auto& ax : chiLocs)
+            {
+                if(ax[4] != oo) continue;
+                mxC[0] = std::max(mxC[0], ax[1] + ax[0] - 1); mxC[1] = std::max(mxC[1], ax[2]); mxC[2] = std::max(mxC[2], ax[3]);
+                mnC[0] = std::min(mnC[0], ax[1]); mnC[1] = std::min(mnC[1], ax[2]); mnC[2] = std::min(mnC[2], ax[3]);
+            }
+            const int sz = mxC[0] - mnC[0] + 3;
+            for(int yy = mnC[1] - 1; yy <= mxC[1] + 1; ++yy)
+                for(int zz = mnC[2] - 1; zz <= mxC[2] + 1; ++zz) P.prev_copy.push_back({{sz, mnC[0] - 1, yy, zz}});
         }
     }
     if(disp && nOrDip > 0)
@@ -781,7 +845,7 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
         // whenever an oriented-dipole object carries electric poles
         const int dOff[3] = {-1, -1, -1}, fEnd[3] = {0, 0, 0};
         ListSet ls;
-        build_lists(IP, g, ras, SPEC_NODE_P, true, dOff, fEnd, g.d[0], g.d[0], P.dielectricMatInPML, true, nthreads, ls);
+        build_lists(IP, g, ras, SPEC_NODE_P, true, dOff, fEnd, g.d[0], g.d[0], P.dielectricMatInPML, P.magMatInPML, true, nthreads, ls);
         P.lists[CHIML_LIST_ORDIPP][0] = std::move(ls.OrDipD);
     }
     // ---- objects ----
@@ -794,6 +858,8 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
                                    "lists for them index z neighbours a 2-D grid does not have (its own parallelGrid::getInd assertion fails)");
         o.eps_inf = obj->eps_infty_; o.mu_inf = obj->mu_infty_;
         o.alpha = obj->alpha_; o.xi = obj->xi_; o.gamma = obj->gamma_;
+        o.magAlpha = obj->magAlpha_; o.magXi = obj->magXi_; o.magGamma = obj->magGamma_;
+        o.chiAlpha = obj->chiAlpha_; o.chiXi = obj->chiXi_; o.chiGamma = obj->chiGamma_; o.chiGammaPrev = obj->chiGammaPrev_;
         o.dip.assign(3 * (size_t)o.npoles, 0.0);
         if(o.use_or_dip)
             for(int p = 0; p < o.npoles; ++p)
@@ -931,6 +997,49 @@ void SlabPlan::write(const std::string& path) const
             ChimlPlanListHdr h; h.kind = kinds[k]; h.comp = comps[k]; h.n = lists[kinds[k]][comps[k]].size();
             app(p, h); app_vec(p, lists[kinds[k]][comps[k]]);
             put_rec(out, "UPLIST", p);
+        }
+    }
+    for(int comp = 0; comp < 6; ++comp)
+    {
+        // upB_ / upLorB_ (B grids) and the chiral lists of either family
+        const int kinds[3] = {CHIML_LIST_D, CHIML_LIST_LORD, CHIML_LIST_CHID};
+        for(int k = 0; k < 3; ++k)
+        {
+            if(comp < 3 && k < 2) continue;
+            if(k < 2 ? !has_B : lists[CHIML_LIST_CHID][comp].empty()) continue;
+            std::string p;
+            ChimlPlanListHdr h; h.kind = kinds[k]; h.comp = comp; h.n = lists[kinds[k]][comp].size();
+            app(p, h); app_vec(p, lists[kinds[k]][comp]);
+            put_rec(out, "UPLIST", p);
+        }
+    }
+    if(has_B)
+    {
+        ChimlPlanMagnetic pm; std::memset(&pm, 0, sizeof(pm));
+        pm.has_B = 1; pm.pml_on_B = magMatInPML ? 1 : 0; pm.n_mag_poles = n_mag_poles;
+        std::string p; app(p, pm); put_rec(out, "MAGNETIC", p);
+        for(size_t oo = 0; oo < objects.size(); ++oo)
+        {
+            const PlanObject& o = objects[oo];
+            ChimlPlanObjMagHdr h; h.obj = (int)oo; h.npoles = (int)o.magGamma.size();
+            std::string q; app(q, h); app_vec(q, o.magAlpha); app_vec(q, o.magXi); app_vec(q, o.magGamma);
+            put_rec(out, "OBJMAG", q);
+        }
+    }
+    {
+        bool anyChi = false;
+        for(const PlanObject& o : objects) anyChi = anyChi || !o.chiGamma.empty();
+        if(anyChi)
+        {
+            for(size_t oo = 0; oo < objects.size(); ++oo)
+            {
+                const PlanObject& o = objects[oo];
+                ChimlPlanObjChiHdr h; h.obj = (int)oo; h.npoles = (int)o.chiGamma.size();
+                std::string q; app(q, h); app_vec(q, o.chiAlpha); app_vec(q, o.chiXi); app_vec(q, o.chiGamma); app_vec(q, o.chiGammaPrev);
+                put_rec(out, "OBJCHI", q);
+            }
+            std::string q; const uint64_t nr = prev_copy.size(); app(q, nr); app_vec(q, prev_copy);
+            put_rec(out, "PREVCOPY", q);
         }
     }
     { std::string p; ChimlPlanListHdr h; h.kind = CHIML_LIST_ORDIPP; h.comp = 0; h.n = lists[CHIML_LIST_ORDIPP][0].size(); app(p, h); app_vec(p, lists[CHIML_LIST_ORDIPP][0]); put_rec(out, "UPLIST", p); }

@@ -20,7 +20,12 @@
 namespace chiml_host {
 
 struct PlanCpml { int comp, part, has_psi; std::vector<ChimlPsiParams> psi; std::vector<ChimlGridParams> grid; };
-struct PlanObject { int npoles, use_or_dip, ml; double eps_inf, mu_inf; std::vector<double> alpha, xi, gamma, dip; };
+struct PlanObject
+{
+    int npoles, use_or_dip, ml; double eps_inf, mu_inf; std::vector<double> alpha, xi, gamma, dip;
+    std::vector<double> magAlpha, magXi, magGamma;                  // magnetic poles (chiml_gpu_set_object_magnetic)
+    std::vector<double> chiAlpha, chiXi, chiGamma, chiGammaPrev;    // chiral poles (chiml_gpu_set_object_chiral)
+};
 struct PlanSource { int field; int32_t loc[3], sz[3]; std::vector<double> amp, amp_im; };     // amp_im: dt * Im(sum pulse), complex fields only
 struct PlanDetector { int detector, field; int32_t loc[3], sz[3], offset[3]; int every, type; double conv, t_conv; };
 
@@ -56,7 +61,7 @@ struct PlanDft
 struct SlabPlan
 {
     ChimlPlanGrid grid;
-    std::vector<ChimlRun> lists[5][6];      // [ChimlListKind][component]
+    std::vector<ChimlRun> lists[6][6];      // [ChimlListKind][component]
     std::vector<PlanObject> objects;
     std::vector<PlanCpml> cpml;
     std::vector<PlanSource> sources;
@@ -67,6 +72,10 @@ struct SlabPlan
     bool cplx = false;                         // complex fields (k-point != 0)
     double k_point[3] = {0.0, 0.0, 0.0};
     bool dielectricMatInPML = false;
+    bool magMatInPML = false;                  // magnetic material reaches the CPML: the H-side CPML acts on B
+    bool has_B = false;                        // B grids exist (magnetic or chiral media)
+    int n_mag_poles = 0;
+    std::vector<std::array<int32_t, 4>> prev_copy;   // copy2PrevFields_ rows {length, x, y, z} (chiral media)
 
     void write(const std::string& path) const;
 };

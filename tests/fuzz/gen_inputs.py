@@ -153,3 +153,53 @@ def rnd_case_rotated(seed, steps=10, pulses="gaussian"):
             rad = o.pop("radius")
             o.update(shape="cylinder", radius=rad * r.uniform(0.6, 1.0), length=rad * r.uniform(1.0, 3.0))
     return cfg
+
+
+def rnd_mag_case(seed, steps=10):
+    """Magnetic-dispersive and chiral media at random places: objects with mu_inf > 1, magnetic poles (sigma_m), chiral poles (tau, 3-D only)
+    beside plain dielectric / Lorentz ones, some of them long enough to reach through the CPML (B grids, the H-side CPML on B, upB_ / upLorB_ /
+    upChiD_ / upChiB_, copy2PrevFields_)."""
+    r=random.Random(7000+seed)
+    mode=r.choice(["3d","3d","te","tm"])
+    if mode=="3d":
+        n=[r.randint(17,25) for _ in range(3)]; pol="Ex"
+    else:
+        n=[r.randint(31,49), r.randint(31,49), 0]; pol="Hz" if mode=="te" else "Ez"
+    size=[k/RES for k in n]
+    pmlc=[r.randint(3,5) for _ in range(3)]
+    if mode!="3d": pmlc[2]=0
+    pml=I.pml([c/RES for c in pmlc], a_max=r.choice([0.25,0.1]), ma=r.choice([1.0,2.0]), m=r.choice([3.0,3.5]), kappa_max=r.choice([1.0,2.5]))
+    objs=[]
+    for k in range(r.randint(1,3)):
+        loc=[r.uniform(-0.25,0.25)*size[j] for j in range(3)]
+        if mode!="3d": loc[2]=0.0
+        kind=r.choice(["mag","mag","chi","mu","lor"]) if mode=="3d" else r.choice(["mag","mag","mu","lor"])
+        if k==0 and kind in ("mu","lor"): kind="mag"
+        pols=[]; mu=1.0
+        if kind=="mag":
+            pols=[I.lorentz_pole(r.choice([0.0, r.uniform(0.3,1.2)]), r.uniform(0.02,0.2), r.uniform(1,3), sigma_m=r.uniform(0.2,1.0)) for _ in range(r.randint(1,2))]
+            mu=r.choice([1.0,1.5,2.0])
+        if kind=="chi":
+            pols=[I.lorentz_pole(r.choice([0.0, r.uniform(0.3,1.2)]), r.uniform(0.02,0.2), r.uniform(1,3), sigma_m=r.choice([0.0, r.uniform(0.2,1.0)]), tau=r.uniform(-0.5,0.5) or 0.1)
+                  for _ in range(r.randint(1,2))]
+            mu=r.choice([1.0,1.5])
+        if kind=="mu": mu=r.choice([1.5,2.0,3.0])
+        if kind=="lor": pols=[I.lorentz_pole(r.uniform(0.3,1.5), r.uniform(0.02,0.2), r.uniform(1,3))]
+        eps=r.choice([1.0,2.0,2.25])
+        if r.random()<0.6:
+            sz=[r.uniform(0.15,0.5)*size[j] for j in range(3)]
+            if r.random()<0.35: sz[r.randrange(3 if mode=="3d" else 2)]=3.0       # through the CPML on both sides
+            if mode!="3d": sz[2]=0.0
+            o=I.block(sz, loc, eps=eps, pols=pols)
+        else:
+            o=I.sphere(r.uniform(0.1,0.25)*min(s for s in size if s>0), loc, eps=eps, pols=pols)
+        objs.append(dict(o, mu=mu))
+    srcpol={"3d":r.choice(["Ex","Ey","Ez","Hx","Hz"]),"te":r.choice(["Hz","Ex","Ey"]),"tm":r.choice(["Ez","Hx","Hy"])}[mode]
+    sloc=[r.uniform(-0.2,0.2)*size[k] for k in range(3)]; ssz=[r.choice([0.0, r.uniform(0,0.3)*size[k]]) for k in range(3)]
+    if mode!="3d": sloc[2]=0.0; ssz[2]=0.0
+    srcs=[I.normal_source(srcpol, sloc, ssz, [I.gaussian_pulse(1.5,1.0,t_0=0.25,cutoff=2.5)])]
+    dpol={"3d":r.choice(["Ex","Ey","Ez","Hx","Hy","Hz"]),"te":r.choice(["Hz","Ex","Ey"]),"tm":r.choice(["Ez","Hx","Hy"])}[mode]
+    dloc=[r.uniform(-0.2,0.2)*size[k] for k in range(3)]
+    if mode!="3d": dloc[2]=0.0
+    dets=[I.detector(dloc, [0.0,0.0,0.0], dpol, f"out/fm{seed}/d", time_int=DT*1.0000001)]
+    return I.config(I.comp_cell(size, RES, steps*DT-0.5*DT, pol), pml, srcs, objs, dets, [])

@@ -60,3 +60,12 @@ def test_gpu_matches_oracle_on_random_media_cells(seed, forced, tmp_path, oracle
 def test_gpu_matches_oracle_on_random_emitter_blocks(seed, forced, tmp_path, oracle_lib):
     import gen_inputs
     run_case(gen_inputs.rnd_ml_case(seed), tmp_path, 12, FORCED[seed % 4] if forced else None)
+
+
+@pytest.mark.parametrize("forced", [False, True], ids=["auto", "march"])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 10, 12, 13, 14, 16, 22])
+def test_gpu_matches_oracle_on_random_magnetic_and_chiral_media(seed, forced, tmp_path, oracle_lib):
+    """tests/fuzz/gen_inputs.rnd_mag_case through this repository's own host setup: magnetic and chiral objects whose faces, edges and corners fall
+    anywhere inside the tiles, some reaching through the CPML (the H-side CPML then acts on B)."""
+    import gen_inputs
+    run_case(gen_inputs.rnd_mag_case(seed, steps=12), tmp_path, 12, FORCED[seed % 4] if forced else None)

@@ -24,6 +24,10 @@ FILES = {"te_vacuum": {"out/te/dtc_field_0.dat": "dtc_field_0.dat"},
                     "out/fq/map_field_3.dat.1.000000": "map_field_3.dat.1.000000", "out/fq/map_field_3.dat.2.000000": "map_field_3.dat.2.000000"},
          # Bloch-periodic runs (k-point != 0, complex fields): two real field sets on the device, coupled by k_wrap_bloch
          "cplx3d": {"out/c3/dtc_field_0.dat": "dtc_field_0.dat"}, "cplx_tm": {"out/ctm/dtc_field_0.dat": "dtc_field_0.dat"},
+         # magnetic-dispersive and chiral media set up by this repository's own host code (B grids, upB_ / upLorB_ / upChiD_ / upChiB_, copy2PrevFields_)
+         "mag3d": {"out/mg/dtc_field_0.dat": "dtc_field_0.dat"}, "mag3d_pml": {"out/mgp/dtc_field_0.dat": "dtc_field_0.dat"},
+         "mag_tm": {"out/mtm/dtc_field_0.dat": "dtc_field_0.dat"},
+         "chi3d": {"out/ch/dtc_field_0.dat": "dtc_field_0.dat"}, "chi3d_pml": {"out/chp/dtc_field_0.dat": "dtc_field_0.dat"},
          "vac3d_bin": {"out/vb/dtc_field_0.dat": "dtc_field_0.dat", "out/vb/dtc_field_1.dat": "dtc_field_1.dat"}}
 
 

@@ -54,7 +54,8 @@ def test_detector_outside_cell(tmp_path):
 @pytest.mark.parametrize("mutate,needle", [
     (lambda c: c.__setitem__("TFSF", [{"dummy": 1}]), "TFSF sources are outside the covered hot path"),
     (lambda c: c["CompCell"].__setitem__("cplxFields", True), "complex fields without periodic boundaries"),
-    (lambda c: c["ObjectList"].append(dict(I.block([0.1, 0.1, 0.0], [0, 0, 0]), mu=2.0)), "magnetic"),
+    (lambda c: c["ObjectList"].append(I.block([0.1, 0.1, 0.0], [0, 0, 0], pols=[I.lorentz_pole(0.5, 0.1, 2.0, sigma_m=0.4, dip_or_m="unidirectional")])), "oriented magnetic"),
+    (lambda c: c["ObjectList"].append(I.block([0.1, 0.1, 0.0], [0, 0, 0], pols=[I.lorentz_pole(0.5, 0.1, 2.0, dip_or_e="normal")])), "surface-normal-relative"),
 ])
 def test_out_of_scope_inputs_fail_loudly(mutate, needle, tmp_path):
     cfg = _base()

@@ -23,9 +23,8 @@ def plan_tool():
 
 # TFSF inputs are set up by the reference's own constructor (the drop-in hands its surface records to the engine); the host-side setup
 # of this repository refuses them
-# (and magnetic / chiral objects: the B / H / M path is fed from the reference's own lists; dipoles oriented relative to the surface normal:
-# the dipole grids are the reference's own, chiml_gpu_set_dip_grid)
-HOST_CASES = [c for c in util.CASES if not c.startswith(("tfsf", "mag", "chi", "dipnorm"))]
+# (and dipoles oriented relative to the surface normal: the dipole grids are the reference's own, chiml_gpu_set_dip_grid)
+HOST_CASES = [c for c in util.CASES if not c.startswith(("tfsf", "dipnorm"))]
 
 
 def test_host_setup_refuses_tfsf_inputs(plan_tool, tmp_path):

@@ -134,3 +134,28 @@ def test_rotated_blocks_and_cylinders_give_the_reference_plan(seed, tmp_path):
     bad = plan_diff.diff(P.read_plan(str(tmp_path / "host.rank0.plan")), P.read_plan(str(tmp_path / "ref.rank0.plan")))
     bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
     assert not bad, "\n".join(bad[:20])
+
+
+MAG_SEEDS = [0, 1, 2, 3, 4, 5, 10, 12, 13, 14, 16, 22]      # (seed 20: the reference's own constructor crashes on a mu-only block beside a magnetic sphere)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="needs the reference build oracle/_ref/chiml_ref")
+@pytest.mark.parametrize("seed", MAG_SEEDS)
+def test_random_magnetic_and_chiral_inputs_give_the_reference_plan(seed, tmp_path):
+    """Magnetic-dispersive and chiral objects at random places (tests/fuzz/gen_inputs.rnd_mag_case), some through the CPML: B grids, magMatInPML_,
+    upB_ / upLorB_ / upChiD_ / upChiB_, magnetic and chiral constants, copy2PrevFields_ and the CPML lists of the host setup equal the reference
+    constructor's record for record."""
+    import gen_inputs
+    import plan_diff
+    from chiml_b200 import inputs as I, plan as P
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
+    cfg = gen_inputs.rnd_mag_case(seed)
+    I.write(cfg, str(tmp_path / "c.json"))
+    r = subprocess.run([REF, "c.json", "--steps", "0", "--plan", str(tmp_path / "ref"), "--quiet", "--no-output"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "host")], check=True)
+    ref = P.read_plan(str(tmp_path / "ref.rank0.plan"))
+    assert ref.has_B
+    bad = plan_diff.diff(P.read_plan(str(tmp_path / "host.rank0.plan")), ref)
+    bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
+    assert not bad, "\n".join(bad[:20])

@@ -50,3 +50,10 @@ def test_oracle_matches_reference_on_random_emitter_blocks(seed, tmp_path, oracl
     cfg = gen_inputs.rnd_ml_case(seed)
     cfg["CompCell"]["tLim"] = 12 * gen_inputs.DT - 0.5 * gen_inputs.DT
     run_case(cfg, tmp_path, 10)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 3, 4, 5, 10, 12, 14, 16, 22, 25, 26])      # (seeds whose source is not overwritten by D->E / B->H of an object around it)
+def test_oracle_matches_reference_on_random_magnetic_and_chiral_media(seed, tmp_path, oracle_lib):
+    """tests/fuzz/gen_inputs.rnd_mag_case: B / H / M cells, chiral cells with their eight-point stencils and prev-field copies, the H-side CPML on B."""
+    import gen_inputs
+    run_case(gen_inputs.rnd_mag_case(seed, steps=12), tmp_path, 5)

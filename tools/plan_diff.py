@@ -19,6 +19,19 @@ def diff(a: P.Plan, b: P.Plan, verbose=True):
     for q, (sa, sb) in enumerate(zip(a.sources, b.sources)):
         if (sa.amp_im is None) != (sb.amp_im is None) or (sa.amp_im is not None and np.asarray(sa.amp_im).tobytes() != np.asarray(sb.amp_im).tobytes()):
             bad.append(f"source {q}: imaginary amplitudes differ")
+    for k in ("has_B", "pml_on_B", "n_mag_poles"):
+        if getattr(a, k) != getattr(b, k):
+            bad.append(f"magnetic.{k}: {getattr(a, k)} != {getattr(b, k)}")
+    for nm in ("mag_objects", "chi_objects"):
+        da, db = getattr(a, nm), getattr(b, nm)
+        if sorted(da) != sorted(db):
+            bad.append(f"{nm}: objects {sorted(da)} != {sorted(db)}")
+        for o in sorted(set(da) & set(db)):
+            for i, (u, v) in enumerate(zip(da[o], db[o])):
+                if np.asarray(u).tobytes() != np.asarray(v).tobytes():
+                    bad.append(f"{nm}[{o}][{i}]: {u} != {v}")
+    if (a.prev_copy is None) != (b.prev_copy is None) or (a.prev_copy is not None and np.asarray(a.prev_copy).tobytes() != np.asarray(b.prev_copy).tobytes()):
+        bad.append(f"prev_copy: {None if a.prev_copy is None else a.prev_copy.shape} != {None if b.prev_copy is None else b.prev_copy.shape}")
     if a.periodic != b.periodic:
         bad.append(f"periodic: {a.periodic} != {b.periodic}")
     for key in sorted(set(a.lists) | set(b.lists)):
