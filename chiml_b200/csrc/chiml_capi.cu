@@ -271,7 +271,6 @@ int chiml_gpu_set_magnetic(ChimlCtx* ctx, int has_B, int pml_on_B)
     if(!ctx) return CHIML_ERR_ARG;
     if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_magnetic after commit");
     if(pml_on_B && !has_B) return fail(ctx, CHIML_ERR_ARG, "set_magnetic: the CPML cannot act on B without B grids");
-    if(has_B && ctx->g.nranks > 1) return fail(ctx, CHIML_ERR_UNSUPPORTED, "magnetic-dispersive media are covered for single-slab runs only");
     ctx->has_B = has_B ? 1 : 0; ctx->pml_on_B = pml_on_B ? 1 : 0;
     return 0;
 }

@@ -749,7 +749,7 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
         if(obj->useOrientedDipols_) nOrDip = std::max(nOrDip, (int)obj->gamma_.size());
     }
     if(chiral && g.twoD) throw std::logic_error("chiral media on a 2-D grid are outside the covered hot path");
-    if((magnetic || chiral) && nranks > 1) throw std::logic_error("magnetic / chiral media are covered for single-slab runs");
+    if(chiral && nranks > 1) throw std::logic_error("chiral media are covered for single-slab runs");
     if(chiral) disp = true;
     P.has_B = magnetic || chiral;
     P.n_mag_poles = P.has_B ? nMag : 0;

@@ -187,7 +187,8 @@ int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* wrap);
  * (parallelFDTDField.cpp:229-246).  With has_B the H components accept the list kinds CHIML_LIST_D (upB_[c]: curl accumulated into B) and
  * CHIML_LIST_LORD (upLorB_[c]: magnetic pole update with H^n at the start of the step, then H = (B - sum M) / mu_inf after the H-side CPML and
  * the sources), comp 3..5.  Magnetic pole constants of an object: Obj::magAlpha() / magXi() / magGamma().  A soft source into H on a cell of
- * upLorB_ is overwritten by B2H as in the reference.  Chiral media and magnetic oriented dipoles are refused. */
+ * upLorB_ is overwritten by B2H as in the reference.  Runs on several slabs too (M and B are cell-local; the H row pushed upward is the one B2H
+ * has written).  Magnetic oriented dipoles are refused. */
 int chiml_gpu_set_magnetic(ChimlCtx* ctx, int has_B, int pml_on_B);
 int chiml_gpu_set_object_magnetic(ChimlCtx* ctx, int obj, int npoles, const double* alpha, const double* xi, const double* gamma);
 /* magnetic pole state lorM_[c][p] / prevLorM_[c][p] (c = 0..2 for Hx..Hz) expanded to the logical full grid */
