@@ -72,6 +72,14 @@ OTHER = {"c1": ("C1: 2-D TE vacuum 512x512, Hz dipole, CPML 20, Hz detector", la
          "c4": ("C4: 3-D 10x10 Au (6-pole) cubes + two-level emitter sheet (1e6 emitters), 768^3", lambda steps: I.c4_plasmonic_ml(n=767, steps=steps))}
 
 
+# the reference on the host cores beside a --workload c1..c4 run: (grid points of the sample, timed steps, input builder).  C1 and C2 are run at
+# their full size; C3 and C4 on a 192 x 512 x 192 sample of the same construction (2 x 2 cubes under a 180 x 180 emitter sheet for C4)
+OTHER_SAMPLE = {"c1": ((512, 512, 1), 200, lambda nx, ny, nz, steps: I.c1_te_vacuum(n=nx - 1, steps=steps)),
+                "c2": ((2048, 2048, 1), 20, lambda nx, ny, nz, steps: I.c2_tm_drude(n=nx - 1, steps=steps, nfreq=64)),
+                "c3": ((192, 512, 192), 10, lambda nx, ny, nz, steps: I.c3_aniso_slab(n=nx - 1, ny=ny - 1, nz=nz - 1, steps=steps)),
+                "c4": ((192, 512, 192), 10, lambda nx, ny, nz, steps: I.c4_plasmonic_ml(n=nx - 1, ny=ny - 1, nz=nz - 1, steps=steps, narray=2, sheet=180))}
+
+
 def workload_cfg(nx_pts: int, ny_pts: int, nz_pts: int, steps: int):
     return I.c5_aniso_ml(nx=nx_pts - 1, ny=ny_pts - 1, nz=nz_pts - 1, steps=steps, sheet=WORKLOAD_HAS_EMITTERS, out="bench_out/c5")
 
@@ -169,9 +177,10 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def run_reference(sample_pts, steps: int, warmup: int, work: str):
+def run_reference(sample_pts, steps: int, warmup: int, work: str, cfg_fn=None):
     """Runs oracle/_ref/chiml_ref (the reference's own sources compiled in place) on a `sample_pts` grid of the workload,
-    one in-process rank (thread) per y-slab.  Returns (Mcell/s, ms_per_step, info)."""
+    one in-process rank (thread) per y-slab.  Returns (Mcell/s, ms_per_step, info).  cfg_fn(nx, ny, nz, steps) builds the input of a
+    workload other than C5 at that grid (ny = 32 rows per rank; 2-D workloads pass nz = 1)."""
     if not os.path.exists(REF_BIN):
         raise RuntimeError(f"{REF_BIN} missing: run `make -C oracle ref` where /root/reference is present")
     cores = host_cores()
@@ -179,7 +188,10 @@ def run_reference(sample_pts, steps: int, warmup: int, work: str):
     # the reference's y-slab ranks must each be taller than the 20-cell CPML: 32 grid rows per rank
     nx, nz = sample_pts[0], sample_pts[2]
     ny = 32 * ranks
-    cfg = workload_cfg(nx, ny, nz, steps + warmup)
+    if cfg_fn is not None and sample_pts[1]:
+        ny = sample_pts[1]                      # the workload's own height (a multiple of the rank count, >= 32 rows per rank)
+        ranks = max(1, min(ranks, ny // 32))
+    cfg = (cfg_fn or workload_cfg)(nx, ny, nz, steps + warmup)
     os.makedirs(work, exist_ok=True)
     jpath = os.path.join(work, "ref_sample.json")
     I.write(cfg, jpath)
@@ -274,7 +286,6 @@ def b200_arm(args):
             if world != 1:
                 raise SystemExit("bench.py: --workload c1..c4 are single-GPU record runs")
             cfg = OTHER[args.workload][1](total_steps)
-            args.no_cpu_baseline = True
         else:
             if args.scaling == "strong":
                 if args.ny_total % world:
@@ -415,7 +426,12 @@ def b200_arm(args):
         sim.close()
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             try:
-                v, cms, info = run_reference((256, 0, 128), 10, 2, work)
+                if args.workload == "c5":
+                    v, cms, info = run_reference((256, 0, 128), 10, 2, work)
+                else:
+                    pts, st, fn = OTHER_SAMPLE[args.workload]
+                    v, cms, info = run_reference(pts, st, 2, work, fn)
+                    info["sample_reduction"] = round(cells_local / info["cells"], 2)
                 line["cpu_baseline"] = dict(info, value=v, unit=UNIT)
             except Exception as e:   # the reference binary is test infrastructure; its absence must not hide the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}

@@ -1005,7 +1005,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                             if(sp.h_xmin[row] >= 0)
                                 std::copy_n(hg.data() + row * ctx->lx + sp.h_xmin[row], std::min(sp.h_xmax[row], ctx->lx - 1) - sp.h_xmin[row] + 1, &tmp[(size_t)sp.h_base[row]]);
                         if((rc = dev_upload(ctx, &ctx->d_dipg[c][p], tmp))) return rc;
-                        ctx->kstat[K_ORDIP_POLES].alg_bytes += 8.0 * (double)sp.total;
+                        // (static data: not part of the algorithmic bytes, like the class tables and CPML coefficients)
                     }
                     std::vector<double>().swap(hg);
                 }
