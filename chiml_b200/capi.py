@@ -434,8 +434,9 @@ class GpuSim:
         """Exchanges the export blobs through torch.distributed (any backend) and binds the neighbours."""
         blobs = [None] * world
         dist.all_gather_object(blobs, self.halo_export())
-        lower = blobs[rank - 1] if rank > 0 else None
-        upper = blobs[rank + 1] if rank < world - 1 else None
+        ring = bool(self.plan.periodic) and world > 1          # a periodic run closes the slabs into a ring (chiml_b200/slab.py)
+        lower = blobs[(rank - 1) % world] if (rank > 0 or ring) else None
+        upper = blobs[(rank + 1) % world] if (rank < world - 1 or ring) else None
         self._chk(lib().chiml_gpu_halo_bind(self.h, lower, len(lower) if lower else 0, upper, len(upper) if upper else 0))
 
     def detector_range(self, index: int, first: int, n: int, out: np.ndarray) -> int:

@@ -322,13 +322,16 @@ int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* w)
     if(ctx->committed) return fail(ctx, CHIML_ERR_STATE, "set_periodic after commit");
     if(comp < 0 || comp > 5 || !w) return fail(ctx, CHIML_ERR_ARG, "set_periodic: component 0..5 and a wrap description");
     if(!field_exists(ctx, comp)) return fail(ctx, CHIML_ERR_ARG, "set_periodic: the component does not exist in this mode");
-    if(ctx->g.nranks > 1) return fail(ctx, CHIML_ERR_UNSUPPORTED, "periodic boundaries are covered for single-slab runs only");
     const bool twoD = ctx->lz == 1;
+    // a slab of several takes the x / z wraps of its owned rows only (ymax = ny = -1): the y direction is the ring of ghost-row pushes
+    const bool slab = ctx->g.nranks > 1;
+    if(slab != (w->ymax < 0)) return fail(ctx, CHIML_ERR_ARG, slab ? "set_periodic: a slab of several takes ymax = ny = -1 (x / z wraps only; y is the slab ring)"
+                                                                   : "set_periodic: ymax = -1 is for slabs of several");
     // the images must lie inside the arrays and the box must have an inside
-    if(w->xmax < 2 || w->ymax < 2 || w->xmax > ctx->lx - 1 || w->ymax > ctx->ly - 1 || w->nx != w->xmax - 1 || w->ny != w->ymax ||
+    if(w->xmax < 2 || (!slab && (w->ymax < 2 || w->ymax > ctx->ly - 1 || w->ny != w->ymax)) || w->xmax > ctx->lx - 1 || w->nx != w->xmax - 1 ||
        (twoD ? (w->zmin != 0) : (w->zmin != 1 || w->zmax < 2 || w->zmax > ctx->lz - 1 || w->nz != w->zmax - 1)))
         return fail(ctx, CHIML_ERR_ARG, "set_periodic: the wrap box does not fit the grid (expected the arguments of applBCE_/applBCH_)");
-    ctx->wrap[comp] = *w; ctx->has_wrap[comp] = true; ctx->periodic = true;
+    ctx->wrap[comp] = *w; ctx->has_wrap[comp] = true; ctx->periodic = true; ctx->ring = slab;
     return 0;
 }
 
@@ -818,6 +821,10 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         if(ordip) return fail(ctx, CHIML_ERR_UNSUPPORTED, "oriented-dipole media under periodic boundaries are outside the covered hot path");
         for(int comp = 0; comp < 6; ++comp)
             if(field_exists(ctx, comp) && !ctx->has_wrap[comp]) return fail(ctx, CHIML_ERR_ARG, "periodic boundaries: set_periodic must be called for every field component");
+        // a ring of slabs carries the field rows the curls read; emitter polarisations, B / M and TFSF corrections across the seam are not built
+        if(ctx->ring && (!ctx->emitters.empty() || ctx->has_B || !ctx->tfsf.empty()))
+            return fail(ctx, CHIML_ERR_UNSUPPORTED, "periodic runs on several slabs are covered without emitters, magnetic / chiral media and TFSF surfaces");
+        if(ctx->ring && ctx->ly < 5) return fail(ctx, CHIML_ERR_UNSUPPORTED, "periodic runs on several slabs need at least three owned rows per slab");
     }
     int rc;
     int* d_err = nullptr;
@@ -1209,7 +1216,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 // work items per SM (a 512 x 512 grid has only ~4600 tiles per half step)
                 // (2-D grids pack ROWS_2D one-row tiles into a block, so they need that many more columns for the same number of blocks)
                 const size_t marchCap = ntiles / (148 * 8 * (ctx->lz > 1 ? 1 : ROWS_2D));
-                const bool hasLo = ctx->g.rank > 0, hasUp = ctx->g.rank < ctx->g.nranks - 1;
+                const bool hasLo = ctx->ring || ctx->g.rank > 0, hasUp = ctx->ring || ctx->g.rank < ctx->g.nranks - 1;
                 auto isBnd = [&](const TileRec& t) { return (hasLo && t.y == 1) || (hasUp && t.y == ctx->ly - 2); };
                 for(int kind = 0; kind < 2; ++kind)      // FAST and UNIFORM lists
                 {
@@ -1251,7 +1258,7 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                 }
             }
             // tiles of a row that a neighbouring slab reads go first: they are launched on their own, ahead of the halo push
-            const bool hasLower = ctx->g.rank > 0, hasUpper = ctx->g.rank < ctx->g.nranks - 1;
+            const bool hasLower = ctx->ring || ctx->g.rank > 0, hasUpper = ctx->ring || ctx->g.rank < ctx->g.nranks - 1;
             for(int k = 0; k < 3; ++k)
             {
                 auto isB = [&](const TileRec& t) { return (hasLower && t.y == 1) || (hasUpper && t.y == ctx->ly - 2); };
@@ -1509,7 +1516,7 @@ struct RowSeg { int y0, y1; };
 int split_rows(const ChimlCtx* ctx, int y0, int y1, int part, RowSeg out[3])
 {
     if(part == 0) { out[0] = {y0, y1}; return y1 > y0 ? 1 : 0; }
-    const int bl = ctx->g.rank > 0 ? 1 : -1, bu = ctx->g.rank < ctx->g.nranks - 1 ? ctx->ly - 2 : -1;
+    const int bl = (ctx->ring || ctx->g.rank > 0) ? 1 : -1, bu = (ctx->ring || ctx->g.rank < ctx->g.nranks - 1) ? ctx->ly - 2 : -1;
     int n = 0;
     if(part == 1)
     {
@@ -1679,7 +1686,7 @@ void launch_wraps(ChimlCtx* ctx, bool isE)
     if(!ctx->periodic) return;
     WrapArgs wa;
     std::memset(&wa, 0, sizeof(wa));
-    wa.lz = ctx->lz; wa.px = ctx->px;
+    wa.lz = ctx->lz; wa.px = ctx->px; wa.ly = ctx->ly;
     long most = 0;
     for(int i = 0; i < 3; ++i)
     {
@@ -1687,8 +1694,9 @@ void launch_wraps(ChimlCtx* ctx, bool isE)
         if(!ctx->has_wrap[comp] || !ctx->d_field[comp]) continue;
         const ChimlWrap& w = ctx->wrap[comp];
         wa.f[wa.n] = ctx->d_field[comp]; wa.w[wa.n] = w; ++wa.n;
-        const long X = w.xmax + 1, Y = w.ymax + 1, Z = w.zmax - w.zmin + 2;
-        most = std::max(most, w.zmin != 0 ? 2 * (X * Z + X * (Y - 2) + (Y - 2) * (Z - 2)) : 2L * (w.xmax - 1 + w.ymax));
+        // (a slab of several, ymax < 0: the owned rows 1 .. ly - 2 play the part of the rows 1 .. ymax - 1 of the shell, without the y faces)
+        const long X = w.xmax + 1, Y = (w.ymax < 0 ? ctx->ly - 1 : w.ymax) + 1, Z = w.zmax - w.zmin + 2;
+        most = std::max(most, w.zmin != 0 ? 2 * (X * Z + X * (Y - 2) + (Y - 2) * (Z - 2)) : 2L * (w.xmax - 1 + (w.ymax < 0 ? ctx->ly : w.ymax)));
     }
     if(wa.n == 0) return;
     LaunchScope ls(ctx, K_WRAP);
@@ -1762,7 +1770,8 @@ void launch_node_poles(ChimlCtx* ctx)
 }
 
 // ---- halo helpers (chiml_halo.cuh) ------------------------------------------------------------------
-void halo_wait(ChimlCtx* ctx, std::initializer_list<std::pair<int, long long>> flags)
+// onHalo: the wait goes in front of a push on the halo stream (the compute stream keeps running)
+void halo_wait(ChimlCtx* ctx, std::initializer_list<std::pair<int, long long>> flags, bool onHalo = false)
 {
     HaloWaitArgs w;
     std::memset(&w, 0, sizeof(w));
@@ -1770,6 +1779,12 @@ void halo_wait(ChimlCtx* ctx, std::initializer_list<std::pair<int, long long>> f
         if(f.second > 0) { w.flag[w.n] = ctx->d_flags + f.first; w.value[w.n] = (int)f.second; ++w.n; }
     if(w.n == 0) return;
     w.error = ctx->d_flags + HF_ERROR;
+    if(onHalo)
+    {
+        ++ctx->launches; ++ctx->kstat[K_HALO_WAIT].launches;
+        k_halo_wait<<<1, 1, 0, ctx->hstream>>>(w);
+        return;
+    }
     LaunchScope ls(ctx, K_HALO_WAIT);
     k_halo_wait<<<1, 1, 0, ctx->stream>>>(w);
 }
@@ -1886,7 +1901,11 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
     const bool lo = ctx->lower.present, up = ctx->upper.present;
     const long rowN = ctx->plane;                                    // one (x, z) plane of doubles, padded
     const long top = (long)(ctx->ly - 2) * ctx->plane, ghostTop = (long)(ctx->ly - 1) * ctx->plane;
-    const bool haveEy = ctx->d_field[CHIML_EY] != nullptr;
+    // a periodic run closes the slabs into a ring (chiml_b200/slab.py): every slab has both neighbours; the last slab's components that are one
+    // row short in y (Hx, Hz, Ey) end at row ly - 3, and its row ly - 2 of Hx, Hz is the wrap image of slab 0's row 1, pushed across the seam.
+    // Ey rows feed oriented-dipole nodes and emitters only, which a ring of slabs does not carry.
+    const bool ring = ctx->ring, lastSlab = ctx->g.rank == ctx->g.nranks - 1, seamTop = ring && lastSlab, seamBottom = ring && ctx->g.rank == 0;
+    const bool haveEy = ctx->d_field[CHIML_EY] != nullptr && !ring;
     const bool needEy = haveEy;
     StepArgs a;
     // pushes of the previous step read rows this step overwrites
@@ -1897,15 +1916,39 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
     fill_step_args(ctx, false, a);
     launch_family<false>(ctx, a, block, 1);
     launch_sources(ctx, k, nsrc, 1);
-    if(up)
-    {
+    auto pushHUp = [&](long srcRow) {
         halo_fork(ctx);
         const HaloPeer& p = ctx->upper;
-        halo_push(ctx, p, {{ctx->d_field[CHIML_HX] ? ctx->d_field[CHIML_HX] + top : nullptr, p.field[CHIML_HX], rowN},
-                           {ctx->d_field[CHIML_HZ] ? ctx->d_field[CHIML_HZ] + top : nullptr, p.field[CHIML_HZ], rowN}}, {HF_H_FROM_LOWER}, kk);
+        halo_push(ctx, p, {{ctx->d_field[CHIML_HX] ? ctx->d_field[CHIML_HX] + srcRow : nullptr, p.field[CHIML_HX], rowN},
+                           {ctx->d_field[CHIML_HZ] ? ctx->d_field[CHIML_HZ] + srcRow : nullptr, p.field[CHIML_HZ], rowN}}, {HF_H_FROM_LOWER}, kk);
+    };
+    if(up && !seamTop) pushHUp(top);
+    if(seamTop)
+    {
+        // the wrap row ly - 2 of Hx, Hz is free: the E half step of the step before has read it, and this step's own (discarded) update of its
+        // cells -- the CPML lists of the reference cover that row, the wrap then overwrites it -- is through: slab 0 may push
+        halo_fork(ctx);
+        halo_push(ctx, ctx->upper, {}, {HF_SEAM_ACK}, kk);
+    }
+    if(seamBottom)
+    {
+        // slab 0's Hx, Hz row 1 into the wrap row ly - 2 of the last slab, once that slab has released the row for this step
+        halo_fork(ctx);
+        halo_wait(ctx, {{HF_SEAM_ACK, kk}}, true);
+        const HaloPeer& p = ctx->lower;
+        const long wrapRow = (long)(p.ly - 2) * ctx->plane;
+        halo_push(ctx, p, {{ctx->d_field[CHIML_HX] ? ctx->d_field[CHIML_HX] + ctx->plane : nullptr, p.field[CHIML_HX] ? p.field[CHIML_HX] + wrapRow : nullptr, rowN},
+                           {ctx->d_field[CHIML_HZ] ? ctx->d_field[CHIML_HZ] + ctx->plane : nullptr, p.field[CHIML_HZ] ? p.field[CHIML_HZ] + wrapRow : nullptr, rowN}},
+                  {HF_H_FROM_UPPER}, kk);
     }
     launch_family<false>(ctx, a, block, 2);
     launch_sources(ctx, k, nsrc, 2);
+    // (the last slab of a ring sends its top owned row of Hx, Hz, row ly - 3: an interior row, ready only now)
+    if(seamTop) pushHUp(top - ctx->plane);
+    // x / z wraps of the owned rows (slabs of a periodic run; nothing otherwise).  The last slab's wrap row arrives with the x / z ghost cells slab 0
+    // had before ITS wrap: wait for the row, then the wrap below redoes them from the row's inner cells
+    if(seamTop) halo_wait(ctx, {{HF_H_FROM_UPPER, kk}});
+    launch_wraps(ctx, false);
 
     // ---- oriented-dipole poles at the nodes (read Ey of ghost row 0: pushed by the slab below after its last E half step)
     if(lo && needEy) halo_wait(ctx, {{HF_EY_FROM_LOWER, kk - 1}});
@@ -1949,6 +1992,7 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
         halo_push(ctx, ctx->upper, {{ctx->d_field[CHIML_EY] + top, ctx->upper.field[CHIML_EY], rowN}}, {HF_EY_FROM_LOWER}, kk);
     launch_family<true>(ctx, a, block, 2);
     for(EmitterDev& em : ctx->emitters) launch_addP(ctx, em, 2);
+    launch_wraps(ctx, true);
 
     // ---- emitter density update (averages Ey[r], Ey[r - y]: needs this step's Ey in ghost row 0)
     if(!ctx->emitters.empty())
@@ -2361,14 +2405,19 @@ static int halo_open_peer(ChimlCtx* ctx, const void* blob, size_t size, bool isL
     HaloBlobHdr h;
     std::memcpy(&h, blob, sizeof(h));
     if(h.magic != HALO_MAGIC) return fail(ctx, CHIML_ERR_ARG, "halo_bind: not a halo blob");
-    if(h.nranks != ctx->g.nranks || h.rank != ctx->g.rank + (isLower ? -1 : 1)) return fail(ctx, CHIML_ERR_ARG, "halo_bind: blob is not from the neighbouring slab");
+    const int nb = ctx->g.rank + (isLower ? -1 : 1);
+    if(h.nranks != ctx->g.nranks || h.rank != (ctx->ring ? (nb + ctx->g.nranks) % ctx->g.nranks : nb)) return fail(ctx, CHIML_ERR_ARG, "halo_bind: blob is not from the neighbouring slab");
     if(h.lx != ctx->lx || h.lz != ctx->lz || h.px != ctx->px) return fail(ctx, CHIML_ERR_ARG, "halo_bind: neighbour has different x / z extents");
     const size_t need = sizeof(HaloBlobHdr) + (7 + MAX_POLES) * sizeof(cudaIpcMemHandle_t) + (size_t)h.nsets * sizeof(HaloBlobSet);
     if(size < need) return fail(ctx, CHIML_ERR_ARG, "halo_bind: truncated blob");
     const cudaIpcMemHandle_t* hs = reinterpret_cast<const cudaIpcMemHandle_t*>((const char*)blob + sizeof(HaloBlobHdr));
     auto open = [&](const cudaIpcMemHandle_t& hh, void** out) -> int {
+        const std::string key(reinterpret_cast<const char*>(&hh), sizeof(hh));
+        auto it = ctx->ipc_cache.find(key);
+        if(it != ctx->ipc_cache.end()) { *out = it->second; return 0; }
         CK(cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess));
         peer.opened.push_back(*out);
+        ctx->ipc_cache[key] = *out;
         return 0;
     };
     int rc;
@@ -2377,7 +2426,9 @@ static int halo_open_peer(ChimlCtx* ctx, const void* blob, size_t size, bool isL
     {
         if(!h.has_field[f]) continue;
         // only the arrays this slab writes into: E_x, E_z of the slab below; H_x, H_z, E_y of the slab above
-        const bool needIt = isLower ? (f == CHIML_EX || f == CHIML_EZ) : (f == CHIML_HX || f == CHIML_HZ || f == CHIML_EY);
+        // (periodic ring: slab 0 also writes H_x, H_z row 1 into the wrap row of the last slab, which is the slab below it)
+        const bool seam = ctx->ring && ctx->g.rank == 0 && isLower && (f == CHIML_HX || f == CHIML_HZ);
+        const bool needIt = seam || (isLower ? (f == CHIML_EX || f == CHIML_EZ) : (f == CHIML_HX || f == CHIML_HZ || f == CHIML_EY));
         if(!needIt) continue;
         void* base = nullptr;
         if((rc = open(hs[f], &base))) return rc;
@@ -2438,9 +2489,10 @@ int chiml_gpu_halo_bind(ChimlCtx* ctx, const void* lower_blob, size_t lower_size
     if(!ctx->committed) return fail(ctx, CHIML_ERR_STATE, "halo_bind before commit");
     if(ctx->halo_bound) return fail(ctx, CHIML_ERR_STATE, "halo_bind called twice");
     CK(cudaSetDevice(ctx->device));
-    const bool needLower = ctx->g.rank > 0, needUpper = ctx->g.rank < ctx->g.nranks - 1;
+    const bool needLower = ctx->ring || ctx->g.rank > 0, needUpper = ctx->ring || ctx->g.rank < ctx->g.nranks - 1;
     if(needLower != (lower_blob != nullptr) || needUpper != (upper_blob != nullptr))
-        return fail(ctx, CHIML_ERR_ARG, "halo_bind: exactly the existing neighbours must be given (none below slab 0, none above the last slab)");
+        return fail(ctx, CHIML_ERR_ARG, "halo_bind: exactly the existing neighbours must be given (none below slab 0, none above the last slab; a periodic "
+                                        "run closes the ring: slab nranks - 1 below slab 0, slab 0 above slab nranks - 1)");
     int rc;
     if(needLower && (rc = halo_open_peer(ctx, lower_blob, lower_size, true, ctx->lower))) return rc;
     if(needUpper && (rc = halo_open_peer(ctx, upper_blob, upper_size, false, ctx->upper))) return rc;

@@ -15,6 +15,8 @@
 #include <array>
 #include <cstdint>
 #include <string>
+#include <map>
+#include <string>
 #include <vector>
 
 #include "../../include/chiml_gpu.h"
@@ -120,7 +122,8 @@ struct EmitterDev
 };
 
 // ---- y-slab halo (chiml_halo.cuh): flags the neighbours write into this context's memory, one 32-bit step counter each
-enum HaloFlag { HF_H_FROM_LOWER = 0, HF_OP_FROM_UPPER, HF_E_FROM_UPPER, HF_EY_FROM_LOWER, HF_QP_FROM_UPPER, HF_ERROR, HF_NFLAGS = 16 };
+// (periodic ring of slabs: HF_H_FROM_UPPER = slab 0's Hx, Hz row 1 has arrived in the last slab's wrap row; HF_SEAM_ACK = the last slab has released that row for the step: read by the E half step before, its own discarded update through)
+enum HaloFlag { HF_H_FROM_LOWER = 0, HF_OP_FROM_UPPER, HF_E_FROM_UPPER, HF_EY_FROM_LOWER, HF_QP_FROM_UPPER, HF_ERROR, HF_H_FROM_UPPER, HF_SEAM_ACK, HF_NFLAGS = 16 };
 constexpr size_t IPC_GRANULE = 2u << 20;     // exported buffers are whole 2 MiB allocations (never sub-allocated by the driver)
 
 struct HaloPeer                   // one neighbouring slab, as mapped into this process
@@ -267,6 +270,8 @@ struct ChimlCtx
     cudaEvent_t ev_main = nullptr, ev_push = nullptr;
     bool push_pending = false;
     int* d_flags = nullptr;                      // HF_NFLAGS ints, exported
+    bool ring = false;                           // periodic run on several slabs: the slabs form a ring (slab 0 <-> slab nranks - 1)
+    std::map<std::string, void*> ipc_cache;      // IPC handles already opened (a ring of two slabs names the same peer twice)
     unsigned* d_push_counter = nullptr;          // block counters of the push kernels
     int push_slot = 0;
     double* d_oPy_ghost[chiml::MAX_POLES] = {};  // dense (lx * lz) ghost row ny+1 of node P_y per pole, written by the slab above

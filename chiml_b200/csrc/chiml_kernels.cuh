@@ -292,7 +292,9 @@ __global__ void k_prev_copy(PrevCopyArgs a)
 // the copies are independent.  3-D: the shell is walked as y faces (whole planes), z faces (rows 1 .. ymax-1), x faces (the rest).
 // 2-D (zmin = 0): rows 0 and ymax over x in [1, xmax-1], columns 0 and xmax over y in [1, ymax] (the cells (0, 0), (xmax, 0) stay as they
 // are, as in the reference).
-struct WrapArgs { double* f[3]; ChimlWrap w[3]; int n; int lz; long px; };
+// A slab of several (ymax < 0; applyBCProcMid, UTIL/FDTD_up_eq.cpp:1036-1061): the x / z ghost cells of the owned rows 1 .. ly - 2 only, each from
+// its image in the same row; the y direction is the ring of ghost-row pushes between the slabs.
+struct WrapArgs { double* f[3]; ChimlWrap w[3]; int n; int lz; long px; int ly; };
 __global__ void k_wrap(WrapArgs a)
 {
     const int c = blockIdx.y;
@@ -301,6 +303,31 @@ __global__ void k_wrap(WrapArgs a)
     const ChimlWrap w = a.w[c];
     const long px = a.px, lz = a.lz;
     const long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x, istep = (long)gridDim.x * blockDim.x;
+    if(w.ymax < 0)
+    {
+        const long R = a.ly - 2;                                   // owned rows
+        if(w.zmin != 0)
+        {
+            const long X = w.xmax + 1, Z = w.zmax - w.zmin + 2;
+            const long nB = 2 * X * R, nC = 2 * R * (Z - 2);
+            for(long i = i0; i < nB + nC; i += istep)
+            {
+                int x, y, z;
+                if(i < nB) { x = (int)(i % X); const long r = i / X; y = (int)(r % R) + 1; z = (r / R) ? w.zmax : w.zmin - 1; }
+                else       { const long j = i - nB; z = (int)(j % (Z - 2)) + w.zmin; const long r = j / (Z - 2); y = (int)(r % R) + 1; x = (r / R) ? w.xmax : 0; }
+                const int sx = x == 0 ? w.xmax - 1 : (x == w.xmax ? 1 : x);
+                const int sz = z == w.zmin - 1 ? w.zmax - 1 : (z == w.zmax ? w.zmin : z);
+                F[x + px * (z + lz * y)] = F[sx + px * (sz + lz * y)];
+            }
+        }
+        else
+            for(long i = i0; i < 2 * R; i += istep)
+            {
+                const int y = (int)(i % R) + 1, x = (i / R) ? w.xmax : 0;
+                F[x + px * (long)y] = F[(x == 0 ? w.xmax - 1 : 1) + px * (long)y];
+            }
+        return;
+    }
     if(w.zmin != 0)
     {
         const long X = w.xmax + 1, Y = w.ymax + 1, Z = w.zmax - w.zmin + 2;

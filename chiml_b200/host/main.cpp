@@ -180,8 +180,9 @@ int main(int argc, char** argv)
             { std::ofstream out((my + ".tmp").c_str(), std::ios::binary); out.write(mine.data(), (std::streamsize)n); }
             std::rename((my + ".tmp").c_str(), my.c_str());
             std::vector<char> lower, upper;
-            if(rank > 0) lower = read_file_when_ready(stem + std::to_string(rank - 1));
-            if(rank + 1 < nranks) upper = read_file_when_ready(stem + std::to_string(rank + 1));
+            const bool ring = !P.periodic.empty();      // a periodic run closes the slabs into a ring: slab nranks - 1 below slab 0
+            if(rank > 0 || ring) lower = read_file_when_ready(stem + std::to_string((rank + nranks - 1) % nranks));
+            if(rank + 1 < nranks || ring) upper = read_file_when_ready(stem + std::to_string((rank + 1) % nranks));
             check(ctx, chiml_gpu_halo_bind(ctx, lower.empty() ? nullptr : lower.data(), lower.size(), upper.empty() ? nullptr : upper.data(), upper.size()), "halo_bind");
         }
         if(rank == 0) std::cout << "made FF" << std::endl;

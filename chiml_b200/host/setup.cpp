@@ -772,8 +772,9 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
     // yEPBC_ / yHPBC_ of the single-process branch (parallelFDTDField.cpp:163-171,329-336) and zMinPBC_ / zMaxPBC_ (hpp:444-445) ----
     if(IP.periodic_)
     {
-        if(nranks > 1) throw std::logic_error("periodic boundaries are covered for single-slab runs (the reference's multi-rank periodic run takes applyBCProcMid on every rank, SURVEY.md B.5)");
         if(nOrDip > 0) throw std::logic_error("oriented-dipole media under periodic boundaries are outside the covered hot path");
+        if(nranks > 1 && (!IP.qes_.empty() || IP.cplxFields_ || magnetic || chiral))
+            throw std::logic_error("periodic runs on several slabs are covered for real fields without emitters and without magnetic / chiral media");
         const int l0 = g.ln[0] - 2, l1 = g.ln[1] - 2;
         const int zMin = g.twoD ? 0 : 1, zMax = g.twoD ? 1 : g.ln[2] - 2;
         // y-limited components (fieldEnd[1] = 1: Ey, Hx, Hz) wrap at row ln_vec_[1], the others at ln_vec_[1] + 1
@@ -782,7 +783,14 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
                                 {l0, yE[2], zMax - 1, l0 + 1, yE[2], zMin, zMax},     {l0, yH[0], zMax - 1, l0 + 1, yH[0], zMin, zMax},
                                 {l0 - 1, yH[1], zMax - 1, l0, yH[1], zMin, zMax},     {l0 - 1, yH[2], zMax, l0, yH[2], zMin, zMax + 1}};
         for(int comp = 0; comp < 6; ++comp)
-            if(comp_exists(mode, comp)) { ChimlPlanPeriodic pp; pp.comp = comp; pp.wrap = w[comp]; P.periodic.push_back(pp); }
+            if(comp_exists(mode, comp))
+            {
+                ChimlPlanPeriodic pp; pp.comp = comp; pp.wrap = w[comp];
+                // a slab of several: the x / z wraps of the owned rows only (applyBCProcMid on every rank); the y direction is the ghost-row ring
+                // between the slabs, slab 0 <-> slab nranks - 1 included (include/chiml_gpu.h chiml_gpu_set_periodic)
+                if(nranks > 1) { pp.wrap.ny = -1; pp.wrap.ymax = -1; }
+                P.periodic.push_back(pp);
+            }
     }
     if(IP.cplxFields_)
     {

@@ -10,6 +10,14 @@ Local rows: 0 = lower ghost, 1 .. ny = owned, ny+1 = upper ghost.  A step is fou
                                                        Ey      row ny UP    (node poles / emitters average Ey[r], Ey[r-y])
   phase 3  emitter density update                  ->  emitter P_y first row  DOWN  (addP of the lower slab's top row)
 
+Periodic runs (CompCell.PBC, real fields) close the slabs into a ring: slab 0's lower neighbour is slab nranks-1 and vice versa, every
+exchange above also crosses that seam, with two differences that come from the reference's wrap rows (applyBC1Proc: F[0] <- F[ymax-1],
+F[ymax] <- F[1] with ymax = ln_y + 1, or ln_y for the components that are one row short in y: Ey, Hx, Hz):
+  * the last slab's top owned row of Hx, Hz (and Ey) is ny - 1, not ny: that is the row it sends UP across the seam;
+  * its row ny of Hx, Hz is the wrap image of slab 0's row 1 -- read by its own E update of row ny -- so after phase 0 slab 0 also
+    sends Hx, Hz row 1 DOWN across the seam into that row.
+The x / z ghost cells are wrapped inside every slab (applyBCProcMid; the checker and the engine do it inside phases 0 and 2).
+
 The CUDA engine implements this protocol natively (peer-to-peer stores + flags, chiml_gpu_halo_*); this module states it once in
 host terms, drives the CPU checker through it in the world_size-2 gloo tests, and gathers slab results onto rank 0.
 """
@@ -49,15 +57,32 @@ def step_slab(sim, plan: P.Plan, amp_step: np.ndarray, send: Callable, recv: Cal
     ny = plan.ln[1] - 2
     lower, upper = plan.rank - 1, plan.rank + 1
     has_lower, has_upper = lower >= 0, upper < plan.nranks
+    ring = bool(plan.periodic) and plan.nranks > 1
+    last = plan.rank == plan.nranks - 1
+    if ring:
+        lower, upper, has_lower, has_upper = lower % plan.nranks, upper % plan.nranks, True, True
     present = plan.fields_present()
     for phase in range(4):
         sim.step_phase(phase, amp_step)
+        if ring and phase == 0:
+            # the seam: slab 0's Hx, Hz row 1 is the wrap image the last slab's E update reads in its row ny
+            for f in (HX, HZ):
+                if f not in present:
+                    continue
+                if plan.rank == 0:
+                    send(plan.nranks - 1, np.ascontiguousarray(sim.field(f)[1]))
+                if last:
+                    buf = np.empty_like(np.ascontiguousarray(sim.field(f)[ny]))
+                    recv(0, buf)
+                    sim.field(f)[ny] = buf
         for ph, kind, fields, direction in PROTOCOL:
             if ph != phase:
                 continue
             rows = []   # (array_view, send_row, recv_row)
             if kind == "field":
-                rows = [(sim.field(f), ny if direction == UP else 1, 0 if direction == UP else ny + 1) for f in fields if f in present]
+                # (ring: the last slab's components that are one row short in y end at row ny - 1)
+                rows = [(sim.field(f), (ny - 1 if ring and last and f in (EY, HX, HZ) else ny) if direction == UP else 1, 0 if direction == UP else ny + 1)
+                        for f in fields if f in present]
             elif kind == "ordip_py":
                 if 1 in present:
                     rows = [(sim.ordip_pole(1, p, 0), 1, ny + 1) for p in range(plan.n_ordip_poles)]

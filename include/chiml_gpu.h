@@ -177,8 +177,12 @@ int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq,
  * first, then columns over rows 1 .. ymax).  The seven numbers are the arguments the reference passes to applBCH_[c] / applBCE_[c]
  * (FDTD_MANAGER/parallelFDTDField.hpp:1267-1269,1285-1287; yHPBC_/yEPBC_/zMinPBC_/zMaxPBC_ from parallelFDTDField.cpp:153-171,
  * 322-336, parallelFDTDField.hpp:444-445): for a component trimmed by one point along an axis (fieldEnd) the last, never updated
- * point of that axis is the upper image.  comp 0..5 = Ex..Hz.  Single slab only (the reference's multi-rank periodic run takes
- * applyBCProcMid on every rank); oriented-dipole media are refused together with it. */
+ * point of that axis is the upper image.  comp 0..5 = Ex..Hz.  Oriented-dipole media are refused together with it.
+ * A slab of several (desc.nranks > 1) passes ymax = ny = -1: the engine then wraps the x / z ghost cells of its owned rows only (applyBCProcMid,
+ * UTIL/FDTD_up_eq.cpp:1036-1061, which the reference takes on every rank), and the y direction is the ring of ghost-row pushes: chiml_gpu_halo_bind
+ * takes the blob of slab nranks - 1 as slab 0's lower neighbour and vice versa; the last slab sends its top owned row of Hx, Hz (ly - 3: these
+ * components are one row short in y) upward across the seam and receives slab 0's row 1 of Hx, Hz in its wrap row ly - 2 (chiml_b200/slab.py).
+ * Interior results equal the single-slab run's bit for bit.  Covered there: real fields, no emitters, no magnetic / chiral media, no TFSF. */
 typedef struct ChimlWrap { int32_t nx, ny, nz, xmax, ymax, zmin, zmax; } ChimlWrap;
 int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* wrap);
 

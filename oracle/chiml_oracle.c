@@ -815,7 +815,8 @@ static void tfsf_add(OracleSim* s, const TfsfSur* q, const double* table)
  * reference's order of dcopy_ calls.  PT(x, y, z) = parallelGrid::point(x, y, z) (GRID/parallelGrid.hpp:363). */
 int oracle_set_periodic(OracleSim* s, int comp, const ChimlWrap* w)
 {
-    if(!s || comp < 0 || comp > 5 || !w || s->g.nranks != 1) return CHIML_ERR_ARG;
+    if(!s || comp < 0 || comp > 5 || !w) return CHIML_ERR_ARG;
+    if((s->g.nranks != 1) != (w->ymax < 0)) return CHIML_ERR_ARG;      /* a slab of several takes the x / z wraps only (ymax = -1) */
     s->wrap[comp] = *w; s->has_wrap[comp] = 1;
     return 0;
 }
@@ -825,6 +826,32 @@ static void apply_bc_1proc(const OracleSim* s, double* F, const ChimlWrap* w)
     const size_t lx = (size_t)s->g.ln[0], lz = (size_t)s->g.ln[2];
 #define PT(x, y, z) (F + ((size_t)(x) + lx * ((size_t)(z) + lz * (size_t)(y))))
     const int nx = w->nx, ny = w->ny, nz = w->nz, xmax = w->xmax, ymax = w->ymax, zmin = w->zmin, zmax = w->zmax;
+    if(ymax < 0)
+    {
+        /* one y-slab of several (applyBCProcMid, UTIL/FDTD_up_eq.cpp:1036-1061): the y direction is the ghost-row ring between the slabs
+         * (transferDat); here only the x / z ghost cells of the owned rows take their periodic images */
+        const int ly = s->g.ln[1];
+        if(zmin != 0)
+        {
+            for(int jj = 1; jj < ly - 1; ++jj)
+            {
+                copy_strided(nz, PT(xmax - 1, jj, 1), lx, PT(0, jj, 1), lx);
+                copy_strided(nz, PT(1, jj, 1), lx, PT(xmax, jj, 1), lx);
+                copy_strided(nx, PT(1, jj, zmax - 1), 1, PT(1, jj, zmin - 1), 1);
+                copy_strided(nx, PT(1, jj, zmin), 1, PT(1, jj, zmax), 1);
+            }
+            copy_strided(ly - 2, PT(1, 1, zmin), lx * lz, PT(xmax, 1, zmax), lx * lz);
+            copy_strided(ly - 2, PT(xmax - 1, 1, zmax - 1), lx * lz, PT(0, 1, zmin - 1), lx * lz);
+            copy_strided(ly - 2, PT(xmax - 1, 1, zmin), lx * lz, PT(0, 1, zmax), lx * lz);
+            copy_strided(ly - 2, PT(1, 1, zmax - 1), lx * lz, PT(xmax, 1, zmin - 1), lx * lz);
+        }
+        else
+        {
+            copy_strided(ly - 2, PT(xmax - 1, 1, 0), lx, PT(0, 1, 0), lx);
+            copy_strided(ly - 2, PT(1, 1, 0), lx, PT(xmax, 1, 0), lx);
+        }
+        return;
+    }
     if(zmin != 0)
     {
         for(int kk = zmin; kk <= nz; ++kk)

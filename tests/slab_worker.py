@@ -81,6 +81,9 @@ def main():
         for n in names:
             got = np.concatenate([g[1][n] for g in gathered], axis=0)
             ref = expect[n][1:-1]
+            if whole.periodic and n == "Ey":
+                # the wrap row of Ey (global row ln_y, the image of row 1): nothing in the step reads it, the slab ring does not carry it
+                got, ref = got[:-1], ref[:-1]
             if not np.array_equal(got, ref):
                 ok = False
                 print(f"MISMATCH {case}/{n}: max |diff| {np.abs(got - ref).max():.3e} of {np.abs(ref).max():.3e}")

@@ -70,11 +70,26 @@ def test_valid_input_builds(tmp_path):
     assert os.path.exists(tmp_path / "out.rank0.plan")
 
 
-def test_periodic_run_on_several_slabs_is_refused(tmp_path):
-    """Real-field periodic boundaries are covered on one slab; the reference's multi-rank periodic run (applyBCProcMid on every rank,
-    SURVEY.md appendix B.5) is not reproduced, so the setup must say so instead of building slab plans."""
+def test_periodic_slab_plans_carry_the_ring_wraps(tmp_path):
+    """A periodic run on several slabs: every slab's PERIODIC records describe the x / z wraps of its owned rows only (ymax = ny = -1; the y
+    direction is the ring of ghost-row pushes, chiml_b200/slab.py); Bloch-periodic (complex) runs on several slabs are refused."""
+    import json
     import shutil
+    import sys
     import util
+    sys.path.insert(0, ROOT)
+    from chiml_b200 import plan as P
     shutil.copy(os.path.join(util.GOLDEN, "pbc3d.json"), tmp_path / "pbc3d.json")
-    r = subprocess.run([TOOL, "pbc3d.json", "out", "--ranks", "2"], cwd=tmp_path, capture_output=True, text=True)
-    assert r.returncode != 0 and "single-slab" in r.stderr, r.stderr
+    r = subprocess.run([TOOL, "pbc3d.json", "out", "--ranks", "3"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    whole = util.load_plan("pbc3d")
+    for rank in range(3):
+        pl = P.read_plan(str(tmp_path / f"out.rank{rank}.plan"))
+        assert sorted(pl.periodic) == sorted(whole.periodic)
+        for comp, w in pl.periodic.items():
+            ref = whole.periodic[comp]
+            assert w[1] == -1 and w[4] == -1 and (w[0], w[2], w[3], w[5], w[6]) == (ref[0], ref[2], ref[3], ref[5], ref[6])
+    cfg = json.load(open(os.path.join(util.GOLDEN, "cplx3d.json")))
+    json.dump(cfg, open(tmp_path / "cplx3d.json", "w"))
+    r = subprocess.run([TOOL, "cplx3d.json", "out2", "--ranks", "2"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "several slabs" in r.stderr, r.stderr

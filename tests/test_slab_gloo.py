@@ -17,6 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
                                         ("aniso_mixed3d", 4), ("aniso_mixed3d", 3),
                                         # magnetic-dispersive media: B / H / M cells cut by slab boundaries, the H-side CPML on B
                                         ("mag3d", 3), ("mag3d_pml", 2), ("mag_tm", 3), ("mag_te", 2),
+                                        # periodic boundaries: the slabs form a ring, the last slab's wrap row comes from slab 0 (chiml_b200/slab.py)
+                                        ("pbc3d", 2), ("pbc3d", 3), ("pbc3d_all", 4), ("pbc_tm", 3), ("pbc_te", 2),
                                         # random inputs (tests/fuzz/gen_inputs.py), expected arrays from the single-rank oracle
                                         ("fuzz:4", 4), ("fuzz:12", 3), ("fuzz:33", 3), ("fuzz:10:ml", 4), ("fuzz:14:ml", 2)])
 def test_slab_protocol_matches_single_rank_reference(case, world):
