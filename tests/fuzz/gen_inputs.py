@@ -203,3 +203,45 @@ def rnd_mag_case(seed, steps=10):
     if mode!="3d": dloc[2]=0.0
     dets=[I.detector(dloc, [0.0,0.0,0.0], dpol, f"out/fm{seed}/d", time_int=DT*1.0000001)]
     return I.config(I.comp_cell(size, RES, steps*DT-0.5*DT, pol), pml, srcs, objs, dets, [])
+
+
+def rnd_pbc_case(seed, steps=14):
+    """Periodic boundaries (CompCell.PBC, real fields) with random media: 3-D grids periodic in x / y with CPML in z (or none at all), 2-D grids with
+    CPML along one axis; blocks that span the periodic faces (crossing the seam between the last and the first y-slab of a multi-slab run), spheres
+    and films with Lorentz / Drude poles."""
+    r=random.Random(9000+seed)
+    mode=r.choice(["3d","3d","te","tm"])
+    if mode=="3d":
+        n=[r.randint(15,23), r.randint(17,25), r.randint(15,25)]; pol="Ex"
+        pmlc=[0,0,r.choice([0,4,6])]
+    else:
+        n=[r.randint(31,49), r.randint(33,49), 0]; pol="Hz" if mode=="te" else "Ez"
+        pmlc=r.choice([[0,6,0],[6,0,0],[0,0,0]])
+    size=[k/RES for k in n]
+    pml=I.pml([c/RES for c in pmlc], a_max=r.choice([0.25,0.1]), ma=r.choice([1.0,2.0]), m=r.choice([3.0,3.5]), kappa_max=r.choice([1.0,2.5]))
+    objs=[]
+    for _ in range(r.randint(1,3)):
+        loc=[r.uniform(-0.4,0.4)*size[k] for k in range(3)]
+        if mode!="3d": loc[2]=0.0
+        kind=r.choice(["eps","lor","drude","lor"])
+        pols=[]
+        if kind=="lor": pols=[I.lorentz_pole(r.uniform(0.3,1.5), r.uniform(0.02,0.2), r.uniform(1,3)) for _ in range(r.randint(1,2))]
+        if kind=="drude": pols=[I.drude_pole(r.uniform(5,9), r.uniform(0.05,0.2))]
+        eps=r.choice([1.0,2.0,2.25,4.0])
+        if r.random()<0.65:
+            sz=[r.uniform(0.1,0.5)*size[k] for k in range(3)]
+            for k in range(2):
+                if r.random()<0.4 and pmlc[k]==0: sz[k]=3.0*size[k]          # spans the periodic faces of that axis
+            if mode!="3d": sz[2]=0.0
+            objs.append(I.block(sz, loc, eps=eps, pols=pols))
+        else:
+            objs.append(I.sphere(r.uniform(0.08,0.25)*min(s for s in size if s>0), loc, eps=eps, pols=pols))
+    srcpol={"3d":r.choice(["Ex","Ey","Ez","Hx","Hz"]),"te":r.choice(["Hz","Ex","Ey"]),"tm":r.choice(["Ez","Hx","Hy"])}[mode]
+    sloc=[r.uniform(-0.3,0.3)*size[k] for k in range(3)]; ssz=[r.choice([0.0, r.uniform(0,0.3)*size[k]]) for k in range(3)]
+    if mode!="3d": sloc[2]=0.0; ssz[2]=0.0
+    srcs=[I.normal_source(srcpol, sloc, ssz, [I.gaussian_pulse(1.5,1.0,t_0=0.25,cutoff=2.5)])]
+    dpol={"3d":r.choice(["Ex","Ey","Ez","Hx","Hy","Hz"]),"te":r.choice(["Hz","Ex","Ey"]),"tm":r.choice(["Ez","Hx","Hy"])}[mode]
+    dloc=[r.uniform(-0.3,0.3)*size[k] for k in range(3)]
+    if mode!="3d": dloc[2]=0.0
+    dets=[I.detector(dloc, [0.0,0.0,0.0], dpol, f"out/fp{seed}/d", time_int=DT*1.0000001)]
+    return I.config(I.comp_cell(size, RES, steps*DT-0.5*DT, pol, pbc=True), pml, srcs, objs, dets, [])

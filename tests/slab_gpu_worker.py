@@ -43,11 +43,27 @@ def run_case(case, rank, world, local, log=print):
     """Returns True when the gathered slabs equal the single-rank result bit for bit (rank 0 decides; other ranks return True).
     `log` receives the per-case verdict and any mismatch lines (bench.py sends them to stderr)."""
     case, pair = (case[:-5], True) if case.endswith("+pair") else (case, False)
-    work = tempfile.mkdtemp(prefix=f"slabgpu_{case}_r{rank}_")
-    subprocess.run([os.path.join(ROOT, "chiml_b200", "chiml_plan"), os.path.join(util.GOLDEN, case + ".json"), os.path.join(work, case),
-                    "--ranks", str(world), "--only", str(rank)], check=True)
+    work = tempfile.mkdtemp(prefix=f"slabgpu_{case.replace(':', '_')}_r{rank}_")
+    tool = os.path.join(ROOT, "chiml_b200", "chiml_plan")
+    fuzz = case.startswith("fuzz:")
+    if fuzz:
+        # fuzz:<seed>:pbc / fuzz:<seed>:mag -- a random periodic / magnetic input (tests/fuzz/gen_inputs.py); expected arrays from the single-rank oracle
+        sys.path.insert(0, os.path.join(ROOT, "tests", "fuzz"))
+        import gen_inputs
+        from chiml_b200 import inputs as I
+        _, seed, kind = case.split(":")
+        cfg = gen_inputs.rnd_pbc_case(int(seed)) if kind == "pbc" else gen_inputs.rnd_mag_case(int(seed), steps=12)
+        src = os.path.join(work, "c.json")
+        I.write(cfg, src)
+        subprocess.run([tool, src, os.path.join(work, "whole")], check=True)
+        whole = P.read_plan(os.path.join(work, "whole.rank0.plan"))
+        label, case = case, "c"
+    else:
+        src = os.path.join(util.GOLDEN, case + ".json")
+        whole = util.load_plan(case)
+        label = case
+    subprocess.run([tool, src, os.path.join(work, case), "--ranks", str(world), "--only", str(rank)], check=True)
     plan = P.read_plan(os.path.join(work, f"{case}.rank{rank}.plan"))
-    whole = util.load_plan(case)
     if pair:
         add_second_species(plan)
         add_second_species(whole)
@@ -75,7 +91,7 @@ def run_case(case, rank, world, local, log=print):
     dist.gather_object((plan.y_start, mine, emit), gathered if rank == 0 else None, dst=0)
     ok = True
     if rank == 0:
-        expect = oracle_expect(whole, util.state_names(whole)) if pair else util.load_expect(case)
+        expect = oracle_expect(whole, util.state_names(whole)) if (pair or fuzz) else util.load_expect(case)
         gathered.sort(key=lambda t: t[0])
         for n in names:
             got = np.concatenate([g[1][n] for g in gathered], axis=0)
@@ -131,7 +147,7 @@ def run_case(case, rank, world, local, log=print):
                 if pops is None or len(pops[d]) != len(ref) or np.abs(pops[d] - ref).max() > 1e-9 * max(np.abs(ref).max(), 1e-300):
                     ok = False
                     log(f"MISMATCH {case}/q{q}pop{d}")
-        log(f"{case}{'+pair' if pair else ''}: {'SLAB_GPU_OK' if ok else 'SLAB_GPU_FAIL'} ({world} slabs, {launches} launches on rank 0)")
+        log(f"{label}{'+pair' if pair else ''}: {'SLAB_GPU_OK' if ok else 'SLAB_GPU_FAIL'} ({world} slabs, {launches} launches on rank 0)")
     return ok
 
 

@@ -31,9 +31,15 @@ def main():
         import gen_inputs
         from chiml_b200 import inputs as I
         parts = case.split(":")
-        cfg = gen_inputs.rnd_ml_case(int(parts[1])) if len(parts) > 2 else gen_inputs.rnd_case(int(parts[1]), steps=12, pulses="random")
-        if len(parts) > 2:
-            cfg["CompCell"]["tLim"] = 12 * gen_inputs.DT - 0.5 * gen_inputs.DT
+        # fuzz:<seed>:pbc -- a periodic run with random media (the slabs form a ring); fuzz:<seed>:mag -- magnetic-dispersive media
+        if len(parts) > 2 and parts[2] == "pbc":
+            cfg = gen_inputs.rnd_pbc_case(int(parts[1]))
+        elif len(parts) > 2 and parts[2] == "mag":
+            cfg = gen_inputs.rnd_mag_case(int(parts[1]), steps=12)
+        else:
+            cfg = gen_inputs.rnd_ml_case(int(parts[1])) if len(parts) > 2 else gen_inputs.rnd_case(int(parts[1]), steps=12, pulses="random")
+            if len(parts) > 2:
+                cfg["CompCell"]["tLim"] = 12 * gen_inputs.DT - 0.5 * gen_inputs.DT
         src = os.path.join(work, "c.json")
         I.write(cfg, src)
         case = "c"

@@ -69,3 +69,11 @@ def test_gpu_matches_oracle_on_random_magnetic_and_chiral_media(seed, forced, tm
     anywhere inside the tiles, some reaching through the CPML (the H-side CPML then acts on B)."""
     import gen_inputs
     run_case(gen_inputs.rnd_mag_case(seed, steps=12), tmp_path, 12, FORCED[seed % 4] if forced else None)
+
+
+@pytest.mark.parametrize("forced", [False, True], ids=["auto", "march"])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 6, 9, 11, 13])
+def test_gpu_matches_oracle_on_random_periodic_inputs(seed, forced, tmp_path, oracle_lib):
+    """tests/fuzz/gen_inputs.rnd_pbc_case on one slab: k_wrap between the half steps (and inside the one-launch 2-D kernel), from a random state."""
+    import gen_inputs
+    run_case(gen_inputs.rnd_pbc_case(seed), tmp_path, 12, FORCED[seed % 4] if forced else None)

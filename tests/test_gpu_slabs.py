@@ -70,3 +70,16 @@ def test_eight_slabs_of_three_rows_match_single_rank_reference():
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
     for c in cases:
         assert f"{c}: SLAB_GPU_OK" in r.stdout, r.stdout[-4000:]
+
+
+@pytest.mark.parametrize("march", [None, "3"], ids=["auto", "ny3"])
+def test_random_periodic_and_magnetic_inputs_on_three_and_four_slabs(march):
+    """tests/fuzz/gen_inputs.rnd_pbc_case / rnd_mag_case on 3 and 4 slabs (sharing however many GPUs there are): periodic runs as a ring of slabs with
+    objects that span the periodic faces, magnetic-dispersive objects cut by slab boundaries; expected arrays from the single-rank oracle."""
+    for world, cases in ((3, ["fuzz:1:pbc", "fuzz:3:pbc", "fuzz:0:pbc", "fuzz:4:mag"]), (4, ["fuzz:6:pbc", "fuzz:4:pbc", "fuzz:9:pbc", "fuzz:0:mag", "fuzz:13:mag"])):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                            "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
+                           capture_output=True, text=True, timeout=900, env=_env(march))
+        assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+        for c in cases:
+            assert f"{c}: SLAB_GPU_OK" in r.stdout, r.stdout[-4000:]

@@ -159,3 +159,23 @@ def test_random_magnetic_and_chiral_inputs_give_the_reference_plan(seed, tmp_pat
     bad = plan_diff.diff(P.read_plan(str(tmp_path / "host.rank0.plan")), ref)
     bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
     assert not bad, "\n".join(bad[:20])
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="needs the reference build oracle/_ref/chiml_ref")
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5, 6, 9, 11, 13])      # (seed 10: the reference's own constructor crashes)
+def test_random_periodic_inputs_give_the_reference_plan(seed, tmp_path):
+    """Periodic boundaries with random media (tests/fuzz/gen_inputs.rnd_pbc_case): lists, CPML and the wrap descriptions of the host setup equal
+    the reference constructor's."""
+    import gen_inputs
+    import plan_diff
+    from chiml_b200 import inputs as I, plan as P
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
+    I.write(gen_inputs.rnd_pbc_case(seed), str(tmp_path / "c.json"))
+    r = subprocess.run([REF, "c.json", "--steps", "0", "--plan", str(tmp_path / "ref"), "--quiet", "--no-output"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "host")], check=True)
+    ref = P.read_plan(str(tmp_path / "ref.rank0.plan"))
+    assert ref.periodic
+    bad = plan_diff.diff(P.read_plan(str(tmp_path / "host.rank0.plan")), ref)
+    bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
+    assert not bad, "\n".join(bad[:20])

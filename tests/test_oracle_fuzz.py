@@ -57,3 +57,10 @@ def test_oracle_matches_reference_on_random_magnetic_and_chiral_media(seed, tmp_
     """tests/fuzz/gen_inputs.rnd_mag_case: B / H / M cells, chiral cells with their eight-point stencils and prev-field copies, the H-side CPML on B."""
     import gen_inputs
     run_case(gen_inputs.rnd_mag_case(seed, steps=12), tmp_path, 5)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 5, 6, 9, 11, 13])
+def test_oracle_matches_reference_on_random_periodic_inputs(seed, tmp_path, oracle_lib):
+    """tests/fuzz/gen_inputs.rnd_pbc_case: the wrap copies of applyBC1Proc with objects that span the periodic faces."""
+    import gen_inputs
+    run_case(gen_inputs.rnd_pbc_case(seed), tmp_path, 5)

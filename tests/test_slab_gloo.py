@@ -20,7 +20,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
                                         # periodic boundaries: the slabs form a ring, the last slab's wrap row comes from slab 0 (chiml_b200/slab.py)
                                         ("pbc3d", 2), ("pbc3d", 3), ("pbc3d_all", 4), ("pbc_tm", 3), ("pbc_te", 2),
                                         # random inputs (tests/fuzz/gen_inputs.py), expected arrays from the single-rank oracle
-                                        ("fuzz:4", 4), ("fuzz:12", 3), ("fuzz:33", 3), ("fuzz:10:ml", 4), ("fuzz:14:ml", 2)])
+                                        ("fuzz:4", 4), ("fuzz:12", 3), ("fuzz:33", 3), ("fuzz:10:ml", 4), ("fuzz:14:ml", 2),
+                                        # random periodic inputs (objects spanning the periodic faces cross the seam of the slab ring) and random magnetic media
+                                        ("fuzz:1:pbc", 3), ("fuzz:3:pbc", 4), ("fuzz:6:pbc", 2), ("fuzz:0:pbc", 3), ("fuzz:4:pbc", 4), ("fuzz:9:pbc", 2),
+                                        ("fuzz:0:mag", 2), ("fuzz:4:mag", 3), ("fuzz:13:mag", 2)])
 def test_slab_protocol_matches_single_rank_reference(case, world):
     subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host")], check=True, stdout=subprocess.DEVNULL)
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, stdout=subprocess.DEVNULL)
