@@ -144,6 +144,14 @@ def cases():
     te["PML"]["thickness"] = [8 / RES, 0.0, 0.0]
     te["ObjectList"] = [I.block([0.1, 1.0, 0.0], [0.08, 0.0, 0.0], eps=2.2, pols=[I.lorentz_pole(0.8, 0.1, 2.0)])]
     c["pbc_te"] = _short_pulse(te)
+    # ---- C4 run periodic, in miniature: a two-level emitter sheet across the whole periodic cell (its polarisation box reaches into the x / y ghost
+    # layers) above a Lorentz film, CPML in z only ----
+    c["pbc_ml3d"] = I.config(I.comp_cell([21 / RES, 17 / RES, 25 / RES], RES, 70 * DT - 0.5 * DT, "Ex", pbc=True), I.pml([0.0, 0.0, 6 / RES]),
+                             [I.normal_source("Ex", [0.0, 0.0, 0.07], [0.21, 0.17, 0.0], [pulse(1.5, 3e13)]),
+                              I.normal_source("Ez", [-0.05, -0.04, -0.04], [0, 0, 0], [pulse(1.2, 2e13)])],
+                             [I.block([0.3, 0.3, 0.04], [0.0, 0.0, -0.03], eps=2.0, pols=[I.lorentz_pole(1.2, 0.1, 2.0)]),
+                              two([0.5, 0.5, 0.02], [0.0, 0.0, 0.025], [3, 1])],
+                             [I.detector([0.03, 0, 0], [0, 0, 0], "Ez", "out/pml/dtc", time_int=DT * 1.0000001)])
     # ---- TFSF plane-wave sources (SOURCE/parallelTFSF.hpp): the surface corrections run on the device, the 1-D incident line is the
     # reference's own (its per-step values are recorded into the plan, record TFSFLINE).  2-D TM along +y over a Drude rod; 2-D TE
     # along (1, 2) (incident strides 1 and 2) over a Lorentz block; 3-D along +z over a Lorentz sphere with a flux box around it

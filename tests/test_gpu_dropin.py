@@ -23,7 +23,7 @@ REF = os.path.join(ROOT, "oracle", "_ref", "chiml_ref")
 pytestmark = pytest.mark.gpu
 
 CASES = ["te_vacuum", "tm_au", "aniso_slab3d", "lorentz3d", "kappa3d", "ml3d_two", "ml_te", "c4_small", "tm_flux", "flux3d", "pbc3d", "pbc_tm", "pbc_te", "tfsf_tm", "tfsf_te",
-         "tfsf3d", "tfsf3d_slab", "freq3d", "mag3d", "mag3d_pml", "mag_tm", "chi3d", "chi3d_pml", "dipnorm3d", "dipnorm3d_pml"]
+         "tfsf3d", "tfsf3d_slab", "freq3d", "mag3d", "mag3d_pml", "mag_tm", "chi3d", "chi3d_pml", "dipnorm3d", "dipnorm3d_pml", "pbc_ml3d"]
 
 
 def _run(case, workdir, gpu):
