@@ -67,7 +67,7 @@ def parse_args():
 
 OTHER = {"c1": ("C1: 2-D TE vacuum 512x512, Hz dipole, CPML 20, Hz detector", lambda steps: I.c1_te_vacuum(n=511, steps=steps)),
          "c2": ("C2: 2-D TM Drude nanorod 2048x2048, CPML 20, Ez line source, 4-edge flux box with 64 frequencies (running DFT every step)",
-                lambda steps: I.c2_tm_drude(n=2047, steps=steps, nfreq=64)),
+                lambda steps: I.c2_tm_drude(n=2047, steps=steps, nfreq=int(os.environ.get("CHIML_BENCH_C2_NFREQ", "64")))),
          "c3": ("C3: 3-D anisotropic (oriented-dipole Lorentz) slab waveguide 512^3, CPML all faces", lambda steps: I.c3_aniso_slab(n=511, steps=steps)),
          "c4": ("C4: 3-D 10x10 Au (6-pole) cubes + two-level emitter sheet (1e6 emitters), 768^3", lambda steps: I.c4_plasmonic_ml(n=767, steps=steps))}
 

@@ -1879,14 +1879,26 @@ int launch_step(ChimlCtx* ctx, long long k, int nsrc, int section = 0)
         size_t per_step = 0;
         std::vector<size_t> goff(ctx->dft_group_nfreq.size(), 0);
         for(size_t g = 0; g < ctx->dft_group_nfreq.size(); ++g) { goff[g] = per_step; per_step += 2 * (size_t)ctx->dft_group_nfreq[g]; }
+        // every set that is due, DFT_BATCH of them per launch (the sets own their accumulators: no two touch the same entry)
+        DftBatchArgs ba;
+        ba.n = 0; ba.lx = ctx->lx; ba.px = ctx->px;
+        size_t most = 0;
+        auto flush = [&]() {
+            if(ba.n == 0) return;
+            LaunchScope ls(ctx, K_DFT);
+            k_dft_batch<<<dim3((unsigned)std::max<size_t>(1, std::min<size_t>((most + 255) / 256, 148 * 2)), (unsigned)ba.n, 1), 256, 0, ctx->stream>>>(ba);
+            ba.n = 0; most = 0;
+        };
         for(DftDev& d : ctx->dfts)
         {
             if(ctx->step_count % d.every != 0 || d.nlines == 0) continue;
-            const size_t n = d.nlines * (size_t)d.npts * d.nfreq;
-            LaunchScope ls(ctx, K_DFT);
-            k_dft<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(
-                ctx->d_field[d.field], d.d_lines, d.nlines, d.npts, d.stride, d.nfreq, ctx->d_tw + (size_t)k * per_step + goff[d.group], d.d_re, d.d_im, ctx->lx, ctx->px);
+            DftBatchSet& o = ba.s[ba.n++];
+            o.field = ctx->d_field[d.field]; o.lines = d.d_lines; o.nlines = d.nlines; o.npts = d.npts; o.stride = d.stride; o.nfreq = d.nfreq;
+            o.tw = ctx->d_tw + (size_t)k * per_step + goff[d.group]; o.re = d.d_re; o.im = d.d_im;
+            most = std::max(most, (size_t)d.nlines * (size_t)d.npts * d.nfreq);
+            if(ba.n == DFT_BATCH) flush();
         }
+        flush();
     }
     return 0;
 }
@@ -2041,6 +2053,9 @@ bool persist_eligible(ChimlCtx* ctx)
     if(ctx->has_B) return false;              // B / M cells take the launch path
     if(!ctx->tfsf.empty()) return false;      // the surface waves are separate launches
     if(ctx->g.mode == CHIML_MODE_3D || ctx->g.nranks > 1 || !ctx->emitters.empty() || ctx->d_info_node) return false;
+    // the resident grid holds 16-32 warps per SM, the launch-per-phase kernels 64: on a large 2-D grid the launches cost less than the lost
+    // parallelism (C2, 2048^2: 0.142 ms per step by launches, 0.159 in one launch; C1, 512^2: 0.066 against 0.039); chiml_gpu_set_persistent(1) forces it
+    if(ctx->persist_mode < 0 && (long)ctx->lx * ctx->ly > 1500000L) return false;
     if((int)ctx->detectors.size() > P2D_MAX_DET || (int)ctx->dfts.size() > P2D_MAX_DFT) return false;
     // sources are injected by one grid-wide pass: two boxes on the same field must not overlap (the launch path adds them one after the other)
     for(size_t i = 0; i < ctx->sources.size(); ++i)
@@ -2058,7 +2073,9 @@ bool persist_eligible(ChimlCtx* ctx)
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
         const int bad = ctx->g.mode == CHIML_MODE_TE ? persist_occupancy<CHIML_MODE_TE>(&perSM) : persist_occupancy<CHIML_MODE_TM>(&perSM);
-        if(coop && !bad && perSM > 0) ctx->persist_blocks = sms * std::min(perSM, 4);
+        int cap = 4;                              // measured on C1 / C2 (profiles/README.md): more resident blocks only lengthen the grid barriers
+        if(const char* ev = std::getenv("CHIML_B200_PERSIST_PER_SM")) cap = std::max(1, std::atoi(ev));
+        if(coop && !bad && perSM > 0) ctx->persist_blocks = sms * std::min(perSM, cap);
         cudaGetLastError();
     }
     return ctx->persist_blocks > 0;

@@ -259,7 +259,7 @@ struct ChimlCtx
     // persistent multi-step kernel of 2-D grids (chiml_persist.cuh)
     void* d_persist_sa = nullptr;                // 3 StepArgs
     int persist_blocks = -1;                     // resident grid size, 0 = not available, -1 = not asked yet
-    int persist_mode = 1;                        // chiml_gpu_set_persistent
+    int persist_mode = -1;                       // -1 automatic (by grid size), 0 / 1 chiml_gpu_set_persistent
 
     long long step_count = 0;
     int64_t launches = 0;

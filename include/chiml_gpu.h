@@ -268,8 +268,10 @@ int chiml_gpu_set_dip_grid(ChimlCtx* ctx, int comp, int pole, const double* grid
 int chiml_gpu_set_march(ChimlCtx* ctx, int fast_planes, int uniform_planes);
 
 /* 2-D grids (single slab, no emitters) run all n steps of a chiml_gpu_step_n call in ONE cooperative launch with grid-wide barriers
- * between the phases of a step (csrc/chiml_persist.cuh) instead of 6-8 launches per step; results are identical.  on = 0 selects
- * the launch-per-phase path (also: environment variable CHIML_B200_NO_PERSIST).  May be called at any time. */
+ * between the phases of a step (csrc/chiml_persist.cuh) instead of 6-8 launches per step; results are identical.  Without this call the
+ * engine chooses by grid size (one launch up to 1.5 M grid points: beyond that the launches cost less than the parallelism the resident
+ * grid gives up); on = 1 forces the one-launch kernel, on = 0 the launch-per-phase path (also: environment variable
+ * CHIML_B200_NO_PERSIST).  May be called at any time. */
 int chiml_gpu_set_persistent(ChimlCtx* ctx, int on);
 
 /* Freeze the setup: paints the per-cell update maps from the lists, builds the CPML coefficient
