@@ -83,8 +83,10 @@ def test_c2_drude_rod_2048sq(march, oracle_lib):
     plan = _plan(I.c2_tm_drude(n=2047, steps=10, nfreq=8, out="mid_out/c2"))
     stats = _compare(plan, march, persistent=False)
     assert stats["k_fast<E>"] > 0 and stats["k_dft"] > 0
-    stats = _compare(plan, march)               # default for 2-D grids: every step in one cooperative launch (csrc/chiml_persist.cuh)
+    stats = _compare(plan, march, persistent=True)      # every step in one cooperative launch (csrc/chiml_persist.cuh), forced
     assert stats["k_steps_2d"] == 1 and stats["k_fast<E>"] == 0
+    stats = _compare(plan, march)                       # the automatic choice for a grid of 4.2 M points: the launch-per-phase path
+    assert stats["k_steps_2d"] == 0 and stats["k_fast<E>"] > 0
 
 
 def test_c1_te_vacuum_1024sq_whole_columns(oracle_lib):
