@@ -435,24 +435,7 @@ __global__ void k_detector(const double* field, int lx0, int lz0, int ly0, int s
 }
 
 // running DFT (DTC/parallelStorageFreqDTC.cpp:21-30): acc[out + f + nfreq*i] += tw[f] * field[ind + i*stride], one rounded product and
-// one rounded sum per entry like the dger_ it replaces; f fastest so that the accumulator traffic is coalesced
-__global__ void k_dft(const double* field, const ChimlDftLine* lines, size_t nlines, int npts, int stride, int nfreq, const double* tw,
-                      double* acc_re, double* acc_im, int lx, long px)
-{
-    const size_t n = nlines * (size_t)npts * (size_t)nfreq;
-    for(size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
-    {
-        const int f = (int)(e % nfreq);
-        const int i = (int)((e / nfreq) % npts);
-        const size_t l = e / ((size_t)nfreq * npts);
-        const long lg = (long)lines[l].ind + (long)i * stride;      // logical index x + lx*(z + lz*y)
-        const double u = field[(lg % lx) + px * (lg / lx)];
-        const size_t o = (size_t)lines[l].out + f + (size_t)nfreq * i;
-        acc_re[o] = da(acc_re[o], dm(tw[2 * f], u));
-        acc_im[o] = da(acc_im[o], dm(tw[2 * f + 1], u));
-    }
-}
-
+// one rounded sum per entry like the dger_ it replaces; f fastest so that the accumulator traffic is coalesced.  Here:
 // all running-DFT sets that are due after a step in one launch (blockIdx.y = set): a flux box is 8 (2-D) to 24 (3-D) stored fields, each a
 // few thousand entries -- one launch per set cost 0.098 ms per step on C2 (4 edges, 64 frequencies), more than the field update itself
 constexpr int DFT_BATCH = 24;

@@ -125,7 +125,7 @@ __device__ __forceinline__ void p2d_samples(const Persist2DArgs& p, const long l
         const unsigned long long n = d.nlines * (unsigned long long)d.npts * (unsigned long long)d.nfreq;
         for(unsigned long long e = gt; e < n; e += nt)
         {
-            // k_dft (chiml_kernels.cuh): acc[out + f + nfreq*i] += tw[f] * field[ind + i*stride]
+            // k_dft_batch (chiml_kernels.cuh): acc[out + f + nfreq*i] += tw[f] * field[ind + i*stride]
             const int fq = (int)(e % d.nfreq), i = (int)((e / d.nfreq) % d.npts);
             const unsigned long long l = e / ((unsigned long long)d.nfreq * d.npts);
             const long lg = (long)d.lines[l].ind + (long)i * d.stride;
