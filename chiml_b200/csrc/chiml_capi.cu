@@ -822,8 +822,8 @@ int chiml_gpu_commit(ChimlCtx* ctx)
         for(int comp = 0; comp < 6; ++comp)
             if(field_exists(ctx, comp) && !ctx->has_wrap[comp]) return fail(ctx, CHIML_ERR_ARG, "periodic boundaries: set_periodic must be called for every field component");
         // a ring of slabs carries the field rows the curls read; emitter polarisations, B / M and TFSF corrections across the seam are not built
-        if(ctx->ring && (!ctx->emitters.empty() || ctx->has_B || !ctx->tfsf.empty()))
-            return fail(ctx, CHIML_ERR_UNSUPPORTED, "periodic runs on several slabs are covered without emitters, magnetic / chiral media and TFSF surfaces");
+        if(ctx->ring && (ctx->has_B || !ctx->tfsf.empty()))
+            return fail(ctx, CHIML_ERR_UNSUPPORTED, "periodic runs on several slabs are covered without magnetic / chiral media and TFSF surfaces");
         if(ctx->ring && ctx->ly < 5) return fail(ctx, CHIML_ERR_UNSUPPORTED, "periodic runs on several slabs need at least three owned rows per slab");
     }
     int rc;
@@ -1917,8 +1917,12 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
     // row short in y (Hx, Hz, Ey) end at row ly - 3, and its row ly - 2 of Hx, Hz is the wrap image of slab 0's row 1, pushed across the seam.
     // Ey rows feed oriented-dipole nodes and emitters only, which a ring of slabs does not carry.
     const bool ring = ctx->ring, lastSlab = ctx->g.rank == ctx->g.nranks - 1, seamTop = ring && lastSlab, seamBottom = ring && ctx->g.rank == 0;
-    const bool haveEy = ctx->d_field[CHIML_EY] != nullptr && !ring;
-    const bool needEy = haveEy;
+    // On a ring Ey rows are carried for emitters only.  The reference updates its emitters BEFORE it wraps E (step() items 16, 17): their
+    // averages Ey[r], Ey[r - y] see the wrap rows of Ey as the step before left them, so the two seam rows of Ey (the last slab's row ly - 3 into
+    // slab 0's row 0, slab 0's row 1 into the last slab's row ly - 2) travel at the END of the step; between the other slabs nothing changes.
+    const bool haveEy = ctx->d_field[CHIML_EY] != nullptr && (!ring || !ctx->emitters.empty());
+    const bool seamEy = ring && haveEy;
+    const bool needEy = haveEy && !ring;
     StepArgs a;
     // pushes of the previous step read rows this step overwrites
     if(ctx->push_pending) { cudaStreamWaitEvent(ctx->stream, ctx->ev_push, 0); ctx->push_pending = false; }
@@ -1988,6 +1992,9 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
         if(up && haveEy && q < ctx->upper.emitPy.size() && ctx->upper.emitPy[q]) recvQP = true;
     halo_wait(ctx, {{HF_H_FROM_LOWER, lo ? kk : 0}, {HF_OP_FROM_UPPER, (up && ctx->nordip > 0 && haveEy) ? kk : 0},
                     {HF_QP_FROM_UPPER, recvQP ? kk - 1 : 0}});
+    // (emitters on a ring: the last slab's wrap row of Ey must hold the row slab 0 sent at the end of the step before BEFORE this half step's own
+    // writes to that row -- the reference's lists cover it -- so that the density update below reads what the reference reads)
+    if(seamEy && seamTop) halo_wait(ctx, {{HF_EY_FROM_UPPER, kk - 1}});
     fill_step_args(ctx, true, a);
     launch_family<true>(ctx, a, block, 1);
     for(EmitterDev& em : ctx->emitters) launch_addP(ctx, em, 1);
@@ -2000,16 +2007,15 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
                            {ctx->d_field[CHIML_EZ] ? ctx->d_field[CHIML_EZ] + ctx->plane : nullptr, p.field[CHIML_EZ] ? p.field[CHIML_EZ] + pg : nullptr, rowN}},
                   {HF_E_FROM_UPPER}, kk);
     }
-    if(up && haveEy)
+    if(up && haveEy && !seamTop)
         halo_push(ctx, ctx->upper, {{ctx->d_field[CHIML_EY] + top, ctx->upper.field[CHIML_EY], rowN}}, {HF_EY_FROM_LOWER}, kk);
     launch_family<true>(ctx, a, block, 2);
     for(EmitterDev& em : ctx->emitters) launch_addP(ctx, em, 2);
-    launch_wraps(ctx, true);
 
-    // ---- emitter density update (averages Ey[r], Ey[r - y]: needs this step's Ey in ghost row 0)
+    // ---- emitter density update (averages Ey[r], Ey[r - y]: needs this step's Ey in ghost row 0; slab 0 of a ring: the wrap row of the step before)
     if(!ctx->emitters.empty())
     {
-        if(lo && haveEy) halo_wait(ctx, {{HF_EY_FROM_LOWER, kk}});
+        if(lo && haveEy) halo_wait(ctx, {{HF_EY_FROM_LOWER, (seamEy && seamBottom) ? kk - 1 : kk}});
         for(EmitterDev& em : ctx->emitters)
         {
             int rc = launch_density_step(ctx, em);
@@ -2031,6 +2037,22 @@ int launch_step_slabs(ChimlCtx* ctx, long long k, int nsrc)
                 else                   halo_push(ctx, ctx->lower, {{em.d_P[1] + rowP, dst, rowP}}, {}, kk);
             }
         }
+    }
+    // periodic boundaries of E (item 17): after the emitters, as in the reference
+    launch_wraps(ctx, true);
+    if(seamEy && (seamTop || seamBottom))
+    {
+        // the seam rows of Ey: each side first releases the row the other writes (its emitters have read it), then waits for the other's release
+        halo_fork(ctx);
+        if(seamTop) halo_push(ctx, ctx->upper, {}, {HF_EY_ACK}, kk);
+        if(seamBottom) halo_push(ctx, ctx->lower, {}, {HF_EY_ACK}, kk);
+        // (a ring of two: both roles on one slab pair; the release flag of either side lives in the other's memory, one word each)
+        halo_wait(ctx, {{HF_EY_ACK, kk}}, true);
+        if(seamTop)
+            halo_push(ctx, ctx->upper, {{ctx->d_field[CHIML_EY] + top - ctx->plane, ctx->upper.field[CHIML_EY], rowN}}, {HF_EY_FROM_LOWER}, kk);
+        if(seamBottom)
+            halo_push(ctx, ctx->lower, {{ctx->d_field[CHIML_EY] + ctx->plane, ctx->lower.field[CHIML_EY] ? ctx->lower.field[CHIML_EY] + (long)(ctx->lower.ly - 2) * ctx->plane : nullptr, rowN}},
+                      {HF_EY_FROM_UPPER}, kk);
     }
     (void)ghostTop;
     if(ctx->push_pending) cudaEventRecord(ctx->ev_push, ctx->hstream);
@@ -2444,7 +2466,7 @@ static int halo_open_peer(ChimlCtx* ctx, const void* blob, size_t size, bool isL
         if(!h.has_field[f]) continue;
         // only the arrays this slab writes into: E_x, E_z of the slab below; H_x, H_z, E_y of the slab above
         // (periodic ring: slab 0 also writes H_x, H_z row 1 into the wrap row of the last slab, which is the slab below it)
-        const bool seam = ctx->ring && ctx->g.rank == 0 && isLower && (f == CHIML_HX || f == CHIML_HZ);
+        const bool seam = ctx->ring && ctx->g.rank == 0 && isLower && (f == CHIML_HX || f == CHIML_HZ || f == CHIML_EY);
         const bool needIt = seam || (isLower ? (f == CHIML_EX || f == CHIML_EZ) : (f == CHIML_HX || f == CHIML_HZ || f == CHIML_EY));
         if(!needIt) continue;
         void* base = nullptr;
@@ -2452,7 +2474,14 @@ static int halo_open_peer(ChimlCtx* ctx, const void* blob, size_t size, bool isL
         peer.field[f] = reinterpret_cast<double*>(base) + h.guard;
     }
     { void* base = nullptr; if((rc = open(hs[6], &base))) return rc; peer.flags = reinterpret_cast<int*>(base); }
-    if(isLower)
+    // the reference does not wrap the emitters' polarisation boxes: across the seam of a periodic ring no emitter set is paired
+    const bool acrossSeam = ctx->ring && ((isLower && ctx->g.rank == 0) || (!isLower && ctx->g.rank == ctx->g.nranks - 1));
+    if(acrossSeam)
+    {
+        peer.emitPy.assign(ctx->emitters.size(), nullptr);
+        peer.emit_bn1.assign(ctx->emitters.size(), 0);
+    }
+    else if(isLower)
     {
         if(h.nordip != ctx->nordip)
             return fail(ctx, CHIML_ERR_ARG, "halo_bind: neighbour counts a different number of oriented-dipole pole grids: give every slab the count of "

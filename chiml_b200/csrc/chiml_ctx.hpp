@@ -122,8 +122,9 @@ struct EmitterDev
 };
 
 // ---- y-slab halo (chiml_halo.cuh): flags the neighbours write into this context's memory, one 32-bit step counter each
+// (HF_EY_FROM_UPPER / HF_EY_ACK: emitters on a ring -- the two seam rows of Ey travel at the END of a step, each side releasing its row first)
 // (periodic ring of slabs: HF_H_FROM_UPPER = slab 0's Hx, Hz row 1 has arrived in the last slab's wrap row; HF_SEAM_ACK = the last slab has released that row for the step: read by the E half step before, its own discarded update through)
-enum HaloFlag { HF_H_FROM_LOWER = 0, HF_OP_FROM_UPPER, HF_E_FROM_UPPER, HF_EY_FROM_LOWER, HF_QP_FROM_UPPER, HF_ERROR, HF_H_FROM_UPPER, HF_SEAM_ACK, HF_NFLAGS = 16 };
+enum HaloFlag { HF_H_FROM_LOWER = 0, HF_OP_FROM_UPPER, HF_E_FROM_UPPER, HF_EY_FROM_LOWER, HF_QP_FROM_UPPER, HF_ERROR, HF_H_FROM_UPPER, HF_SEAM_ACK, HF_EY_FROM_UPPER, HF_EY_ACK, HF_NFLAGS = 16 };
 constexpr size_t IPC_GRANULE = 2u << 20;     // exported buffers are whole 2 MiB allocations (never sub-allocated by the driver)
 
 struct HaloPeer                   // one neighbouring slab, as mapped into this process

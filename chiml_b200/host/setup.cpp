@@ -773,8 +773,8 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
     if(IP.periodic_)
     {
         if(nOrDip > 0) throw std::logic_error("oriented-dipole media under periodic boundaries are outside the covered hot path");
-        if(nranks > 1 && (!IP.qes_.empty() || IP.cplxFields_ || magnetic || chiral))
-            throw std::logic_error("periodic runs on several slabs are covered for real fields without emitters and without magnetic / chiral media");
+        if(nranks > 1 && (IP.cplxFields_ || magnetic || chiral))
+            throw std::logic_error("periodic runs on several slabs are covered for real fields without magnetic / chiral media");
         const int l0 = g.ln[0] - 2, l1 = g.ln[1] - 2;
         const int zMin = g.twoD ? 0 : 1, zMax = g.twoD ? 1 : g.ln[2] - 2;
         // y-limited components (fieldEnd[1] = 1: Ey, Hx, Hz) wrap at row ln_vec_[1], the others at ln_vec_[1] + 1

@@ -16,7 +16,10 @@ F[ymax] <- F[1] with ymax = ln_y + 1, or ln_y for the components that are one ro
   * the last slab's top owned row of Hx, Hz (and Ey) is ny - 1, not ny: that is the row it sends UP across the seam;
   * its row ny of Hx, Hz is the wrap image of slab 0's row 1 -- read by its own E update of row ny -- so after phase 0 slab 0 also
     sends Hx, Hz row 1 DOWN across the seam into that row.
-The x / z ghost cells are wrapped inside every slab (applyBCProcMid; the checker and the engine do it inside phases 0 and 2).
+The x / z ghost cells are wrapped inside every slab (applyBCProcMid; the checker and the engine do it after the H half step and at the end of
+the step).  Emitters on a ring: the reference updates them BEFORE it wraps E, so across the seam their averages of Ey see the wrap rows of the
+step before -- the two seam rows of Ey (last slab's row ny - 1 -> slab 0's row 0, slab 0's row 1 -> last slab's row ny) travel after phase 3;
+emitter polarisation boxes do not cross the seam (the reference does not wrap them).
 
 The CUDA engine implements this protocol natively (peer-to-peer stores + flags, chiml_gpu_halo_*); this module states it once in
 host terms, drives the CPU checker through it in the world_size-2 gloo tests, and gathers slab results onto rank 0.
@@ -75,6 +78,15 @@ def step_slab(sim, plan: P.Plan, amp_step: np.ndarray, send: Callable, recv: Cal
                     buf = np.empty_like(np.ascontiguousarray(sim.field(f)[ny]))
                     recv(0, buf)
                     sim.field(f)[ny] = buf
+        if ring and phase == 3 and EY in present and plan.emitters:
+            # emitters on a ring: the reference updates the emitters BEFORE it wraps E (step() items 16, 17), so their averages Ey[r], Ey[r - y] see
+            # the wrap rows of Ey as of the step before: the two seam rows of Ey travel at the end of the step, not with the E half step
+            if last:
+                send(0, np.ascontiguousarray(sim.field(EY)[ny - 1]))
+                buf = np.empty_like(np.ascontiguousarray(sim.field(EY)[ny])); recv(0, buf); sim.field(EY)[ny] = buf
+            if plan.rank == 0:
+                buf = np.empty_like(np.ascontiguousarray(sim.field(EY)[0])); recv(plan.nranks - 1, buf); sim.field(EY)[0] = buf
+                send(plan.nranks - 1, np.ascontiguousarray(sim.field(EY)[1]))
         for ph, kind, fields, direction in PROTOCOL:
             if ph != phase:
                 continue
@@ -92,10 +104,11 @@ def step_slab(sim, plan: P.Plan, amp_step: np.ndarray, send: Callable, recv: Cal
                         if emitter_sends_down(plan, e) or emitter_receives_from_above(plan, e):
                             rows.append((sim.emitter_P(q, 1), 1 if emitter_sends_down(plan, e) else None,
                                          e.box_n[1] + 1 if emitter_receives_from_above(plan, e) else None))
+            seam_ey = ring and kind == "field" and fields == (EY,) and bool(plan.emitters)
             for arr, srow, rrow in rows:
                 to, frm = (upper, lower) if direction == UP else (lower, upper)
-                can_send = (has_upper if direction == UP else has_lower) and srow is not None
-                can_recv = (has_lower if direction == UP else has_upper) and rrow is not None
+                can_send = (has_upper if direction == UP else has_lower) and srow is not None and not (seam_ey and last)
+                can_recv = (has_lower if direction == UP else has_upper) and rrow is not None and not (seam_ey and plan.rank == 0)
                 # even ranks send first, odd ranks receive first: no deadlock with blocking point-to-point calls
                 ops = [("s", can_send), ("r", can_recv)] if plan.rank % 2 == 0 else [("r", can_recv), ("s", can_send)]
                 for op, ok in ops:

@@ -182,7 +182,8 @@ int chiml_gpu_add_dft(ChimlCtx* ctx, int field, int group, int every, int nfreq,
  * UTIL/FDTD_up_eq.cpp:1036-1061, which the reference takes on every rank), and the y direction is the ring of ghost-row pushes: chiml_gpu_halo_bind
  * takes the blob of slab nranks - 1 as slab 0's lower neighbour and vice versa; the last slab sends its top owned row of Hx, Hz (ly - 3: these
  * components are one row short in y) upward across the seam and receives slab 0's row 1 of Hx, Hz in its wrap row ly - 2 (chiml_b200/slab.py).
- * Interior results equal the single-slab run's bit for bit.  Covered there: real fields, no emitters, no magnetic / chiral media, no TFSF. */
+ * Emitters: the two seam rows of Ey travel at the end of a step (the reference updates its emitters before it wraps E), polarisation boxes do not
+ * cross the seam.  Interior results equal the single-slab run's bit for bit.  Covered there: real fields, no magnetic / chiral media, no TFSF. */
 typedef struct ChimlWrap { int32_t nx, ny, nz, xmax, ymax, zmin, zmax; } ChimlWrap;
 int chiml_gpu_set_periodic(ChimlCtx* ctx, int comp, const ChimlWrap* wrap);
 

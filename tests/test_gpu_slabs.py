@@ -36,7 +36,7 @@ def _env(march):
 def test_two_slabs_over_nvlink_match_single_rank_reference(march):
     if capi.device_count() < 2:
         pytest.skip("needs two GPUs")
-    cases = ["vac3d", "aniso_slab3d", "lorentz3d", "ml3d_two", "ml3d_four", "ml_te", "ml_tm", "tm_au", "te_vacuum", "c4_small", "flux3d", "te_flux", "tm_flux", "aniso_mixed3d", "ml3d_two+pair", "c4_small+pair", "mag3d", "mag3d_pml", "mag_tm", "mag_te", "pbc3d", "pbc3d_all", "pbc_tm", "pbc_te"]
+    cases = ["vac3d", "aniso_slab3d", "lorentz3d", "ml3d_two", "ml3d_four", "ml_te", "ml_tm", "tm_au", "te_vacuum", "c4_small", "flux3d", "te_flux", "tm_flux", "aniso_mixed3d", "ml3d_two+pair", "c4_small+pair", "mag3d", "mag3d_pml", "mag_tm", "mag_te", "pbc3d", "pbc3d_all", "pbc_tm", "pbc_te", "pbc_ml3d"]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
                        capture_output=True, text=True, timeout=900, env=_env(march))
@@ -49,7 +49,7 @@ def test_two_slabs_over_nvlink_match_single_rank_reference(march):
 def test_four_slabs_match_single_rank_reference_even_on_one_gpu(march):
     """Four slabs on however many GPUs there are (ranks wrap around the devices).  c4_small at four slabs has a slab that holds
     only the rim of the emitter sheet (an emitter set without emitters), flux3d has flux surfaces cut by slab boundaries."""
-    cases = ["aniso_slab3d", "ml3d_two", "c4_small", "flux3d", "aniso_mixed3d", "ml3d_two+pair", "ml_te+pair", "mag3d", "mag3d_pml", "mag_tm", "pbc3d", "pbc3d_all", "pbc_tm", "pbc_te"]
+    cases = ["aniso_slab3d", "ml3d_two", "c4_small", "flux3d", "aniso_mixed3d", "ml3d_two+pair", "ml_te+pair", "mag3d", "mag3d_pml", "mag_tm", "pbc3d", "pbc3d_all", "pbc_tm", "pbc_te", "pbc_ml3d"]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
                         "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "slab_gpu_worker.py")] + cases,
                        capture_output=True, text=True, timeout=900, env=_env(march))

@@ -19,6 +19,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
                                         ("mag3d", 3), ("mag3d_pml", 2), ("mag_tm", 3), ("mag_te", 2),
                                         # periodic boundaries: the slabs form a ring, the last slab's wrap row comes from slab 0 (chiml_b200/slab.py)
                                         ("pbc3d", 2), ("pbc3d", 3), ("pbc3d_all", 4), ("pbc_tm", 3), ("pbc_te", 2),
+                                        # ... with an emitter sheet across the whole periodic cell (C4 run periodic, in miniature): the seam rows of Ey travel at the
+                                        # end of the step, the emitters' polarisation boxes do not cross the seam
+                                        ("pbc_ml3d", 2), ("pbc_ml3d", 3), ("pbc_ml3d", 4),
                                         # random inputs (tests/fuzz/gen_inputs.py), expected arrays from the single-rank oracle
                                         ("fuzz:4", 4), ("fuzz:12", 3), ("fuzz:33", 3), ("fuzz:10:ml", 4), ("fuzz:14:ml", 2),
                                         # random periodic inputs (objects spanning the periodic faces cross the seam of the slab ring) and random magnetic media
