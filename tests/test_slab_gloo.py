@@ -30,7 +30,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_slab_protocol_matches_single_rank_reference(case, world):
     subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host")], check=True, stdout=subprocess.DEVNULL)
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, stdout=subprocess.DEVNULL)
-    port = 29650 + (hash((case, world)) % 200)
+    import socket
+    with socket.socket() as so:                 # a free port: parallel test runs (pytest -n) must not meet on one
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "tests", "slab_worker.py"), case],
                        capture_output=True, text=True, timeout=600)
