@@ -19,9 +19,17 @@ from oracle_api import OracleSim  # noqa: E402
 
 
 def main():
-    case = sys.argv[1]
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
+    all_ok = True
+    for case in sys.argv[1:]:          # several cases per launch: the start-up of the process group costs more than a case
+        all_ok = run_case(case, rank, world) and all_ok
+    dist.destroy_process_group()
+    sys.exit(0 if all_ok else 1)
+
+
+def run_case(label, rank, world):
+    case = label
     work = tempfile.mkdtemp(prefix=f"slab_{case.replace(':', '_')}_r{rank}_")
     tool = os.path.join(ROOT, "chiml_b200", "chiml_plan")
     fuzz = case.startswith("fuzz:")
@@ -128,11 +136,11 @@ def main():
             if seen != e.nemit:
                 ok = False
                 print(f"MISMATCH {case}: {seen} emitters over the slabs, {e.nemit} in the single-rank run")
-        print("SLAB_OK" if ok else "SLAB_FAIL")
+        print(f"{label}: " + ("SLAB_OK" if ok else "SLAB_FAIL"), flush=True)
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+    sim.close()
+    return int(flag.item()) == 1
 
 
 if __name__ == "__main__":
