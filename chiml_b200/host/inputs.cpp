@@ -79,7 +79,9 @@ DIPOR string2dipor(const std::string& s)
 {
     if(s == "isotropic") return DIPOR::ISOTROPIC;
     if(s == "unidirectional") return DIPOR::UNIDIRECTIONAL;
-    if(s == "normal" || s == "tangent" || s == "rel_norm" || s == "lat_tangent" || s == "long_tangent") return DIPOR::REL_TO_NORM;
+    if(s == "normal" || s == "tangent" || s == "rel_norm") return DIPOR::REL_TO_NORM;
+    if(s == "lat_tangent") return DIPOR::LAT_TAN;
+    if(s == "long_tangent") return DIPOR::LONG_TAN;
     throw std::logic_error("The dipole orientation style is undefined");
 }
 
@@ -131,6 +133,9 @@ void Obj::setUpConsts(double dt)
         {
             dipOr_.push_back(pol.dipOrE_);
             dipE_.push_back(pol.uVecDipE_);
+            dipNormCompE_.push_back(pol.normCompWeightE_);
+            dipTanLatCompE_.push_back(pol.tangentLatCompWeightE_);
+            dipTanLongCompE_.push_back(pol.tangentLongCompWeightE_);
             alpha_.push_back(((2 - std::pow(pol.omg_ * dt, 2.0)) / (1 + pol.gam_ * dt)));
             xi_.push_back(((pol.gam_ * dt - 1) / (1 + pol.gam_ * dt)));
             gamma_.push_back(((pol.sigP_ * std::pow(pol.omg_ * dt, 2.0)) / (1 + pol.gam_ * dt)));
@@ -150,6 +155,49 @@ void Obj::setUpConsts(double dt)
             chiGammaPrev_.push_back((1.0 / dt) * ((pol.tau_ * std::pow(pol.omg_ * dt, 2.0)) / ((1 + pol.gam_ * dt))));
         }
     }
+}
+
+bool Obj::identityAxes() const
+{
+    for(int i = 0; i < 3; ++i)
+        for(int j = 0; j < 3; ++j)
+            if(coordTransform_[i * 3 + j] != (i == j ? 1.0 : 0.0)) return false;
+    return true;
+}
+
+// Obj::findGradient of the shapes built here (OBJECTS/Obj.cpp:585-596 sphere, :644-653 cylinder, :655-666 block), for objects whose axes are the
+// Cartesian ones: RealSpace2ObjectSpace is then the shift to the centre and ObjectSpace2RealSpace (the LAPACK inverse of the unit matrix) the
+// normalisation alone.  (Rotated objects would need the reference's dgetrf / dgetri inverse bit for bit; the set-up refuses them.)
+std::array<double, 3> Obj::findGradient(const std::array<double, 3>& pt) const
+{
+    auto magSq = [](const std::array<double, 3>& v) { double a = 0.0; for(double x : v) a = a + x * x; return a; };
+    auto normalised = [&](std::array<double, 3> g) {
+        if(magSq(g) < 1e-20) return std::array<double, 3>{{0.0, 0.0, 0.0}};
+        const double norm = std::sqrt(magSq(g));
+        for(double& x : g) x = x / norm;
+        return g;
+    };
+    std::array<double, 3> v;
+    for(int k = 0; k < 3; ++k) v[k] = pt[k] - location_[k];
+    if(shape_ == SHAPE::SPHERE) return normalised(v);
+    // (v_trans = 1 * v_cen + 0 + 0 in the reference's dgemv: exact)
+    std::array<double, 3> grad = {{0.0, 0.0, 0.0}};
+    if(shape_ == SHAPE::BLOCK)
+    {
+        std::array<double, 3> ptRat;
+        for(int k = 0; k < 3; ++k) ptRat[k] = v[k] / geoParam_[k];
+        int mx = 0;                                       // idamax_: first index of the largest magnitude
+        for(int k = 1; k < 3; ++k) if(std::abs(ptRat[k]) > std::abs(ptRat[mx])) mx = k;
+        for(int k = 0; k < 3; ++k)
+            if(ptRat[k] == ptRat[mx]) grad[k] = v[k] >= 0 ? 1.0 : -1.0;
+        return normalised(grad);
+    }
+    // cylinder
+    const double r = std::sqrt(std::pow(v[0], 2.0) + std::pow(v[2], 2.0));
+    const double len = geoParam_[1] * (r / geoParam_[0]);
+    grad = {{v[0], 0.0, v[2]}};
+    if(std::abs(v[1]) >= len / 2.0) grad = {{0.0, v[1] / std::abs(v[1]), 0.0}};
+    return normalised(grad);
 }
 
 void Obj::addMLBuff(double d)
@@ -271,25 +319,54 @@ std::shared_ptr<Obj> Inputs::jsonToObject(const Json& o)
         {
             const Json& p = it.second;
             LorenzDipoleOscillator osc;
-            if(p.get<bool>("tanIso", false) || p.get<bool>("molecular_trans", false))
-                throw std::logic_error("tanIso / molecular_trans poles are outside the covered hot path");
+            if(p.get<bool>("molecular_trans", false)) throw std::logic_error("molecular_trans poles are outside the covered hot path");
+            const bool useTanIso = p.get<bool>("tanIso", false);
             osc.dipOrE_ = string2dipor(p.get<std::string>("dipOrE", "isotropic"));
-            if(osc.dipOrE_ == DIPOR::REL_TO_NORM) throw std::logic_error("surface-normal-relative dipole orientations are outside the covered hot path");
+            if(osc.dipOrE_ == DIPOR::LAT_TAN || osc.dipOrE_ == DIPOR::LONG_TAN)
+                throw std::logic_error("lat_tangent / long_tangent dipole orientations are outside the covered hot path");
+            if(useTanIso && (osc.dipOrE_ == DIPOR::ISOTROPIC || osc.dipOrE_ == DIPOR::UNIDIRECTIONAL))
+                throw std::logic_error("Object can't be isotropic in tangential directions and unidirectional or isotropic");
             osc.gam_ = p.get<double>("gamma") * M_PI;
             osc.omg_ = p.get<double>("omega") * 2 * M_PI;
             osc.sigP_ = p.get<double>("sigma_p", 0.0);
             osc.sigM_ = p.get<double>("sigma_m", 0.0);
             osc.tau_ = p.get<double>("tau", 0.0);
             osc.dipOrM_ = string2dipor(p.get<std::string>("dipOrM", "isotropic"));
+            if(useTanIso && (osc.dipOrM_ == DIPOR::ISOTROPIC || osc.dipOrM_ == DIPOR::UNIDIRECTIONAL))
+                throw std::logic_error("Object can't be isotropic in tangential directions and unidirectional or isotropic");
             if((osc.sigM_ != 0.0 || osc.tau_ != 0.0) && (osc.dipOrE_ != DIPOR::ISOTROPIC || osc.dipOrM_ != DIPOR::ISOTROPIC))
                 throw std::logic_error("oriented magnetic / chiral dipoles are outside the covered hot path");
-            if(osc.dipOrM_ != DIPOR::ISOTROPIC) throw std::logic_error("oriented magnetic dipoles are outside the covered hot path");
+            // (a pole without magnetic / chiral strength carries its dipOrM along unused: only useOrientedDipols_ sees it)
+            // weights of the normal and the tangents (parallelInputs.cpp:1329-1357)
+            {
+                double polAngRelE = p.get<double>("polAngRelNormE", 45.0), azAngRelE = p.get<double>("azAngRelNormE", 45.0);
+                const std::string how = p.get<std::string>("dipOrE", "isotropic");
+                if(how == "normal") polAngRelE = 0.0;
+                else if(how == "tangent") polAngRelE = 90.0;
+                if(useTanIso && ((static_cast<int>(azAngRelE) % 45) != 0 || (static_cast<int>(azAngRelE) % 90) == 0))
+                    throw std::logic_error("isotropic tangent is true, but azimuthal angle of electric dipole is not 45 degrees");
+                osc.normCompWeightE_ = std::cos(polAngRelE * M_PI / 180.0);
+                osc.tangentLatCompWeightE_ = std::sin(polAngRelE * M_PI / 180.0) * std::sin(azAngRelE * M_PI / 180.0);
+                osc.tangentLongCompWeightE_ = std::sin(polAngRelE * M_PI / 180.0) * std::cos(azAngRelE * M_PI / 180.0);
+            }
             if(osc.dipOrE_ == DIPOR::UNIDIRECTIONAL)
             {
                 if(osc.sigP_ > 0.0) { osc.uVecDipE_ = as_ptArr<double>(p, "dirDipE"); normalize3(osc.uVecDipE_); }
                 else osc.uVecDipE_ = {{0.0, 0.0, 0.0}};
             }
             else osc.uVecDipE_ = {{1.0, 1.0, 1.0}};
+            if(useTanIso)
+            {
+                // one pole along each tangent, the normal weight shared (parallelInputs.cpp:1412-1428)
+                LorenzDipoleOscillator oscTanLong(osc), oscTanLat(osc);
+                oscTanLong.tangentLatCompWeightE_ = 0.0;
+                oscTanLat.tangentLongCompWeightE_ = 0.0;
+                oscTanLong.normCompWeightE_ /= std::sqrt(2.0);
+                oscTanLat.normCompWeightE_ /= std::sqrt(2.0);
+                lorPols.push_back(oscTanLat);
+                lorPols.push_back(oscTanLong);
+            }
+            else
             lorPols.push_back(osc);
         }
     }

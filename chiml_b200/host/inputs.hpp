@@ -25,7 +25,7 @@ constexpr double HBAR = 1.054571800139112708622066714857487185100290580423798072
 enum class POLARIZATION { EX, EY, EZ, HX, HY, HZ, L, R };
 enum class PLSSHAPE { GAUSSIAN, BH, RECT, CONTINUOUS, RAMP_CONT, RICKER };
 enum class SHAPE { SPHERE, BLOCK, CYLINDER };
-enum class DIPOR { REL_TO_NORM, ISOTROPIC, UNIDIRECTIONAL };
+enum class DIPOR { REL_TO_NORM, ISOTROPIC, UNIDIRECTIONAL, LAT_TAN, LONG_TAN };
 enum class DTCCLASS { COUT, TXT, BIN, BMP, FREQ };
 // DTCTYPE with the reference's numbering (UTIL/enum.hpp:17)
 enum class DTCTYPE { EX, EY, EZ, HX, HY, HZ, DX, DY, DZ, BX, BY, BZ, EPOW, HPOW, PX, PY, PZ };
@@ -36,6 +36,8 @@ struct LorenzDipoleOscillator
     DIPOR dipOrE_ = DIPOR::ISOTROPIC, dipOrM_ = DIPOR::ISOTROPIC;
     double sigP_ = 0.0, sigM_ = 0.0, tau_ = 0.0, gam_ = 0.0, omg_ = 0.0;
     std::array<double, 3> uVecDipE_ = {{1.0, 1.0, 1.0}};
+    // REL_TO_NORM: weights of the surface normal and of the two tangents (INPUTS/parallelInputs.cpp:1329-1357)
+    double normCompWeightE_ = 0.0, tangentLatCompWeightE_ = 0.0, tangentLongCompWeightE_ = 0.0;
 };
 
 // geometry + material of one object (OBJECTS/Obj.hpp / Obj.cpp); only the shapes the configs use
@@ -57,6 +59,10 @@ public:
     bool constsSet_ = false;
     std::vector<DIPOR> dipOr_;
     std::vector<std::array<double, 3>> dipE_;
+    std::vector<double> dipNormCompE_, dipTanLatCompE_, dipTanLongCompE_;   // per electric pole (REL_TO_NORM orientations)
+    bool identityAxes() const;                                       // the object's axes are the Cartesian ones (coordTransform_ = 1)
+    // Obj::findGradient (OBJECTS/Obj.cpp:585-666): the outward surface normal at pt, for objects whose axes are the Cartesian ones
+    std::array<double, 3> findGradient(const std::array<double, 3>& pt) const;
 
     Obj(SHAPE s, double eps, double mu, std::vector<LorenzDipoleOscillator> pols, bool ML, std::vector<double> geo,
         std::array<double, 3> loc, std::array<std::array<double, 3>, 3> uvec);

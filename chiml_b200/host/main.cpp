@@ -115,6 +115,7 @@ int main(int argc, char** argv)
                     check(c, chiml_gpu_set_object_chiral(c, (int)o, (int)ob.chiGamma.size(), ob.chiAlpha.data(), ob.chiXi.data(), ob.chiGamma.data(), ob.chiGammaPrev.data()), "set_object_chiral");
                 }
             }
+            for(const SlabPlan::DipGrid& dg : P.dip_grids) check(c, chiml_gpu_set_dip_grid(c, dg.comp, dg.pole, dg.grid.data()), "set_dip_grid");
             if(anyChi) check(c, chiml_gpu_set_prev_copy(c, reinterpret_cast<const int32_t*>(P.prev_copy.data()), P.prev_copy.size()), "set_prev_copy");
         };
         handOver(ctx);

@@ -856,6 +856,64 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
         build_lists(IP, g, ras, SPEC_NODE_P, true, dOff, fEnd, g.d[0], g.d[0], P.dielectricMatInPML, P.magMatInPML, true, nthreads, ls);
         P.lists[CHIML_LIST_ORDIPP][0] = std::move(ls.OrDipD);
     }
+    // ---- dipole grids of orientations relative to the surface normal (setupDipMoments, parallelFDTDField.hpp:960-1048; getTangentDip :1058-1093):
+    // evaluated at the cells of the node list -- the only ones the update reads -- for every component and every pole index of the grid
+    {
+        bool relToNorm = false;
+        for(const auto& obj : IP.objArr_)
+            if(obj->useOrientedDipols_)
+                for(DIPOR o : obj->dipOr_) relToNorm = relToNorm || (o != DIPOR::ISOTROPIC && o != DIPOR::UNIDIRECTIONAL);
+        if(relToNorm && disp && nOrDip > 0)
+        {
+            if(g.twoD) throw std::logic_error("oriented-dipole poles on a 2-D grid are outside the covered hot path");
+            const size_t ncell = (size_t)g.ln[0] * g.ln[1] * g.ln[2];
+            for(int c = 0; c < 3; ++c)
+                for(int p = 0; p < nOrDip; ++p) P.dip_grids.push_back({c, p, std::vector<double>(ncell, 0.0)});
+            auto tangentDip = [](const std::array<double, 3>& normVec, double latFact, double longFact) {
+                double magSq = 0.0;
+                for(double x : normVec) magSq = magSq + x * x;
+                const double mag = std::sqrt(magSq);
+                std::array<double, 3> sph = {{mag, std::acos(normVec[2] / mag), std::atan(normVec[1] / normVec[0])}};
+                if(normVec[0] == 0.0) sph[2] = normVec[1] >= 0.0 ? M_PI / 2.0 : -1.0 * M_PI / 2.0;
+                if(normVec[0] < 0) sph[2] += M_PI;
+                if(mag < 1e-20) sph = {{0.0, 0.0, 0.0}};
+                const std::array<double, 3> tLongSph = {{mag, sph[1] + M_PI / 2.0, sph[2]}};
+                const std::array<double, 3> tLong = {{mag * std::sin(tLongSph[1]) * std::cos(tLongSph[2]), mag * std::sin(tLongSph[1]) * std::sin(tLongSph[2]), mag * std::cos(tLongSph[1])}};
+                std::array<double, 3> tLat, out;
+                for(int ii = 0; ii < 3; ++ii) tLat[ii] = normVec[(ii + 1) % 3] * tLong[(ii + 2) % 3] - normVec[(ii + 2) % 3] * tLong[(ii + 1) % 3];
+                for(int ii = 0; ii < 3; ++ii) out[ii] = longFact * tLong[ii] + latFact * tLat[ii];
+                return out;
+            };
+            for(const ChimlRun& r : P.lists[CHIML_LIST_ORDIPP][0])
+            {
+                const Obj& o = *IP.objArr_[r.obj];
+                const int x0 = r.ind % g.ln[0], row = r.ind / g.ln[0], kk = row % g.ln[2], jj = row / g.ln[2];
+                for(int p = 0; p < (int)o.gamma_.size() && p < nOrDip; ++p)
+                {
+                    const DIPOR how = o.dipOr_[p];
+                    if(how == DIPOR::REL_TO_NORM && !o.identityAxes())
+                        throw std::logic_error("surface-normal-relative dipoles of a rotated object are outside the covered hot path");
+                    for(int i = 0; i < r.n; ++i)
+                    {
+                        const int ii = x0 + i;
+                        std::array<double, 3> val = {{0.0, 0.0, 0.0}};
+                        if(how == DIPOR::ISOTROPIC) val = {{1.0, 1.0, 1.0}};
+                        else if(how == DIPOR::UNIDIRECTIONAL) val = o.dipE_[p];
+                        else if(how == DIPOR::REL_TO_NORM)
+                        {
+                            const std::array<double, 3> pt = {{((ii - 1) + 0.0 + g.procLoc(0) - (g.n[0] - g.n[0] % 2) / 2.0) * g.d[0],
+                                                               ((jj - 1) + 0.0 + g.procLoc(1) - (g.n[1] - g.n[1] % 2) / 2.0) * g.d[1],
+                                                               ((kk - 1) + 0.0 + g.procLoc(2) - (g.n[2] - g.n[2] % 2) / 2.0) * g.d[2]}};
+                            const std::array<double, 3> grad = o.findGradient(pt);
+                            const std::array<double, 3> tan = tangentDip(grad, o.dipTanLatCompE_[p], o.dipTanLongCompE_[p]);
+                            for(int c = 0; c < 3; ++c) val[c] = o.dipNormCompE_[p] * grad[c] + tan[c];
+                        }
+                        for(int c = 0; c < 3; ++c) P.dip_grids[(size_t)c * nOrDip + p].grid[(size_t)r.ind + i] = val[c];
+                    }
+                }
+            }
+        }
+    }
     // ---- objects ----
     for(const auto& obj : IP.objArr_)
     {
@@ -871,7 +929,8 @@ SlabPlan build_plan(Inputs& IP, int rank, int nranks, int nthreads, bool referen
         o.dip.assign(3 * (size_t)o.npoles, 0.0);
         if(o.use_or_dip)
             for(int p = 0; p < o.npoles; ++p)
-                for(int k = 0; k < 3; ++k) o.dip[3 * p + k] = obj->dipOr_[p] == DIPOR::ISOTROPIC ? 1.0 : obj->dipE_[p][k];   // setupDipMoments :998-1007
+                for(int k = 0; k < 3; ++k)      // setupDipMoments :998-1007; position-dependent orientations live in the dipole grids (record DIPGRID)
+                    o.dip[3 * p + k] = obj->dipOr_[p] == DIPOR::ISOTROPIC ? 1.0 : (obj->dipOr_[p] == DIPOR::UNIDIRECTIONAL ? obj->dipE_[p][k] : 0.0);
         P.objects.push_back(o);
     }
     // ---- CPML (parallelFDTDField.cpp:60-77,229-246) ----
@@ -1049,6 +1108,11 @@ void SlabPlan::write(const std::string& path) const
             std::string q; const uint64_t nr = prev_copy.size(); app(q, nr); app_vec(q, prev_copy);
             put_rec(out, "PREVCOPY", q);
         }
+    }
+    for(const DipGrid& dg : dip_grids)
+    {
+        std::string q; const int32_t hd[2] = {dg.comp, dg.pole}; app(q, hd); app_vec(q, dg.grid);
+        put_rec(out, "DIPGRID", q);
     }
     { std::string p; ChimlPlanListHdr h; h.kind = CHIML_LIST_ORDIPP; h.comp = 0; h.n = lists[CHIML_LIST_ORDIPP][0].size(); app(p, h); app_vec(p, lists[CHIML_LIST_ORDIPP][0]); put_rec(out, "UPLIST", p); }
     for(size_t oo = 0; oo < objects.size(); ++oo)

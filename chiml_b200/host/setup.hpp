@@ -76,6 +76,8 @@ struct SlabPlan
     bool has_B = false;                        // B grids exist (magnetic or chiral media)
     int n_mag_poles = 0;
     std::vector<std::array<int32_t, 4>> prev_copy;   // copy2PrevFields_ rows {length, x, y, z} (chiral media)
+    struct DipGrid { int comp, pole; std::vector<double> grid; };
+    std::vector<DipGrid> dip_grids;                  // dipP_[comp][pole] at the oriented-dipole node cells (REL_TO_NORM orientations), 0 elsewhere
 
     void write(const std::string& path) const;
 };

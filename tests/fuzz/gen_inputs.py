@@ -245,3 +245,42 @@ def rnd_pbc_case(seed, steps=14):
     if mode!="3d": dloc[2]=0.0
     dets=[I.detector(dloc, [0.0,0.0,0.0], dpol, f"out/fp{seed}/d", time_int=DT*1.0000001)]
     return I.config(I.comp_cell(size, RES, steps*DT-0.5*DT, pol, pbc=True), pml, srcs, objs, dets, [])
+
+
+def rnd_dipnorm_case(seed, steps=10):
+    """Oriented dipoles relative to the surface normal (REL_TO_NORM) at random places: spheres and (unrotated) blocks with "normal", "tangent" and
+    polar / azimuthal-angle poles, optionally tangent-isotropic pairs, beside unidirectional and isotropic-oriented poles."""
+    r=random.Random(11000+seed)
+    n=[r.randint(17,25) for _ in range(3)]
+    size=[k/RES for k in n]
+    pmlc=[r.randint(3,5) for _ in range(3)]
+    pml=I.pml([c/RES for c in pmlc])
+    objs=[]
+    for k in range(r.randint(1,3)):
+        loc=[r.uniform(-0.25,0.25)*size[j] for j in range(3)]
+        pols=[]
+        for _ in range(r.randint(1,2)):
+            how=r.choice(["normal","tangent","rel_norm","unidirectional","taniso"]) if k==0 or r.random()<0.7 else "plain"
+            sp, g, w = r.uniform(0.3,1.5), r.uniform(0.02,0.2), r.uniform(1,3)
+            if how=="plain": pols.append(I.lorentz_pole(sp,g,w)); break
+            if how=="unidirectional":
+                v=[r.uniform(-1,1) for _ in range(3)]; nn=sum(x*x for x in v)**0.5 or 1.0
+                pols.append(I.lorentz_pole(sp,g,w,dip_or_e="unidirectional",dir_dip_e=[x/nn for x in v]))
+            elif how=="rel_norm":
+                pols.append(I.lorentz_pole(sp,g,w,dip_or_e="rel_norm",pol_ang_e=r.choice([20.0,30.0,60.0,75.0]),az_ang_e=r.choice([10.0,45.0,60.0,80.0])))
+            elif how=="taniso":
+                pols.append(I.lorentz_pole(sp,g,w,dip_or_e="tangent",tan_iso=True,dip_or_m="tangent"))
+            else:
+                pols.append(I.lorentz_pole(sp,g,w,dip_or_e=how))
+        eps=r.choice([1.0,2.0,2.25])
+        if r.random()<0.5:
+            sz=[r.uniform(0.15,0.5)*size[j] for j in range(3)]
+            if r.random()<0.3: sz[r.randrange(3)]=3.0
+            objs.append(I.block(sz, loc, eps=eps, pols=pols))
+        else:
+            objs.append(I.sphere(r.uniform(0.1,0.25)*min(size), loc, eps=eps, pols=pols))
+    srcpol=r.choice(["Ex","Ey","Ez"])
+    sloc=[r.uniform(-0.2,0.2)*size[k] for k in range(3)]
+    srcs=[I.normal_source(srcpol, sloc, [0.0,0.0,0.0], [I.gaussian_pulse(1.5,1.0,t_0=0.25,cutoff=2.5)])]
+    dets=[I.detector([r.uniform(-0.2,0.2)*size[k] for k in range(3)], [0.0,0.0,0.0], r.choice(["Ex","Ey","Ez"]), f"out/fd{seed}/d", time_int=DT*1.0000001)]
+    return I.config(I.comp_cell(size, RES, steps*DT-0.5*DT, "Ex"), pml, srcs, objs, dets, [])

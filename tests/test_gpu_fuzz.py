@@ -77,3 +77,11 @@ def test_gpu_matches_oracle_on_random_periodic_inputs(seed, forced, tmp_path, or
     """tests/fuzz/gen_inputs.rnd_pbc_case on one slab: k_wrap between the half steps (and inside the one-launch 2-D kernel), from a random state."""
     import gen_inputs
     run_case(gen_inputs.rnd_pbc_case(seed), tmp_path, 12, FORCED[seed % 4] if forced else None)
+
+
+@pytest.mark.parametrize("forced", [False, True], ids=["auto", "march"])
+@pytest.mark.parametrize("seed", [0, 1, 2, 4, 5, 6, 9, 10, 11, 14])
+def test_gpu_matches_oracle_on_random_surface_normal_dipoles(seed, forced, tmp_path, oracle_lib):
+    """tests/fuzz/gen_inputs.rnd_dipnorm_case through the host setup's own dipole grids: k_ordip_poles<true> reads the dipole vector of every node."""
+    import gen_inputs
+    run_case(gen_inputs.rnd_dipnorm_case(seed, steps=12), tmp_path, 12, FORCED[seed % 4] if forced else None)

@@ -28,6 +28,8 @@ FILES = {"te_vacuum": {"out/te/dtc_field_0.dat": "dtc_field_0.dat"},
          "mag3d": {"out/mg/dtc_field_0.dat": "dtc_field_0.dat"}, "mag3d_pml": {"out/mgp/dtc_field_0.dat": "dtc_field_0.dat"},
          "mag_tm": {"out/mtm/dtc_field_0.dat": "dtc_field_0.dat"},
          "chi3d": {"out/ch/dtc_field_0.dat": "dtc_field_0.dat"}, "chi3d_pml": {"out/chp/dtc_field_0.dat": "dtc_field_0.dat"},
+         # dipoles oriented relative to the surface normal: the host's own findGradient / dipole grids
+         "dipnorm3d": {"out/dn/dtc_field_0.dat": "dtc_field_0.dat"}, "dipnorm3d_pml": {"out/dnp/dtc_field_0.dat": "dtc_field_0.dat"},
          "vac3d_bin": {"out/vb/dtc_field_0.dat": "dtc_field_0.dat", "out/vb/dtc_field_1.dat": "dtc_field_1.dat"}}
 
 

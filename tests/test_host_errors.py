@@ -55,7 +55,8 @@ def test_detector_outside_cell(tmp_path):
     (lambda c: c.__setitem__("TFSF", [{"dummy": 1}]), "TFSF sources are outside the covered hot path"),
     (lambda c: c["CompCell"].__setitem__("cplxFields", True), "complex fields without periodic boundaries"),
     (lambda c: c["ObjectList"].append(I.block([0.1, 0.1, 0.0], [0, 0, 0], pols=[I.lorentz_pole(0.5, 0.1, 2.0, sigma_m=0.4, dip_or_m="unidirectional")])), "oriented magnetic"),
-    (lambda c: c["ObjectList"].append(I.block([0.1, 0.1, 0.0], [0, 0, 0], pols=[I.lorentz_pole(0.5, 0.1, 2.0, dip_or_e="normal")])), "surface-normal-relative"),
+    (lambda c: c["ObjectList"].append(I.block([0.1, 0.1, 0.0], [0, 0, 0], pols=[I.lorentz_pole(0.5, 0.1, 2.0, dip_or_e="normal")])), "2-D grid"),
+    (lambda c: c["ObjectList"].append(I.block([0.1, 0.1, 0.0], [0, 0, 0], pols=[I.lorentz_pole(0.5, 0.1, 2.0, dip_or_e="lat_tangent")])), "lat_tangent"),
 ])
 def test_out_of_scope_inputs_fail_loudly(mutate, needle, tmp_path):
     cfg = _base()

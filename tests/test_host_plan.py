@@ -23,8 +23,7 @@ def plan_tool():
 
 # TFSF inputs are set up by the reference's own constructor (the drop-in hands its surface records to the engine); the host-side setup
 # of this repository refuses them
-# (and dipoles oriented relative to the surface normal: the dipole grids are the reference's own, chiml_gpu_set_dip_grid)
-HOST_CASES = [c for c in util.CASES if not c.startswith(("tfsf", "dipnorm"))]
+HOST_CASES = [c for c in util.CASES if not c.startswith("tfsf")]
 
 
 def test_host_setup_refuses_tfsf_inputs(plan_tool, tmp_path):

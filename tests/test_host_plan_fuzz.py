@@ -179,3 +179,23 @@ def test_random_periodic_inputs_give_the_reference_plan(seed, tmp_path):
     bad = plan_diff.diff(P.read_plan(str(tmp_path / "host.rank0.plan")), ref)
     bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
     assert not bad, "\n".join(bad[:20])
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="needs the reference build oracle/_ref/chiml_ref")
+@pytest.mark.parametrize("seed", [0, 1, 2, 4, 5, 6, 9, 10, 11, 14])
+def test_random_surface_normal_dipoles_give_the_reference_dipole_grids(seed, tmp_path):
+    """tests/fuzz/gen_inputs.rnd_dipnorm_case: findGradient of spheres and blocks, getTangentDip (acos / atan / sin / cos as the reference calls them),
+    tangent-isotropic pole pairs -- the host's dipole grids equal the reference's setupDipMoments at every node of the oriented-dipole list, bit for bit."""
+    import gen_inputs
+    import plan_diff
+    from chiml_b200 import inputs as I, plan as P
+    subprocess.run(["make", "-C", os.path.join(ROOT, "chiml_b200", "host"), os.path.join("..", "chiml_plan")], check=True, stdout=subprocess.DEVNULL)
+    I.write(gen_inputs.rnd_dipnorm_case(seed), str(tmp_path / "c.json"))
+    r = subprocess.run([REF, "c.json", "--steps", "0", "--plan", str(tmp_path / "ref"), "--quiet", "--no-output"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    subprocess.run([TOOL, str(tmp_path / "c.json"), str(tmp_path / "host")], check=True)
+    ref = P.read_plan(str(tmp_path / "ref.rank0.plan"))
+    assert ref.dip_grids
+    bad = plan_diff.diff(P.read_plan(str(tmp_path / "host.rank0.plan")), ref)
+    bad = [b for b in bad if "n_steps" not in b and not (b.startswith("source ") and "amp len" in b)]
+    assert not bad, "\n".join(bad[:20])

@@ -64,3 +64,10 @@ def test_oracle_matches_reference_on_random_periodic_inputs(seed, tmp_path, orac
     """tests/fuzz/gen_inputs.rnd_pbc_case: the wrap copies of applyBC1Proc with objects that span the periodic faces."""
     import gen_inputs
     run_case(gen_inputs.rnd_pbc_case(seed), tmp_path, 5)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 4, 5, 6, 9, 10, 11, 14])
+def test_oracle_matches_reference_on_random_surface_normal_dipoles(seed, tmp_path, oracle_lib):
+    """tests/fuzz/gen_inputs.rnd_dipnorm_case: UpdateLorPolOrDip with position-dependent dipole grids."""
+    import gen_inputs
+    run_case(gen_inputs.rnd_dipnorm_case(seed, steps=12), tmp_path, 5)

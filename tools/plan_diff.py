@@ -32,6 +32,23 @@ def diff(a: P.Plan, b: P.Plan, verbose=True):
                     bad.append(f"{nm}[{o}][{i}]: {u} != {v}")
     if (a.prev_copy is None) != (b.prev_copy is None) or (a.prev_copy is not None and np.asarray(a.prev_copy).tobytes() != np.asarray(b.prev_copy).tobytes()):
         bad.append(f"prev_copy: {None if a.prev_copy is None else a.prev_copy.shape} != {None if b.prev_copy is None else b.prev_copy.shape}")
+    if sorted(a.dip_grids) != sorted(b.dip_grids):
+        bad.append(f"dip grids: {sorted(a.dip_grids)} != {sorted(b.dip_grids)}")
+    else:
+        # compared at the cells of the oriented-dipole node list: the only ones the update reads (the reference's grids hold whatever its
+        # constructor found at the other cells, out-of-range pole indices of other objects included)
+        runs = b.get_list(P.LIST_ORDIPP, 0)
+        npol = {o.obj: o.npoles for o in b.objects}
+        for (comp, pole), gb in sorted(b.dip_grids.items()):
+            ga = a.dip_grids[(comp, pole)]
+            for r in runs:
+                if pole >= npol.get(int(r["obj"]), 0):
+                    continue
+                sl = slice(int(r["ind"]), int(r["ind"]) + int(r["n"]))
+                if np.asarray(ga[sl]).tobytes() != np.asarray(gb[sl]).tobytes():
+                    i = next(i for i in range(int(r["n"])) if ga[sl][i] != gb[sl][i])
+                    bad.append(f"dip grid {(comp, pole)}: cell {int(r['ind']) + i}: {ga[sl][i]!r} != {gb[sl][i]!r}")
+                    break
     if a.periodic != b.periodic:
         bad.append(f"periodic: {a.periodic} != {b.periodic}")
     for key in sorted(set(a.lists) | set(b.lists)):
