@@ -246,9 +246,12 @@ class GpuSim:
             for o in plan.objects:
                 a, x, gm, dp = (np.ascontiguousarray(v, dtype=np.float64) for v in (o.alpha, o.xi, o.gamma, o.dip))
                 self._chk(L.chiml_gpu_set_object(self.h, o.obj, o.npoles, _ptr(a), _ptr(x), _ptr(gm), o.use_or_dip, _ptr(dp)))
+            keep = []                                    # the engine reads the grids at commit: they must outlive this loop
             for (comp, pole), g in sorted(plan.dip_grids.items()):
                 g = np.ascontiguousarray(g, dtype=np.float64)
+                keep.append(g)
                 self._chk(L.chiml_gpu_set_dip_grid(self.h, comp, pole, _ptr(g)))
+            self._dip_keep = keep
             for obj, (a, x, gm) in sorted(plan.mag_objects.items()):
                 a, x, gm = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, x, gm))
                 self._chk(L.chiml_gpu_set_object_magnetic(self.h, obj, len(a), _ptr(a), _ptr(x), _ptr(gm)))

@@ -223,7 +223,7 @@ int chiml_gpu_set_dip_grid(ChimlCtx* ctx, int comp, int pole, const double* grid
     if(comp < 0 || comp > 2 || pole < 0) return fail(ctx, CHIML_ERR_ARG, "set_dip_grid: bad comp/pole");
     if(pole >= MAX_POLES) return fail(ctx, CHIML_ERR_UNSUPPORTED, "set_dip_grid: more than 12 poles per object");
     if(!field_exists(ctx, comp)) return fail(ctx, CHIML_ERR_ARG, "set_dip_grid: the field component does not exist in this mode");
-    ctx->h_dipg[comp][pole].assign(grid, grid + ctx->nlogical);
+    ctx->h_dipg[comp][pole] = grid;
     ctx->has_dipg = true;
     return CHIML_OK;
 }
@@ -1001,8 +1001,8 @@ int chiml_gpu_commit(ChimlCtx* ctx)
             for(int c = 0; c < 3; ++c)
                 for(int p = 0; p < MAX_POLES; ++p)
                 {
-                    std::vector<double>& hg = ctx->h_dipg[c][p];
-                    if(hg.empty()) continue;
+                    const double* hg = ctx->h_dipg[c][p];
+                    if(!hg) continue;
                     if(p < ctx->nordip && field_exists(ctx, c))
                     {
                         const SpanTable& sp = ctx->span_node;
@@ -1010,11 +1010,11 @@ int chiml_gpu_commit(ChimlCtx* ctx)
                         const size_t nrows = (size_t)ctx->ly * ctx->lz;
                         for(size_t row = 0; row < nrows; ++row)
                             if(sp.h_xmin[row] >= 0)
-                                std::copy_n(hg.data() + row * ctx->lx + sp.h_xmin[row], std::min(sp.h_xmax[row], ctx->lx - 1) - sp.h_xmin[row] + 1, &tmp[(size_t)sp.h_base[row]]);
+                                std::copy_n(hg + row * ctx->lx + sp.h_xmin[row], std::min(sp.h_xmax[row], ctx->lx - 1) - sp.h_xmin[row] + 1, &tmp[(size_t)sp.h_base[row]]);
                         if((rc = dev_upload(ctx, &ctx->d_dipg[c][p], tmp))) return rc;
                         // (static data: not part of the algorithmic bytes, like the class tables and CPML coefficients)
                     }
-                    std::vector<double>().swap(hg);
+                    ctx->h_dipg[c][p] = nullptr;
                 }
         }
         else if(ctx->nordip == 0)

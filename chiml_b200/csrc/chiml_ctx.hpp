@@ -220,7 +220,8 @@ struct ChimlCtx
     int nordip = 0;              // pole grids of the whole grid: max(this slab's node list, chiml_gpu_set_ordip_pole_count)
     int nordip_global = 0;
     double* d_oP[3][chiml::MAX_POLES][2] = {};
-    std::vector<double> h_dipg[3][chiml::MAX_POLES];   // chiml_gpu_set_dip_grid: dipP_[c][p] on the logical grid, until commit
+    const double* h_dipg[3][chiml::MAX_POLES] = {};    // chiml_gpu_set_dip_grid: the caller's dipP_[c][p] on the logical grid, read at commit (not copied:
+                                                       // six such grids of a C5-sized run are 25 GB)
     double* d_dipg[3][chiml::MAX_POLES] = {};          // ... gathered over the node spans (same index as d_oP), or nullptr
     bool has_dipg = false;
     long node_off[3] = {};       // logical offsets ind_i-ind, ind_j-ind, ind_k-ind of the node list

@@ -259,7 +259,8 @@ int chiml_gpu_set_ordip_pole_count(ChimlCtx* ctx, int n_poles_global);
  * grid dipP_[comp][pole] that UpdateLorPolOrDip* (UTIL/FDTD_up_eq.cpp:450-631) multiplies with, node by node.  grid = that array, the whole local
  * ghost-inclusive grid (x fastest, then z, then y -- &dipP_[comp][pole]->point(0)); the engine keeps the values at the cells of CHIML_LIST_ORDIPP
  * only.  Where a grid is given it replaces the per-object direction of chiml_gpu_set_object for this (comp, pole) on every node; give it for every
- * component and pole the reference holds as soon as one pole of one object is oriented this way.  Before commit. */
+ * component and pole the reference holds as soon as one pole of one object is oriented this way.  Before commit; the grid is read AT commit and
+ * not copied (the reference's grids live as long as its propagator; six of them on a C5-sized slab are 25 GB): keep it valid until then. */
 int chiml_gpu_set_dip_grid(ChimlCtx* ctx, int comp, int pole, const double* grid);
 
 /* Column length of the y-marching kernels: how many stacked y planes of equal content one thread block walks, carrying the y-coupled
